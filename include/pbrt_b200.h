@@ -1,0 +1,271 @@
+/*
+ * pbrt_b200.h -- C ABI of the B200 render hot path (libpbrt_b200.so).
+ *
+ * This is the drop-in boundary for pbrt-v1's per-pixel render loop.  The one
+ * reference seam it replaces is `void Scene::Render()` (core/scene.h:34,
+ * core/scene.cpp:32-88), entered from pbrtWorldEnd (core/api.cpp:473-476):
+ * the host flattens the Scene it built through the unchanged api.h surface
+ * into the plain arrays below and calls pbrt_b200_render*().  Everything the
+ * reference does per image sample below that seam -- Sampler::GetNextSample,
+ * Camera::GenerateRay, Scene::Intersect/IntersectP (KdTreeAccel), the
+ * SurfaceIntegrator::Li recursion, Film::AddSample and the resolve half of
+ * ImageFilm::WriteImage -- runs on the GPU behind this interface.
+ *
+ * Plain C: pointers + sizes only, no C++/torch types.  All arrays are
+ * borrowed for the duration of the call that receives them.
+ *
+ * Random numbers: the library implements the per-sample keyed counter RNG of
+ * SURVEY.md App. H (oracle/keyed_rng.h is the normative statement) -- there
+ * is no seed argument because the keys are (pixel x, pixel y, sample, stream).
+ */
+#ifndef PBRT_B200_H
+#define PBRT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBRT_B200_ABI_VERSION 1
+
+/* ---- error codes (Scene::Render has none: core/scene.cpp:32; the host maps
+ *      non-zero codes to Severe(), core/util.cpp:90-97) ---- */
+enum {
+  PBRT_B200_OK = 0,
+  PBRT_B200_ERR_INVALID = 1,      /* malformed scene / arguments            */
+  PBRT_B200_ERR_UNSUPPORTED = 2,  /* feature outside the hot-path scope      */
+  PBRT_B200_ERR_CUDA = 3,         /* CUDA runtime failure                    */
+  PBRT_B200_ERR_NO_DEVICE = 4     /* no sm_100 device visible                */
+};
+
+/* ---- kd-tree: accelerators/kdtree.cpp:36-88 (KdAccelNode) ----
+ * 8 bytes.  Interior: `split` float whose 2 low mantissa bits were replaced
+ * by the axis (0..2) exactly as the reference's flags/split union does
+ * (kdtree.cpp:66-72), `above` = index of the above child (below child is
+ * node+1).  Leaf: low 2 bits == 3, nPrims = word0 >> 2; word1 = the single
+ * primitive id when nPrims == 1, else offset of the list in prim_refs[]. */
+typedef struct PbrtB200KdNode {
+  uint32_t word0;
+  uint32_t word1;
+} PbrtB200KdNode;
+
+/* ---- refined primitive: core/primitive.h:72-76 (GeometricPrimitive) with the
+ *      shape data it points at pre-gathered (shapes/trianglemesh.cpp:213-222
+ *      reads mesh->p[v[0..2]]) ---- */
+enum { PBRT_B200_PRIM_TRIANGLE = 0, PBRT_B200_PRIM_SPHERE = 1 };
+enum {
+  PBRT_B200_PF_KIND_MASK = 0x3,
+  PBRT_B200_PF_REVERSE   = 1u << 2,  /* Shape::reverseOrientation            */
+  PBRT_B200_PF_SWAPS     = 1u << 3,  /* Shape::transformSwapsHandedness      */
+  PBRT_B200_PF_HAS_UV    = 1u << 4,
+  PBRT_B200_PF_HAS_N     = 1u << 5,
+  PBRT_B200_PF_HAS_S     = 1u << 6
+};
+typedef struct PbrtB200Prim {     /* 48 bytes, 16-byte aligned records */
+  float    p[9];                   /* triangle: world-space p1,p2,p3; sphere: unused */
+  uint32_t flags;                  /* PBRT_B200_PF_* ; kind in the low 2 bits */
+  uint32_t material;               /* index into materials[]                  */
+  int32_t  light;                  /* area light index or -1                  */
+} PbrtB200Prim;
+
+/* per-primitive side record, read only by shading (never by traversal) */
+typedef struct PbrtB200PrimAux {
+  uint32_t v[3];                   /* triangle: global vertex ids into N/S/UV */
+  uint32_t owner;                  /* triangle: mesh id; sphere: sphere id    */
+} PbrtB200PrimAux;
+
+/* shapes/trianglemesh.cpp:141-169: object<->world of the mesh (only needed to
+ * move per-vertex N/S into world space, trianglemesh.cpp:98-103) */
+typedef struct PbrtB200Mesh {
+  float o2w[16];                   /* ObjectToWorld m, row major              */
+  float w2o[16];                   /* its inverse                             */
+} PbrtB200Mesh;
+
+/* shapes/sphere.cpp:80-97 */
+typedef struct PbrtB200Sphere {
+  float o2w[16];
+  float w2o[16];
+  float radius, zmin, zmax, theta_min, theta_max, phi_max;
+  uint32_t flags;                  /* PBRT_B200_PF_REVERSE | _SWAPS           */
+  uint32_t pad;
+} PbrtB200Sphere;
+
+/* materials/{matte,glass,mirror}.cpp with ConstantTexture operands
+ * (core/texture.h:113-123) */
+enum { PBRT_B200_MAT_MATTE = 0, PBRT_B200_MAT_GLASS = 1, PBRT_B200_MAT_MIRROR = 2 };
+typedef struct PbrtB200Material {
+  int32_t kind;
+  float   kd[3];                   /* matte Kd (already Clamp()ed >= 0); glass/mirror Kr */
+  float   kt[3];                   /* glass Kt                                */
+  float   sigma;                   /* matte: clamped to [0,90] degrees        */
+  float   index;                   /* glass: index of refraction              */
+  float   pad[3];
+} PbrtB200Material;
+
+/* lights/point.cpp:49-54, lights/area.cpp:28-57, core/shape.h:113-147 */
+enum { PBRT_B200_LIGHT_POINT = 0, PBRT_B200_LIGHT_AREA = 1 };
+typedef struct PbrtB200Light {
+  int32_t  kind;
+  int32_t  n_samples;              /* Light::nSamples = max(1, ns)            */
+  float    color[3];               /* point: I ; area: Lemit                  */
+  float    pos[3];                 /* point: LightToWorld(0,0,0)              */
+  uint32_t first_shape;            /* area: range in light_shapes[]/light_cdf[] */
+  uint32_t n_shapes;               /* 1 => the shape itself, >1 => ShapeSet   */
+  float    area;                   /* shape->Area()                           */
+  uint32_t pad;
+} PbrtB200Light;
+
+/* cameras/perspective.cpp:51-82, core/camera.cpp:50-70 */
+typedef struct PbrtB200Camera {
+  float raster_to_camera[16];
+  float camera_to_world[16];
+  float hither, yon;
+  float shutter_open, shutter_close;
+  float lens_radius, focal_distance;
+} PbrtB200Camera;
+
+/* samplers/stratified.cpp:51-86 */
+typedef struct PbrtB200Sampler {
+  int32_t x_samples, y_samples;
+  int32_t jitter;
+} PbrtB200Sampler;
+
+/* integrators/{whitted,directlighting,path}.cpp; volume integrator emission
+ * contributes 2 one-dimensional sample slots (integrators/emission.cpp:42-46) */
+enum { PBRT_B200_INT_WHITTED = 0, PBRT_B200_INT_DIRECT = 1, PBRT_B200_INT_PATH = 2 };
+enum { PBRT_B200_STRATEGY_ALL = 0, PBRT_B200_STRATEGY_ONE = 1 };
+typedef struct PbrtB200Integrator {
+  int32_t kind;
+  int32_t max_depth;
+  int32_t strategy;                /* directlighting only                     */
+  int32_t n_volume_1d;             /* 2 for "emission"                        */
+} PbrtB200Integrator;
+
+/* film/image.cpp:69-102 + the filter it owns (core/sampling.h:118-130) */
+typedef struct PbrtB200Film {
+  int32_t x_resolution, y_resolution;
+  int32_t x_pixel_start, y_pixel_start, x_pixel_count, y_pixel_count; /* crop */
+  float   filter_x_width, filter_y_width, filter_inv_x_width, filter_inv_y_width;
+  float   filter_table[256];       /* 16x16, image.cpp:89-101                 */
+  int32_t premultiply_alpha;
+} PbrtB200Film;
+
+typedef struct PbrtB200Scene {
+  uint32_t abi_version;            /* PBRT_B200_ABI_VERSION                   */
+  /* accelerator */
+  const PbrtB200KdNode *nodes;      uint32_t n_nodes;
+  const uint32_t       *prim_refs;  uint32_t n_prim_refs;
+  float                 bounds[6];  /* KdTreeAccel::bounds pMin, pMax         */
+  /* refined primitives, in the order KdTreeAccel sees them (kdtree.cpp:147-149) */
+  const PbrtB200Prim    *prims;     uint32_t n_prims;
+  const PbrtB200PrimAux *prim_aux;  /* n_prims                                */
+  const PbrtB200Mesh    *meshes;    uint32_t n_meshes;
+  const PbrtB200Sphere  *spheres;   uint32_t n_spheres;
+  /* optional per-vertex shading data, object space, 3/3/2 floats per vertex  */
+  const float *vertex_n; const float *vertex_s; const float *vertex_uv;
+  uint32_t n_vertices;
+  /* shading */
+  const PbrtB200Material *materials; uint32_t n_materials;
+  const PbrtB200Light    *lights;    uint32_t n_lights;
+  const uint32_t *light_shapes;      /* primitive ids, ShapeSet order         */
+  const float    *light_cdf;         /* ShapeSet::areaCDF, same indexing      */
+  uint32_t n_light_shapes;
+  PbrtB200Camera     camera;
+  PbrtB200Sampler    sampler;
+  PbrtB200Integrator integrator;
+  PbrtB200Film       film;
+} PbrtB200Scene;
+
+/* A pixel window [x0,x0+w) x [y0,y0+h) of the film -- the reference's
+ * cropwindow contract (film/image.cpp:79-85,148-156): the window's samples
+ * include the filter apron, so every returned pixel is complete. */
+typedef struct PbrtB200Window {
+  int32_t x0, y0, width, height;
+} PbrtB200Window;
+
+/* Counters: the reference's post-render statistics (core/scene.cpp:80,
+ * core/light.cpp:32, core/primitive.cpp:137, shapes/trianglemesh.cpp:217-247)
+ * plus the kd-walk counters the roofline uses. */
+typedef struct PbrtB200Stats {
+  uint64_t camera_rays;            /* image samples traced                    */
+  uint64_t intersect_rays;         /* Scene::Intersect calls (closest hit)    */
+  uint64_t shadow_rays;            /* Scene::IntersectP calls (any hit)       */
+  uint64_t points_shaded;          /* Intersection::GetBSDF calls             */
+  uint64_t interior_visits, leaf_visits, prim_refs_read, prim_tests;
+  uint64_t nan_samples, negative_samples, infinite_samples; /* scene.cpp:60-74 */
+  double   render_ms;              /* device time of the sample loop          */
+  double   upload_ms, download_ms; /* host<->device copies (e2e calls)        */
+  uint64_t kernel_launches;
+  uint64_t h2d_bytes, d2h_bytes;
+} PbrtB200Stats;
+
+typedef struct PbrtB200Handle PbrtB200Handle;   /* device-resident scene */
+
+/* Library / device queries. */
+int         pbrt_b200_abi_version(void);
+int         pbrt_b200_device_count(void);
+const char *pbrt_b200_last_error(void);
+
+/* Upload a flattened scene to `device` (cudaSetDevice ordinal). */
+int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device,
+                           PbrtB200Handle **out);
+void pbrt_b200_scene_destroy(PbrtB200Handle *h);
+
+/* Render `n_windows` pixel windows of an uploaded scene.  Results stay on the
+ * device; fetch them with pbrt_b200_film_download().  `stats` may be NULL.
+ * Replaces the `while (sampler->GetNextSample(sample))` loop of
+ * core/scene.cpp:43-84 for those windows. */
+int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows,
+                     int n_windows, PbrtB200Stats *stats);
+
+/* Copy the resolved pixels of window `w` of the last render to host memory:
+ * `rgba` receives width*height*4 floats = exactly what ImageFilm::WriteImage
+ * hands to WriteRGBAImage (film/image.cpp:157-209: XYZ round trip, /weightSum,
+ * clamps, premultiply), row major.  `raw` (optional, may be NULL) receives the
+ * unresolved film, 5 floats per pixel: L.r L.g L.b alpha weightSum
+ * (film/image.cpp:57-64). */
+int pbrt_b200_film_download(PbrtB200Handle *h, int w, float *rgba, float *raw);
+
+/* Device pointer (float4 per pixel, row major) of window `w`'s resolved film,
+ * for callers that exchange films GPU-to-GPU (NCCL) without a host bounce. */
+int pbrt_b200_film_device_ptr(PbrtB200Handle *h, int w, void **dptr,
+                              uint64_t *n_floats);
+
+/* One-call form with HOST buffers on both sides: upload scene, render the
+ * windows, download each window's rgba into rgba_out[i] (raw_out may be NULL
+ * or hold NULL entries), free device memory.  This is what the host-side
+ * Scene::Render() calls. */
+int pbrt_b200_render_host(const PbrtB200Scene *scene, int device,
+                          const PbrtB200Window *windows, int n_windows,
+                          float *const *rgba_out, float *const *raw_out,
+                          PbrtB200Stats *stats);
+
+/* Tunables (wave size etc.); returns previous value, value < 0 only queries.
+ * key: 0 = samples per wave. */
+int64_t pbrt_b200_tunable(int key, int64_t value);
+
+/* ---- per-stage entry points used by the parity tests (tests/), each the
+ *      device twin of one reference function ---- */
+
+/* KdTreeAccel::Intersect (kdtree.cpp:313-403) for n rays given as 8 floats
+ * (o.xyz, d.xyz, mint, maxt).  Out per ray: hit_prim (-1 = miss), t, b1, b2
+ * (barycentrics, triangles only). */
+int pbrt_b200_intersect(PbrtB200Handle *h, const float *rays, uint64_t n,
+                        int32_t *hit_prim, float *hit_t, float *hit_b1,
+                        float *hit_b2);
+/* KdTreeAccel::IntersectP (kdtree.cpp:404-488): out 1 = occluded. */
+int pbrt_b200_intersect_p(PbrtB200Handle *h, const float *rays, uint64_t n,
+                          uint8_t *occluded);
+/* Camera rays for the first `n` samples of window w, reference order
+ * (pixel-major, sample-minor): 8 floats per ray + imageX, imageY. */
+int pbrt_b200_camera_rays(PbrtB200Handle *h, const PbrtB200Window *w,
+                          uint64_t n, float *rays, float *image_xy);
+/* Per-sample radiance (after the NaN/neg/inf guards of scene.cpp:60-74) of
+ * window w in reference order: 4 floats (L.rgb, alpha) per sample. */
+int pbrt_b200_sample_radiance(PbrtB200Handle *h, int w, uint64_t n, float *ls);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBRT_B200_H */

@@ -1,0 +1,97 @@
+// ref_glue.cpp -- the pieces linked into the compiled reference (oracle/_ref)
+// in place of what cannot be built here.  Compiled against the REFERENCE's
+// headers by oracle/build_ref.sh; never part of the product.
+//
+//  * WriteRGBAImage / ReadImage: core/exrio.cpp needs OpenEXR (absent).  The
+//    replacement dumps exactly the float arrays ImageFilm::WriteImage hands
+//    over (film/image.cpp:204-207) to "<name>.raw": a 32-byte header
+//    ("PBRTRAW1", xRes, yRes, totalX, totalY, xOff, yOff as int32) followed by
+//    xRes*yRes RGBA float32 quadruples.
+//  * keyed RNG (only when built with -DPBRT_REF_KEYED): genrand_int32 /
+//    genrand_real2 replacements + the reseed hooks that build_ref.sh splices
+//    into copies of samplers/stratified.cpp and core/scene.cpp.
+//  * optional per-sample dump (env PBRT_REF_DUMP_SAMPLES=<file>): imageX,
+//    imageY, L.rgb (after the guards of scene.cpp:60-74), alpha per sample.
+#include "pbrt.h"
+#include "color.h"
+#include "sampling.h"
+#include "keyed_rng.h"
+
+COREDLL void WriteRGBAImage(const string &name, float *pixels, float *alpha, int xRes, int yRes,
+                            int totalXRes, int totalYRes, int xOffset, int yOffset) {
+  string fn = name + ".raw";
+  FILE *f = fopen(fn.c_str(), "wb");
+  if (!f) { Error("Unable to write image file \"%s\"", fn.c_str()); return; }
+  int hdr[6] = {xRes, yRes, totalXRes, totalYRes, xOffset, yOffset};
+  fwrite("PBRTRAW1", 1, 8, f);
+  fwrite(hdr, 4, 6, f);
+  for (int i = 0; i < xRes * yRes; ++i) {
+    float px[4] = {pixels[3 * i], pixels[3 * i + 1], pixels[3 * i + 2], alpha ? alpha[i] : 1.f};
+    fwrite(px, 4, 4, f);
+  }
+  fclose(f);
+}
+COREDLL Spectrum *ReadImage(const string &name, int *, int *) {
+  Error("Unable to read image file \"%s\": no EXR reader in the oracle build", name.c_str());
+  return NULL;
+}
+
+static FILE *gDump = NULL;
+static unsigned long long gSampleCounter = 0;
+static double gRenderSeconds = 0;
+
+#include <sys/time.h>
+static double Now() {
+  struct timeval tv;
+  gettimeofday(&tv, NULL);
+  return tv.tv_sec + 1e-6 * tv.tv_usec;
+}
+static double gRenderStart = 0;
+
+COREDLL void pbrtRefBeginRender() {
+  gSampleCounter = 0;
+  const char *fn = getenv("PBRT_REF_DUMP_SAMPLES");
+  gDump = fn ? fopen(fn, "wb") : NULL;
+  gRenderStart = Now();
+}
+COREDLL void pbrtRefEndRender() {
+  gRenderSeconds = Now() - gRenderStart;
+  if (gDump) fclose(gDump);
+  gDump = NULL;
+  // timing of the sample loop alone (parse, kd build and image write excluded)
+  fprintf(stderr, "PBRT_REF_RENDER_SECONDS %.6f SAMPLES %llu\n", gRenderSeconds, gSampleCounter);
+}
+COREDLL void pbrtRefDumpSample(const Sample *sample, const Spectrum &Ls, float alpha) {
+  if (!gDump) return;
+  float xyz[3];
+  // Spectrum keeps c[] private; recover RGB exactly through operator== is not
+  // possible, so rely on the layout (3 floats first): core/color.h:199.
+  const float *c = (const float *)&Ls;
+  float rec[6] = {sample->imageX, sample->imageY, c[0], c[1], c[2], alpha};
+  (void)xyz;
+  fwrite(rec, 4, 6, gDump);
+}
+
+#ifdef PBRT_REF_KEYED
+static uint64_t gKey = 0, gCtr = 0;
+COREDLL void pbrtReseed(int x, int y, int s, int stream) {
+  gKey = pbrt_keyed_key(x, y, s, stream);
+  gCtr = 0;
+}
+COREDLL unsigned long genrand_int32(void) { return (unsigned long)pbrt_keyed_u32(gKey, ++gCtr); }
+COREDLL float genrand_real2(void) { return (RandomUInt() & 0xffffff) / float(1 << 24); }
+// Called right before Li for every image sample (core/scene.cpp:57).  The
+// (pixel, sample-in-pixel) pair is derived from the running sample count the
+// same way the sampler walks pixels (samplers/stratified.cpp:89-97).
+COREDLL void pbrtRefBeforeLi(const Sampler *sampler) {
+  int spp = sampler->samplesPerPixel;
+  int w = sampler->xPixelEnd - sampler->xPixelStart;
+  unsigned long long pix = gSampleCounter / spp;
+  pbrtReseed(sampler->xPixelStart + (int)(pix % w), sampler->yPixelStart + (int)(pix / w),
+             (int)(gSampleCounter % spp), 1);
+  ++gSampleCounter;
+}
+#else
+COREDLL void pbrtReseed(int, int, int, int) {}
+COREDLL void pbrtRefBeforeLi(const Sampler *) { ++gSampleCounter; }
+#endif

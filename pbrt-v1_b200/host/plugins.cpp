@@ -1,0 +1,371 @@
+// plugins.cpp -- host halves of the in-scope material / light / integrator /
+// camera / sampler plugins and the name -> factory registry that replaces
+// dlopen("<name>.so") (core/dynload.cpp:41-61,272-460).  Parameter names and
+// defaults are those of SURVEY.md App. B (each cited below).
+#include "core.h"
+
+Shape *CreateSphereShape(const Transform &, bool, const ParamSet &);
+Shape *CreateTriangleMeshShape(const Transform &, bool, const ParamSet &);
+Filter *CreateNamedFilter(const string &name, const ParamSet &ps);
+Film *CreateImageFilm(const ParamSet &params, Filter *filter);
+
+namespace {
+
+// ---------------------------------------------------------------- materials
+class Matte : public Material {   // materials/matte.cpp:46-70
+ public:
+  Matte(const Spectrum &kd, float sig) : Kd(kd), sigma(sig) {}
+  void Flatten(PbrtB200Material *out) const {
+    memset(out, 0, sizeof(*out));
+    out->kind = PBRT_B200_MAT_MATTE;
+    Spectrum r = Kd.Clamp();                       // matte.cpp:56
+    for (int i = 0; i < 3; ++i) out->kd[i] = r.c[i];
+    out->sigma = Clamp(sigma, 0.f, 90.f);          // matte.cpp:57
+  }
+  Spectrum Kd; float sigma;
+};
+class Glass : public Material {   // materials/glass.cpp:46-70
+ public:
+  Glass(const Spectrum &r, const Spectrum &t, float ior) : Kr(r), Kt(t), index(ior) {}
+  void Flatten(PbrtB200Material *out) const {
+    memset(out, 0, sizeof(*out));
+    out->kind = PBRT_B200_MAT_GLASS;
+    Spectrum R = Kr.Clamp(), T = Kt.Clamp();
+    for (int i = 0; i < 3; ++i) { out->kd[i] = R.c[i]; out->kt[i] = T.c[i]; }
+    out->index = index;
+  }
+  Spectrum Kr, Kt; float index;
+};
+class Mirror : public Material {  // materials/mirror.cpp:42-60
+ public:
+  Mirror(const Spectrum &r) : Kr(r) {}
+  void Flatten(PbrtB200Material *out) const {
+    memset(out, 0, sizeof(*out));
+    out->kind = PBRT_B200_MAT_MIRROR;
+    Spectrum R = Kr.Clamp();
+    for (int i = 0; i < 3; ++i) out->kd[i] = R.c[i];
+  }
+  Spectrum Kr;
+};
+
+// ------------------------------------------------------------------- lights
+class PointLight : public Light {  // lights/point.cpp:49-54
+ public:
+  PointLight(const Transform &light2world, const Spectrum &intensity)
+      : Light(light2world), Intensity(intensity) {
+    lightPos = LightToWorld(Point(0, 0, 0));
+  }
+  void Flatten(FlatBuilder &, PbrtB200Light *out) const {
+    memset(out, 0, sizeof(*out));
+    out->kind = PBRT_B200_LIGHT_POINT;
+    out->n_samples = nSamples;
+    for (int i = 0; i < 3; ++i) { out->color[i] = Intensity.c[i]; out->pos[i] = lightPos[i]; }
+  }
+  Point lightPos; Spectrum Intensity;
+};
+
+// -------------------------------------------------------------- integrators
+class WhittedIntegrator : public SurfaceIntegrator {  // integrators/whitted.cpp:141-145
+ public:
+  WhittedIntegrator(int md) : maxDepth(md) {}
+  void Flatten(PbrtB200Integrator *out) const {
+    out->kind = PBRT_B200_INT_WHITTED; out->max_depth = maxDepth; out->strategy = 0;
+  }
+  int maxDepth;
+};
+class DirectLighting : public SurfaceIntegrator {     // integrators/directlighting.cpp:195-208
+ public:
+  DirectLighting(int st, int md) : strategy(st), maxDepth(md) {}
+  void Flatten(PbrtB200Integrator *out) const {
+    out->kind = PBRT_B200_INT_DIRECT; out->max_depth = maxDepth; out->strategy = strategy;
+  }
+  int strategy, maxDepth;
+};
+class PathIntegrator : public SurfaceIntegrator {     // integrators/path.cpp:146-149
+ public:
+  PathIntegrator(int md) : maxDepth(md) {}
+  void Flatten(PbrtB200Integrator *out) const {
+    out->kind = PBRT_B200_INT_PATH; out->max_depth = maxDepth; out->strategy = 0;
+  }
+  int maxDepth;
+};
+// integrators/emission.cpp:42-46: no volumes in scope, but its two 1D sample
+// requests shift every sample's random-number stream, so they are exported.
+class EmissionIntegrator : public VolumeIntegrator {
+ public:
+  EmissionIntegrator(float ss) : stepSize(ss) {}
+  int NumSamples1D() const { return 2; }
+  float stepSize;
+};
+
+// ------------------------------------------------------------------- camera
+class PerspectiveCamera : public Camera {
+ public:
+  // core/camera.cpp:50-70 + cameras/perspective.cpp:38-50
+  PerspectiveCamera(const Transform &world2cam, const float Screen[4], float hither, float yon,
+                    float sopen, float sclose, float lensr, float focald, float fov, Film *f)
+      : Camera(world2cam, hither, yon, sopen, sclose, f) {
+    LensRadius = lensr;
+    FocalDistance = focald;
+    Transform CameraToScreen = Perspective(fov, hither, yon);
+    Transform ScreenToRaster =
+        Scale(float(film->xResolution), float(film->yResolution), 1.f) *
+        Scale(1.f / (Screen[1] - Screen[0]), 1.f / (Screen[2] - Screen[3]), 1.f) *
+        Translate(Vector(-Screen[0], -Screen[3], 0.f));
+    Transform RasterToScreen = ScreenToRaster.GetInverse();
+    RasterToCamera = CameraToScreen.GetInverse() * RasterToScreen;
+  }
+  void Flatten(PbrtB200Camera *out) const {
+    memcpy(out->raster_to_camera, RasterToCamera.GetMatrix().m, 16 * sizeof(float));
+    memcpy(out->camera_to_world, CameraToWorld.GetMatrix().m, 16 * sizeof(float));
+    out->hither = ClipHither; out->yon = ClipYon;
+    out->shutter_open = ShutterOpen; out->shutter_close = ShutterClose;
+    out->lens_radius = LensRadius; out->focal_distance = FocalDistance;
+  }
+  Transform RasterToCamera;
+  float LensRadius, FocalDistance;
+};
+
+// ------------------------------------------------------------------ sampler
+class StratifiedSampler : public Sampler {   // samplers/stratified.cpp:51-64
+ public:
+  StratifiedSampler(int xstart, int xend, int ystart, int yend, int xs, int ys, bool jitter)
+      : Sampler(xstart, xend, ystart, yend, xs * ys), xPixelSamples(xs), yPixelSamples(ys),
+        jitterSamples(jitter) {}
+  void Flatten(PbrtB200Sampler *out) const {
+    out->x_samples = xPixelSamples; out->y_samples = yPixelSamples; out->jitter = jitterSamples;
+  }
+  int xPixelSamples, yPixelSamples; bool jitterSamples;
+};
+
+}  // namespace
+
+// core/light.h:88-116 + lights/area.cpp:28-57: a shape that cannot be
+// intersected directly is refined (LIFO) into a ShapeSet.
+AreaLight::AreaLight(const Transform &light2world, const Spectrum &le, int ns,
+                     const Reference<Shape> &s)
+    : Light(light2world, ns) {
+  Lemit = le;
+  if (s->CanIntersect()) {
+    shapes.push_back(s);
+    area = s->Area();
+  } else {
+    vector<Reference<Shape> > todo, done;
+    todo.push_back(s);
+    while (todo.size()) {
+      Reference<Shape> sh = todo.back();
+      todo.pop_back();
+      if (sh->CanIntersect()) done.push_back(sh);
+      else sh->Refine(todo);
+    }
+    if (done.size() == 1) {
+      shapes = done;
+      area = done[0]->Area();
+    } else {
+      if (done.size() > 16)
+        Warning("Area light geometry turned into %d shapes; may be very inefficient.",
+                (int)done.size());
+      // ShapeSet constructor, core/shape.h:122-138
+      shapes = done;
+      area = 0;
+      vector<float> areas;
+      for (u_int i = 0; i < shapes.size(); ++i) {
+        float a = shapes[i]->Area();
+        area += a;
+        areas.push_back(a);
+      }
+      float prevCDF = 0;
+      for (u_int i = 0; i < shapes.size(); ++i) {
+        areaCDF.push_back(prevCDF + areas[i] / area);
+        prevCDF = areaCDF[i];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------- factories
+static Material *CreateMatte(const Transform &, const TextureParams &mp) {
+  Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(1.f));
+  float sigma = mp.GetFloatTexture("sigma", 0.f);
+  mp.GetFloatTexture("bumpmap", 0.f);   // constant 0: Material::Bump degenerates (material.cpp:29-71)
+  return new Matte(Kd, sigma);
+}
+static Material *CreateGlass(const Transform &, const TextureParams &mp) {
+  Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(1.f));
+  Spectrum Kt = mp.GetSpectrumTexture("Kt", Spectrum(1.f));
+  float index = mp.GetFloatTexture("index", 1.5f);
+  mp.GetFloatTexture("bumpmap", 0.f);
+  return new Glass(Kr, Kt, index);
+}
+static Material *CreateMirror(const Transform &, const TextureParams &mp) {
+  Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(1.f));
+  mp.GetFloatTexture("bumpmap", 0.f);
+  return new Mirror(Kr);
+}
+
+static bool gWarnedSearchPath = false;
+void UpdatePluginPath(const string &) {
+  // Plugins are compiled in; SearchPath / PBRT_SEARCHPATH are accepted and ignored.
+  (void)gWarnedSearchPath;
+}
+
+Reference<Shape> MakeShape(const string &name, const Transform &object2world,
+                           bool reverseOrientation, const ParamSet &paramSet) {
+  Shape *s = NULL;
+  if (name == "sphere") s = CreateSphereShape(object2world, reverseOrientation, paramSet);
+  else if (name == "trianglemesh")
+    s = CreateTriangleMeshShape(object2world, reverseOrientation, paramSet);
+  else
+    Error("Shape plugin \"%s\" is outside the B200 hot-path scope (supported: sphere, "
+          "trianglemesh); shape ignored.", name.c_str());
+  return s;
+}
+Reference<Material> MakeMaterial(const string &name, const Transform &mtl2world,
+                                 const TextureParams &mp) {
+  Material *m = NULL;
+  if (name == "matte") m = CreateMatte(mtl2world, mp);
+  else if (name == "glass") m = CreateGlass(mtl2world, mp);
+  else if (name == "mirror") m = CreateMirror(mtl2world, mp);
+  else
+    Error("Material plugin \"%s\" is outside the B200 hot-path scope (supported: matte, glass, "
+          "mirror).", name.c_str());
+  if (m) mp.ReportUnused();   // core/dynload.cpp:299
+  return m;
+}
+Light *MakeLight(const string &name, const Transform &light2world, const ParamSet &paramSet) {
+  if (name == "point") {   // lights/point.cpp:78-84
+    Spectrum I = paramSet.FindOneSpectrum("I", Spectrum(1.0));
+    Point P = paramSet.FindOnePoint("from", Point(0, 0, 0));
+    Transform l2w = Translate(Vector(P.x, P.y, P.z)) * light2world;
+    Light *l = new PointLight(l2w, I);
+    paramSet.ReportUnused();
+    return l;
+  }
+  return NULL;
+}
+AreaLight *MakeAreaLight(const string &name, const Transform &light2world,
+                         const ParamSet &paramSet, const Reference<Shape> &shape) {
+  if (name == "area") {    // lights/area.cpp:106-111
+    Spectrum L = paramSet.FindOneSpectrum("L", Spectrum(1.0));
+    int nSamples = paramSet.FindOneInt("nsamples", 1);
+    AreaLight *a = new AreaLight(light2world, L, nSamples, shape);
+    paramSet.ReportUnused();
+    return a;
+  }
+  Error("Area light plugin \"%s\" unknown.", name.c_str());
+  return NULL;
+}
+VolumeRegion *MakeVolumeRegion(const string &name, const Transform &, const ParamSet &) {
+  Error("Volume plugin \"%s\": participating media are outside the B200 hot-path scope; ignored.",
+        name.c_str());
+  return NULL;
+}
+SurfaceIntegrator *MakeSurfaceIntegrator(const string &name, const ParamSet &params) {
+  SurfaceIntegrator *si = NULL;
+  if (name == "whitted") si = new WhittedIntegrator(params.FindOneInt("maxdepth", 5));
+  else if (name == "path") si = new PathIntegrator(params.FindOneInt("maxdepth", 5));
+  else if (name == "directlighting") {
+    int maxDepth = params.FindOneInt("maxdepth", 5);
+    int strategy;
+    string st = params.FindOneString("strategy", "all");
+    if (st == "one") strategy = PBRT_B200_STRATEGY_ONE;
+    else if (st == "all") strategy = PBRT_B200_STRATEGY_ALL;
+    else if (st == "weighted") {
+      // transport.cpp:71-122 keeps running luminance averages across samples: inherently
+      // serial, outside the scope table.
+      Warning("Strategy \"weighted\" depends on sample order and is not supported on the GPU; "
+              "using \"one\".");
+      strategy = PBRT_B200_STRATEGY_ONE;
+    } else {
+      Warning("Strategy \"%s\" for direct lighting unknown. Using \"all\".", st.c_str());
+      strategy = PBRT_B200_STRATEGY_ALL;
+    }
+    si = new DirectLighting(strategy, maxDepth);
+  } else
+    Error("Surface integrator plugin \"%s\" is outside the B200 hot-path scope (supported: "
+          "whitted, directlighting, path).", name.c_str());
+  if (si) params.ReportUnused();
+  return si;
+}
+VolumeIntegrator *MakeVolumeIntegrator(const string &name, const ParamSet &params) {
+  if (name != "emission")
+    Warning("Volume integrator \"%s\" not supported; using \"emission\" (no volumes in scope).",
+            name.c_str());
+  VolumeIntegrator *vi = new EmissionIntegrator(params.FindOneFloat("stepsize", 1.f));
+  params.ReportUnused();
+  return vi;
+}
+Primitive *MakeAccelerator(const string &name, const vector<Reference<Primitive> > &prims,
+                           const ParamSet &ps) {
+  // "grid" (accelerators/grid.cpp) returns the same closest hits as the
+  // kd-tree, so it aliases the one accelerator the device implements.
+  if (name != "kdtree" && name != "grid") return NULL;
+  int isectCost = ps.FindOneInt("intersectcost", 80);    // kdtree.cpp:489-498
+  int travCost = ps.FindOneInt("traversalcost", 1);
+  float emptyBonus = ps.FindOneFloat("emptybonus", 0.5f);
+  int maxPrims = ps.FindOneInt("maxprims", 1);
+  int maxDepth = ps.FindOneInt("maxdepth", -1);
+  Primitive *p = new KdTreeAccel(prims, isectCost, travCost, emptyBonus, maxPrims, maxDepth);
+  if (name == "kdtree") ps.ReportUnused();
+  return p;
+}
+Camera *MakeCamera(const string &name, const ParamSet &params, const Transform &world2cam,
+                   Film *film) {
+  if (name != "perspective") {
+    Error("Camera plugin \"%s\" is outside the B200 hot-path scope (supported: perspective).",
+          name.c_str());
+    return NULL;
+  }
+  // cameras/perspective.cpp:83-115
+  float hither = max(1e-4f, params.FindOneFloat("hither", 1e-3f));
+  float yon = min(params.FindOneFloat("yon", 1e30f), 1e30f);
+  float shutteropen = params.FindOneFloat("shutteropen", 0.f);
+  float shutterclose = params.FindOneFloat("shutterclose", 1.f);
+  float lensradius = params.FindOneFloat("lensradius", 0.f);
+  float focaldistance = params.FindOneFloat("focaldistance", 1e30f);
+  float frame = params.FindOneFloat("frameaspectratio",
+                                    float(film->xResolution) / float(film->yResolution));
+  float screen[4];
+  if (frame > 1.f) {
+    screen[0] = -frame; screen[1] = frame; screen[2] = -1.f; screen[3] = 1.f;
+  } else {
+    screen[0] = -1.f; screen[1] = 1.f; screen[2] = -1.f / frame; screen[3] = 1.f / frame;
+  }
+  int swi;
+  const float *sw = params.FindFloat("screenwindow", &swi);
+  if (sw && swi == 4) memcpy(screen, sw, 4 * sizeof(float));
+  float fov = params.FindOneFloat("fov", 90.);
+  Camera *c = new PerspectiveCamera(world2cam, screen, hither, yon, shutteropen, shutterclose,
+                                    lensradius, focaldistance, fov, film);
+  params.ReportUnused();
+  return c;
+}
+Sampler *MakeSampler(const string &name, const ParamSet &params, const Film *film) {
+  if (name != "stratified")
+    // bestcandidate/lowdiscrepancy/random are SURVEY.md 8(f) "next"; until then the one
+    // sampler the device implements stands in (different noise, same expectation).
+    Warning("Sampler plugin \"%s\" is not implemented on the GPU yet; using \"stratified\".",
+            name.c_str());
+  bool jitter = params.FindOneBool("jitter", true);      // samplers/stratified.cpp:132-141
+  int xstart, xend, ystart, yend;
+  film->GetSampleExtent(&xstart, &xend, &ystart, &yend);
+  int xsamp = params.FindOneInt("xsamples", 2);
+  int ysamp = params.FindOneInt("ysamples", 2);
+  Sampler *s = new StratifiedSampler(xstart, xend, ystart, yend, xsamp, ysamp, jitter);
+  if (name == "stratified") params.ReportUnused();
+  return s;
+}
+Filter *MakeFilter(const string &name, const ParamSet &paramSet) {
+  Filter *f = CreateNamedFilter(name, paramSet);
+  if (f) paramSet.ReportUnused();
+  return f;
+}
+Film *MakeFilm(const string &name, const ParamSet &paramSet, Filter *filter) {
+  if (name != "image") {
+    Error("Film plugin \"%s\" unknown (supported: image).", name.c_str());
+    return NULL;
+  }
+  Film *f = CreateImageFilm(paramSet, filter);
+  paramSet.ReportUnused();
+  return f;
+}

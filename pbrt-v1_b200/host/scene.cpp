@@ -1,0 +1,277 @@
+// scene.cpp -- Scene construction, export to the C-ABI arrays, and the
+// drop-in Scene::Render() (reference: core/scene.cpp:32-129).
+//
+// Render() does not trace anything on the CPU: it flattens the scene and hands
+// it to libpbrt_b200.so (dlopen'ed like the reference dlopen's its plugins,
+// core/dynload.cpp:462-490).  If that library cannot be loaded the render
+// aborts with Severe() -- there is deliberately no CPU fallback.
+#include "core.h"
+#include <dlfcn.h>
+#include <sys/time.h>
+
+Scene::Scene(Camera *cam, SurfaceIntegrator *si, VolumeIntegrator *vi, Sampler *s,
+             Primitive *accel, const vector<Light *> &lts, VolumeRegion *vr) {
+  lights = lts;
+  aggregate = accel;
+  camera = cam;
+  sampler = s;
+  surfaceIntegrator = si;
+  volumeIntegrator = vi;
+  volumeRegion = vr;
+  if (lts.size() == 0)
+    Warning("No light sources defined in scene; possibly rendering a black image.");
+  bound = aggregate->WorldBound();
+}
+Scene::~Scene() {
+  delete camera;
+  delete sampler;
+  delete surfaceIntegrator;
+  delete volumeIntegrator;
+  delete aggregate;
+  delete volumeRegion;
+  for (u_int i = 0; i < lights.size(); ++i) delete lights[i];
+}
+
+void AreaLight::Flatten(FlatBuilder &fb, PbrtB200Light *out) const {
+  memset(out, 0, sizeof(*out));
+  out->kind = PBRT_B200_LIGHT_AREA;
+  out->n_samples = nSamples;
+  for (int i = 0; i < 3; ++i) out->color[i] = Lemit.c[i];
+  out->first_shape = (uint32_t)fb.lightShapes.size();
+  out->n_shapes = (uint32_t)shapes.size();
+  out->area = area;
+  for (size_t i = 0; i < shapes.size(); ++i) {
+    const void *owner; int index;
+    shapes[i]->Identity(&owner, &index);
+    map<std::pair<const void *, int>, uint32_t>::const_iterator it =
+        fb.shapePrimIds.find(std::make_pair(owner, index));
+    if (it == fb.shapePrimIds.end())
+      Severe("Area light shape has no matching primitive in the accelerator");
+    fb.lightShapes.push_back(it->second);
+    fb.lightCdf.push_back(i < areaCDF.size() ? areaCDF[i] : 1.f);
+  }
+}
+
+void Scene::Flatten(FlatBuilder &fb, PbrtB200Scene *out) const {
+  memset(out, 0, sizeof(*out));
+  out->abi_version = PBRT_B200_ABI_VERSION;
+  KdTreeAccel *accel = dynamic_cast<KdTreeAccel *>(aggregate);
+  if (!accel) Severe("Scene aggregate is not the kd-tree accelerator");
+  for (size_t i = 0; i < lights.size(); ++i)
+    if (lights[i]->IsAreaLight()) fb.lightIds[lights[i]] = (int32_t)i;
+  // primitives in the accelerator's (refined) order
+  fb.prims.resize(accel->prims.size());
+  fb.aux.resize(accel->prims.size());
+  for (size_t i = 0; i < accel->prims.size(); ++i) {
+    const GeometricPrimitive *gp =
+        dynamic_cast<const GeometricPrimitive *>(accel->prims[i].operator->());
+    if (!gp) Severe("Non-geometric primitive reached the accelerator");
+    PbrtB200Prim &pr = fb.prims[i];
+    gp->shape->Flatten(fb, &pr, &fb.aux[i]);
+    const void *owner; int index;
+    gp->shape->Identity(&owner, &index);
+    fb.shapePrimIds[std::make_pair(owner, index)] = (uint32_t)i;
+    const Material *m = gp->material.operator->();
+    map<const void *, uint32_t>::iterator mi = fb.materialIds.find(m);
+    if (mi == fb.materialIds.end()) {
+      PbrtB200Material pm;
+      m->Flatten(&pm);
+      fb.materialIds[m] = pr.material = (uint32_t)fb.materials.size();
+      fb.materials.push_back(pm);
+    } else
+      pr.material = mi->second;
+    pr.light = -1;
+    if (gp->areaLight) {
+      map<const void *, int32_t>::iterator li = fb.lightIds.find(gp->areaLight);
+      if (li != fb.lightIds.end()) pr.light = li->second;
+    }
+  }
+  fb.lights.resize(lights.size());
+  for (size_t i = 0; i < lights.size(); ++i) lights[i]->Flatten(fb, &fb.lights[i]);
+
+  out->nodes = accel->nodes.empty() ? NULL : &accel->nodes[0];
+  out->n_nodes = (uint32_t)accel->nodes.size();
+  out->prim_refs = accel->primRefs.empty() ? NULL : &accel->primRefs[0];
+  out->n_prim_refs = (uint32_t)accel->primRefs.size();
+  for (int i = 0; i < 3; ++i) {
+    out->bounds[i] = accel->bounds.pMin[i];
+    out->bounds[3 + i] = accel->bounds.pMax[i];
+  }
+  out->prims = fb.prims.empty() ? NULL : &fb.prims[0];
+  out->prim_aux = fb.aux.empty() ? NULL : &fb.aux[0];
+  out->n_prims = (uint32_t)fb.prims.size();
+  out->meshes = fb.meshes.empty() ? NULL : &fb.meshes[0];
+  out->n_meshes = (uint32_t)fb.meshes.size();
+  out->spheres = fb.spheres.empty() ? NULL : &fb.spheres[0];
+  out->n_spheres = (uint32_t)fb.spheres.size();
+  out->vertex_n = fb.anyN ? &fb.vertexN[0] : NULL;
+  out->vertex_s = fb.anyS ? &fb.vertexS[0] : NULL;
+  out->vertex_uv = fb.anyUV ? &fb.vertexUV[0] : NULL;
+  out->n_vertices = fb.nVertices;
+  out->materials = fb.materials.empty() ? NULL : &fb.materials[0];
+  out->n_materials = (uint32_t)fb.materials.size();
+  out->lights = fb.lights.empty() ? NULL : &fb.lights[0];
+  out->n_lights = (uint32_t)fb.lights.size();
+  out->light_shapes = fb.lightShapes.empty() ? NULL : &fb.lightShapes[0];
+  out->light_cdf = fb.lightCdf.empty() ? NULL : &fb.lightCdf[0];
+  out->n_light_shapes = (uint32_t)fb.lightShapes.size();
+  camera->Flatten(&out->camera);
+  sampler->Flatten(&out->sampler);
+  surfaceIntegrator->Flatten(&out->integrator);
+  out->integrator.n_volume_1d = volumeIntegrator->NumSamples1D();
+  camera->film->Flatten(&out->film);
+}
+
+// ------------------------------------------------------------ backend
+namespace {
+
+typedef int (*RenderHostFn)(const PbrtB200Scene *, int, const PbrtB200Window *, int,
+                            float *const *, float *const *, PbrtB200Stats *);
+typedef const char *(*LastErrorFn)(void);
+
+int CudaBackend(const PbrtB200Scene *scene, const PbrtB200Window *windows, int nWindows,
+                float *const *rgbaOut, PbrtB200Stats *stats) {
+  static void *lib = NULL;
+  static RenderHostFn renderHost = NULL;
+  static LastErrorFn lastError = NULL;
+  if (!lib) {
+    vector<string> candidates;
+    if (const char *env = getenv("PBRT_B200_LIB")) candidates.push_back(env);
+    Dl_info info;
+    if (dladdr((void *)&CudaBackend, &info) && info.dli_fname) {
+      string dir(info.dli_fname);
+      size_t slash = dir.rfind('/');
+      dir = (slash == string::npos) ? string(".") : dir.substr(0, slash);
+      candidates.push_back(dir + "/libpbrt_b200.so");
+      candidates.push_back(dir + "/../csrc/libpbrt_b200.so");
+    }
+    candidates.push_back("libpbrt_b200.so");
+    string tried;
+    for (size_t i = 0; i < candidates.size() && !lib; ++i) {
+      lib = dlopen(candidates[i].c_str(), RTLD_NOW | RTLD_LOCAL);
+      if (!lib) tried += "\n  " + candidates[i] + ": " + dlerror();
+    }
+    if (!lib)
+      Severe("Unable to load the CUDA render library libpbrt_b200.so (no CPU fallback exists):%s",
+             tried.c_str());
+    renderHost = (RenderHostFn)dlsym(lib, "pbrt_b200_render_host");
+    lastError = (LastErrorFn)dlsym(lib, "pbrt_b200_last_error");
+    if (!renderHost || !lastError) Severe("libpbrt_b200.so does not export the render ABI");
+  }
+  int device = 0;
+  if (const char *d = getenv("PBRT_B200_DEVICE")) device = atoi(d);
+  else if (const char *lr = getenv("LOCAL_RANK")) device = atoi(lr);
+  int rc = renderHost(scene, device, windows, nWindows, rgbaOut, NULL, stats);
+  if (rc != PBRT_B200_OK) Severe("GPU render failed (code %d): %s", rc, lastError());
+  return rc;
+}
+
+PbrtRenderBackend gBackend = CudaBackend;
+
+}  // namespace
+
+void pbrtSetRenderBackend(PbrtRenderBackend fn) { gBackend = fn ? fn : CudaBackend; }
+
+// pbrt_host_load_scene() arms this: the next Render() exports the scene into the
+// capture (deep-copying the kd arrays, which die with the Scene) and returns.
+struct CapturedScene {
+  CapturedScene() { memset(&scene, 0, sizeof(scene)); }
+  FlatBuilder fb;
+  PbrtB200Scene scene;
+  vector<PbrtB200KdNode> nodes;
+  vector<uint32_t> primRefs;
+};
+static CapturedScene *gCapture = NULL;
+
+void Scene::Render() {
+  if (gCapture) {
+    CapturedScene *cap = gCapture;
+    Flatten(cap->fb, &cap->scene);
+    cap->nodes.assign(cap->scene.nodes, cap->scene.nodes + cap->scene.n_nodes);
+    cap->primRefs.assign(cap->scene.prim_refs, cap->scene.prim_refs + cap->scene.n_prim_refs);
+    cap->scene.nodes = cap->nodes.empty() ? NULL : &cap->nodes[0];
+    cap->scene.prim_refs = cap->primRefs.empty() ? NULL : &cap->primRefs[0];
+    return;
+  }
+  FlatBuilder fb;
+  PbrtB200Scene ps;
+  Flatten(fb, &ps);
+  PbrtB200Window win = {ps.film.x_pixel_start, ps.film.y_pixel_start, ps.film.x_pixel_count,
+                        ps.film.y_pixel_count};
+  vector<float> rgba((size_t)win.width * win.height * 4);
+  float *outPtr = &rgba[0];
+  PbrtB200Stats stats;
+  memset(&stats, 0, sizeof(stats));
+  int rc = gBackend(&ps, &win, 1, &outPtr, &stats);
+  if (rc != 0) return;
+  // the reference prints one Error per offending sample (scene.cpp:60-74)
+  if (stats.nan_samples)
+    Error("Not-a-number radiance value returned for %llu image sample(s).  Set to black.",
+          (unsigned long long)stats.nan_samples);
+  if (stats.negative_samples)
+    Error("Negative luminance value returned for %llu image sample(s).  Set to black.",
+          (unsigned long long)stats.negative_samples);
+  if (stats.infinite_samples)
+    Error("Infinite luminance value returned for %llu image sample(s).  Set to black.",
+          (unsigned long long)stats.infinite_samples);
+  camera->film->WriteImage(&rgba[0]);
+  // StatsPrint(stdout) equivalent (api.cpp:479)
+  double rays = double(stats.intersect_rays + stats.shadow_rays);
+  printf("Camera:\n    Camera Rays Traced                            %llu\n",
+         (unsigned long long)stats.camera_rays);
+  printf("Lights:\n    Number of shadow rays traced                  %llu\n",
+         (unsigned long long)stats.shadow_rays);
+  printf("Shading:\n    Number of points shaded                       %llu\n",
+         (unsigned long long)stats.points_shaded);
+  printf("B200:\n    Rays (Intersect + IntersectP)                 %.0f\n", rays);
+  printf("    Render loop (device ms)                       %.3f\n", stats.render_ms);
+  if (stats.render_ms > 0)
+    printf("    Mrays/s                                       %.2f\n",
+           rays / (stats.render_ms * 1e3));
+}
+
+// ------------------------------------------------------ C entry points
+// Used by the Python tests / bench (ctypes) to drive the host front end.
+extern "C" {
+
+// Parse `path`, flatten the scene that WorldEnd would render, and return it
+// without rendering.  Returns NULL on failure.  One scene per file.
+void *pbrt_host_load_scene(const char *path) {
+  CapturedScene *cap = new CapturedScene;
+  gCapture = cap;
+  pbrtInit();
+  bool ok = ParseFile(path);
+  pbrtCleanup();
+  gCapture = NULL;
+  if (!ok || cap->scene.abi_version == 0) {
+    delete cap;
+    return NULL;
+  }
+  return cap;
+}
+const PbrtB200Scene *pbrt_host_scene(void *handle) {
+  return handle ? &((CapturedScene *)handle)->scene : NULL;
+}
+void pbrt_host_free_scene(void *handle) { delete (CapturedScene *)handle; }
+
+// Full pipeline exactly as the `pbrt` executable runs it: parse, build,
+// render on the GPU, write the EXR named by the scene's Film.
+int pbrt_host_render_file(const char *path) {
+  pbrtInit();
+  bool ok = ParseFile(path);
+  pbrtCleanup();
+  return ok ? 0 : 1;
+}
+void pbrt_host_write_exr(const char *name, const float *rgba, int xRes, int yRes, int totalX,
+                         int totalY, int xOff, int yOff) {
+  size_t n = (size_t)xRes * yRes;
+  vector<float> rgb(3 * n), a(n);
+  for (size_t i = 0; i < n; ++i) {
+    rgb[3 * i] = rgba[4 * i]; rgb[3 * i + 1] = rgba[4 * i + 1]; rgb[3 * i + 2] = rgba[4 * i + 2];
+    a[i] = rgba[4 * i + 3];
+  }
+  WriteRGBAImage(name, &rgb[0], &a[0], xRes, yRes, totalX, totalY, xOff, yOff);
+}
+
+}  // extern "C"
+
