@@ -1,0 +1,284 @@
+// twin.cpp -- CPU restatement of the render hot path, sample by sample.
+//
+// TEST INFRASTRUCTURE (oracle/): only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline leg may load this.  The product (libpbrt_b200.so)
+// never links or calls it and has no CPU fallback.
+//
+// What it is: a scalar, single-threaded driver that walks image samples in the
+// reference's order (core/scene.cpp:43-84) and, for each, runs sample
+// generation -> camera ray -> kd-tree closest hit -> integrator vertex ->
+// shadow / MIS-probe rays -> film splat, using the per-stage arithmetic of
+// pbrt-v1_b200/csrc/pb_*.h (each function there cites the reference lines it
+// restates) compiled for the host with gcc -ffp-contract=off.  It exists so
+// that the stage arithmetic can be pinned against the compiled reference
+// (oracle/_ref, built by oracle/build_ref.sh) in the GPU-less build container,
+// and so that GPU results can be compared stage by stage (rays, hits,
+// per-sample radiance) on the GPU box, where /root/reference does not exist.
+//
+// Pinning: tests/test_oracle.py renders the parity scenes with
+// oracle/_ref/pbrt_ref_keyed and compares images and per-sample radiance with
+// this twin; committed fixtures from the same runs live in tests/golden/.
+#include "../pbrt-v1_b200/csrc/pb_integrator.h"
+#include "../pbrt-v1_b200/csrc/pb_camera.h"
+#include "../pbrt-v1_b200/csrc/pb_film.h"
+#include "../pbrt-v1_b200/csrc/pb_setup.h"
+#include <vector>
+#include <string>
+#include <stdio.h>
+#include <stdlib.h>
+#include <chrono>
+
+namespace {
+std::string gError;
+
+bool build_view(const PbrtB200Scene &s, SceneView *sv) {
+  memset(sv, 0, sizeof(*sv));
+  std::string err = pb_setup_view(s, sv);
+  if (!err.empty()) { gError = err; return false; }
+  sv->nodes = s.nodes; sv->primRefs = s.prim_refs;
+  sv->prims = (const PrimQuad *)s.prims; sv->aux = s.prim_aux;
+  sv->meshes = s.meshes; sv->spheres = s.spheres;
+  sv->vertexN = s.vertex_n; sv->vertexS = s.vertex_s; sv->vertexUV = s.vertex_uv;
+  sv->materials = s.materials; sv->lights = s.lights;
+  sv->lightShapes = s.light_shapes; sv->lightCdf = s.light_cdf;
+  return true;
+}
+
+struct Counters {
+  uint64_t intersect, shadow, shaded;
+  KdCounters kd;
+  uint64_t nan, neg, inf;
+};
+
+struct VecFrameIO {
+  std::vector<WdFrame> *frames;
+  WdFrame load(int d) { return (*frames)[d]; }
+  void store(int d, const WdFrame &f) {
+    if ((int)frames->size() <= d) frames->resize(d + 1);
+    (*frames)[d] = f;
+  }
+};
+
+void add_counts(Counters &c, const KdCounters &k) {
+  c.kd.interior += k.interior; c.kd.leaves += k.leaves; c.kd.refs += k.refs; c.kd.tests += k.tests;
+}
+
+bool trace_closest(const SceneView &sv, const Ray &ray, Hit *hit, Counters &c) {
+  KdCounters k = {0, 0, 0, 0};
+  ++c.intersect;
+  bool r = kd_intersect<false, true>(sv, ray, hit, &k);
+  add_counts(c, k);
+  return r;
+}
+bool trace_any(const SceneView &sv, const Ray &ray, Counters &c) {
+  KdCounters k = {0, 0, 0, 0};
+  Hit h;
+  ++c.shadow;
+  bool r = kd_intersect<true, true>(sv, ray, &h, &k);
+  add_counts(c, k);
+  return r;
+}
+
+// resolve the two ray queries of a DirectRec; returns flag bits (1 unoccluded, 2 probe hit)
+uint8_t trace_direct(const SceneView &sv, const DirectRec &rec, Counters &c) {
+  uint8_t f = 0;
+  if (rec.hasShadow && !trace_any(sv, rec.shadow, c)) f |= 1;
+  if (rec.hasProbe) {
+    Hit h;
+    trace_closest(sv, rec.probe, &h, c);
+    if (hit_emits_from_light(sv, rec.probe, h, rec.probeLight)) f |= 2;
+  }
+  return f;
+}
+
+Spec li_path(const SceneView &sv, uint64_t key0, uint64_t key1, const Ray &camRay, float *alpha,
+             Counters &c) {
+  PathState st;
+  st.L = spec(0.f); st.T = spec(1.f); st.pendT = spec(0.f);
+  st.alpha = 0.f; st.depth = 0; st.specularBounce = false;
+  st.rng.key = key1; st.rng.ctr = 0;
+  Ray ray = camRay;
+  for (;;) {
+    Hit hit;
+    trace_closest(sv, ray, &hit, c);
+    PathVertexOut out;
+    path_vertex(sv, key0, st, ray, hit, &out);
+    if (hit.prim >= 0) ++c.shaded;
+    if (out.hasDirect) {
+      uint8_t f = trace_direct(sv, out.direct, c);
+      path_resolve_direct(sv, st, out.direct.termA, out.direct.termB, (f & 1) != 0, (f & 2) != 0);
+    }
+    if (!out.hasNext) break;
+    ray = out.next;
+  }
+  *alpha = st.alpha;
+  return st.L;
+}
+
+Spec li_wd(const SceneView &sv, uint64_t key0, uint64_t key1, const Ray &camRay, float *alpha,
+           Counters &c) {
+  RngStream rng; rng.key = key1; rng.ctr = 0;
+  std::vector<WdFrame> frames(1);
+  VecFrameIO io = {&frames};
+  std::vector<DirectRec> recs(wd_max_records(sv));
+  std::vector<uint8_t> flags(recs.size());
+  Ray ray = camRay;
+  int depth = 0;
+  *alpha = 0.f;
+  for (;;) {
+    Hit hit;
+    trace_closest(sv, ray, &hit, c);
+    WdFrame fr;
+    WdVertexOut out;
+    wd_vertex(sv, key0, ray, hit, rng, depth, depth == 0 ? alpha : (float *)0, &fr, recs.data(), &out);
+    if (hit.prim >= 0) ++c.shaded;
+    for (int r = 0; r < out.nRecs; ++r) flags[r] = trace_direct(sv, recs[r], c);
+    wd_resolve(sv, &fr, recs.data(), flags.data(), out.nRecs);
+    io.store(depth, fr);
+    if (!wd_advance(io, rng, &depth, &ray)) break;
+  }
+  return frames[0].L;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *pbrt_twin_last_error(void) { return gError.c_str(); }
+
+// Render one pixel window exactly like a reference crop-window render.
+//   rgba     width*height*4   what ImageFilm::WriteImage hands to WriteRGBAImage
+//   raw      width*height*5   L.rgb, alpha, weightSum (may be NULL)
+//   samples  nSamples*6       imageX, imageY, L.rgb (after guards), alpha, reference order (may be NULL)
+int pbrt_twin_render(const PbrtB200Scene *scene, const PbrtB200Window *win, float *rgba, float *raw,
+                     float *samples, PbrtB200Stats *stats) {
+  SceneView sv;
+  if (!build_view(*scene, &sv)) return PBRT_B200_ERR_INVALID;
+  int xs, xe, ys, ye;
+  film_sample_extent(sv, win->x0, win->y0, win->width, win->height, &xs, &xe, &ys, &ye);
+  int spp = sv.sampler.x_samples * sv.sampler.y_samples;
+  std::vector<FilmPixel> film((size_t)win->width * win->height);
+  memset(film.data(), 0, film.size() * sizeof(FilmPixel));
+  Counters c;
+  memset(&c, 0, sizeof(c));
+  uint64_t nSamples = 0;
+  auto t0 = std::chrono::steady_clock::now();
+  for (int y = ys; y < ye; ++y)
+    for (int x = xs; x < xe; ++x)
+      for (int k = 0; k < spp; ++k) {
+        CameraSample cs;
+        stratified_camera_sample(sv, x, y, k, &cs);
+        Ray ray;
+        perspective_generate_ray(sv.camera, cs, &ray);
+        uint64_t key0 = pb_key(x, y, k, 0), key1 = pb_key(x, y, k, 1);
+        float alpha = 0.f;
+        Spec Ls = (sv.integrator.kind == PBRT_B200_INT_PATH)
+                      ? li_path(sv, key0, key1, ray, &alpha, c)
+                      : li_wd(sv, key0, key1, ray, &alpha, c);
+        Ls = 1.f * Ls;   // rayWeight * Li, scene.cpp:58
+        cs.imageX = film_image_coord(cs.imageX);
+        cs.imageY = film_image_coord(cs.imageY);
+        int g = sample_guard(&Ls);
+        if (g == 1) ++c.nan; else if (g == 2) ++c.neg; else if (g == 3) ++c.inf;
+        if (samples) {
+          float *o = samples + 6 * nSamples;
+          o[0] = cs.imageX; o[1] = cs.imageY; o[2] = Ls.c[0]; o[3] = Ls.c[1]; o[4] = Ls.c[2]; o[5] = alpha;
+        }
+        ++nSamples;
+        // ImageFilm::AddSample, image.cpp:103-141
+        float dImageX = cs.imageX - 0.5f, dImageY = cs.imageY - 0.5f;
+        int x0 = pb_imax(pb_ceil2int(dImageX - sv.filterXW), win->x0);
+        int x1 = pb_imin(pb_floor2int(dImageX + sv.filterXW), win->x0 + win->width - 1);
+        int y0 = pb_imax(pb_ceil2int(dImageY - sv.filterYW), win->y0);
+        int y1 = pb_imin(pb_floor2int(dImageY + sv.filterYW), win->y0 + win->height - 1);
+        for (int py = y0; py <= y1; ++py)
+          for (int px = x0; px <= x1; ++px) {
+            float wt;
+            if (!film_sample_weight(sv, scene->film.filter_table, cs.imageX, cs.imageY, px, py, &wt))
+              continue;
+            film_pixel_add(&film[(size_t)(py - win->y0) * win->width + (px - win->x0)], wt, Ls.c, alpha);
+          }
+      }
+  auto t1 = std::chrono::steady_clock::now();
+  for (size_t i = 0; i < film.size(); ++i) {
+    film_pixel_resolve(film[i], sv.premultiply != 0, rgba + 4 * i);
+    if (raw) {
+      raw[5 * i] = film[i].L[0]; raw[5 * i + 1] = film[i].L[1]; raw[5 * i + 2] = film[i].L[2];
+      raw[5 * i + 3] = film[i].alpha; raw[5 * i + 4] = film[i].weightSum;
+    }
+  }
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->camera_rays = nSamples;
+    stats->intersect_rays = c.intersect; stats->shadow_rays = c.shadow; stats->points_shaded = c.shaded;
+    stats->interior_visits = c.kd.interior; stats->leaf_visits = c.kd.leaves;
+    stats->prim_refs_read = c.kd.refs; stats->prim_tests = c.kd.tests;
+    stats->nan_samples = c.nan; stats->negative_samples = c.neg; stats->infinite_samples = c.inf;
+    stats->render_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  }
+  return PBRT_B200_OK;
+}
+
+uint64_t pbrt_twin_sample_count(const PbrtB200Scene *scene, const PbrtB200Window *win) {
+  SceneView sv;
+  if (!build_view(*scene, &sv)) return 0;
+  int xs, xe, ys, ye;
+  film_sample_extent(sv, win->x0, win->y0, win->width, win->height, &xs, &xe, &ys, &ye);
+  return (uint64_t)(xe - xs) * (ye - ys) * sv.sampler.x_samples * sv.sampler.y_samples;
+}
+
+// KdTreeAccel::Intersect / IntersectP for explicit rays (8 floats each).
+int pbrt_twin_intersect(const PbrtB200Scene *scene, const float *rays, uint64_t n, int32_t *prim,
+                        float *t, float *b1, float *b2) {
+  SceneView sv;
+  if (!build_view(*scene, &sv)) return PBRT_B200_ERR_INVALID;
+  for (uint64_t i = 0; i < n; ++i) {
+    Ray r;
+    r.o = v3(rays[8 * i], rays[8 * i + 1], rays[8 * i + 2]);
+    r.d = v3(rays[8 * i + 3], rays[8 * i + 4], rays[8 * i + 5]);
+    r.mint = rays[8 * i + 6]; r.maxt = rays[8 * i + 7];
+    Hit h;
+    kd_intersect<false, false>(sv, r, &h, (KdCounters *)0);
+    prim[i] = h.prim;
+    t[i] = h.prim >= 0 ? h.t : 0.f; b1[i] = h.prim >= 0 ? h.b1 : 0.f; b2[i] = h.prim >= 0 ? h.b2 : 0.f;
+  }
+  return PBRT_B200_OK;
+}
+int pbrt_twin_intersect_p(const PbrtB200Scene *scene, const float *rays, uint64_t n, uint8_t *occ) {
+  SceneView sv;
+  if (!build_view(*scene, &sv)) return PBRT_B200_ERR_INVALID;
+  for (uint64_t i = 0; i < n; ++i) {
+    Ray r;
+    r.o = v3(rays[8 * i], rays[8 * i + 1], rays[8 * i + 2]);
+    r.d = v3(rays[8 * i + 3], rays[8 * i + 4], rays[8 * i + 5]);
+    r.mint = rays[8 * i + 6]; r.maxt = rays[8 * i + 7];
+    Hit h;
+    occ[i] = kd_intersect<true, false>(sv, r, &h, (KdCounters *)0) ? 1 : 0;
+  }
+  return PBRT_B200_OK;
+}
+// Camera rays of a window in reference order: 8 floats per ray, 2 per image_xy.
+int pbrt_twin_camera_rays(const PbrtB200Scene *scene, const PbrtB200Window *win, uint64_t n,
+                          float *rays, float *imageXY) {
+  SceneView sv;
+  if (!build_view(*scene, &sv)) return PBRT_B200_ERR_INVALID;
+  int xs, xe, ys, ye;
+  film_sample_extent(sv, win->x0, win->y0, win->width, win->height, &xs, &xe, &ys, &ye);
+  int spp = sv.sampler.x_samples * sv.sampler.y_samples;
+  uint64_t i = 0;
+  for (int y = ys; y < ye && i < n; ++y)
+    for (int x = xs; x < xe && i < n; ++x)
+      for (int k = 0; k < spp && i < n; ++k, ++i) {
+        CameraSample cs;
+        stratified_camera_sample(sv, x, y, k, &cs);
+        Ray r;
+        perspective_generate_ray(sv.camera, cs, &r);
+        float *o = rays + 8 * i;
+        o[0] = r.o.x; o[1] = r.o.y; o[2] = r.o.z; o[3] = r.d.x; o[4] = r.d.y; o[5] = r.d.z;
+        o[6] = r.mint; o[7] = r.maxt;
+        imageXY[2 * i] = cs.imageX; imageXY[2 * i + 1] = cs.imageY;
+      }
+  return PBRT_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,314 @@
+// pb_bsdf.h -- BSDF assembly and evaluation for the in-scope materials.
+//   Material::Bump (constant displacement 0)   core/material.cpp:29-71
+//   Matte / Glass / Mirror ::GetBSDF            materials/{matte,glass,mirror}.cpp
+//   BSDF ctor, f, Sample_f, Pdf                 core/reflection.cpp:402-494
+//   Lambertian, OrenNayar, SpecularReflection,
+//   SpecularTransmission, FresnelDielectric     core/reflection.cpp:31-156, reflection.h:197-276
+//   MC warps                                    core/mc.cpp:92-141, core/mc.h:38-59
+// No arena, no virtual calls: a BSDF is at most two lobes described by the
+// material record.
+#ifndef PB_BSDF_H
+#define PB_BSDF_H
+#include "pb_shapes.h"
+
+// BxDFType, core/reflection.h:54-71
+enum {
+  PB_REFLECTION = 1 << 0, PB_TRANSMISSION = 1 << 1, PB_DIFFUSE = 1 << 2, PB_GLOSSY = 1 << 3,
+  PB_SPECULAR = 1 << 4,
+  PB_ALL_TYPES = PB_DIFFUSE | PB_GLOSSY | PB_SPECULAR,
+  PB_ALL = PB_REFLECTION | PB_TRANSMISSION | PB_ALL_TYPES
+};
+enum { PB_LOBE_LAMBERT = 0, PB_LOBE_ORENNAYAR = 1, PB_LOBE_SPEC_REFL_DIEL = 2,
+       PB_LOBE_SPEC_REFL_NOOP = 3, PB_LOBE_SPEC_TRANS = 4 };
+
+struct Lobe {
+  int kind;
+  int type;      // BxDFType bits
+  Spec R;        // reflectance / transmittance
+  float A, B;    // OrenNayar
+  float etai, etat;
+};
+struct Bsdf {
+  V3 p;          // dgShading.p
+  V3 nn, ng, sn, tn;
+  float eta;
+  int nLobes;
+  Lobe lobes[2];
+};
+
+PB_HD bool lobe_matches(const Lobe &l, int flags) { return (l.type & flags) == l.type; }
+
+// core/mc.cpp:92-135
+PB_HD void concentric_sample_disk(float u1, float u2, float *dx, float *dy) {
+  float r, theta;
+  float sx = 2 * u1 - 1;
+  float sy = 2 * u2 - 1;
+  if (sx == 0.0f && sy == 0.0f) { *dx = 0.0f; *dy = 0.0f; return; }
+  if (sx >= -sy) {
+    if (sx > sy) {
+      r = sx;
+      if (sy > 0.0f) theta = sy / r;
+      else theta = 8.0f + sy / r;
+    } else {
+      r = sy;
+      theta = 2.0f - sx / r;
+    }
+  } else {
+    if (sx <= sy) {
+      r = -sx;
+      theta = 4.0f - sy / r;
+    } else {
+      r = -sy;
+      theta = 6.0f + sx / r;
+    }
+  }
+  theta *= PB_PI / 4.f;
+  *dx = r * pb_cosf(theta);
+  *dy = r * pb_sinf(theta);
+}
+// core/mc.h:38-44
+PB_HD V3 cosine_sample_hemisphere(float u1, float u2) {
+  V3 ret;
+  concentric_sample_disk(u1, u2, &ret.x, &ret.y);
+  ret.z = sqrtf(pb_max(0.f, 1.f - ret.x * ret.x - ret.y * ret.y));
+  return ret;
+}
+// core/mc.h:55-59
+PB_HD float power_heuristic(int nf, float fPdf, int ng, float gPdf) {
+  float f = nf * fPdf, g = ng * gPdf;
+  return (f * f) / (f * f + g * g);
+}
+
+// core/reflection.cpp:31-39 with etai/etat the same in every channel
+PB_HD float fr_diel(float cosi, float cost, float etai, float etat) {
+  float Rparl = ((etat * cosi) - (etai * cost)) / ((etat * cosi) + (etai * cost));
+  float Rperp = ((etai * cosi) - (etat * cost)) / ((etai * cosi) + (etat * cost));
+  return (Rparl * Rparl + Rperp * Rperp) * (1.f / 2.f);   // Spectrum / float
+}
+// core/reflection.cpp:77-95
+PB_HD float fresnel_dielectric(float cosi, float eta_i, float eta_t) {
+  cosi = pb_clamp(cosi, -1.f, 1.f);
+  bool entering = cosi > 0.f;
+  float ei = eta_i, et = eta_t;
+  if (!entering) { float tmp = ei; ei = et; et = tmp; }
+  float sint = ei / et * sqrtf(pb_max(0.f, 1.f - cosi * cosi));
+  if (sint >= 1.f) return 1.f;
+  float cost = sqrtf(pb_max(0.f, 1.f - sint * sint));
+  return fr_diel(fabsf(cosi), cost, ei, et);
+}
+
+// reflection.h:31-52
+PB_HD float sin_theta(const V3 &w) { return sqrtf(pb_max(0.f, 1.f - w.z * w.z)); }
+PB_HD float sin_theta2(const V3 &w) { return pb_max(0.f, 1.f - w.z * w.z); }
+PB_HD float cos_phi(const V3 &w) {
+  float st = sin_theta(w);
+  if (st == 0.f) return 1.f;
+  return pb_clamp(w.x / st, -1.f, 1.f);
+}
+PB_HD float sin_phi(const V3 &w) {
+  float st = sin_theta(w);
+  if (st == 0.f) return 0.f;
+  return pb_clamp(w.y / st, -1.f, 1.f);
+}
+
+// BxDF::f for the non-specular lobes (reflection.cpp:128-156); specular lobes return 0.
+PB_HD Spec lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
+  if (l.kind == PB_LOBE_LAMBERT) return l.R;   // R already holds R * INV_PI (reflection.h:249)
+  if (l.kind == PB_LOBE_ORENNAYAR) {
+    float sinthetai = sin_theta(wi);
+    float sinthetao = sin_theta(wo);
+    float maxcos = 0.f;
+    if (sinthetai > 1e-4 && sinthetao > 1e-4) {
+      float sinphii = sin_phi(wi), cosphii = cos_phi(wi);
+      float sinphio = sin_phi(wo), cosphio = cos_phi(wo);
+      float dcos = cosphii * cosphio + sinphii * sinphio;
+      maxcos = pb_max(0.f, dcos);
+    }
+    float sinalpha, tanbeta;
+    if (fabsf(wi.z) > fabsf(wo.z)) {
+      sinalpha = sinthetao;
+      tanbeta = sinthetai / fabsf(wi.z);
+    } else {
+      sinalpha = sinthetai;
+      tanbeta = sinthetao / fabsf(wo.z);
+    }
+    return l.R * PB_INV_PI * (l.A + l.B * maxcos * sinalpha * tanbeta);
+  }
+  return spec(0.f);
+}
+// BxDF::Pdf (reflection.cpp:226-230); specular lobes return 0 (reflection.h:213,235)
+PB_HD float lobe_pdf(const Lobe &l, const V3 &wo, const V3 &wi) {
+  if (l.type & PB_SPECULAR) return 0.f;
+  return (wo.z * wi.z > 0.f) ? fabsf(wi.z) * PB_INV_PI : 0.f;
+}
+// BxDF::Sample_f for each lobe kind (reflection.cpp:96-127, 219-225)
+PB_HD Spec lobe_sample_f(const Lobe &l, const V3 &wo, V3 *wi, float u1, float u2, float *pdf) {
+  if (l.kind == PB_LOBE_SPEC_REFL_DIEL || l.kind == PB_LOBE_SPEC_REFL_NOOP) {
+    *wi = v3(-wo.x, -wo.y, wo.z);
+    *pdf = 1.f;
+    float F = (l.kind == PB_LOBE_SPEC_REFL_NOOP) ? 1.f : fresnel_dielectric(wo.z, l.etai, l.etat);
+    // fresnel->Evaluate(..) * R / fabsf(CosTheta(*wi))
+    return (spec(F) * l.R) / fabsf(wi->z);
+  }
+  if (l.kind == PB_LOBE_SPEC_TRANS) {
+    bool entering = wo.z > 0.f;
+    float ei = l.etai, et = l.etat;
+    if (!entering) { float tmp = ei; ei = et; et = tmp; }
+    float sini2 = sin_theta2(wo);
+    float eta = ei / et;
+    float sint2 = eta * eta * sini2;
+    if (sint2 >= 1.f) return spec(0.f);   // *pdf stays 0 (set by the caller)
+    float cost = sqrtf(pb_max(0.f, 1.f - sint2));
+    if (entering) cost = -cost;
+    float sintOverSini = eta;
+    *wi = v3(sintOverSini * -wo.x, sintOverSini * -wo.y, cost);
+    *pdf = 1.f;
+    float F = fresnel_dielectric(wo.z, l.etai, l.etat);
+    return ((et * et) / (ei * ei) * (spec(1.f) - spec(F)) * l.R) / fabsf(wi->z);
+  }
+  *wi = cosine_sample_hemisphere(u1, u2);
+  if (wo.z < 0.f) wi->z *= -1.f;
+  *pdf = lobe_pdf(l, wo, *wi);
+  return lobe_f(l, wo, *wi);
+}
+
+PB_HD V3 bsdf_world_to_local(const Bsdf &b, const V3 &v) {
+  return v3(dot(v, b.sn), dot(v, b.tn), dot(v, b.nn));
+}
+PB_HD V3 bsdf_local_to_world(const Bsdf &b, const V3 &v) {
+  return v3(b.sn.x * v.x + b.tn.x * v.y + b.nn.x * v.z, b.sn.y * v.x + b.tn.y * v.y + b.nn.y * v.z,
+            b.sn.z * v.x + b.tn.z * v.y + b.nn.z * v.z);
+}
+PB_HD int bsdf_num_components(const Bsdf &b, int flags) {
+  int n = 0;
+  for (int i = 0; i < b.nLobes; ++i)
+    if (lobe_matches(b.lobes[i], flags)) ++n;
+  return n;
+}
+// BSDF::f, reflection.cpp:480-494
+PB_HD Spec bsdf_f(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags = PB_ALL) {
+  V3 wi = bsdf_world_to_local(b, wiW), wo = bsdf_world_to_local(b, woW);
+  if (dot(wiW, b.ng) * dot(woW, b.ng) > 0) flags &= ~PB_TRANSMISSION;
+  else flags &= ~PB_REFLECTION;
+  Spec f = spec(0.f);
+  for (int i = 0; i < b.nLobes; ++i)
+    if (lobe_matches(b.lobes[i], flags)) f = f + lobe_f(b.lobes[i], wo, wi);
+  return f;
+}
+// BSDF::Pdf, reflection.cpp:458-470
+PB_HD float bsdf_pdf(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags = PB_ALL) {
+  if (b.nLobes == 0) return 0.f;
+  V3 wo = bsdf_world_to_local(b, woW), wi = bsdf_world_to_local(b, wiW);
+  float pdf = 0.f;
+  int matchingComps = 0;
+  for (int i = 0; i < b.nLobes; ++i)
+    if (lobe_matches(b.lobes[i], flags)) {
+      ++matchingComps;
+      pdf += lobe_pdf(b.lobes[i], wo, wi);
+    }
+  return matchingComps > 0 ? pdf / matchingComps : 0.f;
+}
+// BSDF::Sample_f with explicit sample values, reflection.cpp:402-457
+PB_HD Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, float u1, float u2, float u3,
+                         float *pdf, int flags, int *sampledType) {
+  int matchingComps = bsdf_num_components(b, flags);
+  if (matchingComps == 0) {
+    *pdf = 0.f;
+    *sampledType = 0;
+    return spec(0.f);
+  }
+  int which = pb_imin(pb_floor2int(u3 * matchingComps), matchingComps - 1);
+  int chosen = -1;
+  int count = which;
+  for (int i = 0; i < b.nLobes; ++i)
+    if (lobe_matches(b.lobes[i], flags))
+      if (count-- == 0) { chosen = i; break; }
+  const Lobe &bx = b.lobes[chosen];
+  V3 wi = v3(0, 0, 0);
+  V3 wo = bsdf_world_to_local(b, woW);
+  *pdf = 0.f;
+  Spec f = lobe_sample_f(bx, wo, &wi, u1, u2, pdf);
+  if (*pdf == 0.f) {
+    *sampledType = 0;
+    return spec(0.f);
+  }
+  *sampledType = bx.type;
+  *wiW = bsdf_local_to_world(b, wi);
+  if (!(bx.type & PB_SPECULAR) && matchingComps > 1) {
+    for (int i = 0; i < b.nLobes; ++i)
+      if (i != chosen && lobe_matches(b.lobes[i], flags)) *pdf += lobe_pdf(b.lobes[i], wo, wi);
+  }
+  if (matchingComps > 1) *pdf /= matchingComps;
+  if (!(bx.type & PB_SPECULAR)) {
+    f = spec(0.f);
+    if (dot(*wiW, b.ng) * dot(woW, b.ng) > 0) flags &= ~PB_TRANSMISSION;
+    else flags &= ~PB_REFLECTION;
+    for (int i = 0; i < b.nLobes; ++i)
+      if (lobe_matches(b.lobes[i], flags)) f = f + lobe_f(b.lobes[i], wo, wi);
+  }
+  return f;
+}
+
+// Material::Bump with a constant-zero displacement (core/material.cpp:29-71):
+// dpdu/dpdv are unchanged (x + 0*nn + 0*dndu), the normal is re-derived from
+// them, re-oriented by the shape flags and then towards the geometric normal.
+// Followed by the BSDF constructor (reflection.cpp:471-479) and the lobes the
+// material adds.
+PB_HD void make_bsdf(const PbrtB200Material &m, const DiffGeom &dgGeom, const DiffGeom &dgs,
+                     uint32_t shapeFlags, Bsdf *b) {
+  // dgBump->dpdu = dgs.dpdu + (0 - 0) / du * nn + 0 * dndu: evaluated literally so that
+  // signed zeros / non-finite normals behave as in the reference; du = .01 when the
+  // screen-space differentials are zero or unused.
+  float zero_over_du = 0.f / .01f;
+  V3 dpdu = dgs.dpdu + zero_over_du * dgs.nn + 0.f * dgs.dndu;
+  V3 dpdv = dgs.dpdv + zero_over_du * dgs.nn + 0.f * dgs.dndv;
+  V3 nn = normalize(cross(dpdu, dpdv));
+  bool ro = (shapeFlags & PBRT_B200_PF_REVERSE) != 0, sh = (shapeFlags & PBRT_B200_PF_SWAPS) != 0;
+  if (ro ^ sh) nn = nn * -1.f;
+  if (dot(dgGeom.nn, nn) < 0.f) nn = nn * -1.f;
+  b->p = dgs.p;
+  b->ng = dgGeom.nn;
+  b->nn = nn;
+  b->sn = normalize(dpdu);
+  b->tn = cross(b->nn, b->sn);
+  b->eta = 1.f;
+  b->nLobes = 0;
+  Spec R = spec3(m.kd[0], m.kd[1], m.kd[2]);
+  if (m.kind == PBRT_B200_MAT_MATTE) {
+    Lobe &l = b->lobes[b->nLobes++];
+    l.type = PB_REFLECTION | PB_DIFFUSE;
+    l.etai = l.etat = 1.f;
+    if (m.sigma == 0.f) {
+      l.kind = PB_LOBE_LAMBERT;
+      l.R = R * PB_INV_PI;   // Lambertian::RoverPI
+      l.A = l.B = 0.f;
+    } else {
+      l.kind = PB_LOBE_ORENNAYAR;
+      l.R = R;
+      float sigma = (PB_PI / 180.f) * m.sigma;   // Radians()
+      float sigma2 = sigma * sigma;
+      l.A = 1.f - (sigma2 / (2.f * (sigma2 + 0.33f)));
+      l.B = 0.45f * sigma2 / (sigma2 + 0.09f);
+    }
+  } else if (m.kind == PBRT_B200_MAT_GLASS) {
+    b->eta = m.index;
+    Spec T = spec3(m.kt[0], m.kt[1], m.kt[2]);
+    if (!is_black(R)) {
+      Lobe &l = b->lobes[b->nLobes++];
+      l.kind = PB_LOBE_SPEC_REFL_DIEL; l.type = PB_REFLECTION | PB_SPECULAR;
+      l.R = R; l.A = l.B = 0.f; l.etai = 1.f; l.etat = m.index;
+    }
+    if (!is_black(T)) {
+      Lobe &l = b->lobes[b->nLobes++];
+      l.kind = PB_LOBE_SPEC_TRANS; l.type = PB_TRANSMISSION | PB_SPECULAR;
+      l.R = T; l.A = l.B = 0.f; l.etai = 1.f; l.etat = m.index;
+    }
+  } else {   // mirror
+    if (!is_black(R)) {
+      Lobe &l = b->lobes[b->nLobes++];
+      l.kind = PB_LOBE_SPEC_REFL_NOOP; l.type = PB_REFLECTION | PB_SPECULAR;
+      l.R = R; l.A = l.B = 0.f; l.etai = l.etat = 1.f;
+    }
+  }
+}
+#endif

@@ -1,0 +1,74 @@
+// pb_camera.h -- image-sample generation and camera rays.
+//   StratifiedSampler ctor / GetNextSample   samplers/stratified.cpp:51-131
+//   StratifiedSample1D/2D, Shuffle           core/sampling.cpp:72-97
+//   PerspectiveCamera::GenerateRay           cameras/perspective.cpp:51-82
+// One call produces the camera part of image sample k of pixel (x, y) without
+// generating the pixel's other samples (see pb_rng.h for how).
+#ifndef PB_CAMERA_H
+#define PB_CAMERA_H
+#include "pb_bsdf.h"
+
+struct CameraSample {
+  float imageX, imageY, lensU, lensV;
+};
+PB_HD void stratified_camera_sample(const SceneView &sv, int x, int y, int k, CameraSample *cs) {
+  int nx = sv.sampler.x_samples, ny = sv.sampler.y_samples;
+  int n = nx * ny;
+  bool jitter = sv.sampler.jitter != 0;
+  uint64_t key = pb_key(x, y, 0xFFFF, 0);
+  float dx = 1.f / nx, dy = 1.f / ny;
+  // StratifiedSample2D(imageSamples): sample index = sy * nx + sx, jx drawn before jy
+  int sx = k % nx, sy = k / nx;
+  float jx = jitter ? pb_f32(key, 2u * k + 1u) : 0.5f;
+  float jy = jitter ? pb_f32(key, 2u * k + 2u) : 0.5f;
+  cs->imageX = (sx + jx) * dx;
+  cs->imageY = (sy + jy) * dy;
+  cs->imageX += x;
+  cs->imageY += y;
+  cs->lensU = cs->lensV = 0.5f;
+  if (sv.camera.lens_radius > 0.f) {
+    // lens samples: draws 2n+1..4n (jitter), shuffled by the n uints that follow the
+    // 5n jitter draws (image 2n, lens 2n, time n)
+    uint32_t shuffleCtr = jitter ? 5u * n : 0u;
+    int src = pb_shuffle_source(key, shuffleCtr, n, k);
+    int lx = src % nx, ly = src / nx;
+    float lj1 = jitter ? pb_f32(key, 2u * n + 2u * src + 1u) : 0.5f;
+    float lj2 = jitter ? pb_f32(key, 2u * n + 2u * src + 2u) : 0.5f;
+    cs->lensU = (lx + lj1) * dx;
+    cs->lensV = (ly + lj2) * dy;
+  }
+  // the time sample (shuffled likewise) only sets ray.time, which nothing in scope reads
+}
+
+// Scene::Render brackets the two differential-ray calls with ++imageX / --imageX
+// (core/scene.cpp:47-53), so the coordinate ImageFilm::AddSample later sees is
+// (v + 1) - 1, which is not always v in fp32.
+PB_HD float film_image_coord(float v) {
+  float t = v + 1.f;
+  return t - 1.f;
+}
+
+// cameras/perspective.cpp:51-82
+PB_HD void perspective_generate_ray(const PbrtB200Camera &c, const CameraSample &s, Ray *ray) {
+  V3 Pras = v3(s.imageX, s.imageY, 0);
+  V3 Pcamera = xf_point(c.raster_to_camera, Pras);
+  ray->o = Pcamera;
+  ray->d = v3(Pcamera.x, Pcamera.y, Pcamera.z);
+  if (c.lens_radius > 0.f) {
+    float lensU, lensV;
+    concentric_sample_disk(s.lensU, s.lensV, &lensU, &lensV);
+    lensU *= c.lens_radius;
+    lensV *= c.lens_radius;
+    float ft = (c.focal_distance - c.hither) / ray->d.z;
+    V3 Pfocus = ray->o + ray->d * ft;
+    ray->o.x += lensU * (c.focal_distance - c.hither) / c.focal_distance;
+    ray->o.y += lensV * (c.focal_distance - c.hither) / c.focal_distance;
+    ray->d = Pfocus - ray->o;
+  }
+  ray->d = normalize(ray->d);
+  ray->mint = 0.f;
+  ray->maxt = (c.yon - c.hither) / ray->d.z;
+  ray->o = xf_point(c.camera_to_world, ray->o);
+  ray->d = xf_vector(c.camera_to_world, ray->d);
+}
+#endif

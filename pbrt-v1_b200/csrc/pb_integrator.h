@@ -1,0 +1,585 @@
+// pb_integrator.h -- light sampling, the direct-lighting estimator and the
+// per-vertex bodies of the three surface integrators.
+//   PointLight::Sample_L             lights/point.cpp:55-66
+//   AreaLight::Sample_L / Pdf / L    lights/area.cpp:58-72,93-104, core/light.h:93-96
+//   Shape::Pdf(p,wi), ShapeSet       core/shape.h:96-121,150-156
+//   Triangle::Sample                 shapes/trianglemesh.cpp:336-349
+//   Sphere::Sample / Pdf             shapes/sphere.cpp:38-79
+//   VisibilityTester::SetSegment     core/light.h:76-80
+//   EstimateDirect                   core/transport.cpp:123-194
+//   UniformSampleOneLight/AllLights  core/transport.cpp:31-70
+//   PathIntegrator::Li               integrators/path.cpp:58-145
+//   DirectLighting::Li               integrators/directlighting.cpp:91-194
+//   WhittedIntegrator::Li            integrators/whitted.cpp:44-140
+//
+// Everything here is "one path vertex" worth of work: it never traces a ray
+// itself.  Rays it needs (shadow segment, MIS probe, continuation) are
+// returned to the caller, which queues them for the traversal kernels; the
+// radiance terms that depend on those rays are returned as pending records
+// and folded in, in the reference's order of additions, by resolve_*().
+#ifndef PB_INTEGRATOR_H
+#define PB_INTEGRATOR_H
+#include "pb_bsdf.h"
+#include "pb_kd.h"
+
+// ---------------------------------------------------------------- geometry at a hit
+struct Surface {
+  Bsdf bsdf;
+  int32_t light;      // area light of the primitive or -1
+};
+PB_HD void surface_dg(const SceneView &sv, const Ray &ray, const Hit &hit, const TriVerts &tv,
+                      DiffGeom *dg) {
+  if ((tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_TRIANGLE) {
+    tri_dg(sv, (uint32_t)hit.prim, tv, ray, hit.t, hit.b1, hit.b2, dg);
+  } else {
+    const PbrtB200Sphere &s = sv.spheres[sv.aux[hit.prim].owner];
+    Ray r = ray;
+    r.maxt = hit.t;   // re-deriving the accepted root: same branch decisions as when it was found
+    float t, phi; V3 phit;
+    sphere_test(s, r, &t, &phit, &phi);
+    sphere_dg(s, phit, phi, dg);
+  }
+}
+// Intersection::GetBSDF (core/primitive.cpp:126-141)
+PB_HD void surface_at_hit(const SceneView &sv, const Ray &ray, const Hit &hit, Surface *sf) {
+  TriVerts tv = load_prim(sv, (uint32_t)hit.prim);
+  DiffGeom dg, dgs;
+  surface_dg(sv, ray, hit, tv, &dg);
+  if ((tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_TRIANGLE)
+    tri_shading_dg(sv, (uint32_t)hit.prim, tv.flags, dg, &dgs);
+  else
+    dgs = dg;
+  make_bsdf(sv.materials[tv.material], dg, dgs, tv.flags, &sf->bsdf);
+  sf->light = tv.light;
+}
+// Intersection::Le (core/primitive.cpp:142-145) with AreaLight::L (light.h:93-96)
+PB_HD Spec surface_le(const SceneView &sv, const Surface &sf, const V3 &w) {
+  if (sf.light < 0) return spec(0.f);
+  const PbrtB200Light &l = sv.lights[sf.light];
+  return dot(sf.bsdf.ng, w) > 0 ? spec3(l.color[0], l.color[1], l.color[2]) : spec(0.f);
+}
+// `lightIsect.primitive->GetAreaLight() == light ? lightIsect.Le(-wi)` is non-black
+// (transport.cpp:180-182): evaluated by the MIS-probe traversal kernel.
+PB_HD bool hit_emits_from_light(const SceneView &sv, const Ray &ray, const Hit &hit, int light) {
+  if (hit.prim < 0) return false;   // Light::Le(ray) is black for point/area lights
+  TriVerts tv = load_prim(sv, (uint32_t)hit.prim);
+  if (tv.light != light) return false;
+  DiffGeom dg;
+  surface_dg(sv, ray, hit, tv, &dg);
+  return dot(dg.nn, -ray.d) > 0;
+}
+
+// ---------------------------------------------------------------- shape sampling
+// Triangle::Sample, shapes/trianglemesh.cpp:336-349 (+ UniformSampleTriangle mc.cpp:136-141)
+PB_HD V3 triangle_sample(const TriVerts &tv, float u1, float u2, V3 *Ns) {
+  float su1 = sqrtf(u1);
+  float b1 = 1.f - su1;
+  float b2 = u2 * su1;
+  V3 p = b1 * tv.p1 + b2 * tv.p2 + (1.f - b1 - b2) * tv.p3;
+  V3 n = cross(tv.p2 - tv.p1, tv.p3 - tv.p1);
+  *Ns = normalize(n);
+  if (tv.flags & PBRT_B200_PF_REVERSE) *Ns = *Ns * -1.f;
+  return p;
+}
+// core/mc.cpp:74-81
+PB_HD V3 uniform_sample_sphere(float u1, float u2) {
+  float z = 1.f - 2.f * u1;
+  float r = sqrtf(pb_max(0.f, 1.f - z * z));
+  float phi = 2.f * PB_PI * u2;
+  float x = r * pb_cosf(phi);
+  float y = r * pb_sinf(phi);
+  return v3(x, y, z);
+}
+// core/mc.cpp:153-161
+PB_HD V3 uniform_sample_cone(float u1, float u2, float costhetamax, const V3 &x, const V3 &y,
+                             const V3 &z) {
+  float costheta = pb_lerp(u1, costhetamax, 1.f);
+  float sintheta = sqrtf(1.f - costheta * costheta);
+  float phi = u2 * 2.f * PB_PI;
+  return pb_cosf(phi) * sintheta * x + pb_sinf(phi) * sintheta * y + costheta * z;
+}
+// Sphere::Sample(u1,u2,ns), sphere.cpp:38-44
+PB_HD V3 sphere_sample_area(const PbrtB200Sphere &s, float u1, float u2, V3 *ns) {
+  V3 p = v3(0, 0, 0) + s.radius * uniform_sample_sphere(u1, u2);
+  *ns = normalize(xf_normal(s.w2o, p));
+  if (s.flags & PBRT_B200_PF_REVERSE) *ns = *ns * -1.f;
+  return xf_point(s.o2w, p);
+}
+// Sphere::Sample(p,u1,u2,ns), sphere.cpp:45-69
+PB_HD V3 sphere_sample(const PbrtB200Sphere &s, const V3 &p, float u1, float u2, V3 *ns) {
+  V3 Pcenter = xf_point(s.o2w, v3(0, 0, 0));
+  V3 wc = normalize(Pcenter - p);
+  V3 wcX, wcY;
+  coordinate_system(wc, &wcX, &wcY);
+  if (distance_sq(p, Pcenter) - s.radius * s.radius < 1e-4f) return sphere_sample_area(s, u1, u2, ns);
+  float cosThetaMax = sqrtf(pb_max(0.f, 1.f - s.radius * s.radius / distance_sq(p, Pcenter)));
+  Ray r;
+  r.o = p;
+  r.d = uniform_sample_cone(u1, u2, cosThetaMax, wcX, wcY, wc);
+  r.mint = PB_RAY_EPSILON; r.maxt = PB_INFINITY;
+  float thit, phi; V3 phit;
+  if (!sphere_test(s, r, &thit, &phit, &phi)) thit = dot(Pcenter - p, normalize(r.d));
+  V3 ps = ray_at(r, thit);
+  *ns = normalize(ps - Pcenter);
+  if (s.flags & PBRT_B200_PF_REVERSE) *ns = *ns * -1.f;
+  return ps;
+}
+
+// Shape::Pdf(p, wi) (core/shape.h:96-107) over the light's own shape list:
+// a ShapeSet tests every member without shrinking maxt, the last hit wins
+// (core/shape.h:150-156).
+PB_HD float light_shapes_pdf(const SceneView &sv, const PbrtB200Light &l, const V3 &p, const V3 &wi) {
+  Ray ray;
+  ray.o = p; ray.d = wi; ray.mint = PB_RAY_EPSILON; ray.maxt = PB_INFINITY;
+  bool anyHit = false;
+  Hit hit; hit.prim = -1; hit.t = 0.f; hit.b1 = hit.b2 = 0.f;
+  TriVerts htv;
+  for (uint32_t i = 0; i < l.n_shapes; ++i) {
+    uint32_t prim = sv.lightShapes[l.first_shape + i];
+    TriVerts tv = load_prim(sv, prim);
+    float t, b1 = 0.f, b2 = 0.f;
+    bool ok;
+    if ((tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_TRIANGLE)
+      ok = tri_test(tv.p1, tv.p2, tv.p3, ray, &t, &b1, &b2);
+    else {
+      V3 phit; float phi;
+      ok = sphere_test(sv.spheres[sv.aux[prim].owner], ray, &t, &phit, &phi);
+    }
+    if (ok) { anyHit = true; hit.prim = (int32_t)prim; hit.t = t; hit.b1 = b1; hit.b2 = b2; htv = tv; }
+  }
+  if (!anyHit) return 0.f;
+  DiffGeom dg;
+  surface_dg(sv, ray, hit, htv, &dg);
+  float ad = absdot(dg.nn, -wi);
+  float pdf = distance_sq(p, ray_at(ray, hit.t)) / (ad * l.area);
+  if (ad == 0.f) pdf = 0.f;
+  return pdf;
+}
+// Light::Pdf(p, n, wi) for an area light (area.cpp:69-72): the single-sphere
+// light overrides Shape::Pdf (sphere.cpp:70-79).
+PB_HD float area_light_pdf(const SceneView &sv, const PbrtB200Light &l, const V3 &p, const V3 &wi) {
+  if (l.n_shapes == 1) {
+    uint32_t prim = sv.lightShapes[l.first_shape];
+    TriVerts tv = load_prim(sv, prim);
+    if ((tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_SPHERE) {
+      const PbrtB200Sphere &s = sv.spheres[sv.aux[prim].owner];
+      V3 Pcenter = xf_point(s.o2w, v3(0, 0, 0));
+      if (distance_sq(p, Pcenter) - s.radius * s.radius < 1e-4f) return light_shapes_pdf(sv, l, p, wi);
+      float cosThetaMax = sqrtf(pb_max(0.f, 1.f - s.radius * s.radius / distance_sq(p, Pcenter)));
+      return 1.f / (2.f * PB_PI * (1.f - cosThetaMax));   // UniformConePdf, mc.cpp:142-144
+    }
+  }
+  return light_shapes_pdf(sv, l, p, wi);
+}
+// shape->Sample(p, u1, u2, &ns) for the light's shape (area.cpp:63).  A ShapeSet
+// draws one RandomFloat to pick the member by area (core/shape.h:115-121).
+PB_HD V3 area_light_sample_point(const SceneView &sv, const PbrtB200Light &l, const V3 &p, float u1,
+                                 float u2, RngStream &rng, V3 *ns) {
+  uint32_t sn = 0;
+  if (l.n_shapes > 1) {
+    float ls = rng.next_float();
+    for (sn = 0; sn < l.n_shapes - 1; ++sn)
+      if (ls < sv.lightCdf[l.first_shape + sn]) break;
+  }
+  uint32_t prim = sv.lightShapes[l.first_shape + sn];
+  TriVerts tv = load_prim(sv, prim);
+  if ((tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_TRIANGLE)
+    return triangle_sample(tv, u1, u2, ns);
+  const PbrtB200Sphere &s = sv.spheres[sv.aux[prim].owner];
+  if (l.n_shapes > 1) return sphere_sample_area(s, u1, u2, ns);   // Shape::Sample(P,..) default
+  return sphere_sample(s, p, u1, u2, ns);
+}
+
+// ---------------------------------------------------------------- direct lighting
+// One EstimateDirect() call, split at its two ray queries.
+struct DirectRec {
+  Spec termA;        // f * Li * AbsDot(wi,n) [* weight] / lightPdf   -- needs the shadow ray unoccluded
+  Spec termB;        // f * Li * AbsDot(wi,n) * weight / bsdfPdf       -- needs the probe to reach the light
+  bool hasShadow, hasProbe;
+  Ray shadow;        // VisibilityTester segment: [1e-3, 1 - 1e-3] along p2 - p1
+  Ray probe;         // RayDifferential(p, wi): [1e-3, inf)
+  int32_t probeLight;
+};
+PB_HD Spec light_color(const PbrtB200Light &l) { return spec3(l.color[0], l.color[1], l.color[2]); }
+
+PB_HD void set_segment(Ray *r, const V3 &p1, const V3 &p2) {
+  r->o = p1; r->d = p2 - p1; r->mint = PB_RAY_EPSILON; r->maxt = 1.f - PB_RAY_EPSILON;
+}
+
+// transport.cpp:123-194.  ls1..bcs are already chosen by the caller
+// (Sample arrays or RandomFloat, :131-146).
+PB_HD void estimate_direct(const SceneView &sv, int lightNum, const V3 &p, const V3 &n, const V3 &wo,
+                           const Bsdf &bsdf, float ls1, float ls2, float bs1, float bs2, float bcs,
+                           RngStream &rng, DirectRec *rec) {
+  const PbrtB200Light &light = sv.lights[lightNum];
+  rec->hasShadow = rec->hasProbe = false;
+  rec->termA = rec->termB = spec(0.f);
+  rec->probeLight = lightNum;
+  V3 wi;
+  float lightPdf, bsdfPdf;
+  Spec Li;
+  bool isDelta = light.kind == PBRT_B200_LIGHT_POINT;
+  if (isDelta) {
+    V3 lightPos = v3(light.pos[0], light.pos[1], light.pos[2]);
+    lightPdf = 1.f;
+    wi = normalize(lightPos - p);
+    set_segment(&rec->shadow, p, lightPos);
+    Li = light_color(light) / distance_sq(lightPos, p);
+  } else {
+    V3 ns;
+    V3 ps = area_light_sample_point(sv, light, p, ls1, ls2, rng, &ns);
+    wi = normalize(ps - p);
+    lightPdf = area_light_pdf(sv, light, p, wi);
+    set_segment(&rec->shadow, p, ps);
+    Li = dot(ns, -wi) > 0 ? light_color(light) : spec(0.f);
+  }
+  if (lightPdf > 0.f && !is_black(Li)) {
+    Spec f = bsdf_f(bsdf, wo, wi);
+    if (!is_black(f)) {
+      rec->hasShadow = true;
+      // Li *= Transmittance (== 1 without volumes, integrators/emission.cpp:51)
+      Li = Li * spec(1.f);
+      if (isDelta)
+        rec->termA = f * Li * absdot(wi, n) / lightPdf;
+      else {
+        bsdfPdf = bsdf_pdf(bsdf, wo, wi);
+        float weight = power_heuristic(1, lightPdf, 1, bsdfPdf);
+        rec->termA = f * Li * absdot(wi, n) * weight / lightPdf;
+      }
+    }
+  }
+  if (!isDelta) {
+    int sampled;
+    Spec f = bsdf_sample_f(bsdf, wo, &wi, bs1, bs2, bcs, &bsdfPdf, PB_ALL & ~PB_SPECULAR, &sampled);
+    if (!is_black(f) && bsdfPdf > 0.f) {
+      lightPdf = area_light_pdf(sv, light, p, wi);
+      if (lightPdf > 0.f) {
+        float weight = power_heuristic(1, bsdfPdf, 1, lightPdf);
+        rec->hasProbe = true;
+        rec->probe.o = p; rec->probe.d = wi;
+        rec->probe.mint = PB_RAY_EPSILON; rec->probe.maxt = PB_INFINITY;
+        Spec Le = light_color(light) * spec(1.f);   // Li *= scene->Transmittance(ray)
+        rec->termB = f * Le * absdot(wi, n) * weight / bsdfPdf;
+      }
+    }
+  }
+}
+// Ld of one EstimateDirect call once its rays are resolved
+PB_HD Spec direct_value(const Spec &termA, const Spec &termB, bool unoccluded, bool probeHit) {
+  Spec Ld = spec(0.f);
+  if (unoccluded) Ld = Ld + termA;
+  if (probeHit) Ld = Ld + termB;
+  return Ld;
+}
+
+// ---------------------------------------------------------------- sample patterns
+// Index helpers into SceneView::patterns, which the host library lays out as
+// [1D patterns in Add1D order][2D patterns in Add2D order] (core/sampling.cpp:41-70;
+// request order: path.cpp:47-57, directlighting.cpp:39-66, emission.cpp:42-46).
+PB_HD float pat1d(const SceneView &sv, uint64_t key0, int idx, int j) {
+  return pb_lhs_value(key0, sv.patterns[idx], j, 0);
+}
+PB_HD float pat2d(const SceneView &sv, uint64_t key0, int idx, int j, int d) {
+  return pb_lhs_value(key0, sv.patterns[sv.n1D + idx], j, d);
+}
+
+// ---------------------------------------------------------------- path integrator
+struct PathVertexOut {
+  DirectRec direct;
+  bool hasDirect;      // a direct-lighting record was produced (always, when the ray hit)
+  bool hasNext;        // path continues along `next`
+  Ray next;
+};
+struct PathState {
+  Spec L, T;           // radiance so far, pathThroughput
+  Spec pendT;          // throughput the pending direct term is weighted by
+  float alpha;
+  int32_t depth;       // pathLength of the vertex about to be shaded
+  bool specularBounce;
+  RngStream rng;       // stream 1
+};
+// One iteration of the `for (pathLength = 0; ; ++pathLength)` loop body,
+// path.cpp:65-143, after scene->Intersect returned `hit`.
+PB_HD void path_vertex(const SceneView &sv, uint64_t key0, PathState &st, const Ray &ray,
+                       const Hit &hit, PathVertexOut *out) {
+  out->hasDirect = out->hasNext = false;
+  int pathLength = st.depth;
+  if (hit.prim < 0) {
+    // lights[i]->Le(ray) is black for point and area lights (core/light.cpp:41-43)
+    if (pathLength == 0) st.alpha = 0.f;   // L != 0 ? 1 : 0 with L == 0
+    return;
+  }
+  if (pathLength == 0) st.alpha = 1.f;
+  else st.T = st.T * spec(1.f);            // pathThroughput *= scene->Transmittance(ray)
+  Surface sf;
+  surface_at_hit(sv, ray, hit, &sf);
+  if (pathLength == 0 || st.specularBounce) st.L = st.L + st.T * surface_le(sv, sf, -ray.d);
+  const Bsdf &bsdf = sf.bsdf;
+  V3 p = bsdf.p, n = bsdf.nn;
+  V3 wo = -ray.d;
+  int nLights = (int)sv.nLights;
+  if (nLights > 0) {
+    // UniformSampleOneLight, transport.cpp:51-70
+    float ln, ls1, ls2, bs1, bs2, bcs;
+    if (pathLength < 3) {
+      ln = pat1d(sv, key0, 3 * pathLength, 0);
+      ls1 = pat2d(sv, key0, 3 * pathLength, 0, 0);
+      ls2 = pat2d(sv, key0, 3 * pathLength, 0, 1);
+      bs1 = pat2d(sv, key0, 3 * pathLength + 1, 0, 0);
+      bs2 = pat2d(sv, key0, 3 * pathLength + 1, 0, 1);
+      bcs = pat1d(sv, key0, 3 * pathLength + 1, 0);
+    } else {
+      ln = st.rng.next_float();
+      ls1 = st.rng.next_float(); ls2 = st.rng.next_float();
+      bs1 = st.rng.next_float(); bs2 = st.rng.next_float();
+      bcs = st.rng.next_float();
+    }
+    int lightNum = pb_imin(pb_floor2int(ln * nLights), nLights - 1);
+    estimate_direct(sv, lightNum, p, n, wo, bsdf, ls1, ls2, bs1, bs2, bcs, st.rng, &out->direct);
+    out->hasDirect = true;
+    st.pendT = st.T;
+  }
+  // NOTE: with no lights the reference dereferences lights[-1]; such scenes render black here.
+  float os1, os2, ocs;
+  if (pathLength < 3) {
+    os1 = pat2d(sv, key0, 3 * pathLength + 2, 0, 0);
+    os2 = pat2d(sv, key0, 3 * pathLength + 2, 0, 1);
+    ocs = pat1d(sv, key0, 3 * pathLength + 2, 0);
+  } else {
+    os1 = st.rng.next_float(); os2 = st.rng.next_float(); ocs = st.rng.next_float();
+  }
+  V3 wi;
+  float pdf;
+  int flags;
+  Spec f = bsdf_sample_f(bsdf, wo, &wi, os1, os2, ocs, &pdf, PB_ALL, &flags);
+  if (is_black(f) || pdf == 0.f) return;
+  st.specularBounce = (flags & PB_SPECULAR) != 0;
+  st.T = st.T * (f * absdot(wi, n) / pdf);
+  out->next.o = p; out->next.d = wi; out->next.mint = PB_RAY_EPSILON; out->next.maxt = PB_INFINITY;
+  if (pathLength > 3) {
+    float continueProbability = .5f;
+    if (st.rng.next_float() > continueProbability) return;
+    st.T = st.T * (1.f / continueProbability);   // Spectrum::operator/=(float)
+  }
+  if (pathLength == sv.integrator.max_depth) return;
+  out->hasNext = true;
+  st.depth = pathLength + 1;
+}
+// L += pathThroughput * ((float)nLights * Ld), path.cpp:100-112 + transport.cpp:66-69
+PB_HD void path_resolve_direct(const SceneView &sv, PathState &st, const Spec &termA,
+                               const Spec &termB, bool unoccluded, bool probeHit) {
+  Spec Ld = direct_value(termA, termB, unoccluded, probeHit);
+  st.L = st.L + st.pendT * ((float)sv.nLights * Ld);
+}
+
+// ---------------------------------------------------------------- Whitted / DirectLighting
+// Both integrators shade a vertex the same way -- emitted light, a sum over
+// lights, then recursion into specular reflection and transmission
+// (whitted.cpp:66-137, directlighting.cpp:104-183).  The recursion is run as
+// an explicit depth-first walk over per-sample frames so that random numbers
+// are consumed, and child radiance is folded into the parent
+// (`L += Li(child) * f * AbsDot(wi,n)`), in exactly the reference's order.
+struct WdFrame {
+  Spec L;                 // radiance of this Li() call so far
+  V3 p;                   // shading point (origin of both child rays)
+  V3 wiR, wiT;            // specular reflection / transmission directions
+  Spec fR, fT;            // f / pdf of each (BSDF::Sample_f convenience form, reflection.cpp:394-401)
+  float aR, aT;           // AbsDot(wi, n)
+  int32_t stage;          // 0: children not started, 1: reflection done, 2: complete
+  bool reflValid, transValid;
+};
+struct WdVertexOut {
+  int nRecs;              // direct-lighting records written
+};
+// number of EstimateDirect-style records a vertex can produce
+PB_HD int wd_max_records(const SceneView &sv) { return sv.directRecords; }
+
+// Vertex body up to (not including) `if (rayDepth++ < maxDepth)`.  `recs` must hold
+// wd_max_records() entries.  The frame is initialised here.
+PB_HD void wd_vertex(const SceneView &sv, uint64_t key0, const Ray &ray, const Hit &hit,
+                     RngStream &rng, int rayDepth, float *alpha, WdFrame *fr, DirectRec *recs,
+                     WdVertexOut *out) {
+  out->nRecs = 0;
+  fr->L = spec(0.f);
+  fr->stage = 2;
+  fr->reflValid = fr->transValid = false;
+  fr->p = v3(0, 0, 0); fr->wiR = fr->wiT = v3(0, 0, 0);
+  fr->fR = fr->fT = spec(0.f); fr->aR = fr->aT = 0.f;
+  if (hit.prim < 0) {
+    if (alpha) *alpha = 0.f;   // every in-scope light has black Le(ray)
+    return;
+  }
+  if (alpha) *alpha = 1.f;
+  Surface sf;
+  surface_at_hit(sv, ray, hit, &sf);
+  const Bsdf &bsdf = sf.bsdf;
+  V3 p = bsdf.p, n = bsdf.nn;
+  V3 wo = -ray.d;
+  fr->L = fr->L + surface_le(sv, sf, wo);
+  int nLights = (int)sv.nLights;
+  if (sv.integrator.kind == PBRT_B200_INT_WHITTED) {
+    // whitted.cpp:68-76
+    for (int i = 0; i < nLights; ++i) {
+      const PbrtB200Light &light = sv.lights[i];
+      DirectRec *rec = &recs[out->nRecs];
+      rec->hasShadow = rec->hasProbe = false;
+      rec->termA = rec->termB = spec(0.f);
+      rec->probeLight = i;
+      V3 wi; Spec Li;
+      if (light.kind == PBRT_B200_LIGHT_POINT) {
+        V3 lightPos = v3(light.pos[0], light.pos[1], light.pos[2]);
+        wi = normalize(lightPos - p);
+        set_segment(&rec->shadow, p, lightPos);
+        Li = light_color(light) / distance_sq(lightPos, p);
+      } else {
+        // AreaLight::Sample_L(P, &wo, &vis), area.cpp:96-105.  g++ evaluates the two
+        // RandomFloat() arguments right to left: the first draw is u2.
+        float u2 = rng.next_float();
+        float u1 = rng.next_float();
+        V3 Ns;
+        V3 Ps = area_light_sample_point(sv, light, p, u1, u2, rng, &Ns);
+        wi = normalize(Ps - p);
+        set_segment(&rec->shadow, p, Ps);
+        float pdf = area_light_pdf(sv, light, p, wi);
+        if (pdf == 0.f) Li = spec(0.f);
+        else Li = (dot(Ns, -wi) > 0 ? light_color(light) : spec(0.f)) / pdf;
+      }
+      ++out->nRecs;
+      if (is_black(Li)) continue;
+      Spec f = bsdf_f(bsdf, wo, wi);
+      if (!is_black(f)) {
+        rec->hasShadow = true;
+        rec->termA = f * Li * absdot(wi, n) * spec(1.f);
+      }
+    }
+  } else if (nLights > 0) {
+    if (sv.integrator.strategy == PBRT_B200_STRATEGY_ALL) {
+      // UniformSampleAllLights, transport.cpp:31-50; patterns per light i:
+      // 2D {2i: light, 2i+1: bsdf}, 1D {i: component} (directlighting.cpp:46-53)
+      for (int i = 0; i < nLights; ++i) {
+        int nSamples = sv.patterns[sv.n1D + 2 * i].n;
+        for (int j = 0; j < nSamples; ++j) {
+          float ls1 = pat2d(sv, key0, 2 * i, j, 0), ls2 = pat2d(sv, key0, 2 * i, j, 1);
+          float bs1 = pat2d(sv, key0, 2 * i + 1, j, 0), bs2 = pat2d(sv, key0, 2 * i + 1, j, 1);
+          float bcs = pat1d(sv, key0, i, j);
+          estimate_direct(sv, i, p, n, wo, bsdf, ls1, ls2, bs1, bs2, bcs, rng, &recs[out->nRecs]);
+          ++out->nRecs;
+        }
+      }
+    } else {
+      // UniformSampleOneLight; 2D {0: light, 1: bsdf}, 1D {0: lightNum, 1: component}
+      // (directlighting.cpp:58-64)
+      float ln = pat1d(sv, key0, 0, 0);
+      int lightNum = pb_imin(pb_floor2int(ln * nLights), nLights - 1);
+      float ls1 = pat2d(sv, key0, 0, 0, 0), ls2 = pat2d(sv, key0, 0, 0, 1);
+      float bs1 = pat2d(sv, key0, 1, 0, 0), bs2 = pat2d(sv, key0, 1, 0, 1);
+      float bcs = pat1d(sv, key0, 1, 0);
+      estimate_direct(sv, lightNum, p, n, wo, bsdf, ls1, ls2, bs1, bs2, bcs, rng, &recs[0]);
+      out->nRecs = 1;
+    }
+  }
+  // `if (rayDepth++ < maxDepth)`: both specular children are fully determined by the BSDF
+  // (the three RandomFloat()s each BSDF::Sample_f draws never matter: at most one lobe
+  // matches REFLECTION|SPECULAR or TRANSMISSION|SPECULAR); the draws themselves are
+  // accounted for by wd_advance().
+  if (rayDepth < sv.integrator.max_depth) {
+    fr->stage = 0;
+    fr->p = p;
+    float pdf; int sampled;
+    V3 wi = v3(0, 0, 0);
+    Spec f = bsdf_sample_f(bsdf, wo, &wi, 0.5f, 0.5f, 0.5f, &pdf, PB_REFLECTION | PB_SPECULAR, &sampled);
+    if (!is_black(f) && pdf > 0.f) f = f * (1.f / pdf);
+    if (!is_black(f) && absdot(wi, n) > 0.f) {
+      fr->reflValid = true; fr->wiR = wi; fr->fR = f; fr->aR = absdot(wi, n);
+    }
+    wi = v3(0, 0, 0);
+    f = bsdf_sample_f(bsdf, wo, &wi, 0.5f, 0.5f, 0.5f, &pdf, PB_TRANSMISSION | PB_SPECULAR, &sampled);
+    if (!is_black(f) && pdf > 0.f) f = f * (1.f / pdf);
+    if (!is_black(f) && absdot(wi, n) > 0.f) {
+      fr->transValid = true; fr->wiT = wi; fr->fT = f; fr->aT = absdot(wi, n);
+    }
+  }
+}
+// Fold the vertex's resolved direct-lighting records into its frame.
+// flags[r] bit0: shadow ray unoccluded, bit1: MIS probe reached the light.
+PB_HD void wd_resolve(const SceneView &sv, WdFrame *fr, const DirectRec *recs, const uint8_t *flags,
+                      int nRecs) {
+  if (nRecs == 0) return;
+  if (sv.integrator.kind == PBRT_B200_INT_WHITTED) {
+    for (int r = 0; r < nRecs; ++r)
+      if (recs[r].hasShadow && (flags[r] & 1)) fr->L = fr->L + recs[r].termA;
+    return;
+  }
+  int nLights = (int)sv.nLights;
+  if (sv.integrator.strategy == PBRT_B200_STRATEGY_ALL) {
+    Spec L = spec(0.f);
+    int r = 0;
+    for (int i = 0; i < nLights; ++i) {
+      int nSamples = sv.patterns[sv.n1D + 2 * i].n;
+      Spec Ld = spec(0.f);
+      for (int j = 0; j < nSamples; ++j, ++r)
+        Ld = Ld + direct_value(recs[r].termA, recs[r].termB, recs[r].hasShadow && (flags[r] & 1),
+                               recs[r].hasProbe && (flags[r] & 2));
+      L = L + Ld / (float)nSamples;
+    }
+    fr->L = fr->L + L;
+  } else {
+    Spec Ld = direct_value(recs[0].termA, recs[0].termB, recs[0].hasShadow && (flags[0] & 1),
+                           recs[0].hasProbe && (flags[0] & 2));
+    fr->L = fr->L + (float)nLights * Ld;
+  }
+}
+// Depth-first continuation after a vertex's direct lighting is folded in.
+// FrameIO: WdFrame load(int depth); void store(int depth, const WdFrame &).
+// `depth` is the frame of the vertex just shaded (already stored).  Returns true
+// with the next ray and its frame depth, or false when frame 0 is complete.
+template <class FrameIO>
+PB_HD bool wd_advance(FrameIO &io, RngStream &rng, int *depth, Ray *next) {
+  int d = *depth;
+  WdFrame fr = io.load(d);
+  for (;;) {
+    if (fr.stage == 0) {
+      rng.skip(3);            // BSDF::Sample_f(wo,&wi,REFLECTION|SPECULAR) draws
+      if (fr.reflValid) {
+        io.store(d, fr);
+        next->o = fr.p; next->d = fr.wiR; next->mint = PB_RAY_EPSILON; next->maxt = PB_INFINITY;
+        *depth = d + 1;
+        return true;
+      }
+      fr.stage = 1;
+    }
+    if (fr.stage == 1) {
+      rng.skip(3);            // ... TRANSMISSION|SPECULAR draws
+      if (fr.transValid) {
+        fr.stage = 3;         // transmission child in flight
+        io.store(d, fr);
+        next->o = fr.p; next->d = fr.wiT; next->mint = PB_RAY_EPSILON; next->maxt = PB_INFINITY;
+        *depth = d + 1;
+        return true;
+      }
+      fr.stage = 2;
+    }
+    // frame complete: return to the parent
+    if (d == 0) { io.store(0, fr); *depth = 0; return false; }
+    WdFrame parent = io.load(d - 1);
+    if (parent.stage == 0) {
+      parent.L = parent.L + fr.L * parent.fR * parent.aR;   // L += Li(rd) * f * AbsDot(wi,n)
+      parent.stage = 1;
+    } else {
+      parent.L = parent.L + fr.L * parent.fT * parent.aT;
+      parent.stage = 2;
+    }
+    --d;
+    fr = parent;
+  }
+}
+
+// Scene::Render's guards, core/scene.cpp:60-74.  Returns 0 ok, 1 NaN, 2 negative, 3 infinite.
+PB_HD int sample_guard(Spec *Ls) {
+  if (spec_isnan(*Ls)) { *Ls = spec(0.f); return 1; }
+  float y = spec_y(*Ls);
+  if (y < -1e-5) { *Ls = spec(0.f); return 2; }
+  if (isinf(y)) { *Ls = spec(0.f); return 3; }
+  return 0;
+}
+#endif

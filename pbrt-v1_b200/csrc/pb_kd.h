@@ -1,0 +1,142 @@
+// pb_kd.h -- kd-tree walk, the device twin of KdTreeAccel::Intersect
+// (accelerators/kdtree.cpp:313-403) and IntersectP (:404-488), over the packed
+// 8-byte nodes of include/pbrt_b200.h.
+//
+// Same tree, same child ordering, same near/far/both decisions, same
+// `ray.maxt < tmin` early-out, so primitives are tested in the reference's
+// order and equal-t ties resolve the same way (later test wins,
+// shapes/trianglemesh.cpp:245).  The reference's mailboxes
+// (kdtree.cpp:373-377) only skip repeated tests of a primitive that straddles
+// several leaves; a small per-ray ring of recently tested primitive ids plays
+// that role here.
+#ifndef PB_KD_H
+#define PB_KD_H
+#include "pb_shapes.h"
+
+struct KdCounters {
+  uint32_t interior, leaves, refs, tests;
+};
+
+// core/geometry.cpp:51-68
+PB_HD bool bbox_intersect_p(const float *bmin, const float *bmax, const Ray &ray, float *hitt0,
+                            float *hitt1) {
+  float t0 = ray.mint, t1 = ray.maxt;
+  for (int i = 0; i < 3; ++i) {
+    float invRayDir = 1.f / ray.d[i];
+    float tNear = (bmin[i] - ray.o[i]) * invRayDir;
+    float tFar = (bmax[i] - ray.o[i]) * invRayDir;
+    if (tNear > tFar) { float tmp = tNear; tNear = tFar; tFar = tmp; }
+    t0 = tNear > t0 ? tNear : t0;
+    t1 = tFar < t1 ? tFar : t1;
+    if (t0 > t1) return false;
+  }
+  *hitt0 = t0; *hitt1 = t1;
+  return true;
+}
+
+#define PB_MAILBOX 4
+
+// One primitive test: GeometricPrimitive::Intersect (core/primitive.cpp:113-122)
+// shrinks ray.maxt on an accepted hit.
+template <bool ANY>
+PB_HD bool kd_test_prim(const SceneView &sv, uint32_t prim, Ray &ray, Hit *hit) {
+  TriVerts tv = load_prim(sv, prim);
+  float t, b1 = 0.f, b2 = 0.f;
+  bool ok;
+  if ((tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_TRIANGLE) {
+    ok = tri_test(tv.p1, tv.p2, tv.p3, ray, &t, &b1, &b2);
+  } else {
+    V3 phit; float phi;
+    ok = sphere_test(sv.spheres[sv.aux[prim].owner], ray, &t, &phit, &phi);
+  }
+  if (!ok) return false;
+  if (!ANY) {
+    hit->prim = (int32_t)prim; hit->t = t; hit->b1 = b1; hit->b2 = b2;
+    ray.maxt = t;
+  }
+  return true;
+}
+
+// Returns true when something was hit.  ANY=false: closest hit in *hit.
+template <bool ANY, bool COUNT>
+PB_HD bool kd_intersect(const SceneView &sv, Ray ray, Hit *hit, KdCounters *cnt) {
+  if (!ANY) hit->prim = -1;
+  float tmin, tmax;
+  if (sv.nNodes == 0) return false;
+  if (!bbox_intersect_p(sv.bmin, sv.bmax, ray, &tmin, &tmax)) return false;
+  V3 invDir = v3(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
+  uint32_t todoNode[PB_KD_STACK];
+  float todoTmin[PB_KD_STACK], todoTmax[PB_KD_STACK];
+  int todoPos = 0;
+  uint32_t mailbox[PB_MAILBOX];
+#pragma unroll
+  for (int i = 0; i < PB_MAILBOX; ++i) mailbox[i] = 0xffffffffu;
+  int mbPos = 0;
+  bool anyHit = false;
+  uint32_t node = 0;
+  for (;;) {
+    if (!ANY && ray.maxt < tmin) break;
+#ifdef __CUDA_ARCH__
+    uint2 nd = __ldg((const uint2 *)(sv.nodes + node));
+    uint32_t w0 = nd.x, w1 = nd.y;
+#else
+    uint32_t w0 = sv.nodes[node].word0, w1 = sv.nodes[node].word1;
+#endif
+    if ((w0 & 3u) != 3u) {
+      if (COUNT) ++cnt->interior;
+      int axis = (int)(w0 & 3u);
+#ifdef __CUDA_ARCH__
+      float split = __uint_as_float(w0);   // the axis bits stay in the mantissa (kdtree.cpp:66-72)
+#else
+      float split; { uint32_t b = w0; memcpy(&split, &b, 4); }
+#endif
+      float o = ray.o[axis], d = ray.d[axis];
+      float tplane = (split - o) * invDir[axis];
+      bool belowFirst = (o < split) || (o == split && d >= 0);
+      uint32_t firstChild, secondChild;
+      if (belowFirst) { firstChild = node + 1; secondChild = w1; }
+      else { firstChild = w1; secondChild = node + 1; }
+      if (tplane > tmax || tplane <= 0)
+        node = firstChild;
+      else if (tplane < tmin)
+        node = secondChild;
+      else {
+        todoNode[todoPos] = secondChild;
+        todoTmin[todoPos] = tplane;
+        todoTmax[todoPos] = tmax;
+        ++todoPos;
+        node = firstChild;
+        tmax = tplane;
+      }
+    } else {
+      if (COUNT) ++cnt->leaves;
+      uint32_t nPrims = w0 >> 2;
+      for (uint32_t i = 0; i < nPrims; ++i) {
+        uint32_t prim = (nPrims == 1) ? w1 : sv.primRefs[w1 + i];
+        if (COUNT) ++cnt->refs;
+        bool seen = false;
+#pragma unroll
+        for (int k = 0; k < PB_MAILBOX; ++k) seen |= (mailbox[k] == prim);
+        if (seen) continue;
+#pragma unroll
+        for (int k = 0; k < PB_MAILBOX; ++k)
+          if (k == mbPos) mailbox[k] = prim;
+        mbPos = (mbPos + 1) & (PB_MAILBOX - 1);
+        if (COUNT) ++cnt->tests;
+        if (kd_test_prim<ANY>(sv, prim, ray, hit)) {
+          if (ANY) return true;
+          anyHit = true;
+        }
+      }
+      if (todoPos > 0) {
+        --todoPos;
+        node = todoNode[todoPos];
+        tmin = todoTmin[todoPos];
+        tmax = todoTmax[todoPos];
+      } else
+        break;
+    }
+  }
+  return anyHit;
+}
+#endif

@@ -1,0 +1,80 @@
+// pb_rng.h -- the per-sample keyed counter RNG and the stratified sampler's
+// patterns evaluated by random access.
+//
+// Generator: SURVEY.md App. H (normative statement: oracle/keyed_rng.h).  It
+// replaces the reference's global MT19937 (core/util.cpp:318-380) by
+// draw(key, ctr) = hi32(splitmix64(key + ctr * golden)), re-keyed
+//   (x, y, 0xFFFF, 0)  before a pixel's camera pattern  (samplers/stratified.cpp:66-85,98-115)
+//   (x, y, k, 0)       before sample k's LatinHypercube block (stratified.cpp:124-128)
+//   (x, y, k, 1)       before Li of sample k             (core/scene.cpp:57)
+// Because the generator is counter based, draw number n of any stream can be
+// evaluated directly, so one thread per image sample can reproduce the value
+// the reference's *sequential* sampler code hands to that sample: the
+// stratified jitters are plain indexed draws, and a shuffled entry is found
+// by walking the swap sequence backwards (core/sampling.cpp:91-113).
+#ifndef PB_RNG_H
+#define PB_RNG_H
+#include "pb_math.h"
+
+PB_HD uint64_t pb_mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+PB_HD uint64_t pb_key(int x, int y, int s, int stream) {
+  uint64_t k = ((uint64_t)(uint32_t)x << 32) ^ ((uint64_t)(uint32_t)y << 12) ^
+               ((uint64_t)(uint32_t)s << 2) ^ (uint64_t)(uint32_t)stream;
+  return pb_mix64(k);
+}
+// ctr is 1-based (first draw after a re-key has ctr == 1)
+PB_HD uint32_t pb_u32(uint64_t key, uint32_t ctr) {
+  return (uint32_t)(pb_mix64(key + (uint64_t)ctr * 0x9E3779B97F4A7C15ULL) >> 32);
+}
+// RandomFloat(): (u32 & 0xffffff) / 2^24  (core/util.cpp:377-380)
+PB_HD float pb_f32(uint64_t key, uint32_t ctr) {
+  return (float)(pb_u32(key, ctr) & 0xffffff) / (float)(1 << 24);
+}
+
+// Sequential stream used inside Li (stream 1).
+struct RngStream {
+  uint64_t key;
+  uint32_t ctr;   // draws made so far
+  PB_HD float next_float() { return pb_f32(key, ++ctr); }
+  PB_HD void skip(uint32_t n) { ctr += n; }
+};
+
+// Shuffle(samp, count, dims) (core/sampling.cpp:91-97) draws `count` uints
+// starting at ctr0+1: for i in [0,count): swap(i, u_i % count).  Returns the
+// index (before the shuffle) of the entry that ends at position `pos`.
+PB_HD int pb_shuffle_source(uint64_t key, uint32_t ctr0, int count, int pos) {
+  for (int i = count - 1; i >= 0; --i) {
+    int other = (int)(pb_u32(key, ctr0 + 1 + (uint32_t)i) % (uint32_t)count);
+    if (pos == i) pos = other;
+    else if (pos == other) pos = i;
+  }
+  return pos;
+}
+
+// One integrator sample pattern requested through Sample::Add1D/Add2D
+// (core/sampling.h:48-73).  `ctr0` = draws consumed by the patterns generated
+// before it in the same LatinHypercube block (1D patterns first, then 2D:
+// samplers/stratified.cpp:125-128).
+struct SamplePattern {
+  uint32_t ctr0;
+  int32_t n;      // samples in the pattern
+  int32_t dims;   // 1 or 2
+  int32_t pad;
+};
+// LatinHypercube(samples, n, dims) (core/sampling.cpp:98-113): n*dims floats
+// (sample-major), then per dimension n swap draws.  Value of sample j, dim d.
+PB_HD float pb_lhs_value(uint64_t key, const SamplePattern &p, int j, int d) {
+  float delta = 1.f / p.n;
+  int src = j;
+  if (p.n > 1) {
+    uint32_t c = p.ctr0 + (uint32_t)(p.n * p.dims) + (uint32_t)(d * p.n);
+    src = pb_shuffle_source(key, c, p.n, j);
+  }
+  float r = pb_f32(key, p.ctr0 + 1 + (uint32_t)(p.dims * src + d));
+  return (src + r) * delta;
+}
+#endif

@@ -1,0 +1,53 @@
+// pb_scene.h -- device-side view of a flattened scene (the arrays of
+// include/pbrt_b200.h after upload) plus the per-render constants the host
+// library derives from them.
+#ifndef PB_SCENE_H
+#define PB_SCENE_H
+#include "pb_math.h"
+#include "pb_rng.h"
+#include "../../include/pbrt_b200.h"
+
+#define PB_MAX_PATTERNS 64      // sample patterns addressable from constant memory
+#define PB_KD_STACK 64          // MAX_TODO, accelerators/kdtree.cpp:323
+
+// 16-byte view of the 48-byte primitive record: three aligned 128-bit loads
+// fetch a triangle's nine vertex floats plus its flags/material/light words.
+struct PrimQuad {
+  float a, b, c, d;
+};
+
+struct SceneView {
+  const PbrtB200KdNode *nodes;
+  const uint32_t *primRefs;
+  const PrimQuad *prims;            // 3 per primitive
+  const PbrtB200PrimAux *aux;
+  const PbrtB200Mesh *meshes;
+  const PbrtB200Sphere *spheres;
+  const float *vertexN, *vertexS, *vertexUV;
+  const PbrtB200Material *materials;
+  const PbrtB200Light *lights;
+  const uint32_t *lightShapes;
+  const float *lightCdf;
+  uint32_t nNodes, nPrims, nLights;
+  float bmin[3], bmax[3];
+  PbrtB200Camera camera;
+  PbrtB200Sampler sampler;
+  PbrtB200Integrator integrator;
+  // film constants (film/image.cpp:69-102)
+  int32_t xRes, yRes;
+  float filterXW, filterYW, filterInvXW, filterInvYW;
+  int32_t premultiply;
+  // sample patterns (core/sampling.cpp:41-70 layout, see pb_integrator.h)
+  int32_t nPatterns;
+  SamplePattern patterns[PB_MAX_PATTERNS];
+  // per-light pattern indices for directlighting "all" live in patterns[]:
+  // light i uses patterns 2D {2i, 2i+1} and 1D {i}; see PatternIndex helpers.
+  int32_t n1D, n2D;               // pattern counts; 2D patterns start at index n1D
+  int32_t directRecords;          // EstimateDirect calls per shaded vertex
+};
+
+struct Hit {
+  int32_t prim;   // -1 = miss
+  float t, b1, b2;
+};
+#endif

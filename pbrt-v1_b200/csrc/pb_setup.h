@@ -1,0 +1,80 @@
+// pb_setup.h -- host-side derivation of the per-render constants in SceneView
+// from a flattened scene: validation, film constants and the layout of the
+// integrators' sample patterns inside each sample's LatinHypercube block
+// (Sample::Sample, core/sampling.cpp:41-70; request order path.cpp:47-57,
+// directlighting.cpp:39-66, emission.cpp:42-46; generation order
+// samplers/stratified.cpp:125-128: all 1D patterns, then all 2D patterns).
+#ifndef PB_SETUP_H
+#define PB_SETUP_H
+#include "pb_scene.h"
+#include <string.h>
+#include <string>
+
+// Fills everything except the array pointers.  Returns an empty string or an error.
+static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
+  if (s.abi_version != PBRT_B200_ABI_VERSION) return "scene abi_version mismatch";
+  if (s.sampler.x_samples < 1 || s.sampler.y_samples < 1) return "sampler needs >= 1 sample per axis";
+  if (s.film.x_pixel_count < 1 || s.film.y_pixel_count < 1) return "empty film";
+  for (uint32_t i = 0; i < s.n_prims; ++i) {
+    uint32_t kind = s.prims[i].flags & PBRT_B200_PF_KIND_MASK;
+    if (kind != PBRT_B200_PRIM_TRIANGLE && kind != PBRT_B200_PRIM_SPHERE) return "unknown primitive kind";
+    if (s.prims[i].material >= s.n_materials) return "primitive material index out of range";
+    if (s.prims[i].light >= (int32_t)s.n_lights) return "primitive light index out of range";
+  }
+  sv->nNodes = s.n_nodes; sv->nPrims = s.n_prims; sv->nLights = s.n_lights;
+  for (int i = 0; i < 3; ++i) { sv->bmin[i] = s.bounds[i]; sv->bmax[i] = s.bounds[3 + i]; }
+  sv->camera = s.camera; sv->sampler = s.sampler; sv->integrator = s.integrator;
+  sv->xRes = s.film.x_resolution; sv->yRes = s.film.y_resolution;
+  sv->filterXW = s.film.filter_x_width; sv->filterYW = s.film.filter_y_width;
+  sv->filterInvXW = s.film.filter_inv_x_width; sv->filterInvYW = s.film.filter_inv_y_width;
+  sv->premultiply = s.film.premultiply_alpha;
+  int n1[PB_MAX_PATTERNS], n2[PB_MAX_PATTERNS];
+  int c1 = 0, c2 = 0;
+  int kind = s.integrator.kind;
+  if (kind == PBRT_B200_INT_PATH) {
+    for (int i = 0; i < 9; ++i) { n1[c1++] = 1; n2[c2++] = 1; }
+    sv->directRecords = 1;
+  } else if (kind == PBRT_B200_INT_DIRECT) {
+    if (s.integrator.strategy == PBRT_B200_STRATEGY_ALL) {
+      if (s.n_lights * 3 + 2 > PB_MAX_PATTERNS) return "too many lights for directlighting strategy all";
+      int recs = 0;
+      for (uint32_t i = 0; i < s.n_lights; ++i) {
+        int ns = s.lights[i].n_samples < 1 ? 1 : s.lights[i].n_samples;
+        n2[c2++] = ns; n2[c2++] = ns; n1[c1++] = ns;
+        recs += ns;
+      }
+      sv->directRecords = recs;
+    } else {
+      n2[c2++] = 1; n1[c1++] = 1; n2[c2++] = 1; n1[c1++] = 1;
+      sv->directRecords = 1;
+    }
+  } else if (kind == PBRT_B200_INT_WHITTED) {
+    sv->directRecords = (int)s.n_lights;
+  } else
+    return "unknown surface integrator kind";
+  if (sv->directRecords < 1) sv->directRecords = 1;
+  for (int i = 0; i < s.integrator.n_volume_1d; ++i) {
+    if (c1 >= PB_MAX_PATTERNS) return "too many sample patterns";
+    n1[c1++] = 1;
+  }
+  if (c1 + c2 > PB_MAX_PATTERNS) return "too many sample patterns";
+  uint32_t ctr = 0;
+  int k = 0;
+  for (int i = 0; i < c1; ++i, ++k) {
+    sv->patterns[k].ctr0 = ctr; sv->patterns[k].n = n1[i]; sv->patterns[k].dims = 1; sv->patterns[k].pad = 0;
+    ctr += 2u * n1[i];
+  }
+  for (int i = 0; i < c2; ++i, ++k) {
+    sv->patterns[k].ctr0 = ctr; sv->patterns[k].n = n2[i]; sv->patterns[k].dims = 2; sv->patterns[k].pad = 0;
+    ctr += 4u * n2[i];
+  }
+  sv->n1D = c1; sv->n2D = c2; sv->nPatterns = k;
+  return std::string();
+}
+// Do any materials carry a specular lobe (Whitted/DirectLighting then recurse)?
+static inline bool pb_scene_has_specular(const PbrtB200Scene &s) {
+  for (uint32_t i = 0; i < s.n_materials; ++i)
+    if (s.materials[i].kind != PBRT_B200_MAT_MATTE) return true;
+  return false;
+}
+#endif

@@ -253,6 +253,19 @@ const PbrtB200Scene *pbrt_host_scene(void *handle) {
   return handle ? &((CapturedScene *)handle)->scene : NULL;
 }
 void pbrt_host_free_scene(void *handle) { delete (CapturedScene *)handle; }
+// Scalar facts about a captured scene for callers that treat PbrtB200Scene as
+// opaque: out[0..5] = film xres, yres, crop x0, y0, width, height; out[6] =
+// samples per pixel; out[7..11] = #nodes, #prim refs, #prims, #lights, #materials;
+// out[12] = integrator kind.
+void pbrt_host_scene_info(void *handle, int64_t *out) {
+  const PbrtB200Scene &s = ((CapturedScene *)handle)->scene;
+  out[0] = s.film.x_resolution; out[1] = s.film.y_resolution;
+  out[2] = s.film.x_pixel_start; out[3] = s.film.y_pixel_start;
+  out[4] = s.film.x_pixel_count; out[5] = s.film.y_pixel_count;
+  out[6] = (int64_t)s.sampler.x_samples * s.sampler.y_samples;
+  out[7] = s.n_nodes; out[8] = s.n_prim_refs; out[9] = s.n_prims; out[10] = s.n_lights;
+  out[11] = s.n_materials; out[12] = s.integrator.kind;
+}
 
 // Full pipeline exactly as the `pbrt` executable runs it: parse, build,
 // render on the GPU, write the EXR named by the scene's Film.

@@ -1,0 +1,312 @@
+"""ctypes bindings used by tests/, bench.py and __graft_entry__.py.
+
+Three shared libraries, all plain C ABIs:
+
+  host/libpbrt_host.so    front end: .pbrt parser + api.h state machine + kd build;
+                          `load_scene()` parses a scene file and returns the flattened
+                          PbrtB200Scene (opaque pointer) that Scene::Render() would hand
+                          to the GPU library.
+  csrc/libpbrt_b200.so    the product: CUDA render hot path (include/pbrt_b200.h).
+  oracle/_build/libpbrt_twin.so   TEST ONLY: CPU restatement (oracle/twin.cpp).
+
+Nothing here computes anything; it only marshals numpy arrays.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST_LIB = os.path.join(ROOT, "pbrt-v1_b200", "host", "libpbrt_host.so")
+CUDA_LIB = os.path.join(ROOT, "pbrt-v1_b200", "csrc", "libpbrt_b200.so")
+TWIN_LIB = os.environ.get("PBRT_TWIN_LIB", os.path.join(ROOT, "oracle", "_build", "libpbrt_twin.so"))
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+class Window(C.Structure):
+    _fields_ = [("x0", C.c_int32), ("y0", C.c_int32), ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "camera_rays", "intersect_rays", "shadow_rays", "points_shaded", "interior_visits",
+        "leaf_visits", "prim_refs_read", "prim_tests", "nan_samples", "negative_samples",
+        "infinite_samples")] + [("render_ms", C.c_double), ("upload_ms", C.c_double),
+                                ("download_ms", C.c_double), ("kernel_launches", C.c_uint64),
+                                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+_host = None
+
+
+def host():
+    global _host
+    if _host is None:
+        lib = C.CDLL(HOST_LIB, mode=C.RTLD_GLOBAL)
+        lib.pbrt_host_load_scene.restype = C.c_void_p
+        lib.pbrt_host_load_scene.argtypes = [C.c_char_p]
+        lib.pbrt_host_scene.restype = C.c_void_p
+        lib.pbrt_host_scene.argtypes = [C.c_void_p]
+        lib.pbrt_host_free_scene.argtypes = [C.c_void_p]
+        lib.pbrt_host_scene_info.argtypes = [C.c_void_p, C.c_void_p]
+        lib.pbrt_host_render_file.argtypes = [C.c_char_p]
+        lib.pbrt_host_write_exr.argtypes = [C.c_char_p, C.c_void_p] + [C.c_int] * 6
+        _host = lib
+    return _host
+
+
+class Scene:
+    """A parsed + flattened scene (owns the host-side arrays)."""
+
+    def __init__(self, path):
+        self.handle = host().pbrt_host_load_scene(os.fsencode(path))
+        if not self.handle:
+            raise RuntimeError("failed to load scene %s" % path)
+        self.ptr = host().pbrt_host_scene(self.handle)
+        info = np.zeros(16, np.int64)
+        host().pbrt_host_scene_info(self.handle, _fp(info))
+        (self.xres, self.yres, self.x0, self.y0, self.width, self.height, self.spp, self.n_nodes,
+         self.n_prim_refs, self.n_prims, self.n_lights, self.n_materials, self.integrator) = [int(v) for v in info[:13]]
+
+    def full_window(self):
+        return Window(self.x0, self.y0, self.width, self.height)
+
+    def close(self):
+        if self.handle:
+            host().pbrt_host_free_scene(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ----------------------------------------------------------------- CPU twin (tests only)
+_twin = None
+
+
+def twin():
+    global _twin
+    if _twin is None:
+        lib = C.CDLL(TWIN_LIB)
+        lib.pbrt_twin_last_error.restype = C.c_char_p
+        lib.pbrt_twin_sample_count.restype = C.c_uint64
+        lib.pbrt_twin_sample_count.argtypes = [C.c_void_p, C.c_void_p]
+        lib.pbrt_twin_render.argtypes = [C.c_void_p] * 6
+        lib.pbrt_twin_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_void_p] * 4
+        lib.pbrt_twin_intersect_p.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.pbrt_twin_camera_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        _twin = lib
+    return _twin
+
+
+def twin_render(scene, window=None, want_samples=False):
+    w = window or scene.full_window()
+    rgba = np.zeros((w.height, w.width, 4), np.float32)
+    raw = np.zeros((w.height, w.width, 5), np.float32)
+    ns = twin().pbrt_twin_sample_count(scene.ptr, C.byref(w))
+    samples = np.zeros((ns, 6), np.float32) if want_samples else None
+    st = Stats()
+    rc = twin().pbrt_twin_render(scene.ptr, C.byref(w), _fp(rgba), _fp(raw),
+                                 _fp(samples) if want_samples else None, C.byref(st))
+    if rc != 0:
+        raise RuntimeError("twin render failed: %s" % twin().pbrt_twin_last_error().decode())
+    return rgba, raw, samples, st.as_dict()
+
+
+def twin_intersect(scene, rays):
+    rays = np.ascontiguousarray(rays, np.float32)
+    n = rays.shape[0]
+    prim = np.zeros(n, np.int32)
+    t = np.zeros(n, np.float32)
+    b1 = np.zeros(n, np.float32)
+    b2 = np.zeros(n, np.float32)
+    rc = twin().pbrt_twin_intersect(scene.ptr, _fp(rays), n, _fp(prim), _fp(t), _fp(b1), _fp(b2))
+    assert rc == 0
+    return prim, t, b1, b2
+
+
+def twin_intersect_p(scene, rays):
+    rays = np.ascontiguousarray(rays, np.float32)
+    n = rays.shape[0]
+    occ = np.zeros(n, np.uint8)
+    rc = twin().pbrt_twin_intersect_p(scene.ptr, _fp(rays), n, _fp(occ))
+    assert rc == 0
+    return occ
+
+
+def twin_camera_rays(scene, window=None, n=None):
+    w = window or scene.full_window()
+    total = twin().pbrt_twin_sample_count(scene.ptr, C.byref(w))
+    n = total if n is None else min(n, total)
+    rays = np.zeros((n, 8), np.float32)
+    xy = np.zeros((n, 2), np.float32)
+    rc = twin().pbrt_twin_camera_rays(scene.ptr, C.byref(w), n, _fp(rays), _fp(xy))
+    assert rc == 0
+    return rays, xy
+
+
+# ----------------------------------------------------------------- CUDA library (the product)
+_cuda = None
+
+
+def cuda():
+    """Load libpbrt_b200.so.  Raises if it is missing: there is no fallback."""
+    global _cuda
+    if _cuda is None:
+        if not os.path.exists(CUDA_LIB):
+            raise RuntimeError("CUDA library %s not built (run __graft_entry__.build())" % CUDA_LIB)
+        lib = C.CDLL(CUDA_LIB)
+        lib.pbrt_b200_last_error.restype = C.c_char_p
+        lib.pbrt_b200_scene_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        lib.pbrt_b200_scene_destroy.argtypes = [C.c_void_p]
+        lib.pbrt_b200_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        lib.pbrt_b200_film_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.pbrt_b200_film_device_ptr.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.pbrt_b200_render_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]
+        lib.pbrt_b200_tunable.restype = C.c_int64
+        lib.pbrt_b200_tunable.argtypes = [C.c_int, C.c_int64]
+        lib.pbrt_b200_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_void_p] * 4
+        lib.pbrt_b200_intersect_p.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.pbrt_b200_camera_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        lib.pbrt_b200_sample_radiance.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]
+        _cuda = lib
+    return _cuda
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError("pbrt_b200 error %d: %s" % (rc, cuda().pbrt_b200_last_error().decode()))
+
+
+class DeviceScene:
+    """Device-resident scene (pbrt_b200_scene_create / _destroy)."""
+
+    def __init__(self, scene, device=0):
+        self.scene = scene
+        h = C.c_void_p()
+        _check(cuda().pbrt_b200_scene_create(scene.ptr, device, C.byref(h)))
+        self.h = h
+
+    def render(self, windows=None):
+        ws = windows or [self.scene.full_window()]
+        arr = (Window * len(ws))(*ws)
+        st = Stats()
+        _check(cuda().pbrt_b200_render(self.h, arr, len(ws), C.byref(st)))
+        self.windows = ws
+        return st.as_dict()
+
+    def download(self, w=0, want_raw=False):
+        win = self.windows[w]
+        rgba = np.zeros((win.height, win.width, 4), np.float32)
+        raw = np.zeros((win.height, win.width, 5), np.float32) if want_raw else None
+        _check(cuda().pbrt_b200_film_download(self.h, w, _fp(rgba), _fp(raw) if want_raw else None))
+        return (rgba, raw) if want_raw else rgba
+
+    def film_device_ptr(self, w=0):
+        p = C.c_void_p()
+        n = C.c_uint64()
+        _check(cuda().pbrt_b200_film_device_ptr(self.h, w, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def sample_radiance(self, w, n):
+        out = np.zeros((n, 4), np.float32)
+        _check(cuda().pbrt_b200_sample_radiance(self.h, w, n, _fp(out)))
+        return out
+
+    def intersect(self, rays):
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        prim = np.zeros(n, np.int32)
+        t = np.zeros(n, np.float32)
+        b1 = np.zeros(n, np.float32)
+        b2 = np.zeros(n, np.float32)
+        _check(cuda().pbrt_b200_intersect(self.h, _fp(rays), n, _fp(prim), _fp(t), _fp(b1), _fp(b2)))
+        return prim, t, b1, b2
+
+    def intersect_p(self, rays):
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        occ = np.zeros(n, np.uint8)
+        _check(cuda().pbrt_b200_intersect_p(self.h, _fp(rays), n, _fp(occ)))
+        return occ
+
+    def camera_rays(self, window=None, n=None):
+        w = window or self.scene.full_window()
+        total = twin_sample_count(self.scene, w)
+        n = total if n is None else min(n, total)
+        rays = np.zeros((n, 8), np.float32)
+        xy = np.zeros((n, 2), np.float32)
+        _check(cuda().pbrt_b200_camera_rays(self.h, C.byref(w), n, _fp(rays), _fp(xy)))
+        return rays, xy
+
+    def close(self):
+        if self.h:
+            cuda().pbrt_b200_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def twin_sample_count(scene, w):
+    return int(twin().pbrt_twin_sample_count(scene.ptr, C.byref(w)))
+
+
+def render_host(scene, windows=None, device=0, want_raw=False):
+    """pbrt_b200_render_host: HOST buffers in, HOST buffers out (the call Scene::Render makes)."""
+    ws = windows or [scene.full_window()]
+    arr = (Window * len(ws))(*ws)
+    outs = [np.zeros((w.height, w.width, 4), np.float32) for w in ws]
+    raws = [np.zeros((w.height, w.width, 5), np.float32) for w in ws] if want_raw else None
+    optr = (C.c_void_p * len(ws))(*[o.ctypes.data for o in outs])
+    rptr = (C.c_void_p * len(ws))(*[r.ctypes.data for r in raws]) if want_raw else None
+    st = Stats()
+    _check(cuda().pbrt_b200_render_host(scene.ptr, device, arr, len(ws), optr, rptr, C.byref(st)))
+    return outs, raws, st.as_dict()
+
+
+# ----------------------------------------------------------------- compiled reference (oracle/_ref)
+def read_raw(path):
+    """Reads the raw float dump oracle/ref_glue.cpp writes in place of an EXR."""
+    with open(path, "rb") as f:
+        assert f.read(8) == b"PBRTRAW1"
+        hdr = np.frombuffer(f.read(24), np.int32)
+        xres, yres = int(hdr[0]), int(hdr[1])
+        px = np.frombuffer(f.read(), np.float32).reshape(yres, xres, 4)
+    return px.copy(), [int(v) for v in hdr]
+
+
+def have_reference():
+    return os.path.exists(os.path.join(REF_DIR, "pbrt_ref_keyed"))
+
+
+def run_reference(scene_path, keyed=True, dump_samples=None, cwd=None):
+    """Runs the compiled reference on a scene file; returns (stdout+stderr, seconds of the sample loop)."""
+    import subprocess
+    exe = os.path.join(REF_DIR, "pbrt_ref_keyed" if keyed else "pbrt_ref_exact")
+    env = dict(os.environ)
+    env["PBRT_SEARCHPATH"] = os.path.join(REF_DIR, "plugins_keyed" if keyed else "plugins")
+    if dump_samples:
+        env["PBRT_REF_DUMP_SAMPLES"] = dump_samples
+    p = subprocess.run([exe, scene_path], env=env, cwd=cwd, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, check=True)
+    out = p.stdout.decode(errors="replace")
+    secs = None
+    for line in out.splitlines():
+        if "PBRT_REF_RENDER_SECONDS" in line:
+            secs = float(line.split("PBRT_REF_RENDER_SECONDS")[1].split()[0])
+    return out, secs
