@@ -1,0 +1,1146 @@
+// render.cu -- libpbrt_b200.so: the CUDA render hot path behind the C ABI of
+// include/pbrt_b200.h (the drop-in for Scene::Render, core/scene.cpp:32-88).
+//
+// Execution model: a *wavefront*.  The image samples of a pixel window are
+// processed in waves of W consecutive samples (reference order: pixel-major,
+// sample-minor).  Each wave runs
+//
+//   generate   K0  sample + camera ray for every slot          -> ray queue
+//   repeat per path vertex:
+//     intersect  K1  kd-tree closest hit for the ray queue      -> hit records
+//     shade      K2  integrator vertex: BSDF, light sampling    -> shadow queue, probe queue,
+//                                                                  next ray queue (compacted)
+//     shadow     K3  kd-tree any-hit for the shadow queue       -> 1 bit per record
+//     probe      K4  closest hit + "is it the sampled light"    -> 1 bit per record
+//     [advance      Whitted/DirectLighting only: fold direct light, walk the specular
+//                   recursion depth-first, emit the next ray]
+//   finalize   K5a fold the last pending terms, sample guards   -> per-sample radiance
+//   film       K5b gather-accumulate into the pixels, reference order
+//   resolve    K6  RGB->XYZ->RGB, normalise, clamp, premultiply -> float4 film
+//
+// Queues are compacted SoA arrays filled with warp-aggregated atomics
+// (ballot + one atomicAdd per warp).  Kernels are persistent: a fixed grid of
+// numSMs x blocksPerSM CTAs whose warps fetch 32-entry chunks from an atomic
+// work counter, so long and short rays balance across the chip.  Nothing in
+// here runs on the CPU; if no CUDA device is present every entry point fails.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "pb_integrator.h"
+#include "pb_camera.h"
+#include "pb_film.h"
+#include "pb_setup.h"
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+static thread_local std::string g_lastError;
+static int fail(int code, const std::string &msg) {
+  g_lastError = msg;
+  return code;
+}
+#define CU_TRY(expr)                                                                     \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(PBRT_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// tunables (pbrt_b200_tunable)
+static int64_t g_waveSamples = 1 << 22;   // key 0: image samples per wave
+static int64_t g_countKd = 0;             // key 1: collect kd-walk counters (costs a little time)
+static int64_t g_blocksPerSM = 4;         // key 2: resident CTAs per SM for the persistent kernels
+
+#define PB_BLOCK 128
+
+// ------------------------------------------------------------------------------------------
+// device data layout of one wave
+struct RayQueue {        // compacted SoA queue of rays (closest-hit kind)
+  uint32_t *slot;        // owning sample slot
+  float *ox, *oy, *oz, *dx, *dy, *dz, *mint, *maxt;
+  int32_t *hitPrim;      // results, same index
+  float *hitT, *hitB1, *hitB2;
+};
+struct AuxQueue {        // shadow segments / MIS probes
+  uint32_t *rec;         // direct-record index (r * nSlots + slot)
+  float *ox, *oy, *oz, *dx, *dy, *dz;
+  int32_t *light;        // probes only
+};
+struct WaveBuffers {
+  uint32_t nSlots;       // capacity
+  // per-slot path state
+  float *L[3], *T[3], *pendT[3], *alpha;
+  uint32_t *ctr;         // RNG stream-1 draws so far
+  uint32_t *flags;       // bits 0-7 depth, 8 specularBounce, 9 pending direct record
+  float *imageX, *imageY;      // film coordinates of the sample
+  float *outL[3], *outA;       // per-sample radiance after the guards
+  // direct-lighting records: directRecords per slot
+  float *recA[3], *recB[3];
+  uint8_t *recFlags;     // bit0 unoccluded, bit1 probe reached light, bit2 hasShadow, bit3 hasProbe
+  // Whitted / DirectLighting recursion frames: nFrames per slot, 21 floats + 1 word each
+  float *frame;          // [field][frame][slot]
+  uint32_t *frameFlags;  // stage | reflValid<<8 | transValid<<9
+  uint32_t *nRecs;       // records written by the last wd vertex
+  int32_t nFrames;
+  RayQueue q[2];
+  AuxQueue shadowQ, probeQ;
+  // counters (device): [0..] see enum below
+  uint32_t *counts;
+  unsigned long long *stats;
+};
+enum { ST_INTERSECT = 0, ST_SHADOW, ST_SHADED, ST_INTERIOR, ST_LEAVES, ST_REFS, ST_TESTS, ST_NAN,
+       ST_NEG, ST_INF, ST_COUNT };
+// counts[] layout: per iteration it: [4*it+0] main queue size, +1 shadow queue size,
+// +2 probe queue size, +3 unused; work counters follow at PB_WORK_BASE.
+#define PB_MAX_ITERS 1024
+#define PB_WORK_BASE (4 * PB_MAX_ITERS)
+#define PB_COUNTS_TOTAL (PB_WORK_BASE + 8 * PB_MAX_ITERS)
+
+struct WaveDesc {
+  int xs, xe, ys, ye;        // sample extent of the window
+  int spp;
+  uint32_t firstPixel;       // first sample pixel (raster index in the extent) of this wave
+  uint32_t nPixels;          // sample pixels in this wave
+  uint32_t nSlots;           // nPixels * spp
+};
+
+// ------------------------------------------------------------------------------------------
+// persistent-kernel helpers
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+// Each warp claims 32 consecutive work items at a time.
+__device__ __forceinline__ uint32_t warp_claim(uint32_t *counter) {
+  uint32_t base = 0;
+  if (lane_id() == 0) base = atomicAdd(counter, 32u);
+  return __shfl_sync(0xffffffffu, base, 0);
+}
+// Warp-aggregated queue push: returns this lane's index or 0xffffffff.
+__device__ __forceinline__ uint32_t warp_push(uint32_t *count, bool pred) {
+  uint32_t mask = __ballot_sync(0xffffffffu, pred);
+  if (mask == 0) return 0xffffffffu;
+  uint32_t base = 0;
+  int leader = __ffs(mask) - 1;
+  if ((int)lane_id() == leader) base = atomicAdd(count, (uint32_t)__popc(mask));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return pred ? base + __popc(mask & ((1u << lane_id()) - 1u)) : 0xffffffffu;
+}
+__device__ __forceinline__ void warp_stat_add(unsigned long long *stat, uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane_id() == 0 && v) atomicAdd(stat, (unsigned long long)v);
+}
+
+__device__ __forceinline__ Ray queue_ray(const RayQueue &q, uint32_t i) {
+  Ray r;
+  r.o = v3(q.ox[i], q.oy[i], q.oz[i]);
+  r.d = v3(q.dx[i], q.dy[i], q.dz[i]);
+  r.mint = q.mint[i]; r.maxt = q.maxt[i];
+  return r;
+}
+__device__ __forceinline__ void queue_put(const RayQueue &q, uint32_t i, uint32_t slot, const Ray &r) {
+  q.slot[i] = slot;
+  q.ox[i] = r.o.x; q.oy[i] = r.o.y; q.oz[i] = r.o.z;
+  q.dx[i] = r.d.x; q.dy[i] = r.d.y; q.dz[i] = r.d.z;
+  q.mint[i] = r.mint; q.maxt[i] = r.maxt;
+}
+__device__ __forceinline__ void aux_put(const AuxQueue &q, uint32_t i, uint32_t rec, const Ray &r, int light) {
+  q.rec[i] = rec;
+  q.ox[i] = r.o.x; q.oy[i] = r.o.y; q.oz[i] = r.o.z;
+  q.dx[i] = r.d.x; q.dy[i] = r.d.y; q.dz[i] = r.d.z;
+  if (q.light) q.light[i] = light;
+}
+
+// ------------------------------------------------------------------------------------------
+// K0: sample generation + camera rays (samplers/stratified.cpp:87-131, cameras/perspective.cpp:51-82)
+__global__ void __launch_bounds__(PB_BLOCK)
+k_generate(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveDesc wd) {
+  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < wd.nSlots;
+       slot += gridDim.x * blockDim.x) {
+    uint32_t pix = wd.firstPixel + slot / wd.spp;
+    int k = (int)(slot % wd.spp);
+    int ew = wd.xe - wd.xs;
+    int x = wd.xs + (int)(pix % ew), y = wd.ys + (int)(pix / ew);
+    CameraSample cs;
+    stratified_camera_sample(sv, x, y, k, &cs);
+    Ray ray;
+    perspective_generate_ray(sv.camera, cs, &ray);
+    queue_put(wb.q[0], slot, slot, ray);
+    wb.imageX[slot] = film_image_coord(cs.imageX);
+    wb.imageY[slot] = film_image_coord(cs.imageY);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { wb.L[c][slot] = 0.f; wb.T[c][slot] = 1.f; }
+    wb.alpha[slot] = 0.f;
+    wb.ctr[slot] = 0u;
+    wb.flags[slot] = 0u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: closest hit (KdTreeAccel::Intersect, accelerators/kdtree.cpp:313-403)
+template <bool COUNT>
+__global__ void __launch_bounds__(PB_BLOCK)
+k_intersect(const __grid_constant__ SceneView sv, const RayQueue q, const uint32_t *nPtr,
+            uint32_t *work, unsigned long long *stats) {
+  uint32_t n = *nPtr;
+  KdCounters cnt = {0, 0, 0, 0};
+  for (;;) {
+    uint32_t base = warp_claim(work);
+    if (base >= n) break;
+    uint32_t i = base + lane_id();
+    if (i < n) {
+      Ray ray = queue_ray(q, i);
+      Hit hit;
+      kd_intersect<false, COUNT>(sv, ray, &hit, &cnt);
+      q.hitPrim[i] = hit.prim;
+      if (hit.prim >= 0) { q.hitT[i] = hit.t; q.hitB1[i] = hit.b1; q.hitB2[i] = hit.b2; }
+    }
+  }
+  if (COUNT) {
+    warp_stat_add(&stats[ST_INTERIOR], cnt.interior);
+    warp_stat_add(&stats[ST_LEAVES], cnt.leaves);
+    warp_stat_add(&stats[ST_REFS], cnt.refs);
+    warp_stat_add(&stats[ST_TESTS], cnt.tests);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_INTERSECT], (unsigned long long)n);
+}
+
+// K3: shadow rays (KdTreeAccel::IntersectP, kdtree.cpp:404-488; light.cpp:30-36)
+template <bool COUNT>
+__global__ void __launch_bounds__(PB_BLOCK)
+k_shadow(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t *nPtr, uint32_t *work,
+         uint8_t *recFlags, unsigned long long *stats) {
+  uint32_t n = *nPtr;
+  KdCounters cnt = {0, 0, 0, 0};
+  for (;;) {
+    uint32_t base = warp_claim(work);
+    if (base >= n) break;
+    uint32_t i = base + lane_id();
+    if (i < n) {
+      Ray ray;
+      ray.o = v3(q.ox[i], q.oy[i], q.oz[i]);
+      ray.d = v3(q.dx[i], q.dy[i], q.dz[i]);
+      ray.mint = PB_RAY_EPSILON; ray.maxt = 1.f - PB_RAY_EPSILON;   // light.h:78-80
+      Hit hit;
+      bool occluded = kd_intersect<true, COUNT>(sv, ray, &hit, &cnt);
+      if (!occluded) recFlags[q.rec[i]] |= 1;
+    }
+  }
+  if (COUNT) {
+    warp_stat_add(&stats[ST_INTERIOR], cnt.interior);
+    warp_stat_add(&stats[ST_LEAVES], cnt.leaves);
+    warp_stat_add(&stats[ST_REFS], cnt.refs);
+    warp_stat_add(&stats[ST_TESTS], cnt.tests);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_SHADOW], (unsigned long long)n);
+}
+
+// K4: MIS probes (transport.cpp:177-190): closest hit, then "did it reach the sampled light,
+// on its emitting side".
+template <bool COUNT>
+__global__ void __launch_bounds__(PB_BLOCK)
+k_probe(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t *nPtr, uint32_t *work,
+        uint8_t *recFlags, unsigned long long *stats) {
+  uint32_t n = *nPtr;
+  KdCounters cnt = {0, 0, 0, 0};
+  for (;;) {
+    uint32_t base = warp_claim(work);
+    if (base >= n) break;
+    uint32_t i = base + lane_id();
+    if (i < n) {
+      Ray ray;
+      ray.o = v3(q.ox[i], q.oy[i], q.oz[i]);
+      ray.d = v3(q.dx[i], q.dy[i], q.dz[i]);
+      ray.mint = PB_RAY_EPSILON; ray.maxt = PB_INFINITY;
+      Hit hit;
+      kd_intersect<false, COUNT>(sv, ray, &hit, &cnt);
+      if (hit_emits_from_light(sv, ray, hit, q.light[i])) recFlags[q.rec[i]] |= 2;
+    }
+  }
+  if (COUNT) {
+    warp_stat_add(&stats[ST_INTERIOR], cnt.interior);
+    warp_stat_add(&stats[ST_LEAVES], cnt.leaves);
+    warp_stat_add(&stats[ST_REFS], cnt.refs);
+    warp_stat_add(&stats[ST_TESTS], cnt.tests);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_INTERSECT], (unsigned long long)n);
+}
+
+// ------------------------------------------------------------------------------------------
+// per-slot state access
+__device__ __forceinline__ Spec load3(float *const a[3], uint32_t i) { return spec3(a[0][i], a[1][i], a[2][i]); }
+__device__ __forceinline__ void store3(float *const a[3], uint32_t i, const Spec &s) {
+  a[0][i] = s.c[0]; a[1][i] = s.c[1]; a[2][i] = s.c[2];
+}
+__device__ __forceinline__ uint64_t slot_key(const WaveDesc &wd, uint32_t slot, int stream) {
+  uint32_t pix = wd.firstPixel + slot / wd.spp;
+  int k = (int)(slot % wd.spp);
+  int ew = wd.xe - wd.xs;
+  return pb_key(wd.xs + (int)(pix % ew), wd.ys + (int)(pix / ew), k, stream);
+}
+// Fold the slot's pending direct-lighting record (path integrator) into L.
+__device__ __forceinline__ void path_fold_pending(const SceneView &sv, const WaveBuffers &wb,
+                                                  uint32_t slot, uint32_t *flags, Spec *L) {
+  if (!(*flags & (1u << 9))) return;
+  uint8_t rf = wb.recFlags[slot];
+  PathState tmp;
+  tmp.L = *L;
+  tmp.pendT = load3(wb.pendT, slot);
+  path_resolve_direct(sv, tmp, load3(wb.recA, slot), load3(wb.recB, slot),
+                      (rf & 4) && (rf & 1), (rf & 8) && (rf & 2));
+  *L = tmp.L;
+  *flags &= ~(1u << 9);
+}
+
+// K2 (path): one iteration of PathIntegrator::Li's loop (integrators/path.cpp:65-143)
+__global__ void __launch_bounds__(PB_BLOCK)
+k_shade_path(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveDesc wd,
+             const RayQueue qin, const RayQueue qout, const uint32_t *nPtr, uint32_t *work,
+             uint32_t *nextCount, uint32_t *shadowCount, uint32_t *probeCount) {
+  uint32_t n = *nPtr;
+  uint32_t shaded = 0;
+  for (;;) {
+    uint32_t base = warp_claim(work);
+    if (base >= n) break;
+    uint32_t i = base + lane_id();
+    bool valid = i < n;
+    bool pushShadow = false, pushProbe = false, pushNext = false;
+    PathVertexOut out;
+    uint32_t slot = 0;
+    if (valid) {
+      slot = qin.slot[i];
+      Ray ray = queue_ray(qin, i);
+      Hit hit;
+      hit.prim = qin.hitPrim[i];
+      hit.t = 0.f; hit.b1 = hit.b2 = 0.f;
+      if (hit.prim >= 0) { hit.t = qin.hitT[i]; hit.b1 = qin.hitB1[i]; hit.b2 = qin.hitB2[i]; }
+      uint32_t flags = wb.flags[slot];
+      PathState st;
+      st.L = load3(wb.L, slot);
+      path_fold_pending(sv, wb, slot, &flags, &st.L);
+      st.T = load3(wb.T, slot);
+      st.pendT = spec(0.f);
+      st.alpha = wb.alpha[slot];
+      st.depth = (int)(flags & 0xffu);
+      st.specularBounce = (flags >> 8) & 1u;
+      st.rng.key = slot_key(wd, slot, 1);
+      st.rng.ctr = wb.ctr[slot];
+      uint64_t key0 = slot_key(wd, slot, 0);
+      path_vertex(sv, key0, st, ray, hit, &out);
+      if (hit.prim >= 0) ++shaded;
+      store3(wb.L, slot, st.L);
+      store3(wb.T, slot, st.T);
+      wb.alpha[slot] = st.alpha;
+      wb.ctr[slot] = st.rng.ctr;
+      flags = (uint32_t)st.depth | (st.specularBounce ? (1u << 8) : 0u);
+      if (out.hasDirect) {
+        flags |= 1u << 9;
+        store3(wb.pendT, slot, st.pendT);
+        store3(wb.recA, slot, out.direct.termA);
+        store3(wb.recB, slot, out.direct.termB);
+        wb.recFlags[slot] = (out.direct.hasShadow ? 4 : 0) | (out.direct.hasProbe ? 8 : 0);
+        pushShadow = out.direct.hasShadow;
+        pushProbe = out.direct.hasProbe;
+      }
+      wb.flags[slot] = flags;
+      pushNext = out.hasNext;
+    }
+    uint32_t si = warp_push(shadowCount, pushShadow);
+    if (pushShadow) aux_put(wb.shadowQ, si, slot, out.direct.shadow, 0);
+    uint32_t pi = warp_push(probeCount, pushProbe);
+    if (pushProbe) aux_put(wb.probeQ, pi, slot, out.direct.probe, out.direct.probeLight);
+    uint32_t ni = warp_push(nextCount, pushNext);
+    if (pushNext) queue_put(qout, ni, slot, out.next);
+  }
+  warp_stat_add(&wb.stats[ST_SHADED], shaded);
+}
+
+// ------------------------------------------------------------------------------------------
+// Whitted / DirectLighting: frames in SoA
+#define PB_FRAME_FLOATS 21
+struct DevFrameIO {
+  const WaveBuffers *wb;
+  uint32_t slot;
+  __device__ float *fp(int field, int d) const {
+    return wb->frame + ((size_t)field * wb->nFrames + d) * wb->nSlots + slot;
+  }
+  __device__ WdFrame load(int d) const {
+    WdFrame f;
+    int k = 0;
+    for (int c = 0; c < 3; ++c) f.L.c[c] = *fp(k++, d);
+    f.p.x = *fp(k++, d); f.p.y = *fp(k++, d); f.p.z = *fp(k++, d);
+    f.wiR.x = *fp(k++, d); f.wiR.y = *fp(k++, d); f.wiR.z = *fp(k++, d);
+    f.wiT.x = *fp(k++, d); f.wiT.y = *fp(k++, d); f.wiT.z = *fp(k++, d);
+    for (int c = 0; c < 3; ++c) f.fR.c[c] = *fp(k++, d);
+    for (int c = 0; c < 3; ++c) f.fT.c[c] = *fp(k++, d);
+    f.aR = *fp(k++, d); f.aT = *fp(k++, d);
+    uint32_t fl = wb->frameFlags[(size_t)d * wb->nSlots + slot];
+    f.stage = (int)(fl & 0xffu); f.reflValid = (fl >> 8) & 1u; f.transValid = (fl >> 9) & 1u;
+    return f;
+  }
+  __device__ void store(int d, const WdFrame &f) const {
+    int k = 0;
+    for (int c = 0; c < 3; ++c) *fp(k++, d) = f.L.c[c];
+    *fp(k++, d) = f.p.x; *fp(k++, d) = f.p.y; *fp(k++, d) = f.p.z;
+    *fp(k++, d) = f.wiR.x; *fp(k++, d) = f.wiR.y; *fp(k++, d) = f.wiR.z;
+    *fp(k++, d) = f.wiT.x; *fp(k++, d) = f.wiT.y; *fp(k++, d) = f.wiT.z;
+    for (int c = 0; c < 3; ++c) *fp(k++, d) = f.fR.c[c];
+    for (int c = 0; c < 3; ++c) *fp(k++, d) = f.fT.c[c];
+    *fp(k++, d) = f.aR; *fp(k++, d) = f.aT;
+    wb->frameFlags[(size_t)d * wb->nSlots + slot] =
+        (uint32_t)f.stage | (f.reflValid ? (1u << 8) : 0u) | (f.transValid ? (1u << 9) : 0u);
+  }
+};
+
+#define PB_MAX_WD_RECS 16   // per-thread staging of direct records in the wd kernels
+
+// K2 (whitted / directlighting): vertex body up to the specular recursion
+__global__ void __launch_bounds__(PB_BLOCK)
+k_shade_wd(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveDesc wd,
+           const RayQueue qin, const uint32_t *nPtr, uint32_t *work, uint32_t *shadowCount,
+           uint32_t *probeCount) {
+  uint32_t n = *nPtr;
+  uint32_t shaded = 0;
+  for (;;) {
+    uint32_t base = warp_claim(work);
+    if (base >= n) break;
+    uint32_t i = base + lane_id();
+    bool valid = i < n;
+    DirectRec recs[PB_MAX_WD_RECS];
+    int nRecs = 0;
+    uint32_t slot = 0;
+    if (valid) {
+      slot = qin.slot[i];
+      Ray ray = queue_ray(qin, i);
+      Hit hit;
+      hit.prim = qin.hitPrim[i];
+      hit.t = 0.f; hit.b1 = hit.b2 = 0.f;
+      if (hit.prim >= 0) { hit.t = qin.hitT[i]; hit.b1 = qin.hitB1[i]; hit.b2 = qin.hitB2[i]; }
+      uint32_t flags = wb.flags[slot];
+      int depth = (int)(flags & 0xffu);
+      RngStream rng;
+      rng.key = slot_key(wd, slot, 1);
+      rng.ctr = wb.ctr[slot];
+      uint64_t key0 = slot_key(wd, slot, 0);
+      float alpha = 0.f;
+      WdFrame fr;
+      WdVertexOut out;
+      wd_vertex(sv, key0, ray, hit, rng, depth, depth == 0 ? &alpha : (float *)0, &fr, recs, &out);
+      if (hit.prim >= 0) ++shaded;
+      if (depth == 0) wb.alpha[slot] = alpha;
+      wb.ctr[slot] = rng.ctr;
+      nRecs = out.nRecs;
+      wb.nRecs[slot] = (uint32_t)nRecs;
+      DevFrameIO io = {&wb, slot};
+      io.store(depth, fr);
+      for (int r = 0; r < nRecs; ++r) {
+        size_t ri = (size_t)r * wb.nSlots + slot;
+        wb.recA[0][ri] = recs[r].termA.c[0]; wb.recA[1][ri] = recs[r].termA.c[1]; wb.recA[2][ri] = recs[r].termA.c[2];
+        wb.recB[0][ri] = recs[r].termB.c[0]; wb.recB[1][ri] = recs[r].termB.c[1]; wb.recB[2][ri] = recs[r].termB.c[2];
+        wb.recFlags[ri] = (recs[r].hasShadow ? 4 : 0) | (recs[r].hasProbe ? 8 : 0);
+      }
+    }
+    int maxRecs = nRecs;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxRecs = max(maxRecs, __shfl_xor_sync(0xffffffffu, maxRecs, o));
+    for (int r = 0; r < maxRecs; ++r) {
+      bool ps = valid && r < nRecs && recs[r].hasShadow;
+      bool pp = valid && r < nRecs && recs[r].hasProbe;
+      uint32_t ri = (uint32_t)((size_t)r * wb.nSlots + slot);
+      uint32_t si = warp_push(shadowCount, ps);
+      if (ps) aux_put(wb.shadowQ, si, ri, recs[r].shadow, 0);
+      uint32_t pi = warp_push(probeCount, pp);
+      if (pp) aux_put(wb.probeQ, pi, ri, recs[r].probe, recs[r].probeLight);
+    }
+  }
+  warp_stat_add(&wb.stats[ST_SHADED], shaded);
+}
+
+// fold direct lighting into the frame, then continue the depth-first walk
+__global__ void __launch_bounds__(PB_BLOCK)
+k_advance_wd(const __grid_constant__ SceneView sv, const WaveBuffers wb, const RayQueue qin,
+             const RayQueue qout, const uint32_t *nPtr, uint32_t *work, uint32_t *nextCount) {
+  uint32_t n = *nPtr;
+  for (;;) {
+    uint32_t base = warp_claim(work);
+    if (base >= n) break;
+    uint32_t i = base + lane_id();
+    bool valid = i < n;
+    bool pushNext = false;
+    Ray next;
+    uint32_t slot = 0;
+    if (valid) {
+      slot = qin.slot[i];
+      uint32_t flags = wb.flags[slot];
+      int depth = (int)(flags & 0xffu);
+      DevFrameIO io = {&wb, slot};
+      WdFrame fr = io.load(depth);
+      int nRecs = (int)wb.nRecs[slot];
+      DirectRec recs[PB_MAX_WD_RECS];
+      uint8_t rflags[PB_MAX_WD_RECS];
+      for (int r = 0; r < nRecs; ++r) {
+        size_t ri = (size_t)r * wb.nSlots + slot;
+        recs[r].termA = spec3(wb.recA[0][ri], wb.recA[1][ri], wb.recA[2][ri]);
+        recs[r].termB = spec3(wb.recB[0][ri], wb.recB[1][ri], wb.recB[2][ri]);
+        uint8_t f = wb.recFlags[ri];
+        recs[r].hasShadow = (f & 4) != 0; recs[r].hasProbe = (f & 8) != 0;
+        rflags[r] = f & 3;
+      }
+      wd_resolve(sv, &fr, recs, rflags, nRecs);
+      io.store(depth, fr);
+      RngStream rng;
+      rng.key = 0; rng.ctr = wb.ctr[slot];
+      pushNext = wd_advance(io, rng, &depth, &next);
+      wb.ctr[slot] = rng.ctr;
+      wb.flags[slot] = (flags & ~0xffu) | (uint32_t)depth;
+    }
+    uint32_t ni = warp_push(nextCount, pushNext);
+    if (pushNext) queue_put(qout, ni, slot, next);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5a: end of Li -> guards of Scene::Render (core/scene.cpp:58-74)
+__global__ void __launch_bounds__(PB_BLOCK)
+k_finalize(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveDesc wd) {
+  uint32_t nan = 0, neg = 0, inf = 0;
+  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < wd.nSlots;
+       slot += gridDim.x * blockDim.x) {
+    Spec L;
+    if (sv.integrator.kind == PBRT_B200_INT_PATH) {
+      uint32_t flags = wb.flags[slot];
+      L = load3(wb.L, slot);
+      path_fold_pending(sv, wb, slot, &flags, &L);
+    } else {
+      L = spec3(wb.frame[slot], wb.frame[(size_t)wb.nFrames * wb.nSlots + slot],
+                wb.frame[(size_t)2 * wb.nFrames * wb.nSlots + slot]);   // frame 0, fields 0..2
+    }
+    Spec Ls = 1.f * L;   // rayWeight * Li
+    int g = sample_guard(&Ls);
+    nan += g == 1; neg += g == 2; inf += g == 3;
+    store3(wb.outL, slot, Ls);
+    wb.outA[slot] = wb.alpha[slot];
+  }
+  warp_stat_add(&wb.stats[ST_NAN], nan);
+  warp_stat_add(&wb.stats[ST_NEG], neg);
+  warp_stat_add(&wb.stats[ST_INF], inf);
+}
+
+// K5b: ImageFilm::AddSample (film/image.cpp:103-141) as a gather, one thread per pixel.
+// Candidate sample pixels are visited in raster order and their samples in index order:
+// the order in which the reference's serial loop would have splatted them.
+__global__ void __launch_bounds__(PB_BLOCK)
+k_film_gather(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveDesc wd,
+              const float *filterTable, FilmPixel *film, PbrtB200Window win, int rowFirst, int rowCount) {
+  __shared__ float table[256];
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) table[t] = filterTable[t];
+  __syncthreads();
+  int total = rowCount * win.width;
+  int ew = wd.xe - wd.xs;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    int px = win.x0 + idx % win.width;
+    int py = rowFirst + idx / win.width;
+    FilmPixel *fpx = &film[(size_t)(py - win.y0) * win.width + (px - win.x0)];
+    FilmPixel acc = *fpx;
+    int sx0 = max(pb_floor2int(px + .5f - sv.filterXW) - 1, wd.xs);
+    int sx1 = min(pb_floor2int(px + .5f + sv.filterXW) + 1, wd.xe - 1);
+    int sy0 = max(pb_floor2int(py + .5f - sv.filterYW) - 1, wd.ys);
+    int sy1 = min(pb_floor2int(py + .5f + sv.filterYW) + 1, wd.ye - 1);
+    bool touched = false;
+    for (int sy = sy0; sy <= sy1; ++sy)
+      for (int sx = sx0; sx <= sx1; ++sx) {
+        int64_t pix = (int64_t)(sy - wd.ys) * ew + (sx - wd.xs) - (int64_t)wd.firstPixel;
+        if (pix < 0 || pix >= (int64_t)wd.nPixels) continue;
+        uint32_t s0 = (uint32_t)pix * (uint32_t)wd.spp;
+        for (int k = 0; k < wd.spp; ++k) {
+          uint32_t slot = s0 + k;
+          float wt;
+          if (!film_sample_weight(sv, table, wb.imageX[slot], wb.imageY[slot], px, py, &wt)) continue;
+          float L[3] = {wb.outL[0][slot], wb.outL[1][slot], wb.outL[2][slot]};
+          film_pixel_add(&acc, wt, L, wb.outA[slot]);
+          touched = true;
+        }
+      }
+    if (touched) *fpx = acc;
+  }
+}
+
+// K6: ImageFilm::WriteImage up to the WriteRGBAImage call (film/image.cpp:157-203)
+__global__ void k_film_resolve(const FilmPixel *film, float4 *rgba, int n, int premultiply) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float o[4];
+    film_pixel_resolve(film[i], premultiply != 0, o);
+    rgba[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// stand-alone ray kernels behind pbrt_b200_intersect / _intersect_p
+__global__ void k_rays_closest(const __grid_constant__ SceneView sv, const float *rays, uint64_t n,
+                               int32_t *prim, float *t, float *b1, float *b2) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    Ray r;
+    r.o = v3(rays[8 * i], rays[8 * i + 1], rays[8 * i + 2]);
+    r.d = v3(rays[8 * i + 3], rays[8 * i + 4], rays[8 * i + 5]);
+    r.mint = rays[8 * i + 6]; r.maxt = rays[8 * i + 7];
+    Hit h;
+    kd_intersect<false, false>(sv, r, &h, (KdCounters *)0);
+    prim[i] = h.prim;
+    t[i] = h.prim >= 0 ? h.t : 0.f; b1[i] = h.prim >= 0 ? h.b1 : 0.f; b2[i] = h.prim >= 0 ? h.b2 : 0.f;
+  }
+}
+__global__ void k_rays_any(const __grid_constant__ SceneView sv, const float *rays, uint64_t n, uint8_t *occ) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    Ray r;
+    r.o = v3(rays[8 * i], rays[8 * i + 1], rays[8 * i + 2]);
+    r.d = v3(rays[8 * i + 3], rays[8 * i + 4], rays[8 * i + 5]);
+    r.mint = rays[8 * i + 6]; r.maxt = rays[8 * i + 7];
+    Hit h;
+    occ[i] = kd_intersect<true, false>(sv, r, &h, (KdCounters *)0) ? 1 : 0;
+  }
+}
+__global__ void k_camera_rays(const __grid_constant__ SceneView sv, const WaveDesc wd, uint64_t n,
+                              float *rays, float *xy) {
+  for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < n;
+       s += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t pix = s / wd.spp;
+    int k = (int)(s % wd.spp);
+    int ew = wd.xe - wd.xs;
+    CameraSample cs;
+    stratified_camera_sample(sv, wd.xs + (int)(pix % ew), wd.ys + (int)(pix / ew), k, &cs);
+    Ray r;
+    perspective_generate_ray(sv.camera, cs, &r);
+    float *o = rays + 8 * s;
+    o[0] = r.o.x; o[1] = r.o.y; o[2] = r.o.z; o[3] = r.d.x; o[4] = r.d.y; o[5] = r.d.z;
+    o[6] = r.mint; o[7] = r.maxt;
+    xy[2 * s] = cs.imageX; xy[2 * s + 1] = cs.imageY;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+struct WindowFilm {
+  PbrtB200Window win;
+  FilmPixel *film;     // device
+  float4 *rgba;        // device
+  float *sampleOut;    // device: 4 floats per sample (kept only when requested)
+  uint64_t nSamples;
+};
+
+struct PbrtB200Handle {
+  int device;
+  cudaStream_t stream;
+  int numSMs;
+  SceneView sv;                 // device pointers
+  std::vector<void *> allocs;   // scene arrays
+  float *filterTable;
+  bool hasSpecular;
+  int nFrames;
+  uint64_t sceneBytes;
+  // wave arena
+  void *arena;
+  size_t arenaBytes;
+  WaveBuffers wb;
+  std::vector<WindowFilm> films;
+  bool keepSamples;
+};
+
+template <class T>
+static int upload(PbrtB200Handle *h, const T *src, size_t n, const T **dst) {
+  *dst = nullptr;
+  if (n == 0 || !src) return PBRT_B200_OK;
+  void *d = nullptr;
+  CU_TRY(cudaMalloc(&d, n * sizeof(T)));
+  h->allocs.push_back(d);
+  CU_TRY(cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  h->sceneBytes += n * sizeof(T);
+  *dst = (const T *)d;
+  return PBRT_B200_OK;
+}
+
+static void free_wave(PbrtB200Handle *h) {
+  if (h->arena) cudaFree(h->arena);
+  h->arena = nullptr;
+  h->arenaBytes = 0;
+  memset(&h->wb, 0, sizeof(h->wb));
+}
+
+struct Carver {
+  char *base; size_t off;
+  template <class T> T *take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T *p = base ? (T *)(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+static void carve_wave(Carver &c, WaveBuffers &wb, uint32_t nSlots, int directRecords, int nFrames, bool isPath) {
+  wb.nSlots = nSlots;
+  wb.nFrames = nFrames;
+  for (int i = 0; i < 3; ++i) {
+    wb.L[i] = c.take<float>(nSlots); wb.T[i] = c.take<float>(nSlots); wb.pendT[i] = c.take<float>(nSlots);
+    wb.outL[i] = c.take<float>(nSlots);
+    wb.recA[i] = c.take<float>((size_t)nSlots * directRecords);
+    wb.recB[i] = c.take<float>((size_t)nSlots * directRecords);
+  }
+  wb.alpha = c.take<float>(nSlots); wb.outA = c.take<float>(nSlots);
+  wb.ctr = c.take<uint32_t>(nSlots); wb.flags = c.take<uint32_t>(nSlots);
+  wb.imageX = c.take<float>(nSlots); wb.imageY = c.take<float>(nSlots);
+  wb.recFlags = c.take<uint8_t>((size_t)nSlots * directRecords);
+  if (!isPath) {
+    wb.frame = c.take<float>((size_t)PB_FRAME_FLOATS * nFrames * nSlots);
+    wb.frameFlags = c.take<uint32_t>((size_t)nFrames * nSlots);
+    wb.nRecs = c.take<uint32_t>(nSlots);
+  } else {
+    wb.frame = nullptr; wb.frameFlags = nullptr; wb.nRecs = nullptr;
+  }
+  for (int k = 0; k < 2; ++k) {
+    RayQueue &q = wb.q[k];
+    q.slot = c.take<uint32_t>(nSlots);
+    q.ox = c.take<float>(nSlots); q.oy = c.take<float>(nSlots); q.oz = c.take<float>(nSlots);
+    q.dx = c.take<float>(nSlots); q.dy = c.take<float>(nSlots); q.dz = c.take<float>(nSlots);
+    q.mint = c.take<float>(nSlots); q.maxt = c.take<float>(nSlots);
+    q.hitPrim = c.take<int32_t>(nSlots);
+    q.hitT = c.take<float>(nSlots); q.hitB1 = c.take<float>(nSlots); q.hitB2 = c.take<float>(nSlots);
+  }
+  size_t auxN = (size_t)nSlots * directRecords;
+  AuxQueue *aq[2] = {&wb.shadowQ, &wb.probeQ};
+  for (int k = 0; k < 2; ++k) {
+    AuxQueue &q = *aq[k];
+    q.rec = c.take<uint32_t>(auxN);
+    q.ox = c.take<float>(auxN); q.oy = c.take<float>(auxN); q.oz = c.take<float>(auxN);
+    q.dx = c.take<float>(auxN); q.dy = c.take<float>(auxN); q.dz = c.take<float>(auxN);
+    q.light = (k == 1) ? c.take<int32_t>(auxN) : nullptr;
+  }
+  wb.counts = c.take<uint32_t>(PB_COUNTS_TOTAL);
+  wb.stats = c.take<unsigned long long>(ST_COUNT);
+}
+
+static int ensure_wave(PbrtB200Handle *h, uint32_t nSlots) {
+  if (h->arena && h->wb.nSlots >= nSlots) return PBRT_B200_OK;
+  free_wave(h);
+  bool isPath = h->sv.integrator.kind == PBRT_B200_INT_PATH;
+  Carver sizing = {nullptr, 0};
+  WaveBuffers tmp;
+  carve_wave(sizing, tmp, nSlots, h->sv.directRecords, h->nFrames, isPath);
+  size_t bytes = sizing.off + 256;
+  CU_TRY(cudaMalloc(&h->arena, bytes));
+  h->arenaBytes = bytes;
+  Carver c = {(char *)h->arena, 0};
+  carve_wave(c, h->wb, nSlots, h->sv.directRecords, h->nFrames, isPath);
+  return PBRT_B200_OK;
+}
+
+static void free_films(PbrtB200Handle *h) {
+  for (auto &f : h->films) {
+    if (f.film) cudaFree(f.film);
+    if (f.rgba) cudaFree(f.rgba);
+    if (f.sampleOut) cudaFree(f.sampleOut);
+  }
+  h->films.clear();
+}
+
+static int persistent_grid(const PbrtB200Handle *h) { return h->numSMs * (int)g_blocksPerSM; }
+
+// One wave of the path integrator; counts/work indices advance through `it`.
+static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
+  const SceneView &sv = h->sv;
+  WaveBuffers &wb = h->wb;
+  cudaStream_t st = h->stream;
+  int grid = persistent_grid(h);
+  bool count = g_countKd != 0;
+  CU_TRY(cudaMemsetAsync(wb.counts, 0, PB_COUNTS_TOTAL * sizeof(uint32_t), st));
+  CU_TRY(cudaMemcpyAsync(&wb.counts[0], &wd.nSlots, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  int genGrid = (int)std::min<uint64_t>((wd.nSlots + PB_BLOCK - 1) / PB_BLOCK, (uint64_t)h->numSMs * 16);
+  k_generate<<<genGrid, PB_BLOCK, 0, st>>>(sv, wb, wd);
+  ++*launches;
+  uint32_t workIdx = PB_WORK_BASE;
+  auto nextWork = [&]() { return wb.counts + (workIdx++); };
+  bool isPath = sv.integrator.kind == PBRT_B200_INT_PATH;
+  int cur = 0;
+  if (isPath) {
+    int iters = sv.integrator.max_depth + 1;
+    if (iters < 1) iters = 1;
+    if (iters > PB_MAX_ITERS - 1) return fail(PBRT_B200_ERR_UNSUPPORTED, "path maxdepth too large");
+    for (int it = 0; it < iters; ++it) {
+      uint32_t *nMain = &wb.counts[4 * it], *nShadow = &wb.counts[4 * it + 1], *nProbe = &wb.counts[4 * it + 2];
+      uint32_t *nNext = &wb.counts[4 * (it + 1)];
+      if (count) k_intersect<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb.q[cur], nMain, nextWork(), wb.stats);
+      else k_intersect<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb.q[cur], nMain, nextWork(), wb.stats);
+      k_shade_path<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wd, wb.q[cur], wb.q[cur ^ 1], nMain, nextWork(), nNext,
+                                             nShadow, nProbe);
+      if (count) {
+        k_shadow<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb.shadowQ, nShadow, nextWork(), wb.recFlags, wb.stats);
+        k_probe<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb.probeQ, nProbe, nextWork(), wb.recFlags, wb.stats);
+      } else {
+        k_shadow<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb.shadowQ, nShadow, nextWork(), wb.recFlags, wb.stats);
+        k_probe<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb.probeQ, nProbe, nextWork(), wb.recFlags, wb.stats);
+      }
+      *launches += 4;
+      cur ^= 1;
+    }
+  } else {
+    // Whitted / DirectLighting: the recursion depth is data dependent; one host readback of
+    // the queue size per iteration ends the loop.
+    uint32_t nMainHost = wd.nSlots;
+    int it = 0;
+    while (nMainHost > 0) {
+      if (it >= PB_MAX_ITERS - 1) {
+        // recycle the counter block
+        CU_TRY(cudaMemsetAsync(wb.counts, 0, PB_COUNTS_TOTAL * sizeof(uint32_t), st));
+        CU_TRY(cudaMemcpyAsync(&wb.counts[0], &nMainHost, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        it = 0;
+        workIdx = PB_WORK_BASE;
+      }
+      uint32_t *nMain = &wb.counts[4 * it], *nShadow = &wb.counts[4 * it + 1], *nProbe = &wb.counts[4 * it + 2];
+      uint32_t *nNext = &wb.counts[4 * (it + 1)];
+      if (count) k_intersect<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb.q[cur], nMain, nextWork(), wb.stats);
+      else k_intersect<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb.q[cur], nMain, nextWork(), wb.stats);
+      k_shade_wd<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wd, wb.q[cur], nMain, nextWork(), nShadow, nProbe);
+      if (count) {
+        k_shadow<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb.shadowQ, nShadow, nextWork(), wb.recFlags, wb.stats);
+        k_probe<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb.probeQ, nProbe, nextWork(), wb.recFlags, wb.stats);
+      } else {
+        k_shadow<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb.shadowQ, nShadow, nextWork(), wb.recFlags, wb.stats);
+        k_probe<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb.probeQ, nProbe, nextWork(), wb.recFlags, wb.stats);
+      }
+      k_advance_wd<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], wb.q[cur ^ 1], nMain, nextWork(), nNext);
+      *launches += 5;
+      CU_TRY(cudaMemcpyAsync(&nMainHost, nNext, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CU_TRY(cudaStreamSynchronize(st));
+      cur ^= 1;
+      ++it;
+    }
+  }
+  k_finalize<<<genGrid, PB_BLOCK, 0, st>>>(sv, wb, wd);
+  ++*launches;
+  CU_TRY(cudaGetLastError());
+  return PBRT_B200_OK;
+}
+
+static WaveDesc window_desc(const SceneView &sv, const PbrtB200Window &w) {
+  WaveDesc wd;
+  memset(&wd, 0, sizeof(wd));
+  film_sample_extent(sv, w.x0, w.y0, w.width, w.height, &wd.xs, &wd.xe, &wd.ys, &wd.ye);
+  wd.spp = sv.sampler.x_samples * sv.sampler.y_samples;
+  return wd;
+}
+
+extern "C" {
+
+int pbrt_b200_abi_version(void) { return PBRT_B200_ABI_VERSION; }
+int pbrt_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+const char *pbrt_b200_last_error(void) { return g_lastError.c_str(); }
+
+int64_t pbrt_b200_tunable(int key, int64_t value) {
+  int64_t *p = key == 0 ? &g_waveSamples : key == 1 ? &g_countKd : key == 2 ? &g_blocksPerSM : nullptr;
+  if (!p) return -1;
+  int64_t prev = *p;
+  if (value >= 0) *p = value;
+  return prev;
+}
+
+void pbrt_b200_scene_destroy(PbrtB200Handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  free_films(h);
+  free_wave(h);
+  for (void *p : h->allocs) cudaFree(p);
+  if (h->filterTable) cudaFree(h->filterTable);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handle **out) {
+  if (!scene || !out) return fail(PBRT_B200_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int nDev = 0;
+  if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
+    return fail(PBRT_B200_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)");
+  if (device < 0 || device >= nDev) return fail(PBRT_B200_ERR_INVALID, "device ordinal out of range");
+  CU_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(PBRT_B200_ERR_NO_DEVICE, std::string("device is not sm_100 class: ") + prop.name);
+  PbrtB200Handle *h = new PbrtB200Handle();
+  h->device = device; h->stream = nullptr; h->numSMs = prop.multiProcessorCount;
+  h->filterTable = nullptr; h->arena = nullptr; h->arenaBytes = 0; h->sceneBytes = 0; h->keepSamples = false;
+  memset(&h->wb, 0, sizeof(h->wb));
+  memset(&h->sv, 0, sizeof(h->sv));
+  std::string err = pb_setup_view(*scene, &h->sv);
+  if (!err.empty()) { delete h; return fail(PBRT_B200_ERR_INVALID, err); }
+  h->hasSpecular = pb_scene_has_specular(*scene);
+  bool isPath = scene->integrator.kind == PBRT_B200_INT_PATH;
+  h->nFrames = isPath ? 0 : (h->hasSpecular ? std::max(0, scene->integrator.max_depth) + 1 : 1);
+  if (!isPath && h->sv.directRecords > PB_MAX_WD_RECS) {
+    delete h;
+    return fail(PBRT_B200_ERR_UNSUPPORTED, "too many light samples per shaded point for whitted/directlighting");
+  }
+  if (!isPath && h->nFrames > 64) { delete h; return fail(PBRT_B200_ERR_UNSUPPORTED, "maxdepth too large"); }
+  int rc = PBRT_B200_OK;
+  cudaError_t ce = cudaStreamCreate(&h->stream);
+  if (ce != cudaSuccess) { delete h; return fail(PBRT_B200_ERR_CUDA, cudaGetErrorString(ce)); }
+  SceneView &sv = h->sv;
+  const PbrtB200Prim *dprims = nullptr;
+#define UP(expr) do { rc = (expr); if (rc != PBRT_B200_OK) { pbrt_b200_scene_destroy(h); return rc; } } while (0)
+  UP(upload(h, scene->nodes, scene->n_nodes, &sv.nodes));
+  UP(upload(h, scene->prim_refs, scene->n_prim_refs, &sv.primRefs));
+  UP(upload(h, scene->prims, scene->n_prims, &dprims));
+  sv.prims = (const PrimQuad *)dprims;
+  UP(upload(h, scene->prim_aux, scene->n_prims, &sv.aux));
+  UP(upload(h, scene->meshes, scene->n_meshes, &sv.meshes));
+  UP(upload(h, scene->spheres, scene->n_spheres, &sv.spheres));
+  UP(upload(h, scene->vertex_n, (size_t)scene->n_vertices * 3, &sv.vertexN));
+  UP(upload(h, scene->vertex_s, (size_t)scene->n_vertices * 3, &sv.vertexS));
+  UP(upload(h, scene->vertex_uv, (size_t)scene->n_vertices * 2, &sv.vertexUV));
+  UP(upload(h, scene->materials, scene->n_materials, &sv.materials));
+  UP(upload(h, scene->lights, scene->n_lights, &sv.lights));
+  UP(upload(h, scene->light_shapes, scene->n_light_shapes, &sv.lightShapes));
+  UP(upload(h, scene->light_cdf, scene->n_light_shapes, &sv.lightCdf));
+#undef UP
+  ce = cudaMalloc((void **)&h->filterTable, 256 * sizeof(float));
+  if (ce == cudaSuccess)
+    ce = cudaMemcpyAsync(h->filterTable, scene->film.filter_table, 256 * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+  h->sceneBytes += 256 * sizeof(float);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+  if (ce != cudaSuccess) {
+    pbrt_b200_scene_destroy(h);
+    return fail(PBRT_B200_ERR_CUDA, cudaGetErrorString(ce));
+  }
+  *out = h;
+  return PBRT_B200_OK;
+}
+
+int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_windows, PbrtB200Stats *stats) {
+  if (!h || !windows || n_windows < 1) return fail(PBRT_B200_ERR_INVALID, "bad arguments");
+  CU_TRY(cudaSetDevice(h->device));
+  free_films(h);
+  const SceneView &sv = h->sv;
+  uint64_t launches = 0;
+  cudaEvent_t e0, e1;
+  CU_TRY(cudaEventCreate(&e0));
+  CU_TRY(cudaEventCreate(&e1));
+  // size the wave arena for the largest window
+  uint32_t maxSlots = 1;
+  for (int w = 0; w < n_windows; ++w) {
+    const PbrtB200Window &win = windows[w];
+    if (win.width < 1 || win.height < 1) return fail(PBRT_B200_ERR_INVALID, "empty window");
+    WaveDesc wd = window_desc(sv, win);
+    uint64_t nPix = (uint64_t)(wd.xe - wd.xs) * (wd.ye - wd.ys);
+    uint64_t wavePix = std::max<uint64_t>(1, (uint64_t)g_waveSamples / wd.spp);
+    wavePix = std::min(wavePix, nPix);
+    if (wavePix * wd.spp > 0x7fffffffull / 4) return fail(PBRT_B200_ERR_UNSUPPORTED, "wave too large");
+    maxSlots = std::max<uint32_t>(maxSlots, (uint32_t)(wavePix * wd.spp));
+  }
+  int rc = ensure_wave(h, maxSlots);
+  if (rc != PBRT_B200_OK) return rc;
+  CU_TRY(cudaMemsetAsync(h->wb.stats, 0, ST_COUNT * sizeof(unsigned long long), h->stream));
+  uint64_t cameraRays = 0;
+  CU_TRY(cudaEventRecord(e0, h->stream));
+  for (int w = 0; w < n_windows; ++w) {
+    const PbrtB200Window &win = windows[w];
+    WindowFilm wf;
+    wf.win = win; wf.film = nullptr; wf.rgba = nullptr; wf.sampleOut = nullptr;
+    size_t nPixOut = (size_t)win.width * win.height;
+    CU_TRY(cudaMalloc((void **)&wf.film, nPixOut * sizeof(FilmPixel)));
+    CU_TRY(cudaMalloc((void **)&wf.rgba, nPixOut * sizeof(float4)));
+    CU_TRY(cudaMemsetAsync(wf.film, 0, nPixOut * sizeof(FilmPixel), h->stream));
+    WaveDesc wd = window_desc(sv, win);
+    int ew = wd.xe - wd.xs;
+    uint64_t nPix = (uint64_t)ew * (wd.ye - wd.ys);
+    wf.nSamples = nPix * wd.spp;
+    if (h->keepSamples) CU_TRY(cudaMalloc((void **)&wf.sampleOut, wf.nSamples * 4 * sizeof(float)));
+    h->films.push_back(wf);
+    uint64_t wavePix = std::max<uint64_t>(1, (uint64_t)h->wb.nSlots / wd.spp);
+    for (uint64_t p0 = 0; p0 < nPix; p0 += wavePix) {
+      wd.firstPixel = (uint32_t)p0;
+      wd.nPixels = (uint32_t)std::min<uint64_t>(wavePix, nPix - p0);
+      wd.nSlots = wd.nPixels * wd.spp;
+      rc = run_wave(h, wd, &launches);
+      if (rc != PBRT_B200_OK) return rc;
+      // pixel rows this wave's samples can reach
+      int syFirst = wd.ys + (int)(p0 / ew), syLast = wd.ys + (int)((p0 + wd.nPixels - 1) / ew);
+      int rowFirst = std::max(win.y0, (int)floorf(syFirst - 0.5f - sv.filterYW) - 1);
+      int rowLast = std::min(win.y0 + win.height - 1, (int)ceilf(syLast + 1 - 0.5f + sv.filterYW) + 1);
+      if (rowLast >= rowFirst) {
+        int rows = rowLast - rowFirst + 1;
+        int total = rows * win.width;
+        int grid = std::min((total + PB_BLOCK - 1) / PB_BLOCK, h->numSMs * 16);
+        k_film_gather<<<grid, PB_BLOCK, 0, h->stream>>>(sv, h->wb, wd, h->filterTable, wf.film, win, rowFirst, rows);
+        ++launches;
+      }
+      if (wf.sampleOut) {
+        // interleave L.rgb, alpha for the test entry point
+        for (int c = 0; c < 4; ++c) {
+          const float *src = c < 3 ? h->wb.outL[c] : h->wb.outA;
+          CU_TRY(cudaMemcpy2DAsync(wf.sampleOut + (size_t)p0 * wd.spp * 4 + c, 4 * sizeof(float), src,
+                                   sizeof(float), sizeof(float), wd.nSlots, cudaMemcpyDeviceToDevice, h->stream));
+        }
+      }
+      cameraRays += wd.nSlots;
+    }
+    int grid = std::min((int)((nPixOut + 255) / 256), h->numSMs * 16);
+    k_film_resolve<<<grid, 256, 0, h->stream>>>(wf.film, wf.rgba, (int)nPixOut, sv.premultiply);
+    ++launches;
+  }
+  CU_TRY(cudaEventRecord(e1, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  CU_TRY(cudaGetLastError());
+  float ms = 0.f;
+  CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (stats) {
+    unsigned long long hs[ST_COUNT];
+    CU_TRY(cudaMemcpy(hs, h->wb.stats, sizeof(hs), cudaMemcpyDeviceToHost));
+    memset(stats, 0, sizeof(*stats));
+    stats->camera_rays = cameraRays;
+    stats->intersect_rays = hs[ST_INTERSECT]; stats->shadow_rays = hs[ST_SHADOW];
+    stats->points_shaded = hs[ST_SHADED];
+    stats->interior_visits = hs[ST_INTERIOR]; stats->leaf_visits = hs[ST_LEAVES];
+    stats->prim_refs_read = hs[ST_REFS]; stats->prim_tests = hs[ST_TESTS];
+    stats->nan_samples = hs[ST_NAN]; stats->negative_samples = hs[ST_NEG]; stats->infinite_samples = hs[ST_INF];
+    stats->render_ms = ms;
+    stats->kernel_launches = launches;
+  }
+  return PBRT_B200_OK;
+}
+
+int pbrt_b200_film_download(PbrtB200Handle *h, int w, float *rgba, float *raw) {
+  if (!h || w < 0 || w >= (int)h->films.size()) return fail(PBRT_B200_ERR_INVALID, "no such window");
+  CU_TRY(cudaSetDevice(h->device));
+  const WindowFilm &f = h->films[w];
+  size_t n = (size_t)f.win.width * f.win.height;
+  if (rgba) CU_TRY(cudaMemcpy(rgba, f.rgba, n * sizeof(float4), cudaMemcpyDeviceToHost));
+  if (raw) CU_TRY(cudaMemcpy(raw, f.film, n * sizeof(FilmPixel), cudaMemcpyDeviceToHost));
+  return PBRT_B200_OK;
+}
+
+int pbrt_b200_film_device_ptr(PbrtB200Handle *h, int w, void **dptr, uint64_t *n_floats) {
+  if (!h || w < 0 || w >= (int)h->films.size()) return fail(PBRT_B200_ERR_INVALID, "no such window");
+  *dptr = h->films[w].rgba;
+  *n_floats = (uint64_t)h->films[w].win.width * h->films[w].win.height * 4;
+  return PBRT_B200_OK;
+}
+
+int pbrt_b200_render_host(const PbrtB200Scene *scene, int device, const PbrtB200Window *windows,
+                          int n_windows, float *const *rgba_out, float *const *raw_out,
+                          PbrtB200Stats *stats) {
+  PbrtB200Handle *h = nullptr;
+  cudaEvent_t e0, e1, e2, e3;
+  int nDev = 0;
+  if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
+    return fail(PBRT_B200_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)");
+  CU_TRY(cudaSetDevice(device));
+  CU_TRY(cudaEventCreate(&e0)); CU_TRY(cudaEventCreate(&e1));
+  CU_TRY(cudaEventCreate(&e2)); CU_TRY(cudaEventCreate(&e3));
+  CU_TRY(cudaEventRecord(e0, 0));
+  int rc = pbrt_b200_scene_create(scene, device, &h);
+  if (rc != PBRT_B200_OK) return rc;
+  CU_TRY(cudaEventRecord(e1, 0));
+  PbrtB200Stats st;
+  rc = pbrt_b200_render(h, windows, n_windows, &st);
+  if (rc != PBRT_B200_OK) { pbrt_b200_scene_destroy(h); return rc; }
+  CU_TRY(cudaEventRecord(e2, 0));
+  uint64_t d2h = 0;
+  for (int w = 0; w < n_windows; ++w) {
+    rc = pbrt_b200_film_download(h, w, rgba_out ? rgba_out[w] : nullptr, raw_out ? raw_out[w] : nullptr);
+    if (rc != PBRT_B200_OK) { pbrt_b200_scene_destroy(h); return rc; }
+    size_t n = (size_t)windows[w].width * windows[w].height;
+    if (rgba_out && rgba_out[w]) d2h += n * 16;
+    if (raw_out && raw_out[w]) d2h += n * 20;
+  }
+  CU_TRY(cudaEventRecord(e3, 0));
+  CU_TRY(cudaEventSynchronize(e3));
+  float up = 0, down = 0;
+  cudaEventElapsedTime(&up, e0, e1);
+  cudaEventElapsedTime(&down, e2, e3);
+  st.upload_ms = up; st.download_ms = down;
+  st.h2d_bytes = h->sceneBytes; st.d2h_bytes = d2h;
+  if (stats) *stats = st;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+  pbrt_b200_scene_destroy(h);
+  return PBRT_B200_OK;
+}
+
+int pbrt_b200_intersect(PbrtB200Handle *h, const float *rays, uint64_t n, int32_t *hit_prim, float *hit_t,
+                        float *hit_b1, float *hit_b2) {
+  if (!h) return fail(PBRT_B200_ERR_INVALID, "null handle");
+  if (n == 0) return PBRT_B200_OK;
+  CU_TRY(cudaSetDevice(h->device));
+  float *dr; int32_t *dp; float *dt, *d1, *d2;
+  CU_TRY(cudaMalloc((void **)&dr, n * 8 * sizeof(float)));
+  CU_TRY(cudaMalloc((void **)&dp, n * sizeof(int32_t)));
+  CU_TRY(cudaMalloc((void **)&dt, n * sizeof(float)));
+  CU_TRY(cudaMalloc((void **)&d1, n * sizeof(float)));
+  CU_TRY(cudaMalloc((void **)&d2, n * sizeof(float)));
+  CU_TRY(cudaMemcpy(dr, rays, n * 8 * sizeof(float), cudaMemcpyHostToDevice));
+  int grid = (int)std::min<uint64_t>((n + 127) / 128, (uint64_t)h->numSMs * 16);
+  k_rays_closest<<<grid, 128, 0, h->stream>>>(h->sv, dr, n, dp, dt, d1, d2);
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  CU_TRY(cudaMemcpy(hit_prim, dp, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(hit_t, dt, n * sizeof(float), cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(hit_b1, d1, n * sizeof(float), cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(hit_b2, d2, n * sizeof(float), cudaMemcpyDeviceToHost));
+  cudaFree(dr); cudaFree(dp); cudaFree(dt); cudaFree(d1); cudaFree(d2);
+  return PBRT_B200_OK;
+}
+
+int pbrt_b200_intersect_p(PbrtB200Handle *h, const float *rays, uint64_t n, uint8_t *occluded) {
+  if (!h) return fail(PBRT_B200_ERR_INVALID, "null handle");
+  if (n == 0) return PBRT_B200_OK;
+  CU_TRY(cudaSetDevice(h->device));
+  float *dr; uint8_t *docc;
+  CU_TRY(cudaMalloc((void **)&dr, n * 8 * sizeof(float)));
+  CU_TRY(cudaMalloc((void **)&docc, n));
+  CU_TRY(cudaMemcpy(dr, rays, n * 8 * sizeof(float), cudaMemcpyHostToDevice));
+  int grid = (int)std::min<uint64_t>((n + 127) / 128, (uint64_t)h->numSMs * 16);
+  k_rays_any<<<grid, 128, 0, h->stream>>>(h->sv, dr, n, docc);
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  CU_TRY(cudaMemcpy(occluded, docc, n, cudaMemcpyDeviceToHost));
+  cudaFree(dr); cudaFree(docc);
+  return PBRT_B200_OK;
+}
+
+int pbrt_b200_camera_rays(PbrtB200Handle *h, const PbrtB200Window *w, uint64_t n, float *rays, float *image_xy) {
+  if (!h || !w) return fail(PBRT_B200_ERR_INVALID, "null argument");
+  if (n == 0) return PBRT_B200_OK;
+  CU_TRY(cudaSetDevice(h->device));
+  WaveDesc wd = window_desc(h->sv, *w);
+  uint64_t total = (uint64_t)(wd.xe - wd.xs) * (wd.ye - wd.ys) * wd.spp;
+  if (n > total) return fail(PBRT_B200_ERR_INVALID, "more rays requested than the window has samples");
+  float *dr, *dxy;
+  CU_TRY(cudaMalloc((void **)&dr, n * 8 * sizeof(float)));
+  CU_TRY(cudaMalloc((void **)&dxy, n * 2 * sizeof(float)));
+  int grid = (int)std::min<uint64_t>((n + 127) / 128, (uint64_t)h->numSMs * 16);
+  k_camera_rays<<<grid, 128, 0, h->stream>>>(h->sv, wd, n, dr, dxy);
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  CU_TRY(cudaMemcpy(rays, dr, n * 8 * sizeof(float), cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(image_xy, dxy, n * 2 * sizeof(float), cudaMemcpyDeviceToHost));
+  cudaFree(dr); cudaFree(dxy);
+  return PBRT_B200_OK;
+}
+
+int pbrt_b200_sample_radiance(PbrtB200Handle *h, int w, uint64_t n, float *ls) {
+  if (!h) return fail(PBRT_B200_ERR_INVALID, "null handle");
+  if (ls == nullptr) {   // arm: keep per-sample radiance on the next render
+    h->keepSamples = n != 0;
+    return PBRT_B200_OK;
+  }
+  if (w < 0 || w >= (int)h->films.size() || !h->films[w].sampleOut)
+    return fail(PBRT_B200_ERR_INVALID, "per-sample radiance was not kept: call with ls == NULL, n = 1 before rendering");
+  if (n > h->films[w].nSamples) return fail(PBRT_B200_ERR_INVALID, "more samples requested than rendered");
+  CU_TRY(cudaSetDevice(h->device));
+  CU_TRY(cudaMemcpy(ls, h->films[w].sampleOut, n * 4 * sizeof(float), cudaMemcpyDeviceToHost));
+  return PBRT_B200_OK;
+}
+
+}  // extern "C"

@@ -24,11 +24,20 @@ def fmt(v):
     return "%.9g" % float(np.float32(v))
 
 
+LENS = None      # (lensradius, focaldistance) set from the command line
+LIGHT_NSAMPLES = 1
+MIRROR_TALL_BOX = False
+SPHERE_LIGHT = False
+
+
 def header(out, res, spp, integrator, filt, jitter=True, fov=39.3, lookat=None,
            crop=None, filename="pbrt.exr", extra_integrator=""):
     lookat = lookat or (278, 273, -800, 278, 273, 0, 0, 1, 0)
     out.write("LookAt %s\n" % " ".join(fmt(v) for v in lookat))
-    out.write('Camera "perspective" "float fov" [%s]\n' % fmt(fov))
+    cam = 'Camera "perspective" "float fov" [%s]' % fmt(fov)
+    if LENS:
+        cam += ' "float lensradius" [%s] "float focaldistance" [%s]' % (fmt(LENS[0]), fmt(LENS[1]))
+    out.write(cam + "\n")
     film = 'Film "image" "integer xresolution" [%d] "integer yresolution" [%d] "string filename" ["%s"]' % (
         res[0], res[1], filename)
     if crop:
@@ -72,9 +81,12 @@ def cornell_walls(out):
     quad(out, [(0, 0, 0), (0, S, 0), (0, S, S), (0, 0, S)])          # right
     # area light just below the ceiling, facing down
     out.write("AttributeBegin\n")
-    out.write('AreaLightSource "area" "color L" [17 12 4] "integer nsamples" [1]\n')
+    out.write('AreaLightSource "area" "color L" [17 12 4] "integer nsamples" [%d]\n' % LIGHT_NSAMPLES)
     mat((.78, .78, .78))
-    quad(out, [(213, 548.7, 227), (343, 548.7, 227), (343, 548.7, 332), (213, 548.7, 332)])
+    if SPHERE_LIGHT:
+        out.write('Translate 278 480 279\nShape "sphere" "float radius" [40]\n')
+    else:
+        quad(out, [(213, 548.7, 227), (343, 548.7, 227), (343, 548.7, 332), (213, 548.7, 332)])
     out.write("AttributeEnd\n")
     mat(white)
 
@@ -86,6 +98,8 @@ def cornell_boxes(out, short=True, tall=True):
         out.write("AttributeEnd\n")
     if tall:
         out.write("AttributeBegin\nTranslate 368 165 351\nRotate 17 0 1 0\n")
+        if MIRROR_TALL_BOX:
+            out.write('Material "mirror" "color Kr" [.9 .9 .9]\n')
         box(out, 82.5, 165, 82.5)
         out.write("AttributeEnd\n")
 
@@ -163,9 +177,12 @@ def scene_c2(out, a):
 def scene_c3(out, a):
     res = a.res or (1024, 1024)
     spp = a.spp or (8, 8)
+    extra = '"integer maxdepth" [%d]' % a.maxdepth
+    if a.strategy:
+        extra += ' "string strategy" ["%s"]' % a.strategy
     header(out, res, spp, a.integrator or "path", a.filter or "box",
            jitter=a.jitter if a.jitter is not None else True, crop=a.crop, filename=a.filename,
-           extra_integrator='"integer maxdepth" [%d]' % a.maxdepth)
+           extra_integrator=extra)
     out.write("WorldBegin\n")
     cornell_walls(out)
     cornell_boxes(out)
@@ -203,7 +220,16 @@ def main():
     ap.add_argument("--normals", action="store_true")
     ap.add_argument("--nphi", type=int)
     ap.add_argument("--ntheta", type=int)
+    ap.add_argument("--lens", type=float, nargs=2, help="lensradius focaldistance")
+    ap.add_argument("--nsamples", type=int, default=1, help="area light nsamples")
+    ap.add_argument("--mirror", action="store_true", help="tall Cornell box becomes a mirror")
+    ap.add_argument("--spherelight", action="store_true", help="spherical area light instead of the quad")
     a = ap.parse_args()
+    global LENS, LIGHT_NSAMPLES, MIRROR_TALL_BOX, SPHERE_LIGHT
+    LENS = a.lens
+    LIGHT_NSAMPLES = a.nsamples
+    MIRROR_TALL_BOX = a.mirror
+    SPHERE_LIGHT = a.spherelight
     out = sys.stdout if a.output == "-" else open(a.output, "w")
     out.write("# generated by scenes/gen_scenes.py %s\n" % " ".join(sys.argv[1:]))
     if a.scene == "c1":
