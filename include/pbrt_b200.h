@@ -241,9 +241,24 @@ int pbrt_b200_render_host(const PbrtB200Scene *scene, int device,
                           float *const *rgba_out, float *const *raw_out,
                           PbrtB200Stats *stats);
 
-/* Tunables (wave size etc.); returns previous value, value < 0 only queries.
- * key: 0 = samples per wave. */
+/* Tunables; returns the previous value, value < 0 only queries.
+ * key 0: image samples per wave (default 4 Mi)
+ * key 1: collect the kd-walk counters of PbrtB200Stats (default off: they cost time)
+ * key 2: resident CTAs per SM of the persistent kernels
+ * key 3: bracket every kernel launch with CUDA events (pbrt_b200_kernel_stats) */
 int64_t pbrt_b200_tunable(int key, int64_t value);
+
+/* Per-kernel-class totals of the last pbrt_b200_render(): launches, summed
+ * CUDA-event duration (key 3 on) and, for the three traversal kernels, the
+ * kd-walk counters (key 1 on) that the roofline's algorithmic bytes are
+ * computed from. */
+typedef struct PbrtB200KernelStats {
+  char     name[24];
+  uint64_t launches;
+  double   ms;
+  uint64_t rays, interior_visits, leaf_visits, prim_refs_read, prim_tests;
+} PbrtB200KernelStats;
+int pbrt_b200_kernel_stats(PbrtB200Handle *h, PbrtB200KernelStats *out, int max_out, int *n_out);
 
 /* ---- per-stage entry points used by the parity tests (tests/), each the
  *      device twin of one reference function ---- */
@@ -262,7 +277,9 @@ int pbrt_b200_intersect_p(PbrtB200Handle *h, const float *rays, uint64_t n,
 int pbrt_b200_camera_rays(PbrtB200Handle *h, const PbrtB200Window *w,
                           uint64_t n, float *rays, float *image_xy);
 /* Per-sample radiance (after the NaN/neg/inf guards of scene.cpp:60-74) of
- * window w in reference order: 4 floats (L.rgb, alpha) per sample. */
+ * window w in reference order: 4 floats (L.rgb, alpha) per sample.  Keeping
+ * it costs memory, so it is opt-in: call with ls == NULL and n != 0 BEFORE
+ * pbrt_b200_render() to arm it (n == 0 disarms), then with a buffer after. */
 int pbrt_b200_sample_radiance(PbrtB200Handle *h, int w, uint64_t n, float *ls);
 
 #ifdef __cplusplus

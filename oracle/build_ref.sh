@@ -82,6 +82,15 @@ for ln in lines:
 assert n_cam == 2 and n_int == 1, (n_cam, n_int)
 t = '\n'.join(out)
 open(tmp + "/stratified_keyed.cpp", "w").write(t)
+# kdtree.cpp: count calls reaching the kd walk (the metric's "rays": Scene::Intersect + IntersectP)
+k = open(ref + "/accelerators/kdtree.cpp").read()
+k = k.replace('// KdAccelNode Declarations', 'extern unsigned long long gRefIntersectCalls, gRefIntersectPCalls;\n// KdAccelNode Declarations', 1)
+a = 'bool KdTreeAccel::Intersect(const Ray &ray,\n\t\tIntersection *isect) const {\n'
+b = 'bool KdTreeAccel::IntersectP(const Ray &ray) const {\n'
+assert k.count(a) == 1 and k.count(b) == 1
+k = k.replace(a, a + '\t++gRefIntersectCalls;\n').replace(b, b + '\t++gRefIntersectPCalls;\n')
+assert 'extern unsigned long long gRefIntersectCalls' in k
+open(tmp + "/kdtree_counted.cpp", "w").write(k)
 PY
 g++ $FL -c $TMP/scene_hooked.cpp -o $TMP/exact/scene.o
 cp $TMP/exact/scene.o $TMP/keyed/scene.o
@@ -102,6 +111,7 @@ for d in $PLUGDIRS; do
   done
 done
 xargs -P $JOBS -I{} sh -c "{}" < $TMP/cmds_plug
+g++ $FL -I$REF/accelerators -fPIC -shared $TMP/kdtree_counted.cpp -o $OUT/plugins/kdtree.so
 mkdir -p "$OUT/plugins_keyed"
 for f in $OUT/plugins/*.so; do ln -sf ../plugins/$(basename $f) $OUT/plugins_keyed/$(basename $f); done
 rm -f $OUT/plugins_keyed/stratified.so

@@ -36,6 +36,9 @@ COREDLL Spectrum *ReadImage(const string &name, int *, int *) {
   return NULL;
 }
 
+// incremented by the kd-tree plugin built from oracle/build_ref.sh's counted copy
+COREDLL unsigned long long gRefIntersectCalls = 0, gRefIntersectPCalls = 0;
+
 static FILE *gDump = NULL;
 static unsigned long long gSampleCounter = 0;
 static double gRenderSeconds = 0;
@@ -50,6 +53,7 @@ static double gRenderStart = 0;
 
 COREDLL void pbrtRefBeginRender() {
   gSampleCounter = 0;
+  gRefIntersectCalls = gRefIntersectPCalls = 0;
   const char *fn = getenv("PBRT_REF_DUMP_SAMPLES");
   gDump = fn ? fopen(fn, "wb") : NULL;
   gRenderStart = Now();
@@ -60,6 +64,7 @@ COREDLL void pbrtRefEndRender() {
   gDump = NULL;
   // timing of the sample loop alone (parse, kd build and image write excluded)
   fprintf(stderr, "PBRT_REF_RENDER_SECONDS %.6f SAMPLES %llu\n", gRenderSeconds, gSampleCounter);
+  fprintf(stderr, "PBRT_REF_RAYS INTERSECT %llu INTERSECTP %llu\n", gRefIntersectCalls, gRefIntersectPCalls);
 }
 COREDLL void pbrtRefDumpSample(const Sample *sample, const Spectrum &Ls, float alpha) {
   if (!gDump) return;

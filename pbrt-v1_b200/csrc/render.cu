@@ -92,8 +92,16 @@ struct WaveBuffers {
   uint32_t *counts;
   unsigned long long *stats;
 };
-enum { ST_INTERSECT = 0, ST_SHADOW, ST_SHADED, ST_INTERIOR, ST_LEAVES, ST_REFS, ST_TESTS, ST_NAN,
-       ST_NEG, ST_INF, ST_COUNT };
+// device statistics: general counters, then 5 per traversal kind (rays, interior, leaves, refs, tests)
+enum { ST_SHADED = 0, ST_NAN, ST_NEG, ST_INF, ST_KIND_BASE };
+enum { TK_MAIN = 0, TK_SHADOW, TK_PROBE, TK_COUNT };
+enum { TF_RAYS = 0, TF_INTERIOR, TF_LEAVES, TF_REFS, TF_TESTS, TF_COUNT };
+#define ST_COUNT (ST_KIND_BASE + TK_COUNT * TF_COUNT)
+#define ST_K(kind, field) (ST_KIND_BASE + (kind) * TF_COUNT + (field))
+// kernel classes for per-class timing (pbrt_b200_kernel_stats)
+enum { KC_GENERATE = 0, KC_INTERSECT, KC_SHADE, KC_SHADOW, KC_PROBE, KC_ADVANCE, KC_FINALIZE, KC_FILM, KC_COUNT };
+static const char *const kKernelClassNames[KC_COUNT] = {"k_generate", "k_intersect", "k_shade", "k_shadow",
+                                                        "k_probe", "k_advance_wd", "k_finalize", "k_film"};
 // counts[] layout: per iteration it: [4*it+0] main queue size, +1 shadow queue size,
 // +2 probe queue size, +3 unused; work counters follow at PB_WORK_BASE.
 #define PB_MAX_ITERS 1024
@@ -199,12 +207,12 @@ k_intersect(const __grid_constant__ SceneView sv, const RayQueue q, const uint32
     }
   }
   if (COUNT) {
-    warp_stat_add(&stats[ST_INTERIOR], cnt.interior);
-    warp_stat_add(&stats[ST_LEAVES], cnt.leaves);
-    warp_stat_add(&stats[ST_REFS], cnt.refs);
-    warp_stat_add(&stats[ST_TESTS], cnt.tests);
+    warp_stat_add(&stats[ST_K(TK_MAIN, TF_INTERIOR)], cnt.interior);
+    warp_stat_add(&stats[ST_K(TK_MAIN, TF_LEAVES)], cnt.leaves);
+    warp_stat_add(&stats[ST_K(TK_MAIN, TF_REFS)], cnt.refs);
+    warp_stat_add(&stats[ST_K(TK_MAIN, TF_TESTS)], cnt.tests);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_INTERSECT], (unsigned long long)n);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_K(TK_MAIN, TF_RAYS)], (unsigned long long)n);
 }
 
 // K3: shadow rays (KdTreeAccel::IntersectP, kdtree.cpp:404-488; light.cpp:30-36)
@@ -229,12 +237,12 @@ k_shadow(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t 
     }
   }
   if (COUNT) {
-    warp_stat_add(&stats[ST_INTERIOR], cnt.interior);
-    warp_stat_add(&stats[ST_LEAVES], cnt.leaves);
-    warp_stat_add(&stats[ST_REFS], cnt.refs);
-    warp_stat_add(&stats[ST_TESTS], cnt.tests);
+    warp_stat_add(&stats[ST_K(TK_SHADOW, TF_INTERIOR)], cnt.interior);
+    warp_stat_add(&stats[ST_K(TK_SHADOW, TF_LEAVES)], cnt.leaves);
+    warp_stat_add(&stats[ST_K(TK_SHADOW, TF_REFS)], cnt.refs);
+    warp_stat_add(&stats[ST_K(TK_SHADOW, TF_TESTS)], cnt.tests);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_SHADOW], (unsigned long long)n);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_K(TK_SHADOW, TF_RAYS)], (unsigned long long)n);
 }
 
 // K4: MIS probes (transport.cpp:177-190): closest hit, then "did it reach the sampled light,
@@ -260,12 +268,12 @@ k_probe(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t *
     }
   }
   if (COUNT) {
-    warp_stat_add(&stats[ST_INTERIOR], cnt.interior);
-    warp_stat_add(&stats[ST_LEAVES], cnt.leaves);
-    warp_stat_add(&stats[ST_REFS], cnt.refs);
-    warp_stat_add(&stats[ST_TESTS], cnt.tests);
+    warp_stat_add(&stats[ST_K(TK_PROBE, TF_INTERIOR)], cnt.interior);
+    warp_stat_add(&stats[ST_K(TK_PROBE, TF_LEAVES)], cnt.leaves);
+    warp_stat_add(&stats[ST_K(TK_PROBE, TF_REFS)], cnt.refs);
+    warp_stat_add(&stats[ST_K(TK_PROBE, TF_TESTS)], cnt.tests);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_INTERSECT], (unsigned long long)n);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_K(TK_PROBE, TF_RAYS)], (unsigned long long)n);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -646,7 +654,33 @@ struct PbrtB200Handle {
   WaveBuffers wb;
   std::vector<WindowFilm> films;
   bool keepSamples;
+  // per-kernel-class timing (tunable 3): events bracket every launch on h->stream
+  std::vector<cudaEvent_t> evPool;
+  std::vector<int> evClass;         // class of the launch bracketed by events 2i, 2i+1
+  double classMs[KC_COUNT];
+  uint64_t classLaunches[KC_COUNT];
+  unsigned long long lastStats[ST_COUNT];
 };
+
+static int64_t g_profileKernels = 0;   // key 3
+// Brackets one launch with events when profiling is on.
+struct LaunchTimer {
+  PbrtB200Handle *h; int idx;
+  LaunchTimer(PbrtB200Handle *hh, int cls) : h(hh), idx(-1) {
+    ++h->classLaunches[cls];
+    if (!g_profileKernels) return;
+    idx = (int)h->evClass.size();
+    h->evClass.push_back(cls);
+    while ((int)h->evPool.size() < 2 * (idx + 1)) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      h->evPool.push_back(e);
+    }
+    cudaEventRecord(h->evPool[2 * idx], h->stream);
+  }
+  ~LaunchTimer() { if (idx >= 0) cudaEventRecord(h->evPool[2 * idx + 1], h->stream); }
+};
+#define TIMED(cls, launch) do { LaunchTimer lt_(h, cls); launch; } while (0)
 
 template <class T>
 static int upload(PbrtB200Handle *h, const T *src, size_t n, const T **dst) {
@@ -745,7 +779,24 @@ static void free_films(PbrtB200Handle *h) {
 
 static int persistent_grid(const PbrtB200Handle *h) { return h->numSMs * (int)g_blocksPerSM; }
 
-// One wave of the path integrator; counts/work indices advance through `it`.
+static void launch_traversals_a(PbrtB200Handle *h, bool count, int grid, const RayQueue &q, uint32_t *nMain,
+                                uint32_t *work) {
+  if (count) TIMED(KC_INTERSECT, (k_intersect<true><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, q, nMain, work, h->wb.stats)));
+  else TIMED(KC_INTERSECT, (k_intersect<false><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, q, nMain, work, h->wb.stats)));
+}
+static void launch_traversals_b(PbrtB200Handle *h, bool count, int grid, uint32_t *nShadow, uint32_t *nProbe,
+                                uint32_t *workS, uint32_t *workP) {
+  WaveBuffers &wb = h->wb;
+  if (count) {
+    TIMED(KC_SHADOW, (k_shadow<true><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.stats)));
+    TIMED(KC_PROBE, (k_probe<true><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.stats)));
+  } else {
+    TIMED(KC_SHADOW, (k_shadow<false><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.stats)));
+    TIMED(KC_PROBE, (k_probe<false><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.stats)));
+  }
+}
+
+// One wave; counts/work indices advance through `it`.
 static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
   const SceneView &sv = h->sv;
   WaveBuffers &wb = h->wb;
@@ -755,7 +806,7 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
   CU_TRY(cudaMemsetAsync(wb.counts, 0, PB_COUNTS_TOTAL * sizeof(uint32_t), st));
   CU_TRY(cudaMemcpyAsync(&wb.counts[0], &wd.nSlots, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   int genGrid = (int)std::min<uint64_t>((wd.nSlots + PB_BLOCK - 1) / PB_BLOCK, (uint64_t)h->numSMs * 16);
-  k_generate<<<genGrid, PB_BLOCK, 0, st>>>(sv, wb, wd);
+  TIMED(KC_GENERATE, (k_generate<<<genGrid, PB_BLOCK, 0, st>>>(sv, wb, wd)));
   ++*launches;
   uint32_t workIdx = PB_WORK_BASE;
   auto nextWork = [&]() { return wb.counts + (workIdx++); };
@@ -768,17 +819,10 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
     for (int it = 0; it < iters; ++it) {
       uint32_t *nMain = &wb.counts[4 * it], *nShadow = &wb.counts[4 * it + 1], *nProbe = &wb.counts[4 * it + 2];
       uint32_t *nNext = &wb.counts[4 * (it + 1)];
-      if (count) k_intersect<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb.q[cur], nMain, nextWork(), wb.stats);
-      else k_intersect<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb.q[cur], nMain, nextWork(), wb.stats);
-      k_shade_path<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wd, wb.q[cur], wb.q[cur ^ 1], nMain, nextWork(), nNext,
-                                             nShadow, nProbe);
-      if (count) {
-        k_shadow<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb.shadowQ, nShadow, nextWork(), wb.recFlags, wb.stats);
-        k_probe<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb.probeQ, nProbe, nextWork(), wb.recFlags, wb.stats);
-      } else {
-        k_shadow<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb.shadowQ, nShadow, nextWork(), wb.recFlags, wb.stats);
-        k_probe<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb.probeQ, nProbe, nextWork(), wb.recFlags, wb.stats);
-      }
+      launch_traversals_a(h, count, grid, wb.q[cur], nMain, nextWork());
+      TIMED(KC_SHADE, (k_shade_path<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wd, wb.q[cur], wb.q[cur ^ 1], nMain, nextWork(),
+                                                             nNext, nShadow, nProbe)));
+      launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork());
       *launches += 4;
       cur ^= 1;
     }
@@ -797,17 +841,10 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
       }
       uint32_t *nMain = &wb.counts[4 * it], *nShadow = &wb.counts[4 * it + 1], *nProbe = &wb.counts[4 * it + 2];
       uint32_t *nNext = &wb.counts[4 * (it + 1)];
-      if (count) k_intersect<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb.q[cur], nMain, nextWork(), wb.stats);
-      else k_intersect<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb.q[cur], nMain, nextWork(), wb.stats);
-      k_shade_wd<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wd, wb.q[cur], nMain, nextWork(), nShadow, nProbe);
-      if (count) {
-        k_shadow<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb.shadowQ, nShadow, nextWork(), wb.recFlags, wb.stats);
-        k_probe<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb.probeQ, nProbe, nextWork(), wb.recFlags, wb.stats);
-      } else {
-        k_shadow<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb.shadowQ, nShadow, nextWork(), wb.recFlags, wb.stats);
-        k_probe<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb.probeQ, nProbe, nextWork(), wb.recFlags, wb.stats);
-      }
-      k_advance_wd<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], wb.q[cur ^ 1], nMain, nextWork(), nNext);
+      launch_traversals_a(h, count, grid, wb.q[cur], nMain, nextWork());
+      TIMED(KC_SHADE, (k_shade_wd<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wd, wb.q[cur], nMain, nextWork(), nShadow, nProbe)));
+      launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork());
+      TIMED(KC_ADVANCE, (k_advance_wd<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], wb.q[cur ^ 1], nMain, nextWork(), nNext)));
       *launches += 5;
       CU_TRY(cudaMemcpyAsync(&nMainHost, nNext, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
       CU_TRY(cudaStreamSynchronize(st));
@@ -815,7 +852,7 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
       ++it;
     }
   }
-  k_finalize<<<genGrid, PB_BLOCK, 0, st>>>(sv, wb, wd);
+  TIMED(KC_FINALIZE, (k_finalize<<<genGrid, PB_BLOCK, 0, st>>>(sv, wb, wd)));
   ++*launches;
   CU_TRY(cudaGetLastError());
   return PBRT_B200_OK;
@@ -840,7 +877,8 @@ int pbrt_b200_device_count(void) {
 const char *pbrt_b200_last_error(void) { return g_lastError.c_str(); }
 
 int64_t pbrt_b200_tunable(int key, int64_t value) {
-  int64_t *p = key == 0 ? &g_waveSamples : key == 1 ? &g_countKd : key == 2 ? &g_blocksPerSM : nullptr;
+  int64_t *p = key == 0 ? &g_waveSamples : key == 1 ? &g_countKd : key == 2 ? &g_blocksPerSM
+               : key == 3 ? &g_profileKernels : nullptr;
   if (!p) return -1;
   int64_t prev = *p;
   if (value >= 0) *p = value;
@@ -854,6 +892,7 @@ void pbrt_b200_scene_destroy(PbrtB200Handle *h) {
   free_wave(h);
   for (void *p : h->allocs) cudaFree(p);
   if (h->filterTable) cudaFree(h->filterTable);
+  for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -875,6 +914,9 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   h->filterTable = nullptr; h->arena = nullptr; h->arenaBytes = 0; h->sceneBytes = 0; h->keepSamples = false;
   memset(&h->wb, 0, sizeof(h->wb));
   memset(&h->sv, 0, sizeof(h->sv));
+  memset(h->classMs, 0, sizeof(h->classMs));
+  memset(h->classLaunches, 0, sizeof(h->classLaunches));
+  memset(h->lastStats, 0, sizeof(h->lastStats));
   std::string err = pb_setup_view(*scene, &h->sv);
   if (!err.empty()) { delete h; return fail(PBRT_B200_ERR_INVALID, err); }
   h->hasSpecular = pb_scene_has_specular(*scene);
@@ -925,6 +967,9 @@ int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_win
   free_films(h);
   const SceneView &sv = h->sv;
   uint64_t launches = 0;
+  memset(h->classMs, 0, sizeof(h->classMs));
+  memset(h->classLaunches, 0, sizeof(h->classLaunches));
+  h->evClass.clear();
   cudaEvent_t e0, e1;
   CU_TRY(cudaEventCreate(&e0));
   CU_TRY(cudaEventCreate(&e1));
@@ -974,7 +1019,8 @@ int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_win
         int rows = rowLast - rowFirst + 1;
         int total = rows * win.width;
         int grid = std::min((total + PB_BLOCK - 1) / PB_BLOCK, h->numSMs * 16);
-        k_film_gather<<<grid, PB_BLOCK, 0, h->stream>>>(sv, h->wb, wd, h->filterTable, wf.film, win, rowFirst, rows);
+        TIMED(KC_FILM, (k_film_gather<<<grid, PB_BLOCK, 0, h->stream>>>(sv, h->wb, wd, h->filterTable, wf.film, win,
+                                                                        rowFirst, rows)));
         ++launches;
       }
       if (wf.sampleOut) {
@@ -988,7 +1034,7 @@ int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_win
       cameraRays += wd.nSlots;
     }
     int grid = std::min((int)((nPixOut + 255) / 256), h->numSMs * 16);
-    k_film_resolve<<<grid, 256, 0, h->stream>>>(wf.film, wf.rgba, (int)nPixOut, sv.premultiply);
+    TIMED(KC_FILM, (k_film_resolve<<<grid, 256, 0, h->stream>>>(wf.film, wf.rgba, (int)nPixOut, sv.premultiply)));
     ++launches;
   }
   CU_TRY(cudaEventRecord(e1, h->stream));
@@ -998,19 +1044,49 @@ int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_win
   CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  for (size_t i = 0; i < h->evClass.size(); ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, h->evPool[2 * i], h->evPool[2 * i + 1]) == cudaSuccess) h->classMs[h->evClass[i]] += t;
+  }
+  {
+    unsigned long long *hs = h->lastStats;
+    CU_TRY(cudaMemcpy(hs, h->wb.stats, sizeof(h->lastStats), cudaMemcpyDeviceToHost));
+  }
   if (stats) {
-    unsigned long long hs[ST_COUNT];
-    CU_TRY(cudaMemcpy(hs, h->wb.stats, sizeof(hs), cudaMemcpyDeviceToHost));
+    const unsigned long long *hs = h->lastStats;
     memset(stats, 0, sizeof(*stats));
     stats->camera_rays = cameraRays;
-    stats->intersect_rays = hs[ST_INTERSECT]; stats->shadow_rays = hs[ST_SHADOW];
+    stats->intersect_rays = hs[ST_K(TK_MAIN, TF_RAYS)] + hs[ST_K(TK_PROBE, TF_RAYS)];
+    stats->shadow_rays = hs[ST_K(TK_SHADOW, TF_RAYS)];
     stats->points_shaded = hs[ST_SHADED];
-    stats->interior_visits = hs[ST_INTERIOR]; stats->leaf_visits = hs[ST_LEAVES];
-    stats->prim_refs_read = hs[ST_REFS]; stats->prim_tests = hs[ST_TESTS];
+    for (int k = 0; k < TK_COUNT; ++k) {
+      stats->interior_visits += hs[ST_K(k, TF_INTERIOR)]; stats->leaf_visits += hs[ST_K(k, TF_LEAVES)];
+      stats->prim_refs_read += hs[ST_K(k, TF_REFS)]; stats->prim_tests += hs[ST_K(k, TF_TESTS)];
+    }
     stats->nan_samples = hs[ST_NAN]; stats->negative_samples = hs[ST_NEG]; stats->infinite_samples = hs[ST_INF];
     stats->render_ms = ms;
     stats->kernel_launches = launches;
   }
+  return PBRT_B200_OK;
+}
+
+int pbrt_b200_kernel_stats(PbrtB200Handle *h, PbrtB200KernelStats *out, int max_out, int *n_out) {
+  if (!h || !out || !n_out) return fail(PBRT_B200_ERR_INVALID, "null argument");
+  int n = 0;
+  for (int c = 0; c < KC_COUNT && n < max_out; ++c, ++n) {
+    PbrtB200KernelStats &k = out[n];
+    memset(&k, 0, sizeof(k));
+    strncpy(k.name, kKernelClassNames[c], sizeof(k.name) - 1);
+    k.launches = h->classLaunches[c];
+    k.ms = h->classMs[c];
+    int tk = c == KC_INTERSECT ? TK_MAIN : c == KC_SHADOW ? TK_SHADOW : c == KC_PROBE ? TK_PROBE : -1;
+    if (tk >= 0) {
+      k.rays = h->lastStats[ST_K(tk, TF_RAYS)];
+      k.interior_visits = h->lastStats[ST_K(tk, TF_INTERIOR)]; k.leaf_visits = h->lastStats[ST_K(tk, TF_LEAVES)];
+      k.prim_refs_read = h->lastStats[ST_K(tk, TF_REFS)]; k.prim_tests = h->lastStats[ST_K(tk, TF_TESTS)];
+    }
+  }
+  *n_out = n;
   return PBRT_B200_OK;
 }
 

@@ -39,6 +39,12 @@ class Stats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class KernelStats(C.Structure):
+    _fields_ = [("name", C.c_char * 24), ("launches", C.c_uint64), ("ms", C.c_double), ("rays", C.c_uint64),
+                ("interior_visits", C.c_uint64), ("leaf_visits", C.c_uint64), ("prim_refs_read", C.c_uint64),
+                ("prim_tests", C.c_uint64)]
+
+
 def _fp(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -49,7 +55,7 @@ _host = None
 def host():
     global _host
     if _host is None:
-        lib = C.CDLL(HOST_LIB, mode=C.RTLD_GLOBAL)
+        lib = C.CDLL(HOST_LIB)
         lib.pbrt_host_load_scene.restype = C.c_void_p
         lib.pbrt_host_load_scene.argtypes = [C.c_char_p]
         lib.pbrt_host_scene.restype = C.c_void_p
@@ -180,6 +186,7 @@ def cuda():
         lib.pbrt_b200_intersect_p.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.pbrt_b200_camera_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         lib.pbrt_b200_sample_radiance.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]
+        lib.pbrt_b200_kernel_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _cuda = lib
     return _cuda
 
@@ -212,6 +219,16 @@ class DeviceScene:
         raw = np.zeros((win.height, win.width, 5), np.float32) if want_raw else None
         _check(cuda().pbrt_b200_film_download(self.h, w, _fp(rgba), _fp(raw) if want_raw else None))
         return (rgba, raw) if want_raw else rgba
+
+    def kernel_stats(self):
+        arr = (KernelStats * 16)()
+        n = C.c_int()
+        _check(cuda().pbrt_b200_kernel_stats(self.h, arr, 16, C.byref(n)))
+        out = {}
+        for i in range(n.value):
+            k = arr[i]
+            out[k.name.decode()] = {f: getattr(k, f) for f, _ in KernelStats._fields_ if f != "name"}
+        return out
 
     def film_device_ptr(self, w=0):
         p = C.c_void_p()

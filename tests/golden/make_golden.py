@@ -1,0 +1,81 @@
+#!/usr/bin/env python3
+"""Generates the golden fixtures in this directory from the COMPILED REFERENCE.
+
+Run in the build container (needs oracle/_ref, i.e. /root/reference + oracle/build_ref.sh):
+
+    python tests/golden/make_golden.py
+
+For every case below it writes the scene file (<case>.pbrt, produced by scenes/gen_scenes.py)
+and <case>.npz holding what the reference renderer produced for it:
+
+    rgba      float32 [h, w, 4]  the arrays ImageFilm::WriteImage hands to WriteRGBAImage
+    samples   float32 [n, 6]     imageX, imageY, L.rgb (after the scene.cpp:60-74 guards), alpha
+                                 for every image sample in the reference's order
+    stats     int64 [3]          camera rays, shadow rays, points shaded (the reference's own
+                                 post-render statistics)
+
+Cases marked keyed=True come from oracle/_ref/pbrt_ref_keyed (reference + per-sample RNG
+re-keying); "c1_exact" comes from the UNMODIFIED reference
+(pbrt_ref_exact) and pins the one configuration whose result does not depend on the
+random-number stream (Whitted, point light, jitter off).
+"""
+import os
+import re
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from parity_util import gen_scene, load_ffi, read_sample_dump  # noqa: E402
+
+CASES = [
+    # name, generator scene, args, keyed
+    ("c1_exact", "c1", ["--res", "64", "64"], False),
+    ("c1", "c1", ["--res", "64", "64"], True),
+    ("c1_jitter_mitchell", "c1", ["--res", "32", "32", "--spp", "2", "2", "--jitter", "true", "--filter", "mitchell"], True),
+    ("c2", "c2", ["--res", "32", "32", "--spp", "2", "2"], True),
+    ("c2_one", "c2", ["--res", "32", "32", "--spp", "2", "2", "--strategy", "one"], True),
+    ("c2_nsamples4", "c2", ["--res", "24", "24", "--spp", "2", "2", "--nsamples", "4"], True),
+    ("c3", "c3", ["--res", "32", "32", "--spp", "2", "2"], True),
+    ("c3_mitchell", "c3", ["--res", "24", "24", "--spp", "2", "2", "--filter", "mitchell"], True),
+    ("c3_crop", "c3", ["--res", "48", "48", "--spp", "2", "2", "--crop", "0.25", "0.75", "0.5", "1"], True),
+    ("c3_lens", "c3", ["--res", "24", "24", "--spp", "3", "3", "--lens", "20", "900"], True),
+    ("c3_spherelight", "c3", ["--res", "24", "24", "--spp", "2", "2", "--spherelight"], True),
+    ("c3_whitted_mirror", "c3", ["--res", "32", "32", "--spp", "2", "2", "--integrator", "whitted", "--mirror"], True),
+    ("c3_direct_mirror", "c3", ["--res", "32", "32", "--spp", "2", "2", "--integrator", "directlighting", "--mirror"], True),
+    ("c4_blob", "c4", ["--res", "32", "32", "--spp", "2", "2", "--nphi", "48", "--ntheta", "24"], True),
+    ("c4_blob_normals", "c4", ["--res", "32", "32", "--spp", "2", "2", "--nphi", "48", "--ntheta", "24", "--normals"], True),
+]
+
+
+def parse_count(text, label):
+    m = re.search(re.escape(label) + r"\s+([0-9.]+)([kMG]?)", text)
+    if not m:
+        return -1
+    mult = {"": 1, "k": 1e3, "M": 1e6, "G": 1e9}[m.group(2)]
+    return int(float(m.group(1)) * mult)
+
+
+def main():
+    ffi = load_ffi()
+    assert ffi.have_reference(), "oracle/_ref missing: run oracle/build_ref.sh (needs /root/reference)"
+    for name, scene, args, keyed in CASES:
+        sp = os.path.join(HERE, name + ".pbrt")
+        # relative output name so the committed scene file works from any checkout
+        gen_scene(sp, scene, "--filename", name + "_out.exr", *args)
+        dump = os.path.join(HERE, name + ".samples")
+        out, _ = ffi.run_reference(sp, keyed=keyed, dump_samples=dump, cwd=HERE)
+        rgba, _ = ffi.read_raw(os.path.join(HERE, name + "_out.exr.raw"))
+        samples = read_sample_dump(dump)
+        stats = np.array([parse_count(out, "Camera Rays Traced"), parse_count(out, "Number of shadow rays traced"),
+                          parse_count(out, "Number of points shaded")], np.int64)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), rgba=rgba, samples=samples, stats=stats)
+        os.remove(dump)
+        os.remove(os.path.join(HERE, name + "_out.exr.raw"))
+        print("%-22s %s  image %s  samples %d  mean %.6f" % (name, "keyed" if keyed else "exact", rgba.shape[:2],
+                                                             samples.shape[0], float(rgba[..., :3].mean())))
+
+
+if __name__ == "__main__":
+    main()
