@@ -209,7 +209,7 @@ PB_HD float bsdf_pdf(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags = PB
   return matchingComps > 0 ? pdf / matchingComps : 0.f;
 }
 // BSDF::Sample_f with explicit sample values, reflection.cpp:402-457
-PB_HD Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, float u1, float u2, float u3,
+PB_NOINLINE Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, float u1, float u2, float u3,
                          float *pdf, int flags, int *sampledType) {
   int matchingComps = bsdf_num_components(b, flags);
   if (matchingComps == 0) {
@@ -249,6 +249,8 @@ PB_HD Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, float u1, float 
   return f;
 }
 
+struct Bsdf;
+PB_HD void bsdf_set_lobes(const PbrtB200Material &m, Bsdf *b);
 // Material::Bump with a constant-zero displacement (core/material.cpp:29-71):
 // dpdu/dpdv are unchanged (x + 0*nn + 0*dndu), the normal is re-derived from
 // them, re-oriented by the shape flags and then towards the geometric normal.
@@ -271,6 +273,11 @@ PB_HD void make_bsdf(const PbrtB200Material &m, const DiffGeom &dgGeom, const Di
   b->nn = nn;
   b->sn = normalize(dpdu);
   b->tn = cross(b->nn, b->sn);
+  bsdf_set_lobes(m, b);
+}
+// The BxDFs a material adds (materials/{matte,glass,mirror}.cpp); separate from the frame so a
+// kernel can rebuild them from the material record instead of carrying them through memory.
+PB_HD void bsdf_set_lobes(const PbrtB200Material &m, Bsdf *b) {
   b->eta = 1.f;
   b->nLobes = 0;
   Spec R = spec3(m.kd[0], m.kd[1], m.kd[2]);

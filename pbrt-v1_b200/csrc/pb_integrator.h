@@ -26,6 +26,7 @@
 struct Surface {
   Bsdf bsdf;
   int32_t light;      // area light of the primitive or -1
+  uint32_t material;  // index into materials[] (lets a later kernel rebuild the lobes)
 };
 PB_HD void surface_dg(const SceneView &sv, const Ray &ray, const Hit &hit, const TriVerts &tv,
                       DiffGeom *dg) {
@@ -51,6 +52,7 @@ PB_HD void surface_at_hit(const SceneView &sv, const Ray &ray, const Hit &hit, S
     dgs = dg;
   make_bsdf(sv.materials[tv.material], dg, dgs, tv.flags, &sf->bsdf);
   sf->light = tv.light;
+  sf->material = tv.material;
 }
 // Intersection::Le (core/primitive.cpp:142-145) with AreaLight::L (light.h:93-96)
 PB_HD Spec surface_le(const SceneView &sv, const Surface &sf, const V3 &w) {
@@ -106,7 +108,7 @@ PB_HD V3 sphere_sample_area(const PbrtB200Sphere &s, float u1, float u2, V3 *ns)
   return xf_point(s.o2w, p);
 }
 // Sphere::Sample(p,u1,u2,ns), sphere.cpp:45-69
-PB_HD V3 sphere_sample(const PbrtB200Sphere &s, const V3 &p, float u1, float u2, V3 *ns) {
+PB_NOINLINE V3 sphere_sample(const PbrtB200Sphere &s, const V3 &p, float u1, float u2, V3 *ns) {
   V3 Pcenter = xf_point(s.o2w, v3(0, 0, 0));
   V3 wc = normalize(Pcenter - p);
   V3 wcX, wcY;
@@ -128,7 +130,7 @@ PB_HD V3 sphere_sample(const PbrtB200Sphere &s, const V3 &p, float u1, float u2,
 // Shape::Pdf(p, wi) (core/shape.h:96-107) over the light's own shape list:
 // a ShapeSet tests every member without shrinking maxt, the last hit wins
 // (core/shape.h:150-156).
-PB_HD float light_shapes_pdf(const SceneView &sv, const PbrtB200Light &l, const V3 &p, const V3 &wi) {
+PB_NOINLINE float light_shapes_pdf(const SceneView &sv, const PbrtB200Light &l, const V3 &p, const V3 &wi) {
   Ray ray;
   ray.o = p; ray.d = wi; ray.mint = PB_RAY_EPSILON; ray.maxt = PB_INFINITY;
   bool anyHit = false;
@@ -173,7 +175,7 @@ PB_HD float area_light_pdf(const SceneView &sv, const PbrtB200Light &l, const V3
 }
 // shape->Sample(p, u1, u2, &ns) for the light's shape (area.cpp:63).  A ShapeSet
 // draws one RandomFloat to pick the member by area (core/shape.h:115-121).
-PB_HD V3 area_light_sample_point(const SceneView &sv, const PbrtB200Light &l, const V3 &p, float u1,
+PB_NOINLINE V3 area_light_sample_point(const SceneView &sv, const PbrtB200Light &l, const V3 &p, float u1,
                                  float u2, RngStream &rng, V3 *ns) {
   uint32_t sn = 0;
   if (l.n_shapes > 1) {
@@ -299,22 +301,31 @@ struct PathState {
   RngStream rng;       // stream 1
 };
 // One iteration of the `for (pathLength = 0; ; ++pathLength)` loop body,
-// path.cpp:65-143, after scene->Intersect returned `hit`.
-PB_HD void path_vertex(const SceneView &sv, uint64_t key0, PathState &st, const Ray &ray,
-                       const Hit &hit, PathVertexOut *out) {
-  out->hasDirect = out->hasNext = false;
+// path.cpp:65-143, after scene->Intersect returned `hit`, in two halves so a
+// caller can hand the direct-lighting rays on before the continuation is sampled.
+//
+// First half (path.cpp:68-112): miss handling, alpha, emitted light, BSDF, one
+// UniformSampleOneLight record.  Returns false when the ray missed (path ends).
+PB_HD bool path_vertex_surface(const SceneView &sv, PathState &st, const Ray &ray, const Hit &hit,
+                               Surface *sf) {
   int pathLength = st.depth;
   if (hit.prim < 0) {
     // lights[i]->Le(ray) is black for point and area lights (core/light.cpp:41-43)
     if (pathLength == 0) st.alpha = 0.f;   // L != 0 ? 1 : 0 with L == 0
-    return;
+    return false;
   }
   if (pathLength == 0) st.alpha = 1.f;
   else st.T = st.T * spec(1.f);            // pathThroughput *= scene->Transmittance(ray)
-  Surface sf;
-  surface_at_hit(sv, ray, hit, &sf);
-  if (pathLength == 0 || st.specularBounce) st.L = st.L + st.T * surface_le(sv, sf, -ray.d);
-  const Bsdf &bsdf = sf.bsdf;
+  surface_at_hit(sv, ray, hit, sf);
+  if (pathLength == 0 || st.specularBounce) st.L = st.L + st.T * surface_le(sv, *sf, -ray.d);
+  return true;
+}
+// path.cpp:93-112: one UniformSampleOneLight record at the vertex
+PB_HD void path_vertex_direct(const SceneView &sv, uint64_t key0, PathState &st, const Ray &ray,
+                              const Surface *sf, DirectRec *direct, bool *hasDirect) {
+  *hasDirect = false;
+  int pathLength = st.depth;
+  const Bsdf &bsdf = sf->bsdf;
   V3 p = bsdf.p, n = bsdf.nn;
   V3 wo = -ray.d;
   int nLights = (int)sv.nLights;
@@ -335,11 +346,27 @@ PB_HD void path_vertex(const SceneView &sv, uint64_t key0, PathState &st, const 
       bcs = st.rng.next_float();
     }
     int lightNum = pb_imin(pb_floor2int(ln * nLights), nLights - 1);
-    estimate_direct(sv, lightNum, p, n, wo, bsdf, ls1, ls2, bs1, bs2, bcs, st.rng, &out->direct);
-    out->hasDirect = true;
+    estimate_direct(sv, lightNum, p, n, wo, bsdf, ls1, ls2, bs1, bs2, bcs, st.rng, direct);
+    *hasDirect = true;
     st.pendT = st.T;
   }
   // NOTE: with no lights the reference dereferences lights[-1]; such scenes render black here.
+}
+PB_HD bool path_vertex_begin(const SceneView &sv, uint64_t key0, PathState &st, const Ray &ray,
+                             const Hit &hit, Surface *sf, DirectRec *direct, bool *hasDirect) {
+  *hasDirect = false;
+  if (!path_vertex_surface(sv, st, ray, hit, sf)) return false;
+  path_vertex_direct(sv, key0, st, ray, sf, direct, hasDirect);
+  return true;
+}
+// Second half (path.cpp:113-143): sample the BSDF for the next direction, update the
+// throughput, Russian roulette, depth limit.  Returns true when the path continues along *next.
+PB_HD bool path_vertex_continue(const SceneView &sv, uint64_t key0, PathState &st, const Ray &ray,
+                                const Surface &sf, Ray *next) {
+  int pathLength = st.depth;
+  const Bsdf &bsdf = sf.bsdf;
+  V3 p = bsdf.p, n = bsdf.nn;
+  V3 wo = -ray.d;
   float os1, os2, ocs;
   if (pathLength < 3) {
     os1 = pat2d(sv, key0, 3 * pathLength + 2, 0, 0);
@@ -352,18 +379,25 @@ PB_HD void path_vertex(const SceneView &sv, uint64_t key0, PathState &st, const 
   float pdf;
   int flags;
   Spec f = bsdf_sample_f(bsdf, wo, &wi, os1, os2, ocs, &pdf, PB_ALL, &flags);
-  if (is_black(f) || pdf == 0.f) return;
+  if (is_black(f) || pdf == 0.f) return false;
   st.specularBounce = (flags & PB_SPECULAR) != 0;
   st.T = st.T * (f * absdot(wi, n) / pdf);
-  out->next.o = p; out->next.d = wi; out->next.mint = PB_RAY_EPSILON; out->next.maxt = PB_INFINITY;
+  next->o = p; next->d = wi; next->mint = PB_RAY_EPSILON; next->maxt = PB_INFINITY;
   if (pathLength > 3) {
     float continueProbability = .5f;
-    if (st.rng.next_float() > continueProbability) return;
+    if (st.rng.next_float() > continueProbability) return false;
     st.T = st.T * (1.f / continueProbability);   // Spectrum::operator/=(float)
   }
-  if (pathLength == sv.integrator.max_depth) return;
-  out->hasNext = true;
+  if (pathLength == sv.integrator.max_depth) return false;
   st.depth = pathLength + 1;
+  return true;
+}
+PB_HD void path_vertex(const SceneView &sv, uint64_t key0, PathState &st, const Ray &ray,
+                       const Hit &hit, PathVertexOut *out) {
+  out->hasNext = false;
+  Surface sf;
+  if (!path_vertex_begin(sv, key0, st, ray, hit, &sf, &out->direct, &out->hasDirect)) return;
+  out->hasNext = path_vertex_continue(sv, key0, st, ray, sf, &out->next);
 }
 // L += pathThroughput * ((float)nLights * Ld), path.cpp:100-112 + transport.cpp:66-69
 PB_HD void path_resolve_direct(const SceneView &sv, PathState &st, const Spec &termA,

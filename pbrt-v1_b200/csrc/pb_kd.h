@@ -58,6 +58,15 @@ PB_HD bool kd_test_prim(const SceneView &sv, uint32_t prim, Ray &ray, Hit *hit) 
 }
 
 // Returns true when something was hit.  ANY=false: closest hit in *hit.
+//
+// Loop shape ("while-while"): descend through interior nodes until a leaf is
+// reached, then test the leaf's primitives, then pop.  On a GPU this lets the
+// lanes of a warp run the short interior step together and the long triangle
+// tests together instead of interleaving them; per ray the sequence of nodes
+// visited and primitives tested is exactly that of the reference's single loop
+// (kdtree.cpp:328-401).  The reference re-checks `ray.maxt < tmin` at the top of
+// every iteration; neither value changes while descending, so checking after
+// each pop is equivalent.
 template <bool ANY, bool COUNT>
 PB_HD bool kd_intersect(const SceneView &sv, Ray ray, Hit *hit, KdCounters *cnt) {
   if (!ANY) hit->prim = -1;
@@ -75,14 +84,16 @@ PB_HD bool kd_intersect(const SceneView &sv, Ray ray, Hit *hit, KdCounters *cnt)
   bool anyHit = false;
   uint32_t node = 0;
   for (;;) {
-    if (!ANY && ray.maxt < tmin) break;
+    uint32_t w0, w1;
+    // ---- descend to a leaf
+    for (;;) {
 #ifdef __CUDA_ARCH__
-    uint2 nd = __ldg((const uint2 *)(sv.nodes + node));
-    uint32_t w0 = nd.x, w1 = nd.y;
+      uint2 nd = __ldg((const uint2 *)(sv.nodes + node));
+      w0 = nd.x; w1 = nd.y;
 #else
-    uint32_t w0 = sv.nodes[node].word0, w1 = sv.nodes[node].word1;
+      w0 = sv.nodes[node].word0; w1 = sv.nodes[node].word1;
 #endif
-    if ((w0 & 3u) != 3u) {
+      if ((w0 & 3u) == 3u) break;
       if (COUNT) ++cnt->interior;
       int axis = (int)(w0 & 3u);
 #ifdef __CUDA_ARCH__
@@ -93,9 +104,8 @@ PB_HD bool kd_intersect(const SceneView &sv, Ray ray, Hit *hit, KdCounters *cnt)
       float o = ray.o[axis], d = ray.d[axis];
       float tplane = (split - o) * invDir[axis];
       bool belowFirst = (o < split) || (o == split && d >= 0);
-      uint32_t firstChild, secondChild;
-      if (belowFirst) { firstChild = node + 1; secondChild = w1; }
-      else { firstChild = w1; secondChild = node + 1; }
+      uint32_t firstChild = belowFirst ? node + 1 : w1;
+      uint32_t secondChild = belowFirst ? w1 : node + 1;
       if (tplane > tmax || tplane <= 0)
         node = firstChild;
       else if (tplane < tmin)
@@ -108,34 +118,34 @@ PB_HD bool kd_intersect(const SceneView &sv, Ray ray, Hit *hit, KdCounters *cnt)
         node = firstChild;
         tmax = tplane;
       }
-    } else {
-      if (COUNT) ++cnt->leaves;
-      uint32_t nPrims = w0 >> 2;
-      for (uint32_t i = 0; i < nPrims; ++i) {
-        uint32_t prim = (nPrims == 1) ? w1 : sv.primRefs[w1 + i];
-        if (COUNT) ++cnt->refs;
-        bool seen = false;
-#pragma unroll
-        for (int k = 0; k < PB_MAILBOX; ++k) seen |= (mailbox[k] == prim);
-        if (seen) continue;
-#pragma unroll
-        for (int k = 0; k < PB_MAILBOX; ++k)
-          if (k == mbPos) mailbox[k] = prim;
-        mbPos = (mbPos + 1) & (PB_MAILBOX - 1);
-        if (COUNT) ++cnt->tests;
-        if (kd_test_prim<ANY>(sv, prim, ray, hit)) {
-          if (ANY) return true;
-          anyHit = true;
-        }
-      }
-      if (todoPos > 0) {
-        --todoPos;
-        node = todoNode[todoPos];
-        tmin = todoTmin[todoPos];
-        tmax = todoTmax[todoPos];
-      } else
-        break;
     }
+    // ---- leaf
+    if (COUNT) ++cnt->leaves;
+    uint32_t nPrims = w0 >> 2;
+    for (uint32_t i = 0; i < nPrims; ++i) {
+      uint32_t prim = (nPrims == 1) ? w1 : sv.primRefs[w1 + i];
+      if (COUNT) ++cnt->refs;
+      bool seen = false;
+#pragma unroll
+      for (int k = 0; k < PB_MAILBOX; ++k) seen |= (mailbox[k] == prim);
+      if (seen) continue;
+#pragma unroll
+      for (int k = 0; k < PB_MAILBOX; ++k)
+        if (k == mbPos) mailbox[k] = prim;
+      mbPos = (mbPos + 1) & (PB_MAILBOX - 1);
+      if (COUNT) ++cnt->tests;
+      if (kd_test_prim<ANY>(sv, prim, ray, hit)) {
+        if (ANY) return true;
+        anyHit = true;
+      }
+    }
+    // ---- next node from the todo list
+    if (todoPos == 0) break;
+    --todoPos;
+    node = todoNode[todoPos];
+    tmin = todoTmin[todoPos];
+    tmax = todoTmax[todoPos];
+    if (!ANY && ray.maxt < tmin) break;
   }
   return anyHit;
 }

@@ -1,0 +1,160 @@
+// pb_kd_warp.cuh -- warp-scheduled kd-tree walk used by the traversal kernels.
+//
+// Per ray this performs exactly the sequence of node visits and primitive
+// tests of pb_kd.h's kd_intersect() (== KdTreeAccel::Intersect / IntersectP,
+// accelerators/kdtree.cpp:313-488): same tree, same near/far order, same
+// `maxt < tmin` cut, same mailbox ring.  What differs is how a warp's 32 rays
+// are scheduled, because a 1-ray-per-thread transcription of the reference loop
+// measured 3.7 active lanes out of 32 on a path-traced Cornell box (ncu,
+// profiles/r01a_*): rays sit in leaves of different sizes at different times.
+//
+//   * Each lane is a small state machine: DESCEND (interior steps), LEAF
+//     (walk the leaf's primitive list), DONE.
+//   * One trip of the warp loop = every live lane first advances through cheap
+//     steps (interior nodes, leaf bookkeeping, pops) until it holds ONE
+//     primitive that needs testing, then all lanes run the expensive
+//     ray/primitive test together.  The triangle test therefore executes with
+//     every lane that still has work, instead of only the lanes that happen to
+//     be in a leaf in the same iteration.
+//   * Persistent threads with lane refill: when enough lanes have finished
+//     their ray, they claim fresh rays from the queue's atomic work counter
+//     (warp-aggregated), so short rays do not wait for the longest one.
+#ifndef PB_KD_WARP_CUH
+#define PB_KD_WARP_CUH
+#include "pb_kd.h"
+
+#define PB_REFILL_THRESHOLD 8   // refill when at least this many lanes are idle
+
+// Source: Ray load(uint32_t i).   Sink: void done(uint32_t i, const Ray &ray, const Hit &hit, bool anyHit).
+template <bool ANY, bool COUNT, class Source, class Sink>
+__device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n, uint32_t *work,
+                                                 const Source &src, const Sink &sink, KdCounters &cnt) {
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t todoNode[PB_KD_STACK];
+  float todoTmin[PB_KD_STACK], todoTmax[PB_KD_STACK];
+  // lane state
+  bool active = false;        // holds an unfinished ray
+  bool inLeaf = false;
+  bool exhausted = false;     // the queue has no more rays (warp-uniform)
+  uint32_t idx = 0;
+  Ray ray;
+  ray.o = v3(0, 0, 0); ray.d = v3(0, 0, 0); ray.mint = 0.f; ray.maxt = 0.f;
+  V3 invDir = v3(0, 0, 0);
+  float tmin = 0.f, tmax = 0.f;
+  uint32_t node = 0;
+  int todoPos = 0;
+  uint32_t leafW1 = 0, leafI = 0, leafN = 0;
+  uint32_t mailbox[PB_MAILBOX];
+  int mbPos = 0;
+  Hit hit;
+  hit.prim = -1; hit.t = 0.f; hit.b1 = hit.b2 = 0.f;
+  bool anyHit = false;
+
+  for (;;) {
+    // ---- refill idle lanes
+    uint32_t idleMask = __ballot_sync(0xffffffffu, !active);
+    if (!exhausted && (uint32_t)__popc(idleMask) >= (idleMask == 0xffffffffu ? 1u : PB_REFILL_THRESHOLD)) {
+      uint32_t base = 0;
+      uint32_t nIdle = (uint32_t)__popc(idleMask);
+      if (lane == 0) base = atomicAdd(work, nIdle);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base + nIdle >= n) exhausted = true;
+      if (!active) {
+        uint32_t i = base + (uint32_t)__popc(idleMask & ((1u << lane) - 1u));
+        if (i < n) {
+          idx = i;
+          ray = src.load(i);
+          hit.prim = -1;
+          anyHit = false;
+          todoPos = 0;
+          inLeaf = false;
+          node = 0;
+#pragma unroll
+          for (int k = 0; k < PB_MAILBOX; ++k) mailbox[k] = 0xffffffffu;
+          mbPos = 0;
+          active = sv.nNodes != 0 && bbox_intersect_p(sv.bmin, sv.bmax, ray, &tmin, &tmax);
+          invDir = v3(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
+          if (!active) sink.done(idx, ray, hit, false);   // missed the tree's bounds
+        }
+      }
+    }
+    if (__ballot_sync(0xffffffffu, active) == 0) {
+      if (exhausted) break;
+      continue;
+    }
+    // ---- cheap steps until this lane holds one primitive to test
+    bool pending = false;
+    uint32_t prim = 0;
+    while (active && !pending) {
+      if (inLeaf) {
+        if (leafI < leafN) {
+          prim = (leafN == 1) ? leafW1 : __ldg(sv.primRefs + leafW1 + leafI);
+          ++leafI;
+          if (COUNT) ++cnt.refs;
+          bool seen = false;
+#pragma unroll
+          for (int k = 0; k < PB_MAILBOX; ++k) seen |= (mailbox[k] == prim);
+          if (!seen) {
+#pragma unroll
+            for (int k = 0; k < PB_MAILBOX; ++k)
+              if (k == mbPos) mailbox[k] = prim;
+            mbPos = (mbPos + 1) & (PB_MAILBOX - 1);
+            pending = true;
+          }
+        } else {
+          // leaf finished: next node from the todo list (kdtree.cpp:392-399)
+          inLeaf = false;
+          if (todoPos == 0) active = false;
+          else {
+            --todoPos;
+            node = todoNode[todoPos];
+            tmin = todoTmin[todoPos];
+            tmax = todoTmax[todoPos];
+            if (!ANY && ray.maxt < tmin) active = false;   // kdtree.cpp:330
+          }
+          if (!active) sink.done(idx, ray, hit, anyHit);
+        }
+      } else {
+        uint2 nd = __ldg((const uint2 *)(sv.nodes + node));
+        if ((nd.x & 3u) == 3u) {
+          if (COUNT) ++cnt.leaves;
+          inLeaf = true;
+          leafN = nd.x >> 2; leafW1 = nd.y; leafI = 0;
+        } else {
+          if (COUNT) ++cnt.interior;
+          int axis = (int)(nd.x & 3u);
+          float split = __uint_as_float(nd.x);   // axis bits stay in the mantissa (kdtree.cpp:66-72)
+          float o = ray.o[axis], d = ray.d[axis];
+          float tplane = (split - o) * invDir[axis];
+          bool belowFirst = (o < split) || (o == split && d >= 0);
+          uint32_t firstChild = belowFirst ? node + 1 : nd.y;
+          uint32_t secondChild = belowFirst ? nd.y : node + 1;
+          if (tplane > tmax || tplane <= 0)
+            node = firstChild;
+          else if (tplane < tmin)
+            node = secondChild;
+          else {
+            todoNode[todoPos] = secondChild;
+            todoTmin[todoPos] = tplane;
+            todoTmax[todoPos] = tmax;
+            ++todoPos;
+            node = firstChild;
+            tmax = tplane;
+          }
+        }
+      }
+    }
+    // ---- the expensive part, all lanes with work together
+    if (pending) {
+      if (COUNT) ++cnt.tests;
+      if (kd_test_prim<ANY>(sv, prim, ray, &hit)) {
+        anyHit = true;
+        if (ANY) {
+          active = false;
+          sink.done(idx, ray, hit, true);
+        }
+      }
+    }
+  }
+}
+#endif

@@ -22,10 +22,10 @@
 
 #ifdef __CUDACC__
 #define PB_HD __host__ __device__ __forceinline__
-#define PB_HDN __host__ __device__ __noinline__
+#define PB_NOINLINE __host__ __device__ __noinline__
 #else
 #define PB_HD inline
-#define PB_HDN
+#define PB_NOINLINE inline
 #endif
 
 // core/pbrt.h:201-211 -- M_PI is a *float* literal in the reference
@@ -47,10 +47,10 @@ PB_HD float pb_cosf(float x) { return cosf(x); }
 PB_HD float pb_acosf(float x) { return acosf(x); }
 PB_HD float pb_atan2f(float y, float x) { return atan2f(y, x); }
 #else
-PB_HD float pb_sinf(float x) { return (float)sin((double)x); }
-PB_HD float pb_cosf(float x) { return (float)cos((double)x); }
-PB_HD float pb_acosf(float x) { return (float)acos((double)x); }
-PB_HD float pb_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
+PB_NOINLINE float pb_sinf(float x) { return (float)sin((double)x); }
+PB_NOINLINE float pb_cosf(float x) { return (float)cos((double)x); }
+PB_NOINLINE float pb_acosf(float x) { return (float)acos((double)x); }
+PB_NOINLINE float pb_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
 #endif
 
 PB_HD float pb_max(float a, float b) { return a < b ? b : a; }   // std::max(a,b)

@@ -67,14 +67,17 @@ struct SamplePattern {
 };
 // LatinHypercube(samples, n, dims) (core/sampling.cpp:98-113): n*dims floats
 // (sample-major), then per dimension n swap draws.  Value of sample j, dim d.
-PB_HD float pb_lhs_value(uint64_t key, const SamplePattern &p, int j, int d) {
+PB_NOINLINE float pb_lhs_value_general(uint64_t key, const SamplePattern &p, int j, int d) {
   float delta = 1.f / p.n;
-  int src = j;
-  if (p.n > 1) {
-    uint32_t c = p.ctr0 + (uint32_t)(p.n * p.dims) + (uint32_t)(d * p.n);
-    src = pb_shuffle_source(key, c, p.n, j);
-  }
+  uint32_t c = p.ctr0 + (uint32_t)(p.n * p.dims) + (uint32_t)(d * p.n);
+  int src = pb_shuffle_source(key, c, p.n, j);
   float r = pb_f32(key, p.ctr0 + 1 + (uint32_t)(p.dims * src + d));
   return (src + r) * delta;
+}
+PB_HD float pb_lhs_value(uint64_t key, const SamplePattern &p, int j, int d) {
+  // one-sample patterns (every path-integrator pattern): (0 + r) * (1.f / 1) == r exactly, and the
+  // single swap draw exchanges element 0 with itself
+  if (p.n == 1) return pb_f32(key, p.ctr0 + 1 + (uint32_t)d);
+  return pb_lhs_value_general(key, p, j, d);
 }
 #endif

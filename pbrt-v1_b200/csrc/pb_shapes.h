@@ -72,7 +72,7 @@ PB_HD bool quadratic(float A, float B, float C, float *t0, float *t1) {
 
 // Sphere::Intersect up to the accepted hit (sphere.cpp:104-143 == IntersectP
 // :209-249).  Outputs object-space hit point and phi for the DG stage.
-PB_HD bool sphere_test(const PbrtB200Sphere &s, const Ray &r, float *tHit, V3 *phitO, float *phiO) {
+PB_NOINLINE bool sphere_test(const PbrtB200Sphere &s, const Ray &r, float *tHit, V3 *phitO, float *phiO) {
   Ray ray;
   ray.o = xf_point(s.w2o, r.o);
   ray.d = xf_vector(s.w2o, r.d);
@@ -175,7 +175,7 @@ PB_HD bool solve2x2(const float A[2][2], const float B[2], float x[2]) {
 }
 
 // trianglemesh.cpp:71-133: shading geometry from per-vertex N / S.
-PB_HD void tri_shading_dg(const SceneView &sv, uint32_t prim, uint32_t flags, const DiffGeom &dg,
+PB_NOINLINE void tri_shading_dg(const SceneView &sv, uint32_t prim, uint32_t flags, const DiffGeom &dg,
                           DiffGeom *dgs) {
   bool hasN = (flags & PBRT_B200_PF_HAS_N) != 0, hasS = (flags & PBRT_B200_PF_HAS_S) != 0;
   if (!hasN && !hasS) { *dgs = dg; return; }
@@ -235,7 +235,7 @@ PB_HD void tri_shading_dg(const SceneView &sv, uint32_t prim, uint32_t flags, co
 }
 
 // sphere.cpp:144-205: DG of an accepted sphere hit (object-space phit, phi).
-PB_HD void sphere_dg(const PbrtB200Sphere &s, const V3 &phit, float phi, DiffGeom *dg) {
+PB_NOINLINE void sphere_dg(const PbrtB200Sphere &s, const V3 &phit, float phi, DiffGeom *dg) {
   float radius = s.radius, phiMax = s.phi_max, thetaMin = s.theta_min, thetaMax = s.theta_max;
   float u = phi / phiMax;
   float theta = pb_acosf(pb_clamp(phit.z / radius, -1.f, 1.f));

@@ -31,6 +31,7 @@
 #include <algorithm>
 
 #include "pb_integrator.h"
+#include "pb_kd_warp.cuh"
 #include "pb_camera.h"
 #include "pb_film.h"
 #include "pb_setup.h"
@@ -53,7 +54,8 @@ static int fail(int code, const std::string &msg) {
 // tunables (pbrt_b200_tunable)
 static int64_t g_waveSamples = 1 << 22;   // key 0: image samples per wave
 static int64_t g_countKd = 0;             // key 1: collect kd-walk counters (costs a little time)
-static int64_t g_blocksPerSM = 4;         // key 2: resident CTAs per SM for the persistent kernels
+static int64_t g_blocksPerSM = 8;         // key 2: resident CTAs per SM for the persistent kernels
+static int64_t g_shadeBlocks = 4;         // key 4: occupancy target (CTAs/SM) the shade kernel is compiled for: 2, 3 or 4
 
 #define PB_BLOCK 128
 
@@ -88,6 +90,8 @@ struct WaveBuffers {
   int32_t nFrames;
   RayQueue q[2];
   AuxQueue shadowQ, probeQ;
+  float *surf[15];       // BSDF frame records of the vertices being shaded (path), by queue position
+  uint32_t *surfIds;
   // counters (device): [0..] see enum below
   uint32_t *counts;
   unsigned long long *stats;
@@ -99,14 +103,16 @@ enum { TF_RAYS = 0, TF_INTERIOR, TF_LEAVES, TF_REFS, TF_TESTS, TF_COUNT };
 #define ST_COUNT (ST_KIND_BASE + TK_COUNT * TF_COUNT)
 #define ST_K(kind, field) (ST_KIND_BASE + (kind) * TF_COUNT + (field))
 // kernel classes for per-class timing (pbrt_b200_kernel_stats)
-enum { KC_GENERATE = 0, KC_INTERSECT, KC_SHADE, KC_SHADOW, KC_PROBE, KC_ADVANCE, KC_FINALIZE, KC_FILM, KC_COUNT };
-static const char *const kKernelClassNames[KC_COUNT] = {"k_generate", "k_intersect", "k_shade", "k_shadow",
-                                                        "k_probe", "k_advance_wd", "k_finalize", "k_film"};
+enum { KC_GENERATE = 0, KC_INTERSECT, KC_SHADE, KC_SHADE_DIRECT, KC_SHADE_CONT, KC_SHADOW, KC_PROBE, KC_ADVANCE,
+       KC_FINALIZE, KC_FILM, KC_COUNT };
+static const char *const kKernelClassNames[KC_COUNT] = {"k_generate", "k_intersect", "k_shade_surface", "k_shade_direct",
+                                                        "k_shade_continue", "k_shadow", "k_probe", "k_advance_wd",
+                                                        "k_finalize", "k_film"};
 // counts[] layout: per iteration it: [4*it+0] main queue size, +1 shadow queue size,
 // +2 probe queue size, +3 unused; work counters follow at PB_WORK_BASE.
 #define PB_MAX_ITERS 1024
 #define PB_WORK_BASE (4 * PB_MAX_ITERS)
-#define PB_COUNTS_TOTAL (PB_WORK_BASE + 8 * PB_MAX_ITERS)
+#define PB_COUNTS_TOTAL (PB_WORK_BASE + 10 * PB_MAX_ITERS)
 
 struct WaveDesc {
   int xs, xe, ys, ye;        // sample extent of the window
@@ -188,91 +194,97 @@ k_generate(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
 
 // ------------------------------------------------------------------------------------------
 // K1: closest hit (KdTreeAccel::Intersect, accelerators/kdtree.cpp:313-403)
+struct MainSource {
+  RayQueue q;
+  __device__ Ray load(uint32_t i) const { return queue_ray(q, i); }
+};
+struct MainSink {
+  RayQueue q;
+  __device__ void done(uint32_t i, const Ray &, const Hit &hit, bool) const {
+    q.hitPrim[i] = hit.prim;
+    if (hit.prim >= 0) { q.hitT[i] = hit.t; q.hitB1[i] = hit.b1; q.hitB2[i] = hit.b2; }
+  }
+};
+__device__ __forceinline__ void flush_kd_counters(unsigned long long *stats, int kind, const KdCounters &cnt) {
+  warp_stat_add(&stats[ST_K(kind, TF_INTERIOR)], cnt.interior);
+  warp_stat_add(&stats[ST_K(kind, TF_LEAVES)], cnt.leaves);
+  warp_stat_add(&stats[ST_K(kind, TF_REFS)], cnt.refs);
+  warp_stat_add(&stats[ST_K(kind, TF_TESTS)], cnt.tests);
+}
 template <bool COUNT>
 __global__ void __launch_bounds__(PB_BLOCK)
 k_intersect(const __grid_constant__ SceneView sv, const RayQueue q, const uint32_t *nPtr,
             uint32_t *work, unsigned long long *stats) {
   uint32_t n = *nPtr;
   KdCounters cnt = {0, 0, 0, 0};
-  for (;;) {
-    uint32_t base = warp_claim(work);
-    if (base >= n) break;
-    uint32_t i = base + lane_id();
-    if (i < n) {
-      Ray ray = queue_ray(q, i);
-      Hit hit;
-      kd_intersect<false, COUNT>(sv, ray, &hit, &cnt);
-      q.hitPrim[i] = hit.prim;
-      if (hit.prim >= 0) { q.hitT[i] = hit.t; q.hitB1[i] = hit.b1; q.hitB2[i] = hit.b2; }
-    }
-  }
-  if (COUNT) {
-    warp_stat_add(&stats[ST_K(TK_MAIN, TF_INTERIOR)], cnt.interior);
-    warp_stat_add(&stats[ST_K(TK_MAIN, TF_LEAVES)], cnt.leaves);
-    warp_stat_add(&stats[ST_K(TK_MAIN, TF_REFS)], cnt.refs);
-    warp_stat_add(&stats[ST_K(TK_MAIN, TF_TESTS)], cnt.tests);
-  }
+  MainSource src = {q};
+  MainSink sink = {q};
+  kd_warp_traverse<false, COUNT>(sv, n, work, src, sink, cnt);
+  if (COUNT) flush_kd_counters(stats, TK_MAIN, cnt);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_K(TK_MAIN, TF_RAYS)], (unsigned long long)n);
 }
 
 // K3: shadow rays (KdTreeAccel::IntersectP, kdtree.cpp:404-488; light.cpp:30-36)
+struct ShadowSource {
+  AuxQueue q;
+  __device__ Ray load(uint32_t i) const {
+    Ray ray;
+    ray.o = v3(q.ox[i], q.oy[i], q.oz[i]);
+    ray.d = v3(q.dx[i], q.dy[i], q.dz[i]);
+    ray.mint = PB_RAY_EPSILON; ray.maxt = 1.f - PB_RAY_EPSILON;   // light.h:78-80
+    return ray;
+  }
+};
+struct ShadowSink {
+  AuxQueue q;
+  uint8_t *recFlags;
+  __device__ void done(uint32_t i, const Ray &, const Hit &, bool occluded) const {
+    if (!occluded) recFlags[q.rec[i]] |= 1;
+  }
+};
 template <bool COUNT>
 __global__ void __launch_bounds__(PB_BLOCK)
 k_shadow(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t *nPtr, uint32_t *work,
          uint8_t *recFlags, unsigned long long *stats) {
   uint32_t n = *nPtr;
   KdCounters cnt = {0, 0, 0, 0};
-  for (;;) {
-    uint32_t base = warp_claim(work);
-    if (base >= n) break;
-    uint32_t i = base + lane_id();
-    if (i < n) {
-      Ray ray;
-      ray.o = v3(q.ox[i], q.oy[i], q.oz[i]);
-      ray.d = v3(q.dx[i], q.dy[i], q.dz[i]);
-      ray.mint = PB_RAY_EPSILON; ray.maxt = 1.f - PB_RAY_EPSILON;   // light.h:78-80
-      Hit hit;
-      bool occluded = kd_intersect<true, COUNT>(sv, ray, &hit, &cnt);
-      if (!occluded) recFlags[q.rec[i]] |= 1;
-    }
-  }
-  if (COUNT) {
-    warp_stat_add(&stats[ST_K(TK_SHADOW, TF_INTERIOR)], cnt.interior);
-    warp_stat_add(&stats[ST_K(TK_SHADOW, TF_LEAVES)], cnt.leaves);
-    warp_stat_add(&stats[ST_K(TK_SHADOW, TF_REFS)], cnt.refs);
-    warp_stat_add(&stats[ST_K(TK_SHADOW, TF_TESTS)], cnt.tests);
-  }
+  ShadowSource src = {q};
+  ShadowSink sink = {q, recFlags};
+  kd_warp_traverse<true, COUNT>(sv, n, work, src, sink, cnt);
+  if (COUNT) flush_kd_counters(stats, TK_SHADOW, cnt);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_K(TK_SHADOW, TF_RAYS)], (unsigned long long)n);
 }
 
 // K4: MIS probes (transport.cpp:177-190): closest hit, then "did it reach the sampled light,
 // on its emitting side".
+struct ProbeSource {
+  AuxQueue q;
+  __device__ Ray load(uint32_t i) const {
+    Ray ray;
+    ray.o = v3(q.ox[i], q.oy[i], q.oz[i]);
+    ray.d = v3(q.dx[i], q.dy[i], q.dz[i]);
+    ray.mint = PB_RAY_EPSILON; ray.maxt = PB_INFINITY;
+    return ray;
+  }
+};
+struct ProbeSink {
+  const SceneView *sv;
+  AuxQueue q;
+  uint8_t *recFlags;
+  __device__ void done(uint32_t i, const Ray &ray, const Hit &hit, bool) const {
+    if (hit_emits_from_light(*sv, ray, hit, q.light[i])) recFlags[q.rec[i]] |= 2;
+  }
+};
 template <bool COUNT>
 __global__ void __launch_bounds__(PB_BLOCK)
 k_probe(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t *nPtr, uint32_t *work,
         uint8_t *recFlags, unsigned long long *stats) {
   uint32_t n = *nPtr;
   KdCounters cnt = {0, 0, 0, 0};
-  for (;;) {
-    uint32_t base = warp_claim(work);
-    if (base >= n) break;
-    uint32_t i = base + lane_id();
-    if (i < n) {
-      Ray ray;
-      ray.o = v3(q.ox[i], q.oy[i], q.oz[i]);
-      ray.d = v3(q.dx[i], q.dy[i], q.dz[i]);
-      ray.mint = PB_RAY_EPSILON; ray.maxt = PB_INFINITY;
-      Hit hit;
-      kd_intersect<false, COUNT>(sv, ray, &hit, &cnt);
-      if (hit_emits_from_light(sv, ray, hit, q.light[i])) recFlags[q.rec[i]] |= 2;
-    }
-  }
-  if (COUNT) {
-    warp_stat_add(&stats[ST_K(TK_PROBE, TF_INTERIOR)], cnt.interior);
-    warp_stat_add(&stats[ST_K(TK_PROBE, TF_LEAVES)], cnt.leaves);
-    warp_stat_add(&stats[ST_K(TK_PROBE, TF_REFS)], cnt.refs);
-    warp_stat_add(&stats[ST_K(TK_PROBE, TF_TESTS)], cnt.tests);
-  }
+  ProbeSource src = {q};
+  ProbeSink sink = {&sv, q, recFlags};
+  kd_warp_traverse<false, COUNT>(sv, n, work, src, sink, cnt);
+  if (COUNT) flush_kd_counters(stats, TK_PROBE, cnt);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_K(TK_PROBE, TF_RAYS)], (unsigned long long)n);
 }
 
@@ -302,67 +314,161 @@ __device__ __forceinline__ void path_fold_pending(const SceneView &sv, const Wav
   *flags &= ~(1u << 9);
 }
 
-// K2 (path): one iteration of PathIntegrator::Li's loop (integrators/path.cpp:65-143)
-__global__ void __launch_bounds__(PB_BLOCK)
-k_shade_path(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveDesc wd,
-             const RayQueue qin, const RayQueue qout, const uint32_t *nPtr, uint32_t *work,
-             uint32_t *nextCount, uint32_t *shadowCount, uint32_t *probeCount) {
+// K2 (path): one iteration of PathIntegrator::Li's loop (integrators/path.cpp:65-143) as three
+// kernels.  One fused kernel measured 65 % of its issue slots stalled on instruction fetch
+// (8.7 k SASS instructions against a 32 KB instruction cache, profiles/r01a_*), so the vertex is
+// cut where little state crosses:
+//   k_path_surface   fold the previous vertex's direct light, miss handling, hit geometry ->
+//                    BSDF frame record (15 floats + ids), emitted light        path.cpp:66-92
+//   k_path_direct    UniformSampleOneLight / EstimateDirect -> record + shadow / probe rays  :93-112
+//   k_path_continue  BSDF sampling, throughput, Russian roulette -> next ray                 :113-143
+struct SurfaceRecord {       // SoA, indexed by queue position
+  float *f[15];              // p, nn, ng, sn, tn
+  uint32_t *ids;             // material | (light + 1) << 16
+};
+__device__ __forceinline__ void surface_store(const SurfaceRecord &r, uint32_t i, const Surface &sf) {
+  const Bsdf &b = sf.bsdf;
+  r.f[0][i] = b.p.x; r.f[1][i] = b.p.y; r.f[2][i] = b.p.z;
+  r.f[3][i] = b.nn.x; r.f[4][i] = b.nn.y; r.f[5][i] = b.nn.z;
+  r.f[6][i] = b.ng.x; r.f[7][i] = b.ng.y; r.f[8][i] = b.ng.z;
+  r.f[9][i] = b.sn.x; r.f[10][i] = b.sn.y; r.f[11][i] = b.sn.z;
+  r.f[12][i] = b.tn.x; r.f[13][i] = b.tn.y; r.f[14][i] = b.tn.z;
+  r.ids[i] = sf.material | ((uint32_t)(sf.light + 1) << 16);
+}
+__device__ __forceinline__ void surface_load(const SceneView &sv, const SurfaceRecord &r, uint32_t i, Surface *sf) {
+  Bsdf &b = sf->bsdf;
+  b.p = v3(r.f[0][i], r.f[1][i], r.f[2][i]);
+  b.nn = v3(r.f[3][i], r.f[4][i], r.f[5][i]);
+  b.ng = v3(r.f[6][i], r.f[7][i], r.f[8][i]);
+  b.sn = v3(r.f[9][i], r.f[10][i], r.f[11][i]);
+  b.tn = v3(r.f[12][i], r.f[13][i], r.f[14][i]);
+  uint32_t ids = r.ids[i];
+  sf->material = ids & 0xffffu;
+  sf->light = (int32_t)(ids >> 16) - 1;
+  bsdf_set_lobes(sv.materials[sf->material], &b);
+}
+
+__global__ void __launch_bounds__(PB_BLOCK, 4)
+k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const RayQueue qin,
+               const SurfaceRecord rec, const uint32_t *nPtr, uint32_t *work) {
   uint32_t n = *nPtr;
   uint32_t shaded = 0;
   for (;;) {
     uint32_t base = warp_claim(work);
     if (base >= n) break;
     uint32_t i = base + lane_id();
-    bool valid = i < n;
-    bool pushShadow = false, pushProbe = false, pushNext = false;
-    PathVertexOut out;
+    if (i >= n) continue;
+    uint32_t slot = qin.slot[i];
+    Ray ray = queue_ray(qin, i);
+    Hit hit;
+    hit.prim = qin.hitPrim[i];
+    hit.t = 0.f; hit.b1 = hit.b2 = 0.f;
+    if (hit.prim >= 0) { hit.t = qin.hitT[i]; hit.b1 = qin.hitB1[i]; hit.b2 = qin.hitB2[i]; }
+    uint32_t flags = wb.flags[slot];
+    PathState st;
+    st.L = load3(wb.L, slot);
+    path_fold_pending(sv, wb, slot, &flags, &st.L);
+    st.T = load3(wb.T, slot);
+    st.alpha = wb.alpha[slot];
+    st.depth = (int)(flags & 0xffu);
+    st.specularBounce = (flags >> 8) & 1u;
+    Surface sf;
+    if (path_vertex_surface(sv, st, ray, hit, &sf)) {
+      ++shaded;
+      surface_store(rec, i, sf);
+    }
+    store3(wb.L, slot, st.L);
+    wb.alpha[slot] = st.alpha;
+    wb.flags[slot] = flags;
+  }
+  warp_stat_add(&wb.stats[ST_SHADED], shaded);
+}
+
+__global__ void __launch_bounds__(PB_BLOCK, 4)
+k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveDesc wd,
+              const RayQueue qin, const SurfaceRecord rec, const uint32_t *nPtr, uint32_t *work,
+              uint32_t *shadowCount, uint32_t *probeCount) {
+  uint32_t n = *nPtr;
+  for (;;) {
+    uint32_t base = warp_claim(work);
+    if (base >= n) break;
+    uint32_t i = base + lane_id();
+    bool valid = i < n && qin.hitPrim[i] >= 0;
+    bool pushShadow = false, pushProbe = false;
     uint32_t slot = 0;
+    DirectRec direct;
     if (valid) {
       slot = qin.slot[i];
-      Ray ray = queue_ray(qin, i);
-      Hit hit;
-      hit.prim = qin.hitPrim[i];
-      hit.t = 0.f; hit.b1 = hit.b2 = 0.f;
-      if (hit.prim >= 0) { hit.t = qin.hitT[i]; hit.b1 = qin.hitB1[i]; hit.b2 = qin.hitB2[i]; }
+      Ray ray;
+      ray.o = v3(0, 0, 0);
+      ray.d = v3(qin.dx[i], qin.dy[i], qin.dz[i]);   // only wo = -ray.d is needed
+      ray.mint = 0.f; ray.maxt = 0.f;
+      Surface sf;
+      surface_load(sv, rec, i, &sf);
       uint32_t flags = wb.flags[slot];
       PathState st;
-      st.L = load3(wb.L, slot);
-      path_fold_pending(sv, wb, slot, &flags, &st.L);
       st.T = load3(wb.T, slot);
-      st.pendT = spec(0.f);
-      st.alpha = wb.alpha[slot];
+      st.depth = (int)(flags & 0xffu);
+      st.rng.key = slot_key(wd, slot, 1);
+      st.rng.ctr = wb.ctr[slot];
+      uint64_t key0 = slot_key(wd, slot, 0);
+      bool hasDirect;
+      path_vertex_direct(sv, key0, st, ray, &sf, &direct, &hasDirect);
+      wb.ctr[slot] = st.rng.ctr;
+      if (hasDirect) {
+        wb.flags[slot] = flags | (1u << 9);
+        store3(wb.pendT, slot, st.pendT);
+        store3(wb.recA, slot, direct.termA);
+        store3(wb.recB, slot, direct.termB);
+        wb.recFlags[slot] = (direct.hasShadow ? 4 : 0) | (direct.hasProbe ? 8 : 0);
+        pushShadow = direct.hasShadow;
+        pushProbe = direct.hasProbe;
+      }
+    }
+    uint32_t si = warp_push(shadowCount, pushShadow);
+    if (pushShadow) aux_put(wb.shadowQ, si, slot, direct.shadow, 0);
+    uint32_t pi = warp_push(probeCount, pushProbe);
+    if (pushProbe) aux_put(wb.probeQ, pi, slot, direct.probe, direct.probeLight);
+  }
+}
+
+__global__ void __launch_bounds__(PB_BLOCK, 4)
+k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveDesc wd,
+                const RayQueue qin, const RayQueue qout, const SurfaceRecord rec, const uint32_t *nPtr,
+                uint32_t *work, uint32_t *nextCount) {
+  uint32_t n = *nPtr;
+  for (;;) {
+    uint32_t base = warp_claim(work);
+    if (base >= n) break;
+    uint32_t i = base + lane_id();
+    bool valid = i < n && qin.hitPrim[i] >= 0;
+    bool pushNext = false;
+    uint32_t slot = 0;
+    Ray next;
+    if (valid) {
+      slot = qin.slot[i];
+      Ray ray;
+      ray.o = v3(0, 0, 0);
+      ray.d = v3(qin.dx[i], qin.dy[i], qin.dz[i]);
+      ray.mint = 0.f; ray.maxt = 0.f;
+      Surface sf;
+      surface_load(sv, rec, i, &sf);
+      uint32_t flags = wb.flags[slot];
+      PathState st;
+      st.T = load3(wb.T, slot);
       st.depth = (int)(flags & 0xffu);
       st.specularBounce = (flags >> 8) & 1u;
       st.rng.key = slot_key(wd, slot, 1);
       st.rng.ctr = wb.ctr[slot];
       uint64_t key0 = slot_key(wd, slot, 0);
-      path_vertex(sv, key0, st, ray, hit, &out);
-      if (hit.prim >= 0) ++shaded;
-      store3(wb.L, slot, st.L);
+      pushNext = path_vertex_continue(sv, key0, st, ray, sf, &next);
       store3(wb.T, slot, st.T);
-      wb.alpha[slot] = st.alpha;
       wb.ctr[slot] = st.rng.ctr;
-      flags = (uint32_t)st.depth | (st.specularBounce ? (1u << 8) : 0u);
-      if (out.hasDirect) {
-        flags |= 1u << 9;
-        store3(wb.pendT, slot, st.pendT);
-        store3(wb.recA, slot, out.direct.termA);
-        store3(wb.recB, slot, out.direct.termB);
-        wb.recFlags[slot] = (out.direct.hasShadow ? 4 : 0) | (out.direct.hasProbe ? 8 : 0);
-        pushShadow = out.direct.hasShadow;
-        pushProbe = out.direct.hasProbe;
-      }
-      wb.flags[slot] = flags;
-      pushNext = out.hasNext;
+      wb.flags[slot] = (flags & (1u << 9)) | (uint32_t)st.depth | (st.specularBounce ? (1u << 8) : 0u);
     }
-    uint32_t si = warp_push(shadowCount, pushShadow);
-    if (pushShadow) aux_put(wb.shadowQ, si, slot, out.direct.shadow, 0);
-    uint32_t pi = warp_push(probeCount, pushProbe);
-    if (pushProbe) aux_put(wb.probeQ, pi, slot, out.direct.probe, out.direct.probeLight);
     uint32_t ni = warp_push(nextCount, pushNext);
-    if (pushNext) queue_put(qout, ni, slot, out.next);
+    if (pushNext) queue_put(qout, ni, slot, next);
   }
-  warp_stat_add(&wb.stats[ST_SHADED], shaded);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -749,6 +855,8 @@ static void carve_wave(Carver &c, WaveBuffers &wb, uint32_t nSlots, int directRe
     q.dx = c.take<float>(auxN); q.dy = c.take<float>(auxN); q.dz = c.take<float>(auxN);
     q.light = (k == 1) ? c.take<int32_t>(auxN) : nullptr;
   }
+  for (int k = 0; k < 15; ++k) wb.surf[k] = isPath ? c.take<float>(nSlots) : nullptr;
+  wb.surfIds = isPath ? c.take<uint32_t>(nSlots) : nullptr;
   wb.counts = c.take<uint32_t>(PB_COUNTS_TOTAL);
   wb.stats = c.take<unsigned long long>(ST_COUNT);
 }
@@ -820,10 +928,18 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
       uint32_t *nMain = &wb.counts[4 * it], *nShadow = &wb.counts[4 * it + 1], *nProbe = &wb.counts[4 * it + 2];
       uint32_t *nNext = &wb.counts[4 * (it + 1)];
       launch_traversals_a(h, count, grid, wb.q[cur], nMain, nextWork());
-      TIMED(KC_SHADE, (k_shade_path<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wd, wb.q[cur], wb.q[cur ^ 1], nMain, nextWork(),
-                                                             nNext, nShadow, nProbe)));
+      {
+        SurfaceRecord rec;
+        for (int k = 0; k < 15; ++k) rec.f[k] = wb.surf[k];
+        rec.ids = wb.surfIds;
+        TIMED(KC_SHADE, (k_path_surface<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], rec, nMain, nextWork())));
+        TIMED(KC_SHADE_DIRECT, (k_path_direct<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wd, wb.q[cur], rec, nMain, nextWork(),
+                                                                        nShadow, nProbe)));
+        TIMED(KC_SHADE_CONT, (k_path_continue<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wd, wb.q[cur], wb.q[cur ^ 1], rec, nMain,
+                                                                        nextWork(), nNext)));
+      }
       launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork());
-      *launches += 4;
+      *launches += 6;
       cur ^= 1;
     }
   } else {
@@ -878,7 +994,7 @@ const char *pbrt_b200_last_error(void) { return g_lastError.c_str(); }
 
 int64_t pbrt_b200_tunable(int key, int64_t value) {
   int64_t *p = key == 0 ? &g_waveSamples : key == 1 ? &g_countKd : key == 2 ? &g_blocksPerSM
-               : key == 3 ? &g_profileKernels : nullptr;
+               : key == 3 ? &g_profileKernels : key == 4 ? &g_shadeBlocks : nullptr;
   if (!p) return -1;
   int64_t prev = *p;
   if (value >= 0) *p = value;
