@@ -282,3 +282,70 @@ int pbrt_twin_camera_rays(const PbrtB200Scene *scene, const PbrtB200Window *win,
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Developer aid (tools/simt_sim.py): per-ray trace of the kd walk as a string of step codes,
+// I interior step, L leaf entry, R primitive reference skipped by the mailbox, T primitive test,
+// P pop.  Lets warp-scheduling strategies be compared offline.
+extern "C" int pbrt_twin_trace(const PbrtB200Scene *scene, const float *rays, uint64_t n, int any,
+                               uint8_t *codes, uint64_t cap, uint64_t *offsets) {
+  SceneView sv;
+  if (!build_view(*scene, &sv)) return PBRT_B200_ERR_INVALID;
+  uint64_t pos = 0;
+  for (uint64_t r = 0; r < n; ++r) {
+    offsets[r] = pos;
+    Ray ray;
+    ray.o = v3(rays[8 * r], rays[8 * r + 1], rays[8 * r + 2]);
+    ray.d = v3(rays[8 * r + 3], rays[8 * r + 4], rays[8 * r + 5]);
+    ray.mint = rays[8 * r + 6]; ray.maxt = rays[8 * r + 7];
+    float tmin, tmax;
+    if (sv.nNodes == 0 || !bbox_intersect_p(sv.bmin, sv.bmax, ray, &tmin, &tmax)) continue;
+    V3 invDir = v3(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
+    uint32_t todoNode[PB_KD_STACK]; float todoTmin[PB_KD_STACK], todoTmax[PB_KD_STACK];
+    int todoPos = 0;
+    uint32_t mailbox[PB_MAILBOX];
+    for (int i = 0; i < PB_MAILBOX; ++i) mailbox[i] = 0xffffffffu;
+    int mbPos = 0;
+    uint32_t node = 0;
+    Hit hit; hit.prim = -1;
+    bool stop = false;
+    auto put = [&](uint8_t c) { if (pos < cap) codes[pos++] = c; };
+    while (!stop) {
+      uint32_t w0, w1;
+      for (;;) {
+        w0 = sv.nodes[node].word0; w1 = sv.nodes[node].word1;
+        if ((w0 & 3u) == 3u) break;
+        put('I');
+        int axis = (int)(w0 & 3u);
+        float split; { uint32_t b = w0; memcpy(&split, &b, 4); }
+        float o = ray.o[axis], d = ray.d[axis];
+        float tplane = (split - o) * invDir[axis];
+        bool belowFirst = (o < split) || (o == split && d >= 0);
+        uint32_t firstChild = belowFirst ? node + 1 : w1, secondChild = belowFirst ? w1 : node + 1;
+        if (tplane > tmax || tplane <= 0) node = firstChild;
+        else if (tplane < tmin) node = secondChild;
+        else { todoNode[todoPos] = secondChild; todoTmin[todoPos] = tplane; todoTmax[todoPos] = tmax; ++todoPos;
+               node = firstChild; tmax = tplane; }
+      }
+      put('L');
+      uint32_t nPrims = w0 >> 2;
+      for (uint32_t i = 0; i < nPrims && !stop; ++i) {
+        uint32_t prim = (nPrims == 1) ? w1 : sv.primRefs[w1 + i];
+        bool seen = false;
+        for (int k = 0; k < PB_MAILBOX; ++k) seen |= (mailbox[k] == prim);
+        if (seen) { put('R'); continue; }
+        mailbox[mbPos] = prim; mbPos = (mbPos + 1) & (PB_MAILBOX - 1);
+        put('T');
+        bool h = any ? kd_test_prim<true>(sv, prim, ray, &hit) : kd_test_prim<false>(sv, prim, ray, &hit);
+        if (h && any) stop = true;
+      }
+      if (stop) break;
+      put('P');
+      if (todoPos == 0) break;
+      --todoPos; node = todoNode[todoPos]; tmin = todoTmin[todoPos]; tmax = todoTmax[todoPos];
+      if (!any && ray.maxt < tmin) break;
+    }
+  }
+  offsets[n] = pos;
+  return PBRT_B200_OK;
+}

@@ -54,10 +54,13 @@ static int fail(int code, const std::string &msg) {
 // tunables (pbrt_b200_tunable)
 static int64_t g_waveSamples = 1 << 22;   // key 0: image samples per wave
 static int64_t g_countKd = 0;             // key 1: collect kd-walk counters (costs a little time)
-static int64_t g_blocksPerSM = 8;         // key 2: resident CTAs per SM for the persistent kernels
+static int64_t g_blocksPerSM = 12;        // key 2: resident CTAs per SM for the persistent kernels
 static int64_t g_shadeBlocks = 4;         // key 4: occupancy target (CTAs/SM) the shade kernel is compiled for: 2, 3 or 4
 
 #define PB_BLOCK 128
+#ifndef PB_TRAV_MIN_BLOCKS
+#define PB_TRAV_MIN_BLOCKS 10  // <= 48 registers: 40 resident warps per SM for the latency-bound kd walk (measured best of 6/8/10/12)
+#endif
 
 // ------------------------------------------------------------------------------------------
 // device data layout of one wave
@@ -212,7 +215,7 @@ __device__ __forceinline__ void flush_kd_counters(unsigned long long *stats, int
   warp_stat_add(&stats[ST_K(kind, TF_TESTS)], cnt.tests);
 }
 template <bool COUNT>
-__global__ void __launch_bounds__(PB_BLOCK)
+__global__ void __launch_bounds__(PB_BLOCK, PB_TRAV_MIN_BLOCKS)
 k_intersect(const __grid_constant__ SceneView sv, const RayQueue q, const uint32_t *nPtr,
             uint32_t *work, unsigned long long *stats) {
   uint32_t n = *nPtr;
@@ -243,7 +246,7 @@ struct ShadowSink {
   }
 };
 template <bool COUNT>
-__global__ void __launch_bounds__(PB_BLOCK)
+__global__ void __launch_bounds__(PB_BLOCK, PB_TRAV_MIN_BLOCKS)
 k_shadow(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t *nPtr, uint32_t *work,
          uint8_t *recFlags, unsigned long long *stats) {
   uint32_t n = *nPtr;

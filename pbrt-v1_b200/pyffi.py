@@ -18,7 +18,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST_LIB = os.path.join(ROOT, "pbrt-v1_b200", "host", "libpbrt_host.so")
-CUDA_LIB = os.path.join(ROOT, "pbrt-v1_b200", "csrc", "libpbrt_b200.so")
+CUDA_LIB = os.environ.get("PBRT_B200_LIB", os.path.join(ROOT, "pbrt-v1_b200", "csrc", "libpbrt_b200.so"))
 TWIN_LIB = os.environ.get("PBRT_TWIN_LIB", os.path.join(ROOT, "oracle", "_build", "libpbrt_twin.so"))
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
