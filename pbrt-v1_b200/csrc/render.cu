@@ -52,7 +52,7 @@ static int fail(int code, const std::string &msg) {
 
 // ------------------------------------------------------------------------------------------
 // tunables (pbrt_b200_tunable)
-static int64_t g_waveSamples = 1 << 22;   // key 0: image samples per wave
+static int64_t g_waveSamples = 1 << 24;   // key 0: image samples per wave (16 Mi: ~5.4 GB of wave state)
 static int64_t g_countKd = 0;             // key 1: collect kd-walk counters (costs a little time)
 static int64_t g_blocksPerSM = 12;        // key 2: resident CTAs per SM for the persistent kernels
 static int64_t g_shadeBlocks = 4;         // key 4: occupancy target (CTAs/SM) the shade kernel is compiled for: 2, 3 or 4
@@ -81,6 +81,7 @@ struct WaveBuffers {
   float *L[3], *T[3], *pendT[3], *alpha;
   uint32_t *ctr;         // RNG stream-1 draws so far
   uint32_t *flags;       // bits 0-7 depth, 8 specularBounce, 9 pending direct record
+  uint32_t *pixel;             // (x + 32768) | (y + 32768) << 16: sample pixel of the slot (RNG key)
   float *imageX, *imageY;      // film coordinates of the sample
   float *outL[3], *outA;       // per-sample radiance after the guards
   // direct-lighting records: directRecords per slot
@@ -117,12 +118,21 @@ static const char *const kKernelClassNames[KC_COUNT] = {"k_generate", "k_interse
 #define PB_WORK_BASE (4 * PB_MAX_ITERS)
 #define PB_COUNTS_TOTAL (PB_WORK_BASE + 10 * PB_MAX_ITERS)
 
+// A wave is a run of consecutive image samples (reference order) that may span several pixel
+// windows: each part is a range of sample pixels of one window's sample extent.
+#define PB_MAX_PARTS 32
+struct WavePart {
+  int xs, xe, ys, ye;        // sample extent of the part's window (film/image.cpp:148-156)
+  uint32_t firstPixel;       // first sample pixel (raster index inside the extent)
+  uint32_t nPixels;
+  uint32_t slotBase;         // wave slot of the part's first sample (multiple of spp)
+  int32_t window;            // index into the handle's films
+};
 struct WaveDesc {
-  int xs, xe, ys, ye;        // sample extent of the window
   int spp;
-  uint32_t firstPixel;       // first sample pixel (raster index in the extent) of this wave
-  uint32_t nPixels;          // sample pixels in this wave
-  uint32_t nSlots;           // nPixels * spp
+  uint32_t nSlots;
+  int nParts;
+  WavePart parts[PB_MAX_PARTS];
 };
 
 // ------------------------------------------------------------------------------------------
@@ -176,10 +186,14 @@ __global__ void __launch_bounds__(PB_BLOCK)
 k_generate(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveDesc wd) {
   for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < wd.nSlots;
        slot += gridDim.x * blockDim.x) {
-    uint32_t pix = wd.firstPixel + slot / wd.spp;
+    int part = 0;
+    while (part + 1 < wd.nParts && slot >= wd.parts[part + 1].slotBase) ++part;
+    const WavePart &wp = wd.parts[part];
+    uint32_t pix = wp.firstPixel + (slot - wp.slotBase) / wd.spp;
     int k = (int)(slot % wd.spp);
-    int ew = wd.xe - wd.xs;
-    int x = wd.xs + (int)(pix % ew), y = wd.ys + (int)(pix / ew);
+    int ew = wp.xe - wp.xs;
+    int x = wp.xs + (int)(pix % ew), y = wp.ys + (int)(pix / ew);
+    wb.pixel[slot] = (uint32_t)(x + 32768) | ((uint32_t)(y + 32768) << 16);
     CameraSample cs;
     stratified_camera_sample(sv, x, y, k, &cs);
     Ray ray;
@@ -297,11 +311,14 @@ __device__ __forceinline__ Spec load3(float *const a[3], uint32_t i) { return sp
 __device__ __forceinline__ void store3(float *const a[3], uint32_t i, const Spec &s) {
   a[0][i] = s.c[0]; a[1][i] = s.c[1]; a[2][i] = s.c[2];
 }
-__device__ __forceinline__ uint64_t slot_key(const WaveDesc &wd, uint32_t slot, int stream) {
-  uint32_t pix = wd.firstPixel + slot / wd.spp;
-  int k = (int)(slot % wd.spp);
-  int ew = wd.xe - wd.xs;
-  return pb_key(wd.xs + (int)(pix % ew), wd.ys + (int)(pix / ew), k, stream);
+// RNG key of a slot's image sample: (pixel x, pixel y, sample-in-pixel, stream)
+struct WaveKeyInfo {
+  const uint32_t *pixel;
+  int spp;
+};
+__device__ __forceinline__ uint64_t slot_key(const WaveKeyInfo &wd, uint32_t slot, int stream) {
+  uint32_t p = wd.pixel[slot];
+  return pb_key((int)(p & 0xffffu) - 32768, (int)(p >> 16) - 32768, (int)(slot % (uint32_t)wd.spp), stream);
 }
 // Fold the slot's pending direct-lighting record (path integrator) into L.
 __device__ __forceinline__ void path_fold_pending(const SceneView &sv, const WaveBuffers &wb,
@@ -388,7 +405,7 @@ k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const
 }
 
 __global__ void __launch_bounds__(PB_BLOCK, 4)
-k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveDesc wd,
+k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveKeyInfo wd,
               const RayQueue qin, const SurfaceRecord rec, const uint32_t *nPtr, uint32_t *work,
               uint32_t *shadowCount, uint32_t *probeCount) {
   uint32_t n = *nPtr;
@@ -436,7 +453,7 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
 }
 
 __global__ void __launch_bounds__(PB_BLOCK, 4)
-k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveDesc wd,
+k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveKeyInfo wd,
                 const RayQueue qin, const RayQueue qout, const SurfaceRecord rec, const uint32_t *nPtr,
                 uint32_t *work, uint32_t *nextCount) {
   uint32_t n = *nPtr;
@@ -515,7 +532,7 @@ struct DevFrameIO {
 
 // K2 (whitted / directlighting): vertex body up to the specular recursion
 __global__ void __launch_bounds__(PB_BLOCK)
-k_shade_wd(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveDesc wd,
+k_shade_wd(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveKeyInfo wd,
            const RayQueue qin, const uint32_t *nPtr, uint32_t *work, uint32_t *shadowCount,
            uint32_t *probeCount) {
   uint32_t n = *nPtr;
@@ -649,7 +666,7 @@ k_finalize(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
 // Candidate sample pixels are visited in raster order and their samples in index order:
 // the order in which the reference's serial loop would have splatted them.
 __global__ void __launch_bounds__(PB_BLOCK)
-k_film_gather(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveDesc wd,
+k_film_gather(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WavePart wd, int spp,
               const float *filterTable, FilmPixel *film, PbrtB200Window win, int rowFirst, int rowCount) {
   __shared__ float table[256];
   for (int t = threadIdx.x; t < 256; t += blockDim.x) table[t] = filterTable[t];
@@ -670,8 +687,8 @@ k_film_gather(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
       for (int sx = sx0; sx <= sx1; ++sx) {
         int64_t pix = (int64_t)(sy - wd.ys) * ew + (sx - wd.xs) - (int64_t)wd.firstPixel;
         if (pix < 0 || pix >= (int64_t)wd.nPixels) continue;
-        uint32_t s0 = (uint32_t)pix * (uint32_t)wd.spp;
-        for (int k = 0; k < wd.spp; ++k) {
+        uint32_t s0 = wd.slotBase + (uint32_t)pix * (uint32_t)spp;
+        for (int k = 0; k < spp; ++k) {
           uint32_t slot = s0 + k;
           float wt;
           if (!film_sample_weight(sv, table, wb.imageX[slot], wb.imageY[slot], px, py, &wt)) continue;
@@ -719,12 +736,12 @@ __global__ void k_rays_any(const __grid_constant__ SceneView sv, const float *ra
     occ[i] = kd_intersect<true, false>(sv, r, &h, (KdCounters *)0) ? 1 : 0;
   }
 }
-__global__ void k_camera_rays(const __grid_constant__ SceneView sv, const WaveDesc wd, uint64_t n,
+__global__ void k_camera_rays(const __grid_constant__ SceneView sv, const WavePart wd, int spp, uint64_t n,
                               float *rays, float *xy) {
   for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < n;
        s += (uint64_t)gridDim.x * blockDim.x) {
-    uint64_t pix = s / wd.spp;
-    int k = (int)(s % wd.spp);
+    uint64_t pix = s / spp;
+    int k = (int)(s % spp);
     int ew = wd.xe - wd.xs;
     CameraSample cs;
     stratified_camera_sample(sv, wd.xs + (int)(pix % ew), wd.ys + (int)(pix / ew), k, &cs);
@@ -832,6 +849,7 @@ static void carve_wave(Carver &c, WaveBuffers &wb, uint32_t nSlots, int directRe
   wb.alpha = c.take<float>(nSlots); wb.outA = c.take<float>(nSlots);
   wb.ctr = c.take<uint32_t>(nSlots); wb.flags = c.take<uint32_t>(nSlots);
   wb.imageX = c.take<float>(nSlots); wb.imageY = c.take<float>(nSlots);
+  wb.pixel = c.take<uint32_t>(nSlots);
   wb.recFlags = c.take<uint8_t>((size_t)nSlots * directRecords);
   if (!isPath) {
     wb.frame = c.take<float>((size_t)PB_FRAME_FLOATS * nFrames * nSlots);
@@ -898,12 +916,15 @@ static void launch_traversals_a(PbrtB200Handle *h, bool count, int grid, const R
 static void launch_traversals_b(PbrtB200Handle *h, bool count, int grid, uint32_t *nShadow, uint32_t *nProbe,
                                 uint32_t *workS, uint32_t *workP) {
   WaveBuffers &wb = h->wb;
+  // MIS probes are rare (the BSDF sample must point at the light): a small grid avoids paying the
+  // ramp-up of the full persistent grid for a few thousand rays
+  int probeGrid = std::min(grid, h->numSMs * 2);
   if (count) {
     TIMED(KC_SHADOW, (k_shadow<true><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.stats)));
-    TIMED(KC_PROBE, (k_probe<true><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.stats)));
+    TIMED(KC_PROBE, (k_probe<true><<<probeGrid, PB_BLOCK, 0, h->stream>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.stats)));
   } else {
     TIMED(KC_SHADOW, (k_shadow<false><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.stats)));
-    TIMED(KC_PROBE, (k_probe<false><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.stats)));
+    TIMED(KC_PROBE, (k_probe<false><<<probeGrid, PB_BLOCK, 0, h->stream>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.stats)));
   }
 }
 
@@ -923,6 +944,7 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
   auto nextWork = [&]() { return wb.counts + (workIdx++); };
   bool isPath = sv.integrator.kind == PBRT_B200_INT_PATH;
   int cur = 0;
+  WaveKeyInfo wk = {wb.pixel, wd.spp};
   if (isPath) {
     int iters = sv.integrator.max_depth + 1;
     if (iters < 1) iters = 1;
@@ -936,9 +958,9 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
         for (int k = 0; k < 15; ++k) rec.f[k] = wb.surf[k];
         rec.ids = wb.surfIds;
         TIMED(KC_SHADE, (k_path_surface<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], rec, nMain, nextWork())));
-        TIMED(KC_SHADE_DIRECT, (k_path_direct<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wd, wb.q[cur], rec, nMain, nextWork(),
+        TIMED(KC_SHADE_DIRECT, (k_path_direct<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], rec, nMain, nextWork(),
                                                                         nShadow, nProbe)));
-        TIMED(KC_SHADE_CONT, (k_path_continue<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wd, wb.q[cur], wb.q[cur ^ 1], rec, nMain,
+        TIMED(KC_SHADE_CONT, (k_path_continue<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], wb.q[cur ^ 1], rec, nMain,
                                                                         nextWork(), nNext)));
       }
       launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork());
@@ -961,7 +983,7 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
       uint32_t *nMain = &wb.counts[4 * it], *nShadow = &wb.counts[4 * it + 1], *nProbe = &wb.counts[4 * it + 2];
       uint32_t *nNext = &wb.counts[4 * (it + 1)];
       launch_traversals_a(h, count, grid, wb.q[cur], nMain, nextWork());
-      TIMED(KC_SHADE, (k_shade_wd<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wd, wb.q[cur], nMain, nextWork(), nShadow, nProbe)));
+      TIMED(KC_SHADE, (k_shade_wd<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], nMain, nextWork(), nShadow, nProbe)));
       launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork());
       TIMED(KC_ADVANCE, (k_advance_wd<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], wb.q[cur ^ 1], nMain, nextWork(), nNext)));
       *launches += 5;
@@ -977,12 +999,11 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
   return PBRT_B200_OK;
 }
 
-static WaveDesc window_desc(const SceneView &sv, const PbrtB200Window &w) {
-  WaveDesc wd;
-  memset(&wd, 0, sizeof(wd));
-  film_sample_extent(sv, w.x0, w.y0, w.width, w.height, &wd.xs, &wd.xe, &wd.ys, &wd.ye);
-  wd.spp = sv.sampler.x_samples * sv.sampler.y_samples;
-  return wd;
+static WavePart window_part(const SceneView &sv, const PbrtB200Window &w) {
+  WavePart wp;
+  memset(&wp, 0, sizeof(wp));
+  film_sample_extent(sv, w.x0, w.y0, w.width, w.height, &wp.xs, &wp.xe, &wp.ys, &wp.ye);
+  return wp;
 }
 
 extern "C" {
@@ -1092,20 +1113,27 @@ int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_win
   cudaEvent_t e0, e1;
   CU_TRY(cudaEventCreate(&e0));
   CU_TRY(cudaEventCreate(&e1));
-  // size the wave arena for the largest window
-  uint32_t maxSlots = 1;
+  // per-window sample extents; size the wave arena for min(tunable, all samples)
+  const int spp = sv.sampler.x_samples * sv.sampler.y_samples;
+  std::vector<WavePart> ext(n_windows);
+  std::vector<uint64_t> nPixW(n_windows);
+  uint64_t totalSamples = 0;
   for (int w = 0; w < n_windows; ++w) {
     const PbrtB200Window &win = windows[w];
     if (win.width < 1 || win.height < 1) return fail(PBRT_B200_ERR_INVALID, "empty window");
-    WaveDesc wd = window_desc(sv, win);
-    uint64_t nPix = (uint64_t)(wd.xe - wd.xs) * (wd.ye - wd.ys);
-    uint64_t wavePix = std::max<uint64_t>(1, (uint64_t)g_waveSamples / wd.spp);
-    wavePix = std::min(wavePix, nPix);
-    if (wavePix * wd.spp > 0x7fffffffull / 4) return fail(PBRT_B200_ERR_UNSUPPORTED, "wave too large");
-    maxSlots = std::max<uint32_t>(maxSlots, (uint32_t)(wavePix * wd.spp));
+    if (win.x0 < -16384 || win.y0 < -16384 || win.x0 + win.width > 16384 || win.y0 + win.height > 16384)
+      return fail(PBRT_B200_ERR_UNSUPPORTED, "window outside +-16384 pixels");
+    ext[w] = window_part(sv, win);
+    ext[w].window = w;
+    nPixW[w] = (uint64_t)(ext[w].xe - ext[w].xs) * (ext[w].ye - ext[w].ys);
+    totalSamples += nPixW[w] * spp;
   }
-  int rc = ensure_wave(h, maxSlots);
+  uint64_t capSlots = std::max<uint64_t>((uint64_t)spp, std::min<uint64_t>((uint64_t)g_waveSamples, totalSamples));
+  capSlots = (capSlots / spp) * spp;
+  if (capSlots > 0x7fffffffull / 4) return fail(PBRT_B200_ERR_UNSUPPORTED, "wave too large");
+  int rc = ensure_wave(h, (uint32_t)capSlots);
   if (rc != PBRT_B200_OK) return rc;
+  capSlots = (h->wb.nSlots / spp) * (uint64_t)spp;
   CU_TRY(cudaMemsetAsync(h->wb.stats, 0, ST_COUNT * sizeof(unsigned long long), h->stream));
   uint64_t cameraRays = 0;
   CU_TRY(cudaEventRecord(e0, h->stream));
@@ -1117,41 +1145,64 @@ int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_win
     CU_TRY(cudaMalloc((void **)&wf.film, nPixOut * sizeof(FilmPixel)));
     CU_TRY(cudaMalloc((void **)&wf.rgba, nPixOut * sizeof(float4)));
     CU_TRY(cudaMemsetAsync(wf.film, 0, nPixOut * sizeof(FilmPixel), h->stream));
-    WaveDesc wd = window_desc(sv, win);
-    int ew = wd.xe - wd.xs;
-    uint64_t nPix = (uint64_t)ew * (wd.ye - wd.ys);
-    wf.nSamples = nPix * wd.spp;
+    wf.nSamples = nPixW[w] * spp;
     if (h->keepSamples) CU_TRY(cudaMalloc((void **)&wf.sampleOut, wf.nSamples * 4 * sizeof(float)));
     h->films.push_back(wf);
-    uint64_t wavePix = std::max<uint64_t>(1, (uint64_t)h->wb.nSlots / wd.spp);
-    for (uint64_t p0 = 0; p0 < nPix; p0 += wavePix) {
-      wd.firstPixel = (uint32_t)p0;
-      wd.nPixels = (uint32_t)std::min<uint64_t>(wavePix, nPix - p0);
-      wd.nSlots = wd.nPixels * wd.spp;
-      rc = run_wave(h, wd, &launches);
-      if (rc != PBRT_B200_OK) return rc;
-      // pixel rows this wave's samples can reach
-      int syFirst = wd.ys + (int)(p0 / ew), syLast = wd.ys + (int)((p0 + wd.nPixels - 1) / ew);
+  }
+  // waves: consecutive samples in reference order, spanning windows when a window is small
+  int curW = 0;
+  uint64_t curP = 0;
+  while (curW < n_windows) {
+    WaveDesc wd;
+    memset(&wd, 0, sizeof(wd));
+    wd.spp = spp;
+    while (curW < n_windows && wd.nParts < PB_MAX_PARTS && wd.nSlots < capSlots) {
+      uint64_t room = (capSlots - wd.nSlots) / spp;
+      uint64_t take = std::min<uint64_t>(room, nPixW[curW] - curP);
+      if (take == 0) break;
+      WavePart &wp = wd.parts[wd.nParts++];
+      wp = ext[curW];
+      wp.firstPixel = (uint32_t)curP;
+      wp.nPixels = (uint32_t)take;
+      wp.slotBase = wd.nSlots;
+      wd.nSlots += (uint32_t)(take * spp);
+      curP += take;
+      if (curP == nPixW[curW]) { ++curW; curP = 0; }
+    }
+    rc = run_wave(h, wd, &launches);
+    if (rc != PBRT_B200_OK) return rc;
+    for (int pi = 0; pi < wd.nParts; ++pi) {
+      const WavePart &wp = wd.parts[pi];
+      WindowFilm &wf = h->films[wp.window];
+      const PbrtB200Window &win = wf.win;
+      int ew = wp.xe - wp.xs;
+      // pixel rows this part's samples can reach
+      int syFirst = wp.ys + (int)(wp.firstPixel / ew), syLast = wp.ys + (int)((wp.firstPixel + wp.nPixels - 1) / ew);
       int rowFirst = std::max(win.y0, (int)floorf(syFirst - 0.5f - sv.filterYW) - 1);
       int rowLast = std::min(win.y0 + win.height - 1, (int)ceilf(syLast + 1 - 0.5f + sv.filterYW) + 1);
       if (rowLast >= rowFirst) {
         int rows = rowLast - rowFirst + 1;
         int total = rows * win.width;
         int grid = std::min((total + PB_BLOCK - 1) / PB_BLOCK, h->numSMs * 16);
-        TIMED(KC_FILM, (k_film_gather<<<grid, PB_BLOCK, 0, h->stream>>>(sv, h->wb, wd, h->filterTable, wf.film, win,
+        TIMED(KC_FILM, (k_film_gather<<<grid, PB_BLOCK, 0, h->stream>>>(sv, h->wb, wp, spp, h->filterTable, wf.film, win,
                                                                         rowFirst, rows)));
         ++launches;
       }
       if (wf.sampleOut) {
         // interleave L.rgb, alpha for the test entry point
+        uint32_t nS = wp.nPixels * (uint32_t)spp;
         for (int c = 0; c < 4; ++c) {
-          const float *src = c < 3 ? h->wb.outL[c] : h->wb.outA;
-          CU_TRY(cudaMemcpy2DAsync(wf.sampleOut + (size_t)p0 * wd.spp * 4 + c, 4 * sizeof(float), src,
-                                   sizeof(float), sizeof(float), wd.nSlots, cudaMemcpyDeviceToDevice, h->stream));
+          const float *src = (c < 3 ? h->wb.outL[c] : h->wb.outA) + wp.slotBase;
+          CU_TRY(cudaMemcpy2DAsync(wf.sampleOut + (size_t)wp.firstPixel * spp * 4 + c, 4 * sizeof(float), src,
+                                   sizeof(float), sizeof(float), nS, cudaMemcpyDeviceToDevice, h->stream));
         }
       }
-      cameraRays += wd.nSlots;
     }
+    cameraRays += wd.nSlots;
+  }
+  for (int w = 0; w < n_windows; ++w) {
+    WindowFilm &wf = h->films[w];
+    size_t nPixOut = (size_t)wf.win.width * wf.win.height;
     int grid = std::min((int)((nPixOut + 255) / 256), h->numSMs * 16);
     TIMED(KC_FILM, (k_film_resolve<<<grid, 256, 0, h->stream>>>(wf.film, wf.rgba, (int)nPixOut, sv.premultiply)));
     ++launches;
@@ -1309,14 +1360,15 @@ int pbrt_b200_camera_rays(PbrtB200Handle *h, const PbrtB200Window *w, uint64_t n
   if (!h || !w) return fail(PBRT_B200_ERR_INVALID, "null argument");
   if (n == 0) return PBRT_B200_OK;
   CU_TRY(cudaSetDevice(h->device));
-  WaveDesc wd = window_desc(h->sv, *w);
-  uint64_t total = (uint64_t)(wd.xe - wd.xs) * (wd.ye - wd.ys) * wd.spp;
+  WavePart wd = window_part(h->sv, *w);
+  int spp = h->sv.sampler.x_samples * h->sv.sampler.y_samples;
+  uint64_t total = (uint64_t)(wd.xe - wd.xs) * (wd.ye - wd.ys) * spp;
   if (n > total) return fail(PBRT_B200_ERR_INVALID, "more rays requested than the window has samples");
   float *dr, *dxy;
   CU_TRY(cudaMalloc((void **)&dr, n * 8 * sizeof(float)));
   CU_TRY(cudaMalloc((void **)&dxy, n * 2 * sizeof(float)));
   int grid = (int)std::min<uint64_t>((n + 127) / 128, (uint64_t)h->numSMs * 16);
-  k_camera_rays<<<grid, 128, 0, h->stream>>>(h->sv, wd, n, dr, dxy);
+  k_camera_rays<<<grid, 128, 0, h->stream>>>(h->sv, wd, spp, n, dr, dxy);
   CU_TRY(cudaStreamSynchronize(h->stream));
   CU_TRY(cudaMemcpy(rays, dr, n * 8 * sizeof(float), cudaMemcpyDeviceToHost));
   CU_TRY(cudaMemcpy(image_xy, dxy, n * 2 * sizeof(float), cudaMemcpyDeviceToHost));
