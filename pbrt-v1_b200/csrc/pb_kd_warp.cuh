@@ -24,6 +24,9 @@
 #include "pb_kd.h"
 
 #define PB_REFILL_THRESHOLD 8   // refill when at least this many lanes are idle
+#ifndef PB_CHEAP_STEPS
+#define PB_CHEAP_STEPS 4
+#endif
 
 // Source: Ray load(uint32_t i).   Sink: void done(uint32_t i, const Ray &ray, const Hit &hit, bool anyHit).
 template <bool ANY, bool COUNT, class Source, class Sink>
@@ -85,7 +88,9 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
     // ---- cheap steps until this lane holds one primitive to test
     bool pending = false;
     uint32_t prim = 0;
-    while (active && !pending) {
+    // at most PB_CHEAP_STEPS bookkeeping steps per trip: a lane deep in interior nodes must not hold
+    // back 31 lanes that already have a primitive to test (offline SIMT model: tools/simt_sim.py)
+    for (int step = 0; step < PB_CHEAP_STEPS && active && !pending; ++step) {
       if (inLeaf) {
         if (leafI < leafN) {
           prim = (leafN == 1) ? leafW1 : __ldg(sv.primRefs + leafW1 + leafI);

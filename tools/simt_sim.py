@@ -100,3 +100,54 @@ for k, o in orders.items():
     u = sum(sum(COST[c] for c in traces[i]) for i in o[:nw])
     a, b = sim_steploop(o), sim_whilewhile(o)
     print("%-32s step-loop eff %.3f   while-while eff %.3f" % (k, u / (32.0 * a), u / (32.0 * b)))
+
+
+def sim_onestep(order):
+    """each trip every live lane executes exactly one step; the warp pays for every kind present"""
+    total = 0
+    for w in range(0, len(order) - 31, 32):
+        lanes = [traces[i] for i in order[w:w + 32]]
+        L = max(len(t) for t in lanes)
+        for k in range(L):
+            kinds = set(t[k] for t in lanes if k < len(t))
+            total += sum(COST[c] for c in kinds)
+    return total
+
+
+def sim_kcheap(order, K):
+    """per trip: up to K cheap steps per lane (stop early at a test), then the test for lanes that hold one"""
+    total = 0
+    for w in range(0, len(order) - 31, 32):
+        lanes = [traces[i] for i in order[w:w + 32]]
+        pos = [0] * 32
+        while True:
+            maxcheap = 0
+            anytest = False
+            alive = False
+            for l in range(32):
+                tr = lanes[l]
+                c = 0
+                k = 0
+                while pos[l] < len(tr) and tr[pos[l]] != ord('T') and k < K:
+                    c += COST[tr[pos[l]]]
+                    pos[l] += 1
+                    k += 1
+                if pos[l] < len(tr) and tr[pos[l]] == ord('T'):
+                    anytest = True
+                    c += 25
+                    pos[l] += 1
+                if pos[l] < len(tr):
+                    alive = True
+                maxcheap = max(maxcheap, c)
+            total += maxcheap + (90 if anytest else 0)
+            if not alive:
+                break
+    return total
+
+
+o = idx
+nw = (len(o) // 32) * 32
+u = sum(sum(COST[c] for c in traces[i]) for i in o[:nw])
+print("one-step-per-trip eff %.3f" % (u / (32.0 * sim_onestep(o))))
+for K in (1, 2, 3, 4, 6, 8):
+    print("K=%d cheap steps then test: eff %.3f" % (K, u / (32.0 * sim_kcheap(o, K))))
