@@ -325,6 +325,12 @@ __device__ __forceinline__ void path_fold_pending(const SceneView &sv, const Wav
                                                   uint32_t slot, uint32_t *flags, Spec *L) {
   if (!(*flags & (1u << 9))) return;
   uint8_t rf = wb.recFlags[slot];
+  if (rf & 16) {
+    // compact record: recA holds pathThroughput * (nLights * Ld), valid when the shadow ray got through
+    if (rf & 1) *L = *L + load3(wb.recA, slot);
+    *flags &= ~(1u << 9);
+    return;
+  }
   PathState tmp;
   tmp.L = *L;
   tmp.pendT = load3(wb.pendT, slot);
@@ -436,13 +442,23 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
       path_vertex_direct(sv, key0, st, ray, &sf, &direct, &hasDirect);
       wb.ctr[slot] = st.rng.ctr;
       if (hasDirect) {
-        wb.flags[slot] = flags | (1u << 9);
-        store3(wb.pendT, slot, st.pendT);
-        store3(wb.recA, slot, direct.termA);
-        store3(wb.recB, slot, direct.termB);
-        wb.recFlags[slot] = (direct.hasShadow ? 4 : 0) | (direct.hasProbe ? 8 : 0);
         pushShadow = direct.hasShadow;
         pushProbe = direct.hasProbe;
+        if (pushProbe) {
+          // rare: the estimator's value also depends on the MIS probe -> keep both terms pending
+          wb.flags[slot] = flags | (1u << 9);
+          store3(wb.pendT, slot, st.pendT);
+          store3(wb.recA, slot, direct.termA);
+          store3(wb.recB, slot, direct.termB);
+          wb.recFlags[slot] = (direct.hasShadow ? 4 : 0) | 8;
+        } else if (pushShadow) {
+          // common: only the shadow ray decides, so the addend of `L += pathThroughput *
+          // UniformSampleOneLight(..)` (path.cpp:100-112) is known now; 3 floats stay pending, not 9
+          Spec Ld = direct_value(direct.termA, direct.termB, true, false);
+          wb.flags[slot] = flags | (1u << 9);
+          store3(wb.recA, slot, st.pendT * ((float)sv.nLights * Ld));
+          wb.recFlags[slot] = 4 | 16;
+        }
       }
     }
     uint32_t si = warp_push(shadowCount, pushShadow);
@@ -1104,7 +1120,14 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
 int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_windows, PbrtB200Stats *stats) {
   if (!h || !windows || n_windows < 1) return fail(PBRT_B200_ERR_INVALID, "bad arguments");
   CU_TRY(cudaSetDevice(h->device));
-  free_films(h);
+  // keep the film buffers of the previous render when the windows are unchanged (frame loops)
+  bool reuseFilms = (int)h->films.size() == n_windows;
+  for (int w = 0; reuseFilms && w < n_windows; ++w) {
+    const PbrtB200Window &a = h->films[w].win, &b = windows[w];
+    reuseFilms = a.x0 == b.x0 && a.y0 == b.y0 && a.width == b.width && a.height == b.height &&
+                 (h->films[w].sampleOut != nullptr) == h->keepSamples;
+  }
+  if (!reuseFilms) free_films(h);
   const SceneView &sv = h->sv;
   uint64_t launches = 0;
   memset(h->classMs, 0, sizeof(h->classMs));
@@ -1139,9 +1162,13 @@ int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_win
   CU_TRY(cudaEventRecord(e0, h->stream));
   for (int w = 0; w < n_windows; ++w) {
     const PbrtB200Window &win = windows[w];
+    size_t nPixOut = (size_t)win.width * win.height;
+    if (reuseFilms) {
+      CU_TRY(cudaMemsetAsync(h->films[w].film, 0, nPixOut * sizeof(FilmPixel), h->stream));
+      continue;
+    }
     WindowFilm wf;
     wf.win = win; wf.film = nullptr; wf.rgba = nullptr; wf.sampleOut = nullptr;
-    size_t nPixOut = (size_t)win.width * win.height;
     CU_TRY(cudaMalloc((void **)&wf.film, nPixOut * sizeof(FilmPixel)));
     CU_TRY(cudaMalloc((void **)&wf.rgba, nPixOut * sizeof(float4)));
     CU_TRY(cudaMemsetAsync(wf.film, 0, nPixOut * sizeof(FilmPixel), h->stream));
