@@ -120,7 +120,7 @@ PB_NOINLINE V3 sphere_sample(const PbrtB200Sphere &s, const V3 &p, float u1, flo
   r.d = uniform_sample_cone(u1, u2, cosThetaMax, wcX, wcY, wc);
   r.mint = PB_RAY_EPSILON; r.maxt = PB_INFINITY;
   float thit, phi; V3 phit;
-  if (!sphere_test(s, r, &thit, &phit, &phi)) thit = dot(Pcenter - p, normalize(r.d));
+  if (!sphere_test(s, r, &thit, &phit, &phi, false)) thit = dot(Pcenter - p, normalize(r.d));
   V3 ps = ray_at(r, thit);
   *ns = normalize(ps - Pcenter);
   if (s.flags & PBRT_B200_PF_REVERSE) *ns = *ns * -1.f;
@@ -145,7 +145,7 @@ PB_NOINLINE float light_shapes_pdf(const SceneView &sv, const PbrtB200Light &l, 
       ok = tri_test(tv.p1, tv.p2, tv.p3, ray, &t, &b1, &b2);
     else {
       V3 phit; float phi;
-      ok = sphere_test(sv.spheres[sv.aux[prim].owner], ray, &t, &phit, &phi);
+      ok = sphere_test(sv.spheres[sv.aux[prim].owner], ray, &t, &phit, &phi, false);
     }
     if (ok) { anyHit = true; hit.prim = (int32_t)prim; hit.t = t; hit.b1 = b1; hit.b2 = b2; htv = tv; }
   }

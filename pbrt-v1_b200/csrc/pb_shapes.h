@@ -72,7 +72,11 @@ PB_HD bool quadratic(float A, float B, float C, float *t0, float *t1) {
 
 // Sphere::Intersect up to the accepted hit (sphere.cpp:104-143 == IntersectP
 // :209-249).  Outputs object-space hit point and phi for the DG stage.
-PB_NOINLINE bool sphere_test(const PbrtB200Sphere &s, const Ray &r, float *tHit, V3 *phitO, float *phiO) {
+// wantPhi = false lets a pure hit query skip atan2f for an unclipped sphere: phi only feeds the
+// clipping tests (always false when zmin/zmax/phimax do not cut the sphere: phi never exceeds the
+// float 2*pi it is compared with) and the parametric u computed later from a fresh call.
+PB_NOINLINE bool sphere_test(const PbrtB200Sphere &s, const Ray &r, float *tHit, V3 *phitO, float *phiO,
+                             bool wantPhi = true) {
   Ray ray;
   ray.o = xf_point(s.w2o, r.o);
   ray.d = xf_vector(s.w2o, r.d);
@@ -90,6 +94,11 @@ PB_NOINLINE bool sphere_test(const PbrtB200Sphere &s, const Ray &r, float *tHit,
     if (thit > ray.maxt) return false;
   }
   V3 phit = ray_at(ray, thit);
+  bool clipped = s.zmin > -radius || s.zmax < radius || s.phi_max < 2.f * PB_PI;
+  if (!clipped && !wantPhi) {
+    *tHit = thit; *phitO = phit; *phiO = 0.f;
+    return true;
+  }
   float phi = pb_atan2f(phit.y, phit.x);
   if (phi < 0.f) phi += 2.f * PB_PI;
   if ((s.zmin > -radius && phit.z < s.zmin) || (s.zmax < radius && phit.z > s.zmax) ||

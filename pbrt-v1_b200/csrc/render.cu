@@ -144,6 +144,14 @@ __device__ __forceinline__ uint32_t warp_claim(uint32_t *counter) {
   if (lane_id() == 0) base = atomicAdd(counter, 32u);
   return __shfl_sync(0xffffffffu, base, 0);
 }
+// Same, claiming `count` (a multiple of 32) items per atomic: the shading kernels walk their claim in
+// 32-item steps, so the atomic's round trip is paid once per 128 items.
+#define PB_CLAIM 128u
+__device__ __forceinline__ uint32_t warp_claim_n(uint32_t *counter, uint32_t count) {
+  uint32_t base = 0;
+  if (lane_id() == 0) base = atomicAdd(counter, count);
+  return __shfl_sync(0xffffffffu, base, 0);
+}
 // Warp-aggregated queue push: returns this lane's index or 0xffffffff.
 __device__ __forceinline__ uint32_t warp_push(uint32_t *count, bool pred) {
   uint32_t mask = __ballot_sync(0xffffffffu, pred);
@@ -380,32 +388,34 @@ k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const
   uint32_t n = *nPtr;
   uint32_t shaded = 0;
   for (;;) {
-    uint32_t base = warp_claim(work);
-    if (base >= n) break;
-    uint32_t i = base + lane_id();
-    if (i >= n) continue;
-    uint32_t slot = qin.slot[i];
-    Ray ray = queue_ray(qin, i);
-    Hit hit;
-    hit.prim = qin.hitPrim[i];
-    hit.t = 0.f; hit.b1 = hit.b2 = 0.f;
-    if (hit.prim >= 0) { hit.t = qin.hitT[i]; hit.b1 = qin.hitB1[i]; hit.b2 = qin.hitB2[i]; }
-    uint32_t flags = wb.flags[slot];
-    PathState st;
-    st.L = load3(wb.L, slot);
-    path_fold_pending(sv, wb, slot, &flags, &st.L);
-    st.T = load3(wb.T, slot);
-    st.alpha = wb.alpha[slot];
-    st.depth = (int)(flags & 0xffu);
-    st.specularBounce = (flags >> 8) & 1u;
-    Surface sf;
-    if (path_vertex_surface(sv, st, ray, hit, &sf)) {
-      ++shaded;
-      surface_store(rec, i, sf);
-    }
-    store3(wb.L, slot, st.L);
-    wb.alpha[slot] = st.alpha;
-    wb.flags[slot] = flags;
+    uint32_t chunk = warp_claim_n(work, PB_CLAIM);
+    if (chunk >= n) break;
+    for (uint32_t base = chunk; base < chunk + PB_CLAIM && base < n; base += 32) {
+      uint32_t i = base + lane_id();
+      if (i >= n) continue;
+      uint32_t slot = qin.slot[i];
+      Ray ray = queue_ray(qin, i);
+      Hit hit;
+      hit.prim = qin.hitPrim[i];
+      hit.t = 0.f; hit.b1 = hit.b2 = 0.f;
+      if (hit.prim >= 0) { hit.t = qin.hitT[i]; hit.b1 = qin.hitB1[i]; hit.b2 = qin.hitB2[i]; }
+      uint32_t flags = wb.flags[slot];
+      PathState st;
+      st.L = load3(wb.L, slot);
+      path_fold_pending(sv, wb, slot, &flags, &st.L);
+      st.T = load3(wb.T, slot);
+      st.alpha = wb.alpha[slot];
+      st.depth = (int)(flags & 0xffu);
+      st.specularBounce = (flags >> 8) & 1u;
+      Surface sf;
+      if (path_vertex_surface(sv, st, ray, hit, &sf)) {
+        ++shaded;
+        surface_store(rec, i, sf);
+      }
+      store3(wb.L, slot, st.L);
+      wb.alpha[slot] = st.alpha;
+      wb.flags[slot] = flags;
+  }
   }
   warp_stat_add(&wb.stats[ST_SHADED], shaded);
 }
@@ -416,55 +426,57 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
               uint32_t *shadowCount, uint32_t *probeCount) {
   uint32_t n = *nPtr;
   for (;;) {
-    uint32_t base = warp_claim(work);
-    if (base >= n) break;
-    uint32_t i = base + lane_id();
-    bool valid = i < n && qin.hitPrim[i] >= 0;
-    bool pushShadow = false, pushProbe = false;
-    uint32_t slot = 0;
-    DirectRec direct;
-    if (valid) {
-      slot = qin.slot[i];
-      Ray ray;
-      ray.o = v3(0, 0, 0);
-      ray.d = v3(qin.dx[i], qin.dy[i], qin.dz[i]);   // only wo = -ray.d is needed
-      ray.mint = 0.f; ray.maxt = 0.f;
-      Surface sf;
-      surface_load(sv, rec, i, &sf);
-      uint32_t flags = wb.flags[slot];
-      PathState st;
-      st.T = load3(wb.T, slot);
-      st.depth = (int)(flags & 0xffu);
-      st.rng.key = slot_key(wd, slot, 1);
-      st.rng.ctr = wb.ctr[slot];
-      uint64_t key0 = slot_key(wd, slot, 0);
-      bool hasDirect;
-      path_vertex_direct(sv, key0, st, ray, &sf, &direct, &hasDirect);
-      wb.ctr[slot] = st.rng.ctr;
-      if (hasDirect) {
-        pushShadow = direct.hasShadow;
-        pushProbe = direct.hasProbe;
-        if (pushProbe) {
-          // rare: the estimator's value also depends on the MIS probe -> keep both terms pending
-          wb.flags[slot] = flags | (1u << 9);
-          store3(wb.pendT, slot, st.pendT);
-          store3(wb.recA, slot, direct.termA);
-          store3(wb.recB, slot, direct.termB);
-          wb.recFlags[slot] = (direct.hasShadow ? 4 : 0) | 8;
-        } else if (pushShadow) {
-          // common: only the shadow ray decides, so the addend of `L += pathThroughput *
-          // UniformSampleOneLight(..)` (path.cpp:100-112) is known now; 3 floats stay pending, not 9
-          Spec Ld = direct_value(direct.termA, direct.termB, true, false);
-          wb.flags[slot] = flags | (1u << 9);
-          store3(wb.recA, slot, st.pendT * ((float)sv.nLights * Ld));
-          wb.recFlags[slot] = 4 | 16;
+    uint32_t chunk = warp_claim_n(work, PB_CLAIM);
+    if (chunk >= n) break;
+    for (uint32_t base = chunk; base < chunk + PB_CLAIM && base < n; base += 32) {
+      uint32_t i = base + lane_id();
+      bool valid = i < n && qin.hitPrim[i] >= 0;
+      bool pushShadow = false, pushProbe = false;
+      uint32_t slot = 0;
+      DirectRec direct;
+      if (valid) {
+        slot = qin.slot[i];
+        Ray ray;
+        ray.o = v3(0, 0, 0);
+        ray.d = v3(qin.dx[i], qin.dy[i], qin.dz[i]);   // only wo = -ray.d is needed
+        ray.mint = 0.f; ray.maxt = 0.f;
+        Surface sf;
+        surface_load(sv, rec, i, &sf);
+        uint32_t flags = wb.flags[slot];
+        PathState st;
+        st.T = load3(wb.T, slot);
+        st.depth = (int)(flags & 0xffu);
+        st.rng.key = slot_key(wd, slot, 1);
+        st.rng.ctr = wb.ctr[slot];
+        uint64_t key0 = slot_key(wd, slot, 0);
+        bool hasDirect;
+        path_vertex_direct(sv, key0, st, ray, &sf, &direct, &hasDirect);
+        wb.ctr[slot] = st.rng.ctr;
+        if (hasDirect) {
+          pushShadow = direct.hasShadow;
+          pushProbe = direct.hasProbe;
+          if (pushProbe) {
+            // rare: the estimator's value also depends on the MIS probe -> keep both terms pending
+            wb.flags[slot] = flags | (1u << 9);
+            store3(wb.pendT, slot, st.pendT);
+            store3(wb.recA, slot, direct.termA);
+            store3(wb.recB, slot, direct.termB);
+            wb.recFlags[slot] = (direct.hasShadow ? 4 : 0) | 8;
+          } else if (pushShadow) {
+            // common: only the shadow ray decides, so the addend of `L += pathThroughput *
+            // UniformSampleOneLight(..)` (path.cpp:100-112) is known now; 3 floats stay pending, not 9
+            Spec Ld = direct_value(direct.termA, direct.termB, true, false);
+            wb.flags[slot] = flags | (1u << 9);
+            store3(wb.recA, slot, st.pendT * ((float)sv.nLights * Ld));
+            wb.recFlags[slot] = 4 | 16;
+          }
         }
       }
-    }
-    uint32_t si = warp_push(shadowCount, pushShadow);
-    if (pushShadow) aux_put(wb.shadowQ, si, slot, direct.shadow, 0);
-    uint32_t pi = warp_push(probeCount, pushProbe);
-    if (pushProbe) aux_put(wb.probeQ, pi, slot, direct.probe, direct.probeLight);
+      uint32_t si = warp_push(shadowCount, pushShadow);
+      if (pushShadow) aux_put(wb.shadowQ, si, slot, direct.shadow, 0);
+      uint32_t pi = warp_push(probeCount, pushProbe);
+      if (pushProbe) aux_put(wb.probeQ, pi, slot, direct.probe, direct.probeLight);
+  }
   }
 }
 
@@ -474,36 +486,38 @@ k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, cons
                 uint32_t *work, uint32_t *nextCount) {
   uint32_t n = *nPtr;
   for (;;) {
-    uint32_t base = warp_claim(work);
-    if (base >= n) break;
-    uint32_t i = base + lane_id();
-    bool valid = i < n && qin.hitPrim[i] >= 0;
-    bool pushNext = false;
-    uint32_t slot = 0;
-    Ray next;
-    if (valid) {
-      slot = qin.slot[i];
-      Ray ray;
-      ray.o = v3(0, 0, 0);
-      ray.d = v3(qin.dx[i], qin.dy[i], qin.dz[i]);
-      ray.mint = 0.f; ray.maxt = 0.f;
-      Surface sf;
-      surface_load(sv, rec, i, &sf);
-      uint32_t flags = wb.flags[slot];
-      PathState st;
-      st.T = load3(wb.T, slot);
-      st.depth = (int)(flags & 0xffu);
-      st.specularBounce = (flags >> 8) & 1u;
-      st.rng.key = slot_key(wd, slot, 1);
-      st.rng.ctr = wb.ctr[slot];
-      uint64_t key0 = slot_key(wd, slot, 0);
-      pushNext = path_vertex_continue(sv, key0, st, ray, sf, &next);
-      store3(wb.T, slot, st.T);
-      wb.ctr[slot] = st.rng.ctr;
-      wb.flags[slot] = (flags & (1u << 9)) | (uint32_t)st.depth | (st.specularBounce ? (1u << 8) : 0u);
-    }
-    uint32_t ni = warp_push(nextCount, pushNext);
-    if (pushNext) queue_put(qout, ni, slot, next);
+    uint32_t chunk = warp_claim_n(work, PB_CLAIM);
+    if (chunk >= n) break;
+    for (uint32_t base = chunk; base < chunk + PB_CLAIM && base < n; base += 32) {
+      uint32_t i = base + lane_id();
+      bool valid = i < n && qin.hitPrim[i] >= 0;
+      bool pushNext = false;
+      uint32_t slot = 0;
+      Ray next;
+      if (valid) {
+        slot = qin.slot[i];
+        Ray ray;
+        ray.o = v3(0, 0, 0);
+        ray.d = v3(qin.dx[i], qin.dy[i], qin.dz[i]);
+        ray.mint = 0.f; ray.maxt = 0.f;
+        Surface sf;
+        surface_load(sv, rec, i, &sf);
+        uint32_t flags = wb.flags[slot];
+        PathState st;
+        st.T = load3(wb.T, slot);
+        st.depth = (int)(flags & 0xffu);
+        st.specularBounce = (flags >> 8) & 1u;
+        st.rng.key = slot_key(wd, slot, 1);
+        st.rng.ctr = wb.ctr[slot];
+        uint64_t key0 = slot_key(wd, slot, 0);
+        pushNext = path_vertex_continue(sv, key0, st, ray, sf, &next);
+        store3(wb.T, slot, st.T);
+        wb.ctr[slot] = st.rng.ctr;
+        wb.flags[slot] = (flags & (1u << 9)) | (uint32_t)st.depth | (st.specularBounce ? (1u << 8) : 0u);
+      }
+      uint32_t ni = warp_push(nextCount, pushNext);
+      if (pushNext) queue_put(qout, ni, slot, next);
+  }
   }
 }
 
@@ -554,56 +568,58 @@ k_shade_wd(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
   uint32_t n = *nPtr;
   uint32_t shaded = 0;
   for (;;) {
-    uint32_t base = warp_claim(work);
-    if (base >= n) break;
-    uint32_t i = base + lane_id();
-    bool valid = i < n;
-    DirectRec recs[PB_MAX_WD_RECS];
-    int nRecs = 0;
-    uint32_t slot = 0;
-    if (valid) {
-      slot = qin.slot[i];
-      Ray ray = queue_ray(qin, i);
-      Hit hit;
-      hit.prim = qin.hitPrim[i];
-      hit.t = 0.f; hit.b1 = hit.b2 = 0.f;
-      if (hit.prim >= 0) { hit.t = qin.hitT[i]; hit.b1 = qin.hitB1[i]; hit.b2 = qin.hitB2[i]; }
-      uint32_t flags = wb.flags[slot];
-      int depth = (int)(flags & 0xffu);
-      RngStream rng;
-      rng.key = slot_key(wd, slot, 1);
-      rng.ctr = wb.ctr[slot];
-      uint64_t key0 = slot_key(wd, slot, 0);
-      float alpha = 0.f;
-      WdFrame fr;
-      WdVertexOut out;
-      wd_vertex(sv, key0, ray, hit, rng, depth, depth == 0 ? &alpha : (float *)0, &fr, recs, &out);
-      if (hit.prim >= 0) ++shaded;
-      if (depth == 0) wb.alpha[slot] = alpha;
-      wb.ctr[slot] = rng.ctr;
-      nRecs = out.nRecs;
-      wb.nRecs[slot] = (uint32_t)nRecs;
-      DevFrameIO io = {&wb, slot};
-      io.store(depth, fr);
-      for (int r = 0; r < nRecs; ++r) {
-        size_t ri = (size_t)r * wb.nSlots + slot;
-        wb.recA[0][ri] = recs[r].termA.c[0]; wb.recA[1][ri] = recs[r].termA.c[1]; wb.recA[2][ri] = recs[r].termA.c[2];
-        wb.recB[0][ri] = recs[r].termB.c[0]; wb.recB[1][ri] = recs[r].termB.c[1]; wb.recB[2][ri] = recs[r].termB.c[2];
-        wb.recFlags[ri] = (recs[r].hasShadow ? 4 : 0) | (recs[r].hasProbe ? 8 : 0);
+    uint32_t chunk = warp_claim_n(work, PB_CLAIM);
+    if (chunk >= n) break;
+    for (uint32_t base = chunk; base < chunk + PB_CLAIM && base < n; base += 32) {
+      uint32_t i = base + lane_id();
+      bool valid = i < n;
+      DirectRec recs[PB_MAX_WD_RECS];
+      int nRecs = 0;
+      uint32_t slot = 0;
+      if (valid) {
+        slot = qin.slot[i];
+        Ray ray = queue_ray(qin, i);
+        Hit hit;
+        hit.prim = qin.hitPrim[i];
+        hit.t = 0.f; hit.b1 = hit.b2 = 0.f;
+        if (hit.prim >= 0) { hit.t = qin.hitT[i]; hit.b1 = qin.hitB1[i]; hit.b2 = qin.hitB2[i]; }
+        uint32_t flags = wb.flags[slot];
+        int depth = (int)(flags & 0xffu);
+        RngStream rng;
+        rng.key = slot_key(wd, slot, 1);
+        rng.ctr = wb.ctr[slot];
+        uint64_t key0 = slot_key(wd, slot, 0);
+        float alpha = 0.f;
+        WdFrame fr;
+        WdVertexOut out;
+        wd_vertex(sv, key0, ray, hit, rng, depth, depth == 0 ? &alpha : (float *)0, &fr, recs, &out);
+        if (hit.prim >= 0) ++shaded;
+        if (depth == 0) wb.alpha[slot] = alpha;
+        wb.ctr[slot] = rng.ctr;
+        nRecs = out.nRecs;
+        wb.nRecs[slot] = (uint32_t)nRecs;
+        DevFrameIO io = {&wb, slot};
+        io.store(depth, fr);
+        for (int r = 0; r < nRecs; ++r) {
+          size_t ri = (size_t)r * wb.nSlots + slot;
+          wb.recA[0][ri] = recs[r].termA.c[0]; wb.recA[1][ri] = recs[r].termA.c[1]; wb.recA[2][ri] = recs[r].termA.c[2];
+          wb.recB[0][ri] = recs[r].termB.c[0]; wb.recB[1][ri] = recs[r].termB.c[1]; wb.recB[2][ri] = recs[r].termB.c[2];
+          wb.recFlags[ri] = (recs[r].hasShadow ? 4 : 0) | (recs[r].hasProbe ? 8 : 0);
+        }
       }
-    }
-    int maxRecs = nRecs;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxRecs = max(maxRecs, __shfl_xor_sync(0xffffffffu, maxRecs, o));
-    for (int r = 0; r < maxRecs; ++r) {
-      bool ps = valid && r < nRecs && recs[r].hasShadow;
-      bool pp = valid && r < nRecs && recs[r].hasProbe;
-      uint32_t ri = (uint32_t)((size_t)r * wb.nSlots + slot);
-      uint32_t si = warp_push(shadowCount, ps);
-      if (ps) aux_put(wb.shadowQ, si, ri, recs[r].shadow, 0);
-      uint32_t pi = warp_push(probeCount, pp);
-      if (pp) aux_put(wb.probeQ, pi, ri, recs[r].probe, recs[r].probeLight);
-    }
+      int maxRecs = nRecs;
+  #pragma unroll
+      for (int o = 16; o > 0; o >>= 1) maxRecs = max(maxRecs, __shfl_xor_sync(0xffffffffu, maxRecs, o));
+      for (int r = 0; r < maxRecs; ++r) {
+        bool ps = valid && r < nRecs && recs[r].hasShadow;
+        bool pp = valid && r < nRecs && recs[r].hasProbe;
+        uint32_t ri = (uint32_t)((size_t)r * wb.nSlots + slot);
+        uint32_t si = warp_push(shadowCount, ps);
+        if (ps) aux_put(wb.shadowQ, si, ri, recs[r].shadow, 0);
+        uint32_t pi = warp_push(probeCount, pp);
+        if (pp) aux_put(wb.probeQ, pi, ri, recs[r].probe, recs[r].probeLight);
+      }
+  }
   }
   warp_stat_add(&wb.stats[ST_SHADED], shaded);
 }
@@ -614,40 +630,42 @@ k_advance_wd(const __grid_constant__ SceneView sv, const WaveBuffers wb, const R
              const RayQueue qout, const uint32_t *nPtr, uint32_t *work, uint32_t *nextCount) {
   uint32_t n = *nPtr;
   for (;;) {
-    uint32_t base = warp_claim(work);
-    if (base >= n) break;
-    uint32_t i = base + lane_id();
-    bool valid = i < n;
-    bool pushNext = false;
-    Ray next;
-    uint32_t slot = 0;
-    if (valid) {
-      slot = qin.slot[i];
-      uint32_t flags = wb.flags[slot];
-      int depth = (int)(flags & 0xffu);
-      DevFrameIO io = {&wb, slot};
-      WdFrame fr = io.load(depth);
-      int nRecs = (int)wb.nRecs[slot];
-      DirectRec recs[PB_MAX_WD_RECS];
-      uint8_t rflags[PB_MAX_WD_RECS];
-      for (int r = 0; r < nRecs; ++r) {
-        size_t ri = (size_t)r * wb.nSlots + slot;
-        recs[r].termA = spec3(wb.recA[0][ri], wb.recA[1][ri], wb.recA[2][ri]);
-        recs[r].termB = spec3(wb.recB[0][ri], wb.recB[1][ri], wb.recB[2][ri]);
-        uint8_t f = wb.recFlags[ri];
-        recs[r].hasShadow = (f & 4) != 0; recs[r].hasProbe = (f & 8) != 0;
-        rflags[r] = f & 3;
+    uint32_t chunk = warp_claim_n(work, PB_CLAIM);
+    if (chunk >= n) break;
+    for (uint32_t base = chunk; base < chunk + PB_CLAIM && base < n; base += 32) {
+      uint32_t i = base + lane_id();
+      bool valid = i < n;
+      bool pushNext = false;
+      Ray next;
+      uint32_t slot = 0;
+      if (valid) {
+        slot = qin.slot[i];
+        uint32_t flags = wb.flags[slot];
+        int depth = (int)(flags & 0xffu);
+        DevFrameIO io = {&wb, slot};
+        WdFrame fr = io.load(depth);
+        int nRecs = (int)wb.nRecs[slot];
+        DirectRec recs[PB_MAX_WD_RECS];
+        uint8_t rflags[PB_MAX_WD_RECS];
+        for (int r = 0; r < nRecs; ++r) {
+          size_t ri = (size_t)r * wb.nSlots + slot;
+          recs[r].termA = spec3(wb.recA[0][ri], wb.recA[1][ri], wb.recA[2][ri]);
+          recs[r].termB = spec3(wb.recB[0][ri], wb.recB[1][ri], wb.recB[2][ri]);
+          uint8_t f = wb.recFlags[ri];
+          recs[r].hasShadow = (f & 4) != 0; recs[r].hasProbe = (f & 8) != 0;
+          rflags[r] = f & 3;
+        }
+        wd_resolve(sv, &fr, recs, rflags, nRecs);
+        io.store(depth, fr);
+        RngStream rng;
+        rng.key = 0; rng.ctr = wb.ctr[slot];
+        pushNext = wd_advance(io, rng, &depth, &next);
+        wb.ctr[slot] = rng.ctr;
+        wb.flags[slot] = (flags & ~0xffu) | (uint32_t)depth;
       }
-      wd_resolve(sv, &fr, recs, rflags, nRecs);
-      io.store(depth, fr);
-      RngStream rng;
-      rng.key = 0; rng.ctr = wb.ctr[slot];
-      pushNext = wd_advance(io, rng, &depth, &next);
-      wb.ctr[slot] = rng.ctr;
-      wb.flags[slot] = (flags & ~0xffu) | (uint32_t)depth;
-    }
-    uint32_t ni = warp_push(nextCount, pushNext);
-    if (pushNext) queue_put(qout, ni, slot, next);
+      uint32_t ni = warp_push(nextCount, pushNext);
+      if (pushNext) queue_put(qout, ni, slot, next);
+  }
   }
 }
 
