@@ -245,7 +245,8 @@ int pbrt_b200_render_host(const PbrtB200Scene *scene, int device,
  * key 0: image samples per wave (default 4 Mi)
  * key 1: collect the kd-walk counters of PbrtB200Stats (default off: they cost time)
  * key 2: resident CTAs per SM of the persistent kernels
- * key 3: bracket every kernel launch with CUDA events (pbrt_b200_kernel_stats) */
+ * key 3: bracket every kernel launch with CUDA events (pbrt_b200_kernel_stats)
+ * key 5: overlap shadow/probe traversal with the next kernels on a second stream (default off: measured +1 %) */
 int64_t pbrt_b200_tunable(int key, int64_t value);
 
 /* Per-kernel-class totals of the last pbrt_b200_render(): launches, summed

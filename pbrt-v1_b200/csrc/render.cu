@@ -55,6 +55,7 @@ static int fail(int code, const std::string &msg) {
 static int64_t g_waveSamples = 1 << 24;   // key 0: image samples per wave (16 Mi: ~5.4 GB of wave state)
 static int64_t g_countKd = 0;             // key 1: collect kd-walk counters (costs a little time)
 static int64_t g_blocksPerSM = 12;        // key 2: resident CTAs per SM for the persistent kernels
+static int64_t g_overlap = 0;             // key 5: run shadow/probe traversal on a second stream, overlapped (measured +1%: both sides are issue bound, so off by default)
 static int64_t g_shadeBlocks = 4;         // key 4: occupancy target (CTAs/SM) the shade kernel is compiled for: 2, 3 or 4
 
 #define PB_BLOCK 128
@@ -801,6 +802,8 @@ struct WindowFilm {
 struct PbrtB200Handle {
   int device;
   cudaStream_t stream;
+  cudaStream_t auxStream;        // shadow / probe traversal overlaps the main stream's next kernels
+  cudaEvent_t evDirect, evAux;
   int numSMs;
   SceneView sv;                 // device pointers
   std::vector<void *> allocs;   // scene arrays
@@ -826,7 +829,8 @@ static int64_t g_profileKernels = 0;   // key 3
 // Brackets one launch with events when profiling is on.
 struct LaunchTimer {
   PbrtB200Handle *h; int idx;
-  LaunchTimer(PbrtB200Handle *hh, int cls) : h(hh), idx(-1) {
+  cudaStream_t s;
+  LaunchTimer(PbrtB200Handle *hh, int cls, cudaStream_t ss = nullptr) : h(hh), idx(-1), s(ss ? ss : hh->stream) {
     ++h->classLaunches[cls];
     if (!g_profileKernels) return;
     idx = (int)h->evClass.size();
@@ -836,11 +840,12 @@ struct LaunchTimer {
       cudaEventCreate(&e);
       h->evPool.push_back(e);
     }
-    cudaEventRecord(h->evPool[2 * idx], h->stream);
+    cudaEventRecord(h->evPool[2 * idx], s);
   }
-  ~LaunchTimer() { if (idx >= 0) cudaEventRecord(h->evPool[2 * idx + 1], h->stream); }
+  ~LaunchTimer() { if (idx >= 0) cudaEventRecord(h->evPool[2 * idx + 1], s); }
 };
 #define TIMED(cls, launch) do { LaunchTimer lt_(h, cls); launch; } while (0)
+#define TIMED_ON(cls, strm, launch) do { LaunchTimer lt_(h, cls, strm); launch; } while (0)
 
 template <class T>
 static int upload(PbrtB200Handle *h, const T *src, size_t n, const T **dst) {
@@ -855,8 +860,21 @@ static int upload(PbrtB200Handle *h, const T *src, size_t n, const T **dst) {
   return PBRT_B200_OK;
 }
 
+// One retired wave arena per device is kept for the next handle: pbrt_b200_render_host() creates and
+// destroys a handle per call, and a multi-GB cudaMalloc/cudaFree per frame would dominate it.
+#define PB_MAX_DEVICES 64
+static void *g_cachedArena[PB_MAX_DEVICES];
+static size_t g_cachedArenaBytes[PB_MAX_DEVICES];
 static void free_wave(PbrtB200Handle *h) {
-  if (h->arena) cudaFree(h->arena);
+  if (h->arena) {
+    int d = h->device;
+    if (d >= 0 && d < PB_MAX_DEVICES && h->arenaBytes > g_cachedArenaBytes[d]) {
+      if (g_cachedArena[d]) cudaFree(g_cachedArena[d]);
+      g_cachedArena[d] = h->arena;
+      g_cachedArenaBytes[d] = h->arenaBytes;
+    } else
+      cudaFree(h->arena);
+  }
   h->arena = nullptr;
   h->arenaBytes = 0;
   memset(&h->wb, 0, sizeof(h->wb));
@@ -924,8 +942,16 @@ static int ensure_wave(PbrtB200Handle *h, uint32_t nSlots) {
   WaveBuffers tmp;
   carve_wave(sizing, tmp, nSlots, h->sv.directRecords, h->nFrames, isPath);
   size_t bytes = sizing.off + 256;
-  CU_TRY(cudaMalloc(&h->arena, bytes));
-  h->arenaBytes = bytes;
+  int d = h->device;
+  if (d >= 0 && d < PB_MAX_DEVICES && g_cachedArena[d] && g_cachedArenaBytes[d] >= bytes) {
+    h->arena = g_cachedArena[d];
+    h->arenaBytes = g_cachedArenaBytes[d];
+    g_cachedArena[d] = nullptr;
+    g_cachedArenaBytes[d] = 0;
+  } else {
+    CU_TRY(cudaMalloc(&h->arena, bytes));
+    h->arenaBytes = bytes;
+  }
   Carver c = {(char *)h->arena, 0};
   carve_wave(c, h->wb, nSlots, h->sv.directRecords, h->nFrames, isPath);
   return PBRT_B200_OK;
@@ -948,17 +974,17 @@ static void launch_traversals_a(PbrtB200Handle *h, bool count, int grid, const R
   else TIMED(KC_INTERSECT, (k_intersect<false><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, q, nMain, work, h->wb.stats)));
 }
 static void launch_traversals_b(PbrtB200Handle *h, bool count, int grid, uint32_t *nShadow, uint32_t *nProbe,
-                                uint32_t *workS, uint32_t *workP) {
+                                uint32_t *workS, uint32_t *workP, cudaStream_t strm) {
   WaveBuffers &wb = h->wb;
   // MIS probes are rare (the BSDF sample must point at the light): a small grid avoids paying the
   // ramp-up of the full persistent grid for a few thousand rays
   int probeGrid = std::min(grid, h->numSMs * 2);
   if (count) {
-    TIMED(KC_SHADOW, (k_shadow<true><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.stats)));
-    TIMED(KC_PROBE, (k_probe<true><<<probeGrid, PB_BLOCK, 0, h->stream>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.stats)));
+    TIMED_ON(KC_SHADOW, strm, (k_shadow<true><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.stats)));
+    TIMED_ON(KC_PROBE, strm, (k_probe<true><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.stats)));
   } else {
-    TIMED(KC_SHADOW, (k_shadow<false><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.stats)));
-    TIMED(KC_PROBE, (k_probe<false><<<probeGrid, PB_BLOCK, 0, h->stream>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.stats)));
+    TIMED_ON(KC_SHADOW, strm, (k_shadow<false><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.stats)));
+    TIMED_ON(KC_PROBE, strm, (k_probe<false><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.stats)));
   }
 }
 
@@ -979,6 +1005,7 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
   bool isPath = sv.integrator.kind == PBRT_B200_INT_PATH;
   int cur = 0;
   WaveKeyInfo wk = {wb.pixel, wd.spp};
+  bool overlap = g_overlap != 0;
   if (isPath) {
     int iters = sv.integrator.max_depth + 1;
     if (iters < 1) iters = 1;
@@ -987,6 +1014,8 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
       uint32_t *nMain = &wb.counts[4 * it], *nShadow = &wb.counts[4 * it + 1], *nProbe = &wb.counts[4 * it + 2];
       uint32_t *nNext = &wb.counts[4 * (it + 1)];
       launch_traversals_a(h, count, grid, wb.q[cur], nMain, nextWork());
+      // the previous vertex's shadow / probe results are folded in by k_path_surface
+      if (overlap && it > 0) CU_TRY(cudaStreamWaitEvent(st, h->evAux, 0));
       {
         SurfaceRecord rec;
         for (int k = 0; k < 15; ++k) rec.f[k] = wb.surf[k];
@@ -994,13 +1023,22 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
         TIMED(KC_SHADE, (k_path_surface<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], rec, nMain, nextWork())));
         TIMED(KC_SHADE_DIRECT, (k_path_direct<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], rec, nMain, nextWork(),
                                                                         nShadow, nProbe)));
+        if (overlap) {
+          // shadow + probe rays of this vertex run on the aux stream, concurrently with
+          // k_path_continue and the next k_intersect (they share no data)
+          CU_TRY(cudaEventRecord(h->evDirect, st));
+          CU_TRY(cudaStreamWaitEvent(h->auxStream, h->evDirect, 0));
+          launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork(), h->auxStream);
+          CU_TRY(cudaEventRecord(h->evAux, h->auxStream));
+        }
         TIMED(KC_SHADE_CONT, (k_path_continue<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], wb.q[cur ^ 1], rec, nMain,
                                                                         nextWork(), nNext)));
       }
-      launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork());
+      if (!overlap) launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork(), st);
       *launches += 6;
       cur ^= 1;
     }
+    if (overlap) CU_TRY(cudaStreamWaitEvent(st, h->evAux, 0));
   } else {
     // Whitted / DirectLighting: the recursion depth is data dependent; one host readback of
     // the queue size per iteration ends the loop.
@@ -1018,7 +1056,7 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
       uint32_t *nNext = &wb.counts[4 * (it + 1)];
       launch_traversals_a(h, count, grid, wb.q[cur], nMain, nextWork());
       TIMED(KC_SHADE, (k_shade_wd<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], nMain, nextWork(), nShadow, nProbe)));
-      launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork());
+      launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork(), st);
       TIMED(KC_ADVANCE, (k_advance_wd<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], wb.q[cur ^ 1], nMain, nextWork(), nNext)));
       *launches += 5;
       CU_TRY(cudaMemcpyAsync(&nMainHost, nNext, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -1052,7 +1090,7 @@ const char *pbrt_b200_last_error(void) { return g_lastError.c_str(); }
 
 int64_t pbrt_b200_tunable(int key, int64_t value) {
   int64_t *p = key == 0 ? &g_waveSamples : key == 1 ? &g_countKd : key == 2 ? &g_blocksPerSM
-               : key == 3 ? &g_profileKernels : key == 4 ? &g_shadeBlocks : nullptr;
+               : key == 3 ? &g_profileKernels : key == 4 ? &g_shadeBlocks : key == 5 ? &g_overlap : nullptr;
   if (!p) return -1;
   int64_t prev = *p;
   if (value >= 0) *p = value;
@@ -1067,6 +1105,9 @@ void pbrt_b200_scene_destroy(PbrtB200Handle *h) {
   for (void *p : h->allocs) cudaFree(p);
   if (h->filterTable) cudaFree(h->filterTable);
   for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
+  if (h->evDirect) cudaEventDestroy(h->evDirect);
+  if (h->evAux) cudaEventDestroy(h->evAux);
+  if (h->auxStream) cudaStreamDestroy(h->auxStream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1084,7 +1125,8 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   if (prop.major < 10)
     return fail(PBRT_B200_ERR_NO_DEVICE, std::string("device is not sm_100 class: ") + prop.name);
   PbrtB200Handle *h = new PbrtB200Handle();
-  h->device = device; h->stream = nullptr; h->numSMs = prop.multiProcessorCount;
+  h->device = device; h->stream = nullptr; h->auxStream = nullptr; h->evDirect = nullptr; h->evAux = nullptr;
+  h->numSMs = prop.multiProcessorCount;
   h->filterTable = nullptr; h->arena = nullptr; h->arenaBytes = 0; h->sceneBytes = 0; h->keepSamples = false;
   memset(&h->wb, 0, sizeof(h->wb));
   memset(&h->sv, 0, sizeof(h->sv));
@@ -1103,6 +1145,9 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   if (!isPath && h->nFrames > 64) { delete h; return fail(PBRT_B200_ERR_UNSUPPORTED, "maxdepth too large"); }
   int rc = PBRT_B200_OK;
   cudaError_t ce = cudaStreamCreate(&h->stream);
+  if (ce == cudaSuccess) ce = cudaStreamCreate(&h->auxStream);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evDirect, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evAux, cudaEventDisableTiming);
   if (ce != cudaSuccess) { delete h; return fail(PBRT_B200_ERR_CUDA, cudaGetErrorString(ce)); }
   SceneView &sv = h->sv;
   const PbrtB200Prim *dprims = nullptr;
