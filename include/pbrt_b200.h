@@ -246,6 +246,7 @@ int pbrt_b200_render_host(const PbrtB200Scene *scene, int device,
  * key 1: collect the kd-walk counters of PbrtB200Stats (default off: they cost time)
  * key 2: resident CTAs per SM of the persistent kernels
  * key 3: bracket every kernel launch with CUDA events (pbrt_b200_kernel_stats)
+ * key 6: print per-iteration queue sizes of every wave to stderr (profiling aid)
  * key 5: overlap shadow/probe traversal with the next kernels on a second stream (default off: measured +1 %) */
 int64_t pbrt_b200_tunable(int key, int64_t value);
 

@@ -77,6 +77,7 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
           mbPos = 0;
           active = sv.nNodes != 0 && bbox_intersect_p(sv.bmin, sv.bmax, ray, &tmin, &tmax);
           invDir = v3(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
+
           if (!active) sink.done(idx, ray, hit, false);   // missed the tree's bounds
         }
       }

@@ -56,6 +56,7 @@ static int64_t g_waveSamples = 1 << 24;   // key 0: image samples per wave (16 M
 static int64_t g_countKd = 0;             // key 1: collect kd-walk counters (costs a little time)
 static int64_t g_blocksPerSM = 12;        // key 2: resident CTAs per SM for the persistent kernels
 static int64_t g_overlap = 0;             // key 5: run shadow/probe traversal on a second stream, overlapped (measured +1%: both sides are issue bound, so off by default)
+static int64_t g_debugCounts = 0;         // key 6: print each wave's queue sizes per iteration to stderr
 static int64_t g_shadeBlocks = 4;         // key 4: occupancy target (CTAs/SM) the shade kernel is compiled for: 2, 3 or 4
 
 #define PB_BLOCK 128
@@ -82,6 +83,7 @@ struct WaveBuffers {
   float *L[3], *T[3], *pendT[3], *alpha;
   uint32_t *ctr;         // RNG stream-1 draws so far
   uint32_t *flags;       // bits 0-7 depth, 8 specularBounce, 9 pending direct record
+  unsigned long long *reach;   // per sample pixel of the wave: pixel footprint of its samples (k_film_reach)
   uint32_t *pixel;             // (x + 32768) | (y + 32768) << 16: sample pixel of the slot (RNG key)
   float *imageX, *imageY;      // film coordinates of the sample
   float *outL[3], *outA;       // per-sample radiance after the guards
@@ -697,6 +699,24 @@ k_finalize(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
   warp_stat_add(&wb.stats[ST_INF], inf);
 }
 
+// Pixel footprint of each sample pixel of the wave: [min x0, max x1] x [min y0, max y1] over its spp
+// samples (x0..y1 as in ImageFilm::AddSample, film/image.cpp:106-111), packed 4 x int16.  Lets the
+// gather skip whole sample pixels: with the 0.5-wide box filter a neighbouring sample pixel reaches
+// this pixel only through a sample whose coordinate is exactly an integer.
+__global__ void k_film_reach(const __grid_constant__ SceneView sv, const WaveBuffers wb, uint32_t nPix, int spp) {
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < nPix; p += gridDim.x * blockDim.x) {
+    int x0 = 1 << 20, x1 = -(1 << 20), y0 = 1 << 20, y1 = -(1 << 20);
+    uint32_t s0 = p * (uint32_t)spp;
+    for (int k = 0; k < spp; ++k) {
+      float dImageX = wb.imageX[s0 + k] - 0.5f, dImageY = wb.imageY[s0 + k] - 0.5f;
+      x0 = min(x0, pb_ceil2int(dImageX - sv.filterXW)); x1 = max(x1, pb_floor2int(dImageX + sv.filterXW));
+      y0 = min(y0, pb_ceil2int(dImageY - sv.filterYW)); y1 = max(y1, pb_floor2int(dImageY + sv.filterYW));
+    }
+    auto pack = [](int v) { return (unsigned long long)(uint16_t)(max(-32768, min(32767, v)) + 32768); };
+    wb.reach[p] = pack(x0) | (pack(x1) << 16) | (pack(y0) << 32) | (pack(y1) << 48);
+  }
+}
+
 // K5b: ImageFilm::AddSample (film/image.cpp:103-141) as a gather, one thread per pixel.
 // Candidate sample pixels are visited in raster order and their samples in index order:
 // the order in which the reference's serial loop would have splatted them.
@@ -723,6 +743,10 @@ k_film_gather(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
         int64_t pix = (int64_t)(sy - wd.ys) * ew + (sx - wd.xs) - (int64_t)wd.firstPixel;
         if (pix < 0 || pix >= (int64_t)wd.nPixels) continue;
         uint32_t s0 = wd.slotBase + (uint32_t)pix * (uint32_t)spp;
+        unsigned long long rc = wb.reach[s0 / (uint32_t)spp];
+        if (px < (int)(rc & 0xffffu) - 32768 || px > (int)((rc >> 16) & 0xffffu) - 32768 ||
+            py < (int)((rc >> 32) & 0xffffu) - 32768 || py > (int)(rc >> 48) - 32768)
+          continue;
         for (int k = 0; k < spp; ++k) {
           uint32_t slot = s0 + k;
           float wt;
@@ -902,6 +926,7 @@ static void carve_wave(Carver &c, WaveBuffers &wb, uint32_t nSlots, int directRe
   wb.ctr = c.take<uint32_t>(nSlots); wb.flags = c.take<uint32_t>(nSlots);
   wb.imageX = c.take<float>(nSlots); wb.imageY = c.take<float>(nSlots);
   wb.pixel = c.take<uint32_t>(nSlots);
+  wb.reach = c.take<unsigned long long>(nSlots);
   wb.recFlags = c.take<uint8_t>((size_t)nSlots * directRecords);
   if (!isPath) {
     wb.frame = c.take<float>((size_t)PB_FRAME_FLOATS * nFrames * nSlots);
@@ -1067,6 +1092,14 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
   }
   TIMED(KC_FINALIZE, (k_finalize<<<genGrid, PB_BLOCK, 0, st>>>(sv, wb, wd)));
   ++*launches;
+  if (g_debugCounts && isPath) {
+    std::vector<uint32_t> hc(4 * (sv.integrator.max_depth + 2));
+    CU_TRY(cudaMemcpyAsync(hc.data(), wb.counts, hc.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    for (int it = 0; it <= sv.integrator.max_depth; ++it)
+      fprintf(stderr, "pbrt_b200 wave: iteration %d main %u shadow %u probe %u\n", it, hc[4 * it], hc[4 * it + 1],
+              hc[4 * it + 2]);
+  }
   CU_TRY(cudaGetLastError());
   return PBRT_B200_OK;
 }
@@ -1090,7 +1123,7 @@ const char *pbrt_b200_last_error(void) { return g_lastError.c_str(); }
 
 int64_t pbrt_b200_tunable(int key, int64_t value) {
   int64_t *p = key == 0 ? &g_waveSamples : key == 1 ? &g_countKd : key == 2 ? &g_blocksPerSM
-               : key == 3 ? &g_profileKernels : key == 4 ? &g_shadeBlocks : key == 5 ? &g_overlap : nullptr;
+               : key == 3 ? &g_profileKernels : key == 4 ? &g_shadeBlocks : key == 5 ? &g_overlap : key == 6 ? &g_debugCounts : nullptr;
   if (!p) return -1;
   int64_t prev = *p;
   if (value >= 0) *p = value;
@@ -1261,6 +1294,12 @@ int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_win
     }
     rc = run_wave(h, wd, &launches);
     if (rc != PBRT_B200_OK) return rc;
+    {
+      uint32_t nPixWave = wd.nSlots / (uint32_t)spp;
+      int grid = (int)std::min<uint32_t>((nPixWave + 127) / 128, (uint32_t)h->numSMs * 16);
+      TIMED(KC_FILM, (k_film_reach<<<grid, 128, 0, h->stream>>>(sv, h->wb, nPixWave, spp)));
+      ++launches;
+    }
     for (int pi = 0; pi < wd.nParts; ++pi) {
       const WavePart &wp = wd.parts[pi];
       WindowFilm &wf = h->films[wp.window];

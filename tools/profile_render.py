@@ -14,6 +14,8 @@ os.makedirs(out, exist_ok=True)
 sp = gen_scene(os.path.join(out, "prof_%s.pbrt" % name), name, "--filename", os.path.join(out, "prof.exr"), *sys.argv[2:])
 sc = ffi.Scene(sp)
 ds = ffi.DeviceScene(sc)
+if os.environ.get("PBRT_PROFILE_COUNTS"):
+    ffi.cuda().pbrt_b200_tunable(6, 1)
 st = ds.render()
 rays = st["intersect_rays"] + st["shadow_rays"]
 print("render %.2f ms, %.1f Mrays, %.1f Mrays/s, %d launches" % (st["render_ms"], rays / 1e6, rays / st["render_ms"] / 1e3,
