@@ -57,7 +57,7 @@ static int64_t g_countKd = 0;             // key 1: collect kd-walk counters (co
 static int64_t g_blocksPerSM = 12;        // key 2: resident CTAs per SM for the persistent kernels
 static int64_t g_overlap = 0;             // key 5: run shadow/probe traversal on a second stream, overlapped (measured +1%: both sides are issue bound, so off by default)
 static int64_t g_debugCounts = 0;         // key 6: print each wave's queue sizes per iteration to stderr
-static int64_t g_shadeBlocks = 4;         // key 4: occupancy target (CTAs/SM) the shade kernel is compiled for: 2, 3 or 4
+static int64_t g_reserved4 = 0;           // key 4: reserved (was the fused shade kernel's occupancy variant)
 
 #define PB_BLOCK 128
 #ifndef PB_TRAV_MIN_BLOCKS
@@ -1123,7 +1123,7 @@ const char *pbrt_b200_last_error(void) { return g_lastError.c_str(); }
 
 int64_t pbrt_b200_tunable(int key, int64_t value) {
   int64_t *p = key == 0 ? &g_waveSamples : key == 1 ? &g_countKd : key == 2 ? &g_blocksPerSM
-               : key == 3 ? &g_profileKernels : key == 4 ? &g_shadeBlocks : key == 5 ? &g_overlap : key == 6 ? &g_debugCounts : nullptr;
+               : key == 3 ? &g_profileKernels : key == 4 ? &g_reserved4 : key == 5 ? &g_overlap : key == 6 ? &g_debugCounts : nullptr;
   if (!p) return -1;
   int64_t prev = *p;
   if (value >= 0) *p = value;

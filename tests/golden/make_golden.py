@@ -49,6 +49,52 @@ CASES = [
 ]
 
 
+# hand-written scenes (edge cases the generator does not produce): name -> scene text
+INLINE = {
+    "edge_empty_world": """LookAt 0 0 -5 0 0 0 0 1 0
+Camera "perspective" "float fov" [45]
+Film "image" "integer xresolution" [8] "integer yresolution" [8] "string filename" ["edge_empty_world_out.exr"]
+Sampler "stratified" "integer xsamples" [1] "integer ysamples" [1]
+PixelFilter "box"
+SurfaceIntegrator "path"
+WorldBegin
+WorldEnd
+""",
+    "edge_no_lights": """LookAt 0 0 -5 0 0 0 0 1 0
+Camera "perspective" "float fov" [45]
+Film "image" "integer xresolution" [12] "integer yresolution" [8] "string filename" ["edge_no_lights_out.exr"]
+Sampler "stratified" "integer xsamples" [2] "integer ysamples" [1]
+PixelFilter "triangle" "float xwidth" [1.5] "float ywidth" [1]
+SurfaceIntegrator "directlighting"
+WorldBegin
+Shape "sphere" "float radius" [1.2] "float zmin" [-0.5] "float zmax" [0.9] "float phimax" [300]
+WorldEnd
+""",
+    "edge_clipped_sphere_point_lights": """LookAt 0 1 -5 0 0 0 0 1 0
+Camera "perspective" "float fov" [40]
+Film "image" "integer xresolution" [24] "integer yresolution" [20] "string filename" ["edge_clipped_sphere_point_lights_out.exr"]
+Sampler "stratified" "integer xsamples" [2] "integer ysamples" [2]
+PixelFilter "sinc" "float xwidth" [2] "float ywidth" [2]
+SurfaceIntegrator "whitted" "integer maxdepth" [3]
+WorldBegin
+LightSource "point" "color I" [30 20 10] "point from" [3 4 -4]
+LightSource "point" "color I" [5 10 20] "point from" [-3 2 -3]
+AttributeBegin
+Material "matte" "color Kd" [.6 .6 .6] "float sigma" [30]
+Rotate 35 1 0 0
+Shape "sphere" "float radius" [1.2] "float zmin" [-0.7] "float zmax" [0.8] "float phimax" [270]
+AttributeEnd
+AttributeBegin
+Material "mirror"
+ReverseOrientation
+Translate 0 -1.3 0
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-4 0 -4 4 0 -4 4 0 4 -4 0 4]
+AttributeEnd
+WorldEnd
+""",
+}
+
+
 def parse_count(text, label):
     m = re.search(re.escape(label) + r"\s+([0-9.]+)([kMG]?)", text)
     if not m:
@@ -60,10 +106,14 @@ def parse_count(text, label):
 def main():
     ffi = load_ffi()
     assert ffi.have_reference(), "oracle/_ref missing: run oracle/build_ref.sh (needs /root/reference)"
-    for name, scene, args, keyed in CASES:
+    cases = list(CASES) + [(n, None, None, True) for n in INLINE]
+    for name, scene, args, keyed in cases:
         sp = os.path.join(HERE, name + ".pbrt")
         # relative output name so the committed scene file works from any checkout
-        gen_scene(sp, scene, "--filename", name + "_out.exr", *args)
+        if scene is None:
+            open(sp, "w").write(INLINE[name])
+        else:
+            gen_scene(sp, scene, "--filename", name + "_out.exr", *args)
         dump = os.path.join(HERE, name + ".samples")
         out, _ = ffi.run_reference(sp, keyed=keyed, dump_samples=dump, cwd=HERE)
         rgba, _ = ffi.read_raw(os.path.join(HERE, name + "_out.exr.raw"))
