@@ -125,10 +125,12 @@ typedef struct PbrtB200Camera {
   float lens_radius, focal_distance;
 } PbrtB200Camera;
 
-/* samplers/stratified.cpp:51-86 */
+/* samplers/stratified.cpp:51-86, samplers/lowdiscrepancy.cpp:57-74 */
+enum { PBRT_B200_SAMPLER_STRATIFIED = 0, PBRT_B200_SAMPLER_LOWDISCREPANCY = 1 };
 typedef struct PbrtB200Sampler {
-  int32_t x_samples, y_samples;
-  int32_t jitter;
+  int32_t x_samples, y_samples;    /* stratified: strata per axis; lowdiscrepancy: pixelsamples (a power of 2), 1 */
+  int32_t jitter;                  /* stratified only */
+  int32_t kind;                    /* PBRT_B200_SAMPLER_* */
 } PbrtB200Sampler;
 
 /* integrators/{whitted,directlighting,path}.cpp; volume integrator emission

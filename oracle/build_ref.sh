@@ -82,6 +82,13 @@ for ln in lines:
 assert n_cam == 2 and n_int == 1, (n_cam, n_int)
 t = '\n'.join(out)
 open(tmp + "/stratified_keyed.cpp", "w").write(t)
+# lowdiscrepancy.cpp: one re-key per pixel, before its (0,2)-sequence tables are generated
+l = open(ref + "/samplers/lowdiscrepancy.cpp").read()
+l = l.replace('// LDSampler Declarations', 'extern void pbrtReseed(int, int, int, int);\n// LDSampler Declarations', 1)
+mark = '\t\t// Generate low-discrepancy samples for pixel\n'
+assert l.count(mark) == 1
+l = l.replace(mark, '\t\tpbrtReseed(xPos, yPos, 0xFFFF, 0);\n' + mark)
+open(tmp + "/lowdiscrepancy_keyed.cpp", "w").write(l)
 # kdtree.cpp: count calls reaching the kd walk (the metric's "rays": Scene::Intersect + IntersectP)
 k = open(ref + "/accelerators/kdtree.cpp").read()
 k = k.replace('// KdAccelNode Declarations', 'extern unsigned long long gRefIntersectCalls, gRefIntersectPCalls;\n// KdAccelNode Declarations', 1)
@@ -116,6 +123,8 @@ mkdir -p "$OUT/plugins_keyed"
 for f in $OUT/plugins/*.so; do ln -sf ../plugins/$(basename $f) $OUT/plugins_keyed/$(basename $f); done
 rm -f $OUT/plugins_keyed/stratified.so
 g++ $FL -fPIC -shared $TMP/stratified_keyed.cpp -o $OUT/plugins_keyed/stratified.so
+rm -f $OUT/plugins_keyed/lowdiscrepancy.so
+g++ $FL -fPIC -shared $TMP/lowdiscrepancy_keyed.cpp -o $OUT/plugins_keyed/lowdiscrepancy.so
 
 g++ -O2 -msse2 -mfpmath=sse -rdynamic -o $OUT/pbrt_ref_exact $TMP/main.o $TMP/parser.o $TMP/exact/*.o -ldl -lm
 g++ -O2 -msse2 -mfpmath=sse -rdynamic -o $OUT/pbrt_ref_keyed $TMP/main.o $TMP/parser.o $TMP/keyed/*.o -ldl -lm

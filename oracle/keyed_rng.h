@@ -14,6 +14,8 @@
  *
  *   stream 0, s = 0xFFFF : a pixel's camera pattern (image/lens/time strata
  *                          and their shuffles, samplers/stratified.cpp:66-85,98-115)
+ *                          (lowdiscrepancy sampler: ALL of the pixel's tables -- image, lens, time
+ *                          and every integrator pattern -- samplers/lowdiscrepancy.cpp:93-103)
  *   stream 0, s = k      : the LatinHypercube block of the pixel's k-th sample
  *                          (samplers/stratified.cpp:124-128)
  *   stream 1, s = k      : every draw made while evaluating Li for that sample

@@ -91,7 +91,7 @@ uint8_t trace_direct(const SceneView &sv, const DirectRec &rec, Counters &c) {
   return f;
 }
 
-Spec li_path(const SceneView &sv, uint64_t key0, uint64_t key1, const Ray &camRay, float *alpha,
+Spec li_path(const SceneView &sv, const PatternSource &key0, uint64_t key1, const Ray &camRay, float *alpha,
              Counters &c) {
   PathState st;
   st.L = spec(0.f); st.T = spec(1.f); st.pendT = spec(0.f);
@@ -115,7 +115,7 @@ Spec li_path(const SceneView &sv, uint64_t key0, uint64_t key1, const Ray &camRa
   return st.L;
 }
 
-Spec li_wd(const SceneView &sv, uint64_t key0, uint64_t key1, const Ray &camRay, float *alpha,
+Spec li_wd(const SceneView &sv, const PatternSource &key0, uint64_t key1, const Ray &camRay, float *alpha,
            Counters &c) {
   RngStream rng; rng.key = key1; rng.ctr = 0;
   std::vector<WdFrame> frames(1);
@@ -162,15 +162,28 @@ int pbrt_twin_render(const PbrtB200Scene *scene, const PbrtB200Window *win, floa
   Counters c;
   memset(&c, 0, sizeof(c));
   uint64_t nSamples = 0;
+  const bool ld = sv.sampler.kind == PBRT_B200_SAMPLER_LOWDISCREPANCY;
+  std::vector<float> ldTables(ld ? (size_t)sv.ldFloatsPerSample * spp : 0);
   auto t0 = std::chrono::steady_clock::now();
   for (int y = ys; y < ye; ++y)
-    for (int x = xs; x < xe; ++x)
+    for (int x = xs; x < xe; ++x) {
+      if (ld) {
+        // samplers/lowdiscrepancy.cpp:93-103: all of the pixel's tables at once
+        uint64_t keyP = pb_key(x, y, 0xFFFF, 0);
+        for (int t = 0; t < 3; ++t) pb_ld_generate_table(keyP, sv.ldCamera[t], spp, ldTables.data(), spp, 0);
+        for (int t = 0; t < sv.nPatterns; ++t) pb_ld_generate_table(keyP, sv.patterns[t], spp, ldTables.data(), spp, 0);
+      }
       for (int k = 0; k < spp; ++k) {
+        PatternSource key0;
+        key0.key0 = pb_key(x, y, k, 0);
+        key0.ld = ld ? ldTables.data() : (const float *)0;
+        key0.stride = (uint32_t)spp; key0.index = (uint32_t)k;
         CameraSample cs;
-        stratified_camera_sample(sv, x, y, k, &cs);
+        if (ld) ld_camera_sample(sv, key0, x, y, &cs);
+        else stratified_camera_sample(sv, x, y, k, &cs);
         Ray ray;
         perspective_generate_ray(sv.camera, cs, &ray);
-        uint64_t key0 = pb_key(x, y, k, 0), key1 = pb_key(x, y, k, 1);
+        uint64_t key1 = pb_key(x, y, k, 1);
         float alpha = 0.f;
         Spec Ls = (sv.integrator.kind == PBRT_B200_INT_PATH)
                       ? li_path(sv, key0, key1, ray, &alpha, c)
@@ -199,6 +212,7 @@ int pbrt_twin_render(const PbrtB200Scene *scene, const PbrtB200Window *win, floa
             film_pixel_add(&film[(size_t)(py - win->y0) * win->width + (px - win->x0)], wt, Ls.c, alpha);
           }
       }
+    }
   auto t1 = std::chrono::steady_clock::now();
   for (size_t i = 0; i < film.size(); ++i) {
     film_pixel_resolve(film[i], sv.premultiply != 0, rgba + 4 * i);
@@ -270,7 +284,15 @@ int pbrt_twin_camera_rays(const PbrtB200Scene *scene, const PbrtB200Window *win,
     for (int x = xs; x < xe && i < n; ++x)
       for (int k = 0; k < spp && i < n; ++k, ++i) {
         CameraSample cs;
-        stratified_camera_sample(sv, x, y, k, &cs);
+        if (sv.sampler.kind == PBRT_B200_SAMPLER_LOWDISCREPANCY) {
+          std::vector<float> tab((size_t)sv.ldFloatsPerSample * spp);
+          uint64_t keyP = pb_key(x, y, 0xFFFF, 0);
+          for (int t = 0; t < 2; ++t) pb_ld_generate_table(keyP, sv.ldCamera[t], spp, tab.data(), spp, 0);
+          PatternSource ps;
+          ps.key0 = 0; ps.ld = tab.data(); ps.stride = (uint32_t)spp; ps.index = (uint32_t)k;
+          ld_camera_sample(sv, ps, x, y, &cs);
+        } else
+          stratified_camera_sample(sv, x, y, k, &cs);
         Ray r;
         perspective_generate_ray(sv.camera, cs, &r);
         float *o = rays + 8 * i;

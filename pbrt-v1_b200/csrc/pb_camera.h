@@ -11,6 +11,13 @@
 struct CameraSample {
   float imageX, imageY, lensU, lensV;
 };
+// samplers/lowdiscrepancy.cpp:105-110: the sample's camera values come from the pixel's tables
+PB_HD void ld_camera_sample(const SceneView &sv, const PatternSource &ps, int x, int y, CameraSample *cs) {
+  cs->imageX = x + ps.ld[(size_t)(sv.ldCamera[0].offset + 0) * ps.stride + ps.index];
+  cs->imageY = y + ps.ld[(size_t)(sv.ldCamera[0].offset + 1) * ps.stride + ps.index];
+  cs->lensU = ps.ld[(size_t)(sv.ldCamera[1].offset + 0) * ps.stride + ps.index];
+  cs->lensV = ps.ld[(size_t)(sv.ldCamera[1].offset + 1) * ps.stride + ps.index];
+}
 PB_HD void stratified_camera_sample(const SceneView &sv, int x, int y, int k, CameraSample *cs) {
   int nx = sv.sampler.x_samples, ny = sv.sampler.y_samples;
   int n = nx * ny;

@@ -278,11 +278,15 @@ PB_HD Spec direct_value(const Spec &termA, const Spec &termB, bool unoccluded, b
 // Index helpers into SceneView::patterns, which the host library lays out as
 // [1D patterns in Add1D order][2D patterns in Add2D order] (core/sampling.cpp:41-70;
 // request order: path.cpp:47-57, directlighting.cpp:39-66, emission.cpp:42-46).
-PB_HD float pat1d(const SceneView &sv, uint64_t key0, int idx, int j) {
-  return pb_lhs_value(key0, sv.patterns[idx], j, 0);
+PB_HD float pat1d(const SceneView &sv, const PatternSource &key0, int idx, int j) {
+  const SamplePattern &p = sv.patterns[idx];
+  if (key0.ld) return key0.ld[(size_t)(p.offset + j) * key0.stride + key0.index];
+  return pb_lhs_value(key0.key0, p, j, 0);
 }
-PB_HD float pat2d(const SceneView &sv, uint64_t key0, int idx, int j, int d) {
-  return pb_lhs_value(key0, sv.patterns[sv.n1D + idx], j, d);
+PB_HD float pat2d(const SceneView &sv, const PatternSource &key0, int idx, int j, int d) {
+  const SamplePattern &p = sv.patterns[sv.n1D + idx];
+  if (key0.ld) return key0.ld[(size_t)(p.offset + 2 * j + d) * key0.stride + key0.index];
+  return pb_lhs_value(key0.key0, p, j, d);
 }
 
 // ---------------------------------------------------------------- path integrator
@@ -321,7 +325,7 @@ PB_HD bool path_vertex_surface(const SceneView &sv, PathState &st, const Ray &ra
   return true;
 }
 // path.cpp:93-112: one UniformSampleOneLight record at the vertex
-PB_HD void path_vertex_direct(const SceneView &sv, uint64_t key0, PathState &st, const Ray &ray,
+PB_HD void path_vertex_direct(const SceneView &sv, const PatternSource &key0, PathState &st, const Ray &ray,
                               const Surface *sf, DirectRec *direct, bool *hasDirect) {
   *hasDirect = false;
   int pathLength = st.depth;
@@ -352,7 +356,7 @@ PB_HD void path_vertex_direct(const SceneView &sv, uint64_t key0, PathState &st,
   }
   // NOTE: with no lights the reference dereferences lights[-1]; such scenes render black here.
 }
-PB_HD bool path_vertex_begin(const SceneView &sv, uint64_t key0, PathState &st, const Ray &ray,
+PB_HD bool path_vertex_begin(const SceneView &sv, const PatternSource &key0, PathState &st, const Ray &ray,
                              const Hit &hit, Surface *sf, DirectRec *direct, bool *hasDirect) {
   *hasDirect = false;
   if (!path_vertex_surface(sv, st, ray, hit, sf)) return false;
@@ -361,7 +365,7 @@ PB_HD bool path_vertex_begin(const SceneView &sv, uint64_t key0, PathState &st, 
 }
 // Second half (path.cpp:113-143): sample the BSDF for the next direction, update the
 // throughput, Russian roulette, depth limit.  Returns true when the path continues along *next.
-PB_HD bool path_vertex_continue(const SceneView &sv, uint64_t key0, PathState &st, const Ray &ray,
+PB_HD bool path_vertex_continue(const SceneView &sv, const PatternSource &key0, PathState &st, const Ray &ray,
                                 const Surface &sf, Ray *next) {
   int pathLength = st.depth;
   const Bsdf &bsdf = sf.bsdf;
@@ -392,7 +396,7 @@ PB_HD bool path_vertex_continue(const SceneView &sv, uint64_t key0, PathState &s
   st.depth = pathLength + 1;
   return true;
 }
-PB_HD void path_vertex(const SceneView &sv, uint64_t key0, PathState &st, const Ray &ray,
+PB_HD void path_vertex(const SceneView &sv, const PatternSource &key0, PathState &st, const Ray &ray,
                        const Hit &hit, PathVertexOut *out) {
   out->hasNext = false;
   Surface sf;
@@ -430,7 +434,7 @@ PB_HD int wd_max_records(const SceneView &sv) { return sv.directRecords; }
 
 // Vertex body up to (not including) `if (rayDepth++ < maxDepth)`.  `recs` must hold
 // wd_max_records() entries.  The frame is initialised here.
-PB_HD void wd_vertex(const SceneView &sv, uint64_t key0, const Ray &ray, const Hit &hit,
+PB_HD void wd_vertex(const SceneView &sv, const PatternSource &key0, const Ray &ray, const Hit &hit,
                      RngStream &rng, int rayDepth, float *alpha, WdFrame *fr, DirectRec *recs,
                      WdVertexOut *out) {
   out->nRecs = 0;

@@ -63,7 +63,15 @@ struct SamplePattern {
   uint32_t ctr0;
   int32_t n;      // samples in the pattern
   int32_t dims;   // 1 or 2
-  int32_t pad;
+  int32_t offset; // lowdiscrepancy: first float of the pattern in a sample's value record
+};
+// Where an image sample's integrator patterns come from: computed from the key (stratified) or read
+// from the pixel's pre-generated (0,2)-sequence tables (lowdiscrepancy): value e of the sample is
+// ld[e * stride + index].
+struct PatternSource {
+  uint64_t key0;
+  const float *ld;
+  uint32_t stride, index;
 };
 // LatinHypercube(samples, n, dims) (core/sampling.cpp:98-113): n*dims floats
 // (sample-major), then per dimension n swap draws.  Value of sample j, dim d.
@@ -79,5 +87,61 @@ PB_HD float pb_lhs_value(uint64_t key, const SamplePattern &p, int j, int d) {
   // single swap draw exchanges element 0 with itself
   if (p.n == 1) return pb_f32(key, p.ctr0 + 1 + (uint32_t)d);
   return pb_lhs_value_general(key, p, j, d);
+}
+
+// ---- lowdiscrepancy sampler (samplers/lowdiscrepancy.cpp, core/sampling.h:132-174)
+#define PB_LD_MAX_PIXEL_SAMPLES 1024
+#define PB_LD_MAX_PATTERN_SAMPLES 64
+// core/sampling.h:137-146
+PB_HD float pb_van_der_corput(uint32_t n, uint32_t scramble) {
+  n = (n << 16) | (n >> 16);
+  n = ((n & 0x00ff00ffu) << 8) | ((n & 0xff00ff00u) >> 8);
+  n = ((n & 0x0f0f0f0fu) << 4) | ((n & 0xf0f0f0f0u) >> 4);
+  n = ((n & 0x33333333u) << 2) | ((n & 0xccccccccu) >> 2);
+  n = ((n & 0x55555555u) << 1) | ((n & 0xaaaaaaaau) >> 1);
+  n ^= scramble;
+  return (float)n / 4294967296.f;
+}
+// core/sampling.h:147-151
+PB_HD float pb_sobol2(uint32_t n, uint32_t scramble) {
+  for (uint32_t v = 1u << 31; n != 0; n >>= 1, v ^= v >> 1)
+    if (n & 0x1) scramble ^= v;
+  return (float)scramble / 4294967296.f;
+}
+// One LDShuffleScrambled1D / 2D table (core/sampling.h:158-174) for a pixel of nPixel samples,
+// pattern size pat.n: scramble draws, the (0,2)-sequence points, a Shuffle inside every block of
+// pat.n points and a Shuffle of the nPixel blocks.  Point e (0 <= e < pat.n * pat.dims) of the
+// pixel's sample k is written to out[(pat.offset + e) * stride + base + k] -- skipped when
+// pat.offset < 0 (the time table: its draws count, its values are never read).
+PB_HD void pb_ld_generate_table(uint64_t key, const SamplePattern &pat, int nPixel, float *out,
+                                uint32_t stride, uint32_t base) {
+  if (pat.offset < 0) return;
+  uint16_t blockSrc[PB_LD_MAX_PIXEL_SAMPLES];
+  uint8_t inner[PB_LD_MAX_PATTERN_SAMPLES];
+  int n = pat.n, dims = pat.dims;
+  uint32_t ctr = pat.ctr0;
+  uint32_t scr0 = pb_u32(key, ++ctr);
+  uint32_t scr1 = dims == 2 ? pb_u32(key, ++ctr) : 0u;
+  uint32_t ctrInner = ctr;                              // block i's Shuffle draws: ctrInner + i*n + 1 ...
+  uint32_t ctrBlock = ctr + (uint32_t)(nPixel * n);     // the block Shuffle draws follow all of them
+  for (int i = 0; i < nPixel; ++i) blockSrc[i] = (uint16_t)i;
+  for (int i = 0; i < nPixel; ++i) {
+    uint32_t other = pb_u32(key, ctrBlock + 1 + (uint32_t)i) % (uint32_t)nPixel;
+    uint16_t t = blockSrc[i]; blockSrc[i] = blockSrc[other]; blockSrc[other] = t;
+  }
+  for (int k = 0; k < nPixel; ++k) {
+    int b = blockSrc[k];
+    for (int j = 0; j < n; ++j) inner[j] = (uint8_t)j;
+    for (int j = 0; j < n; ++j) {
+      uint32_t other = pb_u32(key, ctrInner + (uint32_t)(b * n) + 1 + (uint32_t)j) % (uint32_t)n;
+      uint8_t t = inner[j]; inner[j] = inner[other]; inner[other] = t;
+    }
+    for (int j = 0; j < n; ++j) {
+      uint32_t i = (uint32_t)(b * n + inner[j]);
+      float *o = out + (size_t)(pat.offset + j * dims) * stride + base + k;
+      o[0] = pb_van_der_corput(i, scr0);
+      if (dims == 2) o[stride] = pb_sobol2(i, scr1);
+    }
+  }
 }
 #endif

@@ -44,6 +44,10 @@ struct SceneView {
   // light i uses patterns 2D {2i, 2i+1} and 1D {i}; see PatternIndex helpers.
   int32_t n1D, n2D;               // pattern counts; 2D patterns start at index n1D
   int32_t directRecords;          // EstimateDirect calls per shaded vertex
+  // lowdiscrepancy sampler: the pixel's camera tables (image, lens, time) and the size of one
+  // sample's value record (image 2 + lens 2 + every integrator pattern)
+  SamplePattern ldCamera[3];
+  int32_t ldFloatsPerSample;
 };
 
 struct Hit {

@@ -14,6 +14,11 @@
 static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
   if (s.abi_version != PBRT_B200_ABI_VERSION) return "scene abi_version mismatch";
   if (s.sampler.x_samples < 1 || s.sampler.y_samples < 1) return "sampler needs >= 1 sample per axis";
+  const bool ld = s.sampler.kind == PBRT_B200_SAMPLER_LOWDISCREPANCY;
+  if (!ld && s.sampler.kind != PBRT_B200_SAMPLER_STRATIFIED) return "unknown sampler kind";
+  if (ld && (s.sampler.y_samples != 1 || (s.sampler.x_samples & (s.sampler.x_samples - 1)) != 0 ||
+             s.sampler.x_samples > PB_LD_MAX_PIXEL_SAMPLES))
+    return "lowdiscrepancy sampler: pixelsamples must be a power of two <= 1024";
   if (s.film.x_pixel_count < 1 || s.film.y_pixel_count < 1) return "empty film";
   for (uint32_t i = 0; i < s.n_prims; ++i) {
     uint32_t kind = s.prims[i].flags & PBRT_B200_PF_KIND_MASK;
@@ -40,6 +45,12 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
       int recs = 0;
       for (uint32_t i = 0; i < s.n_lights; ++i) {
         int ns = s.lights[i].n_samples < 1 ? 1 : s.lights[i].n_samples;
+        if (ld) {   // Sampler::RoundSize: RoundUpPow2 (samplers/lowdiscrepancy.cpp:44-46)
+          int r = 1;
+          while (r < ns) r <<= 1;
+          ns = r;
+          if (ns > PB_LD_MAX_PATTERN_SAMPLES) return "lowdiscrepancy sampler: too many light samples";
+        }
         n2[c2++] = ns; n2[c2++] = ns; n1[c1++] = ns;
         recs += ns;
       }
@@ -60,15 +71,31 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
   if (c1 + c2 > PB_MAX_PATTERNS) return "too many sample patterns";
   uint32_t ctr = 0;
   int k = 0;
+  int32_t off = 0;
+  const uint32_t nPixel = (uint32_t)s.sampler.x_samples;
+  if (ld) {
+    // per pixel: image, lens, time tables first (samplers/lowdiscrepancy.cpp:96-98); a table of
+    // pattern size n draws `dims` scrambles, n per block Shuffle and one per block for the final Shuffle
+    for (int t = 0; t < 3; ++t) {
+      SamplePattern &p = sv->ldCamera[t];
+      p.ctr0 = ctr; p.n = 1; p.dims = t < 2 ? 2 : 1;
+      p.offset = t < 2 ? off : -1;
+      if (t < 2) off += 2;
+      ctr += (uint32_t)p.dims + nPixel * 1u + nPixel;
+    }
+  }
   for (int i = 0; i < c1; ++i, ++k) {
-    sv->patterns[k].ctr0 = ctr; sv->patterns[k].n = n1[i]; sv->patterns[k].dims = 1; sv->patterns[k].pad = 0;
-    ctr += 2u * n1[i];
+    sv->patterns[k].ctr0 = ctr; sv->patterns[k].n = n1[i]; sv->patterns[k].dims = 1; sv->patterns[k].offset = off;
+    ctr += ld ? 1u + nPixel * (uint32_t)n1[i] + nPixel : 2u * n1[i];
+    off += n1[i];
   }
   for (int i = 0; i < c2; ++i, ++k) {
-    sv->patterns[k].ctr0 = ctr; sv->patterns[k].n = n2[i]; sv->patterns[k].dims = 2; sv->patterns[k].pad = 0;
-    ctr += 4u * n2[i];
+    sv->patterns[k].ctr0 = ctr; sv->patterns[k].n = n2[i]; sv->patterns[k].dims = 2; sv->patterns[k].offset = off;
+    ctr += ld ? 2u + nPixel * (uint32_t)n2[i] + nPixel : 4u * n2[i];
+    off += 2 * n2[i];
   }
   sv->n1D = c1; sv->n2D = c2; sv->nPatterns = k;
+  sv->ldFloatsPerSample = ld ? off : 0;
   return std::string();
 }
 // Do any materials carry a specular lobe (Whitted/DirectLighting then recurse)?

@@ -83,6 +83,7 @@ struct WaveBuffers {
   float *L[3], *T[3], *pendT[3], *alpha;
   uint32_t *ctr;         // RNG stream-1 draws so far
   uint32_t *flags;       // bits 0-7 depth, 8 specularBounce, 9 pending direct record
+  float *ld;                   // lowdiscrepancy sampler: value e of slot s at ld[e * nSlots + s]
   unsigned long long *reach;   // per sample pixel of the wave: pixel footprint of its samples (k_film_reach)
   uint32_t *pixel;             // (x + 32768) | (y + 32768) << 16: sample pixel of the slot (RNG key)
   float *imageX, *imageY;      // film coordinates of the sample
@@ -192,6 +193,34 @@ __device__ __forceinline__ void aux_put(const AuxQueue &q, uint32_t i, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------
+// K0a (lowdiscrepancy sampler only): the (0,2)-sequence tables of every sample pixel of the wave
+// (samplers/lowdiscrepancy.cpp:93-103), one thread per (sample pixel, table).
+__global__ void k_ld_tables(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveDesc wd) {
+  uint32_t nPix = wd.nSlots / (uint32_t)wd.spp;
+  uint32_t nTab = 2u + (uint32_t)sv.nPatterns;
+  for (uint64_t id = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; id < (uint64_t)nPix * nTab;
+       id += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t t = (uint32_t)(id / nPix), p = (uint32_t)(id % nPix);
+    uint32_t slot0 = p * (uint32_t)wd.spp;
+    uint32_t px = wb.pixel[slot0];
+    uint64_t key = pb_key((int)(px & 0xffffu) - 32768, (int)(px >> 16) - 32768, 0xFFFF, 0);
+    const SamplePattern &pat = t < 2 ? sv.ldCamera[t] : sv.patterns[t - 2];
+    pb_ld_generate_table(key, pat, wd.spp, wb.ld, wb.nSlots, slot0);
+  }
+}
+// pixel coordinates of every slot of the wave (the RNG keys derive from them)
+__global__ void k_slot_pixels(const WaveBuffers wb, const WaveDesc wd) {
+  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < wd.nSlots; slot += gridDim.x * blockDim.x) {
+    int part = 0;
+    while (part + 1 < wd.nParts && slot >= wd.parts[part + 1].slotBase) ++part;
+    const WavePart &wp = wd.parts[part];
+    uint32_t pix = wp.firstPixel + (slot - wp.slotBase) / wd.spp;
+    int ew = wp.xe - wp.xs;
+    int x = wp.xs + (int)(pix % ew), y = wp.ys + (int)(pix / ew);
+    wb.pixel[slot] = (uint32_t)(x + 32768) | ((uint32_t)(y + 32768) << 16);
+  }
+}
+
 // K0: sample generation + camera rays (samplers/stratified.cpp:87-131, cameras/perspective.cpp:51-82)
 __global__ void __launch_bounds__(PB_BLOCK)
 k_generate(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveDesc wd) {
@@ -206,7 +235,11 @@ k_generate(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
     int x = wp.xs + (int)(pix % ew), y = wp.ys + (int)(pix / ew);
     wb.pixel[slot] = (uint32_t)(x + 32768) | ((uint32_t)(y + 32768) << 16);
     CameraSample cs;
-    stratified_camera_sample(sv, x, y, k, &cs);
+    if (sv.sampler.kind == PBRT_B200_SAMPLER_LOWDISCREPANCY) {
+      PatternSource ps = {0, wb.ld, wb.nSlots, slot};
+      ld_camera_sample(sv, ps, x, y, &cs);
+    } else
+      stratified_camera_sample(sv, x, y, k, &cs);
     Ray ray;
     perspective_generate_ray(sv.camera, cs, &ray);
     queue_put(wb.q[0], slot, slot, ray);
@@ -451,7 +484,7 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
         st.depth = (int)(flags & 0xffu);
         st.rng.key = slot_key(wd, slot, 1);
         st.rng.ctr = wb.ctr[slot];
-        uint64_t key0 = slot_key(wd, slot, 0);
+        PatternSource key0 = {slot_key(wd, slot, 0), wb.ld, wb.nSlots, slot};
         bool hasDirect;
         path_vertex_direct(sv, key0, st, ray, &sf, &direct, &hasDirect);
         wb.ctr[slot] = st.rng.ctr;
@@ -512,7 +545,7 @@ k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, cons
         st.specularBounce = (flags >> 8) & 1u;
         st.rng.key = slot_key(wd, slot, 1);
         st.rng.ctr = wb.ctr[slot];
-        uint64_t key0 = slot_key(wd, slot, 0);
+        PatternSource key0 = {slot_key(wd, slot, 0), wb.ld, wb.nSlots, slot};
         pushNext = path_vertex_continue(sv, key0, st, ray, sf, &next);
         store3(wb.T, slot, st.T);
         wb.ctr[slot] = st.rng.ctr;
@@ -591,7 +624,7 @@ k_shade_wd(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
         RngStream rng;
         rng.key = slot_key(wd, slot, 1);
         rng.ctr = wb.ctr[slot];
-        uint64_t key0 = slot_key(wd, slot, 0);
+        PatternSource key0 = {slot_key(wd, slot, 0), wb.ld, wb.nSlots, slot};
         float alpha = 0.f;
         WdFrame fr;
         WdVertexOut out;
@@ -913,7 +946,8 @@ struct Carver {
     return p;
   }
 };
-static void carve_wave(Carver &c, WaveBuffers &wb, uint32_t nSlots, int directRecords, int nFrames, bool isPath) {
+static void carve_wave(Carver &c, WaveBuffers &wb, uint32_t nSlots, int directRecords, int nFrames, bool isPath,
+                       int ldFloats) {
   wb.nSlots = nSlots;
   wb.nFrames = nFrames;
   for (int i = 0; i < 3; ++i) {
@@ -927,6 +961,7 @@ static void carve_wave(Carver &c, WaveBuffers &wb, uint32_t nSlots, int directRe
   wb.imageX = c.take<float>(nSlots); wb.imageY = c.take<float>(nSlots);
   wb.pixel = c.take<uint32_t>(nSlots);
   wb.reach = c.take<unsigned long long>(nSlots);
+  wb.ld = ldFloats > 0 ? c.take<float>((size_t)ldFloats * nSlots) : nullptr;
   wb.recFlags = c.take<uint8_t>((size_t)nSlots * directRecords);
   if (!isPath) {
     wb.frame = c.take<float>((size_t)PB_FRAME_FLOATS * nFrames * nSlots);
@@ -965,7 +1000,7 @@ static int ensure_wave(PbrtB200Handle *h, uint32_t nSlots) {
   bool isPath = h->sv.integrator.kind == PBRT_B200_INT_PATH;
   Carver sizing = {nullptr, 0};
   WaveBuffers tmp;
-  carve_wave(sizing, tmp, nSlots, h->sv.directRecords, h->nFrames, isPath);
+  carve_wave(sizing, tmp, nSlots, h->sv.directRecords, h->nFrames, isPath, h->sv.ldFloatsPerSample);
   size_t bytes = sizing.off + 256;
   int d = h->device;
   if (d >= 0 && d < PB_MAX_DEVICES && g_cachedArena[d] && g_cachedArenaBytes[d] >= bytes) {
@@ -978,7 +1013,7 @@ static int ensure_wave(PbrtB200Handle *h, uint32_t nSlots) {
     h->arenaBytes = bytes;
   }
   Carver c = {(char *)h->arena, 0};
-  carve_wave(c, h->wb, nSlots, h->sv.directRecords, h->nFrames, isPath);
+  carve_wave(c, h->wb, nSlots, h->sv.directRecords, h->nFrames, isPath, h->sv.ldFloatsPerSample);
   return PBRT_B200_OK;
 }
 
@@ -1023,6 +1058,13 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
   CU_TRY(cudaMemsetAsync(wb.counts, 0, PB_COUNTS_TOTAL * sizeof(uint32_t), st));
   CU_TRY(cudaMemcpyAsync(&wb.counts[0], &wd.nSlots, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   int genGrid = (int)std::min<uint64_t>((wd.nSlots + PB_BLOCK - 1) / PB_BLOCK, (uint64_t)h->numSMs * 16);
+  if (sv.sampler.kind == PBRT_B200_SAMPLER_LOWDISCREPANCY) {
+    TIMED(KC_GENERATE, (k_slot_pixels<<<genGrid, PB_BLOCK, 0, st>>>(wb, wd)));
+    uint64_t nThreads = (uint64_t)(wd.nSlots / wd.spp) * (2 + sv.nPatterns);
+    int tg = (int)std::min<uint64_t>((nThreads + 127) / 128, (uint64_t)h->numSMs * 32);
+    TIMED(KC_GENERATE, (k_ld_tables<<<tg, 128, 0, st>>>(sv, wb, wd)));
+    *launches += 2;
+  }
   TIMED(KC_GENERATE, (k_generate<<<genGrid, PB_BLOCK, 0, st>>>(sv, wb, wd)));
   ++*launches;
   uint32_t workIdx = PB_WORK_BASE;
@@ -1489,6 +1531,8 @@ int pbrt_b200_camera_rays(PbrtB200Handle *h, const PbrtB200Window *w, uint64_t n
   if (!h || !w) return fail(PBRT_B200_ERR_INVALID, "null argument");
   if (n == 0) return PBRT_B200_OK;
   CU_TRY(cudaSetDevice(h->device));
+  if (h->sv.sampler.kind != PBRT_B200_SAMPLER_STRATIFIED)
+    return fail(PBRT_B200_ERR_UNSUPPORTED, "pbrt_b200_camera_rays: stratified sampler only (test entry point)");
   WavePart wd = window_part(h->sv, *w);
   int spp = h->sv.sampler.x_samples * h->sv.sampler.y_samples;
   uint64_t total = (uint64_t)(wd.xe - wd.xs) * (wd.ye - wd.ys) * spp;

@@ -134,8 +134,28 @@ class StratifiedSampler : public Sampler {   // samplers/stratified.cpp:51-64
         jitterSamples(jitter) {}
   void Flatten(PbrtB200Sampler *out) const {
     out->x_samples = xPixelSamples; out->y_samples = yPixelSamples; out->jitter = jitterSamples;
+    out->kind = PBRT_B200_SAMPLER_STRATIFIED;
   }
   int xPixelSamples, yPixelSamples; bool jitterSamples;
+};
+// samplers/lowdiscrepancy.cpp:57-74: (0,2)-sequence sampler, pixelsamples rounded up to a power of 2
+static int RoundUpPow2Int(int v) {
+  u_int x = (u_int)v;
+  x--; x |= x >> 1; x |= x >> 2; x |= x >> 4; x |= x >> 8; x |= x >> 16;
+  return (int)(x + 1);
+}
+class LDSampler : public Sampler {
+ public:
+  LDSampler(int xstart, int xend, int ystart, int yend, int ps)
+      : Sampler(xstart, xend, ystart, yend, RoundUpPow2Int(ps)) {
+    if ((ps & (ps - 1)) != 0) Warning("Pixel samples being rounded up to power of 2");
+    pixelSamples = RoundUpPow2Int(ps);
+  }
+  void Flatten(PbrtB200Sampler *out) const {
+    out->x_samples = pixelSamples; out->y_samples = 1; out->jitter = 0;
+    out->kind = PBRT_B200_SAMPLER_LOWDISCREPANCY;
+  }
+  int pixelSamples;
 };
 
 }  // namespace
@@ -341,9 +361,17 @@ Camera *MakeCamera(const string &name, const ParamSet &params, const Transform &
   return c;
 }
 Sampler *MakeSampler(const string &name, const ParamSet &params, const Film *film) {
+  if (name == "lowdiscrepancy") {   // samplers/lowdiscrepancy.cpp:129-135
+    int xstart, xend, ystart, yend;
+    film->GetSampleExtent(&xstart, &xend, &ystart, &yend);
+    int nsamp = params.FindOneInt("pixelsamples", 4);
+    Sampler *s = new LDSampler(xstart, xend, ystart, yend, nsamp < 1 ? 1 : nsamp);
+    params.ReportUnused();
+    return s;
+  }
   if (name != "stratified")
-    // bestcandidate/lowdiscrepancy/random are SURVEY.md 8(f) "next"; until then the one
-    // sampler the device implements stands in (different noise, same expectation).
+    // bestcandidate/random are SURVEY.md 8(f) "next"; until then the stratified sampler
+    // stands in (different noise, same expectation).
     Warning("Sampler plugin \"%s\" is not implemented on the GPU yet; using \"stratified\".",
             name.c_str());
   bool jitter = params.FindOneBool("jitter", true);      // samplers/stratified.cpp:132-141

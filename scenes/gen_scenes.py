@@ -28,6 +28,7 @@ LENS = None      # (lensradius, focaldistance) set from the command line
 LIGHT_NSAMPLES = 1
 MIRROR_TALL_BOX = False
 SPHERE_LIGHT = False
+LD_SAMPLER = False
 
 
 def header(out, res, spp, integrator, filt, jitter=True, fov=39.3, lookat=None,
@@ -43,8 +44,11 @@ def header(out, res, spp, integrator, filt, jitter=True, fov=39.3, lookat=None,
     if crop:
         film += ' "float cropwindow" [%s]' % " ".join(fmt(c) for c in crop)
     out.write(film + "\n")
-    out.write('Sampler "stratified" "integer xsamples" [%d] "integer ysamples" [%d] "bool jitter" ["%s"]\n' % (
-        spp[0], spp[1], "true" if jitter else "false"))
+    if LD_SAMPLER:
+        out.write('Sampler "lowdiscrepancy" "integer pixelsamples" [%d]\n' % (spp[0] * spp[1]))
+    else:
+        out.write('Sampler "stratified" "integer xsamples" [%d] "integer ysamples" [%d] "bool jitter" ["%s"]\n' % (
+            spp[0], spp[1], "true" if jitter else "false"))
     out.write('PixelFilter "%s"\n' % filt)
     out.write('SurfaceIntegrator "%s" %s\n' % (integrator, extra_integrator))
 
@@ -224,8 +228,10 @@ def main():
     ap.add_argument("--nsamples", type=int, default=1, help="area light nsamples")
     ap.add_argument("--mirror", action="store_true", help="tall Cornell box becomes a mirror")
     ap.add_argument("--spherelight", action="store_true", help="spherical area light instead of the quad")
+    ap.add_argument("--ld", action="store_true", help="lowdiscrepancy sampler with xsamples*ysamples pixel samples")
     a = ap.parse_args()
-    global LENS, LIGHT_NSAMPLES, MIRROR_TALL_BOX, SPHERE_LIGHT
+    global LENS, LIGHT_NSAMPLES, MIRROR_TALL_BOX, SPHERE_LIGHT, LD_SAMPLER
+    LD_SAMPLER = a.ld
     LENS = a.lens
     LIGHT_NSAMPLES = a.nsamples
     MIRROR_TALL_BOX = a.mirror

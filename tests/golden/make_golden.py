@@ -46,6 +46,11 @@ CASES = [
     ("c3_direct_mirror", "c3", ["--res", "32", "32", "--spp", "2", "2", "--integrator", "directlighting", "--mirror"], True),
     ("c4_blob", "c4", ["--res", "32", "32", "--spp", "2", "2", "--nphi", "48", "--ntheta", "24"], True),
     ("c4_blob_normals", "c4", ["--res", "32", "32", "--spp", "2", "2", "--nphi", "48", "--ntheta", "24", "--normals"], True),
+    # lowdiscrepancy sampler ((0,2)-sequences, samplers/lowdiscrepancy.cpp)
+    ("c3_ld", "c3", ["--res", "24", "24", "--spp", "2", "2", "--ld"], True),
+    ("c2_ld_nsamples3", "c2", ["--res", "24", "24", "--spp", "4", "2", "--ld", "--nsamples", "3"], True),
+    ("c3_ld_lens_mitchell", "c3", ["--res", "16", "16", "--spp", "4", "4", "--ld", "--lens", "20", "900", "--filter", "mitchell"], True),
+    ("c3_ld_whitted_mirror", "c3", ["--res", "16", "16", "--spp", "3", "1", "--ld", "--integrator", "whitted", "--mirror"], True),
 ]
 
 
