@@ -93,27 +93,33 @@ typedef struct PbrtB200Sphere {
 
 /* materials/{matte,glass,mirror}.cpp with ConstantTexture operands
  * (core/texture.h:113-123) */
-enum { PBRT_B200_MAT_MATTE = 0, PBRT_B200_MAT_GLASS = 1, PBRT_B200_MAT_MIRROR = 2 };
+enum { PBRT_B200_MAT_MATTE = 0, PBRT_B200_MAT_GLASS = 1, PBRT_B200_MAT_MIRROR = 2,
+       PBRT_B200_MAT_PLASTIC = 3 /* materials/plastic.cpp: Lambertian + Blinn microfacet */ };
 typedef struct PbrtB200Material {
   int32_t kind;
-  float   kd[3];                   /* matte Kd (already Clamp()ed >= 0); glass/mirror Kr */
-  float   kt[3];                   /* glass Kt                                */
+  float   kd[3];                   /* matte/plastic Kd (already Clamp()ed >= 0); glass/mirror Kr */
+  float   kt[3];                   /* glass Kt; plastic Ks                    */
   float   sigma;                   /* matte: clamped to [0,90] degrees        */
   float   index;                   /* glass: index of refraction              */
-  float   pad[3];
+  float   roughness;               /* plastic                                 */
+  float   pad[2];
 } PbrtB200Material;
 
 /* lights/point.cpp:49-54, lights/area.cpp:28-57, core/shape.h:113-147 */
-enum { PBRT_B200_LIGHT_POINT = 0, PBRT_B200_LIGHT_AREA = 1 };
+enum { PBRT_B200_LIGHT_POINT = 0, PBRT_B200_LIGHT_AREA = 1,
+       PBRT_B200_LIGHT_DISTANT = 2 /* lights/distant.cpp */, PBRT_B200_LIGHT_SPOT = 3 /* lights/spot.cpp */ };
 typedef struct PbrtB200Light {
   int32_t  kind;
   int32_t  n_samples;              /* Light::nSamples = max(1, ns)            */
-  float    color[3];               /* point: I ; area: Lemit                  */
-  float    pos[3];                 /* point: LightToWorld(0,0,0)              */
+  float    color[3];               /* point/spot: I ; area: Lemit ; distant: L */
+  float    pos[3];                 /* point/spot: LightToWorld(0,0,0) ; distant: lightDir (normalised, world) */
   uint32_t first_shape;            /* area: range in light_shapes[]/light_cdf[] */
   uint32_t n_shapes;               /* 1 => the shape itself, >1 => ShapeSet   */
   float    area;                   /* shape->Area()                           */
-  uint32_t pad;
+  float    cos_total_width;        /* spot: cosf(Radians(coneangle))          */
+  float    cos_falloff_start;      /* spot: cosf(Radians(coneangle - conedeltaangle)) */
+  float    w2l[9];                 /* spot: upper 3x3 of WorldToLight (rows), for Falloff() */
+  uint32_t pad[2];
 } PbrtB200Light;
 
 /* cameras/perspective.cpp:51-82, core/camera.cpp:50-70 */

@@ -19,7 +19,8 @@ enum {
   PB_ALL = PB_REFLECTION | PB_TRANSMISSION | PB_ALL_TYPES
 };
 enum { PB_LOBE_LAMBERT = 0, PB_LOBE_ORENNAYAR = 1, PB_LOBE_SPEC_REFL_DIEL = 2,
-       PB_LOBE_SPEC_REFL_NOOP = 3, PB_LOBE_SPEC_TRANS = 4 };
+       PB_LOBE_SPEC_REFL_NOOP = 3, PB_LOBE_SPEC_TRANS = 4,
+       PB_LOBE_MICROFACET_BLINN = 5 /* Microfacet(FresnelDielectric, Blinn): A = exponent */ };
 
 struct Lobe {
   int kind;
@@ -111,9 +112,55 @@ PB_HD float sin_phi(const V3 &w) {
   return pb_clamp(w.y / st, -1.f, 1.f);
 }
 
+// Blinn microfacet distribution, core/reflection.h:311-325, reflection.cpp:244-272
+PB_HD float blinn_D(float exponent, const V3 &wh) {
+  float costhetah = fabsf(wh.z);
+  return (exponent + 2) * PB_INV_TWOPI * pb_powf(costhetah, exponent);
+}
+PB_HD float blinn_pdf(float exponent, const V3 &wo, const V3 &wi) {
+  V3 H = normalize(wo + wi);
+  float costheta = fabsf(H.z);
+  float blinn = ((exponent + 1.f) * pb_powf(costheta, exponent)) / (2.f * PB_PI * 4.f * dot(wo, H));
+  if (dot(wo, H) <= 0.f) blinn = 0.f;
+  return blinn;
+}
+PB_HD void blinn_sample_f(float exponent, const V3 &wo, V3 *wi, float u1, float u2, float *pdf) {
+  float costheta = pb_powf(u1, 1.f / (exponent + 1));
+  float sintheta = sqrtf(pb_max(0.f, 1.f - costheta * costheta));
+  float phi = u2 * 2.f * PB_PI;
+  V3 H = v3(sintheta * pb_cosf(phi), sintheta * pb_sinf(phi), costheta);   // SphericalDirection
+  if (!(wo.z * H.z > 0.f)) H = -H;
+  *wi = -wo + 2.f * dot(wo, H) * H;
+  float blinn = ((exponent + 1.f) * pb_powf(costheta, exponent)) / (2.f * PB_PI * 4.f * dot(wo, H));
+  if (dot(wo, H) <= 0.f) blinn = 0.f;
+  *pdf = blinn;
+}
+// Microfacet::G, core/reflection.h:293-301
+PB_HD float microfacet_G(const V3 &wo, const V3 &wi, const V3 &wh) {
+  float NdotWh = fabsf(wh.z);
+  float NdotWo = fabsf(wo.z);
+  float NdotWi = fabsf(wi.z);
+  float WOdotWh = absdot(wo, wh);
+  return pb_min(1.f, pb_min((2.f * NdotWh * NdotWo / WOdotWh), (2.f * NdotWh * NdotWi / WOdotWh)));
+}
+PB_HD float fresnel_dielectric(float cosi, float eta_i, float eta_t);
+// Microfacet::f, core/reflection.cpp:163-175
+PB_NOINLINE Spec microfacet_f(const Spec &R, float exponent, float etai, float etat, const V3 &wo, const V3 &wi) {
+  float cosThetaO = fabsf(wo.z);
+  float cosThetaI = fabsf(wi.z);
+  if (cosThetaI == 0.f || cosThetaO == 0.f) return spec(0.f);
+  V3 wh = wi + wo;
+  if (wh.x == 0.f && wh.y == 0.f && wh.z == 0.f) return spec(0.f);
+  wh = normalize(wh);
+  float cosThetaH = dot(wi, wh);
+  Spec F = spec(fresnel_dielectric(cosThetaH, etai, etat));
+  return R * blinn_D(exponent, wh) * microfacet_G(wo, wi, wh) * F / (4.f * cosThetaI * cosThetaO);
+}
+
 // BxDF::f for the non-specular lobes (reflection.cpp:128-156); specular lobes return 0.
 PB_HD Spec lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
   if (l.kind == PB_LOBE_LAMBERT) return l.R;   // R already holds R * INV_PI (reflection.h:249)
+  if (l.kind == PB_LOBE_MICROFACET_BLINN) return microfacet_f(l.R, l.A, l.etai, l.etat, wo, wi);
   if (l.kind == PB_LOBE_ORENNAYAR) {
     float sinthetai = sin_theta(wi);
     float sinthetao = sin_theta(wo);
@@ -139,6 +186,8 @@ PB_HD Spec lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
 // BxDF::Pdf (reflection.cpp:226-230); specular lobes return 0 (reflection.h:213,235)
 PB_HD float lobe_pdf(const Lobe &l, const V3 &wo, const V3 &wi) {
   if (l.type & PB_SPECULAR) return 0.f;
+  if (l.kind == PB_LOBE_MICROFACET_BLINN)   // Microfacet::Pdf, reflection.cpp:240-243
+    return (wo.z * wi.z > 0.f) ? blinn_pdf(l.A, wo, wi) : 0.f;
   return (wo.z * wi.z > 0.f) ? fabsf(wi.z) * PB_INV_PI : 0.f;
 }
 // BxDF::Sample_f for each lobe kind (reflection.cpp:96-127, 219-225)
@@ -165,6 +214,11 @@ PB_HD Spec lobe_sample_f(const Lobe &l, const V3 &wo, V3 *wi, float u1, float u2
     *pdf = 1.f;
     float F = fresnel_dielectric(wo.z, l.etai, l.etat);
     return ((et * et) / (ei * ei) * (spec(1.f) - spec(F)) * l.R) / fabsf(wi->z);
+  }
+  if (l.kind == PB_LOBE_MICROFACET_BLINN) {   // Microfacet::Sample_f, reflection.cpp:235-239
+    blinn_sample_f(l.A, wo, wi, u1, u2, pdf);
+    if (!(wo.z * wi->z > 0.f)) return spec(0.f);
+    return microfacet_f(l.R, l.A, l.etai, l.etat, wo, *wi);
   }
   *wi = cosine_sample_hemisphere(u1, u2);
   if (wo.z < 0.f) wi->z *= -1.f;
@@ -310,6 +364,17 @@ PB_HD void bsdf_set_lobes(const PbrtB200Material &m, Bsdf *b) {
       l.kind = PB_LOBE_SPEC_TRANS; l.type = PB_TRANSMISSION | PB_SPECULAR;
       l.R = T; l.A = l.B = 0.f; l.etai = 1.f; l.etat = m.index;
     }
+  } else if (m.kind == PBRT_B200_MAT_PLASTIC) {
+    // materials/plastic.cpp:57-67: Lambertian(kd) then Microfacet(ks, FresnelDielectric(1.5, 1), Blinn(1/rough))
+    Lobe &d = b->lobes[b->nLobes++];
+    d.kind = PB_LOBE_LAMBERT; d.type = PB_REFLECTION | PB_DIFFUSE;
+    d.R = R * PB_INV_PI; d.A = d.B = 0.f; d.etai = d.etat = 1.f;
+    Lobe &g = b->lobes[b->nLobes++];
+    g.kind = PB_LOBE_MICROFACET_BLINN; g.type = PB_REFLECTION | PB_GLOSSY;
+    g.R = spec3(m.kt[0], m.kt[1], m.kt[2]);
+    float e = 1.f / m.roughness;
+    if (e > 1000.f || e != e) e = 1000.f;   // Blinn::Blinn, reflection.h:313
+    g.A = e; g.B = 0.f; g.etai = 1.5f; g.etat = 1.f;
   } else {   // mirror
     if (!is_black(R)) {
       Lobe &l = b->lobes[b->nLobes++];

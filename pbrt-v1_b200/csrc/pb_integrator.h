@@ -208,6 +208,36 @@ PB_HD void set_segment(Ray *r, const V3 &p1, const V3 &p2) {
   r->o = p1; r->d = p2 - p1; r->mint = PB_RAY_EPSILON; r->maxt = 1.f - PB_RAY_EPSILON;
 }
 
+// Light::Sample_L(p, &wi, &visibility) of the delta lights: point (lights/point.cpp:55-66), spot
+// (lights/spot.cpp:59-76) and distant (lights/distant.cpp:60-65, whose visibility ray is unbounded).
+PB_HD Spec delta_light_sample(const PbrtB200Light &light, const V3 &p, V3 *wi, Ray *shadow) {
+  if (light.kind == PBRT_B200_LIGHT_DISTANT) {
+    *wi = v3(light.pos[0], light.pos[1], light.pos[2]);
+    shadow->o = p; shadow->d = *wi; shadow->mint = PB_RAY_EPSILON; shadow->maxt = PB_INFINITY;   // SetRay
+    return light_color(light);
+  }
+  V3 lightPos = v3(light.pos[0], light.pos[1], light.pos[2]);
+  *wi = normalize(lightPos - p);
+  set_segment(shadow, p, lightPos);
+  if (light.kind == PBRT_B200_LIGHT_SPOT) {
+    // SpotLight::Falloff(-wi), spot.cpp:66-76
+    V3 w = -*wi;
+    V3 wl = normalize(v3(light.w2l[0] * w.x + light.w2l[1] * w.y + light.w2l[2] * w.z,
+                         light.w2l[3] * w.x + light.w2l[4] * w.y + light.w2l[5] * w.z,
+                         light.w2l[6] * w.x + light.w2l[7] * w.y + light.w2l[8] * w.z));
+    float costheta = wl.z;
+    float falloff;
+    if (costheta < light.cos_total_width) falloff = 0.f;
+    else if (costheta > light.cos_falloff_start) falloff = 1.f;
+    else {
+      float delta = (costheta - light.cos_total_width) / (light.cos_falloff_start - light.cos_total_width);
+      falloff = delta * delta * delta * delta;
+    }
+    return light_color(light) * falloff / distance_sq(lightPos, p);
+  }
+  return light_color(light) / distance_sq(lightPos, p);
+}
+
 // transport.cpp:123-194.  ls1..bcs are already chosen by the caller
 // (Sample arrays or RandomFloat, :131-146).
 PB_HD void estimate_direct(const SceneView &sv, int lightNum, const V3 &p, const V3 &n, const V3 &wo,
@@ -220,13 +250,10 @@ PB_HD void estimate_direct(const SceneView &sv, int lightNum, const V3 &p, const
   V3 wi;
   float lightPdf, bsdfPdf;
   Spec Li;
-  bool isDelta = light.kind == PBRT_B200_LIGHT_POINT;
+  bool isDelta = light.kind != PBRT_B200_LIGHT_AREA;
   if (isDelta) {
-    V3 lightPos = v3(light.pos[0], light.pos[1], light.pos[2]);
     lightPdf = 1.f;
-    wi = normalize(lightPos - p);
-    set_segment(&rec->shadow, p, lightPos);
-    Li = light_color(light) / distance_sq(lightPos, p);
+    Li = delta_light_sample(light, p, &wi, &rec->shadow);
   } else {
     V3 ns;
     V3 ps = area_light_sample_point(sv, light, p, ls1, ls2, rng, &ns);
@@ -464,11 +491,8 @@ PB_HD void wd_vertex(const SceneView &sv, const PatternSource &key0, const Ray &
       rec->termA = rec->termB = spec(0.f);
       rec->probeLight = i;
       V3 wi; Spec Li;
-      if (light.kind == PBRT_B200_LIGHT_POINT) {
-        V3 lightPos = v3(light.pos[0], light.pos[1], light.pos[2]);
-        wi = normalize(lightPos - p);
-        set_segment(&rec->shadow, p, lightPos);
-        Li = light_color(light) / distance_sq(lightPos, p);
+      if (light.kind != PBRT_B200_LIGHT_AREA) {
+        Li = delta_light_sample(light, p, &wi, &rec->shadow);
       } else {
         // AreaLight::Sample_L(P, &wo, &vis), area.cpp:96-105.  g++ evaluates the two
         // RandomFloat() arguments right to left: the first draw is u2.

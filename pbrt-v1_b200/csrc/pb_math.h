@@ -52,6 +52,11 @@ PB_NOINLINE float pb_cosf(float x) { return (float)cos((double)x); }
 PB_NOINLINE float pb_acosf(float x) { return (float)acos((double)x); }
 PB_NOINLINE float pb_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
 #endif
+#if defined(PB_TWIN_LIBM_FLOAT) && !defined(__CUDACC__)
+PB_HD float pb_powf(float x, float y) { return powf(x, y); }
+#else
+PB_NOINLINE float pb_powf(float x, float y) { return (float)pow((double)x, (double)y); }
+#endif
 
 PB_HD float pb_max(float a, float b) { return a < b ? b : a; }   // std::max(a,b)
 PB_HD float pb_min(float a, float b) { return b < a ? b : a; }   // std::min(a,b)

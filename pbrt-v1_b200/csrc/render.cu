@@ -76,6 +76,7 @@ struct AuxQueue {        // shadow segments / MIS probes
   uint32_t *rec;         // direct-record index (r * nSlots + slot)
   float *ox, *oy, *oz, *dx, *dy, *dz;
   int32_t *light;        // probes only
+  float *maxt;           // shadow rays only: 1 - eps for a segment, inf for a distant light's ray
 };
 struct WaveBuffers {
   uint32_t nSlots;       // capacity
@@ -190,6 +191,7 @@ __device__ __forceinline__ void aux_put(const AuxQueue &q, uint32_t i, uint32_t 
   q.ox[i] = r.o.x; q.oy[i] = r.o.y; q.oz[i] = r.o.z;
   q.dx[i] = r.d.x; q.dy[i] = r.d.y; q.dz[i] = r.d.z;
   if (q.light) q.light[i] = light;
+  if (q.maxt) q.maxt[i] = r.maxt;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -292,7 +294,7 @@ struct ShadowSource {
     Ray ray;
     ray.o = v3(q.ox[i], q.oy[i], q.oz[i]);
     ray.d = v3(q.dx[i], q.dy[i], q.dz[i]);
-    ray.mint = PB_RAY_EPSILON; ray.maxt = 1.f - PB_RAY_EPSILON;   // light.h:78-80
+    ray.mint = PB_RAY_EPSILON; ray.maxt = q.maxt[i];   // light.h:78-83 (SetSegment / SetRay)
     return ray;
   }
 };
@@ -987,6 +989,7 @@ static void carve_wave(Carver &c, WaveBuffers &wb, uint32_t nSlots, int directRe
     q.ox = c.take<float>(auxN); q.oy = c.take<float>(auxN); q.oz = c.take<float>(auxN);
     q.dx = c.take<float>(auxN); q.dy = c.take<float>(auxN); q.dz = c.take<float>(auxN);
     q.light = (k == 1) ? c.take<int32_t>(auxN) : nullptr;
+    q.maxt = (k == 0) ? c.take<float>(auxN) : nullptr;
   }
   for (int k = 0; k < 15; ++k) wb.surf[k] = isPath ? c.take<float>(nSlots) : nullptr;
   wb.surfIds = isPath ? c.take<uint32_t>(nSlots) : nullptr;

@@ -67,6 +67,17 @@ inline Vector Cross(const Vector &v1, const Vector &v2) {
                 (v1.x * v2.y) - (v1.y * v2.x));
 }
 inline Vector Normalize(const Vector &v) { return v / v.Length(); }
+// core/geometry.h:320-331 (Cross is spelled out so this does not depend on declaration order)
+inline void CoordinateSystem(const Vector &v1, Vector *v2, Vector *v3) {
+  if (fabsf(v1.x) > fabsf(v1.y)) {
+    float invLen = 1.f / sqrtf(v1.x * v1.x + v1.z * v1.z);
+    *v2 = Vector(-v1.z * invLen, 0.f, v1.x * invLen);
+  } else {
+    float invLen = 1.f / sqrtf(v1.y * v1.y + v1.z * v1.z);
+    *v2 = Vector(0.f, v1.z * invLen, -v1.y * invLen);
+  }
+  *v3 = Vector((v1.y * v2->z) - (v1.z * v2->y), (v1.z * v2->x) - (v1.x * v2->z), (v1.x * v2->y) - (v1.y * v2->x));
+}
 
 // core/geometry.h:235-287, core/geometry.cpp:27-48
 class BBox {

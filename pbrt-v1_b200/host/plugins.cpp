@@ -48,7 +48,55 @@ class Mirror : public Material {  // materials/mirror.cpp:42-60
   Spectrum Kr;
 };
 
+class Plastic : public Material {   // materials/plastic.cpp:28-77
+ public:
+  Plastic(const Spectrum &kd, const Spectrum &ks, float rough) : Kd(kd), Ks(ks), roughness(rough) {}
+  void Flatten(PbrtB200Material *out) const {
+    memset(out, 0, sizeof(*out));
+    out->kind = PBRT_B200_MAT_PLASTIC;
+    Spectrum d = Kd.Clamp(), s = Ks.Clamp();
+    for (int i = 0; i < 3; ++i) { out->kd[i] = d.c[i]; out->kt[i] = s.c[i]; }
+    out->roughness = roughness;
+  }
+  Spectrum Kd, Ks; float roughness;
+};
+
 // ------------------------------------------------------------------- lights
+class DistantLight : public Light {  // lights/distant.cpp:53-59
+ public:
+  DistantLight(const Transform &light2world, const Spectrum &radiance, const Vector &dir)
+      : Light(light2world), L(radiance) {
+    lightDir = Normalize(LightToWorld(dir));
+  }
+  void Flatten(FlatBuilder &, PbrtB200Light *out) const {
+    memset(out, 0, sizeof(*out));
+    out->kind = PBRT_B200_LIGHT_DISTANT;
+    out->n_samples = nSamples;
+    for (int i = 0; i < 3; ++i) { out->color[i] = L.c[i]; out->pos[i] = lightDir[i]; }
+  }
+  Vector lightDir; Spectrum L;
+};
+class SpotLight : public Light {     // lights/spot.cpp:51-58
+ public:
+  SpotLight(const Transform &light2world, const Spectrum &intensity, float width, float fall)
+      : Light(light2world), Intensity(intensity), WorldToLight(light2world.GetInverse()) {
+    lightPos = LightToWorld(Point(0, 0, 0));
+    cosTotalWidth = cosf(Radians(width));
+    cosFalloffStart = cosf(Radians(fall));
+  }
+  void Flatten(FlatBuilder &, PbrtB200Light *out) const {
+    memset(out, 0, sizeof(*out));
+    out->kind = PBRT_B200_LIGHT_SPOT;
+    out->n_samples = nSamples;
+    for (int i = 0; i < 3; ++i) { out->color[i] = Intensity.c[i]; out->pos[i] = lightPos[i]; }
+    out->cos_total_width = cosTotalWidth;
+    out->cos_falloff_start = cosFalloffStart;
+    const Matrix4x4 &m = WorldToLight.GetMatrix();
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) out->w2l[3 * r + c] = m.m[r][c];
+  }
+  Point lightPos; Spectrum Intensity; float cosTotalWidth, cosFalloffStart; Transform WorldToLight;
+};
 class PointLight : public Light {  // lights/point.cpp:49-54
  public:
   PointLight(const Transform &light2world, const Spectrum &intensity)
@@ -217,6 +265,13 @@ static Material *CreateGlass(const Transform &, const TextureParams &mp) {
   mp.GetFloatTexture("bumpmap", 0.f);
   return new Glass(Kr, Kt, index);
 }
+static Material *CreatePlastic(const Transform &, const TextureParams &mp) {
+  Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(1.f));
+  Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(1.f));
+  float roughness = mp.GetFloatTexture("roughness", .1f);
+  mp.GetFloatTexture("bumpmap", 0.f);
+  return new Plastic(Kd, Ks, roughness);
+}
 static Material *CreateMirror(const Transform &, const TextureParams &mp) {
   Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(1.f));
   mp.GetFloatTexture("bumpmap", 0.f);
@@ -246,9 +301,10 @@ Reference<Material> MakeMaterial(const string &name, const Transform &mtl2world,
   if (name == "matte") m = CreateMatte(mtl2world, mp);
   else if (name == "glass") m = CreateGlass(mtl2world, mp);
   else if (name == "mirror") m = CreateMirror(mtl2world, mp);
+  else if (name == "plastic") m = CreatePlastic(mtl2world, mp);
   else
     Error("Material plugin \"%s\" is outside the B200 hot-path scope (supported: matte, glass, "
-          "mirror).", name.c_str());
+          "mirror, plastic).", name.c_str());
   if (m) mp.ReportUnused();   // core/dynload.cpp:299
   return m;
 }
@@ -258,6 +314,31 @@ Light *MakeLight(const string &name, const Transform &light2world, const ParamSe
     Point P = paramSet.FindOnePoint("from", Point(0, 0, 0));
     Transform l2w = Translate(Vector(P.x, P.y, P.z)) * light2world;
     Light *l = new PointLight(l2w, I);
+    paramSet.ReportUnused();
+    return l;
+  }
+  if (name == "distant") {   // lights/distant.cpp:94-101
+    Spectrum L = paramSet.FindOneSpectrum("L", Spectrum(1.0));
+    Point from = paramSet.FindOnePoint("from", Point(0, 0, 0));
+    Point to = paramSet.FindOnePoint("to", Point(0, 0, 1));
+    Vector dir = from - to;
+    Light *l = new DistantLight(light2world, L, dir);
+    paramSet.ReportUnused();
+    return l;
+  }
+  if (name == "spot") {      // lights/spot.cpp:100-121
+    Spectrum I = paramSet.FindOneSpectrum("I", Spectrum(1.0));
+    float coneangle = paramSet.FindOneFloat("coneangle", 30.);
+    float conedelta = paramSet.FindOneFloat("conedeltaangle", 5.);
+    Point from = paramSet.FindOnePoint("from", Point(0, 0, 0));
+    Point to = paramSet.FindOnePoint("to", Point(0, 0, 1));
+    Vector dir = Normalize(to - from);
+    Vector du, dv;
+    CoordinateSystem(dir, &du, &dv);
+    Transform dirToZ = Transform(new Matrix4x4(du.x, du.y, du.z, 0., dv.x, dv.y, dv.z, 0., dir.x, dir.y, dir.z, 0.,
+                                               0, 0, 0, 1.));
+    Transform l2w = light2world * Translate(Vector(from.x, from.y, from.z)) * dirToZ.GetInverse();
+    Light *l = new SpotLight(l2w, I, coneangle, coneangle - conedelta);
     paramSet.ReportUnused();
     return l;
   }

@@ -97,6 +97,78 @@ Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-4 0 -4 4 0 -4 4
 AttributeEnd
 WorldEnd
 """,
+    "plastic_spot_distant_path": """LookAt 278 273 -800 278 273 0 0 1 0
+Camera "perspective" "float fov" [39.3]
+Film "image" "integer xresolution" [32] "integer yresolution" [32] "string filename" ["plastic_spot_distant_path_out.exr"]
+Sampler "stratified" "integer xsamples" [2] "integer ysamples" [2]
+PixelFilter "box"
+SurfaceIntegrator "path" "integer maxdepth" [4]
+WorldBegin
+LightSource "distant" "color L" [2 2 1.5] "point from" [0 600 -300] "point to" [278 0 278]
+LightSource "spot" "color I" [400000 300000 300000] "point from" [100 500 100] "point to" [300 0 300] "float coneangle" [35] "float conedeltaangle" [10]
+AttributeBegin
+AreaLightSource "area" "color L" [17 12 4]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [213 548.7 227 343 548.7 227 343 548.7 332 213 548.7 332]
+AttributeEnd
+Material "plastic" "color Kd" [.3 .5 .3] "color Ks" [.6 .6 .6] "float roughness" [.05]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [0 0 0 0 0 555 555 0 555 555 0 0]
+Material "plastic" "color Kd" [.6 .2 .2] "color Ks" [.3 .3 .3] "float roughness" [.3]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [0 0 555 0 555 555 555 555 555 555 0 555]
+AttributeBegin
+Translate 278 120 300
+Material "plastic" "color Kd" [.2 .2 .7] "float roughness" [.002]
+Shape "sphere" "float radius" [120]
+AttributeEnd
+WorldEnd
+""",
+    "plastic_spot_distant_whitted": """LookAt 278 273 -800 278 273 0 0 1 0
+Camera "perspective" "float fov" [39.3]
+Film "image" "integer xresolution" [32] "integer yresolution" [32] "string filename" ["plastic_spot_distant_whitted_out.exr"]
+Sampler "stratified" "integer xsamples" [2] "integer ysamples" [2]
+PixelFilter "box"
+SurfaceIntegrator "whitted"
+WorldBegin
+LightSource "distant" "color L" [2 2 1.5] "point from" [0 600 -300] "point to" [278 0 278]
+LightSource "spot" "color I" [400000 300000 300000] "point from" [100 500 100] "point to" [300 0 300] "float coneangle" [35] "float conedeltaangle" [10]
+AttributeBegin
+AreaLightSource "area" "color L" [17 12 4]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [213 548.7 227 343 548.7 227 343 548.7 332 213 548.7 332]
+AttributeEnd
+Material "plastic" "color Kd" [.3 .5 .3] "color Ks" [.6 .6 .6] "float roughness" [.05]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [0 0 0 0 0 555 555 0 555 555 0 0]
+Material "plastic" "color Kd" [.6 .2 .2] "color Ks" [.3 .3 .3] "float roughness" [.3]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [0 0 555 0 555 555 555 555 555 555 0 555]
+AttributeBegin
+Translate 278 120 300
+Material "plastic" "color Kd" [.2 .2 .7] "float roughness" [.002]
+Shape "sphere" "float radius" [120]
+AttributeEnd
+WorldEnd
+""",
+    "plastic_spot_distant_direct": """LookAt 278 273 -800 278 273 0 0 1 0
+Camera "perspective" "float fov" [39.3]
+Film "image" "integer xresolution" [32] "integer yresolution" [32] "string filename" ["plastic_spot_distant_direct_out.exr"]
+Sampler "stratified" "integer xsamples" [2] "integer ysamples" [2]
+PixelFilter "box"
+SurfaceIntegrator "directlighting"
+WorldBegin
+LightSource "distant" "color L" [2 2 1.5] "point from" [0 600 -300] "point to" [278 0 278]
+LightSource "spot" "color I" [400000 300000 300000] "point from" [100 500 100] "point to" [300 0 300] "float coneangle" [35] "float conedeltaangle" [10]
+AttributeBegin
+AreaLightSource "area" "color L" [17 12 4]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [213 548.7 227 343 548.7 227 343 548.7 332 213 548.7 332]
+AttributeEnd
+Material "plastic" "color Kd" [.3 .5 .3] "color Ks" [.6 .6 .6] "float roughness" [.05]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [0 0 0 0 0 555 555 0 555 555 0 0]
+Material "plastic" "color Kd" [.6 .2 .2] "color Ks" [.3 .3 .3] "float roughness" [.3]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [0 0 555 0 555 555 555 555 555 555 0 555]
+AttributeBegin
+Translate 278 120 300
+Material "plastic" "color Kd" [.2 .2 .7] "float roughness" [.002]
+Shape "sphere" "float radius" [120]
+AttributeEnd
+WorldEnd
+""",
 }
 
 
