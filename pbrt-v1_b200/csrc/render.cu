@@ -458,6 +458,7 @@ k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const
   warp_stat_add(&wb.stats[ST_SHADED], shaded);
 }
 
+template <bool LD>   // LD: patterns come from the lowdiscrepancy tables; false folds that path away
 __global__ void __launch_bounds__(PB_BLOCK, 4)
 k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveKeyInfo wd,
               const RayQueue qin, const SurfaceRecord rec, const uint32_t *nPtr, uint32_t *work,
@@ -486,7 +487,7 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
         st.depth = (int)(flags & 0xffu);
         st.rng.key = slot_key(wd, slot, 1);
         st.rng.ctr = wb.ctr[slot];
-        PatternSource key0 = {slot_key(wd, slot, 0), wb.ld, wb.nSlots, slot};
+        PatternSource key0 = {slot_key(wd, slot, 0), LD ? wb.ld : (const float *)nullptr, wb.nSlots, slot};
         bool hasDirect;
         path_vertex_direct(sv, key0, st, ray, &sf, &direct, &hasDirect);
         wb.ctr[slot] = st.rng.ctr;
@@ -518,6 +519,7 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
   }
 }
 
+template <bool LD>
 __global__ void __launch_bounds__(PB_BLOCK, 4)
 k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveKeyInfo wd,
                 const RayQueue qin, const RayQueue qout, const SurfaceRecord rec, const uint32_t *nPtr,
@@ -547,7 +549,7 @@ k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, cons
         st.specularBounce = (flags >> 8) & 1u;
         st.rng.key = slot_key(wd, slot, 1);
         st.rng.ctr = wb.ctr[slot];
-        PatternSource key0 = {slot_key(wd, slot, 0), wb.ld, wb.nSlots, slot};
+        PatternSource key0 = {slot_key(wd, slot, 0), LD ? wb.ld : (const float *)nullptr, wb.nSlots, slot};
         pushNext = path_vertex_continue(sv, key0, st, ray, sf, &next);
         store3(wb.T, slot, st.T);
         wb.ctr[slot] = st.rng.ctr;
@@ -1076,6 +1078,7 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
   int cur = 0;
   WaveKeyInfo wk = {wb.pixel, wd.spp};
   bool overlap = g_overlap != 0;
+  const bool isLD = sv.sampler.kind == PBRT_B200_SAMPLER_LOWDISCREPANCY;
   if (isPath) {
     int iters = sv.integrator.max_depth + 1;
     if (iters < 1) iters = 1;
@@ -1091,8 +1094,12 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
         for (int k = 0; k < 15; ++k) rec.f[k] = wb.surf[k];
         rec.ids = wb.surfIds;
         TIMED(KC_SHADE, (k_path_surface<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], rec, nMain, nextWork())));
-        TIMED(KC_SHADE_DIRECT, (k_path_direct<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], rec, nMain, nextWork(),
-                                                                        nShadow, nProbe)));
+        if (isLD)
+          TIMED(KC_SHADE_DIRECT, (k_path_direct<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], rec, nMain,
+                                                                                nextWork(), nShadow, nProbe)));
+        else
+          TIMED(KC_SHADE_DIRECT, (k_path_direct<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], rec, nMain,
+                                                                                 nextWork(), nShadow, nProbe)));
         if (overlap) {
           // shadow + probe rays of this vertex run on the aux stream, concurrently with
           // k_path_continue and the next k_intersect (they share no data)
@@ -1101,8 +1108,12 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
           launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork(), h->auxStream);
           CU_TRY(cudaEventRecord(h->evAux, h->auxStream));
         }
-        TIMED(KC_SHADE_CONT, (k_path_continue<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], wb.q[cur ^ 1], rec, nMain,
-                                                                        nextWork(), nNext)));
+        if (isLD)
+          TIMED(KC_SHADE_CONT, (k_path_continue<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], wb.q[cur ^ 1], rec,
+                                                                                nMain, nextWork(), nNext)));
+        else
+          TIMED(KC_SHADE_CONT, (k_path_continue<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], wb.q[cur ^ 1], rec,
+                                                                                 nMain, nextWork(), nNext)));
       }
       if (!overlap) launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork(), st);
       *launches += 6;

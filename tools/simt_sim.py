@@ -14,7 +14,9 @@ from parity_util import gen_scene, load_ffi  # noqa: E402
 
 ffi = load_ffi()
 name = sys.argv[1] if len(sys.argv) > 1 else "c3"
-sp = gen_scene("/tmp/simt_%s.pbrt" % name, name, "--res", "96", "96", "--spp", "2", "2", "--filename", "/tmp/simt.exr", *sys.argv[2:])
+RES = os.environ.get("SIMT_RES", "96")
+SPP = os.environ.get("SIMT_SPP", "2")
+sp = gen_scene("/tmp/simt_%s.pbrt" % name, name, "--res", RES, RES, "--spp", SPP, SPP, "--filename", "/tmp/simt.exr", *sys.argv[2:])
 sc = ffi.Scene(sp)
 rays, _ = ffi.twin_camera_rays(sc)
 prim, t, _, _ = ffi.twin_intersect(sc, rays)
@@ -95,6 +97,21 @@ for chunk in (256, 1024, 4096):
 cell = (np.clip(p / 555.0 * 4, 0, 3.999).astype(int) * np.array([1, 4, 16])).sum(axis=1)
 orders["global sort (octant, cell4^3)"] = np.lexsort((cell, octant))
 orders["global sort (cell4^3, octant)"] = np.lexsort((octant, cell))
+def morton3(v, bits):
+    out = np.zeros(v.shape[0], np.int64)
+    for b in range(bits):
+        for a in range(3):
+            out |= ((v[:, a] >> b) & 1).astype(np.int64) << (3 * b + a)
+    return out
+
+
+for ob, db in ((3, 2), (4, 3), (5, 4), (6, 5)):
+    oc = np.clip(p / 555.0 * (1 << ob), 0, (1 << ob) - 1).astype(np.int64)
+    dc = np.clip((d * 0.5 + 0.5) * (1 << db), 0, (1 << db) - 1).astype(np.int64)
+    key = (morton3(dc, db) << (3 * ob)) | morton3(oc, ob)
+    orders["sort dir%db/axis then origin%db/axis" % (db, ob)] = np.argsort(key, kind="stable")
+    key2 = (morton3(oc, ob) << (3 * db)) | morton3(dc, db)
+    orders["sort origin%db/axis then dir%db/axis" % (ob, db)] = np.argsort(key2, kind="stable")
 for k, o in orders.items():
     nw = (len(o) // 32) * 32
     u = sum(sum(COST[c] for c in traces[i]) for i in o[:nw])
