@@ -117,7 +117,7 @@ PB_HD float blinn_D(float exponent, const V3 &wh) {
   float costhetah = fabsf(wh.z);
   return (exponent + 2) * PB_INV_TWOPI * pb_powf(costhetah, exponent);
 }
-PB_HD float blinn_pdf(float exponent, const V3 &wo, const V3 &wi) {
+PB_NOINLINE float blinn_pdf(float exponent, const V3 &wo, const V3 &wi) {
   V3 H = normalize(wo + wi);
   float costheta = fabsf(H.z);
   float blinn = ((exponent + 1.f) * pb_powf(costheta, exponent)) / (2.f * PB_PI * 4.f * dot(wo, H));
@@ -157,10 +157,21 @@ PB_NOINLINE Spec microfacet_f(const Spec &R, float exponent, float etai, float e
   return R * blinn_D(exponent, wh) * microfacet_G(wo, wi, wh) * F / (4.f * cosThetaI * cosThetaO);
 }
 
+// Microfacet::Sample_f, reflection.cpp:235-239 (out of line: scenes without glossy materials only
+// pay a branch for it)
+PB_NOINLINE Spec microfacet_sample_f(const Spec &R, float exponent, float etai, float etat, const V3 &wo, V3 *wi,
+                                     float u1, float u2, float *pdf) {
+  blinn_sample_f(exponent, wo, wi, u1, u2, pdf);
+  if (!(wo.z * wi->z > 0.f)) return spec(0.f);
+  return microfacet_f(R, exponent, etai, etat, wo, *wi);
+}
+
 // BxDF::f for the non-specular lobes (reflection.cpp:128-156); specular lobes return 0.
+// G = false compiles the glossy (microfacet) lobe out: kernels for scenes without such materials
+template <bool G = true>
 PB_HD Spec lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
   if (l.kind == PB_LOBE_LAMBERT) return l.R;   // R already holds R * INV_PI (reflection.h:249)
-  if (l.kind == PB_LOBE_MICROFACET_BLINN) return microfacet_f(l.R, l.A, l.etai, l.etat, wo, wi);
+  if (G && l.kind == PB_LOBE_MICROFACET_BLINN) return microfacet_f(l.R, l.A, l.etai, l.etat, wo, wi);
   if (l.kind == PB_LOBE_ORENNAYAR) {
     float sinthetai = sin_theta(wi);
     float sinthetao = sin_theta(wo);
@@ -184,13 +195,15 @@ PB_HD Spec lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
   return spec(0.f);
 }
 // BxDF::Pdf (reflection.cpp:226-230); specular lobes return 0 (reflection.h:213,235)
+template <bool G = true>
 PB_HD float lobe_pdf(const Lobe &l, const V3 &wo, const V3 &wi) {
   if (l.type & PB_SPECULAR) return 0.f;
-  if (l.kind == PB_LOBE_MICROFACET_BLINN)   // Microfacet::Pdf, reflection.cpp:240-243
+  if (G && l.kind == PB_LOBE_MICROFACET_BLINN)   // Microfacet::Pdf, reflection.cpp:240-243
     return (wo.z * wi.z > 0.f) ? blinn_pdf(l.A, wo, wi) : 0.f;
   return (wo.z * wi.z > 0.f) ? fabsf(wi.z) * PB_INV_PI : 0.f;
 }
 // BxDF::Sample_f for each lobe kind (reflection.cpp:96-127, 219-225)
+template <bool G = true>
 PB_HD Spec lobe_sample_f(const Lobe &l, const V3 &wo, V3 *wi, float u1, float u2, float *pdf) {
   if (l.kind == PB_LOBE_SPEC_REFL_DIEL || l.kind == PB_LOBE_SPEC_REFL_NOOP) {
     *wi = v3(-wo.x, -wo.y, wo.z);
@@ -215,15 +228,11 @@ PB_HD Spec lobe_sample_f(const Lobe &l, const V3 &wo, V3 *wi, float u1, float u2
     float F = fresnel_dielectric(wo.z, l.etai, l.etat);
     return ((et * et) / (ei * ei) * (spec(1.f) - spec(F)) * l.R) / fabsf(wi->z);
   }
-  if (l.kind == PB_LOBE_MICROFACET_BLINN) {   // Microfacet::Sample_f, reflection.cpp:235-239
-    blinn_sample_f(l.A, wo, wi, u1, u2, pdf);
-    if (!(wo.z * wi->z > 0.f)) return spec(0.f);
-    return microfacet_f(l.R, l.A, l.etai, l.etat, wo, *wi);
-  }
+  if (G && l.kind == PB_LOBE_MICROFACET_BLINN) return microfacet_sample_f(l.R, l.A, l.etai, l.etat, wo, wi, u1, u2, pdf);
   *wi = cosine_sample_hemisphere(u1, u2);
   if (wo.z < 0.f) wi->z *= -1.f;
-  *pdf = lobe_pdf(l, wo, *wi);
-  return lobe_f(l, wo, *wi);
+  *pdf = lobe_pdf<G>(l, wo, *wi);
+  return lobe_f<G>(l, wo, *wi);
 }
 
 PB_HD V3 bsdf_world_to_local(const Bsdf &b, const V3 &v) {
@@ -240,16 +249,18 @@ PB_HD int bsdf_num_components(const Bsdf &b, int flags) {
   return n;
 }
 // BSDF::f, reflection.cpp:480-494
+template <bool G = true>
 PB_HD Spec bsdf_f(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags = PB_ALL) {
   V3 wi = bsdf_world_to_local(b, wiW), wo = bsdf_world_to_local(b, woW);
   if (dot(wiW, b.ng) * dot(woW, b.ng) > 0) flags &= ~PB_TRANSMISSION;
   else flags &= ~PB_REFLECTION;
   Spec f = spec(0.f);
   for (int i = 0; i < b.nLobes; ++i)
-    if (lobe_matches(b.lobes[i], flags)) f = f + lobe_f(b.lobes[i], wo, wi);
+    if (lobe_matches(b.lobes[i], flags)) f = f + lobe_f<G>(b.lobes[i], wo, wi);
   return f;
 }
 // BSDF::Pdf, reflection.cpp:458-470
+template <bool G = true>
 PB_HD float bsdf_pdf(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags = PB_ALL) {
   if (b.nLobes == 0) return 0.f;
   V3 wo = bsdf_world_to_local(b, woW), wi = bsdf_world_to_local(b, wiW);
@@ -258,11 +269,12 @@ PB_HD float bsdf_pdf(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags = PB
   for (int i = 0; i < b.nLobes; ++i)
     if (lobe_matches(b.lobes[i], flags)) {
       ++matchingComps;
-      pdf += lobe_pdf(b.lobes[i], wo, wi);
+      pdf += lobe_pdf<G>(b.lobes[i], wo, wi);
     }
   return matchingComps > 0 ? pdf / matchingComps : 0.f;
 }
 // BSDF::Sample_f with explicit sample values, reflection.cpp:402-457
+template <bool G = true>
 PB_NOINLINE Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, float u1, float u2, float u3,
                          float *pdf, int flags, int *sampledType) {
   int matchingComps = bsdf_num_components(b, flags);
@@ -281,7 +293,7 @@ PB_NOINLINE Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, float u1, 
   V3 wi = v3(0, 0, 0);
   V3 wo = bsdf_world_to_local(b, woW);
   *pdf = 0.f;
-  Spec f = lobe_sample_f(bx, wo, &wi, u1, u2, pdf);
+  Spec f = lobe_sample_f<G>(bx, wo, &wi, u1, u2, pdf);
   if (*pdf == 0.f) {
     *sampledType = 0;
     return spec(0.f);
@@ -290,7 +302,7 @@ PB_NOINLINE Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, float u1, 
   *wiW = bsdf_local_to_world(b, wi);
   if (!(bx.type & PB_SPECULAR) && matchingComps > 1) {
     for (int i = 0; i < b.nLobes; ++i)
-      if (i != chosen && lobe_matches(b.lobes[i], flags)) *pdf += lobe_pdf(b.lobes[i], wo, wi);
+      if (i != chosen && lobe_matches(b.lobes[i], flags)) *pdf += lobe_pdf<G>(b.lobes[i], wo, wi);
   }
   if (matchingComps > 1) *pdf /= matchingComps;
   if (!(bx.type & PB_SPECULAR)) {
@@ -298,7 +310,7 @@ PB_NOINLINE Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, float u1, 
     if (dot(*wiW, b.ng) * dot(woW, b.ng) > 0) flags &= ~PB_TRANSMISSION;
     else flags &= ~PB_REFLECTION;
     for (int i = 0; i < b.nLobes; ++i)
-      if (lobe_matches(b.lobes[i], flags)) f = f + lobe_f(b.lobes[i], wo, wi);
+      if (lobe_matches(b.lobes[i], flags)) f = f + lobe_f<G>(b.lobes[i], wo, wi);
   }
   return f;
 }

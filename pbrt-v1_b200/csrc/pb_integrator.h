@@ -240,6 +240,7 @@ PB_HD Spec delta_light_sample(const PbrtB200Light &light, const V3 &p, V3 *wi, R
 
 // transport.cpp:123-194.  ls1..bcs are already chosen by the caller
 // (Sample arrays or RandomFloat, :131-146).
+template <bool G = true>
 PB_HD void estimate_direct(const SceneView &sv, int lightNum, const V3 &p, const V3 &n, const V3 &wo,
                            const Bsdf &bsdf, float ls1, float ls2, float bs1, float bs2, float bcs,
                            RngStream &rng, DirectRec *rec) {
@@ -263,7 +264,7 @@ PB_HD void estimate_direct(const SceneView &sv, int lightNum, const V3 &p, const
     Li = dot(ns, -wi) > 0 ? light_color(light) : spec(0.f);
   }
   if (lightPdf > 0.f && !is_black(Li)) {
-    Spec f = bsdf_f(bsdf, wo, wi);
+    Spec f = bsdf_f<G>(bsdf, wo, wi);
     if (!is_black(f)) {
       rec->hasShadow = true;
       // Li *= Transmittance (== 1 without volumes, integrators/emission.cpp:51)
@@ -271,7 +272,7 @@ PB_HD void estimate_direct(const SceneView &sv, int lightNum, const V3 &p, const
       if (isDelta)
         rec->termA = f * Li * absdot(wi, n) / lightPdf;
       else {
-        bsdfPdf = bsdf_pdf(bsdf, wo, wi);
+        bsdfPdf = bsdf_pdf<G>(bsdf, wo, wi);
         float weight = power_heuristic(1, lightPdf, 1, bsdfPdf);
         rec->termA = f * Li * absdot(wi, n) * weight / lightPdf;
       }
@@ -279,7 +280,7 @@ PB_HD void estimate_direct(const SceneView &sv, int lightNum, const V3 &p, const
   }
   if (!isDelta) {
     int sampled;
-    Spec f = bsdf_sample_f(bsdf, wo, &wi, bs1, bs2, bcs, &bsdfPdf, PB_ALL & ~PB_SPECULAR, &sampled);
+    Spec f = bsdf_sample_f<G>(bsdf, wo, &wi, bs1, bs2, bcs, &bsdfPdf, PB_ALL & ~PB_SPECULAR, &sampled);
     if (!is_black(f) && bsdfPdf > 0.f) {
       lightPdf = area_light_pdf(sv, light, p, wi);
       if (lightPdf > 0.f) {
@@ -352,6 +353,7 @@ PB_HD bool path_vertex_surface(const SceneView &sv, PathState &st, const Ray &ra
   return true;
 }
 // path.cpp:93-112: one UniformSampleOneLight record at the vertex
+template <bool G = true>
 PB_HD void path_vertex_direct(const SceneView &sv, const PatternSource &key0, PathState &st, const Ray &ray,
                               const Surface *sf, DirectRec *direct, bool *hasDirect) {
   *hasDirect = false;
@@ -377,7 +379,7 @@ PB_HD void path_vertex_direct(const SceneView &sv, const PatternSource &key0, Pa
       bcs = st.rng.next_float();
     }
     int lightNum = pb_imin(pb_floor2int(ln * nLights), nLights - 1);
-    estimate_direct(sv, lightNum, p, n, wo, bsdf, ls1, ls2, bs1, bs2, bcs, st.rng, direct);
+    estimate_direct<G>(sv, lightNum, p, n, wo, bsdf, ls1, ls2, bs1, bs2, bcs, st.rng, direct);
     *hasDirect = true;
     st.pendT = st.T;
   }
@@ -392,6 +394,7 @@ PB_HD bool path_vertex_begin(const SceneView &sv, const PatternSource &key0, Pat
 }
 // Second half (path.cpp:113-143): sample the BSDF for the next direction, update the
 // throughput, Russian roulette, depth limit.  Returns true when the path continues along *next.
+template <bool G = true>
 PB_HD bool path_vertex_continue(const SceneView &sv, const PatternSource &key0, PathState &st, const Ray &ray,
                                 const Surface &sf, Ray *next) {
   int pathLength = st.depth;
@@ -409,7 +412,7 @@ PB_HD bool path_vertex_continue(const SceneView &sv, const PatternSource &key0, 
   V3 wi;
   float pdf;
   int flags;
-  Spec f = bsdf_sample_f(bsdf, wo, &wi, os1, os2, ocs, &pdf, PB_ALL, &flags);
+  Spec f = bsdf_sample_f<G>(bsdf, wo, &wi, os1, os2, ocs, &pdf, PB_ALL, &flags);
   if (is_black(f) || pdf == 0.f) return false;
   st.specularBounce = (flags & PB_SPECULAR) != 0;
   st.T = st.T * (f * absdot(wi, n) / pdf);

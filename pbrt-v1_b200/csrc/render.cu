@@ -60,6 +60,15 @@ static int64_t g_debugCounts = 0;         // key 6: print each wave's queue size
 static int64_t g_reserved4 = 0;           // key 4: reserved (was the fused shade kernel's occupancy variant)
 
 #define PB_BLOCK 128
+#ifndef PB_DIRECT_MIN_BLOCKS
+#define PB_DIRECT_MIN_BLOCKS 4
+#endif
+#ifndef PB_CONT_MIN_BLOCKS
+#define PB_CONT_MIN_BLOCKS 6
+#endif
+#ifndef PB_SURF_MIN_BLOCKS
+#define PB_SURF_MIN_BLOCKS 6
+#endif
 #ifndef PB_TRAV_MIN_BLOCKS
 #define PB_TRAV_MIN_BLOCKS 10  // <= 48 registers: 40 resident warps per SM for the latency-bound kd walk (measured best of 6/8/10/12)
 #endif
@@ -420,7 +429,7 @@ __device__ __forceinline__ void surface_load(const SceneView &sv, const SurfaceR
   bsdf_set_lobes(sv.materials[sf->material], &b);
 }
 
-__global__ void __launch_bounds__(PB_BLOCK, 4)
+__global__ void __launch_bounds__(PB_BLOCK, PB_SURF_MIN_BLOCKS)
 k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const RayQueue qin,
                const SurfaceRecord rec, const uint32_t *nPtr, uint32_t *work) {
   uint32_t n = *nPtr;
@@ -458,8 +467,10 @@ k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const
   warp_stat_add(&wb.stats[ST_SHADED], shaded);
 }
 
-template <bool LD>   // LD: patterns come from the lowdiscrepancy tables; false folds that path away
-__global__ void __launch_bounds__(PB_BLOCK, 4)
+// LD: patterns come from the lowdiscrepancy tables; G: the scene has glossy (microfacet) materials.
+// false folds that code away, so the common matte/glass scenes do not carry it.
+template <bool LD, bool G>
+__global__ void __launch_bounds__(PB_BLOCK, PB_DIRECT_MIN_BLOCKS)
 k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveKeyInfo wd,
               const RayQueue qin, const SurfaceRecord rec, const uint32_t *nPtr, uint32_t *work,
               uint32_t *shadowCount, uint32_t *probeCount) {
@@ -489,7 +500,7 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
         st.rng.ctr = wb.ctr[slot];
         PatternSource key0 = {slot_key(wd, slot, 0), LD ? wb.ld : (const float *)nullptr, wb.nSlots, slot};
         bool hasDirect;
-        path_vertex_direct(sv, key0, st, ray, &sf, &direct, &hasDirect);
+        path_vertex_direct<G>(sv, key0, st, ray, &sf, &direct, &hasDirect);
         wb.ctr[slot] = st.rng.ctr;
         if (hasDirect) {
           pushShadow = direct.hasShadow;
@@ -519,8 +530,8 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
   }
 }
 
-template <bool LD>
-__global__ void __launch_bounds__(PB_BLOCK, 4)
+template <bool LD, bool G>
+__global__ void __launch_bounds__(PB_BLOCK, PB_CONT_MIN_BLOCKS)
 k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveKeyInfo wd,
                 const RayQueue qin, const RayQueue qout, const SurfaceRecord rec, const uint32_t *nPtr,
                 uint32_t *work, uint32_t *nextCount) {
@@ -550,7 +561,7 @@ k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, cons
         st.rng.key = slot_key(wd, slot, 1);
         st.rng.ctr = wb.ctr[slot];
         PatternSource key0 = {slot_key(wd, slot, 0), LD ? wb.ld : (const float *)nullptr, wb.nSlots, slot};
-        pushNext = path_vertex_continue(sv, key0, st, ray, sf, &next);
+        pushNext = path_vertex_continue<G>(sv, key0, st, ray, sf, &next);
         store3(wb.T, slot, st.T);
         wb.ctr[slot] = st.rng.ctr;
         wb.flags[slot] = (flags & (1u << 9)) | (uint32_t)st.depth | (st.specularBounce ? (1u << 8) : 0u);
@@ -870,6 +881,7 @@ struct PbrtB200Handle {
   std::vector<void *> allocs;   // scene arrays
   float *filterTable;
   bool hasSpecular;
+  bool hasGlossy;
   int nFrames;
   uint64_t sceneBytes;
   // wave arena
@@ -1094,12 +1106,11 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
         for (int k = 0; k < 15; ++k) rec.f[k] = wb.surf[k];
         rec.ids = wb.surfIds;
         TIMED(KC_SHADE, (k_path_surface<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], rec, nMain, nextWork())));
-        if (isLD)
-          TIMED(KC_SHADE_DIRECT, (k_path_direct<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], rec, nMain,
-                                                                                nextWork(), nShadow, nProbe)));
-        else
-          TIMED(KC_SHADE_DIRECT, (k_path_direct<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], rec, nMain,
-                                                                                 nextWork(), nShadow, nProbe)));
+#define PB_LAUNCH_DIRECT(LD_, G_)                                                                              \
+  TIMED(KC_SHADE_DIRECT, (k_path_direct<LD_, G_><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], rec, nMain, \
+                                                                            nextWork(), nShadow, nProbe)))
+        if (isLD) { if (h->hasGlossy) PB_LAUNCH_DIRECT(true, true); else PB_LAUNCH_DIRECT(true, false); }
+        else { if (h->hasGlossy) PB_LAUNCH_DIRECT(false, true); else PB_LAUNCH_DIRECT(false, false); }
         if (overlap) {
           // shadow + probe rays of this vertex run on the aux stream, concurrently with
           // k_path_continue and the next k_intersect (they share no data)
@@ -1108,12 +1119,11 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
           launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork(), h->auxStream);
           CU_TRY(cudaEventRecord(h->evAux, h->auxStream));
         }
-        if (isLD)
-          TIMED(KC_SHADE_CONT, (k_path_continue<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], wb.q[cur ^ 1], rec,
-                                                                                nMain, nextWork(), nNext)));
-        else
-          TIMED(KC_SHADE_CONT, (k_path_continue<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], wb.q[cur ^ 1], rec,
-                                                                                 nMain, nextWork(), nNext)));
+#define PB_LAUNCH_CONT(LD_, G_)                                                                                    \
+  TIMED(KC_SHADE_CONT, (k_path_continue<LD_, G_><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], wb.q[cur ^ 1], rec, \
+                                                                            nMain, nextWork(), nNext)))
+        if (isLD) { if (h->hasGlossy) PB_LAUNCH_CONT(true, true); else PB_LAUNCH_CONT(true, false); }
+        else { if (h->hasGlossy) PB_LAUNCH_CONT(false, true); else PB_LAUNCH_CONT(false, false); }
       }
       if (!overlap) launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork(), st);
       *launches += 6;
@@ -1225,6 +1235,8 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   std::string err = pb_setup_view(*scene, &h->sv);
   if (!err.empty()) { delete h; return fail(PBRT_B200_ERR_INVALID, err); }
   h->hasSpecular = pb_scene_has_specular(*scene);
+  h->hasGlossy = false;
+  for (uint32_t i = 0; i < scene->n_materials; ++i) h->hasGlossy |= scene->materials[i].kind == PBRT_B200_MAT_PLASTIC;
   bool isPath = scene->integrator.kind == PBRT_B200_INT_PATH;
   h->nFrames = isPath ? 0 : (h->hasSpecular ? std::max(0, scene->integrator.max_depth) + 1 : 1);
   if (!isPath && h->sv.directRecords > PB_MAX_WD_RECS) {
