@@ -34,7 +34,9 @@ PB_HD bool bbox_intersect_p(const float *bmin, const float *bmax, const Ray &ray
   return true;
 }
 
-#define PB_MAILBOX 4
+#ifndef PB_MAILBOX
+#define PB_MAILBOX 2   // measured 2 > 4 > 8 on B200: the ring costs more than the few re-tests it avoids
+#endif
 
 // One primitive test: GeometricPrimitive::Intersect (core/primitive.cpp:113-122)
 // shrinks ray.maxt on an accepted hit.

@@ -23,9 +23,14 @@
 #define PB_KD_WARP_CUH
 #include "pb_kd.h"
 
-#define PB_REFILL_THRESHOLD 8   // refill when at least this many lanes are idle
-#ifndef PB_CHEAP_STEPS
-#define PB_CHEAP_STEPS 4
+#ifndef PB_REFILL_THRESHOLD
+#define PB_REFILL_THRESHOLD 16  // refill when at least this many lanes are idle (measured: 1 << 4 << 8 < 16)
+#endif
+#ifndef PB_DESCEND_STEPS
+#define PB_DESCEND_STEPS 2
+#endif
+#ifndef PB_LEAF_STEPS
+#define PB_LEAF_STEPS 2
 #endif
 
 // Source: Ray load(uint32_t i).   Sink: void done(uint32_t i, const Ray &ray, const Hit &hit, bool anyHit).
@@ -86,41 +91,18 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
       if (exhausted) break;
       continue;
     }
-    // ---- cheap steps until this lane holds one primitive to test
+    // ---- bookkeeping, in two uniform phases so that lanes doing the same kind of step run together:
+    //      A. descend: up to PB_DESCEND_STEPS interior nodes (entering the leaf when one is reached)
+    //      B. leaf: up to PB_LEAF_STEPS list entries / pops, until the lane holds one primitive to test
+    // (bounded, so a lane deep in interior nodes never holds back 31 lanes that are ready to test;
+    // offline SIMT model: tools/simt_sim.py)
     bool pending = false;
     uint32_t prim = 0;
-    // at most PB_CHEAP_STEPS bookkeeping steps per trip: a lane deep in interior nodes must not hold
-    // back 31 lanes that already have a primitive to test (offline SIMT model: tools/simt_sim.py)
-    for (int step = 0; step < PB_CHEAP_STEPS && active && !pending; ++step) {
-      if (inLeaf) {
-        if (leafI < leafN) {
-          prim = (leafN == 1) ? leafW1 : __ldg(sv.primRefs + leafW1 + leafI);
-          ++leafI;
-          if (COUNT) ++cnt.refs;
-          bool seen = false;
-#pragma unroll
-          for (int k = 0; k < PB_MAILBOX; ++k) seen |= (mailbox[k] == prim);
-          if (!seen) {
-#pragma unroll
-            for (int k = 0; k < PB_MAILBOX; ++k)
-              if (k == mbPos) mailbox[k] = prim;
-            mbPos = (mbPos + 1) & (PB_MAILBOX - 1);
-            pending = true;
-          }
-        } else {
-          // leaf finished: next node from the todo list (kdtree.cpp:392-399)
-          inLeaf = false;
-          if (todoPos == 0) active = false;
-          else {
-            --todoPos;
-            node = todoNode[todoPos];
-            tmin = todoTmin[todoPos];
-            tmax = todoTmax[todoPos];
-            if (!ANY && ray.maxt < tmin) active = false;   // kdtree.cpp:330
-          }
-          if (!active) sink.done(idx, ray, hit, anyHit);
-        }
-      } else {
+#pragma unroll 1
+    for (int step = 0; step < PB_DESCEND_STEPS; ++step) {
+      bool descending = active && !inLeaf;
+      if (__ballot_sync(0xffffffffu, descending) == 0) break;
+      if (descending) {
         uint2 nd = __ldg((const uint2 *)(sv.nodes + node));
         if ((nd.x & 3u) == 3u) {
           if (COUNT) ++cnt.leaves;
@@ -147,6 +129,40 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
             node = firstChild;
             tmax = tplane;
           }
+        }
+      }
+    }
+#pragma unroll 1
+    for (int step = 0; step < PB_LEAF_STEPS; ++step) {
+      bool walking = active && inLeaf && !pending;
+      if (__ballot_sync(0xffffffffu, walking) == 0) break;
+      if (walking) {
+        if (leafI < leafN) {
+          prim = (leafN == 1) ? leafW1 : __ldg(sv.primRefs + leafW1 + leafI);
+          ++leafI;
+          if (COUNT) ++cnt.refs;
+          bool seen = false;
+#pragma unroll
+          for (int k = 0; k < PB_MAILBOX; ++k) seen |= (mailbox[k] == prim);
+          if (!seen) {
+#pragma unroll
+            for (int k = 0; k < PB_MAILBOX; ++k)
+              if (k == mbPos) mailbox[k] = prim;
+            mbPos = (mbPos + 1) & (PB_MAILBOX - 1);
+            pending = true;
+          }
+        } else {
+          // leaf finished: next node from the todo list (kdtree.cpp:392-399)
+          inLeaf = false;
+          if (todoPos == 0) active = false;
+          else {
+            --todoPos;
+            node = todoNode[todoPos];
+            tmin = todoTmin[todoPos];
+            tmax = todoTmax[todoPos];
+            if (!ANY && ray.maxt < tmin) active = false;   // kdtree.cpp:330
+          }
+          if (!active) sink.done(idx, ray, hit, anyHit);
         }
       }
     }
