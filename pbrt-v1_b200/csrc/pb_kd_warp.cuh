@@ -134,35 +134,21 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
     }
 #pragma unroll 1
     for (int step = 0; step < PB_LEAF_STEPS; ++step) {
-      bool walking = active && inLeaf && !pending;
+      bool walking = active && inLeaf && !pending && leafI < leafN;
       if (__ballot_sync(0xffffffffu, walking) == 0) break;
       if (walking) {
-        if (leafI < leafN) {
-          prim = (leafN == 1) ? leafW1 : __ldg(sv.primRefs + leafW1 + leafI);
-          ++leafI;
-          if (COUNT) ++cnt.refs;
-          bool seen = false;
+        prim = (leafN == 1) ? leafW1 : __ldg(sv.primRefs + leafW1 + leafI);
+        ++leafI;
+        if (COUNT) ++cnt.refs;
+        bool seen = false;
 #pragma unroll
-          for (int k = 0; k < PB_MAILBOX; ++k) seen |= (mailbox[k] == prim);
-          if (!seen) {
+        for (int k = 0; k < PB_MAILBOX; ++k) seen |= (mailbox[k] == prim);
+        if (!seen) {
 #pragma unroll
-            for (int k = 0; k < PB_MAILBOX; ++k)
-              if (k == mbPos) mailbox[k] = prim;
-            mbPos = (mbPos + 1) & (PB_MAILBOX - 1);
-            pending = true;
-          }
-        } else {
-          // leaf finished: next node from the todo list (kdtree.cpp:392-399)
-          inLeaf = false;
-          if (todoPos == 0) active = false;
-          else {
-            --todoPos;
-            node = todoNode[todoPos];
-            tmin = todoTmin[todoPos];
-            tmax = todoTmax[todoPos];
-            if (!ANY && ray.maxt < tmin) active = false;   // kdtree.cpp:330
-          }
-          if (!active) sink.done(idx, ray, hit, anyHit);
+          for (int k = 0; k < PB_MAILBOX; ++k)
+            if (k == mbPos) mailbox[k] = prim;
+          mbPos = (mbPos + 1) & (PB_MAILBOX - 1);
+          pending = true;
         }
       }
     }
@@ -176,6 +162,20 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
           sink.done(idx, ray, hit, true);
         }
       }
+    }
+    // ---- leaf finished (its last test is in): next node from the todo list (kdtree.cpp:392-399), so the
+    //      lane descends again in the next trip instead of spending a trip on the pop
+    if (active && inLeaf && leafI >= leafN) {
+      inLeaf = false;
+      if (todoPos == 0) active = false;
+      else {
+        --todoPos;
+        node = todoNode[todoPos];
+        tmin = todoTmin[todoPos];
+        tmax = todoTmax[todoPos];
+        if (!ANY && ray.maxt < tmin) active = false;   // kdtree.cpp:330
+      }
+      if (!active) sink.done(idx, ray, hit, anyHit);
     }
   }
 }
