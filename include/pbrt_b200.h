@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PBRT_B200_ABI_VERSION 1
+#define PBRT_B200_ABI_VERSION 2
 
 /* ---- error codes (Scene::Render has none: core/scene.cpp:32; the host maps
  *      non-zero codes to Severe(), core/util.cpp:90-97) ---- */
@@ -91,18 +91,23 @@ typedef struct PbrtB200Sphere {
   uint32_t pad;
 } PbrtB200Sphere;
 
-/* materials/{matte,glass,mirror}.cpp with ConstantTexture operands
- * (core/texture.h:113-123) */
+/* materials/{matte,glass,mirror,plastic,uber,shinymetal}.cpp with ConstantTexture
+ * operands (core/texture.h:113-123); spectra are already Clamp()ed >= 0 */
 enum { PBRT_B200_MAT_MATTE = 0, PBRT_B200_MAT_GLASS = 1, PBRT_B200_MAT_MIRROR = 2,
-       PBRT_B200_MAT_PLASTIC = 3 /* materials/plastic.cpp: Lambertian + Blinn microfacet */ };
-typedef struct PbrtB200Material {
+       PBRT_B200_MAT_PLASTIC = 3,    /* materials/plastic.cpp: Lambertian + Blinn microfacet */
+       PBRT_B200_MAT_UBER = 4,       /* materials/uber.cpp: opacity pass-through + Lambertian + microfacet + specular */
+       PBRT_B200_MAT_SHINYMETAL = 5  /* materials/shinymetal.cpp: conductor microfacet + conductor specular */ };
+typedef struct PbrtB200Material {    /* 80 bytes */
   int32_t kind;
-  float   kd[3];                   /* matte/plastic Kd (already Clamp()ed >= 0); glass/mirror Kr */
-  float   kt[3];                   /* glass Kt; plastic Ks                    */
+  float   kd[3];                   /* matte / plastic / uber                  */
+  float   ks[3];                   /* plastic / uber / shinymetal             */
+  float   kr[3];                   /* glass / mirror / uber / shinymetal      */
+  float   kt[3];                   /* glass                                   */
+  float   opacity[3];              /* uber                                    */
   float   sigma;                   /* matte: clamped to [0,90] degrees        */
   float   index;                   /* glass: index of refraction              */
-  float   roughness;               /* plastic                                 */
-  float   pad[2];
+  float   roughness;               /* plastic / uber / shinymetal             */
+  float   pad;
 } PbrtB200Material;
 
 /* lights/point.cpp:49-54, lights/area.cpp:28-57, core/shape.h:113-147 */

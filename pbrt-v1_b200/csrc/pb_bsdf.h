@@ -20,7 +20,13 @@ enum {
 };
 enum { PB_LOBE_LAMBERT = 0, PB_LOBE_ORENNAYAR = 1, PB_LOBE_SPEC_REFL_DIEL = 2,
        PB_LOBE_SPEC_REFL_NOOP = 3, PB_LOBE_SPEC_TRANS = 4,
-       PB_LOBE_MICROFACET_BLINN = 5 /* Microfacet(FresnelDielectric, Blinn): A = exponent */ };
+       PB_LOBE_MICROFACET_BLINN = 5,      /* Microfacet(FresnelDielectric, Blinn): A = exponent */
+       PB_LOBE_SPEC_REFL_COND = 6,        /* SpecularReflection(FresnelConductor(E, k = 0))      */
+       PB_LOBE_MICROFACET_BLINN_COND = 7  /* Microfacet(FresnelConductor(E, k = 0), Blinn)       */ };
+// Lobes a BSDF can hold: 2 covers matte / glass / mirror; the kernels compiled for scenes with
+// glossy materials (template flag G) carry 4 (uber: transmission + Lambertian + microfacet + specular).
+#define PB_MAX_LOBES 4
+template <bool G> struct LobeLimit { static const int n = G ? PB_MAX_LOBES : 2; };
 
 struct Lobe {
   int kind;
@@ -28,13 +34,14 @@ struct Lobe {
   Spec R;        // reflectance / transmittance
   float A, B;    // OrenNayar
   float etai, etat;
+  Spec E;        // conductor lobes: FresnelConductor::eta (k = 0)
 };
 struct Bsdf {
   V3 p;          // dgShading.p
   V3 nn, ng, sn, tn;
   float eta;
   int nLobes;
-  Lobe lobes[2];
+  Lobe lobes[PB_MAX_LOBES];
 };
 
 PB_HD bool lobe_matches(const Lobe &l, int flags) { return (l.type & flags) == l.type; }
@@ -98,6 +105,24 @@ PB_HD float fresnel_dielectric(float cosi, float eta_i, float eta_t) {
   return fr_diel(fabsf(cosi), cost, ei, et);
 }
 
+// core/reflection.cpp:40-51 (FrCond) for FresnelConductor::Evaluate (:74-76) with k = 0 as
+// shinymetal builds it; Spectrum arithmetic channel by channel in the reference's association
+PB_HD Spec fr_cond(float cosi, const Spec &eta) {
+  cosi = fabsf(cosi);
+  Spec k = spec(0.f);
+  Spec tmp = (eta * eta + k * k) * cosi * cosi;
+  Spec Rparl2 = (tmp - (2.f * eta * cosi) + spec(1.f)) / (tmp + (2.f * eta * cosi) + spec(1.f));
+  Spec tmp_f = eta * eta + k * k;
+  Spec Rperp2 = (tmp_f - (2.f * eta * cosi) + spec(cosi * cosi)) / (tmp_f + (2.f * eta * cosi) + spec(cosi * cosi));
+  return (Rparl2 + Rperp2) / 2.f;
+}
+// core/reflection.cpp:52-56
+PB_HD Spec fresnel_approx_eta(const Spec &Fr) {
+  Spec r = spec3(pb_clamp(Fr.c[0], 0.f, .999f), pb_clamp(Fr.c[1], 0.f, .999f), pb_clamp(Fr.c[2], 0.f, .999f));
+  Spec sq = spec3(sqrtf(r.c[0]), sqrtf(r.c[1]), sqrtf(r.c[2]));
+  return (spec(1.f) + sq) / (spec(1.f) - sq);
+}
+
 // reflection.h:31-52
 PB_HD float sin_theta(const V3 &w) { return sqrtf(pb_max(0.f, 1.f - w.z * w.z)); }
 PB_HD float sin_theta2(const V3 &w) { return pb_max(0.f, 1.f - w.z * w.z); }
@@ -145,7 +170,8 @@ PB_HD float microfacet_G(const V3 &wo, const V3 &wi, const V3 &wh) {
 }
 PB_HD float fresnel_dielectric(float cosi, float eta_i, float eta_t);
 // Microfacet::f, core/reflection.cpp:163-175
-PB_NOINLINE Spec microfacet_f(const Spec &R, float exponent, float etai, float etat, const V3 &wo, const V3 &wi) {
+PB_NOINLINE Spec microfacet_f(const Spec &R, float exponent, float etai, float etat, const V3 &wo, const V3 &wi,
+                              const Spec *condEta = nullptr) {
   float cosThetaO = fabsf(wo.z);
   float cosThetaI = fabsf(wi.z);
   if (cosThetaI == 0.f || cosThetaO == 0.f) return spec(0.f);
@@ -153,17 +179,17 @@ PB_NOINLINE Spec microfacet_f(const Spec &R, float exponent, float etai, float e
   if (wh.x == 0.f && wh.y == 0.f && wh.z == 0.f) return spec(0.f);
   wh = normalize(wh);
   float cosThetaH = dot(wi, wh);
-  Spec F = spec(fresnel_dielectric(cosThetaH, etai, etat));
+  Spec F = condEta ? fr_cond(cosThetaH, *condEta) : spec(fresnel_dielectric(cosThetaH, etai, etat));
   return R * blinn_D(exponent, wh) * microfacet_G(wo, wi, wh) * F / (4.f * cosThetaI * cosThetaO);
 }
 
 // Microfacet::Sample_f, reflection.cpp:235-239 (out of line: scenes without glossy materials only
 // pay a branch for it)
 PB_NOINLINE Spec microfacet_sample_f(const Spec &R, float exponent, float etai, float etat, const V3 &wo, V3 *wi,
-                                     float u1, float u2, float *pdf) {
+                                     float u1, float u2, float *pdf, const Spec *condEta = nullptr) {
   blinn_sample_f(exponent, wo, wi, u1, u2, pdf);
   if (!(wo.z * wi->z > 0.f)) return spec(0.f);
-  return microfacet_f(R, exponent, etai, etat, wo, *wi);
+  return microfacet_f(R, exponent, etai, etat, wo, *wi, condEta);
 }
 
 // BxDF::f for the non-specular lobes (reflection.cpp:128-156); specular lobes return 0.
@@ -172,6 +198,7 @@ template <bool G = true>
 PB_HD Spec lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
   if (l.kind == PB_LOBE_LAMBERT) return l.R;   // R already holds R * INV_PI (reflection.h:249)
   if (G && l.kind == PB_LOBE_MICROFACET_BLINN) return microfacet_f(l.R, l.A, l.etai, l.etat, wo, wi);
+  if (G && l.kind == PB_LOBE_MICROFACET_BLINN_COND) return microfacet_f(l.R, l.A, l.etai, l.etat, wo, wi, &l.E);
   if (l.kind == PB_LOBE_ORENNAYAR) {
     float sinthetai = sin_theta(wi);
     float sinthetao = sin_theta(wo);
@@ -198,7 +225,7 @@ PB_HD Spec lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
 template <bool G = true>
 PB_HD float lobe_pdf(const Lobe &l, const V3 &wo, const V3 &wi) {
   if (l.type & PB_SPECULAR) return 0.f;
-  if (G && l.kind == PB_LOBE_MICROFACET_BLINN)   // Microfacet::Pdf, reflection.cpp:240-243
+  if (G && (l.kind == PB_LOBE_MICROFACET_BLINN || l.kind == PB_LOBE_MICROFACET_BLINN_COND))   // Microfacet::Pdf, reflection.cpp:240-243
     return (wo.z * wi.z > 0.f) ? blinn_pdf(l.A, wo, wi) : 0.f;
   return (wo.z * wi.z > 0.f) ? fabsf(wi.z) * PB_INV_PI : 0.f;
 }
@@ -211,6 +238,11 @@ PB_HD Spec lobe_sample_f(const Lobe &l, const V3 &wo, V3 *wi, float u1, float u2
     float F = (l.kind == PB_LOBE_SPEC_REFL_NOOP) ? 1.f : fresnel_dielectric(wo.z, l.etai, l.etat);
     // fresnel->Evaluate(..) * R / fabsf(CosTheta(*wi))
     return (spec(F) * l.R) / fabsf(wi->z);
+  }
+  if (G && l.kind == PB_LOBE_SPEC_REFL_COND) {
+    *wi = v3(-wo.x, -wo.y, wo.z);
+    *pdf = 1.f;
+    return (fr_cond(wo.z, l.E) * l.R) / fabsf(wi->z);
   }
   if (l.kind == PB_LOBE_SPEC_TRANS) {
     bool entering = wo.z > 0.f;
@@ -229,6 +261,8 @@ PB_HD Spec lobe_sample_f(const Lobe &l, const V3 &wo, V3 *wi, float u1, float u2
     return ((et * et) / (ei * ei) * (spec(1.f) - spec(F)) * l.R) / fabsf(wi->z);
   }
   if (G && l.kind == PB_LOBE_MICROFACET_BLINN) return microfacet_sample_f(l.R, l.A, l.etai, l.etat, wo, wi, u1, u2, pdf);
+  if (G && l.kind == PB_LOBE_MICROFACET_BLINN_COND)
+    return microfacet_sample_f(l.R, l.A, l.etai, l.etat, wo, wi, u1, u2, pdf, &l.E);
   *wi = cosine_sample_hemisphere(u1, u2);
   if (wo.z < 0.f) wi->z *= -1.f;
   *pdf = lobe_pdf<G>(l, wo, *wi);
@@ -242,10 +276,12 @@ PB_HD V3 bsdf_local_to_world(const Bsdf &b, const V3 &v) {
   return v3(b.sn.x * v.x + b.tn.x * v.y + b.nn.x * v.z, b.sn.y * v.x + b.tn.y * v.y + b.nn.y * v.z,
             b.sn.z * v.x + b.tn.z * v.y + b.nn.z * v.z);
 }
+template <bool G = true>
 PB_HD int bsdf_num_components(const Bsdf &b, int flags) {
   int n = 0;
-  for (int i = 0; i < b.nLobes; ++i)
-    if (lobe_matches(b.lobes[i], flags)) ++n;
+#pragma unroll
+  for (int i = 0; i < LobeLimit<G>::n; ++i)
+    if (i < b.nLobes && lobe_matches(b.lobes[i], flags)) ++n;
   return n;
 }
 // BSDF::f, reflection.cpp:480-494
@@ -255,8 +291,9 @@ PB_HD Spec bsdf_f(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags = PB_AL
   if (dot(wiW, b.ng) * dot(woW, b.ng) > 0) flags &= ~PB_TRANSMISSION;
   else flags &= ~PB_REFLECTION;
   Spec f = spec(0.f);
-  for (int i = 0; i < b.nLobes; ++i)
-    if (lobe_matches(b.lobes[i], flags)) f = f + lobe_f<G>(b.lobes[i], wo, wi);
+#pragma unroll
+  for (int i = 0; i < LobeLimit<G>::n; ++i)
+    if (i < b.nLobes && lobe_matches(b.lobes[i], flags)) f = f + lobe_f<G>(b.lobes[i], wo, wi);
   return f;
 }
 // BSDF::Pdf, reflection.cpp:458-470
@@ -266,8 +303,9 @@ PB_HD float bsdf_pdf(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags = PB
   V3 wo = bsdf_world_to_local(b, woW), wi = bsdf_world_to_local(b, wiW);
   float pdf = 0.f;
   int matchingComps = 0;
-  for (int i = 0; i < b.nLobes; ++i)
-    if (lobe_matches(b.lobes[i], flags)) {
+#pragma unroll
+  for (int i = 0; i < LobeLimit<G>::n; ++i)
+    if (i < b.nLobes && lobe_matches(b.lobes[i], flags)) {
       ++matchingComps;
       pdf += lobe_pdf<G>(b.lobes[i], wo, wi);
     }
@@ -277,7 +315,7 @@ PB_HD float bsdf_pdf(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags = PB
 template <bool G = true>
 PB_NOINLINE Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, float u1, float u2, float u3,
                          float *pdf, int flags, int *sampledType) {
-  int matchingComps = bsdf_num_components(b, flags);
+  int matchingComps = bsdf_num_components<G>(b, flags);
   if (matchingComps == 0) {
     *pdf = 0.f;
     *sampledType = 0;
@@ -286,10 +324,11 @@ PB_NOINLINE Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, float u1, 
   int which = pb_imin(pb_floor2int(u3 * matchingComps), matchingComps - 1);
   int chosen = -1;
   int count = which;
-  for (int i = 0; i < b.nLobes; ++i)
-    if (lobe_matches(b.lobes[i], flags))
-      if (count-- == 0) { chosen = i; break; }
-  const Lobe &bx = b.lobes[chosen];
+  Lobe bx = b.lobes[0];
+#pragma unroll
+  for (int i = 0; i < LobeLimit<G>::n; ++i)
+    if (chosen < 0 && i < b.nLobes && lobe_matches(b.lobes[i], flags))
+      if (count-- == 0) { chosen = i; bx = b.lobes[i]; }
   V3 wi = v3(0, 0, 0);
   V3 wo = bsdf_world_to_local(b, woW);
   *pdf = 0.f;
@@ -301,27 +340,33 @@ PB_NOINLINE Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, float u1, 
   *sampledType = bx.type;
   *wiW = bsdf_local_to_world(b, wi);
   if (!(bx.type & PB_SPECULAR) && matchingComps > 1) {
-    for (int i = 0; i < b.nLobes; ++i)
-      if (i != chosen && lobe_matches(b.lobes[i], flags)) *pdf += lobe_pdf<G>(b.lobes[i], wo, wi);
+#pragma unroll
+    for (int i = 0; i < LobeLimit<G>::n; ++i)
+      if (i < b.nLobes && i != chosen && lobe_matches(b.lobes[i], flags)) *pdf += lobe_pdf<G>(b.lobes[i], wo, wi);
   }
   if (matchingComps > 1) *pdf /= matchingComps;
   if (!(bx.type & PB_SPECULAR)) {
     f = spec(0.f);
     if (dot(*wiW, b.ng) * dot(woW, b.ng) > 0) flags &= ~PB_TRANSMISSION;
     else flags &= ~PB_REFLECTION;
-    for (int i = 0; i < b.nLobes; ++i)
-      if (lobe_matches(b.lobes[i], flags)) f = f + lobe_f<G>(b.lobes[i], wo, wi);
+#pragma unroll
+    for (int i = 0; i < LobeLimit<G>::n; ++i)
+      if (i < b.nLobes && lobe_matches(b.lobes[i], flags)) f = f + lobe_f<G>(b.lobes[i], wo, wi);
   }
   return f;
 }
 
 struct Bsdf;
+template <bool G = true>
 PB_HD void bsdf_set_lobes(const PbrtB200Material &m, Bsdf *b);
 // Material::Bump with a constant-zero displacement (core/material.cpp:29-71):
 // dpdu/dpdv are unchanged (x + 0*nn + 0*dndu), the normal is re-derived from
 // them, re-oriented by the shape flags and then towards the geometric normal.
 // Followed by the BSDF constructor (reflection.cpp:471-479) and the lobes the
 // material adds.
+// LOBES = false builds only the shading frame (the path integrator's surface kernel stores the frame
+// and a later kernel rebuilds the lobes from the material record).
+template <bool LOBES = true>
 PB_HD void make_bsdf(const PbrtB200Material &m, const DiffGeom &dgGeom, const DiffGeom &dgs,
                      uint32_t shapeFlags, Bsdf *b) {
   // dgBump->dpdu = dgs.dpdu + (0 - 0) / du * nn + 0 * dndu: evaluated literally so that
@@ -339,14 +384,17 @@ PB_HD void make_bsdf(const PbrtB200Material &m, const DiffGeom &dgGeom, const Di
   b->nn = nn;
   b->sn = normalize(dpdu);
   b->tn = cross(b->nn, b->sn);
-  bsdf_set_lobes(m, b);
+  if (LOBES) bsdf_set_lobes<true>(m, b);
+  else { b->eta = 1.f; b->nLobes = 0; }
 }
 // The BxDFs a material adds (materials/{matte,glass,mirror}.cpp); separate from the frame so a
 // kernel can rebuild them from the material record instead of carrying them through memory.
+template <bool G>
 PB_HD void bsdf_set_lobes(const PbrtB200Material &m, Bsdf *b) {
   b->eta = 1.f;
   b->nLobes = 0;
-  Spec R = spec3(m.kd[0], m.kd[1], m.kd[2]);
+  const bool reflects = m.kind == PBRT_B200_MAT_GLASS || m.kind == PBRT_B200_MAT_MIRROR;
+  Spec R = reflects ? spec3(m.kr[0], m.kr[1], m.kr[2]) : spec3(m.kd[0], m.kd[1], m.kd[2]);
   if (m.kind == PBRT_B200_MAT_MATTE) {
     Lobe &l = b->lobes[b->nLobes++];
     l.type = PB_REFLECTION | PB_DIFFUSE;
@@ -376,17 +424,62 @@ PB_HD void bsdf_set_lobes(const PbrtB200Material &m, Bsdf *b) {
       l.kind = PB_LOBE_SPEC_TRANS; l.type = PB_TRANSMISSION | PB_SPECULAR;
       l.R = T; l.A = l.B = 0.f; l.etai = 1.f; l.etat = m.index;
     }
-  } else if (m.kind == PBRT_B200_MAT_PLASTIC) {
+  } else if (G && m.kind == PBRT_B200_MAT_PLASTIC) {
     // materials/plastic.cpp:57-67: Lambertian(kd) then Microfacet(ks, FresnelDielectric(1.5, 1), Blinn(1/rough))
     Lobe &d = b->lobes[b->nLobes++];
     d.kind = PB_LOBE_LAMBERT; d.type = PB_REFLECTION | PB_DIFFUSE;
     d.R = R * PB_INV_PI; d.A = d.B = 0.f; d.etai = d.etat = 1.f;
     Lobe &g = b->lobes[b->nLobes++];
     g.kind = PB_LOBE_MICROFACET_BLINN; g.type = PB_REFLECTION | PB_GLOSSY;
-    g.R = spec3(m.kt[0], m.kt[1], m.kt[2]);
+    g.R = spec3(m.ks[0], m.ks[1], m.ks[2]);
     float e = 1.f / m.roughness;
     if (e > 1000.f || e != e) e = 1000.f;   // Blinn::Blinn, reflection.h:313
     g.A = e; g.B = 0.f; g.etai = 1.5f; g.etat = 1.f;
+  } else if (G && m.kind == PBRT_B200_MAT_UBER) {
+    // materials/uber.cpp:60-83: SpecularTransmission(1 - op, 1, 1) when op != 1, Lambertian(op * Kd),
+    // Microfacet(op * Ks, FresnelDielectric(1.5, 1), Blinn(1/rough)), SpecularReflection(op * Kr, same Fresnel)
+    Spec op = spec3(m.opacity[0], m.opacity[1], m.opacity[2]);
+    if (!(op.c[0] == 1.f && op.c[1] == 1.f && op.c[2] == 1.f)) {
+      Lobe &l = b->lobes[b->nLobes++];
+      l.kind = PB_LOBE_SPEC_TRANS; l.type = PB_TRANSMISSION | PB_SPECULAR;
+      l.R = spec3(-op.c[0], -op.c[1], -op.c[2]) + spec(1.f);
+      l.A = l.B = 0.f; l.etai = 1.f; l.etat = 1.f;
+    }
+    Spec kd = op * spec3(m.kd[0], m.kd[1], m.kd[2]);
+    if (!is_black(kd)) {
+      Lobe &l = b->lobes[b->nLobes++];
+      l.kind = PB_LOBE_LAMBERT; l.type = PB_REFLECTION | PB_DIFFUSE;
+      l.R = kd * PB_INV_PI; l.A = l.B = 0.f; l.etai = l.etat = 1.f;
+    }
+    Spec ks = op * spec3(m.ks[0], m.ks[1], m.ks[2]);
+    if (!is_black(ks)) {
+      Lobe &l = b->lobes[b->nLobes++];
+      l.kind = PB_LOBE_MICROFACET_BLINN; l.type = PB_REFLECTION | PB_GLOSSY;
+      l.R = ks;
+      float e = 1.f / m.roughness;
+      if (e > 1000.f || e != e) e = 1000.f;
+      l.A = e; l.B = 0.f; l.etai = 1.5f; l.etat = 1.f;
+    }
+    Spec kr = op * spec3(m.kr[0], m.kr[1], m.kr[2]);
+    if (!is_black(kr)) {
+      Lobe &l = b->lobes[b->nLobes++];
+      l.kind = PB_LOBE_SPEC_REFL_DIEL; l.type = PB_REFLECTION | PB_SPECULAR;
+      l.R = kr; l.A = l.B = 0.f; l.etai = 1.5f; l.etat = 1.f;
+    }
+  } else if (G && m.kind == PBRT_B200_MAT_SHINYMETAL) {
+    // materials/shinymetal.cpp:54-63: Microfacet(1, FresnelConductor(FresnelApproxEta(Ks), 0), Blinn(1/rough)),
+    // SpecularReflection(1, FresnelConductor(FresnelApproxEta(Kr), 0))
+    Lobe &g = b->lobes[b->nLobes++];
+    g.kind = PB_LOBE_MICROFACET_BLINN_COND; g.type = PB_REFLECTION | PB_GLOSSY;
+    g.R = spec(1.f);
+    float e = 1.f / m.roughness;
+    if (e > 1000.f || e != e) e = 1000.f;
+    g.A = e; g.B = 0.f; g.etai = g.etat = 1.f;
+    g.E = fresnel_approx_eta(spec3(m.ks[0], m.ks[1], m.ks[2]));
+    Lobe &l = b->lobes[b->nLobes++];
+    l.kind = PB_LOBE_SPEC_REFL_COND; l.type = PB_REFLECTION | PB_SPECULAR;
+    l.R = spec(1.f); l.A = l.B = 0.f; l.etai = l.etat = 1.f;
+    l.E = fresnel_approx_eta(spec3(m.kr[0], m.kr[1], m.kr[2]));
   } else {   // mirror
     if (!is_black(R)) {
       Lobe &l = b->lobes[b->nLobes++];

@@ -42,6 +42,7 @@ PB_HD void surface_dg(const SceneView &sv, const Ray &ray, const Hit &hit, const
   }
 }
 // Intersection::GetBSDF (core/primitive.cpp:126-141)
+template <bool LOBES = true>
 PB_HD void surface_at_hit(const SceneView &sv, const Ray &ray, const Hit &hit, Surface *sf) {
   TriVerts tv = load_prim(sv, (uint32_t)hit.prim);
   DiffGeom dg, dgs;
@@ -50,7 +51,7 @@ PB_HD void surface_at_hit(const SceneView &sv, const Ray &ray, const Hit &hit, S
     tri_shading_dg(sv, (uint32_t)hit.prim, tv.flags, dg, &dgs);
   else
     dgs = dg;
-  make_bsdf(sv.materials[tv.material], dg, dgs, tv.flags, &sf->bsdf);
+  make_bsdf<LOBES>(sv.materials[tv.material], dg, dgs, tv.flags, &sf->bsdf);
   sf->light = tv.light;
   sf->material = tv.material;
 }
@@ -338,6 +339,7 @@ struct PathState {
 //
 // First half (path.cpp:68-112): miss handling, alpha, emitted light, BSDF, one
 // UniformSampleOneLight record.  Returns false when the ray missed (path ends).
+template <bool LOBES = true>
 PB_HD bool path_vertex_surface(const SceneView &sv, PathState &st, const Ray &ray, const Hit &hit,
                                Surface *sf) {
   int pathLength = st.depth;
@@ -348,7 +350,7 @@ PB_HD bool path_vertex_surface(const SceneView &sv, PathState &st, const Ray &ra
   }
   if (pathLength == 0) st.alpha = 1.f;
   else st.T = st.T * spec(1.f);            // pathThroughput *= scene->Transmittance(ray)
-  surface_at_hit(sv, ray, hit, sf);
+  surface_at_hit<LOBES>(sv, ray, hit, sf);
   if (pathLength == 0 || st.specularBounce) st.L = st.L + st.T * surface_le(sv, *sf, -ray.d);
   return true;
 }

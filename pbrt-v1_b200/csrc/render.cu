@@ -30,6 +30,7 @@
 #include <vector>
 #include <algorithm>
 
+#define PB_BLOCK 128   // threads per CTA of every persistent kernel
 #include "pb_integrator.h"
 #include "pb_kd_warp.cuh"
 #include "pb_camera.h"
@@ -59,7 +60,6 @@ static int64_t g_overlap = 0;             // key 5: run shadow/probe traversal o
 static int64_t g_debugCounts = 0;         // key 6: print each wave's queue sizes per iteration to stderr
 static int64_t g_reserved4 = 0;           // key 4: reserved (was the fused shade kernel's occupancy variant)
 
-#define PB_BLOCK 128
 #ifndef PB_DIRECT_MIN_BLOCKS
 #define PB_DIRECT_MIN_BLOCKS 4
 #endif
@@ -416,6 +416,7 @@ __device__ __forceinline__ void surface_store(const SurfaceRecord &r, uint32_t i
   r.f[12][i] = b.tn.x; r.f[13][i] = b.tn.y; r.f[14][i] = b.tn.z;
   r.ids[i] = sf.material | ((uint32_t)(sf.light + 1) << 16);
 }
+template <bool G>
 __device__ __forceinline__ void surface_load(const SceneView &sv, const SurfaceRecord &r, uint32_t i, Surface *sf) {
   Bsdf &b = sf->bsdf;
   b.p = v3(r.f[0][i], r.f[1][i], r.f[2][i]);
@@ -426,7 +427,7 @@ __device__ __forceinline__ void surface_load(const SceneView &sv, const SurfaceR
   uint32_t ids = r.ids[i];
   sf->material = ids & 0xffffu;
   sf->light = (int32_t)(ids >> 16) - 1;
-  bsdf_set_lobes(sv.materials[sf->material], &b);
+  bsdf_set_lobes<G>(sv.materials[sf->material], &b);
 }
 
 __global__ void __launch_bounds__(PB_BLOCK, PB_SURF_MIN_BLOCKS)
@@ -455,7 +456,7 @@ k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const
       st.depth = (int)(flags & 0xffu);
       st.specularBounce = (flags >> 8) & 1u;
       Surface sf;
-      if (path_vertex_surface(sv, st, ray, hit, &sf)) {
+      if (path_vertex_surface<false>(sv, st, ray, hit, &sf)) {
         ++shaded;
         surface_store(rec, i, sf);
       }
@@ -491,7 +492,7 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
         ray.d = v3(qin.dx[i], qin.dy[i], qin.dz[i]);   // only wo = -ray.d is needed
         ray.mint = 0.f; ray.maxt = 0.f;
         Surface sf;
-        surface_load(sv, rec, i, &sf);
+        surface_load<G>(sv, rec, i, &sf);
         uint32_t flags = wb.flags[slot];
         PathState st;
         st.T = load3(wb.T, slot);
@@ -552,7 +553,7 @@ k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, cons
         ray.d = v3(qin.dx[i], qin.dy[i], qin.dz[i]);
         ray.mint = 0.f; ray.maxt = 0.f;
         Surface sf;
-        surface_load(sv, rec, i, &sf);
+        surface_load<G>(sv, rec, i, &sf);
         uint32_t flags = wb.flags[slot];
         PathState st;
         st.T = load3(wb.T, slot);
@@ -1236,7 +1237,12 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   if (!err.empty()) { delete h; return fail(PBRT_B200_ERR_INVALID, err); }
   h->hasSpecular = pb_scene_has_specular(*scene);
   h->hasGlossy = false;
-  for (uint32_t i = 0; i < scene->n_materials; ++i) h->hasGlossy |= scene->materials[i].kind == PBRT_B200_MAT_PLASTIC;
+  for (uint32_t i = 0; i < scene->n_materials; ++i) {
+    int k = scene->materials[i].kind;
+    if (k < PBRT_B200_MAT_MATTE || k > PBRT_B200_MAT_SHINYMETAL) { delete h; return fail(PBRT_B200_ERR_INVALID, "unknown material kind"); }
+    // plastic / uber / shinymetal: microfacet lobes and up to 4 lobes per BSDF (kernels instantiated with G = true)
+    h->hasGlossy |= k >= PBRT_B200_MAT_PLASTIC;
+  }
   bool isPath = scene->integrator.kind == PBRT_B200_INT_PATH;
   h->nFrames = isPath ? 0 : (h->hasSpecular ? std::max(0, scene->integrator.max_depth) + 1 : 1);
   if (!isPath && h->sv.directRecords > PB_MAX_WD_RECS) {

@@ -31,7 +31,7 @@ class Glass : public Material {   // materials/glass.cpp:46-70
     memset(out, 0, sizeof(*out));
     out->kind = PBRT_B200_MAT_GLASS;
     Spectrum R = Kr.Clamp(), T = Kt.Clamp();
-    for (int i = 0; i < 3; ++i) { out->kd[i] = R.c[i]; out->kt[i] = T.c[i]; }
+    for (int i = 0; i < 3; ++i) { out->kr[i] = R.c[i]; out->kt[i] = T.c[i]; }
     out->index = index;
   }
   Spectrum Kr, Kt; float index;
@@ -43,7 +43,7 @@ class Mirror : public Material {  // materials/mirror.cpp:42-60
     memset(out, 0, sizeof(*out));
     out->kind = PBRT_B200_MAT_MIRROR;
     Spectrum R = Kr.Clamp();
-    for (int i = 0; i < 3; ++i) out->kd[i] = R.c[i];
+    for (int i = 0; i < 3; ++i) out->kr[i] = R.c[i];
   }
   Spectrum Kr;
 };
@@ -55,10 +55,36 @@ class Plastic : public Material {   // materials/plastic.cpp:28-77
     memset(out, 0, sizeof(*out));
     out->kind = PBRT_B200_MAT_PLASTIC;
     Spectrum d = Kd.Clamp(), s = Ks.Clamp();
-    for (int i = 0; i < 3; ++i) { out->kd[i] = d.c[i]; out->kt[i] = s.c[i]; }
+    for (int i = 0; i < 3; ++i) { out->kd[i] = d.c[i]; out->ks[i] = s.c[i]; }
     out->roughness = roughness;
   }
   Spectrum Kd, Ks; float roughness;
+};
+class UberMaterial : public Material {   // materials/uber.cpp:28-84
+ public:
+  UberMaterial(const Spectrum &kd, const Spectrum &ks, const Spectrum &kr, float rough, const Spectrum &op)
+      : Kd(kd), Ks(ks), Kr(kr), opacity(op), roughness(rough) {}
+  void Flatten(PbrtB200Material *out) const {
+    memset(out, 0, sizeof(*out));
+    out->kind = PBRT_B200_MAT_UBER;
+    // the products with the opacity (uber.cpp:65-83) are formed on the device, per GetBSDF call
+    Spectrum d = Kd.Clamp(), s = Ks.Clamp(), r = Kr.Clamp(), o = opacity.Clamp();
+    for (int i = 0; i < 3; ++i) { out->kd[i] = d.c[i]; out->ks[i] = s.c[i]; out->kr[i] = r.c[i]; out->opacity[i] = o.c[i]; }
+    out->roughness = roughness;
+  }
+  Spectrum Kd, Ks, Kr, opacity; float roughness;
+};
+class ShinyMetal : public Material {   // materials/shinymetal.cpp:28-65
+ public:
+  ShinyMetal(const Spectrum &ks, float rough, const Spectrum &kr) : Ks(ks), Kr(kr), roughness(rough) {}
+  void Flatten(PbrtB200Material *out) const {
+    memset(out, 0, sizeof(*out));
+    out->kind = PBRT_B200_MAT_SHINYMETAL;
+    Spectrum s = Ks.Clamp(), r = Kr.Clamp();
+    for (int i = 0; i < 3; ++i) { out->ks[i] = s.c[i]; out->kr[i] = r.c[i]; }
+    out->roughness = roughness;
+  }
+  Spectrum Ks, Kr; float roughness;
 };
 
 // ------------------------------------------------------------------- lights
@@ -272,6 +298,22 @@ static Material *CreatePlastic(const Transform &, const TextureParams &mp) {
   mp.GetFloatTexture("bumpmap", 0.f);
   return new Plastic(Kd, Ks, roughness);
 }
+static Material *CreateUber(const Transform &, const TextureParams &mp) {   // materials/uber.cpp:86-95
+  Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(1.f));
+  Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(1.f));
+  Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(0.f));
+  float roughness = mp.GetFloatTexture("roughness", .1f);
+  Spectrum opacity = mp.GetSpectrumTexture("opacity", Spectrum(1.f));
+  mp.GetFloatTexture("bumpmap", 0.f);
+  return new UberMaterial(Kd, Ks, Kr, roughness, opacity);
+}
+static Material *CreateShinyMetal(const Transform &, const TextureParams &mp) {   // materials/shinymetal.cpp:66-73
+  Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(1.f));
+  Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(1.f));
+  float roughness = mp.GetFloatTexture("roughness", .1f);
+  mp.GetFloatTexture("bumpmap", 0.f);
+  return new ShinyMetal(Ks, roughness, Kr);
+}
 static Material *CreateMirror(const Transform &, const TextureParams &mp) {
   Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(1.f));
   mp.GetFloatTexture("bumpmap", 0.f);
@@ -302,9 +344,11 @@ Reference<Material> MakeMaterial(const string &name, const Transform &mtl2world,
   else if (name == "glass") m = CreateGlass(mtl2world, mp);
   else if (name == "mirror") m = CreateMirror(mtl2world, mp);
   else if (name == "plastic") m = CreatePlastic(mtl2world, mp);
+  else if (name == "uber") m = CreateUber(mtl2world, mp);
+  else if (name == "shinymetal") m = CreateShinyMetal(mtl2world, mp);
   else
     Error("Material plugin \"%s\" is outside the B200 hot-path scope (supported: matte, glass, "
-          "mirror, plastic).", name.c_str());
+          "mirror, plastic, uber, shinymetal).", name.c_str());
   if (m) mp.ReportUnused();   // core/dynload.cpp:299
   return m;
 }

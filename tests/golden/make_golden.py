@@ -172,6 +172,45 @@ WorldEnd
 }
 
 
+def _uber_shiny(integrator, tag):
+    """uber (opacity pass-through, Lambertian, microfacet, specular) and shinymetal (conductor Fresnel)"""
+    return """LookAt 278 273 -800 278 273 0 0 1 0
+Camera "perspective" "float fov" [39.3]
+Film "image" "integer xresolution" [32] "integer yresolution" [32] "string filename" ["uber_shiny_%s_out.exr"]
+Sampler "stratified" "integer xsamples" [2] "integer ysamples" [2]
+PixelFilter "box"
+SurfaceIntegrator %s
+WorldBegin
+LightSource "point" "color I" [150000 150000 120000] "point from" [400 450 -100]
+AttributeBegin
+AreaLightSource "area" "color L" [17 12 4]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [213 548.7 227 343 548.7 227 343 548.7 332 213 548.7 332]
+AttributeEnd
+Material "uber" "color Kd" [.4 .5 .3] "color Ks" [.5 .5 .5] "color Kr" [.3 .3 .3] "float roughness" [.08]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [0 0 0 0 0 555 555 0 555 555 0 0]
+Material "shinymetal" "color Ks" [.9 .7 .3] "color Kr" [.8 .8 .9] "float roughness" [.15]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [0 0 555 0 555 555 555 555 555 555 0 555]
+Material "matte" "color Kd" [.65 .05 .05]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [0 0 0 0 555 0 0 555 555 0 0 555]
+AttributeBegin
+Translate 200 110 250
+Material "uber" "color Kd" [.2 .3 .8] "color Ks" [.2 .2 .2] "color opacity" [.35 .5 .65] "float roughness" [.2]
+Shape "sphere" "float radius" [110]
+AttributeEnd
+AttributeBegin
+Translate 400 90 150
+Material "shinymetal" "float roughness" [.01]
+Shape "sphere" "float radius" [90]
+AttributeEnd
+WorldEnd
+""" % (tag, integrator)
+
+
+INLINE["uber_shiny_path"] = _uber_shiny('"path" "integer maxdepth" [4]', "path")
+INLINE["uber_shiny_whitted"] = _uber_shiny('"whitted" "integer maxdepth" [3]', "whitted")
+INLINE["uber_shiny_direct"] = _uber_shiny('"directlighting" "integer maxdepth" [3]', "direct")
+
+
 def parse_count(text, label):
     m = re.search(re.escape(label) + r"\s+([0-9.]+)([kMG]?)", text)
     if not m:
@@ -184,6 +223,8 @@ def main():
     ffi = load_ffi()
     assert ffi.have_reference(), "oracle/_ref missing: run oracle/build_ref.sh (needs /root/reference)"
     cases = list(CASES) + [(n, None, None, True) for n in INLINE]
+    if len(sys.argv) > 1:   # only the named cases
+        cases = [c for c in cases if c[0] in sys.argv[1:]]
     for name, scene, args, keyed in cases:
         sp = os.path.join(HERE, name + ".pbrt")
         # relative output name so the committed scene file works from any checkout
