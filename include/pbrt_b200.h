@@ -53,7 +53,7 @@ typedef struct PbrtB200KdNode {
 /* ---- refined primitive: core/primitive.h:72-76 (GeometricPrimitive) with the
  *      shape data it points at pre-gathered (shapes/trianglemesh.cpp:213-222
  *      reads mesh->p[v[0..2]]) ---- */
-enum { PBRT_B200_PRIM_TRIANGLE = 0, PBRT_B200_PRIM_SPHERE = 1 };
+enum { PBRT_B200_PRIM_TRIANGLE = 0, PBRT_B200_PRIM_QUADRIC = 1 /* sphere, cylinder, disk, cone, paraboloid, hyperboloid */ };
 enum {
   PBRT_B200_PF_KIND_MASK = 0x3,
   PBRT_B200_PF_REVERSE   = 1u << 2,  /* Shape::reverseOrientation            */
@@ -63,7 +63,7 @@ enum {
   PBRT_B200_PF_HAS_S     = 1u << 6
 };
 typedef struct PbrtB200Prim {     /* 48 bytes, 16-byte aligned records */
-  float    p[9];                   /* triangle: world-space p1,p2,p3; sphere: unused */
+  float    p[9];                   /* triangle: world-space p1,p2,p3; quadric: unused */
   uint32_t flags;                  /* PBRT_B200_PF_* ; kind in the low 2 bits */
   uint32_t material;               /* index into materials[]                  */
   int32_t  light;                  /* area light index or -1                  */
@@ -72,7 +72,7 @@ typedef struct PbrtB200Prim {     /* 48 bytes, 16-byte aligned records */
 /* per-primitive side record, read only by shading (never by traversal) */
 typedef struct PbrtB200PrimAux {
   uint32_t v[3];                   /* triangle: global vertex ids into N/S/UV */
-  uint32_t owner;                  /* triangle: mesh id; sphere: sphere id    */
+  uint32_t owner;                  /* triangle: mesh id; quadric: quadric id  */
 } PbrtB200PrimAux;
 
 /* shapes/trianglemesh.cpp:141-169: object<->world of the mesh (only needed to
@@ -82,14 +82,25 @@ typedef struct PbrtB200Mesh {
   float w2o[16];                   /* its inverse                             */
 } PbrtB200Mesh;
 
-/* shapes/sphere.cpp:80-97 */
-typedef struct PbrtB200Sphere {
+/* The quadrics: shapes/sphere.cpp:80-97, cylinder.cpp:51-59, disk.cpp:49-57, cone.cpp:41-48,
+ * paraboloid.cpp:43-52, hyperboloid.cpp:46-71.  Intersected in object space (the reference's
+ * WorldToObject(ray)), so each carries both matrices. */
+enum { PBRT_B200_QUADRIC_SPHERE = 0, PBRT_B200_QUADRIC_CYLINDER = 1, PBRT_B200_QUADRIC_DISK = 2,
+       PBRT_B200_QUADRIC_CONE = 3, PBRT_B200_QUADRIC_PARABOLOID = 4, PBRT_B200_QUADRIC_HYPERBOLOID = 5 };
+typedef struct PbrtB200Quadric {
   float o2w[16];
   float w2o[16];
-  float radius, zmin, zmax, theta_min, theta_max, phi_max;
+  float radius;                    /* all but hyperboloid                     */
+  float zmin, zmax;                /* sphere, cylinder, paraboloid, hyperboloid */
+  float theta_min, theta_max;      /* sphere                                  */
+  float phi_max;                   /* radians                                 */
   uint32_t flags;                  /* PBRT_B200_PF_REVERSE | _SWAPS           */
-  uint32_t pad;
-} PbrtB200Sphere;
+  uint32_t kind;                   /* PBRT_B200_QUADRIC_*                     */
+  float height;                    /* disk, cone                              */
+  float inner_radius;              /* disk                                    */
+  float p1[3], p2[3];              /* hyperboloid (after the constructor's swap) */
+  float a, c;                      /* hyperboloid implicit-form coefficients  */
+} PbrtB200Quadric;
 
 /* materials/{matte,glass,mirror,plastic,uber,shinymetal}.cpp with ConstantTexture
  * operands (core/texture.h:113-123); spectra are already Clamp()ed >= 0 */
@@ -174,7 +185,7 @@ typedef struct PbrtB200Scene {
   const PbrtB200Prim    *prims;     uint32_t n_prims;
   const PbrtB200PrimAux *prim_aux;  /* n_prims                                */
   const PbrtB200Mesh    *meshes;    uint32_t n_meshes;
-  const PbrtB200Sphere  *spheres;   uint32_t n_spheres;
+  const PbrtB200Quadric *quadrics;  uint32_t n_quadrics;
   /* optional per-vertex shading data, object space, 3/3/2 floats per vertex  */
   const float *vertex_n; const float *vertex_s; const float *vertex_uv;
   uint32_t n_vertices;

@@ -37,7 +37,7 @@ bool build_view(const PbrtB200Scene &s, SceneView *sv) {
   if (!err.empty()) { gError = err; return false; }
   sv->nodes = s.nodes; sv->primRefs = s.prim_refs;
   sv->prims = (const PrimQuad *)s.prims; sv->aux = s.prim_aux;
-  sv->meshes = s.meshes; sv->spheres = s.spheres;
+  sv->meshes = s.meshes; sv->quadrics = s.quadrics;
   sv->vertexN = s.vertex_n; sv->vertexS = s.vertex_s; sv->vertexUV = s.vertex_uv;
   sv->materials = s.materials; sv->lights = s.lights;
   sv->lightShapes = s.light_shapes; sv->lightCdf = s.light_cdf;

@@ -33,12 +33,12 @@ PB_HD void surface_dg(const SceneView &sv, const Ray &ray, const Hit &hit, const
   if ((tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_TRIANGLE) {
     tri_dg(sv, (uint32_t)hit.prim, tv, ray, hit.t, hit.b1, hit.b2, dg);
   } else {
-    const PbrtB200Sphere &s = sv.spheres[sv.aux[hit.prim].owner];
+    const PbrtB200Quadric &s = sv.quadrics[sv.aux[hit.prim].owner];
     Ray r = ray;
     r.maxt = hit.t;   // re-deriving the accepted root: same branch decisions as when it was found
     float t, phi; V3 phit;
-    sphere_test(s, r, &t, &phit, &phi);
-    sphere_dg(s, phit, phi, dg);
+    quadric_test(s, r, &t, &phit, &phi);
+    quadric_dg(s, phit, phi, dg);
   }
 }
 // Intersection::GetBSDF (core/primitive.cpp:126-141)
@@ -102,14 +102,34 @@ PB_HD V3 uniform_sample_cone(float u1, float u2, float costhetamax, const V3 &x,
   return pb_cosf(phi) * sintheta * x + pb_sinf(phi) * sintheta * y + costheta * z;
 }
 // Sphere::Sample(u1,u2,ns), sphere.cpp:38-44
-PB_HD V3 sphere_sample_area(const PbrtB200Sphere &s, float u1, float u2, V3 *ns) {
+PB_HD V3 sphere_sample_area(const PbrtB200Quadric &s, float u1, float u2, V3 *ns) {
   V3 p = v3(0, 0, 0) + s.radius * uniform_sample_sphere(u1, u2);
   *ns = normalize(xf_normal(s.w2o, p));
   if (s.flags & PBRT_B200_PF_REVERSE) *ns = *ns * -1.f;
   return xf_point(s.o2w, p);
 }
+// Cylinder::Sample(u1,u2,ns), cylinder.cpp:37-44
+PB_NOINLINE V3 cylinder_sample_area(const PbrtB200Quadric &s, float u1, float u2, V3 *ns) {
+  float z = pb_lerp(u1, s.zmin, s.zmax);
+  float t = u2 * s.phi_max;
+  V3 p = v3(s.radius * pb_cosf(t), s.radius * pb_sinf(t), z);
+  *ns = normalize(xf_normal(s.w2o, v3(p.x, p.y, 0.f)));
+  if (s.flags & PBRT_B200_PF_REVERSE) *ns = *ns * -1.f;
+  return xf_point(s.o2w, p);
+}
+// Disk::Sample(u1,u2,ns), disk.cpp:37-46
+PB_NOINLINE V3 disk_sample_area(const PbrtB200Quadric &s, float u1, float u2, V3 *ns) {
+  V3 p;
+  concentric_sample_disk(u1, u2, &p.x, &p.y);
+  p.x *= s.radius;
+  p.y *= s.radius;
+  p.z = s.height;
+  *ns = normalize(xf_normal(s.w2o, v3(0.f, 0.f, 1.f)));
+  if (s.flags & PBRT_B200_PF_REVERSE) *ns = *ns * -1.f;
+  return xf_point(s.o2w, p);
+}
 // Sphere::Sample(p,u1,u2,ns), sphere.cpp:45-69
-PB_NOINLINE V3 sphere_sample(const PbrtB200Sphere &s, const V3 &p, float u1, float u2, V3 *ns) {
+PB_NOINLINE V3 sphere_sample(const PbrtB200Quadric &s, const V3 &p, float u1, float u2, V3 *ns) {
   V3 Pcenter = xf_point(s.o2w, v3(0, 0, 0));
   V3 wc = normalize(Pcenter - p);
   V3 wcX, wcY;
@@ -146,7 +166,7 @@ PB_NOINLINE float light_shapes_pdf(const SceneView &sv, const PbrtB200Light &l, 
       ok = tri_test(tv.p1, tv.p2, tv.p3, ray, &t, &b1, &b2);
     else {
       V3 phit; float phi;
-      ok = sphere_test(sv.spheres[sv.aux[prim].owner], ray, &t, &phit, &phi, false);
+      ok = quadric_test(sv.quadrics[sv.aux[prim].owner], ray, &t, &phit, &phi, false);
     }
     if (ok) { anyHit = true; hit.prim = (int32_t)prim; hit.t = t; hit.b1 = b1; hit.b2 = b2; htv = tv; }
   }
@@ -164,8 +184,9 @@ PB_HD float area_light_pdf(const SceneView &sv, const PbrtB200Light &l, const V3
   if (l.n_shapes == 1) {
     uint32_t prim = sv.lightShapes[l.first_shape];
     TriVerts tv = load_prim(sv, prim);
-    if ((tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_SPHERE) {
-      const PbrtB200Sphere &s = sv.spheres[sv.aux[prim].owner];
+    if ((tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_QUADRIC &&
+        sv.quadrics[sv.aux[prim].owner].kind == PBRT_B200_QUADRIC_SPHERE) {
+      const PbrtB200Quadric &s = sv.quadrics[sv.aux[prim].owner];
       V3 Pcenter = xf_point(s.o2w, v3(0, 0, 0));
       if (distance_sq(p, Pcenter) - s.radius * s.radius < 1e-4f) return light_shapes_pdf(sv, l, p, wi);
       float cosThetaMax = sqrtf(pb_max(0.f, 1.f - s.radius * s.radius / distance_sq(p, Pcenter)));
@@ -188,7 +209,9 @@ PB_NOINLINE V3 area_light_sample_point(const SceneView &sv, const PbrtB200Light 
   TriVerts tv = load_prim(sv, prim);
   if ((tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_TRIANGLE)
     return triangle_sample(tv, u1, u2, ns);
-  const PbrtB200Sphere &s = sv.spheres[sv.aux[prim].owner];
+  const PbrtB200Quadric &s = sv.quadrics[sv.aux[prim].owner];
+  if (s.kind == PBRT_B200_QUADRIC_CYLINDER) return cylinder_sample_area(s, u1, u2, ns);   // Shape::Sample(P,..) default
+  if (s.kind == PBRT_B200_QUADRIC_DISK) return disk_sample_area(s, u1, u2, ns);
   if (l.n_shapes > 1) return sphere_sample_area(s, u1, u2, ns);   // Shape::Sample(P,..) default
   return sphere_sample(s, p, u1, u2, ns);
 }

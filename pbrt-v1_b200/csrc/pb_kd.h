@@ -49,7 +49,7 @@ PB_HD bool kd_test_prim(const SceneView &sv, uint32_t prim, Ray &ray, Hit *hit) 
     ok = tri_test(tv.p1, tv.p2, tv.p3, ray, &t, &b1, &b2);
   } else {
     V3 phit; float phi;
-    ok = sphere_test(sv.spheres[sv.aux[prim].owner], ray, &t, &phit, &phi, false);
+    ok = quadric_test(sv.quadrics[sv.aux[prim].owner], ray, &t, &phit, &phi, false);
   }
   if (!ok) return false;
   if (!ANY) {

@@ -22,7 +22,7 @@ struct SceneView {
   const PrimQuad *prims;            // 3 per primitive
   const PbrtB200PrimAux *aux;
   const PbrtB200Mesh *meshes;
-  const PbrtB200Sphere *spheres;
+  const PbrtB200Quadric *quadrics;
   const float *vertexN, *vertexS, *vertexUV;
   const PbrtB200Material *materials;
   const PbrtB200Light *lights;

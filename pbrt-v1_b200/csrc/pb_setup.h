@@ -22,7 +22,7 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
   if (s.film.x_pixel_count < 1 || s.film.y_pixel_count < 1) return "empty film";
   for (uint32_t i = 0; i < s.n_prims; ++i) {
     uint32_t kind = s.prims[i].flags & PBRT_B200_PF_KIND_MASK;
-    if (kind != PBRT_B200_PRIM_TRIANGLE && kind != PBRT_B200_PRIM_SPHERE) return "unknown primitive kind";
+    if (kind != PBRT_B200_PRIM_TRIANGLE && kind != PBRT_B200_PRIM_QUADRIC) return "unknown primitive kind";
     if (s.prims[i].material >= s.n_materials) return "primitive material index out of range";
     if (s.prims[i].light >= (int32_t)s.n_lights) return "primitive light index out of range";
   }

@@ -75,7 +75,7 @@ PB_HD bool quadratic(float A, float B, float C, float *t0, float *t1) {
 // wantPhi = false lets a pure hit query skip atan2f for an unclipped sphere: phi only feeds the
 // clipping tests (always false when zmin/zmax/phimax do not cut the sphere: phi never exceeds the
 // float 2*pi it is compared with) and the parametric u computed later from a fresh call.
-PB_NOINLINE bool sphere_test(const PbrtB200Sphere &s, const Ray &r, float *tHit, V3 *phitO, float *phiO,
+PB_NOINLINE bool sphere_test(const PbrtB200Quadric &s, const Ray &r, float *tHit, V3 *phitO, float *phiO,
                              bool wantPhi = true) {
   Ray ray;
   ray.o = xf_point(s.w2o, r.o);
@@ -244,7 +244,7 @@ PB_NOINLINE void tri_shading_dg(const SceneView &sv, uint32_t prim, uint32_t fla
 }
 
 // sphere.cpp:144-205: DG of an accepted sphere hit (object-space phit, phi).
-PB_NOINLINE void sphere_dg(const PbrtB200Sphere &s, const V3 &phit, float phi, DiffGeom *dg) {
+PB_NOINLINE void sphere_dg(const PbrtB200Quadric &s, const V3 &phit, float phi, DiffGeom *dg) {
   float radius = s.radius, phiMax = s.phi_max, thetaMin = s.theta_min, thetaMax = s.theta_max;
   float u = phi / phiMax;
   float theta = pb_acosf(pb_clamp(phit.z / radius, -1.f, 1.f));
@@ -280,5 +280,165 @@ PB_NOINLINE void sphere_dg(const PbrtB200Sphere &s, const V3 &phit, float phi, D
   V3 dndv = (g * F - f * G) * invEGF2 * dpdu + (f * F - g * E) * invEGF2 * dpdv;
   dg_init(dg, xf_point(s.o2w, phit), xf_vector(s.o2w, dpdu), xf_vector(s.o2w, dpdv),
           xf_vector(s.o2w, dndu), xf_vector(s.o2w, dndv), u, v, s.flags);
+}
+
+// ---------------------------------------------------------------- the other quadrics
+// Hyperboloid inverse mapping (hyperboloid.cpp:105-112): v along the generating segment, phi from
+// the rotation that takes the segment point to the hit point.
+PB_HD float hyperboloid_phi(const PbrtB200Quadric &q, const V3 &phit, float *vOut) {
+  float v = (phit.z - q.p1[2]) / (q.p2[2] - q.p1[2]);
+  V3 pr = v3((1.f - v) * q.p1[0] + v * q.p2[0], (1.f - v) * q.p1[1] + v * q.p2[1],
+             (1.f - v) * q.p1[2] + v * q.p2[2]);
+  float phi = pb_atan2f(pr.x * phit.y - phit.x * pr.y, phit.x * pr.x + phit.y * pr.y);
+  if (phi < 0) phi += 2 * PB_PI;
+  *vOut = v;
+  return phi;
+}
+// Cylinder / Cone / Paraboloid / Hyperboloid ::Intersect up to the accepted hit
+// (cylinder.cpp:65-110, cone.cpp:54-105, paraboloid.cpp:58-105, hyperboloid.cpp:77-128; the
+// IntersectP bodies are the same text) and Disk::Intersect (disk.cpp:62-84).
+// Outputs the object-space hit point and phi for the DG stage.
+PB_NOINLINE bool quadric_other_test(const PbrtB200Quadric &q, const Ray &r, float *tHit, V3 *phitO, float *phiO) {
+  Ray ray;
+  ray.o = xf_point(q.w2o, r.o);
+  ray.d = xf_vector(q.w2o, r.d);
+  ray.mint = r.mint; ray.maxt = r.maxt;
+  const uint32_t kind = q.kind;
+  if (kind == PBRT_B200_QUADRIC_DISK) {
+    if ((double)fabsf(ray.d.z) < 1e-7) return false;
+    float thit = (q.height - ray.o.z) / ray.d.z;
+    if (thit < ray.mint || thit > ray.maxt) return false;
+    V3 phit = ray_at(ray, thit);
+    float dist2 = phit.x * phit.x + phit.y * phit.y;
+    if (dist2 > q.radius * q.radius || dist2 < q.inner_radius * q.inner_radius) return false;
+    float phi = pb_atan2f(phit.y, phit.x);
+    if (phi < 0) phi = (float)((double)phi + 2. * (double)PB_PI);   // `phi += 2. * M_PI`
+    if (phi > q.phi_max) return false;
+    *tHit = thit; *phitO = phit; *phiO = phi;
+    return true;
+  }
+  float A, B, C;
+  float zlo = q.zmin, zhi = q.zmax;
+  if (kind == PBRT_B200_QUADRIC_CYLINDER) {
+    A = ray.d.x * ray.d.x + ray.d.y * ray.d.y;
+    B = 2 * (ray.d.x * ray.o.x + ray.d.y * ray.o.y);
+    C = ray.o.x * ray.o.x + ray.o.y * ray.o.y - q.radius * q.radius;
+  } else if (kind == PBRT_B200_QUADRIC_CONE) {
+    float height = q.height;
+    float k = q.radius / height;
+    k = k * k;
+    A = ray.d.x * ray.d.x + ray.d.y * ray.d.y - k * ray.d.z * ray.d.z;
+    B = 2 * (ray.d.x * ray.o.x + ray.d.y * ray.o.y - k * ray.d.z * (ray.o.z - height));
+    C = ray.o.x * ray.o.x + ray.o.y * ray.o.y - k * (ray.o.z - height) * (ray.o.z - height);
+    zlo = 0.f; zhi = height;
+  } else if (kind == PBRT_B200_QUADRIC_PARABOLOID) {
+    float k = q.zmax / (q.radius * q.radius);
+    A = k * (ray.d.x * ray.d.x + ray.d.y * ray.d.y);
+    B = 2 * k * (ray.d.x * ray.o.x + ray.d.y * ray.o.y) - ray.d.z;
+    C = k * (ray.o.x * ray.o.x + ray.o.y * ray.o.y) - ray.o.z;
+  } else {   // hyperboloid
+    float a = q.a, c = q.c;
+    A = a * ray.d.x * ray.d.x + a * ray.d.y * ray.d.y - c * ray.d.z * ray.d.z;
+    B = 2.f * (a * ray.d.x * ray.o.x + a * ray.d.y * ray.o.y - c * ray.d.z * ray.o.z);
+    C = a * ray.o.x * ray.o.x + a * ray.o.y * ray.o.y - c * ray.o.z * ray.o.z - 1;
+  }
+  float t0, t1;
+  if (!quadratic(A, B, C, &t0, &t1)) return false;
+  if (t0 > ray.maxt || t1 < ray.mint) return false;
+  float thit = t0;
+  if (t0 < ray.mint) {
+    thit = t1;
+    if (thit > ray.maxt) return false;
+  }
+  const bool hyper = kind == PBRT_B200_QUADRIC_HYPERBOLOID;
+  V3 phit = ray_at(ray, thit);
+  float phi, v;
+  if (hyper) phi = hyperboloid_phi(q, phit, &v);
+  else {
+    phi = pb_atan2f(phit.y, phit.x);
+    if (phi < 0.) phi += 2.f * PB_PI;
+  }
+  if (phit.z < zlo || phit.z > zhi || phi > q.phi_max) {
+    if (thit == t1) return false;
+    thit = t1;
+    if (t1 > ray.maxt) return false;
+    phit = ray_at(ray, thit);
+    if (hyper) phi = hyperboloid_phi(q, phit, &v);
+    else {
+      phi = pb_atan2f(phit.y, phit.x);
+      if (phi < 0.) phi += 2.f * PB_PI;
+    }
+    if (phit.z < zlo || phit.z > zhi || phi > q.phi_max) return false;
+  }
+  *tHit = thit; *phitO = phit; *phiO = phi;
+  return true;
+}
+// Any quadric.  wantPhi as for sphere_test (the other kinds always need phi for their clipping test).
+PB_HD bool quadric_test(const PbrtB200Quadric &q, const Ray &r, float *tHit, V3 *phitO, float *phiO,
+                        bool wantPhi = true) {
+  if (q.kind == PBRT_B200_QUADRIC_SPHERE) return sphere_test(q, r, tHit, phitO, phiO, wantPhi);
+  return quadric_other_test(q, r, tHit, phitO, phiO);
+}
+
+// DG of an accepted hit on the other quadrics: cylinder.cpp:111-145, cone.cpp:106-147,
+// paraboloid.cpp:106-152, hyperboloid.cpp:129-170 (dndu/dndv through the fundamental forms) and
+// disk.cpp:85-103 (dndu = dndv = 0).
+PB_NOINLINE void quadric_other_dg(const PbrtB200Quadric &q, const V3 &phit, float phi, DiffGeom *dg) {
+  const uint32_t kind = q.kind;
+  const float phiMax = q.phi_max;
+  float u = phi / phiMax;
+  float v;
+  V3 dpdu = v3(-phiMax * phit.y, phiMax * phit.x, 0);
+  V3 dpdv, dndu, dndv;
+  if (kind == PBRT_B200_QUADRIC_DISK) {
+    float dist2 = phit.x * phit.x + phit.y * phit.y;
+    v = 1.f - ((sqrtf(dist2) - q.inner_radius) / (q.radius - q.inner_radius));
+    float su = phiMax * PB_INV_TWOPI;
+    dpdu = v3(dpdu.x * su, dpdu.y * su, dpdu.z * su);   // dpdu *= phiMax * INV_TWOPI
+    dpdv = v3(-phit.x / (1 - v), -phit.y / (1 - v), 0.f);
+    float sv = (q.radius - q.inner_radius) / q.radius;
+    dpdv = v3(dpdv.x * sv, dpdv.y * sv, dpdv.z * sv);
+    dndu = dndv = v3(0, 0, 0);
+  } else {
+    V3 d2Pduu = -phiMax * phiMax * v3(phit.x, phit.y, 0);
+    V3 d2Pduv = v3(0, 0, 0), d2Pdvv = v3(0, 0, 0);
+    if (kind == PBRT_B200_QUADRIC_CYLINDER) {
+      v = (phit.z - q.zmin) / (q.zmax - q.zmin);
+      dpdv = v3(0, 0, q.zmax - q.zmin);
+    } else if (kind == PBRT_B200_QUADRIC_CONE) {
+      v = phit.z / q.height;
+      dpdv = v3(-phit.x / (1.f - v), -phit.y / (1.f - v), q.height);
+      d2Pduv = phiMax / (1.f - v) * v3(-phit.y, -phit.x, 0.f);
+    } else if (kind == PBRT_B200_QUADRIC_PARABOLOID) {
+      float zmin = q.zmin, zmax = q.zmax;
+      v = (phit.z - zmin) / (zmax - zmin);
+      dpdv = (zmax - zmin) * v3(phit.x / (2.f * phit.z), phit.y / (2.f * phit.z), 1.f);
+      d2Pduv = (zmax - zmin) * phiMax * v3(-phit.y / (2.f * phit.z), phit.x / (2.f * phit.z), 0);
+      d2Pdvv = -(zmax - zmin) * (zmax - zmin) *
+               v3(phit.x / (4.f * phit.z * phit.z), phit.y / (4.f * phit.z * phit.z), 0.f);
+    } else {   // hyperboloid
+      hyperboloid_phi(q, phit, &v);   // same expression the accepted hit evaluated
+      float cosphi = pb_cosf(phi), sinphi = pb_sinf(phi);
+      float ex = q.p2[0] - q.p1[0], ey = q.p2[1] - q.p1[1], ez = q.p2[2] - q.p1[2];
+      dpdv = v3(ex * cosphi - ey * sinphi, ex * sinphi + ey * cosphi, ez);
+      d2Pduv = phiMax * v3(-dpdv.y, dpdv.x, 0.f);
+    }
+    float E = dot(dpdu, dpdu);
+    float F = dot(dpdu, dpdv);
+    float G = dot(dpdv, dpdv);
+    V3 N = normalize(cross(dpdu, dpdv));
+    float e = dot(N, d2Pduu);
+    float f = dot(N, d2Pduv);
+    float g = dot(N, d2Pdvv);
+    float invEGF2 = 1.f / (E * G - F * F);
+    dndu = (f * F - e * G) * invEGF2 * dpdu + (e * F - f * E) * invEGF2 * dpdv;
+    dndv = (g * F - f * G) * invEGF2 * dpdu + (f * F - g * E) * invEGF2 * dpdv;
+  }
+  dg_init(dg, xf_point(q.o2w, phit), xf_vector(q.o2w, dpdu), xf_vector(q.o2w, dpdv), xf_vector(q.o2w, dndu),
+          xf_vector(q.o2w, dndv), u, v, q.flags);
+}
+PB_HD void quadric_dg(const PbrtB200Quadric &q, const V3 &phit, float phi, DiffGeom *dg) {
+  if (q.kind == PBRT_B200_QUADRIC_SPHERE) sphere_dg(q, phit, phi, dg);
+  else quadric_other_dg(q, phit, phi, dg);
 }
 #endif

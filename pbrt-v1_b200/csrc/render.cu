@@ -1265,7 +1265,7 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   sv.prims = (const PrimQuad *)dprims;
   UP(upload(h, scene->prim_aux, scene->n_prims, &sv.aux));
   UP(upload(h, scene->meshes, scene->n_meshes, &sv.meshes));
-  UP(upload(h, scene->spheres, scene->n_spheres, &sv.spheres));
+  UP(upload(h, scene->quadrics, scene->n_quadrics, &sv.quadrics));
   UP(upload(h, scene->vertex_n, (size_t)scene->n_vertices * 3, &sv.vertexN));
   UP(upload(h, scene->vertex_s, (size_t)scene->n_vertices * 3, &sv.vertexS));
   UP(upload(h, scene->vertex_uv, (size_t)scene->n_vertices * 2, &sv.vertexUV));

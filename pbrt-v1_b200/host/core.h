@@ -177,7 +177,7 @@ struct FlatBuilder {
   vector<PbrtB200Prim> prims;
   vector<PbrtB200PrimAux> aux;
   vector<PbrtB200Mesh> meshes;
-  vector<PbrtB200Sphere> spheres;
+  vector<PbrtB200Quadric> quadrics;
   vector<float> vertexN, vertexS, vertexUV;
   uint32_t nVertices;
   bool anyN, anyS, anyUV;

@@ -30,6 +30,7 @@ class Point {
  public:
   Point(float _x = 0, float _y = 0, float _z = 0) : x(_x), y(_y), z(_z) {}
   Point operator+(const Vector &v) const { return Point(x + v.x, y + v.y, z + v.z); }
+  Point &operator+=(const Vector &v) { x += v.x; y += v.y; z += v.z; return *this; }   // geometry.h:110-113
   Vector operator-(const Point &p) const { return Vector(x - p.x, y - p.y, z - p.z); }
   Point operator-(const Vector &v) const { return Point(x - v.x, y - v.y, z - v.z); }
   Point operator*(float f) const { return Point(f * x, f * y, f * z); }

@@ -5,6 +5,12 @@
 #include "core.h"
 
 Shape *CreateSphereShape(const Transform &, bool, const ParamSet &);
+Shape *CreateCylinderShape(const Transform &, bool, const ParamSet &);
+Shape *CreateDiskShape(const Transform &, bool, const ParamSet &);
+Shape *CreateConeShape(const Transform &, bool, const ParamSet &);
+Shape *CreateParaboloidShape(const Transform &, bool, const ParamSet &);
+Shape *CreateHyperboloidShape(const Transform &, bool, const ParamSet &);
+bool ShapeCanSample(const Shape *s);
 Shape *CreateTriangleMeshShape(const Transform &, bool, const ParamSet &);
 Filter *CreateNamedFilter(const string &name, const ParamSet &ps);
 Film *CreateImageFilm(const ParamSet &params, Filter *filter);
@@ -330,11 +336,16 @@ Reference<Shape> MakeShape(const string &name, const Transform &object2world,
                            bool reverseOrientation, const ParamSet &paramSet) {
   Shape *s = NULL;
   if (name == "sphere") s = CreateSphereShape(object2world, reverseOrientation, paramSet);
+  else if (name == "cylinder") s = CreateCylinderShape(object2world, reverseOrientation, paramSet);
+  else if (name == "disk") s = CreateDiskShape(object2world, reverseOrientation, paramSet);
+  else if (name == "cone") s = CreateConeShape(object2world, reverseOrientation, paramSet);
+  else if (name == "paraboloid") s = CreateParaboloidShape(object2world, reverseOrientation, paramSet);
+  else if (name == "hyperboloid") s = CreateHyperboloidShape(object2world, reverseOrientation, paramSet);
   else if (name == "trianglemesh")
     s = CreateTriangleMeshShape(object2world, reverseOrientation, paramSet);
   else
     Error("Shape plugin \"%s\" is outside the B200 hot-path scope (supported: sphere, "
-          "trianglemesh); shape ignored.", name.c_str());
+          "cylinder, disk, cone, paraboloid, hyperboloid, trianglemesh); shape ignored.", name.c_str());
   return s;
 }
 Reference<Material> MakeMaterial(const string &name, const Transform &mtl2world,
@@ -393,6 +404,8 @@ AreaLight *MakeAreaLight(const string &name, const Transform &light2world,
   if (name == "area") {    // lights/area.cpp:106-111
     Spectrum L = paramSet.FindOneSpectrum("L", Spectrum(1.0));
     int nSamples = paramSet.FindOneInt("nsamples", 1);
+    if (!ShapeCanSample(shape.operator->()))
+      Severe("Unimplemented Shape::Sample method called");   // core/shape.h:85-88: what the reference dies with at the first light sample
     AreaLight *a = new AreaLight(light2world, L, nSamples, shape);
     paramSet.ReportUnused();
     return a;

@@ -102,8 +102,8 @@ void Scene::Flatten(FlatBuilder &fb, PbrtB200Scene *out) const {
   out->n_prims = (uint32_t)fb.prims.size();
   out->meshes = fb.meshes.empty() ? NULL : &fb.meshes[0];
   out->n_meshes = (uint32_t)fb.meshes.size();
-  out->spheres = fb.spheres.empty() ? NULL : &fb.spheres[0];
-  out->n_spheres = (uint32_t)fb.spheres.size();
+  out->quadrics = fb.quadrics.empty() ? NULL : &fb.quadrics[0];
+  out->n_quadrics = (uint32_t)fb.quadrics.size();
   out->vertex_n = fb.anyN ? &fb.vertexN[0] : NULL;
   out->vertex_s = fb.anyS ? &fb.vertexS[0] : NULL;
   out->vertex_uv = fb.anyUV ? &fb.vertexUV[0] : NULL;

@@ -1,4 +1,5 @@
-// shapes.cpp -- "sphere" and "trianglemesh" shape plugins, host half.
+// shapes.cpp -- the quadric ("sphere", "cylinder", "disk", "cone", "paraboloid", "hyperboloid") and
+// "trianglemesh" shape plugins, host half.
 // Parameter handling follows shapes/sphere.cpp:252-263 and
 // shapes/trianglemesh.cpp:350-405; the intersection code of those plugins is
 // what the CUDA kernels implement (pbrt-v1_b200/csrc).
@@ -8,11 +9,32 @@ namespace {
 
 void CopyMatrix(const Matrix4x4 &m, float out[16]) { memcpy(out, m.m, 16 * sizeof(float)); }
 
-// ------------------------------------------------------------------ sphere
-class Sphere : public Shape {
+// ------------------------------------------------------------------ quadrics
+// Common export of a quadric: one PbrtB200Quadric record + a primitive of kind QUADRIC.
+class Quadric : public Shape {
+ public:
+  Quadric(const Transform &o2w, bool ro) : Shape(o2w, ro) {}
+  virtual void Fill(PbrtB200Quadric *q) const = 0;
+  virtual bool CanSample() const { return false; }   // Shape::Sample is only implemented by some (core/shape.h:85-88)
+  void Flatten(FlatBuilder &fb, PbrtB200Prim *prim, PbrtB200PrimAux *aux) const {
+    PbrtB200Quadric q;
+    memset(&q, 0, sizeof(q));
+    CopyMatrix(ObjectToWorld.GetMatrix(), q.o2w);
+    CopyMatrix(WorldToObject.GetMatrix(), q.w2o);
+    q.flags = OrientationFlags();
+    Fill(&q);
+    memset(prim->p, 0, sizeof(prim->p));
+    prim->flags = PBRT_B200_PRIM_QUADRIC | OrientationFlags();
+    aux->v[0] = aux->v[1] = aux->v[2] = 0;
+    aux->owner = (uint32_t)fb.quadrics.size();
+    fb.quadrics.push_back(q);
+  }
+};
+
+class Sphere : public Quadric {
  public:
   // shapes/sphere.cpp:80-92
-  Sphere(const Transform &o2w, bool ro, float rad, float z0, float z1, float pm) : Shape(o2w, ro) {
+  Sphere(const Transform &o2w, bool ro, float rad, float z0, float z1, float pm) : Quadric(o2w, ro) {
     radius = rad;
     zmin = Clamp(min(z0, z1), -radius, radius);
     zmax = Clamp(max(z0, z1), -radius, radius);
@@ -24,22 +46,139 @@ class Sphere : public Shape {
     return BBox(Point(-radius, -radius, zmin), Point(radius, radius, zmax));
   }
   float Area() const { return phiMax * radius * (zmax - zmin); }
-  void Flatten(FlatBuilder &fb, PbrtB200Prim *prim, PbrtB200PrimAux *aux) const {
-    PbrtB200Sphere s;
-    memset(&s, 0, sizeof(s));
-    CopyMatrix(ObjectToWorld.GetMatrix(), s.o2w);
-    CopyMatrix(WorldToObject.GetMatrix(), s.w2o);
-    s.radius = radius; s.zmin = zmin; s.zmax = zmax;
-    s.theta_min = thetaMin; s.theta_max = thetaMax; s.phi_max = phiMax;
-    s.flags = OrientationFlags();
-    memset(prim->p, 0, sizeof(prim->p));
-    prim->flags = PBRT_B200_PRIM_SPHERE | OrientationFlags();
-    aux->v[0] = aux->v[1] = aux->v[2] = 0;
-    aux->owner = (uint32_t)fb.spheres.size();
-    fb.spheres.push_back(s);
+  bool CanSample() const { return true; }
+  void Fill(PbrtB200Quadric *q) const {
+    q->kind = PBRT_B200_QUADRIC_SPHERE;
+    q->radius = radius; q->zmin = zmin; q->zmax = zmax;
+    q->theta_min = thetaMin; q->theta_max = thetaMax; q->phi_max = phiMax;
   }
  private:
   float radius, phiMax, zmin, zmax, thetaMin, thetaMax;
+};
+
+class Cylinder : public Quadric {   // shapes/cylinder.cpp:51-64,218-220
+ public:
+  Cylinder(const Transform &o2w, bool ro, float rad, float z0, float z1, float pm) : Quadric(o2w, ro) {
+    radius = rad;
+    zmin = min(z0, z1);
+    zmax = max(z0, z1);
+    phiMax = Radians(Clamp(pm, 0.0f, 360.0f));
+  }
+  BBox ObjectBound() const { return BBox(Point(-radius, -radius, zmin), Point(radius, radius, zmax)); }
+  float Area() const { return (zmax - zmin) * phiMax * radius; }
+  bool CanSample() const { return true; }
+  void Fill(PbrtB200Quadric *q) const {
+    q->kind = PBRT_B200_QUADRIC_CYLINDER;
+    q->radius = radius; q->zmin = zmin; q->zmax = zmax; q->phi_max = phiMax;
+  }
+ private:
+  float radius, zmin, zmax, phiMax;
+};
+
+class Disk : public Quadric {   // shapes/disk.cpp:49-61,147-150
+ public:
+  Disk(const Transform &o2w, bool ro, float ht, float r, float ri, float tmax) : Quadric(o2w, ro) {
+    height = ht;
+    radius = r;
+    innerRadius = ri;
+    phiMax = Radians(Clamp(tmax, 0.0f, 360.0f));
+  }
+  BBox ObjectBound() const { return BBox(Point(-radius, -radius, height), Point(radius, radius, height)); }
+  float Area() const { return phiMax * 0.5f * (radius * radius - innerRadius * innerRadius); }
+  bool CanSample() const { return true; }
+  void Fill(PbrtB200Quadric *q) const {
+    q->kind = PBRT_B200_QUADRIC_DISK;
+    q->radius = radius; q->height = height; q->inner_radius = innerRadius; q->phi_max = phiMax;
+  }
+ private:
+  float height, radius, innerRadius, phiMax;
+};
+
+class Cone : public Quadric {   // shapes/cone.cpp:41-53,182-186
+ public:
+  Cone(const Transform &o2w, bool ro, float ht, float rad, float tm) : Quadric(o2w, ro) {
+    radius = rad;
+    height = ht;
+    phiMax = Radians(Clamp(tm, 0.0f, 360.0f));
+  }
+  BBox ObjectBound() const { return BBox(Point(-radius, -radius, 0), Point(radius, radius, height)); }
+  float Area() const {
+    return phiMax * height * height * sqrtf((height * height) + (radius * radius)) / (2.0f * radius);
+  }
+  void Fill(PbrtB200Quadric *q) const {
+    q->kind = PBRT_B200_QUADRIC_CONE;
+    q->radius = radius; q->height = height; q->phi_max = phiMax;
+  }
+ private:
+  float radius, height, phiMax;
+};
+
+class Paraboloid : public Quadric {   // shapes/paraboloid.cpp:43-57,187-190
+ public:
+  Paraboloid(const Transform &o2w, bool ro, float rad, float z0, float z1, float tm) : Quadric(o2w, ro) {
+    radius = rad;
+    zmin = min(z0, z1);
+    zmax = max(z0, z1);
+    phiMax = Radians(Clamp(tm, 0.0f, 360.0f));
+  }
+  BBox ObjectBound() const { return BBox(Point(-radius, -radius, zmin), Point(radius, radius, zmax)); }
+  float Area() const { return phiMax / 12.0f * (powf(1 + 4 * zmin, 1.5f) - powf(1 + 4 * zmax, 1.5f)); }
+  void Fill(PbrtB200Quadric *q) const {
+    q->kind = PBRT_B200_QUADRIC_PARABOLOID;
+    q->radius = radius; q->zmin = zmin; q->zmax = zmax; q->phi_max = phiMax;
+  }
+ private:
+  float radius, zmin, zmax, phiMax;
+};
+
+class Hyperboloid : public Quadric {   // shapes/hyperboloid.cpp:46-76,224-237
+ public:
+  Hyperboloid(const Transform &o2w, bool ro, const Point &point1, const Point &point2, float tm)
+      : Quadric(o2w, ro) {
+    p1 = point1;
+    p2 = point2;
+    phiMax = Radians(Clamp(tm, 0.0f, 360.0f));
+    float rad1 = sqrtf(p1.x * p1.x + p1.y * p1.y);
+    float rad2 = sqrtf(p2.x * p2.x + p2.y * p2.y);
+    rmax = max(rad1, rad2);
+    zmin = min(p1.z, p2.z);
+    zmax = max(p1.z, p2.z);
+    // implicit-form coefficients: walk along the generating line until they are finite
+    if (p2.z == 0.) swap(p1, p2);
+    Point pp = p1;
+    float xy1, xy2;
+    do {
+      pp += 2.f * (p2 - p1);
+      xy1 = pp.x * pp.x + pp.y * pp.y;
+      xy2 = p2.x * p2.x + p2.y * p2.y;
+      a = (1.f / xy1 - (pp.z * pp.z) / (xy1 * p2.z * p2.z)) / (1 - (xy2 * pp.z * pp.z) / (xy1 * p2.z * p2.z));
+      c = (a * xy2 - 1) / (p2.z * p2.z);
+    } while (isinf(a) || isnan(a));
+  }
+  BBox ObjectBound() const { return BBox(Point(-rmax, -rmax, zmin), Point(rmax, rmax, zmax)); }
+#define PB_SQR(x) ((x) * (x))
+#define PB_QUAD(x) ((PB_SQR(x)) * (PB_SQR(x)))
+  float Area() const {
+    return phiMax / 6.f *
+           (2.f * PB_QUAD(p1.x) - 2.f * p1.x * p1.x * p1.x * p2.x + 2.f * PB_QUAD(p2.x) +
+            2.f * (p1.y * p1.y + p1.y * p2.y + p2.y * p2.y) * (PB_SQR(p1.y - p2.y) + PB_SQR(p1.z - p2.z)) +
+            p2.x * p2.x * (5.f * p1.y * p1.y + 2.f * p1.y * p2.y - 4.f * p2.y * p2.y + 2.f * PB_SQR(p1.z - p2.z)) +
+            p1.x * p1.x * (-4.f * p1.y * p1.y + 2.f * p1.y * p2.y + 5.f * p2.y * p2.y + 2.f * PB_SQR(p1.z - p2.z)) -
+            2.f * p1.x * p2.x * (p2.x * p2.x - p1.y * p1.y + 5.f * p1.y * p2.y - p2.y * p2.y - p1.z * p1.z +
+                                 2.f * p1.z * p2.z - p2.z * p2.z));
+  }
+#undef PB_SQR
+#undef PB_QUAD
+  void Fill(PbrtB200Quadric *q) const {
+    q->kind = PBRT_B200_QUADRIC_HYPERBOLOID;
+    q->zmin = zmin; q->zmax = zmax; q->phi_max = phiMax; q->radius = rmax;
+    q->p1[0] = p1.x; q->p1[1] = p1.y; q->p1[2] = p1.z;
+    q->p2[0] = p2.x; q->p2[1] = p2.y; q->p2[2] = p2.z;
+    q->a = a; q->c = c;
+  }
+ private:
+  Point p1, p2;
+  float zmin, zmax, phiMax, rmax, a, c;
 };
 
 // ------------------------------------------------------------ trianglemesh
@@ -159,6 +298,50 @@ Shape *CreateSphereShape(const Transform &o2w, bool reverseOrientation, const Pa
   float zmax = params.FindOneFloat("zmax", radius);
   float phimax = params.FindOneFloat("phimax", 360.f);
   return new Sphere(o2w, reverseOrientation, radius, zmin, zmax, phimax);
+}
+
+// shapes/cylinder.cpp:221-228
+Shape *CreateCylinderShape(const Transform &o2w, bool reverseOrientation, const ParamSet &params) {
+  float radius = params.FindOneFloat("radius", 1);
+  float zmin = params.FindOneFloat("zmin", -1);
+  float zmax = params.FindOneFloat("zmax", 1);
+  float phimax = params.FindOneFloat("phimax", 360);
+  return new Cylinder(o2w, reverseOrientation, radius, zmin, zmax, phimax);
+}
+// shapes/disk.cpp:151-158
+Shape *CreateDiskShape(const Transform &o2w, bool reverseOrientation, const ParamSet &params) {
+  float height = params.FindOneFloat("height", 0.);
+  float radius = params.FindOneFloat("radius", 1);
+  float inner_radius = params.FindOneFloat("innerradius", 0);
+  float phimax = params.FindOneFloat("phimax", 360);
+  return new Disk(o2w, reverseOrientation, height, radius, inner_radius, phimax);
+}
+// shapes/cone.cpp:187-193
+Shape *CreateConeShape(const Transform &o2w, bool reverseOrientation, const ParamSet &params) {
+  float radius = params.FindOneFloat("radius", 1);
+  float height = params.FindOneFloat("height", 1);
+  float phimax = params.FindOneFloat("phimax", 360);
+  return new Cone(o2w, reverseOrientation, height, radius, phimax);
+}
+// shapes/paraboloid.cpp:191-198
+Shape *CreateParaboloidShape(const Transform &o2w, bool reverseOrientation, const ParamSet &params) {
+  float radius = params.FindOneFloat("radius", 1);
+  float zmin = params.FindOneFloat("zmin", 0);
+  float zmax = params.FindOneFloat("zmax", 1);
+  float phimax = params.FindOneFloat("phimax", 360);
+  return new Paraboloid(o2w, reverseOrientation, radius, zmin, zmax, phimax);
+}
+// shapes/hyperboloid.cpp:238-244
+Shape *CreateHyperboloidShape(const Transform &o2w, bool reverseOrientation, const ParamSet &params) {
+  Point p1 = params.FindOnePoint("p1", Point(0, 0, 0));
+  Point p2 = params.FindOnePoint("p2", Point(1, 1, 1));
+  float phimax = params.FindOneFloat("phimax", 360);
+  return new Hyperboloid(o2w, reverseOrientation, p1, p2, phimax);
+}
+// Shapes whose Shape::Sample the reference implements (an area light needs it, core/shape.h:85-88)
+bool ShapeCanSample(const Shape *s) {
+  const Quadric *q = dynamic_cast<const Quadric *>(s);
+  return q == NULL || q->CanSample();
 }
 
 // shapes/trianglemesh.cpp:350-405

@@ -211,6 +211,79 @@ INLINE["uber_shiny_whitted"] = _uber_shiny('"whitted" "integer maxdepth" [3]', "
 INLINE["uber_shiny_direct"] = _uber_shiny('"directlighting" "integer maxdepth" [3]', "direct")
 
 
+def _quadrics(integrator, tag, lights):
+    """every quadric (full and clipped by zmin/zmax/phimax, rotated, one reversed), disk and cylinder area lights"""
+    return """LookAt 0 3 -9 0 0.5 0 0 1 0
+Camera "perspective" "float fov" [40]
+Film "image" "integer xresolution" [40] "integer yresolution" [28] "string filename" ["quadrics_%s_out.exr"]
+Sampler "stratified" "integer xsamples" [2] "integer ysamples" [2]
+PixelFilter "box"
+SurfaceIntegrator %s
+WorldBegin
+%s
+Material "matte" "color Kd" [.6 .6 .6]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-8 -1 -8 8 -1 -8 8 -1 8 -8 -1 8]
+AttributeBegin
+Material "matte" "color Kd" [.7 .3 .2]
+Translate -3 0 0
+Rotate -90 1 0 0
+Shape "cylinder" "float radius" [.7] "float zmin" [-1] "float zmax" [1.2] "float phimax" [300]
+AttributeEnd
+AttributeBegin
+Material "plastic" "color Kd" [.2 .6 .3] "color Ks" [.4 .4 .4] "float roughness" [.1]
+Translate -1.2 -1 0.5
+Rotate -90 1 0 0
+Shape "cone" "float radius" [.8] "float height" [2]
+AttributeEnd
+AttributeBegin
+Material "glass" "float index" [1.4]
+Translate 0.6 1.3 0
+Rotate 90 1 0 0
+Rotate 25 0 0 1
+Shape "paraboloid" "float radius" [.9] "float zmin" [.2] "float zmax" [2] "float phimax" [330]
+AttributeEnd
+AttributeBegin
+Material "mirror" "color Kr" [.8 .8 .8]
+Translate 2.6 -1 1
+Rotate -90 1 0 0
+Shape "hyperboloid" "point p1" [.9 0 0] "point p2" [.4 .6 2.2]
+AttributeEnd
+AttributeBegin
+Material "matte" "color Kd" [.3 .3 .8] "float sigma" [20]
+Translate 0 -0.6 -2.5
+Rotate -70 1 0 0
+ReverseOrientation
+Shape "disk" "float radius" [1] "float innerradius" [.35] "float phimax" [270] "float height" [.1]
+AttributeEnd
+AttributeBegin
+Material "matte" "color Kd" [.5 .5 .1]
+Translate 3.5 0.2 -1.5
+Scale 1 1.4 1
+Shape "cone" "float radius" [.5] "float height" [1] "float phimax" [200]
+AttributeEnd
+WorldEnd
+""" % (tag, integrator, lights)
+
+
+_QL_AREA = """AttributeBegin
+AreaLightSource "area" "color L" [14 13 11] "integer nsamples" [2]
+Translate 0 5 0
+Rotate 90 1 0 0
+Shape "disk" "float radius" [1.2]
+AttributeEnd
+AttributeBegin
+AreaLightSource "area" "color L" [6 8 12]
+Translate -4 2.5 2
+Rotate 90 0 1 0
+Shape "cylinder" "float radius" [.25] "float zmin" [-1] "float zmax" [1]
+AttributeEnd"""
+_QL_POINT = """LightSource "point" "color I" [60 60 50] "point from" [2 6 -5]
+LightSource "point" "color I" [20 25 40] "point from" [-5 3 -2]"""
+INLINE["quadrics_path"] = _quadrics('"path" "integer maxdepth" [4]', "path", _QL_AREA)
+INLINE["quadrics_direct"] = _quadrics('"directlighting" "integer maxdepth" [3]', "direct", _QL_AREA)
+INLINE["quadrics_whitted"] = _quadrics('"whitted" "integer maxdepth" [4]', "whitted", _QL_POINT + "\n" + _QL_AREA)
+
+
 def parse_count(text, label):
     m = re.search(re.escape(label) + r"\s+([0-9.]+)([kMG]?)", text)
     if not m:
