@@ -151,6 +151,12 @@ PB_NOINLINE V3 sphere_sample(const PbrtB200Quadric &s, const V3 &p, float u1, fl
 // Shape::Pdf(p, wi) (core/shape.h:96-107) over the light's own shape list:
 // a ShapeSet tests every member without shrinking maxt, the last hit wins
 // (core/shape.h:150-156).
+// LK (light kinds the scene has; kernels for the common all-triangle-area-lights scenes compile the rest
+// out): bit 0 = delta lights (point / spot / distant), bit 1 = area lights over quadrics.
+#define PB_LK_DELTA 1
+#define PB_LK_QUADRIC 2
+#define PB_LK_ALL 3
+template <int LK = PB_LK_ALL>
 PB_NOINLINE float light_shapes_pdf(const SceneView &sv, const PbrtB200Light &l, const V3 &p, const V3 &wi) {
   Ray ray;
   ray.o = p; ray.d = wi; ray.mint = PB_RAY_EPSILON; ray.maxt = PB_INFINITY;
@@ -162,7 +168,7 @@ PB_NOINLINE float light_shapes_pdf(const SceneView &sv, const PbrtB200Light &l, 
     TriVerts tv = load_prim(sv, prim);
     float t, b1 = 0.f, b2 = 0.f;
     bool ok;
-    if ((tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_TRIANGLE)
+    if (!(LK & PB_LK_QUADRIC) || (tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_TRIANGLE)
       ok = tri_test(tv.p1, tv.p2, tv.p3, ray, &t, &b1, &b2);
     else {
       V3 phit; float phi;
@@ -172,7 +178,8 @@ PB_NOINLINE float light_shapes_pdf(const SceneView &sv, const PbrtB200Light &l, 
   }
   if (!anyHit) return 0.f;
   DiffGeom dg;
-  surface_dg(sv, ray, hit, htv, &dg);
+  if (LK & PB_LK_QUADRIC) surface_dg(sv, ray, hit, htv, &dg);
+  else tri_dg(sv, (uint32_t)hit.prim, htv, ray, hit.t, hit.b1, hit.b2, &dg);
   float ad = absdot(dg.nn, -wi);
   float pdf = distance_sq(p, ray_at(ray, hit.t)) / (ad * l.area);
   if (ad == 0.f) pdf = 0.f;
@@ -180,23 +187,25 @@ PB_NOINLINE float light_shapes_pdf(const SceneView &sv, const PbrtB200Light &l, 
 }
 // Light::Pdf(p, n, wi) for an area light (area.cpp:69-72): the single-sphere
 // light overrides Shape::Pdf (sphere.cpp:70-79).
+template <int LK = PB_LK_ALL>
 PB_HD float area_light_pdf(const SceneView &sv, const PbrtB200Light &l, const V3 &p, const V3 &wi) {
-  if (l.n_shapes == 1) {
+  if ((LK & PB_LK_QUADRIC) && l.n_shapes == 1) {
     uint32_t prim = sv.lightShapes[l.first_shape];
     TriVerts tv = load_prim(sv, prim);
     if ((tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_QUADRIC &&
         sv.quadrics[sv.aux[prim].owner].kind == PBRT_B200_QUADRIC_SPHERE) {
       const PbrtB200Quadric &s = sv.quadrics[sv.aux[prim].owner];
       V3 Pcenter = xf_point(s.o2w, v3(0, 0, 0));
-      if (distance_sq(p, Pcenter) - s.radius * s.radius < 1e-4f) return light_shapes_pdf(sv, l, p, wi);
+      if (distance_sq(p, Pcenter) - s.radius * s.radius < 1e-4f) return light_shapes_pdf<LK>(sv, l, p, wi);
       float cosThetaMax = sqrtf(pb_max(0.f, 1.f - s.radius * s.radius / distance_sq(p, Pcenter)));
       return 1.f / (2.f * PB_PI * (1.f - cosThetaMax));   // UniformConePdf, mc.cpp:142-144
     }
   }
-  return light_shapes_pdf(sv, l, p, wi);
+  return light_shapes_pdf<LK>(sv, l, p, wi);
 }
 // shape->Sample(p, u1, u2, &ns) for the light's shape (area.cpp:63).  A ShapeSet
 // draws one RandomFloat to pick the member by area (core/shape.h:115-121).
+template <int LK = PB_LK_ALL>
 PB_NOINLINE V3 area_light_sample_point(const SceneView &sv, const PbrtB200Light &l, const V3 &p, float u1,
                                  float u2, RngStream &rng, V3 *ns) {
   uint32_t sn = 0;
@@ -207,7 +216,7 @@ PB_NOINLINE V3 area_light_sample_point(const SceneView &sv, const PbrtB200Light 
   }
   uint32_t prim = sv.lightShapes[l.first_shape + sn];
   TriVerts tv = load_prim(sv, prim);
-  if ((tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_TRIANGLE)
+  if (!(LK & PB_LK_QUADRIC) || (tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_TRIANGLE)
     return triangle_sample(tv, u1, u2, ns);
   const PbrtB200Quadric &s = sv.quadrics[sv.aux[prim].owner];
   if (s.kind == PBRT_B200_QUADRIC_CYLINDER) return cylinder_sample_area(s, u1, u2, ns);   // Shape::Sample(P,..) default
@@ -264,7 +273,7 @@ PB_HD Spec delta_light_sample(const PbrtB200Light &light, const V3 &p, V3 *wi, R
 
 // transport.cpp:123-194.  ls1..bcs are already chosen by the caller
 // (Sample arrays or RandomFloat, :131-146).
-template <bool G = true>
+template <bool G = true, int LK = PB_LK_ALL>
 PB_HD void estimate_direct(const SceneView &sv, int lightNum, const V3 &p, const V3 &n, const V3 &wo,
                            const Bsdf &bsdf, float ls1, float ls2, float bs1, float bs2, float bcs,
                            RngStream &rng, DirectRec *rec) {
@@ -275,15 +284,15 @@ PB_HD void estimate_direct(const SceneView &sv, int lightNum, const V3 &p, const
   V3 wi;
   float lightPdf, bsdfPdf;
   Spec Li;
-  bool isDelta = light.kind != PBRT_B200_LIGHT_AREA;
+  bool isDelta = (LK & PB_LK_DELTA) && light.kind != PBRT_B200_LIGHT_AREA;
   if (isDelta) {
     lightPdf = 1.f;
     Li = delta_light_sample(light, p, &wi, &rec->shadow);
   } else {
     V3 ns;
-    V3 ps = area_light_sample_point(sv, light, p, ls1, ls2, rng, &ns);
+    V3 ps = area_light_sample_point<LK>(sv, light, p, ls1, ls2, rng, &ns);
     wi = normalize(ps - p);
-    lightPdf = area_light_pdf(sv, light, p, wi);
+    lightPdf = area_light_pdf<LK>(sv, light, p, wi);
     set_segment(&rec->shadow, p, ps);
     Li = dot(ns, -wi) > 0 ? light_color(light) : spec(0.f);
   }
@@ -306,7 +315,7 @@ PB_HD void estimate_direct(const SceneView &sv, int lightNum, const V3 &p, const
     int sampled;
     Spec f = bsdf_sample_f<G>(bsdf, wo, &wi, bs1, bs2, bcs, &bsdfPdf, PB_ALL & ~PB_SPECULAR, &sampled);
     if (!is_black(f) && bsdfPdf > 0.f) {
-      lightPdf = area_light_pdf(sv, light, p, wi);
+      lightPdf = area_light_pdf<LK>(sv, light, p, wi);
       if (lightPdf > 0.f) {
         float weight = power_heuristic(1, bsdfPdf, 1, lightPdf);
         rec->hasProbe = true;
@@ -378,7 +387,7 @@ PB_HD bool path_vertex_surface(const SceneView &sv, PathState &st, const Ray &ra
   return true;
 }
 // path.cpp:93-112: one UniformSampleOneLight record at the vertex
-template <bool G = true>
+template <bool G = true, int LK = PB_LK_ALL>
 PB_HD void path_vertex_direct(const SceneView &sv, const PatternSource &key0, PathState &st, const Ray &ray,
                               const Surface *sf, DirectRec *direct, bool *hasDirect) {
   *hasDirect = false;
@@ -404,7 +413,7 @@ PB_HD void path_vertex_direct(const SceneView &sv, const PatternSource &key0, Pa
       bcs = st.rng.next_float();
     }
     int lightNum = pb_imin(pb_floor2int(ln * nLights), nLights - 1);
-    estimate_direct<G>(sv, lightNum, p, n, wo, bsdf, ls1, ls2, bs1, bs2, bcs, st.rng, direct);
+    estimate_direct<G, LK>(sv, lightNum, p, n, wo, bsdf, ls1, ls2, bs1, bs2, bcs, st.rng, direct);
     *hasDirect = true;
     st.pendT = st.T;
   }

@@ -40,16 +40,22 @@ PB_HD bool bbox_intersect_p(const float *bmin, const float *bmax, const Ray &ray
 
 // One primitive test: GeometricPrimitive::Intersect (core/primitive.cpp:113-122)
 // shrinks ray.maxt on an accepted hit.
-template <bool ANY>
+// QK = the primitive kinds the scene holds, so that traversal kernels for simpler scenes compile the
+// rest out: 0 triangles only, 1 triangles + spheres, 2 every quadric.
+#define PB_QK_TRI 0
+#define PB_QK_SPHERE 1
+#define PB_QK_ALL 2
+template <bool ANY, int QK = PB_QK_ALL>
 PB_HD bool kd_test_prim(const SceneView &sv, uint32_t prim, Ray &ray, Hit *hit) {
   TriVerts tv = load_prim(sv, prim);
   float t, b1 = 0.f, b2 = 0.f;
   bool ok;
-  if ((tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_TRIANGLE) {
+  if (QK == PB_QK_TRI || (tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_TRIANGLE) {
     ok = tri_test(tv.p1, tv.p2, tv.p3, ray, &t, &b1, &b2);
   } else {
     V3 phit; float phi;
-    ok = quadric_test(sv.quadrics[sv.aux[prim].owner], ray, &t, &phit, &phi, false);
+    if (QK == PB_QK_SPHERE) ok = sphere_test(sv.quadrics[sv.aux[prim].owner], ray, &t, &phit, &phi, false);
+    else ok = quadric_test(sv.quadrics[sv.aux[prim].owner], ray, &t, &phit, &phi, false);
   }
   if (!ok) return false;
   if (!ANY) {

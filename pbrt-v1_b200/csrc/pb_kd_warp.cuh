@@ -34,7 +34,7 @@
 #endif
 
 // Source: Ray load(uint32_t i).   Sink: void done(uint32_t i, const Ray &ray, const Hit &hit, bool anyHit).
-template <bool ANY, bool COUNT, class Source, class Sink>
+template <bool ANY, bool COUNT, int QK, class Source, class Sink>
 __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n, uint32_t *work,
                                                  const Source &src, const Sink &sink, KdCounters &cnt) {
   const uint32_t lane = threadIdx.x & 31u;
@@ -155,7 +155,7 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
     // ---- the expensive part, all lanes with work together
     if (pending) {
       if (COUNT) ++cnt.tests;
-      if (kd_test_prim<ANY>(sv, prim, ray, &hit)) {
+      if (kd_test_prim<ANY, QK>(sv, prim, ray, &hit)) {
         anyHit = true;
         if (ANY) {
           active = false;

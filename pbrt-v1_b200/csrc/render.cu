@@ -61,7 +61,7 @@ static int64_t g_debugCounts = 0;         // key 6: print each wave's queue size
 static int64_t g_reserved4 = 0;           // key 4: reserved (was the fused shade kernel's occupancy variant)
 
 #ifndef PB_DIRECT_MIN_BLOCKS
-#define PB_DIRECT_MIN_BLOCKS 4
+#define PB_DIRECT_MIN_BLOCKS 5
 #endif
 #ifndef PB_CONT_MIN_BLOCKS
 #define PB_CONT_MIN_BLOCKS 6
@@ -283,7 +283,7 @@ __device__ __forceinline__ void flush_kd_counters(unsigned long long *stats, int
   warp_stat_add(&stats[ST_K(kind, TF_REFS)], cnt.refs);
   warp_stat_add(&stats[ST_K(kind, TF_TESTS)], cnt.tests);
 }
-template <bool COUNT>
+template <bool COUNT, int QK>
 __global__ void __launch_bounds__(PB_BLOCK, PB_TRAV_MIN_BLOCKS)
 k_intersect(const __grid_constant__ SceneView sv, const RayQueue q, const uint32_t *nPtr,
             uint32_t *work, unsigned long long *stats) {
@@ -291,7 +291,7 @@ k_intersect(const __grid_constant__ SceneView sv, const RayQueue q, const uint32
   KdCounters cnt = {0, 0, 0, 0};
   MainSource src = {q};
   MainSink sink = {q};
-  kd_warp_traverse<false, COUNT>(sv, n, work, src, sink, cnt);
+  kd_warp_traverse<false, COUNT, QK>(sv, n, work, src, sink, cnt);
   if (COUNT) flush_kd_counters(stats, TK_MAIN, cnt);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_K(TK_MAIN, TF_RAYS)], (unsigned long long)n);
 }
@@ -314,7 +314,7 @@ struct ShadowSink {
     if (!occluded) recFlags[q.rec[i]] |= 1;
   }
 };
-template <bool COUNT>
+template <bool COUNT, int QK>
 __global__ void __launch_bounds__(PB_BLOCK, PB_TRAV_MIN_BLOCKS)
 k_shadow(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t *nPtr, uint32_t *work,
          uint8_t *recFlags, unsigned long long *stats) {
@@ -322,7 +322,7 @@ k_shadow(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t 
   KdCounters cnt = {0, 0, 0, 0};
   ShadowSource src = {q};
   ShadowSink sink = {q, recFlags};
-  kd_warp_traverse<true, COUNT>(sv, n, work, src, sink, cnt);
+  kd_warp_traverse<true, COUNT, QK>(sv, n, work, src, sink, cnt);
   if (COUNT) flush_kd_counters(stats, TK_SHADOW, cnt);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_K(TK_SHADOW, TF_RAYS)], (unsigned long long)n);
 }
@@ -355,7 +355,7 @@ k_probe(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t *
   KdCounters cnt = {0, 0, 0, 0};
   ProbeSource src = {q};
   ProbeSink sink = {&sv, q, recFlags};
-  kd_warp_traverse<false, COUNT>(sv, n, work, src, sink, cnt);
+  kd_warp_traverse<false, COUNT, PB_QK_ALL>(sv, n, work, src, sink, cnt);
   if (COUNT) flush_kd_counters(stats, TK_PROBE, cnt);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_K(TK_PROBE, TF_RAYS)], (unsigned long long)n);
 }
@@ -470,7 +470,7 @@ k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const
 
 // LD: patterns come from the lowdiscrepancy tables; G: the scene has glossy (microfacet) materials.
 // false folds that code away, so the common matte/glass scenes do not carry it.
-template <bool LD, bool G>
+template <bool LD, bool G, int LK>
 __global__ void __launch_bounds__(PB_BLOCK, PB_DIRECT_MIN_BLOCKS)
 k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveKeyInfo wd,
               const RayQueue qin, const SurfaceRecord rec, const uint32_t *nPtr, uint32_t *work,
@@ -501,7 +501,7 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
         st.rng.ctr = wb.ctr[slot];
         PatternSource key0 = {slot_key(wd, slot, 0), LD ? wb.ld : (const float *)nullptr, wb.nSlots, slot};
         bool hasDirect;
-        path_vertex_direct<G>(sv, key0, st, ray, &sf, &direct, &hasDirect);
+        path_vertex_direct<G, LK>(sv, key0, st, ray, &sf, &direct, &hasDirect);
         wb.ctr[slot] = st.rng.ctr;
         if (hasDirect) {
           pushShadow = direct.hasShadow;
@@ -883,6 +883,8 @@ struct PbrtB200Handle {
   float *filterTable;
   bool hasSpecular;
   bool hasGlossy;
+  int primKinds;                // PB_QK_*: which primitive tests the traversal kernels need
+  bool triLightsOnly;           // every light is an area light over triangles (kernels drop the other light code)
   int nFrames;
   uint64_t sceneBytes;
   // wave arena
@@ -1048,8 +1050,12 @@ static int persistent_grid(const PbrtB200Handle *h) { return h->numSMs * (int)g_
 
 static void launch_traversals_a(PbrtB200Handle *h, bool count, int grid, const RayQueue &q, uint32_t *nMain,
                                 uint32_t *work) {
-  if (count) TIMED(KC_INTERSECT, (k_intersect<true><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, q, nMain, work, h->wb.stats)));
-  else TIMED(KC_INTERSECT, (k_intersect<false><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, q, nMain, work, h->wb.stats)));
+#define PB_LAUNCH_INTERSECT(C_, QK_) \
+  TIMED(KC_INTERSECT, (k_intersect<C_, QK_><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, q, nMain, work, h->wb.stats)))
+  if (count) PB_LAUNCH_INTERSECT(true, PB_QK_ALL);   // the counting pass is not timed
+  else if (h->primKinds == PB_QK_TRI) PB_LAUNCH_INTERSECT(false, PB_QK_TRI);
+  else if (h->primKinds == PB_QK_SPHERE) PB_LAUNCH_INTERSECT(false, PB_QK_SPHERE);
+  else PB_LAUNCH_INTERSECT(false, PB_QK_ALL);
 }
 static void launch_traversals_b(PbrtB200Handle *h, bool count, int grid, uint32_t *nShadow, uint32_t *nProbe,
                                 uint32_t *workS, uint32_t *workP, cudaStream_t strm) {
@@ -1058,10 +1064,14 @@ static void launch_traversals_b(PbrtB200Handle *h, bool count, int grid, uint32_
   // ramp-up of the full persistent grid for a few thousand rays
   int probeGrid = std::min(grid, h->numSMs * 2);
   if (count) {
-    TIMED_ON(KC_SHADOW, strm, (k_shadow<true><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.stats)));
+    TIMED_ON(KC_SHADOW, strm, (k_shadow<true, PB_QK_ALL><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.stats)));
     TIMED_ON(KC_PROBE, strm, (k_probe<true><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.stats)));
   } else {
-    TIMED_ON(KC_SHADOW, strm, (k_shadow<false><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.stats)));
+#define PB_LAUNCH_SHADOW(QK_) \
+  TIMED_ON(KC_SHADOW, strm, (k_shadow<false, QK_><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.stats)))
+    if (h->primKinds == PB_QK_TRI) PB_LAUNCH_SHADOW(PB_QK_TRI);
+    else if (h->primKinds == PB_QK_SPHERE) PB_LAUNCH_SHADOW(PB_QK_SPHERE);
+    else PB_LAUNCH_SHADOW(PB_QK_ALL);
     TIMED_ON(KC_PROBE, strm, (k_probe<false><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.stats)));
   }
 }
@@ -1107,9 +1117,10 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
         for (int k = 0; k < 15; ++k) rec.f[k] = wb.surf[k];
         rec.ids = wb.surfIds;
         TIMED(KC_SHADE, (k_path_surface<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], rec, nMain, nextWork())));
-#define PB_LAUNCH_DIRECT(LD_, G_)                                                                              \
-  TIMED(KC_SHADE_DIRECT, (k_path_direct<LD_, G_><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], rec, nMain, \
-                                                                            nextWork(), nShadow, nProbe)))
+#define PB_LAUNCH_DIRECT2(LD_, G_, LK_)                                                                             \
+  TIMED(KC_SHADE_DIRECT, (k_path_direct<LD_, G_, LK_><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], rec, nMain, \
+                                                                                 nextWork(), nShadow, nProbe)))
+#define PB_LAUNCH_DIRECT(LD_, G_) do { if (h->triLightsOnly) PB_LAUNCH_DIRECT2(LD_, G_, 0); else PB_LAUNCH_DIRECT2(LD_, G_, PB_LK_ALL); } while (0)
         if (isLD) { if (h->hasGlossy) PB_LAUNCH_DIRECT(true, true); else PB_LAUNCH_DIRECT(true, false); }
         else { if (h->hasGlossy) PB_LAUNCH_DIRECT(false, true); else PB_LAUNCH_DIRECT(false, false); }
         if (overlap) {
@@ -1242,6 +1253,19 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
     if (k < PBRT_B200_MAT_MATTE || k > PBRT_B200_MAT_SHINYMETAL) { delete h; return fail(PBRT_B200_ERR_INVALID, "unknown material kind"); }
     // plastic / uber / shinymetal: microfacet lobes and up to 4 lobes per BSDF (kernels instantiated with G = true)
     h->hasGlossy |= k >= PBRT_B200_MAT_PLASTIC;
+  }
+  h->primKinds = PB_QK_TRI;
+  for (uint32_t i = 0; i < scene->n_quadrics; ++i)
+    h->primKinds = std::max(h->primKinds, scene->quadrics[i].kind == PBRT_B200_QUADRIC_SPHERE ? PB_QK_SPHERE : PB_QK_ALL);
+  h->triLightsOnly = true;
+  for (uint32_t i = 0; i < scene->n_lights; ++i) {
+    const PbrtB200Light &l = scene->lights[i];
+    if (l.kind != PBRT_B200_LIGHT_AREA) { h->triLightsOnly = false; continue; }
+    for (uint32_t k = 0; k < l.n_shapes; ++k) {
+      uint32_t prim = scene->light_shapes[l.first_shape + k];
+      if (prim >= scene->n_prims || (scene->prims[prim].flags & PBRT_B200_PF_KIND_MASK) != PBRT_B200_PRIM_TRIANGLE)
+        h->triLightsOnly = false;
+    }
   }
   bool isPath = scene->integrator.kind == PBRT_B200_INT_PATH;
   h->nFrames = isPath ? 0 : (h->hasSpecular ? std::max(0, scene->integrator.max_depth) + 1 : 1);
