@@ -123,11 +123,12 @@ typedef struct PbrtB200Material {    /* 80 bytes */
 
 /* lights/point.cpp:49-54, lights/area.cpp:28-57, core/shape.h:113-147 */
 enum { PBRT_B200_LIGHT_POINT = 0, PBRT_B200_LIGHT_AREA = 1,
-       PBRT_B200_LIGHT_DISTANT = 2 /* lights/distant.cpp */, PBRT_B200_LIGHT_SPOT = 3 /* lights/spot.cpp */ };
+       PBRT_B200_LIGHT_DISTANT = 2 /* lights/distant.cpp */, PBRT_B200_LIGHT_SPOT = 3 /* lights/spot.cpp */,
+       PBRT_B200_LIGHT_INFINITE = 4 /* lights/infinite.cpp without a radiance map: constant Le */ };
 typedef struct PbrtB200Light {
   int32_t  kind;
   int32_t  n_samples;              /* Light::nSamples = max(1, ns)            */
-  float    color[3];               /* point/spot: I ; area: Lemit ; distant: L */
+  float    color[3];               /* point/spot: I ; area: Lemit ; distant: L ; infinite: Lbase */
   float    pos[3];                 /* point/spot: LightToWorld(0,0,0) ; distant: lightDir (normalised, world) */
   uint32_t first_shape;            /* area: range in light_shapes[]/light_cdf[] */
   uint32_t n_shapes;               /* 1 => the shape itself, >1 => ShapeSet   */

@@ -64,7 +64,9 @@ PB_HD Spec surface_le(const SceneView &sv, const Surface &sf, const V3 &w) {
 // `lightIsect.primitive->GetAreaLight() == light ? lightIsect.Le(-wi)` is non-black
 // (transport.cpp:180-182): evaluated by the MIS-probe traversal kernel.
 PB_HD bool hit_emits_from_light(const SceneView &sv, const Ray &ray, const Hit &hit, int light) {
-  if (hit.prim < 0) return false;   // Light::Le(ray) is black for point/area lights
+  // the probe left the scene: `Li = light->Le(ray)` (transport.cpp:184-185), black except for an infinite light
+  if (hit.prim < 0) return sv.nInfiniteLights != 0 && sv.lights[light].kind == PBRT_B200_LIGHT_INFINITE;
+  if (sv.nInfiniteLights != 0 && sv.lights[light].kind == PBRT_B200_LIGHT_INFINITE) return false;
   TriVerts tv = load_prim(sv, (uint32_t)hit.prim);
   if (tv.light != light) return false;
   DiffGeom dg;
@@ -155,7 +157,8 @@ PB_NOINLINE V3 sphere_sample(const PbrtB200Quadric &s, const V3 &p, float u1, fl
 // out): bit 0 = delta lights (point / spot / distant), bit 1 = area lights over quadrics.
 #define PB_LK_DELTA 1
 #define PB_LK_QUADRIC 2
-#define PB_LK_ALL 3
+#define PB_LK_INFINITE 4
+#define PB_LK_ALL 7
 template <int LK = PB_LK_ALL>
 PB_NOINLINE float light_shapes_pdf(const SceneView &sv, const PbrtB200Light &l, const V3 &p, const V3 &wi) {
   Ray ray;
@@ -271,6 +274,30 @@ PB_HD Spec delta_light_sample(const PbrtB200Light &light, const V3 &p, V3 *wi, R
   return light_color(light) / distance_sq(lightPos, p);
 }
 
+// InfiniteAreaLight::Sample_L(p, n, u1, u2, ..), lights/infinite.cpp:88-109: cosine-weighted direction
+// about n, the hemisphere chosen by one RandomFloat; visibility is an unbounded ray.
+PB_NOINLINE Spec infinite_light_sample_cosine(const PbrtB200Light &light, const V3 &p, const V3 &n, float u1, float u2,
+                                              RngStream &rng, V3 *wi, float *pdf, Ray *shadow) {
+  float x, y, z;
+  concentric_sample_disk(u1, u2, &x, &y);
+  z = sqrtf(pb_max(0.f, 1.f - x * x - y * y));
+  if (rng.next_float() < .5) z *= -1;
+  *pdf = fabsf(z) * PB_INV_TWOPI;
+  V3 v1, v2;
+  coordinate_system(normalize(n), &v1, &v2);
+  *wi = v3(v1.x * x + v2.x * y + n.x * z, v1.y * x + v2.y * y + n.y * z, v1.z * x + v2.z * y + n.z * z);
+  shadow->o = p; shadow->d = *wi; shadow->mint = PB_RAY_EPSILON; shadow->maxt = PB_INFINITY;   // SetRay
+  return light_color(light);
+}
+// Sum of lights[i]->Le(ray) over the scene's lights for a ray that left the scene (black for all but
+// infinite lights; adding a black spectrum changes nothing).
+PB_HD Spec escaped_le(const SceneView &sv) {
+  Spec L = spec(0.f);
+  for (uint32_t i = 0; i < sv.nLights; ++i)
+    if (sv.lights[i].kind == PBRT_B200_LIGHT_INFINITE) L = L + light_color(sv.lights[i]);
+  return L;
+}
+
 // transport.cpp:123-194.  ls1..bcs are already chosen by the caller
 // (Sample arrays or RandomFloat, :131-146).
 template <bool G = true, int LK = PB_LK_ALL>
@@ -284,10 +311,13 @@ PB_HD void estimate_direct(const SceneView &sv, int lightNum, const V3 &p, const
   V3 wi;
   float lightPdf, bsdfPdf;
   Spec Li;
-  bool isDelta = (LK & PB_LK_DELTA) && light.kind != PBRT_B200_LIGHT_AREA;
+  const bool isInfinite = (LK & PB_LK_INFINITE) && light.kind == PBRT_B200_LIGHT_INFINITE;
+  bool isDelta = (LK & PB_LK_DELTA) && light.kind != PBRT_B200_LIGHT_AREA && !isInfinite;
   if (isDelta) {
     lightPdf = 1.f;
     Li = delta_light_sample(light, p, &wi, &rec->shadow);
+  } else if (isInfinite) {
+    Li = infinite_light_sample_cosine(light, p, n, ls1, ls2, rng, &wi, &lightPdf, &rec->shadow);
   } else {
     V3 ns;
     V3 ps = area_light_sample_point<LK>(sv, light, p, ls1, ls2, rng, &ns);
@@ -315,7 +345,8 @@ PB_HD void estimate_direct(const SceneView &sv, int lightNum, const V3 &p, const
     int sampled;
     Spec f = bsdf_sample_f<G>(bsdf, wo, &wi, bs1, bs2, bcs, &bsdfPdf, PB_ALL & ~PB_SPECULAR, &sampled);
     if (!is_black(f) && bsdfPdf > 0.f) {
-      lightPdf = area_light_pdf<LK>(sv, light, p, wi);
+      lightPdf = isInfinite ? absdot(n, wi) * PB_INV_TWOPI   // InfiniteAreaLight::Pdf(p, n, wi), infinite.cpp:110-113
+                            : area_light_pdf<LK>(sv, light, p, wi);
       if (lightPdf > 0.f) {
         float weight = power_heuristic(1, bsdfPdf, 1, lightPdf);
         rec->hasProbe = true;
@@ -376,8 +407,18 @@ PB_HD bool path_vertex_surface(const SceneView &sv, PathState &st, const Ray &ra
                                Surface *sf) {
   int pathLength = st.depth;
   if (hit.prim < 0) {
-    // lights[i]->Le(ray) is black for point and area lights (core/light.cpp:41-43)
+    // path.cpp:69-82.  lights[i]->Le(ray) is black for point and area lights (core/light.cpp:41-43)
     if (pathLength == 0) st.alpha = 0.f;   // L != 0 ? 1 : 0 with L == 0
+    if (sv.nInfiniteLights != 0) {
+      if (pathLength == 0) {
+        for (uint32_t i = 0; i < sv.nLights; ++i)
+          if (sv.lights[i].kind == PBRT_B200_LIGHT_INFINITE) st.L = st.L + light_color(sv.lights[i]);
+        st.alpha = is_black(st.L) ? 0.f : 1.f;
+      } else if (st.specularBounce) {
+        for (uint32_t i = 0; i < sv.nLights; ++i)
+          if (sv.lights[i].kind == PBRT_B200_LIGHT_INFINITE) st.L = st.L + st.T * light_color(sv.lights[i]);
+      }
+    }
     return false;
   }
   if (pathLength == 0) st.alpha = 1.f;
@@ -508,7 +549,12 @@ PB_HD void wd_vertex(const SceneView &sv, const PatternSource &key0, const Ray &
   fr->p = v3(0, 0, 0); fr->wiR = fr->wiT = v3(0, 0, 0);
   fr->fR = fr->fT = spec(0.f); fr->aR = fr->aT = 0.f;
   if (hit.prim < 0) {
-    if (alpha) *alpha = 0.f;   // every in-scope light has black Le(ray)
+    // whitted.cpp:52-59, directlighting.cpp:185-192
+    if (alpha) *alpha = 0.f;
+    if (sv.nInfiniteLights != 0) {
+      fr->L = fr->L + escaped_le(sv);
+      if (alpha && !is_black(fr->L)) *alpha = 1.f;
+    }
     return;
   }
   if (alpha) *alpha = 1.f;
@@ -528,7 +574,16 @@ PB_HD void wd_vertex(const SceneView &sv, const PatternSource &key0, const Ray &
       rec->termA = rec->termB = spec(0.f);
       rec->probeLight = i;
       V3 wi; Spec Li;
-      if (light.kind != PBRT_B200_LIGHT_AREA) {
+      if (light.kind == PBRT_B200_LIGHT_INFINITE) {
+        // InfiniteAreaLight::Sample_L(P, &wi, &vis), infinite.cpp:156-163: uniform direction from two
+        // RandomFloat()s (g++ evaluates the arguments right to left: the first draw is u2), L / pdf
+        float u2 = rng.next_float();
+        float u1 = rng.next_float();
+        wi = uniform_sample_sphere(u1, u2);
+        float pdf = 1.f / (4.f * PB_PI);   // UniformSpherePdf, mc.cpp:82-84
+        rec->shadow.o = p; rec->shadow.d = wi; rec->shadow.mint = PB_RAY_EPSILON; rec->shadow.maxt = PB_INFINITY;
+        Li = light_color(light) / pdf;
+      } else if (light.kind != PBRT_B200_LIGHT_AREA) {
         Li = delta_light_sample(light, p, &wi, &rec->shadow);
       } else {
         // AreaLight::Sample_L(P, &wo, &vis), area.cpp:96-105.  g++ evaluates the two

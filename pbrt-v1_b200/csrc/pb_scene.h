@@ -29,6 +29,7 @@ struct SceneView {
   const uint32_t *lightShapes;
   const float *lightCdf;
   uint32_t nNodes, nPrims, nLights;
+  uint32_t nInfiniteLights;         // lights whose Le(ray) is not black (lights/infinite.cpp)
   float bmin[3], bmax[3];
   PbrtB200Camera camera;
   PbrtB200Sampler sampler;

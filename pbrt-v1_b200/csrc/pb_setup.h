@@ -27,6 +27,11 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
     if (s.prims[i].light >= (int32_t)s.n_lights) return "primitive light index out of range";
   }
   sv->nNodes = s.n_nodes; sv->nPrims = s.n_prims; sv->nLights = s.n_lights;
+  sv->nInfiniteLights = 0;
+  for (uint32_t i = 0; i < s.n_lights; ++i) {
+    if (s.lights[i].kind < PBRT_B200_LIGHT_POINT || s.lights[i].kind > PBRT_B200_LIGHT_INFINITE) return "unknown light kind";
+    if (s.lights[i].kind == PBRT_B200_LIGHT_INFINITE) ++sv->nInfiniteLights;
+  }
   for (int i = 0; i < 3; ++i) { sv->bmin[i] = s.bounds[i]; sv->bmax[i] = s.bounds[3 + i]; }
   sv->camera = s.camera; sv->sampler = s.sampler; sv->integrator = s.integrator;
   sv->xRes = s.film.x_resolution; sv->yRes = s.film.y_resolution;

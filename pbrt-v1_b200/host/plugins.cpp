@@ -108,6 +108,17 @@ class DistantLight : public Light {  // lights/distant.cpp:53-59
   }
   Vector lightDir; Spectrum L;
 };
+class InfiniteAreaLight : public Light {   // lights/infinite.cpp:70-86 (no radiance map: Le is the constant Lbase)
+ public:
+  InfiniteAreaLight(const Transform &light2world, const Spectrum &L, int ns) : Light(light2world, ns), Lbase(L) {}
+  void Flatten(FlatBuilder &, PbrtB200Light *out) const {
+    memset(out, 0, sizeof(*out));
+    out->kind = PBRT_B200_LIGHT_INFINITE;
+    out->n_samples = nSamples;
+    for (int i = 0; i < 3; ++i) out->color[i] = Lbase.c[i];
+  }
+  Spectrum Lbase;
+};
 class SpotLight : public Light {     // lights/spot.cpp:51-58
  public:
   SpotLight(const Transform &light2world, const Spectrum &intensity, float width, float fall)
@@ -369,6 +380,17 @@ Light *MakeLight(const string &name, const Transform &light2world, const ParamSe
     Point P = paramSet.FindOnePoint("from", Point(0, 0, 0));
     Transform l2w = Translate(Vector(P.x, P.y, P.z)) * light2world;
     Light *l = new PointLight(l2w, I);
+    paramSet.ReportUnused();
+    return l;
+  }
+  if (name == "infinite") {   // lights/infinite.cpp:164-170
+    Spectrum L = paramSet.FindOneSpectrum("L", Spectrum(1.0));
+    string texmap = paramSet.FindOneString("mapname", "");
+    int nSamples = paramSet.FindOneInt("nsamples", 1);
+    if (texmap != "")
+      Error("infinite light: radiance maps are outside the B200 hot-path scope (\"%s\" ignored: constant L, as "
+            "the reference does when the map cannot be read).", texmap.c_str());
+    Light *l = new InfiniteAreaLight(light2world, L, nSamples);
     paramSet.ReportUnused();
     return l;
   }

@@ -284,6 +284,49 @@ INLINE["quadrics_direct"] = _quadrics('"directlighting" "integer maxdepth" [3]',
 INLINE["quadrics_whitted"] = _quadrics('"whitted" "integer maxdepth" [4]', "whitted", _QL_POINT + "\n" + _QL_AREA)
 
 
+def _infinite(integrator, tag, extra=""):
+    """constant infinite light (plus an area light): escaping camera, specular and MIS-probe rays"""
+    return """LookAt 0 3 -9 0 0.5 0 0 1 0
+Camera "perspective" "float fov" [40]
+Film "image" "integer xresolution" [36] "integer yresolution" [28] "string filename" ["infinite_%s_out.exr"]
+Sampler "stratified" "integer xsamples" [2] "integer ysamples" [2]
+PixelFilter "box"
+SurfaceIntegrator %s
+WorldBegin
+LightSource "infinite" "color L" [.7 .8 1.1] "integer nsamples" [2]
+%s
+Material "matte" "color Kd" [.6 .6 .6]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-6 -1 -6 6 -1 -6 6 -1 6 -6 -1 6]
+AttributeBegin
+Material "glass" "float index" [1.5]
+Translate -1.6 0 0
+Shape "sphere" "float radius" [1]
+AttributeEnd
+AttributeBegin
+Material "mirror"
+Translate 1.6 0 0.5
+Shape "sphere" "float radius" [1]
+AttributeEnd
+AttributeBegin
+Material "plastic" "color Kd" [.7 .2 .2] "color Ks" [.3 .3 .3] "float roughness" [.05]
+Translate 0 -0.5 -2.2
+Shape "sphere" "float radius" [.5]
+AttributeEnd
+WorldEnd
+""" % (tag, integrator, extra)
+
+
+_INF_AREA = """AttributeBegin
+AreaLightSource "area" "color L" [10 9 7]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-1 4 -1 1 4 -1 1 4 1 -1 4 1]
+AttributeEnd"""
+INLINE["infinite_path"] = _infinite('"path" "integer maxdepth" [4]', "path", _INF_AREA)
+INLINE["infinite_only_path"] = _infinite('"path" "integer maxdepth" [3]', "only_path")
+INLINE["infinite_direct"] = _infinite('"directlighting" "integer maxdepth" [3]', "direct", _INF_AREA)
+INLINE["infinite_direct_one"] = _infinite('"directlighting" "integer maxdepth" [3] "string strategy" ["one"]', "direct_one", _INF_AREA)
+INLINE["infinite_whitted"] = _infinite('"whitted" "integer maxdepth" [3]', "whitted", _INF_AREA)
+
+
 def parse_count(text, label):
     m = re.search(re.escape(label) + r"\s+([0-9.]+)([kMG]?)", text)
     if not m:
