@@ -53,7 +53,8 @@ typedef struct PbrtB200KdNode {
 /* ---- refined primitive: core/primitive.h:72-76 (GeometricPrimitive) with the
  *      shape data it points at pre-gathered (shapes/trianglemesh.cpp:213-222
  *      reads mesh->p[v[0..2]]) ---- */
-enum { PBRT_B200_PRIM_TRIANGLE = 0, PBRT_B200_PRIM_QUADRIC = 1 /* sphere, cylinder, disk, cone, paraboloid, hyperboloid */ };
+enum { PBRT_B200_PRIM_TRIANGLE = 0, PBRT_B200_PRIM_QUADRIC = 1 /* sphere, cylinder, disk, cone, paraboloid, hyperboloid */,
+       PBRT_B200_PRIM_INSTANCE = 2 /* InstancePrimitive, core/primitive.cpp:66-85 */ };
 enum {
   PBRT_B200_PF_KIND_MASK = 0x3,
   PBRT_B200_PF_REVERSE   = 1u << 2,  /* Shape::reverseOrientation            */
@@ -72,7 +73,7 @@ typedef struct PbrtB200Prim {     /* 48 bytes, 16-byte aligned records */
 /* per-primitive side record, read only by shading (never by traversal) */
 typedef struct PbrtB200PrimAux {
   uint32_t v[3];                   /* triangle: global vertex ids into N/S/UV */
-  uint32_t owner;                  /* triangle: mesh id; quadric: quadric id  */
+  uint32_t owner;                  /* triangle: mesh id; quadric: quadric id; instance: instance id */
 } PbrtB200PrimAux;
 
 /* shapes/trianglemesh.cpp:141-169: object<->world of the mesh (only needed to
@@ -101,6 +102,21 @@ typedef struct PbrtB200Quadric {
   float p1[3], p2[3];              /* hyperboloid (after the constructor's swap) */
   float a, c;                      /* hyperboloid implicit-form coefficients  */
 } PbrtB200Quadric;
+
+/* InstancePrimitive (core/primitive.h:93-113, primitive.cpp:66-85; created by pbrtObjectInstance,
+ * core/api.cpp:428-457): a ray is moved into instance space by WorldToInstance and intersected
+ * with the instanced primitive -- the object's own kd-tree (KdTreeAccel over the ObjectBegin/End
+ * block's primitives) or, when the block holds one intersectable shape, that primitive itself.
+ * Nested trees live in the same nodes[] / prim_refs[] / prims[] arrays at the given offsets; their
+ * node child indices, leaf offsets and primitive numbers are relative to those offsets. */
+typedef struct PbrtB200Instance {
+  float i2w[16];                   /* InstanceToWorld m, row major            */
+  float w2i[16];                   /* its inverse (WorldToInstance m)         */
+  float bounds[6];                 /* the nested KdTreeAccel::bounds (instance space) */
+  uint32_t node_base, n_nodes;     /* n_nodes == 0: single primitive prims[prim_base] */
+  uint32_t ref_base;
+  uint32_t prim_base;
+} PbrtB200Instance;
 
 /* materials/{matte,glass,mirror,plastic,uber,shinymetal}.cpp with ConstantTexture
  * operands (core/texture.h:113-123); spectra are already Clamp()ed >= 0 */
@@ -179,14 +195,17 @@ typedef struct PbrtB200Film {
 typedef struct PbrtB200Scene {
   uint32_t abi_version;            /* PBRT_B200_ABI_VERSION                   */
   /* accelerator */
-  const PbrtB200KdNode *nodes;      uint32_t n_nodes;
+  const PbrtB200KdNode *nodes;      uint32_t n_nodes;      /* top-level tree first, then the instanced objects' trees */
+  uint32_t n_top_nodes;             /* nodes of the top-level tree (== n_nodes without instancing) */
   const uint32_t       *prim_refs;  uint32_t n_prim_refs;
   float                 bounds[6];  /* KdTreeAccel::bounds pMin, pMax         */
-  /* refined primitives, in the order KdTreeAccel sees them (kdtree.cpp:147-149) */
+  /* refined primitives, in the order KdTreeAccel sees them (kdtree.cpp:147-149); the top-level
+   * tree's primitives first, then each instanced object's */
   const PbrtB200Prim    *prims;     uint32_t n_prims;
   const PbrtB200PrimAux *prim_aux;  /* n_prims                                */
   const PbrtB200Mesh    *meshes;    uint32_t n_meshes;
   const PbrtB200Quadric *quadrics;  uint32_t n_quadrics;
+  const PbrtB200Instance *instances; uint32_t n_instances;
   /* optional per-vertex shading data, object space, 3/3/2 floats per vertex  */
   const float *vertex_n; const float *vertex_s; const float *vertex_uv;
   uint32_t n_vertices;

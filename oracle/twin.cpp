@@ -37,7 +37,7 @@ bool build_view(const PbrtB200Scene &s, SceneView *sv) {
   if (!err.empty()) { gError = err; return false; }
   sv->nodes = s.nodes; sv->primRefs = s.prim_refs;
   sv->prims = (const PrimQuad *)s.prims; sv->aux = s.prim_aux;
-  sv->meshes = s.meshes; sv->quadrics = s.quadrics;
+  sv->meshes = s.meshes; sv->quadrics = s.quadrics; sv->instances = s.instances;
   sv->vertexN = s.vertex_n; sv->vertexS = s.vertex_s; sv->vertexUV = s.vertex_uv;
   sv->materials = s.materials; sv->lights = s.lights;
   sv->lightShapes = s.light_shapes; sv->lightCdf = s.light_cdf;
@@ -329,7 +329,7 @@ extern "C" int pbrt_twin_trace(const PbrtB200Scene *scene, const float *rays, ui
     for (int i = 0; i < PB_MAILBOX; ++i) mailbox[i] = 0xffffffffu;
     int mbPos = 0;
     uint32_t node = 0;
-    Hit hit; hit.prim = -1;
+    Hit hit; hit.prim = -1; hit.inst = -1;
     bool stop = false;
     auto put = [&](uint8_t c) { if (pos < cap) codes[pos++] = c; };
     while (!stop) {

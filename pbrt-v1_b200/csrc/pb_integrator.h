@@ -28,8 +28,27 @@ struct Surface {
   int32_t light;      // area light of the primitive or -1
   uint32_t material;  // index into materials[] (lets a later kernel rebuild the lobes)
 };
-PB_HD void surface_dg(const SceneView &sv, const Ray &ray, const Hit &hit, const TriVerts &tv,
+// InstancePrimitive::Intersect's tail (core/primitive.cpp:72-83): the instanced shape's DG, computed
+// from the instance-space ray, moved to world space.
+PB_NOINLINE void instance_dg_to_world(const PbrtB200Instance &in, DiffGeom *dg) {
+  dg->p = xf_point(in.i2w, dg->p);
+  dg->nn = normalize(xf_normal(in.w2i, dg->nn));
+  dg->dpdu = xf_vector(in.i2w, dg->dpdu);
+  dg->dpdv = xf_vector(in.i2w, dg->dpdv);
+  dg->dndu = xf_vector(in.i2w, dg->dndu);
+  dg->dndv = xf_vector(in.i2w, dg->dndv);
+}
+// INST = false compiles the instancing code out (kernels for scenes without object instances).
+template <bool INST = true>
+PB_HD void surface_dg(const SceneView &sv, const Ray &rayWorld, const Hit &hit, const TriVerts &tv,
                       DiffGeom *dg) {
+  Ray ray = rayWorld;
+  const bool instanced = INST && sv.nInstances != 0 && hit.inst >= 0;
+  if (instanced) {   // Ray ray = WorldToInstance(r), primitive.cpp:68
+    const PbrtB200Instance &in = sv.instances[hit.inst];
+    ray.o = xf_point(in.w2i, rayWorld.o);
+    ray.d = xf_vector(in.w2i, rayWorld.d);
+  }
   if ((tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_TRIANGLE) {
     tri_dg(sv, (uint32_t)hit.prim, tv, ray, hit.t, hit.b1, hit.b2, dg);
   } else {
@@ -40,15 +59,17 @@ PB_HD void surface_dg(const SceneView &sv, const Ray &ray, const Hit &hit, const
     quadric_test(s, r, &t, &phit, &phi);
     quadric_dg(s, phit, phi, dg);
   }
+  if (instanced) instance_dg_to_world(sv.instances[hit.inst], dg);
 }
 // Intersection::GetBSDF (core/primitive.cpp:126-141)
-template <bool LOBES = true>
+template <bool LOBES = true, bool INST = true>
 PB_HD void surface_at_hit(const SceneView &sv, const Ray &ray, const Hit &hit, Surface *sf) {
   TriVerts tv = load_prim(sv, (uint32_t)hit.prim);
   DiffGeom dg, dgs;
-  surface_dg(sv, ray, hit, tv, &dg);
+  surface_dg<INST>(sv, ray, hit, tv, &dg);
   if ((tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_TRIANGLE)
-    tri_shading_dg(sv, (uint32_t)hit.prim, tv.flags, dg, &dgs);
+    tri_shading_dg<INST>(sv, (uint32_t)hit.prim, tv.flags, dg, &dgs,
+                   (INST && sv.nInstances != 0 && hit.inst >= 0) ? &sv.instances[hit.inst] : (const PbrtB200Instance *)0);
   else
     dgs = dg;
   make_bsdf<LOBES>(sv.materials[tv.material], dg, dgs, tv.flags, &sf->bsdf);
@@ -164,7 +185,7 @@ PB_NOINLINE float light_shapes_pdf(const SceneView &sv, const PbrtB200Light &l, 
   Ray ray;
   ray.o = p; ray.d = wi; ray.mint = PB_RAY_EPSILON; ray.maxt = PB_INFINITY;
   bool anyHit = false;
-  Hit hit; hit.prim = -1; hit.t = 0.f; hit.b1 = hit.b2 = 0.f;
+  Hit hit; hit.prim = -1; hit.t = 0.f; hit.b1 = hit.b2 = 0.f; hit.inst = -1;
   TriVerts htv;
   for (uint32_t i = 0; i < l.n_shapes; ++i) {
     uint32_t prim = sv.lightShapes[l.first_shape + i];
@@ -402,7 +423,7 @@ struct PathState {
 //
 // First half (path.cpp:68-112): miss handling, alpha, emitted light, BSDF, one
 // UniformSampleOneLight record.  Returns false when the ray missed (path ends).
-template <bool LOBES = true>
+template <bool LOBES = true, bool INST = true>
 PB_HD bool path_vertex_surface(const SceneView &sv, PathState &st, const Ray &ray, const Hit &hit,
                                Surface *sf) {
   int pathLength = st.depth;
@@ -423,7 +444,7 @@ PB_HD bool path_vertex_surface(const SceneView &sv, PathState &st, const Ray &ra
   }
   if (pathLength == 0) st.alpha = 1.f;
   else st.T = st.T * spec(1.f);            // pathThroughput *= scene->Transmittance(ray)
-  surface_at_hit<LOBES>(sv, ray, hit, sf);
+  surface_at_hit<LOBES, INST>(sv, ray, hit, sf);
   if (pathLength == 0 || st.specularBounce) st.L = st.L + st.T * surface_le(sv, *sf, -ray.d);
   return true;
 }

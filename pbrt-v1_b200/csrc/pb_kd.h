@@ -38,28 +38,71 @@ PB_HD bool bbox_intersect_p(const float *bmin, const float *bmax, const Ray &ray
 #define PB_MAILBOX 2   // measured 2 > 4 > 8 on B200: the ring costs more than the few re-tests it avoids
 #endif
 
-// One primitive test: GeometricPrimitive::Intersect (core/primitive.cpp:113-122)
-// shrinks ray.maxt on an accepted hit.
+// The scene's top-level tree / an instanced object's tree.
+PB_HD KdTreeView kd_top_tree(const SceneView &sv) {
+  KdTreeView t;
+  t.nodes = sv.nodes; t.primRefs = sv.primRefs; t.nNodes = sv.nNodes; t.primBase = 0;
+  for (int i = 0; i < 3; ++i) { t.bmin[i] = sv.bmin[i]; t.bmax[i] = sv.bmax[i]; }
+  return t;
+}
+PB_HD KdTreeView kd_instance_tree(const SceneView &sv, const PbrtB200Instance &in) {
+  KdTreeView t;
+  t.nodes = sv.nodes + in.node_base; t.primRefs = sv.primRefs + in.ref_base;
+  t.nNodes = in.n_nodes; t.primBase = in.prim_base;
+  for (int i = 0; i < 3; ++i) { t.bmin[i] = in.bounds[i]; t.bmax[i] = in.bounds[3 + i]; }
+  return t;
+}
+
 // QK = the primitive kinds the scene holds, so that traversal kernels for simpler scenes compile the
-// rest out: 0 triangles only, 1 triangles + spheres, 2 every quadric.
+// rest out: 0 triangles only, 1 triangles + spheres, 2 every quadric, 3 + object instances.
 #define PB_QK_TRI 0
 #define PB_QK_SPHERE 1
 #define PB_QK_ALL 2
-template <bool ANY, int QK = PB_QK_ALL>
-PB_HD bool kd_test_prim(const SceneView &sv, uint32_t prim, Ray &ray, Hit *hit) {
+#define PB_QK_INSTANCES 3
+
+template <bool ANY, bool COUNT, int QK>
+PB_HD bool kd_tree_intersect(const SceneView &sv, const KdTreeView &tree, Ray ray, Hit *hit, KdCounters *cnt);
+
+// One primitive test: GeometricPrimitive::Intersect (core/primitive.cpp:113-122)
+// shrinks ray.maxt on an accepted hit.  With QK == PB_QK_INSTANCES a primitive may be an
+// InstancePrimitive (core/primitive.cpp:66-85): the ray goes into instance space, the instanced
+// object's own kd-tree (or single primitive) is intersected, r.maxt = ray.maxt.
+template <bool ANY, int QK = PB_QK_INSTANCES, bool COUNT = false>
+PB_HD bool kd_test_prim(const SceneView &sv, uint32_t prim, Ray &ray, Hit *hit, KdCounters *cnt = nullptr) {
   TriVerts tv = load_prim(sv, prim);
   float t, b1 = 0.f, b2 = 0.f;
   bool ok;
-  if (QK == PB_QK_TRI || (tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_TRIANGLE) {
+  const uint32_t kind = tv.flags & PBRT_B200_PF_KIND_MASK;
+  if (QK == PB_QK_TRI || kind == PBRT_B200_PRIM_TRIANGLE) {
     ok = tri_test(tv.p1, tv.p2, tv.p3, ray, &t, &b1, &b2);
-  } else {
+  } else if (QK != PB_QK_INSTANCES || kind == PBRT_B200_PRIM_QUADRIC) {
     V3 phit; float phi;
     if (QK == PB_QK_SPHERE) ok = sphere_test(sv.quadrics[sv.aux[prim].owner], ray, &t, &phit, &phi, false);
     else ok = quadric_test(sv.quadrics[sv.aux[prim].owner], ray, &t, &phit, &phi, false);
-  }
+  } else if constexpr (QK == PB_QK_INSTANCES) {
+    const uint32_t instId = sv.aux[prim].owner;
+    const PbrtB200Instance &in = sv.instances[instId];
+    Ray r2;
+    r2.o = xf_point(in.w2i, ray.o);
+    r2.d = xf_vector(in.w2i, ray.d);
+    r2.mint = ray.mint; r2.maxt = ray.maxt;
+    Hit h2;
+    h2.prim = -1; h2.t = 0.f; h2.b1 = h2.b2 = 0.f; h2.inst = -1;
+    bool got;
+    if (in.n_nodes == 0) got = kd_test_prim<ANY, PB_QK_ALL>(sv, in.prim_base, r2, &h2);
+    else got = kd_tree_intersect<ANY, COUNT, PB_QK_ALL>(sv, kd_instance_tree(sv, in), r2, &h2, cnt);
+    if (!got) return false;
+    if (!ANY) {
+      *hit = h2;
+      hit->inst = (int32_t)instId;
+      ray.maxt = h2.t;
+    }
+    return true;
+  } else
+    return false;
   if (!ok) return false;
   if (!ANY) {
-    hit->prim = (int32_t)prim; hit->t = t; hit->b1 = b1; hit->b2 = b2;
+    hit->prim = (int32_t)prim; hit->t = t; hit->b1 = b1; hit->b2 = b2; hit->inst = -1;
     ray.maxt = t;
   }
   return true;
@@ -75,12 +118,12 @@ PB_HD bool kd_test_prim(const SceneView &sv, uint32_t prim, Ray &ray, Hit *hit) 
 // (kdtree.cpp:328-401).  The reference re-checks `ray.maxt < tmin` at the top of
 // every iteration; neither value changes while descending, so checking after
 // each pop is equivalent.
-template <bool ANY, bool COUNT>
-PB_HD bool kd_intersect(const SceneView &sv, Ray ray, Hit *hit, KdCounters *cnt) {
+template <bool ANY, bool COUNT, int QK>
+PB_HD bool kd_tree_intersect(const SceneView &sv, const KdTreeView &tree, Ray ray, Hit *hit, KdCounters *cnt) {
   if (!ANY) hit->prim = -1;
   float tmin, tmax;
-  if (sv.nNodes == 0) return false;
-  if (!bbox_intersect_p(sv.bmin, sv.bmax, ray, &tmin, &tmax)) return false;
+  if (tree.nNodes == 0) return false;
+  if (!bbox_intersect_p(tree.bmin, tree.bmax, ray, &tmin, &tmax)) return false;
   V3 invDir = v3(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
   uint32_t todoNode[PB_KD_STACK];
   float todoTmin[PB_KD_STACK], todoTmax[PB_KD_STACK];
@@ -96,10 +139,10 @@ PB_HD bool kd_intersect(const SceneView &sv, Ray ray, Hit *hit, KdCounters *cnt)
     // ---- descend to a leaf
     for (;;) {
 #ifdef __CUDA_ARCH__
-      uint2 nd = __ldg((const uint2 *)(sv.nodes + node));
+      uint2 nd = __ldg((const uint2 *)(tree.nodes + node));
       w0 = nd.x; w1 = nd.y;
 #else
-      w0 = sv.nodes[node].word0; w1 = sv.nodes[node].word1;
+      w0 = tree.nodes[node].word0; w1 = tree.nodes[node].word1;
 #endif
       if ((w0 & 3u) == 3u) break;
       if (COUNT) ++cnt->interior;
@@ -131,7 +174,7 @@ PB_HD bool kd_intersect(const SceneView &sv, Ray ray, Hit *hit, KdCounters *cnt)
     if (COUNT) ++cnt->leaves;
     uint32_t nPrims = w0 >> 2;
     for (uint32_t i = 0; i < nPrims; ++i) {
-      uint32_t prim = (nPrims == 1) ? w1 : sv.primRefs[w1 + i];
+      uint32_t prim = tree.primBase + ((nPrims == 1) ? w1 : tree.primRefs[w1 + i]);
       if (COUNT) ++cnt->refs;
       bool seen = false;
 #pragma unroll
@@ -142,7 +185,7 @@ PB_HD bool kd_intersect(const SceneView &sv, Ray ray, Hit *hit, KdCounters *cnt)
         if (k == mbPos) mailbox[k] = prim;
       mbPos = (mbPos + 1) & (PB_MAILBOX - 1);
       if (COUNT) ++cnt->tests;
-      if (kd_test_prim<ANY>(sv, prim, ray, hit)) {
+      if (kd_test_prim<ANY, QK, COUNT>(sv, prim, ray, hit, cnt)) {
         if (ANY) return true;
         anyHit = true;
       }
@@ -156,5 +199,12 @@ PB_HD bool kd_intersect(const SceneView &sv, Ray ray, Hit *hit, KdCounters *cnt)
     if (!ANY && ray.maxt < tmin) break;
   }
   return anyHit;
+}
+// KdTreeAccel::Intersect / IntersectP on the scene's top-level tree.
+template <bool ANY, bool COUNT>
+PB_HD bool kd_intersect(const SceneView &sv, Ray ray, Hit *hit, KdCounters *cnt) {
+  if (!ANY) { hit->prim = -1; hit->inst = -1; }
+  if (sv.nInstances != 0) return kd_tree_intersect<ANY, COUNT, PB_QK_INSTANCES>(sv, kd_top_tree(sv), ray, hit, cnt);
+  return kd_tree_intersect<ANY, COUNT, PB_QK_ALL>(sv, kd_top_tree(sv), ray, hit, cnt);
 }
 #endif

@@ -55,7 +55,7 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
   uint32_t mailbox[PB_MAILBOX];
   int mbPos = 0;
   Hit hit;
-  hit.prim = -1; hit.t = 0.f; hit.b1 = hit.b2 = 0.f;
+  hit.prim = -1; hit.t = 0.f; hit.b1 = hit.b2 = 0.f; hit.inst = -1;
   bool anyHit = false;
 
   for (;;) {
@@ -155,7 +155,8 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
     // ---- the expensive part, all lanes with work together
     if (pending) {
       if (COUNT) ++cnt.tests;
-      if (kd_test_prim<ANY, QK>(sv, prim, ray, &hit)) {
+      // (an InstancePrimitive runs its nested walk here, per lane: QK == PB_QK_INSTANCES kernels only)
+      if (kd_test_prim<ANY, QK, COUNT>(sv, prim, ray, &hit, &cnt)) {
         anyHit = true;
         if (ANY) {
           active = false;

@@ -23,12 +23,14 @@ struct SceneView {
   const PbrtB200PrimAux *aux;
   const PbrtB200Mesh *meshes;
   const PbrtB200Quadric *quadrics;
+  const PbrtB200Instance *instances;
   const float *vertexN, *vertexS, *vertexUV;
   const PbrtB200Material *materials;
   const PbrtB200Light *lights;
   const uint32_t *lightShapes;
   const float *lightCdf;
-  uint32_t nNodes, nPrims, nLights;
+  uint32_t nNodes, nPrims, nLights;   // nNodes: the top-level tree's
+  uint32_t nInstances;
   uint32_t nInfiniteLights;         // lights whose Le(ray) is not black (lights/infinite.cpp)
   float bmin[3], bmax[3];
   PbrtB200Camera camera;
@@ -54,5 +56,14 @@ struct SceneView {
 struct Hit {
   int32_t prim;   // -1 = miss
   float t, b1, b2;
+  int32_t inst;   // instance the primitive was reached through, or -1
+};
+// One kd-tree inside the scene's node / reference / primitive arrays (the top-level tree or an
+// instanced object's).
+struct KdTreeView {
+  const PbrtB200KdNode *nodes;
+  const uint32_t *primRefs;
+  uint32_t nNodes, primBase;
+  float bmin[3], bmax[3];
 };
 #endif

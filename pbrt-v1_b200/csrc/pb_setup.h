@@ -22,11 +22,22 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
   if (s.film.x_pixel_count < 1 || s.film.y_pixel_count < 1) return "empty film";
   for (uint32_t i = 0; i < s.n_prims; ++i) {
     uint32_t kind = s.prims[i].flags & PBRT_B200_PF_KIND_MASK;
-    if (kind != PBRT_B200_PRIM_TRIANGLE && kind != PBRT_B200_PRIM_QUADRIC) return "unknown primitive kind";
+    if (kind != PBRT_B200_PRIM_TRIANGLE && kind != PBRT_B200_PRIM_QUADRIC && kind != PBRT_B200_PRIM_INSTANCE) return "unknown primitive kind";
+    if (kind == PBRT_B200_PRIM_INSTANCE) {
+      if (s.prim_aux[i].owner >= s.n_instances) return "instance index out of range";
+      continue;
+    }
     if (s.prims[i].material >= s.n_materials) return "primitive material index out of range";
     if (s.prims[i].light >= (int32_t)s.n_lights) return "primitive light index out of range";
   }
-  sv->nNodes = s.n_nodes; sv->nPrims = s.n_prims; sv->nLights = s.n_lights;
+  if (s.n_top_nodes > s.n_nodes) return "n_top_nodes > n_nodes";
+  for (uint32_t i = 0; i < s.n_instances; ++i) {
+    const PbrtB200Instance &in = s.instances[i];
+    if ((uint64_t)in.node_base + in.n_nodes > s.n_nodes || in.ref_base > s.n_prim_refs || in.prim_base >= s.n_prims)
+      return "instance offsets out of range";
+  }
+  sv->nNodes = s.n_top_nodes; sv->nPrims = s.n_prims; sv->nLights = s.n_lights;
+  sv->nInstances = s.n_instances;
   sv->nInfiniteLights = 0;
   for (uint32_t i = 0; i < s.n_lights; ++i) {
     if (s.lights[i].kind < PBRT_B200_LIGHT_POINT || s.lights[i].kind > PBRT_B200_LIGHT_INFINITE) return "unknown light kind";

@@ -184,12 +184,30 @@ PB_HD bool solve2x2(const float A[2][2], const float B[2], float x[2]) {
 }
 
 // trianglemesh.cpp:71-133: shading geometry from per-vertex N / S.
+// Matrix4x4::Mul, core/transform.cpp:78-89 (row major 4x4)
+PB_HD void mat4_mul(const float *m1, const float *m2, float *r) {
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j)
+      r[4 * i + j] = m1[4 * i + 0] * m2[0 * 4 + j] + m1[4 * i + 1] * m2[1 * 4 + j] + m1[4 * i + 2] * m2[2 * 4 + j] +
+                     m1[4 * i + 3] * m2[3 * 4 + j];
+}
+// `inst`: the hit was reached through an InstancePrimitive, so the obj2world handed to
+// GetShadingGeometry is (shape->WorldToObject * WorldToInstance).GetInverse() (primitive.cpp:71,132):
+// m = InstanceToWorld.m * ObjectToWorld.m, inverse = WorldToObject.m * WorldToInstance.m (Transform::operator*).
+template <bool INST = true>
 PB_NOINLINE void tri_shading_dg(const SceneView &sv, uint32_t prim, uint32_t flags, const DiffGeom &dg,
-                          DiffGeom *dgs) {
+                          DiffGeom *dgs, const PbrtB200Instance *inst = nullptr) {
   bool hasN = (flags & PBRT_B200_PF_HAS_N) != 0, hasS = (flags & PBRT_B200_PF_HAS_S) != 0;
   if (!hasN && !hasS) { *dgs = dg; return; }
   const PbrtB200PrimAux &a = sv.aux[prim];
-  const PbrtB200Mesh &mesh = sv.meshes[a.owner];
+  const PbrtB200Mesh &meshOwn = sv.meshes[a.owner];
+  struct { const float *w2o, *o2w; } mesh = {meshOwn.w2o, meshOwn.o2w};
+  float cw2o[INST ? 16 : 1], co2w[INST ? 16 : 1];
+  if (INST && inst) {
+    mat4_mul(meshOwn.w2o, inst->w2i, cw2o);
+    mat4_mul(inst->i2w, meshOwn.o2w, co2w);
+    mesh.w2o = cw2o; mesh.o2w = co2w;
+  }
   float b[3];
   float uv[3][2];
   tri_uvs(sv, prim, flags, uv);
@@ -239,7 +257,7 @@ PB_NOINLINE void tri_shading_dg(const SceneView &sv, uint32_t prim, uint32_t fla
     dndu = dndv = v3(0, 0, 0);
   // `ObjectToWorld(dndu)` on a Vector (trianglemesh.cpp:126-127) is the
   // Triangle's own ObjectToWorld == the mesh's
-  dg_init(dgs, dg.p, ss, ts, xf_vector(mesh.o2w, dndu), xf_vector(mesh.o2w, dndv), dg.u, dg.v,
+  dg_init(dgs, dg.p, ss, ts, xf_vector(meshOwn.o2w, dndu), xf_vector(meshOwn.o2w, dndv), dg.u, dg.v,
           flags);
 }
 

@@ -80,6 +80,7 @@ struct RayQueue {        // compacted SoA queue of rays (closest-hit kind)
   float *ox, *oy, *oz, *dx, *dy, *dz, *mint, *maxt;
   int32_t *hitPrim;      // results, same index
   float *hitT, *hitB1, *hitB2;
+  int32_t *hitInst;      // instance the hit was reached through (scenes with object instances only, else null)
 };
 struct AuxQueue {        // shadow segments / MIS probes
   uint32_t *rec;         // direct-record index (r * nSlots + slot)
@@ -274,7 +275,10 @@ struct MainSink {
   RayQueue q;
   __device__ void done(uint32_t i, const Ray &, const Hit &hit, bool) const {
     q.hitPrim[i] = hit.prim;
-    if (hit.prim >= 0) { q.hitT[i] = hit.t; q.hitB1[i] = hit.b1; q.hitB2[i] = hit.b2; }
+    if (hit.prim >= 0) {
+      q.hitT[i] = hit.t; q.hitB1[i] = hit.b1; q.hitB2[i] = hit.b2;
+      if (q.hitInst) q.hitInst[i] = hit.inst;
+    }
   }
 };
 __device__ __forceinline__ void flush_kd_counters(unsigned long long *stats, int kind, const KdCounters &cnt) {
@@ -355,7 +359,7 @@ k_probe(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t *
   KdCounters cnt = {0, 0, 0, 0};
   ProbeSource src = {q};
   ProbeSink sink = {&sv, q, recFlags};
-  kd_warp_traverse<false, COUNT, PB_QK_ALL>(sv, n, work, src, sink, cnt);
+  kd_warp_traverse<false, COUNT, PB_QK_INSTANCES>(sv, n, work, src, sink, cnt);
   if (COUNT) flush_kd_counters(stats, TK_PROBE, cnt);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_K(TK_PROBE, TF_RAYS)], (unsigned long long)n);
 }
@@ -430,6 +434,7 @@ __device__ __forceinline__ void surface_load(const SceneView &sv, const SurfaceR
   bsdf_set_lobes<G>(sv.materials[sf->material], &b);
 }
 
+template <bool INST>
 __global__ void __launch_bounds__(PB_BLOCK, PB_SURF_MIN_BLOCKS)
 k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const RayQueue qin,
                const SurfaceRecord rec, const uint32_t *nPtr, uint32_t *work) {
@@ -445,8 +450,11 @@ k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const
       Ray ray = queue_ray(qin, i);
       Hit hit;
       hit.prim = qin.hitPrim[i];
-      hit.t = 0.f; hit.b1 = hit.b2 = 0.f;
-      if (hit.prim >= 0) { hit.t = qin.hitT[i]; hit.b1 = qin.hitB1[i]; hit.b2 = qin.hitB2[i]; }
+      hit.t = 0.f; hit.b1 = hit.b2 = 0.f; hit.inst = -1;
+      if (hit.prim >= 0) {
+        hit.t = qin.hitT[i]; hit.b1 = qin.hitB1[i]; hit.b2 = qin.hitB2[i];
+        if (qin.hitInst) hit.inst = qin.hitInst[i];
+      }
       uint32_t flags = wb.flags[slot];
       PathState st;
       st.L = load3(wb.L, slot);
@@ -456,7 +464,7 @@ k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const
       st.depth = (int)(flags & 0xffu);
       st.specularBounce = (flags >> 8) & 1u;
       Surface sf;
-      if (path_vertex_surface<false>(sv, st, ray, hit, &sf)) {
+      if (path_vertex_surface<false, INST>(sv, st, ray, hit, &sf)) {
         ++shaded;
         surface_store(rec, i, sf);
       }
@@ -633,8 +641,11 @@ k_shade_wd(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
         Ray ray = queue_ray(qin, i);
         Hit hit;
         hit.prim = qin.hitPrim[i];
-        hit.t = 0.f; hit.b1 = hit.b2 = 0.f;
-        if (hit.prim >= 0) { hit.t = qin.hitT[i]; hit.b1 = qin.hitB1[i]; hit.b2 = qin.hitB2[i]; }
+        hit.t = 0.f; hit.b1 = hit.b2 = 0.f; hit.inst = -1;
+        if (hit.prim >= 0) {
+          hit.t = qin.hitT[i]; hit.b1 = qin.hitB1[i]; hit.b2 = qin.hitB2[i];
+          if (qin.hitInst) hit.inst = qin.hitInst[i];
+        }
         uint32_t flags = wb.flags[slot];
         int depth = (int)(flags & 0xffu);
         RngStream rng;
@@ -966,7 +977,7 @@ struct Carver {
   }
 };
 static void carve_wave(Carver &c, WaveBuffers &wb, uint32_t nSlots, int directRecords, int nFrames, bool isPath,
-                       int ldFloats) {
+                       int ldFloats, bool hasInstances) {
   wb.nSlots = nSlots;
   wb.nFrames = nFrames;
   for (int i = 0; i < 3; ++i) {
@@ -997,6 +1008,7 @@ static void carve_wave(Carver &c, WaveBuffers &wb, uint32_t nSlots, int directRe
     q.mint = c.take<float>(nSlots); q.maxt = c.take<float>(nSlots);
     q.hitPrim = c.take<int32_t>(nSlots);
     q.hitT = c.take<float>(nSlots); q.hitB1 = c.take<float>(nSlots); q.hitB2 = c.take<float>(nSlots);
+    q.hitInst = hasInstances ? c.take<int32_t>(nSlots) : nullptr;
   }
   size_t auxN = (size_t)nSlots * directRecords;
   AuxQueue *aq[2] = {&wb.shadowQ, &wb.probeQ};
@@ -1020,7 +1032,7 @@ static int ensure_wave(PbrtB200Handle *h, uint32_t nSlots) {
   bool isPath = h->sv.integrator.kind == PBRT_B200_INT_PATH;
   Carver sizing = {nullptr, 0};
   WaveBuffers tmp;
-  carve_wave(sizing, tmp, nSlots, h->sv.directRecords, h->nFrames, isPath, h->sv.ldFloatsPerSample);
+  carve_wave(sizing, tmp, nSlots, h->sv.directRecords, h->nFrames, isPath, h->sv.ldFloatsPerSample, h->sv.nInstances != 0);
   size_t bytes = sizing.off + 256;
   int d = h->device;
   if (d >= 0 && d < PB_MAX_DEVICES && g_cachedArena[d] && g_cachedArenaBytes[d] >= bytes) {
@@ -1033,7 +1045,7 @@ static int ensure_wave(PbrtB200Handle *h, uint32_t nSlots) {
     h->arenaBytes = bytes;
   }
   Carver c = {(char *)h->arena, 0};
-  carve_wave(c, h->wb, nSlots, h->sv.directRecords, h->nFrames, isPath, h->sv.ldFloatsPerSample);
+  carve_wave(c, h->wb, nSlots, h->sv.directRecords, h->nFrames, isPath, h->sv.ldFloatsPerSample, h->sv.nInstances != 0);
   return PBRT_B200_OK;
 }
 
@@ -1052,10 +1064,11 @@ static void launch_traversals_a(PbrtB200Handle *h, bool count, int grid, const R
                                 uint32_t *work) {
 #define PB_LAUNCH_INTERSECT(C_, QK_) \
   TIMED(KC_INTERSECT, (k_intersect<C_, QK_><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, q, nMain, work, h->wb.stats)))
-  if (count) PB_LAUNCH_INTERSECT(true, PB_QK_ALL);   // the counting pass is not timed
+  if (count) PB_LAUNCH_INTERSECT(true, PB_QK_INSTANCES);   // the counting pass is not timed
   else if (h->primKinds == PB_QK_TRI) PB_LAUNCH_INTERSECT(false, PB_QK_TRI);
   else if (h->primKinds == PB_QK_SPHERE) PB_LAUNCH_INTERSECT(false, PB_QK_SPHERE);
-  else PB_LAUNCH_INTERSECT(false, PB_QK_ALL);
+  else if (h->primKinds == PB_QK_ALL) PB_LAUNCH_INTERSECT(false, PB_QK_ALL);
+  else PB_LAUNCH_INTERSECT(false, PB_QK_INSTANCES);
 }
 static void launch_traversals_b(PbrtB200Handle *h, bool count, int grid, uint32_t *nShadow, uint32_t *nProbe,
                                 uint32_t *workS, uint32_t *workP, cudaStream_t strm) {
@@ -1064,14 +1077,15 @@ static void launch_traversals_b(PbrtB200Handle *h, bool count, int grid, uint32_
   // ramp-up of the full persistent grid for a few thousand rays
   int probeGrid = std::min(grid, h->numSMs * 2);
   if (count) {
-    TIMED_ON(KC_SHADOW, strm, (k_shadow<true, PB_QK_ALL><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.stats)));
+    TIMED_ON(KC_SHADOW, strm, (k_shadow<true, PB_QK_INSTANCES><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.stats)));
     TIMED_ON(KC_PROBE, strm, (k_probe<true><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.stats)));
   } else {
 #define PB_LAUNCH_SHADOW(QK_) \
   TIMED_ON(KC_SHADOW, strm, (k_shadow<false, QK_><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.stats)))
     if (h->primKinds == PB_QK_TRI) PB_LAUNCH_SHADOW(PB_QK_TRI);
     else if (h->primKinds == PB_QK_SPHERE) PB_LAUNCH_SHADOW(PB_QK_SPHERE);
-    else PB_LAUNCH_SHADOW(PB_QK_ALL);
+    else if (h->primKinds == PB_QK_ALL) PB_LAUNCH_SHADOW(PB_QK_ALL);
+    else PB_LAUNCH_SHADOW(PB_QK_INSTANCES);
     TIMED_ON(KC_PROBE, strm, (k_probe<false><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.stats)));
   }
 }
@@ -1116,7 +1130,8 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
         SurfaceRecord rec;
         for (int k = 0; k < 15; ++k) rec.f[k] = wb.surf[k];
         rec.ids = wb.surfIds;
-        TIMED(KC_SHADE, (k_path_surface<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], rec, nMain, nextWork())));
+        if (sv.nInstances != 0) TIMED(KC_SHADE, (k_path_surface<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], rec, nMain, nextWork())));
+        else TIMED(KC_SHADE, (k_path_surface<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], rec, nMain, nextWork())));
 #define PB_LAUNCH_DIRECT2(LD_, G_, LK_)                                                                             \
   TIMED(KC_SHADE_DIRECT, (k_path_direct<LD_, G_, LK_><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], rec, nMain, \
                                                                                  nextWork(), nShadow, nProbe)))
@@ -1257,6 +1272,7 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   h->primKinds = PB_QK_TRI;
   for (uint32_t i = 0; i < scene->n_quadrics; ++i)
     h->primKinds = std::max(h->primKinds, scene->quadrics[i].kind == PBRT_B200_QUADRIC_SPHERE ? PB_QK_SPHERE : PB_QK_ALL);
+  if (scene->n_instances != 0) h->primKinds = PB_QK_INSTANCES;
   h->triLightsOnly = true;
   for (uint32_t i = 0; i < scene->n_lights; ++i) {
     const PbrtB200Light &l = scene->lights[i];
@@ -1290,6 +1306,7 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   UP(upload(h, scene->prim_aux, scene->n_prims, &sv.aux));
   UP(upload(h, scene->meshes, scene->n_meshes, &sv.meshes));
   UP(upload(h, scene->quadrics, scene->n_quadrics, &sv.quadrics));
+  UP(upload(h, scene->instances, scene->n_instances, &sv.instances));
   UP(upload(h, scene->vertex_n, (size_t)scene->n_vertices * 3, &sv.vertexN));
   UP(upload(h, scene->vertex_s, (size_t)scene->n_vertices * 3, &sv.vertexS));
   UP(upload(h, scene->vertex_uv, (size_t)scene->n_vertices * 2, &sv.vertexUV));

@@ -310,9 +310,7 @@ void pbrtObjectEnd() {
   renderOptions->currentInstance = NULL;
   pbrtAttributeEnd();
 }
-// api.cpp:428-457.  InstancePrimitive needs a two-level traversal on the
-// device, which is SURVEY.md 8(f) rank 3 ("next"); diagnose instead of
-// silently dropping geometry.
+// api.cpp:428-457
 void pbrtObjectInstance(const string &name) {
   if (!InWorld("ObjectInstance")) return;
   if (renderOptions->currentInstance) {
@@ -323,8 +321,19 @@ void pbrtObjectInstance(const string &name) {
     Error("Unable to find instance named \"%s\"", name.c_str());
     return;
   }
-  Error("ObjectInstance \"%s\": object instancing is not implemented by the B200 hot path yet; "
-        "instance skipped.", name.c_str());
+  vector<Reference<Primitive> > &in = renderOptions->instances[name];
+  if (in.size() == 0) return;
+  if (in.size() > 1 || !in[0]->CanIntersect()) {
+    // Refine instance Primitives and create aggregate
+    Reference<Primitive> accel =
+        MakeAccelerator(renderOptions->AcceleratorName, in, renderOptions->AcceleratorParams);
+    if (!accel) accel = MakeAccelerator("kdtree", in, ParamSet());
+    if (!accel) Severe("Unable to find \"kdtree\" accelerator");
+    in.erase(in.begin(), in.end());
+    in.push_back(accel);
+  }
+  Reference<Primitive> prim = new InstancePrimitive(in[0], curTransform);
+  renderOptions->primitives.push_back(prim);
 }
 void pbrtWorldEnd() {            // api.cpp:458-483
   if (!InWorld("WorldEnd")) return;

@@ -93,6 +93,17 @@ class GeometricPrimitive : public Primitive {
   AreaLight *areaLight;
 };
 
+// core/primitive.h:93-113: an instanced primitive (an object's accelerator, or its single
+// intersectable primitive) placed by InstanceToWorld.  Intersection happens on the device.
+class InstancePrimitive : public Primitive {
+ public:
+  InstancePrimitive(const Reference<Primitive> &i, const Transform &i2w)
+      : instance(i), InstanceToWorld(i2w), WorldToInstance(i2w.GetInverse()) {}
+  BBox WorldBound() const { return InstanceToWorld(instance->WorldBound()); }
+  Reference<Primitive> instance;
+  Transform InstanceToWorld, WorldToInstance;
+};
+
 // kd-tree accelerator (accelerators/kdtree.cpp): host-side SAH build only.
 class KdTreeAccel : public Primitive {
  public:
@@ -178,6 +189,11 @@ struct FlatBuilder {
   vector<PbrtB200PrimAux> aux;
   vector<PbrtB200Mesh> meshes;
   vector<PbrtB200Quadric> quadrics;
+  vector<PbrtB200Instance> instances;
+  vector<PbrtB200KdNode> nodes;        // top-level tree, then the instanced objects' trees (only filled when
+  vector<uint32_t> primRefs;           // the scene has instances; otherwise the accelerator's own arrays are used)
+  map<const void *, uint32_t> objectIds;   // instanced Primitive -> first PbrtB200Instance built for it
+  vector<Reference<Primitive> > keepAlive;
   vector<float> vertexN, vertexS, vertexUV;
   uint32_t nVertices;
   bool anyN, anyS, anyUV;

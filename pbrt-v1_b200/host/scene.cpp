@@ -59,18 +59,64 @@ void Scene::Flatten(FlatBuilder &fb, PbrtB200Scene *out) const {
   if (!accel) Severe("Scene aggregate is not the kd-tree accelerator");
   for (size_t i = 0; i < lights.size(); ++i)
     if (lights[i]->IsAreaLight()) fb.lightIds[lights[i]] = (int32_t)i;
-  // primitives in the accelerator's (refined) order
-  fb.prims.resize(accel->prims.size());
-  fb.aux.resize(accel->prims.size());
-  for (size_t i = 0; i < accel->prims.size(); ++i) {
-    const GeometricPrimitive *gp =
-        dynamic_cast<const GeometricPrimitive *>(accel->prims[i].operator->());
-    if (!gp) Severe("Non-geometric primitive reached the accelerator");
+  // primitives in the accelerator's (refined) order; instanced objects' primitives follow
+  vector<const Primitive *> all;
+  for (size_t i = 0; i < accel->prims.size(); ++i) all.push_back(accel->prims[i].operator->());
+  bool anyInstance = false;
+  for (size_t i = 0; i < all.size(); ++i) anyInstance |= dynamic_cast<const InstancePrimitive *>(all[i]) != NULL;
+  if (anyInstance) {
+    fb.nodes = accel->nodes;
+    fb.primRefs = accel->primRefs;
+  }
+  const size_t nTop = all.size();
+  fb.prims.resize(nTop);
+  fb.aux.resize(nTop);
+  for (size_t i = 0; i < all.size(); ++i) {   // `all` grows while instances are expanded
     PbrtB200Prim &pr = fb.prims[i];
+    if (const InstancePrimitive *ip = dynamic_cast<const InstancePrimitive *>(all[i])) {
+      if (i >= nTop) Severe("Nested object instances are not possible in pbrt-v1 scenes");
+      const Primitive *obj = ip->instance.operator->();
+      PbrtB200Instance in;
+      memset(&in, 0, sizeof(in));
+      map<const void *, uint32_t>::iterator oi = fb.objectIds.find(obj);
+      if (oi != fb.objectIds.end()) {
+        in = fb.instances[oi->second];   // same object placed again: shares tree and primitives
+      } else {
+        fb.objectIds[obj] = (uint32_t)fb.instances.size();
+        in.prim_base = (uint32_t)all.size();
+        if (const KdTreeAccel *oa = dynamic_cast<const KdTreeAccel *>(obj)) {
+          in.node_base = (uint32_t)fb.nodes.size();
+          in.n_nodes = (uint32_t)oa->nodes.size();
+          in.ref_base = (uint32_t)fb.primRefs.size();
+          fb.nodes.insert(fb.nodes.end(), oa->nodes.begin(), oa->nodes.end());
+          fb.primRefs.insert(fb.primRefs.end(), oa->primRefs.begin(), oa->primRefs.end());
+          for (int k = 0; k < 3; ++k) { in.bounds[k] = oa->bounds.pMin[k]; in.bounds[3 + k] = oa->bounds.pMax[k]; }
+          for (size_t k = 0; k < oa->prims.size(); ++k) all.push_back(oa->prims[k].operator->());
+        } else {
+          all.push_back(obj);   // a single intersectable primitive, no accelerator (api.cpp:441)
+        }
+        fb.prims.resize(all.size());
+        fb.aux.resize(all.size());
+      }
+      memcpy(in.i2w, ip->InstanceToWorld.GetMatrix().m, sizeof(in.i2w));
+      memcpy(in.w2i, ip->WorldToInstance.GetMatrix().m, sizeof(in.w2i));
+      PbrtB200Prim &pi = fb.prims[i];   // (fb.prims may have been reallocated)
+      memset(&pi, 0, sizeof(pi));
+      pi.flags = PBRT_B200_PRIM_INSTANCE;
+      pi.light = -1;
+      memset(&fb.aux[i], 0, sizeof(fb.aux[i]));
+      fb.aux[i].owner = (uint32_t)fb.instances.size();
+      fb.instances.push_back(in);
+      continue;
+    }
+    const GeometricPrimitive *gp = dynamic_cast<const GeometricPrimitive *>(all[i]);
+    if (!gp) Severe("Non-geometric primitive reached the accelerator");
     gp->shape->Flatten(fb, &pr, &fb.aux[i]);
-    const void *owner; int index;
-    gp->shape->Identity(&owner, &index);
-    fb.shapePrimIds[std::make_pair(owner, index)] = (uint32_t)i;
+    if (i < nTop) {
+      const void *owner; int index;
+      gp->shape->Identity(&owner, &index);
+      fb.shapePrimIds[std::make_pair(owner, index)] = (uint32_t)i;
+    }
     const Material *m = gp->material.operator->();
     map<const void *, uint32_t>::iterator mi = fb.materialIds.find(m);
     if (mi == fb.materialIds.end()) {
@@ -81,7 +127,7 @@ void Scene::Flatten(FlatBuilder &fb, PbrtB200Scene *out) const {
     } else
       pr.material = mi->second;
     pr.light = -1;
-    if (gp->areaLight) {
+    if (gp->areaLight && i < nTop) {   // instanced shapes cannot be area lights (api.cpp:386)
       map<const void *, int32_t>::iterator li = fb.lightIds.find(gp->areaLight);
       if (li != fb.lightIds.end()) pr.light = li->second;
     }
@@ -89,10 +135,15 @@ void Scene::Flatten(FlatBuilder &fb, PbrtB200Scene *out) const {
   fb.lights.resize(lights.size());
   for (size_t i = 0; i < lights.size(); ++i) lights[i]->Flatten(fb, &fb.lights[i]);
 
-  out->nodes = accel->nodes.empty() ? NULL : &accel->nodes[0];
-  out->n_nodes = (uint32_t)accel->nodes.size();
-  out->prim_refs = accel->primRefs.empty() ? NULL : &accel->primRefs[0];
-  out->n_prim_refs = (uint32_t)accel->primRefs.size();
+  const vector<PbrtB200KdNode> &nodes = anyInstance ? fb.nodes : accel->nodes;
+  const vector<uint32_t> &primRefs = anyInstance ? fb.primRefs : accel->primRefs;
+  out->nodes = nodes.empty() ? NULL : &nodes[0];
+  out->n_nodes = (uint32_t)nodes.size();
+  out->n_top_nodes = (uint32_t)accel->nodes.size();
+  out->prim_refs = primRefs.empty() ? NULL : &primRefs[0];
+  out->n_prim_refs = (uint32_t)primRefs.size();
+  out->instances = fb.instances.empty() ? NULL : &fb.instances[0];
+  out->n_instances = (uint32_t)fb.instances.size();
   for (int i = 0; i < 3; ++i) {
     out->bounds[i] = accel->bounds.pMin[i];
     out->bounds[3 + i] = accel->bounds.pMax[i];

@@ -207,9 +207,33 @@ def scene_blob(out, a, nphi, ntheta, res, spp):
     sys.stderr.write("blob triangles: %d\n" % n)
 
 
+def scene_instances(out, a):
+    """Cornell walls + a 4x4x... grid of instances of one blob object (ObjectBegin/ObjectInstance):
+    27 placements of a 20 k-triangle mesh = 0.55 M instanced triangles from one 20 k-triangle tree."""
+    header(out, a.res or (1024, 1024), a.spp or (8, 8), a.integrator or "path", a.filter or "box",
+           jitter=a.jitter if a.jitter is not None else True, crop=a.crop, filename=a.filename,
+           extra_integrator='"integer maxdepth" [%d]' % a.maxdepth)
+    out.write("WorldBegin\n")
+    cornell_walls(out)
+    out.write('ObjectBegin "blob"\nMaterial "matte" "color Kd" [.6 .55 .4]\n')
+    n = blob(out, a.nphi or 144, a.ntheta or 72, center=(0, 0, 0), radius=1.0, normals=a.normals)
+    out.write("ObjectEnd\n")
+    k = 0
+    for iy in range(3):
+        for iz in range(3):
+            for ix in range(3):
+                s = 55 + 10 * ((ix + 2 * iy + 3 * iz) % 3)
+                out.write("AttributeBegin\nTranslate %g %g %g\nRotate %g 0 1 0\nRotate %g 1 0 0\nScale %g %g %g\n"
+                          'ObjectInstance "blob"\nAttributeEnd\n'
+                          % (120 + 158 * ix, 85 + 150 * iy, 140 + 150 * iz, 37 * k, 23 * k, s, s * (1 + .1 * (k % 3)), s))
+                k += 1
+    out.write("WorldEnd\n")
+    sys.stderr.write("instanced blob triangles: %d x %d\n" % (n, k))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("scene", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("scene", choices=["c1", "c2", "c3", "c4", "c5", "inst"])
     ap.add_argument("-o", "--output", default="-")
     ap.add_argument("--res", type=int, nargs=2)
     ap.add_argument("--spp", type=int, nargs=2)
@@ -244,6 +268,8 @@ def main():
         scene_c2(out, a)
     elif a.scene == "c3":
         scene_c3(out, a)
+    elif a.scene == "inst":
+        scene_instances(out, a)
     elif a.scene == "c4":
         scene_blob(out, a, 320, 160, (1024, 1024), (8, 8))
     else:

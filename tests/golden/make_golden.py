@@ -327,6 +327,113 @@ INLINE["infinite_direct_one"] = _infinite('"directlighting" "integer maxdepth" [
 INLINE["infinite_whitted"] = _infinite('"whitted" "integer maxdepth" [3]', "whitted", _INF_AREA)
 
 
+def _latlong_mesh(nphi, ntheta, rx, ry, rz, normals=True):
+    """a small closed lat-long mesh (optionally with per-vertex N and uv) as a trianglemesh statement"""
+    import math
+    P, N, UV, idx = [], [], [], []
+    for j in range(ntheta + 1):
+        th = math.pi * j / ntheta
+        for i in range(nphi + 1):
+            ph = 2 * math.pi * i / nphi
+            x, y, z = math.sin(th) * math.cos(ph), math.cos(th), math.sin(th) * math.sin(ph)
+            P += [rx * x, ry * y, rz * z]
+            N += [x / rx, y / ry, z / rz]
+            UV += [i / nphi, j / ntheta]
+    for j in range(ntheta):
+        for i in range(nphi):
+            a = j * (nphi + 1) + i
+            b = a + nphi + 1
+            idx += [a, b, a + 1, a + 1, b, b + 1]
+    f = lambda v: " ".join("%.6g" % t for t in v)
+    out = 'Shape "trianglemesh" "integer indices" [%s] "point P" [%s]' % (" ".join(map(str, idx)), f(P))
+    if normals:
+        out += ' "normal N" [%s] "float uv" [%s]' % (f(N), f(UV))
+    return out
+
+
+def _instances(integrator, tag):
+    """object instancing: a multi-primitive object (own kd-tree, mesh with shading normals + quadric), a
+    single-sphere object (no accelerator) and a two-triangle object, placed with translations,
+    rotations, non-uniform scales and a mirroring transform"""
+    return """LookAt 0 4 -11 0 0.8 0 0 1 0
+Camera "perspective" "float fov" [38]
+Film "image" "integer xresolution" [44] "integer yresolution" [30] "string filename" ["instances_%s_out.exr"]
+Sampler "stratified" "integer xsamples" [2] "integer ysamples" [2]
+PixelFilter "box"
+SurfaceIntegrator %s
+WorldBegin
+LightSource "point" "color I" [90 85 80] "point from" [3 7 -6]
+AttributeBegin
+AreaLightSource "area" "color L" [9 9 10]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-2 6 -1 2 6 -1 2 6 2 -2 6 2]
+AttributeEnd
+ObjectBegin "thing"
+Material "plastic" "color Kd" [.7 .4 .2] "color Ks" [.3 .3 .3] "float roughness" [.1]
+%s
+Material "mirror" "color Kr" [.8 .8 .8]
+AttributeBegin
+Translate 0 1.4 0
+Shape "sphere" "float radius" [.45]
+AttributeEnd
+Material "matte" "color Kd" [.2 .5 .7]
+AttributeBegin
+Translate 0 -1.1 0
+Rotate -90 1 0 0
+Shape "cylinder" "float radius" [.35] "float zmin" [0] "float zmax" [.6]
+AttributeEnd
+ObjectEnd
+ObjectBegin "ball"
+Material "glass" "float index" [1.45]
+Shape "sphere" "float radius" [.6]
+ObjectEnd
+ObjectBegin "card"
+Material "matte" "color Kd" [.8 .8 .3]
+%s
+ObjectEnd
+Material "matte" "color Kd" [.6 .6 .6]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-9 -1 -9 9 -1 -9 9 -1 9 -9 -1 9]
+AttributeBegin
+Translate -3.2 0.6 0
+ObjectInstance "thing"
+AttributeEnd
+AttributeBegin
+Translate 0 0.9 1
+Rotate 40 0 1 0
+Scale 1.5 0.8 1.1
+ObjectInstance "thing"
+AttributeEnd
+AttributeBegin
+Translate 3.3 0.7 -0.5
+Rotate 25 0 0 1
+Scale -1 1 1
+ObjectInstance "thing"
+AttributeEnd
+AttributeBegin
+Translate -1.5 -0.4 -2.5
+ObjectInstance "ball"
+AttributeEnd
+AttributeBegin
+Translate 1.6 -0.2 -2.8
+Scale 1 1.5 0.7
+ObjectInstance "ball"
+AttributeEnd
+AttributeBegin
+Translate 0 2.6 3
+Rotate 20 1 0 0
+ObjectInstance "card"
+Translate 2.4 -0.5 0
+Rotate 50 0 1 0
+ObjectInstance "card"
+AttributeEnd
+WorldEnd
+""" % (tag, integrator, _latlong_mesh(8, 5, .9, .7, .8), 'Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-1 -1 0 1 -1 0 1 1 0 -1 1 0]')
+
+
+INLINE["instances_path"] = _instances('"path" "integer maxdepth" [4]', "path")
+INLINE["instances_whitted"] = _instances('"whitted" "integer maxdepth" [4]', "whitted")
+INLINE["instances_direct"] = _instances('"directlighting" "integer maxdepth" [3]', "direct")
+
+
 def parse_count(text, label):
     m = re.search(re.escape(label) + r"\s+([0-9.]+)([kMG]?)", text)
     if not m:

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """BASELINE configs[3] / [4] class scenes (100k / 1M triangle blob): GPU vs oracle twin on a crop, then
 full-size throughput with the kd-walk counters and the roofline arithmetic of SURVEY 8(d).
-usage: big_scene_check.py c4|c5 [--full]"""
+usage: big_scene_check.py c4|c5|inst [--full]   (inst: 27 instances of one 20 k-triangle object)"""
 import os
 import sys
 import time
@@ -16,7 +16,7 @@ ffi = load_ffi()
 name = sys.argv[1]
 out = os.path.join(ROOT, "gpurun_out")
 os.makedirs(out, exist_ok=True)
-res, spp = ((1024, 1024), (8, 8)) if name == "c4" else ((1920, 1080), (16, 16))
+res, spp = ((1024, 1024), (8, 8)) if name in ("c4", "inst") else ((1920, 1080), (16, 16))
 if "--full" not in sys.argv:
     res, spp = (res[0] // 4, res[1] // 4), (2, 2)
 t0 = time.time()
