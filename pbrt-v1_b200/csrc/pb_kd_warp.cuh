@@ -57,6 +57,15 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
   Hit hit;
   hit.prim = -1; hit.t = 0.f; hit.b1 = hit.b2 = 0.f; hit.inst = -1;
   bool anyHit = false;
+  // Object instances (QK == PB_QK_INSTANCES kernels only): while a lane walks an instanced object's
+  // tree its ray is the instance-space ray and node / reference / primitive numbers are relative to
+  // these offsets; the world-space ray, the interrupted leaf walk and the outer mailbox ring wait
+  // in `saved`.  instBase = todo depth at entry (-1: not inside an instance).
+  constexpr bool INSTV = QK == PB_QK_INSTANCES;
+  uint32_t nodeBase = 0, refBase = 0, primBase = 0;
+  int instBase = -1;
+  int32_t instId = -1;
+  float saved[INSTV ? 9 + PB_MAILBOX + 1 : 1];
 
   for (;;) {
     // ---- refill idle lanes
@@ -77,6 +86,7 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
           todoPos = 0;
           inLeaf = false;
           node = 0;
+          if (INSTV) { nodeBase = refBase = primBase = 0; instBase = -1; instId = -1; }
 #pragma unroll
           for (int k = 0; k < PB_MAILBOX; ++k) mailbox[k] = 0xffffffffu;
           mbPos = 0;
@@ -103,7 +113,7 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
       bool descending = active && !inLeaf;
       if (__ballot_sync(0xffffffffu, descending) == 0) break;
       if (descending) {
-        uint2 nd = __ldg((const uint2 *)(sv.nodes + node));
+        uint2 nd = __ldg((const uint2 *)(sv.nodes + (INSTV ? nodeBase : 0u) + node));
         if ((nd.x & 3u) == 3u) {
           if (COUNT) ++cnt.leaves;
           inLeaf = true;
@@ -137,7 +147,7 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
       bool walking = active && inLeaf && !pending && leafI < leafN;
       if (__ballot_sync(0xffffffffu, walking) == 0) break;
       if (walking) {
-        prim = (leafN == 1) ? leafW1 : __ldg(sv.primRefs + leafW1 + leafI);
+        prim = (INSTV ? primBase : 0u) + ((leafN == 1) ? leafW1 : __ldg(sv.primRefs + (INSTV ? refBase : 0u) + leafW1 + leafI));
         ++leafI;
         if (COUNT) ++cnt.refs;
         bool seen = false;
@@ -155,12 +165,56 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
     // ---- the expensive part, all lanes with work together
     if (pending) {
       if (COUNT) ++cnt.tests;
-      // (an InstancePrimitive runs its nested walk here, per lane: QK == PB_QK_INSTANCES kernels only)
-      if (kd_test_prim<ANY, QK, COUNT>(sv, prim, ray, &hit, &cnt)) {
-        anyHit = true;
-        if (ANY) {
-          active = false;
-          sink.done(idx, ray, hit, true);
+      bool entered = false;
+      if (INSTV && instBase < 0 &&
+          (__float_as_uint(__ldg(&sv.prims[3u * prim + 2].b)) & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_INSTANCE) {
+        // InstancePrimitive::Intersect (core/primitive.cpp:66-85): Ray ray = WorldToInstance(r), then
+        // the object's KdTreeAccel::Intersect as part of this lane's state machine
+        const uint32_t id = sv.aux[prim].owner;
+        const PbrtB200Instance &in = sv.instances[id];
+        entered = true;
+        Ray r2;
+        r2.o = xf_point(in.w2i, ray.o);
+        r2.d = xf_vector(in.w2i, ray.d);
+        r2.mint = ray.mint; r2.maxt = ray.maxt;
+        if (in.n_nodes == 0) {
+          // the object is one intersectable primitive (no accelerator, api.cpp:441)
+          Hit h2;
+          h2.prim = -1; h2.t = 0.f; h2.b1 = h2.b2 = 0.f; h2.inst = -1;
+          if (kd_test_prim<ANY, PB_QK_ALL>(sv, in.prim_base, r2, &h2)) {
+            anyHit = true;
+            if (!ANY) { hit = h2; hit.inst = (int32_t)id; ray.maxt = h2.t; }
+            else { active = false; sink.done(idx, ray, hit, true); }
+          }
+        } else {
+          float t0, t1;
+          if (bbox_intersect_p(in.bounds, in.bounds + 3, r2, &t0, &t1)) {
+            saved[0] = ray.o.x; saved[1] = ray.o.y; saved[2] = ray.o.z;
+            saved[3] = ray.d.x; saved[4] = ray.d.y; saved[5] = ray.d.z;
+            saved[6] = __uint_as_float(leafW1); saved[7] = __uint_as_float(leafI); saved[8] = __uint_as_float(leafN);
+#pragma unroll
+            for (int k = 0; k < PB_MAILBOX; ++k) { saved[9 + k] = __uint_as_float(mailbox[k]); mailbox[k] = 0xffffffffu; }
+            saved[9 + PB_MAILBOX] = __int_as_float(mbPos);
+            mbPos = 0;
+            ray = r2;
+            invDir = v3(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
+            tmin = t0; tmax = t1;
+            nodeBase = in.node_base; refBase = in.ref_base; primBase = in.prim_base;
+            instBase = todoPos;
+            instId = (int32_t)id;
+            node = 0;
+            inLeaf = false;
+          }
+        }
+      }
+      if (!entered) {
+        if (kd_test_prim<ANY, (INSTV ? PB_QK_ALL : QK)>(sv, prim, ray, &hit)) {
+          anyHit = true;
+          if (INSTV && !ANY && instBase >= 0) hit.inst = instId;
+          if (ANY) {
+            active = false;
+            sink.done(idx, ray, hit, true);
+          }
         }
       }
     }
@@ -168,15 +222,33 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
     //      lane descends again in the next trip instead of spending a trip on the pop
     if (active && inLeaf && leafI >= leafN) {
       inLeaf = false;
-      if (todoPos == 0) active = false;
+      bool finished = false;   // this tree's walk is over
+      if (todoPos == (INSTV && instBase >= 0 ? instBase : 0)) finished = true;
       else {
         --todoPos;
         node = todoNode[todoPos];
         tmin = todoTmin[todoPos];
         tmax = todoTmax[todoPos];
-        if (!ANY && ray.maxt < tmin) active = false;   // kdtree.cpp:330
+        if (!ANY && ray.maxt < tmin) finished = true;   // kdtree.cpp:330
       }
-      if (!active) sink.done(idx, ray, hit, anyHit);
+      if (INSTV && finished && instBase >= 0) {
+        // the instanced object's walk is over: r.maxt = ray.maxt (primitive.cpp:71), back to the
+        // world-space ray and the leaf that held the instance
+        todoPos = instBase;
+        ray.o = v3(saved[0], saved[1], saved[2]);
+        ray.d = v3(saved[3], saved[4], saved[5]);
+        invDir = v3(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
+        leafW1 = __float_as_uint(saved[6]); leafI = __float_as_uint(saved[7]); leafN = __float_as_uint(saved[8]);
+#pragma unroll
+        for (int k = 0; k < PB_MAILBOX; ++k) mailbox[k] = __float_as_uint(saved[9 + k]);
+        mbPos = __float_as_int(saved[9 + PB_MAILBOX]);
+        nodeBase = refBase = primBase = 0;
+        instBase = -1;
+        inLeaf = true;
+      } else if (finished) {
+        active = false;
+        sink.done(idx, ray, hit, anyHit);
+      }
     }
   }
 }

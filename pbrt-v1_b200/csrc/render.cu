@@ -69,6 +69,12 @@ static int64_t g_reserved4 = 0;           // key 4: reserved (was the fused shad
 #ifndef PB_SURF_MIN_BLOCKS
 #define PB_SURF_MIN_BLOCKS 6
 #endif
+#ifndef PB_TRAV_INST_MIN_BLOCKS
+#define PB_TRAV_INST_MIN_BLOCKS 6   // the two-level walk of scenes with object instances carries more state: 80 registers
+#endif
+#ifndef PB_SHADOW_INST_MIN_BLOCKS
+#define PB_SHADOW_INST_MIN_BLOCKS 8  // (measured on the instanced benchmark scene: closest hit 6 > 8 > 10, any hit 8 > 6 > 10)
+#endif
 #ifndef PB_TRAV_MIN_BLOCKS
 #define PB_TRAV_MIN_BLOCKS 10  // <= 48 registers: 40 resident warps per SM for the latency-bound kd walk (measured best of 6/8/10/12)
 #endif
@@ -288,7 +294,7 @@ __device__ __forceinline__ void flush_kd_counters(unsigned long long *stats, int
   warp_stat_add(&stats[ST_K(kind, TF_TESTS)], cnt.tests);
 }
 template <bool COUNT, int QK>
-__global__ void __launch_bounds__(PB_BLOCK, PB_TRAV_MIN_BLOCKS)
+__global__ void __launch_bounds__(PB_BLOCK, QK == PB_QK_INSTANCES ? PB_TRAV_INST_MIN_BLOCKS : PB_TRAV_MIN_BLOCKS)
 k_intersect(const __grid_constant__ SceneView sv, const RayQueue q, const uint32_t *nPtr,
             uint32_t *work, unsigned long long *stats) {
   uint32_t n = *nPtr;
@@ -319,7 +325,7 @@ struct ShadowSink {
   }
 };
 template <bool COUNT, int QK>
-__global__ void __launch_bounds__(PB_BLOCK, PB_TRAV_MIN_BLOCKS)
+__global__ void __launch_bounds__(PB_BLOCK, QK == PB_QK_INSTANCES ? PB_SHADOW_INST_MIN_BLOCKS : PB_TRAV_MIN_BLOCKS)
 k_shadow(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t *nPtr, uint32_t *work,
          uint8_t *recFlags, unsigned long long *stats) {
   uint32_t n = *nPtr;
