@@ -165,9 +165,12 @@ typedef struct PbrtB200Camera {
 } PbrtB200Camera;
 
 /* samplers/stratified.cpp:51-86, samplers/lowdiscrepancy.cpp:57-74 */
-enum { PBRT_B200_SAMPLER_STRATIFIED = 0, PBRT_B200_SAMPLER_LOWDISCREPANCY = 1 };
+enum { PBRT_B200_SAMPLER_STRATIFIED = 0, PBRT_B200_SAMPLER_LOWDISCREPANCY = 1,
+       PBRT_B200_SAMPLER_BESTCANDIDATE = 2 /* samplers/bestcandidate.cpp: placements of the 4096-entry sample table */ };
+#define PBRT_B200_BC_TABLE_SIZE 4096   /* SAMPLE_TABLE_SIZE, samplers/bestcandidate.cpp:29-31 */
 typedef struct PbrtB200Sampler {
-  int32_t x_samples, y_samples;    /* stratified: strata per axis; lowdiscrepancy: pixelsamples (a power of 2), 1 */
+  int32_t x_samples, y_samples;    /* stratified: strata per axis; lowdiscrepancy: pixelsamples (a power of 2), 1;
+                                      bestcandidate: pixelsamples, 1 */
   int32_t jitter;                  /* stratified only */
   int32_t kind;                    /* PBRT_B200_SAMPLER_* */
 } PbrtB200Sampler;
@@ -215,6 +218,8 @@ typedef struct PbrtB200Scene {
   const uint32_t *light_shapes;      /* primitive ids, ShapeSet order         */
   const float    *light_cdf;         /* ShapeSet::areaCDF, same indexing      */
   uint32_t n_light_shapes;
+  /* bestcandidate sampler only: BestCandidateSampler::sampleTable, 4096 x {imageX, imageY, time, lensU, lensV} */
+  const float *bestcandidate_table;
   PbrtB200Camera     camera;
   PbrtB200Sampler    sampler;
   PbrtB200Integrator integrator;
@@ -327,6 +332,10 @@ int pbrt_b200_camera_rays(PbrtB200Handle *h, const PbrtB200Window *w,
  * it costs memory, so it is opt-in: call with ls == NULL and n != 0 BEFORE
  * pbrt_b200_render() to arm it (n == 0 disarms), then with a buffer after. */
 int pbrt_b200_sample_radiance(PbrtB200Handle *h, int w, uint64_t n, float *ls);
+/* Number of per-sample records window w of the last render holds.  Pixel samplers: the window's
+ * image samples.  bestcandidate: 4096 per table placement, including the entries that fell outside
+ * the sampler's extent and were skipped -- those carry alpha == -1. */
+uint64_t pbrt_b200_sample_slots(PbrtB200Handle *h, int w);
 
 #ifdef __cplusplus
 }

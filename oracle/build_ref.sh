@@ -89,6 +89,16 @@ mark = '\t\t// Generate low-discrepancy samples for pixel\n'
 assert l.count(mark) == 1
 l = l.replace(mark, '\t\tpbrtReseed(xPos, yPos, 0xFFFF, 0);\n' + mark)
 open(tmp + "/lowdiscrepancy_keyed.cpp", "w").write(l)
+# bestcandidate.cpp: one re-key per table placement (sample shifts + LDShuffleScrambled tables) and one
+# per sample (its stratified patterns; also identifies the sample for the Li re-key)
+b = open(ref + "/samplers/bestcandidate.cpp").read()
+b = b.replace('// BestCandidateSampler Declarations', 'extern void pbrtReseed(int, int, int, int);\nextern void pbrtRefBestCandidateSample(int, int, int);\n// BestCandidateSampler Declarations', 1)
+m1 = '\t\t// Update sample shifts\n'
+m2 = '\t// Compute integrator samples for best-candidate sample\n'
+assert b.count(m1) == 1 and b.count(m2) == 1
+b = b.replace(m1, '\t\tpbrtReseed(Floor2Int(xTableCorner), Floor2Int(yTableCorner), 0, 3);\n' + m1)
+b = b.replace(m2, '\tpbrtRefBestCandidateSample(Floor2Int(xTableCorner), Floor2Int(yTableCorner), tableOffset);\n' + m2)
+open(tmp + "/bestcandidate_keyed.cpp", "w").write(b)
 # kdtree.cpp: count calls reaching the kd walk (the metric's "rays": Scene::Intersect + IntersectP)
 k = open(ref + "/accelerators/kdtree.cpp").read()
 k = k.replace('// KdAccelNode Declarations', 'extern unsigned long long gRefIntersectCalls, gRefIntersectPCalls;\n// KdAccelNode Declarations', 1)
@@ -125,6 +135,8 @@ rm -f $OUT/plugins_keyed/stratified.so
 g++ $FL -fPIC -shared $TMP/stratified_keyed.cpp -o $OUT/plugins_keyed/stratified.so
 rm -f $OUT/plugins_keyed/lowdiscrepancy.so
 g++ $FL -fPIC -shared $TMP/lowdiscrepancy_keyed.cpp -o $OUT/plugins_keyed/lowdiscrepancy.so
+rm -f $OUT/plugins_keyed/bestcandidate.so
+g++ $FL -I$REF -fPIC -shared $TMP/bestcandidate_keyed.cpp -o $OUT/plugins_keyed/bestcandidate.so
 
 g++ -O2 -msse2 -mfpmath=sse -rdynamic -o $OUT/pbrt_ref_exact $TMP/main.o $TMP/parser.o $TMP/exact/*.o -ldl -lm
 g++ -O2 -msse2 -mfpmath=sse -rdynamic -o $OUT/pbrt_ref_keyed $TMP/main.o $TMP/parser.o $TMP/keyed/*.o -ldl -lm

@@ -21,6 +21,14 @@
  *   stream 1, s = k      : every draw made while evaluating Li for that sample
  *                          (core/scene.cpp:57 onward)
  *
+ * bestcandidate sampler (samplers/bestcandidate.cpp): its unit is a placement of the 4096-entry
+ * sample table, identified by the integer pixel of its corner (cx, cy); entry `off` of it is a sample:
+ *   stream 3, (cx, cy, 0)        : the placement's three sample shifts and its LDShuffleScrambled tables
+ *   stream 2, bc key (cx,cy,off) : the sample's StratifiedSample1D/2D patterns (patterns of size != 1)
+ *   stream 1, bc key (cx,cy,off) : every draw made while evaluating Li for that sample
+ * where bc key = key(cx ^ ((off >> 10) << 20), cy, off & 1023, stream) keeps the 12-bit entry number
+ * out of the bits y occupies.
+ *
  * draw(ctr) = high 32 bits of splitmix64-finalize(key + ctr * golden), ctr = 1,2,...
  * RandomFloat keeps the reference's mapping (u32 & 0xffffff) / 2^24
  * (core/util.cpp:377-380).
@@ -38,6 +46,9 @@ static inline uint64_t pbrt_keyed_key(int x, int y, int s, int stream) {
   uint64_t k = ((uint64_t)(uint32_t)x << 32) ^ ((uint64_t)(uint32_t)y << 12) ^
                ((uint64_t)(uint32_t)s << 2) ^ (uint64_t)(uint32_t)stream;
   return pbrt_keyed_mix64(k);
+}
+static inline uint64_t pbrt_keyed_key_bc(int cx, int cy, int off, int stream) {
+  return pbrt_keyed_key(cx ^ ((off >> 10) << 20), cy, off & 1023, stream);
 }
 /* ctr is 1-based: the first draw after a reseed uses ctr = 1 */
 static inline uint32_t pbrt_keyed_u32(uint64_t key, uint64_t ctr) {

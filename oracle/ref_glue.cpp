@@ -88,7 +88,22 @@ COREDLL float genrand_real2(void) { return (RandomUInt() & 0xffffff) / float(1 <
 // Called right before Li for every image sample (core/scene.cpp:57).  The
 // (pixel, sample-in-pixel) pair is derived from the running sample count the
 // same way the sampler walks pixels (samplers/stratified.cpp:89-97).
+// bestcandidate sampler: the sampler announces each sample (table placement corner, table entry) right
+// before it generates the sample's integrator patterns; that also keys the following Li.
+static bool gBcSample = false;
+static int gBcX = 0, gBcY = 0, gBcOff = 0;
+COREDLL void pbrtRefBestCandidateSample(int cx, int cy, int off) {
+  gBcSample = true; gBcX = cx; gBcY = cy; gBcOff = off;
+  gKey = pbrt_keyed_key_bc(cx, cy, off, 2);
+  gCtr = 0;
+}
 COREDLL void pbrtRefBeforeLi(const Sampler *sampler) {
+  if (gBcSample) {
+    gKey = pbrt_keyed_key_bc(gBcX, gBcY, gBcOff, 1);
+    gCtr = 0;
+    ++gSampleCounter;
+    return;
+  }
   int spp = sampler->samplesPerPixel;
   int w = sampler->xPixelEnd - sampler->xPixelStart;
   unsigned long long pix = gSampleCounter / spp;
@@ -98,5 +113,6 @@ COREDLL void pbrtRefBeforeLi(const Sampler *sampler) {
 }
 #else
 COREDLL void pbrtReseed(int, int, int, int) {}
+COREDLL void pbrtRefBestCandidateSample(int, int, int) {}
 COREDLL void pbrtRefBeforeLi(const Sampler *) { ++gSampleCounter; }
 #endif

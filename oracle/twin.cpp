@@ -38,6 +38,7 @@ bool build_view(const PbrtB200Scene &s, SceneView *sv) {
   sv->nodes = s.nodes; sv->primRefs = s.prim_refs;
   sv->prims = (const PrimQuad *)s.prims; sv->aux = s.prim_aux;
   sv->meshes = s.meshes; sv->quadrics = s.quadrics; sv->instances = s.instances;
+  sv->bcTable = s.bestcandidate_table;
   sv->vertexN = s.vertex_n; sv->vertexS = s.vertex_s; sv->vertexUV = s.vertex_uv;
   sv->materials = s.materials; sv->lights = s.lights;
   sv->lightShapes = s.light_shapes; sv->lightCdf = s.light_cdf;
@@ -165,6 +166,68 @@ int pbrt_twin_render(const PbrtB200Scene *scene, const PbrtB200Window *win, floa
   const bool ld = sv.sampler.kind == PBRT_B200_SAMPLER_LOWDISCREPANCY;
   std::vector<float> ldTables(ld ? (size_t)sv.ldFloatsPerSample * spp : 0);
   auto t0 = std::chrono::steady_clock::now();
+  // everything after the sampler: camera ray, Li, guards, film (core/scene.cpp:43-78)
+  auto take_sample = [&](CameraSample cs, const PatternSource &key0, uint64_t key1) {
+    Ray ray;
+    perspective_generate_ray(sv.camera, cs, &ray);
+    float alpha = 0.f;
+    Spec Ls = (sv.integrator.kind == PBRT_B200_INT_PATH)
+                  ? li_path(sv, key0, key1, ray, &alpha, c)
+                  : li_wd(sv, key0, key1, ray, &alpha, c);
+    Ls = 1.f * Ls;   // rayWeight * Li, scene.cpp:58
+    cs.imageX = film_image_coord(cs.imageX);
+    cs.imageY = film_image_coord(cs.imageY);
+    int g = sample_guard(&Ls);
+    if (g == 1) ++c.nan; else if (g == 2) ++c.neg; else if (g == 3) ++c.inf;
+    if (samples) {
+      float *o = samples + 6 * nSamples;
+      o[0] = cs.imageX; o[1] = cs.imageY; o[2] = Ls.c[0]; o[3] = Ls.c[1]; o[4] = Ls.c[2]; o[5] = alpha;
+    }
+    ++nSamples;
+    // ImageFilm::AddSample, image.cpp:103-141
+    float dImageX = cs.imageX - 0.5f, dImageY = cs.imageY - 0.5f;
+    int x0 = pb_imax(pb_ceil2int(dImageX - sv.filterXW), win->x0);
+    int x1 = pb_imin(pb_floor2int(dImageX + sv.filterXW), win->x0 + win->width - 1);
+    int y0 = pb_imax(pb_ceil2int(dImageY - sv.filterYW), win->y0);
+    int y1 = pb_imin(pb_floor2int(dImageY + sv.filterYW), win->y0 + win->height - 1);
+    for (int py = y0; py <= y1; ++py)
+      for (int px = x0; px <= x1; ++px) {
+        float wt;
+        if (!film_sample_weight(sv, scene->film.filter_table, cs.imageX, cs.imageY, px, py, &wt))
+          continue;
+        film_pixel_add(&film[(size_t)(py - win->y0) * win->width + (px - win->x0)], wt, Ls.c, alpha);
+      }
+  };
+  if (sv.sampler.kind == PBRT_B200_SAMPLER_BESTCANDIDATE) {
+    // samplers/bestcandidate.cpp:78-171: table placements in scan order, their 4096 entries in order
+    std::vector<float> cxs, cys;
+    pb_bc_placements(xs, xe, ys, ye, sv.bcTableWidth, &cxs, &cys);
+    std::vector<float> tables((size_t)sv.ldFloatsPerSample * PB_BC_TABLE);
+    std::vector<uint16_t> perm(PB_BC_TABLE);
+    for (size_t t = 0; t < cxs.size(); ++t) {
+      int cx = pb_floor2int(cxs[t]), cy = pb_floor2int(cys[t]);
+      uint64_t key3 = pb_key(cx, cy, 0, 3);
+      for (int pi = 0; pi < sv.nPatterns; ++pi) {
+        const SamplePattern &p = sv.patterns[pi];
+        if (p.n != 1) continue;
+        uint32_t scr0 = pb_u32(key3, p.ctr0 + 1), scr1 = p.dims == 2 ? pb_u32(key3, p.ctr0 + 2) : 0u;
+        pb_bc_table_perm(key3, p.ctr0 + (uint32_t)p.dims, perm.data());
+        for (int o = 0; o < PB_BC_TABLE; ++o) {
+          tables[(size_t)p.offset * PB_BC_TABLE + o] = pb_van_der_corput(perm[o], scr0);
+          if (p.dims == 2) tables[(size_t)(p.offset + 1) * PB_BC_TABLE + o] = pb_sobol2(perm[o], scr1);
+        }
+      }
+      for (int o = 0; o < PB_BC_TABLE; ++o) {
+        CameraSample cs;
+        if (!bc_camera_sample(sv, cxs[t], cys[t], o, key3, xs, xe, ys, ye, &cs)) continue;
+        PatternSource key0;
+        key0.key0 = pb_key_bc(cx, cy, o, 2);
+        key0.ld = tables.empty() ? (const float *)0 : tables.data();
+        key0.stride = PB_BC_TABLE; key0.index = (uint32_t)o; key0.bc = 1;
+        take_sample(cs, key0, pb_key_bc(cx, cy, o, 1));
+      }
+    }
+  } else
   for (int y = ys; y < ye; ++y)
     for (int x = xs; x < xe; ++x) {
       if (ld) {
@@ -177,40 +240,11 @@ int pbrt_twin_render(const PbrtB200Scene *scene, const PbrtB200Window *win, floa
         PatternSource key0;
         key0.key0 = pb_key(x, y, k, 0);
         key0.ld = ld ? ldTables.data() : (const float *)0;
-        key0.stride = (uint32_t)spp; key0.index = (uint32_t)k;
+        key0.stride = (uint32_t)spp; key0.index = (uint32_t)k; key0.bc = 0;
         CameraSample cs;
         if (ld) ld_camera_sample(sv, key0, x, y, &cs);
         else stratified_camera_sample(sv, x, y, k, &cs);
-        Ray ray;
-        perspective_generate_ray(sv.camera, cs, &ray);
-        uint64_t key1 = pb_key(x, y, k, 1);
-        float alpha = 0.f;
-        Spec Ls = (sv.integrator.kind == PBRT_B200_INT_PATH)
-                      ? li_path(sv, key0, key1, ray, &alpha, c)
-                      : li_wd(sv, key0, key1, ray, &alpha, c);
-        Ls = 1.f * Ls;   // rayWeight * Li, scene.cpp:58
-        cs.imageX = film_image_coord(cs.imageX);
-        cs.imageY = film_image_coord(cs.imageY);
-        int g = sample_guard(&Ls);
-        if (g == 1) ++c.nan; else if (g == 2) ++c.neg; else if (g == 3) ++c.inf;
-        if (samples) {
-          float *o = samples + 6 * nSamples;
-          o[0] = cs.imageX; o[1] = cs.imageY; o[2] = Ls.c[0]; o[3] = Ls.c[1]; o[4] = Ls.c[2]; o[5] = alpha;
-        }
-        ++nSamples;
-        // ImageFilm::AddSample, image.cpp:103-141
-        float dImageX = cs.imageX - 0.5f, dImageY = cs.imageY - 0.5f;
-        int x0 = pb_imax(pb_ceil2int(dImageX - sv.filterXW), win->x0);
-        int x1 = pb_imin(pb_floor2int(dImageX + sv.filterXW), win->x0 + win->width - 1);
-        int y0 = pb_imax(pb_ceil2int(dImageY - sv.filterYW), win->y0);
-        int y1 = pb_imin(pb_floor2int(dImageY + sv.filterYW), win->y0 + win->height - 1);
-        for (int py = y0; py <= y1; ++py)
-          for (int px = x0; px <= x1; ++px) {
-            float wt;
-            if (!film_sample_weight(sv, scene->film.filter_table, cs.imageX, cs.imageY, px, py, &wt))
-              continue;
-            film_pixel_add(&film[(size_t)(py - win->y0) * win->width + (px - win->x0)], wt, Ls.c, alpha);
-          }
+        take_sample(cs, key0, pb_key(x, y, k, 1));
       }
     }
   auto t1 = std::chrono::steady_clock::now();
@@ -238,6 +272,18 @@ uint64_t pbrt_twin_sample_count(const PbrtB200Scene *scene, const PbrtB200Window
   if (!build_view(*scene, &sv)) return 0;
   int xs, xe, ys, ye;
   film_sample_extent(sv, win->x0, win->y0, win->width, win->height, &xs, &xe, &ys, &ye);
+  if (sv.sampler.kind == PBRT_B200_SAMPLER_BESTCANDIDATE) {
+    // table entries that fall inside the sampler's extent
+    std::vector<float> cxs, cys;
+    pb_bc_placements(xs, xe, ys, ye, sv.bcTableWidth, &cxs, &cys);
+    uint64_t n = 0;
+    for (size_t t = 0; t < cxs.size(); ++t)
+      for (int o = 0; o < PB_BC_TABLE; ++o) {
+        CameraSample cs;
+        if (bc_camera_sample(sv, cxs[t], cys[t], o, 0, xs, xe, ys, ye, &cs)) ++n;
+      }
+    return n;
+  }
   return (uint64_t)(xe - xs) * (ye - ys) * sv.sampler.x_samples * sv.sampler.y_samples;
 }
 

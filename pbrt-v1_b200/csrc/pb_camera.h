@@ -18,6 +18,22 @@ PB_HD void ld_camera_sample(const SceneView &sv, const PatternSource &ps, int x,
   cs->lensU = ps.ld[(size_t)(sv.ldCamera[1].offset + 0) * ps.stride + ps.index];
   cs->lensV = ps.ld[(size_t)(sv.ldCamera[1].offset + 1) * ps.stride + ps.index];
 }
+// samplers/bestcandidate.cpp:107-129: entry `off` of the table placement with corner (cornerX, cornerY).
+// key3 = the placement's stream (its first three draws are the time / lensU / lensV shifts).
+// Returns false when the sample falls outside the sampler's extent [xs,xe) x [ys,ye) (the reference
+// skips such entries).
+PB_HD bool bc_camera_sample(const SceneView &sv, float cornerX, float cornerY, int off, uint64_t key3, int xs,
+                            int xe, int ys, int ye, CameraSample *cs) {
+  const float *e = sv.bcTable + 5 * off;
+  float tw = sv.bcTableWidth;
+  cs->imageX = cornerX + tw * e[0];
+  cs->imageY = cornerY + tw * e[1];
+  float lu = pb_f32(key3, 2u) + e[3];
+  float lv = pb_f32(key3, 3u) + e[4];
+  cs->lensU = lu > 1 ? lu - 1 : lu;   // WRAP
+  cs->lensV = lv > 1 ? lv - 1 : lv;
+  return !(cs->imageX < xs || cs->imageX >= xe || cs->imageY < ys || cs->imageY >= ye);
+}
 PB_HD void stratified_camera_sample(const SceneView &sv, int x, int y, int k, CameraSample *cs) {
   int nx = sv.sampler.x_samples, ny = sv.sampler.y_samples;
   int n = nx * ny;

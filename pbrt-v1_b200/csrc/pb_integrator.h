@@ -393,12 +393,14 @@ PB_HD Spec direct_value(const Spec &termA, const Spec &termB, bool unoccluded, b
 // request order: path.cpp:47-57, directlighting.cpp:39-66, emission.cpp:42-46).
 PB_HD float pat1d(const SceneView &sv, const PatternSource &key0, int idx, int j) {
   const SamplePattern &p = sv.patterns[idx];
-  if (key0.ld) return key0.ld[(size_t)(p.offset + j) * key0.stride + key0.index];
+  if (key0.ld && p.offset >= 0) return key0.ld[(size_t)(p.offset + j) * key0.stride + key0.index];
+  if (key0.bc) return pb_bc_stratified_value(key0.key0, p, j, 0);
   return pb_lhs_value(key0.key0, p, j, 0);
 }
 PB_HD float pat2d(const SceneView &sv, const PatternSource &key0, int idx, int j, int d) {
   const SamplePattern &p = sv.patterns[sv.n1D + idx];
-  if (key0.ld) return key0.ld[(size_t)(p.offset + 2 * j + d) * key0.stride + key0.index];
+  if (key0.ld && p.offset >= 0) return key0.ld[(size_t)(p.offset + 2 * j + d) * key0.stride + key0.index];
+  if (key0.bc) return pb_bc_stratified_value(key0.key0, p, j, d);
   return pb_lhs_value(key0.key0, p, j, d);
 }
 

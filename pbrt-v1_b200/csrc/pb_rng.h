@@ -26,6 +26,11 @@ PB_HD uint64_t pb_key(int x, int y, int s, int stream) {
                ((uint64_t)(uint32_t)s << 2) ^ (uint64_t)(uint32_t)stream;
   return pb_mix64(k);
 }
+// bestcandidate sampler: key of entry `off` of the table placement whose corner pixel is (cx, cy)
+// (oracle/keyed_rng.h: the 12-bit entry number is kept out of the bits y occupies)
+PB_HD uint64_t pb_key_bc(int cx, int cy, int off, int stream) {
+  return pb_key(cx ^ ((off >> 10) << 20), cy, off & 1023, stream);
+}
 // ctr is 1-based (first draw after a re-key has ctr == 1)
 PB_HD uint32_t pb_u32(uint64_t key, uint32_t ctr) {
   return (uint32_t)(pb_mix64(key + (uint64_t)ctr * 0x9E3779B97F4A7C15ULL) >> 32);
@@ -68,10 +73,13 @@ struct SamplePattern {
 // Where an image sample's integrator patterns come from: computed from the key (stratified) or read
 // from the pixel's pre-generated (0,2)-sequence tables (lowdiscrepancy): value e of the sample is
 // ld[e * stride + index].
+// bestcandidate: one-sample patterns are read from the placement's LDShuffleScrambled tables (same
+// record layout), larger ones are StratifiedSample1D/2D draws of the sample's stream 2 (key0).
 struct PatternSource {
   uint64_t key0;
   const float *ld;
   uint32_t stride, index;
+  int32_t bc;
 };
 // LatinHypercube(samples, n, dims) (core/sampling.cpp:98-113): n*dims floats
 // (sample-major), then per dimension n swap draws.  Value of sample j, dim d.
@@ -87,6 +95,20 @@ PB_HD float pb_lhs_value(uint64_t key, const SamplePattern &p, int j, int d) {
   // single swap draw exchanges element 0 with itself
   if (p.n == 1) return pb_f32(key, p.ctr0 + 1 + (uint32_t)d);
   return pb_lhs_value_general(key, p, j, d);
+}
+
+// bestcandidate sampler, patterns of size != 1 (samplers/bestcandidate.cpp:152-168):
+// StratifiedSample1D(n) / StratifiedSample2D(root, root) with jitter (core/sampling.cpp:72-90)
+PB_HD float pb_bc_stratified_value(uint64_t key2, const SamplePattern &p, int j, int d) {
+  if (p.dims == 1) {
+    float invTot = 1.f / p.n;
+    return (j + pb_f32(key2, p.ctr0 + 1u + (uint32_t)j)) * invTot;
+  }
+  int root = 1;
+  while (root * root < p.n) ++root;   // n is a perfect square (BestCandidateSampler::RoundSize)
+  float dxy = 1.f / root;
+  int c = d == 0 ? j % root : j / root;
+  return (c + pb_f32(key2, p.ctr0 + 1u + 2u * (uint32_t)j + (uint32_t)d)) * dxy;
 }
 
 // ---- lowdiscrepancy sampler (samplers/lowdiscrepancy.cpp, core/sampling.h:132-174)
@@ -142,6 +164,20 @@ PB_HD void pb_ld_generate_table(uint64_t key, const SamplePattern &pat, int nPix
       o[0] = pb_van_der_corput(i, scr0);
       if (dims == 2) o[stride] = pb_sobol2(i, scr1);
     }
+  }
+}
+
+// ---- bestcandidate sampler tables (samplers/bestcandidate.cpp:96-105): per table placement one
+// LDShuffleScrambled1D/2D(4096, 1) table per one-sample pattern = scramble draw(s), the (0,2)-sequence
+// points 0..4095, a Shuffle of the 4096 entries and a final one-element Shuffle (one more draw).
+#define PB_BC_TABLE 4096
+// The Shuffle as a permutation: perm[o] = index of the point that ends at entry o.
+// ctrShuffle = draws made before the Shuffle's first.
+PB_HD void pb_bc_table_perm(uint64_t key, uint32_t ctrShuffle, uint16_t *perm) {
+  for (int i = 0; i < PB_BC_TABLE; ++i) perm[i] = (uint16_t)i;
+  for (int i = 0; i < PB_BC_TABLE; ++i) {
+    uint32_t other = pb_u32(key, ctrShuffle + 1u + (uint32_t)i) % (uint32_t)PB_BC_TABLE;
+    uint16_t t = perm[i]; perm[i] = perm[other]; perm[other] = t;
   }
 }
 #endif

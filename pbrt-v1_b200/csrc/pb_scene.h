@@ -51,6 +51,9 @@ struct SceneView {
   // sample's value record (image 2 + lens 2 + every integrator pattern)
   SamplePattern ldCamera[3];
   int32_t ldFloatsPerSample;
+  // bestcandidate sampler: the 4096 x 5 sample table and the width of one placement in pixels
+  const float *bcTable;
+  float bcTableWidth;
 };
 
 struct Hit {

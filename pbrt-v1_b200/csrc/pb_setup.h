@@ -15,7 +15,12 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
   if (s.abi_version != PBRT_B200_ABI_VERSION) return "scene abi_version mismatch";
   if (s.sampler.x_samples < 1 || s.sampler.y_samples < 1) return "sampler needs >= 1 sample per axis";
   const bool ld = s.sampler.kind == PBRT_B200_SAMPLER_LOWDISCREPANCY;
-  if (!ld && s.sampler.kind != PBRT_B200_SAMPLER_STRATIFIED) return "unknown sampler kind";
+  const bool bc = s.sampler.kind == PBRT_B200_SAMPLER_BESTCANDIDATE;
+  if (!ld && !bc && s.sampler.kind != PBRT_B200_SAMPLER_STRATIFIED) return "unknown sampler kind";
+  if (bc && (s.sampler.y_samples != 1 || s.sampler.x_samples > PB_BC_TABLE || !s.bestcandidate_table))
+    return "bestcandidate sampler: pixelsamples must be in [1, 4096] and the sample table present";
+  // tableWidth = SQRT_SAMPLE_TABLE_SIZE / sqrtf(pixelSamples), samplers/bestcandidate.cpp:68-69
+  sv->bcTableWidth = bc ? (float)64 / sqrtf((float)s.sampler.x_samples) : 0.f;
   if (ld && (s.sampler.y_samples != 1 || (s.sampler.x_samples & (s.sampler.x_samples - 1)) != 0 ||
              s.sampler.x_samples > PB_LD_MAX_PIXEL_SAMPLES))
     return "lowdiscrepancy sampler: pixelsamples must be a power of two <= 1024";
@@ -67,6 +72,10 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
           ns = r;
           if (ns > PB_LD_MAX_PATTERN_SAMPLES) return "lowdiscrepancy sampler: too many light samples";
         }
+        if (bc) {   // BestCandidateSampler::RoundSize (samplers/bestcandidate.cpp:45-48)
+          int root = pb_ceil2int(sqrtf((float)ns - .5f));
+          ns = root * root;
+        }
         n2[c2++] = ns; n2[c2++] = ns; n1[c1++] = ns;
         recs += ns;
       }
@@ -100,6 +109,32 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
       ctr += (uint32_t)p.dims + nPixel * 1u + nPixel;
     }
   }
+  if (bc) {
+    // placement stream (3): three sample shifts, then one table per one-sample pattern (1 or 2 scramble
+    // draws, 4096 Shuffle draws, 1 draw of the final one-element Shuffle); sample stream (2): the
+    // stratified draws of the larger patterns, 1D patterns first (samplers/bestcandidate.cpp:96-105,152-168)
+    uint32_t tileCtr = 3, sampleCtr = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      int cnt = pass == 0 ? c1 : c2;
+      const int *nn = pass == 0 ? n1 : n2;
+      int dims = pass + 1;
+      for (int i = 0; i < cnt; ++i, ++k) {
+        SamplePattern &p = sv->patterns[k];
+        p.n = nn[i]; p.dims = dims;
+        if (nn[i] == 1) {
+          p.ctr0 = tileCtr; p.offset = off;
+          tileCtr += (uint32_t)dims + PB_BC_TABLE + 1u;
+          off += dims;
+        } else {
+          p.ctr0 = sampleCtr; p.offset = -1;
+          sampleCtr += (uint32_t)(dims * nn[i]);
+        }
+      }
+    }
+    sv->n1D = c1; sv->n2D = c2; sv->nPatterns = k;
+    sv->ldFloatsPerSample = off;
+    return std::string();
+  }
   for (int i = 0; i < c1; ++i, ++k) {
     sv->patterns[k].ctr0 = ctr; sv->patterns[k].n = n1[i]; sv->patterns[k].dims = 1; sv->patterns[k].offset = off;
     ctr += ld ? 1u + nPixel * (uint32_t)n1[i] + nPixel : 2u * n1[i];
@@ -113,6 +148,27 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
   sv->n1D = c1; sv->n2D = c2; sv->nPatterns = k;
   sv->ldFloatsPerSample = ld ? off : 0;
   return std::string();
+}
+// bestcandidate sampler: corners of the table placements of a sampler over [xs,xe) x [ys,ye), in the
+// order BestCandidateSampler::GetNextSample visits them (samplers/bestcandidate.cpp:66-72,81-90): the
+// corner advances by float additions of tableWidth; the first row starts at (xs - tableWidth) + tableWidth,
+// later rows at xs exactly.
+#include <vector>
+static inline void pb_bc_placements(int xs, int xe, int ys, int ye, float tableWidth, std::vector<float> *cx,
+                                    std::vector<float> *cy) {
+  cx->clear(); cy->clear();
+  float xTableCorner = float(xs) - tableWidth;
+  float yTableCorner = float(ys);
+  for (;;) {
+    xTableCorner += tableWidth;
+    if (xTableCorner >= xe) {
+      xTableCorner = float(xs);
+      yTableCorner += tableWidth;
+      if (yTableCorner >= ye) break;
+    }
+    cx->push_back(xTableCorner);
+    cy->push_back(yTableCorner);
+  }
 }
 // Do any materials carry a specular lobe (Whitted/DirectLighting then recurse)?
 static inline bool pb_scene_has_specular(const PbrtB200Scene &s) {

@@ -122,7 +122,7 @@ struct WaveBuffers {
   unsigned long long *stats;
 };
 // device statistics: general counters, then 5 per traversal kind (rays, interior, leaves, refs, tests)
-enum { ST_SHADED = 0, ST_NAN, ST_NEG, ST_INF, ST_KIND_BASE };
+enum { ST_SHADED = 0, ST_NAN, ST_NEG, ST_INF, ST_CAMERA /* bestcandidate: table entries inside the extent */, ST_KIND_BASE };
 enum { TK_MAIN = 0, TK_SHADOW, TK_PROBE, TK_COUNT };
 enum { TF_RAYS = 0, TF_INTERIOR, TF_LEAVES, TF_REFS, TF_TESTS, TF_COUNT };
 #define ST_COUNT (ST_KIND_BASE + TK_COUNT * TF_COUNT)
@@ -148,9 +148,15 @@ struct WavePart {
   uint32_t nPixels;
   uint32_t slotBase;         // wave slot of the part's first sample (multiple of spp)
   int32_t window;            // index into the handle's films
+  // bestcandidate sampler: the unit is a placement of the 4096-entry sample table instead of a
+  // pixel (firstPixel / nPixels count placements); corners of the window's placements, scan order
+  const float2 *corners;
+  int bcCols;                // placements per row when every row holds the same number, else 0
 };
+#define PB_BC_INVALID_COORD -1.0e6f   // film coordinate of a table entry outside the sampler's extent
 struct WaveDesc {
-  int spp;
+  int spp;                   // samples per unit (pixel; bestcandidate: PB_BC_TABLE per placement)
+  int bc;                    // bestcandidate sampler
   uint32_t nSlots;
   int nParts;
   WavePart parts[PB_MAX_PARTS];
@@ -242,6 +248,7 @@ __global__ void k_slot_pixels(const WaveBuffers wb, const WaveDesc wd) {
 // K0: sample generation + camera rays (samplers/stratified.cpp:87-131, cameras/perspective.cpp:51-82)
 __global__ void __launch_bounds__(PB_BLOCK)
 k_generate(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveDesc wd) {
+  uint32_t nValid = 0;
   for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < wd.nSlots;
        slot += gridDim.x * blockDim.x) {
     int part = 0;
@@ -249,12 +256,37 @@ k_generate(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
     const WavePart &wp = wd.parts[part];
     uint32_t pix = wp.firstPixel + (slot - wp.slotBase) / wd.spp;
     int k = (int)(slot % wd.spp);
+    if (wd.bc) {
+      // samplers/bestcandidate.cpp:107-129: entry k of placement `pix`; entries outside the extent are
+      // skipped (no ray), the others enter the ray queue compacted (nSlots is a multiple of 32, so
+      // whole warps reach the ballot)
+      float2 corner = wp.corners[pix];
+      int cx = pb_floor2int(corner.x), cy = pb_floor2int(corner.y);
+      wb.pixel[slot] = (uint32_t)(cx + 32768) | ((uint32_t)(cy + 32768) << 16);
+      CameraSample cs;
+      bool valid = bc_camera_sample(sv, corner.x, corner.y, k, pb_key(cx, cy, 0, 3), wp.xs, wp.xe, wp.ys, wp.ye, &cs);
+      uint32_t qi = warp_push(&wb.counts[0], valid);
+      if (valid) {
+        Ray ray;
+        perspective_generate_ray(sv.camera, cs, &ray);
+        queue_put(wb.q[0], qi, slot, ray);
+        ++nValid;
+      }
+      wb.imageX[slot] = valid ? film_image_coord(cs.imageX) : PB_BC_INVALID_COORD;
+      wb.imageY[slot] = valid ? film_image_coord(cs.imageY) : PB_BC_INVALID_COORD;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { wb.L[c][slot] = 0.f; wb.T[c][slot] = 1.f; }
+      wb.alpha[slot] = valid ? 0.f : -1.f;   // -1 marks a skipped entry in the per-sample dump
+      wb.ctr[slot] = 0u;
+      wb.flags[slot] = 0u;
+      continue;
+    }
     int ew = wp.xe - wp.xs;
     int x = wp.xs + (int)(pix % ew), y = wp.ys + (int)(pix / ew);
     wb.pixel[slot] = (uint32_t)(x + 32768) | ((uint32_t)(y + 32768) << 16);
     CameraSample cs;
     if (sv.sampler.kind == PBRT_B200_SAMPLER_LOWDISCREPANCY) {
-      PatternSource ps = {0, wb.ld, wb.nSlots, slot};
+      PatternSource ps = {0, wb.ld, wb.nSlots, slot, 0};
       ld_camera_sample(sv, ps, x, y, &cs);
     } else
       stratified_camera_sample(sv, x, y, k, &cs);
@@ -268,6 +300,53 @@ k_generate(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
     wb.alpha[slot] = 0.f;
     wb.ctr[slot] = 0u;
     wb.flags[slot] = 0u;
+  }
+  if (wd.bc) warp_stat_add(&wb.stats[ST_CAMERA], nValid);
+}
+
+// K0b (bestcandidate sampler only): the LDShuffleScrambled1D/2D(4096, 1) tables of every table
+// placement of the wave (samplers/bestcandidate.cpp:96-105), one warp per (placement, one-sample
+// pattern): the Shuffle's 4096 draws in parallel, its swaps by one lane in shared memory, then the
+// (0,2)-sequence points written through the permutation.  Runs after k_generate (reads the
+// placements' corner pixels from wb.pixel).
+#define PB_BC_TABLE_WARPS 2
+__global__ void __launch_bounds__(32 * PB_BC_TABLE_WARPS)
+k_bc_tables(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveDesc wd) {
+  __shared__ uint16_t permS[PB_BC_TABLE_WARPS][PB_BC_TABLE];
+  const uint32_t lane = lane_id(), wib = threadIdx.x >> 5;
+  uint16_t *perm = permS[wib];
+  const uint32_t nUnits = wd.nSlots / PB_BC_TABLE;
+  const uint32_t total = nUnits * (uint32_t)sv.nPatterns;
+  const uint32_t nWarps = gridDim.x * PB_BC_TABLE_WARPS;
+  for (uint32_t w = blockIdx.x * PB_BC_TABLE_WARPS + wib; w < total; w += nWarps) {
+    const SamplePattern &p = sv.patterns[w % (uint32_t)sv.nPatterns];
+    if (p.n != 1) continue;
+    const uint32_t slot0 = (w / (uint32_t)sv.nPatterns) * PB_BC_TABLE;
+    uint32_t px = wb.pixel[slot0];
+    uint64_t key3 = pb_key((int)(px & 0xffffu) - 32768, (int)(px >> 16) - 32768, 0, 3);
+    uint32_t scr0 = pb_u32(key3, p.ctr0 + 1u), scr1 = p.dims == 2 ? pb_u32(key3, p.ctr0 + 2u) : 0u;
+    uint32_t ctrShuffle = p.ctr0 + (uint32_t)p.dims;
+    for (uint32_t i = lane; i < PB_BC_TABLE; i += 32) perm[i] = (uint16_t)i;
+    __syncwarp();
+    // Shuffle (core/sampling.cpp:91-97): 32 swap partners drawn in parallel, the swaps themselves in
+    // order by lane 0 (partners handed over by shuffles, so shared memory only holds the permutation)
+    for (uint32_t base = 0; base < PB_BC_TABLE; base += 32) {
+      uint32_t mine = pb_u32(key3, ctrShuffle + 1u + base + lane) % (uint32_t)PB_BC_TABLE;
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        uint32_t o = __shfl_sync(0xffffffffu, mine, j);
+        if (lane == 0) {
+          uint16_t t = perm[base + j];
+          perm[base + j] = perm[o]; perm[o] = t;
+        }
+      }
+    }
+    __syncwarp();
+    for (uint32_t o = lane; o < PB_BC_TABLE; o += 32) {
+      wb.ld[(size_t)p.offset * wb.nSlots + slot0 + o] = pb_van_der_corput(perm[o], scr0);
+      if (p.dims == 2) wb.ld[(size_t)(p.offset + 1) * wb.nSlots + slot0 + o] = pb_sobol2(perm[o], scr1);
+    }
+    __syncwarp();
   }
 }
 
@@ -380,10 +459,13 @@ __device__ __forceinline__ void store3(float *const a[3], uint32_t i, const Spec
 struct WaveKeyInfo {
   const uint32_t *pixel;
   int spp;
+  int bc;   // bestcandidate sampler: pixel[] holds the placement's corner pixel, slot % spp the table entry
 };
 __device__ __forceinline__ uint64_t slot_key(const WaveKeyInfo &wd, uint32_t slot, int stream) {
   uint32_t p = wd.pixel[slot];
-  return pb_key((int)(p & 0xffffu) - 32768, (int)(p >> 16) - 32768, (int)(slot % (uint32_t)wd.spp), stream);
+  int x = (int)(p & 0xffffu) - 32768, y = (int)(p >> 16) - 32768, k = (int)(slot % (uint32_t)wd.spp);
+  if (wd.bc) return pb_key_bc(x, y, k, stream == 0 ? 2 : stream);   // patterns: the sample's stream 2
+  return pb_key(x, y, k, stream);
 }
 // Fold the slot's pending direct-lighting record (path integrator) into L.
 __device__ __forceinline__ void path_fold_pending(const SceneView &sv, const WaveBuffers &wb,
@@ -513,7 +595,7 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
         st.depth = (int)(flags & 0xffu);
         st.rng.key = slot_key(wd, slot, 1);
         st.rng.ctr = wb.ctr[slot];
-        PatternSource key0 = {slot_key(wd, slot, 0), LD ? wb.ld : (const float *)nullptr, wb.nSlots, slot};
+        PatternSource key0 = {slot_key(wd, slot, 0), LD ? wb.ld : (const float *)nullptr, wb.nSlots, slot, LD ? wd.bc : 0};
         bool hasDirect;
         path_vertex_direct<G, LK>(sv, key0, st, ray, &sf, &direct, &hasDirect);
         wb.ctr[slot] = st.rng.ctr;
@@ -575,7 +657,7 @@ k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, cons
         st.specularBounce = (flags >> 8) & 1u;
         st.rng.key = slot_key(wd, slot, 1);
         st.rng.ctr = wb.ctr[slot];
-        PatternSource key0 = {slot_key(wd, slot, 0), LD ? wb.ld : (const float *)nullptr, wb.nSlots, slot};
+        PatternSource key0 = {slot_key(wd, slot, 0), LD ? wb.ld : (const float *)nullptr, wb.nSlots, slot, LD ? wd.bc : 0};
         pushNext = path_vertex_continue<G>(sv, key0, st, ray, sf, &next);
         store3(wb.T, slot, st.T);
         wb.ctr[slot] = st.rng.ctr;
@@ -657,7 +739,7 @@ k_shade_wd(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
         RngStream rng;
         rng.key = slot_key(wd, slot, 1);
         rng.ctr = wb.ctr[slot];
-        PatternSource key0 = {slot_key(wd, slot, 0), wb.ld, wb.nSlots, slot};
+        PatternSource key0 = {slot_key(wd, slot, 0), wb.ld, wb.nSlots, slot, wd.bc};
         float alpha = 0.f;
         WdFrame fr;
         WdVertexOut out;
@@ -746,6 +828,11 @@ k_finalize(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
   for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < wd.nSlots;
        slot += gridDim.x * blockDim.x) {
     Spec L;
+    if (wd.bc && wb.alpha[slot] == -1.f) {   // bestcandidate: a table entry outside the extent, no sample
+      store3(wb.outL, slot, spec(0.f));
+      wb.outA[slot] = -1.f;
+      continue;
+    }
     if (sv.integrator.kind == PBRT_B200_INT_PATH) {
       uint32_t flags = wb.flags[slot];
       L = load3(wb.L, slot);
@@ -826,6 +913,87 @@ k_film_gather(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
   }
 }
 
+// K5b for the bestcandidate sampler: the samples of a table placement are spread over its whole
+// area, so a pixel visits the placements of the part in order and, for those whose (filter-grown)
+// area contains it, all 4096 entries in order -- the order the reference's serial loop splats them.
+// The table's entries never move inside a placement, so which of the 4096 can reach a pixel is first
+// narrowed with bit masks: the unit square is cut into PB_BC_STRIPS strips per axis and
+// bcMasks[axis][s + 1] has bit k set when entry k lies in a strip <= s (prefix masks, [0] = none);
+// the entries whose x (y) strip is in [lo, hi] are prefix[hi + 1] & ~prefix[lo].  Survivors take the
+// exact test in ascending entry order.
+#define PB_BC_STRIPS 64
+#define PB_BC_WORDS (PB_BC_TABLE / 32)
+__global__ void __launch_bounds__(PB_BLOCK)
+k_film_gather_bc(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WavePart wd,
+                 const float *filterTable, const uint32_t *bcMasks, FilmPixel *film, PbrtB200Window win,
+                 int rowFirst, int rowCount) {
+  __shared__ float table[256];
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) table[t] = filterTable[t];
+  __syncthreads();
+  int total = rowCount * win.width;
+  const float tw = sv.bcTableWidth;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    int px = win.x0 + idx % win.width;
+    int py = rowFirst + idx / win.width;
+    FilmPixel *fpx = &film[(size_t)(py - win.y0) * win.width + (px - win.x0)];
+    FilmPixel acc = *fpx;
+    bool touched = false;
+    // candidate placements: on a regular grid only the few columns / rows around the pixel
+    uint32_t tBegin = 0, tEnd = wd.nPixels;
+    int colLo = 0, colHi = 0x7fffffff;
+    if (wd.bcCols > 0) {
+      float reachX = sv.filterXW + 2.5f, reachY = sv.filterYW + 2.5f;
+      colLo = max(0, (int)floorf((px - reachX - (float)wd.xs) / tw) - 1);
+      colHi = min(wd.bcCols - 1, (int)floorf((px + reachX - (float)wd.xs) / tw) + 1);
+      int rowLo = max(0, (int)floorf((py - reachY - (float)wd.ys) / tw) - 1);
+      int rowHi = (int)floorf((py + reachY - (float)wd.ys) / tw) + 1;
+      long long b = (long long)rowLo * wd.bcCols - (long long)wd.firstPixel;
+      long long e = ((long long)rowHi + 1) * wd.bcCols - (long long)wd.firstPixel;
+      tBegin = (uint32_t)max(0ll, min(b, (long long)wd.nPixels));
+      tEnd = (uint32_t)max(0ll, min(e, (long long)wd.nPixels));
+    }
+    for (uint32_t t = tBegin; t < tEnd; ++t) {
+      if (wd.bcCols > 0) {
+        int col = (int)((wd.firstPixel + t) % (uint32_t)wd.bcCols);
+        if (col < colLo) { t += (uint32_t)(colLo - col) - 1u; continue; }
+        if (col > colHi) { t += (uint32_t)(wd.bcCols - col) - 1u; continue; }
+      }
+      float2 c = wd.corners[wd.firstPixel + t];
+      // sample coordinates of the placement lie in [c, c + tw]; a sample reaches pixels within the
+      // filter width of (coordinate - 0.5)
+      if (px < c.x - 1.5f - sv.filterXW || px > c.x + tw + 0.5f + sv.filterXW ||
+          py < c.y - 1.5f - sv.filterYW || py > c.y + tw + 0.5f + sv.filterYW)
+        continue;
+      uint32_t s0 = wd.slotBase + t * PB_BC_TABLE;
+      // table-space interval of the sample coordinates that can reach the pixel, one strip of slack
+      float invTw = 1.f / tw;
+      int sxLo = (int)floorf((px + 0.5f - sv.filterXW - c.x) * invTw * PB_BC_STRIPS) - 1;
+      int sxHi = (int)floorf((px + 0.5f + sv.filterXW - c.x) * invTw * PB_BC_STRIPS) + 1;
+      int syLo = (int)floorf((py + 0.5f - sv.filterYW - c.y) * invTw * PB_BC_STRIPS) - 1;
+      int syHi = (int)floorf((py + 0.5f + sv.filterYW - c.y) * invTw * PB_BC_STRIPS) + 1;
+      if (sxHi < 0 || syHi < 0 || sxLo >= PB_BC_STRIPS || syLo >= PB_BC_STRIPS) continue;
+      sxLo = max(sxLo, 0); syLo = max(syLo, 0);
+      sxHi = min(sxHi, PB_BC_STRIPS - 1); syHi = min(syHi, PB_BC_STRIPS - 1);
+      const uint32_t *xLoM = bcMasks + (size_t)sxLo * PB_BC_WORDS, *xHiM = bcMasks + (size_t)(sxHi + 1) * PB_BC_WORDS;
+      const uint32_t *yBase = bcMasks + (size_t)(PB_BC_STRIPS + 1) * PB_BC_WORDS;
+      const uint32_t *yLoM = yBase + (size_t)syLo * PB_BC_WORDS, *yHiM = yBase + (size_t)(syHi + 1) * PB_BC_WORDS;
+      for (uint32_t w = 0; w < PB_BC_WORDS; ++w) {
+        uint32_t m = (__ldg(xHiM + w) & ~__ldg(xLoM + w)) & (__ldg(yHiM + w) & ~__ldg(yLoM + w));
+        while (m) {
+          uint32_t slot = s0 + 32u * w + (uint32_t)(__ffs(m) - 1);
+          m &= m - 1u;
+          float wt;
+          if (!film_sample_weight(sv, table, wb.imageX[slot], wb.imageY[slot], px, py, &wt)) continue;
+          float L[3] = {wb.outL[0][slot], wb.outL[1][slot], wb.outL[2][slot]};
+          film_pixel_add(&acc, wt, L, wb.outA[slot]);
+          touched = true;
+        }
+      }
+    }
+    if (touched) *fpx = acc;
+  }
+}
+
 // K6: ImageFilm::WriteImage up to the WriteRGBAImage call (film/image.cpp:157-203)
 __global__ void k_film_resolve(const FilmPixel *film, float4 *rgba, int n, int premultiply) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -887,6 +1055,8 @@ struct WindowFilm {
   float4 *rgba;        // device
   float *sampleOut;    // device: 4 floats per sample (kept only when requested)
   uint64_t nSamples;
+  float2 *corners;     // device: bestcandidate table placements of the window (scan order)
+  std::vector<float2> cornersHost;
 };
 
 struct PbrtB200Handle {
@@ -898,6 +1068,7 @@ struct PbrtB200Handle {
   SceneView sv;                 // device pointers
   std::vector<void *> allocs;   // scene arrays
   float *filterTable;
+  uint32_t *bcMasks;            // bestcandidate: per-axis prefix strip masks of the sample table (k_film_gather_bc)
   bool hasSpecular;
   bool hasGlossy;
   int primKinds;                // PB_QK_*: which primitive tests the traversal kernels need
@@ -940,12 +1111,68 @@ struct LaunchTimer {
 #define TIMED(cls, launch) do { LaunchTimer lt_(h, cls); launch; } while (0)
 #define TIMED_ON(cls, strm, launch) do { LaunchTimer lt_(h, cls, strm); launch; } while (0)
 
+#define PB_MAX_DEVICES 64
+// Small per-device cache of released device blocks: pbrt_b200_render_host() builds and tears down a
+// handle per call (scene arrays, films), and cudaMalloc / cudaFree (which synchronises) per frame
+// showed up as ~10 ms of a 176 ms end-to-end step.  A block is reused for a request of at most its
+// size and at least half of it; the cache is bounded in blocks and bytes.
+#include <mutex>
+#include <unordered_map>
+namespace {
+struct PoolBlock { void *p; size_t bytes; };
+std::mutex g_poolMutex;
+std::vector<PoolBlock> g_pool[PB_MAX_DEVICES];
+std::unordered_map<void *, size_t> g_poolSizes;     // live blocks handed out by pool_alloc
+const size_t kPoolMaxBlocks = 48, kPoolMaxBytes = (size_t)1 << 30;
+}  // namespace
+static cudaError_t pool_alloc(int device, void **out, size_t bytes) {
+  if (bytes == 0) bytes = 1;
+  {
+    std::lock_guard<std::mutex> lock(g_poolMutex);
+    if (device >= 0 && device < PB_MAX_DEVICES) {
+      std::vector<PoolBlock> &pool = g_pool[device];
+      int best = -1;
+      for (int i = 0; i < (int)pool.size(); ++i)
+        if (pool[i].bytes >= bytes && pool[i].bytes <= 2 * bytes + 4096 && (best < 0 || pool[i].bytes < pool[best].bytes)) best = i;
+      if (best >= 0) {
+        *out = pool[best].p;
+        g_poolSizes[*out] = pool[best].bytes;
+        pool.erase(pool.begin() + best);
+        return cudaSuccess;
+      }
+    }
+  }
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e == cudaSuccess) {
+    std::lock_guard<std::mutex> lock(g_poolMutex);
+    g_poolSizes[*out] = bytes;
+  }
+  return e;
+}
+static void pool_free(int device, void *p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lock(g_poolMutex);
+  size_t bytes = 0;
+  auto it = g_poolSizes.find(p);
+  if (it != g_poolSizes.end()) { bytes = it->second; g_poolSizes.erase(it); }
+  if (bytes && device >= 0 && device < PB_MAX_DEVICES) {
+    std::vector<PoolBlock> &pool = g_pool[device];
+    size_t total = bytes;
+    for (const PoolBlock &b : pool) total += b.bytes;
+    if (pool.size() < kPoolMaxBlocks && total <= kPoolMaxBytes) {
+      pool.push_back({p, bytes});
+      return;
+    }
+  }
+  cudaFree(p);
+}
+
 template <class T>
 static int upload(PbrtB200Handle *h, const T *src, size_t n, const T **dst) {
   *dst = nullptr;
   if (n == 0 || !src) return PBRT_B200_OK;
   void *d = nullptr;
-  CU_TRY(cudaMalloc(&d, n * sizeof(T)));
+  CU_TRY(pool_alloc(h->device, &d, n * sizeof(T)));
   h->allocs.push_back(d);
   CU_TRY(cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
   h->sceneBytes += n * sizeof(T);
@@ -955,7 +1182,6 @@ static int upload(PbrtB200Handle *h, const T *src, size_t n, const T **dst) {
 
 // One retired wave arena per device is kept for the next handle: pbrt_b200_render_host() creates and
 // destroys a handle per call, and a multi-GB cudaMalloc/cudaFree per frame would dominate it.
-#define PB_MAX_DEVICES 64
 static void *g_cachedArena[PB_MAX_DEVICES];
 static size_t g_cachedArenaBytes[PB_MAX_DEVICES];
 static void free_wave(PbrtB200Handle *h) {
@@ -1057,9 +1283,10 @@ static int ensure_wave(PbrtB200Handle *h, uint32_t nSlots) {
 
 static void free_films(PbrtB200Handle *h) {
   for (auto &f : h->films) {
-    if (f.film) cudaFree(f.film);
-    if (f.rgba) cudaFree(f.rgba);
-    if (f.sampleOut) cudaFree(f.sampleOut);
+    pool_free(h->device, f.film);
+    pool_free(h->device, f.rgba);
+    pool_free(h->device, f.sampleOut);
+    pool_free(h->device, f.corners);
   }
   h->films.clear();
 }
@@ -1104,7 +1331,8 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
   int grid = persistent_grid(h);
   bool count = g_countKd != 0;
   CU_TRY(cudaMemsetAsync(wb.counts, 0, PB_COUNTS_TOTAL * sizeof(uint32_t), st));
-  CU_TRY(cudaMemcpyAsync(&wb.counts[0], &wd.nSlots, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  // (bestcandidate: k_generate counts the table entries that fall inside the extent itself)
+  if (!wd.bc) CU_TRY(cudaMemcpyAsync(&wb.counts[0], &wd.nSlots, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   int genGrid = (int)std::min<uint64_t>((wd.nSlots + PB_BLOCK - 1) / PB_BLOCK, (uint64_t)h->numSMs * 16);
   if (sv.sampler.kind == PBRT_B200_SAMPLER_LOWDISCREPANCY) {
     TIMED(KC_GENERATE, (k_slot_pixels<<<genGrid, PB_BLOCK, 0, st>>>(wb, wd)));
@@ -1115,13 +1343,20 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
   }
   TIMED(KC_GENERATE, (k_generate<<<genGrid, PB_BLOCK, 0, st>>>(sv, wb, wd)));
   ++*launches;
+  if (wd.bc && sv.ldFloatsPerSample > 0) {
+    uint64_t nWarps = (uint64_t)(wd.nSlots / PB_BC_TABLE) * sv.nPatterns;
+    int tg = (int)std::min<uint64_t>((nWarps + PB_BC_TABLE_WARPS - 1) / PB_BC_TABLE_WARPS, (uint64_t)h->numSMs * 16);
+    TIMED(KC_GENERATE, (k_bc_tables<<<tg, 32 * PB_BC_TABLE_WARPS, 0, st>>>(sv, wb, wd)));
+    ++*launches;
+  }
   uint32_t workIdx = PB_WORK_BASE;
   auto nextWork = [&]() { return wb.counts + (workIdx++); };
   bool isPath = sv.integrator.kind == PBRT_B200_INT_PATH;
   int cur = 0;
-  WaveKeyInfo wk = {wb.pixel, wd.spp};
+  WaveKeyInfo wk = {wb.pixel, wd.spp, wd.bc};
   bool overlap = g_overlap != 0;
-  const bool isLD = sv.sampler.kind == PBRT_B200_SAMPLER_LOWDISCREPANCY;
+  // (LD kernels = patterns read from per-unit tables: lowdiscrepancy and bestcandidate)
+  const bool isLD = sv.sampler.kind == PBRT_B200_SAMPLER_LOWDISCREPANCY || wd.bc;
   if (isPath) {
     int iters = sv.integrator.max_depth + 1;
     if (iters < 1) iters = 1;
@@ -1167,6 +1402,10 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
     // Whitted / DirectLighting: the recursion depth is data dependent; one host readback of
     // the queue size per iteration ends the loop.
     uint32_t nMainHost = wd.nSlots;
+    if (wd.bc) {
+      CU_TRY(cudaMemcpyAsync(&nMainHost, &wb.counts[0], sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CU_TRY(cudaStreamSynchronize(st));
+    }
     int it = 0;
     while (nMainHost > 0) {
       if (it >= PB_MAX_ITERS - 1) {
@@ -1232,10 +1471,14 @@ int64_t pbrt_b200_tunable(int key, int64_t value) {
 void pbrt_b200_scene_destroy(PbrtB200Handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  // (released blocks may still be read by queued work of this handle's streams: drain them first)
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->auxStream) cudaStreamSynchronize(h->auxStream);
   free_films(h);
   free_wave(h);
-  for (void *p : h->allocs) cudaFree(p);
-  if (h->filterTable) cudaFree(h->filterTable);
+  for (void *p : h->allocs) pool_free(h->device, p);
+  pool_free(h->device, h->filterTable);
+  pool_free(h->device, h->bcMasks);
   for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
   if (h->evDirect) cudaEventDestroy(h->evDirect);
   if (h->evAux) cudaEventDestroy(h->evAux);
@@ -1252,14 +1495,20 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
     return fail(PBRT_B200_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)");
   if (device < 0 || device >= nDev) return fail(PBRT_B200_ERR_INVALID, "device ordinal out of range");
   CU_TRY(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  CU_TRY(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10)
-    return fail(PBRT_B200_ERR_NO_DEVICE, std::string("device is not sm_100 class: ") + prop.name);
+  // (cudaGetDeviceProperties costs ~1 ms: asked once per device)
+  static int devMajor[PB_MAX_DEVICES], devSMs[PB_MAX_DEVICES];
+  static bool devKnown[PB_MAX_DEVICES];
+  if (device >= PB_MAX_DEVICES) return fail(PBRT_B200_ERR_INVALID, "device ordinal too large");
+  if (!devKnown[device]) {
+    CU_TRY(cudaDeviceGetAttribute(&devMajor[device], cudaDevAttrComputeCapabilityMajor, device));
+    CU_TRY(cudaDeviceGetAttribute(&devSMs[device], cudaDevAttrMultiProcessorCount, device));
+    devKnown[device] = true;
+  }
+  if (devMajor[device] < 10) return fail(PBRT_B200_ERR_NO_DEVICE, "device is not sm_100 class");
   PbrtB200Handle *h = new PbrtB200Handle();
   h->device = device; h->stream = nullptr; h->auxStream = nullptr; h->evDirect = nullptr; h->evAux = nullptr;
-  h->numSMs = prop.multiProcessorCount;
-  h->filterTable = nullptr; h->arena = nullptr; h->arenaBytes = 0; h->sceneBytes = 0; h->keepSamples = false;
+  h->numSMs = devSMs[device];
+  h->filterTable = nullptr; h->bcMasks = nullptr; h->arena = nullptr; h->arenaBytes = 0; h->sceneBytes = 0; h->keepSamples = false;
   memset(&h->wb, 0, sizeof(h->wb));
   memset(&h->sv, 0, sizeof(h->sv));
   memset(h->classMs, 0, sizeof(h->classMs));
@@ -1313,6 +1562,8 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   UP(upload(h, scene->meshes, scene->n_meshes, &sv.meshes));
   UP(upload(h, scene->quadrics, scene->n_quadrics, &sv.quadrics));
   UP(upload(h, scene->instances, scene->n_instances, &sv.instances));
+  if (scene->sampler.kind == PBRT_B200_SAMPLER_BESTCANDIDATE)
+    UP(upload(h, scene->bestcandidate_table, (size_t)PB_BC_TABLE * 5, &sv.bcTable));
   UP(upload(h, scene->vertex_n, (size_t)scene->n_vertices * 3, &sv.vertexN));
   UP(upload(h, scene->vertex_s, (size_t)scene->n_vertices * 3, &sv.vertexS));
   UP(upload(h, scene->vertex_uv, (size_t)scene->n_vertices * 2, &sv.vertexUV));
@@ -1321,7 +1572,26 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   UP(upload(h, scene->light_shapes, scene->n_light_shapes, &sv.lightShapes));
   UP(upload(h, scene->light_cdf, scene->n_light_shapes, &sv.lightCdf));
 #undef UP
-  ce = cudaMalloc((void **)&h->filterTable, 256 * sizeof(float));
+  if (scene->sampler.kind == PBRT_B200_SAMPLER_BESTCANDIDATE) {
+    // prefix strip masks of the table's image positions (see k_film_gather_bc)
+    std::vector<uint32_t> masks((size_t)2 * (PB_BC_STRIPS + 1) * PB_BC_WORDS, 0u);
+    for (int axis = 0; axis < 2; ++axis) {
+      uint32_t *base = masks.data() + (size_t)axis * (PB_BC_STRIPS + 1) * PB_BC_WORDS;
+      for (int k = 0; k < PB_BC_TABLE; ++k) {
+        int sidx = (int)floorf(scene->bestcandidate_table[5 * k + axis] * PB_BC_STRIPS);
+        sidx = std::min(std::max(sidx, 0), PB_BC_STRIPS - 1);
+        for (int t = sidx + 1; t <= PB_BC_STRIPS; ++t) base[(size_t)t * PB_BC_WORDS + k / 32] |= 1u << (k % 32);
+      }
+    }
+    ce = pool_alloc(h->device, (void **)&h->bcMasks, masks.size() * sizeof(uint32_t));
+    if (ce == cudaSuccess)
+      ce = cudaMemcpy(h->bcMasks, masks.data(), masks.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) {
+      pbrt_b200_scene_destroy(h);
+      return fail(PBRT_B200_ERR_CUDA, cudaGetErrorString(ce));
+    }
+  }
+  ce = pool_alloc(h->device, (void **)&h->filterTable, 256 * sizeof(float));
   if (ce == cudaSuccess)
     ce = cudaMemcpyAsync(h->filterTable, scene->film.filter_table, 256 * sizeof(float), cudaMemcpyHostToDevice, h->stream);
   h->sceneBytes += 256 * sizeof(float);
@@ -1354,7 +1624,10 @@ int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_win
   CU_TRY(cudaEventCreate(&e0));
   CU_TRY(cudaEventCreate(&e1));
   // per-window sample extents; size the wave arena for min(tunable, all samples)
-  const int spp = sv.sampler.x_samples * sv.sampler.y_samples;
+  const bool bc = sv.sampler.kind == PBRT_B200_SAMPLER_BESTCANDIDATE;
+  // samples per unit of work: a pixel's samples, or the 4096 entries of one bestcandidate table placement
+  const int spp = bc ? PB_BC_TABLE : sv.sampler.x_samples * sv.sampler.y_samples;
+  std::vector<std::vector<float2>> placements(n_windows);
   std::vector<WavePart> ext(n_windows);
   std::vector<uint64_t> nPixW(n_windows);
   uint64_t totalSamples = 0;
@@ -1366,6 +1639,14 @@ int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_win
     ext[w] = window_part(sv, win);
     ext[w].window = w;
     nPixW[w] = (uint64_t)(ext[w].xe - ext[w].xs) * (ext[w].ye - ext[w].ys);
+    if (bc) {
+      std::vector<float> cx, cy;
+      pb_bc_placements(ext[w].xs, ext[w].xe, ext[w].ys, ext[w].ye, sv.bcTableWidth, &cx, &cy);
+      placements[w].resize(cx.size());
+      for (size_t i = 0; i < cx.size(); ++i) placements[w][i] = make_float2(cx[i], cy[i]);
+      nPixW[w] = cx.size();
+      if (nPixW[w] == 0) return fail(PBRT_B200_ERR_INVALID, "bestcandidate sampler: window holds no table placement");
+    }
     totalSamples += nPixW[w] * spp;
   }
   uint64_t capSlots = std::max<uint64_t>((uint64_t)spp, std::min<uint64_t>((uint64_t)g_waveSamples, totalSamples));
@@ -1385,12 +1666,18 @@ int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_win
       continue;
     }
     WindowFilm wf;
-    wf.win = win; wf.film = nullptr; wf.rgba = nullptr; wf.sampleOut = nullptr;
-    CU_TRY(cudaMalloc((void **)&wf.film, nPixOut * sizeof(FilmPixel)));
-    CU_TRY(cudaMalloc((void **)&wf.rgba, nPixOut * sizeof(float4)));
+    wf.win = win; wf.film = nullptr; wf.rgba = nullptr; wf.sampleOut = nullptr; wf.corners = nullptr;
+    if (bc) {
+      wf.cornersHost = placements[w];
+      CU_TRY(pool_alloc(h->device, (void **)&wf.corners, placements[w].size() * sizeof(float2)));
+      CU_TRY(cudaMemcpyAsync(wf.corners, wf.cornersHost.data(), placements[w].size() * sizeof(float2),
+                             cudaMemcpyHostToDevice, h->stream));
+    }
+    CU_TRY(pool_alloc(h->device, (void **)&wf.film, nPixOut * sizeof(FilmPixel)));
+    CU_TRY(pool_alloc(h->device, (void **)&wf.rgba, nPixOut * sizeof(float4)));
     CU_TRY(cudaMemsetAsync(wf.film, 0, nPixOut * sizeof(FilmPixel), h->stream));
     wf.nSamples = nPixW[w] * spp;
-    if (h->keepSamples) CU_TRY(cudaMalloc((void **)&wf.sampleOut, wf.nSamples * 4 * sizeof(float)));
+    if (h->keepSamples) CU_TRY(pool_alloc(h->device, (void **)&wf.sampleOut, wf.nSamples * 4 * sizeof(float)));
     h->films.push_back(wf);
   }
   // waves: consecutive samples in reference order, spanning windows when a window is small
@@ -1400,6 +1687,7 @@ int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_win
     WaveDesc wd;
     memset(&wd, 0, sizeof(wd));
     wd.spp = spp;
+    wd.bc = bc ? 1 : 0;
     while (curW < n_windows && wd.nParts < PB_MAX_PARTS && wd.nSlots < capSlots) {
       uint64_t room = (capSlots - wd.nSlots) / spp;
       uint64_t take = std::min<uint64_t>(room, nPixW[curW] - curP);
@@ -1409,13 +1697,25 @@ int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_win
       wp.firstPixel = (uint32_t)curP;
       wp.nPixels = (uint32_t)take;
       wp.slotBase = wd.nSlots;
+      wp.corners = bc ? h->films[curW].corners : nullptr;
+      wp.bcCols = 0;
+      if (bc) {
+        // placements per row, when the window's rows are all alike
+        const std::vector<float2> &pc = h->films[curW].cornersHost;
+        size_t cols = 1;
+        while (cols < pc.size() && pc[cols].y == pc[0].y) ++cols;
+        bool regular = pc.size() % cols == 0;
+        for (size_t r = 0; regular && r < pc.size() / cols; ++r)
+          regular = pc[r * cols].y == pc[r * cols + cols - 1].y && (r == 0 || pc[r * cols].y != pc[r * cols - 1].y);
+        wp.bcCols = regular ? (int)cols : 0;
+      }
       wd.nSlots += (uint32_t)(take * spp);
       curP += take;
       if (curP == nPixW[curW]) { ++curW; curP = 0; }
     }
     rc = run_wave(h, wd, &launches);
     if (rc != PBRT_B200_OK) return rc;
-    {
+    if (!bc) {
       uint32_t nPixWave = wd.nSlots / (uint32_t)spp;
       int grid = (int)std::min<uint32_t>((nPixWave + 127) / 128, (uint32_t)h->numSMs * 16);
       TIMED(KC_FILM, (k_film_reach<<<grid, 128, 0, h->stream>>>(sv, h->wb, nPixWave, spp)));
@@ -1426,11 +1726,29 @@ int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_win
       WindowFilm &wf = h->films[wp.window];
       const PbrtB200Window &win = wf.win;
       int ew = wp.xe - wp.xs;
+      if (bc) {
+        // pixel rows the part's table placements can reach
+        float yMin = 1e30f, yMax = -1e30f;
+        for (uint32_t t = 0; t < wp.nPixels; ++t) {
+          float y = wf.cornersHost[wp.firstPixel + t].y;
+          yMin = std::min(yMin, y); yMax = std::max(yMax, y);
+        }
+        int rowFirst = std::max(win.y0, (int)floorf(yMin - 1.5f - sv.filterYW));
+        int rowLast = std::min(win.y0 + win.height - 1, (int)ceilf(yMax + sv.bcTableWidth + 0.5f + sv.filterYW));
+        if (rowLast >= rowFirst) {
+          int rows = rowLast - rowFirst + 1;
+          int total = rows * win.width;
+          int grid = std::min((total + PB_BLOCK - 1) / PB_BLOCK, h->numSMs * 16);
+          TIMED(KC_FILM, (k_film_gather_bc<<<grid, PB_BLOCK, 0, h->stream>>>(sv, h->wb, wp, h->filterTable, h->bcMasks,
+                                                                             wf.film, win, rowFirst, rows)));
+          ++launches;
+        }
+      }
       // pixel rows this part's samples can reach
       int syFirst = wp.ys + (int)(wp.firstPixel / ew), syLast = wp.ys + (int)((wp.firstPixel + wp.nPixels - 1) / ew);
       int rowFirst = std::max(win.y0, (int)floorf(syFirst - 0.5f - sv.filterYW) - 1);
       int rowLast = std::min(win.y0 + win.height - 1, (int)ceilf(syLast + 1 - 0.5f + sv.filterYW) + 1);
-      if (rowLast >= rowFirst) {
+      if (!bc && rowLast >= rowFirst) {
         int rows = rowLast - rowFirst + 1;
         int total = rows * win.width;
         int grid = std::min((total + PB_BLOCK - 1) / PB_BLOCK, h->numSMs * 16);
@@ -1475,7 +1793,7 @@ int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_win
   if (stats) {
     const unsigned long long *hs = h->lastStats;
     memset(stats, 0, sizeof(*stats));
-    stats->camera_rays = cameraRays;
+    stats->camera_rays = bc ? hs[ST_CAMERA] : cameraRays;
     stats->intersect_rays = hs[ST_K(TK_MAIN, TF_RAYS)] + hs[ST_K(TK_PROBE, TF_RAYS)];
     stats->shadow_rays = hs[ST_K(TK_SHADOW, TF_RAYS)];
     stats->points_shaded = hs[ST_SHADED];
@@ -1626,6 +1944,11 @@ int pbrt_b200_camera_rays(PbrtB200Handle *h, const PbrtB200Window *w, uint64_t n
   CU_TRY(cudaMemcpy(image_xy, dxy, n * 2 * sizeof(float), cudaMemcpyDeviceToHost));
   cudaFree(dr); cudaFree(dxy);
   return PBRT_B200_OK;
+}
+
+uint64_t pbrt_b200_sample_slots(PbrtB200Handle *h, int w) {
+  if (!h || w < 0 || w >= (int)h->films.size()) return 0;
+  return h->films[w].nSamples;
 }
 
 int pbrt_b200_sample_radiance(PbrtB200Handle *h, int w, uint64_t n, float *ls) {

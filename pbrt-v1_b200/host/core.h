@@ -247,6 +247,7 @@ Sampler *MakeSampler(const string &name, const ParamSet &paramSet, const Film *f
 Filter *MakeFilter(const string &name, const ParamSet &paramSet);
 Film *MakeFilm(const string &name, const ParamSet &paramSet, Filter *filter);
 void UpdatePluginPath(const string &newpath);
+const float *BestCandidateTable();   // 4096 x 5 floats (samplers/sampledata.cpp's table, regenerated)
 
 // EXR output (core/exrio.cpp:75-96)
 void WriteRGBAImage(const string &name, const float *pixels, const float *alpha, int xRes,

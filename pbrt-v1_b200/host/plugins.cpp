@@ -248,8 +248,41 @@ class LDSampler : public Sampler {
   }
   int pixelSamples;
 };
+class BestCandidateSampler : public Sampler {   // samplers/bestcandidate.cpp:33-77
+ public:
+  BestCandidateSampler(int xstart, int xend, int ystart, int yend, int ps)
+      : Sampler(xstart, xend, ystart, yend, ps) {}
+  void Flatten(PbrtB200Sampler *out) const {
+    out->x_samples = samplesPerPixel; out->y_samples = 1; out->jitter = 0;
+    out->kind = PBRT_B200_SAMPLER_BESTCANDIDATE;
+  }
+};
 
 }  // namespace
+
+// BestCandidateSampler::sampleTable.  The reference compiles it in as data (samplers/sampledata.cpp);
+// here it is the output of tools/gen_bestcandidate_table.cpp (our restatement of the generator the
+// reference's table came from), stored next to this library as bestcandidate_table.bin.
+#include <dlfcn.h>
+const float *BestCandidateTable() {
+  static vector<float> table;
+  if (!table.empty()) return &table[0];
+  string dir = ".";
+  Dl_info info;
+  if (dladdr((void *)&BestCandidateTable, &info) && info.dli_fname) {
+    dir = info.dli_fname;
+    size_t slash = dir.rfind('/');
+    dir = (slash == string::npos) ? string(".") : dir.substr(0, slash);
+  }
+  string fn = dir + "/bestcandidate_table.bin";
+  FILE *f = fopen(fn.c_str(), "rb");
+  if (!f) Severe("Unable to open the bestcandidate sample table \"%s\"", fn.c_str());
+  table.resize((size_t)PBRT_B200_BC_TABLE_SIZE * 5);
+  size_t got = fread(&table[0], sizeof(float), table.size(), f);
+  fclose(f);
+  if (got != table.size()) Severe("Sample table \"%s\" is truncated", fn.c_str());
+  return &table[0];
+}
 
 // core/light.h:88-116 + lights/area.cpp:28-57: a shape that cannot be
 // intersected directly is refined (LIFO) into a ShapeSet.
@@ -529,10 +562,22 @@ Sampler *MakeSampler(const string &name, const ParamSet &params, const Film *fil
     params.ReportUnused();
     return s;
   }
+  if (name == "bestcandidate") {   // samplers/bestcandidate.cpp:172-178
+    int xstart, xend, ystart, yend;
+    film->GetSampleExtent(&xstart, &xend, &ystart, &yend);
+    int nsamp = params.FindOneInt("pixelsamples", 4);
+    if (nsamp < 1 || nsamp > PBRT_B200_BC_TABLE_SIZE) {
+      Error("bestcandidate sampler: pixelsamples %d outside [1, %d]; using 4.", nsamp, PBRT_B200_BC_TABLE_SIZE);
+      nsamp = 4;
+    }
+    Sampler *s = new BestCandidateSampler(xstart, xend, ystart, yend, nsamp);
+    params.ReportUnused();
+    return s;
+  }
   if (name != "stratified")
-    // bestcandidate/random are SURVEY.md 8(f) "next"; until then the stratified sampler
-    // stands in (different noise, same expectation).
-    Warning("Sampler plugin \"%s\" is not implemented on the GPU yet; using \"stratified\".",
+    // "random" is outside the hot-path scope; the stratified sampler stands in (different noise,
+    // same expectation).
+    Warning("Sampler plugin \"%s\" is not implemented on the GPU; using \"stratified\".",
             name.c_str());
   bool jitter = params.FindOneBool("jitter", true);      // samplers/stratified.cpp:132-141
   int xstart, xend, ystart, yend;

@@ -168,6 +168,7 @@ void Scene::Flatten(FlatBuilder &fb, PbrtB200Scene *out) const {
   out->n_light_shapes = (uint32_t)fb.lightShapes.size();
   camera->Flatten(&out->camera);
   sampler->Flatten(&out->sampler);
+  out->bestcandidate_table = out->sampler.kind == PBRT_B200_SAMPLER_BESTCANDIDATE ? BestCandidateTable() : NULL;
   surfaceIntegrator->Flatten(&out->integrator);
   out->integrator.n_volume_1d = volumeIntegrator->NumSamples1D();
   camera->film->Flatten(&out->film);

@@ -237,9 +237,21 @@ class DeviceScene:
         return p.value, n.value
 
     def sample_radiance(self, w, n):
-        out = np.zeros((n, 4), np.float32)
-        _check(cuda().pbrt_b200_sample_radiance(self.h, w, n, _fp(out)))
-        return out
+        """First n per-sample records (L.rgb, alpha) in reference order.  With the bestcandidate
+        sampler the library keeps one record per table entry; skipped entries (alpha == -1) are dropped."""
+        lib = cuda()
+        lib.pbrt_b200_sample_slots.restype = C.c_uint64
+        lib.pbrt_b200_sample_slots.argtypes = [C.c_void_p, C.c_int]
+        slots = int(lib.pbrt_b200_sample_slots(self.h, w))
+        if slots <= n:
+            out = np.zeros((n, 4), np.float32)
+            _check(lib.pbrt_b200_sample_radiance(self.h, w, n, _fp(out)))
+            return out
+        out = np.zeros((slots, 4), np.float32)
+        _check(lib.pbrt_b200_sample_radiance(self.h, w, slots, _fp(out)))
+        if (out[:, 3] == -1).any():
+            out = out[out[:, 3] != -1]
+        return np.ascontiguousarray(out[:n])
 
     def intersect(self, rays):
         rays = np.ascontiguousarray(rays, np.float32)
@@ -283,11 +295,14 @@ def twin_sample_count(scene, w):
     return int(twin().pbrt_twin_sample_count(scene.ptr, C.byref(w)))
 
 
-def render_host(scene, windows=None, device=0, want_raw=False):
-    """pbrt_b200_render_host: HOST buffers in, HOST buffers out (the call Scene::Render makes)."""
+def render_host(scene, windows=None, device=0, want_raw=False, outs=None):
+    """pbrt_b200_render_host: HOST buffers in, HOST buffers out (the call Scene::Render makes).
+    `outs`: optional preallocated float32 [h, w, 4] arrays (e.g. pinned memory) to receive the frames."""
     ws = windows or [scene.full_window()]
     arr = (Window * len(ws))(*ws)
-    outs = [np.zeros((w.height, w.width, 4), np.float32) for w in ws]
+    if outs is None:
+        outs = [np.zeros((w.height, w.width, 4), np.float32) for w in ws]
+    assert len(outs) == len(ws) and all(o.dtype == np.float32 and o.flags.c_contiguous for o in outs)
     raws = [np.zeros((w.height, w.width, 5), np.float32) for w in ws] if want_raw else None
     optr = (C.c_void_p * len(ws))(*[o.ctypes.data for o in outs])
     rptr = (C.c_void_p * len(ws))(*[r.ctypes.data for r in raws]) if want_raw else None

@@ -29,6 +29,7 @@ LIGHT_NSAMPLES = 1
 MIRROR_TALL_BOX = False
 SPHERE_LIGHT = False
 LD_SAMPLER = False
+BC_SAMPLER = False
 
 
 def header(out, res, spp, integrator, filt, jitter=True, fov=39.3, lookat=None,
@@ -46,6 +47,8 @@ def header(out, res, spp, integrator, filt, jitter=True, fov=39.3, lookat=None,
     out.write(film + "\n")
     if LD_SAMPLER:
         out.write('Sampler "lowdiscrepancy" "integer pixelsamples" [%d]\n' % (spp[0] * spp[1]))
+    elif BC_SAMPLER:
+        out.write('Sampler "bestcandidate" "integer pixelsamples" [%d]\n' % (spp[0] * spp[1]))
     else:
         out.write('Sampler "stratified" "integer xsamples" [%d] "integer ysamples" [%d] "bool jitter" ["%s"]\n' % (
             spp[0], spp[1], "true" if jitter else "false"))
@@ -253,9 +256,11 @@ def main():
     ap.add_argument("--mirror", action="store_true", help="tall Cornell box becomes a mirror")
     ap.add_argument("--spherelight", action="store_true", help="spherical area light instead of the quad")
     ap.add_argument("--ld", action="store_true", help="lowdiscrepancy sampler with xsamples*ysamples pixel samples")
+    ap.add_argument("--bc", action="store_true", help="bestcandidate sampler with xsamples*ysamples pixel samples")
     a = ap.parse_args()
-    global LENS, LIGHT_NSAMPLES, MIRROR_TALL_BOX, SPHERE_LIGHT, LD_SAMPLER
+    global LENS, LIGHT_NSAMPLES, MIRROR_TALL_BOX, SPHERE_LIGHT, LD_SAMPLER, BC_SAMPLER
     LD_SAMPLER = a.ld
+    BC_SAMPLER = a.bc
     LENS = a.lens
     LIGHT_NSAMPLES = a.nsamples
     MIRROR_TALL_BOX = a.mirror

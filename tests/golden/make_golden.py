@@ -434,6 +434,50 @@ INLINE["instances_whitted"] = _instances('"whitted" "integer maxdepth" [4]', "wh
 INLINE["instances_direct"] = _instances('"directlighting" "integer maxdepth" [3]', "direct")
 
 
+def _bestcandidate(integrator, tag, sampler, film='"integer xresolution" [28] "integer yresolution" [20]', lens="", nsamples=1, pfilter='"box"'):
+    """bestcandidate sampler (the reference's default when a scene names none)"""
+    return """LookAt 278 273 -800 278 273 0 0 1 0
+Camera "perspective" "float fov" [39.3] %s
+Film "image" %s "string filename" ["bc_%s_out.exr"]
+%s
+PixelFilter %s
+SurfaceIntegrator %s
+WorldBegin
+AttributeBegin
+AreaLightSource "area" "color L" [17 12 4] "integer nsamples" [%d]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [213 548.7 227 343 548.7 227 343 548.7 332 213 548.7 332]
+AttributeEnd
+Material "matte" "color Kd" [.73 .73 .73]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [0 0 0 0 0 555 555 0 555 555 0 0]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [0 0 555 0 555 555 555 555 555 555 0 555]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [0 555 0 555 555 0 555 555 555 0 555 555]
+Material "matte" "color Kd" [.12 .45 .15]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [0 0 0 0 555 0 0 555 555 0 0 555]
+Material "matte" "color Kd" [.65 .05 .05]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [555 0 0 555 0 555 555 555 555 555 555 0]
+AttributeBegin
+Translate 200 100 250
+Material "glass" "float index" [1.5]
+Shape "sphere" "float radius" [100]
+AttributeEnd
+AttributeBegin
+Translate 400 80 150
+Material "mirror"
+Shape "sphere" "float radius" [80]
+AttributeEnd
+WorldEnd
+""" % (lens, film, tag, sampler, pfilter, integrator, nsamples)
+
+
+INLINE["bc_default_path"] = _bestcandidate('"path" "integer maxdepth" [4]', "default_path", "")   # no Sampler statement at all
+INLINE["bc_path_9spp_mitchell"] = _bestcandidate('"path" "integer maxdepth" [3]', "path_9spp_mitchell", 'Sampler "bestcandidate" "integer pixelsamples" [9]',
+                                                 pfilter='"mitchell"')
+INLINE["bc_direct_nsamples5"] = _bestcandidate('"directlighting"', "direct_nsamples5", 'Sampler "bestcandidate" "integer pixelsamples" [2]', nsamples=5)
+INLINE["bc_whitted_lens_crop"] = _bestcandidate('"whitted" "integer maxdepth" [3]', "whitted_lens_crop", 'Sampler "bestcandidate" "integer pixelsamples" [3]',
+                                                film='"integer xresolution" [40] "integer yresolution" [32] "float cropwindow" [.2 .85 .3 .9]',
+                                                lens='"float lensradius" [15] "float focaldistance" [900]')
+
+
 def parse_count(text, label):
     m = re.search(re.escape(label) + r"\s+([0-9.]+)([kMG]?)", text)
     if not m:

@@ -246,3 +246,21 @@ def test_product_does_not_reference_oracle():
             code = line.split("//")[0]
             assert "oracle/" not in code or "#include" not in code, (path, line)
             assert "libpbrt_twin" not in code, (path, line)
+
+
+def test_bestcandidate_table_matches_reference():
+    """pbrt-v1_b200/host/bestcandidate_table.bin is the output of tools/gen_bestcandidate_table.cpp (our
+    restatement of the generator); it must equal the literals the reference compiles in
+    (samplers/sampledata.cpp), bit for bit as float32.  The reference is only present in the build container."""
+    import re
+    table = np.fromfile(os.path.join(ROOT, "pbrt-v1_b200", "host", "bestcandidate_table.bin"), np.float32)
+    assert table.shape == (4096 * 5,)
+    assert np.isfinite(table).all() and (table >= 0).all() and (table <= 1).all()
+    ref = "/root/reference/samplers/sampledata.cpp"
+    if not os.path.exists(ref):
+        pytest.skip("reference sources not present")
+    lits = re.findall(r"([0-9.]+)f,", open(ref).read())
+    want = np.array([np.float32(v) for v in lits], np.float32)
+    assert want.shape == table.shape
+    assert np.array_equal(want.view(np.uint32), table.view(np.uint32))
+
