@@ -32,6 +32,35 @@
 #ifndef PB_LEAF_STEPS
 #define PB_LEAF_STEPS 2
 #endif
+#ifndef PB_SMEM_NODES
+#define PB_SMEM_NODES 0   // > 0: the first PB_SMEM_NODES nodes of the top-level tree are staged in shared memory
+#endif                    //      by one TMA bulk copy per CTA (experiment)
+
+#if PB_SMEM_NODES > 0
+__device__ __forceinline__ uint32_t pb_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// One thread arms an mbarrier with the byte count and issues cp.async.bulk (TMA, 1-D); everyone waits on it.
+__device__ __forceinline__ void pb_stage_nodes(const PbrtB200KdNode *src, uint2 *dst, unsigned long long *bar, uint32_t nNodes) {
+  const uint32_t bytes = nNodes * 8u;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pb_smem_addr(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (bytes == 0) return;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pb_smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(pb_smem_addr(dst)), "l"(src), "r"(bytes), "r"(pb_smem_addr(bar)) : "memory");
+  }
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "PB_WAIT_NODES:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+      "@!p bra PB_WAIT_NODES;\n"
+      "}\n" ::"r"(pb_smem_addr(bar)) : "memory");
+}
+#endif
 
 // Source: Ray load(uint32_t i).   Sink: void done(uint32_t i, const Ray &ray, const Hit &hit, bool anyHit).
 template <bool ANY, bool COUNT, int QK, class Source, class Sink>
@@ -67,6 +96,12 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
   int32_t instId = -1;
   float saved[INSTV ? 9 + PB_MAILBOX + 1 : 1];
 
+#if PB_SMEM_NODES > 0
+  __shared__ __align__(128) uint2 topNodes[PB_SMEM_NODES];
+  __shared__ __align__(8) unsigned long long topBar;
+  const uint32_t nTop = (sv.nNodes < (uint32_t)PB_SMEM_NODES ? sv.nNodes : (uint32_t)PB_SMEM_NODES) & ~1u;   // 16-byte granules
+  pb_stage_nodes(sv.nodes, topNodes, &topBar, nTop);
+#endif
   for (;;) {
     // ---- refill idle lanes
     uint32_t idleMask = __ballot_sync(0xffffffffu, !active);
@@ -113,7 +148,13 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
       bool descending = active && !inLeaf;
       if (__ballot_sync(0xffffffffu, descending) == 0) break;
       if (descending) {
+#if PB_SMEM_NODES > 0
+        uint2 nd;
+        if (node < nTop && !(INSTV && nodeBase != 0u)) nd = topNodes[node];
+        else nd = __ldg((const uint2 *)(sv.nodes + (INSTV ? nodeBase : 0u) + node));
+#else
         uint2 nd = __ldg((const uint2 *)(sv.nodes + (INSTV ? nodeBase : 0u) + node));
+#endif
         if ((nd.x & 3u) == 3u) {
           if (COUNT) ++cnt.leaves;
           inLeaf = true;

@@ -76,7 +76,10 @@ static int64_t g_reserved4 = 0;           // key 4: reserved (was the fused shad
 #define PB_SHADOW_INST_MIN_BLOCKS 8  // (measured on the instanced benchmark scene: closest hit 6 > 8 > 10, any hit 8 > 6 > 10)
 #endif
 #ifndef PB_TRAV_MIN_BLOCKS
-#define PB_TRAV_MIN_BLOCKS 10  // <= 48 registers: 40 resident warps per SM for the latency-bound kd walk (measured best of 6/8/10/12)
+#define PB_TRAV_MIN_BLOCKS 11  // <= 40 registers, 44 resident warps per SM for the kd walk (C3 closest hit: 11 < 10 < 9; any hit likewise)
+#endif
+#ifndef PB_TRAV_TRI_MIN_BLOCKS
+#define PB_TRAV_TRI_MIN_BLOCKS 9   // triangle-only closest hit: 56 registers (C4 124 ms vs 140 at 10 and 133 at 8; C5 789 vs 882)
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -373,7 +376,8 @@ __device__ __forceinline__ void flush_kd_counters(unsigned long long *stats, int
   warp_stat_add(&stats[ST_K(kind, TF_TESTS)], cnt.tests);
 }
 template <bool COUNT, int QK>
-__global__ void __launch_bounds__(PB_BLOCK, QK == PB_QK_INSTANCES ? PB_TRAV_INST_MIN_BLOCKS : PB_TRAV_MIN_BLOCKS)
+__global__ void __launch_bounds__(PB_BLOCK, QK == PB_QK_INSTANCES ? PB_TRAV_INST_MIN_BLOCKS
+                                            : QK == PB_QK_TRI ? PB_TRAV_TRI_MIN_BLOCKS : PB_TRAV_MIN_BLOCKS)
 k_intersect(const __grid_constant__ SceneView sv, const RayQueue q, const uint32_t *nPtr,
             uint32_t *work, unsigned long long *stats) {
   uint32_t n = *nPtr;
