@@ -120,6 +120,7 @@ struct WaveBuffers {
   AuxQueue shadowQ, probeQ;
   float *surf[15];       // BSDF frame records of the vertices being shaded (path), by queue position
   uint32_t *surfIds;
+  uint32_t *surfQueueIdx;
   // counters (device): [0..] see enum below
   uint32_t *counts;
   unsigned long long *stats;
@@ -137,7 +138,7 @@ static const char *const kKernelClassNames[KC_COUNT] = {"k_generate", "k_interse
                                                         "k_shade_continue", "k_shadow", "k_probe", "k_advance_wd",
                                                         "k_finalize", "k_film"};
 // counts[] layout: per iteration it: [4*it+0] main queue size, +1 shadow queue size,
-// +2 probe queue size, +3 unused; work counters follow at PB_WORK_BASE.
+// +2 probe queue size, +3 rays of the main queue that hit something (path integrator); work counters follow at PB_WORK_BASE.
 #define PB_MAX_ITERS 1024
 #define PB_WORK_BASE (4 * PB_MAX_ITERS)
 #define PB_COUNTS_TOTAL (PB_WORK_BASE + 10 * PB_MAX_ITERS)
@@ -499,9 +500,10 @@ __device__ __forceinline__ void path_fold_pending(const SceneView &sv, const Wav
 //                    BSDF frame record (15 floats + ids), emitted light        path.cpp:66-92
 //   k_path_direct    UniformSampleOneLight / EstimateDirect -> record + shadow / probe rays  :93-112
 //   k_path_continue  BSDF sampling, throughput, Russian roulette -> next ray                 :113-143
-struct SurfaceRecord {       // SoA, indexed by queue position
+struct SurfaceRecord {       // SoA, compacted: record j belongs to the j-th ray of the queue that hit something
   float *f[15];              // p, nn, ng, sn, tn
   uint32_t *ids;             // material | (light + 1) << 16
+  uint32_t *queueIdx;        // queue position of the ray (its slot and direction are read from there)
 };
 __device__ __forceinline__ void surface_store(const SurfaceRecord &r, uint32_t i, const Surface &sf) {
   const Bsdf &b = sf.bsdf;
@@ -529,7 +531,7 @@ __device__ __forceinline__ void surface_load(const SceneView &sv, const SurfaceR
 template <bool INST>
 __global__ void __launch_bounds__(PB_BLOCK, PB_SURF_MIN_BLOCKS)
 k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const RayQueue qin,
-               const SurfaceRecord rec, const uint32_t *nPtr, uint32_t *work) {
+               const SurfaceRecord rec, const uint32_t *nPtr, uint32_t *work, uint32_t *hitCount) {
   uint32_t n = *nPtr;
   uint32_t shaded = 0;
   for (;;) {
@@ -537,7 +539,9 @@ k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const
     if (chunk >= n) break;
     for (uint32_t base = chunk; base < chunk + PB_CLAIM && base < n; base += 32) {
       uint32_t i = base + lane_id();
-      if (i >= n) continue;
+      bool isHit = false;
+      Surface sf;
+      if (i < n) {
       uint32_t slot = qin.slot[i];
       Ray ray = queue_ray(qin, i);
       Hit hit;
@@ -555,14 +559,18 @@ k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const
       st.alpha = wb.alpha[slot];
       st.depth = (int)(flags & 0xffu);
       st.specularBounce = (flags >> 8) & 1u;
-      Surface sf;
-      if (path_vertex_surface<false, INST>(sv, st, ray, hit, &sf)) {
-        ++shaded;
-        surface_store(rec, i, sf);
-      }
+      isHit = path_vertex_surface<false, INST>(sv, st, ray, hit, &sf);
+      if (isHit) ++shaded;
       store3(wb.L, slot, st.L);
       wb.alpha[slot] = st.alpha;
       wb.flags[slot] = flags;
+      }
+      // the shading kernels that follow walk the hits only: full warps instead of ~3/4 full ones
+      uint32_t j = warp_push(hitCount, isHit);
+      if (isHit) {
+        surface_store(rec, j, sf);
+        rec.queueIdx[j] = i;
+      }
   }
   }
   warp_stat_add(&wb.stats[ST_SHADED], shaded);
@@ -580,8 +588,9 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
     uint32_t chunk = warp_claim_n(work, PB_CLAIM);
     if (chunk >= n) break;
     for (uint32_t base = chunk; base < chunk + PB_CLAIM && base < n; base += 32) {
-      uint32_t i = base + lane_id();
-      bool valid = i < n && qin.hitPrim[i] >= 0;
+      uint32_t j = base + lane_id();
+      bool valid = j < n;
+      uint32_t i = valid ? rec.queueIdx[j] : 0u;
       bool pushShadow = false, pushProbe = false;
       uint32_t slot = 0;
       DirectRec direct;
@@ -592,7 +601,7 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
         ray.d = v3(qin.dx[i], qin.dy[i], qin.dz[i]);   // only wo = -ray.d is needed
         ray.mint = 0.f; ray.maxt = 0.f;
         Surface sf;
-        surface_load<G>(sv, rec, i, &sf);
+        surface_load<G>(sv, rec, j, &sf);
         uint32_t flags = wb.flags[slot];
         PathState st;
         st.T = load3(wb.T, slot);
@@ -641,8 +650,9 @@ k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, cons
     uint32_t chunk = warp_claim_n(work, PB_CLAIM);
     if (chunk >= n) break;
     for (uint32_t base = chunk; base < chunk + PB_CLAIM && base < n; base += 32) {
-      uint32_t i = base + lane_id();
-      bool valid = i < n && qin.hitPrim[i] >= 0;
+      uint32_t j = base + lane_id();
+      bool valid = j < n;
+      uint32_t i = valid ? rec.queueIdx[j] : 0u;
       bool pushNext = false;
       uint32_t slot = 0;
       Ray next;
@@ -653,7 +663,7 @@ k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, cons
         ray.d = v3(qin.dx[i], qin.dy[i], qin.dz[i]);
         ray.mint = 0.f; ray.maxt = 0.f;
         Surface sf;
-        surface_load<G>(sv, rec, i, &sf);
+        surface_load<G>(sv, rec, j, &sf);
         uint32_t flags = wb.flags[slot];
         PathState st;
         st.T = load3(wb.T, slot);
@@ -1258,6 +1268,7 @@ static void carve_wave(Carver &c, WaveBuffers &wb, uint32_t nSlots, int directRe
   }
   for (int k = 0; k < 15; ++k) wb.surf[k] = isPath ? c.take<float>(nSlots) : nullptr;
   wb.surfIds = isPath ? c.take<uint32_t>(nSlots) : nullptr;
+  wb.surfQueueIdx = isPath ? c.take<uint32_t>(nSlots) : nullptr;
   wb.counts = c.take<uint32_t>(PB_COUNTS_TOTAL);
   wb.stats = c.take<unsigned long long>(ST_COUNT);
 }
@@ -1375,10 +1386,12 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
         SurfaceRecord rec;
         for (int k = 0; k < 15; ++k) rec.f[k] = wb.surf[k];
         rec.ids = wb.surfIds;
-        if (sv.nInstances != 0) TIMED(KC_SHADE, (k_path_surface<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], rec, nMain, nextWork())));
-        else TIMED(KC_SHADE, (k_path_surface<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], rec, nMain, nextWork())));
+        rec.queueIdx = wb.surfQueueIdx;
+        uint32_t *nHits = &wb.counts[4 * it + 3];
+        if (sv.nInstances != 0) TIMED(KC_SHADE, (k_path_surface<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], rec, nMain, nextWork(), nHits)));
+        else TIMED(KC_SHADE, (k_path_surface<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], rec, nMain, nextWork(), nHits)));
 #define PB_LAUNCH_DIRECT2(LD_, G_, LK_)                                                                             \
-  TIMED(KC_SHADE_DIRECT, (k_path_direct<LD_, G_, LK_><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], rec, nMain, \
+  TIMED(KC_SHADE_DIRECT, (k_path_direct<LD_, G_, LK_><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], rec, nHits, \
                                                                                  nextWork(), nShadow, nProbe)))
 #define PB_LAUNCH_DIRECT(LD_, G_) do { if (h->triLightsOnly) PB_LAUNCH_DIRECT2(LD_, G_, 0); else PB_LAUNCH_DIRECT2(LD_, G_, PB_LK_ALL); } while (0)
         if (isLD) { if (h->hasGlossy) PB_LAUNCH_DIRECT(true, true); else PB_LAUNCH_DIRECT(true, false); }
@@ -1393,7 +1406,7 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
         }
 #define PB_LAUNCH_CONT(LD_, G_)                                                                                    \
   TIMED(KC_SHADE_CONT, (k_path_continue<LD_, G_><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], wb.q[cur ^ 1], rec, \
-                                                                            nMain, nextWork(), nNext)))
+                                                                            nHits, nextWork(), nNext)))
         if (isLD) { if (h->hasGlossy) PB_LAUNCH_CONT(true, true); else PB_LAUNCH_CONT(true, false); }
         else { if (h->hasGlossy) PB_LAUNCH_CONT(false, true); else PB_LAUNCH_CONT(false, false); }
       }
