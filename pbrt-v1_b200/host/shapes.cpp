@@ -5,6 +5,8 @@
 // what the CUDA kernels implement (pbrt-v1_b200/csrc).
 #include "core.h"
 
+Shape *CreateTriangleMeshShape(const Transform &o2w, bool reverseOrientation, const ParamSet &params);
+
 namespace {
 
 void CopyMatrix(const Matrix4x4 &m, float out[16]) { memcpy(out, m.m, 16 * sizeof(float)); }
@@ -284,6 +286,58 @@ class Triangle : public Shape {
   const int *v;
 };
 
+// -------------------------------------------------------------- heightfield
+// shapes/heightfield.cpp:28-109: a shape that only exists to be refined into one triangle mesh over
+// the unit square (two triangles per cell, uv = xy); everything downstream sees triangles.
+class Heightfield : public Shape {
+ public:
+  Heightfield(const Transform &o2w, bool ro, int x, int y, const float *zs) : Shape(o2w, ro), nx(x), ny(y) {
+    z.assign(zs, zs + (size_t)nx * ny);
+  }
+  BBox ObjectBound() const {
+    float minz = z[0], maxz = z[0];
+    for (int i = 1; i < nx * ny; ++i) {
+      if (z[i] < minz) minz = z[i];
+      if (z[i] > maxz) maxz = z[i];
+    }
+    return BBox(Point(0, 0, minz), Point(1, 1, maxz));
+  }
+  bool CanIntersect() const { return false; }
+  float Area() const { Severe("Unimplemented Shape::Area() method called"); return 0.f; }
+  void Flatten(FlatBuilder &, PbrtB200Prim *, PbrtB200PrimAux *) const {
+    Severe("Heightfield must be refined before export");
+  }
+  void Refine(vector<Reference<Shape> > &refined) const {
+    int ntris = 2 * (nx - 1) * (ny - 1);
+    vector<int> verts(3 * (size_t)ntris);
+    vector<Point> P((size_t)nx * ny);
+    vector<float> uvs(2 * (size_t)nx * ny);
+    int pos = 0;
+    for (int y = 0; y < ny; ++y)
+      for (int x = 0; x < nx; ++x) {
+        P[pos].x = uvs[2 * pos] = (float)x / (float)(nx - 1);
+        P[pos].y = uvs[2 * pos + 1] = (float)y / (float)(ny - 1);
+        P[pos].z = z[pos];
+        ++pos;
+      }
+    int *vp = &verts[0];
+    for (int y = 0; y < ny - 1; ++y)
+      for (int x = 0; x < nx - 1; ++x) {
+        int v00 = x + y * nx, v10 = x + 1 + y * nx, v11 = x + 1 + (y + 1) * nx, v01 = x + (y + 1) * nx;
+        *vp++ = v00; *vp++ = v10; *vp++ = v11;
+        *vp++ = v00; *vp++ = v11; *vp++ = v01;
+      }
+    ParamSet paramSet;
+    paramSet.AddInt("indices", &verts[0], 3 * ntris);
+    paramSet.AddFloat("uv", &uvs[0], 2 * nx * ny);
+    paramSet.AddPoint("P", &P[0], nx * ny);
+    refined.push_back(CreateTriangleMeshShape(ObjectToWorld, reverseOrientation, paramSet));
+  }
+ private:
+  int nx, ny;
+  vector<float> z;
+};
+
 void TriangleMesh::Refine(vector<Reference<Shape> > &refined) const {
   for (int i = 0; i < ntris; ++i)
     refined.push_back(new Triangle(ObjectToWorld, reverseOrientation, this, i));
@@ -300,6 +354,18 @@ Shape *CreateSphereShape(const Transform &o2w, bool reverseOrientation, const Pa
   return new Sphere(o2w, reverseOrientation, radius, zmin, zmax, phimax);
 }
 
+// shapes/heightfield.cpp:110-119
+Shape *CreateHeightfieldShape(const Transform &o2w, bool reverseOrientation, const ParamSet &params) {
+  int nu = params.FindOneInt("nu", -1);
+  int nv = params.FindOneInt("nv", -1);
+  int nitems = 0;
+  const float *Pz = params.FindFloat("Pz", &nitems);
+  if (nu < 2 || nv < 2 || Pz == NULL || nitems != nu * nv) {
+    Error("heightfield: \"nu\", \"nv\" (>= 2) and nu*nv \"Pz\" values are required; shape ignored.");
+    return NULL;
+  }
+  return new Heightfield(o2w, reverseOrientation, nu, nv, Pz);
+}
 // shapes/cylinder.cpp:221-228
 Shape *CreateCylinderShape(const Transform &o2w, bool reverseOrientation, const ParamSet &params) {
   float radius = params.FindOneFloat("radius", 1);

@@ -478,6 +478,37 @@ INLINE["bc_whitted_lens_crop"] = _bestcandidate('"whitted" "integer maxdepth" [3
                                                 lens='"float lensradius" [15] "float focaldistance" [900]')
 
 
+def _heightfield():
+    import math
+    nu, nv = 9, 7
+    pz = " ".join("%.6g" % (0.15 * math.sin(1.7 * x) * math.cos(1.3 * y) + 0.05 * ((x * y) % 3)) for y in range(nv) for x in range(nu))
+    return """LookAt 0.5 -1.2 1.4 0.5 0.5 0 0 0 1
+Camera "perspective" "float fov" [45]
+Film "image" "integer xresolution" [36] "integer yresolution" [28] "string filename" ["heightfield_path_out.exr"]
+Sampler "stratified" "integer xsamples" [2] "integer ysamples" [2]
+PixelFilter "box"
+SurfaceIntegrator "path" "integer maxdepth" [3]
+WorldBegin
+LightSource "point" "color I" [6 6 5] "point from" [0.2 -0.5 2]
+AttributeBegin
+AreaLightSource "area" "color L" [5 5 6]
+Translate 0.5 0.5 1.6
+Shape "disk" "float radius" [.4]
+AttributeEnd
+Material "plastic" "color Kd" [.3 .6 .3] "color Ks" [.2 .2 .2] "float roughness" [.2]
+AttributeBegin
+Scale 1 1 1.5
+Shape "heightfield" "integer nu" [%d] "integer nv" [%d] "float Pz" [%s]
+AttributeEnd
+Material "matte" "color Kd" [.5 .5 .5]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-3 -3 -0.4 4 -3 -0.4 4 4 -0.4 -3 4 -0.4]
+WorldEnd
+""" % (nu, nv, pz)
+
+
+INLINE["heightfield_path"] = _heightfield()
+
+
 def parse_count(text, label):
     m = re.search(re.escape(label) + r"\s+([0-9.]+)([kMG]?)", text)
     if not m:
