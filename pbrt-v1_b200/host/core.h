@@ -114,12 +114,8 @@ class KdTreeAccel : public Primitive {
   vector<PbrtB200KdNode> nodes;
   vector<uint32_t> primRefs;
   BBox bounds;
+  struct BoundEdge;   // (kdtree.cpp)
  private:
-  struct BoundEdge;
-  void buildTree(int nodeNum, const BBox &nodeBounds, const vector<BBox> &allPrimBounds,
-                 int *primNums, int nPrims, int depth, BoundEdge *edges[3], int *prims0,
-                 int *prims1, int badRefines);
-  void initLeaf(int nodeNum, int *primNums, int np);
   int isectCost, traversalCost, maxPrims;
   float emptyBonus;
 };

@@ -8,6 +8,7 @@
 // reference.  The output is the packed 8-byte node array of
 // include/pbrt_b200.h instead of the reference's pointer-carrying nodes.
 #include "core.h"
+#include <thread>
 
 void Primitive::FullyRefine(vector<Reference<Primitive> > &refined) const {
   // core/primitive.cpp:40-53: LIFO todo list => a mesh's triangles come out
@@ -41,58 +42,70 @@ struct KdTreeAccel::BoundEdge {
   enum { START, END } type;
 };
 
-KdTreeAccel::KdTreeAccel(const vector<Reference<Primitive> > &p, int icost, int tcost,
-                         float ebonus, int maxp, int maxDepth)
-    : isectCost(icost), traversalCost(tcost), maxPrims(maxp), emptyBonus(ebonus) {
-  for (u_int i = 0; i < p.size(); ++i) p[i]->FullyRefine(prims);
-  if (maxDepth <= 0) maxDepth = Round2Int(8 + 1.3f * Log2Int(float(prims.size())));
-  vector<BBox> primBounds;
-  primBounds.reserve(prims.size());
-  for (u_int i = 0; i < prims.size(); ++i) {
-    BBox b = prims[i]->WorldBound();
-    bounds = Union(bounds, b);
-    primBounds.push_back(b);
-  }
-  size_t np = prims.size();
-  BoundEdge *edges[3];
-  for (int i = 0; i < 3; ++i) edges[i] = new BoundEdge[2 * np + 1];
-  int *prims0 = new int[np + 1];
-  int *prims1 = new int[(size_t)(maxDepth + 1) * np + 1];
-  int *primNums = new int[np + 1];
-  for (u_int i = 0; i < np; ++i) primNums[i] = i;
-  buildTree(0, bounds, primBounds, primNums, (int)np, maxDepth, edges, prims0, prims1, 0);
-  delete[] primNums;
-  for (int i = 0; i < 3; ++i) delete[] edges[i];
-  delete[] prims0;
-  delete[] prims1;
-}
-
-void KdTreeAccel::initLeaf(int nodeNum, int *primNums, int np) {
-  PbrtB200KdNode &n = nodes[nodeNum];
+// ---------------------------------------------------------------------------
+// Build.  The recursion is the reference's (accelerators/kdtree.cpp:172-312); what is added is that
+// a subtree is built into its own node / reference arrays with numbers relative to the subtree, so
+// that the two children of a big node can be built by different threads and spliced afterwards:
+// node numbering is depth first (below child = parent + 1, above child = after the whole below
+// subtree) and leaves append their lists in visiting order, so concatenating
+// [node] + below + above (and the reference lists likewise) and shifting the stored indices
+// reproduces exactly the arrays the sequential build writes.
+namespace {
+struct Subtree {
+  vector<PbrtB200KdNode> nodes;
+  vector<uint32_t> refs;
+};
+struct BuildParams {
+  int isectCost, traversalCost, maxPrims;
+  float emptyBonus;
+  const vector<BBox> *allPrimBounds;
+};
+void init_leaf(Subtree &st, int nodeNum, const int *primNums, int np) {
+  PbrtB200KdNode &n = st.nodes[nodeNum];
   n.word0 = ((uint32_t)np << 2) | 3u;          // kdtree.cpp:53-54
   if (np == 0) n.word1 = 0;
   else if (np == 1) n.word1 = (uint32_t)primNums[0];
   else {
-    n.word1 = (uint32_t)primRefs.size();
-    for (int i = 0; i < np; ++i) primRefs.push_back((uint32_t)primNums[i]);
+    n.word1 = (uint32_t)st.refs.size();
+    for (int i = 0; i < np; ++i) st.refs.push_back((uint32_t)primNums[i]);
   }
 }
-
-void KdTreeAccel::buildTree(int nodeNum, const BBox &nodeBounds,
-                            const vector<BBox> &allPrimBounds, int *primNums, int nPrims,
-                            int depth, BoundEdge *edges[3], int *prims0, int *prims1,
-                            int badRefines) {
-  if ((size_t)nodeNum != nodes.size()) Severe("kd-tree build: node numbering out of sync");
-  PbrtB200KdNode blank = {0u, 0u};
-  nodes.push_back(blank);
-  if (nPrims <= maxPrims || depth == 0) {
-    initLeaf(nodeNum, primNums, nPrims);
-    return;
+// Shift a subtree's stored indices and append it.
+void splice(Subtree &dst, const Subtree &src) {
+  uint32_t nodeBase = (uint32_t)dst.nodes.size(), refBase = (uint32_t)dst.refs.size();
+  for (size_t i = 0; i < src.nodes.size(); ++i) {
+    PbrtB200KdNode n = src.nodes[i];
+    if ((n.word0 & 3u) != 3u) n.word1 += nodeBase;            // interior: above-child index
+    else if ((n.word0 >> 2) > 1u) n.word1 += refBase;         // leaf list offset
+    dst.nodes.push_back(n);
   }
+  dst.refs.insert(dst.refs.end(), src.refs.begin(), src.refs.end());
+}
+}  // namespace
+
+// The split decision of one node (kdtree.cpp:189-299).  Returns false when the node becomes a leaf;
+// otherwise axis / tsplit and the two primitive lists in prims0[0..n0) / prims1[0..n1).
+static bool choose_split(const BuildParams &bp, const BBox &nodeBounds, const int *primNums, int nPrims,
+                         KdTreeAccel::BoundEdge *edges[3], int *prims0, int *prims1, int *badRefines,
+                         int *bestAxisOut, float *tsplitOut, int *n0Out, int *n1Out);
+
+struct KdBuilder {
+  typedef KdTreeAccel::BoundEdge BoundEdge;
+  static void buildTree(const BuildParams &bp, Subtree &st, int nodeNum, const BBox &nodeBounds,
+                        int *primNums, int nPrims, int depth, BoundEdge *edges[3], int *prims0,
+                        int *prims1, int badRefines);
+  static void buildParallel(const BuildParams &bp, Subtree &st, const BBox &nodeBounds, vector<int> &primNums,
+                            int depth, int badRefines, int forkLevels);
+};
+static bool choose_split(const BuildParams &bp, const BBox &nodeBounds, const int *primNums, int nPrims,
+                         KdTreeAccel::BoundEdge *edges[3], int *prims0, int *prims1, int *badRefines,
+                         int *bestAxisOut, float *tsplitOut, int *n0Out, int *n1Out) {
+  typedef KdTreeAccel::BoundEdge BoundEdge;
+  const vector<BBox> &allPrimBounds = *bp.allPrimBounds;
   // choose split: surface-area heuristic over all bounding-box edges
   int bestAxis = -1, bestOffset = -1;
   float bestCost = INFINITY;
-  float oldCost = isectCost * float(nPrims);
+  float oldCost = bp.isectCost * float(nPrims);
   Vector d = nodeBounds.pMax - nodeBounds.pMin;
   float totalSA = (2.f * (d.x * d.y + d.x * d.z + d.y * d.z));
   float invTotalSA = 1.f / totalSA;
@@ -122,8 +135,8 @@ retrySplit:
                            (nodeBounds.pMax[axis] - edget) * (d[otherAxis0] + d[otherAxis1]));
       float pBelow = belowSA * invTotalSA;
       float pAbove = aboveSA * invTotalSA;
-      float eb = (nAbove == 0 || nBelow == 0) ? emptyBonus : 0.f;
-      float cost = traversalCost + isectCost * (1.f - eb) * (pBelow * nBelow + pAbove * nAbove);
+      float eb = (nAbove == 0 || nBelow == 0) ? bp.emptyBonus : 0.f;
+      float cost = bp.traversalCost + bp.isectCost * (1.f - eb) * (pBelow * nBelow + pAbove * nAbove);
       if (cost < bestCost) {
         bestCost = cost;
         bestAxis = axis;
@@ -137,29 +150,124 @@ retrySplit:
     axis = (axis + 1) % 3;
     goto retrySplit;
   }
-  if (bestCost > oldCost) ++badRefines;
-  if ((bestCost > 4.f * oldCost && nPrims < 16) || bestAxis == -1 || badRefines == 3) {
-    initLeaf(nodeNum, primNums, nPrims);
-    return;
-  }
+  if (bestCost > oldCost) ++*badRefines;
+  if ((bestCost > 4.f * oldCost && nPrims < 16) || bestAxis == -1 || *badRefines == 3) return false;
   int n0 = 0, n1 = 0;
   for (int i = 0; i < bestOffset; ++i)
     if (edges[bestAxis][i].type == BoundEdge::START) prims0[n0++] = edges[bestAxis][i].primNum;
   for (int i = bestOffset + 1; i < 2 * nPrims; ++i)
     if (edges[bestAxis][i].type == BoundEdge::END) prims1[n1++] = edges[bestAxis][i].primNum;
-  float tsplit = edges[bestAxis][bestOffset].t;
-  // interior node: split float with the axis in its two low mantissa bits
-  // (kdtree.cpp:66-72: `split = s; flags &= ~3; flags |= axis;`)
-  {
-    uint32_t bits;
-    memcpy(&bits, &tsplit, 4);
-    nodes[nodeNum].word0 = (bits & ~3u) | (uint32_t)bestAxis;
+  *bestAxisOut = bestAxis;
+  *tsplitOut = edges[bestAxis][bestOffset].t;
+  *n0Out = n0; *n1Out = n1;
+  return true;
+}
+
+// interior node: split float with the axis in its two low mantissa bits
+// (kdtree.cpp:66-72: `split = s; flags &= ~3; flags |= axis;`)
+static uint32_t interior_word0(float tsplit, int axis) {
+  uint32_t bits;
+  memcpy(&bits, &tsplit, 4);
+  return (bits & ~3u) | (uint32_t)axis;
+}
+
+void KdBuilder::buildTree(const BuildParams &bp, Subtree &st, int nodeNum, const BBox &nodeBounds,
+                          int *primNums, int nPrims, int depth, BoundEdge *edges[3], int *prims0,
+                          int *prims1, int badRefines) {
+  if ((size_t)nodeNum != st.nodes.size()) Severe("kd-tree build: node numbering out of sync");
+  PbrtB200KdNode blank = {0u, 0u};
+  st.nodes.push_back(blank);
+  if (nPrims <= bp.maxPrims || depth == 0) {
+    init_leaf(st, nodeNum, primNums, nPrims);
+    return;
   }
+  int bestAxis, n0, n1;
+  float tsplit;
+  if (!choose_split(bp, nodeBounds, primNums, nPrims, edges, prims0, prims1, &badRefines, &bestAxis, &tsplit,
+                    &n0, &n1)) {
+    init_leaf(st, nodeNum, primNums, nPrims);
+    return;
+  }
+  st.nodes[nodeNum].word0 = interior_word0(tsplit, bestAxis);
   BBox bounds0 = nodeBounds, bounds1 = nodeBounds;
   bounds0.pMax[bestAxis] = bounds1.pMin[bestAxis] = tsplit;
-  buildTree(nodeNum + 1, bounds0, allPrimBounds, prims0, n0, depth - 1, edges, prims0,
+  buildTree(bp, st, nodeNum + 1, bounds0, prims0, n0, depth - 1, edges, prims0, prims1 + nPrims, badRefines);
+  st.nodes[nodeNum].word1 = (uint32_t)st.nodes.size();
+  buildTree(bp, st, (int)st.nodes[nodeNum].word1, bounds1, prims1, n1, depth - 1, edges, prims0,
             prims1 + nPrims, badRefines);
-  nodes[nodeNum].word1 = (uint32_t)nodes.size();
-  buildTree((int)nodes[nodeNum].word1, bounds1, allPrimBounds, prims1, n1, depth - 1, edges,
-            prims0, prims1 + nPrims, badRefines);
+}
+
+#include <future>
+// A big node: decide its split here, build the two children concurrently, splice.
+void KdBuilder::buildParallel(const BuildParams &bp, Subtree &st, const BBox &nodeBounds, vector<int> &primNums,
+                              int depth, int badRefines, int forkLevels) {
+  const int nPrims = (int)primNums.size();
+  const size_t np = (size_t)nPrims;
+  if (forkLevels <= 0 || nPrims < 4096 || nPrims <= bp.maxPrims || depth == 0) {
+    // sequential build of this subtree, the reference's recursion with its scratch arrays
+    vector<BoundEdge> e0(2 * np + 1), e1(2 * np + 1), e2(2 * np + 1);
+    BoundEdge *edges[3] = {&e0[0], &e1[0], &e2[0]};
+    vector<int> prims0(np + 1), prims1((size_t)(depth + 1) * np + 1);
+    buildTree(bp, st, 0, nodeBounds, nPrims ? &primNums[0] : NULL, nPrims, depth, edges, &prims0[0], &prims1[0],
+              badRefines);
+    return;
+  }
+  PbrtB200KdNode blank = {0u, 0u};
+  st.nodes.push_back(blank);
+  vector<int> below(np + 1), above(np + 1);
+  int bestAxis, n0, n1;
+  float tsplit;
+  bool split;
+  {
+    vector<BoundEdge> e0(2 * np + 1), e1(2 * np + 1), e2(2 * np + 1);
+    BoundEdge *edges[3] = {&e0[0], &e1[0], &e2[0]};
+    split = choose_split(bp, nodeBounds, &primNums[0], nPrims, edges, &below[0], &above[0], &badRefines, &bestAxis,
+                         &tsplit, &n0, &n1);
+  }
+  if (!split) {
+    init_leaf(st, 0, &primNums[0], nPrims);
+    return;
+  }
+  vector<int>().swap(primNums);   // the parent's list is not needed any more
+  below.resize(n0); above.resize(n1);
+  st.nodes[0].word0 = interior_word0(tsplit, bestAxis);
+  BBox bounds0 = nodeBounds, bounds1 = nodeBounds;
+  bounds0.pMax[bestAxis] = bounds1.pMin[bestAxis] = tsplit;
+  Subtree sub0, sub1;
+  std::future<void> other = std::async(std::launch::async, [&]() {
+    buildParallel(bp, sub1, bounds1, above, depth - 1, badRefines, forkLevels - 1);
+  });
+  buildParallel(bp, sub0, bounds0, below, depth - 1, badRefines, forkLevels - 1);
+  other.get();
+  splice(st, sub0);
+  st.nodes[0].word1 = (uint32_t)st.nodes.size();
+  splice(st, sub1);
+}
+
+KdTreeAccel::KdTreeAccel(const vector<Reference<Primitive> > &p, int icost, int tcost,
+                         float ebonus, int maxp, int maxDepth)
+    : isectCost(icost), traversalCost(tcost), maxPrims(maxp), emptyBonus(ebonus) {
+  for (u_int i = 0; i < p.size(); ++i) p[i]->FullyRefine(prims);
+  if (maxDepth <= 0) maxDepth = Round2Int(8 + 1.3f * Log2Int(float(prims.size())));
+  vector<BBox> primBounds;
+  primBounds.reserve(prims.size());
+  for (u_int i = 0; i < prims.size(); ++i) {
+    BBox b = prims[i]->WorldBound();
+    bounds = Union(bounds, b);
+    primBounds.push_back(b);
+  }
+  size_t np = prims.size();
+  vector<int> primNums(np);
+  for (u_int i = 0; i < np; ++i) primNums[i] = i;
+  BuildParams bp = {isectCost, traversalCost, maxPrims, emptyBonus, &primBounds};
+  // PBRT_KD_THREADS=1 forces the sequential build; default: as many fork levels as the cores warrant
+  int threads = (int)std::thread::hardware_concurrency();
+  if (const char *e = getenv("PBRT_KD_THREADS")) threads = atoi(e);
+  int forkLevels = 0;
+  while ((1 << forkLevels) < threads) ++forkLevels;
+  if (threads > 1) forkLevels += 2;   // children differ in size: over-decompose a little
+  Subtree st;
+  KdBuilder::buildParallel(bp, st, bounds, primNums, maxDepth, 0, forkLevels);
+  nodes.swap(st.nodes);
+  primRefs.swap(st.refs);
 }

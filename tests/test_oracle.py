@@ -16,6 +16,7 @@ import glob
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -263,4 +264,32 @@ def test_bestcandidate_table_matches_reference():
     want = np.array([np.float32(v) for v in lits], np.float32)
     assert want.shape == table.shape
     assert np.array_equal(want.view(np.uint32), table.view(np.uint32))
+
+
+def test_parallel_kd_build_equals_sequential(ffi, tmp_path):
+    """The host kd build forks big nodes' children onto threads and splices the subtrees; the arrays must be
+    the sequential build's (== the reference's tree), bit for bit."""
+    import hashlib
+    import subprocess
+    sp = gen_scene(str(tmp_path / "kd.pbrt"), "c4", "--res", "16", "16", "--spp", "1", "1", "--nphi", "200", "--ntheta", "100",
+                   "--filename", str(tmp_path / "kd.exr"))
+    code = (
+        "import sys, hashlib, ctypes as C\n"
+        "sys.path.insert(0, %r)\n"
+        "from parity_util import load_ffi\n"
+        "ffi = load_ffi()\n"
+        "sc = ffi.Scene(sys.argv[1])\n"
+        "class Head(C.Structure):\n"
+        "    _fields_ = [('abi', C.c_uint32), ('nodes', C.c_void_p), ('n_nodes', C.c_uint32), ('n_top', C.c_uint32),\n"
+        "                ('refs', C.c_void_p), ('n_refs', C.c_uint32)]\n"
+        "h = Head.from_address(sc.ptr)\n"
+        "a = C.string_at(h.nodes, 8 * h.n_nodes); b = C.string_at(h.refs, 4 * h.n_refs)\n"
+        "print(h.n_nodes, h.n_refs, hashlib.md5(a).hexdigest(), hashlib.md5(b).hexdigest())\n" % os.path.join(ROOT, "tests"))
+    outs = []
+    for threads in ("1", "8"):
+        env = dict(os.environ, PBRT_KD_THREADS=threads)
+        r = subprocess.run([sys.executable, "-c", code, sp], env=env, capture_output=True, text=True, check=True)
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1], outs
+    assert int(outs[0].split()[0]) > 10000
 
