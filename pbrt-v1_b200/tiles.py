@@ -7,9 +7,9 @@ every pixel it owns is complete.  With the per-sample keyed RNG a tile rendered 
 bit-identical to the same pixels of a full-frame render, so the exchange is a pure gather:
 no arithmetic, one collective.
 
-One process per GPU (torch.distributed): rank r renders tiles r, r+world, r+2*world, ... of
-the raster-ordered tile list (round-robin balances cheap ceiling tiles against expensive
-glass tiles), packs their resolved RGBA pixels into one buffer and takes part in a single
+One process per GPU (torch.distributed): the raster-ordered tile list is dealt round-robin with
+the start shifted by one per tile row (diagonals: balances cheap ceiling tiles against expensive
+glass tiles in both directions), packs their resolved RGBA pixels into one buffer and takes part in a single
 `all_gather_into_tensor`; rank 0 pastes tiles into the frame.
 """
 import numpy as np
@@ -25,7 +25,13 @@ def make_tiles(x0, y0, width, height, tile=128):
 
 
 def tiles_of_rank(tiles, rank, world):
-    return tiles[rank::world]
+    """Tile i (raster order) goes to rank (i + row(i)) % world: round-robin with the start shifted by one per
+    tile row, so that a rank's tiles lie on diagonals instead of in one column of the image (with 8 tiles
+    per row and 8 ranks plain round-robin hands one rank the whole glass-sphere column)."""
+    if world <= 1 or not tiles:
+        return list(tiles)
+    ncols = sum(1 for t in tiles if t[1] == tiles[0][1])
+    return [t for i, t in enumerate(tiles) if (i + i // ncols) % world == rank]
 
 
 def slot_floats(tiles, world):
