@@ -555,14 +555,17 @@ k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const
       PathState st;
       st.L = load3(wb.L, slot);
       path_fold_pending(sv, wb, slot, &flags, &st.L);
-      st.T = load3(wb.T, slot);
-      st.alpha = wb.alpha[slot];
       st.depth = (int)(flags & 0xffu);
       st.specularBounce = (flags >> 8) & 1u;
+      // the throughput only matters where emitted light can be added (path.cpp:74-82,90-91), alpha only
+      // at the first vertex
+      const bool mayEmit = st.depth == 0 || st.specularBounce;
+      st.T = mayEmit ? load3(wb.T, slot) : spec(0.f);
+      st.alpha = 0.f;
       isHit = path_vertex_surface<false, INST>(sv, st, ray, hit, &sf);
       if (isHit) ++shaded;
       store3(wb.L, slot, st.L);
-      wb.alpha[slot] = st.alpha;
+      if (st.depth == 0) wb.alpha[slot] = st.alpha;
       wb.flags[slot] = flags;
       }
       // the shading kernels that follow walk the hits only: full warps instead of ~3/4 full ones
