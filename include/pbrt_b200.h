@@ -155,9 +155,13 @@ typedef struct PbrtB200Light {
   uint32_t pad[2];
 } PbrtB200Light;
 
-/* cameras/perspective.cpp:51-82, core/camera.cpp:50-70 */
+/* cameras/perspective.cpp:51-82, cameras/orthographic.cpp:49-78, cameras/environment.cpp:49-63,
+ * core/camera.cpp:50-70 */
+enum { PBRT_B200_CAMERA_PERSPECTIVE = 0, PBRT_B200_CAMERA_ORTHOGRAPHIC = 1, PBRT_B200_CAMERA_ENVIRONMENT = 2 };
 typedef struct PbrtB200Camera {
-  float raster_to_camera[16];
+  int32_t kind;                    /* PBRT_B200_CAMERA_*                      */
+  float ray_origin[3];             /* environment: CameraToWorld(0,0,0)       */
+  float raster_to_camera[16];      /* projective cameras                      */
   float camera_to_world[16];
   float hither, yon;
   float shutter_open, shutter_close;

@@ -169,7 +169,7 @@ int pbrt_twin_render(const PbrtB200Scene *scene, const PbrtB200Window *win, floa
   // everything after the sampler: camera ray, Li, guards, film (core/scene.cpp:43-78)
   auto take_sample = [&](CameraSample cs, const PatternSource &key0, uint64_t key1) {
     Ray ray;
-    perspective_generate_ray(sv.camera, cs, &ray);
+    perspective_generate_ray(sv.camera, cs, &ray, sv.xRes, sv.yRes);
     float alpha = 0.f;
     Spec Ls = (sv.integrator.kind == PBRT_B200_INT_PATH)
                   ? li_path(sv, key0, key1, ray, &alpha, c)
@@ -340,7 +340,7 @@ int pbrt_twin_camera_rays(const PbrtB200Scene *scene, const PbrtB200Window *win,
         } else
           stratified_camera_sample(sv, x, y, k, &cs);
         Ray r;
-        perspective_generate_ray(sv.camera, cs, &r);
+        perspective_generate_ray(sv.camera, cs, &r, sv.xRes, sv.yRes);
         float *o = rays + 8 * i;
         o[0] = r.o.x; o[1] = r.o.y; o[2] = r.o.z; o[3] = r.d.x; o[4] = r.d.y; o[5] = r.d.z;
         o[6] = r.mint; o[7] = r.maxt;

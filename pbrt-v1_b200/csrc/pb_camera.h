@@ -71,12 +71,29 @@ PB_HD float film_image_coord(float v) {
   return t - 1.f;
 }
 
+// cameras/environment.cpp:49-63: latitude / longitude directions from the film position (needs the
+// film resolution); cameras/orthographic.cpp:49-78 differs from the perspective camera in the ray
+// direction (0,0,1) and maxt.
+PB_NOINLINE void environment_generate_ray(const PbrtB200Camera &c, const CameraSample &s, int xRes, int yRes, Ray *ray) {
+  ray->o = v3(c.ray_origin[0], c.ray_origin[1], c.ray_origin[2]);
+  float theta = PB_PI * s.imageY / yRes;
+  float phi = 2 * PB_PI * s.imageX / xRes;
+  V3 dir = v3(pb_sinf(theta) * pb_cosf(phi), pb_cosf(theta), pb_sinf(theta) * pb_sinf(phi));
+  ray->d = xf_vector(c.camera_to_world, dir);
+  ray->mint = c.hither;
+  ray->maxt = c.yon;
+}
 // cameras/perspective.cpp:51-82
-PB_HD void perspective_generate_ray(const PbrtB200Camera &c, const CameraSample &s, Ray *ray) {
+PB_HD void perspective_generate_ray(const PbrtB200Camera &c, const CameraSample &s, Ray *ray, int xRes = 0, int yRes = 0) {
+  if (c.kind == PBRT_B200_CAMERA_ENVIRONMENT) {
+    environment_generate_ray(c, s, xRes, yRes, ray);
+    return;
+  }
+  const bool ortho = c.kind == PBRT_B200_CAMERA_ORTHOGRAPHIC;
   V3 Pras = v3(s.imageX, s.imageY, 0);
   V3 Pcamera = xf_point(c.raster_to_camera, Pras);
   ray->o = Pcamera;
-  ray->d = v3(Pcamera.x, Pcamera.y, Pcamera.z);
+  ray->d = ortho ? v3(0, 0, 1) : v3(Pcamera.x, Pcamera.y, Pcamera.z);
   if (c.lens_radius > 0.f) {
     float lensU, lensV;
     concentric_sample_disk(s.lensU, s.lensV, &lensU, &lensV);
@@ -90,7 +107,7 @@ PB_HD void perspective_generate_ray(const PbrtB200Camera &c, const CameraSample 
   }
   ray->d = normalize(ray->d);
   ray->mint = 0.f;
-  ray->maxt = (c.yon - c.hither) / ray->d.z;
+  ray->maxt = ortho ? c.yon - c.hither : (c.yon - c.hither) / ray->d.z;
   ray->o = xf_point(c.camera_to_world, ray->o);
   ray->d = xf_vector(c.camera_to_world, ray->d);
 }

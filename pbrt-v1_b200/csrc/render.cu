@@ -272,7 +272,7 @@ k_generate(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
       uint32_t qi = warp_push(&wb.counts[0], valid);
       if (valid) {
         Ray ray;
-        perspective_generate_ray(sv.camera, cs, &ray);
+        perspective_generate_ray(sv.camera, cs, &ray, sv.xRes, sv.yRes);
         queue_put(wb.q[0], qi, slot, ray);
         ++nValid;
       }
@@ -295,7 +295,7 @@ k_generate(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
     } else
       stratified_camera_sample(sv, x, y, k, &cs);
     Ray ray;
-    perspective_generate_ray(sv.camera, cs, &ray);
+    perspective_generate_ray(sv.camera, cs, &ray, sv.xRes, sv.yRes);
     queue_put(wb.q[0], slot, slot, ray);
     wb.imageX[slot] = film_image_coord(cs.imageX);
     wb.imageY[slot] = film_image_coord(cs.imageY);
@@ -1056,7 +1056,7 @@ __global__ void k_camera_rays(const __grid_constant__ SceneView sv, const WavePa
     CameraSample cs;
     stratified_camera_sample(sv, wd.xs + (int)(pix % ew), wd.ys + (int)(pix / ew), k, &cs);
     Ray r;
-    perspective_generate_ray(sv.camera, cs, &r);
+    perspective_generate_ray(sv.camera, cs, &r, sv.xRes, sv.yRes);
     float *o = rays + 8 * s;
     o[0] = r.o.x; o[1] = r.o.y; o[2] = r.o.z; o[3] = r.d.x; o[4] = r.d.y; o[5] = r.d.z;
     o[6] = r.mint; o[7] = r.maxt;

@@ -191,15 +191,19 @@ class EmissionIntegrator : public VolumeIntegrator {
 };
 
 // ------------------------------------------------------------------- camera
-class PerspectiveCamera : public Camera {
+// core/transform.cpp:177-180
+static Transform Orthographic(float znear, float zfar) {
+  return Scale(1.f, 1.f, 1.f / (zfar - znear)) * Translate(Vector(0.f, 0.f, -znear));
+}
+class PerspectiveCamera : public Camera {   // also the orthographic camera: both are ProjectiveCameras
  public:
-  // core/camera.cpp:50-70 + cameras/perspective.cpp:38-50
+  // core/camera.cpp:50-70 + cameras/perspective.cpp:38-50 / cameras/orthographic.cpp:38-48
   PerspectiveCamera(const Transform &world2cam, const float Screen[4], float hither, float yon,
-                    float sopen, float sclose, float lensr, float focald, float fov, Film *f)
-      : Camera(world2cam, hither, yon, sopen, sclose, f) {
+                    float sopen, float sclose, float lensr, float focald, float fov, Film *f, bool ortho = false)
+      : Camera(world2cam, hither, yon, sopen, sclose, f), orthographic(ortho) {
     LensRadius = lensr;
     FocalDistance = focald;
-    Transform CameraToScreen = Perspective(fov, hither, yon);
+    Transform CameraToScreen = ortho ? Orthographic(hither, yon) : Perspective(fov, hither, yon);
     Transform ScreenToRaster =
         Scale(float(film->xResolution), float(film->yResolution), 1.f) *
         Scale(1.f / (Screen[1] - Screen[0]), 1.f / (Screen[2] - Screen[3]), 1.f) *
@@ -208,6 +212,8 @@ class PerspectiveCamera : public Camera {
     RasterToCamera = CameraToScreen.GetInverse() * RasterToScreen;
   }
   void Flatten(PbrtB200Camera *out) const {
+    memset(out, 0, sizeof(*out));
+    out->kind = orthographic ? PBRT_B200_CAMERA_ORTHOGRAPHIC : PBRT_B200_CAMERA_PERSPECTIVE;
     memcpy(out->raster_to_camera, RasterToCamera.GetMatrix().m, 16 * sizeof(float));
     memcpy(out->camera_to_world, CameraToWorld.GetMatrix().m, 16 * sizeof(float));
     out->hither = ClipHither; out->yon = ClipYon;
@@ -216,6 +222,23 @@ class PerspectiveCamera : public Camera {
   }
   Transform RasterToCamera;
   float LensRadius, FocalDistance;
+  bool orthographic;
+};
+class EnvironmentCamera : public Camera {   // cameras/environment.cpp:28-63
+ public:
+  EnvironmentCamera(const Transform &world2cam, float hither, float yon, float sopen, float sclose, Film *f)
+      : Camera(world2cam, hither, yon, sopen, sclose, f) {
+    rayOrigin = CameraToWorld(Point(0, 0, 0));
+  }
+  void Flatten(PbrtB200Camera *out) const {
+    memset(out, 0, sizeof(*out));
+    out->kind = PBRT_B200_CAMERA_ENVIRONMENT;
+    out->ray_origin[0] = rayOrigin.x; out->ray_origin[1] = rayOrigin.y; out->ray_origin[2] = rayOrigin.z;
+    memcpy(out->camera_to_world, CameraToWorld.GetMatrix().m, 16 * sizeof(float));
+    out->hither = ClipHither; out->yon = ClipYon;
+    out->shutter_open = ShutterOpen; out->shutter_close = ShutterClose;
+  }
+  Point rayOrigin;
 };
 
 // ------------------------------------------------------------------ sampler
@@ -526,12 +549,11 @@ Primitive *MakeAccelerator(const string &name, const vector<Reference<Primitive>
 }
 Camera *MakeCamera(const string &name, const ParamSet &params, const Transform &world2cam,
                    Film *film) {
-  if (name != "perspective") {
-    Error("Camera plugin \"%s\" is outside the B200 hot-path scope (supported: perspective).",
-          name.c_str());
+  if (name != "perspective" && name != "orthographic" && name != "environment") {
+    Error("Camera plugin \"%s\" unknown (supported: perspective, orthographic, environment).", name.c_str());
     return NULL;
   }
-  // cameras/perspective.cpp:83-115
+  // cameras/perspective.cpp:83-115, orthographic.cpp:79-112, environment.cpp:64-99 (same parameter block)
   float hither = max(1e-4f, params.FindOneFloat("hither", 1e-3f));
   float yon = min(params.FindOneFloat("yon", 1e30f), 1e30f);
   float shutteropen = params.FindOneFloat("shutteropen", 0.f);
@@ -549,9 +571,17 @@ Camera *MakeCamera(const string &name, const ParamSet &params, const Transform &
   int swi;
   const float *sw = params.FindFloat("screenwindow", &swi);
   if (sw && swi == 4) memcpy(screen, sw, 4 * sizeof(float));
-  float fov = params.FindOneFloat("fov", 90.);
-  Camera *c = new PerspectiveCamera(world2cam, screen, hither, yon, shutteropen, shutterclose,
-                                    lensradius, focaldistance, fov, film);
+  Camera *c;
+  if (name == "environment")
+    c = new EnvironmentCamera(world2cam, hither, yon, shutteropen, shutterclose, film);
+  else if (name == "orthographic")
+    c = new PerspectiveCamera(world2cam, screen, hither, yon, shutteropen, shutterclose, lensradius, focaldistance,
+                              0.f, film, true);
+  else {
+    float fov = params.FindOneFloat("fov", 90.);
+    c = new PerspectiveCamera(world2cam, screen, hither, yon, shutteropen, shutterclose, lensradius, focaldistance,
+                              fov, film);
+  }
   params.ReportUnused();
   return c;
 }

@@ -509,6 +509,42 @@ WorldEnd
 INLINE["heightfield_path"] = _heightfield()
 
 
+def _camera(cam, tag, extra=""):
+    """orthographic (with depth of field) and environment cameras"""
+    return """LookAt 278 273 -300 278 273 0 0 1 0
+Camera %s
+Film "image" "integer xresolution" [32] "integer yresolution" [24] "string filename" ["camera_%s_out.exr"]
+Sampler "stratified" "integer xsamples" [2] "integer ysamples" [2]
+PixelFilter "box"
+SurfaceIntegrator "path" "integer maxdepth" [3]
+WorldBegin
+AttributeBegin
+AreaLightSource "area" "color L" [17 12 4]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [213 548.7 227 343 548.7 227 343 548.7 332 213 548.7 332]
+AttributeEnd
+Material "matte" "color Kd" [.73 .73 .73]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [0 0 0 0 0 555 555 0 555 555 0 0]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [0 0 555 0 555 555 555 555 555 555 0 555]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [0 555 0 555 555 0 555 555 555 0 555 555]
+Material "matte" "color Kd" [.12 .45 .15]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [0 0 0 0 555 0 0 555 555 0 0 555]
+Material "matte" "color Kd" [.65 .05 .05]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [555 0 0 555 0 555 555 555 555 555 555 0]
+AttributeBegin
+Translate 200 100 250
+Material "glass" "float index" [1.5]
+Shape "sphere" "float radius" [100]
+AttributeEnd
+%s
+WorldEnd
+""" % (cam, tag, extra)
+
+
+INLINE["camera_orthographic"] = _camera('"orthographic" "float screenwindow" [-300 300 -225 225]', "orthographic")
+INLINE["camera_orthographic_lens"] = _camera('"orthographic" "float screenwindow" [-300 300 -225 225] "float lensradius" [12] "float focaldistance" [550]', "orthographic_lens")
+INLINE["camera_environment"] = _camera('"environment"', "environment")
+
+
 def parse_count(text, label):
     m = re.search(re.escape(label) + r"\s+([0-9.]+)([kMG]?)", text)
     if not m:
