@@ -170,7 +170,8 @@ typedef struct PbrtB200Camera {
 
 /* samplers/stratified.cpp:51-86, samplers/lowdiscrepancy.cpp:57-74 */
 enum { PBRT_B200_SAMPLER_STRATIFIED = 0, PBRT_B200_SAMPLER_LOWDISCREPANCY = 1,
-       PBRT_B200_SAMPLER_BESTCANDIDATE = 2 /* samplers/bestcandidate.cpp: placements of the 4096-entry sample table */ };
+       PBRT_B200_SAMPLER_BESTCANDIDATE = 2 /* samplers/bestcandidate.cpp: placements of the 4096-entry sample table */,
+       PBRT_B200_SAMPLER_RANDOM = 3 /* samplers/random.cpp: x_samples * y_samples uniform samples per pixel */ };
 #define PBRT_B200_BC_TABLE_SIZE 4096   /* SAMPLE_TABLE_SIZE, samplers/bestcandidate.cpp:29-31 */
 typedef struct PbrtB200Sampler {
   int32_t x_samples, y_samples;    /* stratified: strata per axis; lowdiscrepancy: pixelsamples (a power of 2), 1;

@@ -99,6 +99,21 @@ assert b.count(m1) == 1 and b.count(m2) == 1
 b = b.replace(m1, '\t\tpbrtReseed(Floor2Int(xTableCorner), Floor2Int(yTableCorner), 0, 3);\n' + m1)
 b = b.replace(m2, '\tpbrtRefBestCandidateSample(Floor2Int(xTableCorner), Floor2Int(yTableCorner), tableOffset);\n' + m2)
 open(tmp + "/bestcandidate_keyed.cpp", "w").write(b)
+# random.cpp: same two re-key points as the stratified sampler (pixel pattern: constructor and
+# GetNextSample; integrator samples of each image sample)
+r = open(ref + "/samplers/random.cpp").read()
+r = r.replace('class RandomSampler : public Sampler {', 'extern void pbrtReseed(int, int, int, int);\nclass RandomSampler : public Sampler {', 1)
+lines = r.split('\n')
+out = []
+n_pix = n_int = 0
+for i, ln in enumerate(lines):
+    if ln.strip() == 'for (int i = 0;' and lines[i + 1].strip() == 'i < 5 * xPixelSamples * yPixelSamples;':
+        out.append(ln[:len(ln) - len(ln.lstrip())] + 'pbrtReseed(xPos, yPos, 0xFFFF, 0);'); n_pix += 1
+    if ln.strip() == '// Generate stratified samples for integrators':
+        out.append(ln[:len(ln) - len(ln.lstrip())] + 'pbrtReseed(xPos, yPos, samplePos, 0);'); n_int += 1
+    out.append(ln)
+assert n_pix == 2 and n_int == 1, (n_pix, n_int)
+open(tmp + "/random_keyed.cpp", "w").write('\n'.join(out))
 # kdtree.cpp: count calls reaching the kd walk (the metric's "rays": Scene::Intersect + IntersectP)
 k = open(ref + "/accelerators/kdtree.cpp").read()
 k = k.replace('// KdAccelNode Declarations', 'extern unsigned long long gRefIntersectCalls, gRefIntersectPCalls;\n// KdAccelNode Declarations', 1)
@@ -135,6 +150,8 @@ rm -f $OUT/plugins_keyed/stratified.so
 g++ $FL -fPIC -shared $TMP/stratified_keyed.cpp -o $OUT/plugins_keyed/stratified.so
 rm -f $OUT/plugins_keyed/lowdiscrepancy.so
 g++ $FL -fPIC -shared $TMP/lowdiscrepancy_keyed.cpp -o $OUT/plugins_keyed/lowdiscrepancy.so
+rm -f $OUT/plugins_keyed/random.so
+g++ $FL -fPIC -shared $TMP/random_keyed.cpp -o $OUT/plugins_keyed/random.so
 rm -f $OUT/plugins_keyed/bestcandidate.so
 g++ $FL -I$REF -fPIC -shared $TMP/bestcandidate_keyed.cpp -o $OUT/plugins_keyed/bestcandidate.so
 

@@ -240,7 +240,8 @@ int pbrt_twin_render(const PbrtB200Scene *scene, const PbrtB200Window *win, floa
         PatternSource key0;
         key0.key0 = pb_key(x, y, k, 0);
         key0.ld = ld ? ldTables.data() : (const float *)0;
-        key0.stride = (uint32_t)spp; key0.index = (uint32_t)k; key0.bc = 0;
+        key0.stride = (uint32_t)spp; key0.index = (uint32_t)k;
+        key0.bc = sv.sampler.kind == PBRT_B200_SAMPLER_RANDOM ? 2 : 0;
         CameraSample cs;
         if (ld) ld_camera_sample(sv, key0, x, y, &cs);
         else stratified_camera_sample(sv, x, y, k, &cs);

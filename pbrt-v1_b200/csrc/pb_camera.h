@@ -37,6 +37,17 @@ PB_HD bool bc_camera_sample(const SceneView &sv, float cornerX, float cornerY, i
 PB_HD void stratified_camera_sample(const SceneView &sv, int x, int y, int k, CameraSample *cs) {
   int nx = sv.sampler.x_samples, ny = sv.sampler.y_samples;
   int n = nx * ny;
+  if (sv.sampler.kind == PBRT_B200_SAMPLER_RANDOM) {
+    // samplers/random.cpp:77-100: 5n uniform draws per pixel: image (2n), lens (2n), time (n)
+    uint64_t keyR = pb_key(x, y, 0xFFFF, 0);
+    cs->imageX = pb_f32(keyR, 2u * k + 1u);
+    cs->imageY = pb_f32(keyR, 2u * k + 2u);
+    cs->imageX += x;
+    cs->imageY += y;
+    cs->lensU = pb_f32(keyR, 2u * n + 2u * k + 1u);
+    cs->lensV = pb_f32(keyR, 2u * n + 2u * k + 2u);
+    return;
+  }
   bool jitter = sv.sampler.jitter != 0;
   uint64_t key = pb_key(x, y, 0xFFFF, 0);
   float dx = 1.f / nx, dy = 1.f / ny;

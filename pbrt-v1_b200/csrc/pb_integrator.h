@@ -394,12 +394,14 @@ PB_HD Spec direct_value(const Spec &termA, const Spec &termB, bool unoccluded, b
 PB_HD float pat1d(const SceneView &sv, const PatternSource &key0, int idx, int j) {
   const SamplePattern &p = sv.patterns[idx];
   if (key0.ld && p.offset >= 0) return key0.ld[(size_t)(p.offset + j) * key0.stride + key0.index];
+  if (key0.bc == 2) return pb_f32(key0.key0, p.ctr0 + 1u + (uint32_t)j);   // samplers/random.cpp:103-105
   if (key0.bc) return pb_bc_stratified_value(key0.key0, p, j, 0);
   return pb_lhs_value(key0.key0, p, j, 0);
 }
 PB_HD float pat2d(const SceneView &sv, const PatternSource &key0, int idx, int j, int d) {
   const SamplePattern &p = sv.patterns[sv.n1D + idx];
   if (key0.ld && p.offset >= 0) return key0.ld[(size_t)(p.offset + 2 * j + d) * key0.stride + key0.index];
+  if (key0.bc == 2) return pb_f32(key0.key0, p.ctr0 + 1u + 2u * (uint32_t)j + (uint32_t)d);   // random.cpp:106-108
   if (key0.bc) return pb_bc_stratified_value(key0.key0, p, j, d);
   return pb_lhs_value(key0.key0, p, j, d);
 }

@@ -79,7 +79,7 @@ struct PatternSource {
   uint64_t key0;
   const float *ld;
   uint32_t stride, index;
-  int32_t bc;
+  int32_t bc;   // 0 LatinHypercube patterns (stratified) or tables (lowdiscrepancy), 1 bestcandidate, 2 random sampler
 };
 // LatinHypercube(samples, n, dims) (core/sampling.cpp:98-113): n*dims floats
 // (sample-major), then per dimension n swap draws.  Value of sample j, dim d.

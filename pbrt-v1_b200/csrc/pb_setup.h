@@ -16,7 +16,8 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
   if (s.sampler.x_samples < 1 || s.sampler.y_samples < 1) return "sampler needs >= 1 sample per axis";
   const bool ld = s.sampler.kind == PBRT_B200_SAMPLER_LOWDISCREPANCY;
   const bool bc = s.sampler.kind == PBRT_B200_SAMPLER_BESTCANDIDATE;
-  if (!ld && !bc && s.sampler.kind != PBRT_B200_SAMPLER_STRATIFIED) return "unknown sampler kind";
+  const bool rnd = s.sampler.kind == PBRT_B200_SAMPLER_RANDOM;
+  if (!ld && !bc && !rnd && s.sampler.kind != PBRT_B200_SAMPLER_STRATIFIED) return "unknown sampler kind";
   if (bc && (s.sampler.y_samples != 1 || s.sampler.x_samples > PB_BC_TABLE || !s.bestcandidate_table))
     return "bestcandidate sampler: pixelsamples must be in [1, 4096] and the sample table present";
   // tableWidth = SQRT_SAMPLE_TABLE_SIZE / sqrtf(pixelSamples), samplers/bestcandidate.cpp:68-69
@@ -137,11 +138,13 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
   }
   for (int i = 0; i < c1; ++i, ++k) {
     sv->patterns[k].ctr0 = ctr; sv->patterns[k].n = n1[i]; sv->patterns[k].dims = 1; sv->patterns[k].offset = off;
+    if (rnd) { ctr += (uint32_t)n1[i]; continue; }   // one RandomFloat per value (samplers/random.cpp:103-105)
     ctr += ld ? 1u + nPixel * (uint32_t)n1[i] + nPixel : 2u * n1[i];
     off += n1[i];
   }
   for (int i = 0; i < c2; ++i, ++k) {
     sv->patterns[k].ctr0 = ctr; sv->patterns[k].n = n2[i]; sv->patterns[k].dims = 2; sv->patterns[k].offset = off;
+    if (rnd) { ctr += 2u * (uint32_t)n2[i]; continue; }
     ctr += ld ? 2u + nPixel * (uint32_t)n2[i] + nPixel : 4u * n2[i];
     off += 2 * n2[i];
   }

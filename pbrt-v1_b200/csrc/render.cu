@@ -464,12 +464,12 @@ __device__ __forceinline__ void store3(float *const a[3], uint32_t i, const Spec
 struct WaveKeyInfo {
   const uint32_t *pixel;
   int spp;
-  int bc;   // bestcandidate sampler: pixel[] holds the placement's corner pixel, slot % spp the table entry
+  int bc;   // 1 bestcandidate sampler: pixel[] holds the placement's corner pixel, slot % spp the table entry; 2 random sampler
 };
 __device__ __forceinline__ uint64_t slot_key(const WaveKeyInfo &wd, uint32_t slot, int stream) {
   uint32_t p = wd.pixel[slot];
   int x = (int)(p & 0xffffu) - 32768, y = (int)(p >> 16) - 32768, k = (int)(slot % (uint32_t)wd.spp);
-  if (wd.bc) return pb_key_bc(x, y, k, stream == 0 ? 2 : stream);   // patterns: the sample's stream 2
+  if (wd.bc == 1) return pb_key_bc(x, y, k, stream == 0 ? 2 : stream);   // patterns: the sample's stream 2
   return pb_key(x, y, k, stream);
 }
 // Fold the slot's pending direct-lighting record (path integrator) into L.
@@ -611,7 +611,7 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
         st.depth = (int)(flags & 0xffu);
         st.rng.key = slot_key(wd, slot, 1);
         st.rng.ctr = wb.ctr[slot];
-        PatternSource key0 = {slot_key(wd, slot, 0), LD ? wb.ld : (const float *)nullptr, wb.nSlots, slot, LD ? wd.bc : 0};
+        PatternSource key0 = {slot_key(wd, slot, 0), LD ? wb.ld : (const float *)nullptr, wb.nSlots, slot, LD ? wd.bc : (wd.bc == 2 ? 2 : 0)};
         bool hasDirect;
         path_vertex_direct<G, LK>(sv, key0, st, ray, &sf, &direct, &hasDirect);
         wb.ctr[slot] = st.rng.ctr;
@@ -674,7 +674,7 @@ k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, cons
         st.specularBounce = (flags >> 8) & 1u;
         st.rng.key = slot_key(wd, slot, 1);
         st.rng.ctr = wb.ctr[slot];
-        PatternSource key0 = {slot_key(wd, slot, 0), LD ? wb.ld : (const float *)nullptr, wb.nSlots, slot, LD ? wd.bc : 0};
+        PatternSource key0 = {slot_key(wd, slot, 0), LD ? wb.ld : (const float *)nullptr, wb.nSlots, slot, LD ? wd.bc : (wd.bc == 2 ? 2 : 0)};
         pushNext = path_vertex_continue<G>(sv, key0, st, ray, sf, &next);
         store3(wb.T, slot, st.T);
         wb.ctr[slot] = st.rng.ctr;
@@ -1371,7 +1371,7 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
   auto nextWork = [&]() { return wb.counts + (workIdx++); };
   bool isPath = sv.integrator.kind == PBRT_B200_INT_PATH;
   int cur = 0;
-  WaveKeyInfo wk = {wb.pixel, wd.spp, wd.bc};
+  WaveKeyInfo wk = {wb.pixel, wd.spp, wd.bc ? 1 : (sv.sampler.kind == PBRT_B200_SAMPLER_RANDOM ? 2 : 0)};
   bool overlap = g_overlap != 0;
   // (LD kernels = patterns read from per-unit tables: lowdiscrepancy and bestcandidate)
   const bool isLD = sv.sampler.kind == PBRT_B200_SAMPLER_LOWDISCREPANCY || wd.bc;

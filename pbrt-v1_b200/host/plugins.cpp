@@ -272,6 +272,16 @@ class LDSampler : public Sampler {
   }
   int pixelSamples;
 };
+class RandomSampler : public Sampler {   // samplers/random.cpp:28-76
+ public:
+  RandomSampler(int xstart, int xend, int ystart, int yend, int xs, int ys)
+      : Sampler(xstart, xend, ystart, yend, xs * ys), xPixelSamples(xs), yPixelSamples(ys) {}
+  void Flatten(PbrtB200Sampler *out) const {
+    out->x_samples = xPixelSamples; out->y_samples = yPixelSamples; out->jitter = 0;
+    out->kind = PBRT_B200_SAMPLER_RANDOM;
+  }
+  int xPixelSamples, yPixelSamples;
+};
 class BestCandidateSampler : public Sampler {   // samplers/bestcandidate.cpp:33-77
  public:
   BestCandidateSampler(int xstart, int xend, int ystart, int yend, int ps)
@@ -606,11 +616,17 @@ Sampler *MakeSampler(const string &name, const ParamSet &params, const Film *fil
     params.ReportUnused();
     return s;
   }
+  if (name == "random") {   // samplers/random.cpp:113-122
+    int xsamp = params.FindOneInt("xsamples", 2);
+    int ysamp = params.FindOneInt("ysamples", 2);
+    int xstart, xend, ystart, yend;
+    film->GetSampleExtent(&xstart, &xend, &ystart, &yend);
+    Sampler *s = new RandomSampler(xstart, xend, ystart, yend, xsamp < 1 ? 1 : xsamp, ysamp < 1 ? 1 : ysamp);
+    params.ReportUnused();
+    return s;
+  }
   if (name != "stratified")
-    // "random" is outside the hot-path scope; the stratified sampler stands in (different noise,
-    // same expectation).
-    Warning("Sampler plugin \"%s\" is not implemented on the GPU; using \"stratified\".",
-            name.c_str());
+    Warning("Sampler plugin \"%s\" unknown; using \"stratified\".", name.c_str());
   bool jitter = params.FindOneBool("jitter", true);      // samplers/stratified.cpp:132-141
   int xstart, xend, ystart, yend;
   film->GetSampleExtent(&xstart, &xend, &ystart, &yend);

@@ -544,6 +544,11 @@ INLINE["camera_orthographic"] = _camera('"orthographic" "float screenwindow" [-3
 INLINE["camera_orthographic_lens"] = _camera('"orthographic" "float screenwindow" [-300 300 -225 225] "float lensradius" [12] "float focaldistance" [550]', "orthographic_lens")
 INLINE["camera_environment"] = _camera('"environment"', "environment")
 
+INLINE["random_sampler_path_lens"] = _bestcandidate('"path" "integer maxdepth" [4]', "random_path_lens", 'Sampler "random" "integer xsamples" [2] "integer ysamples" [2]',
+                                                    lens='"float lensradius" [15] "float focaldistance" [900]').replace("bc_random_path_lens_out", "random_sampler_path_lens_out")
+INLINE["random_sampler_direct_nsamples3"] = _bestcandidate('"directlighting"', "random_direct", 'Sampler "random" "integer xsamples" [3] "integer ysamples" [1]',
+                                                           nsamples=3).replace("bc_random_direct_out", "random_sampler_direct_nsamples3_out")
+
 
 def parse_count(text, label):
     m = re.search(re.escape(label) + r"\s+([0-9.]+)([kMG]?)", text)
