@@ -123,7 +123,9 @@ typedef struct PbrtB200Instance {
 enum { PBRT_B200_MAT_MATTE = 0, PBRT_B200_MAT_GLASS = 1, PBRT_B200_MAT_MIRROR = 2,
        PBRT_B200_MAT_PLASTIC = 3,    /* materials/plastic.cpp: Lambertian + Blinn microfacet */
        PBRT_B200_MAT_UBER = 4,       /* materials/uber.cpp: opacity pass-through + Lambertian + microfacet + specular */
-       PBRT_B200_MAT_SHINYMETAL = 5  /* materials/shinymetal.cpp: conductor microfacet + conductor specular */ };
+       PBRT_B200_MAT_SHINYMETAL = 5, /* materials/shinymetal.cpp: conductor microfacet + conductor specular */
+       PBRT_B200_MAT_TRANSLUCENT = 6 /* materials/translucent.cpp: Lambertian + microfacet, reflected (kr = reflect) and
+                                        transmitted through BRDFToBTDF (kt = transmit) */ };
 typedef struct PbrtB200Material {    /* 80 bytes */
   int32_t kind;
   float   kd[3];                   /* matte / plastic / uber                  */

@@ -35,6 +35,7 @@ struct Lobe {
   float A, B;    // OrenNayar
   float etai, etat;
   Spec E;        // conductor lobes: FresnelConductor::eta (k = 0)
+  int btdf;      // wrapped in BRDFToBTDF (core/reflection.h:143-167): evaluated with the other hemisphere's wi
 };
 struct Bsdf {
   V3 p;          // dgShading.p
@@ -195,7 +196,7 @@ PB_NOINLINE Spec microfacet_sample_f(const Spec &R, float exponent, float etai, 
 // BxDF::f for the non-specular lobes (reflection.cpp:128-156); specular lobes return 0.
 // G = false compiles the glossy (microfacet) lobe out: kernels for scenes without such materials
 template <bool G = true>
-PB_HD Spec lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
+PB_HD Spec lobe_f_brdf(const Lobe &l, const V3 &wo, const V3 &wi) {
   if (l.kind == PB_LOBE_LAMBERT) return l.R;   // R already holds R * INV_PI (reflection.h:249)
   if (G && l.kind == PB_LOBE_MICROFACET_BLINN) return microfacet_f(l.R, l.A, l.etai, l.etat, wo, wi);
   if (G && l.kind == PB_LOBE_MICROFACET_BLINN_COND) return microfacet_f(l.R, l.A, l.etai, l.etat, wo, wi, &l.E);
@@ -222,16 +223,28 @@ PB_HD Spec lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
   return spec(0.f);
 }
 // BxDF::Pdf (reflection.cpp:226-230); specular lobes return 0 (reflection.h:213,235)
+// BRDFToBTDF::f (reflection.cpp:63-66): the wrapped BRDF with wi mirrored into wo's hemisphere
 template <bool G = true>
-PB_HD float lobe_pdf(const Lobe &l, const V3 &wo, const V3 &wi) {
+PB_HD Spec lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
+  if (G && l.btdf) return lobe_f_brdf<G>(l, wo, v3(wi.x, wi.y, -wi.z));
+  return lobe_f_brdf<G>(l, wo, wi);
+}
+template <bool G = true>
+PB_HD float lobe_pdf_brdf(const Lobe &l, const V3 &wo, const V3 &wi) {
   if (l.type & PB_SPECULAR) return 0.f;
   if (G && (l.kind == PB_LOBE_MICROFACET_BLINN || l.kind == PB_LOBE_MICROFACET_BLINN_COND))   // Microfacet::Pdf, reflection.cpp:240-243
     return (wo.z * wi.z > 0.f) ? blinn_pdf(l.A, wo, wi) : 0.f;
   return (wo.z * wi.z > 0.f) ? fabsf(wi.z) * PB_INV_PI : 0.f;
 }
+// BRDFToBTDF::Pdf (reflection.cpp:231-234): brdf->Pdf(wo, -wi)
+template <bool G = true>
+PB_HD float lobe_pdf(const Lobe &l, const V3 &wo, const V3 &wi) {
+  if (G && l.btdf) return lobe_pdf_brdf<G>(l, wo, -wi);
+  return lobe_pdf_brdf<G>(l, wo, wi);
+}
 // BxDF::Sample_f for each lobe kind (reflection.cpp:96-127, 219-225)
 template <bool G = true>
-PB_HD Spec lobe_sample_f(const Lobe &l, const V3 &wo, V3 *wi, float u1, float u2, float *pdf) {
+PB_HD Spec lobe_sample_f_brdf(const Lobe &l, const V3 &wo, V3 *wi, float u1, float u2, float *pdf) {
   if (l.kind == PB_LOBE_SPEC_REFL_DIEL || l.kind == PB_LOBE_SPEC_REFL_NOOP) {
     *wi = v3(-wo.x, -wo.y, wo.z);
     *pdf = 1.f;
@@ -265,8 +278,15 @@ PB_HD Spec lobe_sample_f(const Lobe &l, const V3 &wo, V3 *wi, float u1, float u2
     return microfacet_sample_f(l.R, l.A, l.etai, l.etat, wo, wi, u1, u2, pdf, &l.E);
   *wi = cosine_sample_hemisphere(u1, u2);
   if (wo.z < 0.f) wi->z *= -1.f;
-  *pdf = lobe_pdf<G>(l, wo, *wi);
-  return lobe_f<G>(l, wo, *wi);
+  *pdf = lobe_pdf_brdf<G>(l, wo, *wi);
+  return lobe_f_brdf<G>(l, wo, *wi);
+}
+// BRDFToBTDF::Sample_f (reflection.cpp:67-72): sample the BRDF, then mirror wi
+template <bool G = true>
+PB_HD Spec lobe_sample_f(const Lobe &l, const V3 &wo, V3 *wi, float u1, float u2, float *pdf) {
+  Spec f = lobe_sample_f_brdf<G>(l, wo, wi, u1, u2, pdf);
+  if (G && l.btdf) *wi = v3(wi->x, wi->y, -wi->z);
+  return f;
 }
 
 PB_HD V3 bsdf_world_to_local(const Bsdf &b, const V3 &v) {
@@ -393,6 +413,8 @@ template <bool G>
 PB_HD void bsdf_set_lobes(const PbrtB200Material &m, Bsdf *b) {
   b->eta = 1.f;
   b->nLobes = 0;
+#pragma unroll
+  for (int i = 0; i < LobeLimit<G>::n; ++i) b->lobes[i].btdf = 0;
   const bool reflects = m.kind == PBRT_B200_MAT_GLASS || m.kind == PBRT_B200_MAT_MIRROR;
   Spec R = reflects ? spec3(m.kr[0], m.kr[1], m.kr[2]) : spec3(m.kd[0], m.kd[1], m.kd[2]);
   if (m.kind == PBRT_B200_MAT_MATTE) {
@@ -465,6 +487,40 @@ PB_HD void bsdf_set_lobes(const PbrtB200Material &m, Bsdf *b) {
       Lobe &l = b->lobes[b->nLobes++];
       l.kind = PB_LOBE_SPEC_REFL_DIEL; l.type = PB_REFLECTION | PB_SPECULAR;
       l.R = kr; l.A = l.B = 0.f; l.etai = 1.5f; l.etat = 1.f;
+    }
+  } else if (G && m.kind == PBRT_B200_MAT_TRANSLUCENT) {
+    // materials/translucent.cpp:52-82: Lambertian(r * kd), BRDFToBTDF(Lambertian(t * kd)),
+    // Microfacet(r * ks, FresnelDielectric(1.5, 1), Blinn(1/rough)), BRDFToBTDF(Microfacet(t * ks, ..))
+    Spec r = spec3(m.kr[0], m.kr[1], m.kr[2]), t = spec3(m.kt[0], m.kt[1], m.kt[2]);
+    if (!(is_black(r) && is_black(t))) {
+      Spec kd = spec3(m.kd[0], m.kd[1], m.kd[2]);
+      if (!is_black(kd)) {
+        if (!is_black(r)) {
+          Lobe &l = b->lobes[b->nLobes++];
+          l.kind = PB_LOBE_LAMBERT; l.type = PB_REFLECTION | PB_DIFFUSE;
+          l.R = (r * kd) * PB_INV_PI; l.A = l.B = 0.f; l.etai = l.etat = 1.f;
+        }
+        if (!is_black(t)) {
+          Lobe &l = b->lobes[b->nLobes++];
+          l.kind = PB_LOBE_LAMBERT; l.type = PB_TRANSMISSION | PB_DIFFUSE; l.btdf = 1;
+          l.R = (t * kd) * PB_INV_PI; l.A = l.B = 0.f; l.etai = l.etat = 1.f;
+        }
+      }
+      Spec ks = spec3(m.ks[0], m.ks[1], m.ks[2]);
+      if (!is_black(ks)) {
+        float e = 1.f / m.roughness;
+        if (e > 1000.f || e != e) e = 1000.f;
+        if (!is_black(r)) {
+          Lobe &l = b->lobes[b->nLobes++];
+          l.kind = PB_LOBE_MICROFACET_BLINN; l.type = PB_REFLECTION | PB_GLOSSY;
+          l.R = r * ks; l.A = e; l.B = 0.f; l.etai = 1.5f; l.etat = 1.f;
+        }
+        if (!is_black(t)) {
+          Lobe &l = b->lobes[b->nLobes++];
+          l.kind = PB_LOBE_MICROFACET_BLINN; l.type = PB_TRANSMISSION | PB_GLOSSY; l.btdf = 1;
+          l.R = t * ks; l.A = e; l.B = 0.f; l.etai = 1.5f; l.etat = 1.f;
+        }
+      }
     }
   } else if (G && m.kind == PBRT_B200_MAT_SHINYMETAL) {
     // materials/shinymetal.cpp:54-63: Microfacet(1, FresnelConductor(FresnelApproxEta(Ks), 0), Blinn(1/rough)),

@@ -229,8 +229,11 @@ void pbrtTexture(const string &name, const string &type, const string &texname,
     Error("Texture type \"%s\" unknown.", type.c_str());
     return;
   }
-  if (texname != "constant") {
-    Error("Texture class \"%s\" is outside the B200 hot-path scope (supported: constant); "
+  // Every texture in scope evaluates to one value: "constant" (textures/constant.cpp), and "scale" /
+  // "mix" of such textures (textures/scale.cpp:38-41, textures/mix.cpp:40-44), whose Evaluate() is the
+  // same float expression at every point -- folded here once.
+  if (texname != "constant" && texname != "scale" && texname != "mix") {
+    Error("Texture class \"%s\" is outside the B200 hot-path scope (supported: constant, scale, mix); "
           "texture \"%s\" not created.", texname.c_str(), name.c_str());
     return;
   }
@@ -238,13 +241,27 @@ void pbrtTexture(const string &name, const string &type, const string &texname,
     if (graphicsState.floatTextures.find(name) != graphicsState.floatTextures.end())
       Warning("Texture \"%s\" being redefined", name.c_str());
     FloatTexture *ft = new FloatTexture;
-    ft->value = tp.FindFloat("value", 1.f);
+    if (texname == "constant") ft->value = tp.FindFloat("value", 1.f);
+    else if (texname == "scale") ft->value = tp.GetFloatTexture("tex1", 1.f) * tp.GetFloatTexture("tex2", 1.f);
+    else {
+      float t1 = tp.GetFloatTexture("tex1", 0.f), t2 = tp.GetFloatTexture("tex2", 1.f);
+      float amt = tp.GetFloatTexture("amount", 0.5f);
+      ft->value = (1.f - amt) * t1 + amt * t2;
+    }
     graphicsState.floatTextures[name] = ft;
   } else {
     if (graphicsState.spectrumTextures.find(name) != graphicsState.spectrumTextures.end())
       Warning("Texture \"%s\" being redefined", name.c_str());
     SpectrumTexture *st = new SpectrumTexture;
-    st->value = tp.FindSpectrum("value", Spectrum(1.f));
+    if (texname == "constant") st->value = tp.FindSpectrum("value", Spectrum(1.f));
+    else if (texname == "scale") {
+      Spectrum a = tp.GetSpectrumTexture("tex1", Spectrum(1.f)), b = tp.GetSpectrumTexture("tex2", Spectrum(1.f));
+      for (int i = 0; i < COLOR_SAMPLES; ++i) st->value.c[i] = a.c[i] * b.c[i];
+    } else {
+      Spectrum t1 = tp.GetSpectrumTexture("tex1", Spectrum(0.f)), t2 = tp.GetSpectrumTexture("tex2", Spectrum(1.f));
+      float amt = tp.GetFloatTexture("amount", 0.5f);
+      for (int i = 0; i < COLOR_SAMPLES; ++i) st->value.c[i] = t1.c[i] * (1.f - amt) + t2.c[i] * amt;
+    }
     graphicsState.spectrumTextures[name] = st;
   }
   tp.ReportUnused();

@@ -81,6 +81,19 @@ class UberMaterial : public Material {   // materials/uber.cpp:28-84
   }
   Spectrum Kd, Ks, Kr, opacity; float roughness;
 };
+class Translucent : public Material {   // materials/translucent.cpp:28-84
+ public:
+  Translucent(const Spectrum &kd, const Spectrum &ks, float rough, const Spectrum &refl, const Spectrum &trans)
+      : Kd(kd), Ks(ks), reflect(refl), transmit(trans), roughness(rough) {}
+  void Flatten(PbrtB200Material *out) const {
+    memset(out, 0, sizeof(*out));
+    out->kind = PBRT_B200_MAT_TRANSLUCENT;
+    Spectrum d = Kd.Clamp(), s = Ks.Clamp(), r = reflect.Clamp(), t = transmit.Clamp();
+    for (int i = 0; i < 3; ++i) { out->kd[i] = d.c[i]; out->ks[i] = s.c[i]; out->kr[i] = r.c[i]; out->kt[i] = t.c[i]; }
+    out->roughness = roughness;
+  }
+  Spectrum Kd, Ks, reflect, transmit; float roughness;
+};
 class ShinyMetal : public Material {   // materials/shinymetal.cpp:28-65
  public:
   ShinyMetal(const Spectrum &ks, float rough, const Spectrum &kr) : Ks(ks), Kr(kr), roughness(rough) {}
@@ -391,6 +404,15 @@ static Material *CreateUber(const Transform &, const TextureParams &mp) {   // m
   mp.GetFloatTexture("bumpmap", 0.f);
   return new UberMaterial(Kd, Ks, Kr, roughness, opacity);
 }
+static Material *CreateTranslucent(const Transform &, const TextureParams &mp) {   // materials/translucent.cpp:85-94
+  Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(1.f));
+  Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(1.f));
+  Spectrum reflect = mp.GetSpectrumTexture("reflect", Spectrum(0.5f));
+  Spectrum transmit = mp.GetSpectrumTexture("transmit", Spectrum(0.5f));
+  float roughness = mp.GetFloatTexture("roughness", .1f);
+  mp.GetFloatTexture("bumpmap", 0.f);
+  return new Translucent(Kd, Ks, roughness, reflect, transmit);
+}
 static Material *CreateShinyMetal(const Transform &, const TextureParams &mp) {   // materials/shinymetal.cpp:66-73
   Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(1.f));
   Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(1.f));
@@ -436,9 +458,10 @@ Reference<Material> MakeMaterial(const string &name, const Transform &mtl2world,
   else if (name == "plastic") m = CreatePlastic(mtl2world, mp);
   else if (name == "uber") m = CreateUber(mtl2world, mp);
   else if (name == "shinymetal") m = CreateShinyMetal(mtl2world, mp);
+  else if (name == "translucent") m = CreateTranslucent(mtl2world, mp);
   else
     Error("Material plugin \"%s\" is outside the B200 hot-path scope (supported: matte, glass, "
-          "mirror, plastic, uber, shinymetal).", name.c_str());
+          "mirror, plastic, uber, shinymetal, translucent).", name.c_str());
   if (m) mp.ReportUnused();   // core/dynload.cpp:299
   return m;
 }

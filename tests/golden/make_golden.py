@@ -550,6 +550,43 @@ INLINE["random_sampler_direct_nsamples3"] = _bestcandidate('"directlighting"', "
                                                            nsamples=3).replace("bc_random_direct_out", "random_sampler_direct_nsamples3_out")
 
 
+def _translucent(integrator, tag):
+    """translucent material (BRDFToBTDF lobes) lit from behind and in front; scale / mix textures of constants"""
+    return """LookAt 278 273 -800 278 273 0 0 1 0
+Camera "perspective" "float fov" [39.3]
+Film "image" "integer xresolution" [32] "integer yresolution" [32] "string filename" ["translucent_%s_out.exr"]
+Sampler "stratified" "integer xsamples" [2] "integer ysamples" [2]
+PixelFilter "box"
+SurfaceIntegrator %s
+WorldBegin
+LightSource "point" "color I" [300000 280000 250000] "point from" [278 300 500]
+AttributeBegin
+AreaLightSource "area" "color L" [17 12 4]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [213 548.7 227 343 548.7 227 343 548.7 332 213 548.7 332]
+AttributeEnd
+Texture "base" "color" "constant" "color value" [.8 .7 .5]
+Texture "tint" "color" "scale" "texture tex1" "base" "color tex2" [.9 .5 .9]
+Texture "blend" "color" "mix" "texture tex1" "base" "color tex2" [.1 .2 .9] "float amount" [.3]
+Texture "rough" "float" "mix" "float tex1" [.05] "float tex2" [.4] "float amount" [.25]
+Material "matte" "texture Kd" "blend"
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [0 0 0 0 0 555 555 0 555 555 0 0]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [0 0 555 0 555 555 555 555 555 555 0 555]
+Material "translucent" "texture Kd" "tint" "color Ks" [.4 .4 .4] "color reflect" [.4 .4 .4] "color transmit" [.6 .6 .5] "texture roughness" "rough"
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [80 20 300 480 20 300 480 420 330 80 420 330]
+AttributeBegin
+Translate 400 100 150
+Material "translucent" "color Kd" [.2 .6 .3] "color Ks" [0 0 0] "color transmit" [.9 .9 .9] "color reflect" [0 0 0]
+Shape "sphere" "float radius" [90]
+AttributeEnd
+WorldEnd
+""" % (tag, integrator)
+
+
+INLINE["translucent_path"] = _translucent('"path" "integer maxdepth" [4]', "path")
+INLINE["translucent_direct"] = _translucent('"directlighting"', "direct")
+INLINE["translucent_whitted"] = _translucent('"whitted"', "whitted")
+
+
 def parse_count(text, label):
     m = re.search(re.escape(label) + r"\s+([0-9.]+)([kMG]?)", text)
     if not m:
