@@ -124,8 +124,10 @@ enum { PBRT_B200_MAT_MATTE = 0, PBRT_B200_MAT_GLASS = 1, PBRT_B200_MAT_MIRROR = 
        PBRT_B200_MAT_PLASTIC = 3,    /* materials/plastic.cpp: Lambertian + Blinn microfacet */
        PBRT_B200_MAT_UBER = 4,       /* materials/uber.cpp: opacity pass-through + Lambertian + microfacet + specular */
        PBRT_B200_MAT_SHINYMETAL = 5, /* materials/shinymetal.cpp: conductor microfacet + conductor specular */
-       PBRT_B200_MAT_TRANSLUCENT = 6 /* materials/translucent.cpp: Lambertian + microfacet, reflected (kr = reflect) and
-                                        transmitted through BRDFToBTDF (kt = transmit) */ };
+       PBRT_B200_MAT_TRANSLUCENT = 6,/* materials/translucent.cpp: Lambertian + microfacet, reflected (kr = reflect) and
+                                        transmitted through BRDFToBTDF (kt = transmit) */
+       PBRT_B200_MAT_SUBSTRATE = 7   /* materials/substrate.cpp: FresnelBlend(Kd, Ks, Anisotropic(1/uroughness, 1/vroughness));
+                                        roughness = uroughness, sigma = vroughness */ };
 typedef struct PbrtB200Material {    /* 80 bytes */
   int32_t kind;
   float   kd[3];                   /* matte / plastic / uber                  */

@@ -22,7 +22,8 @@ enum { PB_LOBE_LAMBERT = 0, PB_LOBE_ORENNAYAR = 1, PB_LOBE_SPEC_REFL_DIEL = 2,
        PB_LOBE_SPEC_REFL_NOOP = 3, PB_LOBE_SPEC_TRANS = 4,
        PB_LOBE_MICROFACET_BLINN = 5,      /* Microfacet(FresnelDielectric, Blinn): A = exponent */
        PB_LOBE_SPEC_REFL_COND = 6,        /* SpecularReflection(FresnelConductor(E, k = 0))      */
-       PB_LOBE_MICROFACET_BLINN_COND = 7  /* Microfacet(FresnelConductor(E, k = 0), Blinn)       */ };
+       PB_LOBE_MICROFACET_BLINN_COND = 7, /* Microfacet(FresnelConductor(E, k = 0), Blinn)       */
+       PB_LOBE_FRESNEL_BLEND = 8          /* FresnelBlend(R = Rd, E = Rs, Anisotropic(A, B))     */ };
 // Lobes a BSDF can hold: 2 covers matte / glass / mirror; the kernels compiled for scenes with
 // glossy materials (template flag G) carry 4 (uber: transmission + Lambertian + microfacet + specular).
 #define PB_MAX_LOBES 4
@@ -193,6 +194,70 @@ PB_NOINLINE Spec microfacet_sample_f(const Spec &R, float exponent, float etai, 
   return microfacet_f(R, exponent, etai, etat, wo, *wi, condEta);
 }
 
+// Anisotropic microfacet distribution (core/reflection.h:326-345, reflection.cpp:273-332)
+PB_HD float aniso_D(float ex, float ey, const V3 &wh) {
+  float costhetah = fabsf(wh.z);
+  float d = (1.f - costhetah * costhetah);
+  if (d == 0.f) return 0.f;
+  float e = (ex * wh.x * wh.x + ey * wh.y * wh.y) / d;
+  return sqrtf((ex + 2.f) * (ey + 2.f)) * PB_INV_TWOPI * pb_powf(costhetah, e);
+}
+PB_HD float aniso_pdf_H(float ex, float ey, const V3 &wo, const V3 &H) {
+  float costhetah = fabsf(H.z);
+  float ds = 1.f - costhetah * costhetah;
+  float anisotropic_pdf = 0.f;
+  if (ds > 0.f && dot(wo, H) > 0.f) {
+    float e = (ex * H.x * H.x + ey * H.y * H.y) / ds;
+    float d = sqrtf((ex + 1.f) * (ey + 1.f)) * PB_INV_TWOPI * pb_powf(costhetah, e);
+    anisotropic_pdf = d / (4.f * dot(wo, H));
+  }
+  return anisotropic_pdf;
+}
+PB_HD void aniso_first_quadrant(float ex, float ey, float u1, float u2, float *phi, float *costheta) {
+  if (ex == ey) *phi = PB_PI * u1 * 0.5f;
+  else *phi = pb_atanf(sqrtf((ex + 1) / (ey + 1)) * pb_tanf(PB_PI * u1 * 0.5f));
+  float cosphi = pb_cosf(*phi), sinphi = pb_sinf(*phi);
+  *costheta = pb_powf(u2, 1.f / (ex * cosphi * cosphi + ey * sinphi * sinphi + 1));
+}
+PB_NOINLINE void aniso_sample_f(float ex, float ey, const V3 &wo, V3 *wi, float u1, float u2, float *pdf) {
+  float phi, costheta;
+  if (u1 < .25f) {
+    aniso_first_quadrant(ex, ey, 4.f * u1, u2, &phi, &costheta);
+  } else if (u1 < .5f) {
+    u1 = 4.f * (.5f - u1);
+    aniso_first_quadrant(ex, ey, u1, u2, &phi, &costheta);
+    phi = PB_PI - phi;
+  } else if (u1 < .75f) {
+    u1 = 4.f * (u1 - .5f);
+    aniso_first_quadrant(ex, ey, u1, u2, &phi, &costheta);
+    phi += PB_PI;
+  } else {
+    u1 = 4.f * (1.f - u1);
+    aniso_first_quadrant(ex, ey, u1, u2, &phi, &costheta);
+    phi = 2.f * PB_PI - phi;
+  }
+  float sintheta = sqrtf(pb_max(0.f, 1.f - costheta * costheta));
+  V3 H = v3(sintheta * pb_cosf(phi), sintheta * pb_sinf(phi), costheta);   // SphericalDirection
+  if (!(wo.z * H.z > 0.f)) H = -H;
+  *wi = -wo + 2.f * dot(wo, H) * H;
+  *pdf = aniso_pdf_H(ex, ey, wo, H);
+}
+// FresnelBlend (core/reflection.cpp:199-218,333-355, reflection.h:359-376): Rd = l.R, Rs = l.E
+PB_NOINLINE Spec fresnel_blend_f(const Lobe &l, const V3 &wo, const V3 &wi) {
+  const Spec Rd = l.R, Rs = l.E;
+  Spec diffuse = (28.f / (23.f * PB_PI)) * Rd * (spec(1.f) - Rs) * (1 - pb_powf(1 - .5f * fabsf(wi.z), 5)) *
+                 (1 - pb_powf(1 - .5f * fabsf(wo.z), 5));
+  V3 H = normalize(wi + wo);
+  float costheta = dot(wi, H);
+  Spec schlick = Rs + pb_powf(1 - costheta, 5.f) * (spec(1.f) - Rs);
+  Spec specular = aniso_D(l.A, l.B, H) / (4.f * absdot(wi, H) * pb_max(fabsf(wi.z), fabsf(wo.z))) * schlick;
+  return diffuse + specular;
+}
+PB_HD float fresnel_blend_pdf(const Lobe &l, const V3 &wo, const V3 &wi) {
+  if (!(wo.z * wi.z > 0.f)) return 0.f;
+  return .5f * (fabsf(wi.z) * PB_INV_PI + aniso_pdf_H(l.A, l.B, wo, normalize(wo + wi)));
+}
+
 // BxDF::f for the non-specular lobes (reflection.cpp:128-156); specular lobes return 0.
 // G = false compiles the glossy (microfacet) lobe out: kernels for scenes without such materials
 template <bool G = true>
@@ -200,6 +265,7 @@ PB_HD Spec lobe_f_brdf(const Lobe &l, const V3 &wo, const V3 &wi) {
   if (l.kind == PB_LOBE_LAMBERT) return l.R;   // R already holds R * INV_PI (reflection.h:249)
   if (G && l.kind == PB_LOBE_MICROFACET_BLINN) return microfacet_f(l.R, l.A, l.etai, l.etat, wo, wi);
   if (G && l.kind == PB_LOBE_MICROFACET_BLINN_COND) return microfacet_f(l.R, l.A, l.etai, l.etat, wo, wi, &l.E);
+  if (G && l.kind == PB_LOBE_FRESNEL_BLEND) return fresnel_blend_f(l, wo, wi);
   if (l.kind == PB_LOBE_ORENNAYAR) {
     float sinthetai = sin_theta(wi);
     float sinthetao = sin_theta(wo);
@@ -234,6 +300,7 @@ PB_HD float lobe_pdf_brdf(const Lobe &l, const V3 &wo, const V3 &wi) {
   if (l.type & PB_SPECULAR) return 0.f;
   if (G && (l.kind == PB_LOBE_MICROFACET_BLINN || l.kind == PB_LOBE_MICROFACET_BLINN_COND))   // Microfacet::Pdf, reflection.cpp:240-243
     return (wo.z * wi.z > 0.f) ? blinn_pdf(l.A, wo, wi) : 0.f;
+  if (G && l.kind == PB_LOBE_FRESNEL_BLEND) return fresnel_blend_pdf(l, wo, wi);
   return (wo.z * wi.z > 0.f) ? fabsf(wi.z) * PB_INV_PI : 0.f;
 }
 // BRDFToBTDF::Pdf (reflection.cpp:231-234): brdf->Pdf(wo, -wi)
@@ -276,6 +343,19 @@ PB_HD Spec lobe_sample_f_brdf(const Lobe &l, const V3 &wo, V3 *wi, float u1, flo
   if (G && l.kind == PB_LOBE_MICROFACET_BLINN) return microfacet_sample_f(l.R, l.A, l.etai, l.etat, wo, wi, u1, u2, pdf);
   if (G && l.kind == PB_LOBE_MICROFACET_BLINN_COND)
     return microfacet_sample_f(l.R, l.A, l.etai, l.etat, wo, wi, u1, u2, pdf, &l.E);
+  if (G && l.kind == PB_LOBE_FRESNEL_BLEND) {   // FresnelBlend::Sample_f, reflection.cpp:333-348
+    if (u1 < .5) {
+      u1 = 2.f * u1;
+      *wi = cosine_sample_hemisphere(u1, u2);
+      if (wo.z < 0.f) wi->z *= -1.f;
+    } else {
+      u1 = 2.f * (u1 - .5f);
+      aniso_sample_f(l.A, l.B, wo, wi, u1, u2, pdf);
+      if (!(wo.z * wi->z > 0.f)) return spec(0.f);   // (*pdf keeps the distribution's value)
+    }
+    *pdf = fresnel_blend_pdf(l, wo, *wi);
+    return fresnel_blend_f(l, wo, *wi);
+  }
   *wi = cosine_sample_hemisphere(u1, u2);
   if (wo.z < 0.f) wi->z *= -1.f;
   *pdf = lobe_pdf_brdf<G>(l, wo, *wi);
@@ -522,6 +602,17 @@ PB_HD void bsdf_set_lobes(const PbrtB200Material &m, Bsdf *b) {
         }
       }
     }
+  } else if (G && m.kind == PBRT_B200_MAT_SUBSTRATE) {
+    // materials/substrate.cpp:58-62: FresnelBlend(d, s, Anisotropic(1/u, 1/v)); exponents capped at
+    // 1000 (reflection.h:329-332)
+    Lobe &l = b->lobes[b->nLobes++];
+    l.kind = PB_LOBE_FRESNEL_BLEND; l.type = PB_REFLECTION | PB_GLOSSY;
+    l.R = spec3(m.kd[0], m.kd[1], m.kd[2]);
+    l.E = spec3(m.ks[0], m.ks[1], m.ks[2]);
+    float ex = 1.f / m.roughness, ey = 1.f / m.sigma;
+    if (ex > 1000.f || ex != ex) ex = 1000.f;
+    if (ey > 1000.f || ey != ey) ey = 1000.f;
+    l.A = ex; l.B = ey; l.etai = l.etat = 1.f;
   } else if (G && m.kind == PBRT_B200_MAT_SHINYMETAL) {
     // materials/shinymetal.cpp:54-63: Microfacet(1, FresnelConductor(FresnelApproxEta(Ks), 0), Blinn(1/rough)),
     // SpecularReflection(1, FresnelConductor(FresnelApproxEta(Kr), 0))

@@ -46,11 +46,15 @@ PB_HD float pb_sinf(float x) { return sinf(x); }
 PB_HD float pb_cosf(float x) { return cosf(x); }
 PB_HD float pb_acosf(float x) { return acosf(x); }
 PB_HD float pb_atan2f(float y, float x) { return atan2f(y, x); }
+PB_HD float pb_tanf(float x) { return tanf(x); }
+PB_HD float pb_atanf(float x) { return atanf(x); }
 #else
 PB_NOINLINE float pb_sinf(float x) { return (float)sin((double)x); }
 PB_NOINLINE float pb_cosf(float x) { return (float)cos((double)x); }
 PB_NOINLINE float pb_acosf(float x) { return (float)acos((double)x); }
 PB_NOINLINE float pb_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
+PB_NOINLINE float pb_tanf(float x) { return (float)tan((double)x); }
+PB_NOINLINE float pb_atanf(float x) { return (float)atan((double)x); }
 #endif
 #if defined(PB_TWIN_LIBM_FLOAT) && !defined(__CUDACC__)
 PB_HD float pb_powf(float x, float y) { return powf(x, y); }

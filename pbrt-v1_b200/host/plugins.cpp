@@ -94,6 +94,19 @@ class Translucent : public Material {   // materials/translucent.cpp:28-84
   }
   Spectrum Kd, Ks, reflect, transmit; float roughness;
 };
+class Substrate : public Material {   // materials/substrate.cpp:28-73
+ public:
+  Substrate(const Spectrum &kd, const Spectrum &ks, float u, float v) : Kd(kd), Ks(ks), nu(u), nv(v) {}
+  void Flatten(PbrtB200Material *out) const {
+    memset(out, 0, sizeof(*out));
+    out->kind = PBRT_B200_MAT_SUBSTRATE;
+    Spectrum d = Kd.Clamp(), s = Ks.Clamp();
+    for (int i = 0; i < 3; ++i) { out->kd[i] = d.c[i]; out->ks[i] = s.c[i]; }
+    out->roughness = nu;   // uroughness
+    out->sigma = nv;       // vroughness
+  }
+  Spectrum Kd, Ks; float nu, nv;
+};
 class ShinyMetal : public Material {   // materials/shinymetal.cpp:28-65
  public:
   ShinyMetal(const Spectrum &ks, float rough, const Spectrum &kr) : Ks(ks), Kr(kr), roughness(rough) {}
@@ -413,6 +426,14 @@ static Material *CreateTranslucent(const Transform &, const TextureParams &mp) {
   mp.GetFloatTexture("bumpmap", 0.f);
   return new Translucent(Kd, Ks, roughness, reflect, transmit);
 }
+static Material *CreateSubstrate(const Transform &, const TextureParams &mp) {   // materials/substrate.cpp:64-73
+  Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(.5f));
+  Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(.5f));
+  float uroughness = mp.GetFloatTexture("uroughness", .1f);
+  float vroughness = mp.GetFloatTexture("vroughness", .1f);
+  mp.GetFloatTexture("bumpmap", 0.f);
+  return new Substrate(Kd, Ks, uroughness, vroughness);
+}
 static Material *CreateShinyMetal(const Transform &, const TextureParams &mp) {   // materials/shinymetal.cpp:66-73
   Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(1.f));
   Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(1.f));
@@ -459,9 +480,10 @@ Reference<Material> MakeMaterial(const string &name, const Transform &mtl2world,
   else if (name == "uber") m = CreateUber(mtl2world, mp);
   else if (name == "shinymetal") m = CreateShinyMetal(mtl2world, mp);
   else if (name == "translucent") m = CreateTranslucent(mtl2world, mp);
+  else if (name == "substrate") m = CreateSubstrate(mtl2world, mp);
   else
     Error("Material plugin \"%s\" is outside the B200 hot-path scope (supported: matte, glass, "
-          "mirror, plastic, uber, shinymetal, translucent).", name.c_str());
+          "mirror, plastic, uber, shinymetal, translucent, substrate).", name.c_str());
   if (m) mp.ReportUnused();   // core/dynload.cpp:299
   return m;
 }

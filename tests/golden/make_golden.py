@@ -586,6 +586,15 @@ INLINE["translucent_path"] = _translucent('"path" "integer maxdepth" [4]', "path
 INLINE["translucent_direct"] = _translucent('"directlighting"', "direct")
 INLINE["translucent_whitted"] = _translucent('"whitted"', "whitted")
 
+INLINE["substrate_path"] = _uber_shiny('"path" "integer maxdepth" [4]', "path").replace("uber_shiny_path_out", "substrate_path_out") \
+    .replace('Material "shinymetal" "color Ks" [.9 .7 .3] "color Kr" [.8 .8 .9] "float roughness" [.15]',
+             'Material "substrate" "color Kd" [.3 .4 .7] "color Ks" [.3 .3 .3] "float uroughness" [.05] "float vroughness" [.3]') \
+    .replace('Material "shinymetal" "float roughness" [.01]', 'Material "substrate" "float uroughness" [.0005] "float vroughness" [.0005]') \
+    .replace('Material "uber" "color Kd" [.4 .5 .3] "color Ks" [.5 .5 .5] "color Kr" [.3 .3 .3] "float roughness" [.08]',
+             'Material "substrate" "color Kd" [.6 .5 .3] "color Ks" [.1 .1 .1] "float uroughness" [.2] "float vroughness" [.2]')
+INLINE["substrate_direct"] = INLINE["substrate_path"].replace('SurfaceIntegrator "path" "integer maxdepth" [4]', 'SurfaceIntegrator "directlighting"') \
+    .replace("substrate_path_out", "substrate_direct_out")
+
 
 def parse_count(text, label):
     m = re.search(re.escape(label) + r"\s+([0-9.]+)([kMG]?)", text)
