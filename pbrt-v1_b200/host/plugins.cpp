@@ -11,6 +11,7 @@ Shape *CreateConeShape(const Transform &, bool, const ParamSet &);
 Shape *CreateParaboloidShape(const Transform &, bool, const ParamSet &);
 Shape *CreateHyperboloidShape(const Transform &, bool, const ParamSet &);
 Shape *CreateHeightfieldShape(const Transform &, bool, const ParamSet &);
+Shape *CreateLoopSubdivShape(const Transform &, bool, const ParamSet &);
 bool ShapeCanSample(const Shape *s);
 Shape *CreateTriangleMeshShape(const Transform &, bool, const ParamSet &);
 Filter *CreateNamedFilter(const string &name, const ParamSet &ps);
@@ -463,11 +464,12 @@ Reference<Shape> MakeShape(const string &name, const Transform &object2world,
   else if (name == "paraboloid") s = CreateParaboloidShape(object2world, reverseOrientation, paramSet);
   else if (name == "hyperboloid") s = CreateHyperboloidShape(object2world, reverseOrientation, paramSet);
   else if (name == "heightfield") s = CreateHeightfieldShape(object2world, reverseOrientation, paramSet);
+  else if (name == "loopsubdiv") s = CreateLoopSubdivShape(object2world, reverseOrientation, paramSet);
   else if (name == "trianglemesh")
     s = CreateTriangleMeshShape(object2world, reverseOrientation, paramSet);
   else
     Error("Shape plugin \"%s\" is outside the B200 hot-path scope (supported: sphere, "
-          "cylinder, disk, cone, paraboloid, hyperboloid, heightfield, trianglemesh); shape ignored.", name.c_str());
+          "cylinder, disk, cone, paraboloid, hyperboloid, heightfield, loopsubdiv, trianglemesh); shape ignored.", name.c_str());
   return s;
 }
 Reference<Material> MakeMaterial(const string &name, const Transform &mtl2world,

@@ -596,6 +596,67 @@ INLINE["substrate_direct"] = INLINE["substrate_path"].replace('SurfaceIntegrator
     .replace("substrate_path_out", "substrate_direct_out")
 
 
+def _loopsubdiv():
+    """Loop subdivision surfaces: a closed octahedron (irregular interior vertices), an open bumpy grid
+    (boundary vertices of valence 2, 3, 4, regular interior ones) and an open fan (boundary vertex of valence 6)"""
+    import math
+    grid_p, grid_i = [], []
+    n = 4
+    for y in range(n):
+        for x in range(n):
+            grid_p += [x - 1.5, 0.3 * math.sin(2.1 * x + 0.7 * y), y - 1.5]
+    for y in range(n - 1):
+        for x in range(n - 1):
+            a = y * n + x
+            grid_i += [a, a + n, a + 1, a + 1, a + n, a + n + 1]
+    fan_p = [0, 0, 0]
+    for k in range(6):
+        t = math.pi * k / 5
+        fan_p += [math.cos(t), 0.2 * (k % 2), math.sin(t)]
+    fan_i = []
+    for k in range(5):
+        fan_i += [0, k + 2, k + 1]
+    f = lambda v: " ".join("%.6g" % t for t in v)
+    return """LookAt 0 4 -9 0 0.3 0 0 1 0
+Camera "perspective" "float fov" [38]
+Film "image" "integer xresolution" [44] "integer yresolution" [30] "string filename" ["loopsubdiv_path_out.exr"]
+Sampler "stratified" "integer xsamples" [2] "integer ysamples" [2]
+PixelFilter "box"
+SurfaceIntegrator "path" "integer maxdepth" [3]
+WorldBegin
+LightSource "point" "color I" [70 65 60] "point from" [3 7 -6]
+AttributeBegin
+AreaLightSource "area" "color L" [8 8 9]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-2 6 -1 2 6 -1 2 6 2 -2 6 2]
+AttributeEnd
+Material "matte" "color Kd" [.6 .6 .6]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-9 -1.2 -9 9 -1.2 -9 9 -1.2 9 -9 -1.2 9]
+AttributeBegin
+Material "plastic" "color Kd" [.7 .3 .2] "color Ks" [.3 .3 .3] "float roughness" [.08]
+Translate -3 0.5 0
+Shape "loopsubdiv" "integer nlevels" [2] "integer indices" [0 2 4 2 1 4 1 3 4 3 0 4 2 0 5 1 2 5 3 1 5 0 3 5]
+  "point P" [1 0 0 -1 0 0 0 0 1 0 0 -1 0 1.3 0 0 -1 0]
+AttributeEnd
+AttributeBegin
+Material "matte" "color Kd" [.2 .5 .7]
+Translate 0.3 -0.3 0.5
+Rotate 20 1 0 0
+Shape "loopsubdiv" "integer nlevels" [2] "integer indices" [%s] "point P" [%s]
+AttributeEnd
+AttributeBegin
+Material "mirror" "color Kr" [.8 .8 .8]
+Translate 3.4 -0.2 -0.5
+Rotate -60 1 0 0
+Scale 1.3 1.3 1.3
+Shape "loopsubdiv" "integer nlevels" [3] "integer indices" [%s] "point P" [%s]
+AttributeEnd
+WorldEnd
+""" % (" ".join(map(str, grid_i)), f(grid_p), " ".join(map(str, fan_i)), f(fan_p))
+
+
+INLINE["loopsubdiv_path"] = _loopsubdiv()
+
+
 def parse_count(text, label):
     m = re.search(re.escape(label) + r"\s+([0-9.]+)([kMG]?)", text)
     if not m:
