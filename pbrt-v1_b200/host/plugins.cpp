@@ -12,6 +12,7 @@ Shape *CreateParaboloidShape(const Transform &, bool, const ParamSet &);
 Shape *CreateHyperboloidShape(const Transform &, bool, const ParamSet &);
 Shape *CreateHeightfieldShape(const Transform &, bool, const ParamSet &);
 Shape *CreateLoopSubdivShape(const Transform &, bool, const ParamSet &);
+Shape *CreateNURBSShape(const Transform &, bool, const ParamSet &);
 bool ShapeCanSample(const Shape *s);
 Shape *CreateTriangleMeshShape(const Transform &, bool, const ParamSet &);
 Filter *CreateNamedFilter(const string &name, const ParamSet &ps);
@@ -465,11 +466,12 @@ Reference<Shape> MakeShape(const string &name, const Transform &object2world,
   else if (name == "hyperboloid") s = CreateHyperboloidShape(object2world, reverseOrientation, paramSet);
   else if (name == "heightfield") s = CreateHeightfieldShape(object2world, reverseOrientation, paramSet);
   else if (name == "loopsubdiv") s = CreateLoopSubdivShape(object2world, reverseOrientation, paramSet);
+  else if (name == "nurbs") s = CreateNURBSShape(object2world, reverseOrientation, paramSet);
   else if (name == "trianglemesh")
     s = CreateTriangleMeshShape(object2world, reverseOrientation, paramSet);
   else
     Error("Shape plugin \"%s\" is outside the B200 hot-path scope (supported: sphere, "
-          "cylinder, disk, cone, paraboloid, hyperboloid, heightfield, loopsubdiv, trianglemesh); shape ignored.", name.c_str());
+          "cylinder, disk, cone, paraboloid, hyperboloid, heightfield, loopsubdiv, nurbs, trianglemesh); shape ignored.", name.c_str());
   return s;
 }
 Reference<Material> MakeMaterial(const string &name, const Transform &mtl2world,

@@ -657,6 +657,56 @@ WorldEnd
 INLINE["loopsubdiv_path"] = _loopsubdiv()
 
 
+def _nurbs():
+    """NURBS patches: a bicubic 5 x 4 patch (non-homogeneous control points, interior knots) and a
+    rational quadratic one (Pw, weights: a quarter cylinder swept along a bent profile)"""
+    import math
+    P = []
+    for v in range(4):
+        for u in range(5):
+            P += [u - 2.0, 0.6 * math.sin(1.3 * u) * math.cos(0.9 * v) + 0.2 * v, v - 1.5]
+    w = math.sqrt(0.5)
+    prof = [(1, 0, 1), (1, 1, w), (0, 1, 1)]
+    Pw = []
+    for v, (z, bend) in enumerate([(-1.5, 0.0), (0.0, 0.5), (1.5, 0.0)]):
+        for (x, y, wt) in prof:
+            Pw += [(x + bend) * wt, y * wt, z * wt, wt]
+    f = lambda v: " ".join("%.7g" % t for t in v)
+    return """LookAt 0 4 -9 0 0.3 0 0 1 0
+Camera "perspective" "float fov" [36]
+Film "image" "integer xresolution" [40] "integer yresolution" [28] "string filename" ["nurbs_path_out.exr"]
+Sampler "stratified" "integer xsamples" [2] "integer ysamples" [2]
+PixelFilter "box"
+SurfaceIntegrator "path" "integer maxdepth" [3]
+WorldBegin
+LightSource "point" "color I" [70 65 60] "point from" [3 7 -6]
+AttributeBegin
+AreaLightSource "area" "color L" [8 8 9]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-2 6 -1 2 6 -1 2 6 2 -2 6 2]
+AttributeEnd
+Material "matte" "color Kd" [.6 .6 .6]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-9 -1.2 -9 9 -1.2 -9 9 -1.2 9 -9 -1.2 9]
+AttributeBegin
+Material "plastic" "color Kd" [.3 .6 .7] "color Ks" [.3 .3 .3] "float roughness" [.1]
+Translate -1.8 0 0.5
+Shape "nurbs" "integer nu" [5] "integer uorder" [4] "float uknots" [0 0 0 0 .5 1 1 1 1]
+  "integer nv" [4] "integer vorder" [4] "float vknots" [0 0 0 0 1 1 1 1] "point P" [%s]
+AttributeEnd
+AttributeBegin
+Material "shinymetal" "float roughness" [.05]
+Translate 2.6 -0.6 0
+Rotate -30 0 1 0
+Scale 1.4 1.4 1.4
+Shape "nurbs" "integer nu" [3] "integer uorder" [3] "float uknots" [0 0 0 1 1 1] "float u0" [.05] "float u1" [.95]
+  "integer nv" [3] "integer vorder" [3] "float vknots" [0 0 0 1 1 1] "float Pw" [%s]
+AttributeEnd
+WorldEnd
+""" % (f(P), f(Pw))
+
+
+INLINE["nurbs_path"] = _nurbs()
+
+
 def parse_count(text, label):
     m = re.search(re.escape(label) + r"\s+([0-9.]+)([kMG]?)", text)
     if not m:
