@@ -145,6 +145,30 @@ def test_tiles_are_independent_and_wave_size_invariant(ffi, scene_dir):
     ds.close()
 
 
+def test_bestcandidate_windows_equal_reference_crop_renders(ffi, scene_dir):
+    """bestcandidate sampler, several windows in one call (one wave spans them): every window equals the
+    twin's (== the reference's) crop render of that window -- the sampler's table placements start at the
+    window's own sample extent, exactly as in a reference crop render -- also with tiny ragged waves."""
+    sp = gen_scene(os.path.join(scene_dir, "bcwin.pbrt"), "c3", "--res", "40", "36", "--spp", "3", "1", "--bc", "--filter",
+                   "mitchell", "--filename", os.path.join(scene_dir, "bcwin.exr"))
+    scene = ffi.Scene(sp)
+    wins = [ffi.Window(0, 0, 17, 36), ffi.Window(17, 0, 23, 20), ffi.Window(17, 20, 23, 16)]
+    for wave in (-1, 5000):
+        prev = ffi.cuda().pbrt_b200_tunable(0, wave)
+        try:
+            ds = ffi.DeviceScene(scene)
+            ds.render(wins)
+            for i, w in enumerate(wins):
+                tile, raw = ds.download(i, want_raw=True)
+                rt, rawt, _, _ = ffi.twin_render(scene, w)
+                assert np.array_equal(raw.view(np.uint32), rawt.view(np.uint32)), (wave, i)
+                assert np.array_equal(tile.view(np.uint32), rt.view(np.uint32)), (wave, i)
+            ds.close()
+        finally:
+            if wave >= 0:
+                ffi.cuda().pbrt_b200_tunable(0, prev)
+
+
 def test_render_host_end_to_end_and_exr(ffi, scene_dir):
     """pbrt_b200_render_host (host buffers both sides) and the full front end: parse -> GPU -> EXR."""
     os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
