@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PBRT_B200_ABI_VERSION 2
+#define PBRT_B200_ABI_VERSION 3
 
 /* ---- error codes (Scene::Render has none: core/scene.cpp:32; the host maps
  *      non-zero codes to Severe(), core/util.cpp:90-97) ---- */
@@ -224,6 +224,10 @@ typedef struct PbrtB200Scene {
   /* shading */
   const PbrtB200Material *materials; uint32_t n_materials;
   const PbrtB200Light    *lights;    uint32_t n_lights;
+  /* area lights attached to shapes inside an ObjectBegin block follow the n_lights sampled ones in `lights`:
+   * pbrtShape keeps them on the primitive but leaves them out of the scene's light vector
+   * (core/api.cpp:383-387), so they only emit when hit (Intersection::Le) and are never sampled */
+  uint32_t n_unsampled_lights;
   const uint32_t *light_shapes;      /* primitive ids, ShapeSet order         */
   const float    *light_cdf;         /* ShapeSet::areaCDF, same indexing      */
   uint32_t n_light_shapes;

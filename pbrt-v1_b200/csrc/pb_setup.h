@@ -34,7 +34,7 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
       continue;
     }
     if (s.prims[i].material >= s.n_materials) return "primitive material index out of range";
-    if (s.prims[i].light >= (int32_t)s.n_lights) return "primitive light index out of range";
+    if (s.prims[i].light >= (int32_t)(s.n_lights + s.n_unsampled_lights)) return "primitive light index out of range";
   }
   if (s.n_top_nodes > s.n_nodes) return "n_top_nodes > n_nodes";
   for (uint32_t i = 0; i < s.n_instances; ++i) {

@@ -1588,7 +1588,7 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   UP(upload(h, scene->vertex_s, (size_t)scene->n_vertices * 3, &sv.vertexS));
   UP(upload(h, scene->vertex_uv, (size_t)scene->n_vertices * 2, &sv.vertexUV));
   UP(upload(h, scene->materials, scene->n_materials, &sv.materials));
-  UP(upload(h, scene->lights, scene->n_lights, &sv.lights));
+  UP(upload(h, scene->lights, scene->n_lights + scene->n_unsampled_lights, &sv.lights));
   UP(upload(h, scene->light_shapes, scene->n_light_shapes, &sv.lightShapes));
   UP(upload(h, scene->light_cdf, scene->n_light_shapes, &sv.lightCdf));
 #undef UP

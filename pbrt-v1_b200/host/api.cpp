@@ -33,6 +33,7 @@ void Severe(const char *format, ...) {
 }
 
 // ------------------------------------------------------------------ state
+bool ShapeCanSample(const Shape *s);   // shapes.cpp
 namespace {
 
 struct RenderOptions {          // core/api.cpp:39-88
@@ -302,7 +303,11 @@ void pbrtShape(const string &name, const ParamSet &params) {   // api.cpp:354-39
     renderOptions->currentInstance->push_back(prim);
   } else {
     renderOptions->primitives.push_back(prim);
-    if (area != NULL) renderOptions->lights.push_back(area);
+    if (area != NULL) {
+      if (!ShapeCanSample(shape.operator->()))   // core/shape.h:85-88: what the reference dies with at the first light sample
+        Severe("Unimplemented Shape::Sample method called");
+      renderOptions->lights.push_back(area);
+    }
   }
 }
 void pbrtReverseOrientation() {

@@ -13,7 +13,6 @@ Shape *CreateHyperboloidShape(const Transform &, bool, const ParamSet &);
 Shape *CreateHeightfieldShape(const Transform &, bool, const ParamSet &);
 Shape *CreateLoopSubdivShape(const Transform &, bool, const ParamSet &);
 Shape *CreateNURBSShape(const Transform &, bool, const ParamSet &);
-bool ShapeCanSample(const Shape *s);
 Shape *CreateTriangleMeshShape(const Transform &, bool, const ParamSet &);
 Filter *CreateNamedFilter(const string &name, const ParamSet &ps);
 Film *CreateImageFilm(const ParamSet &params, Filter *filter);
@@ -543,8 +542,6 @@ AreaLight *MakeAreaLight(const string &name, const Transform &light2world,
   if (name == "area") {    // lights/area.cpp:106-111
     Spectrum L = paramSet.FindOneSpectrum("L", Spectrum(1.0));
     int nSamples = paramSet.FindOneInt("nsamples", 1);
-    if (!ShapeCanSample(shape.operator->()))
-      Severe("Unimplemented Shape::Sample method called");   // core/shape.h:85-88: what the reference dies with at the first light sample
     AreaLight *a = new AreaLight(light2world, L, nSamples, shape);
     paramSet.ReportUnused();
     return a;

@@ -69,6 +69,7 @@ void Scene::Flatten(FlatBuilder &fb, PbrtB200Scene *out) const {
     fb.primRefs = accel->primRefs;
   }
   const size_t nTop = all.size();
+  vector<const AreaLight *> unsampled;
   fb.prims.resize(nTop);
   fb.aux.resize(nTop);
   for (size_t i = 0; i < all.size(); ++i) {   // `all` grows while instances are expanded
@@ -127,13 +128,26 @@ void Scene::Flatten(FlatBuilder &fb, PbrtB200Scene *out) const {
     } else
       pr.material = mi->second;
     pr.light = -1;
-    if (gp->areaLight && i < nTop) {   // instanced shapes cannot be area lights (api.cpp:386)
+    if (gp->areaLight) {
       map<const void *, int32_t>::iterator li = fb.lightIds.find(gp->areaLight);
-      if (li != fb.lightIds.end()) pr.light = li->second;
+      if (li != fb.lightIds.end())
+        pr.light = li->second;
+      else if (i >= nTop) {
+        // a shape inside ObjectBegin keeps its AreaLight (it emits when hit, Intersection::Le) but the
+        // light never joins the scene's light vector (api.cpp:383-387): an unsampled emitter
+        fb.lightIds[gp->areaLight] = pr.light = (int32_t)(lights.size() + unsampled.size());
+        unsampled.push_back(gp->areaLight);
+      }
     }
   }
-  fb.lights.resize(lights.size());
+  fb.lights.resize(lights.size() + unsampled.size());
   for (size_t i = 0; i < lights.size(); ++i) lights[i]->Flatten(fb, &fb.lights[i]);
+  for (size_t i = 0; i < unsampled.size(); ++i) {
+    PbrtB200Light *pl = &fb.lights[lights.size() + i];
+    memset(pl, 0, sizeof(*pl));
+    pl->kind = PBRT_B200_LIGHT_AREA;
+    for (int c = 0; c < 3; ++c) pl->color[c] = unsampled[i]->Lemit.c[c];
+  }
 
   const vector<PbrtB200KdNode> &nodes = anyInstance ? fb.nodes : accel->nodes;
   const vector<uint32_t> &primRefs = anyInstance ? fb.primRefs : accel->primRefs;
@@ -162,7 +176,8 @@ void Scene::Flatten(FlatBuilder &fb, PbrtB200Scene *out) const {
   out->materials = fb.materials.empty() ? NULL : &fb.materials[0];
   out->n_materials = (uint32_t)fb.materials.size();
   out->lights = fb.lights.empty() ? NULL : &fb.lights[0];
-  out->n_lights = (uint32_t)fb.lights.size();
+  out->n_lights = (uint32_t)lights.size();
+  out->n_unsampled_lights = (uint32_t)unsampled.size();
   out->light_shapes = fb.lightShapes.empty() ? NULL : &fb.lightShapes[0];
   out->light_cdf = fb.lightCdf.empty() ? NULL : &fb.lightCdf[0];
   out->n_light_shapes = (uint32_t)fb.lightShapes.size();

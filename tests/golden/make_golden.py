@@ -434,6 +434,64 @@ INLINE["instances_whitted"] = _instances('"whitted" "integer maxdepth" [4]', "wh
 INLINE["instances_direct"] = _instances('"directlighting" "integer maxdepth" [3]', "direct")
 
 
+def _instanced_emitters(integrator, tag):
+    """area-lit shapes inside ObjectBegin: the reference keeps the AreaLight on the primitive (it emits when a
+    camera or specular ray hits it) but never adds it to the light vector (api.cpp:383-387)"""
+    return """LookAt 0 3 -9 0 0.8 0 0 1 0
+Camera "perspective" "float fov" [40]
+Film "image" "integer xresolution" [40] "integer yresolution" [28] "string filename" ["instances_emitter_%s_out.exr"]
+Sampler "stratified" "integer xsamples" [2] "integer ysamples" [2]
+PixelFilter "mitchell"
+SurfaceIntegrator %s
+WorldBegin
+LightSource "point" "color I" [40 40 45] "point from" [-3 6 -5]
+ObjectBegin "lamp"
+AttributeBegin
+AreaLightSource "area" "color L" [6 5 3] "integer nsamples" [2]
+Material "matte" "color Kd" [.5 .5 .5]
+Shape "sphere" "float radius" [.5]
+Translate 0 1.2 0
+Rotate 30 1 0 0
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-.6 -.6 0 .6 -.6 0 .6 .6 0 -.6 .6 0]
+AttributeEnd
+Material "plastic" "color Kd" [.2 .6 .3] "color Ks" [.4 .4 .4] "float roughness" [.05]
+AttributeBegin
+Translate 0 -0.9 0
+Rotate -90 1 0 0
+Shape "cone" "float radius" [.5] "float height" [.6]
+AttributeEnd
+ObjectEnd
+Material "matte" "color Kd" [.6 .6 .6]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-9 -1 -9 9 -1 -9 9 -1 9 -9 -1 9]
+AttributeBegin
+Material "mirror" "color Kr" [.9 .9 .9]
+Translate 0 0.4 2.5
+Shape "sphere" "float radius" [1.4]
+AttributeEnd
+AttributeBegin
+Material "glass" "float index" [1.5]
+Translate 0.2 -0.3 -3
+Shape "sphere" "float radius" [.6]
+AttributeEnd
+AttributeBegin
+Translate -2.6 0.5 0
+ObjectInstance "lamp"
+AttributeEnd
+AttributeBegin
+Translate 2.5 0.7 -0.5
+Rotate 35 0 0 1
+Scale -1.2 1 0.8
+ObjectInstance "lamp"
+AttributeEnd
+WorldEnd
+""" % (tag, integrator)
+
+
+INLINE["instances_emitter_path"] = _instanced_emitters('"path" "integer maxdepth" [4]', "path")
+INLINE["instances_emitter_whitted"] = _instanced_emitters('"whitted" "integer maxdepth" [4]', "whitted")
+INLINE["instances_emitter_direct"] = _instanced_emitters('"directlighting" "integer maxdepth" [3]', "direct")
+
+
 def _bestcandidate(integrator, tag, sampler, film='"integer xresolution" [28] "integer yresolution" [20]', lens="", nsamples=1, pfilter='"box"'):
     """bestcandidate sampler (the reference's default when a scene names none)"""
     return """LookAt 278 273 -800 278 273 0 0 1 0

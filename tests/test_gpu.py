@@ -82,6 +82,28 @@ def test_render_bit_identical_to_twin(ffi, name):
     ds.close()
 
 
+@pytest.mark.parametrize("seed", range(32))
+def test_fuzz_scenes_bit_identical_to_twin(ffi, tmp_path, seed):
+    """Random scenes mixing every supported plugin (tests/fuzz_scenes.py; tests/test_oracle.py pins the twin
+    to the compiled reference on the same generator): CUDA path == twin, samples, film and counters."""
+    import random
+    from fuzz_scenes import scene as fuzz_scene
+    sp = str(tmp_path / ("fuzz_%d.pbrt" % seed))
+    open(sp, "w").write(fuzz_scene(random.Random(500009 + seed), seed))
+    scene = ffi.Scene(sp)
+    ds, st = gpu_render(ffi, scene)
+    rgba, raw = ds.download(0, want_raw=True)
+    rgba_t, raw_t, samples_t, st_t = ffi.twin_render(scene, want_samples=True)
+    ls = ds.sample_radiance(0, samples_t.shape[0])
+    assert np.array_equal(ls[:, :3].view(np.uint32), samples_t[:, 2:5].view(np.uint32))
+    assert np.array_equal(raw.view(np.uint32), raw_t.view(np.uint32))
+    assert np.array_equal(rgba.view(np.uint32), rgba_t.view(np.uint32))
+    for k in ("camera_rays", "intersect_rays", "shadow_rays", "points_shaded", "interior_visits", "leaf_visits",
+              "prim_refs_read", "prim_tests", "nan_samples", "negative_samples", "infinite_samples"):
+        assert st[k] == st_t[k], (k, st[k], st_t[k])
+    ds.close()
+
+
 def test_camera_rays_and_traversal_bit_exact(ffi, scene_dir):
     sp = gen_scene(os.path.join(scene_dir, "trav.pbrt"), "c4", "--res", "48", "48", "--spp", "2", "2", "--nphi", "96",
                    "--ntheta", "48", "--lens", "5", "700", "--filename", os.path.join(scene_dir, "trav.exr"))

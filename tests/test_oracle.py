@@ -137,6 +137,25 @@ def test_live_reference_when_built(ffi, scene_dir):
     assert np.array_equal(rgba.view(np.uint32), ref.view(np.uint32))
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_scenes_twin_equals_live_reference(ffi, tmp_path, seed):
+    """Random scenes mixing every supported plugin (tests/fuzz_scenes.py): compiled reference == libm twin,
+    every sample and every pixel, bit for bit.  tools/fuzz_parity.py runs the same check over hundreds."""
+    if not ffi.have_reference():
+        pytest.skip("oracle/_ref not built in this checkout")
+    import random
+    from fuzz_scenes import scene as fuzz_scene
+    sp = str(tmp_path / ("fuzz_%d.pbrt" % seed))
+    open(sp, "w").write(fuzz_scene(random.Random(900001 + seed), seed))
+    dump = str(tmp_path / "fuzz.samples")
+    ffi.run_reference(sp, keyed=True, dump_samples=dump, cwd=str(tmp_path))
+    ref, _ = ffi.read_raw(str(tmp_path / ("fuzz_%d.exr.raw" % seed)))
+    rs = read_sample_dump(dump)
+    rgba, samples, _ = twin_with(ffi, "libpbrt_twin_libm.so")(ffi.Scene(sp))
+    assert np.array_equal(samples.view(np.uint32), rs.view(np.uint32))
+    assert np.array_equal(rgba.view(np.uint32), ref.view(np.uint32))
+
+
 # ---------------------------------------------------------------- keyed RNG known answers
 def _mix64(z):
     z &= (1 << 64) - 1
@@ -220,7 +239,7 @@ def test_c_abi_exports_every_declared_symbol():
     lib = C.CDLL(lib_path)
     for name in declared:
         assert hasattr(lib, name), "missing export " + name
-    assert lib.pbrt_b200_abi_version() == 2
+    assert lib.pbrt_b200_abi_version() == 3
 
 
 def test_product_fails_loudly_without_gpu(ffi, scene_dir):
