@@ -128,7 +128,36 @@ enum { PBRT_B200_MAT_MATTE = 0, PBRT_B200_MAT_GLASS = 1, PBRT_B200_MAT_MIRROR = 
                                         transmitted through BRDFToBTDF (kt = transmit) */
        PBRT_B200_MAT_SUBSTRATE = 7   /* materials/substrate.cpp: FresnelBlend(Kd, Ks, Anisotropic(1/uroughness, 1/vroughness));
                                         roughness = uroughness, sigma = vroughness */ };
-typedef struct PbrtB200Material {    /* 80 bytes */
+/* Texture operands of the materials: a small expression graph whose leaves are constants and image maps
+ * (textures/{constant,scale,mix,imagemap}.cpp).  A material slot whose tex[] entry is >= 0 is evaluated at
+ * every hit (Material::GetBSDF's `Kd->Evaluate(dgs)`), the others keep the constant in the record.
+ * Operand nodes always come before the node that uses them; graphs are at most 3 operators deep. */
+enum { PBRT_B200_TEX_CONSTANT = 0, PBRT_B200_TEX_IMAGEMAP = 1, PBRT_B200_TEX_SCALE = 2, PBRT_B200_TEX_MIX = 3 };
+enum { PBRT_B200_TEXMAP_UV = 0, PBRT_B200_TEXMAP_SPHERICAL = 1, PBRT_B200_TEXMAP_CYLINDRICAL = 2,
+       PBRT_B200_TEXMAP_PLANAR = 3 };                       /* core/texture.cpp:66-149 */
+enum { PBRT_B200_TEXWRAP_REPEAT = 0, PBRT_B200_TEXWRAP_BLACK = 1, PBRT_B200_TEXWRAP_CLAMP = 2 };   /* core/mipmap.h:30-34 */
+#define PBRT_B200_EWA_LUT_SIZE 128                           /* WEIGHT_LUT_SIZE, core/mipmap.h:80 */
+typedef struct PbrtB200TexLevel {    /* one level of a MIPMap pyramid (core/mipmap.h:136-152) */
+  uint64_t offset;                   /* first float of the level in `texels`; row-major, `channels` floats per texel */
+  uint32_t width, height;
+} PbrtB200TexLevel;
+typedef struct PbrtB200Texture {
+  uint32_t kind;
+  uint32_t channels;                 /* 3: Texture<Spectrum>, 1: Texture<float> */
+  int32_t  arg[3];                   /* SCALE: tex1, tex2; MIX: tex1, tex2, amount */
+  float    value[3];                 /* CONSTANT (a float constant repeats its value) */
+  /* IMAGEMAP (textures/imagemap.cpp:130-195) */
+  uint32_t mapping, wrap, trilinear;
+  float    max_anisotropy;
+  float    su, sv, du, dv;           /* uv: uscale, vscale, udelta, vdelta; planar: du, dv = udelta, vdelta */
+  float    v1[3], v2[3];             /* planar */
+  float    world_to_texture[16];     /* spherical / cylindrical */
+  uint32_t first_level, n_levels;    /* tex_levels[first_level .. first_level + n_levels), finest first */
+} PbrtB200Texture;
+enum { PBRT_B200_TEXSLOT_KD = 0, PBRT_B200_TEXSLOT_KS = 1, PBRT_B200_TEXSLOT_KR = 2, PBRT_B200_TEXSLOT_KT = 3,
+       PBRT_B200_TEXSLOT_OPACITY = 4, PBRT_B200_TEXSLOT_SIGMA = 5, PBRT_B200_TEXSLOT_INDEX = 6,
+       PBRT_B200_TEXSLOT_ROUGHNESS = 7, PBRT_B200_TEXSLOTS = 8 };
+typedef struct PbrtB200Material {    /* 112 bytes */
   int32_t kind;
   float   kd[3];                   /* matte / plastic / uber                  */
   float   ks[3];                   /* plastic / uber / shinymetal             */
@@ -138,6 +167,7 @@ typedef struct PbrtB200Material {    /* 80 bytes */
   float   sigma;                   /* matte: clamped to [0,90] degrees        */
   float   index;                   /* glass: index of refraction              */
   float   roughness;               /* plastic / uber / shinymetal             */
+  int32_t tex[PBRT_B200_TEXSLOTS]; /* texture node per operand (PBRT_B200_TEXSLOT_*), -1 = the constant above */
   float   pad;
 } PbrtB200Material;
 
@@ -228,6 +258,11 @@ typedef struct PbrtB200Scene {
    * pbrtShape keeps them on the primitive but leaves them out of the scene's light vector
    * (core/api.cpp:383-387), so they only emit when hit (Intersection::Le) and are never sampled */
   uint32_t n_unsampled_lights;
+  /* texture graphs and MIPMap pyramids (path integrator only; NULL / 0 when every operand is constant) */
+  const PbrtB200Texture  *textures;   uint32_t n_textures;
+  const PbrtB200TexLevel *tex_levels; uint32_t n_tex_levels;
+  const float *texels;                uint64_t n_texel_floats;
+  const float *ewa_weight_lut;        /* PBRT_B200_EWA_LUT_SIZE floats, MIPMap::weightLut (core/mipmap.h:167-176) */
   const uint32_t *light_shapes;      /* primitive ids, ShapeSet order         */
   const float    *light_cdf;         /* ShapeSet::areaCDF, same indexing      */
   uint32_t n_light_shapes;

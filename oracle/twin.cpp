@@ -39,6 +39,7 @@ bool build_view(const PbrtB200Scene &s, SceneView *sv) {
   sv->prims = (const PrimQuad *)s.prims; sv->aux = s.prim_aux;
   sv->meshes = s.meshes; sv->quadrics = s.quadrics; sv->instances = s.instances;
   sv->bcTable = s.bestcandidate_table;
+  sv->textures = s.textures; sv->texLevels = s.tex_levels; sv->texels = s.texels; sv->ewaLut = s.ewa_weight_lut;
   sv->vertexN = s.vertex_n; sv->vertexS = s.vertex_s; sv->vertexUV = s.vertex_uv;
   sv->materials = s.materials; sv->lights = s.lights;
   sv->lightShapes = s.light_shapes; sv->lightCdf = s.light_cdf;
@@ -92,8 +93,8 @@ uint8_t trace_direct(const SceneView &sv, const DirectRec &rec, Counters &c) {
   return f;
 }
 
-Spec li_path(const SceneView &sv, const PatternSource &key0, uint64_t key1, const Ray &camRay, float *alpha,
-             Counters &c) {
+Spec li_path(const SceneView &sv, const PatternSource &key0, uint64_t key1, const Ray &camRay, const RayDiff &camDiff,
+             float *alpha, Counters &c) {
   PathState st;
   st.L = spec(0.f); st.T = spec(1.f); st.pendT = spec(0.f);
   st.alpha = 0.f; st.depth = 0; st.specularBounce = false;
@@ -103,7 +104,8 @@ Spec li_path(const SceneView &sv, const PatternSource &key0, uint64_t key1, cons
     Hit hit;
     trace_closest(sv, ray, &hit, c);
     PathVertexOut out;
-    path_vertex(sv, key0, st, ray, hit, &out);
+    // only the camera ray has differentials: path.cpp:133 continues with `RayDifferential(p, wi)`
+    path_vertex<true>(sv, key0, st, ray, hit, &out, st.depth == 0 ? &camDiff : (const RayDiff *)0);
     if (hit.prim >= 0) ++c.shaded;
     if (out.hasDirect) {
       uint8_t f = trace_direct(sv, out.direct, c);
@@ -170,9 +172,11 @@ int pbrt_twin_render(const PbrtB200Scene *scene, const PbrtB200Window *win, floa
   auto take_sample = [&](CameraSample cs, const PatternSource &key0, uint64_t key1) {
     Ray ray;
     perspective_generate_ray(sv.camera, cs, &ray, sv.xRes, sv.yRes);
+    RayDiff camDiff;
+    camera_ray_differentials(sv, cs, &camDiff);
     float alpha = 0.f;
     Spec Ls = (sv.integrator.kind == PBRT_B200_INT_PATH)
-                  ? li_path(sv, key0, key1, ray, &alpha, c)
+                  ? li_path(sv, key0, key1, ray, camDiff, &alpha, c)
                   : li_wd(sv, key0, key1, ray, &alpha, c);
     Ls = 1.f * Ls;   // rayWeight * Li, scene.cpp:58
     cs.imageX = film_image_coord(cs.imageX);

@@ -7,6 +7,7 @@
 #ifndef PB_CAMERA_H
 #define PB_CAMERA_H
 #include "pb_bsdf.h"
+#include "pb_texture.h"
 
 struct CameraSample {
   float imageX, imageY, lensU, lensV;
@@ -121,5 +122,20 @@ PB_HD void perspective_generate_ray(const PbrtB200Camera &c, const CameraSample 
   ray->maxt = ortho ? c.yon - c.hither : (c.yon - c.hither) / ray->d.z;
   ray->o = xf_point(c.camera_to_world, ray->o);
   ray->d = xf_vector(c.camera_to_world, ray->d);
+}
+// Scene::Render's differential rays (core/scene.cpp:46-53): rx from imageX + 1; imageX is then restored by
+// `--`, i.e. to (x + 1) - 1, before ry is generated from imageY + 1.  Both weights are 1 for the cameras in
+// scope, so hasDifferentials is always set.
+PB_HD void camera_ray_differentials(const SceneView &sv, const CameraSample &cs, RayDiff *rd) {
+  CameraSample s = cs;
+  Ray r;
+  s.imageX = cs.imageX + 1.f;
+  perspective_generate_ray(sv.camera, s, &r, sv.xRes, sv.yRes);
+  rd->rxo = r.o; rd->rxd = r.d;
+  s.imageX = s.imageX - 1.f;
+  s.imageY = cs.imageY + 1.f;
+  perspective_generate_ray(sv.camera, s, &r, sv.xRes, sv.yRes);
+  rd->ryo = r.o; rd->ryd = r.d;
+  rd->has = true;
 }
 #endif

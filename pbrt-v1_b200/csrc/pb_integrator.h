@@ -21,6 +21,7 @@
 #define PB_INTEGRATOR_H
 #include "pb_bsdf.h"
 #include "pb_kd.h"
+#include "pb_texture.h"
 
 // ---------------------------------------------------------------- geometry at a hit
 struct Surface {
@@ -62,8 +63,12 @@ PB_HD void surface_dg(const SceneView &sv, const Ray &rayWorld, const Hit &hit, 
   if (instanced) instance_dg_to_world(sv.instances[hit.inst], dg);
 }
 // Intersection::GetBSDF (core/primitive.cpp:126-141)
-template <bool LOBES = true, bool INST = true>
-PB_HD void surface_at_hit(const SceneView &sv, const Ray &ray, const Hit &hit, Surface *sf) {
+// TEX = true evaluates the material's texture operands at the hit (dg.ComputeDifferentials(ray) and the
+// `Kd->Evaluate(dgs)` calls of Material::GetBSDF); `rd` holds the ray's differentials or is null, `evalMat`
+// (optional) receives the material record with every textured operand replaced by its value here.
+template <bool LOBES = true, bool INST = true, bool TEX = false>
+PB_HD void surface_at_hit(const SceneView &sv, const Ray &ray, const Hit &hit, Surface *sf,
+                          const RayDiff *rd = (const RayDiff *)0, PbrtB200Material *evalMat = (PbrtB200Material *)0) {
   TriVerts tv = load_prim(sv, (uint32_t)hit.prim);
   DiffGeom dg, dgs;
   surface_dg<INST>(sv, ray, hit, tv, &dg);
@@ -72,7 +77,17 @@ PB_HD void surface_at_hit(const SceneView &sv, const Ray &ray, const Hit &hit, S
                    (INST && sv.nInstances != 0 && hit.inst >= 0) ? &sv.instances[hit.inst] : (const PbrtB200Instance *)0);
   else
     dgs = dg;
-  make_bsdf<LOBES>(sv.materials[tv.material], dg, dgs, tv.flags, &sf->bsdf);
+  if (TEX) {
+    // the shading geometry inherits u, v, p and the screen-space derivatives of the geometric one
+    // (trianglemesh.cpp:130-132, shape.h:77-80), so the operands are evaluated from `dg`
+    PbrtB200Material m = sv.materials[tv.material];
+    DgDiff dd;
+    compute_differentials(dg, rd, &dd);
+    material_eval_textures(sv, dg, dd, &m);
+    make_bsdf<LOBES>(m, dg, dgs, tv.flags, &sf->bsdf);
+    if (evalMat) *evalMat = m;
+  } else
+    make_bsdf<LOBES>(sv.materials[tv.material], dg, dgs, tv.flags, &sf->bsdf);
   sf->light = tv.light;
   sf->material = tv.material;
 }
@@ -427,9 +442,10 @@ struct PathState {
 //
 // First half (path.cpp:68-112): miss handling, alpha, emitted light, BSDF, one
 // UniformSampleOneLight record.  Returns false when the ray missed (path ends).
-template <bool LOBES = true, bool INST = true>
+template <bool LOBES = true, bool INST = true, bool TEX = false>
 PB_HD bool path_vertex_surface(const SceneView &sv, PathState &st, const Ray &ray, const Hit &hit,
-                               Surface *sf) {
+                               Surface *sf, const RayDiff *rd = (const RayDiff *)0,
+                               PbrtB200Material *evalMat = (PbrtB200Material *)0) {
   int pathLength = st.depth;
   if (hit.prim < 0) {
     // path.cpp:69-82.  lights[i]->Le(ray) is black for point and area lights (core/light.cpp:41-43)
@@ -448,7 +464,7 @@ PB_HD bool path_vertex_surface(const SceneView &sv, PathState &st, const Ray &ra
   }
   if (pathLength == 0) st.alpha = 1.f;
   else st.T = st.T * spec(1.f);            // pathThroughput *= scene->Transmittance(ray)
-  surface_at_hit<LOBES, INST>(sv, ray, hit, sf);
+  surface_at_hit<LOBES, INST, TEX>(sv, ray, hit, sf, rd, evalMat);
   if (pathLength == 0 || st.specularBounce) st.L = st.L + st.T * surface_le(sv, *sf, -ray.d);
   return true;
 }
@@ -485,10 +501,12 @@ PB_HD void path_vertex_direct(const SceneView &sv, const PatternSource &key0, Pa
   }
   // NOTE: with no lights the reference dereferences lights[-1]; such scenes render black here.
 }
+template <bool TEX = false>
 PB_HD bool path_vertex_begin(const SceneView &sv, const PatternSource &key0, PathState &st, const Ray &ray,
-                             const Hit &hit, Surface *sf, DirectRec *direct, bool *hasDirect) {
+                             const Hit &hit, Surface *sf, DirectRec *direct, bool *hasDirect,
+                             const RayDiff *rd = (const RayDiff *)0) {
   *hasDirect = false;
-  if (!path_vertex_surface(sv, st, ray, hit, sf)) return false;
+  if (!path_vertex_surface<true, true, TEX>(sv, st, ray, hit, sf, rd)) return false;
   path_vertex_direct(sv, key0, st, ray, sf, direct, hasDirect);
   return true;
 }
@@ -526,11 +544,13 @@ PB_HD bool path_vertex_continue(const SceneView &sv, const PatternSource &key0, 
   st.depth = pathLength + 1;
   return true;
 }
+// `rd`: the differentials of `ray` (the camera ray's; path.cpp:133 continues with plain rays)
+template <bool TEX = false>
 PB_HD void path_vertex(const SceneView &sv, const PatternSource &key0, PathState &st, const Ray &ray,
-                       const Hit &hit, PathVertexOut *out) {
+                       const Hit &hit, PathVertexOut *out, const RayDiff *rd = (const RayDiff *)0) {
   out->hasNext = false;
   Surface sf;
-  if (!path_vertex_begin(sv, key0, st, ray, hit, &sf, &out->direct, &out->hasDirect)) return;
+  if (!path_vertex_begin<TEX>(sv, key0, st, ray, hit, &sf, &out->direct, &out->hasDirect, rd)) return;
   out->hasNext = path_vertex_continue(sv, key0, st, ray, sf, &out->next);
 }
 // L += pathThroughput * ((float)nLights * Ld), path.cpp:100-112 + transport.cpp:66-69

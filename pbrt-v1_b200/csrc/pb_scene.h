@@ -54,6 +54,12 @@ struct SceneView {
   // bestcandidate sampler: the 4096 x 5 sample table and the width of one placement in pixels
   const float *bcTable;
   float bcTableWidth;
+  // texture operands (pb_texture.h): node table, MIPMap levels, texels, EWA weight table
+  const PbrtB200Texture *textures;
+  const PbrtB200TexLevel *texLevels;
+  const float *texels;
+  const float *ewaLut;
+  uint32_t nTextures;
 };
 
 struct Hit {

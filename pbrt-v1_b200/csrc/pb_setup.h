@@ -36,6 +36,34 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
     if (s.prims[i].material >= s.n_materials) return "primitive material index out of range";
     if (s.prims[i].light >= (int32_t)(s.n_lights + s.n_unsampled_lights)) return "primitive light index out of range";
   }
+  // texture operands: indices in range, operands before their users, image maps with complete pyramids
+  sv->nTextures = s.n_textures;
+  bool textured = false;
+  for (uint32_t i = 0; i < s.n_materials; ++i)
+    for (int k = 0; k < PBRT_B200_TEXSLOTS; ++k) {
+      if (s.materials[i].tex[k] >= (int32_t)s.n_textures) return "material texture index out of range";
+      textured |= s.materials[i].tex[k] >= 0;
+    }
+  for (uint32_t i = 0; i < s.n_textures; ++i) {
+    const PbrtB200Texture &t = s.textures[i];
+    if (t.kind > PBRT_B200_TEX_MIX || (t.channels != 1 && t.channels != 3)) return "unknown texture kind";
+    if (t.kind == PBRT_B200_TEX_SCALE || t.kind == PBRT_B200_TEX_MIX)
+      for (int k = 0; k < (t.kind == PBRT_B200_TEX_MIX ? 3 : 2); ++k)
+        if (t.arg[k] < 0 || t.arg[k] >= (int32_t)i) return "texture operand must precede its user";
+    if (t.kind == PBRT_B200_TEX_IMAGEMAP) {
+      if (t.n_levels < 1 || (uint64_t)t.first_level + t.n_levels > s.n_tex_levels || !s.ewa_weight_lut) return "image map without a pyramid";
+      if (t.mapping > PBRT_B200_TEXMAP_PLANAR || t.wrap > PBRT_B200_TEXWRAP_CLAMP) return "unknown texture mapping or wrap mode";
+      for (uint32_t l = 0; l < t.n_levels; ++l) {
+        const PbrtB200TexLevel &lv = s.tex_levels[t.first_level + l];
+        if (lv.width < 1 || lv.height < 1 || lv.offset + (uint64_t)lv.width * lv.height * t.channels > s.n_texel_floats)
+          return "texture level outside the texel array";
+      }
+    }
+  }
+  // ray differentials are carried for camera rays only; the specular-bounce transfer of whitted.cpp:86-134 /
+  // directlighting.cpp:131-181 is not implemented, so those integrators refuse textured scenes
+  if (textured && s.integrator.kind != PBRT_B200_INT_PATH)
+    return "image-map textures are supported under the path integrator only";
   if (s.n_top_nodes > s.n_nodes) return "n_top_nodes > n_nodes";
   for (uint32_t i = 0; i < s.n_instances; ++i) {
     const PbrtB200Instance &in = s.instances[i];

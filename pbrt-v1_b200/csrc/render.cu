@@ -121,6 +121,10 @@ struct WaveBuffers {
   float *surf[15];       // BSDF frame records of the vertices being shaded (path), by queue position
   uint32_t *surfIds;
   uint32_t *surfQueueIdx;
+  // scenes with texture operands only: the camera ray's differentials (rx.o, rx.d, ry.o, ry.d: value e of slot
+  // s at camDiff[e * nSlots + s]) and, per hit record, the material with its operands evaluated at the hit
+  float *camDiff;
+  PbrtB200Material *surfMat;
   // counters (device): [0..] see enum below
   uint32_t *counts;
   unsigned long long *stats;
@@ -220,6 +224,22 @@ __device__ __forceinline__ void aux_put(const AuxQueue &q, uint32_t i, uint32_t 
   if (q.maxt) q.maxt[i] = r.maxt;
 }
 
+// camera-ray differentials of a slot (textured scenes), SoA over the wave
+__device__ __forceinline__ void cam_diff_store(const SceneView &sv, const WaveBuffers &wb, uint32_t slot, const CameraSample &cs) {
+  RayDiff rd;
+  camera_ray_differentials(sv, cs, &rd);
+  const float v[12] = {rd.rxo.x, rd.rxo.y, rd.rxo.z, rd.rxd.x, rd.rxd.y, rd.rxd.z,
+                       rd.ryo.x, rd.ryo.y, rd.ryo.z, rd.ryd.x, rd.ryd.y, rd.ryd.z};
+#pragma unroll
+  for (int e = 0; e < 12; ++e) wb.camDiff[(size_t)e * wb.nSlots + slot] = v[e];
+}
+__device__ __forceinline__ void cam_diff_load(const WaveBuffers &wb, uint32_t slot, RayDiff *rd) {
+  float v[12];
+#pragma unroll
+  for (int e = 0; e < 12; ++e) v[e] = wb.camDiff[(size_t)e * wb.nSlots + slot];
+  rd->rxo = v3(v[0], v[1], v[2]); rd->rxd = v3(v[3], v[4], v[5]);
+  rd->ryo = v3(v[6], v[7], v[8]); rd->ryd = v3(v[9], v[10], v[11]);
+}
 // ------------------------------------------------------------------------------------------
 // K0a (lowdiscrepancy sampler only): the (0,2)-sequence tables of every sample pixel of the wave
 // (samplers/lowdiscrepancy.cpp:93-103), one thread per (sample pixel, table).
@@ -274,6 +294,7 @@ k_generate(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
         Ray ray;
         perspective_generate_ray(sv.camera, cs, &ray, sv.xRes, sv.yRes);
         queue_put(wb.q[0], qi, slot, ray);
+        if (wb.camDiff) cam_diff_store(sv, wb, slot, cs);
         ++nValid;
       }
       wb.imageX[slot] = valid ? film_image_coord(cs.imageX) : PB_BC_INVALID_COORD;
@@ -297,6 +318,7 @@ k_generate(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
     Ray ray;
     perspective_generate_ray(sv.camera, cs, &ray, sv.xRes, sv.yRes);
     queue_put(wb.q[0], slot, slot, ray);
+    if (wb.camDiff) cam_diff_store(sv, wb, slot, cs);
     wb.imageX[slot] = film_image_coord(cs.imageX);
     wb.imageY[slot] = film_image_coord(cs.imageY);
 #pragma unroll
@@ -504,6 +526,7 @@ struct SurfaceRecord {       // SoA, compacted: record j belongs to the j-th ray
   float *f[15];              // p, nn, ng, sn, tn
   uint32_t *ids;             // material | (light + 1) << 16
   uint32_t *queueIdx;        // queue position of the ray (its slot and direction are read from there)
+  PbrtB200Material *mat;     // textured scenes: the material record evaluated at the hit, else null
 };
 __device__ __forceinline__ void surface_store(const SurfaceRecord &r, uint32_t i, const Surface &sf) {
   const Bsdf &b = sf.bsdf;
@@ -525,10 +548,11 @@ __device__ __forceinline__ void surface_load(const SceneView &sv, const SurfaceR
   uint32_t ids = r.ids[i];
   sf->material = ids & 0xffffu;
   sf->light = (int32_t)(ids >> 16) - 1;
-  bsdf_set_lobes<G>(sv.materials[sf->material], &b);
+  bsdf_set_lobes<G>(r.mat ? r.mat[i] : sv.materials[sf->material], &b);
 }
 
-template <bool INST>
+// TEX: the scene has texture operands (ray differentials of the camera ray, operand evaluation at the hit)
+template <bool INST, bool TEX>
 __global__ void __launch_bounds__(PB_BLOCK, PB_SURF_MIN_BLOCKS)
 k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const RayQueue qin,
                const SurfaceRecord rec, const uint32_t *nPtr, uint32_t *work, uint32_t *hitCount) {
@@ -541,6 +565,7 @@ k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const
       uint32_t i = base + lane_id();
       bool isHit = false;
       Surface sf;
+      PbrtB200Material evalMat;
       if (i < n) {
       uint32_t slot = qin.slot[i];
       Ray ray = queue_ray(qin, i);
@@ -562,7 +587,13 @@ k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const
       const bool mayEmit = st.depth == 0 || st.specularBounce;
       st.T = mayEmit ? load3(wb.T, slot) : spec(0.f);
       st.alpha = 0.f;
-      isHit = path_vertex_surface<false, INST>(sv, st, ray, hit, &sf);
+      if (TEX) {
+        RayDiff rd;
+        rd.has = st.depth == 0;   // path.cpp:133 continues with plain rays
+        if (rd.has) cam_diff_load(wb, slot, &rd);
+        isHit = path_vertex_surface<false, INST, true>(sv, st, ray, hit, &sf, &rd, &evalMat);
+      } else
+        isHit = path_vertex_surface<false, INST, false>(sv, st, ray, hit, &sf);
       if (isHit) ++shaded;
       store3(wb.L, slot, st.L);
       if (st.depth == 0) wb.alpha[slot] = st.alpha;
@@ -573,6 +604,7 @@ k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const
       if (isHit) {
         surface_store(rec, j, sf);
         rec.queueIdx[j] = i;
+        if (TEX) rec.mat[j] = evalMat;
       }
   }
   }
@@ -1088,6 +1120,7 @@ struct PbrtB200Handle {
   uint32_t *bcMasks;            // bestcandidate: per-axis prefix strip masks of the sample table (k_film_gather_bc)
   bool hasSpecular;
   bool hasGlossy;
+  bool textured;          // some material operand is a texture node (pb_texture.h)
   int primKinds;                // PB_QK_*: which primitive tests the traversal kernels need
   bool triLightsOnly;           // every light is an area light over triangles (kernels drop the other light code)
   int nFrames;
@@ -1226,7 +1259,7 @@ struct Carver {
   }
 };
 static void carve_wave(Carver &c, WaveBuffers &wb, uint32_t nSlots, int directRecords, int nFrames, bool isPath,
-                       int ldFloats, bool hasInstances) {
+                       int ldFloats, bool hasInstances, bool textured) {
   wb.nSlots = nSlots;
   wb.nFrames = nFrames;
   for (int i = 0; i < 3; ++i) {
@@ -1272,6 +1305,8 @@ static void carve_wave(Carver &c, WaveBuffers &wb, uint32_t nSlots, int directRe
   for (int k = 0; k < 15; ++k) wb.surf[k] = isPath ? c.take<float>(nSlots) : nullptr;
   wb.surfIds = isPath ? c.take<uint32_t>(nSlots) : nullptr;
   wb.surfQueueIdx = isPath ? c.take<uint32_t>(nSlots) : nullptr;
+  wb.camDiff = textured ? c.take<float>((size_t)12 * nSlots) : nullptr;
+  wb.surfMat = textured ? c.take<PbrtB200Material>(nSlots) : nullptr;
   wb.counts = c.take<uint32_t>(PB_COUNTS_TOTAL);
   wb.stats = c.take<unsigned long long>(ST_COUNT);
 }
@@ -1282,7 +1317,7 @@ static int ensure_wave(PbrtB200Handle *h, uint32_t nSlots) {
   bool isPath = h->sv.integrator.kind == PBRT_B200_INT_PATH;
   Carver sizing = {nullptr, 0};
   WaveBuffers tmp;
-  carve_wave(sizing, tmp, nSlots, h->sv.directRecords, h->nFrames, isPath, h->sv.ldFloatsPerSample, h->sv.nInstances != 0);
+  carve_wave(sizing, tmp, nSlots, h->sv.directRecords, h->nFrames, isPath, h->sv.ldFloatsPerSample, h->sv.nInstances != 0, h->textured);
   size_t bytes = sizing.off + 256;
   int d = h->device;
   if (d >= 0 && d < PB_MAX_DEVICES && g_cachedArena[d] && g_cachedArenaBytes[d] >= bytes) {
@@ -1295,7 +1330,7 @@ static int ensure_wave(PbrtB200Handle *h, uint32_t nSlots) {
     h->arenaBytes = bytes;
   }
   Carver c = {(char *)h->arena, 0};
-  carve_wave(c, h->wb, nSlots, h->sv.directRecords, h->nFrames, isPath, h->sv.ldFloatsPerSample, h->sv.nInstances != 0);
+  carve_wave(c, h->wb, nSlots, h->sv.directRecords, h->nFrames, isPath, h->sv.ldFloatsPerSample, h->sv.nInstances != 0, h->textured);
   return PBRT_B200_OK;
 }
 
@@ -1390,9 +1425,12 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
         for (int k = 0; k < 15; ++k) rec.f[k] = wb.surf[k];
         rec.ids = wb.surfIds;
         rec.queueIdx = wb.surfQueueIdx;
+        rec.mat = wb.surfMat;
         uint32_t *nHits = &wb.counts[4 * it + 3];
-        if (sv.nInstances != 0) TIMED(KC_SHADE, (k_path_surface<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], rec, nMain, nextWork(), nHits)));
-        else TIMED(KC_SHADE, (k_path_surface<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], rec, nMain, nextWork(), nHits)));
+#define PB_LAUNCH_SURF(INST, TEX) TIMED(KC_SHADE, (k_path_surface<INST, TEX><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], rec, nMain, nextWork(), nHits)))
+        if (h->textured) { if (sv.nInstances != 0) PB_LAUNCH_SURF(true, true); else PB_LAUNCH_SURF(false, true); }
+        else { if (sv.nInstances != 0) PB_LAUNCH_SURF(true, false); else PB_LAUNCH_SURF(false, false); }
+#undef PB_LAUNCH_SURF
 #define PB_LAUNCH_DIRECT2(LD_, G_, LK_)                                                                             \
   TIMED(KC_SHADE_DIRECT, (k_path_direct<LD_, G_, LK_><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], rec, nHits, \
                                                                                  nextWork(), nShadow, nProbe)))
@@ -1538,11 +1576,13 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   if (!err.empty()) { delete h; return fail(PBRT_B200_ERR_INVALID, err); }
   h->hasSpecular = pb_scene_has_specular(*scene);
   h->hasGlossy = false;
+  h->textured = false;
   for (uint32_t i = 0; i < scene->n_materials; ++i) {
     int k = scene->materials[i].kind;
     if (k < PBRT_B200_MAT_MATTE || k > PBRT_B200_MAT_SUBSTRATE) { delete h; return fail(PBRT_B200_ERR_INVALID, "unknown material kind"); }
     // plastic / uber / shinymetal / translucent: microfacet lobes and up to 4 lobes per BSDF (kernels instantiated with G = true)
     h->hasGlossy |= k >= PBRT_B200_MAT_PLASTIC;
+    for (int t = 0; t < PBRT_B200_TEXSLOTS; ++t) h->textured |= scene->materials[i].tex[t] >= 0;
   }
   h->primKinds = PB_QK_TRI;
   for (uint32_t i = 0; i < scene->n_quadrics; ++i)
@@ -1591,6 +1631,10 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   UP(upload(h, scene->lights, scene->n_lights + scene->n_unsampled_lights, &sv.lights));
   UP(upload(h, scene->light_shapes, scene->n_light_shapes, &sv.lightShapes));
   UP(upload(h, scene->light_cdf, scene->n_light_shapes, &sv.lightCdf));
+  UP(upload(h, scene->textures, scene->n_textures, &sv.textures));
+  UP(upload(h, scene->tex_levels, scene->n_tex_levels, &sv.texLevels));
+  UP(upload(h, scene->texels, (size_t)scene->n_texel_floats, &sv.texels));
+  if (scene->n_textures) UP(upload(h, scene->ewa_weight_lut, (size_t)PBRT_B200_EWA_LUT_SIZE, &sv.ewaLut));
 #undef UP
   if (scene->sampler.kind == PBRT_B200_SAMPLER_BESTCANDIDATE) {
     // prefix strip masks of the table's image positions (see k_film_gather_bc)

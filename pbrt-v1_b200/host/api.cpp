@@ -42,6 +42,7 @@ struct RenderOptions {          // core/api.cpp:39-88
         AcceleratorName("kdtree"), SurfIntegratorName("directlighting"),
         VolIntegratorName("emission"), CameraName("perspective"), currentInstance(NULL) {}
   Scene *MakeScene() const;
+  TextureStore textures;          // nodes referenced by this world block's materials
   string FilterName; ParamSet FilterParams;
   string FilmName; ParamSet FilmParams;
   string SamplerName; ParamSet SamplerParams;
@@ -220,8 +221,19 @@ void pbrtTransformEnd() {
   curTransform = pushedTransforms.back();
   pushedTransforms.pop_back();
 }
-// api.cpp:305-332.  Only the "constant" texture class (textures/constant.cpp)
-// is inside the scope table; it is what literal Kd/sigma/index values become.
+// api.cpp:305-332.  Texture classes in scope: "constant" (textures/constant.cpp), "imagemap"
+// (textures/imagemap.cpp), and "scale" / "mix" over them (textures/scale.cpp:38-41, textures/mix.cpp:40-44).
+// An expression whose operands are all constant has the same value at every point and is folded here once;
+// anything that depends on an image map becomes a node of the scene's texture table (texture.h).
+namespace {
+int OperandNode(TextureStore &st, const Spectrum &v, int32_t node) {
+  return node >= 0 ? node : st.AddConstant(v.c, 3);
+}
+int OperandNode(TextureStore &st, float v, int32_t node) {
+  float c[3] = {v, v, v};
+  return node >= 0 ? node : st.AddConstant(c, 1);
+}
+}  // namespace
 void pbrtTexture(const string &name, const string &type, const string &texname,
                  const ParamSet &params) {
   if (!InWorld("Texture")) return;
@@ -230,41 +242,56 @@ void pbrtTexture(const string &name, const string &type, const string &texname,
     Error("Texture type \"%s\" unknown.", type.c_str());
     return;
   }
-  // Every texture in scope evaluates to one value: "constant" (textures/constant.cpp), and "scale" /
-  // "mix" of such textures (textures/scale.cpp:38-41, textures/mix.cpp:40-44), whose Evaluate() is the
-  // same float expression at every point -- folded here once.
-  if (texname != "constant" && texname != "scale" && texname != "mix") {
-    Error("Texture class \"%s\" is outside the B200 hot-path scope (supported: constant, scale, mix); "
+  if (texname != "constant" && texname != "scale" && texname != "mix" && texname != "imagemap") {
+    Error("Texture class \"%s\" is outside the B200 hot-path scope (supported: constant, scale, mix, imagemap); "
           "texture \"%s\" not created.", texname.c_str(), name.c_str());
     return;
   }
+  TextureStore &store = renderOptions->textures;
+  int node = -1;
   if (type == "float") {
     if (graphicsState.floatTextures.find(name) != graphicsState.floatTextures.end())
       Warning("Texture \"%s\" being redefined", name.c_str());
     FloatTexture *ft = new FloatTexture;
     if (texname == "constant") ft->value = tp.FindFloat("value", 1.f);
-    else if (texname == "scale") ft->value = tp.GetFloatTexture("tex1", 1.f) * tp.GetFloatTexture("tex2", 1.f);
-    else {
-      float t1 = tp.GetFloatTexture("tex1", 0.f), t2 = tp.GetFloatTexture("tex2", 1.f);
-      float amt = tp.GetFloatTexture("amount", 0.5f);
-      ft->value = (1.f - amt) * t1 + amt * t2;
+    else if (texname == "imagemap") node = store.AddImageMap(curTransform, tp, 1);
+    else if (texname == "scale") {
+      int32_t n1, n2;
+      float a = tp.GetFloatTexture("tex1", 1.f, &n1), b = tp.GetFloatTexture("tex2", 1.f, &n2);
+      if (n1 < 0 && n2 < 0) ft->value = a * b;
+      else node = store.AddScale(OperandNode(store, a, n1), OperandNode(store, b, n2), 1);
+    } else {
+      int32_t n1, n2, na;
+      float t1 = tp.GetFloatTexture("tex1", 0.f, &n1), t2 = tp.GetFloatTexture("tex2", 1.f, &n2);
+      float amt = tp.GetFloatTexture("amount", 0.5f, &na);
+      if (n1 < 0 && n2 < 0 && na < 0) ft->value = (1.f - amt) * t1 + amt * t2;
+      else node = store.AddMix(OperandNode(store, t1, n1), OperandNode(store, t2, n2), OperandNode(store, amt, na), 1);
     }
+    ft->node = node;
     graphicsState.floatTextures[name] = ft;
   } else {
     if (graphicsState.spectrumTextures.find(name) != graphicsState.spectrumTextures.end())
       Warning("Texture \"%s\" being redefined", name.c_str());
     SpectrumTexture *st = new SpectrumTexture;
     if (texname == "constant") st->value = tp.FindSpectrum("value", Spectrum(1.f));
+    else if (texname == "imagemap") node = store.AddImageMap(curTransform, tp, 3);
     else if (texname == "scale") {
-      Spectrum a = tp.GetSpectrumTexture("tex1", Spectrum(1.f)), b = tp.GetSpectrumTexture("tex2", Spectrum(1.f));
-      for (int i = 0; i < COLOR_SAMPLES; ++i) st->value.c[i] = a.c[i] * b.c[i];
+      int32_t n1, n2;
+      Spectrum a = tp.GetSpectrumTexture("tex1", Spectrum(1.f), &n1), b = tp.GetSpectrumTexture("tex2", Spectrum(1.f), &n2);
+      if (n1 < 0 && n2 < 0) for (int i = 0; i < COLOR_SAMPLES; ++i) st->value.c[i] = a.c[i] * b.c[i];
+      else node = store.AddScale(OperandNode(store, a, n1), OperandNode(store, b, n2), 3);
     } else {
-      Spectrum t1 = tp.GetSpectrumTexture("tex1", Spectrum(0.f)), t2 = tp.GetSpectrumTexture("tex2", Spectrum(1.f));
-      float amt = tp.GetFloatTexture("amount", 0.5f);
-      for (int i = 0; i < COLOR_SAMPLES; ++i) st->value.c[i] = t1.c[i] * (1.f - amt) + t2.c[i] * amt;
+      int32_t n1, n2, na;
+      Spectrum t1 = tp.GetSpectrumTexture("tex1", Spectrum(0.f), &n1), t2 = tp.GetSpectrumTexture("tex2", Spectrum(1.f), &n2);
+      float amt = tp.GetFloatTexture("amount", 0.5f, &na);
+      if (n1 < 0 && n2 < 0 && na < 0) for (int i = 0; i < COLOR_SAMPLES; ++i) st->value.c[i] = t1.c[i] * (1.f - amt) + t2.c[i] * amt;
+      else node = store.AddMix(OperandNode(store, t1, n1), OperandNode(store, t2, n2), OperandNode(store, amt, na), 3);
     }
+    st->node = node;
     graphicsState.spectrumTextures[name] = st;
   }
+  if (node >= 0 && store.Depth(node) > 3)
+    Severe("Texture \"%s\": expressions more than 3 scale/mix operators deep are not supported", name.c_str());
   tp.ReportUnused();
 }
 void pbrtMaterial(const string &name, const ParamSet &params) {
@@ -367,6 +394,7 @@ void pbrtWorldEnd() {            // api.cpp:458-483
   Scene *scene = renderOptions->MakeScene();
   if (scene) scene->Render();
   delete scene;
+  renderOptions->textures.Clear();
   currentApiState = STATE_OPTIONS_BLOCK;
   curTransform = Transform();
   namedCoordinateSystems.erase(namedCoordinateSystems.begin(), namedCoordinateSystems.end());
@@ -396,6 +424,7 @@ Scene *RenderOptions::MakeScene() const {
   }
   Scene *ret = new Scene(camera, surfaceIntegrator, volumeIntegrator, sampler, accelerator, lights,
                          volumeRegion);
+  ret->textures = textures;
   primitives.erase(primitives.begin(), primitives.end());
   lights.erase(lights.begin(), lights.end());
   volumeRegions.erase(volumeRegions.begin(), volumeRegions.end());

@@ -12,6 +12,7 @@
 #include "geometry.h"
 #include "transform.h"
 #include "paramset.h"
+#include "texture.h"
 #include "../../include/pbrt_b200.h"
 
 // ---------------------------------------------------------------- shapes
@@ -44,8 +45,16 @@ class Shape : public ReferenceCounted {
 // ------------------------------------------------------------- materials
 class Material : public ReferenceCounted {
  public:
+  Material() { for (int i = 0; i < PBRT_B200_TEXSLOTS; ++i) tex[i] = -1; }
   virtual ~Material() {}
   virtual void Flatten(PbrtB200Material *out) const = 0;
+  // texture node (TextureStore index) per operand slot, -1 where the operand is a constant
+  int32_t tex[PBRT_B200_TEXSLOTS];
+ protected:
+  void InitRecord(PbrtB200Material *out) const {
+    memset(out, 0, sizeof(*out));
+    for (int i = 0; i < PBRT_B200_TEXSLOTS; ++i) out->tex[i] = tex[i];
+  }
 };
 
 // ---------------------------------------------------------------- lights
@@ -200,6 +209,7 @@ struct FlatBuilder {
   map<const void *, uint32_t> meshIds, meshVertexBase, materialIds;
   map<std::pair<const void *, int>, uint32_t> shapePrimIds;
   map<const void *, int32_t> lightIds;
+  TextureStore textures;
   FlatBuilder() : nVertices(0), anyN(false), anyS(false), anyUV(false) {}
 };
 
@@ -219,6 +229,7 @@ class Scene {
   VolumeIntegrator *volumeIntegrator;
   Sampler *sampler;
   BBox bound;
+  TextureStore textures;   // texture table of the world block this scene was made from
 };
 
 // ------------------------------------------------- plugin registry

@@ -107,16 +107,26 @@ class ParamSet {
 // a "texture" parameter names a previously declared texture, otherwise the
 // literal becomes a ConstantTexture (core/paramset.cpp:435-465).  Only
 // constant textures are inside the hot-path scope, so a texture is its value.
-struct FloatTexture : public ReferenceCounted { float value; };
-struct SpectrumTexture : public ReferenceCounted { Spectrum value; };
+// `node` >= 0: the texture varies over the surface (image maps and expressions over them); it is entry
+// `node` of the scene's texture table (texture.h) and `value` is unused.
+struct FloatTexture : public ReferenceCounted { FloatTexture() : value(0.f), node(-1) {} float value; int node; };
+struct SpectrumTexture : public ReferenceCounted { SpectrumTexture() : node(-1) {} Spectrum value; int node; };
 class TextureParams {
  public:
   TextureParams(const ParamSet &geomp, const ParamSet &matp,
                 map<string, Reference<FloatTexture> > &ft,
                 map<string, Reference<SpectrumTexture> > &st)
       : geomParams(geomp), materialParams(matp), floatTextures(ft), spectrumTextures(st) {}
-  Spectrum GetSpectrumTexture(const string &name, const Spectrum &def) const;
-  float GetFloatTexture(const string &name, float def) const;
+  // *node receives the texture-table entry when the operand is not constant (the returned value is then unused)
+  Spectrum GetSpectrumTexture(const string &name, const Spectrum &def, int32_t *node = NULL) const;
+  float GetFloatTexture(const string &name, float def, int32_t *node = NULL) const;
+  string FindString(const string &n, const string &d = "") const {
+    return geomParams.FindOneString(n, materialParams.FindOneString(n, d));
+  }
+  bool FindBool(const string &n, bool d) const { return geomParams.FindOneBool(n, materialParams.FindOneBool(n, d)); }
+  Vector FindVector(const string &n, const Vector &d) const {
+    return geomParams.FindOneVector(n, materialParams.FindOneVector(n, d));
+  }
   float FindFloat(const string &n, float d) const {
     return geomParams.FindOneFloat(n, materialParams.FindOneFloat(n, d));
   }

@@ -479,9 +479,24 @@ class Parser {
 }  // namespace
 
 // core/parser.cpp:27-51
+// Data files named in a scene (image maps) are opened as given, relative to the working directory like the
+// reference does; when that fails, a relative name is also tried beside the scene file being parsed.
+static string gSceneDir;
+string ResolveDataFile(const string &name) {
+  if (name.empty() || name[0] == '/' || gSceneDir.empty()) return name;
+  FILE *f = fopen(name.c_str(), "rb");
+  if (f) { fclose(f); return name; }
+  string alt = gSceneDir + "/" + name;
+  f = fopen(alt.c_str(), "rb");
+  if (f) { fclose(f); return alt; }
+  return name;
+}
 bool ParseFile(const char *filename) {
   FILE *fp = (strcmp(filename, "-") == 0) ? stdin : fopen(filename, "r");
   if (fp != NULL) {
+    string fn(filename);
+    size_t slash = fn.rfind('/');
+    gSceneDir = (fp != stdin && slash != string::npos) ? fn.substr(0, slash) : string("");
     current_file = filename;
     if (fp == stdin) current_file = "<standard input>";
     line_num = 1;

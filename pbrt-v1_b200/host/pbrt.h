@@ -58,6 +58,7 @@ void Severe(const char *, ...) __attribute__((__format__(__printf__, 1, 2)));
 void pbrtInit();
 void pbrtCleanup();
 bool ParseFile(const char *filename);
+std::string ResolveDataFile(const std::string &name);   // parser.cpp
 
 #define Assert(expr) ((void)0)
 

@@ -24,7 +24,7 @@ class Matte : public Material {   // materials/matte.cpp:46-70
  public:
   Matte(const Spectrum &kd, float sig) : Kd(kd), sigma(sig) {}
   void Flatten(PbrtB200Material *out) const {
-    memset(out, 0, sizeof(*out));
+    InitRecord(out);
     out->kind = PBRT_B200_MAT_MATTE;
     Spectrum r = Kd.Clamp();                       // matte.cpp:56
     for (int i = 0; i < 3; ++i) out->kd[i] = r.c[i];
@@ -36,7 +36,7 @@ class Glass : public Material {   // materials/glass.cpp:46-70
  public:
   Glass(const Spectrum &r, const Spectrum &t, float ior) : Kr(r), Kt(t), index(ior) {}
   void Flatten(PbrtB200Material *out) const {
-    memset(out, 0, sizeof(*out));
+    InitRecord(out);
     out->kind = PBRT_B200_MAT_GLASS;
     Spectrum R = Kr.Clamp(), T = Kt.Clamp();
     for (int i = 0; i < 3; ++i) { out->kr[i] = R.c[i]; out->kt[i] = T.c[i]; }
@@ -48,7 +48,7 @@ class Mirror : public Material {  // materials/mirror.cpp:42-60
  public:
   Mirror(const Spectrum &r) : Kr(r) {}
   void Flatten(PbrtB200Material *out) const {
-    memset(out, 0, sizeof(*out));
+    InitRecord(out);
     out->kind = PBRT_B200_MAT_MIRROR;
     Spectrum R = Kr.Clamp();
     for (int i = 0; i < 3; ++i) out->kr[i] = R.c[i];
@@ -60,7 +60,7 @@ class Plastic : public Material {   // materials/plastic.cpp:28-77
  public:
   Plastic(const Spectrum &kd, const Spectrum &ks, float rough) : Kd(kd), Ks(ks), roughness(rough) {}
   void Flatten(PbrtB200Material *out) const {
-    memset(out, 0, sizeof(*out));
+    InitRecord(out);
     out->kind = PBRT_B200_MAT_PLASTIC;
     Spectrum d = Kd.Clamp(), s = Ks.Clamp();
     for (int i = 0; i < 3; ++i) { out->kd[i] = d.c[i]; out->ks[i] = s.c[i]; }
@@ -73,7 +73,7 @@ class UberMaterial : public Material {   // materials/uber.cpp:28-84
   UberMaterial(const Spectrum &kd, const Spectrum &ks, const Spectrum &kr, float rough, const Spectrum &op)
       : Kd(kd), Ks(ks), Kr(kr), opacity(op), roughness(rough) {}
   void Flatten(PbrtB200Material *out) const {
-    memset(out, 0, sizeof(*out));
+    InitRecord(out);
     out->kind = PBRT_B200_MAT_UBER;
     // the products with the opacity (uber.cpp:65-83) are formed on the device, per GetBSDF call
     Spectrum d = Kd.Clamp(), s = Ks.Clamp(), r = Kr.Clamp(), o = opacity.Clamp();
@@ -87,7 +87,7 @@ class Translucent : public Material {   // materials/translucent.cpp:28-84
   Translucent(const Spectrum &kd, const Spectrum &ks, float rough, const Spectrum &refl, const Spectrum &trans)
       : Kd(kd), Ks(ks), reflect(refl), transmit(trans), roughness(rough) {}
   void Flatten(PbrtB200Material *out) const {
-    memset(out, 0, sizeof(*out));
+    InitRecord(out);
     out->kind = PBRT_B200_MAT_TRANSLUCENT;
     Spectrum d = Kd.Clamp(), s = Ks.Clamp(), r = reflect.Clamp(), t = transmit.Clamp();
     for (int i = 0; i < 3; ++i) { out->kd[i] = d.c[i]; out->ks[i] = s.c[i]; out->kr[i] = r.c[i]; out->kt[i] = t.c[i]; }
@@ -99,7 +99,7 @@ class Substrate : public Material {   // materials/substrate.cpp:28-73
  public:
   Substrate(const Spectrum &kd, const Spectrum &ks, float u, float v) : Kd(kd), Ks(ks), nu(u), nv(v) {}
   void Flatten(PbrtB200Material *out) const {
-    memset(out, 0, sizeof(*out));
+    InitRecord(out);
     out->kind = PBRT_B200_MAT_SUBSTRATE;
     Spectrum d = Kd.Clamp(), s = Ks.Clamp();
     for (int i = 0; i < 3; ++i) { out->kd[i] = d.c[i]; out->ks[i] = s.c[i]; }
@@ -112,7 +112,7 @@ class ShinyMetal : public Material {   // materials/shinymetal.cpp:28-65
  public:
   ShinyMetal(const Spectrum &ks, float rough, const Spectrum &kr) : Ks(ks), Kr(kr), roughness(rough) {}
   void Flatten(PbrtB200Material *out) const {
-    memset(out, 0, sizeof(*out));
+    InitRecord(out);
     out->kind = PBRT_B200_MAT_SHINYMETAL;
     Spectrum s = Ks.Clamp(), r = Kr.Clamp();
     for (int i = 0; i < 3; ++i) { out->ks[i] = s.c[i]; out->kr[i] = r.c[i]; }
@@ -389,63 +389,82 @@ AreaLight::AreaLight(const Transform &light2world, const Spectrum &le, int ns,
 }
 
 // ------------------------------------------------------------- factories
+// Operand slots a factory found to vary over the surface (TextureParams reports the texture-table entry).
+struct TexSlots {
+  TexSlots() { for (int i = 0; i < PBRT_B200_TEXSLOTS; ++i) t[i] = -1; }
+  Material *Attach(Material *m) const { memcpy(m->tex, t, sizeof(t)); return m; }
+  int32_t t[PBRT_B200_TEXSLOTS];
+};
+static void NoBump(const TextureParams &mp) {   // constant 0: Material::Bump degenerates (material.cpp:29-71)
+  int32_t node;
+  mp.GetFloatTexture("bumpmap", 0.f, &node);
+  if (node >= 0) Error("Bump mapping is outside the B200 hot-path scope; \"bumpmap\" ignored.");
+}
 static Material *CreateMatte(const Transform &, const TextureParams &mp) {
-  Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(1.f));
-  float sigma = mp.GetFloatTexture("sigma", 0.f);
-  mp.GetFloatTexture("bumpmap", 0.f);   // constant 0: Material::Bump degenerates (material.cpp:29-71)
-  return new Matte(Kd, sigma);
+  TexSlots ts;
+  Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KD]);
+  float sigma = mp.GetFloatTexture("sigma", 0.f, &ts.t[PBRT_B200_TEXSLOT_SIGMA]);
+  NoBump(mp);
+  return ts.Attach(new Matte(Kd, sigma));
 }
 static Material *CreateGlass(const Transform &, const TextureParams &mp) {
-  Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(1.f));
-  Spectrum Kt = mp.GetSpectrumTexture("Kt", Spectrum(1.f));
-  float index = mp.GetFloatTexture("index", 1.5f);
-  mp.GetFloatTexture("bumpmap", 0.f);
-  return new Glass(Kr, Kt, index);
+  TexSlots ts;
+  Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KR]);
+  Spectrum Kt = mp.GetSpectrumTexture("Kt", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KT]);
+  float index = mp.GetFloatTexture("index", 1.5f, &ts.t[PBRT_B200_TEXSLOT_INDEX]);
+  NoBump(mp);
+  return ts.Attach(new Glass(Kr, Kt, index));
 }
 static Material *CreatePlastic(const Transform &, const TextureParams &mp) {
-  Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(1.f));
-  Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(1.f));
-  float roughness = mp.GetFloatTexture("roughness", .1f);
-  mp.GetFloatTexture("bumpmap", 0.f);
-  return new Plastic(Kd, Ks, roughness);
+  TexSlots ts;
+  Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KD]);
+  Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KS]);
+  float roughness = mp.GetFloatTexture("roughness", .1f, &ts.t[PBRT_B200_TEXSLOT_ROUGHNESS]);
+  NoBump(mp);
+  return ts.Attach(new Plastic(Kd, Ks, roughness));
 }
 static Material *CreateUber(const Transform &, const TextureParams &mp) {   // materials/uber.cpp:86-95
-  Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(1.f));
-  Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(1.f));
-  Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(0.f));
-  float roughness = mp.GetFloatTexture("roughness", .1f);
-  Spectrum opacity = mp.GetSpectrumTexture("opacity", Spectrum(1.f));
-  mp.GetFloatTexture("bumpmap", 0.f);
-  return new UberMaterial(Kd, Ks, Kr, roughness, opacity);
+  TexSlots ts;
+  Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KD]);
+  Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KS]);
+  Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(0.f), &ts.t[PBRT_B200_TEXSLOT_KR]);
+  float roughness = mp.GetFloatTexture("roughness", .1f, &ts.t[PBRT_B200_TEXSLOT_ROUGHNESS]);
+  Spectrum opacity = mp.GetSpectrumTexture("opacity", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_OPACITY]);
+  NoBump(mp);
+  return ts.Attach(new UberMaterial(Kd, Ks, Kr, roughness, opacity));
 }
 static Material *CreateTranslucent(const Transform &, const TextureParams &mp) {   // materials/translucent.cpp:85-94
-  Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(1.f));
-  Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(1.f));
-  Spectrum reflect = mp.GetSpectrumTexture("reflect", Spectrum(0.5f));
-  Spectrum transmit = mp.GetSpectrumTexture("transmit", Spectrum(0.5f));
-  float roughness = mp.GetFloatTexture("roughness", .1f);
-  mp.GetFloatTexture("bumpmap", 0.f);
-  return new Translucent(Kd, Ks, roughness, reflect, transmit);
+  TexSlots ts;
+  Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KD]);
+  Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KS]);
+  Spectrum reflect = mp.GetSpectrumTexture("reflect", Spectrum(0.5f), &ts.t[PBRT_B200_TEXSLOT_KR]);
+  Spectrum transmit = mp.GetSpectrumTexture("transmit", Spectrum(0.5f), &ts.t[PBRT_B200_TEXSLOT_KT]);
+  float roughness = mp.GetFloatTexture("roughness", .1f, &ts.t[PBRT_B200_TEXSLOT_ROUGHNESS]);
+  NoBump(mp);
+  return ts.Attach(new Translucent(Kd, Ks, roughness, reflect, transmit));
 }
 static Material *CreateSubstrate(const Transform &, const TextureParams &mp) {   // materials/substrate.cpp:64-73
-  Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(.5f));
-  Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(.5f));
-  float uroughness = mp.GetFloatTexture("uroughness", .1f);
-  float vroughness = mp.GetFloatTexture("vroughness", .1f);
-  mp.GetFloatTexture("bumpmap", 0.f);
-  return new Substrate(Kd, Ks, uroughness, vroughness);
+  TexSlots ts;
+  Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(.5f), &ts.t[PBRT_B200_TEXSLOT_KD]);
+  Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(.5f), &ts.t[PBRT_B200_TEXSLOT_KS]);
+  float uroughness = mp.GetFloatTexture("uroughness", .1f, &ts.t[PBRT_B200_TEXSLOT_ROUGHNESS]);
+  float vroughness = mp.GetFloatTexture("vroughness", .1f, &ts.t[PBRT_B200_TEXSLOT_SIGMA]);
+  NoBump(mp);
+  return ts.Attach(new Substrate(Kd, Ks, uroughness, vroughness));
 }
 static Material *CreateShinyMetal(const Transform &, const TextureParams &mp) {   // materials/shinymetal.cpp:66-73
-  Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(1.f));
-  Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(1.f));
-  float roughness = mp.GetFloatTexture("roughness", .1f);
-  mp.GetFloatTexture("bumpmap", 0.f);
-  return new ShinyMetal(Ks, roughness, Kr);
+  TexSlots ts;
+  Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KR]);
+  Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KS]);
+  float roughness = mp.GetFloatTexture("roughness", .1f, &ts.t[PBRT_B200_TEXSLOT_ROUGHNESS]);
+  NoBump(mp);
+  return ts.Attach(new ShinyMetal(Ks, roughness, Kr));
 }
 static Material *CreateMirror(const Transform &, const TextureParams &mp) {
-  Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(1.f));
-  mp.GetFloatTexture("bumpmap", 0.f);
-  return new Mirror(Kr);
+  TexSlots ts;
+  Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KR]);
+  NoBump(mp);
+  return ts.Attach(new Mirror(Kr));
 }
 
 static bool gWarnedSearchPath = false;

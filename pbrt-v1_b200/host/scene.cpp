@@ -178,6 +178,16 @@ void Scene::Flatten(FlatBuilder &fb, PbrtB200Scene *out) const {
   out->lights = fb.lights.empty() ? NULL : &fb.lights[0];
   out->n_lights = (uint32_t)lights.size();
   out->n_unsampled_lights = (uint32_t)unsampled.size();
+  fb.textures = textures;
+  if (!fb.textures.nodes.empty()) {
+    out->textures = &fb.textures.nodes[0];
+    out->n_textures = (uint32_t)fb.textures.nodes.size();
+    out->tex_levels = fb.textures.levels.empty() ? NULL : &fb.textures.levels[0];
+    out->n_tex_levels = (uint32_t)fb.textures.levels.size();
+    out->texels = fb.textures.texels.empty() ? NULL : &fb.textures.texels[0];
+    out->n_texel_floats = fb.textures.texels.size();
+    out->ewa_weight_lut = fb.textures.ewaLut;
+  }
   out->light_shapes = fb.lightShapes.empty() ? NULL : &fb.lightShapes[0];
   out->light_cdf = fb.lightCdf.empty() ? NULL : &fb.lightCdf[0];
   out->n_light_shapes = (uint32_t)fb.lightShapes.size();

@@ -1,0 +1,28 @@
+// texture.h -- host half of the texture operands: the node table the materials refer to, image loading
+// and MIPMap pyramid construction (core/mipmap.h:89-177, textures/imagemap.cpp:75-121, core/exrio.cpp:40-73).
+#ifndef PBRT_B200_HOST_TEXTURE_H
+#define PBRT_B200_HOST_TEXTURE_H
+#include "paramset.h"
+#include "transform.h"
+#include "../../include/pbrt_b200.h"
+#include <map>
+#include <vector>
+
+struct TextureStore {
+  TextureStore();
+  std::vector<PbrtB200Texture> nodes;
+  std::vector<PbrtB200TexLevel> levels;
+  std::vector<float> texels;
+  float ewaLut[PBRT_B200_EWA_LUT_SIZE];
+  // ImageTexture::GetTexture's cache (imagemap.cpp:75-89): one pyramid per (file, filter, anisotropy, wrap, type)
+  std::map<string, std::pair<uint32_t, uint32_t> > pyramids;
+  void Clear() { nodes.clear(); levels.clear(); texels.clear(); pyramids.clear(); }
+  int AddConstant(const float v[3], int channels);
+  int AddImageMap(const Transform &tex2world, const TextureParams &tp, int channels);
+  int AddScale(int a, int b, int channels);
+  int AddMix(int a, int b, int amount, int channels);
+  int Depth(int node) const;
+};
+// Spectrum texels of an OpenEXR file (R, G, B read as HALF), NULL with an error message when unreadable
+Spectrum *ReadImage(const string &name, int *width, int *height);
+#endif

@@ -2,6 +2,10 @@
 integrators, filters, instancing, constant textures) at thumbnail size: input for the differential tests
 (compiled reference vs oracle twin on the CPU; CUDA path vs twin on the GPU).  scene(random.Random, idx) -> text."""
 import math
+import os
+import re
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def f(*v):
@@ -35,6 +39,46 @@ def material(r):
             rnd_color(r), r.choice(["0 0 0", rnd_color(r, 0, .5)]), r.choice(["0 0 0", rnd_color(r)]), r.choice(["0 0 0", rnd_color(r)]), f(r.uniform(.02, .5)))
     return 'Material "substrate" "color Kd" [%s] "color Ks" [%s] "float uroughness" [%s] "float vroughness" [%s]' % (
         rnd_color(r), rnd_color(r, .05, .5), f(r.choice([.001, .05, .3])), f(r.choice([.001, .05, .3])))
+
+
+def textures(r):
+    """image-map textures (and scale / mix expressions over them) for a world block; returns the statements and
+    the names usable as color / float operands"""
+    out, color, flt = [], [], []
+    files = ["tex13x7.exr", "tex8x16.exr", "tex5x5.exr"]
+    for i in range(r.randint(1, 3)):
+        for typ, names in (("color", color), ("float", flt)):
+            m = r.choice(["uv", "uv", "spherical", "cylindrical", "planar"])
+            p = '"string mapping" ["%s"]' % m
+            if m == "uv":
+                p += ' "float uscale" [%s] "float vscale" [%s] "float udelta" [%s]' % (f(r.choice([1, 2, 7, 30])), f(r.choice([1, 3, 11])), f(r.uniform(-1, 1)))
+            if m == "planar":
+                p += ' "vector v1" [%s] "vector v2" [%s]' % (f(r.uniform(-.5, .5), 0, r.uniform(-.5, .5)), f(0, r.uniform(-.5, .5), r.uniform(-.5, .5)))
+            p += r.choice(["", ' "string wrap" ["clamp"]', ' "string wrap" ["black"]', ' "bool trilinear" ["true"]', ' "float maxanisotropy" [%s]' % f(r.choice([1, 2, 20]))])
+            pre = r.choice(["", "Rotate %s 1 1 0\n" % f(r.uniform(0, 360)), "Scale 1 %s 1\nTranslate .3 .2 .1\n" % f(r.uniform(.5, 2))])
+            name = "%s%d" % (typ[0], i)
+            out.append('TransformBegin\n%sTexture "%s" "%s" "imagemap" "string filename" ["%s"] %s\nTransformEnd' % (
+                pre, name, typ, os.path.join(GOLDEN, r.choice(files)), p))
+            names.append(name)
+    out.append('Texture "cs" "color" "scale" "texture tex1" "%s" "color tex2" [%s]' % (r.choice(color), rnd_color(r)))
+    out.append('Texture "cm" "color" "mix" "texture tex1" "cs" "texture tex2" "%s" "texture amount" "%s"' % (r.choice(color), r.choice(flt)))
+    color += ["cs", "cm"]
+    out.append('Texture "frough" "float" "mix" "float tex1" [.02] "float tex2" [.5] "texture amount" "%s"' % r.choice(flt))
+    out.append('Texture "findex" "float" "mix" "float tex1" [1.2] "float tex2" [1.8] "texture amount" "%s"' % r.choice(flt))
+    out.append('Texture "fsigma" "float" "scale" "texture tex1" "%s" "float tex2" [50]' % r.choice(flt))
+    return out, color
+
+
+def retexture(r, mat, color):
+    """swaps some constant operands of a Material statement for textures"""
+    def csub(m):
+        return '"texture %s" "%s"' % (m.group(1), r.choice(color)) if r.random() < .5 else m.group(0)
+
+    def fsub(m):
+        name = {"sigma": "fsigma", "index": "findex"}.get(m.group(1), "frough")
+        return '"texture %s" "%s"' % (m.group(1), name) if r.random() < .5 else m.group(0)
+    mat = re.sub(r'"color (Kd|Ks|Kr|Kt|opacity|reflect|transmit)" \[[^\]]*\]', csub, mat)
+    return re.sub(r'"float (sigma|index|roughness|uroughness|vroughness)" \[[^\]]*\]', fsub, mat)
 
 
 def shape(r):
@@ -146,6 +190,16 @@ def scene(r, idx):
                        'Shape "cylinder" "float radius" [.2] "float zmin" [-.8] "float zmax" [.8]'])
         out.append('AttributeBegin\nAreaLightSource "area" "color L" [%s] "integer nsamples" [%d]\nTranslate %s\nRotate %s 1 0 0\n%s\nAttributeEnd' % (
             rnd_color(r, 4, 15), r.randint(1, 3), f(r.uniform(-3, 3), r.uniform(3.5, 6), r.uniform(-2, 2)), f(r.choice([90, 90, 60, 200])), sh))
+    color = None
+    if r.random() < .35:   # textures need the path integrator
+        integ = 'SurfaceIntegrator "path" "integer maxdepth" [%d]' % r.randint(1, 5)
+        out[5] = integ
+        stmts, color = textures(r)
+        out += stmts
+
+    def mat():
+        m = material(r)
+        return retexture(r, m, color) if color else m
     out.append('Texture "tc" "color" "constant" "color value" [%s]' % rnd_color(r))
     out.append('Texture "tm" "color" "mix" "texture tex1" "tc" "color tex2" [%s] "float amount" [%s]' % (rnd_color(r), f(r.uniform(0, 1))))
     out.append('Material "matte" "texture Kd" "tm"')
@@ -155,12 +209,12 @@ def scene(r, idx):
         out.append('ObjectBegin "obj"')
         for _ in range(r.randint(1, 3)):
             lit = 'AreaLightSource "area" "color L" [%s]\n' % rnd_color(r, 1, 6) if r.random() < .2 else ""
-            out.append("AttributeBegin\n" + lit + material(r) + "\n" + xform(r).replace("Translate", "Translate 0 0 0 Translate", 1) + shape(r) + "\nAttributeEnd")
+            out.append("AttributeBegin\n" + lit + mat() + "\n" + xform(r).replace("Translate", "Translate 0 0 0 Translate", 1) + shape(r) + "\nAttributeEnd")
         out.append("ObjectEnd")
     for _ in range(r.randint(2, 6)):
         if has_obj and r.random() < .35:
             out.append("AttributeBegin\n" + xform(r) + 'ObjectInstance "obj"\nAttributeEnd')
         else:
-            out.append("AttributeBegin\n" + material(r) + "\n" + xform(r) + shape(r) + "\nAttributeEnd")
+            out.append("AttributeBegin\n" + mat() + "\n" + xform(r) + shape(r) + "\nAttributeEnd")
     out.append("WorldEnd")
     return "\n".join(out) + "\n"

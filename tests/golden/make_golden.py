@@ -27,7 +27,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
-from parity_util import gen_scene, load_ffi, read_sample_dump  # noqa: E402
+from parity_util import gen_scene, load_ffi, read_sample_dump, write_exr  # noqa: E402
 
 CASES = [
     # name, generator scene, args, keyed
@@ -492,6 +492,180 @@ INLINE["instances_emitter_whitted"] = _instanced_emitters('"whitted" "integer ma
 INLINE["instances_emitter_direct"] = _instanced_emitters('"directlighting" "integer maxdepth" [3]', "direct")
 
 
+def make_textures():
+    """image maps of the tex_* fixtures (committed beside them): non-power-of-two, non-square, tiny"""
+    rng = np.random.RandomState(20260117)
+    a = rng.rand(7, 13, 3).astype(np.float32)
+    a[::2, ::3] *= 0.1
+    write_exr(os.path.join(HERE, "tex13x7.exr"), a)
+    b = rng.rand(16, 8, 3).astype(np.float32)
+    yy, xx = np.mgrid[0:16, 0:8]
+    b *= (((xx // 2 + yy // 4) % 2) * 0.8 + 0.2)[..., None].astype(np.float32)
+    write_exr(os.path.join(HERE, "tex8x16.exr"), b)
+    c = (rng.rand(5, 5, 3) * 1.5).astype(np.float32)
+    write_exr(os.path.join(HERE, "tex5x5.exr"), c)
+
+
+_TEX_HEAD = """LookAt 0 3 -8 0 0.5 0 0 1 0
+Camera %s
+Film "image" "integer xresolution" [40] "integer yresolution" [28] %s "string filename" ["%s_out.exr"]
+%s
+PixelFilter %s
+SurfaceIntegrator "path" "integer maxdepth" [%d]
+WorldBegin
+"""
+
+_TEX_LIGHTS = """LightSource "point" "color I" [50 50 50] "point from" [2 6 -5]
+AttributeBegin
+AreaLightSource "area" "color L" [8 8 7] "integer nsamples" [1]
+Translate -2 5 0
+Rotate 90 1 0 0
+Shape "disk" "radius" [1.2]
+AttributeEnd
+"""
+
+
+def _tex_scene(tag, body, camera='"perspective" "float fov" [40]', film="", sampler='Sampler "stratified" "integer xsamples" [2] "integer ysamples" [2]',
+               pfilter='"box"', depth=3):
+    return _TEX_HEAD % (camera, film, tag, sampler, pfilter, depth) + _TEX_LIGHTS.replace('"radius"', '"float radius"') + body + "WorldEnd\n"
+
+
+# uv mapping with scale/offset on a plane (EWA, strongly anisotropic towards the horizon), a pow2 map on a
+# sphere, a glass ball and a mirror so textured surfaces are also reached by rays without differentials
+INLINE["tex_uv_ewa_path"] = _tex_scene("tex_uv_ewa_path", """Texture "img" "color" "imagemap" "string filename" ["tex13x7.exr"] "float uscale" [4] "float vscale" [3] "float udelta" [.25] "float vdelta" [-.4]
+Material "matte" "texture Kd" "img"
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-9 -1 -9 9 -1 -9 9 -1 9 -9 -1 9] "float uv" [0 0 1 0 1 1 0 1]
+AttributeBegin
+Texture "img2" "color" "imagemap" "string filename" ["tex8x16.exr"]
+Material "matte" "texture Kd" "img2"
+Translate -1.2 0.5 0.5
+Shape "sphere" "float radius" [1.5]
+AttributeEnd
+AttributeBegin
+Material "glass" "float index" [1.5]
+Translate 1.6 0 -2
+Shape "sphere" "float radius" [.9]
+AttributeEnd
+AttributeBegin
+Material "mirror"
+Translate 3 1 2
+Rotate -30 0 1 0
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-1.5 -2 0 1.5 -2 0 1.5 2 0 -1.5 2 0]
+AttributeEnd
+""", depth=4)
+
+# the three other mappings (under rotated / scaled texture spaces), trilinear filtering, the three wrap modes
+INLINE["tex_mappings_path"] = _tex_scene("tex_mappings_path", """TransformBegin
+Rotate 25 1 0 1
+Scale 1 1.3 .8
+Texture "sph" "color" "imagemap" "string filename" ["tex8x16.exr"] "string mapping" ["spherical"] "string wrap" ["clamp"]
+TransformEnd
+TransformBegin
+Translate .5 0 0
+Rotate 90 1 0 0
+Texture "cyl" "color" "imagemap" "string filename" ["tex13x7.exr"] "string mapping" ["cylindrical"] "bool trilinear" ["true"]
+Texture "cyl2" "color" "imagemap" "string filename" ["tex8x16.exr"] "string mapping" ["cylindrical"] "float maxanisotropy" [16]
+TransformEnd
+Texture "pla" "color" "imagemap" "string filename" ["tex5x5.exr"] "string mapping" ["planar"] "vector v1" [.3 0 .1] "vector v2" [0 .1 .35] "float udelta" [.1] "float vdelta" [.2] "string wrap" ["black"] "float maxanisotropy" [3]
+Material "matte" "texture Kd" "pla"
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-9 -1 -9 9 -1 -9 9 -1 9 -9 -1 9]
+AttributeBegin
+Material "plastic" "texture Kd" "sph" "color Ks" [.2 .2 .2] "float roughness" [.05]
+Translate -1.8 0.5 0
+Shape "sphere" "float radius" [1.4]
+AttributeEnd
+AttributeBegin
+Material "matte" "texture Kd" "cyl"
+Translate 1.8 -1 0.5
+Rotate -90 1 0 0
+Shape "cylinder" "float radius" [1] "float zmin" [0] "float zmax" [2.5]
+AttributeEnd
+AttributeBegin
+Material "matte" "texture Kd" "cyl2"
+Translate 0.2 -0.4 -3
+Shape "sphere" "float radius" [.6]
+AttributeEnd
+""")
+
+# float image maps (sigma, roughness, mix amount), scale / mix expressions over image maps, opacity, and a
+# texture on every operand kind
+INLINE["tex_float_mix_path"] = _tex_scene("tex_float_mix_path", """Texture "a" "color" "imagemap" "string filename" ["tex13x7.exr"] "float uscale" [2] "float vscale" [2]
+Texture "b" "color" "imagemap" "string filename" ["tex8x16.exr"] "string wrap" ["clamp"]
+Texture "fa" "float" "imagemap" "string filename" ["tex5x5.exr"]
+Texture "fb" "float" "imagemap" "string filename" ["tex8x16.exr"] "bool trilinear" ["true"] "float uscale" [3] "float vscale" [3]
+Texture "deg" "float" "scale" "texture tex1" "fa" "float tex2" [60]
+Texture "rough" "float" "mix" "float tex1" [.02] "float tex2" [.4] "texture amount" "fb"
+Texture "ab" "color" "scale" "texture tex1" "a" "texture tex2" "b"
+Texture "mixed" "color" "mix" "texture tex1" "ab" "color tex2" [.9 .2 .1] "texture amount" "fa"
+Material "matte" "texture Kd" "mixed" "texture sigma" "deg"
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-9 -1 -9 9 -1 -9 9 -1 9 -9 -1 9] "float uv" [0 0 3 0 3 3 0 3]
+AttributeBegin
+Material "plastic" "texture Kd" "a" "texture Ks" "b" "texture roughness" "rough"
+Translate -2.2 0.4 0
+Shape "sphere" "float radius" [1.3]
+AttributeEnd
+AttributeBegin
+Material "uber" "texture Kd" "b" "color Ks" [.3 .3 .3] "texture Kr" "a" "texture opacity" "b" "texture roughness" "rough"
+Translate 0.6 0.2 -1.5
+Shape "sphere" "float radius" [1]
+AttributeEnd
+AttributeBegin
+Material "substrate" "texture Kd" "a" "texture Ks" "ab" "texture uroughness" "rough" "float vroughness" [.2]
+Translate 2.8 0.3 1
+Shape "sphere" "float radius" [1.2]
+AttributeEnd
+AttributeBegin
+Material "glass" "texture Kr" "b" "texture Kt" "a" "texture index" "fa"
+Translate -0.5 -0.3 -3.5
+Shape "sphere" "float radius" [.6]
+AttributeEnd
+""", depth=4)
+
+# a textured mesh with shading normals inside instanced objects, the lowdiscrepancy sampler, depth of field,
+# a Mitchell filter and a crop window
+INLINE["tex_instances_ld_path"] = _tex_scene("tex_instances_ld_path", """Texture "img" "color" "imagemap" "string filename" ["tex13x7.exr"]
+Texture "chk" "color" "imagemap" "string filename" ["tex8x16.exr"] "float uscale" [6] "float vscale" [6]
+Material "shinymetal" "texture Ks" "chk" "texture Kr" "img" "float roughness" [.1]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-9 -1 -9 9 -1 -9 9 -1 9 -9 -1 9] "float uv" [0 0 1 0 1 1 0 1]
+ObjectBegin "blob"
+Material "matte" "texture Kd" "img"
+%s
+Material "translucent" "texture Kd" "chk" "color Ks" [.2 .2 .2] "texture reflect" "img" "color transmit" [.6 .6 .6]
+AttributeBegin
+Translate 0 1.5 0
+Shape "disk" "float radius" [.8]
+AttributeEnd
+ObjectEnd
+AttributeBegin
+Translate -2 0.3 0
+ObjectInstance "blob"
+AttributeEnd
+AttributeBegin
+Translate 2 0.5 1
+Rotate 40 0 1 1
+Scale -1.3 .9 1.1
+ObjectInstance "blob"
+AttributeEnd
+""" % _latlong_mesh(8, 5, 1.0, .8, .9), camera='"perspective" "float fov" [40] "float lensradius" [.15] "float focaldistance" [8]',
+    film='"float cropwindow" [.1 .9 .15 .95]', sampler='Sampler "lowdiscrepancy" "integer pixelsamples" [4]', pfilter='"mitchell"')
+
+# bestcandidate sampler + orthographic camera; environment camera + random sampler
+_TEX_SMALL = """Texture "img" "color" "imagemap" "string filename" ["tex5x5.exr"] "float uscale" [5] "float vscale" [5] "string wrap" ["clamp"]
+Material "matte" "texture Kd" "img"
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-9 -1 -9 9 -1 -9 9 -1 9 -9 -1 9] "float uv" [0 0 1 0 1 1 0 1]
+AttributeBegin
+Texture "s" "color" "imagemap" "string filename" ["tex13x7.exr"] "string mapping" ["spherical"]
+Material "plastic" "texture Kd" "s" "color Ks" [.3 .3 .3]
+Translate 0 0.6 0
+Shape "sphere" "float radius" [1.6]
+AttributeEnd
+"""
+INLINE["tex_bc_ortho_path"] = _tex_scene("tex_bc_ortho_path", _TEX_SMALL, camera='"orthographic" "float screenwindow" [-4 4 -2.8 2.8]',
+                                         sampler='Sampler "bestcandidate" "integer pixelsamples" [3]', pfilter='"gaussian"')
+INLINE["tex_env_random_path"] = _tex_scene("tex_env_random_path", _TEX_SMALL, camera='"environment"',
+                                           sampler='Sampler "random" "integer xsamples" [2] "integer ysamples" [1]')
+
+
 def _bestcandidate(integrator, tag, sampler, film='"integer xresolution" [28] "integer yresolution" [20]', lens="", nsamples=1, pfilter='"box"'):
     """bestcandidate sampler (the reference's default when a scene names none)"""
     return """LookAt 278 273 -800 278 273 0 0 1 0
@@ -777,6 +951,7 @@ def main():
     ffi = load_ffi()
     assert ffi.have_reference(), "oracle/_ref missing: run oracle/build_ref.sh (needs /root/reference)"
     cases = list(CASES) + [(n, None, None, True) for n in INLINE]
+    make_textures()
     if len(sys.argv) > 1:   # only the named cases
         cases = [c for c in cases if c[0] in sys.argv[1:]]
     for name, scene, args, keyed in cases:

@@ -44,3 +44,35 @@ def image_error_stats(a, b):
         "frac_gt_1e-2": float((d > 1e-2).mean()),
         "mean_rel": float(abs(a[..., :3].mean() - b[..., :3].mean()) / max(abs(b[..., :3].mean()), 1e-30)),
     }
+
+
+def write_exr(path, rgb):
+    """Uncompressed scan-line OpenEXR file, HALF channels B, G, R, from a float array [h, w, 3] (texture
+    fixtures; what oracle/ref_glue.cpp's and the host front end's ReadImage both accept)."""
+    import struct
+    rgb = np.asarray(rgb, np.float32)
+    h, w, _ = rgb.shape
+    half = rgb.astype(np.float16)
+
+    def attr(name, typ, data):
+        return name.encode() + b"\0" + typ.encode() + b"\0" + struct.pack("<i", len(data)) + data
+    chlist = b"".join(n + b"\0" + struct.pack("<iBBBBii", 1, 0, 0, 0, 0, 1, 1) for n in (b"B", b"G", b"R")) + b"\0"
+    hdr = struct.pack("<II", 20000630, 2)
+    hdr += attr("channels", "chlist", chlist)
+    hdr += attr("compression", "compression", b"\0")
+    hdr += attr("dataWindow", "box2i", struct.pack("<4i", 0, 0, w - 1, h - 1))
+    hdr += attr("displayWindow", "box2i", struct.pack("<4i", 0, 0, w - 1, h - 1))
+    hdr += attr("lineOrder", "lineOrder", b"\0")
+    hdr += attr("pixelAspectRatio", "float", struct.pack("<f", 1.0))
+    hdr += attr("screenWindowCenter", "v2f", struct.pack("<2f", 0.0, 0.0))
+    hdr += attr("screenWindowWidth", "float", struct.pack("<f", 1.0))
+    hdr += b"\0"
+    row_bytes = 8 + 3 * 2 * w
+    base = len(hdr) + 8 * h
+    out = [hdr, b"".join(struct.pack("<Q", base + y * row_bytes) for y in range(h))]
+    for y in range(h):
+        out.append(struct.pack("<ii", y, 3 * 2 * w))
+        for c in (2, 1, 0):
+            out.append(half[y, :, c].tobytes())
+    with open(path, "wb") as f:
+        f.write(b"".join(out))

@@ -82,7 +82,7 @@ def test_render_bit_identical_to_twin(ffi, name):
     ds.close()
 
 
-@pytest.mark.parametrize("seed", range(32))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("PBRT_FUZZ_SCENES", "32"))))
 def test_fuzz_scenes_bit_identical_to_twin(ffi, tmp_path, seed):
     """Random scenes mixing every supported plugin (tests/fuzz_scenes.py; tests/test_oracle.py pins the twin
     to the compiled reference on the same generator): CUDA path == twin, samples, film and counters."""
