@@ -118,8 +118,8 @@ Spec li_path(const SceneView &sv, const PatternSource &key0, uint64_t key1, cons
   return st.L;
 }
 
-Spec li_wd(const SceneView &sv, const PatternSource &key0, uint64_t key1, const Ray &camRay, float *alpha,
-           Counters &c) {
+Spec li_wd(const SceneView &sv, const PatternSource &key0, uint64_t key1, const Ray &camRay, const RayDiff &camDiff,
+           float *alpha, Counters &c) {
   RngStream rng; rng.key = key1; rng.ctr = 0;
   std::vector<WdFrame> frames(1);
   VecFrameIO io = {&frames};
@@ -133,7 +133,9 @@ Spec li_wd(const SceneView &sv, const PatternSource &key0, uint64_t key1, const 
     trace_closest(sv, ray, &hit, c);
     WdFrame fr;
     WdVertexOut out;
-    wd_vertex(sv, key0, ray, hit, rng, depth, depth == 0 ? alpha : (float *)0, &fr, recs.data(), &out);
+    // the ray into depth d is the reflection (parent stage 0) or transmission child of frame d - 1
+    const RayDiff *rd = depth == 0 ? &camDiff : (frames[depth - 1].stage == 0 ? &frames[depth - 1].dR : &frames[depth - 1].dT);
+    wd_vertex<true>(sv, key0, ray, hit, rng, depth, depth == 0 ? alpha : (float *)0, &fr, recs.data(), &out, rd);
     if (hit.prim >= 0) ++c.shaded;
     for (int r = 0; r < out.nRecs; ++r) flags[r] = trace_direct(sv, recs[r], c);
     wd_resolve(sv, &fr, recs.data(), flags.data(), out.nRecs);
@@ -177,7 +179,7 @@ int pbrt_twin_render(const PbrtB200Scene *scene, const PbrtB200Window *win, floa
     float alpha = 0.f;
     Spec Ls = (sv.integrator.kind == PBRT_B200_INT_PATH)
                   ? li_path(sv, key0, key1, ray, camDiff, &alpha, c)
-                  : li_wd(sv, key0, key1, ray, &alpha, c);
+                  : li_wd(sv, key0, key1, ray, camDiff, &alpha, c);
     Ls = 1.f * Ls;   // rayWeight * Li, scene.cpp:58
     cs.imageX = film_image_coord(cs.imageX);
     cs.imageY = film_image_coord(cs.imageY);

@@ -36,8 +36,10 @@ PB_NOINLINE void instance_dg_to_world(const PbrtB200Instance &in, DiffGeom *dg) 
   dg->nn = normalize(xf_normal(in.w2i, dg->nn));
   dg->dpdu = xf_vector(in.i2w, dg->dpdu);
   dg->dpdv = xf_vector(in.i2w, dg->dpdv);
-  dg->dndu = xf_vector(in.i2w, dg->dndu);
-  dg->dndv = xf_vector(in.i2w, dg->dndv);
+  // DifferentialGeometry::dndu / dndv are declared Normal (core/shape.h:46): this step transforms them as
+  // normals (inverse transpose), unlike the shapes' own `ObjectToWorld(dndu)` on a Vector
+  dg->dndu = xf_normal(in.w2i, dg->dndu);
+  dg->dndv = xf_normal(in.w2i, dg->dndv);
 }
 // INST = false compiles the instancing code out (kernels for scenes without object instances).
 template <bool INST = true>
@@ -66,9 +68,16 @@ PB_HD void surface_dg(const SceneView &sv, const Ray &rayWorld, const Hit &hit, 
 // TEX = true evaluates the material's texture operands at the hit (dg.ComputeDifferentials(ray) and the
 // `Kd->Evaluate(dgs)` calls of Material::GetBSDF); `rd` holds the ray's differentials or is null, `evalMat`
 // (optional) receives the material record with every textured operand replaced by its value here.
+// What the specular-bounce transfer of ray differentials reads at a vertex (whitted.cpp:86-131): the geometric
+// dg's dpdx / dpdy, and the shading dg's dndu / dndv with the (inherited) du/dx ... dv/dy.
+struct SurfaceDiff {
+  DgDiff dd;
+  V3 dndu, dndv;
+};
 template <bool LOBES = true, bool INST = true, bool TEX = false>
 PB_HD void surface_at_hit(const SceneView &sv, const Ray &ray, const Hit &hit, Surface *sf,
-                          const RayDiff *rd = (const RayDiff *)0, PbrtB200Material *evalMat = (PbrtB200Material *)0) {
+                          const RayDiff *rd = (const RayDiff *)0, PbrtB200Material *evalMat = (PbrtB200Material *)0,
+                          SurfaceDiff *sd = (SurfaceDiff *)0) {
   TriVerts tv = load_prim(sv, (uint32_t)hit.prim);
   DiffGeom dg, dgs;
   surface_dg<INST>(sv, ray, hit, tv, &dg);
@@ -86,6 +95,7 @@ PB_HD void surface_at_hit(const SceneView &sv, const Ray &ray, const Hit &hit, S
     material_eval_textures(sv, dg, dd, &m);
     make_bsdf<LOBES>(m, dg, dgs, tv.flags, &sf->bsdf);
     if (evalMat) *evalMat = m;
+    if (sd) { sd->dd = dd; sd->dndu = dgs.dndu; sd->dndv = dgs.dndv; }
   } else
     make_bsdf<LOBES>(sv.materials[tv.material], dg, dgs, tv.flags, &sf->bsdf);
   sf->light = tv.light;
@@ -575,6 +585,7 @@ struct WdFrame {
   float aR, aT;           // AbsDot(wi, n)
   int32_t stage;          // 0: children not started, 1: reflection done, 2: complete
   bool reflValid, transValid;
+  RayDiff dR, dT;         // textured scenes: the differentials of the two child rays
 };
 struct WdVertexOut {
   int nRecs;              // direct-lighting records written
@@ -584,9 +595,11 @@ PB_HD int wd_max_records(const SceneView &sv) { return sv.directRecords; }
 
 // Vertex body up to (not including) `if (rayDepth++ < maxDepth)`.  `recs` must hold
 // wd_max_records() entries.  The frame is initialised here.
+// TEX: texture operands are evaluated with `rd`, the differentials of `ray`, and the children's are derived.
+template <bool TEX = false>
 PB_HD void wd_vertex(const SceneView &sv, const PatternSource &key0, const Ray &ray, const Hit &hit,
                      RngStream &rng, int rayDepth, float *alpha, WdFrame *fr, DirectRec *recs,
-                     WdVertexOut *out) {
+                     WdVertexOut *out, const RayDiff *rd = (const RayDiff *)0) {
   out->nRecs = 0;
   fr->L = spec(0.f);
   fr->stage = 2;
@@ -604,7 +617,8 @@ PB_HD void wd_vertex(const SceneView &sv, const PatternSource &key0, const Ray &
   }
   if (alpha) *alpha = 1.f;
   Surface sf;
-  surface_at_hit(sv, ray, hit, &sf);
+  SurfaceDiff sd;
+  surface_at_hit<true, true, TEX>(sv, ray, hit, &sf, rd, (PbrtB200Material *)0, &sd);
   const Bsdf &bsdf = sf.bsdf;
   V3 p = bsdf.p, n = bsdf.nn;
   V3 wo = -ray.d;
@@ -690,12 +704,46 @@ PB_HD void wd_vertex(const SceneView &sv, const PatternSource &key0, const Ray &
     if (!is_black(f) && pdf > 0.f) f = f * (1.f / pdf);
     if (!is_black(f) && absdot(wi, n) > 0.f) {
       fr->reflValid = true; fr->wiR = wi; fr->fR = f; fr->aR = absdot(wi, n);
+      if (TEX) {
+        // ray differential for specular reflection, whitted.cpp:86-103 / directlighting.cpp:133-150
+        RayDiff &c = fr->dR;
+        c.has = true;
+        c.rxo = p + sd.dd.dpdx;
+        c.ryo = p + sd.dd.dpdy;
+        V3 dndx = sd.dndu * sd.dd.dudx + sd.dndv * sd.dd.dvdx;
+        V3 dndy = sd.dndu * sd.dd.dudy + sd.dndv * sd.dd.dvdy;
+        V3 dwodx = -rd->rxd - wo, dwody = -rd->ryd - wo;
+        float dDNdx = dot(dwodx, n) + dot(wo, dndx);
+        float dDNdy = dot(dwody, n) + dot(wo, dndy);
+        c.rxd = wi - dwodx + 2.f * (dot(wo, n) * dndx + dDNdx * n);
+        c.ryd = wi - dwody + 2.f * (dot(wo, n) * dndy + dDNdy * n);
+      }
     }
     wi = v3(0, 0, 0);
     f = bsdf_sample_f(bsdf, wo, &wi, 0.5f, 0.5f, 0.5f, &pdf, PB_TRANSMISSION | PB_SPECULAR, &sampled);
     if (!is_black(f) && pdf > 0.f) f = f * (1.f / pdf);
     if (!is_black(f) && absdot(wi, n) > 0.f) {
       fr->transValid = true; fr->wiT = wi; fr->fT = f; fr->aT = absdot(wi, n);
+      if (TEX) {
+        // ray differential for specular transmission, whitted.cpp:108-131 / directlighting.cpp:156-179
+        RayDiff &c = fr->dT;
+        c.has = true;
+        c.rxo = p + sd.dd.dpdx;
+        c.ryo = p + sd.dd.dpdy;
+        float eta = bsdf.eta;
+        V3 w = -wo;
+        if (dot(wo, n) < 0) eta = 1.f / eta;
+        V3 dndx = sd.dndu * sd.dd.dudx + sd.dndv * sd.dd.dvdx;
+        V3 dndy = sd.dndu * sd.dd.dudy + sd.dndv * sd.dd.dvdy;
+        V3 dwodx = -rd->rxd - wo, dwody = -rd->ryd - wo;
+        float dDNdx = dot(dwodx, n) + dot(wo, dndx);
+        float dDNdy = dot(dwody, n) + dot(wo, dndy);
+        float mu = eta * dot(w, n) - dot(wi, n);
+        float dmudx = (eta - (eta * eta * dot(w, n)) / dot(wi, n)) * dDNdx;
+        float dmudy = (eta - (eta * eta * dot(w, n)) / dot(wi, n)) * dDNdy;
+        c.rxd = wi + eta * dwodx - (mu * dndx + dmudx * n);
+        c.ryd = wi + eta * dwody - (mu * dndy + dmudy * n);
+      }
     }
   }
 }

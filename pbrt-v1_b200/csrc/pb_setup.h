@@ -60,10 +60,7 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
       }
     }
   }
-  // ray differentials are carried for camera rays only; the specular-bounce transfer of whitted.cpp:86-134 /
-  // directlighting.cpp:131-181 is not implemented, so those integrators refuse textured scenes
-  if (textured && s.integrator.kind != PBRT_B200_INT_PATH)
-    return "image-map textures are supported under the path integrator only";
+  (void)textured;
   if (s.n_top_nodes > s.n_nodes) return "n_top_nodes > n_nodes";
   for (uint32_t i = 0; i < s.n_instances; ++i) {
     const PbrtB200Instance &in = s.instances[i];

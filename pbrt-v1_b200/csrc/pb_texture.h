@@ -227,6 +227,9 @@ PB_HD Spec mip_lookup(const SceneView &sv, const PbrtB200Texture &t, float s, fl
 PB_NOINLINE Spec tex_image_eval(const SceneView &sv, const PbrtB200Texture &t, const DiffGeom &dg, const DgDiff &dd) {
   float s, tt, dsdx, dtdx, dsdy, dtdy;
   tex_map(t, dg, dd, &s, &tt, &dsdx, &dtdx, &dsdy, &dtdy);
+#if defined(PB_TEX_DEBUG) && !defined(__CUDACC__)   // trace for diffing against an instrumented reference plugin
+  fprintf(stderr, "TEX %a %a %a %a %a %a -> %a\n", s, tt, dsdx, dtdx, dsdy, dtdy, mip_lookup(sv, t, s, tt, dsdx, dtdx, dsdy, dtdy).c[0]);
+#endif
   return mip_lookup(sv, t, s, tt, dsdx, dtdx, dsdy, dtdy);
 }
 // Operands always precede the node that uses them and the host refuses graphs more than PB_TEX_MAX_DEPTH

@@ -125,6 +125,7 @@ struct WaveBuffers {
   // s at camDiff[e * nSlots + s]) and, per hit record, the material with its operands evaluated at the hit
   float *camDiff;
   PbrtB200Material *surfMat;
+  float *frameDiff;      // whitted / directlighting: the two child-ray differentials of each frame, [24][frame][slot]
   // counters (device): [0..] see enum below
   uint32_t *counts;
   unsigned long long *stats;
@@ -727,6 +728,25 @@ struct DevFrameIO {
   __device__ float *fp(int field, int d) const {
     return wb->frame + ((size_t)field * wb->nFrames + d) * wb->nSlots + slot;
   }
+  __device__ float *dp(int field, int d) const {
+    return wb->frameDiff + ((size_t)field * wb->nFrames + d) * wb->nSlots + slot;
+  }
+  // child 0: reflection, 1: transmission
+  __device__ void load_diff(int d, int child, RayDiff *r) const {
+    int k = 12 * child;
+    r->has = true;
+    r->rxo.x = *dp(k++, d); r->rxo.y = *dp(k++, d); r->rxo.z = *dp(k++, d);
+    r->rxd.x = *dp(k++, d); r->rxd.y = *dp(k++, d); r->rxd.z = *dp(k++, d);
+    r->ryo.x = *dp(k++, d); r->ryo.y = *dp(k++, d); r->ryo.z = *dp(k++, d);
+    r->ryd.x = *dp(k++, d); r->ryd.y = *dp(k++, d); r->ryd.z = *dp(k++, d);
+  }
+  __device__ void store_diff(int d, int child, const RayDiff &r) const {
+    int k = 12 * child;
+    *dp(k++, d) = r.rxo.x; *dp(k++, d) = r.rxo.y; *dp(k++, d) = r.rxo.z;
+    *dp(k++, d) = r.rxd.x; *dp(k++, d) = r.rxd.y; *dp(k++, d) = r.rxd.z;
+    *dp(k++, d) = r.ryo.x; *dp(k++, d) = r.ryo.y; *dp(k++, d) = r.ryo.z;
+    *dp(k++, d) = r.ryd.x; *dp(k++, d) = r.ryd.y; *dp(k++, d) = r.ryd.z;
+  }
   __device__ WdFrame load(int d) const {
     WdFrame f;
     int k = 0;
@@ -758,6 +778,7 @@ struct DevFrameIO {
 #define PB_MAX_WD_RECS 16   // per-thread staging of direct records in the wd kernels
 
 // K2 (whitted / directlighting): vertex body up to the specular recursion
+template <bool TEX>
 __global__ void __launch_bounds__(PB_BLOCK)
 k_shade_wd(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveKeyInfo wd,
            const RayQueue qin, const uint32_t *nPtr, uint32_t *work, uint32_t *shadowCount,
@@ -792,14 +813,26 @@ k_shade_wd(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
         float alpha = 0.f;
         WdFrame fr;
         WdVertexOut out;
-        wd_vertex(sv, key0, ray, hit, rng, depth, depth == 0 ? &alpha : (float *)0, &fr, recs, &out);
+        DevFrameIO io = {&wb, slot};
+        if (TEX) {
+          // the ray into depth d is the reflection (parent stage 0) or transmission child of frame d - 1
+          RayDiff rd;
+          rd.has = true;
+          if (depth == 0) cam_diff_load(wb, slot, &rd);
+          else io.load_diff(depth - 1, (wb.frameFlags[(size_t)(depth - 1) * wb.nSlots + slot] & 0xffu) == 0 ? 0 : 1, &rd);
+          wd_vertex<true>(sv, key0, ray, hit, rng, depth, depth == 0 ? &alpha : (float *)0, &fr, recs, &out, &rd);
+        } else
+          wd_vertex<false>(sv, key0, ray, hit, rng, depth, depth == 0 ? &alpha : (float *)0, &fr, recs, &out);
         if (hit.prim >= 0) ++shaded;
         if (depth == 0) wb.alpha[slot] = alpha;
         wb.ctr[slot] = rng.ctr;
         nRecs = out.nRecs;
         wb.nRecs[slot] = (uint32_t)nRecs;
-        DevFrameIO io = {&wb, slot};
         io.store(depth, fr);
+        if (TEX) {
+          if (fr.reflValid) io.store_diff(depth, 0, fr.dR);
+          if (fr.transValid) io.store_diff(depth, 1, fr.dT);
+        }
         for (int r = 0; r < nRecs; ++r) {
           size_t ri = (size_t)r * wb.nSlots + slot;
           wb.recA[0][ri] = recs[r].termA.c[0]; wb.recA[1][ri] = recs[r].termA.c[1]; wb.recA[2][ri] = recs[r].termA.c[2];
@@ -1306,7 +1339,8 @@ static void carve_wave(Carver &c, WaveBuffers &wb, uint32_t nSlots, int directRe
   wb.surfIds = isPath ? c.take<uint32_t>(nSlots) : nullptr;
   wb.surfQueueIdx = isPath ? c.take<uint32_t>(nSlots) : nullptr;
   wb.camDiff = textured ? c.take<float>((size_t)12 * nSlots) : nullptr;
-  wb.surfMat = textured ? c.take<PbrtB200Material>(nSlots) : nullptr;
+  wb.surfMat = (textured && isPath) ? c.take<PbrtB200Material>(nSlots) : nullptr;
+  wb.frameDiff = (textured && !isPath) ? c.take<float>((size_t)24 * nFrames * nSlots) : nullptr;
   wb.counts = c.take<uint32_t>(PB_COUNTS_TOTAL);
   wb.stats = c.take<unsigned long long>(ST_COUNT);
 }
@@ -1476,7 +1510,8 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
       uint32_t *nMain = &wb.counts[4 * it], *nShadow = &wb.counts[4 * it + 1], *nProbe = &wb.counts[4 * it + 2];
       uint32_t *nNext = &wb.counts[4 * (it + 1)];
       launch_traversals_a(h, count, grid, wb.q[cur], nMain, nextWork());
-      TIMED(KC_SHADE, (k_shade_wd<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], nMain, nextWork(), nShadow, nProbe)));
+      if (h->textured) TIMED(KC_SHADE, (k_shade_wd<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], nMain, nextWork(), nShadow, nProbe)));
+      else TIMED(KC_SHADE, (k_shade_wd<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], nMain, nextWork(), nShadow, nProbe)));
       launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork(), st);
       TIMED(KC_ADVANCE, (k_advance_wd<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], wb.q[cur ^ 1], nMain, nextWork(), nNext)));
       *launches += 5;

@@ -191,9 +191,7 @@ def scene(r, idx):
         out.append('AttributeBegin\nAreaLightSource "area" "color L" [%s] "integer nsamples" [%d]\nTranslate %s\nRotate %s 1 0 0\n%s\nAttributeEnd' % (
             rnd_color(r, 4, 15), r.randint(1, 3), f(r.uniform(-3, 3), r.uniform(3.5, 6), r.uniform(-2, 2)), f(r.choice([90, 90, 60, 200])), sh))
     color = None
-    if r.random() < .35:   # textures need the path integrator
-        integ = 'SurfaceIntegrator "path" "integer maxdepth" [%d]' % r.randint(1, 5)
-        out[5] = integ
+    if r.random() < .4:
         stmts, color = textures(r)
         out += stmts
 

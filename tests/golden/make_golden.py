@@ -511,7 +511,7 @@ Camera %s
 Film "image" "integer xresolution" [40] "integer yresolution" [28] %s "string filename" ["%s_out.exr"]
 %s
 PixelFilter %s
-SurfaceIntegrator "path" "integer maxdepth" [%d]
+SurfaceIntegrator %s
 WorldBegin
 """
 
@@ -526,8 +526,8 @@ AttributeEnd
 
 
 def _tex_scene(tag, body, camera='"perspective" "float fov" [40]', film="", sampler='Sampler "stratified" "integer xsamples" [2] "integer ysamples" [2]',
-               pfilter='"box"', depth=3):
-    return _TEX_HEAD % (camera, film, tag, sampler, pfilter, depth) + _TEX_LIGHTS.replace('"radius"', '"float radius"') + body + "WorldEnd\n"
+               pfilter='"box"', depth=3, integrator=None):
+    return _TEX_HEAD % (camera, film, tag, sampler, pfilter, integrator or '"path" "integer maxdepth" [%d]' % depth) + _TEX_LIGHTS.replace('"radius"', '"float radius"') + body + "WorldEnd\n"
 
 
 # uv mapping with scale/offset on a plane (EWA, strongly anisotropic towards the horizon), a pow2 map on a
@@ -664,6 +664,72 @@ INLINE["tex_bc_ortho_path"] = _tex_scene("tex_bc_ortho_path", _TEX_SMALL, camera
                                          sampler='Sampler "bestcandidate" "integer pixelsamples" [3]', pfilter='"gaussian"')
 INLINE["tex_env_random_path"] = _tex_scene("tex_env_random_path", _TEX_SMALL, camera='"environment"',
                                            sampler='Sampler "random" "integer xsamples" [2] "integer ysamples" [1]')
+
+
+# Whitted / DirectLighting: ray differentials carried through specular reflection and refraction
+# (whitted.cpp:86-131): curved mirrors and glass (dndu, dndv of quadrics), a mirror mesh with shading
+# normals, an instanced mirror, nested transmission, all looking at image-mapped surfaces
+_TEX_SPECULAR = """Texture "img" "color" "imagemap" "string filename" ["tex13x7.exr"] "float uscale" [6] "float vscale" [6]
+Texture "chk" "color" "imagemap" "string filename" ["tex8x16.exr"] "float uscale" [3] "float vscale" [2] %s
+Texture "fr" "float" "imagemap" "string filename" ["tex5x5.exr"]
+Material "matte" "texture Kd" "img"
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-9 -1 -9 9 -1 -9 9 -1 9 -9 -1 9] "float uv" [0 0 1 0 1 1 0 1]
+Material "plastic" "texture Kd" "chk" "color Ks" [.1 .1 .1]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-9 -1 6 9 -1 6 9 8 6 -9 8 6] "float uv" [0 0 1 0 1 1 0 1]
+AttributeBegin
+Material "mirror" "texture Kr" "chk"
+Translate -2.3 0.6 0.5
+Shape "sphere" "float radius" [1.5]
+AttributeEnd
+AttributeBegin
+Material "glass" "float index" [1.4] "color Kr" [.7 .7 .7]
+Translate 1.2 0.1 -2.2
+Scale 1 1.2 .8
+Shape "sphere" "float radius" [1]
+AttributeEnd
+AttributeBegin
+Material "uber" "texture Kd" "img" "color Ks" [.1 .1 .1] "color Kr" [.6 .6 .6] "texture roughness" "fr"
+Translate 3 -1 1.5
+Rotate -90 1 0 0
+Shape "cylinder" "float radius" [.9] "float zmin" [0] "float zmax" [2.6]
+AttributeEnd
+ObjectBegin "m"
+Material "mirror"
+%s
+ObjectEnd
+AttributeBegin
+Translate 0.3 1.2 3.5
+Rotate 20 0 1 0
+Scale 1.2 1 -1
+ObjectInstance "m"
+AttributeEnd
+ObjectBegin "c"
+AttributeBegin
+Material "shinymetal" "color Ks" [.7 .5 .9] "color Kr" [.9 .5 .4] "float roughness" [.1]
+Rotate -70 1 0 0
+Shape "cone" "float radius" [.8] "float height" [1.2]
+AttributeEnd
+ObjectEnd
+AttributeBegin
+Translate 2.2 0.2 -2.6
+Rotate 30 0 0 1
+Scale -1.1 1.4 .8
+ObjectInstance "c"
+AttributeEnd
+AttributeBegin
+Material "glass" "texture Kt" "chk" "float index" [1.6]
+Translate -0.6 -0.6 -3.6
+Rotate 30 1 1 0
+Shape "paraboloid" "float radius" [.5] "float zmax" [.8]
+AttributeEnd
+"""
+INLINE["tex_whitted"] = _tex_scene("tex_whitted", _TEX_SPECULAR % ("", _latlong_mesh(8, 5, 1.1, .9, 1.0)), integrator='"whitted" "integer maxdepth" [4]')
+INLINE["tex_direct_all"] = _tex_scene("tex_direct_all", _TEX_SPECULAR % ('"bool trilinear" ["true"]', _latlong_mesh(8, 5, 1.1, .9, 1.0)),
+                                      integrator='"directlighting" "integer maxdepth" [3] "string strategy" ["all"]', pfilter='"mitchell"')
+INLINE["tex_direct_one_dof"] = _tex_scene("tex_direct_one_dof", _TEX_SPECULAR % ('"string wrap" ["clamp"]', _latlong_mesh(8, 5, 1.1, .9, 1.0)),
+                                          camera='"perspective" "float fov" [40] "float lensradius" [.1] "float focaldistance" [8]',
+                                          sampler='Sampler "lowdiscrepancy" "integer pixelsamples" [4]',
+                                          integrator='"directlighting" "integer maxdepth" [4] "string strategy" ["one"]')
 
 
 def _bestcandidate(integrator, tag, sampler, film='"integer xresolution" [28] "integer yresolution" [20]', lens="", nsamples=1, pfilter='"box"'):
