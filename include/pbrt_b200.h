@@ -185,8 +185,10 @@ typedef struct PbrtB200Light {
   float    area;                   /* shape->Area()                           */
   float    cos_total_width;        /* spot: cosf(Radians(coneangle))          */
   float    cos_falloff_start;      /* spot: cosf(Radians(coneangle - conedeltaangle)) */
-  float    w2l[9];                 /* spot: upper 3x3 of WorldToLight (rows), for Falloff() */
-  uint32_t pad[2];
+  float    w2l[9];                 /* spot, infinite: upper 3x3 of WorldToLight (rows): Falloff(), radiance-map lookup */
+  uint32_t radiance_map;           /* infinite: 1 + index in textures[] of the IMAGEMAP node holding the "mapname"
+                                      pyramid (lights/infinite.cpp:63-86), 0 = constant Lbase */
+  uint32_t pad;
 } PbrtB200Light;
 
 /* cameras/perspective.cpp:51-82, cameras/orthographic.cpp:49-78, cameras/environment.cpp:49-63,

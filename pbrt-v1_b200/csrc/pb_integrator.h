@@ -322,7 +322,23 @@ PB_HD Spec delta_light_sample(const PbrtB200Light &light, const V3 &p, V3 *wi, R
 
 // InfiniteAreaLight::Sample_L(p, n, u1, u2, ..), lights/infinite.cpp:88-109: cosine-weighted direction
 // about n, the hemisphere chosen by one RandomFloat; visibility is an unbounded ray.
-PB_NOINLINE Spec infinite_light_sample_cosine(const PbrtB200Light &light, const V3 &p, const V3 &n, float u1, float u2,
+// InfiniteAreaLight::Le, lights/infinite.cpp:75-87: Lbase, times the radiance map looked up (MIPMap::Lookup(s, t),
+// i.e. filter width 0) at the direction's spherical coordinates in light space
+PB_NOINLINE Spec infinite_le(const SceneView &sv, const PbrtB200Light &l, const V3 &w) {
+  Spec L = spec3(l.color[0], l.color[1], l.color[2]);
+  if (l.radiance_map != 0) {
+    V3 wl = v3(l.w2l[0] * w.x + l.w2l[1] * w.y + l.w2l[2] * w.z, l.w2l[3] * w.x + l.w2l[4] * w.y + l.w2l[5] * w.z,
+               l.w2l[6] * w.x + l.w2l[7] * w.y + l.w2l[8] * w.z);
+    V3 wh = normalize(wl);
+    float ph = pb_atan2f(wh.y, wh.x);
+    float phi = (ph < 0.f) ? ph + 2.f * PB_PI : ph;
+    float s = phi * PB_INV_TWOPI;
+    float t = pb_acosf(pb_clamp(wh.z, -1.f, 1.f)) * PB_INV_PI;
+    L = L * mip_lookup_width(sv, sv.textures[l.radiance_map - 1], s, t, 0.f);
+  }
+  return L;
+}
+PB_NOINLINE Spec infinite_light_sample_cosine(const SceneView &sv, const PbrtB200Light &light, const V3 &p, const V3 &n, float u1, float u2,
                                               RngStream &rng, V3 *wi, float *pdf, Ray *shadow) {
   float x, y, z;
   concentric_sample_disk(u1, u2, &x, &y);
@@ -333,14 +349,14 @@ PB_NOINLINE Spec infinite_light_sample_cosine(const PbrtB200Light &light, const 
   coordinate_system(normalize(n), &v1, &v2);
   *wi = v3(v1.x * x + v2.x * y + n.x * z, v1.y * x + v2.y * y + n.y * z, v1.z * x + v2.z * y + n.z * z);
   shadow->o = p; shadow->d = *wi; shadow->mint = PB_RAY_EPSILON; shadow->maxt = PB_INFINITY;   // SetRay
-  return light_color(light);
+  return infinite_le(sv, light, *wi);   // Le(RayDifferential(p, *wi))
 }
 // Sum of lights[i]->Le(ray) over the scene's lights for a ray that left the scene (black for all but
 // infinite lights; adding a black spectrum changes nothing).
-PB_HD Spec escaped_le(const SceneView &sv) {
+PB_HD Spec escaped_le(const SceneView &sv, const V3 &d) {
   Spec L = spec(0.f);
   for (uint32_t i = 0; i < sv.nLights; ++i)
-    if (sv.lights[i].kind == PBRT_B200_LIGHT_INFINITE) L = L + light_color(sv.lights[i]);
+    if (sv.lights[i].kind == PBRT_B200_LIGHT_INFINITE) L = L + infinite_le(sv, sv.lights[i], d);
   return L;
 }
 
@@ -363,7 +379,7 @@ PB_HD void estimate_direct(const SceneView &sv, int lightNum, const V3 &p, const
     lightPdf = 1.f;
     Li = delta_light_sample(light, p, &wi, &rec->shadow);
   } else if (isInfinite) {
-    Li = infinite_light_sample_cosine(light, p, n, ls1, ls2, rng, &wi, &lightPdf, &rec->shadow);
+    Li = infinite_light_sample_cosine(sv, light, p, n, ls1, ls2, rng, &wi, &lightPdf, &rec->shadow);
   } else {
     V3 ns;
     V3 ps = area_light_sample_point<LK>(sv, light, p, ls1, ls2, rng, &ns);
@@ -398,7 +414,8 @@ PB_HD void estimate_direct(const SceneView &sv, int lightNum, const V3 &p, const
         rec->hasProbe = true;
         rec->probe.o = p; rec->probe.d = wi;
         rec->probe.mint = PB_RAY_EPSILON; rec->probe.maxt = PB_INFINITY;
-        Spec Le = light_color(light) * spec(1.f);   // Li *= scene->Transmittance(ray)
+        // the probe left the scene: light->Le(ray) (transport.cpp:184-185); constant for an area light
+        Spec Le = (isInfinite ? infinite_le(sv, light, wi) : light_color(light)) * spec(1.f);   // Li *= scene->Transmittance(ray)
         rec->termB = f * Le * absdot(wi, n) * weight / bsdfPdf;
       }
     }
@@ -463,11 +480,11 @@ PB_HD bool path_vertex_surface(const SceneView &sv, PathState &st, const Ray &ra
     if (sv.nInfiniteLights != 0) {
       if (pathLength == 0) {
         for (uint32_t i = 0; i < sv.nLights; ++i)
-          if (sv.lights[i].kind == PBRT_B200_LIGHT_INFINITE) st.L = st.L + light_color(sv.lights[i]);
+          if (sv.lights[i].kind == PBRT_B200_LIGHT_INFINITE) st.L = st.L + infinite_le(sv, sv.lights[i], ray.d);
         st.alpha = is_black(st.L) ? 0.f : 1.f;
       } else if (st.specularBounce) {
         for (uint32_t i = 0; i < sv.nLights; ++i)
-          if (sv.lights[i].kind == PBRT_B200_LIGHT_INFINITE) st.L = st.L + st.T * light_color(sv.lights[i]);
+          if (sv.lights[i].kind == PBRT_B200_LIGHT_INFINITE) st.L = st.L + st.T * infinite_le(sv, sv.lights[i], ray.d);
       }
     }
     return false;
@@ -610,7 +627,7 @@ PB_HD void wd_vertex(const SceneView &sv, const PatternSource &key0, const Ray &
     // whitted.cpp:52-59, directlighting.cpp:185-192
     if (alpha) *alpha = 0.f;
     if (sv.nInfiniteLights != 0) {
-      fr->L = fr->L + escaped_le(sv);
+      fr->L = fr->L + escaped_le(sv, ray.d);
       if (alpha && !is_black(fr->L)) *alpha = 1.f;
     }
     return;
@@ -641,7 +658,7 @@ PB_HD void wd_vertex(const SceneView &sv, const PatternSource &key0, const Ray &
         wi = uniform_sample_sphere(u1, u2);
         float pdf = 1.f / (4.f * PB_PI);   // UniformSpherePdf, mc.cpp:82-84
         rec->shadow.o = p; rec->shadow.d = wi; rec->shadow.mint = PB_RAY_EPSILON; rec->shadow.maxt = PB_INFINITY;
-        Li = light_color(light) / pdf;
+        Li = infinite_le(sv, light, wi) / pdf;
       } else if (light.kind != PBRT_B200_LIGHT_AREA) {
         Li = delta_light_sample(light, p, &wi, &rec->shadow);
       } else {

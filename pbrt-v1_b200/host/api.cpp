@@ -234,6 +234,7 @@ int OperandNode(TextureStore &st, float v, int32_t node) {
   return node >= 0 ? node : st.AddConstant(c, 1);
 }
 }  // namespace
+TextureStore &CurrentTextureStore() { return renderOptions->textures; }
 void pbrtTexture(const string &name, const string &type, const string &texname,
                  const ParamSet &params) {
   if (!InWorld("Texture")) return;

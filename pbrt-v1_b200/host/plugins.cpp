@@ -136,16 +136,25 @@ class DistantLight : public Light {  // lights/distant.cpp:53-59
   }
   Vector lightDir; Spectrum L;
 };
-class InfiniteAreaLight : public Light {   // lights/infinite.cpp:70-86 (no radiance map: Le is the constant Lbase)
+class InfiniteAreaLight : public Light {   // lights/infinite.cpp:63-87
  public:
-  InfiniteAreaLight(const Transform &light2world, const Spectrum &L, int ns) : Light(light2world, ns), Lbase(L) {}
+  InfiniteAreaLight(const Transform &light2world, const Spectrum &L, int ns, const string &texmap)
+      : Light(light2world, ns), Lbase(L), radianceMap(-1) {
+    if (texmap != "") radianceMap = CurrentTextureStore().AddRadianceMap(texmap);
+  }
   void Flatten(FlatBuilder &, PbrtB200Light *out) const {
     memset(out, 0, sizeof(*out));
     out->kind = PBRT_B200_LIGHT_INFINITE;
     out->n_samples = nSamples;
     for (int i = 0; i < 3; ++i) out->color[i] = Lbase.c[i];
+    out->radiance_map = (uint32_t)(radianceMap + 1);
+    Transform WorldToLight = LightToWorld.GetInverse();
+    const Matrix4x4 &m = WorldToLight.GetMatrix();
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) out->w2l[3 * i + j] = m.m[i][j];
   }
   Spectrum Lbase;
+  int radianceMap;   // texture-table entry holding the pyramid, or -1
 };
 class SpotLight : public Light {     // lights/spot.cpp:51-58
  public:
@@ -522,10 +531,7 @@ Light *MakeLight(const string &name, const Transform &light2world, const ParamSe
     Spectrum L = paramSet.FindOneSpectrum("L", Spectrum(1.0));
     string texmap = paramSet.FindOneString("mapname", "");
     int nSamples = paramSet.FindOneInt("nsamples", 1);
-    if (texmap != "")
-      Error("infinite light: radiance maps are outside the B200 hot-path scope (\"%s\" ignored: constant L, as "
-            "the reference does when the map cannot be read).", texmap.c_str());
-    Light *l = new InfiniteAreaLight(light2world, L, nSamples);
+    Light *l = new InfiniteAreaLight(light2world, L, nSamples, texmap);
     paramSet.ReportUnused();
     return l;
   }

@@ -385,3 +385,32 @@ int TextureStore::AddImageMap(const Transform &tex2world, const TextureParams &t
   nodes.push_back(t);
   return (int)nodes.size() - 1;
 }
+int TextureStore::AddRadianceMap(const string &filename) {
+  PbrtB200Texture t;
+  memset(&t, 0, sizeof(t));
+  t.kind = PBRT_B200_TEX_IMAGEMAP;
+  t.channels = 3;
+  for (int i = 0; i < 3; ++i) t.arg[i] = -1;
+  t.mapping = PBRT_B200_TEXMAP_UV;
+  t.su = t.sv = 1.f;
+  t.wrap = PBRT_B200_TEXWRAP_REPEAT;
+  t.max_anisotropy = 8.f;
+  string key = filename + "|0|3";   // same pyramid as a repeat-wrapped color image map of the file
+  std::map<string, std::pair<uint32_t, uint32_t> >::iterator it = pyramids.find(key);
+  if (it == pyramids.end()) {
+    int width = 0, height = 0;
+    Spectrum *texels = ReadImage(ResolveDataFile(filename), &width, &height);
+    if (!texels) return -1;
+    Plane img;
+    img.w = width; img.h = height; img.ch = 3;
+    img.v.resize((size_t)width * height * 3);
+    for (int i = 0; i < width * height; ++i)
+      for (int c = 0; c < 3; ++c) img.v[3 * (size_t)i + c] = texels[i].c[c];
+    delete[] texels;
+    it = pyramids.insert(std::make_pair(key, BuildPyramid(*this, img, PBRT_B200_TEXWRAP_REPEAT))).first;
+  }
+  t.first_level = it->second.first;
+  t.n_levels = it->second.second;
+  nodes.push_back(t);
+  return (int)nodes.size() - 1;
+}

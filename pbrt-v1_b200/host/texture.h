@@ -19,10 +19,14 @@ struct TextureStore {
   void Clear() { nodes.clear(); levels.clear(); texels.clear(); pyramids.clear(); }
   int AddConstant(const float v[3], int channels);
   int AddImageMap(const Transform &tex2world, const TextureParams &tp, int channels);
+  // InfiniteAreaLight's radiance map: `new MIPMap<Spectrum>(w, h, texels)` with the constructor's defaults
+  // (lights/infinite.cpp:63-73); -1 when the file cannot be read (the light then keeps its constant Lbase)
+  int AddRadianceMap(const string &filename);
   int AddScale(int a, int b, int channels);
   int AddMix(int a, int b, int amount, int channels);
   int Depth(int node) const;
 };
 // Spectrum texels of an OpenEXR file (R, G, B read as HALF), NULL with an error message when unreadable
 Spectrum *ReadImage(const string &name, int *width, int *height);
+TextureStore &CurrentTextureStore();   // the texture table of the world block being described (api.cpp)
 #endif

@@ -183,7 +183,11 @@ def scene(r, idx):
         elif k == "distant":
             out.append('LightSource "distant" "color L" [%s] "point from" [%s] "point to" [0 0 0]' % (rnd_color(r, .5, 2), f(r.uniform(-3, 3), 5, r.uniform(-5, 0))))
         else:
-            out.append('LightSource "infinite" "color L" [%s] "integer nsamples" [%d]' % (rnd_color(r, .2, 1), r.randint(1, 3)))
+            lmap = ""
+            if r.random() < .5:
+                lmap = ' "string mapname" ["%s"]' % os.path.join(GOLDEN, r.choice(["tex13x7.exr", "tex8x16.exr", "tex5x5.exr"]))
+            out.append('AttributeBegin\nRotate %s 1 .3 0\nLightSource "infinite" "color L" [%s] "integer nsamples" [%d]%s\nAttributeEnd' % (
+                f(r.uniform(0, 360)), rnd_color(r, .2, 1), r.randint(1, 3), lmap))
     for _ in range(r.randint(0 if nl else 1, 2)):
         sh = r.choice(['Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-1 0 -1 1 0 -1 1 0 1 -1 0 1]',
                        'Shape "sphere" "float radius" [.5]', 'Shape "disk" "float radius" [.9]',

@@ -327,6 +327,21 @@ INLINE["infinite_direct_one"] = _infinite('"directlighting" "integer maxdepth" [
 INLINE["infinite_whitted"] = _infinite('"whitted" "integer maxdepth" [3]', "whitted", _INF_AREA)
 
 
+
+def _infinite_map(integrator, tag, extra=""):
+    """radiance-mapped infinite light ("mapname", lights/infinite.cpp:63-87) under a rotated, scaled light space"""
+    return _infinite(integrator, tag, extra).replace(
+        'LightSource "infinite" "color L" [.7 .8 1.1] "integer nsamples" [2]',
+        'AttributeBegin\nRotate -90 1 0 0\nRotate 40 0 0 1\nScale 1 1.5 -1\n'
+        'LightSource "infinite" "color L" [1.4 1.3 1.2] "integer nsamples" [2] "string mapname" ["tex8x16.exr"]\nAttributeEnd')
+
+
+INLINE["infinite_map_path"] = _infinite_map('"path" "integer maxdepth" [4]', "map_path", _INF_AREA)
+INLINE["infinite_map_direct"] = _infinite_map('"directlighting" "integer maxdepth" [3]', "map_direct")
+INLINE["infinite_map_direct_one"] = _infinite_map('"directlighting" "integer maxdepth" [3] "string strategy" ["one"]', "map_direct_one", _INF_AREA)
+INLINE["infinite_map_whitted"] = _infinite_map('"whitted" "integer maxdepth" [3]', "map_whitted", _INF_AREA)
+
+
 def _latlong_mesh(nphi, ntheta, rx, ry, rz, normals=True):
     """a small closed lat-long mesh (optionally with per-vertex N and uv) as a trianglemesh statement"""
     import math
