@@ -156,7 +156,10 @@ typedef struct PbrtB200Texture {
 } PbrtB200Texture;
 enum { PBRT_B200_TEXSLOT_KD = 0, PBRT_B200_TEXSLOT_KS = 1, PBRT_B200_TEXSLOT_KR = 2, PBRT_B200_TEXSLOT_KT = 3,
        PBRT_B200_TEXSLOT_OPACITY = 4, PBRT_B200_TEXSLOT_SIGMA = 5, PBRT_B200_TEXSLOT_INDEX = 6,
-       PBRT_B200_TEXSLOT_ROUGHNESS = 7, PBRT_B200_TEXSLOTS = 8 };
+       PBRT_B200_TEXSLOT_ROUGHNESS = 7,
+       PBRT_B200_TEXSLOT_BUMP = 8,   /* "bumpmap": the displacement of Material::Bump (core/material.cpp:29-71); has no
+                                        constant in the record -- absent (-1) means the reference's default constant 0 */
+       PBRT_B200_TEXSLOTS = 9 };
 typedef struct PbrtB200Material {    /* 112 bytes */
   int32_t kind;
   float   kd[3];                   /* matte / plastic / uber                  */
@@ -168,7 +171,6 @@ typedef struct PbrtB200Material {    /* 112 bytes */
   float   index;                   /* glass: index of refraction              */
   float   roughness;               /* plastic / uber / shinymetal             */
   int32_t tex[PBRT_B200_TEXSLOTS]; /* texture node per operand (PBRT_B200_TEXSLOT_*), -1 = the constant above */
-  float   pad;
 } PbrtB200Material;
 
 /* lights/point.cpp:49-54, lights/area.cpp:28-57, core/shape.h:113-147 */

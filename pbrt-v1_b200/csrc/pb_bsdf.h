@@ -466,15 +466,22 @@ PB_HD void bsdf_set_lobes(const PbrtB200Material &m, Bsdf *b);
 // material adds.
 // LOBES = false builds only the shading frame (the path integrator's surface kernel stores the frame
 // and a later kernel rebuilds the lobes from the material record).
+// The displacement samples of Material::Bump (core/material.cpp:33-56).  Every material calls Bump(): an absent
+// "bumpmap" is the constant texture 0 (materials/*.cpp CreateMaterial), for which all three samples are 0.
+struct BumpSamples {
+  float du, dv;               // shift distances (.01 when the screen-space derivatives are zero)
+  float uDisplace, vDisplace, displace;
+};
 template <bool LOBES = true>
 PB_HD void make_bsdf(const PbrtB200Material &m, const DiffGeom &dgGeom, const DiffGeom &dgs,
-                     uint32_t shapeFlags, Bsdf *b) {
-  // dgBump->dpdu = dgs.dpdu + (0 - 0) / du * nn + 0 * dndu: evaluated literally so that
-  // signed zeros / non-finite normals behave as in the reference; du = .01 when the
-  // screen-space differentials are zero or unused.
-  float zero_over_du = 0.f / .01f;
-  V3 dpdu = dgs.dpdu + zero_over_du * dgs.nn + 0.f * dgs.dndu;
-  V3 dpdv = dgs.dpdv + zero_over_du * dgs.nn + 0.f * dgs.dndv;
+                     uint32_t shapeFlags, Bsdf *b, const BumpSamples *bump = (const BumpSamples *)0) {
+  // dgBump->dpdu = dgs.dpdu + (uDisplace - displace) / du * nn + displace * dndu (material.cpp:58-63),
+  // evaluated literally also for the constant-0 displacement so that signed zeros / non-finite normals
+  // behave as in the reference (0 / du is the same 0 for every du)
+  float du = .01f, dv = .01f, uDisplace = 0.f, vDisplace = 0.f, displace = 0.f;
+  if (bump) { du = bump->du; dv = bump->dv; uDisplace = bump->uDisplace; vDisplace = bump->vDisplace; displace = bump->displace; }
+  V3 dpdu = dgs.dpdu + (uDisplace - displace) / du * dgs.nn + displace * dgs.dndu;
+  V3 dpdv = dgs.dpdv + (vDisplace - displace) / dv * dgs.nn + displace * dgs.dndv;
   V3 nn = normalize(cross(dpdu, dpdv));
   bool ro = (shapeFlags & PBRT_B200_PF_REVERSE) != 0, sh = (shapeFlags & PBRT_B200_PF_SWAPS) != 0;
   if (ro ^ sh) nn = nn * -1.f;

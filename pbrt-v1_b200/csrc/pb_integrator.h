@@ -65,6 +65,25 @@ PB_HD void surface_dg(const SceneView &sv, const Ray &rayWorld, const Hit &hit, 
   if (instanced) instance_dg_to_world(sv.instances[hit.inst], dg);
 }
 // Intersection::GetBSDF (core/primitive.cpp:126-141)
+// Material::Bump's three evaluations of the displacement texture (core/material.cpp:33-56): at the point
+// shifted along the shading dpdu, along dpdv, and at the point itself.  Of the shifted
+// DifferentialGeometry only p, u, v and the inherited screen-space derivatives reach a texture in scope.
+PB_NOINLINE void bump_samples(const SceneView &sv, int32_t node, const DiffGeom &dgs, const DgDiff &dd, BumpSamples *o) {
+  DiffGeom e = dgs;
+  float du = .5f * (fabsf(dd.dudx) + fabsf(dd.dudy));
+  if (du == 0.f) du = .01f;
+  e.p = dgs.p + du * dgs.dpdu;
+  e.u = dgs.u + du;
+  o->uDisplace = tex_eval<PB_TEX_MAX_DEPTH>(sv, node, e, dd).c[0];
+  float dv = .5f * (fabsf(dd.dvdx) + fabsf(dd.dvdy));
+  if (dv == 0.f) dv = .01f;
+  e.p = dgs.p + dv * dgs.dpdv;
+  e.u = dgs.u;
+  e.v = dgs.v + dv;
+  o->vDisplace = tex_eval<PB_TEX_MAX_DEPTH>(sv, node, e, dd).c[0];
+  o->displace = tex_eval<PB_TEX_MAX_DEPTH>(sv, node, dgs, dd).c[0];
+  o->du = du; o->dv = dv;
+}
 // TEX = true evaluates the material's texture operands at the hit (dg.ComputeDifferentials(ray) and the
 // `Kd->Evaluate(dgs)` calls of Material::GetBSDF); `rd` holds the ray's differentials or is null, `evalMat`
 // (optional) receives the material record with every textured operand replaced by its value here.
@@ -93,7 +112,10 @@ PB_HD void surface_at_hit(const SceneView &sv, const Ray &ray, const Hit &hit, S
     DgDiff dd;
     compute_differentials(dg, rd, &dd);
     material_eval_textures(sv, dg, dd, &m);
-    make_bsdf<LOBES>(m, dg, dgs, tv.flags, &sf->bsdf);
+    BumpSamples bump;
+    const bool bumped = m.tex[PBRT_B200_TEXSLOT_BUMP] >= 0;
+    if (bumped) bump_samples(sv, m.tex[PBRT_B200_TEXSLOT_BUMP], dgs, dd, &bump);
+    make_bsdf<LOBES>(m, dg, dgs, tv.flags, &sf->bsdf, bumped ? &bump : (const BumpSamples *)0);
     if (evalMat) *evalMat = m;
     if (sd) { sd->dd = dd; sd->dndu = dgs.dndu; sd->dndv = dgs.dndv; }
   } else

@@ -257,7 +257,7 @@ PB_NOINLINE void material_eval_textures(const SceneView &sv, const DiffGeom &dg,
 #pragma unroll 1
   for (int i = 0; i < PBRT_B200_TEXSLOTS; ++i) {
     int32_t id = m->tex[i];
-    if (id < 0) continue;
+    if (id < 0 || i == PBRT_B200_TEXSLOT_BUMP) continue;   // the displacement is sampled by bump_samples()
     Spec v = tex_eval<PB_TEX_MAX_DEPTH>(sv, id, dg, dd);
     if (i <= PBRT_B200_TEXSLOT_OPACITY) {
       float *dst = i == PBRT_B200_TEXSLOT_KD ? m->kd : i == PBRT_B200_TEXSLOT_KS ? m->ks : i == PBRT_B200_TEXSLOT_KR ? m->kr

@@ -404,16 +404,22 @@ struct TexSlots {
   Material *Attach(Material *m) const { memcpy(m->tex, t, sizeof(t)); return m; }
   int32_t t[PBRT_B200_TEXSLOTS];
 };
-static void NoBump(const TextureParams &mp) {   // constant 0: Material::Bump degenerates (material.cpp:29-71)
+// "bumpmap" (Material::Bump, core/material.cpp:29-71): the default constant 0 leaves the slot empty (the device
+// evaluates Bump with zero displacement); any other constant becomes a constant node
+static void Bumpmap(const TextureParams &mp, TexSlots *ts) {
   int32_t node;
-  mp.GetFloatTexture("bumpmap", 0.f, &node);
-  if (node >= 0) Error("Bump mapping is outside the B200 hot-path scope; \"bumpmap\" ignored.");
+  float v = mp.GetFloatTexture("bumpmap", 0.f, &node);
+  if (node < 0 && v != 0.f) {
+    float c[3] = {v, v, v};
+    node = CurrentTextureStore().AddConstant(c, 1);
+  }
+  ts->t[PBRT_B200_TEXSLOT_BUMP] = node;
 }
 static Material *CreateMatte(const Transform &, const TextureParams &mp) {
   TexSlots ts;
   Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KD]);
   float sigma = mp.GetFloatTexture("sigma", 0.f, &ts.t[PBRT_B200_TEXSLOT_SIGMA]);
-  NoBump(mp);
+  Bumpmap(mp, &ts);
   return ts.Attach(new Matte(Kd, sigma));
 }
 static Material *CreateGlass(const Transform &, const TextureParams &mp) {
@@ -421,7 +427,7 @@ static Material *CreateGlass(const Transform &, const TextureParams &mp) {
   Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KR]);
   Spectrum Kt = mp.GetSpectrumTexture("Kt", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KT]);
   float index = mp.GetFloatTexture("index", 1.5f, &ts.t[PBRT_B200_TEXSLOT_INDEX]);
-  NoBump(mp);
+  Bumpmap(mp, &ts);
   return ts.Attach(new Glass(Kr, Kt, index));
 }
 static Material *CreatePlastic(const Transform &, const TextureParams &mp) {
@@ -429,7 +435,7 @@ static Material *CreatePlastic(const Transform &, const TextureParams &mp) {
   Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KD]);
   Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KS]);
   float roughness = mp.GetFloatTexture("roughness", .1f, &ts.t[PBRT_B200_TEXSLOT_ROUGHNESS]);
-  NoBump(mp);
+  Bumpmap(mp, &ts);
   return ts.Attach(new Plastic(Kd, Ks, roughness));
 }
 static Material *CreateUber(const Transform &, const TextureParams &mp) {   // materials/uber.cpp:86-95
@@ -439,7 +445,7 @@ static Material *CreateUber(const Transform &, const TextureParams &mp) {   // m
   Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(0.f), &ts.t[PBRT_B200_TEXSLOT_KR]);
   float roughness = mp.GetFloatTexture("roughness", .1f, &ts.t[PBRT_B200_TEXSLOT_ROUGHNESS]);
   Spectrum opacity = mp.GetSpectrumTexture("opacity", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_OPACITY]);
-  NoBump(mp);
+  Bumpmap(mp, &ts);
   return ts.Attach(new UberMaterial(Kd, Ks, Kr, roughness, opacity));
 }
 static Material *CreateTranslucent(const Transform &, const TextureParams &mp) {   // materials/translucent.cpp:85-94
@@ -449,7 +455,7 @@ static Material *CreateTranslucent(const Transform &, const TextureParams &mp) {
   Spectrum reflect = mp.GetSpectrumTexture("reflect", Spectrum(0.5f), &ts.t[PBRT_B200_TEXSLOT_KR]);
   Spectrum transmit = mp.GetSpectrumTexture("transmit", Spectrum(0.5f), &ts.t[PBRT_B200_TEXSLOT_KT]);
   float roughness = mp.GetFloatTexture("roughness", .1f, &ts.t[PBRT_B200_TEXSLOT_ROUGHNESS]);
-  NoBump(mp);
+  Bumpmap(mp, &ts);
   return ts.Attach(new Translucent(Kd, Ks, roughness, reflect, transmit));
 }
 static Material *CreateSubstrate(const Transform &, const TextureParams &mp) {   // materials/substrate.cpp:64-73
@@ -458,7 +464,7 @@ static Material *CreateSubstrate(const Transform &, const TextureParams &mp) {  
   Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(.5f), &ts.t[PBRT_B200_TEXSLOT_KS]);
   float uroughness = mp.GetFloatTexture("uroughness", .1f, &ts.t[PBRT_B200_TEXSLOT_ROUGHNESS]);
   float vroughness = mp.GetFloatTexture("vroughness", .1f, &ts.t[PBRT_B200_TEXSLOT_SIGMA]);
-  NoBump(mp);
+  Bumpmap(mp, &ts);
   return ts.Attach(new Substrate(Kd, Ks, uroughness, vroughness));
 }
 static Material *CreateShinyMetal(const Transform &, const TextureParams &mp) {   // materials/shinymetal.cpp:66-73
@@ -466,13 +472,13 @@ static Material *CreateShinyMetal(const Transform &, const TextureParams &mp) { 
   Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KR]);
   Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KS]);
   float roughness = mp.GetFloatTexture("roughness", .1f, &ts.t[PBRT_B200_TEXSLOT_ROUGHNESS]);
-  NoBump(mp);
+  Bumpmap(mp, &ts);
   return ts.Attach(new ShinyMetal(Ks, roughness, Kr));
 }
 static Material *CreateMirror(const Transform &, const TextureParams &mp) {
   TexSlots ts;
   Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KR]);
-  NoBump(mp);
+  Bumpmap(mp, &ts);
   return ts.Attach(new Mirror(Kr));
 }
 

@@ -66,6 +66,7 @@ def textures(r):
     out.append('Texture "frough" "float" "mix" "float tex1" [.02] "float tex2" [.5] "texture amount" "%s"' % r.choice(flt))
     out.append('Texture "findex" "float" "mix" "float tex1" [1.2] "float tex2" [1.8] "texture amount" "%s"' % r.choice(flt))
     out.append('Texture "fsigma" "float" "scale" "texture tex1" "%s" "float tex2" [50]' % r.choice(flt))
+    out.append('Texture "fbump" "float" "scale" "texture tex1" "%s" "float tex2" [%s]' % (r.choice(flt), f(r.uniform(-.3, .3))))
     return out, color
 
 
@@ -77,6 +78,8 @@ def retexture(r, mat, color):
     def fsub(m):
         name = {"sigma": "fsigma", "index": "findex"}.get(m.group(1), "frough")
         return '"texture %s" "%s"' % (m.group(1), name) if r.random() < .5 else m.group(0)
+    if r.random() < .3:
+        mat += ' "texture bumpmap" "%s"' % r.choice(["fbump", "frough"])
     mat = re.sub(r'"color (Kd|Ks|Kr|Kt|opacity|reflect|transmit)" \[[^\]]*\]', csub, mat)
     return re.sub(r'"float (sigma|index|roughness|uroughness|vroughness)" \[[^\]]*\]', fsub, mat)
 
@@ -201,7 +204,9 @@ def scene(r, idx):
 
     def mat():
         m = material(r)
-        return retexture(r, m, color) if color else m
+        if color:
+            return retexture(r, m, color)
+        return m + (' "float bumpmap" [%s]' % f(r.uniform(-.2, .2)) if r.random() < .1 else "")
     out.append('Texture "tc" "color" "constant" "color value" [%s]' % rnd_color(r))
     out.append('Texture "tm" "color" "mix" "texture tex1" "tc" "color tex2" [%s] "float amount" [%s]' % (rnd_color(r), f(r.uniform(0, 1))))
     out.append('Material "matte" "texture Kd" "tm"')

@@ -747,6 +747,49 @@ INLINE["tex_direct_one_dof"] = _tex_scene("tex_direct_one_dof", _TEX_SPECULAR % 
                                           integrator='"directlighting" "integer maxdepth" [4] "string strategy" ["one"]')
 
 
+# bump mapping (Material::Bump, core/material.cpp:29-71): image-mapped, expression and constant non-zero
+# displacements on a plane, quadrics, a mesh with shading normals and an instanced object, seen directly, in a
+# mirror (Whitted: the bumped shading normal drives the reflected differentials) and after diffuse bounces
+_TEX_BUMP = """Texture "img" "color" "imagemap" "string filename" ["tex13x7.exr"] "float uscale" [4] "float vscale" [4]
+Texture "h1" "float" "imagemap" "string filename" ["tex8x16.exr"] "float uscale" [5] "float vscale" [5]
+Texture "h2" "float" "imagemap" "string filename" ["tex5x5.exr"] "string mapping" ["spherical"] "bool trilinear" ["true"]
+Texture "h3" "float" "scale" "texture tex1" "h1" "float tex2" [.15]
+Texture "h4" "float" "mix" "float tex1" [-.05] "float tex2" [.1] "texture amount" "h2"
+Material "matte" "texture Kd" "img" "texture bumpmap" "h3"
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-9 -1 -9 9 -1 -9 9 -1 9 -9 -1 9] "float uv" [0 0 1 0 1 1 0 1]
+AttributeBegin
+Material "plastic" "color Kd" [.7 .3 .2] "color Ks" [.4 .4 .4] "float roughness" [.05] "texture bumpmap" "h4"
+Translate -2.2 0.5 0
+Shape "sphere" "float radius" [1.4]
+AttributeEnd
+AttributeBegin
+Material "mirror" "texture bumpmap" "h3"
+Translate 1.2 0.2 1.5
+Rotate -90 1 0 0
+Shape "cylinder" "float radius" [1.1] "float zmin" [-1.2] "float zmax" [1.6]
+AttributeEnd
+AttributeBegin
+Material "matte" "color Kd" [.3 .5 .7] "float bumpmap" [.2]
+Translate 0.2 -0.4 -3
+Shape "sphere" "float radius" [.6]
+AttributeEnd
+ObjectBegin "b"
+Material "uber" "color Kd" [.5 .5 .2] "color Ks" [.2 .2 .2] "color Kr" [.3 .3 .3] "texture bumpmap" "h1"
+%s
+ObjectEnd
+AttributeBegin
+Translate 3.2 0.4 -1
+Rotate 35 0 1 1
+Scale .9 1.2 -.8
+ObjectInstance "b"
+AttributeEnd
+"""
+INLINE["tex_bump_path"] = _tex_scene("tex_bump_path", _TEX_BUMP % _latlong_mesh(8, 5, .9, .8, .9), depth=3)
+INLINE["tex_bump_whitted"] = _tex_scene("tex_bump_whitted", _TEX_BUMP % _latlong_mesh(8, 5, .9, .8, .9), integrator='"whitted" "integer maxdepth" [3]')
+INLINE["tex_bump_direct"] = _tex_scene("tex_bump_direct", _TEX_BUMP % _latlong_mesh(8, 5, .9, .8, .9), integrator='"directlighting" "integer maxdepth" [3]',
+                                       sampler='Sampler "bestcandidate" "integer pixelsamples" [4]')
+
+
 def _bestcandidate(integrator, tag, sampler, film='"integer xresolution" [28] "integer yresolution" [20]', lens="", nsamples=1, pfilter='"box"'):
     """bestcandidate sampler (the reference's default when a scene names none)"""
     return """LookAt 278 273 -800 278 273 0 0 1 0
