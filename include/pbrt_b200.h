@@ -132,7 +132,17 @@ enum { PBRT_B200_MAT_MATTE = 0, PBRT_B200_MAT_GLASS = 1, PBRT_B200_MAT_MIRROR = 
  * (textures/{constant,scale,mix,imagemap}.cpp).  A material slot whose tex[] entry is >= 0 is evaluated at
  * every hit (Material::GetBSDF's `Kd->Evaluate(dgs)`), the others keep the constant in the record.
  * Operand nodes always come before the node that uses them; graphs are at most 3 operators deep. */
-enum { PBRT_B200_TEX_CONSTANT = 0, PBRT_B200_TEX_IMAGEMAP = 1, PBRT_B200_TEX_SCALE = 2, PBRT_B200_TEX_MIX = 3 };
+enum { PBRT_B200_TEX_CONSTANT = 0, PBRT_B200_TEX_IMAGEMAP = 1, PBRT_B200_TEX_SCALE = 2, PBRT_B200_TEX_MIX = 3,
+       /* procedural textures: textures/{uv,bilerp,checkerboard,dots,fbm,wrinkled,windy,marble}.cpp */
+       PBRT_B200_TEX_UV = 4,            /* 2D mapping only */
+       PBRT_B200_TEX_BILERP = 5,        /* param[0..11] = v00, v01, v10, v11 (3 floats each; a float texture repeats its value) */
+       PBRT_B200_TEX_CHECKERBOARD = 6,  /* 2D; arg[0], arg[1] = tex1, tex2; iparam[0] = aamode (PBRT_B200_CHECKER_*) */
+       PBRT_B200_TEX_DOTS = 7,          /* arg[0] = the "inside" parameter, arg[1] = "outside" (used swapped, like dots.cpp:38-42,89-90) */
+       PBRT_B200_TEX_FBM = 8,           /* 3D: world_to_texture holds IdentityMapping3D's matrix; iparam[0] = octaves, param[0] = roughness */
+       PBRT_B200_TEX_WRINKLED = 9,      /* as FBM, Turbulence() */
+       PBRT_B200_TEX_WINDY = 10,
+       PBRT_B200_TEX_MARBLE = 11        /* iparam[0] = octaves, param[0] = roughness, param[1] = scale, param[2] = variation */ };
+enum { PBRT_B200_CHECKER_NONE = 0, PBRT_B200_CHECKER_CLOSEDFORM = 2 };   /* "supersample" draws random numbers: not supported */
 enum { PBRT_B200_TEXMAP_UV = 0, PBRT_B200_TEXMAP_SPHERICAL = 1, PBRT_B200_TEXMAP_CYLINDRICAL = 2,
        PBRT_B200_TEXMAP_PLANAR = 3 };                       /* core/texture.cpp:66-149 */
 enum { PBRT_B200_TEXWRAP_REPEAT = 0, PBRT_B200_TEXWRAP_BLACK = 1, PBRT_B200_TEXWRAP_CLAMP = 2 };   /* core/mipmap.h:30-34 */
@@ -153,6 +163,8 @@ typedef struct PbrtB200Texture {
   float    v1[3], v2[3];             /* planar */
   float    world_to_texture[16];     /* spherical / cylindrical */
   uint32_t first_level, n_levels;    /* tex_levels[first_level .. first_level + n_levels), finest first */
+  float    param[12];                /* procedural textures, see PBRT_B200_TEX_* */
+  int32_t  iparam[2];
 } PbrtB200Texture;
 enum { PBRT_B200_TEXSLOT_KD = 0, PBRT_B200_TEXSLOT_KS = 1, PBRT_B200_TEXSLOT_KR = 2, PBRT_B200_TEXSLOT_KT = 3,
        PBRT_B200_TEXSLOT_OPACITY = 4, PBRT_B200_TEXSLOT_SIGMA = 5, PBRT_B200_TEXSLOT_INDEX = 6,

@@ -22,6 +22,7 @@
 #include "../pbrt-v1_b200/csrc/pb_camera.h"
 #include "../pbrt-v1_b200/csrc/pb_film.h"
 #include "../pbrt-v1_b200/csrc/pb_setup.h"
+#include "../pbrt-v1_b200/csrc/pb_noise_table.h"
 #include <vector>
 #include <string>
 #include <stdio.h>
@@ -40,6 +41,9 @@ bool build_view(const PbrtB200Scene &s, SceneView *sv) {
   sv->meshes = s.meshes; sv->quadrics = s.quadrics; sv->instances = s.instances;
   sv->bcTable = s.bestcandidate_table;
   sv->textures = s.textures; sv->texLevels = s.tex_levels; sv->texels = s.texels; sv->ewaLut = s.ewa_weight_lut;
+  static unsigned char noisePerm[2 * PB_NOISE_PERM_SIZE];
+  pb_noise_perm_fill(noisePerm);
+  sv->noisePerm = noisePerm;
   sv->vertexN = s.vertex_n; sv->vertexS = s.vertex_s; sv->vertexUV = s.vertex_uv;
   sv->materials = s.materials; sv->lights = s.lights;
   sv->lightShapes = s.light_shapes; sv->lightCdf = s.light_cdf;

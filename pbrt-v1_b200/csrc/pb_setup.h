@@ -46,8 +46,12 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
     }
   for (uint32_t i = 0; i < s.n_textures; ++i) {
     const PbrtB200Texture &t = s.textures[i];
-    if (t.kind > PBRT_B200_TEX_MIX || (t.channels != 1 && t.channels != 3)) return "unknown texture kind";
-    if (t.kind == PBRT_B200_TEX_SCALE || t.kind == PBRT_B200_TEX_MIX)
+    if (t.kind > PBRT_B200_TEX_MARBLE || (t.channels != 1 && t.channels != 3)) return "unknown texture kind";
+    if ((t.kind == PBRT_B200_TEX_UV || t.kind == PBRT_B200_TEX_BILERP || t.kind == PBRT_B200_TEX_CHECKERBOARD ||
+         t.kind == PBRT_B200_TEX_DOTS) && t.mapping > PBRT_B200_TEXMAP_PLANAR) return "unknown texture mapping or wrap mode";
+    if (t.kind == PBRT_B200_TEX_CHECKERBOARD && t.iparam[0] != PBRT_B200_CHECKER_NONE && t.iparam[0] != PBRT_B200_CHECKER_CLOSEDFORM)
+      return "checkerboard: unsupported anti-aliasing mode";
+    if (t.kind == PBRT_B200_TEX_SCALE || t.kind == PBRT_B200_TEX_MIX || t.kind == PBRT_B200_TEX_CHECKERBOARD || t.kind == PBRT_B200_TEX_DOTS)
       for (int k = 0; k < (t.kind == PBRT_B200_TEX_MIX ? 3 : 2); ++k)
         if (t.arg[k] < 0 || t.arg[k] >= (int32_t)i) return "texture operand must precede its user";
     if (t.kind == PBRT_B200_TEX_IMAGEMAP) {

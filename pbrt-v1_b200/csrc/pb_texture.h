@@ -222,6 +222,77 @@ PB_HD Spec mip_lookup(const SceneView &sv, const PbrtB200Texture &t, float s, fl
          d * mip_ewa(sv, t, s, tt, ds0, dt0, ds1, dt1, ilod + 1);
 }
 
+// ---------------------------------------------------------------- Perlin noise (core/texture.cpp:156-238)
+PB_HD float noise_grad(const unsigned char *perm, int x, int y, int z, float dx, float dy, float dz) {
+  int h = perm[perm[perm[x] + y] + z];
+  h &= 15;
+  float u = h < 8 || h == 12 || h == 13 ? dx : dy;
+  float v = h < 4 || h == 12 || h == 13 ? dy : dz;
+  return ((h & 1) ? -u : u) + ((h & 2) ? -v : v);
+}
+PB_HD float noise_weight(float t) {
+  float t3 = t * t * t;
+  float t4 = t3 * t;
+  return 6.f * t4 * t - 15.f * t4 + 10.f * t3;
+}
+PB_NOINLINE float pb_noise(const unsigned char *perm, float x, float y, float z) {
+  int ix = pb_floor2int(x), iy = pb_floor2int(y), iz = pb_floor2int(z);
+  float dx = x - ix, dy = y - iy, dz = z - iz;
+  ix &= 255; iy &= 255; iz &= 255;
+  float w000 = noise_grad(perm, ix, iy, iz, dx, dy, dz);
+  float w100 = noise_grad(perm, ix + 1, iy, iz, dx - 1, dy, dz);
+  float w010 = noise_grad(perm, ix, iy + 1, iz, dx, dy - 1, dz);
+  float w110 = noise_grad(perm, ix + 1, iy + 1, iz, dx - 1, dy - 1, dz);
+  float w001 = noise_grad(perm, ix, iy, iz + 1, dx, dy, dz - 1);
+  float w101 = noise_grad(perm, ix + 1, iy, iz + 1, dx - 1, dy, dz - 1);
+  float w011 = noise_grad(perm, ix, iy + 1, iz + 1, dx, dy - 1, dz - 1);
+  float w111 = noise_grad(perm, ix + 1, iy + 1, iz + 1, dx - 1, dy - 1, dz - 1);
+  float wx = noise_weight(dx), wy = noise_weight(dy), wz = noise_weight(dz);
+  float x00 = pb_lerp(wx, w000, w100), x10 = pb_lerp(wx, w010, w110);
+  float x01 = pb_lerp(wx, w001, w101), x11 = pb_lerp(wx, w011, w111);
+  float y0 = pb_lerp(wy, x00, x10), y1 = pb_lerp(wy, x01, x11);
+  return pb_lerp(wz, y0, y1);
+}
+PB_HD float pb_smoothstep(float mn, float mx, float value) {   // core/pbrt.h:660-663
+  float v = pb_clamp((value - mn) / (mx - mn), 0.f, 1.f);
+  return v * v * (-2.f * v + 3.f);
+}
+// FBm / Turbulence (TURB takes |Noise|), core/texture.cpp:203-238
+template <bool TURB>
+PB_NOINLINE float pb_fbm(const unsigned char *perm, const V3 &P, const V3 &dpdx, const V3 &dpdy, float omega, int maxOctaves) {
+  float s2 = pb_max(length_sq(dpdx), length_sq(dpdy));
+  float foctaves = pb_min((float)maxOctaves, 1.f - .5f * pb_log2(s2));
+  int octaves = pb_floor2int(foctaves);
+  float sum = 0.f, lambda = 1.f, o = 1.f;
+  for (int i = 0; i < octaves; ++i) {
+    float n = pb_noise(perm, lambda * P.x, lambda * P.y, lambda * P.z);
+    sum += o * (TURB ? fabsf(n) : n);
+    lambda *= 1.99f;
+    o *= omega;
+  }
+  float partialOctave = foctaves - octaves;
+  float n = pb_noise(perm, lambda * P.x, lambda * P.y, lambda * P.z);
+  sum += o * pb_smoothstep(.3f, .7f, partialOctave) * (TURB ? fabsf(n) : n);
+  return sum;
+}
+// MarbleTexture::Evaluate's colour spline, textures/marble.cpp:47-69
+PB_NOINLINE Spec marble_color(float marble) {
+  float t = .5f + .5f * pb_sinf(marble);
+  const float c[9][3] = {{.58f, .58f, .6f}, {.58f, .58f, .6f}, {.58f, .58f, .6f}, {.5f, .5f, .5f}, {.6f, .59f, .58f},
+                         {.58f, .58f, .6f}, {.58f, .58f, .6f}, {.2f, .2f, .33f}, {.58f, .58f, .6f}};
+  const int nseg = 9 - 3;
+  int first = pb_floor2int(t * nseg);
+  t = (t * nseg - first);
+  Spec c0 = spec3(c[first][0], c[first][1], c[first][2]), c1 = spec3(c[first + 1][0], c[first + 1][1], c[first + 1][2]);
+  Spec c2 = spec3(c[first + 2][0], c[first + 2][1], c[first + 2][2]), c3 = spec3(c[first + 3][0], c[first + 3][1], c[first + 3][2]);
+  Spec s0 = (1.f - t) * c0 + t * c1;
+  Spec s1 = (1.f - t) * c1 + t * c2;
+  Spec s2 = (1.f - t) * c2 + t * c3;
+  s0 = (1.f - t) * s0 + t * s1;
+  s1 = (1.f - t) * s1 + t * s2;
+  return 1.5f * ((1.f - t) * s0 + t * s1);
+}
+
 // ---------------------------------------------------------------- texture graphs
 // ImageTexture::Evaluate, textures/imagemap.cpp:122-128
 PB_NOINLINE Spec tex_image_eval(const SceneView &sv, const PbrtB200Texture &t, const DiffGeom &dg, const DgDiff &dd) {
@@ -232,6 +303,33 @@ PB_NOINLINE Spec tex_image_eval(const SceneView &sv, const PbrtB200Texture &t, c
 #endif
   return mip_lookup(sv, t, s, tt, dsdx, dtdx, dsdy, dtdy);
 }
+// The procedural leaves: textures/{uv,bilerp,fbm,wrinkled,windy,marble}.cpp
+PB_NOINLINE Spec tex_procedural_eval(const SceneView &sv, const PbrtB200Texture &t, const DiffGeom &dg, const DgDiff &dd) {
+  if (t.kind == PBRT_B200_TEX_UV || t.kind == PBRT_B200_TEX_BILERP) {
+    float s, tt, dsdx, dtdx, dsdy, dtdy;
+    tex_map(t, dg, dd, &s, &tt, &dsdx, &dtdx, &dsdy, &dtdy);
+    if (t.kind == PBRT_B200_TEX_UV) return spec3(s - pb_floor2int(s), tt - pb_floor2int(tt), 0.f);   // uv.cpp:39-46
+    const float *v = t.param;                                                                     // bilerp.cpp:45-52
+    return (1 - s) * (1 - tt) * spec3(v[0], v[1], v[2]) + (1 - s) * (tt) * spec3(v[3], v[4], v[5]) +
+           (s) * (1 - tt) * spec3(v[6], v[7], v[8]) + (s) * (tt) * spec3(v[9], v[10], v[11]);
+  }
+  // IdentityMapping3D::Map, core/texture.cpp:150-155
+  V3 P = xf_point(t.world_to_texture, dg.p);
+  V3 dpdx = xf_vector(t.world_to_texture, dd.dpdx), dpdy = xf_vector(t.world_to_texture, dd.dpdy);
+  const unsigned char *perm = sv.noisePerm;
+  if (t.kind == PBRT_B200_TEX_FBM) return spec(pb_fbm<false>(perm, P, dpdx, dpdy, t.param[0], t.iparam[0]));
+  if (t.kind == PBRT_B200_TEX_WRINKLED) return spec(pb_fbm<true>(perm, P, dpdx, dpdy, t.param[0], t.iparam[0]));
+  if (t.kind == PBRT_B200_TEX_WINDY) {   // windy.cpp:38-46
+    float windStrength = pb_fbm<false>(perm, .1f * P, .1f * dpdx, .1f * dpdy, .5f, 3);
+    float waveHeight = pb_fbm<false>(perm, P, dpdx, dpdy, .5f, 6);
+    return spec(fabsf(windStrength) * waveHeight);
+  }
+  // marble.cpp:42-46
+  float scale = t.param[1], variation = t.param[2];
+  P = v3(P.x * scale, P.y * scale, P.z * scale);
+  float marble = P.y + variation * pb_fbm<false>(perm, P, scale * dpdx, scale * dpdy, t.param[0], t.iparam[0]);
+  return marble_color(marble);
+}
 // Operands always precede the node that uses them and the host refuses graphs more than PB_TEX_MAX_DEPTH
 // operators deep, so the recursion is a fixed chain of (non-inlined) instances.
 #define PB_TEX_MAX_DEPTH 3
@@ -240,12 +338,50 @@ PB_NOINLINE Spec tex_eval(const SceneView &sv, int32_t id, const DiffGeom &dg, c
   const PbrtB200Texture &t = sv.textures[id];
   if (t.kind == PBRT_B200_TEX_IMAGEMAP) return tex_image_eval(sv, t, dg, dd);
   if (t.kind == PBRT_B200_TEX_CONSTANT) return spec3(t.value[0], t.value[1], t.value[2]);
+  if (t.kind == PBRT_B200_TEX_UV || t.kind == PBRT_B200_TEX_BILERP || t.kind >= PBRT_B200_TEX_FBM)
+    return tex_procedural_eval(sv, t, dg, dd);
   if (DEPTH > 0) {
-    Spec a = tex_eval<(DEPTH > 0 ? DEPTH - 1 : 0)>(sv, t.arg[0], dg, dd);
-    Spec b = tex_eval<(DEPTH > 0 ? DEPTH - 1 : 0)>(sv, t.arg[1], dg, dd);
-    if (t.kind == PBRT_B200_TEX_SCALE) return a * b;
-    float amt = tex_eval<(DEPTH > 0 ? DEPTH - 1 : 0)>(sv, t.arg[2], dg, dd).c[0];
-    return (1.f - amt) * a + amt * b;
+    const int D = DEPTH > 0 ? DEPTH - 1 : 0;
+    if (t.kind == PBRT_B200_TEX_SCALE) return tex_eval<D>(sv, t.arg[0], dg, dd) * tex_eval<D>(sv, t.arg[1], dg, dd);
+    if (t.kind == PBRT_B200_TEX_MIX) {
+      Spec a = tex_eval<D>(sv, t.arg[0], dg, dd);
+      Spec b = tex_eval<D>(sv, t.arg[1], dg, dd);
+      float amt = tex_eval<D>(sv, t.arg[2], dg, dd).c[0];
+      return (1.f - amt) * a + amt * b;
+    }
+    float s, tt, dsdx, dtdx, dsdy, dtdy;
+    tex_map(t, dg, dd, &s, &tt, &dsdx, &dtdx, &dsdy, &dtdy);
+    if (t.kind == PBRT_B200_TEX_DOTS) {   // dots.cpp:43-61; arg[0] plays outsideDot, arg[1] insideDot
+      const unsigned char *perm = sv.noisePerm;
+      int sCell = pb_floor2int(s + .5f), tCell = pb_floor2int(tt + .5f);
+      if (pb_noise(perm, sCell + .5f, tCell + .5f, .5f) > 0) {
+        float radius = .35f;
+        float maxShift = 0.5f - radius;
+        float sCenter = sCell + maxShift * pb_noise(perm, sCell + 1.5f, tCell + 2.8f, .5f);
+        float tCenter = tCell + maxShift * pb_noise(perm, sCell + 4.5f, tCell + 9.8f, .5f);
+        float ds = s - sCenter, dt = tt - tCenter;
+        if (ds * ds + dt * dt < radius * radius) return tex_eval<D>(sv, t.arg[1], dg, dd);
+      }
+      return tex_eval<D>(sv, t.arg[0], dg, dd);
+    }
+    // Checkerboard2D, checkerboard.cpp:57-87,128-131
+    bool even = (pb_floor2int(s) + pb_floor2int(tt)) % 2 == 0;
+    if (t.iparam[0] == PBRT_B200_CHECKER_CLOSEDFORM) {
+      float ds = pb_max(fabsf(dsdx), fabsf(dsdy));
+      float dt = pb_max(fabsf(dtdx), fabsf(dtdy));
+      float s0 = s - ds, s1 = s + ds;
+      float t0 = tt - dt, t1 = tt + dt;
+      if (!(pb_floor2int(s0) == pb_floor2int(s1) && pb_floor2int(t0) == pb_floor2int(t1))) {
+#define PB_BUMPINT(x) (pb_floor2int((x) / 2) + 2.f * pb_max(((x) / 2) - pb_floor2int((x) / 2) - .5f, 0.f))
+        float sint = (PB_BUMPINT(s1) - PB_BUMPINT(s0)) / (2.f * ds);
+        float tint = (PB_BUMPINT(t1) - PB_BUMPINT(t0)) / (2.f * dt);
+#undef PB_BUMPINT
+        float area2 = sint + tint - 2.f * sint * tint;
+        if (ds > 1.f || dt > 1.f) area2 = .5f;
+        return (1.f - area2) * tex_eval<D>(sv, t.arg[0], dg, dd) + area2 * tex_eval<D>(sv, t.arg[1], dg, dd);
+      }
+    }
+    return tex_eval<D>(sv, even ? t.arg[0] : t.arg[1], dg, dd);
   }
   return spec(0.f);
 }

@@ -36,6 +36,7 @@
 #include "pb_camera.h"
 #include "pb_film.h"
 #include "pb_setup.h"
+#include "pb_noise_table.h"
 
 // ------------------------------------------------------------------------------------------
 // error plumbing
@@ -1670,6 +1671,15 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   UP(upload(h, scene->tex_levels, scene->n_tex_levels, &sv.texLevels));
   UP(upload(h, scene->texels, (size_t)scene->n_texel_floats, &sv.texels));
   if (scene->n_textures) UP(upload(h, scene->ewa_weight_lut, (size_t)PBRT_B200_EWA_LUT_SIZE, &sv.ewaLut));
+  {
+    bool noise = false;
+    for (uint32_t i = 0; i < scene->n_textures; ++i) noise |= scene->textures[i].kind >= PBRT_B200_TEX_DOTS;
+    if (noise) {
+      unsigned char perm[2 * PB_NOISE_PERM_SIZE];
+      pb_noise_perm_fill(perm);
+      UP(upload(h, perm, sizeof(perm), &sv.noisePerm));
+    }
+  }
 #undef UP
   if (scene->sampler.kind == PBRT_B200_SAMPLER_BESTCANDIDATE) {
     // prefix strip masks of the table's image positions (see k_film_gather_bc)

@@ -243,13 +243,51 @@ void pbrtTexture(const string &name, const string &type, const string &texname,
     Error("Texture type \"%s\" unknown.", type.c_str());
     return;
   }
-  if (texname != "constant" && texname != "scale" && texname != "mix" && texname != "imagemap") {
-    Error("Texture class \"%s\" is outside the B200 hot-path scope (supported: constant, scale, mix, imagemap); "
-          "texture \"%s\" not created.", texname.c_str(), name.c_str());
+  const bool procedural = texname == "uv" || texname == "bilerp" || texname == "checkerboard" || texname == "dots" ||
+                          texname == "fbm" || texname == "wrinkled" || texname == "windy" || texname == "marble";
+  if (texname != "constant" && texname != "scale" && texname != "mix" && texname != "imagemap" && !procedural) {
+    Error("Texture plugin \"%s\" unknown; texture \"%s\" not created.", texname.c_str(), name.c_str());
     return;
   }
   TextureStore &store = renderOptions->textures;
   int node = -1;
+  if (procedural) {
+    // checkerboard.cpp:178-179,223-224: tex1 = 1, tex2 = 0; dots.cpp:89-90,116-117: inside = 1, outside = 0
+    const bool two = texname == "checkerboard" || texname == "dots";
+    const char *n0 = texname == "dots" ? "inside" : "tex1", *n1 = texname == "dots" ? "outside" : "tex2";
+    int a0 = -1, a1 = -1;
+    if (two && type == "float") {
+      int32_t m0, m1;
+      float v0 = tp.GetFloatTexture(n0, 1.f, &m0), v1 = tp.GetFloatTexture(n1, 0.f, &m1);
+      a0 = OperandNode(store, v0, m0); a1 = OperandNode(store, v1, m1);
+    } else if (two) {
+      int32_t m0, m1;
+      Spectrum v0 = tp.GetSpectrumTexture(n0, Spectrum(1.f), &m0), v1 = tp.GetSpectrumTexture(n1, Spectrum(0.f), &m1);
+      a0 = OperandNode(store, v0, m0); a1 = OperandNode(store, v1, m1);
+    }
+    node = store.AddProcedural(texname, curTransform, tp, type == "float" ? 1 : 3, a0, a1);
+    if (node < 0) {
+      Error("Unable to create %s texture \"%s\" of class \"%s\".", type.c_str(), name.c_str(), texname.c_str());
+      return;
+    }
+    if (type == "float") {
+      if (graphicsState.floatTextures.find(name) != graphicsState.floatTextures.end())
+        Warning("Texture \"%s\" being redefined", name.c_str());
+      FloatTexture *ft = new FloatTexture;
+      ft->node = node;
+      graphicsState.floatTextures[name] = ft;
+    } else {
+      if (graphicsState.spectrumTextures.find(name) != graphicsState.spectrumTextures.end())
+        Warning("Texture \"%s\" being redefined", name.c_str());
+      SpectrumTexture *st = new SpectrumTexture;
+      st->node = node;
+      graphicsState.spectrumTextures[name] = st;
+    }
+    if (store.Depth(node) > 3)
+      Severe("Texture \"%s\": expressions more than 3 operators deep are not supported", name.c_str());
+    tp.ReportUnused();
+    return;
+  }
   if (type == "float") {
     if (graphicsState.floatTextures.find(name) != graphicsState.floatTextures.end())
       Warning("Texture \"%s\" being redefined", name.c_str());

@@ -123,6 +123,7 @@ class TextureParams {
   string FindString(const string &n, const string &d = "") const {
     return geomParams.FindOneString(n, materialParams.FindOneString(n, d));
   }
+  int FindInt(const string &n, int d) const { return geomParams.FindOneInt(n, materialParams.FindOneInt(n, d)); }
   bool FindBool(const string &n, bool d) const { return geomParams.FindOneBool(n, materialParams.FindOneBool(n, d)); }
   Vector FindVector(const string &n, const Vector &d) const {
     return geomParams.FindOneVector(n, materialParams.FindOneVector(n, d));

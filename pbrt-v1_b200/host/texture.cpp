@@ -305,11 +305,101 @@ int TextureStore::AddMix(int a, int b, int amount, int channels) {
 }
 int TextureStore::Depth(int node) const {
   const PbrtB200Texture &t = nodes[node];
-  if (t.kind != PBRT_B200_TEX_SCALE && t.kind != PBRT_B200_TEX_MIX) return 0;
+  if (t.kind != PBRT_B200_TEX_SCALE && t.kind != PBRT_B200_TEX_MIX && t.kind != PBRT_B200_TEX_CHECKERBOARD &&
+      t.kind != PBRT_B200_TEX_DOTS) return 0;
   int d = 0;
   for (int i = 0; i < 3; ++i)
     if (t.arg[i] >= 0) d = max(d, Depth(t.arg[i]));
   return d + 1;
+}
+// the "mapping" block every 2D texture plugin starts with (e.g. textures/imagemap.cpp:133-151)
+static void ParseMapping2D(const Transform &tex2world, const TextureParams &tp, PbrtB200Texture *t) {
+  string type = tp.FindString("mapping");
+  t->mapping = PBRT_B200_TEXMAP_UV;
+  t->su = t->sv = 1.f;
+  if (type == "" || type == "uv") {
+    t->su = tp.FindFloat("uscale", 1.);
+    t->sv = tp.FindFloat("vscale", 1.);
+    t->du = tp.FindFloat("udelta", 0.);
+    t->dv = tp.FindFloat("vdelta", 0.);
+  } else if (type == "spherical" || type == "cylindrical") {
+    t->mapping = type == "spherical" ? PBRT_B200_TEXMAP_SPHERICAL : PBRT_B200_TEXMAP_CYLINDRICAL;
+    Transform w2t = tex2world.GetInverse();
+    const Matrix4x4 &M = w2t.GetMatrix();
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) t->world_to_texture[4 * i + j] = M.m[i][j];
+  } else if (type == "planar") {
+    t->mapping = PBRT_B200_TEXMAP_PLANAR;
+    Vector v1 = tp.FindVector("v1", Vector(1, 0, 0)), v2 = tp.FindVector("v2", Vector(0, 1, 0));
+    t->v1[0] = v1.x; t->v1[1] = v1.y; t->v1[2] = v1.z;
+    t->v2[0] = v2.x; t->v2[1] = v2.y; t->v2[2] = v2.z;
+    t->du = tp.FindFloat("udelta", 0.f);
+    t->dv = tp.FindFloat("vdelta", 0.f);
+  } else
+    Error("2D texture mapping \"%s\" unknown", type.c_str());
+}
+int TextureStore::AddProcedural(const string &texname, const Transform &tex2world, const TextureParams &tp,
+                                int channels, int arg0, int arg1) {
+  PbrtB200Texture t;
+  memset(&t, 0, sizeof(t));
+  t.channels = (uint32_t)channels;
+  t.arg[0] = arg0; t.arg[1] = arg1; t.arg[2] = -1;
+  if (texname == "uv" || texname == "bilerp" || texname == "checkerboard" || texname == "dots") {
+    if (texname == "uv" && channels != 3) return -1;   // uv.cpp:49-52: no float version
+    if (texname == "checkerboard") {
+      int dim = tp.FindInt("dimension", 2);
+      if (dim != 2) {
+        Error("checkerboard: only the 2D texture is supported (the 3D one supersamples with random numbers)");
+        return -1;
+      }
+    }
+    ParseMapping2D(tex2world, tp, &t);
+    if (texname == "uv") t.kind = PBRT_B200_TEX_UV;
+    else if (texname == "bilerp") {
+      t.kind = PBRT_B200_TEX_BILERP;
+      const char *names[4] = {"v00", "v01", "v10", "v11"};
+      for (int k = 0; k < 4; ++k) {
+        float dflt = (k & 1) ? 1.f : 0.f;   // bilerp.cpp:77-79,105-107
+        if (channels == 3) {
+          Spectrum v = tp.FindSpectrum(names[k], Spectrum(dflt));
+          for (int c = 0; c < 3; ++c) t.param[3 * k + c] = v.c[c];
+        } else {
+          float v = tp.FindFloat(names[k], dflt);
+          for (int c = 0; c < 3; ++c) t.param[3 * k + c] = v;
+        }
+      }
+    } else if (texname == "checkerboard") {
+      t.kind = PBRT_B200_TEX_CHECKERBOARD;
+      string aamode = tp.FindString("aamode");
+      if (aamode == "" || aamode == "closedform") t.iparam[0] = PBRT_B200_CHECKER_CLOSEDFORM;
+      else if (aamode == "none") t.iparam[0] = PBRT_B200_CHECKER_NONE;
+      else {
+        Error("checkerboard: anti-aliasing mode \"%s\" draws random numbers inside the texture and is not "
+              "supported (use closedform or none)", aamode.c_str());
+        return -1;
+      }
+    } else
+      t.kind = PBRT_B200_TEX_DOTS;
+  } else {
+    if (texname == "marble" && channels != 3) return -1;   // marble.cpp:79-82
+    t.kind = texname == "fbm" ? PBRT_B200_TEX_FBM : texname == "wrinkled" ? PBRT_B200_TEX_WRINKLED
+           : texname == "windy" ? PBRT_B200_TEX_WINDY : PBRT_B200_TEX_MARBLE;
+    // `new IdentityMapping3D(tex2world)`: the plugins hand the texture-to-world transform to a mapping that
+    // applies it as world-to-texture (fbm.cpp:56, core/texture.h:96-97); kept as is
+    const Matrix4x4 &M = tex2world.GetMatrix();
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) t.world_to_texture[4 * i + j] = M.m[i][j];
+    if (t.kind != PBRT_B200_TEX_WINDY) {
+      t.iparam[0] = tp.FindInt("octaves", 8);
+      t.param[0] = tp.FindFloat("roughness", .5f);
+    }
+    if (t.kind == PBRT_B200_TEX_MARBLE) {
+      t.param[1] = tp.FindFloat("scale", 1.f);
+      t.param[2] = tp.FindFloat("variation", .2f);
+    }
+  }
+  nodes.push_back(t);
+  return (int)nodes.size() - 1;
 }
 // CreateFloatTexture / CreateSpectrumTexture, textures/imagemap.cpp:130-195
 int TextureStore::AddImageMap(const Transform &tex2world, const TextureParams &tp, int channels) {
@@ -318,29 +408,7 @@ int TextureStore::AddImageMap(const Transform &tex2world, const TextureParams &t
   t.kind = PBRT_B200_TEX_IMAGEMAP;
   t.channels = (uint32_t)channels;
   for (int i = 0; i < 3; ++i) t.arg[i] = -1;
-  string type = tp.FindString("mapping");
-  t.mapping = PBRT_B200_TEXMAP_UV;
-  t.su = t.sv = 1.f;
-  if (type == "" || type == "uv") {
-    t.su = tp.FindFloat("uscale", 1.);
-    t.sv = tp.FindFloat("vscale", 1.);
-    t.du = tp.FindFloat("udelta", 0.);
-    t.dv = tp.FindFloat("vdelta", 0.);
-  } else if (type == "spherical" || type == "cylindrical") {
-    t.mapping = type == "spherical" ? PBRT_B200_TEXMAP_SPHERICAL : PBRT_B200_TEXMAP_CYLINDRICAL;
-    Transform w2t = tex2world.GetInverse();
-    const Matrix4x4 &M = w2t.GetMatrix();
-    for (int i = 0; i < 4; ++i)
-      for (int j = 0; j < 4; ++j) t.world_to_texture[4 * i + j] = M.m[i][j];
-  } else if (type == "planar") {
-    t.mapping = PBRT_B200_TEXMAP_PLANAR;
-    Vector v1 = tp.FindVector("v1", Vector(1, 0, 0)), v2 = tp.FindVector("v2", Vector(0, 1, 0));
-    t.v1[0] = v1.x; t.v1[1] = v1.y; t.v1[2] = v1.z;
-    t.v2[0] = v2.x; t.v2[1] = v2.y; t.v2[2] = v2.z;
-    t.du = tp.FindFloat("udelta", 0.f);
-    t.dv = tp.FindFloat("vdelta", 0.f);
-  } else
-    Error("2D texture mapping \"%s\" unknown", type.c_str());
+  ParseMapping2D(tex2world, tp, &t);
   t.max_anisotropy = tp.FindFloat("maxanisotropy", 8.f);
   t.trilinear = tp.FindBool("trilinear", false) ? 1u : 0u;
   string wrap = tp.FindString("wrap");

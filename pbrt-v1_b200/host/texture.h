@@ -23,6 +23,10 @@ struct TextureStore {
   // (lights/infinite.cpp:63-73); -1 when the file cannot be read (the light then keeps its constant Lbase)
   int AddRadianceMap(const string &filename);
   int AddScale(int a, int b, int channels);
+  // textures/{uv,bilerp,checkerboard,dots,fbm,wrinkled,windy,marble}.cpp; -1 (with an error message) when the
+  // parameters ask for something outside the scope (3D or supersampled checkerboards, float uv / marble)
+  int AddProcedural(const string &texname, const Transform &tex2world, const TextureParams &tp, int channels,
+                    int arg0, int arg1);
   int AddMix(int a, int b, int amount, int channels);
   int Depth(int node) const;
 };

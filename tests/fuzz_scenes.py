@@ -60,6 +60,22 @@ def textures(r):
             out.append('TransformBegin\n%sTexture "%s" "%s" "imagemap" "string filename" ["%s"] %s\nTransformEnd' % (
                 pre, name, typ, os.path.join(GOLDEN, r.choice(files)), p))
             names.append(name)
+    # procedural textures (textures/{uv,bilerp,checkerboard,dots,fbm,wrinkled,windy,marble}.cpp)
+    m2 = lambda: r.choice(['', ' "string mapping" ["spherical"]', ' "string mapping" ["cylindrical"]',
+                           ' "float uscale" [%s] "float vscale" [%s]' % (f(r.choice([2, 6, 15])), f(r.choice([3, 9])))])
+    pre3 = "TransformBegin\nRotate %s 1 0 1\nScale %s 1 %s\n" % (f(r.uniform(0, 360)), f(r.uniform(.5, 3)), f(r.uniform(.5, 3)))
+    out.append('Texture "p_uv" "color" "uv"%s' % m2())
+    out.append('Texture "p_bil" "color" "bilerp" "color v00" [%s] "color v11" [%s]%s' % (rnd_color(r), rnd_color(r), m2()))
+    out.append('Texture "p_fbil" "float" "bilerp" "float v01" [%s]%s' % (f(r.uniform(0, 1)), m2()))
+    out.append('Texture "p_chk" "color" "checkerboard" "texture tex1" "%s" "color tex2" [%s]%s%s' % (
+        r.choice(color + ["p_uv", "p_bil"]), rnd_color(r), r.choice(['', ' "string aamode" ["none"]']), m2()))
+    out.append('Texture "p_fchk" "float" "checkerboard" "float tex1" [.1] "texture tex2" "p_fbil"%s' % m2())
+    out.append('Texture "p_dot" "color" "dots" "texture inside" "%s" "color outside" [%s]%s' % (r.choice(color), rnd_color(r), m2()))
+    out.append(pre3 + 'Texture "p_fbm" "color" "fbm" "integer octaves" [%d] "float roughness" [%s]\nTexture "p_ffbm" "float" "fbm"\n'
+               'Texture "p_wr" "color" "wrinkled"\nTexture "p_wi" "float" "windy"\nTexture "p_mar" "color" "marble" "float scale" [%s]\nTransformEnd' % (
+                   r.randint(1, 8), f(r.uniform(.3, .7)), f(r.uniform(.5, 4))))
+    color += ["p_uv", "p_bil", "p_chk", "p_dot", "p_fbm", "p_wr", "p_mar"]
+    flt += ["p_fbil", "p_fchk", "p_wi"]
     out.append('Texture "cs" "color" "scale" "texture tex1" "%s" "color tex2" [%s]' % (r.choice(color), rnd_color(r)))
     out.append('Texture "cm" "color" "mix" "texture tex1" "cs" "texture tex2" "%s" "texture amount" "%s"' % (r.choice(color), r.choice(flt)))
     color += ["cs", "cm"]

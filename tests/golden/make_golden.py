@@ -790,6 +790,61 @@ INLINE["tex_bump_direct"] = _tex_scene("tex_bump_direct", _TEX_BUMP % _latlong_m
                                        sampler='Sampler "bestcandidate" "integer pixelsamples" [4]')
 
 
+# the procedural textures: uv, bilerp, checkerboard (closed-form and point-sampled, nested), dots, fbm, wrinkled,
+# windy, marble -- colour and float versions, every 2D mapping, rotated / scaled texture spaces for the 3D ones
+_TEX_PROC = """Texture "chk" "color" "checkerboard" "float uscale" [8] "float vscale" [8] "color tex1" [.9 .9 .9] "color tex2" [.1 .1 .4]
+Texture "chk2" "color" "checkerboard" "string aamode" ["none"] "float uscale" [3] "float vscale" [5] "texture tex1" "chk" "color tex2" [.7 .2 .1]
+Texture "uvt" "color" "uv" "float uscale" [3] "float vscale" [2]
+Texture "bil" "color" "bilerp" "color v00" [.1 .2 .9] "color v01" [.9 .8 .1] "color v10" [.2 .9 .3] "color v11" [.9 .1 .6] "string mapping" ["spherical"]
+Texture "fbil" "float" "bilerp" "float v00" [.02] "float v01" [.4] "float v10" [.1] "float v11" [.3]
+Texture "dot" "color" "dots" "float uscale" [10] "float vscale" [10] "texture inside" "uvt" "color outside" [.8 .8 .2]
+Texture "fdot" "float" "dots" "float uscale" [6] "float vscale" [6] "float inside" [.05] "float outside" [.5]
+TransformBegin
+Rotate 30 1 1 0
+Scale 2 3 1.5
+Texture "fb" "color" "fbm" "integer octaves" [5] "float roughness" [.6]
+Texture "ffb" "float" "fbm"
+Texture "wr" "color" "wrinkled" "integer octaves" [6]
+Texture "fwr" "float" "wrinkled" "float roughness" [.4]
+Texture "wi" "float" "windy"
+Texture "mar" "color" "marble" "float scale" [2] "float variation" [.4]
+TransformEnd
+Texture "fchk" "float" "checkerboard" "string mapping" ["planar"] "vector v1" [.5 0 0] "vector v2" [0 0 .5] "float tex1" [.02] "texture tex2" "fbil"
+Texture "bump" "float" "scale" "texture tex1" "fwr" "float tex2" [.2]
+Texture "wibump" "float" "scale" "texture tex1" "wi" "float tex2" [.3]
+Material "matte" "texture Kd" "chk2"
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-9 -1 -9 9 -1 -9 9 -1 9 -9 -1 9] "float uv" [0 0 1 0 1 1 0 1]
+Material "matte" "texture Kd" "mar" "texture bumpmap" "wibump"
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-9 -1 6 9 -1 6 9 8 6 -9 8 6] "float uv" [0 0 1 0 1 1 0 1]
+AttributeBegin
+Material "plastic" "texture Kd" "bil" "color Ks" [.3 .3 .3] "texture roughness" "fchk"
+Translate -2.4 0.5 0
+Shape "sphere" "float radius" [1.4]
+AttributeEnd
+AttributeBegin
+Material "matte" "texture Kd" "dot" "texture bumpmap" "bump"
+Translate 0.6 0 1
+Rotate -90 1 0 0
+Shape "cylinder" "float radius" [1] "float zmin" [-1] "float zmax" [1.8]
+AttributeEnd
+AttributeBegin
+Material "uber" "texture Kd" "fb" "texture Ks" "wr" "color Kr" [.2 .2 .2] "texture roughness" "fdot"
+Translate 3 0.2 -0.5
+Shape "sphere" "float radius" [1.1]
+AttributeEnd
+AttributeBegin
+Material "matte" "texture Kd" "wr" "texture sigma" "ffb"
+Translate -0.4 -0.4 -3.2
+Shape "disk" "float radius" [.9]
+AttributeEnd
+"""
+INLINE["tex_procedural_path"] = _tex_scene("tex_procedural_path", _TEX_PROC, depth=3)
+INLINE["tex_procedural_whitted"] = _tex_scene("tex_procedural_whitted", _TEX_PROC, integrator='"whitted" "integer maxdepth" [3]',
+                                              camera='"orthographic" "float screenwindow" [-4 4 -2.8 2.8]')
+INLINE["tex_procedural_direct"] = _tex_scene("tex_procedural_direct", _TEX_PROC, integrator='"directlighting" "integer maxdepth" [2] "string strategy" ["one"]',
+                                             sampler='Sampler "lowdiscrepancy" "integer pixelsamples" [2]', pfilter='"gaussian"')
+
+
 def _bestcandidate(integrator, tag, sampler, film='"integer xresolution" [28] "integer yresolution" [20]', lens="", nsamples=1, pfilter='"box"'):
     """bestcandidate sampler (the reference's default when a scene names none)"""
     return """LookAt 278 273 -800 278 273 0 0 1 0

@@ -285,6 +285,20 @@ def test_bestcandidate_table_matches_reference():
     assert np.array_equal(want.view(np.uint32), table.view(np.uint32))
 
 
+def test_noise_permutation_matches_reference():
+    """pb_noise_table.h states Perlin's published permutation; where the reference is present, compare it with
+    the array the reference's Noise() indexes (core/texture.cpp:31-61)."""
+    import re
+    ref_src = "/root/reference/core/texture.cpp"
+    if not os.path.exists(ref_src):
+        pytest.skip("reference sources not present")
+    body = re.search(r"NoisePerm\[2 \* NOISE_PERM_SIZE\] = \{(.*?)\};", open(ref_src).read(), re.S).group(1)
+    ref = [int(x) for x in re.findall(r"\d+", re.sub(r"//.*", "", body))]
+    mine_src = open(os.path.join(ROOT, "pbrt-v1_b200", "csrc", "pb_noise_table.h")).read()
+    mine = [int(x) for x in re.findall(r"\d+", re.search(r"PB_NOISE_PERM_HALF\[PB_NOISE_PERM_SIZE\] = \{(.*?)\};", mine_src, re.S).group(1))]
+    assert len(mine) == 256 and ref == mine + mine
+
+
 def test_parallel_kd_build_equals_sequential(ffi, tmp_path):
     """The host kd build forks big nodes' children onto threads and splices the subtrees; the arrays must be
     the sequential build's (== the reference's tree), bit for bit."""
