@@ -188,7 +188,9 @@ typedef struct PbrtB200Material {    /* 112 bytes */
 /* lights/point.cpp:49-54, lights/area.cpp:28-57, core/shape.h:113-147 */
 enum { PBRT_B200_LIGHT_POINT = 0, PBRT_B200_LIGHT_AREA = 1,
        PBRT_B200_LIGHT_DISTANT = 2 /* lights/distant.cpp */, PBRT_B200_LIGHT_SPOT = 3 /* lights/spot.cpp */,
-       PBRT_B200_LIGHT_INFINITE = 4 /* lights/infinite.cpp without a radiance map: constant Le */ };
+       PBRT_B200_LIGHT_INFINITE = 4 /* lights/infinite.cpp: constant Lbase, or Lbase x radiance map */,
+       PBRT_B200_LIGHT_GONIOMETRIC = 5 /* lights/goniometric.cpp: point light x map at the direction's (phi, theta), y/z swapped */,
+       PBRT_B200_LIGHT_PROJECTION = 6  /* lights/projection.cpp: point light x map at the projected direction */ };
 typedef struct PbrtB200Light {
   int32_t  kind;
   int32_t  n_samples;              /* Light::nSamples = max(1, ns)            */
@@ -200,9 +202,11 @@ typedef struct PbrtB200Light {
   float    cos_total_width;        /* spot: cosf(Radians(coneangle))          */
   float    cos_falloff_start;      /* spot: cosf(Radians(coneangle - conedeltaangle)) */
   float    w2l[9];                 /* spot, infinite: upper 3x3 of WorldToLight (rows): Falloff(), radiance-map lookup */
-  uint32_t radiance_map;           /* infinite: 1 + index in textures[] of the IMAGEMAP node holding the "mapname"
-                                      pyramid (lights/infinite.cpp:63-86), 0 = constant Lbase */
+  uint32_t radiance_map;           /* infinite, goniometric, projection: 1 + index in textures[] of the IMAGEMAP node
+                                      holding the "mapname" pyramid (lights/infinite.cpp:63-86), 0 = no map (factor 1) */
   uint32_t pad;
+  float    projection[16];         /* projection: lightProjection = Perspective(fov, 1e-3, 1e30) (projection.cpp:80-82) */
+  float    screen[4];              /* projection: screenX0, screenX1, screenY0, screenY1 (projection.cpp:71-78) */
 } PbrtB200Light;
 
 /* cameras/perspective.cpp:51-82, cameras/orthographic.cpp:49-78, cameras/environment.cpp:49-63,

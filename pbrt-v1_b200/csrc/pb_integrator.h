@@ -314,7 +314,31 @@ PB_HD void set_segment(Ray *r, const V3 &p1, const V3 &p2) {
 
 // Light::Sample_L(p, &wi, &visibility) of the delta lights: point (lights/point.cpp:55-66), spot
 // (lights/spot.cpp:59-76) and distant (lights/distant.cpp:60-65, whose visibility ray is unbounded).
-PB_HD Spec delta_light_sample(const PbrtB200Light &light, const V3 &p, V3 *wi, Ray *shadow) {
+// GonioPhotometricLight::Scale (goniometric.cpp:39-46) and ProjectionLight::Projection (projection.cpp:100-113):
+// the factor on a point light's intensity towards world direction w (MIPMap::Lookup(s, t), filter width 0)
+PB_NOINLINE Spec mapped_light_scale(const SceneView &sv, const PbrtB200Light &l, const V3 &w) {
+  V3 wl = v3(l.w2l[0] * w.x + l.w2l[1] * w.y + l.w2l[2] * w.z, l.w2l[3] * w.x + l.w2l[4] * w.y + l.w2l[5] * w.z,
+             l.w2l[6] * w.x + l.w2l[7] * w.y + l.w2l[8] * w.z);
+  float s, t;
+  if (l.kind == PBRT_B200_LIGHT_GONIOMETRIC) {
+    V3 wp = normalize(wl);
+    float tmp = wp.y; wp.y = wp.z; wp.z = tmp;
+    float theta = pb_acosf(pb_clamp(wp.z, -1.f, 1.f));
+    float ph = pb_atan2f(wp.y, wp.x);
+    float phi = (ph < 0.f) ? ph + 2.f * PB_PI : ph;
+    s = phi * PB_INV_TWOPI; t = theta * PB_INV_PI;
+    if (l.radiance_map == 0) return spec(1.f);
+  } else {
+    if (wl.z < PB_RAY_EPSILON) return spec(0.f);   // hither
+    V3 Pl = xf_point(l.projection, wl);
+    if (Pl.x < l.screen[0] || Pl.x > l.screen[1] || Pl.y < l.screen[2] || Pl.y > l.screen[3]) return spec(0.f);
+    if (l.radiance_map == 0) return spec(1.f);
+    s = (Pl.x - l.screen[0]) / (l.screen[1] - l.screen[0]);
+    t = (Pl.y - l.screen[2]) / (l.screen[3] - l.screen[2]);
+  }
+  return mip_lookup_width(sv, sv.textures[l.radiance_map - 1], s, t, 0.f);
+}
+PB_HD Spec delta_light_sample(const SceneView &sv, const PbrtB200Light &light, const V3 &p, V3 *wi, Ray *shadow) {
   if (light.kind == PBRT_B200_LIGHT_DISTANT) {
     *wi = v3(light.pos[0], light.pos[1], light.pos[2]);
     shadow->o = p; shadow->d = *wi; shadow->mint = PB_RAY_EPSILON; shadow->maxt = PB_INFINITY;   // SetRay
@@ -339,6 +363,8 @@ PB_HD Spec delta_light_sample(const PbrtB200Light &light, const V3 &p, V3 *wi, R
     }
     return light_color(light) * falloff / distance_sq(lightPos, p);
   }
+  if (light.kind >= PBRT_B200_LIGHT_GONIOMETRIC)   // Intensity * Scale(-wi) / DistanceSquared(lightPos, p)
+    return light_color(light) * mapped_light_scale(sv, light, -*wi) / distance_sq(lightPos, p);
   return light_color(light) / distance_sq(lightPos, p);
 }
 
@@ -399,7 +425,7 @@ PB_HD void estimate_direct(const SceneView &sv, int lightNum, const V3 &p, const
   bool isDelta = (LK & PB_LK_DELTA) && light.kind != PBRT_B200_LIGHT_AREA && !isInfinite;
   if (isDelta) {
     lightPdf = 1.f;
-    Li = delta_light_sample(light, p, &wi, &rec->shadow);
+    Li = delta_light_sample(sv, light, p, &wi, &rec->shadow);
   } else if (isInfinite) {
     Li = infinite_light_sample_cosine(sv, light, p, n, ls1, ls2, rng, &wi, &lightPdf, &rec->shadow);
   } else {
@@ -682,7 +708,7 @@ PB_HD void wd_vertex(const SceneView &sv, const PatternSource &key0, const Ray &
         rec->shadow.o = p; rec->shadow.d = wi; rec->shadow.mint = PB_RAY_EPSILON; rec->shadow.maxt = PB_INFINITY;
         Li = infinite_le(sv, light, wi) / pdf;
       } else if (light.kind != PBRT_B200_LIGHT_AREA) {
-        Li = delta_light_sample(light, p, &wi, &rec->shadow);
+        Li = delta_light_sample(sv, light, p, &wi, &rec->shadow);
       } else {
         // AreaLight::Sample_L(P, &wo, &vis), area.cpp:96-105.  g++ evaluates the two
         // RandomFloat() arguments right to left: the first draw is u2.

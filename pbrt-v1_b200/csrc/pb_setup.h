@@ -75,12 +75,12 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
   sv->nInstances = s.n_instances;
   sv->nInfiniteLights = 0;
   for (uint32_t i = 0; i < s.n_lights; ++i) {
-    if (s.lights[i].kind < PBRT_B200_LIGHT_POINT || s.lights[i].kind > PBRT_B200_LIGHT_INFINITE) return "unknown light kind";
+    if (s.lights[i].kind < PBRT_B200_LIGHT_POINT || s.lights[i].kind > PBRT_B200_LIGHT_PROJECTION) return "unknown light kind";
     if (s.lights[i].kind == PBRT_B200_LIGHT_INFINITE) ++sv->nInfiniteLights;
-    if (s.lights[i].kind == PBRT_B200_LIGHT_INFINITE && s.lights[i].radiance_map != 0 &&
+    if (s.lights[i].kind >= PBRT_B200_LIGHT_INFINITE && s.lights[i].radiance_map != 0 &&
         (s.lights[i].radiance_map > s.n_textures || s.textures[s.lights[i].radiance_map - 1].kind != PBRT_B200_TEX_IMAGEMAP ||
          s.textures[s.lights[i].radiance_map - 1].channels != 3))
-      return "infinite light radiance map is not an image-map texture node";
+      return "light map is not an image-map texture node";
   }
   for (int i = 0; i < 3; ++i) { sv->bmin[i] = s.bounds[i]; sv->bmax[i] = s.bounds[3 + i]; }
   sv->camera = s.camera; sv->sampler = s.sampler; sv->integrator = s.integrator;

@@ -192,6 +192,46 @@ class PointLight : public Light {  // lights/point.cpp:49-54
   Point lightPos; Spectrum Intensity;
 };
 
+// lights/goniometric.cpp:31-83 and lights/projection.cpp:31-99: point lights whose intensity is scaled by an image
+// looked up at the direction towards the receiver
+class MappedPointLight : public Light {
+ public:
+  MappedPointLight(int kind_, const Transform &light2world, const Spectrum &intensity, const string &texname, float fov)
+      : Light(light2world), kind(kind_), Intensity(intensity), map(-1) {
+    lightPos = LightToWorld(Point(0, 0, 0));
+    TextureStore &store = CurrentTextureStore();
+    if (texname != "") map = store.AddRadianceMap(texname);
+    float aspect = 1.f;
+    if (map >= 0) aspect = float(store.imageSizes[texname].first) / float(store.imageSizes[texname].second);
+    else if (kind == PBRT_B200_LIGHT_PROJECTION)
+      Warning("projection light without a readable \"mapname\": the reference reads an uninitialised image size "
+              "here; a square projection window is used");
+    if (aspect > 1.f) { screen[0] = -aspect; screen[1] = aspect; screen[2] = -1.f; screen[3] = 1.f; }
+    else { screen[0] = -1.f; screen[1] = 1.f; screen[2] = -1.f / aspect; screen[3] = 1.f / aspect; }
+    lightProjection = Perspective(fov, RAY_EPSILON, 1e30f);
+  }
+  void Flatten(FlatBuilder &, PbrtB200Light *out) const {
+    memset(out, 0, sizeof(*out));
+    out->kind = kind;
+    out->n_samples = nSamples;
+    for (int i = 0; i < 3; ++i) { out->color[i] = Intensity.c[i]; out->pos[i] = lightPos[i]; }
+    out->radiance_map = (uint32_t)(map + 1);
+    Transform WorldToLight = LightToWorld.GetInverse();
+    const Matrix4x4 &m = WorldToLight.GetMatrix();
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) out->w2l[3 * i + j] = m.m[i][j];
+    const Matrix4x4 &pm = lightProjection.GetMatrix();
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) out->projection[4 * i + j] = pm.m[i][j];
+    for (int i = 0; i < 4; ++i) out->screen[i] = screen[i];
+  }
+  int kind;
+  Point lightPos; Spectrum Intensity;
+  int map;
+  Transform lightProjection;
+  float screen[4];
+};
+
 // -------------------------------------------------------------- integrators
 class WhittedIntegrator : public SurfaceIntegrator {  // integrators/whitted.cpp:141-145
  public:
@@ -530,6 +570,15 @@ Light *MakeLight(const string &name, const Transform &light2world, const ParamSe
     Point P = paramSet.FindOnePoint("from", Point(0, 0, 0));
     Transform l2w = Translate(Vector(P.x, P.y, P.z)) * light2world;
     Light *l = new PointLight(l2w, I);
+    paramSet.ReportUnused();
+    return l;
+  }
+  if (name == "goniometric" || name == "projection") {   // lights/goniometric.cpp:84-89, lights/projection.cpp:133-139
+    Spectrum I = paramSet.FindOneSpectrum("I", Spectrum(1.0));
+    float fov = name == "projection" ? paramSet.FindOneFloat("fov", 45.) : 45.f;
+    string texname = paramSet.FindOneString("mapname", "");
+    Light *l = new MappedPointLight(name == "projection" ? PBRT_B200_LIGHT_PROJECTION : PBRT_B200_LIGHT_GONIOMETRIC,
+                                    light2world, I, texname, fov);
     paramSet.ReportUnused();
     return l;
   }

@@ -427,6 +427,7 @@ int TextureStore::AddImageMap(const Transform &tex2world, const TextureParams &t
     Plane img;
     std::pair<uint32_t, uint32_t> pyr;
     if (texels) {
+      imageSizes[filename] = std::make_pair(width, height);
       img.w = width; img.h = height; img.ch = channels;
       img.v.resize((size_t)width * height * channels);
       for (int i = 0; i < width * height; ++i) {
@@ -469,6 +470,7 @@ int TextureStore::AddRadianceMap(const string &filename) {
     int width = 0, height = 0;
     Spectrum *texels = ReadImage(ResolveDataFile(filename), &width, &height);
     if (!texels) return -1;
+    imageSizes[filename] = std::make_pair(width, height);
     Plane img;
     img.w = width; img.h = height; img.ch = 3;
     img.v.resize((size_t)width * height * 3);

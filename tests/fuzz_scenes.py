@@ -192,13 +192,20 @@ def scene(r, idx):
            samp, filt, integ, "WorldBegin"]
     nl = 0
     for _ in range(r.randint(0, 2)):
-        k = r.choice(["point", "spot", "distant", "infinite"])
+        k = r.choice(["point", "spot", "distant", "infinite", "goniometric", "projection"])
         nl += 1
         if k == "point":
             out.append('LightSource "point" "color I" [%s] "point from" [%s]' % (rnd_color(r, 20, 60), f(r.uniform(-4, 4), r.uniform(3, 7), r.uniform(-6, 0))))
         elif k == "spot":
             out.append('LightSource "spot" "color I" [%s] "point from" [%s] "point to" [0 0 0] "float coneangle" [%s] "float conedeltaangle" [%s]' % (
                 rnd_color(r, 40, 120), f(r.uniform(-4, 4), r.uniform(3, 7), r.uniform(-6, 0)), f(r.uniform(20, 50)), f(r.uniform(2, 15))))
+        elif k in ("goniometric", "projection"):
+            mapn = ' "string mapname" ["%s"]' % os.path.join(GOLDEN, r.choice(["tex13x7.exr", "tex8x16.exr", "tex5x5.exr"]))
+            if k == "goniometric" and r.random() < .3:
+                mapn = ""
+            out.append('AttributeBegin\nTranslate %s\nRotate %s 1 0 .5\nLightSource "%s" "color I" [%s]%s%s\nAttributeEnd' % (
+                f(r.uniform(-4, 4), r.uniform(3, 7), r.uniform(-6, 0)), f(r.uniform(40, 140)), k, rnd_color(r, 40, 150), mapn,
+                ' "float fov" [%s]' % f(r.uniform(30, 90)) if k == "projection" else ""))
         elif k == "distant":
             out.append('LightSource "distant" "color L" [%s] "point from" [%s] "point to" [0 0 0]' % (rnd_color(r, .5, 2), f(r.uniform(-3, 3), 5, r.uniform(-5, 0))))
         else:

@@ -845,6 +845,58 @@ INLINE["tex_procedural_direct"] = _tex_scene("tex_procedural_direct", _TEX_PROC,
                                              sampler='Sampler "lowdiscrepancy" "integer pixelsamples" [2]', pfilter='"gaussian"')
 
 
+def _mapped_lights(integrator, tag):
+    """goniometric and projection lights (lights/goniometric.cpp, lights/projection.cpp): image-scaled point lights
+    under rotated light spaces, one goniometric light without a map; wide and tall projection images"""
+    return """LookAt 0 3 -9 0 0.5 0 0 1 0
+Camera "perspective" "float fov" [40]
+Film "image" "integer xresolution" [36] "integer yresolution" [28] "string filename" ["lights_%s_out.exr"]
+Sampler "stratified" "integer xsamples" [2] "integer ysamples" [2]
+PixelFilter "box"
+SurfaceIntegrator %s
+WorldBegin
+AttributeBegin
+Translate -2 4 -1
+Rotate 35 1 0 1
+LightSource "goniometric" "color I" [40 38 30] "string mapname" ["tex8x16.exr"]
+AttributeEnd
+AttributeBegin
+Translate 3 2 -3
+LightSource "goniometric" "color I" [6 8 10]
+AttributeEnd
+AttributeBegin
+Translate 0 5 -2
+Rotate 100 1 0 0
+Rotate 20 0 0 1
+LightSource "projection" "color I" [160 160 160] "float fov" [50] "string mapname" ["tex13x7.exr"]
+AttributeEnd
+AttributeBegin
+Translate 2.5 3 1
+Rotate 60 1 0 0
+LightSource "projection" "color I" [60 40 40] "float fov" [70] "string mapname" ["tex8x16.exr"]
+AttributeEnd
+Material "matte" "color Kd" [.6 .6 .6]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-6 -1 -6 6 -1 -6 6 -1 6 -6 -1 6]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-6 -1 5 6 -1 5 6 7 5 -6 7 5]
+AttributeBegin
+Material "glass" "float index" [1.5]
+Translate -1.6 0 0
+Shape "sphere" "float radius" [1]
+AttributeEnd
+AttributeBegin
+Material "plastic" "color Kd" [.7 .2 .2] "color Ks" [.3 .3 .3] "float roughness" [.05]
+Translate 1.4 -0.2 0.5
+Shape "sphere" "float radius" [.8]
+AttributeEnd
+WorldEnd
+""" % (tag, integrator)
+
+
+INLINE["lights_mapped_path"] = _mapped_lights('"path" "integer maxdepth" [3]', "mapped_path")
+INLINE["lights_mapped_direct"] = _mapped_lights('"directlighting" "integer maxdepth" [3]', "mapped_direct")
+INLINE["lights_mapped_whitted"] = _mapped_lights('"whitted" "integer maxdepth" [3]', "mapped_whitted")
+
+
 def _bestcandidate(integrator, tag, sampler, film='"integer xresolution" [28] "integer yresolution" [20]', lens="", nsamples=1, pfilter='"box"'):
     """bestcandidate sampler (the reference's default when a scene names none)"""
     return """LookAt 278 273 -800 278 273 0 0 1 0
