@@ -74,8 +74,10 @@ PB_HD float pb_clamp(float val, float low, float high) {
   else return val;
 }
 // core/pbrt.h:622-635 (FAST_INT is off): the argument is promoted to double
-PB_HD int pb_floor2int(float v) { return (int)floor((double)v); }
-PB_HD int pb_ceil2int(float v) { return (int)ceil((double)v); }
+// Floor2Int / Ceil2Int (core/pbrt.h:622-635) take a double; for a float argument floorf / ceilf give the same
+// integer exactly (the floor of a float is a float), without the fp64 round trip
+PB_HD int pb_floor2int(float v) { return (int)floorf(v); }
+PB_HD int pb_ceil2int(float v) { return (int)ceilf(v); }
 
 struct V3 {
   float x, y, z;

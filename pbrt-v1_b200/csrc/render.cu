@@ -67,6 +67,9 @@ static int64_t g_reserved4 = 0;           // key 4: reserved (was the fused shad
 #ifndef PB_CONT_MIN_BLOCKS
 #define PB_CONT_MIN_BLOCKS 6
 #endif
+#ifndef PB_SURF_TEX_MIN_BLOCKS
+#define PB_SURF_TEX_MIN_BLOCKS 6   // the texture-evaluating instances of k_path_surface
+#endif
 #ifndef PB_SURF_MIN_BLOCKS
 #define PB_SURF_MIN_BLOCKS 6
 #endif
@@ -555,7 +558,7 @@ __device__ __forceinline__ void surface_load(const SceneView &sv, const SurfaceR
 
 // TEX: the scene has texture operands (ray differentials of the camera ray, operand evaluation at the hit)
 template <bool INST, bool TEX>
-__global__ void __launch_bounds__(PB_BLOCK, PB_SURF_MIN_BLOCKS)
+__global__ void __launch_bounds__(PB_BLOCK, TEX ? PB_SURF_TEX_MIN_BLOCKS : PB_SURF_MIN_BLOCKS)
 k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const RayQueue qin,
                const SurfaceRecord rec, const uint32_t *nPtr, uint32_t *work, uint32_t *hitCount) {
   uint32_t n = *nPtr;

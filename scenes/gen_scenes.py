@@ -71,11 +71,27 @@ def box(out, hx, hy, hz):
     quad(out, [(x1, y0, z0), (x1, y1, z0), (x1, y1, z1), (x1, y0, z1)])  # x1
 
 
+TEXTURE_FILE = None   # --textured FILE: walls get image-map / checkerboard / marble colours and an fbm bump map
+
+
 def cornell_walls(out):
     white, green, red = (.73, .73, .73), (.12, .45, .15), (.65, .05, .05)
     S = 555.0
+    if TEXTURE_FILE:
+        out.write('Texture "img" "color" "imagemap" "string filename" ["%s"] "string mapping" ["planar"] '
+                  '"vector v1" [.004 0 .001] "vector v2" [0 .004 .003]\n' % TEXTURE_FILE)
+        out.write('Texture "chk" "color" "checkerboard" "string mapping" ["planar"] "vector v1" [.012 0 0] '
+                  '"vector v2" [0 .012 .012] "texture tex1" "img" "color tex2" [.73 .73 .73]\n')
+        out.write('TransformBegin\nScale 40 40 40\nTexture "mar" "color" "marble"\nTexture "fb" "float" "fbm"\nTransformEnd\n')
+        out.write('Texture "bump" "float" "scale" "texture tex1" "fb" "float tex2" [3]\n')
+        out.write('Texture "greenimg" "color" "scale" "texture tex1" "img" "color tex2" [.3 .9 .35]\n')
 
     def mat(c):
+        if TEXTURE_FILE:
+            kd = {white: "chk", green: "greenimg", red: "mar"}.get(c)
+            if kd:
+                out.write('Material "matte" "texture Kd" "%s" "texture bumpmap" "bump"\n' % kd)
+                return
         out.write('Material "matte" "color Kd" [%s]\n' % " ".join(fmt(v) for v in c))
 
     mat(white)
@@ -248,6 +264,7 @@ def main():
     ap.add_argument("--integrator")
     ap.add_argument("--maxdepth", type=int, default=5)
     ap.add_argument("--noglass", action="store_true")
+    ap.add_argument("--textured", metavar="EXR", help="texture the Cornell walls from this image (absolute path)")
     ap.add_argument("--normals", action="store_true")
     ap.add_argument("--nphi", type=int)
     ap.add_argument("--ntheta", type=int)
@@ -258,13 +275,14 @@ def main():
     ap.add_argument("--ld", action="store_true", help="lowdiscrepancy sampler with xsamples*ysamples pixel samples")
     ap.add_argument("--bc", action="store_true", help="bestcandidate sampler with xsamples*ysamples pixel samples")
     a = ap.parse_args()
-    global LENS, LIGHT_NSAMPLES, MIRROR_TALL_BOX, SPHERE_LIGHT, LD_SAMPLER, BC_SAMPLER
+    global LENS, LIGHT_NSAMPLES, MIRROR_TALL_BOX, SPHERE_LIGHT, LD_SAMPLER, BC_SAMPLER, TEXTURE_FILE
     LD_SAMPLER = a.ld
     BC_SAMPLER = a.bc
     LENS = a.lens
     LIGHT_NSAMPLES = a.nsamples
     MIRROR_TALL_BOX = a.mirror
     SPHERE_LIGHT = a.spherelight
+    TEXTURE_FILE = a.textured
     out = sys.stdout if a.output == "-" else open(a.output, "w")
     out.write("# generated by scenes/gen_scenes.py %s\n" % " ".join(sys.argv[1:]))
     if a.scene == "c1":
