@@ -204,7 +204,10 @@ typedef struct PbrtB200Light {
   float    w2l[9];                 /* spot, infinite: upper 3x3 of WorldToLight (rows): Falloff(), radiance-map lookup */
   uint32_t radiance_map;           /* infinite, goniometric, projection: 1 + index in textures[] of the IMAGEMAP node
                                       holding the "mapname" pyramid (lights/infinite.cpp:63-86), 0 = no map (factor 1) */
-  uint32_t pad;
+  uint32_t dist_offset;            /* infinite with importance sampling (lights/infinitesample.cpp): first float of
+                                      the light's tables in light_distributions, laid out
+                                      uFunc[nu] uCdf[nu+1] uFuncInt vFuncInt[nu] { vFunc[nv] vCdf[nv+1] } x nu */
+  uint32_t dist_nu, dist_nv;       /* 0 = the plain "infinite" light (cosine / uniform sampling) */
   float    projection[16];         /* projection: lightProjection = Perspective(fov, 1e-3, 1e30) (projection.cpp:80-82) */
   float    screen[4];              /* projection: screenX0, screenX1, screenY0, screenY1 (projection.cpp:71-78) */
 } PbrtB200Light;
@@ -283,6 +286,7 @@ typedef struct PbrtB200Scene {
   const PbrtB200TexLevel *tex_levels; uint32_t n_tex_levels;
   const float *texels;                uint64_t n_texel_floats;
   const float *ewa_weight_lut;        /* PBRT_B200_EWA_LUT_SIZE floats, MIPMap::weightLut (core/mipmap.h:167-176) */
+  const float *light_distributions;   uint64_t n_light_distribution_floats;   /* "infinitesample" lights' Distribution1Ds */
   const uint32_t *light_shapes;      /* primitive ids, ShapeSet order         */
   const float    *light_cdf;         /* ShapeSet::areaCDF, same indexing      */
   uint32_t n_light_shapes;

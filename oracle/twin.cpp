@@ -41,6 +41,7 @@ bool build_view(const PbrtB200Scene &s, SceneView *sv) {
   sv->meshes = s.meshes; sv->quadrics = s.quadrics; sv->instances = s.instances;
   sv->bcTable = s.bestcandidate_table;
   sv->textures = s.textures; sv->texLevels = s.tex_levels; sv->texels = s.texels; sv->ewaLut = s.ewa_weight_lut;
+  sv->lightDist = s.light_distributions;
   static unsigned char noisePerm[2 * PB_NOISE_PERM_SIZE];
   pb_noise_perm_fill(noisePerm);
   sv->noisePerm = noisePerm;

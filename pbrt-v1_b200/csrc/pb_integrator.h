@@ -386,6 +386,72 @@ PB_NOINLINE Spec infinite_le(const SceneView &sv, const PbrtB200Light &l, const 
   }
   return L;
 }
+// ---- InfiniteAreaLightIS (lights/infinitesample.cpp): the "infinite" light with piecewise-constant
+// importance sampling of its radiance map.  Tables: see PbrtB200Light::dist_offset.
+struct InfDist {
+  const float *uFunc, *uCdf, *vFuncInt, *vBase;
+  float uFuncInt;
+  int nu, nv;
+  PB_HD const float *vFunc(int u) const { return vBase + (size_t)u * (2 * nv + 1); }
+  PB_HD const float *vCdf(int u) const { return vBase + (size_t)u * (2 * nv + 1) + nv; }
+};
+PB_HD InfDist inf_dist(const SceneView &sv, const PbrtB200Light &l) {
+  InfDist d;
+  d.nu = (int)l.dist_nu; d.nv = (int)l.dist_nv;
+  const float *b = sv.lightDist + l.dist_offset;
+  d.uFunc = b; d.uCdf = b + d.nu; d.uFuncInt = b[2 * d.nu + 1];
+  d.vFuncInt = b + 2 * d.nu + 2;
+  d.vBase = b + 3 * d.nu + 2;
+  return d;
+}
+// Distribution1D::Sample, infinitesample.cpp:43-52 (std::upper_bound: first cdf entry greater than u)
+PB_HD float dist1d_sample(const float *func, const float *cdf, int count, float funcInt, float u, float *pdf) {
+  int lo = 0, n = count + 1;
+  while (n > 0) {
+    int half = n >> 1;
+    if (!(u < cdf[lo + half])) { lo += half + 1; n -= half + 1; }
+    else n = half;
+  }
+  int offset = pb_imax(0, lo - 1);
+  u = (u - cdf[offset]) / (cdf[offset + 1] - cdf[offset]);
+  *pdf = func[offset] * (1.f / funcInt);
+  return offset + u;
+}
+// InfiniteAreaLightIS::Sample_L(p, u1, u2, wi, pdf, vis), infinitesample.cpp:149-175
+PB_NOINLINE Spec infinite_light_sample_is(const SceneView &sv, const PbrtB200Light &light, const V3 &p, float u1, float u2,
+                                          V3 *wi, float *pdf, Ray *shadow) {
+  InfDist d = inf_dist(sv, light);
+  float pdfs[2];
+  float fu = dist1d_sample(d.uFunc, d.uCdf, d.nu, d.uFuncInt, u1, &pdfs[0]);
+  int u = pb_imin(pb_imax((int)fu, 0), d.nu - 1);
+  float fv = dist1d_sample(d.vFunc(u), d.vCdf(u), d.nv, d.vFuncInt[u], u2, &pdfs[1]);
+  *wi = v3(0, 0, 0);
+  if (pdfs[0] == 0.f || pdfs[1] == 0.f) { *pdf = 0.f; return spec(0.f); }
+  float invNu = 1.f / d.nu, invNv = 1.f / d.nv;
+  float theta = fv * invNv * PB_PI;
+  float phi = fu * invNu * 2.f * PB_PI;
+  float costheta = pb_cosf(theta), sintheta = pb_sinf(theta);
+  if (sintheta == 0.f) { *pdf = 0.f; return spec(0.f); }
+  float sinphi = pb_sinf(phi), cosphi = pb_cosf(phi);
+  // LightToWorld(Vector): the inverse of the w2l rows held in the record is not stored; l2w travels in `projection`
+  V3 wl = v3(sintheta * cosphi, sintheta * sinphi, costheta);
+  *wi = xf_vector(light.projection, wl);
+  *pdf = (float)((double)(pdfs[0] * pdfs[1]) / (2. * (double)PB_PI * (double)PB_PI * (double)sintheta));
+  shadow->o = p; shadow->d = *wi; shadow->mint = PB_RAY_EPSILON; shadow->maxt = PB_INFINITY;   // SetRay
+  return light_color(light) * mip_lookup_width(sv, sv.textures[light.radiance_map - 1], fu * invNu, fv * invNv, 0.f);
+}
+// InfiniteAreaLightIS::Pdf(p, w), infinitesample.cpp:176-187
+PB_NOINLINE float infinite_light_pdf_is(const SceneView &sv, const PbrtB200Light &l, const V3 &w) {
+  InfDist d = inf_dist(sv, l);
+  V3 wi = v3(l.w2l[0] * w.x + l.w2l[1] * w.y + l.w2l[2] * w.z, l.w2l[3] * w.x + l.w2l[4] * w.y + l.w2l[5] * w.z,
+             l.w2l[6] * w.x + l.w2l[7] * w.y + l.w2l[8] * w.z);
+  float theta = pb_acosf(pb_clamp(wi.z, -1.f, 1.f));
+  float ph = pb_atan2f(wi.y, wi.x);
+  float phi = (ph < 0.f) ? ph + 2.f * PB_PI : ph;
+  int u = pb_imin(pb_imax((int)(phi * PB_INV_TWOPI * d.nu), 0), d.nu - 1);
+  int v = pb_imin(pb_imax((int)(theta * PB_INV_PI * d.nv), 0), d.nv - 1);
+  return (d.uFunc[u] * d.vFunc(u)[v]) / (d.uFuncInt * d.vFuncInt[u]) * 1.f / (2.f * PB_PI * PB_PI * pb_sinf(theta));
+}
 PB_NOINLINE Spec infinite_light_sample_cosine(const SceneView &sv, const PbrtB200Light &light, const V3 &p, const V3 &n, float u1, float u2,
                                               RngStream &rng, V3 *wi, float *pdf, Ray *shadow) {
   float x, y, z;
@@ -427,7 +493,8 @@ PB_HD void estimate_direct(const SceneView &sv, int lightNum, const V3 &p, const
     lightPdf = 1.f;
     Li = delta_light_sample(sv, light, p, &wi, &rec->shadow);
   } else if (isInfinite) {
-    Li = infinite_light_sample_cosine(sv, light, p, n, ls1, ls2, rng, &wi, &lightPdf, &rec->shadow);
+    if (light.dist_nu != 0) Li = infinite_light_sample_is(sv, light, p, ls1, ls2, &wi, &lightPdf, &rec->shadow);
+    else Li = infinite_light_sample_cosine(sv, light, p, n, ls1, ls2, rng, &wi, &lightPdf, &rec->shadow);
   } else {
     V3 ns;
     V3 ps = area_light_sample_point<LK>(sv, light, p, ls1, ls2, rng, &ns);
@@ -455,7 +522,8 @@ PB_HD void estimate_direct(const SceneView &sv, int lightNum, const V3 &p, const
     int sampled;
     Spec f = bsdf_sample_f<G>(bsdf, wo, &wi, bs1, bs2, bcs, &bsdfPdf, PB_ALL & ~PB_SPECULAR, &sampled);
     if (!is_black(f) && bsdfPdf > 0.f) {
-      lightPdf = isInfinite ? absdot(n, wi) * PB_INV_TWOPI   // InfiniteAreaLight::Pdf(p, n, wi), infinite.cpp:110-113
+      lightPdf = isInfinite ? (light.dist_nu != 0 ? infinite_light_pdf_is(sv, light, wi)
+                                                   : absdot(n, wi) * PB_INV_TWOPI)   // InfiniteAreaLight::Pdf(p, n, wi), infinite.cpp:110-113
                             : area_light_pdf<LK>(sv, light, p, wi);
       if (lightPdf > 0.f) {
         float weight = power_heuristic(1, bsdfPdf, 1, lightPdf);
@@ -703,10 +771,16 @@ PB_HD void wd_vertex(const SceneView &sv, const PatternSource &key0, const Ray &
         // RandomFloat()s (g++ evaluates the arguments right to left: the first draw is u2), L / pdf
         float u2 = rng.next_float();
         float u1 = rng.next_float();
+        if (light.dist_nu != 0) {   // InfiniteAreaLightIS::Sample_L(P, &wi, &vis), infinitesample.cpp:208-215
+          float pdf;
+          Spec L = infinite_light_sample_is(sv, light, p, u1, u2, &wi, &pdf, &rec->shadow);
+          Li = pdf == 0.f ? spec(0.f) : L / pdf;
+        } else {
         wi = uniform_sample_sphere(u1, u2);
         float pdf = 1.f / (4.f * PB_PI);   // UniformSpherePdf, mc.cpp:82-84
         rec->shadow.o = p; rec->shadow.d = wi; rec->shadow.mint = PB_RAY_EPSILON; rec->shadow.maxt = PB_INFINITY;
         Li = infinite_le(sv, light, wi) / pdf;
+        }
       } else if (light.kind != PBRT_B200_LIGHT_AREA) {
         Li = delta_light_sample(sv, light, p, &wi, &rec->shadow);
       } else {

@@ -59,6 +59,7 @@ struct SceneView {
   const PbrtB200TexLevel *texLevels;
   const float *texels;
   const float *ewaLut;
+  const float *lightDist;           // Distribution1D tables of the importance-sampled infinite lights
   const unsigned char *noisePerm;   // Perlin permutation, 512 entries (pb_noise_table.h), when a texture needs it
   uint32_t nTextures;
 };

@@ -81,6 +81,13 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
         (s.lights[i].radiance_map > s.n_textures || s.textures[s.lights[i].radiance_map - 1].kind != PBRT_B200_TEX_IMAGEMAP ||
          s.textures[s.lights[i].radiance_map - 1].channels != 3))
       return "light map is not an image-map texture node";
+    if (s.lights[i].dist_nu != 0) {
+      const PbrtB200Light &l = s.lights[i];
+      uint64_t need = 3ull * l.dist_nu + 2 + (uint64_t)l.dist_nu * (2ull * l.dist_nv + 1);
+      if (l.kind != PBRT_B200_LIGHT_INFINITE || l.radiance_map == 0 || l.dist_nv == 0 ||
+          l.dist_offset + need > s.n_light_distribution_floats)
+        return "importance-sampled infinite light without complete distribution tables";
+    }
   }
   for (int i = 0; i < 3; ++i) { sv->bmin[i] = s.bounds[i]; sv->bmax[i] = s.bounds[3 + i]; }
   sv->camera = s.camera; sv->sampler = s.sampler; sv->integrator = s.integrator;

@@ -1674,6 +1674,7 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   UP(upload(h, scene->tex_levels, scene->n_tex_levels, &sv.texLevels));
   UP(upload(h, scene->texels, (size_t)scene->n_texel_floats, &sv.texels));
   if (scene->n_textures) UP(upload(h, scene->ewa_weight_lut, (size_t)PBRT_B200_EWA_LUT_SIZE, &sv.ewaLut));
+  UP(upload(h, scene->light_distributions, (size_t)scene->n_light_distribution_floats, &sv.lightDist));
   {
     bool noise = false;
     for (uint32_t i = 0; i < scene->n_textures; ++i) noise |= scene->textures[i].kind >= PBRT_B200_TEX_DOTS;

@@ -136,11 +136,56 @@ class DistantLight : public Light {  // lights/distant.cpp:53-59
   }
   Vector lightDir; Spectrum L;
 };
-class InfiniteAreaLight : public Light {   // lights/infinite.cpp:63-87
+// ComputeStep1dCDF, core/mc.cpp:31-42
+static void ComputeStep1dCDF(const float *f, int nSteps, float *c, float *cdf) {
+  int i;
+  cdf[0] = 0.;
+  for (i = 1; i < nSteps + 1; ++i) cdf[i] = cdf[i - 1] + f[i - 1] / nSteps;
+  *c = cdf[nSteps];
+  for (i = 1; i < nSteps + 1; ++i) cdf[i] /= *c;
+}
+class InfiniteAreaLight : public Light {   // lights/infinite.cpp:63-87; importance = lights/infinitesample.cpp:88-137
  public:
-  InfiniteAreaLight(const Transform &light2world, const Spectrum &L, int ns, const string &texmap)
-      : Light(light2world, ns), Lbase(L), radianceMap(-1) {
-    if (texmap != "") radianceMap = CurrentTextureStore().AddRadianceMap(texmap);
+  InfiniteAreaLight(const Transform &light2world, const Spectrum &L, int ns, const string &texmap, bool importance = false)
+      : Light(light2world, ns), Lbase(L), radianceMap(-1), distOffset(0), nu(0), nv(0) {
+    TextureStore &store = CurrentTextureStore();
+    if (texmap != "") radianceMap = store.AddRadianceMap(texmap);
+    if (!importance) return;
+    if (radianceMap < 0) Severe("infinitesample light: a readable \"mapname\" is required (the reference crashes without one)");
+    int width = store.imageSizes[texmap].first, height = store.imageSizes[texmap].second;
+    // scalar-valued image from the environment map
+    float filter = 1.f / max(width, height);
+    nu = width; nv = height;
+    vector<float> img((size_t)width * height);
+    for (int x = 0; x < nu; ++x) {
+      float xp = (float)x / (float)nu;
+      for (int y = 0; y < nv; ++y) {
+        float yp = (float)y / (float)nv;
+        float rgb[3];
+        store.LookupWidth(radianceMap, xp, yp, filter, rgb);
+        const float YWeight[3] = {0.212671f, 0.715160f, 0.072169f};   // Spectrum::y(), core/color.h:141-146
+        float v = 0.;
+        for (int c = 0; c < 3; ++c) v += YWeight[c] * rgb[c];
+        img[y + x * nv] = v;
+      }
+    }
+    vector<float> func(max(nu, nv)), sinVals(nv);
+    for (int i = 0; i < nv; ++i) sinVals[i] = sin(M_PI * float(i + .5) / float(nv));
+    // tables: uFunc[nu] uCdf[nu+1] uFuncInt vFuncInt[nu] { vFunc[nv] vCdf[nv+1] } x nu
+    vector<float> &T = store.lightDistributions;
+    distOffset = (uint32_t)T.size();
+    T.resize(T.size() + 3 * (size_t)nu + 2 + (size_t)nu * (2 * (size_t)nv + 1));
+    float *b = &T[distOffset];
+    float *uFunc = b, *uCdf = b + nu, *uFuncInt = b + 2 * nu + 1, *vFuncInt = b + 2 * nu + 2, *vBase = b + 3 * nu + 2;
+    for (int u = 0; u < nu; ++u) {
+      for (int v = 0; v < nv; ++v) func[v] = img[u * nv + v] *= sinVals[v];
+      float *vFunc = vBase + (size_t)u * (2 * nv + 1), *vCdf = vFunc + nv;
+      memcpy(vFunc, &func[0], nv * sizeof(float));
+      ComputeStep1dCDF(vFunc, nv, &vFuncInt[u], vCdf);
+    }
+    for (int u = 0; u < nu; ++u) func[u] = vFuncInt[u];
+    memcpy(uFunc, &func[0], nu * sizeof(float));
+    ComputeStep1dCDF(uFunc, nu, uFuncInt, uCdf);
   }
   void Flatten(FlatBuilder &, PbrtB200Light *out) const {
     memset(out, 0, sizeof(*out));
@@ -152,9 +197,17 @@ class InfiniteAreaLight : public Light {   // lights/infinite.cpp:63-87
     const Matrix4x4 &m = WorldToLight.GetMatrix();
     for (int i = 0; i < 3; ++i)
       for (int j = 0; j < 3; ++j) out->w2l[3 * i + j] = m.m[i][j];
+    out->dist_offset = distOffset; out->dist_nu = (uint32_t)nu; out->dist_nv = (uint32_t)nv;
+    if (nu) {   // LightToWorld for the sampled directions (the projection matrix is unused by this light kind)
+      const Matrix4x4 &l2w = LightToWorld.GetMatrix();
+      for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) out->projection[4 * i + j] = l2w.m[i][j];
+    }
   }
   Spectrum Lbase;
   int radianceMap;   // texture-table entry holding the pyramid, or -1
+  uint32_t distOffset;
+  int nu, nv;
 };
 class SpotLight : public Light {     // lights/spot.cpp:51-58
  public:
@@ -582,11 +635,11 @@ Light *MakeLight(const string &name, const Transform &light2world, const ParamSe
     paramSet.ReportUnused();
     return l;
   }
-  if (name == "infinite") {   // lights/infinite.cpp:164-170
+  if (name == "infinite" || name == "infinitesample") {   // lights/infinite.cpp:164-170, lights/infinitesample.cpp:217-224
     Spectrum L = paramSet.FindOneSpectrum("L", Spectrum(1.0));
     string texmap = paramSet.FindOneString("mapname", "");
     int nSamples = paramSet.FindOneInt("nsamples", 1);
-    Light *l = new InfiniteAreaLight(light2world, L, nSamples, texmap);
+    Light *l = new InfiniteAreaLight(light2world, L, nSamples, texmap, name == "infinitesample");
     paramSet.ReportUnused();
     return l;
   }

@@ -188,6 +188,10 @@ void Scene::Flatten(FlatBuilder &fb, PbrtB200Scene *out) const {
     out->n_texel_floats = fb.textures.texels.size();
     out->ewa_weight_lut = fb.textures.ewaLut;
   }
+  if (!fb.textures.lightDistributions.empty()) {
+    out->light_distributions = &fb.textures.lightDistributions[0];
+    out->n_light_distribution_floats = fb.textures.lightDistributions.size();
+  }
   out->light_shapes = fb.lightShapes.empty() ? NULL : &fb.lightShapes[0];
   out->light_cdf = fb.lightCdf.empty() ? NULL : &fb.lightCdf[0];
   out->n_light_shapes = (uint32_t)fb.lightShapes.size();

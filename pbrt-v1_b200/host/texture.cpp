@@ -3,6 +3,9 @@
 // constructors: reading the image (core/exrio.cpp:40-73), resampling it to a power of two with Lanczos weights
 // and box-filtering the pyramid (core/mipmap.h:89-165), filling the EWA weight table (:167-176).
 #include "texture.h"
+// the lookup arithmetic itself is the device's stage code, compiled here with glibc's float libm like the reference
+#define PB_TWIN_LIBM_FLOAT 1
+#include "../csrc/pb_texture.h"
 #include <errno.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -483,4 +486,14 @@ int TextureStore::AddRadianceMap(const string &filename) {
   t.n_levels = it->second.second;
   nodes.push_back(t);
   return (int)nodes.size() - 1;
+}
+void TextureStore::LookupWidth(int node, float s, float t, float width, float rgb[3]) const {
+  SceneView sv;
+  memset(&sv, 0, sizeof(sv));
+  sv.textures = &nodes[0];
+  sv.texLevels = &levels[0];
+  sv.texels = &texels[0];
+  sv.ewaLut = ewaLut;
+  Spec v = mip_lookup_width(sv, nodes[node], s, t, width);
+  for (int c = 0; c < 3; ++c) rgb[c] = v.c[c];
 }

@@ -16,12 +16,16 @@ struct TextureStore {
   float ewaLut[PBRT_B200_EWA_LUT_SIZE];
   // ImageTexture::GetTexture's cache (imagemap.cpp:75-89): one pyramid per (file, filter, anisotropy, wrap, type)
   std::map<string, std::pair<uint32_t, uint32_t> > pyramids;
-  void Clear() { nodes.clear(); levels.clear(); texels.clear(); pyramids.clear(); imageSizes.clear(); }
+  void Clear() { nodes.clear(); levels.clear(); texels.clear(); pyramids.clear(); imageSizes.clear(); lightDistributions.clear(); }
   int AddConstant(const float v[3], int channels);
   int AddImageMap(const Transform &tex2world, const TextureParams &tp, int channels);
   // InfiniteAreaLight's radiance map: `new MIPMap<Spectrum>(w, h, texels)` with the constructor's defaults
   // (lights/infinite.cpp:63-73); -1 when the file cannot be read (the light then keeps its constant Lbase)
   int AddRadianceMap(const string &filename);
+  // MIPMap::Lookup(s, t, width) (trilinear) of an image-map node, on the host: InfiniteAreaLightIS's constructor
+  // resamples its radiance map with it (lights/infinitesample.cpp:103-111)
+  void LookupWidth(int node, float s, float t, float width, float rgb[3]) const;
+  std::vector<float> lightDistributions;   // Distribution1D tables of the "infinitesample" lights
   // level-0 size of a pyramid's source image before resampling (ProjectionLight's aspect ratio)
   std::map<string, std::pair<int, int> > imageSizes;
   int AddScale(int a, int b, int channels);

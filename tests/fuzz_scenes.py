@@ -212,8 +212,8 @@ def scene(r, idx):
             lmap = ""
             if r.random() < .5:
                 lmap = ' "string mapname" ["%s"]' % os.path.join(GOLDEN, r.choice(["tex13x7.exr", "tex8x16.exr", "tex5x5.exr"]))
-            out.append('AttributeBegin\nRotate %s 1 .3 0\nLightSource "infinite" "color L" [%s] "integer nsamples" [%d]%s\nAttributeEnd' % (
-                f(r.uniform(0, 360)), rnd_color(r, .2, 1), r.randint(1, 3), lmap))
+            out.append('AttributeBegin\nRotate %s 1 .3 0\nLightSource "%s" "color L" [%s] "integer nsamples" [%d]%s\nAttributeEnd' % (
+                f(r.uniform(0, 360)), "infinitesample" if lmap and r.random() < .5 else "infinite", rnd_color(r, .2, 1), r.randint(1, 3), lmap))
     for _ in range(r.randint(0 if nl else 1, 2)):
         sh = r.choice(['Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-1 0 -1 1 0 -1 1 0 1 -1 0 1]',
                        'Shape "sphere" "float radius" [.5]', 'Shape "disk" "float radius" [.9]',

@@ -336,6 +336,14 @@ def _infinite_map(integrator, tag, extra=""):
         'LightSource "infinite" "color L" [1.4 1.3 1.2] "integer nsamples" [2] "string mapname" ["tex8x16.exr"]\nAttributeEnd')
 
 
+def _infinite_is(integrator, tag, extra=""):
+    """importance-sampled radiance map (lights/infinitesample.cpp)"""
+    return _infinite_map(integrator, tag, extra).replace('LightSource "infinite"', 'LightSource "infinitesample"')
+
+
+INLINE["infinite_is_path"] = _infinite_is('"path" "integer maxdepth" [4]', "is_path", _INF_AREA)
+INLINE["infinite_is_direct"] = _infinite_is('"directlighting" "integer maxdepth" [3]', "is_direct")
+INLINE["infinite_is_whitted"] = _infinite_is('"whitted" "integer maxdepth" [3]', "is_whitted", _INF_AREA)
 INLINE["infinite_map_path"] = _infinite_map('"path" "integer maxdepth" [4]', "map_path", _INF_AREA)
 INLINE["infinite_map_direct"] = _infinite_map('"directlighting" "integer maxdepth" [3]', "map_direct")
 INLINE["infinite_map_direct_one"] = _infinite_map('"directlighting" "integer maxdepth" [3] "string strategy" ["one"]', "map_direct_one", _INF_AREA)
