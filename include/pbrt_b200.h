@@ -126,8 +126,12 @@ enum { PBRT_B200_MAT_MATTE = 0, PBRT_B200_MAT_GLASS = 1, PBRT_B200_MAT_MIRROR = 
        PBRT_B200_MAT_SHINYMETAL = 5, /* materials/shinymetal.cpp: conductor microfacet + conductor specular */
        PBRT_B200_MAT_TRANSLUCENT = 6,/* materials/translucent.cpp: Lambertian + microfacet, reflected (kr = reflect) and
                                         transmitted through BRDFToBTDF (kt = transmit) */
-       PBRT_B200_MAT_SUBSTRATE = 7   /* materials/substrate.cpp: FresnelBlend(Kd, Ks, Anisotropic(1/uroughness, 1/vroughness));
-                                        roughness = uroughness, sigma = vroughness */ };
+       PBRT_B200_MAT_SUBSTRATE = 7,  /* materials/substrate.cpp: FresnelBlend(Kd, Ks, Anisotropic(1/uroughness, 1/vroughness));
+                                        roughness = uroughness, sigma = vroughness */
+       PBRT_B200_MAT_MEASURED = 8    /* materials/{bluepaint,brushedmetal,clay,felt,primer,skin}.cpp: one three-lobe Lafortune
+                                        BRDF with fixed fitted coefficients; index = which (PBRT_B200_MEASURED_*) */ };
+enum { PBRT_B200_MEASURED_BLUEPAINT = 0, PBRT_B200_MEASURED_BRUSHEDMETAL = 1, PBRT_B200_MEASURED_CLAY = 2,
+       PBRT_B200_MEASURED_FELT = 3, PBRT_B200_MEASURED_PRIMER = 4, PBRT_B200_MEASURED_SKIN = 5 };
 /* Texture operands of the materials: a small expression graph whose leaves are constants and image maps
  * (textures/{constant,scale,mix,imagemap}.cpp).  A material slot whose tex[] entry is >= 0 is evaluated at
  * every hit (Material::GetBSDF's `Kd->Evaluate(dgs)`), the others keep the constant in the record.

@@ -23,7 +23,8 @@ enum { PB_LOBE_LAMBERT = 0, PB_LOBE_ORENNAYAR = 1, PB_LOBE_SPEC_REFL_DIEL = 2,
        PB_LOBE_MICROFACET_BLINN = 5,      /* Microfacet(FresnelDielectric, Blinn): A = exponent */
        PB_LOBE_SPEC_REFL_COND = 6,        /* SpecularReflection(FresnelConductor(E, k = 0))      */
        PB_LOBE_MICROFACET_BLINN_COND = 7, /* Microfacet(FresnelConductor(E, k = 0), Blinn)       */
-       PB_LOBE_FRESNEL_BLEND = 8          /* FresnelBlend(R = Rd, E = Rs, Anisotropic(A, B))     */ };
+       PB_LOBE_FRESNEL_BLEND = 8,         /* FresnelBlend(R = Rd, E = Rs, Anisotropic(A, B))     */
+       PB_LOBE_LAFORTUNE = 9              /* Lafortune(R = diffuse, three lobes): A = row of the coefficient table */ };
 // Lobes a BSDF can hold: 2 covers matte / glass / mirror; the kernels compiled for scenes with
 // glossy materials (template flag G) carry 4 (uber: transmission + Lambertian + microfacet + specular).
 #define PB_MAX_LOBES 4
@@ -258,6 +259,56 @@ PB_HD float fresnel_blend_pdf(const Lobe &l, const V3 &wo, const V3 &wi) {
   return .5f * (fabsf(wi.z) * PB_INV_PI + aniso_pdf_H(l.A, l.B, wo, normalize(wo + wi)));
 }
 
+// The measured materials (materials/{bluepaint,brushedmetal,clay,felt,primer,skin}.cpp): Lafortune et al.'s fits to
+// the Cornell reflectance measurements, three cosine lobes each.  Row = PBRT_B200_MEASURED_*; per row: diffuse rgb,
+// then for each lobe its xy, z and exponent rgb triples.  These numbers are the materials' definition (published
+// measurement data, as quoted by the reference's plugins); the code around them is not.
+#define PB_LAFORTUNE_ROWS { \
+  {0.3094f, 0.39667f, 0.70837f, 0.870567f, 0.857255f, 0.670982f, 0.803624f, 0.774290f, 0.586674f, 21.820103f, 18.597755f, 7.472717f, \
+   -0.451218f, -0.406681f, -0.477976f, 0.023123f, 0.017625f, 0.227295f, 2.774499f, 2.581499f, 3.677653f, \
+   -1.031545f, -1.029426f, -1.026588f, 0.706734f, 0.696530f, 0.687715f, 66.899060f, 63.767912f, 57.489181f}, \
+  {0.f, 0.f, 0.f, -1.11854f, -1.11845f, -1.11999f, 1.01272f, 1.01469f, 1.01942f, 15.8708f, 15.6489f, 15.4571f, \
+   -1.05334f, -1.06409f, -1.08378f, 0.69541f, 0.662178f, 0.626672f, 111.267f, 88.9222f, 65.2179f, \
+   -1.01684f, -1.01635f, -1.01529f, 1.00132f, 1.00112f, 1.00108f, 180.181f, 184.152f, 195.773f}, \
+  {0.383626f, 0.260749f, 0.274207f, -1.089701f, -1.102701f, -1.107603f, -1.354682f, -2.714801f, -1.569866f, 17.968505f, 11.024489f, 21.270282f, \
+   -0.733381f, -0.793320f, -0.848206f, 0.676108f, 0.679314f, 0.726031f, 8.219745f, 9.055139f, 11.261951f, \
+   -1.010548f, -1.012378f, -1.011263f, 0.910783f, 0.885239f, 0.892451f, 152.912795f, 141.937171f, 201.046802f}, \
+  {0.025865f, 0.025865f, 0.025865f, -0.304075f, -0.304075f, -0.304075f, -0.065992f, -0.065992f, -0.065992f, 3.047892f, 3.047892f, 3.047892f, \
+   -0.749561f, -0.749561f, -0.749561f, -1.167929f, -1.167929f, -1.167929f, 6.931827f, 6.931827f, 6.931827f, \
+   1.004921f, 1.004921f, 1.004921f, -0.205529f, -0.205529f, -0.205529f, 94.117332f, 94.117332f, 94.117332f}, \
+  {0.118230f, 0.121218f, 0.133209f, -0.399286f, -1.033473f, -1.058104f, 0.167504f, 0.009545f, -0.068002f, 2.466633f, 7.637253f, 8.117645f, \
+   -1.041861f, -1.100108f, -1.087779f, 0.014375f, -0.198147f, -0.053605f, 7.993722f, 29.446268f, 41.988990f, \
+   -1.098605f, -0.379883f, -0.449038f, -0.145110f, 0.159127f, 0.173224f, 31.899719f, 2.372852f, 2.636161f}, \
+  {0.428425f, 0.301341f, 0.331054f, -1.131747f, -1.016939f, -0.966018f, -1.209182f, -1.462488f, -1.222419f, 6.421658f, 3.699932f, 3.524889f, \
+   -0.546570f, -0.643533f, -0.638934f, 0.380123f, 0.410559f, 0.437367f, 3.685044f, 4.266495f, 4.539742f, \
+   -0.998888f, -1.020153f, -1.027479f, 0.857998f, 0.703913f, 0.573625f, 64.208486f, 63.919687f, 43.809866f}}
+#ifdef __CUDACC__
+static __device__ const float pb_lafortune_dev[6][30] = PB_LAFORTUNE_ROWS;
+#endif
+PB_HD const float *lafortune_row(int which) {
+#ifdef __CUDA_ARCH__
+  return pb_lafortune_dev[which];
+#else
+  static const float rows[6][30] = PB_LAFORTUNE_ROWS;
+  return rows[which];
+#endif
+}
+// Lafortune::f, core/reflection.cpp:188-198 (Spectrum::Pow: c > 0 ? powf(c, e) : 0, color.h:141-147)
+PB_NOINLINE Spec lafortune_f(const Lobe &l, const V3 &wo, const V3 &wi) {
+  const float *t = lafortune_row((int)l.A);
+  Spec ret = l.R * PB_INV_PI;
+  for (int i = 0; i < 3; ++i) {
+    const float *xy = t + 3 + 9 * i, *z = xy + 3, *e = xy + 6;
+    Spec v;
+    for (int c = 0; c < 3; ++c) {
+      float vc = xy[c] * wo.x * wi.x + xy[c] * wo.y * wi.y + z[c] * wo.z * wi.z;
+      v.c[c] = vc > 0 ? pb_powf(vc, e[c]) : 0.f;
+    }
+    ret = ret + v;
+  }
+  return ret;
+}
+
 // BxDF::f for the non-specular lobes (reflection.cpp:128-156); specular lobes return 0.
 // G = false compiles the glossy (microfacet) lobe out: kernels for scenes without such materials
 template <bool G = true>
@@ -266,6 +317,7 @@ PB_HD Spec lobe_f_brdf(const Lobe &l, const V3 &wo, const V3 &wi) {
   if (G && l.kind == PB_LOBE_MICROFACET_BLINN) return microfacet_f(l.R, l.A, l.etai, l.etat, wo, wi);
   if (G && l.kind == PB_LOBE_MICROFACET_BLINN_COND) return microfacet_f(l.R, l.A, l.etai, l.etat, wo, wi, &l.E);
   if (G && l.kind == PB_LOBE_FRESNEL_BLEND) return fresnel_blend_f(l, wo, wi);
+  if (G && l.kind == PB_LOBE_LAFORTUNE) return lafortune_f(l, wo, wi);
   if (l.kind == PB_LOBE_ORENNAYAR) {
     float sinthetai = sin_theta(wi);
     float sinthetao = sin_theta(wo);
@@ -634,6 +686,15 @@ PB_HD void bsdf_set_lobes(const PbrtB200Material &m, Bsdf *b) {
     l.kind = PB_LOBE_SPEC_REFL_COND; l.type = PB_REFLECTION | PB_SPECULAR;
     l.R = spec(1.f); l.A = l.B = 0.f; l.etai = l.etat = 1.f;
     l.E = fresnel_approx_eta(spec3(m.kr[0], m.kr[1], m.kr[2]));
+  } else if (G && m.kind == PBRT_B200_MAT_MEASURED) {
+    // e.g. materials/bluepaint.cpp:54-56: Lafortune(diffuse, 3, xy, xy, z, e, REFLECTION | DIFFUSE); brushedmetal's is GLOSSY
+    int which = (int)m.index;
+    const float *t = lafortune_row(which);
+    Lobe &l = b->lobes[b->nLobes++];
+    l.kind = PB_LOBE_LAFORTUNE;
+    l.type = PB_REFLECTION | (which == PBRT_B200_MEASURED_BRUSHEDMETAL ? PB_GLOSSY : PB_DIFFUSE);
+    l.R = spec3(t[0], t[1], t[2]);
+    l.A = (float)which; l.B = 0.f; l.etai = l.etat = 1.f;
   } else {   // mirror
     if (!is_black(R)) {
       Lobe &l = b->lobes[b->nLobes++];

@@ -1618,7 +1618,7 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   h->textured = false;
   for (uint32_t i = 0; i < scene->n_materials; ++i) {
     int k = scene->materials[i].kind;
-    if (k < PBRT_B200_MAT_MATTE || k > PBRT_B200_MAT_SUBSTRATE) { delete h; return fail(PBRT_B200_ERR_INVALID, "unknown material kind"); }
+    if (k < PBRT_B200_MAT_MATTE || k > PBRT_B200_MAT_MEASURED) { delete h; return fail(PBRT_B200_ERR_INVALID, "unknown material kind"); }
     // plastic / uber / shinymetal / translucent: microfacet lobes and up to 4 lobes per BSDF (kernels instantiated with G = true)
     h->hasGlossy |= k >= PBRT_B200_MAT_PLASTIC;
     for (int t = 0; t < PBRT_B200_TEXSLOTS; ++t) h->textured |= scene->materials[i].tex[t] >= 0;

@@ -108,6 +108,16 @@ class Substrate : public Material {   // materials/substrate.cpp:28-73
   }
   Spectrum Kd, Ks; float nu, nv;
 };
+class Measured : public Material {   // materials/{bluepaint,brushedmetal,clay,felt,primer,skin}.cpp
+ public:
+  Measured(int w) : which(w) {}
+  void Flatten(PbrtB200Material *out) const {
+    InitRecord(out);
+    out->kind = PBRT_B200_MAT_MEASURED;
+    out->index = (float)which;
+  }
+  int which;
+};
 class ShinyMetal : public Material {   // materials/shinymetal.cpp:28-65
  public:
   ShinyMetal(const Spectrum &ks, float rough, const Spectrum &kr) : Ks(ks), Kr(kr), roughness(rough) {}
@@ -568,6 +578,11 @@ static Material *CreateShinyMetal(const Transform &, const TextureParams &mp) { 
   Bumpmap(mp, &ts);
   return ts.Attach(new ShinyMetal(Ks, roughness, Kr));
 }
+static Material *CreateMeasured(int which, const TextureParams &mp) {   // e.g. materials/bluepaint.cpp:60-64
+  TexSlots ts;
+  Bumpmap(mp, &ts);
+  return ts.Attach(new Measured(which));
+}
 static Material *CreateMirror(const Transform &, const TextureParams &mp) {
   TexSlots ts;
   Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(1.f), &ts.t[PBRT_B200_TEXSLOT_KR]);
@@ -611,9 +626,15 @@ Reference<Material> MakeMaterial(const string &name, const Transform &mtl2world,
   else if (name == "shinymetal") m = CreateShinyMetal(mtl2world, mp);
   else if (name == "translucent") m = CreateTranslucent(mtl2world, mp);
   else if (name == "substrate") m = CreateSubstrate(mtl2world, mp);
+  else if (name == "bluepaint") m = CreateMeasured(PBRT_B200_MEASURED_BLUEPAINT, mp);
+  else if (name == "brushedmetal") m = CreateMeasured(PBRT_B200_MEASURED_BRUSHEDMETAL, mp);
+  else if (name == "clay") m = CreateMeasured(PBRT_B200_MEASURED_CLAY, mp);
+  else if (name == "felt") m = CreateMeasured(PBRT_B200_MEASURED_FELT, mp);
+  else if (name == "primer") m = CreateMeasured(PBRT_B200_MEASURED_PRIMER, mp);
+  else if (name == "skin") m = CreateMeasured(PBRT_B200_MEASURED_SKIN, mp);
   else
-    Error("Material plugin \"%s\" is outside the B200 hot-path scope (supported: matte, glass, "
-          "mirror, plastic, uber, shinymetal, translucent, substrate).", name.c_str());
+    Error("Material plugin \"%s\" unknown (supported: matte, glass, "
+          "mirror, plastic, uber, shinymetal, translucent, substrate, bluepaint, brushedmetal, clay, felt, primer, skin).", name.c_str());
   if (m) mp.ReportUnused();   // core/dynload.cpp:299
   return m;
 }

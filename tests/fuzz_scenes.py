@@ -17,7 +17,9 @@ def rnd_color(r, lo=0.05, hi=0.95):
 
 
 def material(r):
-    k = r.choice(["matte", "matte_on", "glass", "mirror", "plastic", "uber", "shinymetal", "translucent", "substrate"])
+    k = r.choice(["matte", "matte_on", "glass", "mirror", "plastic", "uber", "shinymetal", "translucent", "substrate", "measured"])
+    if k == "measured":
+        return 'Material "%s"' % r.choice(["bluepaint", "brushedmetal", "clay", "felt", "primer", "skin"])
     if k == "matte":
         return 'Material "matte" "color Kd" [%s]' % rnd_color(r)
     if k == "matte_on":

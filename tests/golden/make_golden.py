@@ -905,6 +905,36 @@ INLINE["lights_mapped_direct"] = _mapped_lights('"directlighting" "integer maxde
 INLINE["lights_mapped_whitted"] = _mapped_lights('"whitted" "integer maxdepth" [3]', "mapped_whitted")
 
 
+def _measured(integrator, tag):
+    """the six measured (Lafortune) materials, one of them bump-mapped"""
+    mats = ["bluepaint", "brushedmetal", "clay", "felt", "primer", "skin"]
+    body = ""
+    for i, m in enumerate(mats):
+        body += 'AttributeBegin\nMaterial "%s"%s\nTranslate %g %g %g\nShape "sphere" "float radius" [.8]\nAttributeEnd\n' % (
+            m, ' "float bumpmap" [.15]' if m == "clay" else "", -3.2 + 2.1 * (i % 3) + 1.1, 0.1 + 1.9 * (i // 3), (i // 3) * 1.5 - 1)
+    return """LookAt 0 3 -9 0 0.8 0 0 1 0
+Camera "perspective" "float fov" [40]
+Film "image" "integer xresolution" [36] "integer yresolution" [28] "string filename" ["measured_%s_out.exr"]
+Sampler "stratified" "integer xsamples" [2] "integer ysamples" [2]
+PixelFilter "box"
+SurfaceIntegrator %s
+WorldBegin
+LightSource "point" "color I" [70 70 70] "point from" [3 7 -6]
+AttributeBegin
+AreaLightSource "area" "color L" [9 9 9]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-2 6 -1 2 6 -1 2 6 2 -2 6 2]
+AttributeEnd
+Material "brushedmetal"
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-9 -1 -9 9 -1 -9 9 -1 9 -9 -1 9]
+%sWorldEnd
+""" % (tag, integrator, body)
+
+
+INLINE["measured_path"] = _measured('"path" "integer maxdepth" [4]', "path")
+INLINE["measured_direct"] = _measured('"directlighting" "integer maxdepth" [3]', "direct")
+INLINE["measured_whitted"] = _measured('"whitted" "integer maxdepth" [3]', "whitted")
+
+
 def _bestcandidate(integrator, tag, sampler, film='"integer xresolution" [28] "integer yresolution" [20]', lens="", nsamples=1, pfilter='"box"'):
     """bestcandidate sampler (the reference's default when a scene names none)"""
     return """LookAt 278 273 -800 278 273 0 0 1 0
