@@ -142,11 +142,19 @@ def test_camera_rays_and_traversal_bit_exact(ffi, scene_dir):
     ds.close()
 
 
-def test_tiles_are_independent_and_wave_size_invariant(ffi, scene_dir):
+@pytest.mark.parametrize("variant", ["plain", "textured", "textured_whitted"])
+def test_tiles_are_independent_and_wave_size_invariant(ffi, scene_dir, variant):
     """A window rendered alone == the same pixels of the full frame, bit for bit (Mitchell filter: the
-    tile re-traces its apron), and the result does not depend on how samples are split into waves."""
-    sp = gen_scene(os.path.join(scene_dir, "tiles.pbrt"), "c3", "--res", "48", "40", "--spp", "2", "2", "--filter",
-                   "mitchell", "--filename", os.path.join(scene_dir, "tiles.exr"))
+    tile re-traces its apron), and the result does not depend on how samples are split into waves.  The
+    textured variants carry per-slot camera-ray differentials and per-hit evaluated materials (path) or
+    per-frame child differentials (whitted) through the same waves."""
+    extra = []
+    if variant != "plain":
+        extra += ["--textured", os.path.join(GOLDEN, "tex13x7.exr"), "--mirror"]
+    if variant == "textured_whitted":
+        extra += ["--integrator", "whitted"]
+    sp = gen_scene(os.path.join(scene_dir, "tiles_%s.pbrt" % variant), "c3", "--res", "48", "40", "--spp", "2", "2", "--filter",
+                   "mitchell", "--filename", os.path.join(scene_dir, "tiles.exr"), *extra)
     scene = ffi.Scene(sp)
     ds = ffi.DeviceScene(scene)
     ds.render()
