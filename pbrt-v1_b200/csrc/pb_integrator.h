@@ -593,14 +593,18 @@ PB_HD bool path_vertex_surface(const SceneView &sv, PathState &st, const Ray &ra
   if (hit.prim < 0) {
     // path.cpp:69-82.  lights[i]->Le(ray) is black for point and area lights (core/light.cpp:41-43)
     if (pathLength == 0) st.alpha = 0.f;   // L != 0 ? 1 : 0 with L == 0
+    // (TEX = false instances serve scenes without any texture node, hence without radiance maps: Le is Lbase,
+    // and the map lookup's call stays out of those kernels)
     if (sv.nInfiniteLights != 0) {
       if (pathLength == 0) {
         for (uint32_t i = 0; i < sv.nLights; ++i)
-          if (sv.lights[i].kind == PBRT_B200_LIGHT_INFINITE) st.L = st.L + infinite_le(sv, sv.lights[i], ray.d);
+          if (sv.lights[i].kind == PBRT_B200_LIGHT_INFINITE)
+            st.L = st.L + (TEX ? infinite_le(sv, sv.lights[i], ray.d) : light_color(sv.lights[i]));
         st.alpha = is_black(st.L) ? 0.f : 1.f;
       } else if (st.specularBounce) {
         for (uint32_t i = 0; i < sv.nLights; ++i)
-          if (sv.lights[i].kind == PBRT_B200_LIGHT_INFINITE) st.L = st.L + st.T * infinite_le(sv, sv.lights[i], ray.d);
+          if (sv.lights[i].kind == PBRT_B200_LIGHT_INFINITE)
+            st.L = st.L + st.T * (TEX ? infinite_le(sv, sv.lights[i], ray.d) : light_color(sv.lights[i]));
       }
     }
     return false;

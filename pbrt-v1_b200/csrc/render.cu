@@ -1615,7 +1615,7 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   if (!err.empty()) { delete h; return fail(PBRT_B200_ERR_INVALID, err); }
   h->hasSpecular = pb_scene_has_specular(*scene);
   h->hasGlossy = false;
-  h->textured = false;
+  h->textured = scene->n_textures != 0;   // material operands (below) or light maps
   for (uint32_t i = 0; i < scene->n_materials; ++i) {
     int k = scene->materials[i].kind;
     if (k < PBRT_B200_MAT_MATTE || k > PBRT_B200_MAT_MEASURED) { delete h; return fail(PBRT_B200_ERR_INVALID, "unknown material kind"); }
