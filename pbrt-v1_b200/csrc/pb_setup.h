@@ -38,12 +38,10 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
   }
   // texture operands: indices in range, operands before their users, image maps with complete pyramids
   sv->nTextures = s.n_textures;
-  bool textured = false;
   for (uint32_t i = 0; i < s.n_materials; ++i)
-    for (int k = 0; k < PBRT_B200_TEXSLOTS; ++k) {
+    for (int k = 0; k < PBRT_B200_TEXSLOTS; ++k)
       if (s.materials[i].tex[k] >= (int32_t)s.n_textures) return "material texture index out of range";
-      textured |= s.materials[i].tex[k] >= 0;
-    }
+  std::string texDepth(s.n_textures, '\0');   // operators above the deepest leaf, per node (operands come first)
   for (uint32_t i = 0; i < s.n_textures; ++i) {
     const PbrtB200Texture &t = s.textures[i];
     if (t.kind > PBRT_B200_TEX_MARBLE || (t.channels != 1 && t.channels != 3)) return "unknown texture kind";
@@ -53,7 +51,11 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
       return "checkerboard: unsupported anti-aliasing mode";
     if (t.kind == PBRT_B200_TEX_SCALE || t.kind == PBRT_B200_TEX_MIX || t.kind == PBRT_B200_TEX_CHECKERBOARD || t.kind == PBRT_B200_TEX_DOTS)
       for (int k = 0; k < (t.kind == PBRT_B200_TEX_MIX ? 3 : 2); ++k)
+      {
         if (t.arg[k] < 0 || t.arg[k] >= (int32_t)i) return "texture operand must precede its user";
+        if (texDepth[t.arg[k]] + 1 > texDepth[i]) texDepth[i] = (char)(texDepth[t.arg[k]] + 1);
+        if (texDepth[i] > 3) return "texture expression more than 3 operators deep";   // PB_TEX_MAX_DEPTH
+      }
     if (t.kind == PBRT_B200_TEX_IMAGEMAP) {
       if (t.n_levels < 1 || (uint64_t)t.first_level + t.n_levels > s.n_tex_levels || !s.ewa_weight_lut) return "image map without a pyramid";
       if (t.mapping > PBRT_B200_TEXMAP_PLANAR || t.wrap > PBRT_B200_TEXWRAP_CLAMP) return "unknown texture mapping or wrap mode";
@@ -64,7 +66,6 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
       }
     }
   }
-  (void)textured;
   if (s.n_top_nodes > s.n_nodes) return "n_top_nodes > n_nodes";
   for (uint32_t i = 0; i < s.n_instances; ++i) {
     const PbrtB200Instance &in = s.instances[i];
