@@ -39,9 +39,10 @@
 #define PB_INFINITY ((float)INFINITY)
 #endif
 
-#if defined(PB_TWIN_LIBM_FLOAT) && !defined(__CUDACC__)
-// test-only variant of the CPU twin: call glibc's float functions directly, to
-// separate "libm rounding" differences from logic differences
+#if (defined(PB_TWIN_LIBM_FLOAT) || defined(PB_HOST_LIBM_FLOAT)) && !defined(__CUDACC__)
+// CPU builds that must round like the reference: the oracle twin's bit-comparison variant
+// (PB_TWIN_LIBM_FLOAT) and the host front end's scene-load code (PB_HOST_LIBM_FLOAT, host/texture.cpp)
+// call glibc's float functions directly
 PB_HD float pb_sinf(float x) { return sinf(x); }
 PB_HD float pb_cosf(float x) { return cosf(x); }
 PB_HD float pb_acosf(float x) { return acosf(x); }
@@ -56,7 +57,7 @@ PB_NOINLINE float pb_atan2f(float y, float x) { return (float)atan2((double)y, (
 PB_NOINLINE float pb_tanf(float x) { return (float)tan((double)x); }
 PB_NOINLINE float pb_atanf(float x) { return (float)atan((double)x); }
 #endif
-#if defined(PB_TWIN_LIBM_FLOAT) && !defined(__CUDACC__)
+#if (defined(PB_TWIN_LIBM_FLOAT) || defined(PB_HOST_LIBM_FLOAT)) && !defined(__CUDACC__)
 PB_HD float pb_powf(float x, float y) { return powf(x, y); }
 #else
 PB_NOINLINE float pb_powf(float x, float y) { return (float)pow((double)x, (double)y); }

@@ -12,7 +12,7 @@
 #define PB_TEXTURE_H
 #include "pb_shapes.h"
 
-#if defined(PB_TWIN_LIBM_FLOAT) && !defined(__CUDACC__)
+#if (defined(PB_TWIN_LIBM_FLOAT) || defined(PB_HOST_LIBM_FLOAT)) && !defined(__CUDACC__)
 PB_HD float pb_logf(float x) { return logf(x); }
 #else
 PB_NOINLINE float pb_logf(float x) { return (float)log((double)x); }

@@ -3,8 +3,10 @@
 // constructors: reading the image (core/exrio.cpp:40-73), resampling it to a power of two with Lanczos weights
 // and box-filtering the pyramid (core/mipmap.h:89-165), filling the EWA weight table (:167-176).
 #include "texture.h"
-// the lookup arithmetic itself is the device's stage code, compiled here with glibc's float libm like the reference
-#define PB_TWIN_LIBM_FLOAT 1
+// The lookup arithmetic is the device's stage code (csrc/pb_texture.h).  This host copy runs inside constructors
+// whose results the reference computes with glibc's float libm (logf in MIPMap::Lookup), so it is compiled against
+// the float functions rather than the device's double-rounded ones.
+#define PB_HOST_LIBM_FLOAT 1
 #include "../csrc/pb_texture.h"
 #include <errno.h>
 #include <stdint.h>
