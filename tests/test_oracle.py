@@ -285,6 +285,32 @@ def test_bestcandidate_table_matches_reference():
     assert np.array_equal(want.view(np.uint32), table.view(np.uint32))
 
 
+def test_unsupported_texture_modes_are_reported_not_rendered(ffi, tmp_path, capfd):
+    """Checkerboards that draw random numbers inside the texture (supersampled, 3D) are refused at parse time:
+    an error is reported, the texture is not created and the material falls back to its default operand,
+    as the reference does for any texture it cannot create (api.cpp:318-331)."""
+    sp = str(tmp_path / "unsupported.pbrt")
+    open(sp, "w").write("""LookAt 0 0 -5 0 0 0 0 1 0
+Camera "perspective" "float fov" [40]
+Film "image" "integer xresolution" [8] "integer yresolution" [8] "string filename" ["u.exr"]
+Sampler "stratified" "integer xsamples" [1] "integer ysamples" [1]
+SurfaceIntegrator "path"
+WorldBegin
+LightSource "point" "color I" [10 10 10] "point from" [0 3 -3]
+Texture "a" "color" "checkerboard" "string aamode" ["supersample"]
+Texture "b" "color" "checkerboard" "integer dimension" [3]
+Texture "c" "color" "checkerboard"
+Material "matte" "texture Kd" "c"
+Shape "sphere" "float radius" [1]
+WorldEnd
+""")
+    scene = ffi.Scene(sp)
+    err = capfd.readouterr().err
+    assert "supersample" in err or "random numbers" in err
+    assert err.count("Unable to create color texture") == 2
+    assert scene.n_prims == 1
+
+
 def test_noise_permutation_matches_reference():
     """pb_noise_table.h states Perlin's published permutation; where the reference is present, compare it with
     the array the reference's Noise() indexes (core/texture.cpp:31-61)."""
