@@ -122,6 +122,13 @@ b = 'bool KdTreeAccel::IntersectP(const Ray &ray) const {\n'
 assert k.count(a) == 1 and k.count(b) == 1
 k = k.replace(a, a + '\t++gRefIntersectCalls;\n').replace(b, b + '\t++gRefIntersectPCalls;\n')
 assert 'extern unsigned long long gRefIntersectCalls' in k
+# ... and hand the finished tree to the glue (exact node / reference counts on stderr; with
+# PBRT_REF_DUMP_KD=<file> the whole tree: tests compare the host build's arrays with it word for word)
+k = k.replace('// KdAccelNode Declarations', 'extern void pbrtRefKdBuilt(const void *nodes, int nNodes, const void *mailboxBase, int mailboxStride, int nPrims, const float *bounds);\n// KdAccelNode Declarations', 1)
+m = '\t// Free working memory for kd-tree construction\n'
+assert k.count(m) == 1
+k = k.replace(m, '\t{ float b6[6] = { bounds.pMin.x, bounds.pMin.y, bounds.pMin.z, bounds.pMax.x, bounds.pMax.y, bounds.pMax.z };\n'
+                 '\t  pbrtRefKdBuilt(nodes, nextFreeNode, mailboxPrims, (int)sizeof(MailboxPrim), (int)nMailboxes, b6); }\n' + m)
 open(tmp + "/kdtree_counted.cpp", "w").write(k)
 PY
 g++ $FL -c $TMP/scene_hooked.cpp -o $TMP/exact/scene.o

@@ -159,6 +159,57 @@ COREDLL void pbrtRefEndRender() {
   fprintf(stderr, "PBRT_REF_RENDER_SECONDS %.6f SAMPLES %llu\n", gRenderSeconds, gSampleCounter);
   fprintf(stderr, "PBRT_REF_RAYS INTERSECT %llu INTERSECTP %llu\n", gRefIntersectCalls, gRefIntersectPCalls);
 }
+// Called by the counted kdtree.cpp copy when a KdTreeAccel has been built (see build_ref.sh).  Prints the
+// exact node / leaf-reference counts (the reference's own statistics round them to 3-4 digits,
+// core/util.cpp:263-276) and, with PBRT_REF_DUMP_KD=<file>, appends the tree in the flat form of
+// include/pbrt_b200.h: per node {word0 = the reference's flags|split|nPrims word, word1 = above child |
+// primitive number | offset into the reference list}, then the leaves' reference lists in node order.
+COREDLL void pbrtRefKdBuilt(const void *nodes, int nNodes, const void *mailboxBase, int mailboxStride, int nPrims,
+                            const float *bounds) {
+  const unsigned char *nb = (const unsigned char *)nodes;
+  unsigned long long nRefs = 0, nLeaves = 0;
+  for (int i = 0; i < nNodes; ++i) {
+    unsigned int w0;
+    memcpy(&w0, nb + 16 * (size_t)i, 4);
+    if ((w0 & 3u) == 3u) { ++nLeaves; if ((w0 >> 2) > 1) nRefs += w0 >> 2; }
+  }
+  fprintf(stderr, "PBRT_REF_KD NODES %d LEAVES %llu REFS %llu PRIMS %d\n", nNodes, nLeaves, nRefs, nPrims);
+  const char *fn = getenv("PBRT_REF_DUMP_KD");
+  if (!fn) return;
+  FILE *f = fopen(fn, "ab");
+  if (!f) return;
+  unsigned int hdr[4] = {0x4b445452u, (unsigned int)nNodes, (unsigned int)nRefs, (unsigned int)nPrims};
+  fwrite(hdr, 4, 4, f);
+  fwrite(bounds, 4, 6, f);
+  unsigned int *words = new unsigned int[2 * (size_t)nNodes];
+  unsigned int *refs = new unsigned int[nRefs ? nRefs : 1];
+  unsigned long long off = 0;
+  for (int i = 0; i < nNodes; ++i) {
+    unsigned int w0;
+    memcpy(&w0, nb + 16 * (size_t)i, 4);
+    words[2 * i] = w0;
+    if ((w0 & 3u) != 3u) {
+      memcpy(&words[2 * i + 1], nb + 16 * (size_t)i + 8, 4);   // aboveChild
+      continue;
+    }
+    unsigned int np = w0 >> 2;
+    const unsigned char *ptr;
+    memcpy(&ptr, nb + 16 * (size_t)i + 8, sizeof(ptr));
+    if (np == 0) words[2 * i + 1] = 0;
+    else if (np == 1) words[2 * i + 1] = (unsigned int)((ptr - (const unsigned char *)mailboxBase) / mailboxStride);
+    else {
+      words[2 * i + 1] = (unsigned int)off;
+      const unsigned char *const *list = (const unsigned char *const *)ptr;
+      for (unsigned int k = 0; k < np; ++k)
+        refs[off++] = (unsigned int)((list[k] - (const unsigned char *)mailboxBase) / mailboxStride);
+    }
+  }
+  fwrite(words, 4, 2 * (size_t)nNodes, f);
+  fwrite(refs, 4, nRefs, f);
+  delete[] words;
+  delete[] refs;
+  fclose(f);
+}
 COREDLL void pbrtRefDumpSample(const Sample *sample, const Spectrum &Ls, float alpha) {
   if (!gDump) return;
   float xyz[3];

@@ -1,0 +1,157 @@
+"""GPU parity at the BASELINE configurations' real sizes (-m gpu), against the compiled reference run LIVE
+on this box (oracle/_ref travels with the snapshot; /root/reference is not needed at run time).
+
+The reference is single-threaded; it is run the only way it parallelises: as concurrent `cropwindow`
+processes over the host cores (film/image.cpp:79-85,148-156), each with the per-sample keyed RNG
+("O-keyed").  Everything on the GPU side goes through the C ABI.
+
+  C3  Cornell + glass sphere, path maxdepth 5, 1024x1024, 64 spp, box filter -- the WHOLE frame
+  C4  101 k-triangle blob, path, 1024x1024 64 spp                             -- a 128x128 crop, per sample
+  C5  998 k-triangle blob, path, 1920x1080 256 spp                            -- a 128x96 crop, per sample
+  + the kd-trees of C4 / C5 (2.6 M / 18.9 M nodes) equal the reference's word for word.
+
+Stated tolerance on the fp32 film handed to WriteRGBAImage: |delta| <= max(2^-10 |ref|, 1e-3)
+for >= 90 % of the pixels, every outlier <= 4 * Lmax / spp (a few flipped samples: one sample moves a pixel
+by up to Lmax / spp), image mean within 2e-3 relative.  The cause of any difference is the documented one:
+sinf / cosf / atan2f / acosf are evaluated in double and rounded once on the device, glibc's float
+versions on the reference.  Integer work (sample positions, ray counts of the camera
+rays, the trees) is bit exact.  The histograms are printed and written to gpurun_out/ for the record.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from parity_util import (ROOT, error_histogram, gen_scene, host_cores, host_kd_arrays, read_kd_dump,
+                         reference_statistic, row_strips, run_reference_windows)
+
+pytestmark = pytest.mark.gpu
+
+LIGHT_MAX = 17.0   # the Cornell light's largest emitted radiance channel (scenes/gen_scenes.py)
+
+
+def _record(name, obj):
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_%s.json" % name), "w") as f:
+            json.dump(obj, f, indent=1)
+    except OSError:
+        pass
+    print("PARITY %s %s" % (name, json.dumps(obj)))
+
+
+def _need_reference(ffi):
+    if not ffi.have_reference():
+        pytest.skip("oracle/_ref not present in this snapshot")
+
+
+def _assert_film(h, spp):
+    assert h["frac_within_tol"] >= 0.90, h
+    assert h["outliers_over_bound"] == 0, h
+    assert h["mean_rel"] <= 2e-3, h
+
+
+def _gpu_windows(ffi, scene, wins, keep_samples):
+    ds = ffi.DeviceScene(scene)
+    ffi.cuda().pbrt_b200_sample_radiance(ds.h, 0, 1 if keep_samples else 0, None)
+    st = ds.render([ffi.Window(*w) for w in wins])
+    return ds, st
+
+
+def test_c3_full_frame_vs_live_reference(ffi, scene_dir):
+    """BASELINE configs[2], the headline workload, whole frame: 67.2 M samples, ~409 M rays."""
+    _need_reference(ffi)
+    sp = gen_scene(os.path.join(scene_dir, "c3full.pbrt"), "c3", "--filename", os.path.join(scene_dir, "c3full.exr"))
+    strips = row_strips((0, 0, 1024, 1024), host_cores())
+    res, wall = run_reference_windows(ffi, sp, 1024, 1024, strips, scene_dir, keyed=True, tag="c3ref")
+    ref = np.concatenate([r["rgba"] for r in res], axis=0)
+    scene = ffi.Scene(sp)
+    # the product call: host buffers in, host buffers out
+    outs, _, st = ffi.render_host(scene)
+    gpu = outs[0]
+    h = error_histogram(gpu, ref, LIGHT_MAX, 64)
+    # the same frame as the reference's strips (its rays include each strip's one-row sample apron)
+    ds, st2 = _gpu_windows(ffi, scene, strips, False)
+    tiles = np.concatenate([ds.download(i) for i in range(len(strips))], axis=0)
+    ds.close()
+    assert np.array_equal(tiles.view(np.uint32), gpu.view(np.uint32)), "strip renders differ from the full frame"
+    ref_i = sum(r["intersect"] for r in res)
+    ref_p = sum(r["intersect_p"] for r in res)
+    h.update({"config": "C3 1024x1024 64spp path maxdepth 5 box filter, whole frame", "reference_wall_s": wall,
+              "reference_processes": len(strips), "rays_reference": [ref_i, ref_p],
+              "rays_gpu": [st2["intersect_rays"], st2["shadow_rays"]], "camera_rays": st["camera_rays"]})
+    _record("c3_full", h)
+    assert st["camera_rays"] == 1025 * 1025 * 64
+    assert st["nan_samples"] == 0 and st["infinite_samples"] == 0
+    _assert_film(h, 64)
+    assert h["frac_identical"] >= 0.5, h   # most pixels do not even hold a sample that differs in the last bit
+    assert abs(st2["intersect_rays"] - ref_i) <= 2e-4 * ref_i, (st2["intersect_rays"], ref_i)
+    assert abs(st2["shadow_rays"] - ref_p) <= 2e-4 * ref_p, (st2["shadow_rays"], ref_p)
+
+
+def _big_scene_crop(ffi, scene_dir, name, res, spp, win, nproc, tris):
+    sp = gen_scene(os.path.join(scene_dir, "%s_scale.pbrt" % name), name, "--filename",
+                   os.path.join(scene_dir, "%s_scale.exr" % name))
+    strips = row_strips(win, nproc)
+    kd = os.path.join(scene_dir, "%s_kd.bin" % name)
+    out, wall = run_reference_windows(ffi, sp, res[0], res[1], strips, scene_dir, keyed=True, dump_samples=True,
+                                      dump_kd=kd, tag=name + "ref")
+    scene = ffi.Scene(sp)
+    assert scene.n_prims == tris
+    # (iii) the tree: node / reference counts and every word
+    b, nodes, refs, ntop = host_kd_arrays(scene)
+    rb, rnodes, rrefs, rprims = read_kd_dump(kd)
+    os.remove(kd)
+    assert out[0]["kd"] == (nodes.shape[0], int(((nodes[:, 0] & 3) == 3).sum()), refs.shape[0], scene.n_prims)
+    for stat, mine in (("Interior kd-tree nodes made", int(((nodes[:, 0] & 3) != 3).sum())),
+                       ("Leaf kd-tree nodes made", int(((nodes[:, 0] & 3) == 3).sum()))):
+        v, tol = reference_statistic(out[0]["statistics"], stat)
+        assert v is not None and abs(v - mine) <= tol, (stat, v, mine)
+    assert np.array_equal(b, rb) and np.array_equal(nodes, rnodes) and np.array_equal(refs, rrefs)
+    del rnodes, rrefs
+    ds, st = _gpu_windows(ffi, scene, strips, True)
+    nspp = spp[0] * spp[1]
+    ident, n_all, worst = 0, 0, 0.0
+    gpu_tiles = []
+    for i, r in enumerate(out):
+        g = ds.download(i)
+        gpu_tiles.append(g)
+        rs = r["samples"]
+        ls = ds.sample_radiance(i, rs.shape[0])
+        d = np.abs(ls[:, :3] - rs[:, 2:5]).max(axis=1)
+        ident += int((d == 0).sum()); n_all += d.size; worst = max(worst, float(d.max()))
+        assert np.array_equal(ls[:, 3], rs[:, 5]), "alpha differs"
+    ds.close()
+    gpu = np.concatenate(gpu_tiles, axis=0)
+    ref = np.concatenate([r["rgba"] for r in out], axis=0)
+    h = error_histogram(gpu, ref, LIGHT_MAX, nspp)
+    ref_i = sum(r["intersect"] for r in out)
+    ref_p = sum(r["intersect_p"] for r in out)
+    shaded_ref = [reference_statistic(r["statistics"], "Number of points shaded") for r in out]
+    h.update({"config": "%s %dx%d %dspp path, crop %s, %d triangles, %d kd nodes" % (name, res[0], res[1], nspp, list(win),
+                                                                                    tris, nodes.shape[0]),
+              "samples": n_all, "samples_identical": ident / n_all, "sample_linf": worst, "reference_wall_s": wall,
+              "rays_reference": [ref_i, ref_p], "rays_gpu": [st["intersect_rays"], st["shadow_rays"]],
+              "points_shaded_gpu": st["points_shaded"], "points_shaded_reference": sum(v for v, _ in shaded_ref),
+              "kd_tree_identical": True})
+    _record(name + "_crop", h)
+    assert st["camera_rays"] == n_all
+    _assert_film(h, nspp)
+    assert ident / n_all >= 0.97, h
+    assert abs(st["intersect_rays"] - ref_i) <= 1e-3 * ref_i and abs(st["shadow_rays"] - ref_p) <= 1e-3 * ref_p
+    assert abs(st["points_shaded"] - sum(v for v, _ in shaded_ref)) <= sum(t for _, t in shaded_ref) + 1e-3 * st["points_shaded"]
+
+
+def test_c4_crop_vs_live_reference(ffi, scene_dir):
+    """BASELINE configs[3]: 101 k-triangle blob, 1024x1024, 64 spp -- 128x128 crop over the blob's silhouette."""
+    _need_reference(ffi)
+    _big_scene_crop(ffi, scene_dir, "c4", (1024, 1024), (8, 8), (256, 560, 128, 128), host_cores(), 101772)
+
+
+def test_c5_crop_vs_live_reference(ffi, scene_dir):
+    """BASELINE configs[4]: 998 k-triangle blob, 1920x1080, 256 spp -- 128x96 crop; each reference process
+    builds the 18.9 M-node tree itself (~15 s, ~1 GB), so at most 16 run at once."""
+    _need_reference(ffi)
+    _big_scene_crop(ffi, scene_dir, "c5", (1920, 1080), (16, 16), (720, 600, 128, 96), min(16, host_cores()), 998012)

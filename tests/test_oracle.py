@@ -352,3 +352,34 @@ def test_parallel_kd_build_equals_sequential(ffi, tmp_path):
     assert outs[0] == outs[1], outs
     assert int(outs[0].split()[0]) > 10000
 
+
+
+def test_c4_scale_tree_and_crop_vs_reference(ffi, tmp_path):
+    """BASELINE configs[3] geometry at its real size (101 k triangles, 2.6 M kd nodes): the host front end's
+    kd-tree equals the one the compiled reference builds word for word (every split, child index and leaf
+    list: accelerators/kdtree.cpp:141-312, incl. the maxDepth formula and the badRefines / retry paths a deep
+    tree exercises), and a crop rendered as concurrent cropwindow processes of the reference equals the libm
+    twin bit for bit, sample by sample."""
+    if not ffi.have_reference():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    from parity_util import host_kd_arrays, read_kd_dump, row_strips, run_reference_windows
+    td = str(tmp_path)
+    sp = gen_scene(os.path.join(td, "c4.pbrt"), "c4", "--res", "256", "256", "--spp", "2", "2", "--filename",
+                   os.path.join(td, "c4.exr"))
+    win = (116, 116, 24, 24)
+    kd = os.path.join(td, "kd.bin")
+    res, _ = run_reference_windows(ffi, sp, 256, 256, row_strips(win, 3), td, keyed=True, dump_samples=True, dump_kd=kd)
+    scene = ffi.Scene(sp)
+    b, nodes, refs, ntop = host_kd_arrays(scene)
+    rb, rnodes, rrefs, rprims = read_kd_dump(kd)
+    assert rprims == scene.n_prims == 101772
+    assert res[0]["kd"][0] == nodes.shape[0] == ntop and res[0]["kd"][2] == refs.shape[0]
+    assert np.array_equal(b, rb)
+    assert np.array_equal(nodes, rnodes)
+    assert np.array_equal(refs, rrefs)
+    render = twin_with(ffi, "libpbrt_twin_libm.so")
+    for r in res:
+        rgba, samples, st = render(scene, ffi.Window(*r["window"]))
+        assert np.array_equal(rgba.view(np.uint32), r["rgba"].view(np.uint32)), r["window"]
+        assert np.array_equal(samples.view(np.uint32), r["samples"].view(np.uint32)), r["window"]
+        assert st["intersect_rays"] == r["intersect"] and st["shadow_rays"] == r["intersect_p"]
