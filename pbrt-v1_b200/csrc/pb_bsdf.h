@@ -508,6 +508,54 @@ PB_NOINLINE Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, float u1, 
   return f;
 }
 
+// ---- A BSDF holding exactly one Lambertian lobe: matte with sigma == 0 (materials/matte.cpp:46-64), the
+// material of most path vertices.  bsdf_f / bsdf_pdf / bsdf_sample_f above specialised by hand for nLobes == 1,
+// lobes[0] = {PB_LOBE_LAMBERT, PB_REFLECTION | PB_DIFFUSE, R = Kd * INV_PI}: the same operations on the values
+// that reach a result (a Lambertian lobe reads only the z components of the local directions), without the
+// lobe table.  The kernels use it where the material allows; the CPU twin always runs the general code, so the
+// GPU == twin tests pin the two forms to each other.
+struct LambertBsdf {
+  V3 p;
+  V3 nn, ng, sn, tn;
+  Spec R;   // Lambertian::RoverPI
+};
+PB_HD V3 bsdf_local_to_world(const LambertBsdf &b, const V3 &v) {
+  return v3(b.sn.x * v.x + b.tn.x * v.y + b.nn.x * v.z, b.sn.y * v.x + b.tn.y * v.y + b.nn.y * v.z,
+            b.sn.z * v.x + b.tn.z * v.y + b.nn.z * v.z);
+}
+template <bool G = true>
+PB_HD Spec bsdf_f(const LambertBsdf &b, const V3 &woW, const V3 &wiW, int = PB_ALL) {
+  Spec f = spec(0.f);
+  if (dot(wiW, b.ng) * dot(woW, b.ng) > 0) f = f + b.R;   // the reflection lobe counts on the same side only
+  return f;
+}
+template <bool G = true>
+PB_HD float bsdf_pdf(const LambertBsdf &b, const V3 &woW, const V3 &wiW, int = PB_ALL) {
+  float woz = dot(woW, b.nn), wiz = dot(wiW, b.nn);
+  float pdf = 0.f;
+  pdf += (woz * wiz > 0.f) ? fabsf(wiz) * PB_INV_PI : 0.f;
+  return pdf;   // (/ matchingComps == 1)
+}
+// (the component choice min(Floor2Int(u3 * 1), 0) is 0 for every u3 in [0, 1); the single diffuse lobe matches
+// both flag sets the path integrator passes: BSDF_ALL and BSDF_ALL & ~BSDF_SPECULAR)
+template <bool G = true>
+PB_HD Spec bsdf_sample_f(const LambertBsdf &b, const V3 &woW, V3 *wiW, float u1, float u2, float, float *pdf,
+                         int, int *sampledType) {
+  float woz = dot(woW, b.nn);
+  V3 wi = cosine_sample_hemisphere(u1, u2);
+  if (woz < 0.f) wi.z *= -1.f;
+  *pdf = (woz * wi.z > 0.f) ? fabsf(wi.z) * PB_INV_PI : 0.f;
+  if (*pdf == 0.f) {
+    *sampledType = 0;
+    return spec(0.f);
+  }
+  *sampledType = PB_REFLECTION | PB_DIFFUSE;
+  *wiW = bsdf_local_to_world(b, wi);
+  Spec f = spec(0.f);
+  if (dot(*wiW, b.ng) * dot(woW, b.ng) > 0) f = f + b.R;
+  return f;
+}
+
 struct Bsdf;
 template <bool G = true>
 PB_HD void bsdf_set_lobes(const PbrtB200Material &m, Bsdf *b);

@@ -29,6 +29,11 @@ struct Surface {
   int32_t light;      // area light of the primitive or -1
   uint32_t material;  // index into materials[] (lets a later kernel rebuild the lobes)
 };
+struct LambertSurface {   // same, for a vertex whose material is matte with sigma == 0 (pb_bsdf.h: LambertBsdf)
+  LambertBsdf bsdf;
+  int32_t light;
+  uint32_t material;
+};
 // InstancePrimitive::Intersect's tail (core/primitive.cpp:72-83): the instanced shape's DG, computed
 // from the instance-space ray, moved to world space.
 PB_NOINLINE void instance_dg_to_world(const PbrtB200Instance &in, DiffGeom *dg) {
@@ -97,6 +102,25 @@ template <bool LOBES = true, bool INST = true, bool TEX = false>
 PB_HD void surface_at_hit(const SceneView &sv, const Ray &ray, const Hit &hit, Surface *sf,
                           const RayDiff *rd = (const RayDiff *)0, PbrtB200Material *evalMat = (PbrtB200Material *)0,
                           SurfaceDiff *sd = (SurfaceDiff *)0) {
+#ifdef __CUDA_ARCH__
+  if (!TEX && sv.primFrame) {
+    // flat triangle: the frame was computed once by k_prim_frames with this very function (see pb_scene.h)
+    const float4 tail = __ldg((const float4 *)(sv.prims + 3u * (uint32_t)hit.prim + 2));
+    const uint32_t pflags = __float_as_uint(tail.y);
+    if ((pflags & PB_PF_DEV_FRAME) && !(INST && hit.inst >= 0)) {
+      const float4 *fr = sv.primFrame + 3u * (uint32_t)hit.prim;
+      const float4 a = __ldg(fr), b = __ldg(fr + 1), c = __ldg(fr + 2);
+      Bsdf &bs = sf->bsdf;
+      bs.p = ray_at(ray, hit.t);
+      bs.ng = v3(a.x, a.y, a.z); bs.nn = v3(a.w, b.x, b.y); bs.sn = v3(b.z, b.w, c.x); bs.tn = v3(c.y, c.z, c.w);
+      sf->material = __float_as_uint(tail.z);
+      sf->light = __float_as_int(tail.w);
+      if (LOBES) bsdf_set_lobes<true>(sv.materials[sf->material], &bs);
+      else { bs.eta = 1.f; bs.nLobes = 0; }
+      return;
+    }
+  }
+#endif
   TriVerts tv = load_prim(sv, (uint32_t)hit.prim);
   DiffGeom dg, dgs;
   surface_dg<INST>(sv, ray, hit, tv, &dg);
@@ -144,11 +168,19 @@ PB_HD bool hit_emits_from_light(const SceneView &sv, const Ray &ray, const Hit &
 
 // ---------------------------------------------------------------- shape sampling
 // Triangle::Sample, shapes/trianglemesh.cpp:336-349 (+ UniformSampleTriangle mc.cpp:136-141)
-PB_HD V3 triangle_sample(const TriVerts &tv, float u1, float u2, V3 *Ns) {
+// `frame`: the light-shape entry's precomputed pair (SceneView::lightFrame) or null
+PB_HD V3 triangle_sample(const TriVerts &tv, float u1, float u2, V3 *Ns, const float4 *frame = (const float4 *)0) {
   float su1 = sqrtf(u1);
   float b1 = 1.f - su1;
   float b2 = u2 * su1;
   V3 p = b1 * tv.p1 + b2 * tv.p2 + (1.f - b1 - b2) * tv.p3;
+#ifdef __CUDA_ARCH__
+  if (frame) {
+    const float4 f = __ldg(frame + 1);
+    *Ns = v3(f.x, f.y, f.z);
+    return p;
+  }
+#endif
   V3 n = cross(tv.p2 - tv.p1, tv.p3 - tv.p1);
   *Ns = normalize(n);
   if (tv.flags & PBRT_B200_PF_REVERSE) *Ns = *Ns * -1.f;
@@ -234,6 +266,7 @@ PB_NOINLINE float light_shapes_pdf(const SceneView &sv, const PbrtB200Light &l, 
   bool anyHit = false;
   Hit hit; hit.prim = -1; hit.t = 0.f; hit.b1 = hit.b2 = 0.f; hit.inst = -1;
   TriVerts htv;
+  uint32_t hitShape = 0;
   for (uint32_t i = 0; i < l.n_shapes; ++i) {
     uint32_t prim = sv.lightShapes[l.first_shape + i];
     TriVerts tv = load_prim(sv, prim);
@@ -245,10 +278,16 @@ PB_NOINLINE float light_shapes_pdf(const SceneView &sv, const PbrtB200Light &l, 
       V3 phit; float phi;
       ok = quadric_test(sv.quadrics[sv.aux[prim].owner], ray, &t, &phit, &phi, false);
     }
-    if (ok) { anyHit = true; hit.prim = (int32_t)prim; hit.t = t; hit.b1 = b1; hit.b2 = b2; htv = tv; }
+    if (ok) { anyHit = true; hit.prim = (int32_t)prim; hit.t = t; hit.b1 = b1; hit.b2 = b2; htv = tv; hitShape = l.first_shape + i; }
   }
   if (!anyHit) return 0.f;
   DiffGeom dg;
+#ifdef __CUDA_ARCH__
+  if (sv.lightFrame && (htv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_TRIANGLE) {
+    const float4 f = __ldg(sv.lightFrame + 2u * hitShape);   // dg.nn of this triangle: hit independent (k_light_frames)
+    dg.nn = v3(f.x, f.y, f.z);
+  } else
+#endif
   if (LK & PB_LK_QUADRIC) surface_dg(sv, ray, hit, htv, &dg);
   else tri_dg(sv, (uint32_t)hit.prim, htv, ray, hit.t, hit.b1, hit.b2, &dg);
   float ad = absdot(dg.nn, -wi);
@@ -288,7 +327,7 @@ PB_NOINLINE V3 area_light_sample_point(const SceneView &sv, const PbrtB200Light 
   uint32_t prim = sv.lightShapes[l.first_shape + sn];
   TriVerts tv = load_prim(sv, prim);
   if (!(LK & PB_LK_QUADRIC) || (tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_TRIANGLE)
-    return triangle_sample(tv, u1, u2, ns);
+    return triangle_sample(tv, u1, u2, ns, sv.lightFrame ? sv.lightFrame + 2u * (l.first_shape + sn) : (const float4 *)0);
   const PbrtB200Quadric &s = sv.quadrics[sv.aux[prim].owner];
   if (s.kind == PBRT_B200_QUADRIC_CYLINDER) return cylinder_sample_area(s, u1, u2, ns);   // Shape::Sample(P,..) default
   if (s.kind == PBRT_B200_QUADRIC_DISK) return disk_sample_area(s, u1, u2, ns);
@@ -476,9 +515,9 @@ PB_HD Spec escaped_le(const SceneView &sv, const V3 &d) {
 
 // transport.cpp:123-194.  ls1..bcs are already chosen by the caller
 // (Sample arrays or RandomFloat, :131-146).
-template <bool G = true, int LK = PB_LK_ALL>
+template <bool G = true, int LK = PB_LK_ALL, class BS = Bsdf>
 PB_HD void estimate_direct(const SceneView &sv, int lightNum, const V3 &p, const V3 &n, const V3 &wo,
-                           const Bsdf &bsdf, float ls1, float ls2, float bs1, float bs2, float bcs,
+                           const BS &bsdf, float ls1, float ls2, float bs1, float bs2, float bcs,
                            RngStream &rng, DirectRec *rec) {
   const PbrtB200Light &light = sv.lights[lightNum];
   rec->hasShadow = rec->hasProbe = false;
@@ -616,12 +655,12 @@ PB_HD bool path_vertex_surface(const SceneView &sv, PathState &st, const Ray &ra
   return true;
 }
 // path.cpp:93-112: one UniformSampleOneLight record at the vertex
-template <bool G = true, int LK = PB_LK_ALL>
+template <bool G = true, int LK = PB_LK_ALL, class SF = Surface>
 PB_HD void path_vertex_direct(const SceneView &sv, const PatternSource &key0, PathState &st, const Ray &ray,
-                              const Surface *sf, DirectRec *direct, bool *hasDirect) {
+                              const SF *sf, DirectRec *direct, bool *hasDirect) {
   *hasDirect = false;
   int pathLength = st.depth;
-  const Bsdf &bsdf = sf->bsdf;
+  const auto &bsdf = sf->bsdf;
   V3 p = bsdf.p, n = bsdf.nn;
   V3 wo = -ray.d;
   int nLights = (int)sv.nLights;
@@ -648,6 +687,22 @@ PB_HD void path_vertex_direct(const SceneView &sv, const PatternSource &key0, Pa
   }
   // NOTE: with no lights the reference dereferences lights[-1]; such scenes render black here.
 }
+// The RandomFloat() draws of path_vertex_direct at a vertex whose BSDF has no non-specular component, without
+// the estimate: there bsdf_f is black for every wi and Sample_f(~BSDF_SPECULAR) matches nothing, so
+// UniformSampleOneLight traces no ray and adds nothing (transport.cpp:51-70,153-155,171-174) -- but past
+// depth 3 it still drew its six sample values (transport.cpp:141-146), and the chosen light's Sample_L may
+// draw one more (ShapeSet::Sample, shape.h:115-121; InfiniteAreaLight::Sample_L, infinite.cpp:96).
+PB_HD void path_vertex_direct_skip(const SceneView &sv, const PatternSource &key0, PathState &st) {
+  int nLights = (int)sv.nLights;
+  if (nLights <= 0) return;
+  float ln;
+  if (st.depth < 3) ln = pat1d(sv, key0, 3 * st.depth, 0);
+  else { ln = st.rng.next_float(); st.rng.skip(5); }
+  int lightNum = pb_imin(pb_floor2int(ln * nLights), nLights - 1);
+  const PbrtB200Light &light = sv.lights[lightNum];
+  if (light.kind == PBRT_B200_LIGHT_AREA) { if (light.n_shapes > 1) st.rng.skip(1); }
+  else if (light.kind == PBRT_B200_LIGHT_INFINITE && light.dist_nu == 0) st.rng.skip(1);
+}
 template <bool TEX = false>
 PB_HD bool path_vertex_begin(const SceneView &sv, const PatternSource &key0, PathState &st, const Ray &ray,
                              const Hit &hit, Surface *sf, DirectRec *direct, bool *hasDirect,
@@ -659,11 +714,11 @@ PB_HD bool path_vertex_begin(const SceneView &sv, const PatternSource &key0, Pat
 }
 // Second half (path.cpp:113-143): sample the BSDF for the next direction, update the
 // throughput, Russian roulette, depth limit.  Returns true when the path continues along *next.
-template <bool G = true>
+template <bool G = true, class SF = Surface>
 PB_HD bool path_vertex_continue(const SceneView &sv, const PatternSource &key0, PathState &st, const Ray &ray,
-                                const Surface &sf, Ray *next) {
+                                const SF &sf, Ray *next) {
   int pathLength = st.depth;
-  const Bsdf &bsdf = sf.bsdf;
+  const auto &bsdf = sf.bsdf;
   V3 p = bsdf.p, n = bsdf.nn;
   V3 wo = -ray.d;
   float os1, os2, ocs;

@@ -6,6 +6,9 @@
 #include "pb_math.h"
 #include "pb_rng.h"
 #include "../../include/pbrt_b200.h"
+#ifndef __CUDACC__
+struct float4 { float x, y, z, w; };   // (host builds of the shared headers: the twin never dereferences these tables)
+#endif
 
 #define PB_MAX_PATTERNS 64      // sample patterns addressable from constant memory
 #define PB_KD_STACK 64          // MAX_TODO, accelerators/kdtree.cpp:323
@@ -62,7 +65,19 @@ struct SceneView {
   const float *lightDist;           // Distribution1D tables of the importance-sampled infinite lights
   const unsigned char *noisePerm;   // Perlin permutation, 512 entries (pb_noise_table.h), when a texture needs it
   uint32_t nTextures;
+  // Device-only tables, filled once per pbrt_b200_scene_create by k_prim_frames / k_light_frames with the very
+  // code a hit would run (null in the CPU twin, which evaluates every hit from scratch):
+  //   primFrame   3 x float4 per primitive: the BSDF frame (ng | nn | sn | tn) of a flat triangle (no per-vertex
+  //               N / S).  It depends on the triangle only -- dpdu / dpdv come from the vertices and uvs
+  //               (trianglemesh.cpp:248-268), Bump with the constant displacement 0 and the BSDF constructor
+  //               (material.cpp:29-71, reflection.cpp:471-479) add nothing hit dependent -- so a hit reads 48 bytes
+  //               instead of re-deriving it.  Valid where the primitive's device flags carry PB_PF_DEV_FRAME.
+  //   lightFrame  2 x float4 per entry of lightShapes[] that is a triangle: the DifferentialGeometry normal
+  //               Shape::Pdf uses (shape.h:96-107) and the Ns Triangle::Sample returns (trianglemesh.cpp:336-349).
+  const float4 *primFrame;
+  const float4 *lightFrame;
 };
+#define PB_PF_DEV_FRAME (1u << 31)
 
 struct Hit {
   int32_t prim;   // -1 = miss

@@ -60,6 +60,7 @@ static int64_t g_blocksPerSM = 12;        // key 2: resident CTAs per SM for the
 static int64_t g_overlap = 0;             // key 5: run shadow/probe traversal on a second stream, overlapped (measured +1%: both sides are issue bound, so off by default)
 static int64_t g_debugCounts = 0;         // key 6: print each wave's queue sizes per iteration to stderr
 static int64_t g_reserved4 = 0;           // key 4: reserved (was the fused shade kernel's occupancy variant)
+static int64_t g_primFrames = 1;          // key 7: precompute hit-independent BSDF / light-triangle frames at scene create (0: evaluate per hit)
 
 #ifndef PB_DIRECT_MIN_BLOCKS
 #define PB_DIRECT_MIN_BLOCKS 5
@@ -556,11 +557,29 @@ __device__ __forceinline__ void surface_load(const SceneView &sv, const SurfaceR
   bsdf_set_lobes<G>(r.mat ? r.mat[i] : sv.materials[sf->material], &b);
 }
 
+// The frame only; the caller adds the lobes (general Bsdf) or the reflectance (LambertBsdf).
+template <class B>
+__device__ __forceinline__ uint32_t surface_load_frame(const SurfaceRecord &r, uint32_t i, B *b) {
+  b->p = v3(r.f[0][i], r.f[1][i], r.f[2][i]);
+  b->nn = v3(r.f[3][i], r.f[4][i], r.f[5][i]);
+  b->ng = v3(r.f[6][i], r.f[7][i], r.f[8][i]);
+  b->sn = v3(r.f[9][i], r.f[10][i], r.f[11][i]);
+  b->tn = v3(r.f[12][i], r.f[13][i], r.f[14][i]);
+  return r.ids[i];
+}
+#ifndef PB_LAMBERT_PATH
+#define PB_LAMBERT_PATH 1   // 0: every vertex goes through the general lobe table (A/B switch for the profiles)
+#endif
+// matte with sigma == 0: one Lambertian lobe (materials/matte.cpp:59-62)
+__device__ __forceinline__ bool material_is_lambert(const PbrtB200Material &m) {
+  return PB_LAMBERT_PATH && m.kind == PBRT_B200_MAT_MATTE && m.sigma == 0.f;
+}
+
 // TEX: the scene has texture operands (ray differentials of the camera ray, operand evaluation at the hit)
 template <bool INST, bool TEX>
 __global__ void __launch_bounds__(PB_BLOCK, TEX ? PB_SURF_TEX_MIN_BLOCKS : PB_SURF_MIN_BLOCKS)
 k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const RayQueue qin,
-               const SurfaceRecord rec, const uint32_t *nPtr, uint32_t *work, uint32_t *hitCount) {
+               const SurfaceRecord rec, const uint32_t *nPtr, uint32_t *work, uint32_t *hitCount, uint32_t *specCount) {
   uint32_t n = *nPtr;
   uint32_t shaded = 0;
   for (;;) {
@@ -604,8 +623,18 @@ k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const
       if (st.depth == 0) wb.alpha[slot] = st.alpha;
       wb.flags[slot] = flags;
       }
-      // the shading kernels that follow walk the hits only: full warps instead of ~3/4 full ones
-      uint32_t j = warp_push(hitCount, isHit);
+      // The shading kernels that follow walk the hits only, and the hits are binned by material class so that
+      // their warps do not mix glass / mirror vertices with diffuse ones: vertices whose BSDF has a non-specular
+      // component fill the record arrays from the front (k_path_direct walks exactly these), specular-only ones
+      // (glass, mirror: UniformSampleOneLight cannot contribute there) from the back.
+      bool specOnly = false;
+      if (isHit) {
+        const int kind = TEX ? evalMat.kind : sv.materials[sf.material].kind;
+        specOnly = kind == PBRT_B200_MAT_GLASS || kind == PBRT_B200_MAT_MIRROR;
+      }
+      uint32_t j = warp_push(hitCount, isHit && !specOnly);
+      uint32_t js = warp_push(specCount, isHit && specOnly);
+      if (specOnly) j = wb.nSlots - 1u - js;
       if (isHit) {
         surface_store(rec, j, sf);
         rec.queueIdx[j] = i;
@@ -640,8 +669,6 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
         ray.o = v3(0, 0, 0);
         ray.d = v3(qin.dx[i], qin.dy[i], qin.dz[i]);   // only wo = -ray.d is needed
         ray.mint = 0.f; ray.maxt = 0.f;
-        Surface sf;
-        surface_load<G>(sv, rec, j, &sf);
         uint32_t flags = wb.flags[slot];
         PathState st;
         st.T = load3(wb.T, slot);
@@ -650,7 +677,18 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
         st.rng.ctr = wb.ctr[slot];
         PatternSource key0 = {slot_key(wd, slot, 0), LD ? wb.ld : (const float *)nullptr, wb.nSlots, slot, LD ? wd.bc : (wd.bc == 2 ? 2 : 0)};
         bool hasDirect;
-        path_vertex_direct<G, LK>(sv, key0, st, ray, &sf, &direct, &hasDirect);
+        const PbrtB200Material &mat = rec.mat ? rec.mat[j] : sv.materials[rec.ids[j] & 0xffffu];
+        if (material_is_lambert(mat)) {
+          LambertSurface ls;
+          uint32_t ids = surface_load_frame(rec, j, &ls.bsdf);
+          ls.material = ids & 0xffffu; ls.light = (int32_t)(ids >> 16) - 1;
+          ls.bsdf.R = spec3(mat.kd[0], mat.kd[1], mat.kd[2]) * PB_INV_PI;
+          path_vertex_direct<G, LK>(sv, key0, st, ray, &ls, &direct, &hasDirect);
+        } else {
+          Surface sf;
+          surface_load<G>(sv, rec, j, &sf);
+          path_vertex_direct<G, LK>(sv, key0, st, ray, &sf, &direct, &hasDirect);
+        }
         wb.ctr[slot] = st.rng.ctr;
         if (hasDirect) {
           pushShadow = direct.hasShadow;
@@ -684,14 +722,18 @@ template <bool LD, bool G>
 __global__ void __launch_bounds__(PB_BLOCK, PB_CONT_MIN_BLOCKS)
 k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveKeyInfo wd,
                 const RayQueue qin, const RayQueue qout, const SurfaceRecord rec, const uint32_t *nPtr,
-                uint32_t *work, uint32_t *nextCount) {
-  uint32_t n = *nPtr;
+                const uint32_t *nSpecPtr, uint32_t *work, uint32_t *nextCount) {
+  const uint32_t nDiff = *nPtr;
+  const uint32_t n = nDiff + *nSpecPtr;
   for (;;) {
     uint32_t chunk = warp_claim_n(work, PB_CLAIM);
     if (chunk >= n) break;
     for (uint32_t base = chunk; base < chunk + PB_CLAIM && base < n; base += 32) {
-      uint32_t j = base + lane_id();
-      bool valid = j < n;
+      uint32_t w = base + lane_id();
+      bool valid = w < n;
+      // records [0, nDiff) from the front, then the specular-only ones from the back of the arrays
+      const bool specOnly = valid && w >= nDiff;
+      uint32_t j = specOnly ? wb.nSlots - 1u - (w - nDiff) : w;
       uint32_t i = valid ? rec.queueIdx[j] : 0u;
       bool pushNext = false;
       uint32_t slot = 0;
@@ -702,8 +744,6 @@ k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, cons
         ray.o = v3(0, 0, 0);
         ray.d = v3(qin.dx[i], qin.dy[i], qin.dz[i]);
         ray.mint = 0.f; ray.maxt = 0.f;
-        Surface sf;
-        surface_load<G>(sv, rec, j, &sf);
         uint32_t flags = wb.flags[slot];
         PathState st;
         st.T = load3(wb.T, slot);
@@ -712,7 +752,19 @@ k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, cons
         st.rng.key = slot_key(wd, slot, 1);
         st.rng.ctr = wb.ctr[slot];
         PatternSource key0 = {slot_key(wd, slot, 0), LD ? wb.ld : (const float *)nullptr, wb.nSlots, slot, LD ? wd.bc : (wd.bc == 2 ? 2 : 0)};
-        pushNext = path_vertex_continue<G>(sv, key0, st, ray, sf, &next);
+        const PbrtB200Material &mat = rec.mat ? rec.mat[j] : sv.materials[rec.ids[j] & 0xffffu];
+        if (!specOnly && material_is_lambert(mat)) {
+          LambertSurface ls;
+          uint32_t ids = surface_load_frame(rec, j, &ls.bsdf);
+          ls.material = ids & 0xffffu; ls.light = (int32_t)(ids >> 16) - 1;
+          ls.bsdf.R = spec3(mat.kd[0], mat.kd[1], mat.kd[2]) * PB_INV_PI;
+          pushNext = path_vertex_continue<G>(sv, key0, st, ray, ls, &next);
+        } else {
+          Surface sf;
+          surface_load<G>(sv, rec, j, &sf);
+          if (specOnly) path_vertex_direct_skip(sv, key0, st);   // k_path_direct never saw this vertex
+          pushNext = path_vertex_continue<G>(sv, key0, st, ray, sf, &next);
+        }
         store3(wb.T, slot, st.T);
         wb.ctr[slot] = st.rng.ctr;
         wb.flags[slot] = (flags & (1u << 9)) | (uint32_t)st.depth | (st.specularBounce ? (1u << 8) : 0u);
@@ -1134,6 +1186,47 @@ __global__ void k_camera_rays(const __grid_constant__ SceneView sv, const WavePa
 }
 
 // ------------------------------------------------------------------------------------------
+// Per-scene tables (SceneView::primFrame / lightFrame), computed once at pbrt_b200_scene_create by the code a
+// hit would run, so that the values are the same bits the per-hit evaluation produces.
+__global__ void k_prim_frames(const __grid_constant__ SceneView sv, float4 *frames, PrimQuad *prims) {
+  for (uint32_t prim = blockIdx.x * blockDim.x + threadIdx.x; prim < sv.nPrims; prim += gridDim.x * blockDim.x) {
+    TriVerts tv = load_prim(sv, prim);
+    if ((tv.flags & PBRT_B200_PF_KIND_MASK) != PBRT_B200_PRIM_TRIANGLE) continue;
+    if (tv.flags & (PBRT_B200_PF_HAS_N | PBRT_B200_PF_HAS_S)) continue;   // shading frame interpolates per hit
+    if (sv.materials[tv.material].tex[PBRT_B200_TEXSLOT_BUMP] >= 0) continue;
+    Ray ray;
+    ray.o = v3(0, 0, 0); ray.d = v3(0, 0, 1); ray.mint = 0.f; ray.maxt = PB_INFINITY;
+    Hit hit;
+    hit.prim = (int32_t)prim; hit.t = 1.f; hit.b1 = hit.b2 = 1.f / 3.f; hit.inst = -1;
+    Surface sf;
+    surface_at_hit<false, false, false>(sv, ray, hit, &sf);   // (launched with sv.primFrame == nullptr)
+    const Bsdf &b = sf.bsdf;
+    frames[3 * prim] = make_float4(b.ng.x, b.ng.y, b.ng.z, b.nn.x);
+    frames[3 * prim + 1] = make_float4(b.nn.y, b.nn.z, b.sn.x, b.sn.y);
+    frames[3 * prim + 2] = make_float4(b.sn.z, b.tn.x, b.tn.y, b.tn.z);
+    prims[3 * prim + 2].b = __uint_as_float(tv.flags | PB_PF_DEV_FRAME);
+  }
+}
+__global__ void k_light_frames(const __grid_constant__ SceneView sv, uint32_t nShapes, float4 *frames) {
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nShapes; j += gridDim.x * blockDim.x) {
+    uint32_t prim = sv.lightShapes[j];
+    TriVerts tv = load_prim(sv, prim);
+    float4 a = make_float4(0, 0, 0, 0), b = a;
+    if ((tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_TRIANGLE) {
+      Ray ray;
+      ray.o = v3(0, 0, 0); ray.d = v3(0, 0, 1); ray.mint = 0.f; ray.maxt = PB_INFINITY;
+      DiffGeom dg;
+      tri_dg(sv, prim, tv, ray, 1.f, 1.f / 3.f, 1.f / 3.f, &dg);
+      V3 ns;
+      triangle_sample(tv, .5f, .5f, &ns);
+      a = make_float4(dg.nn.x, dg.nn.y, dg.nn.z, 0.f);
+      b = make_float4(ns.x, ns.y, ns.z, 0.f);
+    }
+    frames[2 * j] = a; frames[2 * j + 1] = b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 struct WindowFilm {
   PbrtB200Window win;
@@ -1465,7 +1558,8 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
         rec.queueIdx = wb.surfQueueIdx;
         rec.mat = wb.surfMat;
         uint32_t *nHits = &wb.counts[4 * it + 3];
-#define PB_LAUNCH_SURF(INST, TEX) TIMED(KC_SHADE, (k_path_surface<INST, TEX><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], rec, nMain, nextWork(), nHits)))
+        uint32_t *nSpec = nextWork();   // specular-only hits (second bin of the surface records)
+#define PB_LAUNCH_SURF(INST, TEX) TIMED(KC_SHADE, (k_path_surface<INST, TEX><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], rec, nMain, nextWork(), nHits, nSpec)))
         if (h->textured) { if (sv.nInstances != 0) PB_LAUNCH_SURF(true, true); else PB_LAUNCH_SURF(false, true); }
         else { if (sv.nInstances != 0) PB_LAUNCH_SURF(true, false); else PB_LAUNCH_SURF(false, false); }
 #undef PB_LAUNCH_SURF
@@ -1485,7 +1579,7 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
         }
 #define PB_LAUNCH_CONT(LD_, G_)                                                                                    \
   TIMED(KC_SHADE_CONT, (k_path_continue<LD_, G_><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], wb.q[cur ^ 1], rec, \
-                                                                            nHits, nextWork(), nNext)))
+                                                                            nHits, nSpec, nextWork(), nNext)))
         if (isLD) { if (h->hasGlossy) PB_LAUNCH_CONT(true, true); else PB_LAUNCH_CONT(true, false); }
         else { if (h->hasGlossy) PB_LAUNCH_CONT(false, true); else PB_LAUNCH_CONT(false, false); }
       }
@@ -1558,7 +1652,8 @@ const char *pbrt_b200_last_error(void) { return g_lastError.c_str(); }
 
 int64_t pbrt_b200_tunable(int key, int64_t value) {
   int64_t *p = key == 0 ? &g_waveSamples : key == 1 ? &g_countKd : key == 2 ? &g_blocksPerSM
-               : key == 3 ? &g_profileKernels : key == 4 ? &g_reserved4 : key == 5 ? &g_overlap : key == 6 ? &g_debugCounts : nullptr;
+               : key == 3 ? &g_profileKernels : key == 4 ? &g_reserved4 : key == 5 ? &g_overlap : key == 6 ? &g_debugCounts
+               : key == 7 ? &g_primFrames : nullptr;
   if (!p) return -1;
   int64_t prev = *p;
   if (value >= 0) *p = value;
@@ -1702,6 +1797,29 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
     if (ce != cudaSuccess) {
       pbrt_b200_scene_destroy(h);
       return fail(PBRT_B200_ERR_CUDA, cudaGetErrorString(ce));
+    }
+  }
+  if (g_primFrames) {
+    // hit-independent BSDF frames of flat triangles and the light triangles' normals (pb_scene.h)
+    void *pf = nullptr, *lf = nullptr;
+    ce = cudaSuccess;
+    if (!h->textured && scene->n_prims) ce = pool_alloc(h->device, &pf, (size_t)scene->n_prims * 3 * sizeof(float4));
+    if (ce == cudaSuccess && scene->n_light_shapes) ce = pool_alloc(h->device, &lf, (size_t)scene->n_light_shapes * 2 * sizeof(float4));
+    if (pf) h->allocs.push_back(pf);
+    if (lf) h->allocs.push_back(lf);
+    if (ce != cudaSuccess) {
+      pbrt_b200_scene_destroy(h);
+      return fail(PBRT_B200_ERR_CUDA, cudaGetErrorString(ce));
+    }
+    if (pf) {
+      int grid = (int)std::min<uint64_t>(((uint64_t)scene->n_prims + 127) / 128, (uint64_t)h->numSMs * 16);
+      k_prim_frames<<<grid, 128, 0, h->stream>>>(sv, (float4 *)pf, (PrimQuad *)sv.prims);   // (sv.primFrame still null)
+      sv.primFrame = (const float4 *)pf;
+    }
+    if (lf) {
+      int grid = (int)std::min<uint64_t>(((uint64_t)scene->n_light_shapes + 127) / 128, (uint64_t)h->numSMs * 16);
+      k_light_frames<<<grid, 128, 0, h->stream>>>(sv, scene->n_light_shapes, (float4 *)lf);
+      sv.lightFrame = (const float4 *)lf;
     }
   }
   ce = pool_alloc(h->device, (void **)&h->filterTable, 256 * sizeof(float));

@@ -14,8 +14,8 @@ from parity_util import gen_scene, load_ffi  # noqa: E402
 
 ffi = load_ffi()
 name = sys.argv[1]
-out = os.path.join(ROOT, "gpurun_out")
-os.makedirs(out, exist_ok=True)
+import tempfile
+out = tempfile.mkdtemp(prefix="pbrt_tool_")   # (scene files are large: keep them out of gpurun_out/)
 res, spp = ((1024, 1024), (8, 8)) if name in ("c4", "inst") else ((1920, 1080), (16, 16))
 if "--full" not in sys.argv:
     res, spp = (res[0] // 4, res[1] // 4), (2, 2)

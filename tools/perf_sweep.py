@@ -16,8 +16,8 @@ if "--" in argv:
 else:
     gen, variants = argv, [""]
 name = gen[0] if gen else "c3"
-out = os.path.join(ROOT, "gpurun_out")
-os.makedirs(out, exist_ok=True)
+import tempfile
+out = tempfile.mkdtemp(prefix="pbrt_tool_")   # (scene files are large: keep them out of gpurun_out/)
 sp = gen_scene(os.path.join(out, "sweep_%s.pbrt" % name), name, "--filename", os.path.join(out, "sweep.exr"), *gen[1:])
 sc = ffi.Scene(sp)
 lib = ffi.cuda()

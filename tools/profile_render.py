@@ -9,8 +9,8 @@ from parity_util import gen_scene, load_ffi  # noqa: E402
 
 ffi = load_ffi()
 name = sys.argv[1] if len(sys.argv) > 1 else "c3"
-out = os.path.join(ROOT, "gpurun_out")
-os.makedirs(out, exist_ok=True)
+import tempfile
+out = tempfile.mkdtemp(prefix="pbrt_tool_")   # (scene files are large: keep them out of gpurun_out/)
 sp = gen_scene(os.path.join(out, "prof_%s.pbrt" % name), name, "--filename", os.path.join(out, "prof.exr"), *sys.argv[2:])
 sc = ffi.Scene(sp)
 ds = ffi.DeviceScene(sc)
