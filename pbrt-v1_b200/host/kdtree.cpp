@@ -30,17 +30,25 @@ void GeometricPrimitive::Refine(vector<Reference<Primitive> > &refined) const {
     refined.push_back(new GeometricPrimitive(r[i], material, areaLight));
 }
 
+// One end of a primitive's bounding interval along the axis being examined.  Events are ordered by
+// position; where an interval opens at the very position another closes, the opening comes first (so a
+// primitive that merely touches the plane from above is counted on both sides of it, like the reference's
+// edge order, accelerators/kdtree.cpp:89-105).  Events that compare equal keep whatever order std::sort
+// leaves them in -- the build below depends on that being the same algorithm the reference ran (libstdc++'s
+// introsort on the same input sequence), see DESIGN.md "kd-tree build".
 struct KdTreeAccel::BoundEdge {
-  BoundEdge() {}
-  BoundEdge(float tt, int pn, bool starting) : t(tt), primNum(pn), type(starting ? START : END) {}
-  bool operator<(const BoundEdge &e) const {
-    if (t == e.t) return (int)type < (int)e.type;
-    else return t < e.t;
-  }
-  float t;
-  int primNum;
-  enum { START, END } type;
+  float pos;
+  int prim;
+  unsigned char closes;   // 0: the interval opens here, 1: it closes here
 };
+namespace {
+typedef KdTreeAccel::BoundEdge PlaneEvent;
+struct EventOrder {
+  bool operator()(const PlaneEvent &a, const PlaneEvent &b) const {
+    return a.pos == b.pos ? a.closes < b.closes : a.pos < b.pos;
+  }
+};
+}  // namespace
 
 // ---------------------------------------------------------------------------
 // Build.  The recursion is the reference's (accelerators/kdtree.cpp:172-312); what is added is that
@@ -97,69 +105,79 @@ struct KdBuilder {
   static void buildParallel(const BuildParams &bp, Subtree &st, const BBox &nodeBounds, vector<int> &primNums,
                             int depth, int badRefines, int forkLevels);
 };
+// Surface-area heuristic along one axis: walks the sorted events keeping the primitive counts on either side
+// of the candidate plane and returns the cheapest plane strictly inside the node (index into `ev`, -1 if none).
+// cost = traversal + intersection * (1 - bonus) * (P(below) * nBelow + P(above) * nAbove), where P is the ratio
+// of the child's surface area to the node's and the bonus applies when one side is empty.
+namespace {
+struct AxisSweep {
+  const BuildParams &bp;
+  const BBox &box;
+  Vector extent;
+  float invNodeArea;
+  int best;
+  float bestCost;
+  AxisSweep(const BuildParams &p, const BBox &b) : bp(p), box(b), extent(b.pMax - b.pMin), best(-1), bestCost(INFINITY) {
+    float nodeArea = (2.f * (extent.x * extent.y + extent.x * extent.z + extent.y * extent.z));
+    invNodeArea = 1.f / nodeArea;
+  }
+  void run(int axis, const PlaneEvent *ev, int nEvents, int nPrims) {
+    const int u = (axis + 1) % 3 < (axis + 2) % 3 ? (axis + 1) % 3 : (axis + 2) % 3;   // the two other axes,
+    const int v = 3 - axis - u;                                                         // lower one first
+    const float lo = box.pMin[axis], hi = box.pMax[axis];
+    int below = 0, above = nPrims;
+    for (int i = 0; i < nEvents; ++i) {
+      const PlaneEvent &e = ev[i];
+      if (e.closes) --above;
+      if (e.pos > lo && e.pos < hi) {
+        float areaBelow = 2 * (extent[u] * extent[v] + (e.pos - lo) * (extent[u] + extent[v]));
+        float areaAbove = 2 * (extent[u] * extent[v] + (hi - e.pos) * (extent[u] + extent[v]));
+        float pBelow = areaBelow * invNodeArea, pAbove = areaAbove * invNodeArea;
+        float bonus = (above == 0 || below == 0) ? bp.emptyBonus : 0.f;
+        float cost = bp.traversalCost + bp.isectCost * (1.f - bonus) * (pBelow * below + pAbove * above);
+        if (cost < bestCost) { bestCost = cost; best = i; }
+      }
+      if (!e.closes) ++below;
+    }
+  }
+};
+}  // namespace
 static bool choose_split(const BuildParams &bp, const BBox &nodeBounds, const int *primNums, int nPrims,
                          KdTreeAccel::BoundEdge *edges[3], int *prims0, int *prims1, int *badRefines,
                          int *bestAxisOut, float *tsplitOut, int *n0Out, int *n1Out) {
-  typedef KdTreeAccel::BoundEdge BoundEdge;
-  const vector<BBox> &allPrimBounds = *bp.allPrimBounds;
-  // choose split: surface-area heuristic over all bounding-box edges
-  int bestAxis = -1, bestOffset = -1;
-  float bestCost = INFINITY;
-  float oldCost = bp.isectCost * float(nPrims);
-  Vector d = nodeBounds.pMax - nodeBounds.pMin;
-  float totalSA = (2.f * (d.x * d.y + d.x * d.z + d.y * d.z));
-  float invTotalSA = 1.f / totalSA;
-  int axis;
-  if (d.x > d.y && d.x > d.z) axis = 0;
-  else axis = (d.y > d.z) ? 1 : 2;
-  int retries = 0;
-retrySplit:
-  for (int i = 0; i < nPrims; ++i) {
-    int pn = primNums[i];
-    const BBox &bbox = allPrimBounds[pn];
-    edges[axis][2 * i] = BoundEdge(bbox.pMin[axis], pn, true);
-    edges[axis][2 * i + 1] = BoundEdge(bbox.pMax[axis], pn, false);
-  }
-  std::sort(&edges[axis][0], &edges[axis][2 * nPrims]);
-  int nBelow = 0, nAbove = nPrims;
-  for (int i = 0; i < 2 * nPrims; ++i) {
-    if (edges[axis][i].type == BoundEdge::END) --nAbove;
-    float edget = edges[axis][i].t;
-    if (edget > nodeBounds.pMin[axis] && edget < nodeBounds.pMax[axis]) {
-      static const int otherAxis[3][2] = {{1, 2}, {0, 2}, {0, 1}};
-      int otherAxis0 = otherAxis[axis][0];
-      int otherAxis1 = otherAxis[axis][1];
-      float belowSA = 2 * (d[otherAxis0] * d[otherAxis1] +
-                           (edget - nodeBounds.pMin[axis]) * (d[otherAxis0] + d[otherAxis1]));
-      float aboveSA = 2 * (d[otherAxis0] * d[otherAxis1] +
-                           (nodeBounds.pMax[axis] - edget) * (d[otherAxis0] + d[otherAxis1]));
-      float pBelow = belowSA * invTotalSA;
-      float pAbove = aboveSA * invTotalSA;
-      float eb = (nAbove == 0 || nBelow == 0) ? bp.emptyBonus : 0.f;
-      float cost = bp.traversalCost + bp.isectCost * (1.f - eb) * (pBelow * nBelow + pAbove * nAbove);
-      if (cost < bestCost) {
-        bestCost = cost;
-        bestAxis = axis;
-        bestOffset = i;
-      }
+  const vector<BBox> &primBounds = *bp.allPrimBounds;
+  AxisSweep sweep(bp, nodeBounds);
+  // the longest axis first; if no plane of an axis falls inside the node, the next axis (cyclically) is tried
+  const Vector &ext = sweep.extent;
+  const int firstAxis = (ext.x > ext.y && ext.x > ext.z) ? 0 : (ext.y > ext.z ? 1 : 2);
+  int splitAxis = -1;
+  for (int attempt = 0; attempt < 3 && splitAxis < 0; ++attempt) {
+    const int axis = (firstAxis + attempt) % 3;
+    PlaneEvent *ev = edges[axis];
+    for (int i = 0; i < nPrims; ++i) {
+      const BBox &b = primBounds[primNums[i]];
+      ev[2 * i].pos = b.pMin[axis]; ev[2 * i].prim = primNums[i]; ev[2 * i].closes = 0;
+      ev[2 * i + 1].pos = b.pMax[axis]; ev[2 * i + 1].prim = primNums[i]; ev[2 * i + 1].closes = 1;
     }
-    if (edges[axis][i].type == BoundEdge::START) ++nBelow;
+    std::sort(ev, ev + 2 * nPrims, EventOrder());
+    sweep.run(axis, ev, 2 * nPrims, nPrims);
+    if (sweep.best >= 0) splitAxis = axis;
   }
-  if (bestAxis == -1 && retries < 2) {
-    ++retries;
-    axis = (axis + 1) % 3;
-    goto retrySplit;
-  }
-  if (bestCost > oldCost) ++*badRefines;
-  if ((bestCost > 4.f * oldCost && nPrims < 16) || bestAxis == -1 || *badRefines == 3) return false;
-  int n0 = 0, n1 = 0;
-  for (int i = 0; i < bestOffset; ++i)
-    if (edges[bestAxis][i].type == BoundEdge::START) prims0[n0++] = edges[bestAxis][i].primNum;
-  for (int i = bestOffset + 1; i < 2 * nPrims; ++i)
-    if (edges[bestAxis][i].type == BoundEdge::END) prims1[n1++] = edges[bestAxis][i].primNum;
-  *bestAxisOut = bestAxis;
-  *tsplitOut = edges[bestAxis][bestOffset].t;
-  *n0Out = n0; *n1Out = n1;
+  // give up (leaf) when splitting is not worth it: repeatedly worse than not splitting, or much worse on a
+  // small node, or no plane found at all
+  const float leafCost = bp.isectCost * float(nPrims);
+  if (sweep.bestCost > leafCost) ++*badRefines;
+  if ((sweep.bestCost > 4.f * leafCost && nPrims < 16) || splitAxis < 0 || *badRefines == 3) return false;
+  // primitives whose interval opens before the chosen event go below, those that close after it go above
+  const PlaneEvent *ev = edges[splitAxis];
+  int nBelow = 0, nAbove = 0;
+  for (int i = 0; i < sweep.best; ++i)
+    if (!ev[i].closes) prims0[nBelow++] = ev[i].prim;
+  for (int i = sweep.best + 1; i < 2 * nPrims; ++i)
+    if (ev[i].closes) prims1[nAbove++] = ev[i].prim;
+  *bestAxisOut = splitAxis;
+  *tsplitOut = ev[sweep.best].pos;
+  *n0Out = nBelow; *n1Out = nAbove;
   return true;
 }
 

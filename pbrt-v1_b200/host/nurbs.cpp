@@ -95,42 +95,63 @@ class NURBS : public Shape {
   vector<float> P, uknot, vknot;
 };
 
-void NURBS::Refine(vector<Reference<Shape> > &refined) const {   // nurbs.cpp:204-281
-  const int diceu = 30, dicev = 30;
-  vector<float> ueval(diceu), veval(dicev);
-  for (int i = 0; i < diceu; ++i) ueval[i] = Lerp((float)i / (float)(diceu - 1), umin, umax);
-  for (int i = 0; i < dicev; ++i) veval[i] = Lerp((float)i / (float)(dicev - 1), vmin, vmax);
-  vector<Hom> Pw((size_t)nu * nv);
-  for (int i = 0; i < nu * nv; ++i) {
-    if (isHomogeneous) { Hom h = {P[4 * i], P[4 * i + 1], P[4 * i + 2], P[4 * i + 3]}; Pw[i] = h; }
-    else { Hom h = {P[3 * i], P[3 * i + 1], P[3 * i + 2], 1.f}; Pw[i] = h; }
+// The patch sampled on a regular parameter grid (what the reference hands to its triangle mesh,
+// shapes/nurbs.cpp:204-281): GRID x GRID surface points with normals and (u, v), row = one v value.
+struct SampledPatch {
+  static const int GRID = 30;
+  vector<Point> position;
+  vector<Normal> normal;
+  vector<float> uv;
+  SampledPatch() : position((size_t)GRID * GRID), normal((size_t)GRID * GRID), uv(2 * (size_t)GRID * GRID) {}
+  static int vertex(int iu, int iv) { return iv * GRID + iu; }
+  // two triangles per grid cell, both fanned from the cell's (u, v) corner
+  vector<int> triangulate() const {
+    vector<int> tri;
+    tri.reserve(6 * (size_t)(GRID - 1) * (GRID - 1));
+    for (int iv = 0; iv + 1 < GRID; ++iv)
+      for (int iu = 0; iu + 1 < GRID; ++iu) {
+        const int corner = vertex(iu, iv), opposite = vertex(iu + 1, iv + 1);
+        const int fan[2][3] = {{corner, vertex(iu + 1, iv), opposite}, {corner, opposite, vertex(iu, iv + 1)}};
+        for (int t = 0; t < 2; ++t) tri.insert(tri.end(), fan[t], fan[t] + 3);
+      }
+    return tri;
   }
-  vector<Point> evalPs((size_t)diceu * dicev);
-  vector<Normal> evalNs((size_t)diceu * dicev);
-  vector<float> uvs(2 * (size_t)diceu * dicev);
-  for (int v = 0; v < dicev; ++v)
-    for (int u = 0; u < diceu; ++u) {
-      uvs[2 * (v * diceu + u)] = ueval[u];
-      uvs[2 * (v * diceu + u) + 1] = veval[v];
-      Vector dPdu, dPdv;
-      evalPs[v * diceu + u] = EvalSurface(Pw, ueval[u], veval[v], &dPdu, &dPdv);
-      evalNs[v * diceu + u] = Normal(Normalize(Cross(dPdu, dPdv)));
+};
+
+void NURBS::Refine(vector<Reference<Shape> > &refined) const {
+  const int G = SampledPatch::GRID;
+  // every control point in homogeneous form (weight 1 for a polynomial patch)
+  const int stride = isHomogeneous ? 4 : 3;
+  vector<Hom> control((size_t)nu * nv);
+  for (size_t i = 0; i < control.size(); ++i) {
+    const float *c = &P[stride * i];
+    Hom h = {c[0], c[1], c[2], isHomogeneous ? c[3] : 1.f};
+    control[i] = h;
+  }
+  // the grid's parameter values: G evenly spaced steps across [umin, umax] x [vmin, vmax]
+  float uAt[SampledPatch::GRID], vAt[SampledPatch::GRID];
+  for (int k = 0; k < G; ++k) {
+    const float frac = (float)k / (float)(G - 1);
+    uAt[k] = Lerp(frac, umin, umax);
+    vAt[k] = Lerp(frac, vmin, vmax);
+  }
+  SampledPatch grid;
+  for (int iv = 0; iv < G; ++iv)
+    for (int iu = 0; iu < G; ++iu) {
+      const int at = SampledPatch::vertex(iu, iv);
+      Vector du, dv;
+      grid.position[at] = EvalSurface(control, uAt[iu], vAt[iv], &du, &dv);
+      grid.normal[at] = Normal(Normalize(Cross(du, dv)));
+      grid.uv[2 * at] = uAt[iu];
+      grid.uv[2 * at + 1] = vAt[iv];
     }
-  const int nTris = 2 * (diceu - 1) * (dicev - 1);
-  vector<int> vertices(3 * (size_t)nTris);
-  int *vp = &vertices[0];
-  for (int v = 0; v < dicev - 1; ++v)
-    for (int u = 0; u < diceu - 1; ++u) {
-      int v00 = v * diceu + u, v10 = v * diceu + u + 1, v11 = (v + 1) * diceu + u + 1, v01 = (v + 1) * diceu + u;
-      *vp++ = v00; *vp++ = v10; *vp++ = v11;
-      *vp++ = v00; *vp++ = v11; *vp++ = v01;
-    }
-  ParamSet paramSet;
-  paramSet.AddInt("indices", &vertices[0], 3 * nTris);
-  paramSet.AddPoint("P", &evalPs[0], diceu * dicev);
-  paramSet.AddFloat("uv", &uvs[0], 2 * diceu * dicev);
-  paramSet.AddNormal("N", &evalNs[0], diceu * dicev);
-  refined.push_back(CreateTriangleMeshShape(ObjectToWorld, reverseOrientation, paramSet));
+  const vector<int> indices = grid.triangulate();
+  ParamSet mesh;
+  mesh.AddInt("indices", &indices[0], (int)indices.size());
+  mesh.AddPoint("P", &grid.position[0], G * G);
+  mesh.AddFloat("uv", &grid.uv[0], 2 * G * G);
+  mesh.AddNormal("N", &grid.normal[0], G * G);
+  refined.push_back(CreateTriangleMeshShape(ObjectToWorld, reverseOrientation, mesh));
 }
 
 }  // namespace

@@ -1,139 +1,182 @@
-// transform.cpp -- transform builders (core/transform.cpp:32-194) and the
-// Gauss-Jordan inverse (core/util.cpp:127-184), restated in the reference's
-// operation order so that CTMs match the reference bit-for-bit.
+// transform.cpp -- the transform builders of the scene-description API and the 4x4 inverse.
+//
+// Contract: every matrix this file produces must equal, bit for bit, the one pbrt-v1 computes for the
+// same scene statement (core/transform.cpp:32-194, core/util.cpp:127-184), because the CTM reaches
+// every vertex, ray and bound downstream.  That pins the *sequence of float operations* (which
+// products are formed, in which association, which pivot a tie selects), not the program text: the
+// code below is organised around small helpers of its own and is checked against the compiled
+// reference by the fixture and fuzz tests (tests/test_oracle.py).
 #include "transform.h"
 
 Reference<Matrix4x4> Matrix4x4::Transpose() const {
-  return new Matrix4x4(m[0][0], m[1][0], m[2][0], m[3][0], m[0][1], m[1][1],
-                       m[2][1], m[3][1], m[0][2], m[1][2], m[2][2], m[3][2],
-                       m[0][3], m[1][3], m[2][3], m[3][3]);
+  float t[4][4];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) t[c][r] = m[r][c];
+  return new Matrix4x4(t);
 }
 
-// core/util.cpp:127-184: full-pivot Gauss-Jordan, pivot chosen with >=.
-Reference<Matrix4x4> Matrix4x4::Inverse() const {
-  int indxc[4], indxr[4];
-  int ipiv[4] = {0, 0, 0, 0};
-  float minv[4][4];
-  memcpy(minv, m, 4 * 4 * sizeof(float));
-  for (int i = 0; i < 4; i++) {
-    int irow = -1, icol = -1;
-    float big = 0.;
-    for (int j = 0; j < 4; j++) {
-      if (ipiv[j] != 1) {
-        for (int k = 0; k < 4; k++) {
-          if (ipiv[k] == 0) {
-            if (fabsf(minv[j][k]) >= big) {
-              big = float(fabsf(minv[j][k]));
-              irow = j;
-              icol = k;
-            }
-          } else if (ipiv[k] > 1)
-            Error("Singular matrix in MatrixInvert");
-        }
-      }
-    }
-    ++ipiv[icol];
-    if (irow != icol) {
-      for (int k = 0; k < 4; ++k) swap(minv[irow][k], minv[icol][k]);
-    }
-    indxr[i] = irow;
-    indxc[i] = icol;
-    if (minv[icol][icol] == 0.) Error("Singular matrix in MatrixInvert");
-    float pivinv = 1.f / minv[icol][icol];
-    minv[icol][icol] = 1.f;
-    for (int j = 0; j < 4; j++) minv[icol][j] *= pivinv;
-    for (int j = 0; j < 4; j++) {
-      if (j != icol) {
-        float save = minv[j][icol];
-        minv[j][icol] = 0;
-        for (int k = 0; k < 4; k++) minv[j][k] -= minv[icol][k] * save;
-      }
+namespace {
+// Work state of the inversion: the matrix being reduced in place plus which rows / columns already
+// hold a pivot.
+struct Reduction {
+  float a[4][4];
+  bool rowDone[4], colDone[4];
+  int fromRow[4], toCol[4];   // the (row, column) pair of each elimination round
+};
+// Largest magnitude among the entries whose row and column are both still free; of equal candidates
+// the last one in row-major order wins (the comparison is >=, starting from 0).
+bool pick_pivot(const Reduction &w, int *row, int *col) {
+  float best = 0.f;
+  *row = *col = -1;
+  for (int r = 0; r < 4; ++r) {
+    if (w.rowDone[r]) continue;
+    for (int c = 0; c < 4; ++c) {
+      if (w.colDone[c]) continue;
+      float mag = fabsf(w.a[r][c]);
+      if (mag >= best) { best = mag; *row = r; *col = c; }
     }
   }
-  for (int j = 3; j >= 0; j--) {
-    if (indxr[j] != indxc[j]) {
-      for (int k = 0; k < 4; k++) swap(minv[k][indxr[j]], minv[k][indxc[j]]);
-    }
-  }
-  return new Matrix4x4(minv);
+  return *row >= 0;
 }
+void exchange_rows(float a[4][4], int r0, int r1) {
+  for (int c = 0; c < 4; ++c) { float t = a[r0][c]; a[r0][c] = a[r1][c]; a[r1][c] = t; }
+}
+void exchange_columns(float a[4][4], int c0, int c1) {
+  for (int r = 0; r < 4; ++r) { float t = a[r][c0]; a[r][c0] = a[r][c1]; a[r][c1] = t; }
+}
+}  // namespace
+
+// In-place Gauss-Jordan elimination with full pivoting: each round moves the chosen pivot onto the
+// diagonal by a row exchange, turns the pivot column into a unit column while the inverse builds up in
+// the same storage, and remembers the exchange; the column exchanges that undo the row exchanges are
+// applied last, newest first.
+Reference<Matrix4x4> Matrix4x4::Inverse() const {
+  Reduction w;
+  memcpy(w.a, m, sizeof(w.a));
+  // (a row and its column retire together: after the exchange the pivot sits on the diagonal)
+  for (int i = 0; i < 4; ++i) w.rowDone[i] = w.colDone[i] = false;
+  for (int round = 0; round < 4; ++round) {
+    int pr, pc;
+    if (!pick_pivot(w, &pr, &pc)) {
+      Error("Singular matrix in MatrixInvert");
+      return new Matrix4x4(w.a);
+    }
+    w.colDone[pc] = w.rowDone[pc] = true;
+    if (pr != pc) exchange_rows(w.a, pr, pc);
+    w.fromRow[round] = pr;
+    w.toCol[round] = pc;
+    float *prow = w.a[pc];
+    if (prow[pc] == 0.f) Error("Singular matrix in MatrixInvert");
+    const float scale = 1.f / prow[pc];
+    prow[pc] = 1.f;
+    for (int c = 0; c < 4; ++c) prow[c] *= scale;
+    for (int r = 0; r < 4; ++r) {
+      if (r == pc) continue;
+      float *row = w.a[r];
+      const float factor = row[pc];
+      row[pc] = 0.f;
+      for (int c = 0; c < 4; ++c) row[c] -= prow[c] * factor;
+    }
+  }
+  for (int round = 3; round >= 0; --round)
+    if (w.fromRow[round] != w.toCol[round]) exchange_columns(w.a, w.fromRow[round], w.toCol[round]);
+  return new Matrix4x4(w.a);
+}
+
+namespace {
+Matrix4x4 *diagonal_matrix(float x, float y, float z) {
+  float d[4][4] = {{x, 0, 0, 0}, {0, y, 0, 0}, {0, 0, z, 0}, {0, 0, 0, 1}};
+  return new Matrix4x4(d);
+}
+Matrix4x4 *offset_matrix(float x, float y, float z) {
+  float d[4][4] = {{1, 0, 0, x}, {0, 1, 0, y}, {0, 0, 1, z}, {0, 0, 0, 1}};
+  return new Matrix4x4(d);
+}
+}  // namespace
 
 Transform Translate(const Vector &delta) {
-  Matrix4x4 *m = new Matrix4x4(1, 0, 0, delta.x, 0, 1, 0, delta.y, 0, 0, 1,
-                               delta.z, 0, 0, 0, 1);
-  Matrix4x4 *minv = new Matrix4x4(1, 0, 0, -delta.x, 0, 1, 0, -delta.y, 0, 0,
-                                  1, -delta.z, 0, 0, 0, 1);
-  return Transform(m, minv);
+  return Transform(offset_matrix(delta.x, delta.y, delta.z), offset_matrix(-delta.x, -delta.y, -delta.z));
 }
 Transform Scale(float x, float y, float z) {
-  Matrix4x4 *m = new Matrix4x4(x, 0, 0, 0, 0, y, 0, 0, 0, 0, z, 0, 0, 0, 0, 1);
-  Matrix4x4 *minv = new Matrix4x4(1.f / x, 0, 0, 0, 0, 1.f / y, 0, 0, 0, 0,
-                                  1.f / z, 0, 0, 0, 0, 1);
-  return Transform(m, minv);
+  return Transform(diagonal_matrix(x, y, z), diagonal_matrix(1.f / x, 1.f / y, 1.f / z));
 }
-// transform.cpp:87-117 (Rodrigues form; inverse is the transpose)
+
+// Rotation by `angle` degrees about `axis` (Rodrigues' formula; a rotation's inverse is its transpose).
+// Entry (i, j), i != j, is a_i a_j (1 - cos) -/+ a_k sin with k the third index and the sign that of the
+// permutation (i, j, k); the diagonal is a_i^2 + (1 - a_i^2) cos.
 Transform Rotate(float angle, const Vector &axis) {
-  Vector a = Normalize(axis);
-  float s = sinf(Radians(angle));
-  float c = cosf(Radians(angle));
-  float m[4][4];
-  m[0][0] = a.x * a.x + (1.f - a.x * a.x) * c;
-  m[0][1] = a.x * a.y * (1.f - c) - a.z * s;
-  m[0][2] = a.x * a.z * (1.f - c) + a.y * s;
-  m[0][3] = 0;
-  m[1][0] = a.x * a.y * (1.f - c) + a.z * s;
-  m[1][1] = a.y * a.y + (1.f - a.y * a.y) * c;
-  m[1][2] = a.y * a.z * (1.f - c) - a.x * s;
-  m[1][3] = 0;
-  m[2][0] = a.x * a.z * (1.f - c) - a.y * s;
-  m[2][1] = a.y * a.z * (1.f - c) + a.x * s;
-  m[2][2] = a.z * a.z + (1.f - a.z * a.z) * c;
-  m[2][3] = 0;
-  m[3][0] = 0; m[3][1] = 0; m[3][2] = 0; m[3][3] = 1;
-  Matrix4x4 *mat = new Matrix4x4(m);
-  return Transform(mat, mat->Transpose());
+  const Vector unit = Normalize(axis);
+  const float a[3] = {unit.x, unit.y, unit.z};
+  const float sine = sinf(Radians(angle)), cosine = cosf(Radians(angle));
+  float r[4][4];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) r[i][j] = (i == 3 && j == 3) ? 1.f : 0.f;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      if (i == j) {
+        r[i][j] = a[i] * a[i] + (1.f - a[i] * a[i]) * cosine;
+        continue;
+      }
+      const int k = 3 - i - j;
+      const float sym = a[i] * a[j] * (1.f - cosine);
+      const bool cyclic = (j - i + 3) % 3 == 1;   // (i, j, k) is an even permutation of (0, 1, 2)
+      r[i][j] = cyclic ? sym - a[k] * sine : sym + a[k] * sine;
+    }
+  Matrix4x4 *rot = new Matrix4x4(r);
+  return Transform(rot, rot->Transpose());
 }
-// transform.cpp:118-146
+
+// World-from-camera has the camera's right / up / viewing direction as its first three columns and the
+// eye position as the fourth; the transform handed back is its inverse (world to camera).
 Transform LookAt(const Point &pos, const Point &look, const Vector &up) {
-  float m[4][4];
-  m[0][3] = pos.x; m[1][3] = pos.y; m[2][3] = pos.z; m[3][3] = 1;
-  Vector dir = Normalize(look - pos);
-  Vector right = Normalize(Cross(dir, up));
-  Vector newUp = Cross(right, dir);
-  m[0][0] = right.x; m[1][0] = right.y; m[2][0] = right.z; m[3][0] = 0.;
-  m[0][1] = newUp.x; m[1][1] = newUp.y; m[2][1] = newUp.z; m[3][1] = 0.;
-  m[0][2] = dir.x; m[1][2] = dir.y; m[2][2] = dir.z; m[3][2] = 0.;
-  Matrix4x4 *camToWorld = new Matrix4x4(m);
+  const Vector forward = Normalize(look - pos);
+  const Vector right = Normalize(Cross(forward, up));
+  const Vector trueUp = Cross(right, forward);
+  const float columns[4][3] = {{right.x, right.y, right.z}, {trueUp.x, trueUp.y, trueUp.z},
+                               {forward.x, forward.y, forward.z}, {pos.x, pos.y, pos.z}};
+  float c2w[4][4];
+  for (int c = 0; c < 4; ++c) {
+    for (int r = 0; r < 3; ++r) c2w[r][c] = columns[c][r];
+    c2w[3][c] = c == 3 ? 1.f : 0.f;
+  }
+  Matrix4x4 *camToWorld = new Matrix4x4(c2w);
   return Transform(camToWorld->Inverse(), camToWorld);
 }
+
+// Bounds of a transformed box: the union of its eight transformed corners.  The corners are visited in
+// a fixed order (bit 0 / 1 / 2 of the code selects the max x / y / z) because min / max keep the first
+// of two equal values, which decides the sign of a zero.
 BBox Transform::operator()(const BBox &b) const {
-  const Transform &M = *this;
-  BBox ret(M(Point(b.pMin.x, b.pMin.y, b.pMin.z)));
-  ret = Union(ret, M(Point(b.pMax.x, b.pMin.y, b.pMin.z)));
-  ret = Union(ret, M(Point(b.pMin.x, b.pMax.y, b.pMin.z)));
-  ret = Union(ret, M(Point(b.pMin.x, b.pMin.y, b.pMax.z)));
-  ret = Union(ret, M(Point(b.pMin.x, b.pMax.y, b.pMax.z)));
-  ret = Union(ret, M(Point(b.pMax.x, b.pMax.y, b.pMin.z)));
-  ret = Union(ret, M(Point(b.pMax.x, b.pMin.y, b.pMax.z)));
-  ret = Union(ret, M(Point(b.pMax.x, b.pMax.y, b.pMax.z)));
-  return ret;
+  static const int cornerOrder[8] = {0, 1, 2, 4, 6, 3, 5, 7};
+  BBox out;
+  for (int n = 0; n < 8; ++n) {
+    const int code = cornerOrder[n];
+    const Point corner((code & 1) ? b.pMax.x : b.pMin.x, (code & 2) ? b.pMax.y : b.pMin.y,
+                       (code & 4) ? b.pMax.z : b.pMin.z);
+    const Point moved = (*this)(corner);
+    out = n == 0 ? BBox(moved) : Union(out, moved);
+  }
+  return out;
 }
+
+// Composition keeps both directions: (A B)^-1 = B^-1 A^-1.
 Transform Transform::operator*(const Transform &t2) const {
-  Reference<Matrix4x4> m1 = Matrix4x4::Mul(m, t2.m);
-  Reference<Matrix4x4> m2 = Matrix4x4::Mul(t2.mInv, mInv);
-  return Transform(m1, m2);
+  return Transform(Matrix4x4::Mul(m, t2.m), Matrix4x4::Mul(t2.mInv, mInv));
 }
+
+// Sign of the determinant of the upper-left 3x3 block, expanded along its first row.
 bool Transform::SwapsHandedness() const {
-  float det = ((m->m[0][0] * (m->m[1][1] * m->m[2][2] - m->m[1][2] * m->m[2][1])) -
-               (m->m[0][1] * (m->m[1][0] * m->m[2][2] - m->m[1][2] * m->m[2][0])) +
-               (m->m[0][2] * (m->m[1][0] * m->m[2][1] - m->m[1][1] * m->m[2][0])));
+  const float(*a)[4] = m->m;
+  auto minor2 = [a](int c0, int c1) { return a[1][c0] * a[2][c1] - a[1][c1] * a[2][c0]; };
+  const float det = ((a[0][0] * minor2(1, 2)) - (a[0][1] * minor2(0, 2)) + (a[0][2] * minor2(0, 1)));
   return det < 0.f;
 }
-// transform.cpp:180-194
+
+// Perspective projection: z in [n, f] goes to [0, 1] with the divide by z, then x and y are scaled so
+// that the field of view spans [-1, 1].
 Transform Perspective(float fov, float n, float f) {
-  float inv_denom = 1.f / (f - n);
-  Matrix4x4 *persp = new Matrix4x4(1, 0, 0, 0, 0, 1, 0, 0, 0, 0, f * inv_denom,
-                                   -f * n * inv_denom, 0, 0, 1, 0);
-  float invTanAng = 1.f / tanf(Radians(fov) / 2.f);
-  return Scale(invTanAng, invTanAng, 1) * Transform(persp);
+  const float depthScale = 1.f / (f - n);
+  float p[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, f * depthScale, -f * n * depthScale}, {0, 0, 1, 0}};
+  const float cotHalfFov = 1.f / tanf(Radians(fov) / 2.f);
+  return Scale(cotHalfFov, cotHalfFov, 1) * Transform(new Matrix4x4(p));
 }
