@@ -98,16 +98,18 @@ struct SurfaceDiff {
   DgDiff dd;
   V3 dndu, dndv;
 };
-template <bool LOBES = true, bool INST = true, bool TEX = false>
+// FLATONLY: the caller has established that the primitive carries a precomputed frame (PB_PF_DEV_FRAME) and
+// was not reached through an instance; the general evaluation is then compiled out of the call site.
+template <bool LOBES = true, bool INST = true, bool TEX = false, bool FLATONLY = false>
 PB_HD void surface_at_hit(const SceneView &sv, const Ray &ray, const Hit &hit, Surface *sf,
                           const RayDiff *rd = (const RayDiff *)0, PbrtB200Material *evalMat = (PbrtB200Material *)0,
                           SurfaceDiff *sd = (SurfaceDiff *)0) {
 #ifdef __CUDA_ARCH__
-  if (!TEX && sv.primFrame) {
+  if (FLATONLY || (!TEX && sv.primFrame)) {
     // flat triangle: the frame was computed once by k_prim_frames with this very function (see pb_scene.h)
     const float4 tail = __ldg((const float4 *)(sv.prims + 3u * (uint32_t)hit.prim + 2));
     const uint32_t pflags = __float_as_uint(tail.y);
-    if ((pflags & PB_PF_DEV_FRAME) && !(INST && hit.inst >= 0)) {
+    if (FLATONLY || ((pflags & PB_PF_DEV_FRAME) && !(INST && hit.inst >= 0))) {
       const float4 *fr = sv.primFrame + 3u * (uint32_t)hit.prim;
       const float4 a = __ldg(fr), b = __ldg(fr + 1), c = __ldg(fr + 2);
       Bsdf &bs = sf->bsdf;
@@ -121,6 +123,7 @@ PB_HD void surface_at_hit(const SceneView &sv, const Ray &ray, const Hit &hit, S
     }
   }
 #endif
+  if (FLATONLY) return;
   TriVerts tv = load_prim(sv, (uint32_t)hit.prim);
   DiffGeom dg, dgs;
   surface_dg<INST>(sv, ray, hit, tv, &dg);
@@ -624,7 +627,7 @@ struct PathState {
 //
 // First half (path.cpp:68-112): miss handling, alpha, emitted light, BSDF, one
 // UniformSampleOneLight record.  Returns false when the ray missed (path ends).
-template <bool LOBES = true, bool INST = true, bool TEX = false>
+template <bool LOBES = true, bool INST = true, bool TEX = false, bool FLATONLY = false>
 PB_HD bool path_vertex_surface(const SceneView &sv, PathState &st, const Ray &ray, const Hit &hit,
                                Surface *sf, const RayDiff *rd = (const RayDiff *)0,
                                PbrtB200Material *evalMat = (PbrtB200Material *)0) {
@@ -650,7 +653,7 @@ PB_HD bool path_vertex_surface(const SceneView &sv, PathState &st, const Ray &ra
   }
   if (pathLength == 0) st.alpha = 1.f;
   else st.T = st.T * spec(1.f);            // pathThroughput *= scene->Transmittance(ray)
-  surface_at_hit<LOBES, INST, TEX>(sv, ray, hit, sf, rd, evalMat);
+  surface_at_hit<LOBES, INST, TEX, FLATONLY>(sv, ray, hit, sf, rd, evalMat);
   if (pathLength == 0 || st.specularBounce) st.L = st.L + st.T * surface_le(sv, *sf, -ray.d);
   return true;
 }

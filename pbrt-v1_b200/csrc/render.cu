@@ -104,7 +104,13 @@ struct AuxQueue {        // shadow segments / MIS probes
 };
 struct WaveBuffers {
   uint32_t nSlots;       // capacity
-  // per-slot path state
+  // Path integrator: the per-slot state lives in three 16-byte records instead (null for whitted /
+  // directlighting).  By the second bounce a warp's 32 vertices belong to 32 unrelated slots, so every per-slot
+  // FIELD costs a 32-byte sector per lane; grouping what a kernel reads together makes that one sector per record.
+  float4 *ptc;           // pathThroughput rgb | RNG stream-1 draws so far (bits)
+  float4 *plf;           // L rgb | flags (bits)
+  float4 *prec;          // pending direct term rgb | record flags (bits 0-3 as recFlags, bit 4 compact record)
+  // per-slot state (whitted / directlighting; the path integrator uses pendT, alpha and recB of these)
   float *L[3], *T[3], *pendT[3], *alpha;
   uint32_t *ctr;         // RNG stream-1 draws so far
   uint32_t *flags;       // bits 0-7 depth, 8 specularBounce, 9 pending direct record
@@ -275,6 +281,18 @@ __global__ void k_slot_pixels(const WaveBuffers wb, const WaveDesc wd) {
   }
 }
 
+// L = 0, pathThroughput = 1, no draws, depth 0
+__device__ __forceinline__ void wave_state_init(const WaveBuffers &wb, uint32_t slot) {
+  if (wb.ptc) {
+    wb.ptc[slot] = make_float4(1.f, 1.f, 1.f, __uint_as_float(0u));
+    wb.plf[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+    return;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { wb.L[c][slot] = 0.f; wb.T[c][slot] = 1.f; }
+  wb.ctr[slot] = 0u;
+  wb.flags[slot] = 0u;
+}
 // K0: sample generation + camera rays (samplers/stratified.cpp:87-131, cameras/perspective.cpp:51-82)
 __global__ void __launch_bounds__(PB_BLOCK)
 k_generate(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveDesc wd) {
@@ -305,11 +323,8 @@ k_generate(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
       }
       wb.imageX[slot] = valid ? film_image_coord(cs.imageX) : PB_BC_INVALID_COORD;
       wb.imageY[slot] = valid ? film_image_coord(cs.imageY) : PB_BC_INVALID_COORD;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { wb.L[c][slot] = 0.f; wb.T[c][slot] = 1.f; }
+      wave_state_init(wb, slot);
       wb.alpha[slot] = valid ? 0.f : -1.f;   // -1 marks a skipped entry in the per-sample dump
-      wb.ctr[slot] = 0u;
-      wb.flags[slot] = 0u;
       continue;
     }
     int ew = wp.xe - wp.xs;
@@ -327,11 +342,8 @@ k_generate(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
     if (wb.camDiff) cam_diff_store(sv, wb, slot, cs);
     wb.imageX[slot] = film_image_coord(cs.imageX);
     wb.imageY[slot] = film_image_coord(cs.imageY);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { wb.L[c][slot] = 0.f; wb.T[c][slot] = 1.f; }
+    wave_state_init(wb, slot);
     wb.alpha[slot] = 0.f;
-    wb.ctr[slot] = 0u;
-    wb.flags[slot] = 0u;
   }
   if (wd.bc) warp_stat_add(&wb.stats[ST_CAMERA], nValid);
 }
@@ -429,21 +441,31 @@ struct ShadowSource {
     return ray;
   }
 };
+// record flag bits live in a byte array (whitted / directlighting: several records per slot) or in the w word of
+// the path integrator's per-slot record
+__device__ __forceinline__ void rec_flag_set(uint8_t *recFlags, float4 *prec, uint32_t rec, uint32_t bit) {
+  if (prec) {
+    uint32_t *w = reinterpret_cast<uint32_t *>(&prec[rec]) + 3;
+    *w |= bit;
+  } else
+    recFlags[rec] |= (uint8_t)bit;
+}
 struct ShadowSink {
   AuxQueue q;
   uint8_t *recFlags;
+  float4 *prec;
   __device__ void done(uint32_t i, const Ray &, const Hit &, bool occluded) const {
-    if (!occluded) recFlags[q.rec[i]] |= 1;
+    if (!occluded) rec_flag_set(recFlags, prec, q.rec[i], 1u);
   }
 };
 template <bool COUNT, int QK>
 __global__ void __launch_bounds__(PB_BLOCK, QK == PB_QK_INSTANCES ? PB_SHADOW_INST_MIN_BLOCKS : PB_TRAV_MIN_BLOCKS)
 k_shadow(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t *nPtr, uint32_t *work,
-         uint8_t *recFlags, unsigned long long *stats) {
+         uint8_t *recFlags, float4 *prec, unsigned long long *stats) {
   uint32_t n = *nPtr;
   KdCounters cnt = {0, 0, 0, 0};
   ShadowSource src = {q};
-  ShadowSink sink = {q, recFlags};
+  ShadowSink sink = {q, recFlags, prec};
   kd_warp_traverse<true, COUNT, QK>(sv, n, work, src, sink, cnt);
   if (COUNT) flush_kd_counters(stats, TK_SHADOW, cnt);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_K(TK_SHADOW, TF_RAYS)], (unsigned long long)n);
@@ -465,18 +487,19 @@ struct ProbeSink {
   const SceneView *sv;
   AuxQueue q;
   uint8_t *recFlags;
+  float4 *prec;
   __device__ void done(uint32_t i, const Ray &ray, const Hit &hit, bool) const {
-    if (hit_emits_from_light(*sv, ray, hit, q.light[i])) recFlags[q.rec[i]] |= 2;
+    if (hit_emits_from_light(*sv, ray, hit, q.light[i])) rec_flag_set(recFlags, prec, q.rec[i], 2u);
   }
 };
 template <bool COUNT>
 __global__ void __launch_bounds__(PB_BLOCK)
 k_probe(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t *nPtr, uint32_t *work,
-        uint8_t *recFlags, unsigned long long *stats) {
+        uint8_t *recFlags, float4 *prec, unsigned long long *stats) {
   uint32_t n = *nPtr;
   KdCounters cnt = {0, 0, 0, 0};
   ProbeSource src = {q};
-  ProbeSink sink = {&sv, q, recFlags};
+  ProbeSink sink = {&sv, q, recFlags, prec};
   kd_warp_traverse<false, COUNT, PB_QK_INSTANCES>(sv, n, work, src, sink, cnt);
   if (COUNT) flush_kd_counters(stats, TK_PROBE, cnt);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_K(TK_PROBE, TF_RAYS)], (unsigned long long)n);
@@ -504,20 +527,19 @@ __device__ __forceinline__ uint64_t slot_key(const WaveKeyInfo &wd, uint32_t slo
 __device__ __forceinline__ void path_fold_pending(const SceneView &sv, const WaveBuffers &wb,
                                                   uint32_t slot, uint32_t *flags, Spec *L) {
   if (!(*flags & (1u << 9))) return;
-  uint8_t rf = wb.recFlags[slot];
+  *flags &= ~(1u << 9);
+  const float4 r = wb.prec[slot];
+  const uint32_t rf = __float_as_uint(r.w);
   if (rf & 16) {
-    // compact record: recA holds pathThroughput * (nLights * Ld), valid when the shadow ray got through
-    if (rf & 1) *L = *L + load3(wb.recA, slot);
-    *flags &= ~(1u << 9);
+    // compact record: rgb holds pathThroughput * (nLights * Ld), valid when the shadow ray got through
+    if (rf & 1) *L = *L + spec3(r.x, r.y, r.z);
     return;
   }
   PathState tmp;
   tmp.L = *L;
   tmp.pendT = load3(wb.pendT, slot);
-  path_resolve_direct(sv, tmp, load3(wb.recA, slot), load3(wb.recB, slot),
-                      (rf & 4) && (rf & 1), (rf & 8) && (rf & 2));
+  path_resolve_direct(sv, tmp, spec3(r.x, r.y, r.z), load3(wb.recB, slot), (rf & 4) && (rf & 1), (rf & 8) && (rf & 2));
   *L = tmp.L;
-  *flags &= ~(1u << 9);
 }
 
 // K2 (path): one iteration of PathIntegrator::Li's loop (integrators/path.cpp:65-143) as three
@@ -575,72 +597,120 @@ __device__ __forceinline__ bool material_is_lambert(const PbrtB200Material &m) {
   return PB_LAMBERT_PATH && m.kind == PBRT_B200_MAT_MATTE && m.sigma == 0.f;
 }
 
+// One vertex of k_path_surface for queue entry i.  GENERAL = false: the caller knows the ray missed or hit a
+// triangle that carries a precomputed frame, and the shape / shading-geometry code is compiled out.
 // TEX: the scene has texture operands (ray differentials of the camera ray, operand evaluation at the hit)
+template <bool INST, bool TEX, bool GENERAL>
+__device__ __forceinline__ void path_surface_vertex(const SceneView &sv, const WaveBuffers &wb, const RayQueue &qin,
+                                                    const SurfaceRecord &rec, uint32_t i, bool valid,
+                                                    uint32_t *hitCount, uint32_t *specCount, uint32_t &shaded) {
+  bool isHit = false;
+  Surface sf;
+  PbrtB200Material evalMat;
+  if (valid) {
+    uint32_t slot = qin.slot[i];
+    Ray ray = queue_ray(qin, i);
+    Hit hit;
+    hit.prim = qin.hitPrim[i];
+    hit.t = 0.f; hit.b1 = hit.b2 = 0.f; hit.inst = -1;
+    if (hit.prim >= 0) {
+      hit.t = qin.hitT[i]; hit.b1 = qin.hitB1[i]; hit.b2 = qin.hitB2[i];
+      if (qin.hitInst) hit.inst = qin.hitInst[i];
+    }
+    const float4 lf = wb.plf[slot];
+    uint32_t flags = __float_as_uint(lf.w);
+    PathState st;
+    st.L = spec3(lf.x, lf.y, lf.z);
+    path_fold_pending(sv, wb, slot, &flags, &st.L);
+    st.depth = (int)(flags & 0xffu);
+    st.specularBounce = (flags >> 8) & 1u;
+    // the throughput only matters where emitted light can be added (path.cpp:74-82,90-91), alpha only
+    // at the first vertex
+    const bool mayEmit = st.depth == 0 || st.specularBounce;
+    st.T = spec(0.f);
+    if (mayEmit) { const float4 tc = wb.ptc[slot]; st.T = spec3(tc.x, tc.y, tc.z); }
+    st.alpha = 0.f;
+    if (TEX) {
+      RayDiff rd;
+      rd.has = st.depth == 0;   // path.cpp:133 continues with plain rays
+      if (rd.has) cam_diff_load(wb, slot, &rd);
+      isHit = path_vertex_surface<false, INST, true>(sv, st, ray, hit, &sf, &rd, &evalMat);
+    } else
+      isHit = path_vertex_surface<false, INST, false, !GENERAL>(sv, st, ray, hit, &sf);
+    if (isHit) ++shaded;
+    wb.plf[slot] = make_float4(st.L.c[0], st.L.c[1], st.L.c[2], __uint_as_float(flags));
+    if (st.depth == 0) wb.alpha[slot] = st.alpha;
+  }
+  // The shading kernels that follow walk the hits only, and the hits are binned by material class so that
+  // their warps do not mix glass / mirror vertices with diffuse ones: vertices whose BSDF has a non-specular
+  // component fill the record arrays from the front (k_path_direct walks exactly these), specular-only ones
+  // (glass, mirror: UniformSampleOneLight cannot contribute there) from the back.
+  bool specOnly = false;
+  if (isHit) {
+    const int kind = TEX ? evalMat.kind : sv.materials[sf.material].kind;
+    specOnly = kind == PBRT_B200_MAT_GLASS || kind == PBRT_B200_MAT_MIRROR;
+  }
+  uint32_t j = warp_push(hitCount, isHit && !specOnly);
+  uint32_t js = warp_push(specCount, isHit && specOnly);
+  if (specOnly) j = wb.nSlots - 1u - js;
+  if (isHit) {
+    surface_store(rec, j, sf);
+    rec.queueIdx[j] = i;
+    if (TEX) rec.mat[j] = evalMat;
+  }
+}
+
+// K2a.  Untextured scenes: most hits are flat triangles whose frame is a 48-byte table read, a few are quadrics or
+// triangles with per-vertex shading data whose geometry takes hundreds of instructions (ncu, r02a: the glass
+// sphere's lanes ran that code at 1.7 active lanes per instruction and made up over half of the kernel's
+// instructions).  So a warp shades the cheap vertices of its 32 rays at once and parks the expensive ones in a
+// small shared-memory list, which it works off 32 at a time with every lane busy.
 template <bool INST, bool TEX>
 __global__ void __launch_bounds__(PB_BLOCK, TEX ? PB_SURF_TEX_MIN_BLOCKS : PB_SURF_MIN_BLOCKS)
 k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const RayQueue qin,
                const SurfaceRecord rec, const uint32_t *nPtr, uint32_t *work, uint32_t *hitCount, uint32_t *specCount) {
+  __shared__ uint32_t parkedAll[PB_BLOCK / 32][64];
+  uint32_t *parked = parkedAll[threadIdx.x >> 5];
+  uint32_t nParked = 0;   // warp uniform
+  const uint32_t lane = lane_id();
   uint32_t n = *nPtr;
   uint32_t shaded = 0;
   for (;;) {
     uint32_t chunk = warp_claim_n(work, PB_CLAIM);
     if (chunk >= n) break;
     for (uint32_t base = chunk; base < chunk + PB_CLAIM && base < n; base += 32) {
-      uint32_t i = base + lane_id();
-      bool isHit = false;
-      Surface sf;
-      PbrtB200Material evalMat;
-      if (i < n) {
-      uint32_t slot = qin.slot[i];
-      Ray ray = queue_ray(qin, i);
-      Hit hit;
-      hit.prim = qin.hitPrim[i];
-      hit.t = 0.f; hit.b1 = hit.b2 = 0.f; hit.inst = -1;
-      if (hit.prim >= 0) {
-        hit.t = qin.hitT[i]; hit.b1 = qin.hitB1[i]; hit.b2 = qin.hitB2[i];
-        if (qin.hitInst) hit.inst = qin.hitInst[i];
+      uint32_t i = base + lane;
+      const bool valid = i < n;
+      if (TEX || !sv.primFrame) {
+        path_surface_vertex<INST, TEX, true>(sv, wb, qin, rec, i, valid, hitCount, specCount, shaded);
+        continue;
       }
-      uint32_t flags = wb.flags[slot];
-      PathState st;
-      st.L = load3(wb.L, slot);
-      path_fold_pending(sv, wb, slot, &flags, &st.L);
-      st.depth = (int)(flags & 0xffu);
-      st.specularBounce = (flags >> 8) & 1u;
-      // the throughput only matters where emitted light can be added (path.cpp:74-82,90-91), alpha only
-      // at the first vertex
-      const bool mayEmit = st.depth == 0 || st.specularBounce;
-      st.T = mayEmit ? load3(wb.T, slot) : spec(0.f);
-      st.alpha = 0.f;
-      if (TEX) {
-        RayDiff rd;
-        rd.has = st.depth == 0;   // path.cpp:133 continues with plain rays
-        if (rd.has) cam_diff_load(wb, slot, &rd);
-        isHit = path_vertex_surface<false, INST, true>(sv, st, ray, hit, &sf, &rd, &evalMat);
-      } else
-        isHit = path_vertex_surface<false, INST, false>(sv, st, ray, hit, &sf);
-      if (isHit) ++shaded;
-      store3(wb.L, slot, st.L);
-      if (st.depth == 0) wb.alpha[slot] = st.alpha;
-      wb.flags[slot] = flags;
+      bool expensive = false;
+      if (valid) {
+        int32_t prim = qin.hitPrim[i];
+        if (prim >= 0) {
+          uint32_t pflags = __float_as_uint(__ldg(&sv.prims[3u * (uint32_t)prim + 2].b));
+          expensive = !(pflags & PB_PF_DEV_FRAME) || (INST && qin.hitInst && qin.hitInst[i] >= 0);
+        }
       }
-      // The shading kernels that follow walk the hits only, and the hits are binned by material class so that
-      // their warps do not mix glass / mirror vertices with diffuse ones: vertices whose BSDF has a non-specular
-      // component fill the record arrays from the front (k_path_direct walks exactly these), specular-only ones
-      // (glass, mirror: UniformSampleOneLight cannot contribute there) from the back.
-      bool specOnly = false;
-      if (isHit) {
-        const int kind = TEX ? evalMat.kind : sv.materials[sf.material].kind;
-        specOnly = kind == PBRT_B200_MAT_GLASS || kind == PBRT_B200_MAT_MIRROR;
+      path_surface_vertex<INST, false, false>(sv, wb, qin, rec, i, valid && !expensive, hitCount, specCount, shaded);
+      const uint32_t mask = __ballot_sync(0xffffffffu, expensive);
+      if (mask) {
+        if (expensive) parked[nParked + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = i;
+        nParked += (uint32_t)__popc(mask);
+        __syncwarp();
+        if (nParked >= 32u) {
+          nParked -= 32u;
+          uint32_t pi = parked[nParked + lane];
+          __syncwarp();
+          path_surface_vertex<INST, false, true>(sv, wb, qin, rec, pi, true, hitCount, specCount, shaded);
+        }
       }
-      uint32_t j = warp_push(hitCount, isHit && !specOnly);
-      uint32_t js = warp_push(specCount, isHit && specOnly);
-      if (specOnly) j = wb.nSlots - 1u - js;
-      if (isHit) {
-        surface_store(rec, j, sf);
-        rec.queueIdx[j] = i;
-        if (TEX) rec.mat[j] = evalMat;
-      }
+    }
   }
+  if (nParked) {
+    uint32_t pi = lane < nParked ? parked[lane] : 0u;
+    path_surface_vertex<INST, false, true>(sv, wb, qin, rec, pi, lane < nParked, hitCount, specCount, shaded);
   }
   warp_stat_add(&wb.stats[ST_SHADED], shaded);
 }
@@ -669,12 +739,13 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
         ray.o = v3(0, 0, 0);
         ray.d = v3(qin.dx[i], qin.dy[i], qin.dz[i]);   // only wo = -ray.d is needed
         ray.mint = 0.f; ray.maxt = 0.f;
-        uint32_t flags = wb.flags[slot];
+        const float4 tc = wb.ptc[slot];
+        const uint32_t flags = __float_as_uint(wb.plf[slot].w);
         PathState st;
-        st.T = load3(wb.T, slot);
+        st.T = spec3(tc.x, tc.y, tc.z);
         st.depth = (int)(flags & 0xffu);
         st.rng.key = slot_key(wd, slot, 1);
-        st.rng.ctr = wb.ctr[slot];
+        st.rng.ctr = __float_as_uint(tc.w);
         PatternSource key0 = {slot_key(wd, slot, 0), LD ? wb.ld : (const float *)nullptr, wb.nSlots, slot, LD ? wd.bc : (wd.bc == 2 ? 2 : 0)};
         bool hasDirect;
         const PbrtB200Material &mat = rec.mat ? rec.mat[j] : sv.materials[rec.ids[j] & 0xffffu];
@@ -689,24 +760,24 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
           surface_load<G>(sv, rec, j, &sf);
           path_vertex_direct<G, LK>(sv, key0, st, ray, &sf, &direct, &hasDirect);
         }
-        wb.ctr[slot] = st.rng.ctr;
+        if (st.rng.ctr != __float_as_uint(tc.w)) reinterpret_cast<uint32_t *>(&wb.ptc[slot])[3] = st.rng.ctr;
         if (hasDirect) {
           pushShadow = direct.hasShadow;
           pushProbe = direct.hasProbe;
           if (pushProbe) {
             // rare: the estimator's value also depends on the MIS probe -> keep both terms pending
-            wb.flags[slot] = flags | (1u << 9);
+            reinterpret_cast<uint32_t *>(&wb.plf[slot])[3] = flags | (1u << 9);
             store3(wb.pendT, slot, st.pendT);
-            store3(wb.recA, slot, direct.termA);
             store3(wb.recB, slot, direct.termB);
-            wb.recFlags[slot] = (direct.hasShadow ? 4 : 0) | 8;
+            wb.prec[slot] = make_float4(direct.termA.c[0], direct.termA.c[1], direct.termA.c[2],
+                                        __uint_as_float((direct.hasShadow ? 4u : 0u) | 8u));
           } else if (pushShadow) {
             // common: only the shadow ray decides, so the addend of `L += pathThroughput *
-            // UniformSampleOneLight(..)` (path.cpp:100-112) is known now; 3 floats stay pending, not 9
+            // UniformSampleOneLight(..)` (path.cpp:100-112) is known now; one 16-byte record stays pending
             Spec Ld = direct_value(direct.termA, direct.termB, true, false);
-            wb.flags[slot] = flags | (1u << 9);
-            store3(wb.recA, slot, st.pendT * ((float)sv.nLights * Ld));
-            wb.recFlags[slot] = 4 | 16;
+            Spec add = st.pendT * ((float)sv.nLights * Ld);
+            reinterpret_cast<uint32_t *>(&wb.plf[slot])[3] = flags | (1u << 9);
+            wb.prec[slot] = make_float4(add.c[0], add.c[1], add.c[2], __uint_as_float(4u | 16u));
           }
         }
       }
@@ -744,13 +815,14 @@ k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, cons
         ray.o = v3(0, 0, 0);
         ray.d = v3(qin.dx[i], qin.dy[i], qin.dz[i]);
         ray.mint = 0.f; ray.maxt = 0.f;
-        uint32_t flags = wb.flags[slot];
+        const float4 tc = wb.ptc[slot];
+        const uint32_t flags = __float_as_uint(wb.plf[slot].w);
         PathState st;
-        st.T = load3(wb.T, slot);
+        st.T = spec3(tc.x, tc.y, tc.z);
         st.depth = (int)(flags & 0xffu);
         st.specularBounce = (flags >> 8) & 1u;
         st.rng.key = slot_key(wd, slot, 1);
-        st.rng.ctr = wb.ctr[slot];
+        st.rng.ctr = __float_as_uint(tc.w);
         PatternSource key0 = {slot_key(wd, slot, 0), LD ? wb.ld : (const float *)nullptr, wb.nSlots, slot, LD ? wd.bc : (wd.bc == 2 ? 2 : 0)};
         const PbrtB200Material &mat = rec.mat ? rec.mat[j] : sv.materials[rec.ids[j] & 0xffffu];
         if (!specOnly && material_is_lambert(mat)) {
@@ -765,9 +837,9 @@ k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, cons
           if (specOnly) path_vertex_direct_skip(sv, key0, st);   // k_path_direct never saw this vertex
           pushNext = path_vertex_continue<G>(sv, key0, st, ray, sf, &next);
         }
-        store3(wb.T, slot, st.T);
-        wb.ctr[slot] = st.rng.ctr;
-        wb.flags[slot] = (flags & (1u << 9)) | (uint32_t)st.depth | (st.specularBounce ? (1u << 8) : 0u);
+        wb.ptc[slot] = make_float4(st.T.c[0], st.T.c[1], st.T.c[2], __uint_as_float(st.rng.ctr));
+        reinterpret_cast<uint32_t *>(&wb.plf[slot])[3] =
+            (flags & (1u << 9)) | (uint32_t)st.depth | (st.specularBounce ? (1u << 8) : 0u);
       }
       uint32_t ni = warp_push(nextCount, pushNext);
       if (pushNext) queue_put(qout, ni, slot, next);
@@ -972,8 +1044,9 @@ k_finalize(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
       continue;
     }
     if (sv.integrator.kind == PBRT_B200_INT_PATH) {
-      uint32_t flags = wb.flags[slot];
-      L = load3(wb.L, slot);
+      const float4 lf = wb.plf[slot];
+      uint32_t flags = __float_as_uint(lf.w);
+      L = spec3(lf.x, lf.y, lf.z);
       path_fold_pending(sv, wb, slot, &flags, &L);
     } else {
       L = spec3(wb.frame[slot], wb.frame[(size_t)wb.nFrames * wb.nSlots + slot],
@@ -1392,19 +1465,25 @@ static void carve_wave(Carver &c, WaveBuffers &wb, uint32_t nSlots, int directRe
                        int ldFloats, bool hasInstances, bool textured) {
   wb.nSlots = nSlots;
   wb.nFrames = nFrames;
+  wb.ptc = isPath ? c.take<float4>(nSlots) : nullptr;
+  wb.plf = isPath ? c.take<float4>(nSlots) : nullptr;
+  wb.prec = isPath ? c.take<float4>(nSlots) : nullptr;
   for (int i = 0; i < 3; ++i) {
-    wb.L[i] = c.take<float>(nSlots); wb.T[i] = c.take<float>(nSlots); wb.pendT[i] = c.take<float>(nSlots);
+    wb.L[i] = isPath ? nullptr : c.take<float>(nSlots);
+    wb.T[i] = isPath ? nullptr : c.take<float>(nSlots);
+    wb.pendT[i] = c.take<float>(nSlots);
     wb.outL[i] = c.take<float>(nSlots);
-    wb.recA[i] = c.take<float>((size_t)nSlots * directRecords);
+    wb.recA[i] = isPath ? nullptr : c.take<float>((size_t)nSlots * directRecords);
     wb.recB[i] = c.take<float>((size_t)nSlots * directRecords);
   }
   wb.alpha = c.take<float>(nSlots); wb.outA = c.take<float>(nSlots);
-  wb.ctr = c.take<uint32_t>(nSlots); wb.flags = c.take<uint32_t>(nSlots);
+  wb.ctr = isPath ? nullptr : c.take<uint32_t>(nSlots);
+  wb.flags = isPath ? nullptr : c.take<uint32_t>(nSlots);
   wb.imageX = c.take<float>(nSlots); wb.imageY = c.take<float>(nSlots);
   wb.pixel = c.take<uint32_t>(nSlots);
   wb.reach = c.take<unsigned long long>(nSlots);
   wb.ld = ldFloats > 0 ? c.take<float>((size_t)ldFloats * nSlots) : nullptr;
-  wb.recFlags = c.take<uint8_t>((size_t)nSlots * directRecords);
+  wb.recFlags = isPath ? nullptr : c.take<uint8_t>((size_t)nSlots * directRecords);
   if (!isPath) {
     wb.frame = c.take<float>((size_t)PB_FRAME_FLOATS * nFrames * nSlots);
     wb.frameFlags = c.take<uint32_t>((size_t)nFrames * nSlots);
@@ -1494,16 +1573,16 @@ static void launch_traversals_b(PbrtB200Handle *h, bool count, int grid, uint32_
   // ramp-up of the full persistent grid for a few thousand rays
   int probeGrid = std::min(grid, h->numSMs * 2);
   if (count) {
-    TIMED_ON(KC_SHADOW, strm, (k_shadow<true, PB_QK_INSTANCES><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.stats)));
-    TIMED_ON(KC_PROBE, strm, (k_probe<true><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.stats)));
+    TIMED_ON(KC_SHADOW, strm, (k_shadow<true, PB_QK_INSTANCES><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.prec, wb.stats)));
+    TIMED_ON(KC_PROBE, strm, (k_probe<true><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.prec, wb.stats)));
   } else {
 #define PB_LAUNCH_SHADOW(QK_) \
-  TIMED_ON(KC_SHADOW, strm, (k_shadow<false, QK_><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.stats)))
+  TIMED_ON(KC_SHADOW, strm, (k_shadow<false, QK_><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.prec, wb.stats)))
     if (h->primKinds == PB_QK_TRI) PB_LAUNCH_SHADOW(PB_QK_TRI);
     else if (h->primKinds == PB_QK_SPHERE) PB_LAUNCH_SHADOW(PB_QK_SPHERE);
     else if (h->primKinds == PB_QK_ALL) PB_LAUNCH_SHADOW(PB_QK_ALL);
     else PB_LAUNCH_SHADOW(PB_QK_INSTANCES);
-    TIMED_ON(KC_PROBE, strm, (k_probe<false><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.stats)));
+    TIMED_ON(KC_PROBE, strm, (k_probe<false><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.prec, wb.stats)));
   }
 }
 
