@@ -458,8 +458,12 @@ struct ShadowSink {
     if (!occluded) rec_flag_set(recFlags, prec, q.rec[i], 1u);
   }
 };
+#ifndef PB_SHADOW_TRI_MIN_BLOCKS
+#define PB_SHADOW_TRI_MIN_BLOCKS PB_TRAV_MIN_BLOCKS
+#endif
 template <bool COUNT, int QK>
-__global__ void __launch_bounds__(PB_BLOCK, QK == PB_QK_INSTANCES ? PB_SHADOW_INST_MIN_BLOCKS : PB_TRAV_MIN_BLOCKS)
+__global__ void __launch_bounds__(PB_BLOCK, QK == PB_QK_INSTANCES ? PB_SHADOW_INST_MIN_BLOCKS
+                                            : QK == PB_QK_TRI ? PB_SHADOW_TRI_MIN_BLOCKS : PB_TRAV_MIN_BLOCKS)
 k_shadow(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t *nPtr, uint32_t *work,
          uint8_t *recFlags, float4 *prec, unsigned long long *stats) {
   uint32_t n = *nPtr;
@@ -589,6 +593,9 @@ __device__ __forceinline__ uint32_t surface_load_frame(const SurfaceRecord &r, u
   b->tn = v3(r.f[12][i], r.f[13][i], r.f[14][i]);
   return r.ids[i];
 }
+#ifndef PB_FUSE_DIFFUSE
+#define PB_FUSE_DIFFUSE 0   // 1: k_path_direct also samples the continuation of its (diffuse-class) vertices
+#endif
 #ifndef PB_LAMBERT_PATH
 #define PB_LAMBERT_PATH 1   // 0: every vertex goes through the general lobe table (A/B switch for the profiles)
 #endif
@@ -721,7 +728,7 @@ template <bool LD, bool G, int LK>
 __global__ void __launch_bounds__(PB_BLOCK, PB_DIRECT_MIN_BLOCKS)
 k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveKeyInfo wd,
               const RayQueue qin, const SurfaceRecord rec, const uint32_t *nPtr, uint32_t *work,
-              uint32_t *shadowCount, uint32_t *probeCount) {
+              uint32_t *shadowCount, uint32_t *probeCount, const RayQueue qout, uint32_t *nextCount) {
   uint32_t n = *nPtr;
   for (;;) {
     uint32_t chunk = warp_claim_n(work, PB_CLAIM);
@@ -733,6 +740,10 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
       bool pushShadow = false, pushProbe = false;
       uint32_t slot = 0;
       DirectRec direct;
+#if PB_FUSE_DIFFUSE
+      bool pushNext = false;
+      Ray next;
+#endif
       if (valid) {
         slot = qin.slot[i];
         Ray ray;
@@ -740,7 +751,7 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
         ray.d = v3(qin.dx[i], qin.dy[i], qin.dz[i]);   // only wo = -ray.d is needed
         ray.mint = 0.f; ray.maxt = 0.f;
         const float4 tc = wb.ptc[slot];
-        const uint32_t flags = __float_as_uint(wb.plf[slot].w);
+        uint32_t flags = __float_as_uint(wb.plf[slot].w);
         PathState st;
         st.T = spec3(tc.x, tc.y, tc.z);
         st.depth = (int)(flags & 0xffu);
@@ -755,12 +766,27 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
           ls.material = ids & 0xffffu; ls.light = (int32_t)(ids >> 16) - 1;
           ls.bsdf.R = spec3(mat.kd[0], mat.kd[1], mat.kd[2]) * PB_INV_PI;
           path_vertex_direct<G, LK>(sv, key0, st, ray, &ls, &direct, &hasDirect);
+#if PB_FUSE_DIFFUSE
+          st.specularBounce = (flags >> 8) & 1u;
+          pushNext = path_vertex_continue<G>(sv, key0, st, ray, ls, &next);
+#endif
         } else {
           Surface sf;
           surface_load<G>(sv, rec, j, &sf);
           path_vertex_direct<G, LK>(sv, key0, st, ray, &sf, &direct, &hasDirect);
+#if PB_FUSE_DIFFUSE
+          st.specularBounce = (flags >> 8) & 1u;
+          pushNext = path_vertex_continue<G>(sv, key0, st, ray, sf, &next);
+#endif
         }
+#if PB_FUSE_DIFFUSE
+        // (the continuation of path.cpp:113-143 in the same pass: throughput, draw count and depth go back together)
+        wb.ptc[slot] = make_float4(st.T.c[0], st.T.c[1], st.T.c[2], __uint_as_float(st.rng.ctr));
+        flags = (uint32_t)st.depth | (st.specularBounce ? (1u << 8) : 0u);
+        reinterpret_cast<uint32_t *>(&wb.plf[slot])[3] = flags;
+#else
         if (st.rng.ctr != __float_as_uint(tc.w)) reinterpret_cast<uint32_t *>(&wb.ptc[slot])[3] = st.rng.ctr;
+#endif
         if (hasDirect) {
           pushShadow = direct.hasShadow;
           pushProbe = direct.hasProbe;
@@ -785,6 +811,10 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
       if (pushShadow) aux_put(wb.shadowQ, si, slot, direct.shadow, 0);
       uint32_t pi = warp_push(probeCount, pushProbe);
       if (pushProbe) aux_put(wb.probeQ, pi, slot, direct.probe, direct.probeLight);
+#if PB_FUSE_DIFFUSE
+      uint32_t ni = warp_push(nextCount, pushNext);
+      if (pushNext) queue_put(qout, ni, slot, next);
+#endif
   }
   }
 }
@@ -796,8 +826,10 @@ k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, cons
                 const uint32_t *nSpecPtr, uint32_t *work, uint32_t *nextCount) {
   const uint32_t nDiff = *nPtr;
   const uint32_t n = nDiff + *nSpecPtr;
+  // (PB_FUSE_DIFFUSE: k_path_direct already continued the diffuse-class vertices; only the specular-only ones are left)
+  const uint32_t first = PB_FUSE_DIFFUSE ? nDiff : 0u;
   for (;;) {
-    uint32_t chunk = warp_claim_n(work, PB_CLAIM);
+    uint32_t chunk = first + warp_claim_n(work, PB_CLAIM);
     if (chunk >= n) break;
     for (uint32_t base = chunk; base < chunk + PB_CLAIM && base < n; base += 32) {
       uint32_t w = base + lane_id();
@@ -1644,7 +1676,7 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
 #undef PB_LAUNCH_SURF
 #define PB_LAUNCH_DIRECT2(LD_, G_, LK_)                                                                             \
   TIMED(KC_SHADE_DIRECT, (k_path_direct<LD_, G_, LK_><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], rec, nHits, \
-                                                                                 nextWork(), nShadow, nProbe)))
+                                                                                 nextWork(), nShadow, nProbe, wb.q[cur ^ 1], nNext)))
 #define PB_LAUNCH_DIRECT(LD_, G_) do { if (h->triLightsOnly) PB_LAUNCH_DIRECT2(LD_, G_, 0); else PB_LAUNCH_DIRECT2(LD_, G_, PB_LK_ALL); } while (0)
         if (isLD) { if (h->hasGlossy) PB_LAUNCH_DIRECT(true, true); else PB_LAUNCH_DIRECT(true, false); }
         else { if (h->hasGlossy) PB_LAUNCH_DIRECT(false, true); else PB_LAUNCH_DIRECT(false, false); }
