@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PBRT_B200_ABI_VERSION 3
+#define PBRT_B200_ABI_VERSION 4
 
 /* ---- error codes (Scene::Render has none: core/scene.cpp:32; the host maps
  *      non-zero codes to Severe(), core/util.cpp:90-97) ---- */
@@ -343,6 +343,46 @@ void pbrt_b200_scene_destroy(PbrtB200Handle *h);
  * core/scene.cpp:43-84 for those windows. */
 int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows,
                      int n_windows, PbrtB200Stats *stats);
+
+/* The same for TILES of one frame.  Every window must lie inside the scene's film window
+ * (film/image.cpp:79-85).  A crop render (above) samples the reference's crop extent (image.cpp:148-156),
+ * which misses the rare sample of the pixel row / column before the window whose coordinate rounds up to
+ * the window's first integer coordinate (it splats into both pixels, image.cpp:108-111).  A tile instead
+ * draws from every sample pixel of the FRAME's extent that can reach it and traces exactly the samples
+ * whose filter footprint touches one of its pixels: its pixels are bit-identical to the same pixels of the
+ * whole frame, and apron samples that contribute nothing are not traced.  This is the unit of the multi-GPU
+ * partition below; the reference's counterpart is cropwindow renders pasted by tools/exrassemble.cpp:53-66.
+ * Not available with the bestcandidate sampler (PBRT_B200_ERR_UNSUPPORTED). */
+int pbrt_b200_render_tiles(PbrtB200Handle *h, const PbrtB200Window *tiles,
+                           int n_tiles, PbrtB200Stats *stats);
+
+/* ---- one frame on several GPUs (pbrt-v1_b200/csrc/multi.cuh) -------------------------------------------
+ * A communicator names this rank among `world` ranks, one GPU each: processes of one node (torchrun: rank 0
+ * calls pbrt_b200_comm_unique_id and broadcasts the 128 bytes) or threads of one process.  NCCL is loaded at
+ * run time; without it these return PBRT_B200_ERR_UNSUPPORTED and single-GPU rendering is unaffected. */
+typedef struct PbrtB200Comm PbrtB200Comm;
+int  pbrt_b200_comm_unique_id(void *id128);
+int  pbrt_b200_comm_create(const void *id128, int rank, int world, int device, PbrtB200Comm **out);
+void pbrt_b200_comm_destroy(PbrtB200Comm *comm);
+/* Render the scene's whole film window: the window is cut into square tiles (`tile_edge` pixels, 0 = chosen
+ * from the frame size and the rank count), dealt statically to the ranks; each rank renders its share as
+ * tiles (above) and ONE exchange -- an ncclSend of the rank's contiguous tile block, matched by grouped
+ * ncclRecv's on rank 0 -- plus one paste kernel assemble the frame on rank 0's device, bit-identical to the
+ * single-GPU frame.  rank 0: `rgba_host` (may be NULL) receives width*height*4 floats; other ranks ignore it.
+ * comm == NULL renders on this device alone.  `stats` describes THIS rank's share. */
+int pbrt_b200_render_frame(PbrtB200Handle *h, PbrtB200Comm *comm, int tile_edge, float *rgba_host,
+                           PbrtB200Stats *stats);
+/* The partition pbrt_b200_render_frame uses (pure host arithmetic): tiles of `frame` in raster order and the
+ * rank that owns each; returns the number of tiles, writes at most max_tiles entries. */
+int pbrt_b200_frame_partition(const PbrtB200Window *frame, int world, int tile_edge,
+                              PbrtB200Window *tiles_out, int32_t *owner_out, int max_tiles);
+/* rank 0: device pointer of the frame assembled by the last pbrt_b200_render_frame (float4 per pixel). */
+int pbrt_b200_frame_device_ptr(PbrtB200Handle *h, void **dptr, uint64_t *n_floats);
+/* Host-buffer call for `n_devices` GPUs of this process -- what Scene::Render() makes when PBRT_GPUS > 1
+ * (SURVEY.md section 5): one thread per device uploads the scene, renders its tiles and joins the exchange;
+ * `rgba_out` receives the film window; statistics are summed over the devices. */
+int pbrt_b200_render_host_multi(const PbrtB200Scene *scene, const int *devices, int n_devices,
+                                float *rgba_out, PbrtB200Stats *stats);
 
 /* Copy the resolved pixels of window `w` of the last render to host memory:
  * `rgba` receives width*height*4 floats = exactly what ImageFilm::WriteImage

@@ -160,12 +160,24 @@ const char *pbrt_twin_last_error(void) { return gError.c_str(); }
 //   rgba     width*height*4   what ImageFilm::WriteImage hands to WriteRGBAImage
 //   raw      width*height*5   L.rgb, alpha, weightSum (may be NULL)
 //   samples  nSamples*6       imageX, imageY, L.rgb (after guards), alpha, reference order (may be NULL)
-int pbrt_twin_render(const PbrtB200Scene *scene, const PbrtB200Window *win, float *rgba, float *raw,
-                     float *samples, PbrtB200Stats *stats) {
+// `frame` != NULL: `win` is a TILE of the frame window (include/pbrt_b200.h, pbrt_b200_render_tiles): the extent
+// holds every sample pixel of the frame's extent that can reach the tile, and samples whose filter footprint
+// misses the tile are skipped before they are traced.
+static int twin_render_impl(const PbrtB200Scene *scene, const PbrtB200Window *win, const PbrtB200Window *frame,
+                            float *rgba, float *raw, float *samples, PbrtB200Stats *stats) {
   SceneView sv;
   if (!build_view(*scene, &sv)) return PBRT_B200_ERR_INVALID;
   int xs, xe, ys, ye;
   film_sample_extent(sv, win->x0, win->y0, win->width, win->height, &xs, &xe, &ys, &ye);
+  if (frame) {
+    if (sv.sampler.kind == PBRT_B200_SAMPLER_BESTCANDIDATE) return PBRT_B200_ERR_UNSUPPORTED;
+    int fxs, fxe, fys, fye;
+    film_sample_extent(sv, frame->x0, frame->y0, frame->width, frame->height, &fxs, &fxe, &fys, &fye);
+    xs = pb_imax(fxs, pb_floor2int(win->x0 + .5f - sv.filterXW) - 1);
+    xe = pb_imin(fxe, pb_floor2int(win->x0 + win->width - 1 + .5f + sv.filterXW) + 2);
+    ys = pb_imax(fys, pb_floor2int(win->y0 + .5f - sv.filterYW) - 1);
+    ye = pb_imin(fye, pb_floor2int(win->y0 + win->height - 1 + .5f + sv.filterYW) + 2);
+  }
   int spp = sv.sampler.x_samples * sv.sampler.y_samples;
   std::vector<FilmPixel> film((size_t)win->width * win->height);
   memset(film.data(), 0, film.size() * sizeof(FilmPixel));
@@ -177,6 +189,12 @@ int pbrt_twin_render(const PbrtB200Scene *scene, const PbrtB200Window *win, floa
   auto t0 = std::chrono::steady_clock::now();
   // everything after the sampler: camera ray, Li, guards, film (core/scene.cpp:43-78)
   auto take_sample = [&](CameraSample cs, const PatternSource &key0, uint64_t key1) {
+    if (frame) {
+      float dX = film_image_coord(cs.imageX) - 0.5f, dY = film_image_coord(cs.imageY) - 0.5f;
+      if (pb_floor2int(dX + sv.filterXW) < win->x0 || pb_ceil2int(dX - sv.filterXW) >= win->x0 + win->width ||
+          pb_floor2int(dY + sv.filterYW) < win->y0 || pb_ceil2int(dY - sv.filterYW) >= win->y0 + win->height)
+        return;
+    }
     Ray ray;
     perspective_generate_ray(sv.camera, cs, &ray, sv.xRes, sv.yRes);
     RayDiff camDiff;
@@ -277,6 +295,15 @@ int pbrt_twin_render(const PbrtB200Scene *scene, const PbrtB200Window *win, floa
     stats->render_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
   }
   return PBRT_B200_OK;
+}
+
+int pbrt_twin_render(const PbrtB200Scene *scene, const PbrtB200Window *win, float *rgba, float *raw,
+                     float *samples, PbrtB200Stats *stats) {
+  return twin_render_impl(scene, win, (const PbrtB200Window *)0, rgba, raw, samples, stats);
+}
+int pbrt_twin_render_tile(const PbrtB200Scene *scene, const PbrtB200Window *frame, const PbrtB200Window *tile,
+                          float *rgba, float *raw, PbrtB200Stats *stats) {
+  return twin_render_impl(scene, tile, frame, rgba, raw, (float *)0, stats);
 }
 
 uint64_t pbrt_twin_sample_count(const PbrtB200Scene *scene, const PbrtB200Window *win) {

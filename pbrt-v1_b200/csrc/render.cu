@@ -60,6 +60,7 @@ static int64_t g_blocksPerSM = 12;        // key 2: resident CTAs per SM for the
 static int64_t g_overlap = 0;             // key 5: run shadow/probe traversal on a second stream, overlapped (measured +1%: both sides are issue bound, so off by default)
 static int64_t g_debugCounts = 0;         // key 6: print each wave's queue sizes per iteration to stderr
 static int64_t g_reserved4 = 0;           // key 4: reserved (was the fused shade kernel's occupancy variant)
+static int64_t g_fastPath = 1;            // key 8: k_path_fast shades flat-triangle / matte vertices in one pass (0: general three-kernel pipeline only)
 static int64_t g_primFrames = 1;          // key 7: precompute hit-independent BSDF / light-triangle frames at scene create (0: evaluate per hit)
 
 #ifndef PB_DIRECT_MIN_BLOCKS
@@ -129,6 +130,7 @@ struct WaveBuffers {
   int32_t nFrames;
   RayQueue q[2];
   AuxQueue shadowQ, probeQ;
+  uint32_t *subset;      // path: queue indices k_path_fast leaves to the general shading kernels
   float *surf[15];       // BSDF frame records of the vertices being shaded (path), by queue position
   uint32_t *surfIds;
   uint32_t *surfQueueIdx;
@@ -149,10 +151,10 @@ enum { TF_RAYS = 0, TF_INTERIOR, TF_LEAVES, TF_REFS, TF_TESTS, TF_COUNT };
 #define ST_K(kind, field) (ST_KIND_BASE + (kind) * TF_COUNT + (field))
 // kernel classes for per-class timing (pbrt_b200_kernel_stats)
 enum { KC_GENERATE = 0, KC_INTERSECT, KC_SHADE, KC_SHADE_DIRECT, KC_SHADE_CONT, KC_SHADOW, KC_PROBE, KC_ADVANCE,
-       KC_FINALIZE, KC_FILM, KC_COUNT };
+       KC_FINALIZE, KC_FILM, KC_SHADE_FAST, KC_COUNT };
 static const char *const kKernelClassNames[KC_COUNT] = {"k_generate", "k_intersect", "k_shade_surface", "k_shade_direct",
                                                         "k_shade_continue", "k_shadow", "k_probe", "k_advance_wd",
-                                                        "k_finalize", "k_film"};
+                                                        "k_finalize", "k_film", "k_shade_fast"};
 // counts[] layout: per iteration it: [4*it+0] main queue size, +1 shadow queue size,
 // +2 probe queue size, +3 rays of the main queue that hit something (path integrator); work counters follow at PB_WORK_BASE.
 #define PB_MAX_ITERS 1024
@@ -172,11 +174,16 @@ struct WavePart {
   // pixel (firstPixel / nPixels count placements); corners of the window's placements, scan order
   const float2 *corners;
   int bcCols;                // placements per row when every row holds the same number, else 0
+  // tile mode (pbrt_b200_render_tiles): the window is a TILE of the scene's film window.  Its sample extent holds
+  // every sample pixel of the frame's extent that could reach the tile, and a sample is traced only if its filter
+  // footprint (film/image.cpp:106-111) really touches a pixel of [tx0, tx1) x [ty0, ty1)
+  int tile, tx0, ty0, tx1, ty1;
 };
 #define PB_BC_INVALID_COORD -1.0e6f   // film coordinate of a table entry outside the sampler's extent
 struct WaveDesc {
   int spp;                   // samples per unit (pixel; bestcandidate: PB_BC_TABLE per placement)
   int bc;                    // bestcandidate sampler
+  int tiles;                 // tile mode (see WavePart)
   uint32_t nSlots;
   int nParts;
   WavePart parts[PB_MAX_PARTS];
@@ -297,12 +304,15 @@ __device__ __forceinline__ void wave_state_init(const WaveBuffers &wb, uint32_t 
 __global__ void __launch_bounds__(PB_BLOCK)
 k_generate(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveDesc wd) {
   uint32_t nValid = 0;
-  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < wd.nSlots;
+  // (tile mode compacts the ray queue with warp ballots: the loop bound is rounded up so that whole warps iterate)
+  const uint32_t nLoop = wd.tiles ? ((wd.nSlots + 31u) & ~31u) : wd.nSlots;
+  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < nLoop;
        slot += gridDim.x * blockDim.x) {
+    const bool inWave = slot < wd.nSlots;
     int part = 0;
     while (part + 1 < wd.nParts && slot >= wd.parts[part + 1].slotBase) ++part;
     const WavePart &wp = wd.parts[part];
-    uint32_t pix = wp.firstPixel + (slot - wp.slotBase) / wd.spp;
+    uint32_t pix = inWave ? wp.firstPixel + (slot - wp.slotBase) / wd.spp : 0u;
     int k = (int)(slot % wd.spp);
     if (wd.bc) {
       // samplers/bestcandidate.cpp:107-129: entry k of placement `pix`; entries outside the extent are
@@ -329,13 +339,40 @@ k_generate(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
     }
     int ew = wp.xe - wp.xs;
     int x = wp.xs + (int)(pix % ew), y = wp.ys + (int)(pix / ew);
-    wb.pixel[slot] = (uint32_t)(x + 32768) | ((uint32_t)(y + 32768) << 16);
     CameraSample cs;
-    if (sv.sampler.kind == PBRT_B200_SAMPLER_LOWDISCREPANCY) {
-      PatternSource ps = {0, wb.ld, wb.nSlots, slot, 0};
-      ld_camera_sample(sv, ps, x, y, &cs);
-    } else
-      stratified_camera_sample(sv, x, y, k, &cs);
+    if (inWave) {
+      wb.pixel[slot] = (uint32_t)(x + 32768) | ((uint32_t)(y + 32768) << 16);
+      if (sv.sampler.kind == PBRT_B200_SAMPLER_LOWDISCREPANCY) {
+        PatternSource ps = {0, wb.ld, wb.nSlots, slot, 0};
+        ld_camera_sample(sv, ps, x, y, &cs);
+      } else
+        stratified_camera_sample(sv, x, y, k, &cs);
+    }
+    if (wd.tiles) {
+      // tile of a larger frame: the sample is traced when ImageFilm::AddSample would touch a pixel of the tile
+      bool valid = false;
+      if (inWave) {
+        float dImageX = film_image_coord(cs.imageX) - 0.5f, dImageY = film_image_coord(cs.imageY) - 0.5f;
+        int x0 = pb_ceil2int(dImageX - sv.filterXW), x1 = pb_floor2int(dImageX + sv.filterXW);
+        int y0 = pb_ceil2int(dImageY - sv.filterYW), y1 = pb_floor2int(dImageY + sv.filterYW);
+        valid = x1 >= wp.tx0 && x0 < wp.tx1 && y1 >= wp.ty0 && y0 < wp.ty1;
+      }
+      uint32_t qi = warp_push(&wb.counts[0], valid);
+      if (valid) {
+        Ray ray;
+        perspective_generate_ray(sv.camera, cs, &ray, sv.xRes, sv.yRes);
+        queue_put(wb.q[0], qi, slot, ray);
+        if (wb.camDiff) cam_diff_store(sv, wb, slot, cs);
+        ++nValid;
+      }
+      if (inWave) {
+        wb.imageX[slot] = valid ? film_image_coord(cs.imageX) : PB_BC_INVALID_COORD;
+        wb.imageY[slot] = valid ? film_image_coord(cs.imageY) : PB_BC_INVALID_COORD;
+        wave_state_init(wb, slot);
+        wb.alpha[slot] = valid ? 0.f : -1.f;
+      }
+      continue;
+    }
     Ray ray;
     perspective_generate_ray(sv.camera, cs, &ray, sv.xRes, sv.yRes);
     queue_put(wb.q[0], slot, slot, ray);
@@ -345,7 +382,7 @@ k_generate(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
     wave_state_init(wb, slot);
     wb.alpha[slot] = 0.f;
   }
-  if (wd.bc) warp_stat_add(&wb.stats[ST_CAMERA], nValid);
+  if (wd.bc || wd.tiles) warp_stat_add(&wb.stats[ST_CAMERA], nValid);
 }
 
 // K0b (bestcandidate sampler only): the LDShuffleScrambled1D/2D(4096, 1) tables of every table
@@ -675,7 +712,8 @@ __device__ __forceinline__ void path_surface_vertex(const SceneView &sv, const W
 template <bool INST, bool TEX>
 __global__ void __launch_bounds__(PB_BLOCK, TEX ? PB_SURF_TEX_MIN_BLOCKS : PB_SURF_MIN_BLOCKS)
 k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const RayQueue qin,
-               const SurfaceRecord rec, const uint32_t *nPtr, uint32_t *work, uint32_t *hitCount, uint32_t *specCount) {
+               const SurfaceRecord rec, const uint32_t *nPtr, uint32_t *work, uint32_t *hitCount, uint32_t *specCount,
+               const uint32_t *subset) {
   __shared__ uint32_t parkedAll[PB_BLOCK / 32][64];
   uint32_t *parked = parkedAll[threadIdx.x >> 5];
   uint32_t nParked = 0;   // warp uniform
@@ -688,6 +726,7 @@ k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const
     for (uint32_t base = chunk; base < chunk + PB_CLAIM && base < n; base += 32) {
       uint32_t i = base + lane;
       const bool valid = i < n;
+      if (subset) i = valid ? subset[i] : 0u;   // the queue entries k_path_fast left to this pipeline
       if (TEX || !sv.primFrame) {
         path_surface_vertex<INST, TEX, true>(sv, wb, qin, rec, i, valid, hitCount, specCount, shaded);
         continue;
@@ -718,6 +757,130 @@ k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const
   if (nParked) {
     uint32_t pi = lane < nParked ? parked[lane] : 0u;
     path_surface_vertex<INST, false, true>(sv, wb, qin, rec, pi, lane < nParked, hitCount, specCount, shaded);
+  }
+  warp_stat_add(&wb.stats[ST_SHADED], shaded);
+}
+
+// K2 fast path (untextured scenes).  Most path vertices are a ray that hit a flat triangle with a plain matte
+// material: for those the whole loop body of PathIntegrator::Li (path.cpp:66-143) -- fold the previous
+// vertex's direct light, emitted light, the UniformSampleOneLight record, the next direction -- runs here in
+// registers, from the ray and hit records straight to the shadow / probe / next-ray queues, with no surface
+// record through HBM in between (three kernels and ~470 bytes of traffic per vertex before).  Every other hit
+// (quadrics, per-vertex shading normals, instances, glass / mirror / glossy / Oren-Nayar materials) is passed
+// on: its queue index goes to `subset`, which the general k_path_surface / _direct / _continue pipeline then
+// shades.  Misses end here.  The arithmetic is the general kernels' (same inlined functions, LambertBsdf).
+#ifndef PB_FAST_MIN_BLOCKS
+#define PB_FAST_MIN_BLOCKS 4
+#endif
+template <bool LD, int LK>
+__global__ void __launch_bounds__(PB_BLOCK, PB_FAST_MIN_BLOCKS)
+k_path_fast(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveKeyInfo wd, const RayQueue qin,
+            const RayQueue qout, const uint32_t *nPtr, uint32_t *work, uint32_t *shadowCount, uint32_t *probeCount,
+            uint32_t *nextCount, uint32_t *subset, uint32_t *subsetCount) {
+  const uint32_t n = *nPtr;
+  uint32_t shaded = 0;
+  for (;;) {
+    uint32_t chunk = warp_claim_n(work, PB_CLAIM);
+    if (chunk >= n) break;
+    for (uint32_t base = chunk; base < chunk + PB_CLAIM && base < n; base += 32) {
+      const uint32_t i = base + lane_id();
+      const bool valid = i < n;
+      bool pass = false, pushShadow = false, pushProbe = false, pushNext = false;
+      uint32_t slot = 0;
+      DirectRec direct;
+      Ray next;
+      if (valid) {
+        const int32_t prim = qin.hitPrim[i];
+        float4 tail = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (prim >= 0) {
+          tail = __ldg((const float4 *)(sv.prims + 3u * (uint32_t)prim + 2));
+          pass = !(__float_as_uint(tail.y) & PB_PF_DEV_FRAME) || (qin.hitInst && qin.hitInst[i] >= 0) ||
+                 !material_is_lambert(sv.materials[__float_as_uint(tail.z)]);
+        }
+        if (!pass) {
+          slot = qin.slot[i];
+          const float4 lf = wb.plf[slot];
+          uint32_t flags = __float_as_uint(lf.w);
+          PathState st;
+          st.L = spec3(lf.x, lf.y, lf.z);
+          path_fold_pending(sv, wb, slot, &flags, &st.L);
+          st.depth = (int)(flags & 0xffu);
+          st.specularBounce = (flags >> 8) & 1u;
+          st.alpha = 0.f;
+          Ray ray = queue_ray(qin, i);
+          if (prim < 0) {
+            // the ray left the scene (path.cpp:69-82)
+            const bool mayEmit = st.depth == 0 || st.specularBounce;
+            st.T = spec(0.f);
+            if (mayEmit) { const float4 tc = wb.ptc[slot]; st.T = spec3(tc.x, tc.y, tc.z); }
+            Hit miss; miss.prim = -1; miss.t = 0.f; miss.b1 = miss.b2 = 0.f; miss.inst = -1;
+            Surface none;
+            path_vertex_surface<false, false, false, true>(sv, st, ray, miss, &none);
+            wb.plf[slot] = make_float4(st.L.c[0], st.L.c[1], st.L.c[2], __uint_as_float(flags));
+            if (st.depth == 0) wb.alpha[slot] = st.alpha;
+          } else {
+            const float4 tc = wb.ptc[slot];
+            st.T = spec3(tc.x, tc.y, tc.z);
+            st.rng.ctr = __float_as_uint(tc.w);
+            // path.cpp:83-92: alpha, the frame (k_prim_frames' table), emitted light
+            if (st.depth == 0) st.alpha = 1.f;
+            else st.T = st.T * spec(1.f);
+            LambertSurface ls;
+            const float4 *fr = sv.primFrame + 3u * (uint32_t)prim;
+            const float4 a = __ldg(fr), b = __ldg(fr + 1), c = __ldg(fr + 2);
+            ls.bsdf.p = ray_at(ray, qin.hitT[i]);
+            ls.bsdf.ng = v3(a.x, a.y, a.z); ls.bsdf.nn = v3(a.w, b.x, b.y);
+            ls.bsdf.sn = v3(b.z, b.w, c.x); ls.bsdf.tn = v3(c.y, c.z, c.w);
+            ls.material = __float_as_uint(tail.z);
+            ls.light = __float_as_int(tail.w);
+            const PbrtB200Material &mat = sv.materials[ls.material];
+            ls.bsdf.R = spec3(mat.kd[0], mat.kd[1], mat.kd[2]) * PB_INV_PI;
+            if (st.depth == 0 || st.specularBounce) {
+              Spec Le = spec(0.f);   // Intersection::Le (primitive.cpp:142-145)
+              if (ls.light >= 0 && dot(ls.bsdf.ng, -ray.d) > 0) Le = light_color(sv.lights[ls.light]);
+              st.L = st.L + st.T * Le;
+            }
+            ++shaded;
+            // path.cpp:93-112
+            st.rng.key = slot_key(wd, slot, 1);
+            PatternSource key0 = {slot_key(wd, slot, 0), LD ? wb.ld : (const float *)nullptr, wb.nSlots, slot, LD ? wd.bc : (wd.bc == 2 ? 2 : 0)};
+            bool hasDirect;
+            path_vertex_direct<false, LK>(sv, key0, st, ray, &ls, &direct, &hasDirect);
+            const Spec pendT = st.pendT;
+            // path.cpp:113-143
+            pushNext = path_vertex_continue<false>(sv, key0, st, ray, ls, &next);
+            flags = (uint32_t)st.depth | (st.specularBounce ? (1u << 8) : 0u);
+            if (hasDirect) {
+              pushShadow = direct.hasShadow;
+              pushProbe = direct.hasProbe;
+              if (pushProbe) {
+                flags |= 1u << 9;
+                store3(wb.pendT, slot, pendT);
+                store3(wb.recB, slot, direct.termB);
+                wb.prec[slot] = make_float4(direct.termA.c[0], direct.termA.c[1], direct.termA.c[2],
+                                            __uint_as_float((direct.hasShadow ? 4u : 0u) | 8u));
+              } else if (pushShadow) {
+                Spec Ld = direct_value(direct.termA, direct.termB, true, false);
+                Spec add = pendT * ((float)sv.nLights * Ld);
+                flags |= 1u << 9;
+                wb.prec[slot] = make_float4(add.c[0], add.c[1], add.c[2], __uint_as_float(4u | 16u));
+              }
+            }
+            wb.plf[slot] = make_float4(st.L.c[0], st.L.c[1], st.L.c[2], __uint_as_float(flags));
+            wb.ptc[slot] = make_float4(st.T.c[0], st.T.c[1], st.T.c[2], __uint_as_float(st.rng.ctr));
+            if (st.alpha != 0.f) wb.alpha[slot] = st.alpha;   // (depth 0 only; k_generate wrote 0)
+          }
+        }
+      }
+      uint32_t pj = warp_push(subsetCount, pass);
+      if (pass) subset[pj] = i;
+      uint32_t si = warp_push(shadowCount, pushShadow);
+      if (pushShadow) aux_put(wb.shadowQ, si, slot, direct.shadow, 0);
+      uint32_t pi = warp_push(probeCount, pushProbe);
+      if (pushProbe) aux_put(wb.probeQ, pi, slot, direct.probe, direct.probeLight);
+      uint32_t ni = warp_push(nextCount, pushNext);
+      if (pushNext) queue_put(qout, ni, slot, next);
+    }
   }
   warp_stat_add(&wb.stats[ST_SHADED], shaded);
 }
@@ -1070,7 +1233,7 @@ k_finalize(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
   for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < wd.nSlots;
        slot += gridDim.x * blockDim.x) {
     Spec L;
-    if (wd.bc && wb.alpha[slot] == -1.f) {   // bestcandidate: a table entry outside the extent, no sample
+    if ((wd.bc || wd.tiles) && wb.alpha[slot] == -1.f) {   // a table entry outside the extent / a culled apron sample: no sample
       store3(wb.outL, slot, spec(0.f));
       wb.outA[slot] = -1.f;
       continue;
@@ -1104,6 +1267,7 @@ __global__ void k_film_reach(const __grid_constant__ SceneView sv, const WaveBuf
     int x0 = 1 << 20, x1 = -(1 << 20), y0 = 1 << 20, y1 = -(1 << 20);
     uint32_t s0 = p * (uint32_t)spp;
     for (int k = 0; k < spp; ++k) {
+      if (wb.imageX[s0 + k] == PB_BC_INVALID_COORD) continue;   // culled (tile mode)
       float dImageX = wb.imageX[s0 + k] - 0.5f, dImageY = wb.imageY[s0 + k] - 0.5f;
       x0 = min(x0, pb_ceil2int(dImageX - sv.filterXW)); x1 = max(x1, pb_floor2int(dImageX + sv.filterXW));
       y0 = min(y0, pb_ceil2int(dImageY - sv.filterYW)); y1 = max(y1, pb_floor2int(dImageY + sv.filterYW));
@@ -1366,6 +1530,13 @@ struct PbrtB200Handle {
   WaveBuffers wb;
   std::vector<WindowFilm> films;
   bool keepSamples;
+  PbrtB200Window frameWin;   // the scene film's pixel window (crop window), what tiles are tiles of
+  float4 *rgbaSlab;          // when the windows' resolved pixels were allocated as one block (tile renders): its base
+  size_t rgbaSlabFloats;
+  // multi-GPU frames (multi.cuh), rank 0: the assembled frame + staging for the other ranks' tile blocks, tile table
+  float4 *gather; size_t gatherFloats;
+  float4 *frame;             // last assembled frame (points into `gather`, or at the single window's pixels)
+  void *tileTable; size_t tileTableCap;
   // per-kernel-class timing (tunable 3): events bracket every launch on h->stream
   std::vector<cudaEvent_t> evPool;
   std::vector<int> evClass;         // class of the launch bracketed by events 2i, 2i+1
@@ -1545,6 +1716,7 @@ static void carve_wave(Carver &c, WaveBuffers &wb, uint32_t nSlots, int directRe
   }
   for (int k = 0; k < 15; ++k) wb.surf[k] = isPath ? c.take<float>(nSlots) : nullptr;
   wb.surfIds = isPath ? c.take<uint32_t>(nSlots) : nullptr;
+  wb.subset = isPath ? c.take<uint32_t>(nSlots) : nullptr;
   wb.surfQueueIdx = isPath ? c.take<uint32_t>(nSlots) : nullptr;
   wb.camDiff = textured ? c.take<float>((size_t)12 * nSlots) : nullptr;
   wb.surfMat = (textured && isPath) ? c.take<PbrtB200Material>(nSlots) : nullptr;
@@ -1579,11 +1751,14 @@ static int ensure_wave(PbrtB200Handle *h, uint32_t nSlots) {
 static void free_films(PbrtB200Handle *h) {
   for (auto &f : h->films) {
     pool_free(h->device, f.film);
-    pool_free(h->device, f.rgba);
+    if (!h->rgbaSlab) pool_free(h->device, f.rgba);
     pool_free(h->device, f.sampleOut);
     pool_free(h->device, f.corners);
   }
   h->films.clear();
+  pool_free(h->device, h->rgbaSlab);
+  h->rgbaSlab = nullptr;
+  h->rgbaSlabFloats = 0;
 }
 
 static int persistent_grid(const PbrtB200Handle *h) { return h->numSMs * (int)g_blocksPerSM; }
@@ -1627,7 +1802,7 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
   bool count = g_countKd != 0;
   CU_TRY(cudaMemsetAsync(wb.counts, 0, PB_COUNTS_TOTAL * sizeof(uint32_t), st));
   // (bestcandidate: k_generate counts the table entries that fall inside the extent itself)
-  if (!wd.bc) CU_TRY(cudaMemcpyAsync(&wb.counts[0], &wd.nSlots, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  if (!wd.bc && !wd.tiles) CU_TRY(cudaMemcpyAsync(&wb.counts[0], &wd.nSlots, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   int genGrid = (int)std::min<uint64_t>((wd.nSlots + PB_BLOCK - 1) / PB_BLOCK, (uint64_t)h->numSMs * 16);
   if (sv.sampler.kind == PBRT_B200_SAMPLER_LOWDISCREPANCY) {
     TIMED(KC_GENERATE, (k_slot_pixels<<<genGrid, PB_BLOCK, 0, st>>>(wb, wd)));
@@ -1670,7 +1845,23 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
         rec.mat = wb.surfMat;
         uint32_t *nHits = &wb.counts[4 * it + 3];
         uint32_t *nSpec = nextWork();   // specular-only hits (second bin of the surface records)
-#define PB_LAUNCH_SURF(INST, TEX) TIMED(KC_SHADE, (k_path_surface<INST, TEX><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], rec, nMain, nextWork(), nHits, nSpec)))
+        // untextured scenes: k_path_fast shades the plain vertices outright and leaves the rest as a subset
+        const bool fast = g_fastPath && !h->textured && sv.primFrame != nullptr;
+        const uint32_t *nGeneral = nMain;
+        const uint32_t *subset = nullptr;
+        if (fast) {
+          uint32_t *nSub = nextWork();
+#define PB_LAUNCH_FAST(LD_, LK_)                                                                                      \
+  TIMED(KC_SHADE_FAST, (k_path_fast<LD_, LK_><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], wb.q[cur ^ 1], nMain, \
+                                                                        nextWork(), nShadow, nProbe, nNext, wb.subset, nSub)))
+          if (isLD) { if (h->triLightsOnly) PB_LAUNCH_FAST(true, 0); else PB_LAUNCH_FAST(true, PB_LK_ALL); }
+          else { if (h->triLightsOnly) PB_LAUNCH_FAST(false, 0); else PB_LAUNCH_FAST(false, PB_LK_ALL); }
+#undef PB_LAUNCH_FAST
+          nGeneral = nSub;
+          subset = wb.subset;
+          ++*launches;
+        }
+#define PB_LAUNCH_SURF(INST, TEX) TIMED(KC_SHADE, (k_path_surface<INST, TEX><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], rec, nGeneral, nextWork(), nHits, nSpec, subset)))
         if (h->textured) { if (sv.nInstances != 0) PB_LAUNCH_SURF(true, true); else PB_LAUNCH_SURF(false, true); }
         else { if (sv.nInstances != 0) PB_LAUNCH_SURF(true, false); else PB_LAUNCH_SURF(false, false); }
 #undef PB_LAUNCH_SURF
@@ -1703,7 +1894,7 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
     // Whitted / DirectLighting: the recursion depth is data dependent; one host readback of
     // the queue size per iteration ends the loop.
     uint32_t nMainHost = wd.nSlots;
-    if (wd.bc) {
+    if (wd.bc || wd.tiles) {
       CU_TRY(cudaMemcpyAsync(&nMainHost, &wb.counts[0], sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
       CU_TRY(cudaStreamSynchronize(st));
     }
@@ -1764,7 +1955,7 @@ const char *pbrt_b200_last_error(void) { return g_lastError.c_str(); }
 int64_t pbrt_b200_tunable(int key, int64_t value) {
   int64_t *p = key == 0 ? &g_waveSamples : key == 1 ? &g_countKd : key == 2 ? &g_blocksPerSM
                : key == 3 ? &g_profileKernels : key == 4 ? &g_reserved4 : key == 5 ? &g_overlap : key == 6 ? &g_debugCounts
-               : key == 7 ? &g_primFrames : nullptr;
+               : key == 7 ? &g_primFrames : key == 8 ? &g_fastPath : nullptr;
   if (!p) return -1;
   int64_t prev = *p;
   if (value >= 0) *p = value;
@@ -1782,6 +1973,8 @@ void pbrt_b200_scene_destroy(PbrtB200Handle *h) {
   for (void *p : h->allocs) pool_free(h->device, p);
   pool_free(h->device, h->filterTable);
   pool_free(h->device, h->bcMasks);
+  pool_free(h->device, h->gather);
+  pool_free(h->device, h->tileTable);
   for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
   if (h->evDirect) cudaEventDestroy(h->evDirect);
   if (h->evAux) cudaEventDestroy(h->evAux);
@@ -1819,6 +2012,10 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   memset(h->lastStats, 0, sizeof(h->lastStats));
   std::string err = pb_setup_view(*scene, &h->sv);
   if (!err.empty()) { delete h; return fail(PBRT_B200_ERR_INVALID, err); }
+  h->frameWin.x0 = scene->film.x_pixel_start; h->frameWin.y0 = scene->film.y_pixel_start;
+  h->frameWin.width = scene->film.x_pixel_count; h->frameWin.height = scene->film.y_pixel_count;
+  h->rgbaSlab = nullptr; h->rgbaSlabFloats = 0;
+  h->gather = nullptr; h->gatherFloats = 0; h->frame = nullptr; h->tileTable = nullptr; h->tileTableCap = 0;
   h->hasSpecular = pb_scene_has_specular(*scene);
   h->hasGlossy = false;
   h->textured = scene->n_textures != 0;   // material operands (below) or light maps
@@ -1946,11 +2143,42 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   return PBRT_B200_OK;
 }
 
+// The sample extent of a TILE of the frame window `frame`: every sample pixel of the frame's own extent
+// (film/image.cpp:148-156) that can reach a pixel of the tile -- one more column / row towards lower coordinates
+// than a crop render of the same pixels would sample (a sample whose coordinate rounds up to the next integer
+// splats into the next pixel as well, image.cpp:108-111), so that the tile's pixels receive exactly the samples
+// they receive in the whole frame.  k_generate culls the samples of this extent that do not reach the tile.
+static WavePart tile_part(const SceneView &sv, const PbrtB200Window &frame, const PbrtB200Window &t) {
+  WavePart wp;
+  memset(&wp, 0, sizeof(wp));
+  int fxs, fxe, fys, fye;
+  film_sample_extent(sv, frame.x0, frame.y0, frame.width, frame.height, &fxs, &fxe, &fys, &fye);
+  wp.xs = std::max(fxs, pb_floor2int(t.x0 + .5f - sv.filterXW) - 1);
+  wp.xe = std::min(fxe, pb_floor2int(t.x0 + t.width - 1 + .5f + sv.filterXW) + 2);
+  wp.ys = std::max(fys, pb_floor2int(t.y0 + .5f - sv.filterYW) - 1);
+  wp.ye = std::min(fye, pb_floor2int(t.y0 + t.height - 1 + .5f + sv.filterYW) + 2);
+  wp.tile = 1;
+  wp.tx0 = t.x0; wp.ty0 = t.y0; wp.tx1 = t.x0 + t.width; wp.ty1 = t.y0 + t.height;
+  return wp;
+}
+
+static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int n_windows, PbrtB200Stats *stats,
+                          bool tiles);
 int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_windows, PbrtB200Stats *stats) {
+  return render_windows(h, windows, n_windows, stats, false);
+}
+int pbrt_b200_render_tiles(PbrtB200Handle *h, const PbrtB200Window *tiles, int n_tiles, PbrtB200Stats *stats) {
+  if (h && h->sv.sampler.kind == PBRT_B200_SAMPLER_BESTCANDIDATE)
+    return fail(PBRT_B200_ERR_UNSUPPORTED, "tile mode: the bestcandidate sampler's table placements are tied to the "
+                                           "window they start in (samplers/bestcandidate.cpp:81-105)");
+  return render_windows(h, tiles, n_tiles, stats, true);
+}
+static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int n_windows, PbrtB200Stats *stats,
+                          bool tiles) {
   if (!h || !windows || n_windows < 1) return fail(PBRT_B200_ERR_INVALID, "bad arguments");
   CU_TRY(cudaSetDevice(h->device));
   // keep the film buffers of the previous render when the windows are unchanged (frame loops)
-  bool reuseFilms = (int)h->films.size() == n_windows;
+  bool reuseFilms = (int)h->films.size() == n_windows && (h->rgbaSlab != nullptr) == tiles;
   for (int w = 0; reuseFilms && w < n_windows; ++w) {
     const PbrtB200Window &a = h->films[w].win, &b = windows[w];
     reuseFilms = a.x0 == b.x0 && a.y0 == b.y0 && a.width == b.width && a.height == b.height &&
@@ -1978,7 +2206,13 @@ int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_win
     if (win.width < 1 || win.height < 1) return fail(PBRT_B200_ERR_INVALID, "empty window");
     if (win.x0 < -16384 || win.y0 < -16384 || win.x0 + win.width > 16384 || win.y0 + win.height > 16384)
       return fail(PBRT_B200_ERR_UNSUPPORTED, "window outside +-16384 pixels");
-    ext[w] = window_part(sv, win);
+    if (tiles) {
+      const PbrtB200Window &f = h->frameWin;
+      if (win.x0 < f.x0 || win.y0 < f.y0 || win.x0 + win.width > f.x0 + f.width || win.y0 + win.height > f.y0 + f.height)
+        return fail(PBRT_B200_ERR_INVALID, "tile outside the scene's film window");
+      ext[w] = tile_part(sv, f, win);
+    } else
+      ext[w] = window_part(sv, win);
     ext[w].window = w;
     nPixW[w] = (uint64_t)(ext[w].xe - ext[w].xs) * (ext[w].ye - ext[w].ys);
     if (bc) {
@@ -2016,7 +2250,20 @@ int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_win
                              cudaMemcpyHostToDevice, h->stream));
     }
     CU_TRY(pool_alloc(h->device, (void **)&wf.film, nPixOut * sizeof(FilmPixel)));
-    CU_TRY(pool_alloc(h->device, (void **)&wf.rgba, nPixOut * sizeof(float4)));
+    if (tiles) {
+      // tile renders resolve into ONE block, window after window, so that a rank's finished tiles leave in a
+      // single transfer (multi.cuh)
+      if (w == 0) {
+        size_t total = 0;
+        for (int k = 0; k < n_windows; ++k) total += (size_t)windows[k].width * windows[k].height;
+        CU_TRY(pool_alloc(h->device, (void **)&h->rgbaSlab, total * sizeof(float4)));
+        h->rgbaSlabFloats = total * 4;
+      }
+      size_t before = 0;
+      for (int k = 0; k < w; ++k) before += (size_t)windows[k].width * windows[k].height;
+      wf.rgba = h->rgbaSlab + before;
+    } else
+      CU_TRY(pool_alloc(h->device, (void **)&wf.rgba, nPixOut * sizeof(float4)));
     CU_TRY(cudaMemsetAsync(wf.film, 0, nPixOut * sizeof(FilmPixel), h->stream));
     wf.nSamples = nPixW[w] * spp;
     if (h->keepSamples) CU_TRY(pool_alloc(h->device, (void **)&wf.sampleOut, wf.nSamples * 4 * sizeof(float)));
@@ -2030,6 +2277,7 @@ int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_win
     memset(&wd, 0, sizeof(wd));
     wd.spp = spp;
     wd.bc = bc ? 1 : 0;
+    wd.tiles = tiles ? 1 : 0;
     while (curW < n_windows && wd.nParts < PB_MAX_PARTS && wd.nSlots < capSlots) {
       uint64_t room = (capSlots - wd.nSlots) / spp;
       uint64_t take = std::min<uint64_t>(room, nPixW[curW] - curP);
@@ -2135,7 +2383,7 @@ int pbrt_b200_render(PbrtB200Handle *h, const PbrtB200Window *windows, int n_win
   if (stats) {
     const unsigned long long *hs = h->lastStats;
     memset(stats, 0, sizeof(*stats));
-    stats->camera_rays = bc ? hs[ST_CAMERA] : cameraRays;
+    stats->camera_rays = (bc || tiles) ? hs[ST_CAMERA] : cameraRays;
     stats->intersect_rays = hs[ST_K(TK_MAIN, TF_RAYS)] + hs[ST_K(TK_PROBE, TF_RAYS)];
     stats->shadow_rays = hs[ST_K(TK_SHADOW, TF_RAYS)];
     stats->points_shaded = hs[ST_SHADED];
@@ -2308,3 +2556,5 @@ int pbrt_b200_sample_radiance(PbrtB200Handle *h, int w, uint64_t n, float *ls) {
 }
 
 }  // extern "C"
+
+#include "multi.cuh"

@@ -209,12 +209,16 @@ namespace {
 typedef int (*RenderHostFn)(const PbrtB200Scene *, int, const PbrtB200Window *, int,
                             float *const *, float *const *, PbrtB200Stats *);
 typedef const char *(*LastErrorFn)(void);
+typedef int (*RenderHostMultiFn)(const PbrtB200Scene *, const int *, int, float *, PbrtB200Stats *);
+typedef int (*DeviceCountFn)(void);
 
 int CudaBackend(const PbrtB200Scene *scene, const PbrtB200Window *windows, int nWindows,
                 float *const *rgbaOut, PbrtB200Stats *stats) {
   static void *lib = NULL;
   static RenderHostFn renderHost = NULL;
   static LastErrorFn lastError = NULL;
+  static RenderHostMultiFn renderHostMulti = NULL;
+  static DeviceCountFn deviceCount = NULL;
   if (!lib) {
     vector<string> candidates;
     if (const char *env = getenv("PBRT_B200_LIB")) candidates.push_back(env);
@@ -237,7 +241,36 @@ int CudaBackend(const PbrtB200Scene *scene, const PbrtB200Window *windows, int n
              tried.c_str());
     renderHost = (RenderHostFn)dlsym(lib, "pbrt_b200_render_host");
     lastError = (LastErrorFn)dlsym(lib, "pbrt_b200_last_error");
-    if (!renderHost || !lastError) Severe("libpbrt_b200.so does not export the render ABI");
+    renderHostMulti = (RenderHostMultiFn)dlsym(lib, "pbrt_b200_render_host_multi");
+    deviceCount = (DeviceCountFn)dlsym(lib, "pbrt_b200_device_count");
+    if (!renderHost || !lastError || !renderHostMulti || !deviceCount) Severe("libpbrt_b200.so does not export the render ABI");
+  }
+  // PBRT_GPUS=n: the frame is cut into tiles over the first n GPUs of this machine (or the ones listed in
+  // PBRT_B200_DEVICES, comma separated) and assembled by one NCCL exchange -- no change to the scene file.
+  // The reference's counterpart is n cropwindow renders pasted with tools/exrassemble.cpp.
+  if (const char *g = getenv("PBRT_GPUS")) {
+    int n = atoi(g);
+    if (n > 1 && nWindows == 1) {
+      vector<int> devices;
+      if (const char *list = getenv("PBRT_B200_DEVICES")) {
+        for (const char *q = list; *q;) {
+          devices.push_back(atoi(q));
+          while (*q && *q != ',') ++q;
+          if (*q == ',') ++q;
+        }
+      } else
+        for (int i = 0; i < n; ++i) devices.push_back(i);
+      int have = deviceCount();
+      if ((int)devices.size() < n || n > have) {
+        Warning("PBRT_GPUS=%d but %d CUDA device(s) usable; rendering on %d", n, have, std::max(1, std::min(have, (int)devices.size())));
+        n = std::max(1, std::min(have, (int)devices.size()));
+      }
+      if (n > 1) {
+        int rc = renderHostMulti(scene, &devices[0], n, rgbaOut[0], stats);
+        if (rc != PBRT_B200_OK) Severe("multi-GPU render failed (code %d): %s", rc, lastError());
+        return rc;
+      }
+    }
   }
   int device = 0;
   if (const char *d = getenv("PBRT_B200_DEVICE")) device = atoi(d);

@@ -187,6 +187,13 @@ def cuda():
         lib.pbrt_b200_camera_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         lib.pbrt_b200_sample_radiance.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]
         lib.pbrt_b200_kernel_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        lib.pbrt_b200_render_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        lib.pbrt_b200_comm_unique_id.argtypes = [C.c_void_p]
+        lib.pbrt_b200_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        lib.pbrt_b200_comm_destroy.argtypes = [C.c_void_p]
+        lib.pbrt_b200_render_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.pbrt_b200_frame_device_ptr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pbrt_b200_render_host_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _cuda = lib
     return _cuda
 
@@ -212,6 +219,28 @@ class DeviceScene:
         _check(cuda().pbrt_b200_render(self.h, arr, len(ws), C.byref(st)))
         self.windows = ws
         return st.as_dict()
+
+    def render_tiles(self, tiles):
+        """pbrt_b200_render_tiles: the windows are tiles of the scene's film window (bit-identical to the frame)."""
+        arr = (Window * len(tiles))(*tiles)
+        st = Stats()
+        _check(cuda().pbrt_b200_render_tiles(self.h, arr, len(tiles), C.byref(st)))
+        self.windows = list(tiles)
+        return st.as_dict()
+
+    def render_frame(self, comm=None, tile_edge=0, out=None):
+        """pbrt_b200_render_frame: this rank's share of the whole film window + the one exchange; rank 0 may pass a
+        float32 [h, w, 4] array (e.g. pinned) to receive the frame."""
+        st = Stats()
+        _check(cuda().pbrt_b200_render_frame(self.h, comm.c if comm else None, tile_edge,
+                                             out.ctypes.data if out is not None else None, C.byref(st)))
+        return st.as_dict()
+
+    def frame_device_ptr(self):
+        p = C.c_void_p()
+        n = C.c_uint64()
+        _check(cuda().pbrt_b200_frame_device_ptr(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
 
     def download(self, w=0, want_raw=False):
         win = self.windows[w]
@@ -289,6 +318,63 @@ class DeviceScene:
             self.close()
         except Exception:
             pass
+
+
+class Comm:
+    """pbrt_b200_comm_*: this rank among `world` ranks (one GPU each).  `unique_id` = the 128 bytes rank 0 got from
+    Comm.unique_id(), broadcast by the caller (torch.distributed, MPI, a file ...)."""
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * 128)()
+        _check(cuda().pbrt_b200_comm_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, unique_id, rank, world, device):
+        c = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(cuda().pbrt_b200_comm_create(buf, rank, world, device, C.byref(c)))
+        self.c = c
+        self.rank, self.world = rank, world
+
+    def close(self):
+        if self.c:
+            cuda().pbrt_b200_comm_destroy(self.c)
+            self.c = None
+
+
+def frame_partition(window, world, tile_edge=0):
+    """pbrt_b200_frame_partition: [(Window, owner rank)] of the multi-GPU partition of `window` (no GPU needed)."""
+    lib = cuda()
+    lib.pbrt_b200_frame_partition.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    n = lib.pbrt_b200_frame_partition(C.byref(window), world, tile_edge, None, None, 0)
+    tiles = (Window * n)()
+    owners = (C.c_int32 * n)()
+    lib.pbrt_b200_frame_partition(C.byref(window), world, tile_edge, tiles, owners, n)
+    return [(Window(t.x0, t.y0, t.width, t.height), int(o)) for t, o in zip(tiles, owners)]
+
+
+def twin_render_tile(scene, frame, tile):
+    """TEST ONLY: the oracle twin's restatement of tile semantics (pbrt_b200_render_tiles)."""
+    lib = twin()
+    lib.pbrt_twin_render_tile.argtypes = [C.c_void_p] * 6
+    rgba = np.zeros((tile.height, tile.width, 4), np.float32)
+    st = Stats()
+    rc = lib.pbrt_twin_render_tile(scene.ptr, C.byref(frame), C.byref(tile), _fp(rgba), None, C.byref(st))
+    if rc != 0:
+        raise RuntimeError("twin tile render failed (%d)" % rc)
+    return rgba, st.as_dict()
+
+
+def render_host_multi(scene, devices, out=None):
+    """pbrt_b200_render_host_multi: HOST buffers both sides, one thread per device inside the library."""
+    w = scene.full_window()
+    if out is None:
+        out = np.zeros((w.height, w.width, 4), np.float32)
+    dev = (C.c_int * len(devices))(*devices)
+    st = Stats()
+    _check(cuda().pbrt_b200_render_host_multi(scene.ptr, dev, len(devices), out.ctypes.data, C.byref(st)))
+    return out, st.as_dict()
 
 
 def twin_sample_count(scene, w):

@@ -267,3 +267,92 @@ def test_full_size_properties(ffi, scene_dir):
     ds.render([ffi.Window(200, 0, 64, 512)])
     assert np.array_equal(ds.download(0).view(np.uint32), rgba[:, 200:264].view(np.uint32))
     ds.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# tile mode and the multi-GPU frame (pbrt_b200_render_tiles / _render_frame / _render_host_multi)
+@pytest.mark.parametrize("variant", ["box", "mitchell", "ld", "whitted"])
+def test_tile_mode_equals_full_frame(ffi, scene_dir, variant):
+    """Tiles of the film window are bit-identical to the same pixels of the whole frame, and trace (box filter)
+    practically no apron samples."""
+    args = ["--res", "200", "152", "--spp", "3", "3"]
+    if variant == "mitchell":
+        args += ["--filter", "mitchell"]
+    elif variant == "ld":
+        args += ["--ld"]
+    elif variant == "whitted":
+        args += ["--integrator", "whitted", "--mirror"]
+    sp = gen_scene(os.path.join(scene_dir, "tile_%s.pbrt" % variant), "c3", "--filename",
+                   os.path.join(scene_dir, "tile.exr"), *args)
+    scene = ffi.Scene(sp)
+    ds = ffi.DeviceScene(scene)
+    st_full = ds.render()
+    full = ds.download(0)
+    part = ffi.frame_partition(scene.full_window(), 3, 48)
+    tiles = [t for t, _ in part]
+    st = ds.render_tiles(tiles)
+    for i, t in enumerate(tiles):
+        got = ds.download(i)
+        want = full[t.y0:t.y0 + t.height, t.x0:t.x0 + t.width]
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (variant, i)
+    if variant == "box":
+        assert st_full["camera_rays"] <= st["camera_rays"] <= st_full["camera_rays"] * 1.001
+    else:
+        assert st["camera_rays"] >= st_full["camera_rays"]
+    # single-rank pbrt_b200_render_frame is the plain frame
+    ds.render_frame()
+    ptr, n = ds.frame_device_ptr()
+    assert n == full.size
+    ds.close()
+
+
+def test_tile_mode_full_size_frame(ffi, scene_dir):
+    """BASELINE configs[2] at full size: row strips rendered as TILES equal the frame bit for bit -- including the
+    handful of pixels a crop render of the same strips gets differently (tests/test_gpu_scale.py)."""
+    sp = gen_scene(os.path.join(scene_dir, "c3tiles.pbrt"), "c3", "--filename", os.path.join(scene_dir, "c3tiles.exr"))
+    scene = ffi.Scene(sp)
+    ds = ffi.DeviceScene(scene)
+    st_full = ds.render()
+    full = ds.download(0)
+    part = ffi.frame_partition(scene.full_window(), 8, 0)
+    tiles = [t for t, _ in part]
+    assert 150 <= len(tiles) <= 400
+    for lo in range(0, len(tiles), 32):
+        chunk = tiles[lo:lo + 32]
+        ds.render_tiles(chunk)
+        for i, t in enumerate(chunk):
+            got = ds.download(i)
+            assert np.array_equal(got.view(np.uint32), full[t.y0:t.y0 + t.height, t.x0:t.x0 + t.width].view(np.uint32)), t.y0
+    ds.close()
+
+
+def _n_devices(ffi):
+    return int(ffi.cuda().pbrt_b200_device_count())
+
+
+def test_multi_gpu_frame_bit_identical(ffi, scene_dir):
+    """pbrt_b200_render_host_multi on 2 (and all) GPUs of this box == the one-GPU frame, bit for bit; PBRT_GPUS drives
+    the same path from the scene-file front end."""
+    n = _n_devices(ffi)
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    exr = os.path.join(scene_dir, "multi.exr")
+    sp = gen_scene(os.path.join(scene_dir, "multi.pbrt"), "c3", "--res", "512", "384", "--spp", "4", "4", "--filename", exr)
+    scene = ffi.Scene(sp)
+    one, _, st1 = ffi.render_host(scene)
+    for k in sorted({2, n}):
+        frame, st = ffi.render_host_multi(scene, list(range(k)))
+        assert np.array_equal(frame.view(np.uint32), one[0].view(np.uint32)), k
+        assert st1["camera_rays"] <= st["camera_rays"] <= st1["camera_rays"] * 1.001
+        assert abs(st["intersect_rays"] + st["shadow_rays"] - st1["intersect_rays"] - st1["shadow_rays"]) <= 1e-3 * st1["intersect_rays"]
+    # the `pbrt scene.pbrt` path with PBRT_GPUS=2 writes the same EXR as with one GPU
+    outs = []
+    for gpus in ("1", "2"):
+        os.environ["PBRT_GPUS"] = gpus
+        try:
+            assert ffi.host().pbrt_host_render_file(os.fsencode(sp)) == 0
+        finally:
+            del os.environ["PBRT_GPUS"]
+        outs.append(open(exr, "rb").read())
+    assert outs[0] == outs[1]

@@ -239,7 +239,7 @@ def test_c_abi_exports_every_declared_symbol():
     lib = C.CDLL(lib_path)
     for name in declared:
         assert hasattr(lib, name), "missing export " + name
-    assert lib.pbrt_b200_abi_version() == 3
+    assert lib.pbrt_b200_abi_version() == 4
 
 
 def test_product_fails_loudly_without_gpu(ffi, scene_dir):
