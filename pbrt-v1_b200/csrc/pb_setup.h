@@ -25,13 +25,32 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
   if (ld && (s.sampler.y_samples != 1 || (s.sampler.x_samples & (s.sampler.x_samples - 1)) != 0 ||
              s.sampler.x_samples > PB_LD_MAX_PIXEL_SAMPLES))
     return "lowdiscrepancy sampler: pixelsamples must be a power of two <= 1024";
+  // The keyed RNG packs the sample index into 10 bits next to the pixel's y (pb_rng.h: pb_key); the camera
+  // pattern's key uses index 0xFFFF, whose low field equals sample 1023's.  Up to 1023 samples per pixel no two
+  // keys coincide; beyond that different pixels would share LatinHypercube blocks.
+  if (!bc && !ld && (int64_t)s.sampler.x_samples * s.sampler.y_samples > 1023)
+    return "stratified / random sampler: more than 1023 samples per pixel";
   if (s.film.x_pixel_count < 1 || s.film.y_pixel_count < 1) return "empty film";
+  // (ImageFilm keeps the path depth in 8 bits of the per-sample flag word)
+  if (s.integrator.kind == PBRT_B200_INT_PATH && s.integrator.max_depth > 254) return "path integrator: maxdepth > 254";
+  if ((s.n_nodes && !s.nodes) || (s.n_prim_refs && !s.prim_refs) || (s.n_prims && (!s.prims || !s.prim_aux)) ||
+      (s.n_materials && !s.materials) || ((s.n_lights + s.n_unsampled_lights) && !s.lights))
+    return "scene array pointer is null";
   for (uint32_t i = 0; i < s.n_prims; ++i) {
     uint32_t kind = s.prims[i].flags & PBRT_B200_PF_KIND_MASK;
     if (kind != PBRT_B200_PRIM_TRIANGLE && kind != PBRT_B200_PRIM_QUADRIC && kind != PBRT_B200_PRIM_INSTANCE) return "unknown primitive kind";
     if (kind == PBRT_B200_PRIM_INSTANCE) {
       if (s.prim_aux[i].owner >= s.n_instances) return "instance index out of range";
       continue;
+    }
+    if (kind == PBRT_B200_PRIM_QUADRIC && (!s.quadrics || s.prim_aux[i].owner >= s.n_quadrics)) return "quadric index out of range";
+    if (kind == PBRT_B200_PRIM_TRIANGLE && (s.prims[i].flags & (PBRT_B200_PF_HAS_UV | PBRT_B200_PF_HAS_N | PBRT_B200_PF_HAS_S))) {
+      const PbrtB200PrimAux &a = s.prim_aux[i];
+      if (a.v[0] >= s.n_vertices || a.v[1] >= s.n_vertices || a.v[2] >= s.n_vertices) return "triangle vertex index out of range";
+      if ((s.prims[i].flags & (PBRT_B200_PF_HAS_N | PBRT_B200_PF_HAS_S)) && (!s.meshes || a.owner >= s.n_meshes)) return "triangle mesh index out of range";
+      if (((s.prims[i].flags & PBRT_B200_PF_HAS_UV) && !s.vertex_uv) || ((s.prims[i].flags & PBRT_B200_PF_HAS_N) && !s.vertex_n) ||
+          ((s.prims[i].flags & PBRT_B200_PF_HAS_S) && !s.vertex_s))
+        return "per-vertex array missing";
     }
     if (s.prims[i].material >= s.n_materials) return "primitive material index out of range";
     if (s.prims[i].light >= (int32_t)(s.n_lights + s.n_unsampled_lights)) return "primitive light index out of range";
@@ -67,6 +86,35 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
     }
   }
   if (s.n_top_nodes > s.n_nodes) return "n_top_nodes > n_nodes";
+  // kd-trees: every interior node's above child and every leaf's primitives must stay inside the tree they
+  // belong to (the top-level tree, or an instanced object's, whose indices are relative to its offsets)
+  {
+    auto check_tree = [&](uint32_t nodeBase, uint32_t nNodes, uint32_t refBase, uint32_t refLimit, uint32_t primBase,
+                          uint32_t primLimit) -> const char * {
+      for (uint32_t i = 0; i < nNodes; ++i) {
+        const PbrtB200KdNode &n = s.nodes[nodeBase + i];
+        if ((n.word0 & 3u) != 3u) {
+          if (n.word1 <= i || n.word1 >= nNodes || i + 1 >= nNodes) return "kd node child index out of range";
+        } else {
+          uint32_t np = n.word0 >> 2;
+          if (np == 1) { if ((uint64_t)primBase + n.word1 >= primLimit) return "kd leaf primitive out of range"; }
+          else if (np > 1) {
+            if ((uint64_t)refBase + n.word1 + np > refLimit) return "kd leaf reference list out of range";
+            for (uint32_t k = 0; k < np; ++k)
+              if ((uint64_t)primBase + s.prim_refs[refBase + n.word1 + k] >= primLimit) return "kd leaf primitive out of range";
+          }
+        }
+      }
+      return (const char *)0;
+    };
+    if (const char *e = check_tree(0, s.n_top_nodes, 0, s.n_prim_refs, 0, s.n_prims)) return e;
+    for (uint32_t i = 0; i < s.n_instances; ++i) {
+      const PbrtB200Instance &in = s.instances[i];
+      if ((uint64_t)in.node_base + in.n_nodes > s.n_nodes || in.ref_base > s.n_prim_refs || in.prim_base >= s.n_prims)
+        return "instance offsets out of range";
+      if (const char *e = check_tree(in.node_base, in.n_nodes, in.ref_base, s.n_prim_refs, in.prim_base, s.n_prims)) return e;
+    }
+  }
   for (uint32_t i = 0; i < s.n_instances; ++i) {
     const PbrtB200Instance &in = s.instances[i];
     if ((uint64_t)in.node_base + in.n_nodes > s.n_nodes || in.ref_base > s.n_prim_refs || in.prim_base >= s.n_prims)
@@ -78,6 +126,19 @@ static inline std::string pb_setup_view(const PbrtB200Scene &s, SceneView *sv) {
   for (uint32_t i = 0; i < s.n_lights; ++i) {
     if (s.lights[i].kind < PBRT_B200_LIGHT_POINT || s.lights[i].kind > PBRT_B200_LIGHT_PROJECTION) return "unknown light kind";
     if (s.lights[i].kind == PBRT_B200_LIGHT_INFINITE) ++sv->nInfiniteLights;
+    if (s.lights[i].kind == PBRT_B200_LIGHT_AREA) {
+      // AreaLight over a ShapeSet (lights/area.cpp, core/shape.h:108-156): its shape list and area CDF
+      const PbrtB200Light &l = s.lights[i];
+      if (l.n_shapes < 1 || !s.light_shapes || !s.light_cdf || (uint64_t)l.first_shape + l.n_shapes > s.n_light_shapes)
+        return "area light shape list out of range";
+      for (uint32_t k = 0; k < l.n_shapes; ++k) {
+        uint32_t prim = s.light_shapes[l.first_shape + k];
+        if (prim >= s.n_prims) return "area light shape is not a primitive of the scene";
+        uint32_t pk = s.prims[prim].flags & PBRT_B200_PF_KIND_MASK;
+        if (pk == PBRT_B200_PRIM_INSTANCE) return "area light shape is an object instance";
+        if (pk == PBRT_B200_PRIM_QUADRIC && s.prim_aux[prim].owner >= s.n_quadrics) return "area light quadric index out of range";
+      }
+    }
     if (s.lights[i].kind >= PBRT_B200_LIGHT_INFINITE && s.lights[i].radiance_map != 0 &&
         (s.lights[i].radiance_map > s.n_textures || s.textures[s.lights[i].radiance_map - 1].kind != PBRT_B200_TEX_IMAGEMAP ||
          s.textures[s.lights[i].radiance_map - 1].channels != 3))

@@ -1567,6 +1567,20 @@ struct LaunchTimer {
 #define TIMED(cls, launch) do { LaunchTimer lt_(h, cls); launch; } while (0)
 #define TIMED_ON(cls, strm, launch) do { LaunchTimer lt_(h, cls, strm); launch; } while (0)
 
+// CUDA events that are destroyed on every exit path
+struct ScopedEvents {
+  cudaEvent_t e[4];
+  int n;
+  ScopedEvents() : n(0) {}
+  ~ScopedEvents() { for (int i = 0; i < n; ++i) cudaEventDestroy(e[i]); }
+  cudaError_t create(int count) {
+    for (; n < count; ++n) {
+      cudaError_t err = cudaEventCreate(&e[n]);
+      if (err != cudaSuccess) return err;
+    }
+    return cudaSuccess;
+  }
+};
 #define PB_MAX_DEVICES 64
 // Small per-device cache of released device blocks: pbrt_b200_render_host() builds and tears down a
 // handle per call (scene arrays, films), and cudaMalloc / cudaFree (which synchronises) per frame
@@ -1579,7 +1593,7 @@ struct PoolBlock { void *p; size_t bytes; };
 std::mutex g_poolMutex;
 std::vector<PoolBlock> g_pool[PB_MAX_DEVICES];
 std::unordered_map<void *, size_t> g_poolSizes;     // live blocks handed out by pool_alloc
-const size_t kPoolMaxBlocks = 48, kPoolMaxBytes = (size_t)1 << 30;
+const size_t kPoolMaxBlocks = 512, kPoolMaxBytes = (size_t)2 << 30;
 }  // namespace
 static cudaError_t pool_alloc(int device, void **out, size_t bytes) {
   if (bytes == 0) bytes = 1;
@@ -1642,6 +1656,7 @@ static void *g_cachedArena[PB_MAX_DEVICES];
 static size_t g_cachedArenaBytes[PB_MAX_DEVICES];
 static void free_wave(PbrtB200Handle *h) {
   if (h->arena) {
+    std::lock_guard<std::mutex> lock(g_poolMutex);   // (handles of several host threads share the per-device cache)
     int d = h->device;
     if (d >= 0 && d < PB_MAX_DEVICES && h->arenaBytes > g_cachedArenaBytes[d]) {
       if (g_cachedArena[d]) cudaFree(g_cachedArena[d]);
@@ -1734,12 +1749,16 @@ static int ensure_wave(PbrtB200Handle *h, uint32_t nSlots) {
   carve_wave(sizing, tmp, nSlots, h->sv.directRecords, h->nFrames, isPath, h->sv.ldFloatsPerSample, h->sv.nInstances != 0, h->textured);
   size_t bytes = sizing.off + 256;
   int d = h->device;
-  if (d >= 0 && d < PB_MAX_DEVICES && g_cachedArena[d] && g_cachedArenaBytes[d] >= bytes) {
-    h->arena = g_cachedArena[d];
-    h->arenaBytes = g_cachedArenaBytes[d];
-    g_cachedArena[d] = nullptr;
-    g_cachedArenaBytes[d] = 0;
-  } else {
+  {
+    std::lock_guard<std::mutex> lock(g_poolMutex);
+    if (d >= 0 && d < PB_MAX_DEVICES && g_cachedArena[d] && g_cachedArenaBytes[d] >= bytes) {
+      h->arena = g_cachedArena[d];
+      h->arenaBytes = g_cachedArenaBytes[d];
+      g_cachedArena[d] = nullptr;
+      g_cachedArenaBytes[d] = 0;
+    }
+  }
+  if (!h->arena) {
     CU_TRY(cudaMalloc(&h->arena, bytes));
     h->arenaBytes = bytes;
   }
@@ -2190,9 +2209,9 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
   memset(h->classMs, 0, sizeof(h->classMs));
   memset(h->classLaunches, 0, sizeof(h->classLaunches));
   h->evClass.clear();
-  cudaEvent_t e0, e1;
-  CU_TRY(cudaEventCreate(&e0));
-  CU_TRY(cudaEventCreate(&e1));
+  ScopedEvents ev;
+  CU_TRY(ev.create(2));
+  const cudaEvent_t e0 = ev.e[0], e1 = ev.e[1];
   // per-window sample extents; size the wave arena for min(tunable, all samples)
   const bool bc = sv.sampler.kind == PBRT_B200_SAMPLER_BESTCANDIDATE;
   // samples per unit of work: a pixel's samples, or the 4096 entries of one bestcandidate table placement
@@ -2241,7 +2260,8 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
       CU_TRY(cudaMemsetAsync(h->films[w].film, 0, nPixOut * sizeof(FilmPixel), h->stream));
       continue;
     }
-    WindowFilm wf;
+    h->films.push_back(WindowFilm());
+    WindowFilm &wf = h->films.back();   // registered first: an allocation failure below leaves it to free_films
     wf.win = win; wf.film = nullptr; wf.rgba = nullptr; wf.sampleOut = nullptr; wf.corners = nullptr;
     if (bc) {
       wf.cornersHost = placements[w];
@@ -2267,7 +2287,6 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
     CU_TRY(cudaMemsetAsync(wf.film, 0, nPixOut * sizeof(FilmPixel), h->stream));
     wf.nSamples = nPixW[w] * spp;
     if (h->keepSamples) CU_TRY(pool_alloc(h->device, (void **)&wf.sampleOut, wf.nSamples * 4 * sizeof(float)));
-    h->films.push_back(wf);
   }
   // waves: consecutive samples in reference order, spanning windows when a window is small
   int curW = 0;
@@ -2370,8 +2389,6 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
   CU_TRY(cudaGetLastError());
   float ms = 0.f;
   CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   for (size_t i = 0; i < h->evClass.size(); ++i) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, h->evPool[2 * i], h->evPool[2 * i + 1]) == cudaSuccess) h->classMs[h->evClass[i]] += t;
@@ -2439,25 +2456,29 @@ int pbrt_b200_render_host(const PbrtB200Scene *scene, int device, const PbrtB200
                           int n_windows, float *const *rgba_out, float *const *raw_out,
                           PbrtB200Stats *stats) {
   PbrtB200Handle *h = nullptr;
-  cudaEvent_t e0, e1, e2, e3;
   int nDev = 0;
   if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
     return fail(PBRT_B200_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)");
   CU_TRY(cudaSetDevice(device));
-  CU_TRY(cudaEventCreate(&e0)); CU_TRY(cudaEventCreate(&e1));
-  CU_TRY(cudaEventCreate(&e2)); CU_TRY(cudaEventCreate(&e3));
+  ScopedEvents ev;
+  CU_TRY(ev.create(4));
+  const cudaEvent_t e0 = ev.e[0], e1 = ev.e[1], e2 = ev.e[2], e3 = ev.e[3];
   CU_TRY(cudaEventRecord(e0, 0));
   int rc = pbrt_b200_scene_create(scene, device, &h);
   if (rc != PBRT_B200_OK) return rc;
+  struct HandleGuard {
+    PbrtB200Handle *&h;
+    ~HandleGuard() { if (h) pbrt_b200_scene_destroy(h); }
+  } guard = {h};
   CU_TRY(cudaEventRecord(e1, 0));
   PbrtB200Stats st;
   rc = pbrt_b200_render(h, windows, n_windows, &st);
-  if (rc != PBRT_B200_OK) { pbrt_b200_scene_destroy(h); return rc; }
+  if (rc != PBRT_B200_OK) return rc;
   CU_TRY(cudaEventRecord(e2, 0));
   uint64_t d2h = 0;
   for (int w = 0; w < n_windows; ++w) {
     rc = pbrt_b200_film_download(h, w, rgba_out ? rgba_out[w] : nullptr, raw_out ? raw_out[w] : nullptr);
-    if (rc != PBRT_B200_OK) { pbrt_b200_scene_destroy(h); return rc; }
+    if (rc != PBRT_B200_OK) return rc;
     size_t n = (size_t)windows[w].width * windows[w].height;
     if (rgba_out && rgba_out[w]) d2h += n * 16;
     if (raw_out && raw_out[w]) d2h += n * 20;
@@ -2470,8 +2491,8 @@ int pbrt_b200_render_host(const PbrtB200Scene *scene, int device, const PbrtB200
   st.upload_ms = up; st.download_ms = down;
   st.h2d_bytes = h->sceneBytes; st.d2h_bytes = d2h;
   if (stats) *stats = st;
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
   pbrt_b200_scene_destroy(h);
+  h = nullptr;
   return PBRT_B200_OK;
 }
 
