@@ -407,12 +407,16 @@ int pbrt_b200_render_host(const PbrtB200Scene *scene, int device,
                           PbrtB200Stats *stats);
 
 /* Tunables; returns the previous value, value < 0 only queries.
- * key 0: image samples per wave (default 4 Mi)
+ * key 0: image samples per wave (default 16 Mi = ~5.4 GB of wave state for the path integrator; a frame whose
+ *        sample count exceeds it is cut into equal waves)
  * key 1: collect the kd-walk counters of PbrtB200Stats (default off: they cost time)
  * key 2: resident CTAs per SM of the persistent kernels
  * key 3: bracket every kernel launch with CUDA events (pbrt_b200_kernel_stats)
+ * key 5: overlap shadow/probe traversal with the next kernels on a second stream (default off: measured +1 %)
  * key 6: print per-iteration queue sizes of every wave to stderr (profiling aid)
- * key 5: overlap shadow/probe traversal with the next kernels on a second stream (default off: measured +1 %) */
+ * key 7: precompute the hit-independent BSDF frames of flat triangles and the light triangles' normals at
+ *        scene create (default on; 0 evaluates them at every hit -- same bits, A/B switch for the profiles)
+ * key 8: shade plain vertices (flat triangle, matte material) in the single-pass kernel k_path_fast (default on) */
 int64_t pbrt_b200_tunable(int key, int64_t value);
 
 /* Per-kernel-class totals of the last pbrt_b200_render(): launches, summed

@@ -63,7 +63,9 @@ __device__ __forceinline__ void pb_stage_nodes(const PbrtB200KdNode *src, uint2 
 #endif
 
 // Source: Ray load(uint32_t i).   Sink: void done(uint32_t i, const Ray &ray, const Hit &hit, bool anyHit).
-template <bool ANY, bool COUNT, int QK, class Source, class Sink>
+// DS: interior steps per trip (PB_DESCEND_STEPS for small trees; trees with > ~100 k nodes visit 3-4 interior
+// nodes per primitive test and run 3-4 % faster with 4: profiles/r02c_sweep.log, r02d_sweep.log)
+template <bool ANY, bool COUNT, int QK, int DS, class Source, class Sink>
 __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n, uint32_t *work,
                                                  const Source &src, const Sink &sink, KdCounters &cnt) {
   const uint32_t lane = threadIdx.x & 31u;
@@ -144,7 +146,7 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
     bool pending = false;
     uint32_t prim = 0;
 #pragma unroll 1
-    for (int step = 0; step < PB_DESCEND_STEPS; ++step) {
+    for (int step = 0; step < DS; ++step) {
       bool descending = active && !inLeaf;
       if (__ballot_sync(0xffffffffu, descending) == 0) break;
       if (descending) {

@@ -453,7 +453,11 @@ __device__ __forceinline__ void flush_kd_counters(unsigned long long *stats, int
   warp_stat_add(&stats[ST_K(kind, TF_REFS)], cnt.refs);
   warp_stat_add(&stats[ST_K(kind, TF_TESTS)], cnt.tests);
 }
-template <bool COUNT, int QK>
+#ifndef PB_DESCEND_STEPS_BIG
+#define PB_DESCEND_STEPS_BIG 4
+#endif
+#define PB_BIG_TREE_NODES 100000u   // top-level trees above this many nodes use PB_DESCEND_STEPS_BIG
+template <bool COUNT, int QK, int DS>
 __global__ void __launch_bounds__(PB_BLOCK, QK == PB_QK_INSTANCES ? PB_TRAV_INST_MIN_BLOCKS
                                             : QK == PB_QK_TRI ? PB_TRAV_TRI_MIN_BLOCKS : PB_TRAV_MIN_BLOCKS)
 k_intersect(const __grid_constant__ SceneView sv, const RayQueue q, const uint32_t *nPtr,
@@ -462,7 +466,7 @@ k_intersect(const __grid_constant__ SceneView sv, const RayQueue q, const uint32
   KdCounters cnt = {0, 0, 0, 0};
   MainSource src = {q};
   MainSink sink = {q};
-  kd_warp_traverse<false, COUNT, QK>(sv, n, work, src, sink, cnt);
+  kd_warp_traverse<false, COUNT, QK, DS>(sv, n, work, src, sink, cnt);
   if (COUNT) flush_kd_counters(stats, TK_MAIN, cnt);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_K(TK_MAIN, TF_RAYS)], (unsigned long long)n);
 }
@@ -498,7 +502,7 @@ struct ShadowSink {
 #ifndef PB_SHADOW_TRI_MIN_BLOCKS
 #define PB_SHADOW_TRI_MIN_BLOCKS PB_TRAV_MIN_BLOCKS
 #endif
-template <bool COUNT, int QK>
+template <bool COUNT, int QK, int DS>
 __global__ void __launch_bounds__(PB_BLOCK, QK == PB_QK_INSTANCES ? PB_SHADOW_INST_MIN_BLOCKS
                                             : QK == PB_QK_TRI ? PB_SHADOW_TRI_MIN_BLOCKS : PB_TRAV_MIN_BLOCKS)
 k_shadow(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t *nPtr, uint32_t *work,
@@ -507,7 +511,7 @@ k_shadow(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t 
   KdCounters cnt = {0, 0, 0, 0};
   ShadowSource src = {q};
   ShadowSink sink = {q, recFlags, prec};
-  kd_warp_traverse<true, COUNT, QK>(sv, n, work, src, sink, cnt);
+  kd_warp_traverse<true, COUNT, QK, DS>(sv, n, work, src, sink, cnt);
   if (COUNT) flush_kd_counters(stats, TK_SHADOW, cnt);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_K(TK_SHADOW, TF_RAYS)], (unsigned long long)n);
 }
@@ -541,7 +545,7 @@ k_probe(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t *
   KdCounters cnt = {0, 0, 0, 0};
   ProbeSource src = {q};
   ProbeSink sink = {&sv, q, recFlags, prec};
-  kd_warp_traverse<false, COUNT, PB_QK_INSTANCES>(sv, n, work, src, sink, cnt);
+  kd_warp_traverse<false, COUNT, PB_QK_INSTANCES, PB_DESCEND_STEPS>(sv, n, work, src, sink, cnt);
   if (COUNT) flush_kd_counters(stats, TK_PROBE, cnt);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_K(TK_PROBE, TF_RAYS)], (unsigned long long)n);
 }
@@ -770,35 +774,121 @@ k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const
 // on: its queue index goes to `subset`, which the general k_path_surface / _direct / _continue pipeline then
 // shades.  Misses end here.  The arithmetic is the general kernels' (same inlined functions, LambertBsdf).
 #ifndef PB_FAST_MIN_BLOCKS
-#define PB_FAST_MIN_BLOCKS 4
+#define PB_FAST_MIN_BLOCKS 6   // 80 registers (r02d_sweep.log: 3 / 4 / 5 / 6 CTAs per SM: 54.3 / 43.8 / 40.9 / 38.2 ms per C3 frame)
 #endif
+// One plain vertex (flat triangle, matte): queue entry i, all in registers.
+template <bool LD, int LK>
+__device__ __forceinline__ void path_fast_vertex(const SceneView &sv, const WaveBuffers &wb, const WaveKeyInfo &wd,
+                                                 const RayQueue &qin, const RayQueue &qout, uint32_t i, bool valid,
+                                                 uint32_t *shadowCount, uint32_t *probeCount, uint32_t *nextCount,
+                                                 uint32_t &shaded) {
+  bool pushShadow = false, pushProbe = false, pushNext = false;
+  uint32_t slot = 0;
+  DirectRec direct;
+  Ray next;
+  if (valid) {
+    const uint32_t prim = (uint32_t)qin.hitPrim[i];
+    const float4 tail = __ldg((const float4 *)(sv.prims + 3u * prim + 2));
+    slot = qin.slot[i];
+    const float4 lf = wb.plf[slot];
+    uint32_t flags = __float_as_uint(lf.w);
+    PathState st;
+    st.L = spec3(lf.x, lf.y, lf.z);
+    path_fold_pending(sv, wb, slot, &flags, &st.L);
+    st.depth = (int)(flags & 0xffu);
+    st.specularBounce = (flags >> 8) & 1u;
+    st.alpha = 0.f;
+    Ray ray = queue_ray(qin, i);
+    const float4 tc = wb.ptc[slot];
+    st.T = spec3(tc.x, tc.y, tc.z);
+    st.rng.ctr = __float_as_uint(tc.w);
+    // path.cpp:83-92: alpha, the frame (k_prim_frames' table), emitted light
+    if (st.depth == 0) st.alpha = 1.f;
+    else st.T = st.T * spec(1.f);
+    LambertSurface ls;
+    const float4 *fr = sv.primFrame + 3u * prim;
+    const float4 a = __ldg(fr), b = __ldg(fr + 1), c = __ldg(fr + 2);
+    ls.bsdf.p = ray_at(ray, qin.hitT[i]);
+    ls.bsdf.ng = v3(a.x, a.y, a.z); ls.bsdf.nn = v3(a.w, b.x, b.y);
+    ls.bsdf.sn = v3(b.z, b.w, c.x); ls.bsdf.tn = v3(c.y, c.z, c.w);
+    ls.material = __float_as_uint(tail.z);
+    ls.light = __float_as_int(tail.w);
+    const PbrtB200Material &mat = sv.materials[ls.material];
+    ls.bsdf.R = spec3(mat.kd[0], mat.kd[1], mat.kd[2]) * PB_INV_PI;
+    if (st.depth == 0 || st.specularBounce) {
+      Spec Le = spec(0.f);   // Intersection::Le (primitive.cpp:142-145)
+      if (ls.light >= 0 && dot(ls.bsdf.ng, -ray.d) > 0) Le = light_color(sv.lights[ls.light]);
+      st.L = st.L + st.T * Le;
+    }
+    ++shaded;
+    // path.cpp:93-112
+    st.rng.key = slot_key(wd, slot, 1);
+    PatternSource key0 = {slot_key(wd, slot, 0), LD ? wb.ld : (const float *)nullptr, wb.nSlots, slot, LD ? wd.bc : (wd.bc == 2 ? 2 : 0)};
+    bool hasDirect;
+    path_vertex_direct<false, LK>(sv, key0, st, ray, &ls, &direct, &hasDirect);
+    const Spec pendT = st.pendT;
+    // path.cpp:113-143
+    pushNext = path_vertex_continue<false>(sv, key0, st, ray, ls, &next);
+    flags = (uint32_t)st.depth | (st.specularBounce ? (1u << 8) : 0u);
+    if (hasDirect) {
+      pushShadow = direct.hasShadow;
+      pushProbe = direct.hasProbe;
+      if (pushProbe) {
+        flags |= 1u << 9;
+        store3(wb.pendT, slot, pendT);
+        store3(wb.recB, slot, direct.termB);
+        wb.prec[slot] = make_float4(direct.termA.c[0], direct.termA.c[1], direct.termA.c[2],
+                                    __uint_as_float((direct.hasShadow ? 4u : 0u) | 8u));
+      } else if (pushShadow) {
+        Spec Ld = direct_value(direct.termA, direct.termB, true, false);
+        Spec add = pendT * ((float)sv.nLights * Ld);
+        flags |= 1u << 9;
+        wb.prec[slot] = make_float4(add.c[0], add.c[1], add.c[2], __uint_as_float(4u | 16u));
+      }
+    }
+    wb.plf[slot] = make_float4(st.L.c[0], st.L.c[1], st.L.c[2], __uint_as_float(flags));
+    wb.ptc[slot] = make_float4(st.T.c[0], st.T.c[1], st.T.c[2], __uint_as_float(st.rng.ctr));
+    if (st.alpha != 0.f) wb.alpha[slot] = st.alpha;   // (depth 0 only; k_generate wrote 0)
+  }
+  uint32_t si = warp_push(shadowCount, pushShadow);
+  if (pushShadow) aux_put(wb.shadowQ, si, slot, direct.shadow, 0);
+  uint32_t pi = warp_push(probeCount, pushProbe);
+  if (pushProbe) aux_put(wb.probeQ, pi, slot, direct.probe, direct.probeLight);
+  uint32_t ni = warp_push(nextCount, pushNext);
+  if (pushNext) queue_put(qout, ni, slot, next);
+}
+
 template <bool LD, int LK>
 __global__ void __launch_bounds__(PB_BLOCK, PB_FAST_MIN_BLOCKS)
 k_path_fast(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WaveKeyInfo wd, const RayQueue qin,
             const RayQueue qout, const uint32_t *nPtr, uint32_t *work, uint32_t *shadowCount, uint32_t *probeCount,
             uint32_t *nextCount, uint32_t *subset, uint32_t *subsetCount) {
+  // a warp sorts its 32 rays into: missed (finished here, a few memory operations), to be passed on to the
+  // general kernels, and plain hits -- the latter wait in a shared-memory list and are shaded 32 at a time, so that
+  // the ~1700-instruction vertex body always runs with full warps (r02d ncu: 20 of 32 lanes active without this)
+  __shared__ uint32_t parkedAll[PB_BLOCK / 32][64];
+  uint32_t *parked = parkedAll[threadIdx.x >> 5];
+  uint32_t nParked = 0;   // warp uniform
+  const uint32_t lane = lane_id();
   const uint32_t n = *nPtr;
   uint32_t shaded = 0;
   for (;;) {
     uint32_t chunk = warp_claim_n(work, PB_CLAIM);
     if (chunk >= n) break;
     for (uint32_t base = chunk; base < chunk + PB_CLAIM && base < n; base += 32) {
-      const uint32_t i = base + lane_id();
+      const uint32_t i = base + lane;
       const bool valid = i < n;
-      bool pass = false, pushShadow = false, pushProbe = false, pushNext = false;
-      uint32_t slot = 0;
-      DirectRec direct;
-      Ray next;
+      bool pass = false, plain = false;
       if (valid) {
         const int32_t prim = qin.hitPrim[i];
-        float4 tail = make_float4(0.f, 0.f, 0.f, 0.f);
         if (prim >= 0) {
-          tail = __ldg((const float4 *)(sv.prims + 3u * (uint32_t)prim + 2));
+          const float4 tail = __ldg((const float4 *)(sv.prims + 3u * (uint32_t)prim + 2));
           pass = !(__float_as_uint(tail.y) & PB_PF_DEV_FRAME) || (qin.hitInst && qin.hitInst[i] >= 0) ||
                  !material_is_lambert(sv.materials[__float_as_uint(tail.z)]);
-        }
-        if (!pass) {
-          slot = qin.slot[i];
+          plain = !pass;
+        } else {
+          // the ray left the scene (path.cpp:69-82): fold the pending direct light, emitted light of infinite lights
+          const uint32_t slot = qin.slot[i];
           const float4 lf = wb.plf[slot];
           uint32_t flags = __float_as_uint(lf.w);
           PathState st;
@@ -807,80 +897,35 @@ k_path_fast(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wa
           st.depth = (int)(flags & 0xffu);
           st.specularBounce = (flags >> 8) & 1u;
           st.alpha = 0.f;
+          st.T = spec(0.f);
+          if (st.depth == 0 || st.specularBounce) { const float4 tc = wb.ptc[slot]; st.T = spec3(tc.x, tc.y, tc.z); }
           Ray ray = queue_ray(qin, i);
-          if (prim < 0) {
-            // the ray left the scene (path.cpp:69-82)
-            const bool mayEmit = st.depth == 0 || st.specularBounce;
-            st.T = spec(0.f);
-            if (mayEmit) { const float4 tc = wb.ptc[slot]; st.T = spec3(tc.x, tc.y, tc.z); }
-            Hit miss; miss.prim = -1; miss.t = 0.f; miss.b1 = miss.b2 = 0.f; miss.inst = -1;
-            Surface none;
-            path_vertex_surface<false, false, false, true>(sv, st, ray, miss, &none);
-            wb.plf[slot] = make_float4(st.L.c[0], st.L.c[1], st.L.c[2], __uint_as_float(flags));
-            if (st.depth == 0) wb.alpha[slot] = st.alpha;
-          } else {
-            const float4 tc = wb.ptc[slot];
-            st.T = spec3(tc.x, tc.y, tc.z);
-            st.rng.ctr = __float_as_uint(tc.w);
-            // path.cpp:83-92: alpha, the frame (k_prim_frames' table), emitted light
-            if (st.depth == 0) st.alpha = 1.f;
-            else st.T = st.T * spec(1.f);
-            LambertSurface ls;
-            const float4 *fr = sv.primFrame + 3u * (uint32_t)prim;
-            const float4 a = __ldg(fr), b = __ldg(fr + 1), c = __ldg(fr + 2);
-            ls.bsdf.p = ray_at(ray, qin.hitT[i]);
-            ls.bsdf.ng = v3(a.x, a.y, a.z); ls.bsdf.nn = v3(a.w, b.x, b.y);
-            ls.bsdf.sn = v3(b.z, b.w, c.x); ls.bsdf.tn = v3(c.y, c.z, c.w);
-            ls.material = __float_as_uint(tail.z);
-            ls.light = __float_as_int(tail.w);
-            const PbrtB200Material &mat = sv.materials[ls.material];
-            ls.bsdf.R = spec3(mat.kd[0], mat.kd[1], mat.kd[2]) * PB_INV_PI;
-            if (st.depth == 0 || st.specularBounce) {
-              Spec Le = spec(0.f);   // Intersection::Le (primitive.cpp:142-145)
-              if (ls.light >= 0 && dot(ls.bsdf.ng, -ray.d) > 0) Le = light_color(sv.lights[ls.light]);
-              st.L = st.L + st.T * Le;
-            }
-            ++shaded;
-            // path.cpp:93-112
-            st.rng.key = slot_key(wd, slot, 1);
-            PatternSource key0 = {slot_key(wd, slot, 0), LD ? wb.ld : (const float *)nullptr, wb.nSlots, slot, LD ? wd.bc : (wd.bc == 2 ? 2 : 0)};
-            bool hasDirect;
-            path_vertex_direct<false, LK>(sv, key0, st, ray, &ls, &direct, &hasDirect);
-            const Spec pendT = st.pendT;
-            // path.cpp:113-143
-            pushNext = path_vertex_continue<false>(sv, key0, st, ray, ls, &next);
-            flags = (uint32_t)st.depth | (st.specularBounce ? (1u << 8) : 0u);
-            if (hasDirect) {
-              pushShadow = direct.hasShadow;
-              pushProbe = direct.hasProbe;
-              if (pushProbe) {
-                flags |= 1u << 9;
-                store3(wb.pendT, slot, pendT);
-                store3(wb.recB, slot, direct.termB);
-                wb.prec[slot] = make_float4(direct.termA.c[0], direct.termA.c[1], direct.termA.c[2],
-                                            __uint_as_float((direct.hasShadow ? 4u : 0u) | 8u));
-              } else if (pushShadow) {
-                Spec Ld = direct_value(direct.termA, direct.termB, true, false);
-                Spec add = pendT * ((float)sv.nLights * Ld);
-                flags |= 1u << 9;
-                wb.prec[slot] = make_float4(add.c[0], add.c[1], add.c[2], __uint_as_float(4u | 16u));
-              }
-            }
-            wb.plf[slot] = make_float4(st.L.c[0], st.L.c[1], st.L.c[2], __uint_as_float(flags));
-            wb.ptc[slot] = make_float4(st.T.c[0], st.T.c[1], st.T.c[2], __uint_as_float(st.rng.ctr));
-            if (st.alpha != 0.f) wb.alpha[slot] = st.alpha;   // (depth 0 only; k_generate wrote 0)
-          }
+          Hit miss; miss.prim = -1; miss.t = 0.f; miss.b1 = miss.b2 = 0.f; miss.inst = -1;
+          Surface none;
+          path_vertex_surface<false, false, false, true>(sv, st, ray, miss, &none);
+          wb.plf[slot] = make_float4(st.L.c[0], st.L.c[1], st.L.c[2], __uint_as_float(flags));
+          if (st.depth == 0) wb.alpha[slot] = st.alpha;
         }
       }
       uint32_t pj = warp_push(subsetCount, pass);
       if (pass) subset[pj] = i;
-      uint32_t si = warp_push(shadowCount, pushShadow);
-      if (pushShadow) aux_put(wb.shadowQ, si, slot, direct.shadow, 0);
-      uint32_t pi = warp_push(probeCount, pushProbe);
-      if (pushProbe) aux_put(wb.probeQ, pi, slot, direct.probe, direct.probeLight);
-      uint32_t ni = warp_push(nextCount, pushNext);
-      if (pushNext) queue_put(qout, ni, slot, next);
+      const uint32_t mask = __ballot_sync(0xffffffffu, plain);
+      if (mask) {
+        if (plain) parked[nParked + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = i;
+        nParked += (uint32_t)__popc(mask);
+        __syncwarp();
+        if (nParked >= 32u) {
+          nParked -= 32u;
+          const uint32_t pi = parked[nParked + lane];
+          __syncwarp();
+          path_fast_vertex<LD, LK>(sv, wb, wd, qin, qout, pi, true, shadowCount, probeCount, nextCount, shaded);
+        }
+      }
     }
+  }
+  if (nParked) {
+    const uint32_t pi = lane < nParked ? parked[lane] : 0u;
+    path_fast_vertex<LD, LK>(sv, wb, wd, qin, qout, pi, lane < nParked, shadowCount, probeCount, nextCount, shaded);
   }
   warp_stat_add(&wb.stats[ST_SHADED], shaded);
 }
@@ -1784,8 +1829,13 @@ static int persistent_grid(const PbrtB200Handle *h) { return h->numSMs * (int)g_
 
 static void launch_traversals_a(PbrtB200Handle *h, bool count, int grid, const RayQueue &q, uint32_t *nMain,
                                 uint32_t *work) {
-#define PB_LAUNCH_INTERSECT(C_, QK_) \
-  TIMED(KC_INTERSECT, (k_intersect<C_, QK_><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, q, nMain, work, h->wb.stats)))
+#define PB_LAUNCH_INTERSECT(C_, QK_)                                                                                             \
+  do {                                                                                                                         \
+    if (h->sv.nNodes > PB_BIG_TREE_NODES)                                                                                      \
+      TIMED(KC_INTERSECT, (k_intersect<C_, QK_, PB_DESCEND_STEPS_BIG><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, q, nMain, work, h->wb.stats))); \
+    else                                                                                                                       \
+      TIMED(KC_INTERSECT, (k_intersect<C_, QK_, PB_DESCEND_STEPS><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, q, nMain, work, h->wb.stats)));     \
+  } while (0)
   if (count) PB_LAUNCH_INTERSECT(true, PB_QK_INSTANCES);   // the counting pass is not timed
   else if (h->primKinds == PB_QK_TRI) PB_LAUNCH_INTERSECT(false, PB_QK_TRI);
   else if (h->primKinds == PB_QK_SPHERE) PB_LAUNCH_INTERSECT(false, PB_QK_SPHERE);
@@ -1799,11 +1849,16 @@ static void launch_traversals_b(PbrtB200Handle *h, bool count, int grid, uint32_
   // ramp-up of the full persistent grid for a few thousand rays
   int probeGrid = std::min(grid, h->numSMs * 2);
   if (count) {
-    TIMED_ON(KC_SHADOW, strm, (k_shadow<true, PB_QK_INSTANCES><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.prec, wb.stats)));
+    TIMED_ON(KC_SHADOW, strm, (k_shadow<true, PB_QK_INSTANCES, PB_DESCEND_STEPS><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.prec, wb.stats)));
     TIMED_ON(KC_PROBE, strm, (k_probe<true><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.prec, wb.stats)));
   } else {
-#define PB_LAUNCH_SHADOW(QK_) \
-  TIMED_ON(KC_SHADOW, strm, (k_shadow<false, QK_><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.prec, wb.stats)))
+#define PB_LAUNCH_SHADOW(QK_)                                                                                                    \
+  do {                                                                                                                         \
+    if (h->sv.nNodes > PB_BIG_TREE_NODES)                                                                                      \
+      TIMED_ON(KC_SHADOW, strm, (k_shadow<false, QK_, PB_DESCEND_STEPS_BIG><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.prec, wb.stats))); \
+    else                                                                                                                       \
+      TIMED_ON(KC_SHADOW, strm, (k_shadow<false, QK_, PB_DESCEND_STEPS><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.prec, wb.stats)));     \
+  } while (0)
     if (h->primKinds == PB_QK_TRI) PB_LAUNCH_SHADOW(PB_QK_TRI);
     else if (h->primKinds == PB_QK_SPHERE) PB_LAUNCH_SHADOW(PB_QK_SPHERE);
     else if (h->primKinds == PB_QK_ALL) PB_LAUNCH_SHADOW(PB_QK_ALL);
@@ -2244,12 +2299,17 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
     }
     totalSamples += nPixW[w] * spp;
   }
-  uint64_t capSlots = std::max<uint64_t>((uint64_t)spp, std::min<uint64_t>((uint64_t)g_waveSamples, totalSamples));
-  capSlots = (capSlots / spp) * spp;
+  // Waves of equal size: the frame's units (pixels / table placements) are split over the fewest waves the
+  // tunable allows, and a remainder of less than 1/16 wave is absorbed by growing the waves instead of paying a
+  // whole extra round of ~40 launches for it (C3: 67.24 M samples = 4 waves of 16.81 M, not 4 x 16.78 M + 0.13 M).
+  const uint64_t units = totalSamples / spp;
+  const uint64_t unitCap = std::max<uint64_t>(1, (uint64_t)g_waveSamples / spp);
+  uint64_t nWaves = std::max<uint64_t>(1, (units + unitCap - 1) / unitCap);
+  if (nWaves > 1 && units - (nWaves - 1) * unitCap <= unitCap / 16) --nWaves;
+  uint64_t capSlots = ((units + nWaves - 1) / nWaves) * spp;
   if (capSlots > 0x7fffffffull / 4) return fail(PBRT_B200_ERR_UNSUPPORTED, "wave too large");
   int rc = ensure_wave(h, (uint32_t)capSlots);
   if (rc != PBRT_B200_OK) return rc;
-  capSlots = (h->wb.nSlots / spp) * (uint64_t)spp;
   CU_TRY(cudaMemsetAsync(h->wb.stats, 0, ST_COUNT * sizeof(unsigned long long), h->stream));
   uint64_t cameraRays = 0;
   CU_TRY(cudaEventRecord(e0, h->stream));

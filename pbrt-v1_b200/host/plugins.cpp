@@ -825,15 +825,19 @@ Sampler *MakeSampler(const string &name, const ParamSet &params, const Film *fil
     params.ReportUnused();
     return s;
   }
-  if (name != "stratified")
-    Warning("Sampler plugin \"%s\" unknown; using \"stratified\".", name.c_str());
+  if (name != "stratified") {
+    // the reference's MakeSampler returns NULL for a plug-in it cannot load (core/dynload.cpp:208-216) and
+    // MakeScene then aborts with "missing plug-ins" (core/api.cpp:494-497): same here
+    Error("Sampler plugin \"%s\" unknown (supported: stratified, lowdiscrepancy, bestcandidate, random).", name.c_str());
+    return NULL;
+  }
   bool jitter = params.FindOneBool("jitter", true);      // samplers/stratified.cpp:132-141
   int xstart, xend, ystart, yend;
   film->GetSampleExtent(&xstart, &xend, &ystart, &yend);
   int xsamp = params.FindOneInt("xsamples", 2);
   int ysamp = params.FindOneInt("ysamples", 2);
   Sampler *s = new StratifiedSampler(xstart, xend, ystart, yend, xsamp, ysamp, jitter);
-  if (name == "stratified") params.ReportUnused();
+  params.ReportUnused();
   return s;
 }
 Filter *MakeFilter(const string &name, const ParamSet &paramSet) {

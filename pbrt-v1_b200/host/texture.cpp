@@ -93,10 +93,14 @@ Spectrum *ReadImage(const string &name, int *width, int *height) {
     pos += 4;
     if (size < 0 || pos + (size_t)size > buf.size()) { why = "truncated header"; break; }
     if (attr == "channels") {
+      // channel list: name\0, then 16 bytes (pixel type, pLinear + reserved, x / y sampling); every read stays
+      // inside the attribute's `size` bytes
       size_t p = pos;
-      while (p < pos + size && buf[p]) {
+      const size_t end = pos + (size_t)size;
+      while (p < end && buf[p]) {
         ExrChannel ch;
-        while (buf[p]) ch.name += (char)buf[p++];
+        while (p < end && buf[p]) ch.name += (char)buf[p++];
+        if (p >= end || end - (p + 1) < 16) { why = "truncated channel list"; break; }
         ++p;
         int32_t type;
         memcpy(&type, &buf[p], 4);
@@ -104,6 +108,7 @@ Spectrum *ReadImage(const string &name, int *width, int *height) {
         p += 16;
         channels.push_back(ch);
       }
+      if (why) break;
     } else if (attr == "compression") compression = buf[pos];
     else if (attr == "dataWindow" && size == 16) memcpy(dw, &buf[pos], 16);
     pos += (size_t)size;
@@ -114,7 +119,15 @@ Spectrum *ReadImage(const string &name, int *width, int *height) {
     Error("Unable to read image file \"%s\": %s", name.c_str(), why);
     return NULL;
   }
-  int w = dw[2] - dw[0] + 1, h = dw[3] - dw[1] + 1;
+  // (sizes in 64 bits: a hostile data window must not wrap the pixel count)
+  const int64_t w64 = (int64_t)dw[2] - dw[0] + 1, h64 = (int64_t)dw[3] - dw[1] + 1;
+  if (w64 < 1 || h64 < 1 || w64 > (1 << 20) || h64 > (1 << 20) || (uint64_t)(w64 * h64) > (uint64_t)buf.size()) {
+    // an uncompressed file holds at least 2 bytes per pixel and channel: more pixels than bytes cannot be real
+    Error("Unable to read image file \"%s\": data window %lld x %lld does not fit the file", name.c_str(),
+          (long long)w64, (long long)h64);
+    return NULL;
+  }
+  int w = (int)w64, h = (int)h64;
   size_t rowBytes = 0;
   for (size_t c = 0; c < channels.size(); ++c) {
     if (channels[c].type != 1 && channels[c].type != 2) {
@@ -123,13 +136,25 @@ Spectrum *ReadImage(const string &name, int *width, int *height) {
     }
     rowBytes += (size_t)w * (channels[c].type == 1 ? 2 : 4);
   }
-  Spectrum *ret = new Spectrum[(size_t)w * h];
-  for (int i = 0; i < w * h; ++i) ret[i] = Spectrum(0.f);
+  // the scan-line offset table and every scan line it points at must lie inside the file (OpenEXR throws on a
+  // truncated file and the reference's ReadImage returns NULL, core/exrio.cpp:40-73)
+  if (pos > buf.size() || (buf.size() - pos) / 8 < (size_t)h || rowBytes > buf.size()) {
+    Error("Unable to read image file \"%s\": truncated scan-line offset table", name.c_str());
+    return NULL;
+  }
   for (int row = 0; row < h; ++row) {
     uint64_t off;
-    if (pos + 8 * (size_t)(row + 1) > buf.size()) break;
     memcpy(&off, &buf[pos + 8 * (size_t)row], 8);
-    if (off + 8 + rowBytes > buf.size()) break;
+    if (off > buf.size() || buf.size() - off < 8 + rowBytes) {
+      Error("Unable to read image file \"%s\": scan line %d lies outside the file", name.c_str(), row);
+      return NULL;
+    }
+  }
+  Spectrum *ret = new Spectrum[(size_t)w * h];
+  for (size_t i = 0; i < (size_t)w * h; ++i) ret[i] = Spectrum(0.f);
+  for (int row = 0; row < h; ++row) {
+    uint64_t off;
+    memcpy(&off, &buf[pos + 8 * (size_t)row], 8);
     int32_t y;
     memcpy(&y, &buf[off], 4);
     if (y < dw[1] || y > dw[3]) continue;
