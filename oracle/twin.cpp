@@ -456,3 +456,71 @@ extern "C" int pbrt_twin_trace(const PbrtB200Scene *scene, const float *rays, ui
   offsets[n] = pos;
   return PBRT_B200_OK;
 }
+
+// Mailbox study (test infrastructure): primitive tests per ray of the closest-hit / any-hit walk under different
+// "already tested" filters -- none, the shipped 2-entry ring, direct-mapped tables of 4..64 entries indexed by a
+// multiplicative hash of the primitive number, and the reference's exact per-primitive mailboxes (accelerators/kdtree.cpp:373-377).
+// Every filter only skips repeats, so hits are identical; out[k] = total tests with filter k over all rays.
+extern "C" int pbrt_twin_mailbox_study(const PbrtB200Scene *scene, const float *rays, uint64_t n, int any,
+                                       uint64_t *out /* [8]: none, ring2, dm4, dm8, dm16, dm32, dm64, exact */) {
+  SceneView sv;
+  if (!build_view(*scene, &sv)) return PBRT_B200_ERR_INVALID;
+  for (int k = 0; k < 8; ++k) out[k] = 0;
+  std::vector<uint32_t> stamp(sv.nPrims, 0xffffffffu);
+  for (uint64_t r = 0; r < n; ++r) {
+    Ray ray;
+    ray.o = v3(rays[8 * r], rays[8 * r + 1], rays[8 * r + 2]);
+    ray.d = v3(rays[8 * r + 3], rays[8 * r + 4], rays[8 * r + 5]);
+    ray.mint = rays[8 * r + 6]; ray.maxt = rays[8 * r + 7];
+    float tmin, tmax;
+    if (sv.nNodes == 0 || !bbox_intersect_p(sv.bmin, sv.bmax, ray, &tmin, &tmax)) continue;
+    V3 invDir = v3(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
+    uint32_t todoNode[PB_KD_STACK]; float todoTmin[PB_KD_STACK], todoTmax[PB_KD_STACK];
+    int todoPos = 0;
+    uint32_t ring[2] = {0xffffffffu, 0xffffffffu};
+    int ringPos = 0;
+    uint32_t dm[5][64];
+    for (int k = 0; k < 5; ++k) for (int i = 0; i < 64; ++i) dm[k][i] = 0xffffffffu;
+    uint32_t node = 0;
+    Hit hit; hit.prim = -1; hit.inst = -1;
+    bool stop = false;
+    while (!stop) {
+      uint32_t w0, w1;
+      for (;;) {
+        w0 = sv.nodes[node].word0; w1 = sv.nodes[node].word1;
+        if ((w0 & 3u) == 3u) break;
+        int axis = (int)(w0 & 3u);
+        float split; { uint32_t b = w0; memcpy(&split, &b, 4); }
+        float o = ray.o[axis], d = ray.d[axis];
+        float tplane = (split - o) * invDir[axis];
+        bool belowFirst = (o < split) || (o == split && d >= 0);
+        uint32_t firstChild = belowFirst ? node + 1 : w1, secondChild = belowFirst ? w1 : node + 1;
+        if (tplane > tmax || tplane <= 0) node = firstChild;
+        else if (tplane < tmin) node = secondChild;
+        else { todoNode[todoPos] = secondChild; todoTmin[todoPos] = tplane; todoTmax[todoPos] = tmax; ++todoPos;
+               node = firstChild; tmax = tplane; }
+      }
+      uint32_t nPrims = w0 >> 2;
+      for (uint32_t i = 0; i < nPrims && !stop; ++i) {
+        uint32_t prim = (nPrims == 1) ? w1 : sv.primRefs[w1 + i];
+        ++out[0];
+        if (ring[0] != prim && ring[1] != prim) { ++out[1]; ring[ringPos] = prim; ringPos ^= 1; }
+        for (int k = 0; k < 5; ++k) {
+          uint32_t slot = (prim * 0x9E3779B1u) >> (30 - k);   // multiplicative hash: mesh neighbours differ by a row stride
+          if (dm[k][slot] != prim) { ++out[2 + k]; dm[k][slot] = prim; }
+        }
+        bool fresh = stamp[prim] != (uint32_t)r;
+        if (fresh) { ++out[7]; stamp[prim] = (uint32_t)r; }
+        // the walk itself follows the exact filter (the reference's)
+        if (!fresh) continue;
+        bool h = any ? kd_test_prim<true>(sv, prim, ray, &hit) : kd_test_prim<false>(sv, prim, ray, &hit);
+        if (h && any) stop = true;
+      }
+      if (stop) break;
+      if (todoPos == 0) break;
+      --todoPos; node = todoNode[todoPos]; tmin = todoTmin[todoPos]; tmax = todoTmax[todoPos];
+      if (!any && ray.maxt < tmin) break;
+    }
+  }
+  return PBRT_B200_OK;
+}

@@ -37,6 +37,22 @@ PB_HD bool bbox_intersect_p(const float *bmin, const float *bmax, const Ray &ray
 #ifndef PB_MAILBOX
 #define PB_MAILBOX 2   // measured 2 > 4 > 8 on B200: the ring costs more than the few re-tests it avoids
 #endif
+// Scenes without object instances filter repeats with a direct-mapped table of PB_MB_SLOTS recently tested
+// primitives per ray instead (slot = multiplicative hash of the primitive number; an entry is only ever compared
+// for equality, so a collision costs a repeated test, never a skipped one).  oracle/twin.cpp's
+// pbrt_twin_mailbox_study on C4's bounce rays: tests per closest-hit ray 14.5 with the 2-entry ring, 8.75 / 8.30 with
+// 8 / 16 slots, 8.21 with the reference's exact per-primitive mailboxes (kdtree.cpp:373-377); C3 13.0 / 9.8 / 9.0 /
+// 8.8.  The warp walk keeps the table in shared memory (pb_kd_warp.cuh), this per-thread walk in a local array.
+// 0 = the ring everywhere.
+#ifndef PB_MB_SLOTS
+#define PB_MB_SLOTS 16
+#endif
+#if PB_MB_SLOTS != 0 && PB_MB_SLOTS != 4 && PB_MB_SLOTS != 8 && PB_MB_SLOTS != 16 && PB_MB_SLOTS != 32
+#error "PB_MB_SLOTS: 0, 4, 8, 16 or 32"
+#endif
+PB_HD uint32_t pb_mb_slot(uint32_t prim) {
+  return (prim * 0x9E3779B1u) >> (PB_MB_SLOTS == 32 ? 27 : PB_MB_SLOTS == 16 ? 28 : PB_MB_SLOTS == 8 ? 29 : 30);
+}
 
 // The scene's top-level tree / an instanced object's tree.
 PB_HD KdTreeView kd_top_tree(const SceneView &sv) {
@@ -60,7 +76,7 @@ PB_HD KdTreeView kd_instance_tree(const SceneView &sv, const PbrtB200Instance &i
 #define PB_QK_ALL 2
 #define PB_QK_INSTANCES 3
 
-template <bool ANY, bool COUNT, int QK>
+template <bool ANY, bool COUNT, int QK, bool TABLE = false>
 PB_HD bool kd_tree_intersect(const SceneView &sv, const KdTreeView &tree, Ray ray, Hit *hit, KdCounters *cnt);
 
 // One primitive test: GeometricPrimitive::Intersect (core/primitive.cpp:113-122)
@@ -118,7 +134,7 @@ PB_HD bool kd_test_prim(const SceneView &sv, uint32_t prim, Ray &ray, Hit *hit, 
 // (kdtree.cpp:328-401).  The reference re-checks `ray.maxt < tmin` at the top of
 // every iteration; neither value changes while descending, so checking after
 // each pop is equivalent.
-template <bool ANY, bool COUNT, int QK>
+template <bool ANY, bool COUNT, int QK, bool TABLE>
 PB_HD bool kd_tree_intersect(const SceneView &sv, const KdTreeView &tree, Ray ray, Hit *hit, KdCounters *cnt) {
   if (!ANY) hit->prim = -1;
   float tmin, tmax;
@@ -132,6 +148,10 @@ PB_HD bool kd_tree_intersect(const SceneView &sv, const KdTreeView &tree, Ray ra
 #pragma unroll
   for (int i = 0; i < PB_MAILBOX; ++i) mailbox[i] = 0xffffffffu;
   int mbPos = 0;
+  constexpr bool HASHED = TABLE && PB_MB_SLOTS != 0;
+  uint32_t tested[HASHED ? PB_MB_SLOTS : 1];
+  if (HASHED)
+    for (int i = 0; i < PB_MB_SLOTS; ++i) tested[i] = 0xffffffffu;
   bool anyHit = false;
   uint32_t node = 0;
   for (;;) {
@@ -176,14 +196,20 @@ PB_HD bool kd_tree_intersect(const SceneView &sv, const KdTreeView &tree, Ray ra
     for (uint32_t i = 0; i < nPrims; ++i) {
       uint32_t prim = tree.primBase + ((nPrims == 1) ? w1 : tree.primRefs[w1 + i]);
       if (COUNT) ++cnt->refs;
-      bool seen = false;
+      if (HASHED) {
+        const uint32_t slot = pb_mb_slot(prim);
+        if (tested[slot] == prim) continue;
+        tested[slot] = prim;
+      } else {
+        bool seen = false;
 #pragma unroll
-      for (int k = 0; k < PB_MAILBOX; ++k) seen |= (mailbox[k] == prim);
-      if (seen) continue;
+        for (int k = 0; k < PB_MAILBOX; ++k) seen |= (mailbox[k] == prim);
+        if (seen) continue;
 #pragma unroll
-      for (int k = 0; k < PB_MAILBOX; ++k)
-        if (k == mbPos) mailbox[k] = prim;
-      mbPos = (mbPos + 1) & (PB_MAILBOX - 1);
+        for (int k = 0; k < PB_MAILBOX; ++k)
+          if (k == mbPos) mailbox[k] = prim;
+        mbPos = (mbPos + 1) & (PB_MAILBOX - 1);
+      }
       if (COUNT) ++cnt->tests;
       if (kd_test_prim<ANY, QK, COUNT>(sv, prim, ray, hit, cnt)) {
         if (ANY) return true;
@@ -205,6 +231,6 @@ template <bool ANY, bool COUNT>
 PB_HD bool kd_intersect(const SceneView &sv, Ray ray, Hit *hit, KdCounters *cnt) {
   if (!ANY) { hit->prim = -1; hit->inst = -1; }
   if (sv.nInstances != 0) return kd_tree_intersect<ANY, COUNT, PB_QK_INSTANCES>(sv, kd_top_tree(sv), ray, hit, cnt);
-  return kd_tree_intersect<ANY, COUNT, PB_QK_ALL>(sv, kd_top_tree(sv), ray, hit, cnt);
+  return kd_tree_intersect<ANY, COUNT, PB_QK_ALL, true>(sv, kd_top_tree(sv), ray, hit, cnt);
 }
 #endif

@@ -295,4 +295,201 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// The walk of scenes without object instances (every BASELINE configuration), written for issue slots: round-2
+// ncu of the general loop above on C5 (profiles/r02e_ncu_trav_*) shows 333 warp instructions per trip at 12 / 6 / 8
+// active lanes in the interior / leaf-list / test steps, 58 of them per interior step (the per-axis operands were
+// picked by branches, the lane flags lived in byte registers).  Same per-ray visit and test sequence; differences:
+//   * lane state is one word (idle / descending / in a leaf / finished), the per-axis operands of an interior step
+//     come from predicated selects, the 2-entry mailbox ring is a shift register;
+//   * an EMPTY leaf (43 % of the leaves C4's bounce rays reach) is popped inside the interior step that finds it,
+//     so the lane keeps descending in the same trip instead of idling until the trip's end;
+//   * the interior phase runs while at least PB_DESCEND_LANES lanes are still descending (at most PB_DESCEND_MAX
+//     steps) instead of a fixed step count (tools/simt_sim2.py: -17 % issued instructions on C4's bounce rays);
+//   * hit.t is not carried: it always equals ray.maxt once something was hit.
+#ifndef PB_DESCEND_LANES
+#define PB_DESCEND_LANES 12
+#endif
+#ifndef PB_DESCEND_MAX
+#define PB_DESCEND_MAX 8
+#endif
+#ifndef PB_LEAN_LEAF_STEPS
+#define PB_LEAN_LEAF_STEPS 2
+#endif
+// o[axis], invDir[axis] with two compares and four selects
+__device__ __forceinline__ void pb_pick_axis(uint32_t axis, const V3 &o, const V3 &inv, float *oa, float *ia) {
+  asm("{\n\t.reg .pred p0, p1;\n\t"
+      "setp.eq.u32 p0, %2, 0;\n\t"
+      "setp.eq.u32 p1, %2, 1;\n\t"
+      "selp.f32 %0, %4, %5, p1;\n\t"
+      "selp.f32 %1, %7, %8, p1;\n\t"
+      "selp.f32 %0, %3, %0, p0;\n\t"
+      "selp.f32 %1, %6, %1, p0;\n\t}"
+      : "=&f"(*oa), "=&f"(*ia)
+      : "r"(axis), "f"(o.x), "f"(o.y), "f"(o.z), "f"(inv.x), "f"(inv.y), "f"(inv.z));
+}
+enum { PB_LS_IDLE = 0, PB_LS_DESCEND = 1, PB_LS_LEAF = 2, PB_LS_FINISHED = 3 };
+
+template <bool ANY, bool COUNT, int QK, class Source, class Sink>
+__device__ __forceinline__ void kd_warp_traverse_lean(const SceneView &sv, uint32_t n, uint32_t *work,
+                                                      const Source &src, const Sink &sink, KdCounters &cnt) {
+  static_assert(QK != PB_QK_INSTANCES, "object instances use kd_warp_traverse");
+  static_assert(PB_MAILBOX == 2, "the shift-register mailbox holds two entries");
+#if PB_MB_SLOTS != 0
+  // per-lane table of recently tested primitives (pb_kd.h): column threadIdx.x, so a warp's accesses never conflict
+  __shared__ uint32_t testedAll[PB_MB_SLOTS][PB_BLOCK];
+  uint32_t *const tested = &testedAll[0][threadIdx.x];
+#endif
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t todoNode[PB_KD_STACK];
+  float todoTmin[PB_KD_STACK], todoTmax[PB_KD_STACK];
+  uint32_t state = PB_LS_IDLE;
+  bool exhausted = false;     // the queue has no more rays (warp-uniform)
+  uint32_t idx = 0;
+  Ray ray;
+  ray.o = v3(0, 0, 0); ray.d = v3(0, 0, 0); ray.mint = 0.f; ray.maxt = 0.f;
+  V3 invDir = v3(0, 0, 0);
+  uint32_t dirNeg = 0;        // bit a: !(ray.d[a] >= 0)
+  float tmin = 0.f, tmax = 0.f;
+  uint32_t node = 0;
+  int todoPos = 0;
+  uint32_t leafW1 = 0, leafI = 0, leafN = 0;
+  uint32_t mb0 = 0xffffffffu, mb1 = 0xffffffffu;   // the two most recently tested primitives
+  Hit hit;
+  hit.prim = -1; hit.t = 0.f; hit.b1 = hit.b2 = 0.f; hit.inst = -1;
+  const uint2 *nodes = (const uint2 *)sv.nodes;
+  for (;;) {
+    // ---- refill idle lanes
+    const uint32_t idleMask = __ballot_sync(0xffffffffu, state == PB_LS_IDLE);
+    if (!exhausted && (uint32_t)__popc(idleMask) >= (idleMask == 0xffffffffu ? 1u : PB_REFILL_THRESHOLD)) {
+      uint32_t base = 0;
+      const uint32_t nIdle = (uint32_t)__popc(idleMask);
+      if (lane == 0) base = atomicAdd(work, nIdle);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base + nIdle >= n) exhausted = true;
+      if (state == PB_LS_IDLE) {
+        const uint32_t i = base + (uint32_t)__popc(idleMask & ((1u << lane) - 1u));
+        if (i < n) {
+          idx = i;
+          ray = src.load(i);
+          hit.prim = -1;
+          todoPos = 0;
+          node = 0;
+          mb0 = mb1 = 0xffffffffu;
+#if PB_MB_SLOTS != 0
+#pragma unroll
+          for (int k = 0; k < PB_MB_SLOTS; ++k) tested[k * PB_BLOCK] = 0xffffffffu;
+#endif
+          const bool in = sv.nNodes != 0 && bbox_intersect_p(sv.bmin, sv.bmax, ray, &tmin, &tmax);
+          invDir = v3(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
+          dirNeg = (ray.d.x >= 0 ? 0u : 1u) | (ray.d.y >= 0 ? 0u : 2u) | (ray.d.z >= 0 ? 0u : 4u);
+          if (in) state = PB_LS_DESCEND;
+          else sink.done(idx, ray, hit, false);   // missed the tree's bounds
+        }
+      }
+    }
+    if (idleMask == 0xffffffffu && __ballot_sync(0xffffffffu, state != PB_LS_IDLE) == 0) {
+      if (exhausted) break;
+      continue;
+    }
+    // ---- A. interior steps (while the queue drains, the bar follows the number of lanes that still hold a ray)
+    const uint32_t descendLanes = exhausted ? min((uint32_t)PB_DESCEND_LANES, (32u - (uint32_t)__popc(idleMask)) >> 1)
+                                            : (uint32_t)PB_DESCEND_LANES;
+#pragma unroll 1
+    for (int step = 0; step < PB_DESCEND_MAX; ++step) {
+      const bool descending = state == PB_LS_DESCEND;
+      const uint32_t m = __ballot_sync(0xffffffffu, descending);
+      if (m == 0 || (step != 0 && (uint32_t)__popc(m) < descendLanes)) break;
+      if (descending) {
+        const uint2 nd = __ldg(nodes + node);
+        const uint32_t axis = nd.x & 3u;
+        if (axis == 3u) {
+          if (COUNT) ++cnt.leaves;
+          leafN = nd.x >> 2; leafW1 = nd.y; leafI = 0;
+          if (leafN != 0) state = PB_LS_LEAF;
+          else if (todoPos == 0) state = PB_LS_FINISHED;
+          else {
+            // empty leaf: next node from the todo list right away (kdtree.cpp:392-399, :330)
+            --todoPos;
+            node = todoNode[todoPos];
+            tmin = todoTmin[todoPos];
+            tmax = todoTmax[todoPos];
+            if (!ANY && ray.maxt < tmin) state = PB_LS_FINISHED;
+          }
+        } else {
+          if (COUNT) ++cnt.interior;
+          const float split = __uint_as_float(nd.x);   // axis bits stay in the mantissa (kdtree.cpp:66-72)
+          float o, inv;
+          pb_pick_axis(axis, ray.o, invDir, &o, &inv);
+          const float tplane = (split - o) * inv;
+          const bool belowFirst = (o < split) || (o == split && !((dirNeg >> axis) & 1u));
+          const uint32_t below = node + 1u, above = nd.y;
+          const uint32_t firstChild = belowFirst ? below : above;
+          const uint32_t secondChild = belowFirst ? above : below;
+          if (tplane > tmax || tplane <= 0)
+            node = firstChild;
+          else if (tplane < tmin)
+            node = secondChild;
+          else {
+            todoNode[todoPos] = secondChild;
+            todoTmin[todoPos] = tplane;
+            todoTmax[todoPos] = tmax;
+            ++todoPos;
+            node = firstChild;
+            tmax = tplane;
+          }
+        }
+      }
+    }
+    // ---- B. leaf-list steps until the lane holds one primitive to test
+    bool pending = false;
+    uint32_t prim = 0;
+#pragma unroll 1
+    for (int step = 0; step < PB_LEAN_LEAF_STEPS; ++step) {
+      const bool walking = state == PB_LS_LEAF && !pending && leafI < leafN;
+      if (__ballot_sync(0xffffffffu, walking) == 0) break;
+      if (walking) {
+        prim = (leafN == 1) ? leafW1 : __ldg(sv.primRefs + leafW1 + leafI);
+        ++leafI;
+        if (COUNT) ++cnt.refs;
+#if PB_MB_SLOTS != 0
+        uint32_t *const entry = tested + pb_mb_slot(prim) * PB_BLOCK;
+        if (*entry != prim) {
+          *entry = prim;
+          pending = true;
+        }
+#else
+        if (prim != mb0 && prim != mb1) {
+          mb1 = mb0; mb0 = prim;
+          pending = true;
+        }
+#endif
+      }
+    }
+    // ---- C. the expensive part, all lanes with work together
+    if (pending) {
+      if (COUNT) ++cnt.tests;
+      if (kd_test_prim<ANY, QK>(sv, prim, ray, &hit)) {
+        if (ANY) { hit.prim = 0; state = PB_LS_FINISHED; }
+      }
+    }
+    // ---- D. leaf finished: next node from the todo list (kdtree.cpp:392-399)
+    if (state == PB_LS_LEAF && leafI >= leafN) {
+      if (todoPos == 0) state = PB_LS_FINISHED;
+      else {
+        --todoPos;
+        node = todoNode[todoPos];
+        tmin = todoTmin[todoPos];
+        tmax = todoTmax[todoPos];
+        state = (!ANY && ray.maxt < tmin) ? PB_LS_FINISHED : PB_LS_DESCEND;   // kdtree.cpp:330
+      }
+    }
+    if (state == PB_LS_FINISHED) {
+      state = PB_LS_IDLE;
+      hit.t = ray.maxt;
+      sink.done(idx, ray, hit, hit.prim >= 0);
+    }
+  }
+}
 #endif

@@ -456,6 +456,12 @@ __device__ __forceinline__ void flush_kd_counters(unsigned long long *stats, int
 #ifndef PB_DESCEND_STEPS_BIG
 #define PB_DESCEND_STEPS_BIG 4
 #endif
+#ifndef PB_PROBE_CTAS_BIG
+#define PB_PROBE_CTAS_BIG 2   // CTAs per SM of the probe kernel on big trees
+#endif
+#ifndef PB_LEAN_WALK
+#define PB_LEAN_WALK 1   // scenes without object instances walk with kd_warp_traverse_lean (0: the general loop, for A/B)
+#endif
 #define PB_BIG_TREE_NODES 100000u   // top-level trees above this many nodes use PB_DESCEND_STEPS_BIG
 template <bool COUNT, int QK, int DS>
 __global__ void __launch_bounds__(PB_BLOCK, QK == PB_QK_INSTANCES ? PB_TRAV_INST_MIN_BLOCKS
@@ -466,7 +472,8 @@ k_intersect(const __grid_constant__ SceneView sv, const RayQueue q, const uint32
   KdCounters cnt = {0, 0, 0, 0};
   MainSource src = {q};
   MainSink sink = {q};
-  kd_warp_traverse<false, COUNT, QK, DS>(sv, n, work, src, sink, cnt);
+  if constexpr (PB_LEAN_WALK && QK != PB_QK_INSTANCES) kd_warp_traverse_lean<false, COUNT, QK>(sv, n, work, src, sink, cnt);
+  else kd_warp_traverse<false, COUNT, QK, DS>(sv, n, work, src, sink, cnt);
   if (COUNT) flush_kd_counters(stats, TK_MAIN, cnt);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_K(TK_MAIN, TF_RAYS)], (unsigned long long)n);
 }
@@ -511,7 +518,8 @@ k_shadow(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t 
   KdCounters cnt = {0, 0, 0, 0};
   ShadowSource src = {q};
   ShadowSink sink = {q, recFlags, prec};
-  kd_warp_traverse<true, COUNT, QK, DS>(sv, n, work, src, sink, cnt);
+  if constexpr (PB_LEAN_WALK && QK != PB_QK_INSTANCES) kd_warp_traverse_lean<true, COUNT, QK>(sv, n, work, src, sink, cnt);
+  else kd_warp_traverse<true, COUNT, QK, DS>(sv, n, work, src, sink, cnt);
   if (COUNT) flush_kd_counters(stats, TK_SHADOW, cnt);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_K(TK_SHADOW, TF_RAYS)], (unsigned long long)n);
 }
@@ -537,7 +545,7 @@ struct ProbeSink {
     if (hit_emits_from_light(*sv, ray, hit, q.light[i])) rec_flag_set(recFlags, prec, q.rec[i], 2u);
   }
 };
-template <bool COUNT>
+template <bool COUNT, bool INST>
 __global__ void __launch_bounds__(PB_BLOCK)
 k_probe(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t *nPtr, uint32_t *work,
         uint8_t *recFlags, float4 *prec, unsigned long long *stats) {
@@ -545,7 +553,8 @@ k_probe(const __grid_constant__ SceneView sv, const AuxQueue q, const uint32_t *
   KdCounters cnt = {0, 0, 0, 0};
   ProbeSource src = {q};
   ProbeSink sink = {&sv, q, recFlags, prec};
-  kd_warp_traverse<false, COUNT, PB_QK_INSTANCES, PB_DESCEND_STEPS>(sv, n, work, src, sink, cnt);
+  if constexpr (PB_LEAN_WALK && !INST) kd_warp_traverse_lean<false, COUNT, PB_QK_ALL>(sv, n, work, src, sink, cnt);
+  else kd_warp_traverse<false, COUNT, PB_QK_INSTANCES, PB_DESCEND_STEPS>(sv, n, work, src, sink, cnt);
   if (COUNT) flush_kd_counters(stats, TK_PROBE, cnt);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[ST_K(TK_PROBE, TF_RAYS)], (unsigned long long)n);
 }
@@ -1836,8 +1845,10 @@ static void launch_traversals_a(PbrtB200Handle *h, bool count, int grid, const R
     else                                                                                                                       \
       TIMED(KC_INTERSECT, (k_intersect<C_, QK_, PB_DESCEND_STEPS><<<grid, PB_BLOCK, 0, h->stream>>>(h->sv, q, nMain, work, h->wb.stats)));     \
   } while (0)
-  if (count) PB_LAUNCH_INTERSECT(true, PB_QK_INSTANCES);   // the counting pass is not timed
-  else if (h->primKinds == PB_QK_TRI) PB_LAUNCH_INTERSECT(false, PB_QK_TRI);
+  if (count) {   // the counting pass is not timed; it walks like the timed kernels (same counters as the twin's)
+    if (h->primKinds == PB_QK_INSTANCES) PB_LAUNCH_INTERSECT(true, PB_QK_INSTANCES);
+    else PB_LAUNCH_INTERSECT(true, PB_QK_ALL);
+  } else if (h->primKinds == PB_QK_TRI) PB_LAUNCH_INTERSECT(false, PB_QK_TRI);
   else if (h->primKinds == PB_QK_SPHERE) PB_LAUNCH_INTERSECT(false, PB_QK_SPHERE);
   else if (h->primKinds == PB_QK_ALL) PB_LAUNCH_INTERSECT(false, PB_QK_ALL);
   else PB_LAUNCH_INTERSECT(false, PB_QK_INSTANCES);
@@ -1847,10 +1858,16 @@ static void launch_traversals_b(PbrtB200Handle *h, bool count, int grid, uint32_
   WaveBuffers &wb = h->wb;
   // MIS probes are rare (the BSDF sample must point at the light): a small grid avoids paying the
   // ramp-up of the full persistent grid for a few thousand rays
-  int probeGrid = std::min(grid, h->numSMs * 2);
+  int probeGrid = std::min(grid, h->numSMs * (h->sv.nNodes > PB_BIG_TREE_NODES ? PB_PROBE_CTAS_BIG : 2));
   if (count) {
-    TIMED_ON(KC_SHADOW, strm, (k_shadow<true, PB_QK_INSTANCES, PB_DESCEND_STEPS><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.prec, wb.stats)));
-    TIMED_ON(KC_PROBE, strm, (k_probe<true><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.prec, wb.stats)));
+    if (h->primKinds == PB_QK_INSTANCES)
+      TIMED_ON(KC_SHADOW, strm, (k_shadow<true, PB_QK_INSTANCES, PB_DESCEND_STEPS><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.prec, wb.stats)));
+    else
+      TIMED_ON(KC_SHADOW, strm, (k_shadow<true, PB_QK_ALL, PB_DESCEND_STEPS><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.prec, wb.stats)));
+    if (h->primKinds == PB_QK_INSTANCES)
+      TIMED_ON(KC_PROBE, strm, (k_probe<true, true><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.prec, wb.stats)));
+    else
+      TIMED_ON(KC_PROBE, strm, (k_probe<true, false><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.prec, wb.stats)));
   } else {
 #define PB_LAUNCH_SHADOW(QK_)                                                                                                    \
   do {                                                                                                                         \
@@ -1863,7 +1880,10 @@ static void launch_traversals_b(PbrtB200Handle *h, bool count, int grid, uint32_
     else if (h->primKinds == PB_QK_SPHERE) PB_LAUNCH_SHADOW(PB_QK_SPHERE);
     else if (h->primKinds == PB_QK_ALL) PB_LAUNCH_SHADOW(PB_QK_ALL);
     else PB_LAUNCH_SHADOW(PB_QK_INSTANCES);
-    TIMED_ON(KC_PROBE, strm, (k_probe<false><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.prec, wb.stats)));
+    if (h->primKinds == PB_QK_INSTANCES)
+      TIMED_ON(KC_PROBE, strm, (k_probe<false, true><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.prec, wb.stats)));
+    else
+      TIMED_ON(KC_PROBE, strm, (k_probe<false, false><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.prec, wb.stats)));
   }
 }
 
