@@ -23,6 +23,7 @@
 #include "../pbrt-v1_b200/csrc/pb_film.h"
 #include "../pbrt-v1_b200/csrc/pb_setup.h"
 #include "../pbrt-v1_b200/csrc/pb_noise_table.h"
+#include "../pbrt-v1_b200/csrc/pb_treelet.h"
 #include <vector>
 #include <string>
 #include <stdio.h>
@@ -338,6 +339,35 @@ int pbrt_twin_intersect(const PbrtB200Scene *scene, const float *rays, uint64_t 
     r.mint = rays[8 * i + 6]; r.maxt = rays[8 * i + 7];
     Hit h;
     kd_intersect<false, false>(sv, r, &h, (KdCounters *)0);
+    prim[i] = h.prim;
+    t[i] = h.prim >= 0 ? h.t : 0.f; b1[i] = h.prim >= 0 ? h.b1 : 0.f; b2[i] = h.prim >= 0 ? h.b2 : 0.f;
+  }
+  return PBRT_B200_OK;
+}
+// The same walk over the device-side node order (csrc/pb_treelet.h): checks, on the CPU, that re-ordering the
+// nodes changes no hit and no counter.  counters[4] = interior visits, leaf visits, references read, tests (summed).
+int pbrt_twin_intersect_treelets(const PbrtB200Scene *scene, const float *rays, uint64_t n, int32_t *prim,
+                                 float *t, float *b1, float *b2, uint64_t *counters, int paired) {
+  SceneView sv;
+  if (!build_view(*scene, &sv)) return PBRT_B200_ERR_INVALID;
+  std::vector<PbrtB200KdNode> ordered;
+  if (paired) {
+    if (scene->n_instances != 0 || scene->n_nodes < 2) return PBRT_B200_ERR_UNSUPPORTED;
+    pb_treelet_order(scene->nodes, scene->n_nodes, &ordered);
+    sv.nodes = ordered.data();
+    sv.pairedNodes = 1;
+  }
+  KdCounters k = {0, 0, 0, 0};
+  for (int c = 0; c < 4; ++c) counters[c] = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    Ray r;
+    r.o = v3(rays[8 * i], rays[8 * i + 1], rays[8 * i + 2]);
+    r.d = v3(rays[8 * i + 3], rays[8 * i + 4], rays[8 * i + 5]);
+    r.mint = rays[8 * i + 6]; r.maxt = rays[8 * i + 7];
+    Hit h;
+    k.interior = k.leaves = k.refs = k.tests = 0;
+    kd_intersect<false, true>(sv, r, &h, &k);
+    counters[0] += k.interior; counters[1] += k.leaves; counters[2] += k.refs; counters[3] += k.tests;
     prim[i] = h.prim;
     t[i] = h.prim >= 0 ? h.t : 0.f; b1[i] = h.prim >= 0 ? h.b1 : 0.f; b2[i] = h.prim >= 0 ? h.b2 : 0.f;
   }

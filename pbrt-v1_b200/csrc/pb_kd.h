@@ -45,26 +45,28 @@ PB_HD bool bbox_intersect_p(const float *bmin, const float *bmax, const Ray &ray
 // 8.8.  The warp walk keeps the table in shared memory (pb_kd_warp.cuh), this per-thread walk in a local array.
 // 0 = the ring everywhere.
 #ifndef PB_MB_SLOTS
-#define PB_MB_SLOTS 16
+#define PB_MB_SLOTS 16          // closest-hit walks (Scene::Intersect, MIS probes)
 #endif
-#if PB_MB_SLOTS != 0 && PB_MB_SLOTS != 4 && PB_MB_SLOTS != 8 && PB_MB_SLOTS != 16 && PB_MB_SLOTS != 32
-#error "PB_MB_SLOTS: 0, 4, 8, 16 or 32"
+#ifndef PB_MB_SLOTS_ANY
+#define PB_MB_SLOTS_ANY PB_MB_SLOTS   // any-hit walks (Scene::IntersectP)
 #endif
+template <int SLOTS>
 PB_HD uint32_t pb_mb_slot(uint32_t prim) {
-  return (prim * 0x9E3779B1u) >> (PB_MB_SLOTS == 32 ? 27 : PB_MB_SLOTS == 16 ? 28 : PB_MB_SLOTS == 8 ? 29 : 30);
+  static_assert(SLOTS == 4 || SLOTS == 8 || SLOTS == 16 || SLOTS == 32, "mailbox table: 4, 8, 16 or 32 slots (0: the ring)");
+  return (prim * 0x9E3779B1u) >> (SLOTS == 32 ? 27 : SLOTS == 16 ? 28 : SLOTS == 8 ? 29 : 30);
 }
 
 // The scene's top-level tree / an instanced object's tree.
 PB_HD KdTreeView kd_top_tree(const SceneView &sv) {
   KdTreeView t;
-  t.nodes = sv.nodes; t.primRefs = sv.primRefs; t.nNodes = sv.nNodes; t.primBase = 0;
+  t.nodes = sv.nodes; t.primRefs = sv.primRefs; t.nNodes = sv.nNodes; t.primBase = 0; t.paired = sv.pairedNodes;
   for (int i = 0; i < 3; ++i) { t.bmin[i] = sv.bmin[i]; t.bmax[i] = sv.bmax[i]; }
   return t;
 }
 PB_HD KdTreeView kd_instance_tree(const SceneView &sv, const PbrtB200Instance &in) {
   KdTreeView t;
   t.nodes = sv.nodes + in.node_base; t.primRefs = sv.primRefs + in.ref_base;
-  t.nNodes = in.n_nodes; t.primBase = in.prim_base;
+  t.nNodes = in.n_nodes; t.primBase = in.prim_base; t.paired = 0;
   for (int i = 0; i < 3; ++i) { t.bmin[i] = in.bounds[i]; t.bmax[i] = in.bounds[3 + i]; }
   return t;
 }
@@ -148,10 +150,11 @@ PB_HD bool kd_tree_intersect(const SceneView &sv, const KdTreeView &tree, Ray ra
 #pragma unroll
   for (int i = 0; i < PB_MAILBOX; ++i) mailbox[i] = 0xffffffffu;
   int mbPos = 0;
-  constexpr bool HASHED = TABLE && PB_MB_SLOTS != 0;
-  uint32_t tested[HASHED ? PB_MB_SLOTS : 1];
+  constexpr int MBS = !TABLE ? 0 : (ANY ? PB_MB_SLOTS_ANY : PB_MB_SLOTS);
+  constexpr bool HASHED = MBS != 0;
+  uint32_t tested[HASHED ? MBS : 1];
   if (HASHED)
-    for (int i = 0; i < PB_MB_SLOTS; ++i) tested[i] = 0xffffffffu;
+    for (int i = 0; i < MBS; ++i) tested[i] = 0xffffffffu;
   bool anyHit = false;
   uint32_t node = 0;
   for (;;) {
@@ -175,8 +178,9 @@ PB_HD bool kd_tree_intersect(const SceneView &sv, const KdTreeView &tree, Ray ra
       float o = ray.o[axis], d = ray.d[axis];
       float tplane = (split - o) * invDir[axis];
       bool belowFirst = (o < split) || (o == split && d >= 0);
-      uint32_t firstChild = belowFirst ? node + 1 : w1;
-      uint32_t secondChild = belowFirst ? w1 : node + 1;
+      const uint32_t below = tree.paired ? w1 : node + 1, above = tree.paired ? w1 + 1 : w1;   // (pb_treelet.h)
+      uint32_t firstChild = belowFirst ? below : above;
+      uint32_t secondChild = belowFirst ? above : below;
       if (tplane > tmax || tplane <= 0)
         node = firstChild;
       else if (tplane < tmin)
@@ -197,7 +201,7 @@ PB_HD bool kd_tree_intersect(const SceneView &sv, const KdTreeView &tree, Ray ra
       uint32_t prim = tree.primBase + ((nPrims == 1) ? w1 : tree.primRefs[w1 + i]);
       if (COUNT) ++cnt->refs;
       if (HASHED) {
-        const uint32_t slot = pb_mb_slot(prim);
+        const uint32_t slot = pb_mb_slot<HASHED ? MBS : 4>(prim);
         if (tested[slot] == prim) continue;
         tested[slot] = prim;
       } else {

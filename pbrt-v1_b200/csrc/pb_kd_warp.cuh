@@ -314,6 +314,9 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
 #ifndef PB_DESCEND_MAX
 #define PB_DESCEND_MAX 8
 #endif
+#ifndef PB_LEAN_INLINE_POP
+#define PB_LEAN_INLINE_POP 1
+#endif
 #ifndef PB_LEAN_LEAF_STEPS
 #define PB_LEAN_LEAF_STEPS 2
 #endif
@@ -336,14 +339,16 @@ __device__ __forceinline__ void kd_warp_traverse_lean(const SceneView &sv, uint3
                                                       const Source &src, const Sink &sink, KdCounters &cnt) {
   static_assert(QK != PB_QK_INSTANCES, "object instances use kd_warp_traverse");
   static_assert(PB_MAILBOX == 2, "the shift-register mailbox holds two entries");
-#if PB_MB_SLOTS != 0
   // per-lane table of recently tested primitives (pb_kd.h): column threadIdx.x, so a warp's accesses never conflict
-  __shared__ uint32_t testedAll[PB_MB_SLOTS][PB_BLOCK];
-  uint32_t *const tested = &testedAll[0][threadIdx.x];
-#endif
+  constexpr int MBS = ANY ? PB_MB_SLOTS_ANY : PB_MB_SLOTS;
+  __shared__ uint32_t testedAll[MBS ? MBS : 1][MBS ? PB_BLOCK : 1];
+  uint32_t *const tested = &testedAll[0][MBS ? threadIdx.x : 0];
   const uint32_t lane = threadIdx.x & 31u;
-  uint32_t todoNode[PB_KD_STACK];
-  float todoTmin[PB_KD_STACK], todoTmax[PB_KD_STACK];
+  // todo list, 8 bytes per entry: (node, tmax).  The reference's entry also holds tmin (kdtree.cpp:318-322), but the
+  // interval that is current when an entry is popped always ends where that entry's begins -- a push sets
+  // tmax = tplane = the new entry's tmin, single-child steps leave tmax alone, and a pop restores the tmax that was
+  // current at the push, which is the tmin of the entry below -- so the popped tmin is the value tmax already holds.
+  uint2 todo[PB_KD_STACK];
   uint32_t state = PB_LS_IDLE;
   bool exhausted = false;     // the queue has no more rays (warp-uniform)
   uint32_t idx = 0;
@@ -377,10 +382,10 @@ __device__ __forceinline__ void kd_warp_traverse_lean(const SceneView &sv, uint3
           todoPos = 0;
           node = 0;
           mb0 = mb1 = 0xffffffffu;
-#if PB_MB_SLOTS != 0
+          if (MBS) {
 #pragma unroll
-          for (int k = 0; k < PB_MB_SLOTS; ++k) tested[k * PB_BLOCK] = 0xffffffffu;
-#endif
+            for (int k = 0; k < MBS; ++k) tested[k * PB_BLOCK] = 0xffffffffu;
+          }
           const bool in = sv.nNodes != 0 && bbox_intersect_p(sv.bmin, sv.bmax, ray, &tmin, &tmax);
           invDir = v3(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
           dirNeg = (ray.d.x >= 0 ? 0u : 1u) | (ray.d.y >= 0 ? 0u : 2u) | (ray.d.z >= 0 ? 0u : 4u);
@@ -408,13 +413,15 @@ __device__ __forceinline__ void kd_warp_traverse_lean(const SceneView &sv, uint3
           if (COUNT) ++cnt.leaves;
           leafN = nd.x >> 2; leafW1 = nd.y; leafI = 0;
           if (leafN != 0) state = PB_LS_LEAF;
+          else if (!PB_LEAN_INLINE_POP) state = PB_LS_LEAF;
           else if (todoPos == 0) state = PB_LS_FINISHED;
           else {
             // empty leaf: next node from the todo list right away (kdtree.cpp:392-399, :330)
             --todoPos;
-            node = todoNode[todoPos];
-            tmin = todoTmin[todoPos];
-            tmax = todoTmax[todoPos];
+            const uint2 e = todo[todoPos];
+            node = e.x;
+            tmin = tmax;
+            tmax = __uint_as_float(e.y);
             if (!ANY && ray.maxt < tmin) state = PB_LS_FINISHED;
           }
         } else {
@@ -424,7 +431,8 @@ __device__ __forceinline__ void kd_warp_traverse_lean(const SceneView &sv, uint3
           pb_pick_axis(axis, ray.o, invDir, &o, &inv);
           const float tplane = (split - o) * inv;
           const bool belowFirst = (o < split) || (o == split && !((dirNeg >> axis) & 1u));
-          const uint32_t below = node + 1u, above = nd.y;
+          const uint32_t below = sv.pairedNodes ? nd.y : node + 1u;        // (pb_treelet.h)
+          const uint32_t above = sv.pairedNodes ? nd.y + 1u : nd.y;
           const uint32_t firstChild = belowFirst ? below : above;
           const uint32_t secondChild = belowFirst ? above : below;
           if (tplane > tmax || tplane <= 0)
@@ -432,9 +440,7 @@ __device__ __forceinline__ void kd_warp_traverse_lean(const SceneView &sv, uint3
           else if (tplane < tmin)
             node = secondChild;
           else {
-            todoNode[todoPos] = secondChild;
-            todoTmin[todoPos] = tplane;
-            todoTmax[todoPos] = tmax;
+            todo[todoPos] = make_uint2(secondChild, __float_as_uint(tmax));
             ++todoPos;
             node = firstChild;
             tmax = tplane;
@@ -453,18 +459,16 @@ __device__ __forceinline__ void kd_warp_traverse_lean(const SceneView &sv, uint3
         prim = (leafN == 1) ? leafW1 : __ldg(sv.primRefs + leafW1 + leafI);
         ++leafI;
         if (COUNT) ++cnt.refs;
-#if PB_MB_SLOTS != 0
-        uint32_t *const entry = tested + pb_mb_slot(prim) * PB_BLOCK;
-        if (*entry != prim) {
-          *entry = prim;
-          pending = true;
-        }
-#else
-        if (prim != mb0 && prim != mb1) {
+        if (MBS) {
+          uint32_t *const entry = tested + pb_mb_slot<MBS ? MBS : 4>(prim) * PB_BLOCK;
+          if (*entry != prim) {
+            *entry = prim;
+            pending = true;
+          }
+        } else if (prim != mb0 && prim != mb1) {
           mb1 = mb0; mb0 = prim;
           pending = true;
         }
-#endif
       }
     }
     // ---- C. the expensive part, all lanes with work together
@@ -479,9 +483,10 @@ __device__ __forceinline__ void kd_warp_traverse_lean(const SceneView &sv, uint3
       if (todoPos == 0) state = PB_LS_FINISHED;
       else {
         --todoPos;
-        node = todoNode[todoPos];
-        tmin = todoTmin[todoPos];
-        tmax = todoTmax[todoPos];
+        const uint2 e = todo[todoPos];
+        node = e.x;
+        tmin = tmax;
+        tmax = __uint_as_float(e.y);
         state = (!ANY && ray.maxt < tmin) ? PB_LS_FINISHED : PB_LS_DESCEND;   // kdtree.cpp:330
       }
     }

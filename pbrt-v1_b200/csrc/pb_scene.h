@@ -33,6 +33,7 @@ struct SceneView {
   const uint32_t *lightShapes;
   const float *lightCdf;
   uint32_t nNodes, nPrims, nLights;   // nNodes: the top-level tree's
+  uint32_t pairedNodes;               // device copy in treelet order (pb_treelet.h): word1 = below child, above = below + 1
   uint32_t nInstances;
   uint32_t nInfiniteLights;         // lights whose Le(ray) is not black (lights/infinite.cpp)
   float bmin[3], bmax[3];
@@ -90,6 +91,7 @@ struct KdTreeView {
   const PbrtB200KdNode *nodes;
   const uint32_t *primRefs;
   uint32_t nNodes, primBase;
+  uint32_t paired;   // node order of pb_treelet.h (device copy of the top-level tree only)
   float bmin[3], bmax[3];
 };
 #endif

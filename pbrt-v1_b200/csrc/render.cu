@@ -37,6 +37,7 @@
 #include "pb_film.h"
 #include "pb_setup.h"
 #include "pb_noise_table.h"
+#include "pb_treelet.h"
 
 // ------------------------------------------------------------------------------------------
 // error plumbing
@@ -61,6 +62,7 @@ static int64_t g_overlap = 0;             // key 5: run shadow/probe traversal o
 static int64_t g_debugCounts = 0;         // key 6: print each wave's queue sizes per iteration to stderr
 static int64_t g_reserved4 = 0;           // key 4: reserved (was the fused shade kernel's occupancy variant)
 static int64_t g_fastPath = 1;            // key 8: k_path_fast shades flat-triangle / matte vertices in one pass (0: general three-kernel pipeline only)
+static int64_t g_treelets = 1;            // key 9: device node order of the top-level tree: sibling pairs in line-sized treelets (pb_treelet.h; 0: the reference's depth-first array)
 static int64_t g_primFrames = 1;          // key 7: precompute hit-independent BSDF / light-triangle frames at scene create (0: evaluate per hit)
 
 #ifndef PB_DIRECT_MIN_BLOCKS
@@ -2049,7 +2051,7 @@ const char *pbrt_b200_last_error(void) { return g_lastError.c_str(); }
 int64_t pbrt_b200_tunable(int key, int64_t value) {
   int64_t *p = key == 0 ? &g_waveSamples : key == 1 ? &g_countKd : key == 2 ? &g_blocksPerSM
                : key == 3 ? &g_profileKernels : key == 4 ? &g_reserved4 : key == 5 ? &g_overlap : key == 6 ? &g_debugCounts
-               : key == 7 ? &g_primFrames : key == 8 ? &g_fastPath : nullptr;
+               : key == 7 ? &g_primFrames : key == 8 ? &g_fastPath : key == 9 ? &g_treelets : nullptr;
   if (!p) return -1;
   int64_t prev = *p;
   if (value >= 0) *p = value;
@@ -2150,7 +2152,17 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   SceneView &sv = h->sv;
   const PbrtB200Prim *dprims = nullptr;
 #define UP(expr) do { rc = (expr); if (rc != PBRT_B200_OK) { pbrt_b200_scene_destroy(h); return rc; } } while (0)
-  UP(upload(h, scene->nodes, scene->n_nodes, &sv.nodes));
+  if (PB_LEAN_WALK && g_treelets && scene->n_instances == 0 && scene->n_nodes > 1) {
+    std::vector<PbrtB200KdNode> ordered;
+    pb_treelet_order(scene->nodes, scene->n_nodes, &ordered);
+    UP(upload(h, ordered.data(), ordered.size(), &sv.nodes));
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) {   // (`ordered` is about to go away)
+      pbrt_b200_scene_destroy(h);
+      return fail(PBRT_B200_ERR_CUDA, "upload of the kd-tree nodes failed");
+    }
+    sv.pairedNodes = 1;
+  } else
+    UP(upload(h, scene->nodes, scene->n_nodes, &sv.nodes));
   UP(upload(h, scene->prim_refs, scene->n_prim_refs, &sv.primRefs));
   UP(upload(h, scene->prims, scene->n_prims, &dprims));
   sv.prims = (const PrimQuad *)dprims;

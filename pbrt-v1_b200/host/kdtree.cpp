@@ -9,6 +9,10 @@
 // include/pbrt_b200.h instead of the reference's pointer-carrying nodes.
 #include "core.h"
 #include <thread>
+#include <chrono>
+static double host_seconds() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 void Primitive::FullyRefine(vector<Reference<Primitive> > &refined) const {
   // core/primitive.cpp:40-53: LIFO todo list => a mesh's triangles come out
@@ -159,8 +163,12 @@ static bool choose_split(const BuildParams &bp, const BBox &nodeBounds, const in
       ev[2 * i].pos = b.pMin[axis]; ev[2 * i].prim = primNums[i]; ev[2 * i].closes = 0;
       ev[2 * i + 1].pos = b.pMax[axis]; ev[2 * i + 1].prim = primNums[i]; ev[2 * i + 1].closes = 1;
     }
+    const bool tm = nPrims > 900000 && getenv("PBRT_HOST_TIMING");
+    double ta = tm ? host_seconds() : 0;
     std::sort(ev, ev + 2 * nPrims, EventOrder());
+    double tb = tm ? host_seconds() : 0;
     sweep.run(axis, ev, 2 * nPrims, nPrims);
+    if (tm) fprintf(stderr, "  root axis %d: sort %.3f s, sweep %.3f s\n", axis, tb - ta, host_seconds() - tb);
     if (sweep.best >= 0) splitAxis = axis;
   }
   // give up (leaf) when splitting is not worth it: repeatedly worse than not splitting, or much worse on a
@@ -265,6 +273,8 @@ void KdBuilder::buildParallel(const BuildParams &bp, Subtree &st, const BBox &no
 KdTreeAccel::KdTreeAccel(const vector<Reference<Primitive> > &p, int icost, int tcost,
                          float ebonus, int maxp, int maxDepth)
     : isectCost(icost), traversalCost(tcost), maxPrims(maxp), emptyBonus(ebonus) {
+  const bool timing = getenv("PBRT_HOST_TIMING") != NULL;
+  const double t0 = host_seconds();
   for (u_int i = 0; i < p.size(); ++i) p[i]->FullyRefine(prims);
   if (maxDepth <= 0) maxDepth = Round2Int(8 + 1.3f * Log2Int(float(prims.size())));
   vector<BBox> primBounds;
@@ -274,6 +284,7 @@ KdTreeAccel::KdTreeAccel(const vector<Reference<Primitive> > &p, int icost, int 
     bounds = Union(bounds, b);
     primBounds.push_back(b);
   }
+  const double t1 = host_seconds();
   size_t np = prims.size();
   vector<int> primNums(np);
   for (u_int i = 0; i < np; ++i) primNums[i] = i;
@@ -288,4 +299,7 @@ KdTreeAccel::KdTreeAccel(const vector<Reference<Primitive> > &p, int icost, int 
   KdBuilder::buildParallel(bp, st, bounds, primNums, maxDepth, 0, forkLevels);
   nodes.swap(st.nodes);
   primRefs.swap(st.refs);
+  if (timing)
+    fprintf(stderr, "kd-tree: %zu primitives, refine + bounds %.3f s, build %.3f s (%d threads), %zu nodes\n", np,
+            t1 - t0, host_seconds() - t1, threads, nodes.size());
 }

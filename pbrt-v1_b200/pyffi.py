@@ -1,13 +1,13 @@
 """ctypes bindings used by tests/, bench.py and __graft_entry__.py.
 
-Three shared libraries, all plain C ABIs:
+Two shared libraries, both plain C ABIs (the bindings of the test-only CPU twin, oracle/_build/libpbrt_twin.so,
+live in tests/twin_ffi.py; tests/parity_util.load_ffi() attaches them to this module for the tests' convenience):
 
   host/libpbrt_host.so    front end: .pbrt parser + api.h state machine + kd build;
                           `load_scene()` parses a scene file and returns the flattened
                           PbrtB200Scene (opaque pointer) that Scene::Render() would hand
                           to the GPU library.
   csrc/libpbrt_b200.so    the product: CUDA render hot path (include/pbrt_b200.h).
-  oracle/_build/libpbrt_twin.so   TEST ONLY: CPU restatement (oracle/twin.cpp).
 
 Nothing here computes anything; it only marshals numpy arrays.
 """
@@ -19,7 +19,6 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST_LIB = os.path.join(ROOT, "pbrt-v1_b200", "host", "libpbrt_host.so")
 CUDA_LIB = os.environ.get("PBRT_B200_LIB", os.path.join(ROOT, "pbrt-v1_b200", "csrc", "libpbrt_b200.so"))
-TWIN_LIB = os.environ.get("PBRT_TWIN_LIB", os.path.join(ROOT, "oracle", "_build", "libpbrt_twin.so"))
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 
@@ -94,71 +93,6 @@ class Scene:
             self.close()
         except Exception:
             pass
-
-
-# ----------------------------------------------------------------- CPU twin (tests only)
-_twin = None
-
-
-def twin():
-    global _twin
-    if _twin is None:
-        lib = C.CDLL(TWIN_LIB)
-        lib.pbrt_twin_last_error.restype = C.c_char_p
-        lib.pbrt_twin_sample_count.restype = C.c_uint64
-        lib.pbrt_twin_sample_count.argtypes = [C.c_void_p, C.c_void_p]
-        lib.pbrt_twin_render.argtypes = [C.c_void_p] * 6
-        lib.pbrt_twin_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_void_p] * 4
-        lib.pbrt_twin_intersect_p.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
-        lib.pbrt_twin_camera_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
-        _twin = lib
-    return _twin
-
-
-def twin_render(scene, window=None, want_samples=False):
-    w = window or scene.full_window()
-    rgba = np.zeros((w.height, w.width, 4), np.float32)
-    raw = np.zeros((w.height, w.width, 5), np.float32)
-    ns = twin().pbrt_twin_sample_count(scene.ptr, C.byref(w))
-    samples = np.zeros((ns, 6), np.float32) if want_samples else None
-    st = Stats()
-    rc = twin().pbrt_twin_render(scene.ptr, C.byref(w), _fp(rgba), _fp(raw),
-                                 _fp(samples) if want_samples else None, C.byref(st))
-    if rc != 0:
-        raise RuntimeError("twin render failed: %s" % twin().pbrt_twin_last_error().decode())
-    return rgba, raw, samples, st.as_dict()
-
-
-def twin_intersect(scene, rays):
-    rays = np.ascontiguousarray(rays, np.float32)
-    n = rays.shape[0]
-    prim = np.zeros(n, np.int32)
-    t = np.zeros(n, np.float32)
-    b1 = np.zeros(n, np.float32)
-    b2 = np.zeros(n, np.float32)
-    rc = twin().pbrt_twin_intersect(scene.ptr, _fp(rays), n, _fp(prim), _fp(t), _fp(b1), _fp(b2))
-    assert rc == 0
-    return prim, t, b1, b2
-
-
-def twin_intersect_p(scene, rays):
-    rays = np.ascontiguousarray(rays, np.float32)
-    n = rays.shape[0]
-    occ = np.zeros(n, np.uint8)
-    rc = twin().pbrt_twin_intersect_p(scene.ptr, _fp(rays), n, _fp(occ))
-    assert rc == 0
-    return occ
-
-
-def twin_camera_rays(scene, window=None, n=None):
-    w = window or scene.full_window()
-    total = twin().pbrt_twin_sample_count(scene.ptr, C.byref(w))
-    n = total if n is None else min(n, total)
-    rays = np.zeros((n, 8), np.float32)
-    xy = np.zeros((n, 2), np.float32)
-    rc = twin().pbrt_twin_camera_rays(scene.ptr, C.byref(w), n, _fp(rays), _fp(xy))
-    assert rc == 0
-    return rays, xy
 
 
 # ----------------------------------------------------------------- CUDA library (the product)
@@ -299,10 +233,10 @@ class DeviceScene:
         _check(cuda().pbrt_b200_intersect_p(self.h, _fp(rays), n, _fp(occ)))
         return occ
 
-    def camera_rays(self, window=None, n=None):
+    def camera_rays(self, n, window=None):
+        """The first n camera rays of a window (pbrt_b200_camera_rays, a test entry point); the caller knows the
+        window's sample count."""
         w = window or self.scene.full_window()
-        total = twin_sample_count(self.scene, w)
-        n = total if n is None else min(n, total)
         rays = np.zeros((n, 8), np.float32)
         xy = np.zeros((n, 2), np.float32)
         _check(cuda().pbrt_b200_camera_rays(self.h, C.byref(w), n, _fp(rays), _fp(xy)))
@@ -354,18 +288,6 @@ def frame_partition(window, world, tile_edge=0):
     return [(Window(t.x0, t.y0, t.width, t.height), int(o)) for t, o in zip(tiles, owners)]
 
 
-def twin_render_tile(scene, frame, tile):
-    """TEST ONLY: the oracle twin's restatement of tile semantics (pbrt_b200_render_tiles)."""
-    lib = twin()
-    lib.pbrt_twin_render_tile.argtypes = [C.c_void_p] * 6
-    rgba = np.zeros((tile.height, tile.width, 4), np.float32)
-    st = Stats()
-    rc = lib.pbrt_twin_render_tile(scene.ptr, C.byref(frame), C.byref(tile), _fp(rgba), None, C.byref(st))
-    if rc != 0:
-        raise RuntimeError("twin tile render failed (%d)" % rc)
-    return rgba, st.as_dict()
-
-
 def render_host_multi(scene, devices, out=None):
     """pbrt_b200_render_host_multi: HOST buffers both sides, one thread per device inside the library."""
     w = scene.full_window()
@@ -375,10 +297,6 @@ def render_host_multi(scene, devices, out=None):
     st = Stats()
     _check(cuda().pbrt_b200_render_host_multi(scene.ptr, dev, len(devices), out.ctypes.data, C.byref(st)))
     return out, st.as_dict()
-
-
-def twin_sample_count(scene, w):
-    return int(twin().pbrt_twin_sample_count(scene.ptr, C.byref(w)))
 
 
 def render_host(scene, windows=None, device=0, want_raw=False, outs=None):

@@ -16,6 +16,13 @@ def load_ffi():
         mod = importlib.util.module_from_spec(spec)
         sys.modules["pbrt_b200_pyffi"] = mod
         spec.loader.exec_module(mod)
+    if not hasattr(mod, "twin"):
+        # the CPU twin's bindings are test infrastructure and live here, not in the product package
+        tspec = importlib.util.spec_from_file_location("pbrt_twin_ffi", os.path.join(ROOT, "tests", "twin_ffi.py"))
+        tmod = importlib.util.module_from_spec(tspec)
+        sys.modules["pbrt_twin_ffi"] = tmod
+        tspec.loader.exec_module(tmod)
+        tmod.attach(mod)
     return mod
 
 

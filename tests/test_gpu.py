@@ -110,7 +110,7 @@ def test_camera_rays_and_traversal_bit_exact(ffi, scene_dir):
     scene = ffi.Scene(sp)
     ds = ffi.DeviceScene(scene)
     rays_t, xy_t = ffi.twin_camera_rays(scene)
-    rays_g, xy_g = ds.camera_rays()
+    rays_g, xy_g = ds.camera_rays(ffi.twin_sample_count(scene, scene.full_window()))
     assert np.array_equal(rays_t.view(np.uint32), rays_g.view(np.uint32))
     assert np.array_equal(xy_t.view(np.uint32), xy_g.view(np.uint32))
     rng = np.random.default_rng(11)

@@ -383,3 +383,29 @@ def test_c4_scale_tree_and_crop_vs_reference(ffi, tmp_path):
         assert np.array_equal(rgba.view(np.uint32), r["rgba"].view(np.uint32)), r["window"]
         assert np.array_equal(samples.view(np.uint32), r["samples"].view(np.uint32)), r["window"]
         assert st["intersect_rays"] == r["intersect"] and st["shadow_rays"] == r["intersect_p"]
+
+
+def test_treelet_node_order_changes_no_hit_and_no_counter(ffi, tmp_path):
+    """csrc/pb_treelet.h re-orders the device copy of the top-level tree (sibling pairs in line-sized treelets);
+    the walk over it must return the same hits and visit / test counts as over the reference's depth-first array."""
+    for name, extra in (("c3", ()), ("c4", ("--nphi", "160", "--ntheta", "80"))):
+        sp = gen_scene(str(tmp_path / ("tl_%s.pbrt" % name)), name, "--res", "40", "40", "--spp", "2", "2",
+                       "--filename", str(tmp_path / "tl.exr"), *extra)
+        scene = ffi.Scene(sp)
+        rays, _ = ffi.twin_camera_rays(scene)
+        prim, t, _, _ = ffi.twin_intersect(scene, rays)
+        ok = prim >= 0
+        rng = np.random.default_rng(5)
+        p = rays[ok, :3] + rays[ok, 3:6] * t[ok, None]
+        d = rng.normal(size=p.shape).astype(np.float32)
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        sec = np.zeros((p.shape[0], 8), np.float32)
+        sec[:, :3] = p; sec[:, 3:6] = d; sec[:, 6] = 1e-3; sec[:, 7] = np.inf
+        allrays = np.concatenate([rays, sec])
+        a = ffi.twin_intersect_treelets(scene, allrays, 0)
+        b = ffi.twin_intersect_treelets(scene, allrays, 1)
+        assert np.array_equal(a[0], b[0])
+        for k in (1, 2, 3):
+            assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32))
+        assert np.array_equal(a[4], b[4]) and a[4][0] > 0
+        scene.close()

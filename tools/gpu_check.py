@@ -21,7 +21,7 @@ def check(name, *args):
     sc = ffi.Scene(sp)
     ds = ffi.DeviceScene(sc)
     rays_t, xy_t = ffi.twin_camera_rays(sc)
-    rays_g, xy_g = ds.camera_rays()
+    rays_g, xy_g = ds.camera_rays(ffi.twin_sample_count(scene, scene.full_window()))
     print(name, "camera rays identical:", bool((rays_t.view(np.uint32) == rays_g.view(np.uint32)).all()),
           bool((xy_t == xy_g).all()))
     pt, tt, b1t, b2t = ffi.twin_intersect(sc, rays_t)
