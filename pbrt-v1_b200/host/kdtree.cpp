@@ -9,6 +9,8 @@
 // include/pbrt_b200.h instead of the reference's pointer-carrying nodes.
 #include "core.h"
 #include <thread>
+#include <atomic>
+#include <climits>
 #include <chrono>
 static double host_seconds() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -71,6 +73,7 @@ struct BuildParams {
   int isectCost, traversalCost, maxPrims;
   float emptyBonus;
   const vector<BBox> *allPrimBounds;
+  int sortThreads;   // threads a big node's event sort may use (sort_events)
 };
 void init_leaf(Subtree &st, int nodeNum, const int *primNums, int np) {
   PbrtB200KdNode &n = st.nodes[nodeNum];
@@ -82,17 +85,6 @@ void init_leaf(Subtree &st, int nodeNum, const int *primNums, int np) {
     for (int i = 0; i < np; ++i) st.refs.push_back((uint32_t)primNums[i]);
   }
 }
-// Shift a subtree's stored indices and append it.
-void splice(Subtree &dst, const Subtree &src) {
-  uint32_t nodeBase = (uint32_t)dst.nodes.size(), refBase = (uint32_t)dst.refs.size();
-  for (size_t i = 0; i < src.nodes.size(); ++i) {
-    PbrtB200KdNode n = src.nodes[i];
-    if ((n.word0 & 3u) != 3u) n.word1 += nodeBase;            // interior: above-child index
-    else if ((n.word0 >> 2) > 1u) n.word1 += refBase;         // leaf list offset
-    dst.nodes.push_back(n);
-  }
-  dst.refs.insert(dst.refs.end(), src.refs.begin(), src.refs.end());
-}
 }  // namespace
 
 // The split decision of one node (kdtree.cpp:189-299).  Returns false when the node becomes a leaf;
@@ -101,13 +93,14 @@ static bool choose_split(const BuildParams &bp, const BBox &nodeBounds, const in
                          KdTreeAccel::BoundEdge *edges[3], int *prims0, int *prims1, int *badRefines,
                          int *bestAxisOut, float *tsplitOut, int *n0Out, int *n1Out);
 
+namespace { struct Piece; }
 struct KdBuilder {
   typedef KdTreeAccel::BoundEdge BoundEdge;
   static void buildTree(const BuildParams &bp, Subtree &st, int nodeNum, const BBox &nodeBounds,
                         int *primNums, int nPrims, int depth, BoundEdge *edges[3], int *prims0,
                         int *prims1, int badRefines);
-  static void buildParallel(const BuildParams &bp, Subtree &st, const BBox &nodeBounds, vector<int> &primNums,
-                            int depth, int badRefines, int forkLevels);
+  static void buildParallel(const BuildParams &bp, Piece &pc, const BBox &nodeBounds, vector<int> &primNums,
+                            int depth, int badRefines, int forkPrims);
 };
 // Surface-area heuristic along one axis: walks the sorted events keeping the primitive counts on either side
 // of the candidate plane and returns the cheapest plane strictly inside the node (index into `ev`, -1 if none).
@@ -146,6 +139,55 @@ struct AxisSweep {
   }
 };
 }  // namespace
+// std::sort's result, computed by several threads.  The order std::sort leaves EQUAL events in decides which
+// primitives land in which child (and in which order), so the sort of a big node cannot be replaced by another
+// algorithm -- but it can be run concurrently: libstdc++'s std::sort is
+//     __introsort_loop(first, last, 2 * lg(n));  __final_insertion_sort(first, last);
+// and the introsort loop (bits/stl_algo.h) partitions [first, last) around a median-of-three pivot, recurses into the
+// upper part and continues with the lower one.  The two parts are disjoint ranges and nothing else is shared, so
+// handing the upper part of a large range to another thread changes no comparison and no swap.  The functions
+// called are the library's own (same pivot rule, same heap-sort fallback at depth 0), hence the same bytes out; the
+// final insertion sort then runs once over the whole range as in std::sort.
+// (tests/test_oracle.py::test_parallel_kd_build_equals_sequential compares the trees.)
+#if defined(__GLIBCXX__)
+#include <future>
+namespace {
+template <class It, class Cmp>
+void introsort_loop_parallel(It first, It last, long depthLimit, Cmp cmp, int forks) {
+  std::vector<std::future<void> > pending;
+  while (last - first > 16) {   // _S_threshold
+    if (depthLimit == 0) {
+      std::__partial_sort(first, last, last, cmp);
+      break;
+    }
+    --depthLimit;
+    It cut = std::__unguarded_partition_pivot(first, last, cmp);
+    if (forks > 0 && last - cut > 32768) {
+      --forks;
+      const int f = forks;
+      pending.push_back(std::async(std::launch::async, [=]() { introsort_loop_parallel(cut, last, depthLimit, cmp, f); }));
+    } else
+      std::__introsort_loop(cut, last, depthLimit, cmp);
+    last = cut;
+  }
+  for (size_t i = 0; i < pending.size(); ++i) pending[i].get();
+}
+}  // namespace
+static void sort_events(PlaneEvent *first, PlaneEvent *last, int threads) {
+  if (threads <= 1 || last - first < 131072) {
+    std::sort(first, last, EventOrder());
+    return;
+  }
+  auto cmp = __gnu_cxx::__ops::__iter_comp_iter(EventOrder());
+  int forks = 0;
+  while ((1 << forks) < threads) ++forks;
+  introsort_loop_parallel(first, last, std::__lg(last - first) * 2, cmp, forks + 1);
+  std::__final_insertion_sort(first, last, cmp);
+}
+#else
+static void sort_events(PlaneEvent *first, PlaneEvent *last, int) { std::sort(first, last, EventOrder()); }
+#endif
+
 static bool choose_split(const BuildParams &bp, const BBox &nodeBounds, const int *primNums, int nPrims,
                          KdTreeAccel::BoundEdge *edges[3], int *prims0, int *prims1, int *badRefines,
                          int *bestAxisOut, float *tsplitOut, int *n0Out, int *n1Out) {
@@ -163,12 +205,8 @@ static bool choose_split(const BuildParams &bp, const BBox &nodeBounds, const in
       ev[2 * i].pos = b.pMin[axis]; ev[2 * i].prim = primNums[i]; ev[2 * i].closes = 0;
       ev[2 * i + 1].pos = b.pMax[axis]; ev[2 * i + 1].prim = primNums[i]; ev[2 * i + 1].closes = 1;
     }
-    const bool tm = nPrims > 900000 && getenv("PBRT_HOST_TIMING");
-    double ta = tm ? host_seconds() : 0;
-    std::sort(ev, ev + 2 * nPrims, EventOrder());
-    double tb = tm ? host_seconds() : 0;
+    sort_events(ev, ev + 2 * nPrims, bp.sortThreads);
     sweep.run(axis, ev, 2 * nPrims, nPrims);
-    if (tm) fprintf(stderr, "  root axis %d: sort %.3f s, sweep %.3f s\n", axis, tb - ta, host_seconds() - tb);
     if (sweep.best >= 0) splitAxis = axis;
   }
   // give up (leaf) when splitting is not worth it: repeatedly worse than not splitting, or much worse on a
@@ -224,12 +262,76 @@ void KdBuilder::buildTree(const BuildParams &bp, Subtree &st, int nodeNum, const
 }
 
 #include <future>
-// A big node: decide its split here, build the two children concurrently, splice.
-void KdBuilder::buildParallel(const BuildParams &bp, Subtree &st, const BBox &nodeBounds, vector<int> &primNums,
-                              int depth, int badRefines, int forkLevels) {
+#include <memory>
+// A big node: decide its split here and build the two children concurrently.  The result is a tree of pieces -- a
+// forked node holds only its own split, a piece built sequentially holds its whole subtree with subtree-relative
+// numbers -- which assemble_pieces() lays out afterwards: node numbering is depth first (a node, its whole below
+// subtree, its above subtree) and leaves append their reference lists in the same order, so every piece's position
+// in the final arrays follows from the sizes of the pieces before it, and the pieces are copied (indices shifted)
+// by all threads at once.  Same arrays as the sequential build, bit for bit.
+namespace {
+struct Piece {
+  Subtree st;                       // a sequentially built subtree (or a single leaf); unused for a fork
+  bool fork = false;
+  uint32_t word0 = 0;               // fork: the node's split word
+  std::unique_ptr<Piece> below, above;
+  size_t nodeBase = 0, refBase = 0, nNodes = 0, nRefs = 0;
+};
+void measure_pieces(Piece &pc, size_t nodeBase, size_t refBase, vector<Piece *> *leaves) {
+  pc.nodeBase = nodeBase; pc.refBase = refBase;
+  if (!pc.fork) {
+    pc.nNodes = pc.st.nodes.size(); pc.nRefs = pc.st.refs.size();
+    leaves->push_back(&pc);
+    return;
+  }
+  measure_pieces(*pc.below, nodeBase + 1, refBase, leaves);
+  measure_pieces(*pc.above, nodeBase + 1 + pc.below->nNodes, refBase + pc.below->nRefs, leaves);
+  pc.nNodes = 1 + pc.below->nNodes + pc.above->nNodes;
+  pc.nRefs = pc.below->nRefs + pc.above->nRefs;
+}
+void write_forks(const Piece &pc, vector<PbrtB200KdNode> &nodes) {
+  if (!pc.fork) return;
+  nodes[pc.nodeBase].word0 = pc.word0;
+  nodes[pc.nodeBase].word1 = (uint32_t)pc.above->nodeBase;
+  write_forks(*pc.below, nodes);
+  write_forks(*pc.above, nodes);
+}
+void assemble_pieces(Piece &root, int threads, vector<PbrtB200KdNode> *nodes, vector<uint32_t> *refs) {
+  vector<Piece *> leaves;
+  measure_pieces(root, 0, 0, &leaves);
+  PbrtB200KdNode blank = {0u, 0u};
+  nodes->assign(root.nNodes, blank);
+  refs->assign(root.nRefs, 0u);
+  write_forks(root, *nodes);
+  std::atomic<size_t> next(0);
+  auto worker = [&]() {
+    for (;;) {
+      size_t i = next.fetch_add(1);
+      if (i >= leaves.size()) return;
+      const Piece &pc = *leaves[i];
+      const uint32_t nodeBase = (uint32_t)pc.nodeBase, refBase = (uint32_t)pc.refBase;
+      PbrtB200KdNode *dst = nodes->data() + pc.nodeBase;
+      for (size_t k = 0; k < pc.st.nodes.size(); ++k) {
+        PbrtB200KdNode n = pc.st.nodes[k];
+        if ((n.word0 & 3u) != 3u) n.word1 += nodeBase;            // interior: above-child index
+        else if ((n.word0 >> 2) > 1u) n.word1 += refBase;         // leaf list offset
+        dst[k] = n;
+      }
+      if (!pc.st.refs.empty()) memcpy(refs->data() + pc.refBase, pc.st.refs.data(), pc.st.refs.size() * sizeof(uint32_t));
+    }
+  };
+  vector<std::thread> pool;
+  for (int t = 1; t < std::max(1, threads); ++t) pool.emplace_back(worker);
+  worker();
+  for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+}
+}  // namespace
+void KdBuilder::buildParallel(const BuildParams &bp, Piece &pc, const BBox &nodeBounds, vector<int> &primNums,
+                              int depth, int badRefines, int forkPrims) {
   const int nPrims = (int)primNums.size();
   const size_t np = (size_t)nPrims;
-  if (forkLevels <= 0 || nPrims < 4096 || nPrims <= bp.maxPrims || depth == 0) {
+  Subtree &st = pc.st;
+  if (nPrims < forkPrims || nPrims <= bp.maxPrims || depth == 0) {
     // sequential build of this subtree, the reference's recursion with its scratch arrays
     vector<BoundEdge> e0(2 * np + 1), e1(2 * np + 1), e2(2 * np + 1);
     BoundEdge *edges[3] = {&e0[0], &e1[0], &e2[0]};
@@ -238,8 +340,6 @@ void KdBuilder::buildParallel(const BuildParams &bp, Subtree &st, const BBox &no
               badRefines);
     return;
   }
-  PbrtB200KdNode blank = {0u, 0u};
-  st.nodes.push_back(blank);
   vector<int> below(np + 1), above(np + 1);
   int bestAxis, n0, n1;
   float tsplit;
@@ -251,23 +351,25 @@ void KdBuilder::buildParallel(const BuildParams &bp, Subtree &st, const BBox &no
                          &tsplit, &n0, &n1);
   }
   if (!split) {
+    PbrtB200KdNode blank = {0u, 0u};
+    st.nodes.push_back(blank);
     init_leaf(st, 0, &primNums[0], nPrims);
     return;
   }
   vector<int>().swap(primNums);   // the parent's list is not needed any more
   below.resize(n0); above.resize(n1);
-  st.nodes[0].word0 = interior_word0(tsplit, bestAxis);
+  pc.fork = true;
+  pc.word0 = interior_word0(tsplit, bestAxis);
+  pc.below.reset(new Piece);
+  pc.above.reset(new Piece);
   BBox bounds0 = nodeBounds, bounds1 = nodeBounds;
   bounds0.pMax[bestAxis] = bounds1.pMin[bestAxis] = tsplit;
-  Subtree sub0, sub1;
-  std::future<void> other = std::async(std::launch::async, [&]() {
-    buildParallel(bp, sub1, bounds1, above, depth - 1, badRefines, forkLevels - 1);
+  Piece *pa = pc.above.get();
+  std::future<void> other = std::async(std::launch::async, [&, pa]() {
+    buildParallel(bp, *pa, bounds1, above, depth - 1, badRefines, forkPrims);
   });
-  buildParallel(bp, sub0, bounds0, below, depth - 1, badRefines, forkLevels - 1);
+  buildParallel(bp, *pc.below, bounds0, below, depth - 1, badRefines, forkPrims);
   other.get();
-  splice(st, sub0);
-  st.nodes[0].word1 = (uint32_t)st.nodes.size();
-  splice(st, sub1);
 }
 
 KdTreeAccel::KdTreeAccel(const vector<Reference<Primitive> > &p, int icost, int tcost,
@@ -288,17 +390,19 @@ KdTreeAccel::KdTreeAccel(const vector<Reference<Primitive> > &p, int icost, int 
   size_t np = prims.size();
   vector<int> primNums(np);
   for (u_int i = 0; i < np; ++i) primNums[i] = i;
-  BuildParams bp = {isectCost, traversalCost, maxPrims, emptyBonus, &primBounds};
-  // PBRT_KD_THREADS=1 forces the sequential build; default: as many fork levels as the cores warrant
+  // PBRT_KD_THREADS=1 forces the sequential build; default: one thread per core
   int threads = (int)std::thread::hardware_concurrency();
   if (const char *e = getenv("PBRT_KD_THREADS")) threads = atoi(e);
-  int forkLevels = 0;
-  while ((1 << forkLevels) < threads) ++forkLevels;
-  if (threads > 1) forkLevels += 2;   // children differ in size: over-decompose a little
-  Subtree st;
-  KdBuilder::buildParallel(bp, st, bounds, primNums, maxDepth, 0, forkLevels);
-  nodes.swap(st.nodes);
-  primRefs.swap(st.refs);
+  threads = std::max(1, threads);
+  BuildParams bp = {isectCost, traversalCost, maxPrims, emptyBonus, &primBounds, threads};
+  // nodes with at least forkPrims primitives fork their children onto threads: about 16 sequential pieces per
+  // thread, so that pieces of different cost still balance
+  const int forkPrims = threads > 1 ? std::max(4096, (int)(np / (16 * (size_t)threads))) : INT_MAX;
+  Piece root;
+  KdBuilder::buildParallel(bp, root, bounds, primNums, maxDepth, 0, forkPrims);
+  const double t2 = host_seconds();
+  assemble_pieces(root, threads, &nodes, &primRefs);
+  if (timing) fprintf(stderr, "kd-tree: pieces built in %.3f s, assembled in %.3f s\n", t2 - t1, host_seconds() - t2);
   if (timing)
     fprintf(stderr, "kd-tree: %zu primitives, refine + bounds %.3f s, build %.3f s (%d threads), %zu nodes\n", np,
             t1 - t0, host_seconds() - t1, threads, nodes.size());
