@@ -416,7 +416,9 @@ int pbrt_b200_render_host(const PbrtB200Scene *scene, int device,
  * key 6: print per-iteration queue sizes of every wave to stderr (profiling aid)
  * key 7: precompute the hit-independent BSDF frames of flat triangles and the light triangles' normals at
  *        scene create (default on; 0 evaluates them at every hit -- same bits, A/B switch for the profiles)
- * key 8: shade plain vertices (flat triangle, matte material) in the single-pass kernel k_path_fast (default on) */
+ * key 8: shade plain vertices (flat triangle, matte material) in the single-pass kernel k_path_fast (default on)
+ * key 9: node order of the device copy of the top-level kd-tree, read at pbrt_b200_scene_create: 0 = the array as
+ *        given (depth first, default), 1 = sibling pairs packed in 128-byte treelets (same tree, same visits) */
 int64_t pbrt_b200_tunable(int key, int64_t value);
 
 /* Per-kernel-class totals of the last pbrt_b200_render(): launches, summed

@@ -303,8 +303,13 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
 // picked by branches, the lane flags lived in byte registers).  Same per-ray visit and test sequence; differences:
 //   * lane state is one word (idle / descending / in a leaf / finished), the per-axis operands of an interior step
 //     come from predicated selects, the 2-entry mailbox ring is a shift register;
-//   * an EMPTY leaf (43 % of the leaves C4's bounce rays reach) is popped inside the interior step that finds it,
-//     so the lane keeps descending in the same trip instead of idling until the trip's end;
+//   * the todo list holds 8-byte entries (node, tmax) -- the popped tmin is the current tmax, see below;
+//   * repeats are filtered by a hashed table of recently tested primitives in shared memory (pb_kd.h);
+//   * (PB_LEAN_INLINE_POP, off) an EMPTY leaf -- 43 % of the leaves C4's bounce rays reach -- can be popped inside
+//     the interior step that finds it, so that the lane keeps descending in the same trip.  The instruction-count
+//     model liked it (-7 %), the GPU did not: the pop's local-memory loads sit in the divergent leaf branch of every
+//     interior step and their latency is exposed there (C4 closest hit 117.5 ms with, 108.2 ms without;
+//     profiles/r02g_sweep_walk_variants.log);
 //   * the interior phase runs while at least PB_DESCEND_LANES lanes are still descending (at most PB_DESCEND_MAX
 //     steps) instead of a fixed step count (tools/simt_sim2.py: -17 % issued instructions on C4's bounce rays);
 //   * hit.t is not carried: it always equals ray.maxt once something was hit.
@@ -315,7 +320,7 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
 #define PB_DESCEND_MAX 8
 #endif
 #ifndef PB_LEAN_INLINE_POP
-#define PB_LEAN_INLINE_POP 1
+#define PB_LEAN_INLINE_POP 0   // pop an empty leaf inside the interior step that finds it (measured: slower, see below)
 #endif
 #ifndef PB_LEAN_LEAF_STEPS
 #define PB_LEAN_LEAF_STEPS 2

@@ -14,6 +14,12 @@
 //   * treelets are written breadth first, which keeps the top of the tree -- shared by every ray -- contiguous.
 // Lines are packed first-fit in that order (a treelet that does not fit the rest of the current line starts the
 // next one); unused entries are empty leaves nothing points to.
+//
+// MEASURED (profiles/r02g_sweep_walk_variants.log, rows "[default]" = treelets, "[9=0]" = depth first): no gain on
+// any configuration -- C4 248.6 vs 247.4 ms, C5 1587.8 vs 1591.1 ms per frame.  The wait after a node fetch is the
+// latency of the slowest of a warp's ~14 concurrent fetches into an L2-resident tree, which a better line layout
+// does not shorten; the L1 misses come from the per-lane todo lists and primitive data.  Kept behind tunable 9
+// (default off) with its CPU test (tests/test_oracle.py::test_treelet_node_order_changes_no_hit_and_no_counter).
 #ifndef PB_TREELET_H
 #define PB_TREELET_H
 #include <stdint.h>

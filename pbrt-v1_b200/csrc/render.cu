@@ -62,7 +62,7 @@ static int64_t g_overlap = 0;             // key 5: run shadow/probe traversal o
 static int64_t g_debugCounts = 0;         // key 6: print each wave's queue sizes per iteration to stderr
 static int64_t g_reserved4 = 0;           // key 4: reserved (was the fused shade kernel's occupancy variant)
 static int64_t g_fastPath = 1;            // key 8: k_path_fast shades flat-triangle / matte vertices in one pass (0: general three-kernel pipeline only)
-static int64_t g_treelets = 1;            // key 9: device node order of the top-level tree: sibling pairs in line-sized treelets (pb_treelet.h; 0: the reference's depth-first array)
+static int64_t g_treelets = 0;            // key 9: device node order of the top-level tree: 1 = sibling pairs in line-sized treelets (pb_treelet.h), 0 = the reference's depth-first array (default: the re-ordering measured no gain, profiles/r02g_sweep_walk_variants.log)
 static int64_t g_primFrames = 1;          // key 7: precompute hit-independent BSDF / light-triangle frames at scene create (0: evaluate per hit)
 
 #ifndef PB_DIRECT_MIN_BLOCKS
