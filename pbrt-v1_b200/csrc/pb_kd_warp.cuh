@@ -314,7 +314,18 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
 //     steps) instead of a fixed step count (tools/simt_sim2.py: -17 % issued instructions on C4's bounce rays);
 //   * hit.t is not carried: it always equals ray.maxt once something was hit.
 #ifndef PB_DESCEND_LANES
-#define PB_DESCEND_LANES 12
+#define PB_DESCEND_LANES 8    // (profiles/r02h_sweep_walk_tuning.log: 8 < 12 < 16 on C3, C4 and C5)
+#endif
+// Idle lanes fetch new rays once this many of the warp's lanes are idle.  Small trees (C3: 61 nodes) like full
+// refills, big ones earlier ones: C4 247.7 -> 237.1 ms and C5 1592 -> 1535 ms with 8 instead of 16, C3 127.8 -> 130.1.
+#ifndef PB_REFILL_SMALL
+#define PB_REFILL_SMALL PB_REFILL_THRESHOLD
+#endif
+#ifndef PB_REFILL_BIG
+#define PB_REFILL_BIG 8
+#endif
+#ifndef PB_BIG_TREE_NODES
+#define PB_BIG_TREE_NODES 100000u
 #endif
 #ifndef PB_DESCEND_MAX
 #define PB_DESCEND_MAX 8
@@ -337,7 +348,10 @@ __device__ __forceinline__ void pb_pick_axis(uint32_t axis, const V3 &o, const V
       : "=&f"(*oa), "=&f"(*ia)
       : "r"(axis), "f"(o.x), "f"(o.y), "f"(o.z), "f"(inv.x), "f"(inv.y), "f"(inv.z));
 }
-enum { PB_LS_IDLE = 0, PB_LS_DESCEND = 1, PB_LS_LEAF = 2, PB_LS_FINISHED = 3 };
+enum { PB_LS_IDLE = 0, PB_LS_DESCEND = 1, PB_LS_LEAF = 2, PB_LS_FINISHED = 3, PB_LS_QUADRIC = 4 };
+#ifndef PB_QUADRIC_LANES
+#define PB_QUADRIC_LANES 4   // parked quadric tests run once this many lanes of the warp hold one
+#endif
 
 template <bool ANY, bool COUNT, int QK, class Source, class Sink>
 __device__ __forceinline__ void kd_warp_traverse_lean(const SceneView &sv, uint32_t n, uint32_t *work,
@@ -368,11 +382,13 @@ __device__ __forceinline__ void kd_warp_traverse_lean(const SceneView &sv, uint3
   uint32_t mb0 = 0xffffffffu, mb1 = 0xffffffffu;   // the two most recently tested primitives
   Hit hit;
   hit.prim = -1; hit.t = 0.f; hit.b1 = hit.b2 = 0.f; hit.inst = -1;
+  uint32_t parkedPrim = 0;    // PB_LS_QUADRIC: the quadric waiting to be tested
   const uint2 *nodes = (const uint2 *)sv.nodes;
+  const uint32_t refillAt = sv.nNodes > PB_BIG_TREE_NODES ? (uint32_t)PB_REFILL_BIG : (uint32_t)PB_REFILL_SMALL;
   for (;;) {
     // ---- refill idle lanes
     const uint32_t idleMask = __ballot_sync(0xffffffffu, state == PB_LS_IDLE);
-    if (!exhausted && (uint32_t)__popc(idleMask) >= (idleMask == 0xffffffffu ? 1u : PB_REFILL_THRESHOLD)) {
+    if (!exhausted && (uint32_t)__popc(idleMask) >= (idleMask == 0xffffffffu ? 1u : refillAt)) {
       uint32_t base = 0;
       const uint32_t nIdle = (uint32_t)__popc(idleMask);
       if (lane == 0) base = atomicAdd(work, nIdle);
@@ -476,11 +492,44 @@ __device__ __forceinline__ void kd_warp_traverse_lean(const SceneView &sv, uint3
         }
       }
     }
-    // ---- C. the expensive part, all lanes with work together
+    // ---- C. the expensive part, all lanes with work together.  Scenes with quadrics: a lane whose primitive is
+    //      not a triangle parks (PB_LS_QUADRIC) instead of testing at once -- the quadric test is ~800 instructions
+    //      (object-space transform, IEEE divisions and square root) and the lanes that need it are few: ncu on C3's
+    //      closest-hit kernel showed it running with ONE active lane in a sixth of the trips, a third of all issued
+    //      instructions (profiles/r02h_ncu_trav_def_c3.txt).  Parked lanes are tested together once PB_QUADRIC_LANES
+    //      of them wait or nothing else in the warp can advance; a parked lane simply resumes later, so its own
+    //      sequence of tests is unchanged.
     if (pending) {
       if (COUNT) ++cnt.tests;
-      if (kd_test_prim<ANY, QK>(sv, prim, ray, &hit)) {
-        if (ANY) { hit.prim = 0; state = PB_LS_FINISHED; }
+      if (QK == PB_QK_TRI) {
+        if (kd_test_prim<ANY, PB_QK_TRI>(sv, prim, ray, &hit)) {
+          if (ANY) { hit.prim = 0; state = PB_LS_FINISHED; }
+        }
+      } else {
+        const TriVerts tv = load_prim(sv, prim);
+        if ((tv.flags & PBRT_B200_PF_KIND_MASK) == PBRT_B200_PRIM_TRIANGLE) {
+          float t, b1, b2;
+          if (tri_test(tv.p1, tv.p2, tv.p3, ray, &t, &b1, &b2)) {
+            if (ANY) { hit.prim = 0; state = PB_LS_FINISHED; }
+            else { hit.prim = (int32_t)prim; hit.b1 = b1; hit.b2 = b2; ray.maxt = t; }
+          }
+        } else {
+          parkedPrim = prim;
+          state = PB_LS_QUADRIC;
+        }
+      }
+    }
+    if (QK != PB_QK_TRI) {
+      const uint32_t qm = __ballot_sync(0xffffffffu, state == PB_LS_QUADRIC);
+      if (qm != 0u) {
+        bool run = (uint32_t)__popc(qm) >= (uint32_t)PB_QUADRIC_LANES || exhausted;
+        if (!run) run = __ballot_sync(0xffffffffu, state == PB_LS_DESCEND || (state == PB_LS_LEAF && leafI < leafN)) == 0u;
+        if (run && state == PB_LS_QUADRIC) {
+          state = PB_LS_LEAF;
+          if (kd_test_prim<ANY, QK>(sv, parkedPrim, ray, &hit)) {
+            if (ANY) { hit.prim = 0; state = PB_LS_FINISHED; }
+          }
+        }
       }
     }
     // ---- D. leaf finished: next node from the todo list (kdtree.cpp:392-399)

@@ -464,7 +464,9 @@ __device__ __forceinline__ void flush_kd_counters(unsigned long long *stats, int
 #ifndef PB_LEAN_WALK
 #define PB_LEAN_WALK 1   // scenes without object instances walk with kd_warp_traverse_lean (0: the general loop, for A/B)
 #endif
+#ifndef PB_BIG_TREE_NODES
 #define PB_BIG_TREE_NODES 100000u   // top-level trees above this many nodes use PB_DESCEND_STEPS_BIG
+#endif
 template <bool COUNT, int QK, int DS>
 __global__ void __launch_bounds__(PB_BLOCK, QK == PB_QK_INSTANCES ? PB_TRAV_INST_MIN_BLOCKS
                                             : QK == PB_QK_TRI ? PB_TRAV_TRI_MIN_BLOCKS : PB_TRAV_MIN_BLOCKS)
