@@ -350,7 +350,7 @@ __device__ __forceinline__ void pb_pick_axis(uint32_t axis, const V3 &o, const V
 }
 enum { PB_LS_IDLE = 0, PB_LS_DESCEND = 1, PB_LS_LEAF = 2, PB_LS_FINISHED = 3, PB_LS_QUADRIC = 4 };
 #ifndef PB_QUADRIC_LANES
-#define PB_QUADRIC_LANES 4   // parked quadric tests run once this many lanes of the warp hold one
+#define PB_QUADRIC_LANES 1   // > 1: quadric tests are parked until this many lanes of the warp hold one (measured: slower)
 #endif
 
 template <bool ANY, bool COUNT, int QK, class Source, class Sink>
@@ -492,17 +492,16 @@ __device__ __forceinline__ void kd_warp_traverse_lean(const SceneView &sv, uint3
         }
       }
     }
-    // ---- C. the expensive part, all lanes with work together.  Scenes with quadrics: a lane whose primitive is
-    //      not a triangle parks (PB_LS_QUADRIC) instead of testing at once -- the quadric test is ~800 instructions
-    //      (object-space transform, IEEE divisions and square root) and the lanes that need it are few: ncu on C3's
-    //      closest-hit kernel showed it running with ONE active lane in a sixth of the trips, a third of all issued
-    //      instructions (profiles/r02h_ncu_trav_def_c3.txt).  Parked lanes are tested together once PB_QUADRIC_LANES
-    //      of them wait or nothing else in the warp can advance; a parked lane simply resumes later, so its own
-    //      sequence of tests is unchanged.
+    // ---- C. the expensive part, all lanes with work together.  (PB_QUADRIC_LANES > 1, an experiment: a lane whose
+    //      primitive is not a triangle parks in PB_LS_QUADRIC and the parked lanes are tested together once that
+    //      many wait or nothing else in the warp can advance -- the quadric test is several hundred instructions and
+    //      on C3's bounce rays it runs with one or two active lanes.  A parked lane resumes later with its own
+    //      sequence of tests unchanged, but its idle trips cost more than the fuller quadric tests return: C3 frame
+    //      128.3 / 128.6 / 130.2 / 134.6 ms with 1 / 2 / 4 / 8 lanes, profiles/r02i_sweep_quadric_parking.log.)
     if (pending) {
       if (COUNT) ++cnt.tests;
-      if (QK == PB_QK_TRI) {
-        if (kd_test_prim<ANY, PB_QK_TRI>(sv, prim, ray, &hit)) {
+      if (QK == PB_QK_TRI || PB_QUADRIC_LANES <= 1) {
+        if (kd_test_prim<ANY, QK>(sv, prim, ray, &hit)) {
           if (ANY) { hit.prim = 0; state = PB_LS_FINISHED; }
         }
       } else {
@@ -519,7 +518,7 @@ __device__ __forceinline__ void kd_warp_traverse_lean(const SceneView &sv, uint3
         }
       }
     }
-    if (QK != PB_QK_TRI) {
+    if (QK != PB_QK_TRI && PB_QUADRIC_LANES > 1) {
       const uint32_t qm = __ballot_sync(0xffffffffu, state == PB_LS_QUADRIC);
       if (qm != 0u) {
         bool run = (uint32_t)__popc(qm) >= (uint32_t)PB_QUADRIC_LANES || exhausted;

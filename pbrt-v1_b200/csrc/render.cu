@@ -58,7 +58,7 @@ static int fail(int code, const std::string &msg) {
 static int64_t g_waveSamples = 1 << 24;   // key 0: image samples per wave (16 Mi: ~5.4 GB of wave state)
 static int64_t g_countKd = 0;             // key 1: collect kd-walk counters (costs a little time)
 static int64_t g_blocksPerSM = 12;        // key 2: resident CTAs per SM for the persistent kernels
-static int64_t g_overlap = 0;             // key 5: run shadow/probe traversal on a second stream, overlapped (measured +1%: both sides are issue bound, so off by default)
+static int64_t g_overlap = 0;             // key 5: 1 = shadow + probe traversal on a second stream beside the next kernels (measured +1 %: both sides are issue bound), 2 = only the MIS probes on the second stream, beside the shadow rays
 static int64_t g_debugCounts = 0;         // key 6: print each wave's queue sizes per iteration to stderr
 static int64_t g_reserved4 = 0;           // key 4: reserved (was the fused shade kernel's occupancy variant)
 static int64_t g_fastPath = 1;            // key 8: k_path_fast shades flat-triangle / matte vertices in one pass (0: general three-kernel pipeline only)
@@ -497,8 +497,9 @@ struct ShadowSource {
 // the path integrator's per-slot record
 __device__ __forceinline__ void rec_flag_set(uint8_t *recFlags, float4 *prec, uint32_t rec, uint32_t bit) {
   if (prec) {
-    uint32_t *w = reinterpret_cast<uint32_t *>(&prec[rec]) + 3;
-    *w |= bit;
+    // (atomic: the shadow and the probe kernel of one vertex may run concurrently, tunable 5, and a record can
+    // be waiting for both)
+    atomicOr(reinterpret_cast<uint32_t *>(&prec[rec]) + 3, bit);
   } else
     recFlags[rec] |= (uint8_t)bit;
 }
@@ -1858,7 +1859,7 @@ static void launch_traversals_a(PbrtB200Handle *h, bool count, int grid, const R
   else PB_LAUNCH_INTERSECT(false, PB_QK_INSTANCES);
 }
 static void launch_traversals_b(PbrtB200Handle *h, bool count, int grid, uint32_t *nShadow, uint32_t *nProbe,
-                                uint32_t *workS, uint32_t *workP, cudaStream_t strm) {
+                                uint32_t *workS, uint32_t *workP, cudaStream_t strm, cudaStream_t probeStrm) {
   WaveBuffers &wb = h->wb;
   // MIS probes are rare (the BSDF sample must point at the light): a small grid avoids paying the
   // ramp-up of the full persistent grid for a few thousand rays
@@ -1869,9 +1870,9 @@ static void launch_traversals_b(PbrtB200Handle *h, bool count, int grid, uint32_
     else
       TIMED_ON(KC_SHADOW, strm, (k_shadow<true, PB_QK_ALL, PB_DESCEND_STEPS><<<grid, PB_BLOCK, 0, strm>>>(h->sv, wb.shadowQ, nShadow, workS, wb.recFlags, wb.prec, wb.stats)));
     if (h->primKinds == PB_QK_INSTANCES)
-      TIMED_ON(KC_PROBE, strm, (k_probe<true, true><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.prec, wb.stats)));
+      TIMED_ON(KC_PROBE, probeStrm, (k_probe<true, true><<<probeGrid, PB_BLOCK, 0, probeStrm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.prec, wb.stats)));
     else
-      TIMED_ON(KC_PROBE, strm, (k_probe<true, false><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.prec, wb.stats)));
+      TIMED_ON(KC_PROBE, probeStrm, (k_probe<true, false><<<probeGrid, PB_BLOCK, 0, probeStrm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.prec, wb.stats)));
   } else {
 #define PB_LAUNCH_SHADOW(QK_)                                                                                                    \
   do {                                                                                                                         \
@@ -1885,9 +1886,9 @@ static void launch_traversals_b(PbrtB200Handle *h, bool count, int grid, uint32_
     else if (h->primKinds == PB_QK_ALL) PB_LAUNCH_SHADOW(PB_QK_ALL);
     else PB_LAUNCH_SHADOW(PB_QK_INSTANCES);
     if (h->primKinds == PB_QK_INSTANCES)
-      TIMED_ON(KC_PROBE, strm, (k_probe<false, true><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.prec, wb.stats)));
+      TIMED_ON(KC_PROBE, probeStrm, (k_probe<false, true><<<probeGrid, PB_BLOCK, 0, probeStrm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.prec, wb.stats)));
     else
-      TIMED_ON(KC_PROBE, strm, (k_probe<false, false><<<probeGrid, PB_BLOCK, 0, strm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.prec, wb.stats)));
+      TIMED_ON(KC_PROBE, probeStrm, (k_probe<false, false><<<probeGrid, PB_BLOCK, 0, probeStrm>>>(h->sv, wb.probeQ, nProbe, workP, wb.recFlags, wb.prec, wb.stats)));
   }
 }
 
@@ -1922,7 +1923,8 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
   bool isPath = sv.integrator.kind == PBRT_B200_INT_PATH;
   int cur = 0;
   WaveKeyInfo wk = {wb.pixel, wd.spp, wd.bc ? 1 : (sv.sampler.kind == PBRT_B200_SAMPLER_RANDOM ? 2 : 0)};
-  bool overlap = g_overlap != 0;
+  const bool overlap = g_overlap == 1;                 // shadow + probe on the aux stream, beside the next closest-hit launch
+  const bool probeAside = g_overlap == 2 && !count;    // only the probes on the aux stream, beside the shadow rays
   // (LD kernels = patterns read from per-unit tables: lowdiscrepancy and bestcandidate)
   const bool isLD = sv.sampler.kind == PBRT_B200_SAMPLER_LOWDISCREPANCY || wd.bc;
   if (isPath) {
@@ -1934,7 +1936,7 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
       uint32_t *nNext = &wb.counts[4 * (it + 1)];
       launch_traversals_a(h, count, grid, wb.q[cur], nMain, nextWork());
       // the previous vertex's shadow / probe results are folded in by k_path_surface
-      if (overlap && it > 0) CU_TRY(cudaStreamWaitEvent(st, h->evAux, 0));
+      if ((overlap || probeAside) && it > 0) CU_TRY(cudaStreamWaitEvent(st, h->evAux, 0));
       {
         SurfaceRecord rec;
         for (int k = 0; k < 15; ++k) rec.f[k] = wb.surf[k];
@@ -1974,7 +1976,7 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
           // k_path_continue and the next k_intersect (they share no data)
           CU_TRY(cudaEventRecord(h->evDirect, st));
           CU_TRY(cudaStreamWaitEvent(h->auxStream, h->evDirect, 0));
-          launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork(), h->auxStream);
+          launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork(), h->auxStream, h->auxStream);
           CU_TRY(cudaEventRecord(h->evAux, h->auxStream));
         }
 #define PB_LAUNCH_CONT(LD_, G_)                                                                                    \
@@ -1983,11 +1985,19 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
         if (isLD) { if (h->hasGlossy) PB_LAUNCH_CONT(true, true); else PB_LAUNCH_CONT(true, false); }
         else { if (h->hasGlossy) PB_LAUNCH_CONT(false, true); else PB_LAUNCH_CONT(false, false); }
       }
-      if (!overlap) launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork(), st);
+      if (probeAside) {
+        // the few MIS probes of this vertex (a latency-bound launch that leaves most of the GPU idle) run on the aux
+        // stream beside the shadow rays and the next closest-hit launch; the next vertex's shading waits for them
+        CU_TRY(cudaEventRecord(h->evDirect, st));
+        CU_TRY(cudaStreamWaitEvent(h->auxStream, h->evDirect, 0));
+        launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork(), st, h->auxStream);
+        CU_TRY(cudaEventRecord(h->evAux, h->auxStream));
+      } else if (!overlap)
+        launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork(), st, st);
       *launches += 6;
       cur ^= 1;
     }
-    if (overlap) CU_TRY(cudaStreamWaitEvent(st, h->evAux, 0));
+    if (overlap || probeAside) CU_TRY(cudaStreamWaitEvent(st, h->evAux, 0));
   } else {
     // Whitted / DirectLighting: the recursion depth is data dependent; one host readback of
     // the queue size per iteration ends the loop.
@@ -2010,7 +2020,7 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
       launch_traversals_a(h, count, grid, wb.q[cur], nMain, nextWork());
       if (h->textured) TIMED(KC_SHADE, (k_shade_wd<true><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], nMain, nextWork(), nShadow, nProbe)));
       else TIMED(KC_SHADE, (k_shade_wd<false><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], nMain, nextWork(), nShadow, nProbe)));
-      launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork(), st);
+      launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork(), st, st);
       TIMED(KC_ADVANCE, (k_advance_wd<<<grid, PB_BLOCK, 0, st>>>(sv, wb, wb.q[cur], wb.q[cur ^ 1], nMain, nextWork(), nNext)));
       *launches += 5;
       CU_TRY(cudaMemcpyAsync(&nMainHost, nNext, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
