@@ -412,7 +412,9 @@ int pbrt_b200_render_host(const PbrtB200Scene *scene, int device,
  * key 1: collect the kd-walk counters of PbrtB200Stats (default off: they cost time)
  * key 2: resident CTAs per SM of the persistent kernels
  * key 3: bracket every kernel launch with CUDA events (pbrt_b200_kernel_stats)
- * key 5: overlap shadow/probe traversal with the next kernels on a second stream (default off: measured +1 %)
+ * key 5: streams of one wave: 0 = one; 1 (default) = a path vertex's shadow + probe traversal on a second stream,
+ *        beside the continuation kernel and the next closest-hit launch; 2 = only the probes on the second stream;
+ *        3 = like 1 with the probes on a third stream
  * key 6: print per-iteration queue sizes of every wave to stderr (profiling aid)
  * key 7: precompute the hit-independent BSDF frames of flat triangles and the light triangles' normals at
  *        scene create (default on; 0 evaluates them at every hit -- same bits, A/B switch for the profiles)

@@ -58,7 +58,7 @@ static int fail(int code, const std::string &msg) {
 static int64_t g_waveSamples = 1 << 24;   // key 0: image samples per wave (16 Mi: ~5.4 GB of wave state)
 static int64_t g_countKd = 0;             // key 1: collect kd-walk counters (costs a little time)
 static int64_t g_blocksPerSM = 12;        // key 2: resident CTAs per SM for the persistent kernels
-static int64_t g_overlap = 0;             // key 5: 1 = shadow + probe traversal on a second stream beside the next kernels (measured +1 %: both sides are issue bound), 2 = only the MIS probes on the second stream, beside the shadow rays
+static int64_t g_overlap = 1;             // key 5: 0 = one stream; 1 (default) = a vertex's shadow + probe traversal on a second stream beside k_path_continue and the next closest-hit launch; 2 = only the MIS probes on the second stream, beside the shadow rays; 3 = 1 with the probes on a third stream.  C3 is issue bound (+1 %), the big trees wait on L2 and two traversal kernels side by side fill each other's stalls: C4 237.3 -> 224.8 ms, C5 1542 -> 1396 ms per frame (profiles/r02j_sweep_streams.log)
 static int64_t g_debugCounts = 0;         // key 6: print each wave's queue sizes per iteration to stderr
 static int64_t g_reserved4 = 0;           // key 4: reserved (was the fused shade kernel's occupancy variant)
 static int64_t g_fastPath = 1;            // key 8: k_path_fast shades flat-triangle / matte vertices in one pass (0: general three-kernel pipeline only)
@@ -1570,7 +1570,8 @@ struct PbrtB200Handle {
   int device;
   cudaStream_t stream;
   cudaStream_t auxStream;        // shadow / probe traversal overlaps the main stream's next kernels
-  cudaEvent_t evDirect, evAux;
+  cudaStream_t auxStream2;       // (tunable 5 = 3: the probes' own stream)
+  cudaEvent_t evDirect, evAux, evAux2;
   int numSMs;
   SceneView sv;                 // device pointers
   std::vector<void *> allocs;   // scene arrays
@@ -1923,7 +1924,8 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
   bool isPath = sv.integrator.kind == PBRT_B200_INT_PATH;
   int cur = 0;
   WaveKeyInfo wk = {wb.pixel, wd.spp, wd.bc ? 1 : (sv.sampler.kind == PBRT_B200_SAMPLER_RANDOM ? 2 : 0)};
-  const bool overlap = g_overlap == 1;                 // shadow + probe on the aux stream, beside the next closest-hit launch
+  const bool overlap3 = g_overlap == 3 && !count;      // like 1, and the probes on a third stream beside the shadow rays
+  const bool overlap = g_overlap == 1 || overlap3;     // shadow + probe on the aux stream, beside the next closest-hit launch
   const bool probeAside = g_overlap == 2 && !count;    // only the probes on the aux stream, beside the shadow rays
   // (LD kernels = patterns read from per-unit tables: lowdiscrepancy and bestcandidate)
   const bool isLD = sv.sampler.kind == PBRT_B200_SAMPLER_LOWDISCREPANCY || wd.bc;
@@ -1937,6 +1939,7 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
       launch_traversals_a(h, count, grid, wb.q[cur], nMain, nextWork());
       // the previous vertex's shadow / probe results are folded in by k_path_surface
       if ((overlap || probeAside) && it > 0) CU_TRY(cudaStreamWaitEvent(st, h->evAux, 0));
+      if (overlap3 && it > 0) CU_TRY(cudaStreamWaitEvent(st, h->evAux2, 0));
       {
         SurfaceRecord rec;
         for (int k = 0; k < 15; ++k) rec.f[k] = wb.surf[k];
@@ -1976,8 +1979,11 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
           // k_path_continue and the next k_intersect (they share no data)
           CU_TRY(cudaEventRecord(h->evDirect, st));
           CU_TRY(cudaStreamWaitEvent(h->auxStream, h->evDirect, 0));
-          launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork(), h->auxStream, h->auxStream);
+          if (overlap3) CU_TRY(cudaStreamWaitEvent(h->auxStream2, h->evDirect, 0));
+          launch_traversals_b(h, count, grid, nShadow, nProbe, nextWork(), nextWork(), h->auxStream,
+                              overlap3 ? h->auxStream2 : h->auxStream);
           CU_TRY(cudaEventRecord(h->evAux, h->auxStream));
+          if (overlap3) CU_TRY(cudaEventRecord(h->evAux2, h->auxStream2));
         }
 #define PB_LAUNCH_CONT(LD_, G_)                                                                                    \
   TIMED(KC_SHADE_CONT, (k_path_continue<LD_, G_><<<grid, PB_BLOCK, 0, st>>>(sv, wb, wk, wb.q[cur], wb.q[cur ^ 1], rec, \
@@ -1998,6 +2004,7 @@ static int run_wave(PbrtB200Handle *h, const WaveDesc &wd, uint64_t *launches) {
       cur ^= 1;
     }
     if (overlap || probeAside) CU_TRY(cudaStreamWaitEvent(st, h->evAux, 0));
+    if (overlap3) CU_TRY(cudaStreamWaitEvent(st, h->evAux2, 0));
   } else {
     // Whitted / DirectLighting: the recursion depth is data dependent; one host readback of
     // the queue size per iteration ends the loop.
@@ -2076,6 +2083,7 @@ void pbrt_b200_scene_destroy(PbrtB200Handle *h) {
   // (released blocks may still be read by queued work of this handle's streams: drain them first)
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->auxStream) cudaStreamSynchronize(h->auxStream);
+  if (h->auxStream2) cudaStreamSynchronize(h->auxStream2);
   free_films(h);
   free_wave(h);
   for (void *p : h->allocs) pool_free(h->device, p);
@@ -2086,7 +2094,9 @@ void pbrt_b200_scene_destroy(PbrtB200Handle *h) {
   for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
   if (h->evDirect) cudaEventDestroy(h->evDirect);
   if (h->evAux) cudaEventDestroy(h->evAux);
+  if (h->evAux2) cudaEventDestroy(h->evAux2);
   if (h->auxStream) cudaStreamDestroy(h->auxStream);
+  if (h->auxStream2) cudaStreamDestroy(h->auxStream2);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -2110,7 +2120,7 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   }
   if (devMajor[device] < 10) return fail(PBRT_B200_ERR_NO_DEVICE, "device is not sm_100 class");
   PbrtB200Handle *h = new PbrtB200Handle();
-  h->device = device; h->stream = nullptr; h->auxStream = nullptr; h->evDirect = nullptr; h->evAux = nullptr;
+  h->device = device; h->stream = nullptr; h->auxStream = nullptr; h->auxStream2 = nullptr; h->evDirect = nullptr; h->evAux = nullptr; h->evAux2 = nullptr;
   h->numSMs = devSMs[device];
   h->filterTable = nullptr; h->bcMasks = nullptr; h->arena = nullptr; h->arenaBytes = 0; h->sceneBytes = 0; h->keepSamples = false;
   memset(&h->wb, 0, sizeof(h->wb));
@@ -2158,6 +2168,8 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   int rc = PBRT_B200_OK;
   cudaError_t ce = cudaStreamCreate(&h->stream);
   if (ce == cudaSuccess) ce = cudaStreamCreate(&h->auxStream);
+  if (ce == cudaSuccess) ce = cudaStreamCreate(&h->auxStream2);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evAux2, cudaEventDisableTiming);
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evDirect, cudaEventDisableTiming);
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evAux, cudaEventDisableTiming);
   if (ce != cudaSuccess) { delete h; return fail(PBRT_B200_ERR_CUDA, cudaGetErrorString(ce)); }
