@@ -407,14 +407,15 @@ int pbrt_b200_render_host(const PbrtB200Scene *scene, int device,
                           PbrtB200Stats *stats);
 
 /* Tunables; returns the previous value, value < 0 only queries.
- * key 0: image samples per wave (default 16 Mi = ~5.4 GB of wave state for the path integrator; a frame whose
- *        sample count exceeds it is cut into equal waves)
+ * key 0: image samples per wave (default 64 Mi = ~21.6 GB of wave state for the path integrator, 16 Mi for whitted /
+ *        directlighting; never more than half of the device's free memory; a frame whose sample count exceeds it
+ *        is cut into equal waves)
  * key 1: collect the kd-walk counters of PbrtB200Stats (default off: they cost time)
  * key 2: resident CTAs per SM of the persistent kernels
  * key 3: bracket every kernel launch with CUDA events (pbrt_b200_kernel_stats)
- * key 5: streams of one wave: 0 = one; 1 (default) = a path vertex's shadow + probe traversal on a second stream,
+ * key 5: streams of one wave: 0 = one; 1 = a path vertex's shadow + probe traversal on a second stream,
  *        beside the continuation kernel and the next closest-hit launch; 2 = only the probes on the second stream;
- *        3 = like 1 with the probes on a third stream
+ *        3 (default) = like 1 with the probes on a third stream
  * key 6: print per-iteration queue sizes of every wave to stderr (profiling aid)
  * key 7: precompute the hit-independent BSDF frames of flat triangles and the light triangles' normals at
  *        scene create (default on; 0 evaluates them at every hit -- same bits, A/B switch for the profiles)

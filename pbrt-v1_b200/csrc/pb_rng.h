@@ -16,7 +16,12 @@
 #define PB_RNG_H
 #include "pb_math.h"
 
-PB_HD uint64_t pb_mix64(uint64_t z) {
+#ifdef PB_MIX_NOINLINE   // experiment: one out-of-line copy of the mixer instead of ~20 inlined ones per shading kernel
+PB_NOINLINE
+#else
+PB_HD
+#endif
+uint64_t pb_mix64(uint64_t z) {
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
   return z ^ (z >> 31);

@@ -55,10 +55,10 @@ static int fail(int code, const std::string &msg) {
 
 // ------------------------------------------------------------------------------------------
 // tunables (pbrt_b200_tunable)
-static int64_t g_waveSamples = 1 << 24;   // key 0: image samples per wave (16 Mi: ~5.4 GB of wave state)
+static int64_t g_waveSamples = 1 << 26;   // key 0: image samples per wave, path integrator (64 Mi: ~21.6 GB of wave state on a 180 GB part; C5 1387 / 1274 / 1225 ms per frame with 16 / 32 / 64 Mi, profiles/r02k_sweep_streams_waves.log: a wave is ~46 launches whose tails run almost empty, so fewer, larger waves waste less)
 static int64_t g_countKd = 0;             // key 1: collect kd-walk counters (costs a little time)
 static int64_t g_blocksPerSM = 12;        // key 2: resident CTAs per SM for the persistent kernels
-static int64_t g_overlap = 1;             // key 5: 0 = one stream; 1 (default) = a vertex's shadow + probe traversal on a second stream beside k_path_continue and the next closest-hit launch; 2 = only the MIS probes on the second stream, beside the shadow rays; 3 = 1 with the probes on a third stream.  C3 is issue bound (+1 %), the big trees wait on L2 and two traversal kernels side by side fill each other's stalls: C4 237.3 -> 224.8 ms, C5 1542 -> 1396 ms per frame (profiles/r02j_sweep_streams.log)
+static int64_t g_overlap = 3;             // key 5: 0 = one stream; 1 = a vertex's shadow + probe traversal on a second stream beside k_path_continue and the next closest-hit launch; 2 = only the MIS probes on the second stream, beside the shadow rays; 3 (default) = 1 with the probes on a third stream.  C3 is issue bound (+1 %), the big trees wait on L2 and two traversal kernels side by side fill each other's stalls: C4 237.3 -> 224.8 ms, C5 1542 -> 1396 ms per frame (profiles/r02j_sweep_streams.log)
 static int64_t g_debugCounts = 0;         // key 6: print each wave's queue sizes per iteration to stderr
 static int64_t g_reserved4 = 0;           // key 4: reserved (was the fused shade kernel's occupancy variant)
 static int64_t g_fastPath = 1;            // key 8: k_path_fast shades flat-triangle / matte vertices in one pass (0: general three-kernel pipeline only)
@@ -2359,7 +2359,32 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
   // tunable allows, and a remainder of less than 1/16 wave is absorbed by growing the waves instead of paying a
   // whole extra round of ~40 launches for it (C3: 67.24 M samples = 4 waves of 16.81 M, not 4 x 16.78 M + 0.13 M).
   const uint64_t units = totalSamples / spp;
-  const uint64_t unitCap = std::max<uint64_t>(1, (uint64_t)g_waveSamples / spp);
+  // The tunable bounds a wave; so do the 32-bit record index of the whitted / directlighting queues
+  // (record * nSlots + slot) and the device's memory: a wave's arena may take half of what is free now (plus
+  // this device's retired arena, which ensure_wave() would reuse).  The per-slot state of whitted / directlighting
+  // (recursion frames) is several times the path integrator's: they keep the 16 Mi-sample bound of round 1.
+  uint64_t waveSamples = (uint64_t)g_waveSamples;
+  if (h->sv.integrator.kind != PBRT_B200_INT_PATH) waveSamples = std::min<uint64_t>(waveSamples, 1ull << 24);
+  waveSamples = std::min<uint64_t>(waveSamples, 0xffffffffull / (uint64_t)std::max(1, h->sv.directRecords));
+  {
+    Carver sizing = {nullptr, 0};
+    WaveBuffers tmp;
+    const uint32_t probe = 1u << 20;
+    carve_wave(sizing, tmp, probe, h->sv.directRecords, h->nFrames, h->sv.integrator.kind == PBRT_B200_INT_PATH,
+               h->sv.ldFloatsPerSample, h->sv.nInstances != 0, h->textured);
+    const double bytesPerSlot = (double)sizing.off / probe;
+    size_t freeB = 0, totalB = 0;
+    if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
+      size_t reusable = h->arenaBytes;
+      {
+        std::lock_guard<std::mutex> lock(g_poolMutex);
+        if (h->device >= 0 && h->device < PB_MAX_DEVICES) reusable = std::max(reusable, g_cachedArenaBytes[h->device]);
+      }
+      const double budget = std::max(0.5 * (double)freeB, (double)reusable);
+      waveSamples = std::min<uint64_t>(waveSamples, std::max<uint64_t>(1u << 20, (uint64_t)(budget / bytesPerSlot)));
+    }
+  }
+  const uint64_t unitCap = std::max<uint64_t>(1, waveSamples / spp);
   uint64_t nWaves = std::max<uint64_t>(1, (units + unitCap - 1) / unitCap);
   if (nWaves > 1 && units - (nWaves - 1) * unitCap <= unitCap / 16) --nWaves;
   uint64_t capSlots = ((units + nWaves - 1) / nWaves) * spp;
