@@ -407,3 +407,24 @@ KdTreeAccel::KdTreeAccel(const vector<Reference<Primitive> > &p, int icost, int 
     fprintf(stderr, "kd-tree: %zu primitives, refine + bounds %.3f s, build %.3f s (%d threads), %zu nodes\n", np,
             t1 - t0, host_seconds() - t1, threads, nodes.size());
 }
+
+// Test hook (tests/test_oracle.py): sort_events() on `threads` threads against std::sort on the same input --
+// n events at pseudo-random positions drawn from `distinct` values, so that runs of equal keys are long.
+// Returns the number of positions where the two results differ (0 = same permutation).
+extern "C" long pbrt_host_test_sort_events(long n, long distinct, unsigned seed, int threads) {
+  vector<PlaneEvent> a((size_t)n), b;
+  unsigned s = seed * 2654435761u + 12345u;
+  for (long i = 0; i < n; ++i) {
+    s = s * 1664525u + 1013904223u;
+    a[(size_t)i].pos = (float)((s >> 8) % (unsigned)distinct) * 0.25f;
+    s = s * 1664525u + 1013904223u;
+    a[(size_t)i].closes = (unsigned char)((s >> 16) & 1u);
+    a[(size_t)i].prim = (int)i;
+  }
+  b = a;
+  std::sort(a.begin(), a.end(), EventOrder());
+  sort_events(&b[0], &b[0] + n, threads);
+  long diff = 0;
+  for (long i = 0; i < n; ++i) diff += a[(size_t)i].prim != b[(size_t)i].prim;
+  return diff;
+}

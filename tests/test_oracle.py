@@ -409,3 +409,14 @@ def test_treelet_node_order_changes_no_hit_and_no_counter(ffi, tmp_path):
             assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32))
         assert np.array_equal(a[4], b[4]) and a[4][0] > 0
         scene.close()
+
+
+def test_threaded_event_sort_is_std_sort(ffi):
+    """host/kdtree.cpp sorts a big node's events with libstdc++'s introsort run on several threads; the result must
+    be std::sort's permutation exactly, equal keys included (their order decides which child a primitive lands in)."""
+    lib = ffi.host()
+    lib.pbrt_host_test_sort_events.restype = C.c_long
+    lib.pbrt_host_test_sort_events.argtypes = [C.c_long, C.c_long, C.c_uint, C.c_int]
+    for n, distinct, seed, threads in ((200000, 50, 1, 4), (300000, 3000, 2, 8), (150001, 7, 3, 3), (400000, 400000, 4, 16),
+                                       (1000, 10, 5, 8)):
+        assert lib.pbrt_host_test_sort_events(n, distinct, seed, threads) == 0, (n, distinct, seed, threads)
