@@ -10,8 +10,8 @@
 // posts the matching ncclRecv's in one group and pastes all tiles into the frame with one kernel.  No
 // arithmetic happens in the exchange, so the assembled frame is bit-identical to the one-GPU frame.
 //
-// Partition: square tiles of about (pixels / (28 * ranks))^(1/2) on a side, dealt in raster order to rank
-// (i + row(i)) % ranks.  The deal is static on purpose: a wave of a path-traced frame costs ~40 kernel launches
+// Partition: square tiles of about (pixels / (28 * ranks))^(1/2) on a side, tile (col, row) to rank
+// (col + row * shift) % ranks (tile_shift below).  The deal is static on purpose: a wave of a path-traced frame costs ~40 kernel launches
 // whose tails run almost empty, so a rank that fetched its work in many small dynamic batches would pay that
 // fixed cost per batch (measured: ~0.3 ms per wave against a 20 ms frame share at 8 GPUs); ~30 small tiles per
 // rank spread over the whole image balance to within a few per cent and render as ONE wave.  Tile mode culls
@@ -109,7 +109,22 @@ static void frame_tiles(const PbrtB200Window &f, int edge, std::vector<PbrtB200W
       tiles->push_back(t);
     }
 }
-static inline int tile_owner(int i, int cols, int world) { return (i + i / cols) % world; }
+// Owner of tile (col, row): (col + row * shift) mod world, a lattice.  Every rank's tiles are spread evenly over the
+// image in both directions when shift is coprime to world and near world * 0.618 (for 8 ranks: 5).  The round-1 rule
+// (i + i / cols) mod world is this lattice with shift = cols + 1, which degenerates to vertical stripes whenever
+// world divides cols + 1: 4 ranks on a 1024-pixel frame (11 columns of 96-pixel tiles) left one rank with 2 of the
+// 11 columns -- 23.9 ms of work beside 39.3 ms on its neighbour (profiles/r02s_scale_n4.json).
+static inline int tile_shift(int world) {
+  if (world <= 2) return 1;
+  auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+  int s = (int)(world * 0.6180339887 + 0.5);
+  for (int d = 0; d < world; ++d) {
+    if (s + d < world && gcd(s + d, world) == 1) return s + d;
+    if (s - d > 0 && gcd(s - d, world) == 1) return s - d;
+  }
+  return 1;
+}
+static inline int tile_owner(int i, int cols, int world) { return (i % cols + (i / cols) * tile_shift(world)) % world; }
 
 extern "C" {
 

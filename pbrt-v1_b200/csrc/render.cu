@@ -1339,12 +1339,9 @@ __global__ void k_film_reach(const __grid_constant__ SceneView sv, const WaveBuf
 // K5b: ImageFilm::AddSample (film/image.cpp:103-141) as a gather, one thread per pixel.
 // Candidate sample pixels are visited in raster order and their samples in index order:
 // the order in which the reference's serial loop would have splatted them.
-__global__ void __launch_bounds__(PB_BLOCK)
-k_film_gather(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WavePart wd, int spp,
-              const float *filterTable, FilmPixel *film, PbrtB200Window win, int rowFirst, int rowCount) {
-  __shared__ float table[256];
-  for (int t = threadIdx.x; t < 256; t += blockDim.x) table[t] = filterTable[t];
-  __syncthreads();
+__device__ __forceinline__ void film_gather_part(const SceneView &sv, const WaveBuffers &wb, const WavePart &wd, int spp,
+                                                 const float *table, FilmPixel *film, const PbrtB200Window &win,
+                                                 int rowFirst, int rowCount) {
   int total = rowCount * win.width;
   int ew = wd.xe - wd.xs;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -1377,6 +1374,32 @@ k_film_gather(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
       }
     if (touched) *fpx = acc;
   }
+}
+__global__ void __launch_bounds__(PB_BLOCK)
+k_film_gather(const __grid_constant__ SceneView sv, const WaveBuffers wb, const WavePart wd, int spp,
+              const float *filterTable, FilmPixel *film, PbrtB200Window win, int rowFirst, int rowCount) {
+  __shared__ float table[256];
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) table[t] = filterTable[t];
+  __syncthreads();
+  film_gather_part(sv, wb, wd, spp, table, film, win, rowFirst, rowCount);
+}
+// The same for every part of a wave in one launch (blockIdx.y = part): a multi-GPU rank's share of a frame is ~30
+// small tiles in one wave, and one launch per tile made the film the only kernel class that did not shrink with the
+// rank count (8 GPUs: 1.87 ms of a 17.9 ms frame share, profiles/r02s_scale_n8.json).
+struct FilmTargets {
+  FilmPixel *film[PB_MAX_PARTS];
+  PbrtB200Window win[PB_MAX_PARTS];
+  int rowFirst[PB_MAX_PARTS], rowCount[PB_MAX_PARTS];
+};
+__global__ void __launch_bounds__(PB_BLOCK)
+k_film_gather_parts(const __grid_constant__ SceneView sv, const WaveBuffers wb, const __grid_constant__ WaveDesc wd,
+                    const float *filterTable, const __grid_constant__ FilmTargets tg) {
+  __shared__ float table[256];
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) table[t] = filterTable[t];
+  __syncthreads();
+  const int p = blockIdx.y;
+  if (tg.rowCount[p] > 0)
+    film_gather_part(sv, wb, wd.parts[p], wd.spp, table, tg.film[p], tg.win[p], tg.rowFirst[p], tg.rowCount[p]);
 }
 
 // K5b for the bestcandidate sampler: the samples of a table placement are spread over its whole
@@ -1591,6 +1614,7 @@ struct PbrtB200Handle {
   std::vector<WindowFilm> films;
   bool keepSamples;
   PbrtB200Window frameWin;   // the scene film's pixel window (crop window), what tiles are tiles of
+  FilmPixel *filmSlab;       // tile renders: the windows' unresolved films as one block too (one memset, one resolve)
   float4 *rgbaSlab;          // when the windows' resolved pixels were allocated as one block (tile renders): its base
   size_t rgbaSlabFloats;
   // multi-GPU frames (multi.cuh), rank 0: the assembled frame + staging for the other ranks' tile blocks, tile table
@@ -1829,14 +1853,16 @@ static int ensure_wave(PbrtB200Handle *h, uint32_t nSlots) {
 
 static void free_films(PbrtB200Handle *h) {
   for (auto &f : h->films) {
-    pool_free(h->device, f.film);
+    if (!h->filmSlab) pool_free(h->device, f.film);
     if (!h->rgbaSlab) pool_free(h->device, f.rgba);
     pool_free(h->device, f.sampleOut);
     pool_free(h->device, f.corners);
   }
   h->films.clear();
   pool_free(h->device, h->rgbaSlab);
+  pool_free(h->device, h->filmSlab);
   h->rgbaSlab = nullptr;
+  h->filmSlab = nullptr;
   h->rgbaSlabFloats = 0;
 }
 
@@ -2132,7 +2158,7 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   if (!err.empty()) { delete h; return fail(PBRT_B200_ERR_INVALID, err); }
   h->frameWin.x0 = scene->film.x_pixel_start; h->frameWin.y0 = scene->film.y_pixel_start;
   h->frameWin.width = scene->film.x_pixel_count; h->frameWin.height = scene->film.y_pixel_count;
-  h->rgbaSlab = nullptr; h->rgbaSlabFloats = 0;
+  h->rgbaSlab = nullptr; h->rgbaSlabFloats = 0; h->filmSlab = nullptr;
   h->gather = nullptr; h->gatherFloats = 0; h->frame = nullptr; h->tileTable = nullptr; h->tileTableCap = 0;
   h->hasSpecular = pb_scene_has_specular(*scene);
   h->hasGlossy = false;
@@ -2398,7 +2424,8 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
     const PbrtB200Window &win = windows[w];
     size_t nPixOut = (size_t)win.width * win.height;
     if (reuseFilms) {
-      CU_TRY(cudaMemsetAsync(h->films[w].film, 0, nPixOut * sizeof(FilmPixel), h->stream));
+      if (!h->filmSlab) CU_TRY(cudaMemsetAsync(h->films[w].film, 0, nPixOut * sizeof(FilmPixel), h->stream));
+      else if (w == 0) CU_TRY(cudaMemsetAsync(h->filmSlab, 0, h->rgbaSlabFloats / 4 * sizeof(FilmPixel), h->stream));
       continue;
     }
     h->films.push_back(WindowFilm());
@@ -2410,7 +2437,7 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
       CU_TRY(cudaMemcpyAsync(wf.corners, wf.cornersHost.data(), placements[w].size() * sizeof(float2),
                              cudaMemcpyHostToDevice, h->stream));
     }
-    CU_TRY(pool_alloc(h->device, (void **)&wf.film, nPixOut * sizeof(FilmPixel)));
+    if (!tiles) CU_TRY(pool_alloc(h->device, (void **)&wf.film, nPixOut * sizeof(FilmPixel)));
     if (tiles) {
       // tile renders resolve into ONE block, window after window, so that a rank's finished tiles leave in a
       // single transfer (multi.cuh)
@@ -2419,13 +2446,16 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
         for (int k = 0; k < n_windows; ++k) total += (size_t)windows[k].width * windows[k].height;
         CU_TRY(pool_alloc(h->device, (void **)&h->rgbaSlab, total * sizeof(float4)));
         h->rgbaSlabFloats = total * 4;
+        CU_TRY(pool_alloc(h->device, (void **)&h->filmSlab, total * sizeof(FilmPixel)));
+        CU_TRY(cudaMemsetAsync(h->filmSlab, 0, total * sizeof(FilmPixel), h->stream));
       }
       size_t before = 0;
       for (int k = 0; k < w; ++k) before += (size_t)windows[k].width * windows[k].height;
       wf.rgba = h->rgbaSlab + before;
+      wf.film = h->filmSlab + before;
     } else
       CU_TRY(pool_alloc(h->device, (void **)&wf.rgba, nPixOut * sizeof(float4)));
-    CU_TRY(cudaMemsetAsync(wf.film, 0, nPixOut * sizeof(FilmPixel), h->stream));
+    if (!tiles) CU_TRY(cudaMemsetAsync(wf.film, 0, nPixOut * sizeof(FilmPixel), h->stream));
     wf.nSamples = nPixW[w] * spp;
     if (h->keepSamples) CU_TRY(pool_alloc(h->device, (void **)&wf.sampleOut, wf.nSamples * 4 * sizeof(float)));
   }
@@ -2471,6 +2501,9 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
       TIMED(KC_FILM, (k_film_reach<<<grid, 128, 0, h->stream>>>(sv, h->wb, nPixWave, spp)));
       ++launches;
     }
+    const bool gatherTogether = !bc && wd.nParts > 1;
+    FilmTargets tg;
+    int tgMaxTotal = 0;
     for (int pi = 0; pi < wd.nParts; ++pi) {
       const WavePart &wp = wd.parts[pi];
       WindowFilm &wf = h->films[wp.window];
@@ -2498,7 +2531,11 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
       int syFirst = wp.ys + (int)(wp.firstPixel / ew), syLast = wp.ys + (int)((wp.firstPixel + wp.nPixels - 1) / ew);
       int rowFirst = std::max(win.y0, (int)floorf(syFirst - 0.5f - sv.filterYW) - 1);
       int rowLast = std::min(win.y0 + win.height - 1, (int)ceilf(syLast + 1 - 0.5f + sv.filterYW) + 1);
-      if (!bc && rowLast >= rowFirst) {
+      if (gatherTogether) {
+        tg.film[pi] = wf.film; tg.win[pi] = win; tg.rowFirst[pi] = rowFirst;
+        tg.rowCount[pi] = std::max(0, rowLast - rowFirst + 1);
+        tgMaxTotal = std::max(tgMaxTotal, tg.rowCount[pi] * win.width);
+      } else if (!bc && rowLast >= rowFirst) {
         int rows = rowLast - rowFirst + 1;
         int total = rows * win.width;
         int grid = std::min((total + PB_BLOCK - 1) / PB_BLOCK, h->numSMs * 16);
@@ -2516,9 +2553,22 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
         }
       }
     }
+    if (gatherTogether && tgMaxTotal > 0) {
+      // (parts of one wave never share a pixel of the same window twice in a launch: a window's parts are
+      // consecutive pixel ranges of ONE window only when the window spans waves, and then it is a single part here)
+      dim3 grid((unsigned)std::min((tgMaxTotal + PB_BLOCK - 1) / PB_BLOCK, h->numSMs * 4), (unsigned)wd.nParts);
+      TIMED(KC_FILM, (k_film_gather_parts<<<grid, PB_BLOCK, 0, h->stream>>>(sv, h->wb, wd, h->filterTable, tg)));
+      ++launches;
+    }
     cameraRays += wd.nSlots;
   }
-  for (int w = 0; w < n_windows; ++w) {
+  if (h->filmSlab) {
+    const size_t total = h->rgbaSlabFloats / 4;
+    int grid = std::min((int)((total + 255) / 256), h->numSMs * 16);
+    TIMED(KC_FILM, (k_film_resolve<<<grid, 256, 0, h->stream>>>(h->filmSlab, h->rgbaSlab, (int)total, sv.premultiply)));
+    ++launches;
+  }
+  for (int w = 0; w < n_windows && !h->filmSlab; ++w) {
     WindowFilm &wf = h->films[w];
     size_t nPixOut = (size_t)wf.win.width * wf.win.height;
     int grid = std::min((int)((nPixOut + 255) / 256), h->numSMs * 16);

@@ -14,6 +14,8 @@ out = tempfile.mkdtemp(prefix="pbrt_tool_")   # (scene files are large: keep the
 sp = gen_scene(os.path.join(out, "prof_%s.pbrt" % name), name, "--filename", os.path.join(out, "prof.exr"), *sys.argv[2:])
 sc = ffi.Scene(sp)
 ds = ffi.DeviceScene(sc)
+if os.environ.get("PBRT_PROFILE_WAVE"):   # (ncu's kernel replay saves and restores the wave arena: keep it small)
+    ffi.cuda().pbrt_b200_tunable(0, int(os.environ["PBRT_PROFILE_WAVE"]))
 if os.environ.get("PBRT_PROFILE_COUNTS"):
     ffi.cuda().pbrt_b200_tunable(6, 1)
 st = ds.render()
