@@ -175,6 +175,36 @@ def test_tiles_are_independent_and_wave_size_invariant(ffi, scene_dir, variant):
     ds.close()
 
 
+@pytest.mark.parametrize("name", ["c3", "c4_blob", "c3_spherelight"])
+def test_stream_modes_and_tree_order_change_no_bit(ffi, name):
+    """How a wave's kernels are spread over streams (tunable 5: one stream; shadow + probe traversal beside the next
+    closest-hit launch; probes alone beside the shadow rays; three streams) and the device-side node order of the
+    tree (tunable 9: treelets) are scheduling / layout choices: same image, same samples, same ray counts."""
+    scene, _, _, _ = load_case(ffi, name)
+    lib = ffi.cuda()
+    prev5, prev9 = lib.pbrt_b200_tunable(5, -1), lib.pbrt_b200_tunable(9, -1)
+    ref = None
+    try:
+        for mode, treelets in ((0, 0), (1, 0), (2, 0), (3, 0), (3, 1), (0, 1)):
+            lib.pbrt_b200_tunable(5, mode)
+            lib.pbrt_b200_tunable(9, treelets)
+            ds, st = gpu_render(ffi, scene, count=False)   # (the counting pass keeps the wave on fewer streams)
+            rgba, raw = ds.download(0, want_raw=True)
+            ls = ds.sample_radiance(0, st["camera_rays"])
+            got = (rgba.copy(), raw.copy(), ls.copy(),
+                   tuple(st[k] for k in ("camera_rays", "intersect_rays", "shadow_rays", "points_shaded")))
+            ds.close()
+            if ref is None:
+                ref = got
+                continue
+            for a, b in zip(got[:3], ref[:3]):
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (mode, treelets)
+            assert got[3] == ref[3], (mode, treelets)
+    finally:
+        lib.pbrt_b200_tunable(5, prev5)
+        lib.pbrt_b200_tunable(9, prev9)
+
+
 def test_bestcandidate_windows_equal_reference_crop_renders(ffi, scene_dir):
     """bestcandidate sampler, several windows in one call (one wave spans them): every window equals the
     twin's (== the reference's) crop render of that window -- the sampler's table placements start at the
