@@ -62,6 +62,7 @@ static int64_t g_overlap = 3;             // key 5: 0 = one stream; 1 = a vertex
 static int64_t g_debugCounts = 0;         // key 6: print each wave's queue sizes per iteration to stderr
 static int64_t g_reserved4 = 0;           // key 4: reserved (was the fused shade kernel's occupancy variant)
 static int64_t g_fastPath = 1;            // key 8: k_path_fast shades flat-triangle / matte vertices in one pass (0: general three-kernel pipeline only)
+static int64_t g_lanes = 2;               // key 10: waves of a frame in flight at once: 1, or 2 (path integrator, frames of at least PB_LANE_MIN_SAMPLES samples; 3 = two lanes whatever the size, for tests)
 static int64_t g_treelets = 0;            // key 9: device node order of the top-level tree: 1 = sibling pairs in line-sized treelets (pb_treelet.h), 0 = the reference's depth-first array (default: the re-ordering measured no gain, profiles/r02g_sweep_walk_variants.log)
 static int64_t g_primFrames = 1;          // key 7: precompute hit-independent BSDF / light-triangle frames at scene create (0: evaluate per hit)
 
@@ -457,6 +458,9 @@ __device__ __forceinline__ void flush_kd_counters(unsigned long long *stats, int
 }
 #ifndef PB_DESCEND_STEPS_BIG
 #define PB_DESCEND_STEPS_BIG 4
+#endif
+#ifndef PB_LANE_MIN_SAMPLES
+#define PB_LANE_MIN_SAMPLES (1u << 21)   // frames below this many image samples render as one wave on one lane
 #endif
 #ifndef PB_PROBE_CTAS_BIG
 #define PB_PROBE_CTAS_BIG 2   // CTAs per SM of the probe kernel on big trees
@@ -1611,6 +1615,16 @@ struct PbrtB200Handle {
   void *arena;
   size_t arenaBytes;
   WaveBuffers wb;
+  // A second "lane": its own arena, streams and events, so that two waves of a frame can be in flight at once and
+  // the almost empty tails of one wave's launches are filled by the other's kernels (tunable 10).  The code below
+  // always works on the handle's primary fields; swap_lane() exchanges them with the parked set between waves.
+  struct Lane {
+    void *arena; size_t arenaBytes; WaveBuffers wb;
+    cudaStream_t stream, auxStream, auxStream2;
+    cudaEvent_t evDirect, evAux, evAux2;
+  } parked;
+  bool parkedReady;
+  cudaEvent_t evFilm[2], evStart;
   std::vector<WindowFilm> films;
   bool keepSamples;
   PbrtB200Window frameWin;   // the scene film's pixel window (crop window), what tiles are tiles of
@@ -1736,22 +1750,52 @@ static int upload(PbrtB200Handle *h, const T *src, size_t n, const T **dst) {
 
 // One retired wave arena per device is kept for the next handle: pbrt_b200_render_host() creates and
 // destroys a handle per call, and a multi-GB cudaMalloc/cudaFree per frame would dominate it.
-static void *g_cachedArena[PB_MAX_DEVICES];
-static size_t g_cachedArenaBytes[PB_MAX_DEVICES];
+static void *g_cachedArena[PB_MAX_DEVICES][2];       // (two: a handle may run two wave lanes)
+static size_t g_cachedArenaBytes[PB_MAX_DEVICES][2];
 static void free_wave(PbrtB200Handle *h) {
   if (h->arena) {
     std::lock_guard<std::mutex> lock(g_poolMutex);   // (handles of several host threads share the per-device cache)
     int d = h->device;
-    if (d >= 0 && d < PB_MAX_DEVICES && h->arenaBytes > g_cachedArenaBytes[d]) {
-      if (g_cachedArena[d]) cudaFree(g_cachedArena[d]);
-      g_cachedArena[d] = h->arena;
-      g_cachedArenaBytes[d] = h->arenaBytes;
+    if (d >= 0 && d < PB_MAX_DEVICES) {
+      // keep it in the smaller (or an empty) one of the device's two cache slots if it is larger than that one
+      int slot = g_cachedArenaBytes[d][0] <= g_cachedArenaBytes[d][1] ? 0 : 1;
+      if (h->arenaBytes > g_cachedArenaBytes[d][slot]) {
+        if (g_cachedArena[d][slot]) cudaFree(g_cachedArena[d][slot]);
+        g_cachedArena[d][slot] = h->arena;
+        g_cachedArenaBytes[d][slot] = h->arenaBytes;
+      } else
+        cudaFree(h->arena);
     } else
       cudaFree(h->arena);
   }
   h->arena = nullptr;
   h->arenaBytes = 0;
   memset(&h->wb, 0, sizeof(h->wb));
+}
+// Exchanges the handle's working lane (arena, wave buffers, streams, events) with the parked one.
+static void swap_lane(PbrtB200Handle *h) {
+  PbrtB200Handle::Lane cur = {h->arena, h->arenaBytes, h->wb, h->stream, h->auxStream, h->auxStream2,
+                              h->evDirect, h->evAux, h->evAux2};
+  const PbrtB200Handle::Lane &o = h->parked;
+  h->arena = o.arena; h->arenaBytes = o.arenaBytes; h->wb = o.wb;
+  h->stream = o.stream; h->auxStream = o.auxStream; h->auxStream2 = o.auxStream2;
+  h->evDirect = o.evDirect; h->evAux = o.evAux; h->evAux2 = o.evAux2;
+  h->parked = cur;
+}
+static int ensure_parked_lane(PbrtB200Handle *h) {
+  if (h->parkedReady) return PBRT_B200_OK;
+  PbrtB200Handle::Lane &l = h->parked;
+  CU_TRY(cudaStreamCreate(&l.stream));
+  CU_TRY(cudaStreamCreate(&l.auxStream));
+  CU_TRY(cudaStreamCreate(&l.auxStream2));
+  CU_TRY(cudaEventCreateWithFlags(&l.evDirect, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&l.evAux, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&l.evAux2, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&h->evFilm[0], cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&h->evFilm[1], cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&h->evStart, cudaEventDisableTiming));
+  h->parkedReady = true;
+  return PBRT_B200_OK;
 }
 
 struct Carver {
@@ -1835,11 +1879,19 @@ static int ensure_wave(PbrtB200Handle *h, uint32_t nSlots) {
   int d = h->device;
   {
     std::lock_guard<std::mutex> lock(g_poolMutex);
-    if (d >= 0 && d < PB_MAX_DEVICES && g_cachedArena[d] && g_cachedArenaBytes[d] >= bytes) {
-      h->arena = g_cachedArena[d];
-      h->arenaBytes = g_cachedArenaBytes[d];
-      g_cachedArena[d] = nullptr;
-      g_cachedArenaBytes[d] = 0;
+    if (d >= 0 && d < PB_MAX_DEVICES) {
+      // the smallest cached arena that is large enough
+      int best = -1;
+      for (int k = 0; k < 2; ++k)
+        if (g_cachedArena[d][k] && g_cachedArenaBytes[d][k] >= bytes &&
+            (best < 0 || g_cachedArenaBytes[d][k] < g_cachedArenaBytes[d][best]))
+          best = k;
+      if (best >= 0) {
+        h->arena = g_cachedArena[d][best];
+        h->arenaBytes = g_cachedArenaBytes[d][best];
+        g_cachedArena[d][best] = nullptr;
+        g_cachedArenaBytes[d][best] = 0;
+      }
     }
   }
   if (!h->arena) {
@@ -2096,7 +2148,7 @@ const char *pbrt_b200_last_error(void) { return g_lastError.c_str(); }
 int64_t pbrt_b200_tunable(int key, int64_t value) {
   int64_t *p = key == 0 ? &g_waveSamples : key == 1 ? &g_countKd : key == 2 ? &g_blocksPerSM
                : key == 3 ? &g_profileKernels : key == 4 ? &g_reserved4 : key == 5 ? &g_overlap : key == 6 ? &g_debugCounts
-               : key == 7 ? &g_primFrames : key == 8 ? &g_fastPath : key == 9 ? &g_treelets : nullptr;
+               : key == 7 ? &g_primFrames : key == 8 ? &g_fastPath : key == 9 ? &g_treelets : key == 10 ? &g_lanes : nullptr;
   if (!p) return -1;
   int64_t prev = *p;
   if (value >= 0) *p = value;
@@ -2112,6 +2164,17 @@ void pbrt_b200_scene_destroy(PbrtB200Handle *h) {
   if (h->auxStream2) cudaStreamSynchronize(h->auxStream2);
   free_films(h);
   free_wave(h);
+  if (h->parkedReady) {
+    cudaStreamSynchronize(h->parked.stream);
+    cudaStreamSynchronize(h->parked.auxStream);
+    cudaStreamSynchronize(h->parked.auxStream2);
+    swap_lane(h);
+    free_wave(h);
+    swap_lane(h);
+    cudaEventDestroy(h->parked.evDirect); cudaEventDestroy(h->parked.evAux); cudaEventDestroy(h->parked.evAux2);
+    cudaEventDestroy(h->evFilm[0]); cudaEventDestroy(h->evFilm[1]); cudaEventDestroy(h->evStart);
+    cudaStreamDestroy(h->parked.auxStream); cudaStreamDestroy(h->parked.auxStream2); cudaStreamDestroy(h->parked.stream);
+  }
   for (void *p : h->allocs) pool_free(h->device, p);
   pool_free(h->device, h->filterTable);
   pool_free(h->device, h->bcMasks);
@@ -2147,6 +2210,7 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
   if (devMajor[device] < 10) return fail(PBRT_B200_ERR_NO_DEVICE, "device is not sm_100 class");
   PbrtB200Handle *h = new PbrtB200Handle();
   h->device = device; h->stream = nullptr; h->auxStream = nullptr; h->auxStream2 = nullptr; h->evDirect = nullptr; h->evAux = nullptr; h->evAux2 = nullptr;
+  memset(&h->parked, 0, sizeof(h->parked)); h->parkedReady = false;
   h->numSMs = devSMs[device];
   h->filterTable = nullptr; h->bcMasks = nullptr; h->arena = nullptr; h->arenaBytes = 0; h->sceneBytes = 0; h->keepSamples = false;
   memset(&h->wb, 0, sizeof(h->wb));
@@ -2404,19 +2468,34 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
       size_t reusable = h->arenaBytes;
       {
         std::lock_guard<std::mutex> lock(g_poolMutex);
-        if (h->device >= 0 && h->device < PB_MAX_DEVICES) reusable = std::max(reusable, g_cachedArenaBytes[h->device]);
+        if (h->device >= 0 && h->device < PB_MAX_DEVICES)
+          reusable = std::max(reusable, std::max(g_cachedArenaBytes[h->device][0], g_cachedArenaBytes[h->device][1]));
       }
       const double budget = std::max(0.5 * (double)freeB, (double)reusable);
       waveSamples = std::min<uint64_t>(waveSamples, std::max<uint64_t>(1u << 20, (uint64_t)(budget / bytesPerSlot)));
     }
   }
+  // two lanes: the frame is cut into an even number of waves (at least two), each lane's arena holds one
+  const bool twoLanes = h->sv.integrator.kind == PBRT_B200_INT_PATH && !bc &&
+                        (g_lanes == 3 || (g_lanes == 2 && totalSamples >= PB_LANE_MIN_SAMPLES)) && units >= 2;
+  if (twoLanes) waveSamples = std::max<uint64_t>(waveSamples / 2, (uint64_t)spp);   // (the memory bound above is for both)
   const uint64_t unitCap = std::max<uint64_t>(1, waveSamples / spp);
   uint64_t nWaves = std::max<uint64_t>(1, (units + unitCap - 1) / unitCap);
   if (nWaves > 1 && units - (nWaves - 1) * unitCap <= unitCap / 16) --nWaves;
+  if (twoLanes) nWaves = std::max<uint64_t>(2, nWaves + (nWaves & 1));
   uint64_t capSlots = ((units + nWaves - 1) / nWaves) * spp;
   if (capSlots > 0x7fffffffull / 4) return fail(PBRT_B200_ERR_UNSUPPORTED, "wave too large");
   int rc = ensure_wave(h, (uint32_t)capSlots);
   if (rc != PBRT_B200_OK) return rc;
+  if (twoLanes) {
+    rc = ensure_parked_lane(h);
+    if (rc != PBRT_B200_OK) return rc;
+    swap_lane(h);
+    rc = ensure_wave(h, (uint32_t)capSlots);
+    if (rc == PBRT_B200_OK) CU_TRY(cudaMemsetAsync(h->wb.stats, 0, ST_COUNT * sizeof(unsigned long long), h->stream));
+    swap_lane(h);
+    if (rc != PBRT_B200_OK) return rc;
+  }
   CU_TRY(cudaMemsetAsync(h->wb.stats, 0, ST_COUNT * sizeof(unsigned long long), h->stream));
   uint64_t cameraRays = 0;
   CU_TRY(cudaEventRecord(e0, h->stream));
@@ -2462,7 +2541,21 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
   // waves: consecutive samples in reference order, spanning windows when a window is small
   int curW = 0;
   uint64_t curP = 0;
+  int waveIdx = 0;
+  if (twoLanes) {
+    // the other lane starts after the film buffers are cleared
+    CU_TRY(cudaEventRecord(h->evStart, h->stream));
+    CU_TRY(cudaStreamWaitEvent(h->parked.stream, h->evStart, 0));
+  }
   while (curW < n_windows) {
+    // odd waves run on the second lane; the film accumulates wave after wave whichever lane a wave ran on
+    // (a pixel's sum takes its samples in the reference's order, film/image.cpp:103-141)
+    const bool otherLane = twoLanes && (waveIdx & 1);
+    if (otherLane) swap_lane(h);
+    struct LaneGuard {   // back to the first lane on every way out of this iteration
+      PbrtB200Handle *h; bool on;
+      ~LaneGuard() { if (on) swap_lane(h); }
+    } laneGuard = {h, otherLane};
     WaveDesc wd;
     memset(&wd, 0, sizeof(wd));
     wd.spp = spp;
@@ -2501,6 +2594,7 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
       TIMED(KC_FILM, (k_film_reach<<<grid, 128, 0, h->stream>>>(sv, h->wb, nPixWave, spp)));
       ++launches;
     }
+    if (twoLanes && waveIdx > 0) CU_TRY(cudaStreamWaitEvent(h->stream, h->evFilm[(waveIdx - 1) & 1], 0));
     const bool gatherTogether = !bc && wd.nParts > 1;
     FilmTargets tg;
     int tgMaxTotal = 0;
@@ -2560,8 +2654,11 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
       TIMED(KC_FILM, (k_film_gather_parts<<<grid, PB_BLOCK, 0, h->stream>>>(sv, h->wb, wd, h->filterTable, tg)));
       ++launches;
     }
+    if (twoLanes) CU_TRY(cudaEventRecord(h->evFilm[waveIdx & 1], h->stream));
     cameraRays += wd.nSlots;
+    ++waveIdx;
   }
+  if (twoLanes && waveIdx > 0) CU_TRY(cudaStreamWaitEvent(h->stream, h->evFilm[(waveIdx - 1) & 1], 0));
   if (h->filmSlab) {
     const size_t total = h->rgbaSlabFloats / 4;
     int grid = std::min((int)((total + 255) / 256), h->numSMs * 16);
@@ -2587,6 +2684,11 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
   {
     unsigned long long *hs = h->lastStats;
     CU_TRY(cudaMemcpy(hs, h->wb.stats, sizeof(h->lastStats), cudaMemcpyDeviceToHost));
+    if (twoLanes) {
+      unsigned long long other[ST_COUNT];
+      CU_TRY(cudaMemcpy(other, h->parked.wb.stats, sizeof(other), cudaMemcpyDeviceToHost));
+      for (int k = 0; k < ST_COUNT; ++k) hs[k] += other[k];
+    }
   }
   if (stats) {
     const unsigned long long *hs = h->lastStats;

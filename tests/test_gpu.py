@@ -177,17 +177,19 @@ def test_tiles_are_independent_and_wave_size_invariant(ffi, scene_dir, variant):
 
 @pytest.mark.parametrize("name", ["c3", "c4_blob", "c3_spherelight"])
 def test_stream_modes_and_tree_order_change_no_bit(ffi, name):
-    """How a wave's kernels are spread over streams (tunable 5: one stream; shadow + probe traversal beside the next
+    """How many waves of a frame are in flight (tunable 10), how a wave's kernels are spread over streams (tunable 5: one stream; shadow + probe traversal beside the next
     closest-hit launch; probes alone beside the shadow rays; three streams) and the device-side node order of the
     tree (tunable 9: treelets) are scheduling / layout choices: same image, same samples, same ray counts."""
     scene, _, _, _ = load_case(ffi, name)
     lib = ffi.cuda()
-    prev5, prev9 = lib.pbrt_b200_tunable(5, -1), lib.pbrt_b200_tunable(9, -1)
+    prev5, prev9, prev10 = lib.pbrt_b200_tunable(5, -1), lib.pbrt_b200_tunable(9, -1), lib.pbrt_b200_tunable(10, -1)
     ref = None
     try:
-        for mode, treelets in ((0, 0), (1, 0), (2, 0), (3, 0), (3, 1), (0, 1)):
+        # (lanes: 1 = one wave at a time, 3 = two waves in flight on two lanes whatever the frame's size)
+        for mode, treelets, lanes in ((0, 0, 1), (1, 0, 1), (2, 0, 1), (3, 0, 1), (3, 1, 1), (0, 1, 1), (3, 0, 3), (0, 0, 3)):
             lib.pbrt_b200_tunable(5, mode)
             lib.pbrt_b200_tunable(9, treelets)
+            lib.pbrt_b200_tunable(10, lanes)
             ds, st = gpu_render(ffi, scene, count=False)   # (the counting pass keeps the wave on fewer streams)
             rgba, raw = ds.download(0, want_raw=True)
             ls = ds.sample_radiance(0, st["camera_rays"])
@@ -198,11 +200,12 @@ def test_stream_modes_and_tree_order_change_no_bit(ffi, name):
                 ref = got
                 continue
             for a, b in zip(got[:3], ref[:3]):
-                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (mode, treelets)
-            assert got[3] == ref[3], (mode, treelets)
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (mode, treelets, lanes)
+            assert got[3] == ref[3], (mode, treelets, lanes)
     finally:
         lib.pbrt_b200_tunable(5, prev5)
         lib.pbrt_b200_tunable(9, prev9)
+        lib.pbrt_b200_tunable(10, prev10)
 
 
 def test_bestcandidate_windows_equal_reference_crop_renders(ffi, scene_dir):
