@@ -422,7 +422,7 @@ int pbrt_b200_render_host(const PbrtB200Scene *scene, int device,
  * key 8: shade plain vertices (flat triangle, matte material) in the single-pass kernel k_path_fast (default on)
  * key 9: node order of the device copy of the top-level kd-tree, read at pbrt_b200_scene_create: 0 = the array as
  *        given (depth first, default), 1 = sibling pairs packed in 128-byte treelets (same tree, same visits)
- * key 10: waves of one frame in flight at once (path integrator): 1, or 2 = frames of 2 Mi samples and more are cut
+ * key 10: waves of one frame in flight at once (path integrator): 1 (default; 2 measured no gain), or 2 = frames of 2 Mi samples and more are cut
  *        into an even number of waves that alternate between two lanes (arena + streams each), so that one wave's
  *        nearly empty last launches overlap the other's kernels; 3 = two lanes whatever the size (tests) */
 int64_t pbrt_b200_tunable(int key, int64_t value);

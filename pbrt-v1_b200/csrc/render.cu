@@ -62,7 +62,7 @@ static int64_t g_overlap = 3;             // key 5: 0 = one stream; 1 = a vertex
 static int64_t g_debugCounts = 0;         // key 6: print each wave's queue sizes per iteration to stderr
 static int64_t g_reserved4 = 0;           // key 4: reserved (was the fused shade kernel's occupancy variant)
 static int64_t g_fastPath = 1;            // key 8: k_path_fast shades flat-triangle / matte vertices in one pass (0: general three-kernel pipeline only)
-static int64_t g_lanes = 2;               // key 10: waves of a frame in flight at once: 1, or 2 (path integrator, frames of at least PB_LANE_MIN_SAMPLES samples; 3 = two lanes whatever the size, for tests)
+static int64_t g_lanes = 1;               // key 10: waves of a frame in flight at once: 1 (default), or 2 (path integrator, frames of at least PB_LANE_MIN_SAMPLES samples; 3 = two lanes whatever the size, for tests).  Measured (profiles/r02n_sweep_lanes.log): two lanes with half-size waves C3 121.3 vs 119.8 ms, C4 211.9 vs 210.8, C5 1204.9 vs 1216.9, an 8-GPU rank's share (8.4 M samples) 16.07 vs 15.81 ms -- the three streams of one wave already fill most of what a second wave could, and persistent grids leave the other lane's CTAs little room before a launch's tail
 static int64_t g_treelets = 0;            // key 9: device node order of the top-level tree: 1 = sibling pairs in line-sized treelets (pb_treelet.h), 0 = the reference's depth-first array (default: the re-ordering measured no gain, profiles/r02g_sweep_walk_variants.log)
 static int64_t g_primFrames = 1;          // key 7: precompute hit-independent BSDF / light-triangle frames at scene create (0: evaluate per hit)
 
