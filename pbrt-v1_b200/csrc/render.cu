@@ -2456,7 +2456,9 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
   uint64_t waveSamples = (uint64_t)g_waveSamples;
   if (h->sv.integrator.kind != PBRT_B200_INT_PATH) waveSamples = std::min<uint64_t>(waveSamples, 1ull << 24);
   waveSamples = std::min<uint64_t>(waveSamples, 0xffffffffull / (uint64_t)std::max(1, h->sv.directRecords));
-  {
+  // (the device is only asked when the arena at hand cannot hold the frame's samples or the tunable's wave anyway:
+  // a frame loop pays cudaMemGetInfo once)
+  if ((uint64_t)h->wb.nSlots < std::min<uint64_t>(waveSamples, totalSamples)) {
     Carver sizing = {nullptr, 0};
     WaveBuffers tmp;
     const uint32_t probe = 1u << 20;
