@@ -32,6 +32,18 @@
 #ifndef PB_LEAF_STEPS
 #define PB_LEAF_STEPS 2
 #endif
+#ifndef PB_GENERAL_ADAPTIVE
+#define PB_GENERAL_ADAPTIVE 1   // instance-capable walk: adaptive interior phase and early refills like the lean walk (the
+#endif                          // 27-placement scene: 916 -> 781 ms per frame, profiles/r02p_inst_variants.log)
+#ifndef PB_GENERAL_REFILL
+#define PB_GENERAL_REFILL 8
+#endif
+#ifndef PB_GENERAL_DESCEND_LANES
+#define PB_GENERAL_DESCEND_LANES 8
+#endif
+#ifndef PB_GENERAL_DESCEND_MAX
+#define PB_GENERAL_DESCEND_MAX 8
+#endif
 #ifndef PB_SMEM_NODES
 #define PB_SMEM_NODES 0   // > 0: the first PB_SMEM_NODES nodes of the top-level tree are staged in shared memory
 #endif                    //      by one TMA bulk copy per CTA (experiment)
@@ -107,7 +119,7 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
   for (;;) {
     // ---- refill idle lanes
     uint32_t idleMask = __ballot_sync(0xffffffffu, !active);
-    if (!exhausted && (uint32_t)__popc(idleMask) >= (idleMask == 0xffffffffu ? 1u : PB_REFILL_THRESHOLD)) {
+    if (!exhausted && (uint32_t)__popc(idleMask) >= (idleMask == 0xffffffffu ? 1u : (uint32_t)PB_GENERAL_REFILL)) {
       uint32_t base = 0;
       uint32_t nIdle = (uint32_t)__popc(idleMask);
       if (lane == 0) base = atomicAdd(work, nIdle);
@@ -146,9 +158,12 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
     bool pending = false;
     uint32_t prim = 0;
 #pragma unroll 1
-    for (int step = 0; step < DS; ++step) {
+    for (int step = 0; step < (PB_GENERAL_ADAPTIVE ? PB_GENERAL_DESCEND_MAX : DS); ++step) {
       bool descending = active && !inLeaf;
-      if (__ballot_sync(0xffffffffu, descending) == 0) break;
+      const uint32_t dm = __ballot_sync(0xffffffffu, descending);
+      if (dm == 0) break;
+      // (PB_GENERAL_ADAPTIVE: like the lean walk, the interior phase goes on while enough lanes still descend)
+      if (PB_GENERAL_ADAPTIVE && step != 0 && (uint32_t)__popc(dm) < (uint32_t)PB_GENERAL_DESCEND_LANES) break;
       if (descending) {
 #if PB_SMEM_NODES > 0
         uint2 nd;
