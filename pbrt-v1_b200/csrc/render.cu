@@ -2456,23 +2456,25 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
   uint64_t waveSamples = (uint64_t)g_waveSamples;
   if (h->sv.integrator.kind != PBRT_B200_INT_PATH) waveSamples = std::min<uint64_t>(waveSamples, 1ull << 24);
   waveSamples = std::min<uint64_t>(waveSamples, 0xffffffffull / (uint64_t)std::max(1, h->sv.directRecords));
-  // (the device is only asked when the arena at hand cannot hold the frame's samples or the tunable's wave anyway:
-  // a frame loop pays cudaMemGetInfo once)
-  if ((uint64_t)h->wb.nSlots < std::min<uint64_t>(waveSamples, totalSamples)) {
+  // (the device is asked only when neither the arena at hand nor a retired one of this device holds the wave the
+  // tunable allows: frame loops and the per-call handles of pbrt_b200_render_host skip cudaMemGetInfo, whose latency
+  // is erratic next to tens of GB of allocations)
+  {
     Carver sizing = {nullptr, 0};
     WaveBuffers tmp;
     const uint32_t probe = 1u << 20;
     carve_wave(sizing, tmp, probe, h->sv.directRecords, h->nFrames, h->sv.integrator.kind == PBRT_B200_INT_PATH,
                h->sv.ldFloatsPerSample, h->sv.nInstances != 0, h->textured);
     const double bytesPerSlot = (double)sizing.off / probe;
+    size_t reusable = h->arenaBytes;
+    {
+      std::lock_guard<std::mutex> lock(g_poolMutex);
+      if (h->device >= 0 && h->device < PB_MAX_DEVICES)
+        reusable = std::max(reusable, std::max(g_cachedArenaBytes[h->device][0], g_cachedArenaBytes[h->device][1]));
+    }
+    const double wanted = (double)std::min<uint64_t>(waveSamples, totalSamples) * bytesPerSlot * 1.08 + (1 << 20);
     size_t freeB = 0, totalB = 0;
-    if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
-      size_t reusable = h->arenaBytes;
-      {
-        std::lock_guard<std::mutex> lock(g_poolMutex);
-        if (h->device >= 0 && h->device < PB_MAX_DEVICES)
-          reusable = std::max(reusable, std::max(g_cachedArenaBytes[h->device][0], g_cachedArenaBytes[h->device][1]));
-      }
+    if ((double)reusable < wanted && cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
       const double budget = std::max(0.5 * (double)freeB, (double)reusable);
       waveSamples = std::min<uint64_t>(waveSamples, std::max<uint64_t>(1u << 20, (uint64_t)(budget / bytesPerSlot)));
     }

@@ -26,3 +26,22 @@ for resident in (False, True):
             resident, i, 1e3 * (t1 - t0), st["render_ms"], st["upload_ms"], st["download_ms"]))
     if ds:
         ds.close()
+
+# the same steps spelled out through the resident-scene calls, to see which one a slow step spends its time in
+ds = ffi.DeviceScene(sc)
+ds.render()
+for i in range(8):
+    t0 = time.perf_counter()
+    d2 = ffi.DeviceScene(sc)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    st = d2.render()
+    t2 = time.perf_counter()
+    img = d2.download(0)
+    t3 = time.perf_counter()
+    d2.close()
+    torch.cuda.synchronize()
+    t4 = time.perf_counter()
+    print("spelled out step %d: create %.2f ms  render %.2f (device %.2f)  download %.2f  destroy %.2f" % (
+        i, 1e3 * (t1 - t0), 1e3 * (t2 - t1), st["render_ms"], 1e3 * (t3 - t2), 1e3 * (t4 - t3)))
+ds.close()
