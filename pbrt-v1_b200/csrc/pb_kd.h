@@ -108,7 +108,7 @@ PB_HD bool kd_test_prim(const SceneView &sv, uint32_t prim, Ray &ray, Hit *hit, 
     h2.prim = -1; h2.t = 0.f; h2.b1 = h2.b2 = 0.f; h2.inst = -1;
     bool got;
     if (in.n_nodes == 0) got = kd_test_prim<ANY, PB_QK_ALL>(sv, in.prim_base, r2, &h2);
-    else got = kd_tree_intersect<ANY, COUNT, PB_QK_ALL>(sv, kd_instance_tree(sv, in), r2, &h2, cnt);
+    else got = kd_tree_intersect<ANY, COUNT, PB_QK_ALL, true>(sv, kd_instance_tree(sv, in), r2, &h2, cnt);   // (table per object walk)
     if (!got) return false;
     if (!ANY) {
       *hit = h2;

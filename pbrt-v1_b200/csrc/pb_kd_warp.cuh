@@ -81,8 +81,10 @@ template <bool ANY, bool COUNT, int QK, int DS, class Source, class Sink>
 __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n, uint32_t *work,
                                                  const Source &src, const Sink &sink, KdCounters &cnt) {
   const uint32_t lane = threadIdx.x & 31u;
-  uint32_t todoNode[PB_KD_STACK];
-  float todoTmin[PB_KD_STACK], todoTmax[PB_KD_STACK];
+  // todo list of 8-byte entries (node, tmax): the popped tmin is the tmax that is current at the pop (see the lean
+  // walk below); entering an instanced object parks the outer tmax in saved[], because the object's walk runs with
+  // its own interval
+  uint2 todo[PB_KD_STACK];
   // lane state
   bool active = false;        // holds an unfinished ray
   bool inLeaf = false;
@@ -108,7 +110,12 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
   uint32_t nodeBase = 0, refBase = 0, primBase = 0;
   int instBase = -1;
   int32_t instId = -1;
-  float saved[INSTV ? 9 + PB_MAILBOX + 1 : 1];
+  float saved[INSTV ? 10 : 1];
+  // repeats inside an instanced object's tree are filtered by the hashed table of pb_kd.h (cleared at every entry);
+  // the top-level tree, which holds the placements and a few loose primitives, keeps the 2-entry ring
+  constexpr int MBS = INSTV ? (ANY ? PB_MB_SLOTS_ANY : PB_MB_SLOTS) : 0;
+  __shared__ uint32_t testedAll[MBS ? MBS : 1][MBS ? PB_BLOCK : 1];
+  uint32_t *const tested = &testedAll[0][MBS ? threadIdx.x : 0];
 
 #if PB_SMEM_NODES > 0
   __shared__ __align__(128) uint2 topNodes[PB_SMEM_NODES];
@@ -190,9 +197,7 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
           else if (tplane < tmin)
             node = secondChild;
           else {
-            todoNode[todoPos] = secondChild;
-            todoTmin[todoPos] = tplane;
-            todoTmax[todoPos] = tmax;
+            todo[todoPos] = make_uint2(secondChild, __float_as_uint(tmax));
             ++todoPos;
             node = firstChild;
             tmax = tplane;
@@ -208,15 +213,23 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
         prim = (INSTV ? primBase : 0u) + ((leafN == 1) ? leafW1 : __ldg(sv.primRefs + (INSTV ? refBase : 0u) + leafW1 + leafI));
         ++leafI;
         if (COUNT) ++cnt.refs;
-        bool seen = false;
+        if (MBS != 0 && instBase >= 0) {
+          uint32_t *const entry = tested + pb_mb_slot<MBS ? MBS : 4>(prim) * PB_BLOCK;
+          if (*entry != prim) {
+            *entry = prim;
+            pending = true;
+          }
+        } else {
+          bool seen = false;
 #pragma unroll
-        for (int k = 0; k < PB_MAILBOX; ++k) seen |= (mailbox[k] == prim);
-        if (!seen) {
+          for (int k = 0; k < PB_MAILBOX; ++k) seen |= (mailbox[k] == prim);
+          if (!seen) {
 #pragma unroll
-          for (int k = 0; k < PB_MAILBOX; ++k)
-            if (k == mbPos) mailbox[k] = prim;
-          mbPos = (mbPos + 1) & (PB_MAILBOX - 1);
-          pending = true;
+            for (int k = 0; k < PB_MAILBOX; ++k)
+              if (k == mbPos) mailbox[k] = prim;
+            mbPos = (mbPos + 1) & (PB_MAILBOX - 1);
+            pending = true;
+          }
         }
       }
     }
@@ -250,10 +263,13 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
             saved[0] = ray.o.x; saved[1] = ray.o.y; saved[2] = ray.o.z;
             saved[3] = ray.d.x; saved[4] = ray.d.y; saved[5] = ray.d.z;
             saved[6] = __uint_as_float(leafW1); saved[7] = __uint_as_float(leafI); saved[8] = __uint_as_float(leafN);
+            saved[9] = tmax;
+            if (MBS != 0) {
 #pragma unroll
-            for (int k = 0; k < PB_MAILBOX; ++k) { saved[9 + k] = __uint_as_float(mailbox[k]); mailbox[k] = 0xffffffffu; }
-            saved[9 + PB_MAILBOX] = __int_as_float(mbPos);
-            mbPos = 0;
+              for (int k = 0; k < MBS; ++k) tested[k * PB_BLOCK] = 0xffffffffu;
+            } else {
+              // (no table: the object's walk would need the ring; not a configuration that is built)
+            }
             ray = r2;
             invDir = v3(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
             tmin = t0; tmax = t1;
@@ -284,9 +300,10 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
       if (todoPos == (INSTV && instBase >= 0 ? instBase : 0)) finished = true;
       else {
         --todoPos;
-        node = todoNode[todoPos];
-        tmin = todoTmin[todoPos];
-        tmax = todoTmax[todoPos];
+        const uint2 e = todo[todoPos];
+        node = e.x;
+        tmin = tmax;
+        tmax = __uint_as_float(e.y);
         if (!ANY && ray.maxt < tmin) finished = true;   // kdtree.cpp:330
       }
       if (INSTV && finished && instBase >= 0) {
@@ -297,9 +314,7 @@ __device__ __forceinline__ void kd_warp_traverse(const SceneView &sv, uint32_t n
         ray.d = v3(saved[3], saved[4], saved[5]);
         invDir = v3(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
         leafW1 = __float_as_uint(saved[6]); leafI = __float_as_uint(saved[7]); leafN = __float_as_uint(saved[8]);
-#pragma unroll
-        for (int k = 0; k < PB_MAILBOX; ++k) mailbox[k] = __float_as_uint(saved[9 + k]);
-        mbPos = __float_as_int(saved[9 + PB_MAILBOX]);
+        tmax = saved[9];
         nodeBase = refBase = primBase = 0;
         instBase = -1;
         inLeaf = true;
