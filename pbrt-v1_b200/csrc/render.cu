@@ -791,6 +791,10 @@ k_path_surface(const __grid_constant__ SceneView sv, const WaveBuffers wb, const
 // (quadrics, per-vertex shading normals, instances, glass / mirror / glossy / Oren-Nayar materials) is passed
 // on: its queue index goes to `subset`, which the general k_path_surface / _direct / _continue pipeline then
 // shades.  Misses end here.  The arithmetic is the general kernels' (same inlined functions, LambertBsdf).
+#ifndef PB_FAST_PREFETCH
+#define PB_FAST_PREFETCH 0   // prefetch a parked hit's state records and frame into L1 (measured: no effect, 35.3 vs
+#endif                       // 35.1 ms per C3 frame, profiles/r02v_sweep_fast_prefetch.log -- the kernel waits on
+                             // instruction fetch and issue, not on these loads)
 #ifndef PB_FAST_MIN_BLOCKS
 #define PB_FAST_MIN_BLOCKS 6   // 80 registers (r02d_sweep.log: 3 / 4 / 5 / 6 CTAs per SM: 54.3 / 43.8 / 40.9 / 38.2 ms per C3 frame)
 #endif
@@ -929,7 +933,17 @@ k_path_fast(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wa
       if (pass) subset[pj] = i;
       const uint32_t mask = __ballot_sync(0xffffffffu, plain);
       if (mask) {
-        if (plain) parked[nParked + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = i;
+        if (plain) {
+          parked[nParked + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = i;
+#if PB_FAST_PREFETCH
+          // the records the vertex will read, on their way while the hit waits in the list: the slot's two 16-byte
+          // state records and the primitive's 48-byte frame are scattered reads
+          const uint32_t pslot = qin.slot[i];
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(wb.plf + pslot));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(wb.ptc + pslot));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(sv.primFrame + 3u * (uint32_t)qin.hitPrim[i]));
+#endif
+        }
         nParked += (uint32_t)__popc(mask);
         __syncwarp();
         if (nParked >= 32u) {
