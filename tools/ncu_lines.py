@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Per-source-line dynamic instruction and stall histogram from an ncu report + the matching .so.
-usage: ncu_lines.py report.ncu-rep lib.so kernel_substring [topN]"""
+usage: ncu_lines.py report.ncu-rep lib.so kernel_substring [topN [mangled_substring]]
+(mangled_substring picks the template instance in the disassembly, e.g. k_path_fastILb0ELi0E)"""
 import collections
 import csv
 import io
@@ -31,7 +32,7 @@ td = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=td, capture_output=True)
 cubin = [f for f in os.listdir(td) if f.endswith(".cubin")][0]
 dis = subprocess.run(["nvdisasm", "-g", os.path.join(td, cubin)], capture_output=True, text=True).stdout.split("\n")
-mangled = re.sub(r"[^A-Za-z0-9_]", "", kname)
+mangled = sys.argv[5] if len(sys.argv) > 5 else re.sub(r"[^A-Za-z0-9_]", "", kname)
 start = [i for i, l in enumerate(dis) if l.startswith(".text.") and mangled in l][0]
 end = [i for i, l in enumerate(dis) if l.startswith("//--------------------- .text.") and i > start][0]
 curl, sass = None, []
