@@ -29,6 +29,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <chrono>
 
 #define PB_BLOCK 128   // threads per CTA of every persistent kernel
 #include "pb_integrator.h"
@@ -2410,6 +2411,11 @@ int pbrt_b200_render_tiles(PbrtB200Handle *h, const PbrtB200Window *tiles, int n
 static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int n_windows, PbrtB200Stats *stats,
                           bool tiles) {
   if (!h || !windows || n_windows < 1) return fail(PBRT_B200_ERR_INVALID, "bad arguments");
+  // PBRT_HOST_PHASES=1: host wall clock of this call's phases to stderr (where a frame's time outside kernels goes)
+  static const bool hostPhases = getenv("PBRT_HOST_PHASES") != nullptr;
+  auto hostNow = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double hp0 = hostPhases ? hostNow() : 0.0;
+  double hp1 = 0, hp2 = 0, hp3 = 0;
   CU_TRY(cudaSetDevice(h->device));
   // keep the film buffers of the previous render when the windows are unchanged (frame loops)
   bool reuseFilms = (int)h->films.size() == n_windows && (h->rgbaSlab != nullptr) == tiles;
@@ -2470,38 +2476,47 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
   uint64_t waveSamples = (uint64_t)g_waveSamples;
   if (h->sv.integrator.kind != PBRT_B200_INT_PATH) waveSamples = std::min<uint64_t>(waveSamples, 1ull << 24);
   waveSamples = std::min<uint64_t>(waveSamples, 0xffffffffull / (uint64_t)std::max(1, h->sv.directRecords));
-  // (the device is asked only when neither the arena at hand nor a retired one of this device holds the wave the
-  // tunable allows: frame loops and the per-call handles of pbrt_b200_render_host skip cudaMemGetInfo, whose latency
-  // is erratic next to tens of GB of allocations)
-  {
+  // two lanes: the frame is cut into an even number of waves (at least two), each lane's arena holds one
+  const bool twoLanes = h->sv.integrator.kind == PBRT_B200_INT_PATH && !bc &&
+                        (g_lanes == 3 || (g_lanes == 2 && totalSamples >= PB_LANE_MIN_SAMPLES)) && units >= 2;
+  // slots of one wave when a wave may hold `ws` samples: equal waves, a remainder below 1/16 wave absorbed
+  auto wave_slots = [&](uint64_t ws) {
+    if (twoLanes) ws = std::max<uint64_t>(ws / 2, (uint64_t)spp);   // (the bounds are for both lanes together)
+    const uint64_t unitCap = std::max<uint64_t>(1, ws / spp);
+    uint64_t nWaves = std::max<uint64_t>(1, (units + unitCap - 1) / unitCap);
+    if (nWaves > 1 && units - (nWaves - 1) * unitCap <= unitCap / 16) --nWaves;
+    if (twoLanes) nWaves = std::max<uint64_t>(2, nWaves + (nWaves & 1));
+    return ((units + nWaves - 1) / nWaves) * spp;
+  };
+  auto arena_bytes = [&](uint64_t slots) {
     Carver sizing = {nullptr, 0};
     WaveBuffers tmp;
-    const uint32_t probe = 1u << 20;
-    carve_wave(sizing, tmp, probe, h->sv.directRecords, h->nFrames, h->sv.integrator.kind == PBRT_B200_INT_PATH,
+    carve_wave(sizing, tmp, (uint32_t)slots, h->sv.directRecords, h->nFrames, h->sv.integrator.kind == PBRT_B200_INT_PATH,
                h->sv.ldFloatsPerSample, h->sv.nInstances != 0, h->textured);
-    const double bytesPerSlot = (double)sizing.off / probe;
+    return sizing.off + 256;
+  };
+  uint64_t capSlots = wave_slots(waveSamples);
+  // The device is asked for its free memory only when neither the arena at hand nor a retired one of this device
+  // holds that wave: frame loops and the per-call handles of pbrt_b200_render_host never call cudaMemGetInfo, whose
+  // latency next to tens of GB of allocations is erratic (0.1 ms, then 7-44 ms in a quarter of the calls:
+  // profiles/r02z_host_gap.log).
+  if (capSlots <= 0x7fffffffull / 4 && !(h->arena && (uint64_t)h->wb.nSlots >= capSlots)) {
+    const size_t need = arena_bytes(capSlots) * (twoLanes ? 2 : 1);
     size_t reusable = h->arenaBytes;
     {
       std::lock_guard<std::mutex> lock(g_poolMutex);
       if (h->device >= 0 && h->device < PB_MAX_DEVICES)
-        reusable = std::max(reusable, std::max(g_cachedArenaBytes[h->device][0], g_cachedArenaBytes[h->device][1]));
+        reusable = twoLanes ? g_cachedArenaBytes[h->device][0] + g_cachedArenaBytes[h->device][1]
+                            : std::max(reusable, std::max(g_cachedArenaBytes[h->device][0], g_cachedArenaBytes[h->device][1]));
     }
-    const double wanted = (double)std::min<uint64_t>(waveSamples, totalSamples) * bytesPerSlot * 1.08 + (1 << 20);
     size_t freeB = 0, totalB = 0;
-    if ((double)reusable < wanted && cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
+    if (reusable < need && cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
+      const double bytesPerSlot = (double)arena_bytes(1u << 20) / (double)(1u << 20);
       const double budget = std::max(0.5 * (double)freeB, (double)reusable);
       waveSamples = std::min<uint64_t>(waveSamples, std::max<uint64_t>(1u << 20, (uint64_t)(budget / bytesPerSlot)));
+      capSlots = wave_slots(waveSamples);
     }
   }
-  // two lanes: the frame is cut into an even number of waves (at least two), each lane's arena holds one
-  const bool twoLanes = h->sv.integrator.kind == PBRT_B200_INT_PATH && !bc &&
-                        (g_lanes == 3 || (g_lanes == 2 && totalSamples >= PB_LANE_MIN_SAMPLES)) && units >= 2;
-  if (twoLanes) waveSamples = std::max<uint64_t>(waveSamples / 2, (uint64_t)spp);   // (the memory bound above is for both)
-  const uint64_t unitCap = std::max<uint64_t>(1, waveSamples / spp);
-  uint64_t nWaves = std::max<uint64_t>(1, (units + unitCap - 1) / unitCap);
-  if (nWaves > 1 && units - (nWaves - 1) * unitCap <= unitCap / 16) --nWaves;
-  if (twoLanes) nWaves = std::max<uint64_t>(2, nWaves + (nWaves & 1));
-  uint64_t capSlots = ((units + nWaves - 1) / nWaves) * spp;
   if (capSlots > 0x7fffffffull / 4) return fail(PBRT_B200_ERR_UNSUPPORTED, "wave too large");
   int rc = ensure_wave(h, (uint32_t)capSlots);
   if (rc != PBRT_B200_OK) return rc;
@@ -2556,6 +2571,7 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
     wf.nSamples = nPixW[w] * spp;
     if (h->keepSamples) CU_TRY(pool_alloc(h->device, (void **)&wf.sampleOut, wf.nSamples * 4 * sizeof(float)));
   }
+  if (hostPhases) hp1 = hostNow();
   // waves: consecutive samples in reference order, spanning windows when a window is small
   int curW = 0;
   uint64_t curP = 0;
@@ -2691,7 +2707,9 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
     ++launches;
   }
   CU_TRY(cudaEventRecord(e1, h->stream));
+  if (hostPhases) hp2 = hostNow();
   CU_TRY(cudaStreamSynchronize(h->stream));
+  if (hostPhases) hp3 = hostNow();
   CU_TRY(cudaGetLastError());
   float ms = 0.f;
   CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
@@ -2723,6 +2741,9 @@ static int render_windows(PbrtB200Handle *h, const PbrtB200Window *windows, int 
     stats->render_ms = ms;
     stats->kernel_launches = launches;
   }
+  if (hostPhases)
+    fprintf(stderr, "pbrt_b200 host phases: setup %.3f ms, enqueue %.3f ms, wait %.3f ms, wrap-up %.3f ms; device %.3f ms, "
+                    "%llu launches\n", hp1 - hp0, hp2 - hp1, hp3 - hp2, hostNow() - hp3, ms, (unsigned long long)launches);
   return PBRT_B200_OK;
 }
 
