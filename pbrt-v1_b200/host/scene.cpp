@@ -5,6 +5,7 @@
 // it to libpbrt_b200.so (dlopen'ed like the reference dlopen's its plugins,
 // core/dynload.cpp:462-490).  If that library cannot be loaded the render
 // aborts with Severe() -- there is deliberately no CPU fallback.
+#include <chrono>
 #include "core.h"
 #include <dlfcn.h>
 #include <sys/time.h>
@@ -113,7 +114,9 @@ void Scene::Flatten(FlatBuilder &fb, PbrtB200Scene *out) const {
     const GeometricPrimitive *gp = dynamic_cast<const GeometricPrimitive *>(all[i]);
     if (!gp) Severe("Non-geometric primitive reached the accelerator");
     gp->shape->Flatten(fb, &pr, &fb.aux[i]);
-    if (i < nTop) {
+    if (i < nTop && gp->areaLight) {
+      // (only emitters are looked up again, by AreaLight::Flatten: a map entry for each of a million triangles
+      // was a third of a second of the load)
       const void *owner; int index;
       gp->shape->Identity(&owner, &index);
       fb.shapePrimIds[std::make_pair(owner, index)] = (uint32_t)i;
@@ -300,9 +303,23 @@ static CapturedScene *gCapture = NULL;
 void Scene::Render() {
   if (gCapture) {
     CapturedScene *cap = gCapture;
+    const auto f0 = std::chrono::steady_clock::now();
     Flatten(cap->fb, &cap->scene);
-    cap->nodes.assign(cap->scene.nodes, cap->scene.nodes + cap->scene.n_nodes);
-    cap->primRefs.assign(cap->scene.prim_refs, cap->scene.prim_refs + cap->scene.n_prim_refs);
+    const auto f1 = std::chrono::steady_clock::now();
+    // the kd arrays die with the Scene: take them over when they are the accelerator's own vectors (no instancing),
+    // copy them when Flatten assembled them in the builder
+    KdTreeAccel *accel = dynamic_cast<KdTreeAccel *>(aggregate);
+    if (accel && !accel->nodes.empty() && cap->scene.nodes == &accel->nodes[0] &&
+        (accel->primRefs.empty() || cap->scene.prim_refs == &accel->primRefs[0])) {
+      cap->nodes.swap(accel->nodes);
+      cap->primRefs.swap(accel->primRefs);
+    } else {
+      cap->nodes.assign(cap->scene.nodes, cap->scene.nodes + cap->scene.n_nodes);
+      cap->primRefs.assign(cap->scene.prim_refs, cap->scene.prim_refs + cap->scene.n_prim_refs);
+    }
+    if (getenv("PBRT_HOST_TIMING"))
+      fprintf(stderr, "load: flatten %.3f s, copy of the kd arrays %.3f s\n", std::chrono::duration<double>(f1 - f0).count(),
+              std::chrono::duration<double>(std::chrono::steady_clock::now() - f1).count());
     cap->scene.nodes = cap->nodes.empty() ? NULL : &cap->nodes[0];
     cap->scene.prim_refs = cap->primRefs.empty() ? NULL : &cap->primRefs[0];
     return;
@@ -353,10 +370,17 @@ extern "C" {
 void *pbrt_host_load_scene(const char *path) {
   CapturedScene *cap = new CapturedScene;
   gCapture = cap;
+  const bool timing = getenv("PBRT_HOST_TIMING") != NULL;
+  const auto t0 = std::chrono::steady_clock::now();
   pbrtInit();
   bool ok = ParseFile(path);
+  const auto t1 = std::chrono::steady_clock::now();
   pbrtCleanup();
   gCapture = NULL;
+  if (timing)
+    fprintf(stderr, "load: parse + WorldEnd (kd build, flatten) %.3f s, cleanup %.3f s\n",
+            std::chrono::duration<double>(t1 - t0).count(),
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
   if (!ok || cap->scene.abi_version == 0) {
     delete cap;
     return NULL;
