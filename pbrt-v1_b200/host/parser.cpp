@@ -528,3 +528,21 @@ bool ParseFile(const char *filename) {
   line_num = 0;
   return (fp != NULL);
 }
+
+// Test hook (tests/test_oracle.py): the NUMBER tokens of `text`, as the tokenizer reads them (pbrtlex.l:96:
+// (float)atof(yytext)).  Returns how many were written to out[0..max).
+extern "C" int pbrt_host_test_scan_numbers(const char *text, float *out, int max) {
+  FILE *f = fmemopen((void *)text, strlen(text), "r");
+  if (!f) return -1;
+  int n = 0;
+  {
+    Lexer lex(f);
+    for (;;) {
+      Token t = lex.Next();
+      if (t.kind == T_EOF) break;
+      if (t.kind == T_NUM && n < max) out[n++] = t.num;
+    }
+  }
+  fclose(f);
+  return n;
+}

@@ -420,3 +420,29 @@ def test_threaded_event_sort_is_std_sort(ffi):
     for n, distinct, seed, threads in ((200000, 50, 1, 4), (300000, 3000, 2, 8), (150001, 7, 3, 3), (400000, 400000, 4, 16),
                                        (1000, 10, 5, 8)):
         assert lib.pbrt_host_test_sort_events(n, distinct, seed, threads) == 0, (n, distinct, seed, threads)
+
+
+def test_tokenizer_numbers_round_like_atof(ffi):
+    """The scene tokenizer reads a NUMBER as (float)atof(text) (pbrtlex.l:96): the correctly rounded double, then
+    rounded to float.  host/parser.cpp gets that double from std::from_chars; Python's float() is the same correctly
+    rounded double, so every literal must come out as np.float32(float(literal)) bit for bit -- incl. halfway cases
+    of the float grid, denormals, overflow, leading '+', '.5', '5.', exponents."""
+    lib = ffi.host()
+    lib.pbrt_host_test_scan_numbers.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(7)
+    lits = ["0", "-0", "+5", "-.5", "5.", ".25", "1e5", "1E-5", "1e+5", "3.4028235e38", "3.4028236e38", "1e39", "-1e39",
+            "1.17549435e-38", "1e-45", "7e-46", "1e-50", "0.1", "0.30000001192092896", "16777217", "16777219",
+            "1.00000005960464477539", "1.00000005960464477540", "123456789.987654321", "555.0", "0.000001"]
+    for _ in range(4000):
+        mant = "%d.%s" % (rng.integers(0, 1000), "".join(str(d) for d in rng.integers(0, 10, rng.integers(1, 18))))
+        lits.append(("-" if rng.random() < 0.3 else "") + mant + ("e%d" % rng.integers(-44, 39) if rng.random() < 0.5 else ""))
+    for x in rng.random(2000).astype(np.float32):     # halfway points between neighbouring floats, written exactly
+        lo = float(x); hi = float(np.nextafter(x, np.float32(2.0)))
+        lits.append("%.60g" % ((lo + hi) / 2))
+    out = np.zeros(len(lits), np.float32)
+    n = lib.pbrt_host_test_scan_numbers(" ".join(lits).encode(), out.ctypes.data, len(lits))
+    assert n == len(lits)
+    with np.errstate(over="ignore"):
+        want = np.array([np.float32(float(s)) for s in lits], np.float32)
+    bad = [(lits[i], out[i], want[i]) for i in range(n) if out[i].view(np.uint32) != want[i].view(np.uint32)]
+    assert not bad, bad[:5]
