@@ -407,7 +407,7 @@ int pbrt_b200_render_host(const PbrtB200Scene *scene, int device,
                           PbrtB200Stats *stats);
 
 /* Tunables; returns the previous value, value < 0 only queries.
- * key 0: image samples per wave (default 64 Mi = ~21.6 GB of wave state for the path integrator, 16 Mi for whitted /
+ * key 0: image samples per wave (default 128 Mi = up to ~43 GB of wave state for the path integrator, 16 Mi for whitted /
  *        directlighting; never more than half of the device's free memory; a frame whose sample count exceeds it
  *        is cut into equal waves)
  * key 1: collect the kd-walk counters of PbrtB200Stats (default off: they cost time)

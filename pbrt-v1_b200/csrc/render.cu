@@ -56,7 +56,7 @@ static int fail(int code, const std::string &msg) {
 
 // ------------------------------------------------------------------------------------------
 // tunables (pbrt_b200_tunable)
-static int64_t g_waveSamples = 1 << 26;   // key 0: image samples per wave, path integrator (64 Mi: ~21.6 GB of wave state on a 180 GB part; C5 1387 / 1274 / 1225 ms per frame with 16 / 32 / 64 Mi, profiles/r02k_sweep_streams_waves.log: a wave is ~46 launches whose tails run almost empty, so fewer, larger waves waste less)
+static int64_t g_waveSamples = 1 << 27;   // key 0: image samples per wave, path integrator (128 Mi: up to ~43 GB of wave state on a 180 GB part, never more than half of the free memory; C5 1387 / 1274 / 1225 / 1194 / 1184 ms per frame with 16 / 32 / 64 / 128 / 256 Mi, profiles/r02k_sweep_streams_waves.log, r02l_sweep_waves.log: a wave is ~46 launches whose tails run almost empty, so fewer, larger waves waste less)
 static int64_t g_countKd = 0;             // key 1: collect kd-walk counters (costs a little time)
 static int64_t g_blocksPerSM = 12;        // key 2: resident CTAs per SM for the persistent kernels
 static int64_t g_overlap = 3;             // key 5: 0 = one stream; 1 = a vertex's shadow + probe traversal on a second stream beside k_path_continue and the next closest-hit launch; 2 = only the MIS probes on the second stream, beside the shadow rays; 3 (default) = 1 with the probes on a third stream.  C3 is issue bound (+1 %), the big trees wait on L2 and two traversal kernels side by side fill each other's stalls: C4 237.3 -> 224.8 ms, C5 1542 -> 1396 ms per frame (profiles/r02j_sweep_streams.log)
