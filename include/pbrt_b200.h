@@ -424,7 +424,9 @@ int pbrt_b200_render_host(const PbrtB200Scene *scene, int device,
  *        given (depth first, default), 1 = sibling pairs packed in 128-byte treelets (same tree, same visits)
  * key 10: waves of one frame in flight at once (path integrator): 1 (default; 2 measured no gain), or 2 = frames of 2 Mi samples and more are cut
  *        into an even number of waves that alternate between two lanes (arena + streams each), so that one wave's
- *        nearly empty last launches overlap the other's kernels; 3 = two lanes whatever the size (tests) */
+ *        nearly empty last launches overlap the other's kernels; 3 = two lanes whatever the size (tests)
+ * key 11: percent of the L2 set aside as a persisting access window over the kd-tree nodes, read at
+ *        pbrt_b200_scene_create (default 0 = off; measured no gain) */
 int64_t pbrt_b200_tunable(int key, int64_t value);
 
 /* Per-kernel-class totals of the last pbrt_b200_render(): launches, summed

@@ -64,6 +64,7 @@ static int64_t g_debugCounts = 0;         // key 6: print each wave's queue size
 static int64_t g_reserved4 = 0;           // key 4: reserved (was the fused shade kernel's occupancy variant)
 static int64_t g_fastPath = 1;            // key 8: k_path_fast shades flat-triangle / matte vertices in one pass (0: general three-kernel pipeline only)
 static int64_t g_lanes = 1;               // key 10: waves of a frame in flight at once: 1 (default), or 2 (path integrator, frames of at least PB_LANE_MIN_SAMPLES samples; 3 = two lanes whatever the size, for tests).  Measured (profiles/r02n_sweep_lanes.log): two lanes with half-size waves C3 121.3 vs 119.8 ms, C4 211.9 vs 210.8, C5 1204.9 vs 1216.9, an 8-GPU rank's share (8.4 M samples) 16.07 vs 15.81 ms -- the three streams of one wave already fill most of what a second wave could, and persistent grids leave the other lane's CTAs little room before a launch's tail
+static int64_t g_l2Persist = 0;           // key 11: percent of the L2 set aside for a persisting access window over the kd-tree nodes (0: off, the default -- measured: 25 % changes nothing, 50 / 75 % cost C4 3 / 23 % and C5 5 / 38 % because the queues' streaming traffic loses the L2 it used; profiles/r02aa_sweep_l2_persist.log)
 static int64_t g_treelets = 0;            // key 9: device node order of the top-level tree: 1 = sibling pairs in line-sized treelets (pb_treelet.h), 0 = the reference's depth-first array (default: the re-ordering measured no gain, profiles/r02g_sweep_walk_variants.log)
 static int64_t g_primFrames = 1;          // key 7: precompute hit-independent BSDF / light-triangle frames at scene create (0: evaluate per hit)
 
@@ -2163,7 +2164,7 @@ const char *pbrt_b200_last_error(void) { return g_lastError.c_str(); }
 int64_t pbrt_b200_tunable(int key, int64_t value) {
   int64_t *p = key == 0 ? &g_waveSamples : key == 1 ? &g_countKd : key == 2 ? &g_blocksPerSM
                : key == 3 ? &g_profileKernels : key == 4 ? &g_reserved4 : key == 5 ? &g_overlap : key == 6 ? &g_debugCounts
-               : key == 7 ? &g_primFrames : key == 8 ? &g_fastPath : key == 9 ? &g_treelets : key == 10 ? &g_lanes : nullptr;
+               : key == 7 ? &g_primFrames : key == 8 ? &g_fastPath : key == 9 ? &g_treelets : key == 10 ? &g_lanes : key == 11 ? &g_l2Persist : nullptr;
   if (!p) return -1;
   int64_t prev = *p;
   if (value >= 0) *p = value;
@@ -2292,6 +2293,28 @@ int pbrt_b200_scene_create(const PbrtB200Scene *scene, int device, PbrtB200Handl
     sv.pairedNodes = 1;
   } else
     UP(upload(h, scene->nodes, scene->n_nodes, &sv.nodes));
+  if (g_l2Persist > 0 && scene->n_nodes > 0) {
+    // tunable 11: the kd-tree nodes as a persisting-L2 access window of this handle's streams, so that the wave's
+    // streaming queue traffic does not evict them (experiment; percent of the L2 the device may set aside)
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+      const size_t setAside = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize,
+                                               (size_t)prop.l2CacheSize * (size_t)std::min<int64_t>(g_l2Persist, 100) / 100);
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setAside);
+      const size_t bytes = (size_t)scene->n_nodes * sizeof(PbrtB200KdNode);
+      cudaStreamAttrValue attr;
+      memset(&attr, 0, sizeof(attr));
+      attr.accessPolicyWindow.base_ptr = (void *)sv.nodes;
+      attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+      attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)setAside / (double)attr.accessPolicyWindow.num_bytes);
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+      cudaStreamSetAttribute(h->auxStream, cudaStreamAttributeAccessPolicyWindow, &attr);
+      cudaStreamSetAttribute(h->auxStream2, cudaStreamAttributeAccessPolicyWindow, &attr);
+      cudaGetLastError();
+    }
+  }
   UP(upload(h, scene->prim_refs, scene->n_prim_refs, &sv.primRefs));
   UP(upload(h, scene->prims, scene->n_prims, &dprims));
   sv.prims = (const PrimQuad *)dprims;

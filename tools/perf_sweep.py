@@ -21,7 +21,7 @@ out = tempfile.mkdtemp(prefix="pbrt_tool_")   # (scene files are large: keep the
 sp = gen_scene(os.path.join(out, "sweep_%s.pbrt" % name), name, "--filename", os.path.join(out, "sweep.exr"), *gen[1:])
 sc = ffi.Scene(sp)
 lib = ffi.cuda()
-defaults = {k: lib.pbrt_b200_tunable(k, -1) for k in range(11)}
+defaults = {k: lib.pbrt_b200_tunable(k, -1) for k in range(12)}
 for var in variants:
     for k, v in defaults.items():
         if v >= 0:
