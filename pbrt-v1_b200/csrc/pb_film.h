@@ -17,15 +17,15 @@ PB_HD bool film_sample_weight(const SceneView &sv, const float *filterTable, flo
                               float imageY, int x, int y, float *wt) {
   float dImageX = imageX - 0.5f;
   float dImageY = imageY - 0.5f;
-  int x0 = pb_ceil2int(dImageX - sv.filterXW);
-  int x1 = pb_floor2int(dImageX + sv.filterXW);
-  int y0 = pb_ceil2int(dImageY - sv.filterYW);
-  int y1 = pb_floor2int(dImageY + sv.filterYW);
+  int x0 = pb_ceil2int_fin(dImageX - sv.filterXW);
+  int x1 = pb_floor2int_fin(dImageX + sv.filterXW);
+  int y0 = pb_ceil2int_fin(dImageY - sv.filterYW);
+  int y1 = pb_floor2int_fin(dImageY + sv.filterYW);
   if (x < x0 || x > x1 || y < y0 || y > y1) return false;
   float fx = fabsf((x - dImageX) * sv.filterInvXW * PB_FILTER_TABLE_SIZE);
-  int ifx = pb_imin(pb_floor2int(fx), PB_FILTER_TABLE_SIZE - 1);
+  int ifx = pb_imin(pb_floor2int_fin(fx), PB_FILTER_TABLE_SIZE - 1);
   float fy = fabsf((y - dImageY) * sv.filterInvYW * PB_FILTER_TABLE_SIZE);
-  int ify = pb_imin(pb_floor2int(fy), PB_FILTER_TABLE_SIZE - 1);
+  int ify = pb_imin(pb_floor2int_fin(fy), PB_FILTER_TABLE_SIZE - 1);
   *wt = filterTable[ify * PB_FILTER_TABLE_SIZE + ifx];
   return true;
 }
@@ -70,9 +70,9 @@ PB_HD void film_pixel_resolve(const FilmPixel &px, bool premultiply, float rgba[
 // film/image.cpp:148-156 for a pixel window used as the crop
 PB_HD void film_sample_extent(const SceneView &sv, int px0, int py0, int pw, int ph, int *xstart,
                               int *xend, int *ystart, int *yend) {
-  *xstart = pb_floor2int(px0 + .5f - sv.filterXW);
-  *xend = pb_floor2int(px0 + .5f + pw + sv.filterXW);
-  *ystart = pb_floor2int(py0 + .5f - sv.filterYW);
-  *yend = pb_floor2int(py0 + .5f + ph + sv.filterYW);
+  *xstart = pb_floor2int_fin(px0 + .5f - sv.filterXW);
+  *xend = pb_floor2int_fin(px0 + .5f + pw + sv.filterXW);
+  *ystart = pb_floor2int_fin(py0 + .5f - sv.filterYW);
+  *yend = pb_floor2int_fin(py0 + .5f + ph + sv.filterYW);
 }
 #endif

@@ -465,7 +465,7 @@ PB_NOINLINE Spec infinite_light_sample_is(const SceneView &sv, const PbrtB200Lig
   InfDist d = inf_dist(sv, light);
   float pdfs[2];
   float fu = dist1d_sample(d.uFunc, d.uCdf, d.nu, d.uFuncInt, u1, &pdfs[0]);
-  int u = pb_imin(pb_imax((int)fu, 0), d.nu - 1);
+  int u = pb_imin(pb_imax(pb_f2i(fu), 0), d.nu - 1);
   float fv = dist1d_sample(d.vFunc(u), d.vCdf(u), d.nv, d.vFuncInt[u], u2, &pdfs[1]);
   *wi = v3(0, 0, 0);
   if (pdfs[0] == 0.f || pdfs[1] == 0.f) { *pdf = 0.f; return spec(0.f); }
@@ -490,8 +490,8 @@ PB_NOINLINE float infinite_light_pdf_is(const SceneView &sv, const PbrtB200Light
   float theta = pb_acosf(pb_clamp(wi.z, -1.f, 1.f));
   float ph = pb_atan2f(wi.y, wi.x);
   float phi = (ph < 0.f) ? ph + 2.f * PB_PI : ph;
-  int u = pb_imin(pb_imax((int)(phi * PB_INV_TWOPI * d.nu), 0), d.nu - 1);
-  int v = pb_imin(pb_imax((int)(theta * PB_INV_PI * d.nv), 0), d.nv - 1);
+  int u = pb_imin(pb_imax(pb_f2i(phi * PB_INV_TWOPI * d.nu), 0), d.nu - 1);
+  int v = pb_imin(pb_imax(pb_f2i(theta * PB_INV_PI * d.nv), 0), d.nv - 1);
   return (d.uFunc[u] * d.vFunc(u)[v]) / (d.uFuncInt * d.vFuncInt[u]) * 1.f / (2.f * PB_PI * PB_PI * pb_sinf(theta));
 }
 PB_NOINLINE Spec infinite_light_sample_cosine(const SceneView &sv, const PbrtB200Light &light, const V3 &p, const V3 &n, float u1, float u2,

@@ -77,8 +77,23 @@ PB_HD float pb_clamp(float val, float low, float high) {
 // core/pbrt.h:622-635 (FAST_INT is off): the argument is promoted to double
 // Floor2Int / Ceil2Int (core/pbrt.h:622-635) take a double; for a float argument floorf / ceilf give the same
 // integer exactly (the floor of a float is a float), without the fp64 round trip
-PB_HD int pb_floor2int(float v) { return (int)floorf(v); }
-PB_HD int pb_ceil2int(float v) { return (int)ceilf(v); }
+// (int)x as the reference's x86 build performs it: cvttss2si returns the "integer indefinite" 0x80000000 for a NaN
+// and for every value outside [-2^31, 2^31); the device's cvt.rzi.s32.f32 returns 0 for a NaN and saturates.  Only
+// degenerate inputs differ (a NaN texture coordinate, an infinite film coordinate), but they decide which texel or
+// pixel such a sample lands on.
+PB_HD int pb_f2i(float v) {
+#ifdef __CUDA_ARCH__
+  return (v >= -2147483648.f && v < 2147483648.f) ? (int)v : (int)0x80000000;
+#else
+  return (int)v;
+#endif
+}
+PB_HD int pb_floor2int(float v) { return pb_f2i(floorf(v)); }
+PB_HD int pb_ceil2int(float v) { return pb_f2i(ceilf(v)); }
+// the same for arguments the caller knows to be finite and far inside the int range (film and sample coordinates):
+// the plain conversion, without the range test (the film gather converts per sample and pixel)
+PB_HD int pb_floor2int_fin(float v) { return (int)floorf(v); }
+PB_HD int pb_ceil2int_fin(float v) { return (int)ceilf(v); }
 
 struct V3 {
   float x, y, z;

@@ -188,7 +188,7 @@ PB_NOINLINE Spec mip_ewa(const SceneView &sv, const PbrtB200Texture &t, float s,
       float ss = is - s;
       float r2 = A * ss * ss + B * ss * t_ + C * t_ * t_;
       if (r2 < 1.f) {
-        float weight = sv.ewaLut[pb_imin((int)(r2 * PBRT_B200_EWA_LUT_SIZE), PBRT_B200_EWA_LUT_SIZE - 1)];
+        float weight = sv.ewaLut[pb_imin(pb_f2i(r2 * PBRT_B200_EWA_LUT_SIZE), PBRT_B200_EWA_LUT_SIZE - 1)];
         num = num + mip_texel(sv, t, level, is, it) * weight;
         den += weight;
       }

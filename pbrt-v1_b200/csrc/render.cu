@@ -324,7 +324,7 @@ k_generate(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
       // skipped (no ray), the others enter the ray queue compacted (nSlots is a multiple of 32, so
       // whole warps reach the ballot)
       float2 corner = wp.corners[pix];
-      int cx = pb_floor2int(corner.x), cy = pb_floor2int(corner.y);
+      int cx = pb_floor2int_fin(corner.x), cy = pb_floor2int_fin(corner.y);
       wb.pixel[slot] = (uint32_t)(cx + 32768) | ((uint32_t)(cy + 32768) << 16);
       CameraSample cs;
       bool valid = bc_camera_sample(sv, corner.x, corner.y, k, pb_key(cx, cy, 0, 3), wp.xs, wp.xe, wp.ys, wp.ye, &cs);
@@ -358,8 +358,8 @@ k_generate(const __grid_constant__ SceneView sv, const WaveBuffers wb, const Wav
       bool valid = false;
       if (inWave) {
         float dImageX = film_image_coord(cs.imageX) - 0.5f, dImageY = film_image_coord(cs.imageY) - 0.5f;
-        int x0 = pb_ceil2int(dImageX - sv.filterXW), x1 = pb_floor2int(dImageX + sv.filterXW);
-        int y0 = pb_ceil2int(dImageY - sv.filterYW), y1 = pb_floor2int(dImageY + sv.filterYW);
+        int x0 = pb_ceil2int_fin(dImageX - sv.filterXW), x1 = pb_floor2int_fin(dImageX + sv.filterXW);
+        int y0 = pb_ceil2int_fin(dImageY - sv.filterYW), y1 = pb_floor2int_fin(dImageY + sv.filterYW);
         valid = x1 >= wp.tx0 && x0 < wp.tx1 && y1 >= wp.ty0 && y0 < wp.ty1;
       }
       uint32_t qi = warp_push(&wb.counts[0], valid);
@@ -588,6 +588,25 @@ __device__ __forceinline__ uint64_t slot_key(const WaveKeyInfo &wd, uint32_t slo
   if (wd.bc == 1) return pb_key_bc(x, y, k, stream == 0 ? 2 : stream);   // patterns: the sample's stream 2
   return pb_key(x, y, k, stream);
 }
+// `L += pathThroughput * UniformSampleOneLight(...)` (path.cpp:100-112) runs at EVERY vertex of the reference's loop,
+// also when the estimate is black: x * 0 is 0 for a finite throughput and NaN for a NaN or infinite one, so a path
+// whose throughput went bad (a degenerate BSDF) turns its sample into a NaN sample -- which Scene::Render then reports
+// and sets to black (scene.cpp:58-74) -- at the next vertex.  The wavefront skips adding black estimates, so it adds
+// that NaN explicitly: pb_bad_channels() of the throughput travels in bits 5-7 of a compact pending record, and a
+// vertex that leaves no record applies it at once.  (Found by the 4000-seed GPU fuzz: two scenes where the twin
+// counted NaN samples and the GPU kept a finite value, profiles/r02ac_fuzz_*.log.)
+__device__ __forceinline__ uint32_t pb_bad_channels(const Spec &t) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    if (!(fabsf(t.c[c]) <= 3.402823466e+38f)) m |= 1u << c;   // NaN or +-inf
+  return m;
+}
+__device__ __forceinline__ void pb_add_bad_zero(Spec *L, uint32_t mask) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    if (mask & (1u << c)) L->c[c] = L->c[c] + __uint_as_float(0x7fc00000u);
+}
 // Fold the slot's pending direct-lighting record (path integrator) into L.
 __device__ __forceinline__ void path_fold_pending(const SceneView &sv, const WaveBuffers &wb,
                                                   uint32_t slot, uint32_t *flags, Spec *L) {
@@ -596,8 +615,10 @@ __device__ __forceinline__ void path_fold_pending(const SceneView &sv, const Wav
   const float4 r = wb.prec[slot];
   const uint32_t rf = __float_as_uint(r.w);
   if (rf & 16) {
-    // compact record: rgb holds pathThroughput * (nLights * Ld), valid when the shadow ray got through
+    // compact record: rgb holds pathThroughput * (nLights * Ld), valid when the shadow ray got through; otherwise
+    // the reference added pathThroughput * 0 (bits 5-7: channels where that is not 0)
     if (rf & 1) *L = *L + spec3(r.x, r.y, r.z);
+    else if (rf & 0xe0u) pb_add_bad_zero(L, (rf >> 5) & 7u);
     return;
   }
   PathState tmp;
@@ -867,8 +888,9 @@ __device__ __forceinline__ void path_fast_vertex(const SceneView &sv, const Wave
         Spec Ld = direct_value(direct.termA, direct.termB, true, false);
         Spec add = pendT * ((float)sv.nLights * Ld);
         flags |= 1u << 9;
-        wb.prec[slot] = make_float4(add.c[0], add.c[1], add.c[2], __uint_as_float(4u | 16u));
-      }
+        wb.prec[slot] = make_float4(add.c[0], add.c[1], add.c[2], __uint_as_float(4u | 16u | (pb_bad_channels(pendT) << 5)));
+      } else
+        pb_add_bad_zero(&st.L, pb_bad_channels(pendT));   // black estimate, no ray: L += pathThroughput * 0 now
     }
     wb.plf[slot] = make_float4(st.L.c[0], st.L.c[1], st.L.c[2], __uint_as_float(flags));
     wb.ptc[slot] = make_float4(st.T.c[0], st.T.c[1], st.T.c[2], __uint_as_float(st.rng.ctr));
@@ -1045,7 +1067,15 @@ k_path_direct(const __grid_constant__ SceneView sv, const WaveBuffers wb, const 
             Spec Ld = direct_value(direct.termA, direct.termB, true, false);
             Spec add = st.pendT * ((float)sv.nLights * Ld);
             reinterpret_cast<uint32_t *>(&wb.plf[slot])[3] = flags | (1u << 9);
-            wb.prec[slot] = make_float4(add.c[0], add.c[1], add.c[2], __uint_as_float(4u | 16u));
+            wb.prec[slot] = make_float4(add.c[0], add.c[1], add.c[2],
+                                        __uint_as_float(4u | 16u | (pb_bad_channels(st.pendT) << 5)));
+          } else if (const uint32_t bad = pb_bad_channels(st.pendT)) {
+            // black estimate, no ray, and a throughput that is not finite: L += pathThroughput * 0 is a NaN
+            // (rare: L lives in the slot's record, which this kernel otherwise only reads the flag word of)
+            const float4 lf = wb.plf[slot];
+            Spec L = spec3(lf.x, lf.y, lf.z);
+            pb_add_bad_zero(&L, bad);
+            wb.plf[slot] = make_float4(L.c[0], L.c[1], L.c[2], lf.w);
           }
         }
       }
@@ -1108,7 +1138,17 @@ k_path_continue(const __grid_constant__ SceneView sv, const WaveBuffers wb, cons
         } else {
           Surface sf;
           surface_load<G>(sv, rec, j, &sf);
-          if (specOnly) path_vertex_direct_skip(sv, key0, st);   // k_path_direct never saw this vertex
+          if (specOnly) {
+            path_vertex_direct_skip(sv, key0, st);   // k_path_direct never saw this vertex
+            // (its estimate is black; the reference still added pathThroughput * 0 to L)
+            if (sv.nLights != 0)
+              if (const uint32_t bad = pb_bad_channels(st.T)) {
+                const float4 lf = wb.plf[slot];
+                Spec L = spec3(lf.x, lf.y, lf.z);
+                pb_add_bad_zero(&L, bad);
+                wb.plf[slot] = make_float4(L.c[0], L.c[1], L.c[2], lf.w);
+              }
+          }
           pushNext = path_vertex_continue<G>(sv, key0, st, ray, sf, &next);
         }
         wb.ptc[slot] = make_float4(st.T.c[0], st.T.c[1], st.T.c[2], __uint_as_float(st.rng.ctr));
@@ -1348,8 +1388,8 @@ __global__ void k_film_reach(const __grid_constant__ SceneView sv, const WaveBuf
     for (int k = 0; k < spp; ++k) {
       if (wb.imageX[s0 + k] == PB_BC_INVALID_COORD) continue;   // culled (tile mode)
       float dImageX = wb.imageX[s0 + k] - 0.5f, dImageY = wb.imageY[s0 + k] - 0.5f;
-      x0 = min(x0, pb_ceil2int(dImageX - sv.filterXW)); x1 = max(x1, pb_floor2int(dImageX + sv.filterXW));
-      y0 = min(y0, pb_ceil2int(dImageY - sv.filterYW)); y1 = max(y1, pb_floor2int(dImageY + sv.filterYW));
+      x0 = min(x0, pb_ceil2int_fin(dImageX - sv.filterXW)); x1 = max(x1, pb_floor2int_fin(dImageX + sv.filterXW));
+      y0 = min(y0, pb_ceil2int_fin(dImageY - sv.filterYW)); y1 = max(y1, pb_floor2int_fin(dImageY + sv.filterYW));
     }
     auto pack = [](int v) { return (unsigned long long)(uint16_t)(max(-32768, min(32767, v)) + 32768); };
     wb.reach[p] = pack(x0) | (pack(x1) << 16) | (pack(y0) << 32) | (pack(y1) << 48);
@@ -1369,10 +1409,10 @@ __device__ __forceinline__ void film_gather_part(const SceneView &sv, const Wave
     int py = rowFirst + idx / win.width;
     FilmPixel *fpx = &film[(size_t)(py - win.y0) * win.width + (px - win.x0)];
     FilmPixel acc = *fpx;
-    int sx0 = max(pb_floor2int(px + .5f - sv.filterXW) - 1, wd.xs);
-    int sx1 = min(pb_floor2int(px + .5f + sv.filterXW) + 1, wd.xe - 1);
-    int sy0 = max(pb_floor2int(py + .5f - sv.filterYW) - 1, wd.ys);
-    int sy1 = min(pb_floor2int(py + .5f + sv.filterYW) + 1, wd.ye - 1);
+    int sx0 = max(pb_floor2int_fin(px + .5f - sv.filterXW) - 1, wd.xs);
+    int sx1 = min(pb_floor2int_fin(px + .5f + sv.filterXW) + 1, wd.xe - 1);
+    int sy0 = max(pb_floor2int_fin(py + .5f - sv.filterYW) - 1, wd.ys);
+    int sy1 = min(pb_floor2int_fin(py + .5f + sv.filterYW) + 1, wd.ye - 1);
     bool touched = false;
     for (int sy = sy0; sy <= sy1; ++sy)
       for (int sx = sx0; sx <= sx1; ++sx) {
@@ -2411,10 +2451,10 @@ static WavePart tile_part(const SceneView &sv, const PbrtB200Window &frame, cons
   memset(&wp, 0, sizeof(wp));
   int fxs, fxe, fys, fye;
   film_sample_extent(sv, frame.x0, frame.y0, frame.width, frame.height, &fxs, &fxe, &fys, &fye);
-  wp.xs = std::max(fxs, pb_floor2int(t.x0 + .5f - sv.filterXW) - 1);
-  wp.xe = std::min(fxe, pb_floor2int(t.x0 + t.width - 1 + .5f + sv.filterXW) + 2);
-  wp.ys = std::max(fys, pb_floor2int(t.y0 + .5f - sv.filterYW) - 1);
-  wp.ye = std::min(fye, pb_floor2int(t.y0 + t.height - 1 + .5f + sv.filterYW) + 2);
+  wp.xs = std::max(fxs, pb_floor2int_fin(t.x0 + .5f - sv.filterXW) - 1);
+  wp.xe = std::min(fxe, pb_floor2int_fin(t.x0 + t.width - 1 + .5f + sv.filterXW) + 2);
+  wp.ys = std::max(fys, pb_floor2int_fin(t.y0 + .5f - sv.filterYW) - 1);
+  wp.ye = std::min(fye, pb_floor2int_fin(t.y0 + t.height - 1 + .5f + sv.filterYW) + 2);
   wp.tile = 1;
   wp.tx0 = t.x0; wp.ty0 = t.y0; wp.tx1 = t.x0 + t.width; wp.ty1 = t.y0 + t.height;
   return wp;

@@ -25,5 +25,6 @@ diff = np.any(a.view(np.uint32) != b.view(np.uint32), axis=1)
 print("lib %s: %d of %d samples differ" % (os.environ.get("PBRT_B200_LIB", "default"), int(diff.sum()), len(diff)))
 for i in np.nonzero(diff)[0][:8]:
     print("  sample %d: gpu %s twin %s  ulp diff %s" % (i, a[i], b[i], np.abs(a[i].view(np.int32).astype(np.int64) - b[i].view(np.int32).astype(np.int64))))
-for k in ("camera_rays", "intersect_rays", "shadow_rays", "points_shaded", "interior_visits", "leaf_visits", "prim_refs_read", "prim_tests"):
+for k in ("camera_rays", "intersect_rays", "shadow_rays", "points_shaded", "interior_visits", "leaf_visits", "prim_refs_read", "prim_tests",
+          "nan_samples", "negative_samples", "infinite_samples"):
     print("  %-16s gpu %d twin %d %s" % (k, st[k], st_t[k], "" if st[k] == st_t[k] else "<-- differs"))
