@@ -494,3 +494,56 @@ def test_parser_vocabulary_and_numbers_follow_the_reference_lexer(ffi):
         assert np.array_equal(out[:n].view(np.uint32), exp.view(np.uint32)), (text, want, out[:n])
         compared += 1
     assert compared >= 500, compared
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/core/pbrtparse.y"), reason="needs the reference tree")
+def test_parser_statement_shapes_follow_the_reference_grammar(tmp_path):
+    """The shapes of the statements, read off the TEXT of core/pbrtparse.y:294-574: which directives take a quoted
+    name + parameter list, which a fixed count of numbers, which a 16-entry array.  A scene that follows the
+    grammar loads; the same scene with one number too few in a fixed-count directive does not."""
+    import subprocess
+    y = open("/root/reference/core/pbrtparse.y").read()
+    rules = dict((m.group(1), m.group(2).split()) for m in
+                 re.finditer(r"^(?:ri_stmt:|\|)\s*([A-Z]+)((?:[ \t]+(?:STRING|paramlist|num_array|real_num_array|NUM))*)[ \t]*$", y, re.M))
+    assert rules["LOOKAT"] == ["NUM"] * 9 and rules["ROTATE"] == ["NUM"] * 4 and rules["SCALE"] == ["NUM"] * 3
+    assert rules["TRANSLATE"] == ["NUM"] * 3 and rules["CONCATTRANSFORM"] == ["num_array"] and rules["TRANSFORM"] == ["real_num_array"]
+    for d in ("ACCELERATOR", "AREALIGHTSOURCE", "CAMERA", "FILM", "LIGHTSOURCE", "MATERIAL", "PIXELFILTER", "SAMPLER", "SHAPE",
+              "SURFACEINTEGRATOR", "VOLUMEINTEGRATOR", "VOLUME"):
+        assert rules[d] == ["STRING", "paramlist"], d
+    for d in ("COORDINATESYSTEM", "COORDSYSTRANSFORM", "OBJECTBEGIN", "OBJECTINSTANCE", "SEARCHPATH"):
+        assert rules[d] == ["STRING"], d
+    for d in ("ATTRIBUTEBEGIN", "ATTRIBUTEEND", "IDENTITY", "OBJECTEND", "REVERSEORIENTATION", "TRANSFORMBEGIN", "TRANSFORMEND",
+              "WORLDBEGIN", "WORLDEND"):
+        assert rules[d] == [], d
+    names = {"LOOKAT": "LookAt", "ROTATE": "Rotate", "SCALE": "Scale", "TRANSLATE": "Translate",
+             "CONCATTRANSFORM": "ConcatTransform", "TRANSFORM": "Transform"}
+    ident16 = "1 0 0 0 0 1 0 0 0 0 1 0 0 0 0 1"
+
+    def stmt(d, drop=0):
+        if rules[d] in (["num_array"], ["real_num_array"]):
+            vals = ident16.split()
+            return "%s [%s]" % (names[d], " ".join(vals[:16 - drop]))
+        n = len(rules[d]) - drop
+        base = {"LOOKAT": "0 0 5 0 0 0 0 1 0", "ROTATE": "30 0 1 0", "SCALE": "1 2 1", "TRANSLATE": "0 .5 0"}[d].split()
+        return "%s %s" % (names[d], " ".join(base[:n]))
+
+    def scene(bad=None):
+        pre = [stmt("LOOKAT", 1 if bad == "LOOKAT" else 0)]
+        body = [stmt(d, 1 if bad == d else 0) for d in ("ROTATE", "SCALE", "TRANSLATE", "CONCATTRANSFORM", "TRANSFORM")]
+        return "\n".join(pre + ['Camera "perspective" "float fov" [40]', 'Film "image" "integer xresolution" [4] "integer yresolution" [4] "string filename" ["g.exr"]',
+                                 'Sampler "stratified" "integer xsamples" [1] "integer ysamples" [1]', 'SurfaceIntegrator "whitted"', "WorldBegin",
+                                 'LightSource "point" "color I" [1 1 1]', "AttributeBegin", 'CoordinateSystem "here"'] + body +
+                         ['CoordSysTransform "here"', 'Material "matte"', 'Shape "sphere" "float radius" [1]', "AttributeEnd", "WorldEnd"]) + "\n"
+
+    code = ("import sys; sys.path.insert(0, %r)\nfrom parity_util import load_ffi\nffi = load_ffi()\n"
+            "sc = ffi.Scene(sys.argv[1]); print('loaded', sc.n_prims)\n" % os.path.join(ROOT, "tests"))
+
+    def loads(text, tag):
+        p = tmp_path / ("g_%s.pbrt" % tag)
+        p.write_text(text)
+        r = subprocess.run([sys.executable, "-c", code, str(p)], capture_output=True, text=True)
+        return r.returncode == 0 and "loaded 1" in r.stdout
+
+    assert loads(scene(), "ok")
+    for d in ("LOOKAT", "ROTATE", "SCALE", "TRANSLATE", "CONCATTRANSFORM", "TRANSFORM"):
+        assert not loads(scene(bad=d), d), d
