@@ -515,6 +515,13 @@ def test_parser_statement_shapes_follow_the_reference_grammar(tmp_path):
     for d in ("ATTRIBUTEBEGIN", "ATTRIBUTEEND", "IDENTITY", "OBJECTEND", "REVERSEORIENTATION", "TRANSFORMBEGIN", "TRANSFORMEND",
               "WORLDBEGIN", "WORLDEND"):
         assert rules[d] == [], d
+    # parameter-list type words (pbrtparse.y:557-565), in the reference's decoding order -- it matters: the test is
+    # a prefix match (strncmp), and "float" / "integer" ... share no prefix, so the set is what must agree
+    types = re.findall(r'TRY_DECODING_TYPE\("([a-z]+)",', y)
+    assert sorted(types) == sorted(["float", "integer", "bool", "point", "vector", "normal", "string", "texture", "color"])
+    psrc = open(os.path.join(ROOT, "pbrt-v1_b200", "host", "parser.cpp")).read()
+    for tname in types:
+        assert ('{"%s", PT_' % tname) in psrc, tname
     names = {"LOOKAT": "LookAt", "ROTATE": "Rotate", "SCALE": "Scale", "TRANSLATE": "Translate",
              "CONCATTRANSFORM": "ConcatTransform", "TRANSFORM": "Transform"}
     ident16 = "1 0 0 0 0 1 0 0 0 0 1 0 0 0 0 1"
