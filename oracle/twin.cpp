@@ -554,3 +554,58 @@ extern "C" int pbrt_twin_mailbox_study(const PbrtB200Scene *scene, const float *
   }
   return PBRT_B200_OK;
 }
+
+// The 8-byte todo entries of the GPU walk (csrc/pb_kd_warp.cuh) rest on an invariant of KdTreeAccel::Intersect's loop
+// (accelerators/kdtree.cpp:313-403): whenever an entry is popped, its stored tmin equals the tmax that is current at
+// that moment, bit for bit.  This walks the reference's loop with full 12-byte entries and counts the pops where that
+// is not so (returns the count; pops[0] = number of pops examined).
+extern "C" uint64_t pbrt_twin_stack_invariant(const PbrtB200Scene *scene, const float *rays, uint64_t n, uint64_t *pops) {
+  SceneView sv;
+  *pops = 0;
+  if (!build_view(*scene, &sv) || sv.nInstances != 0) return ~0ull;
+  uint64_t bad = 0;
+  for (uint64_t r = 0; r < n; ++r) {
+    Ray ray;
+    ray.o = v3(rays[8 * r], rays[8 * r + 1], rays[8 * r + 2]);
+    ray.d = v3(rays[8 * r + 3], rays[8 * r + 4], rays[8 * r + 5]);
+    ray.mint = rays[8 * r + 6]; ray.maxt = rays[8 * r + 7];
+    float tmin, tmax;
+    if (sv.nNodes == 0 || !bbox_intersect_p(sv.bmin, sv.bmax, ray, &tmin, &tmax)) continue;
+    V3 invDir = v3(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
+    uint32_t todoNode[PB_KD_STACK]; float todoTmin[PB_KD_STACK], todoTmax[PB_KD_STACK];
+    int todoPos = 0;
+    uint32_t node = 0;
+    Hit hit; hit.prim = -1; hit.inst = -1;
+    for (;;) {
+      uint32_t w0, w1;
+      for (;;) {
+        w0 = sv.nodes[node].word0; w1 = sv.nodes[node].word1;
+        if ((w0 & 3u) == 3u) break;
+        int axis = (int)(w0 & 3u);
+        float split; { uint32_t b = w0; memcpy(&split, &b, 4); }
+        float o = ray.o[axis], d = ray.d[axis];
+        float tplane = (split - o) * invDir[axis];
+        bool belowFirst = (o < split) || (o == split && d >= 0);
+        uint32_t firstChild = belowFirst ? node + 1 : w1, secondChild = belowFirst ? w1 : node + 1;
+        if (tplane > tmax || tplane <= 0) node = firstChild;
+        else if (tplane < tmin) node = secondChild;
+        else { todoNode[todoPos] = secondChild; todoTmin[todoPos] = tplane; todoTmax[todoPos] = tmax; ++todoPos;
+               node = firstChild; tmax = tplane; }
+      }
+      uint32_t nPrims = w0 >> 2;
+      for (uint32_t i = 0; i < nPrims; ++i) {
+        uint32_t prim = (nPrims == 1) ? w1 : sv.primRefs[w1 + i];
+        kd_test_prim<false>(sv, prim, ray, &hit);
+      }
+      if (todoPos == 0) break;
+      --todoPos;
+      ++*pops;
+      uint32_t a, b;
+      memcpy(&a, &todoTmin[todoPos], 4); memcpy(&b, &tmax, 4);
+      if (a != b) ++bad;
+      node = todoNode[todoPos]; tmin = todoTmin[todoPos]; tmax = todoTmax[todoPos];
+      if (ray.maxt < tmin) break;
+    }
+  }
+  return bad;
+}

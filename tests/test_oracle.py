@@ -554,3 +554,30 @@ def test_parser_statement_shapes_follow_the_reference_grammar(tmp_path):
     assert loads(scene(), "ok")
     for d in ("LOOKAT", "ROTATE", "SCALE", "TRANSLATE", "CONCATTRANSFORM", "TRANSFORM"):
         assert not loads(scene(bad=d), d), d
+
+
+def test_todo_entry_tmin_is_the_current_tmax(ffi, tmp_path):
+    """The GPU walk keeps 8-byte todo entries (node, tmax) instead of the reference's (node, tmin, tmax): when an
+    entry is popped, its tmin is -- bit for bit -- the tmax current at that moment.  Checked on the reference's own
+    loop over camera and random bounce rays of two trees."""
+    lib = ffi.twin()
+    lib.pbrt_twin_stack_invariant.restype = C.c_uint64
+    lib.pbrt_twin_stack_invariant.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    for name, extra in (("c3", ()), ("c4", ("--nphi", "160", "--ntheta", "80"))):
+        sp = gen_scene(str(tmp_path / ("inv_%s.pbrt" % name)), name, "--res", "48", "48", "--spp", "2", "2",
+                       "--filename", str(tmp_path / "inv.exr"), *extra)
+        scene = ffi.Scene(sp)
+        rays, _ = ffi.twin_camera_rays(scene)
+        prim, t, _, _ = ffi.twin_intersect(scene, rays)
+        ok = prim >= 0
+        rng = np.random.default_rng(9)
+        p = rays[ok, :3] + rays[ok, 3:6] * t[ok, None]
+        d = rng.normal(size=p.shape).astype(np.float32)
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        sec = np.zeros((p.shape[0], 8), np.float32)
+        sec[:, :3] = p; sec[:, 3:6] = d; sec[:, 6] = 1e-3; sec[:, 7] = np.inf
+        allrays = np.ascontiguousarray(np.concatenate([rays, sec]), np.float32)
+        pops = C.c_uint64(0)
+        bad = lib.pbrt_twin_stack_invariant(scene.ptr, allrays.ctypes.data, allrays.shape[0], C.byref(pops))
+        assert bad == 0 and pops.value > 1000, (name, bad, pops.value)
+        scene.close()
